@@ -1,0 +1,126 @@
+"""ctypes binding of oracle/liboracle.so (the plain-C restatement, oracle/osm_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/osm_oracle.h for the parity-pinning statement.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+WIN = {"rect": 0, "han": 1, "ham": 2, "gau": 3, "sin": 4, "tri": 5, "bar": 6}
+
+
+class Frontend(C.Structure):
+    _fields_ = [("sample_rate", C.c_double), ("frame_size_sec", C.c_double),
+                ("frame_step_sec", C.c_double), ("preemph_on", C.c_int),
+                ("preemph_k", C.c_double), ("win_func", C.c_int), ("win_sigma", C.c_double),
+                ("win_gain", C.c_double), ("win_offset", C.c_double),
+                ("zero_pad_symmetric", C.c_int)]
+
+
+class Melspec(C.Structure):
+    _fields_ = [("n_bands", C.c_int), ("lofreq", C.c_double), ("hifreq", C.c_double),
+                ("use_power", C.c_int), ("htkcompatible", C.c_int)]
+
+
+class Mfcc(C.Structure):
+    _fields_ = [("first_mfcc", C.c_int), ("last_mfcc", C.c_int), ("cep_lifter", C.c_double),
+                ("melfloor", C.c_double), ("htkcompatible", C.c_int)]
+
+
+class Plp(C.Structure):
+    _fields_ = [("lp_order", C.c_int), ("first_cc", C.c_int), ("last_cc", C.c_int),
+                ("do_log", C.c_int), ("do_aud", C.c_int), ("do_inv_log", C.c_int),
+                ("do_idft", C.c_int), ("do_lp", C.c_int), ("do_lp_to_ceps", C.c_int),
+                ("rasta", C.c_int), ("new_rasta", C.c_int), ("rasta_upper", C.c_double),
+                ("rasta_lower", C.c_double), ("cep_lifter", C.c_double),
+                ("compression", C.c_double), ("melfloor", C.c_double),
+                ("htkcompatible", C.c_int)]
+
+
+def build(force=False):
+    """Compile liboracle.so with gcc (oracle/Makefile)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    src = [os.path.join(_HERE, f) for f in ("osm_oracle.c", "osm_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.osm_or_frame_size_samples.restype = C.c_long
+        L.osm_or_frame_step_samples.restype = C.c_long
+        L.osm_or_fft_size.restype = C.c_long
+        L.osm_or_fft_size.argtypes = [C.c_long]
+        L.osm_or_num_frames.restype = C.c_long
+        L.osm_or_num_frames.argtypes = [C.c_long, C.c_long, C.c_long]
+        L.osm_or_fft_frame_size_sec.restype = C.c_double
+        L.osm_or_mfcc_d_a.restype = C.c_long
+        L.osm_or_plp_d_a.restype = C.c_long
+        L.osm_or_delta.restype = C.c_long
+        L.osm_or_sma.restype = C.c_long
+    return _LIB
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float)) if a is not None else None
+
+
+# ---- config presets mirroring the shipped .conf files (values read from
+# /root/reference/config/mfcc/MFCC12_0_D_A.conf, config/plp/PLP_0_D_A.conf) ----
+
+def mfcc12_0_d_a(sample_rate):
+    fe = Frontend(sample_rate, 0.025, 0.010, 1, 0.97, WIN["ham"], 0.4, 1.0, 0.0, 0)
+    ms = Melspec(26, 0.0, 8000.0, 1, 1)
+    mf = Mfcc(0, 12, 22.0, 1e-8, 1)
+    return fe, ms, mf
+
+
+def geometry(fe, n_samples):
+    L = lib()
+    N = L.osm_or_frame_size_samples(C.byref(fe))
+    H = L.osm_or_frame_step_samples(C.byref(fe))
+    nfft = L.osm_or_fft_size(N)
+    T = L.osm_or_num_frames(n_samples, N, H)
+    return N, H, nfft, T
+
+
+def mfcc_d_a(pcm, sample_rate, n_chan=1, taps=False, cfg=None, delta_win=2, accel_win=2):
+    """int16 PCM [L*n_chan] -> float32 [T, 3*nMfcc] (static | delta | accel)."""
+    fe, ms, mf = cfg if cfg is not None else mfcc12_0_d_a(sample_rate)
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nS = pcm.size // n_chan
+    N, H, nfft, T = geometry(fe, nS)
+    K = mf.last_mfcc - mf.first_mfcc + 1
+    out = np.zeros((max(T, 0), 3 * K), np.float32)
+    tap_mag = np.zeros((max(T, 0), nfft // 2 + 1), np.float32) if taps else None
+    tap_mel = np.zeros((max(T, 0), ms.n_bands), np.float32) if taps else None
+    r = lib().osm_or_mfcc_d_a(C.byref(fe), C.byref(ms), C.byref(mf), C.c_int(delta_win),
+                              C.c_int(accel_win), pcm.ctypes.data_as(C.POINTER(C.c_int16)),
+                              C.c_long(nS), C.c_int(n_chan), _fp(out), _fp(tap_mag), _fp(tap_mel))
+    assert r == max(T, 0), (r, T)
+    return (out, tap_mag, tap_mel) if taps else out
+
+
+def delta(x, win):
+    x = np.ascontiguousarray(x, np.float32)
+    T, K = x.shape
+    out = np.zeros((T + win, K), np.float32)
+    r = lib().osm_or_delta(_fp(x), C.c_long(T), C.c_int(K), C.c_int(win), _fp(out))
+    return out[:r]
+
+
+def sma(x, sma_win=3, no_zero_sma=0):
+    x = np.ascontiguousarray(x, np.float32)
+    T, K = x.shape
+    out = np.zeros((T + (sma_win - 1) // 2, K), np.float32)
+    r = lib().osm_or_sma(_fp(x), C.c_long(T), C.c_int(K), C.c_int(sma_win), C.c_int(no_zero_sma), _fp(out))
+    return out[:r]

@@ -1,0 +1,473 @@
+/*
+ * osm_oracle.c -- CPU restatement of openSMILE's LLD hot path (see osm_oracle.h).
+ * TEST INFRASTRUCTURE ONLY: never linked into or imported by the product.
+ * All `file:line` citations are relative to /root/reference/src.
+ */
+#include "osm_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ------------------------------------------------------------------ geometry */
+
+/* core/winToVecProcessor.cpp:439-441: frameSizeFrames = (long)round(frameSize / T),
+ * T = 1/sampleRate as a double (level period). C round() = half away from zero. */
+long osm_or_frame_size_samples(const osm_or_frontend *fe)
+{
+  double T = 1.0 / fe->sample_rate;
+  return (long)round(fe->frame_size_sec / T);
+}
+
+/* core/winToVecProcessor.cpp:443-456 */
+long osm_or_frame_step_samples(const osm_or_frontend *fe)
+{
+  double T = 1.0 / fe->sample_rate;
+  double step = fe->frame_step_sec;
+  if (step == 0.0) step = fe->frame_size_sec;
+  long s = (long)round(step / T);
+  if (s == 0) s = osm_or_frame_size_samples(fe);
+  return s;
+}
+
+/* dspcore/transformFft.cpp:124-129 (+ smileutil/smileUtil.c:691-731): next power of two
+ * >= n, at least 4 */
+long osm_or_fft_size(long n)
+{
+  long p = 1;
+  while (p < n) p <<= 1;
+  if (p < 4) p = 4;
+  return p;
+}
+
+/* core/winToVecProcessor.cpp:868-877 with noPostEOIprocessing=1 + frameCenterSpecial=left:
+ * only complete frames are emitted: T = floor((L - size)/step) + 1 for L >= size else 0 */
+long osm_or_num_frames(long n_samples, long frame_size, long frame_step)
+{
+  if (n_samples < frame_size || frame_size <= 0 || frame_step <= 0) return 0;
+  return (n_samples - frame_size) / frame_step + 1;
+}
+
+/* dspcore/transformFft.cpp:78-85: the level's frameSizeSec is multiplied by nfft/frameSize
+ * (NOT replaced by nfft/fs) -- SURVEY.md H2 */
+double osm_or_fft_frame_size_sec(const osm_or_frontend *fe)
+{
+  long n = osm_or_frame_size_samples(fe);
+  long nfft = osm_or_fft_size(n);
+  double fss = fe->frame_size_sec; /* winToVecProcessor.cpp:563-564: c.frameSizeSec = frameSize */
+  if (nfft != n) fss *= (double)nfft / (double)n;
+  return fss;
+}
+
+/* ------------------------------------------------------------------ a-1 PCM -> float */
+
+/* smileutil/smileUtil.c:2520-2534 (monoMixdown=1, 16 bit): tmp = sum_c (float)x_c ;
+ * out = (tmp / (float)nChan) / (float)32767.0 */
+void osm_or_pcm16_to_float(const int16_t *pcm, long n_samples, int n_chan, float *out)
+{
+  for (long i = 0; i < n_samples; i++) {
+    float tmp = 0.0f;
+    for (int c = 0; c < n_chan; c++) tmp += (float)pcm[i * n_chan + c];
+    out[i] = (tmp / (float)n_chan) / (float)32767.0;
+  }
+}
+
+/* ------------------------------------------------------------------ a-4 window table */
+
+/* smileutil/smileUtil.c:1218-1349, dspcore/windower.cpp:159-217 (gain only; no sqrt /
+ * fade / xshift in the BASELINE configs) */
+void osm_or_window_table(int win_func, long N, double sigma, double gain, double *w)
+{
+  double NN = (double)N;
+  for (long n = 0; n < N; n++) {
+    double i = (double)n;
+    switch (win_func) {
+      case OSM_OR_WIN_HANN:  /* :1277-1288 */
+        w[n] = 0.5 * (1.0 - cos((2.0 * M_PI * i) / (NN - 1.0))); break;
+      case OSM_OR_WIN_HAMM:  /* :1291-1303 */
+        w[n] = 0.54 - 0.46 * cos((2.0 * M_PI * i) / (NN - 1.0)); break;
+      case OSM_OR_WIN_GAUSS: { /* :1334-1349 */
+        double s = sigma;
+        if (s <= 0.0) s = 0.01;
+        if (s > 0.5) s = 0.5;
+        double tmp = (i - (NN - 1.0) / 2.0) / (s * (NN - 1.0) / 2.0);
+        w[n] = exp(-0.5 * (tmp * tmp));
+        break; }
+      case OSM_OR_WIN_SINE:  /* :1306-1317 */
+        w[n] = sin((1.0 * M_PI * i) / (NN - 1.0)); break;
+      case OSM_OR_WIN_TRI:   /* :1232-1246 */
+        if (n < N / 2) w[n] = 2.0 * (double)(n + 1) / (double)N;
+        else w[n] = 2.0 * (double)(N - n) / (double)N;
+        break;
+      case OSM_OR_WIN_BARTLETT: /* :1261-1274 */
+        if (n < N / 2) w[n] = 2.0 * (double)n / (double)(N - 1);
+        else w[n] = 2.0 * (double)(N - 1 - n) / (double)(N - 1);
+        break;
+      default: w[n] = 1.0; break; /* rectangle :1218-1228 */
+    }
+  }
+  if (gain != 1.0) for (long n = 0; n < N; n++) w[n] *= gain; /* windower.cpp:192-196 */
+}
+
+/* ------------------------------------------------------------------ a-5 FFT */
+
+/* Real DFT with Ooura's output convention (dspcore/fftsg.c:104-122):
+ *   a[2k] = R[k] = sum_j x[j] cos(2 pi j k / n),  a[2k+1] = I[k] = sum_j x[j] sin(2 pi j k / n)
+ *   (0 < k < n/2),  a[0] = R[0],  a[1] = R[n/2].
+ * Computed in double with an iterative radix-2 complex FFT, rounded to float at the end. */
+static void fft_c2c_double(double *re, double *im, long n)
+{
+  /* bit reversal */
+  for (long i = 1, j = 0; i < n; i++) {
+    long bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { double t = re[i]; re[i] = re[j]; re[j] = t; t = im[i]; im[i] = im[j]; im[j] = t; }
+  }
+  for (long len = 2; len <= n; len <<= 1) {
+    double ang = 2.0 * M_PI / (double)len; /* e^{+i ang}: Ooura's forward sign */
+    for (long i = 0; i < n; i += len) {
+      for (long k = 0; k < len / 2; k++) {
+        double wr = cos(ang * (double)k), wi = sin(ang * (double)k);
+        double ur = re[i + k], ui = im[i + k];
+        double vr = re[i + k + len / 2] * wr - im[i + k + len / 2] * wi;
+        double vi = re[i + k + len / 2] * wi + im[i + k + len / 2] * wr;
+        re[i + k] = ur + vr; im[i + k] = ui + vi;
+        re[i + k + len / 2] = ur - vr; im[i + k + len / 2] = ui - vi;
+      }
+    }
+  }
+}
+
+static void rdft_packed(const float *x, long n, float *a)
+{
+  double *re = (double *)malloc(sizeof(double) * n);
+  double *im = (double *)calloc(n, sizeof(double));
+  for (long i = 0; i < n; i++) re[i] = (double)x[i];
+  fft_c2c_double(re, im, n);
+  a[0] = (float)re[0];
+  a[1] = (float)re[n / 2];
+  for (long k = 1; k < n / 2; k++) { a[2 * k] = (float)re[k]; a[2 * k + 1] = (float)im[k]; }
+  free(re); free(im);
+}
+
+/* one frame through a-3 .. a-6 */
+void osm_or_frame_to_mag(const osm_or_frontend *fe, const float *x, long N, long nfft,
+                         const double *win, float *fft_packed, float *mag)
+{
+  float *y = (float *)malloc(sizeof(float) * N);
+  float *z = (float *)calloc(nfft, sizeof(float));
+  float *a = fft_packed ? fft_packed : (float *)malloc(sizeof(float) * nfft);
+
+  /* a-3 dspcore/vectorPreemphasis.cpp:89-108 (de=0): y[0]=(1-k)*x[0]; y[n]=x[n]-k*x[n-1] */
+  if (fe->preemph_on) {
+    float k = (float)fe->preemph_k; /* :55 k = (FLOAT_DMEM)getDouble("k") */
+    y[0] = (1 - k) * x[0];
+    for (long n = 1; n < N; n++) y[n] = x[n] - k * x[n - 1];
+  } else {
+    memcpy(y, x, sizeof(float) * N);
+  }
+  /* a-4 dspcore/windower.cpp:221-229: dst = src * (float)w + (float)offset */
+  float off = (float)fe->win_offset;
+  for (long n = 0; n < N; n++) y[n] = y[n] * (float)win[n] + off;
+
+  /* a-5 dspcore/transformFft.cpp:175-196: zero padding (end, or symmetric) */
+  long pad = fe->zero_pad_symmetric ? (nfft - N) / 2 : 0;
+  for (long n = 0; n < N; n++) z[n + pad] = y[n];
+  rdft_packed(z, nfft, a);
+
+  /* a-6 dspcore/fftmagphase.cpp:215-221 */
+  mag[0] = fabsf(a[0]);
+  for (long n = 2; n < nfft; n += 2) mag[n / 2] = sqrtf(a[n] * a[n] + a[n + 1] * a[n + 1]);
+  mag[nfft / 2] = fabsf(a[1]);
+
+  if (!fft_packed) free(a);
+  free(y); free(z);
+}
+
+/* ------------------------------------------------------------------ a-7 mel filterbank */
+
+typedef struct {
+  long n_bins, n_lo, n_hi;
+  int n_bands;
+  float *coef;      /* per bin rising-slope weight */
+  long *chan_map;   /* per bin: lower band index, -1, or -3 */
+  float *cfs;       /* nBands+2 centre frequencies in mel */
+  double *band_hz;  /* nBands band centres in Hz (field info, used by cPlp) */
+} mel_bank;
+
+/* smileutil/smileUtil.c:1139-1142 (SPECTSCALE_MEL fwd) */
+static double mel_fwd(double x) { return x > 0.0 ? 1127.0 * log(1.0 + x / 700.0) : 0.0; }
+/* smileutil/smileUtil.c:1197-1198 (inverse) */
+static double mel_inv(double x) { return 700.0 * (exp(x / 1127.0) - 1.0); }
+
+/* lldcore/melspec.cpp:184-455, standard (non-ERB) triangular bank, specScale=mel.
+ * float/double casts follow the reference line by line. */
+static void mel_design(const osm_or_melspec *ms, long blocksize, double frame_size_sec, mel_bank *mb)
+{
+  int nBands = ms->n_bands;
+  mb->n_bins = blocksize; mb->n_bands = nBands;
+  mb->coef = (float *)calloc(blocksize, sizeof(float));
+  mb->chan_map = (long *)malloc(sizeof(long) * blocksize);
+  mb->cfs = (float *)malloc(sizeof(float) * (nBands + 2));
+  mb->band_hz = (double *)malloc(sizeof(double) * nBands);
+
+  float N = (float)((blocksize - 1) * 2);                 /* :217 */
+  float F0 = (float)(1.0 / frame_size_sec);               /* :220 */
+  float Fs = (float)(N / frame_size_sec);                 /* :221 */
+  float M = (float)nBands;
+  float lofreq = (float)ms->lofreq, hifreq = (float)ms->hifreq; /* melspec.hpp:48 FLOAT_DMEM */
+  if ((lofreq < 0.0) || (lofreq > Fs / 2.0) || (lofreq > hifreq)) lofreq = 0.0;      /* :224-225 */
+  if ((hifreq < lofreq) || (hifreq > Fs / 2.0) || (hifreq <= 0.0)) hifreq = Fs / (float)2.0; /* :226-227 */
+  float LoF = (float)mel_fwd(lofreq);                     /* :228-229 */
+  float HiF = (float)mel_fwd(hifreq);                     /* :230-231 */
+  long nLoF = (long)round((double)(lofreq / F0));         /* :232 + melspec.hpp:107-110 */
+  long nHiF = (long)round((double)(hifreq / F0));
+  if (nLoF > blocksize) nLoF = blocksize;
+  if (nHiF > blocksize) nHiF = blocksize;
+  if (nLoF < 0) nLoF = 0;
+  if (nHiF < 0) nHiF = 0;
+  mb->n_lo = nLoF; mb->n_hi = nHiF;
+
+  float mBandw = (HiF - LoF) / (M + (float)1.0);          /* :394 */
+  for (int m = 0; m <= nBands + 1; m++) mb->cfs[m] = LoF + (float)m * mBandw; /* :395-397 */
+  for (int m = 1; m <= nBands; m++) mb->band_hz[m - 1] = mel_inv(mb->cfs[m]); /* :408-411 */
+
+  /* channel map :427-438 ; NtoFmel(n,F0) = (float)mel_fwd((float)n * F0) (melspec.hpp:119-122) */
+  int m = 0;
+  for (long n = 0; n < blocksize; n++) {
+    if ((n <= nLoF) || (n >= nHiF)) mb->chan_map[n] = -3;
+    else {
+      while (mb->cfs[m] < (float)mel_fwd(((float)n) * F0)) {
+        if (m > nBands) break;
+        m++;
+      }
+      mb->chan_map[n] = m - 2;
+    }
+  }
+  /* rising slope weights :441-447 */
+  m = 0;
+  for (long n = nLoF; n < nHiF; n++) {
+    float nM = (float)mel_fwd(((float)n) * F0);
+    while ((nM > mb->cfs[m + 1]) && (m <= nBands)) m++;
+    mb->coef[n] = (mb->cfs[m + 1] - nM) / (mb->cfs[m + 1] - mb->cfs[m]);
+  }
+}
+
+static void mel_free(mel_bank *mb) { free(mb->coef); free(mb->chan_map); free(mb->cfs); free(mb->band_hz); }
+
+/* lldcore/melspec.cpp:519-570 */
+static void mel_apply(const osm_or_melspec *ms, const mel_bank *mb, const float *mag, float *dst)
+{
+  long Nsrc = mb->n_bins;
+  float *p = (float *)malloc(sizeof(float) * Nsrc);
+  if (ms->use_power) for (long n = 0; n < Nsrc; n++) p[n] = mag[n] * mag[n]; /* :520-527 */
+  else memcpy(p, mag, sizeof(float) * Nsrc);
+  memset(dst, 0, sizeof(float) * mb->n_bands);
+  for (long n = mb->n_lo; n < mb->n_hi; n++) {            /* :543-553 */
+    long m = mb->chan_map[n];
+    double a = (double)p[n] * (double)mb->coef[n];
+    if (m > -2) {
+      if (m > -1) dst[m] += (float)a;
+      if (m < mb->n_bands - 1) dst[m + 1] += p[n] - (float)a;
+    }
+  }
+  if (ms->htkcompatible) {                                /* :559-569 */
+    for (int m = 0; m < mb->n_bands; m++) {
+      if (ms->use_power) dst[m] *= (float)(32767.0 * 32767.0);
+      else dst[m] *= (float)32767.0;
+    }
+  }
+  free(p);
+}
+
+/* ------------------------------------------------------------------ a-8 MFCC */
+
+/* lldcore/mfcc.cpp:136-170 (tables) + :238-273 (per frame) */
+static void mfcc_apply(const osm_or_mfcc *mf, const float *mel, int nBands, float *dst)
+{
+  int first = mf->first_mfcc, last = mf->last_mfcc, nM = last - first + 1;
+  float melfloor = (float)mf->melfloor;
+  if (mf->htkcompatible) melfloor = 1.0f;                 /* :88-91 */
+  float cepLifter = (float)mf->cep_lifter;
+  float *cost = (float *)malloc(sizeof(float) * nBands * nM);
+  float *sint = (float *)malloc(sizeof(float) * nM);
+  double fnM = (double)nBands;
+  for (int i = first; i <= last; i++) {                   /* :146-152 */
+    double fi = (double)i;
+    for (int m = 0; m < nBands; m++)
+      cost[m + (i - first) * nBands] = (float)cos((double)M_PI * (fi / fnM) * ((double)m + 0.5));
+  }
+  for (int i = first; i <= last; i++) {                   /* :158-166 */
+    if (cepLifter > 0.0)
+      sint[i - first] = ((float)1.0 + cepLifter / (float)2.0 * sinf((float)M_PI * ((float)i) / cepLifter));
+    else sint[i - first] = 1.0f;
+  }
+  float *l = (float *)malloc(sizeof(float) * nBands);
+  for (int i = 0; i < nBands; i++) {                      /* :239-243 */
+    if (mel[i] < melfloor) l[i] = logf(melfloor);
+    else l[i] = logf(mel[i]);
+  }
+  float factor = (float)sqrt((double)2.0 / (double)nBands); /* :251 */
+  for (int i = first; i <= last; i++) {                   /* :252-272 */
+    int i0 = i - first;
+    float *outc = dst + i0;
+    if (mf->htkcompatible && (first == 0)) {
+      if (i == last) i0 = 0; else i0 += 1;
+    }
+    *outc = 0.0f;
+    for (int m = 0; m < nBands; m++) *outc += l[m] * cost[m + i0 * nBands];
+    *outc *= sint[i0] * factor;
+  }
+  free(cost); free(sint); free(l);
+}
+
+/* ------------------------------------------------------------------ a-13 / a-14 */
+
+static const float *row_clamped(const float *x, long T, int K, long t)
+{
+  /* core/dataMemoryLevel.cpp:1687-1708: indices < 0 replicate frame 0; at EOI indices >= T
+   * replicate frame T-1 */
+  if (t < 0) t = 0;
+  if (t > T - 1) t = T - 1;
+  return x + t * K;
+}
+
+/* dspcore/deltaRegression.cpp:139-146 over core/windowProcessor.cpp:85-119,167-230:
+ * reader window [t-W, t+W]; frames are emitted while the end padding is shorter than the
+ * window (core/dataMemoryLevel.cpp:1022-1026) => t = 0 .. T+W-1. */
+long osm_or_delta(const float *in, long T, int K, int W, float *out)
+{
+  if (T <= 0) return 0;
+  float norm = 0.0f;
+  for (int i = 1; i <= W; i++) norm += (float)i * (float)i; /* :77-79 */
+  norm *= 2.0;
+  long To = T + W;
+  for (long t = 0; t < To; t++) {
+    for (int k = 0; k < K; k++) {
+      if (W > 0) {
+        float num = 0.0f;
+        for (int i = 1; i <= W; i++) {
+          float delta = row_clamped(in, T, K, t + i)[k] - row_clamped(in, T, K, t - i)[k];
+          num += (float)i * delta;
+        }
+        out[t * K + k] = num / norm;
+      } else {
+        out[t * K + k] = row_clamped(in, T, K, t)[k] - row_clamped(in, T, K, t - 1)[k];
+      }
+    }
+  }
+  return To;
+}
+
+/* dspcore/contourSmoother.cpp:84-117 (window smaWin, centred) with the same edge rules */
+long osm_or_sma(const float *in, long T, int K, int smaWin, int noZeroSma, float *out)
+{
+  if (T <= 0) return 0;
+  int W = (smaWin - 1) / 2;
+  long To = T + W;
+  for (long t = 0; t < To; t++) {
+    for (int k = 0; k < K; k++) {
+      float x0 = row_clamped(in, T, K, t)[k];
+      if (noZeroSma) {
+        if (x0 != 0.0f) {
+          float sum = 0.0f; int cnt = 0;
+          for (int j = -W; j <= W; j++) {
+            float v = row_clamped(in, T, K, t + j)[k];
+            if (v != 0.0f) { sum += v; cnt++; }
+          }
+          out[t * K + k] = sum / (float)cnt;
+        } else out[t * K + k] = 0.0f;
+      } else {
+        float sum = 0.0f;
+        for (int j = -W; j <= W; j++) sum += row_clamped(in, T, K, t + j)[k];
+        out[t * K + k] = sum / (float)smaWin;
+      }
+    }
+  }
+  return To;
+}
+
+/* ------------------------------------------------------------------ whole chains */
+
+/* static features for all frames of one utterance via a per-frame callback */
+typedef void (*frame_fn)(void *ctx, const float *mag, long n_bins, float *dst);
+
+static long run_frames(const osm_or_frontend *fe, const int16_t *pcm, long L, int n_chan,
+                       frame_fn fn, void *ctx, int n_static, float *stat, float *tap_mag)
+{
+  long N = osm_or_frame_size_samples(fe), H = osm_or_frame_step_samples(fe);
+  long nfft = osm_or_fft_size(N), nb = nfft / 2 + 1;
+  long T = osm_or_num_frames(L, N, H);
+  if (T <= 0) return 0;
+  float *x = (float *)malloc(sizeof(float) * L);
+  osm_or_pcm16_to_float(pcm, L, n_chan, x);
+  double *win = (double *)malloc(sizeof(double) * N);
+  osm_or_window_table(fe->win_func, N, fe->win_sigma, fe->win_gain, win);
+  float *mag = (float *)malloc(sizeof(float) * nb);
+  for (long t = 0; t < T; t++) {
+    osm_or_frame_to_mag(fe, x + t * H, N, nfft, win, NULL, mag); /* a-2: frame t = [t*H, t*H+N) */
+    if (tap_mag) memcpy(tap_mag + t * nb, mag, sizeof(float) * nb);
+    fn(ctx, mag, nb, stat + t * n_static);
+  }
+  free(x); free(win); free(mag);
+  return T;
+}
+
+/* static [T x K] -> [T x 3K] = static | delta | delta-delta, concat truncated to T
+ * (other/vectorConcat.cpp:48-53 via core/dataReader.cpp:375-380: min over levels) */
+static void add_deltas(const float *stat, long T, int K, int dW, int aW, float *out)
+{
+  float *d = (float *)malloc(sizeof(float) * (T + dW) * K);
+  float *dd = (float *)malloc(sizeof(float) * (T + dW + aW) * K);
+  long Td = osm_or_delta(stat, T, K, dW, d);
+  osm_or_delta(d, Td, K, aW, dd);
+  for (long t = 0; t < T; t++) {
+    memcpy(out + t * 3 * K, stat + t * K, sizeof(float) * K);
+    memcpy(out + t * 3 * K + K, d + t * K, sizeof(float) * K);
+    memcpy(out + t * 3 * K + 2 * K, dd + t * K, sizeof(float) * K);
+  }
+  free(d); free(dd);
+}
+
+typedef struct { const osm_or_melspec *ms; const osm_or_mfcc *mf; mel_bank mb; float *mel; float *tap_mel; long t; } mfcc_ctx;
+
+static void mfcc_frame(void *vctx, const float *mag, long nb, float *dst)
+{
+  mfcc_ctx *c = (mfcc_ctx *)vctx;
+  (void)nb;
+  mel_apply(c->ms, &c->mb, mag, c->mel);
+  if (c->tap_mel) memcpy(c->tap_mel + c->t * c->ms->n_bands, c->mel, sizeof(float) * c->ms->n_bands);
+  mfcc_apply(c->mf, c->mel, c->ms->n_bands, dst);
+  c->t++;
+}
+
+long osm_or_mfcc_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const osm_or_mfcc *mf,
+                     int dW, int aW, const int16_t *pcm, long L, int n_chan,
+                     float *out, float *tap_mag, float *tap_mel)
+{
+  long N = osm_or_frame_size_samples(fe), H = osm_or_frame_step_samples(fe);
+  long nfft = osm_or_fft_size(N);
+  long T = osm_or_num_frames(L, N, H);
+  if (T <= 0) return 0;
+  int K = mf->last_mfcc - mf->first_mfcc + 1;
+  mfcc_ctx c; c.ms = ms; c.mf = mf; c.tap_mel = tap_mel; c.t = 0;
+  mel_design(ms, nfft / 2 + 1, osm_or_fft_frame_size_sec(fe), &c.mb);
+  c.mel = (float *)malloc(sizeof(float) * ms->n_bands);
+  float *stat = (float *)malloc(sizeof(float) * T * K);
+  run_frames(fe, pcm, L, n_chan, mfcc_frame, &c, K, stat, tap_mag);
+  add_deltas(stat, T, K, dW, aW, out);
+  free(stat); free(c.mel); mel_free(&c.mb);
+  return T;
+}
+
+long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const osm_or_plp *pl,
+                    int dW, int aW, const int16_t *pcm, long L, int n_chan,
+                    float *out, float *tap_mel)
+{
+  (void)fe; (void)ms; (void)pl; (void)dW; (void)aW; (void)pcm; (void)L; (void)n_chan; (void)out; (void)tap_mel;
+  return -1; /* filled in with the PLP row (a-9) */
+}
