@@ -1,0 +1,295 @@
+/*
+ * osm_b200.h -- C ABI of libosm_b200.so: the B200 (sm_100a) back end for openSMILE's
+ * per-frame low-level-descriptor (LLD) extraction path.
+ *
+ * Boundary.  In the reference every LLD component is a cSmileComponent
+ * subclass whose per-frame hook is called once per tick by cComponentManager::tick
+ * (src/core/componentManager.cpp:1233-1262):
+ *     cWinToVecProcessor::doProcess        src/include/core/winToVecProcessor.hpp:124-126
+ *     cVectorProcessor::processVector      src/include/core/vectorProcessor.hpp:98-129
+ *     cWindowProcessor::processBuffer      src/core/windowProcessor.cpp:124-146
+ * This library replaces the *numerics* of that sub-graph (wave level -> lld level) by block
+ * execution: the host side describes the component chain exactly as the .conf file does
+ * (one osm_b200_component per [instance:cType] section, same field names and defaults as
+ * the reference's ConfigType), osm_b200_plan_create() resolves
+ * the reader.dmLevel / writer.dmLevel wiring and compiles it into one fused CUDA plan, and
+ * osm_b200_plan_run_*() pushes a whole batch of utterances through it.
+ *
+ * Conventions (same spirit as progsrc/include/smileapi/SMILEapi.h:16-26,82-153):
+ *   - plain C, no exceptions cross the boundary, every call returns osm_b200_status;
+ *     osm_b200_last_error() returns a message owned by the library (thread local);
+ *   - plan handles are owned by the caller (create/destroy);
+ *   - *_device entry points take device pointers and a cudaStream_t passed as void*
+ *     (NULL = default stream) and are asynchronous; *_host entry points take host
+ *     buffers, do H2D / D2H themselves and return when the result is in `out`;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails
+ *     with OSM_B200_ERR_CUDA.
+ *
+ * Data layout.  PCM: all utterances of a batch packed back to back in one buffer,
+ * utterance u starting at sample-frame offset utt_offsets[u] (units: sample frames, i.e.
+ * one sample of every channel) and ending at utt_offsets[u+1]; interleaved channels,
+ * int16 little endian (cWaveSource, src/iocore/waveSource.cpp:217-345).  Offsets that are
+ * multiples of 8 sample frames get 16-byte vector loads, anything else still works.
+ * Output: float32 rows, row-major, one row per LLD frame (`lld` level layout,
+ * src/include/core/dataMemoryLevel.hpp:178-179), utterance u's rows starting at
+ * frame_offsets[u]; number of rows per utterance follows the reference's framer / EOI
+ * rules and is returned by osm_b200_plan_num_frames().
+ */
+#ifndef OSM_B200_H
+#define OSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSM_B200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define OSM_B200_API __attribute__((visibility("default")))
+#else
+#define OSM_B200_API
+#endif
+#define OSM_B200_NAME_LEN 64
+#define OSM_B200_MAX_INPUTS 8
+#define OSM_B200_MAX_LIST 16
+
+typedef enum {
+  OSM_B200_OK = 0,
+  OSM_B200_ERR_INVALID = 1,      /* bad argument / malformed graph          (cf. SMILE_INVALID_ARG) */
+  OSM_B200_ERR_UNSUPPORTED = 2,  /* valid openSMILE graph this back end does not fuse (yet)      */
+  OSM_B200_ERR_CUDA = 3,         /* CUDA runtime / device error, no device  (cf. SMILE_FAIL)       */
+  OSM_B200_ERR_NOMEM = 4
+} osm_b200_status;
+
+/* component types; names = the reference's registered component names
+ * (src/include/core/componentList.hpp:172-390) */
+typedef enum {
+  OSM_B200_C_WAVESOURCE = 0,     /* cWaveSource / cExternalAudioSource: defines the `wave` level */
+  OSM_B200_C_FRAMER,             /* cFramer             src/dspcore/framer.cpp:54-68               */
+  OSM_B200_C_VECTORPREEMPHASIS,  /* cVectorPreemphasis  src/dspcore/vectorPreemphasis.cpp:89-108  */
+  OSM_B200_C_WINDOWER,           /* cWindower           src/dspcore/windower.cpp:159-229          */
+  OSM_B200_C_TRANSFORMFFT,       /* cTransformFFT       src/dspcore/transformFft.cpp:165-223      */
+  OSM_B200_C_FFTMAGPHASE,        /* cFFTmagphase        src/dspcore/fftmagphase.cpp:179-292       */
+  OSM_B200_C_MELSPEC,            /* cMelspec            src/lldcore/melspec.cpp:184-573           */
+  OSM_B200_C_MFCC,               /* cMfcc               src/lldcore/mfcc.cpp:136-281              */
+  OSM_B200_C_PLP,                /* cPlp                src/lldcore/plp.cpp:276-593               */
+  OSM_B200_C_SPECTRAL,           /* cSpectral           src/lldcore/spectral.cpp:586-1555         */
+  OSM_B200_C_ENERGY,             /* cEnergy             src/lldcore/energy.cpp:152-187            */
+  OSM_B200_C_MZCR,               /* cMZcr               src/lldcore/mzcr.cpp:109-157              */
+  OSM_B200_C_ACF,                /* cAcf                src/dspcore/acf.cpp:170-354               */
+  OSM_B200_C_PITCHACF,           /* cPitchACF           src/lldcore/pitchACF.cpp:137-361          */
+  OSM_B200_C_DELTAREGRESSION,    /* cDeltaRegression    src/dspcore/deltaRegression.cpp:113-175   */
+  OSM_B200_C_CONTOURSMOOTHER,    /* cContourSmoother    src/dspcore/contourSmoother.cpp:84-117    */
+  OSM_B200_C_VECTORCONCAT,       /* cVectorConcat       src/other/vectorConcat.cpp:48-53          */
+  OSM_B200_C_VECTOROPERATION,    /* cVectorOperation    src/other/vectorOperation.cpp:130 (ll1)   */
+  OSM_B200_C_COUNT_
+} osm_b200_component_type;
+
+/* window functions, cWindower.winFunc (src/dspcore/windower.cpp:60-80) */
+typedef enum {
+  OSM_B200_WIN_RECTANGLE = 0, OSM_B200_WIN_HANNING, OSM_B200_WIN_HAMMING, OSM_B200_WIN_GAUSS,
+  OSM_B200_WIN_SINE, OSM_B200_WIN_TRIANGLE, OSM_B200_WIN_BARTLETT
+} osm_b200_winfunc;
+
+typedef enum { OSM_B200_PCM_S16 = 0, OSM_B200_PCM_F32 = 1 } osm_b200_pcm_format;
+
+/* ---- per-type parameter blocks.  Field names and defaults = the reference's config
+ * schema; osm_b200_component_defaults() fills the defaults. ---- */
+
+typedef struct {            /* cWaveSource (src/iocore/waveSource.cpp) */
+  double  sampleRate;       /* Hz, from the WAV header                                   */
+  int32_t nChannels;        /* channels in the PCM buffer                                */
+  int32_t monoMixdown;      /* 1: average channels (config/shared/standard_wave_input.conf.inc:19) */
+  int32_t format;           /* osm_b200_pcm_format                                       */
+  char    outFieldName[OSM_B200_NAME_LEN]; /* "pcm" (standard_wave_input.conf.inc:20)     */
+} osm_b200_wavesource;
+
+typedef struct {            /* cFramer */
+  double  frameSize;        /* 0.025 */
+  double  frameStep;        /* 0 = frameSize */
+  int32_t frameCenterSpecialLeft; /* 1 (only `left` is supported) */
+  int32_t noPostEOIprocessing;    /* 1 */
+} osm_b200_framer;
+
+typedef struct { double k; int32_t de; } osm_b200_vectorpreemphasis;  /* 0.97, 0 */
+
+typedef struct {            /* cWindower */
+  int32_t winFunc;          /* osm_b200_winfunc, default Hanning */
+  double  gain, offset, sigma;    /* 1, 0, 0.4 */
+} osm_b200_windower;
+
+typedef struct { int32_t inverse; int32_t zeroPadSymmetric; } osm_b200_transformfft; /* 0, 1 */
+
+typedef struct {            /* cFFTmagphase */
+  int32_t magnitude, phase, normalise, power, dBpsd;  /* 1,0,0,0,0 */
+} osm_b200_fftmagphase;
+
+typedef struct {            /* cMelspec */
+  int32_t nBands;           /* 26 */
+  double  lofreq, hifreq;   /* 20, 8000 */
+  int32_t usePower;         /* 0 */
+  int32_t htkcompatible;    /* 1 */
+} osm_b200_melspec;
+
+typedef struct {            /* cMfcc */
+  int32_t firstMfcc, lastMfcc;  /* 1, 12 */
+  double  melfloor;         /* 1e-8 */
+  int32_t doLog;            /* 1 */
+  double  cepLifter;        /* 22 */
+  int32_t htkcompatible;    /* 1 */
+} osm_b200_mfcc;
+
+typedef struct {            /* cPlp */
+  int32_t lpOrder;          /* 5 */
+  int32_t nCeps;            /* -1 */
+  int32_t firstCC, lastCC;  /* 1, -1 */
+  int32_t doLog, doAud, RASTA, newRASTA, doInvLog, doIDFT, doLP, doLpToCeps; /* 1,1,0,0,1,1,1,1 */
+  double  rastaUpperCutoff, rastaLowerCutoff;  /* 29, 1 */
+  double  cepLifter;        /* 0 */
+  double  compression;      /* 0.33 */
+  double  melfloor;         /* 9.3e-10 */
+  int32_t htkcompatible;    /* 1 */
+} osm_b200_plp;
+
+typedef struct {            /* cSpectral (subset of switches used by eGeMAPS / ComParE) */
+  int32_t squareInput;      /* 1 */
+  int32_t nBands;  double bandLo[OSM_B200_MAX_LIST], bandHi[OSM_B200_MAX_LIST];   /* bands[] */
+  int32_t nSlopes; double slopeLo[OSM_B200_MAX_LIST], slopeHi[OSM_B200_MAX_LIST]; /* slopes[] */
+  int32_t nRollOff; double rollOff[OSM_B200_MAX_LIST];                            /* rollOff[] */
+  int32_t flux, centroid, maxPos, minPos, entropy, standardDeviation, variance, skewness,
+          kurtosis, slope, alphaRatio, hammarbergIndex, sharpness, harmonicity, flatness;
+  int32_t normBandEnergies, buggyRollOff, oldSlopeScale, useLogSpectrum;
+  double  freqRangeLo, freqRangeHi;  /* freqRange = lo-hi, 0-0 = full */
+  double  specFloor;        /* 1e-7 */
+} osm_b200_spectral;
+
+typedef struct {            /* cEnergy */
+  int32_t htkcompatible, rms, energy2, log;  /* 0,1,0,1 */
+  double  escaleLog, escaleRms, escaleSquare, ebiasLog, ebiasRms, ebiasSquare; /* 1,1,1,0,0,0 */
+} osm_b200_energy;
+
+typedef struct { int32_t zcr, mcr, amax, maxmin, dc; } osm_b200_mzcr; /* 1,1,1,1,0 */
+
+typedef struct {            /* cAcf */
+  int32_t usePower, cepstrum, inverse, cosLifterCepstrum, expBeforeAbs, symmetricData,
+          acfCepsNormOutput, oldCompatCepstrum, absCepstrum; /* 1,0,0,0,1,1,1,0,0 */
+} osm_b200_acf;
+
+typedef struct {            /* cPitchACF */
+  double  maxPitch;         /* 500 */
+  int32_t voiceProb, voiceQual, HNR, HNRdB, linHNR, F0, F0raw, F0env; /* 1,0,0,0,0,0,0,0 */
+  double  voicingCutoff;    /* 0.55 */
+} osm_b200_pitchacf;
+
+typedef struct {            /* cDeltaRegression */
+  int32_t deltawin;         /* 2 */
+  int32_t absOutput, halfWaveRect, onlyInSegments, zeroSegBound, relativeDelta; /* 0,0,0,1,0 */
+} osm_b200_deltaregression;
+
+typedef struct { int32_t smaWin; int32_t noZeroSma; } osm_b200_contoursmoother; /* 3, 0 */
+
+typedef struct { int32_t operation; } osm_b200_vectoroperation; /* 0 = ll1 (L1 norm / sum) */
+
+/* one `[name:cType]` section */
+typedef struct {
+  int32_t type;                                  /* osm_b200_component_type */
+  char    name[OSM_B200_NAME_LEN];               /* instance name (diagnostics only) */
+  int32_t n_inputs;                              /* reader.dmLevel = a;b;c */
+  char    reader_dmLevel[OSM_B200_MAX_INPUTS][OSM_B200_NAME_LEN];
+  char    writer_dmLevel[OSM_B200_NAME_LEN];
+  /* cDataProcessor naming fields (src/core/dataProcessor.cpp:41-48,249-325).  nameAppend ""
+   * selects the type's default ("mfcc", "de", "sma", "fftMag", ...); copyInputName default 1. */
+  char    nameAppend[OSM_B200_NAME_LEN];
+  int32_t copyInputName;
+  union {
+    osm_b200_wavesource wavesource;
+    osm_b200_framer framer;
+    osm_b200_vectorpreemphasis vectorpreemphasis;
+    osm_b200_windower windower;
+    osm_b200_transformfft transformfft;
+    osm_b200_fftmagphase fftmagphase;
+    osm_b200_melspec melspec;
+    osm_b200_mfcc mfcc;
+    osm_b200_plp plp;
+    osm_b200_spectral spectral;
+    osm_b200_energy energy;
+    osm_b200_mzcr mzcr;
+    osm_b200_acf acf;
+    osm_b200_pitchacf pitchacf;
+    osm_b200_deltaregression deltaregression;
+    osm_b200_contoursmoother contoursmoother;
+    osm_b200_vectoroperation vectoroperation;
+  } u;
+} osm_b200_component;
+
+typedef struct osm_b200_plan osm_b200_plan;
+
+/* ---- library ---- */
+OSM_B200_API int32_t     osm_b200_abi_version(void);
+/* sizeof(osm_b200_component) as compiled into the library: bindings in other languages
+ * (ctypes, cgo, JNI) assert it against their own mirror of the struct */
+OSM_B200_API int32_t     osm_b200_sizeof_component(void);
+OSM_B200_API const char *osm_b200_last_error(void);
+/* number of usable CUDA devices (0 = none; compute entry points will then fail) */
+OSM_B200_API int32_t     osm_b200_device_count(void);
+
+/* fill `c` with the reference's defaults for `type` (everything else zeroed) */
+OSM_B200_API osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c);
+
+/* ---- plan ---- */
+/* Compile the component graph that produces `output_level` into a fused plan bound to CUDA
+ * device `device`.  The graph must contain exactly one OSM_B200_C_WAVESOURCE.
+ * device < 0 creates a description-only plan (element names, geometry, frame-count rules)
+ * without touching CUDA; its run_* calls fail with OSM_B200_ERR_CUDA. */
+OSM_B200_API osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_comps,
+                                     const char *output_level, int32_t device,
+                                     osm_b200_plan **plan);
+OSM_B200_API void            osm_b200_plan_destroy(osm_b200_plan *plan);
+
+/* output row width (elements of the output level) and names of its elements, formed by the
+ * reference's naming rules (src/core/dataProcessor.cpp:249-325), e.g. "pcm_fftMag_mfcc[1]" */
+OSM_B200_API int32_t     osm_b200_plan_num_elements(const osm_b200_plan *plan);
+OSM_B200_API const char *osm_b200_plan_element_name(const osm_b200_plan *plan, int32_t idx);
+/* frame period of the output level in seconds (cFramer.frameStep) */
+OSM_B200_API double      osm_b200_plan_frame_period(const osm_b200_plan *plan);
+/* geometry resolved at plan time */
+OSM_B200_API int32_t     osm_b200_plan_frame_size_samples(const osm_b200_plan *plan);
+OSM_B200_API int32_t     osm_b200_plan_frame_step_samples(const osm_b200_plan *plan);
+OSM_B200_API int32_t     osm_b200_plan_fft_size(const osm_b200_plan *plan);
+
+/* rows the reference would emit on the output level for an utterance of n sample frames
+ * (bit-exact integer rule: framer with noPostEOIprocessing, window processors' EOI padding,
+ * concat = min over inputs) */
+OSM_B200_API int64_t     osm_b200_plan_num_frames(const osm_b200_plan *plan, int64_t n_sample_frames);
+
+/* exclusive prefix sums over utterances: frame_offsets[0..n_utt] (host arrays) */
+OSM_B200_API osm_b200_status osm_b200_plan_frame_offsets(const osm_b200_plan *plan,
+                                            const int64_t *utt_offsets, int32_t n_utt,
+                                            int64_t *frame_offsets);
+
+/* ---- execution ---- */
+/* Device-resident batch.  d_pcm / d_out are device pointers; utt_offsets / frame_offsets are
+ * HOST arrays of n_utt+1 entries (frame_offsets as returned by osm_b200_plan_frame_offsets).
+ * Asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+OSM_B200_API osm_b200_status osm_b200_plan_run_device(osm_b200_plan *plan, const void *d_pcm,
+                                         const int64_t *utt_offsets, int32_t n_utt,
+                                         const int64_t *frame_offsets, float *d_out,
+                                         void *stream);
+
+/* Host buffers: copies PCM to the device, runs, copies the rows back into `out`
+ * (frame_offsets[n_utt] * num_elements floats) and synchronises. */
+OSM_B200_API osm_b200_status osm_b200_plan_run_host(osm_b200_plan *plan, const void *pcm,
+                                       const int64_t *utt_offsets, int32_t n_utt,
+                                       const int64_t *frame_offsets, float *out);
+
+/* number of CUDA kernels the last run_* call launched (for bench.py's gpu_launches) */
+OSM_B200_API int32_t     osm_b200_plan_last_launch_count(const osm_b200_plan *plan);
+/* device time in ms of the fused LLD kernel(s) of the last run_* call, measured with CUDA
+ * events on the run's stream; blocks until the run has finished.  <0 if unavailable. */
+OSM_B200_API float       osm_b200_plan_last_kernel_ms(osm_b200_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSM_B200_H */

@@ -1,0 +1,10 @@
+"""opensmile_b200 -- B200 (sm_100a) back end for openSMILE's per-frame LLD extraction path.
+
+The compute path is the in-tree CUDA library libosm_b200.so behind the C ABI in
+include/osm_b200.h; importing this package does not load it, the first use of
+`opensmile_b200.plan.Plan` does (and fails loudly if it has not been built).
+"""
+from . import capi  # noqa: F401
+from .plan import Plan, components_mfcc12_0_d_a, pack_utterances  # noqa: F401
+
+__all__ = ["Plan", "components_mfcc12_0_d_a", "pack_utterances", "capi"]

@@ -1,0 +1,533 @@
+// api.cu -- the C ABI of libosm_b200.so (include/osm_b200.h): plan objects, device tables,
+// batch bookkeeping (tile lists, row offsets) and kernel launches.  No CPU fallback: every
+// compute entry point fails with OSM_B200_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace osm;
+
+namespace {
+
+thread_local std::string g_err;
+
+osm_b200_status fail(osm_b200_status st, const std::string &msg)
+{
+  g_err = msg;
+  return st;
+}
+
+osm_b200_status cuda_fail(cudaError_t e, const char *what)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error in %s: %s", what, cudaGetErrorString(e));
+  return fail(OSM_B200_ERR_CUDA, buf);
+}
+
+#define CU(call)                                              \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;   // elements
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n)
+  {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 64;
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct osm_b200_plan {
+  PlanDesc d;
+  int device = 0;
+  int numSMs = 0;
+  // constant tables on the device (one blob)
+  unsigned char *dConst = nullptr;
+  LldParams kp;            // template: table pointers + geometry filled at create
+  PostParams pp;
+  int tileF = 32;
+  bool staticDirect = false;   // static rows are written straight into the output rows
+  int identityOutCol = 0;
+  // batch bookkeeping
+  std::vector<int64_t> cachedUttOff;
+  PinBuf<long long> hMeta;     // uttOff | rowOff | statOff
+  PinBuf<TileRef> hTiles;
+  DevBuf<long long> dMeta;
+  DevBuf<TileRef> dTiles;
+  DevBuf<float> dStat;
+  size_t nTiles = 0;
+  long long totalRows = 0, totalStat = 0, totalSamples = 0;
+  cudaEvent_t evMetaDone = nullptr, evK0 = nullptr, evK1 = nullptr;
+  bool metaPending = false, timed = false;
+  // run_host buffers
+  DevBuf<int16_t> dPcm;
+  DevBuf<float> dOut;
+  cudaStream_t hostStream = nullptr;
+  int lastLaunches = 0;
+  LldLaunchInfo lastInfo{};
+};
+
+extern "C" {
+
+int32_t osm_b200_abi_version(void) { return OSM_B200_ABI_VERSION; }
+int32_t osm_b200_sizeof_component(void) { return (int32_t)sizeof(osm_b200_component); }
+
+const char *osm_b200_last_error(void) { return g_err.c_str(); }
+
+int32_t osm_b200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// defaults = the reference's ConfigType defaults
+osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
+{
+  if (!c || type < 0 || type >= OSM_B200_C_COUNT_) return fail(OSM_B200_ERR_INVALID, "bad component type");
+  memset(c, 0, sizeof *c);
+  c->type = type;
+  c->copyInputName = 1;
+  switch (type) {
+    case OSM_B200_C_WAVESOURCE:
+      c->u.wavesource.sampleRate = 16000; c->u.wavesource.nChannels = 1; c->u.wavesource.monoMixdown = 1;
+      c->u.wavesource.format = OSM_B200_PCM_S16; strcpy(c->u.wavesource.outFieldName, "pcm");
+      break;
+    case OSM_B200_C_FRAMER:
+      c->u.framer.frameSize = 0.025; c->u.framer.frameStep = 0.0;
+      c->u.framer.frameCenterSpecialLeft = 1; c->u.framer.noPostEOIprocessing = 1;
+      break;
+    case OSM_B200_C_VECTORPREEMPHASIS: c->u.vectorpreemphasis.k = 0.97; c->u.vectorpreemphasis.de = 0; break;
+    case OSM_B200_C_WINDOWER:
+      c->u.windower.winFunc = OSM_B200_WIN_HANNING; c->u.windower.gain = 1.0; c->u.windower.offset = 0.0;
+      c->u.windower.sigma = 0.4;
+      break;
+    case OSM_B200_C_TRANSFORMFFT: c->u.transformfft.inverse = 0; c->u.transformfft.zeroPadSymmetric = 1; break;
+    case OSM_B200_C_FFTMAGPHASE: c->u.fftmagphase.magnitude = 1; break;
+    case OSM_B200_C_MELSPEC:
+      c->u.melspec.nBands = 26; c->u.melspec.lofreq = 20; c->u.melspec.hifreq = 8000;
+      c->u.melspec.usePower = 0; c->u.melspec.htkcompatible = 1;
+      break;
+    case OSM_B200_C_MFCC:
+      c->u.mfcc.firstMfcc = 1; c->u.mfcc.lastMfcc = 12; c->u.mfcc.melfloor = 1e-8; c->u.mfcc.doLog = 1;
+      c->u.mfcc.cepLifter = 22; c->u.mfcc.htkcompatible = 1;
+      break;
+    case OSM_B200_C_PLP: {
+      auto &p = c->u.plp;
+      p.lpOrder = 5; p.nCeps = -1; p.firstCC = 1; p.lastCC = -1; p.doLog = 1; p.doAud = 1; p.RASTA = 0;
+      p.newRASTA = 0; p.doInvLog = 1; p.doIDFT = 1; p.doLP = 1; p.doLpToCeps = 1; p.rastaUpperCutoff = 29;
+      p.rastaLowerCutoff = 1; p.cepLifter = 0; p.compression = 0.33; p.melfloor = 9.3e-10; p.htkcompatible = 1;
+      break;
+    }
+    case OSM_B200_C_SPECTRAL: {
+      auto &s = c->u.spectral;
+      s.squareInput = 1; s.flux = 1; s.centroid = 1; s.maxPos = 1; s.minPos = 1; s.oldSlopeScale = 1;
+      s.specFloor = 1e-7;
+      break;
+    }
+    case OSM_B200_C_ENERGY: {
+      auto &e = c->u.energy;
+      e.rms = 1; e.log = 1; e.escaleLog = e.escaleRms = e.escaleSquare = 1.0;
+      break;
+    }
+    case OSM_B200_C_MZCR: c->u.mzcr.zcr = 1; c->u.mzcr.mcr = 1; c->u.mzcr.amax = 1; c->u.mzcr.maxmin = 1; break;
+    case OSM_B200_C_ACF: {
+      auto &a = c->u.acf;
+      a.usePower = 1; a.expBeforeAbs = 1; a.symmetricData = 1; a.acfCepsNormOutput = 1;
+      break;
+    }
+    case OSM_B200_C_PITCHACF: c->u.pitchacf.maxPitch = 500; c->u.pitchacf.voiceProb = 1; c->u.pitchacf.voicingCutoff = 0.55; break;
+    case OSM_B200_C_DELTAREGRESSION: c->u.deltaregression.deltawin = 2; c->u.deltaregression.zeroSegBound = 1; break;
+    case OSM_B200_C_CONTOURSMOOTHER: c->u.contoursmoother.smaWin = 3; break;
+    default: break;
+  }
+  return OSM_B200_OK;
+}
+
+static void build_twiddles(int M, std::vector<float2> &tw, int twOff[4])
+{
+  // factorisation must match Fact<M> in kernels.cu
+  int R[3] = {0, 0, 0}, ns = 0;
+  if (M == 256) { R[0] = 16; R[1] = 16; ns = 2; }
+  else if (M == 512) { R[0] = 8; R[1] = 8; R[2] = 8; ns = 3; }
+  else { R[0] = 16; R[1] = 16; R[2] = 4; ns = 3; }
+  int MS = M;
+  tw.clear();
+  for (int s = 0; s < 4; s++) twOff[s] = 0;
+  for (int s = 0; s < ns - 1; s++) {       // the last stage has no twiddles
+    const int stride = MS / R[s];
+    twOff[s] = (int)tw.size();
+    for (int j = 0; j < stride; j++)
+      for (int q = 0; q < R[s]; q++) {
+        const double ang = -2.0 * M_PI * (double)j * (double)q / (double)MS;
+        tw.push_back(make_float2((float)cos(ang), (float)sin(ang)));
+      }
+    MS = stride;
+  }
+}
+
+osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_comps,
+                                     const char *output_level, int32_t device, osm_b200_plan **out)
+{
+  if (!comps || n_comps <= 0 || !out) return fail(OSM_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  osm_b200_plan *pl = new (std::nothrow) osm_b200_plan();
+  if (!pl) return fail(OSM_B200_ERR_NOMEM, "out of memory");
+  std::string err;
+  osm_b200_status st = compile_graph(comps, n_comps, output_level, pl->d, err);
+  if (st != OSM_B200_OK) { delete pl; return fail(st, err); }
+  const PlanDesc &d = pl->d;
+  if (!lld_supported_fft(d.fe.nfft)) {
+    delete pl;
+    return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(d.fe.nfft) + " not supported (512, 1024, 2048)");
+  }
+  if (d.ops.size() != 1 || d.ops[0].kind != SOP_MFCC) { delete pl; return fail(OSM_B200_ERR_UNSUPPORTED, "only a single cMfcc static producer is supported"); }
+
+  if (device < 0) {
+    // description-only plan: geometry, names and frame-count rules without touching CUDA
+    // (used by host-side tooling and CPU-only tests); it can never run.
+    pl->device = -1;
+    *out = pl;
+    return OSM_B200_OK;
+  }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    delete pl;
+    return fail(OSM_B200_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) { delete pl; return fail(OSM_B200_ERR_INVALID, "bad device index"); }
+  pl->device = device;
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { osm_b200_plan_destroy(pl); return cuda_fail(e_, #call); } } while (0)
+  CUP(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUP(cudaGetDeviceProperties(&prop, device));
+  pl->numSMs = prop.multiProcessorCount;
+
+  // ---- pack constant tables ----
+  const FrontEnd &fe = d.fe;
+  const int M = fe.nfft / 2;
+  const MelBank &mb = d.mels[d.ops[0].mfcc.melIdx];
+  const MfccOp &mf = d.ops[0].mfcc;
+  pl->tileF = lld_tile_frames(fe.nfft);
+
+  LldParams &kp = pl->kp;
+  memset(&kp, 0, sizeof kp);
+  kp.nChan = fe.nChan;
+  kp.frameSize = fe.frameSize; kp.frameStep = fe.frameStep;
+  kp.sPad = (fe.frameStep % 2 == 0) ? 1 : 0;     // make the per-lane smem stride odd
+  kp.preemph = fe.preemph; kp.preDe = fe.preDe; kp.preK = fe.preK;
+  kp.oneMinusK = 1 - fe.preK;                     // (1-k), float arithmetic (vectorPreemphasis.cpp:94)
+  kp.winOffset = fe.winOffset; kp.hasWinOffset = fe.winOffset != 0.f;
+
+  std::vector<float2> winPairs(M, make_float2(0.f, 0.f));
+  std::vector<int> lut(M, 0);
+  for (int e = 0; e < M; e++) {
+    const int n = 2 * e;
+    if (n < fe.frameSize) winPairs[e].x = fe.window[n];
+    if (n + 1 < fe.frameSize) winPairs[e].y = fe.window[n + 1];
+    lut[e] = n + (n / fe.frameStep) * kp.sPad;
+  }
+  std::vector<float2> tw;
+  build_twiddles(M, tw, kp.twOff);
+  kp.twCount = (int)tw.size();
+  std::vector<float2> split(M / 2 + 1);
+  for (int k = 0; k <= M / 2; k++) {
+    const double ang = -2.0 * M_PI * (double)k / (double)fe.nfft;
+    split[k] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  kp.nBands = mb.nBands; kp.melScale = mb.outScale; kp.melUsePower = mb.usePower;
+  kp.nMfcc = mf.nMfcc; kp.melfloor = mf.melfloor; kp.logMelfloor = mf.logMelfloor; kp.doLog = mf.doLog;
+  // split the bands over the virtual warps, balancing visited bins (ranges bs..be)
+  {
+    const int nvw = lld_virtual_warps(fe.nfft);
+    const int totalBins = mb.rangeBegin[mb.nBands + 1] - mb.rangeBegin[0];
+    int b = 0;
+    kp.melSplit[0] = 0;
+    for (int w = 1; w <= nvw; w++) {
+      // advance b until the cumulative bin count reaches w/nvw of the total
+      const double target = (double)totalBins * w / nvw;
+      while (b < mb.nBands && (mb.rangeBegin[b + 1] - mb.rangeBegin[0]) < target) b++;
+      if (w == nvw) b = mb.nBands;
+      kp.melSplit[w] = b;
+    }
+    for (int w = nvw + 1; w <= kMaxVW; w++) kp.melSplit[w] = mb.nBands;
+  }
+
+  auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+  size_t o = 0;
+  const size_t oWin = o; o = up16(o + winPairs.size() * sizeof(float2));
+  const size_t oLut = o; o = up16(o + lut.size() * sizeof(int));
+  const size_t oTw = o; o = up16(o + (tw.size() + 1) * sizeof(float2));
+  const size_t oSplit = o; o = up16(o + split.size() * sizeof(float2));
+  const size_t oCoef = o; o = up16(o + mb.coef.size() * sizeof(float));
+  const size_t oRange = o; o = up16(o + mb.rangeBegin.size() * sizeof(int));
+  const size_t oDct = o; o = up16(o + mf.cosT.size() * sizeof(float));
+  const size_t oLift = o; o = up16(o + mf.liftFactor.size() * sizeof(float));
+  std::vector<unsigned char> blob(o, 0);
+  memcpy(&blob[oWin], winPairs.data(), winPairs.size() * sizeof(float2));
+  memcpy(&blob[oLut], lut.data(), lut.size() * sizeof(int));
+  if (!tw.empty()) memcpy(&blob[oTw], tw.data(), tw.size() * sizeof(float2));
+  memcpy(&blob[oSplit], split.data(), split.size() * sizeof(float2));
+  memcpy(&blob[oCoef], mb.coef.data(), mb.coef.size() * sizeof(float));
+  memcpy(&blob[oRange], mb.rangeBegin.data(), mb.rangeBegin.size() * sizeof(int));
+  memcpy(&blob[oDct], mf.cosT.data(), mf.cosT.size() * sizeof(float));
+  memcpy(&blob[oLift], mf.liftFactor.data(), mf.liftFactor.size() * sizeof(float));
+  CUP(cudaMalloc(&pl->dConst, o));
+  CUP(cudaMemcpy(pl->dConst, blob.data(), o, cudaMemcpyHostToDevice));
+  kp.winPairs = reinterpret_cast<const float2 *>(pl->dConst + oWin);
+  kp.sampLut = reinterpret_cast<const int *>(pl->dConst + oLut);
+  kp.twiddles = reinterpret_cast<const float2 *>(pl->dConst + oTw);
+  kp.splitTw = reinterpret_cast<const float2 *>(pl->dConst + oSplit);
+  kp.melCoef = reinterpret_cast<const float *>(pl->dConst + oCoef);
+  kp.melRange = reinterpret_cast<const int *>(pl->dConst + oRange);
+  kp.dctCos = reinterpret_cast<const float *>(pl->dConst + oDct);
+  kp.dctLift = reinterpret_cast<const float *>(pl->dConst + oLift);
+
+  const size_t smemNeed = lld_smem_bytes(kp, fe.nfft);
+  if (smemNeed > (size_t)prop.sharedMemPerBlockOptin) {
+    osm_b200_plan_destroy(pl);
+    return fail(OSM_B200_ERR_UNSUPPORTED, "configuration needs more shared memory than the device offers");
+  }
+
+  // ---- output groups ----
+  PostParams &pp = pl->pp;
+  memset(&pp, 0, sizeof pp);
+  pl->staticDirect = false;
+  for (const auto &g : d.groups)
+    if (g.stages.empty() && g.srcCol == 0 && g.n == d.nStatic) { pl->staticDirect = true; pl->identityOutCol = g.outCol; break; }
+  for (const auto &g : d.groups) {
+    if (g.stages.empty() && pl->staticDirect && g.srcCol == 0 && g.n == d.nStatic && g.outCol == pl->identityOutCol) continue;
+    if (pp.nGroups >= kMaxPostGroups) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many output groups"); }
+    PostGroup &pg = pp.groups[pp.nGroups++];
+    pg.srcCol = g.srcCol; pg.n = g.n; pg.outCol = g.outCol; pg.nStages = (int)g.stages.size();
+    for (size_t i = 0; i < g.stages.size(); i++) { pg.kind[i] = g.stages[i].kind; pg.win[i] = g.stages[i].win; pg.flags[i] = g.stages[i].flags; }
+  }
+  pp.frameSize = fe.frameSize; pp.frameStep = fe.frameStep;
+
+  CUP(cudaEventCreateWithFlags(&pl->evMetaDone, cudaEventDisableTiming));
+  CUP(cudaEventCreate(&pl->evK0));
+  CUP(cudaEventCreate(&pl->evK1));
+#undef CUP
+  *out = pl;
+  return OSM_B200_OK;
+}
+
+void osm_b200_plan_destroy(osm_b200_plan *pl)
+{
+  if (!pl) return;
+  if (pl->device < 0) { delete pl; return; }
+  cudaSetDevice(pl->device);
+  if (pl->hostStream) { cudaStreamSynchronize(pl->hostStream); cudaStreamDestroy(pl->hostStream); }
+  cudaDeviceSynchronize();
+  if (pl->dConst) cudaFree(pl->dConst);
+  pl->hMeta.release(); pl->hTiles.release(); pl->dMeta.release(); pl->dTiles.release(); pl->dStat.release();
+  pl->dPcm.release(); pl->dOut.release();
+  if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
+  if (pl->evK0) cudaEventDestroy(pl->evK0);
+  if (pl->evK1) cudaEventDestroy(pl->evK1);
+  delete pl;
+}
+
+int32_t osm_b200_plan_num_elements(const osm_b200_plan *pl) { return pl ? pl->d.nOut : 0; }
+
+const char *osm_b200_plan_element_name(const osm_b200_plan *pl, int32_t idx)
+{
+  if (!pl || idx < 0 || idx >= (int)pl->d.names.size()) return nullptr;
+  return pl->d.names[idx].c_str();
+}
+
+double osm_b200_plan_frame_period(const osm_b200_plan *pl) { return pl ? pl->d.fe.frameStepSec : 0.0; }
+int32_t osm_b200_plan_frame_size_samples(const osm_b200_plan *pl) { return pl ? pl->d.fe.frameSize : 0; }
+int32_t osm_b200_plan_frame_step_samples(const osm_b200_plan *pl) { return pl ? pl->d.fe.frameStep : 0; }
+int32_t osm_b200_plan_fft_size(const osm_b200_plan *pl) { return pl ? pl->d.fe.nfft : 0; }
+
+int64_t osm_b200_plan_num_frames(const osm_b200_plan *pl, int64_t n) { return pl ? desc_num_frames(pl->d, n) : 0; }
+
+osm_b200_status osm_b200_plan_frame_offsets(const osm_b200_plan *pl, const int64_t *utt_offsets, int32_t n_utt,
+                                            int64_t *frame_offsets)
+{
+  if (!pl || !utt_offsets || !frame_offsets || n_utt < 0) return fail(OSM_B200_ERR_INVALID, "null argument");
+  frame_offsets[0] = 0;
+  for (int u = 0; u < n_utt; u++) {
+    if (utt_offsets[u + 1] < utt_offsets[u]) return fail(OSM_B200_ERR_INVALID, "utt_offsets must be non-decreasing");
+    frame_offsets[u + 1] = frame_offsets[u] + desc_num_frames(pl->d, utt_offsets[u + 1] - utt_offsets[u]);
+  }
+  return OSM_B200_OK;
+}
+
+// (re)build the per-batch tables when the utterance layout changed
+static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, int nUtt, const int64_t *frameOff,
+                                     cudaStream_t st)
+{
+  const PlanDesc &d = pl->d;
+  const bool same = (int)pl->cachedUttOff.size() == nUtt + 1 &&
+                    memcmp(pl->cachedUttOff.data(), uttOff, sizeof(int64_t) * (nUtt + 1)) == 0;
+  if (!same) {
+    if (pl->metaPending) { CU(cudaEventSynchronize(pl->evMetaDone)); pl->metaPending = false; }
+    const size_t nm = (size_t)(nUtt + 1);
+    CU(pl->hMeta.reserve(3 * nm));
+    long long *hU = pl->hMeta.p, *hR = hU + nm, *hS = hR + nm;
+    size_t nTiles = 0;
+    hR[0] = 0; hS[0] = 0;
+    for (int u = 0; u < nUtt; u++) {
+      if (uttOff[u + 1] < uttOff[u]) return fail(OSM_B200_ERR_INVALID, "utt_offsets must be non-decreasing");
+      const int64_t L = uttOff[u + 1] - uttOff[u];
+      const int64_t T = desc_num_static_frames(d, L);
+      hU[u] = uttOff[u];
+      hR[u + 1] = hR[u] + desc_num_frames(d, L);
+      hS[u + 1] = hS[u] + T;
+      nTiles += (size_t)((T + pl->tileF - 1) / pl->tileF);
+    }
+    hU[nUtt] = uttOff[nUtt];
+    CU(pl->hTiles.reserve(nTiles + 1));
+    size_t ti = 0;
+    for (int u = 0; u < nUtt; u++) {
+      const int64_t T = hS[u + 1] - hS[u];
+      for (int64_t f0 = 0; f0 < T; f0 += pl->tileF) pl->hTiles.p[ti++] = TileRef{u, (int32_t)f0};
+    }
+    pl->nTiles = nTiles;
+    pl->totalRows = hR[nUtt];
+    pl->totalStat = hS[nUtt];
+    pl->totalSamples = uttOff[nUtt];
+    CU(pl->dMeta.reserve(3 * nm));
+    CU(pl->dTiles.reserve(nTiles + 1));
+    CU(cudaMemcpyAsync(pl->dMeta.p, pl->hMeta.p, 3 * nm * sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (nTiles) CU(cudaMemcpyAsync(pl->dTiles.p, pl->hTiles.p, nTiles * sizeof(TileRef), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(pl->evMetaDone, st));
+    pl->metaPending = true;
+    pl->cachedUttOff.assign(uttOff, uttOff + nUtt + 1);
+  }
+  if (frameOff) {
+    // the caller's row offsets must be the ones the plan derives (bit-exact integer rule)
+    const size_t nm = (size_t)(nUtt + 1);
+    const long long *hR = pl->hMeta.p + nm;
+    for (int u = 0; u <= nUtt; u++)
+      if ((long long)frameOff[u] != hR[u]) return fail(OSM_B200_ERR_INVALID, "frame_offsets do not match osm_b200_plan_frame_offsets()");
+  }
+  return OSM_B200_OK;
+}
+
+osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, const int64_t *utt_offsets,
+                                         int32_t n_utt, const int64_t *frame_offsets, float *d_out, void *stream)
+{
+  if (!pl || !utt_offsets || n_utt < 0) return fail(OSM_B200_ERR_INVALID, "null argument");
+  if (pl->device < 0) return fail(OSM_B200_ERR_CUDA, "description-only plan (device < 0) cannot run; no CPU fallback");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CU(cudaSetDevice(pl->device));
+  pl->lastLaunches = 0;
+  pl->timed = false;
+  osm_b200_status s = prepare_batch(pl, utt_offsets, n_utt, frame_offsets, st);
+  if (s != OSM_B200_OK) return s;
+  if (pl->totalRows == 0 || pl->nTiles == 0) return OSM_B200_OK;
+  if (!d_pcm || !d_out) return fail(OSM_B200_ERR_INVALID, "null device buffer");
+
+  const size_t nm = (size_t)(n_utt + 1);
+  const long long *dU = pl->dMeta.p, *dR = dU + nm, *dS = dR + nm;
+  LldParams kp = pl->kp;
+  kp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
+  kp.uttOff = dU;
+  kp.tiles = pl->dTiles.p;
+  kp.nTiles = (int)pl->nTiles;
+  PostParams pp = pl->pp;
+  if (pl->staticDirect) {
+    kp.out = d_out; kp.outStride = pl->d.nOut; kp.outCol = pl->identityOutCol; kp.rowOff = dR;
+    pp.stat = d_out + pl->identityOutCol; pp.statStride = pl->d.nOut; pp.statOff = dR;
+  } else {
+    CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic));
+    kp.out = pl->dStat.p; kp.outStride = pl->d.nStatic; kp.outCol = 0; kp.rowOff = dS;
+    pp.stat = pl->dStat.p; pp.statStride = pl->d.nStatic; pp.statOff = dS;
+  }
+  pp.out = d_out; pp.outStride = pl->d.nOut; pp.rowOff = dR; pp.uttOff = dU; pp.nUtt = n_utt;
+  pp.totalRows = pl->totalRows;
+
+  CU(cudaEventRecord(pl->evK0, st));
+  CU(launch_lld(kp, pl->d.fe.nfft, pl->numSMs, st, &pl->lastInfo));
+  pl->lastLaunches++;
+  if (pp.nGroups > 0) {
+    CU(launch_post(pp, st));
+    pl->lastLaunches++;
+  }
+  CU(cudaEventRecord(pl->evK1, st));
+  pl->timed = true;
+  return OSM_B200_OK;
+}
+
+osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const int64_t *utt_offsets, int32_t n_utt,
+                                       const int64_t *frame_offsets, float *out)
+{
+  if (!pl || !utt_offsets || n_utt < 0) return fail(OSM_B200_ERR_INVALID, "null argument");
+  if (pl->device < 0) return fail(OSM_B200_ERR_CUDA, "description-only plan (device < 0) cannot run; no CPU fallback");
+  CU(cudaSetDevice(pl->device));
+  if (!pl->hostStream) CU(cudaStreamCreateWithFlags(&pl->hostStream, cudaStreamNonBlocking));
+  cudaStream_t st = pl->hostStream;
+  const int64_t nSamp = utt_offsets[n_utt] * pl->d.fe.nChan;
+  std::vector<int64_t> fo;
+  if (!frame_offsets) {
+    fo.resize(n_utt + 1);
+    osm_b200_status s = osm_b200_plan_frame_offsets(pl, utt_offsets, n_utt, fo.data());
+    if (s != OSM_B200_OK) return s;
+    frame_offsets = fo.data();
+  }
+  const int64_t rows = frame_offsets[n_utt];
+  if (rows == 0) return OSM_B200_OK;
+  if (!pcm || !out) return fail(OSM_B200_ERR_INVALID, "null host buffer");
+  CU(pl->dPcm.reserve((size_t)nSamp + 8));
+  CU(pl->dOut.reserve((size_t)rows * pl->d.nOut));
+  CU(cudaMemcpyAsync(pl->dPcm.p, pcm, (size_t)nSamp * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  osm_b200_status s = osm_b200_plan_run_device(pl, pl->dPcm.p, utt_offsets, n_utt, frame_offsets, pl->dOut.p, st);
+  if (s != OSM_B200_OK) return s;
+  CU(cudaMemcpyAsync(out, pl->dOut.p, (size_t)rows * pl->d.nOut * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return OSM_B200_OK;
+}
+
+int32_t osm_b200_plan_last_launch_count(const osm_b200_plan *pl) { return pl ? pl->lastLaunches : 0; }
+
+float osm_b200_plan_last_kernel_ms(osm_b200_plan *pl)
+{
+  if (!pl || !pl->timed) return -1.f;
+  if (cudaEventSynchronize(pl->evK1) != cudaSuccess) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, pl->evK0, pl->evK1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+}  // extern "C"

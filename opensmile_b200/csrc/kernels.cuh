@@ -1,0 +1,87 @@
+// kernels.cuh -- parameter blocks and launchers of the fused LLD kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace osm {
+
+constexpr int kMaxVW = 32;   // virtual warps (F-lane groups) per CTA
+
+struct TileRef { int32_t utt; int32_t f0; };   // <= F consecutive frames of one utterance
+
+// Everything the fused per-frame kernel needs.  Pointers are device pointers; the table
+// pointers reference one packed constant blob uploaded at plan creation.
+struct LldParams {
+  // ---- input ----
+  const int16_t *pcm;
+  const long long *uttOff;       // [nUtt+1] sample-frame offsets
+  const long long *rowOff;       // [nUtt+1] first output row of each utterance
+  const TileRef *tiles;
+  int nTiles;
+  int nChan;
+  // ---- front end ----
+  int frameSize, frameStep, sPad;
+  int preemph, preDe;
+  float preK, oneMinusK;
+  int hasWinOffset;
+  float winOffset;
+  const float2 *winPairs;        // [M] (w[2e], w[2e+1]), zero beyond frameSize
+  const int *sampLut;            // [M] smem offset of sample 2e relative to the frame base
+  const float2 *twiddles;        // per-stage tables, concatenated
+  int twOff[4];                  // offset (in float2) of each stage's table
+  int twCount;                   // total float2 in twiddles
+  const float2 *splitTw;         // [M/2+1] exp(-2 pi i k / N)
+  // ---- mel + mfcc op ----
+  const float *melCoef;          // [nBins]
+  const int *melRange;           // [nBands+2]
+  int nBands;
+  float melScale;
+  int melUsePower;
+  int melSplit[kMaxVW + 1];      // virtual warp w computes bands [melSplit[w], melSplit[w+1])
+  const float *dctCos;           // [nMfcc][nBands], output order
+  const float *dctLift;          // [nMfcc]
+  int nMfcc;
+  float melfloor, logMelfloor;
+  int doLog;
+  // ---- output ----
+  float *out;
+  int outStride, outCol;
+};
+
+// temporal post-processing (cDeltaRegression / cContourSmoother chains)
+struct PostGroup {
+  int srcCol, n, outCol;
+  int nStages;
+  int kind[3];                   // 0 = delta, 1 = sma
+  int win[3];
+  int flags[3];
+};
+constexpr int kMaxPostGroups = 16;
+struct PostParams {
+  const float *stat;             // static rows
+  int statStride;
+  const long long *statOff;      // [nUtt+1] static row offsets
+  float *out;
+  int outStride;
+  const long long *rowOff;       // [nUtt+1] output row offsets
+  const long long *uttOff;       // [nUtt+1] sample-frame offsets (to derive T)
+  int frameSize, frameStep;
+  int nUtt;
+  int nGroups;
+  PostGroup groups[kMaxPostGroups];
+  long long totalRows;
+};
+
+struct LldLaunchInfo { int grid, block; size_t smem; };
+
+// returns cudaSuccess or the launch error; fills `info`
+cudaError_t launch_lld(const LldParams &p, int nfft, int numSMs, cudaStream_t st, LldLaunchInfo *info);
+cudaError_t launch_post(const PostParams &p, cudaStream_t st);
+// smem bytes the fused kernel needs for a given geometry (host helper, used for diagnostics)
+size_t lld_smem_bytes(const LldParams &p, int nfft);
+// frames per tile / virtual warps per CTA for a given FFT size
+int lld_tile_frames(int nfft);
+int lld_virtual_warps(int nfft);
+bool lld_supported_fft(int nfft);
+
+}  // namespace osm

@@ -67,6 +67,8 @@ def lib():
         L.osm_or_plp_d_a.restype = C.c_long
         L.osm_or_delta.restype = C.c_long
         L.osm_or_sma.restype = C.c_long
+        L.osm_or_delta_chained.restype = C.c_long
+        L.osm_or_sma_chained.restype = C.c_long
     return _LIB
 
 
@@ -116,6 +118,17 @@ def delta(x, win):
     out = np.zeros((T + win, K), np.float32)
     r = lib().osm_or_delta(_fp(x), C.c_long(T), C.c_int(K), C.c_int(win), _fp(out))
     return out[:r]
+
+
+def delta_chained(x, win, n0):
+    """Stage reading a level of which only n0 frames exist when EOI is raised.
+    Returns (out, c0) with c0 = the same quantity for the produced level."""
+    x = np.ascontiguousarray(x, np.float32)
+    T, K = x.shape
+    out = np.zeros((T + win, K), np.float32)
+    c0 = C.c_long(0)
+    r = lib().osm_or_delta_chained(_fp(x), C.c_long(T), C.c_long(n0), C.c_int(K), C.c_int(win), _fp(out), C.byref(c0))
+    return out[:r], c0.value
 
 
 def sma(x, sma_win=3, no_zero_sma=0):

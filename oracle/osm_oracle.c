@@ -327,68 +327,125 @@ static void mfcc_apply(const osm_or_mfcc *mf, const float *mel, int nBands, floa
 
 /* ------------------------------------------------------------------ a-13 / a-14 */
 
-static const float *row_clamped(const float *x, long T, int K, long t)
+static const float kZeroRow[256] = {0};
+
+/* Tick-order model of chained window processors (cWindowProcessor, core/windowProcessor.cpp:
+ * 85-119,167-230; blocksize=1 => one frame per tick; components tick in data-flow order,
+ * core/componentManager.cpp:1233-1262).
+ *
+ * A level is described by (T = final number of frames, n0 = frames already written when EOI is
+ * raised).  The static level has n0 = T.  A window processor with half window W reading it has,
+ * before EOI, produced c0 = max(n0 - W, 0) frames (it needs t+W < n0); during EOI processing
+ * producer and consumer both advance one frame per tick, producer first, so when the consumer
+ * computes frame t >= c0 the producer holds  navail(t) = min(n0 + (t - c0) + 1, T)  frames.
+ *
+ * Reads of the input matrix for output frame t (core/dataMemoryLevel.cpp:1651-1738 getMatrix,
+ * :1005-1045 validateIdxRangeR):
+ *   window start t-W >= 0 : rows >= navail replicate row navail-1 (end padding, :1698-1708);
+ *   window start t-W <  0 : rows < 0 replicate row 0 (:1687-1693), but rows >= navail are read
+ *                           straight from the zero-initialised, not-yet-written level buffer
+ *                           (:1694-1697 loops to the unclamped vIdxEnd) => 0.0.
+ * For n0 >= W this reduces to the closed form "clamp to [0, T-1]" (SURVEY.md 8a-13); the other
+ * branch is only reachable for utterances of fewer than W1+W2 frames and is reproduced because
+ * the reference does it (verified against oracle/_ref for T = 1..5). */
+static long win_navail(long t, long n0, long c0, long T)
 {
-  /* core/dataMemoryLevel.cpp:1687-1708: indices < 0 replicate frame 0; at EOI indices >= T
-   * replicate frame T-1 */
-  if (t < 0) t = 0;
-  if (t > T - 1) t = T - 1;
-  return x + t * K;
+  if (t < c0) return T;              /* computed before EOI: everything it needs is there */
+  long n = n0 + (t - c0) + 1;
+  return n < T ? n : T;
 }
 
-/* dspcore/deltaRegression.cpp:139-146 over core/windowProcessor.cpp:85-119,167-230:
- * reader window [t-W, t+W]; frames are emitted while the end padding is shorter than the
- * window (core/dataMemoryLevel.cpp:1022-1026) => t = 0 .. T+W-1. */
-long osm_or_delta(const float *in, long T, int K, int W, float *out)
+static const float *row_win(const float *x, long navail, int K, long t, int W, long i)
 {
+  if (t - W < 0) {
+    if (i < 0) return x;
+    if (i >= navail) return kZeroRow;
+    return x + i * K;
+  }
+  if (i > navail - 1) i = navail - 1;
+  return x + i * K;
+}
+
+/* dspcore/deltaRegression.cpp:139-146.  in: T x K with n0 frames written before EOI.
+ * out: (T + W) x K; *c0_out = frames of the output level produced before EOI. */
+static long delta_stage(const float *in, long T, long n0, int K, int W, float *out, long *c0_out)
+{
+  long c0 = n0 - W > 0 ? n0 - W : 0;
+  if (c0_out) *c0_out = c0;
   if (T <= 0) return 0;
   float norm = 0.0f;
   for (int i = 1; i <= W; i++) norm += (float)i * (float)i; /* :77-79 */
   norm *= 2.0;
   long To = T + W;
   for (long t = 0; t < To; t++) {
+    long na = win_navail(t, n0, c0, T);
     for (int k = 0; k < K; k++) {
-      if (W > 0) {
-        float num = 0.0f;
-        for (int i = 1; i <= W; i++) {
-          float delta = row_clamped(in, T, K, t + i)[k] - row_clamped(in, T, K, t - i)[k];
-          num += (float)i * delta;
-        }
-        out[t * K + k] = num / norm;
+      float num = 0.0f;
+      for (int i = 1; i <= W; i++) {
+        float delta = row_win(in, na, K, t, W, t + i)[k] - row_win(in, na, K, t, W, t - i)[k];
+        num += (float)i * delta;
+      }
+      out[t * K + k] = num / norm;
+    }
+  }
+  return To;
+}
+
+/* dspcore/contourSmoother.cpp:84-117: y = x[n]; y += x[n-w]; y += x[n+w] (w = 1..smaWin/2);
+ * y /= smaWin  (noZeroSma: zeros are skipped and the divisor is the count) */
+static long sma_stage(const float *in, long T, long n0, int K, int smaWin, int noZeroSma, float *out, long *c0_out)
+{
+  int W = smaWin / 2;
+  long c0 = n0 - W > 0 ? n0 - W : 0;
+  if (c0_out) *c0_out = c0;
+  if (T <= 0) return 0;
+  long To = T + W;
+  for (long t = 0; t < To; t++) {
+    long na = win_navail(t, n0, c0, T);
+    for (int k = 0; k < K; k++) {
+      float x0 = row_win(in, na, K, t, W, t)[k];
+      if (noZeroSma) {
+        if (x0 != 0.0f) {
+          long N = 1;
+          float y = x0;
+          for (int w = 1; w <= W; w++) {
+            float a = row_win(in, na, K, t, W, t - w)[k], b = row_win(in, na, K, t, W, t + w)[k];
+            if (a != 0.0f) { y += a; N++; }
+            if (b != 0.0f) { y += b; N++; }
+          }
+          out[t * K + k] = y / (float)N;
+        } else out[t * K + k] = 0.0f;
       } else {
-        out[t * K + k] = row_clamped(in, T, K, t)[k] - row_clamped(in, T, K, t - 1)[k];
+        float y = x0;
+        for (int w = 1; w <= W; w++) {
+          y += row_win(in, na, K, t, W, t - w)[k];
+          y += row_win(in, na, K, t, W, t + w)[k];
+        }
+        out[t * K + k] = y / (float)smaWin;
       }
     }
   }
   return To;
 }
 
-/* dspcore/contourSmoother.cpp:84-117 (window smaWin, centred) with the same edge rules */
+/* public single-stage helpers: the input level is complete (n0 = T), as for a stage that
+ * reads a static LLD level */
+long osm_or_delta(const float *in, long T, int K, int W, float *out)
+{
+  return delta_stage(in, T, T, K, W, out, NULL);
+}
 long osm_or_sma(const float *in, long T, int K, int smaWin, int noZeroSma, float *out)
 {
-  if (T <= 0) return 0;
-  int W = (smaWin - 1) / 2;
-  long To = T + W;
-  for (long t = 0; t < To; t++) {
-    for (int k = 0; k < K; k++) {
-      float x0 = row_clamped(in, T, K, t)[k];
-      if (noZeroSma) {
-        if (x0 != 0.0f) {
-          float sum = 0.0f; int cnt = 0;
-          for (int j = -W; j <= W; j++) {
-            float v = row_clamped(in, T, K, t + j)[k];
-            if (v != 0.0f) { sum += v; cnt++; }
-          }
-          out[t * K + k] = sum / (float)cnt;
-        } else out[t * K + k] = 0.0f;
-      } else {
-        float sum = 0.0f;
-        for (int j = -W; j <= W; j++) sum += row_clamped(in, T, K, t + j)[k];
-        out[t * K + k] = sum / (float)smaWin;
-      }
-    }
-  }
-  return To;
+  return sma_stage(in, T, T, K, smaWin, noZeroSma, out, NULL);
+}
+/* chained stage: n0 = frames of `in` written before EOI (see the model above) */
+long osm_or_delta_chained(const float *in, long T, long n0, int K, int W, float *out, long *c0_out)
+{
+  return delta_stage(in, T, n0, K, W, out, c0_out);
+}
+long osm_or_sma_chained(const float *in, long T, long n0, int K, int smaWin, int noZeroSma, float *out, long *c0_out)
+{
+  return sma_stage(in, T, n0, K, smaWin, noZeroSma, out, c0_out);
 }
 
 /* ------------------------------------------------------------------ whole chains */
@@ -423,8 +480,9 @@ static void add_deltas(const float *stat, long T, int K, int dW, int aW, float *
 {
   float *d = (float *)malloc(sizeof(float) * (T + dW) * K);
   float *dd = (float *)malloc(sizeof(float) * (T + dW + aW) * K);
-  long Td = osm_or_delta(stat, T, K, dW, d);
-  osm_or_delta(d, Td, K, aW, dd);
+  long c0 = 0;
+  long Td = delta_stage(stat, T, T, K, dW, d, &c0);
+  delta_stage(d, Td, c0, K, aW, dd, NULL);
   for (long t = 0; t < T; t++) {
     memcpy(out + t * 3 * K, stat + t * K, sizeof(float) * K);
     memcpy(out + t * 3 * K + K, d + t * K, sizeof(float) * K);

@@ -104,6 +104,10 @@ long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const o
 long osm_or_delta(const float *in, long T, int K, int win, float *out);
 /* cContourSmoother: in T x K ; out (T + (smaWin-1)/2) x K */
 long osm_or_sma(const float *in, long T, int K, int sma_win, int no_zero_sma, float *out);
+/* chained variants: `n0` = frames of the input level already written when EOI is raised
+ * (tick-order model, see osm_oracle.c); *c0_out = the same quantity for the output level */
+long osm_or_delta_chained(const float *in, long T, long n0, int K, int win, float *out, long *c0_out);
+long osm_or_sma_chained(const float *in, long T, long n0, int K, int sma_win, int no_zero_sma, float *out, long *c0_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,83 @@
+"""CPU tests: the oracle (plain-C restatement) against the golden vectors produced by the
+unmodified reference, and -- when oracle/_ref is built -- against the reference itself."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, rel_to_frame_scale
+from opensmile_b200.synth import voiced_pcm
+from oracle import oracle, refrun
+
+TOL = 1e-5   # of the per-frame vector scale (north_star: 1e-5 relative, float32)
+
+
+def test_geometry_known_answers():
+    # SURVEY.md 8(a'): frame-count known answers measured on the reference
+    fe, _, _ = oracle.mfcc12_0_d_a(16000.0)
+    assert oracle.geometry(fe, 80000) == (400, 160, 512, 498)
+    assert oracle.geometry(fe, 9600000)[3] == 59998
+    fe, _, _ = oracle.mfcc12_0_d_a(44100.0)
+    assert oracle.geometry(fe, 90112) == (1103, 441, 2048, 202)
+    assert oracle.geometry(fe, 1102)[3] == 0
+    assert oracle.geometry(fe, 1103)[3] == 1
+
+
+def test_oracle_vs_golden_example_wav():
+    g = np.load(os.path.join(GOLD, "mfcc_example_44k1.npz"))
+    out = oracle.mfcc_d_a(g["pcm"], float(g["sample_rate"]))
+    assert out.shape == g["lld"].shape == (202, 39)
+    assert rel_to_frame_scale(out, g["lld"]) < TOL
+
+
+def test_oracle_vs_golden_synth16k():
+    g = np.load(os.path.join(GOLD, "mfcc_synth16k_s0.npz"))
+    pcm = voiced_pcm(80000, 16000, seed=0)
+    assert int(pcm.astype(np.int64).sum()) == int(g["crc"]), "synthetic generator drifted"
+    out = oracle.mfcc_d_a(pcm, 16000.0)
+    assert out.shape == g["lld"].shape == (498, 39)
+    assert rel_to_frame_scale(out, g["lld"]) < TOL
+
+
+def test_oracle_taps_vs_golden():
+    g = np.load(os.path.join(GOLD, "mfcc_taps16k_s1.npz"))
+    pcm = voiced_pcm(16000, 16000, seed=1)
+    out, mag, mel = oracle.mfcc_d_a(pcm, 16000.0, taps=True)
+    assert mag.shape[0] == int(g["n_frames"])
+    n = g["fftmag"].shape[0]
+    assert rel_to_frame_scale(mag[:n], g["fftmag"]) < 2e-6
+    assert rel_to_frame_scale(mel[:n], g["melspec"]) < 2e-6
+    assert rel_to_frame_scale(out[:n, :13], g["ft0"]) < TOL
+
+
+def test_delta_is_bit_exact_on_reference_statics():
+    # the regression stages are float arithmetic in a fixed order: given the reference's own
+    # static features the oracle must reproduce delta / delta-delta bit for bit, including
+    # the phantom frames at the end
+    for name in ("mfcc_example_44k1.npz", "mfcc_synth16k_s0.npz"):
+        lld = np.load(os.path.join(GOLD, name))["lld"]
+        T = lld.shape[0]
+        d = oracle.delta(lld[:, :13], 2)
+        dd = oracle.delta(d, 2)
+        assert d.shape[0] == T + 2 and dd.shape[0] == T + 4
+        assert np.array_equal(d[:T], lld[:, 13:26])
+        assert np.array_equal(dd[:T], lld[:, 26:39])
+
+
+@pytest.mark.skipif(not refrun.available(), reason="oracle/_ref not built (make -C oracle ref)")
+@pytest.mark.parametrize("sr,n,seed", [(16000, 40000, 3), (44100, 30000, 4), (16000, 400, 5), (16000, 561, 6)])
+def test_oracle_vs_live_reference(sr, n, seed):
+    pcm = voiced_pcm(n, sr, seed=seed)
+    ref = refrun.extract("mfcc/MFCC12_0_D_A.conf", pcm, sr)
+    out = oracle.mfcc_d_a(pcm, float(sr))
+    assert out.shape == ref.shape
+    assert rel_to_frame_scale(out, ref) < TOL
+
+
+@pytest.mark.skipif(not refrun.available(), reason="oracle/_ref not built")
+def test_oracle_vs_live_reference_stereo():
+    pcm = voiced_pcm(20000, 16000, seed=7, n_chan=2)
+    ref = refrun.extract("mfcc/MFCC12_0_D_A.conf", pcm, 16000, n_chan=2)
+    out = oracle.mfcc_d_a(pcm, 16000.0, n_chan=2)
+    assert out.shape == ref.shape
+    assert rel_to_frame_scale(out, ref) < TOL

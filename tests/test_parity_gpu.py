@@ -1,0 +1,130 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (a) the golden vectors
+the unmodified reference produced and (b) the CPU oracle on seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, rel_to_frame_scale
+from opensmile_b200 import Plan, components_mfcc12_0_d_a, pack_utterances
+from opensmile_b200.synth import voiced_pcm
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5   # relative to the per-frame vector scale, float32 (north_star)
+
+
+@pytest.fixture(scope="module")
+def plan16():
+    p = Plan(components_mfcc12_0_d_a(16000.0), "lld", device=0)
+    yield p
+    p.close()
+
+
+@pytest.fixture(scope="module")
+def plan44():
+    p = Plan(components_mfcc12_0_d_a(44100.0), "lld", device=0)
+    yield p
+    p.close()
+
+
+def test_golden_example_wav_config0(plan44):
+    g = np.load(os.path.join(GOLD, "mfcc_example_44k1.npz"))
+    out = plan44.run_host(g["pcm"], np.array([0, g["pcm"].size], np.int64))
+    assert out.shape == (202, 39)                       # bit-exact frame count
+    assert rel_to_frame_scale(out, g["lld"]) < TOL
+
+
+def test_golden_synth16k(plan16):
+    g = np.load(os.path.join(GOLD, "mfcc_synth16k_s0.npz"))
+    pcm = voiced_pcm(80000, 16000, seed=0)
+    out = plan16.run_host(pcm, np.array([0, pcm.size], np.int64))
+    assert out.shape == (498, 39)
+    assert rel_to_frame_scale(out, g["lld"]) < TOL
+    # the regression stages are exact float arithmetic on the statics: recomputing them on the
+    # CPU from the GPU's own statics must match the GPU's delta columns bit for bit
+    d = oracle.delta(out[:, :13], 2)
+    dd = oracle.delta(d, 2)
+    assert np.array_equal(d[:498], out[:, 13:26])
+    assert np.array_equal(dd[:498], out[:, 26:39])
+
+
+@pytest.mark.parametrize("lens", [
+    [16000, 8123, 400, 399, 0, 561, 5000],       # ragged, too-short and empty utterances
+    [80240] * 5,                                  # exactly 500 frames each (BASELINE cfg 2 shape)
+    [400 + 160 * 31, 400 + 160 * 32, 400 + 160 * 33],   # tile boundaries (32 frames per tile)
+])
+def test_batch_vs_oracle_16k(plan16, lens):
+    utts = [voiced_pcm(n, 16000, seed=100 + i) for i, n in enumerate(lens)]
+    pcm, off = pack_utterances(utts)
+    out = plan16.run_host(pcm, off)
+    fo = plan16.frame_offsets(off)
+    assert out.shape[0] == fo[-1]
+    for u, x in enumerate(utts):
+        ref = oracle.mfcc_d_a(x, 16000.0)
+        got = out[fo[u]:fo[u + 1]]
+        assert got.shape == ref.shape
+        if ref.shape[0]:
+            assert rel_to_frame_scale(got, ref) < TOL
+
+
+def test_batch_vs_oracle_44k1_stereo():
+    comps = components_mfcc12_0_d_a(44100.0, n_channels=2)
+    p = Plan(comps, "lld", device=0)
+    utts = [voiced_pcm(n, 44100, seed=200 + i, n_chan=2) for i, n in enumerate([30000, 1103, 20011])]
+    pcm, off = pack_utterances(utts, n_chan=2)
+    out = p.run_host(pcm, off)
+    fo = p.frame_offsets(off)
+    for u, x in enumerate(utts):
+        ref = oracle.mfcc_d_a(x, 44100.0, n_chan=2)
+        got = out[fo[u]:fo[u + 1]]
+        assert got.shape == ref.shape
+        assert rel_to_frame_scale(got, ref) < TOL
+    p.close()
+
+
+def test_extreme_inputs(plan16):
+    # silence (log floor path), full-scale square wave, single impulse
+    n = 400 + 160 * 40
+    sil = np.zeros(n, np.int16)
+    sq = (np.where((np.arange(n) // 40) % 2 == 0, 32767, -32768)).astype(np.int16)
+    imp = np.zeros(n, np.int16); imp[1234] = 32767
+    pcm, off = pack_utterances([sil, sq, imp])
+    out = plan16.run_host(pcm, off)
+    fo = plan16.frame_offsets(off)
+    assert np.isfinite(out).all()
+    for u, x in enumerate([sil, sq, imp]):
+        ref = oracle.mfcc_d_a(x, 16000.0)
+        assert rel_to_frame_scale(out[fo[u]:fo[u + 1]], ref) < TOL
+
+
+def test_device_resident_entry_point_and_determinism(plan16):
+    import torch
+    utts = [voiced_pcm(80240, 16000, seed=300 + i) for i in range(4)]
+    pcm, off = pack_utterances(utts)
+    host = plan16.run_host(pcm, off)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    a = plan16.run_device(d_pcm, off)
+    b = plan16.run_device(d_pcm, off)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)                                  # run-to-run bit identical
+    assert np.array_equal(a.cpu().numpy(), host)              # host and device entry points agree
+    assert plan16.last_launch_count() >= 1
+    assert plan16.last_kernel_ms() > 0
+
+
+def test_full_size_properties(plan16):
+    """BASELINE cfg 2 scale (a slice of it: 200 x 500 frames), size-independent properties:
+    batching invariance (an utterance's rows do not depend on its neighbours) and linearity of
+    the regression stages."""
+    import torch
+    n_utt, L = 200, 80240
+    base = voiced_pcm(L * 4, 16000, seed=999)
+    pcm = np.tile(base, n_utt // 4)
+    off = np.arange(n_utt + 1, dtype=np.int64) * L
+    out = plan16.run_host(pcm, off)
+    assert out.shape == (n_utt * 500, 39)
+    blk = out.reshape(n_utt // 4, 4 * 500, 39)
+    assert np.array_equal(blk[0], blk[-1]) and np.array_equal(blk[0], blk[len(blk) // 2])
+    single = plan16.run_host(base[:L], np.array([0, L], np.int64))
+    assert np.array_equal(single, out[:500])
