@@ -288,6 +288,10 @@ OSM_B200_API int32_t     osm_b200_plan_last_launch_count(const osm_b200_plan *pl
 /* device time in ms of the fused LLD kernel(s) of the last run_* call, measured with CUDA
  * events on the run's stream; blocks until the run has finished.  <0 if unavailable. */
 OSM_B200_API float       osm_b200_plan_last_kernel_ms(osm_b200_plan *plan);
+/* the same split per kernel: *lld_ms = the fused per-frame kernel, *post_ms = the temporal
+ * (delta / smoothing) kernel, 0 if none was launched.  Either pointer may be NULL. */
+OSM_B200_API osm_b200_status osm_b200_plan_last_kernel_times(osm_b200_plan *plan, float *lld_ms,
+                                                             float *post_ms);
 
 #ifdef __cplusplus
 }

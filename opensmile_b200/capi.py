@@ -165,6 +165,7 @@ EXPORTS = [
     "osm_b200_plan_frame_step_samples", "osm_b200_plan_fft_size", "osm_b200_plan_num_frames",
     "osm_b200_plan_frame_offsets", "osm_b200_plan_run_device", "osm_b200_plan_run_host",
     "osm_b200_plan_last_launch_count", "osm_b200_plan_last_kernel_ms",
+    "osm_b200_plan_last_kernel_times",
 ]
 
 _lib = None
@@ -208,6 +209,7 @@ def lib():
     L.osm_b200_plan_run_host.argtypes = [vp, vp, i64p, i32, i64p, vp]
     L.osm_b200_plan_last_kernel_ms.argtypes = [vp]
     L.osm_b200_plan_last_kernel_ms.restype = C.c_float
+    L.osm_b200_plan_last_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     if L.osm_b200_sizeof_component() != C.sizeof(Component):
         raise RuntimeError("ABI mismatch: sizeof(osm_b200_component) = %d, ctypes mirror = %d"
                            % (L.osm_b200_sizeof_component(), C.sizeof(Component)))

@@ -93,7 +93,7 @@ struct osm_b200_plan {
   DevBuf<float> dStat;
   size_t nTiles = 0;
   long long totalRows = 0, totalStat = 0, totalSamples = 0;
-  cudaEvent_t evMetaDone = nullptr, evK0 = nullptr, evK1 = nullptr;
+  cudaEvent_t evMetaDone = nullptr, evK0 = nullptr, evKm = nullptr, evK1 = nullptr;
   bool metaPending = false, timed = false;
   // run_host buffers
   DevBuf<int16_t> dPcm;
@@ -345,6 +345,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   CUP(cudaEventCreateWithFlags(&pl->evMetaDone, cudaEventDisableTiming));
   CUP(cudaEventCreate(&pl->evK0));
   CUP(cudaEventCreate(&pl->evK1));
+  CUP(cudaEventCreate(&pl->evKm));
 #undef CUP
   *out = pl;
   return OSM_B200_OK;
@@ -363,6 +364,7 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
   if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
   if (pl->evK0) cudaEventDestroy(pl->evK0);
   if (pl->evK1) cudaEventDestroy(pl->evK1);
+  if (pl->evKm) cudaEventDestroy(pl->evKm);
   delete pl;
 }
 
@@ -481,6 +483,7 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
   CU(cudaEventRecord(pl->evK0, st));
   CU(launch_lld(kp, pl->d.fe.nfft, pl->numSMs, st, &pl->lastInfo));
   pl->lastLaunches++;
+  CU(cudaEventRecord(pl->evKm, st));
   if (pp.nGroups > 0) {
     CU(launch_post(pp, st));
     pl->lastLaunches++;
@@ -528,6 +531,18 @@ float osm_b200_plan_last_kernel_ms(osm_b200_plan *pl)
   float ms = -1.f;
   if (cudaEventElapsedTime(&ms, pl->evK0, pl->evK1) != cudaSuccess) return -1.f;
   return ms;
+}
+
+osm_b200_status osm_b200_plan_last_kernel_times(osm_b200_plan *pl, float *lld_ms, float *post_ms)
+{
+  if (!pl || !pl->timed) return fail(OSM_B200_ERR_INVALID, "no timed run");
+  CU(cudaEventSynchronize(pl->evK1));
+  float a = 0.f, b = 0.f;
+  CU(cudaEventElapsedTime(&a, pl->evK0, pl->evKm));
+  CU(cudaEventElapsedTime(&b, pl->evKm, pl->evK1));
+  if (lld_ms) *lld_ms = a;
+  if (post_ms) *post_ms = b;
+  return OSM_B200_OK;
 }
 
 }  // extern "C"

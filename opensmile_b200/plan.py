@@ -144,6 +144,14 @@ class Plan:
     def last_kernel_ms(self):
         return float(self._L.osm_b200_plan_last_kernel_ms(self._h))
 
+    def last_kernel_times(self):
+        """(fused per-frame kernel ms, temporal kernel ms) of the last run, CUDA events."""
+        a, b = C.c_float(0), C.c_float(0)
+        st = self._L.osm_b200_plan_last_kernel_times(self._h, C.byref(a), C.byref(b))
+        if st != capi.OK:
+            raise RuntimeError(capi.last_error())
+        return a.value, b.value
+
 
 def _addr(buf):
     if hasattr(buf, "data_ptr"):
