@@ -87,7 +87,8 @@ struct osm_b200_plan {
   // batch bookkeeping
   std::vector<int64_t> cachedUttOff;
   PinBuf<long long> hMeta;     // uttOff | rowOff | statOff
-  PinBuf<TileRef> hTiles;
+  PinBuf<TileRef> hTiles;      // lld tiles | post tiles
+  size_t nPostTiles = 0;
   DevBuf<long long> dMeta;
   DevBuf<TileRef> dTiles;
   DevBuf<float> dStat;
@@ -252,18 +253,20 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   memset(&kp, 0, sizeof kp);
   kp.nChan = fe.nChan;
   kp.frameSize = fe.frameSize; kp.frameStep = fe.frameStep;
-  kp.sPad = (fe.frameStep % 2 == 0) ? 1 : 0;     // make the per-lane smem stride odd
+  // per-lane stride S = frameStep + sPad of the shared-memory sample tile: odd S (scalar loads)
+  // or even S with S/2 odd (64-bit sample-pair loads) is bank-conflict free across the lanes
+  kp.sPad = (fe.frameStep % 2 != 0) ? 0 : (((fe.frameStep / 2) % 2 != 0) ? 0 : 2);
   kp.preemph = fe.preemph; kp.preDe = fe.preDe; kp.preK = fe.preK;
   kp.oneMinusK = 1 - fe.preK;                     // (1-k), float arithmetic (vectorPreemphasis.cpp:94)
   kp.winOffset = fe.winOffset; kp.hasWinOffset = fe.winOffset != 0.f;
 
-  std::vector<float2> winPairs(M, make_float2(0.f, 0.f));
-  std::vector<int> lut(M, 0);
+  std::vector<float4> winLut(M, make_float4(0.f, 0.f, 0.f, 0.f));
   for (int e = 0; e < M; e++) {
     const int n = 2 * e;
-    if (n < fe.frameSize) winPairs[e].x = fe.window[n];
-    if (n + 1 < fe.frameSize) winPairs[e].y = fe.window[n + 1];
-    lut[e] = n + (n / fe.frameStep) * kp.sPad;
+    if (n < fe.frameSize) winLut[e].x = fe.window[n];
+    if (n + 1 < fe.frameSize) winLut[e].y = fe.window[n + 1];
+    const int off = n + (n / fe.frameStep) * kp.sPad;
+    memcpy(&winLut[e].z, &off, sizeof(int));
   }
   std::vector<float2> tw;
   build_twiddles(M, tw, kp.twOff);
@@ -293,8 +296,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
 
   auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
   size_t o = 0;
-  const size_t oWin = o; o = up16(o + winPairs.size() * sizeof(float2));
-  const size_t oLut = o; o = up16(o + lut.size() * sizeof(int));
+  const size_t oWin = o; o = up16(o + winLut.size() * sizeof(float4));
   const size_t oTw = o; o = up16(o + (tw.size() + 1) * sizeof(float2));
   const size_t oSplit = o; o = up16(o + split.size() * sizeof(float2));
   const size_t oCoef = o; o = up16(o + mb.coef.size() * sizeof(float));
@@ -302,8 +304,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   const size_t oDct = o; o = up16(o + mf.cosT.size() * sizeof(float));
   const size_t oLift = o; o = up16(o + mf.liftFactor.size() * sizeof(float));
   std::vector<unsigned char> blob(o, 0);
-  memcpy(&blob[oWin], winPairs.data(), winPairs.size() * sizeof(float2));
-  memcpy(&blob[oLut], lut.data(), lut.size() * sizeof(int));
+  memcpy(&blob[oWin], winLut.data(), winLut.size() * sizeof(float4));
   if (!tw.empty()) memcpy(&blob[oTw], tw.data(), tw.size() * sizeof(float2));
   memcpy(&blob[oSplit], split.data(), split.size() * sizeof(float2));
   memcpy(&blob[oCoef], mb.coef.data(), mb.coef.size() * sizeof(float));
@@ -312,8 +313,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   memcpy(&blob[oLift], mf.liftFactor.data(), mf.liftFactor.size() * sizeof(float));
   CUP(cudaMalloc(&pl->dConst, o));
   CUP(cudaMemcpy(pl->dConst, blob.data(), o, cudaMemcpyHostToDevice));
-  kp.winPairs = reinterpret_cast<const float2 *>(pl->dConst + oWin);
-  kp.sampLut = reinterpret_cast<const int *>(pl->dConst + oLut);
+  kp.winLut = reinterpret_cast<const float4 *>(pl->dConst + oWin);
   kp.twiddles = reinterpret_cast<const float2 *>(pl->dConst + oTw);
   kp.splitTw = reinterpret_cast<const float2 *>(pl->dConst + oSplit);
   kp.melCoef = reinterpret_cast<const float *>(pl->dConst + oCoef);
@@ -341,6 +341,14 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     for (size_t i = 0; i < g.stages.size(); i++) { pg.kind[i] = g.stages[i].kind; pg.win[i] = g.stages[i].win; pg.flags[i] = g.stages[i].flags; }
   }
   pp.frameSize = fe.frameSize; pp.frameStep = fe.frameStep;
+  pp.nStat = d.nStatic; pp.maxN = 1; pp.halo = 0;
+  for (int g = 0; g < pp.nGroups; g++) {
+    int h = 0;
+    for (int s2 = 0; s2 < pp.groups[g].nStages; s2++) h += pp.groups[g].win[s2];
+    if (h > pp.halo) pp.halo = h;
+    if (pp.groups[g].n > pp.maxN) pp.maxN = pp.groups[g].n;
+  }
+  if (pp.halo > 12) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "summed temporal half windows exceed 12 frames"); }
 
   CUP(cudaEventCreateWithFlags(&pl->evMetaDone, cudaEventDisableTiming));
   CUP(cudaEventCreate(&pl->evK0));
@@ -407,7 +415,8 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
     const size_t nm = (size_t)(nUtt + 1);
     CU(pl->hMeta.reserve(3 * nm));
     long long *hU = pl->hMeta.p, *hR = hU + nm, *hS = hR + nm;
-    size_t nTiles = 0;
+    size_t nTiles = 0, nPost = 0;
+    const int PR = post_tile_rows();
     hR[0] = 0; hS[0] = 0;
     for (int u = 0; u < nUtt; u++) {
       if (uttOff[u + 1] < uttOff[u]) return fail(OSM_B200_ERR_INVALID, "utt_offsets must be non-decreasing");
@@ -417,22 +426,28 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
       hR[u + 1] = hR[u] + desc_num_frames(d, L);
       hS[u + 1] = hS[u] + T;
       nTiles += (size_t)((T + pl->tileF - 1) / pl->tileF);
+      nPost += (size_t)((hR[u + 1] - hR[u] + PR - 1) / PR);
     }
     hU[nUtt] = uttOff[nUtt];
-    CU(pl->hTiles.reserve(nTiles + 1));
+    CU(pl->hTiles.reserve(nTiles + nPost + 1));
     size_t ti = 0;
     for (int u = 0; u < nUtt; u++) {
       const int64_t T = hS[u + 1] - hS[u];
       for (int64_t f0 = 0; f0 < T; f0 += pl->tileF) pl->hTiles.p[ti++] = TileRef{u, (int32_t)f0};
     }
+    for (int u = 0; u < nUtt; u++) {
+      const int64_t To = hR[u + 1] - hR[u];
+      for (int64_t r0 = 0; r0 < To; r0 += PR) pl->hTiles.p[ti++] = TileRef{u, (int32_t)r0};
+    }
     pl->nTiles = nTiles;
+    pl->nPostTiles = nPost;
     pl->totalRows = hR[nUtt];
     pl->totalStat = hS[nUtt];
     pl->totalSamples = uttOff[nUtt];
     CU(pl->dMeta.reserve(3 * nm));
-    CU(pl->dTiles.reserve(nTiles + 1));
+    CU(pl->dTiles.reserve(nTiles + nPost + 1));
     CU(cudaMemcpyAsync(pl->dMeta.p, pl->hMeta.p, 3 * nm * sizeof(long long), cudaMemcpyHostToDevice, st));
-    if (nTiles) CU(cudaMemcpyAsync(pl->dTiles.p, pl->hTiles.p, nTiles * sizeof(TileRef), cudaMemcpyHostToDevice, st));
+    if (nTiles + nPost) CU(cudaMemcpyAsync(pl->dTiles.p, pl->hTiles.p, (nTiles + nPost) * sizeof(TileRef), cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(pl->evMetaDone, st));
     pl->metaPending = true;
     pl->cachedUttOff.assign(uttOff, uttOff + nUtt + 1);
@@ -478,7 +493,7 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
     pp.stat = pl->dStat.p; pp.statStride = pl->d.nStatic; pp.statOff = dS;
   }
   pp.out = d_out; pp.outStride = pl->d.nOut; pp.rowOff = dR; pp.uttOff = dU; pp.nUtt = n_utt;
-  pp.totalRows = pl->totalRows;
+  pp.tiles = pl->dTiles.p + pl->nTiles; pp.nTiles = (int)pl->nPostTiles;
 
   CU(cudaEventRecord(pl->evK0, st));
   CU(launch_lld(kp, pl->d.fe.nfft, pl->numSMs, st, &pl->lastInfo));

@@ -32,12 +32,14 @@ namespace osm {
 // shared memory layout (identical computation on host and device)
 // ------------------------------------------------------------------------------------------
 struct SmemLayout {
-  int zbuf, samp, raw, winPairs, sampLut, tw, splitTw, melCoef, melRange, dctCos, dctLift, melS, mfccS;
+  int zbuf, samp, raw, rawPcm, mbar, winLut, tw, splitTw, melCoef, melRange, dctCos, dctLift, melS, mfccS;
   int total;
-  int sampFloats;
+  int sampFloats, rawPcmBytes;
 };
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+constexpr int kLeadFrames = 8;   // sample frames fetched ahead of a tile (x[n-1] for pre-emphasis)
 
 __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int F)
 {
@@ -49,9 +51,12 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
   L.samp = o; o += L.sampFloats * 4;
   L.raw = o; o += F * 4;
   o = align_up(o, 16);
-  L.winPairs = o; o += M * 8;
-  L.sampLut = o; o += M * 4;
-  o = align_up(o, 16);
+  // raw PCM landing zone of the bulk (TMA) prefetch: <=15 bytes of alignment slack, the lead
+  // frames, the tile's sample frames, rounded up to 16
+  L.rawPcmBytes = align_up(16 + (kLeadFrames + (F - 1) * p.frameStep + p.frameSize) * p.nChan * 2, 16);
+  L.rawPcm = o; o += L.rawPcmBytes;
+  L.mbar = o; o += 16;
+  L.winLut = o; o += M * 16;
   L.tw = o; o += p.twCount * 8;
   L.splitTw = o; o += (M / 2 + 1) * 8;
   o = align_up(o, 16);
@@ -70,22 +75,97 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
 // ------------------------------------------------------------------------------------------
 // PCM conversion, smileutil/smileUtil.c:2520-2534 : ((sum_c (float)x_c) / nChan) / 32767
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float pcm_to_float(const int16_t *s, int nChan)
+// x / 32767 with one reciprocal multiply and two FMAs (Markstein refinement).  Checked
+// exhaustively against IEEE division for every int16 and every half-integer k/2 (stereo mix)
+// |k| <= 65536: bit-identical (tests/test_host_cpu.py::test_div32767_trick).
+__device__ __forceinline__ float div32767(float x)
+{
+  const float rc = 3.0518509447574615e-05f;   // fl(1/32767)
+  const float q0 = __fmul_rn(x, rc);
+  const float r = __fmaf_rn(-q0, 32767.0f, x);
+  return __fmaf_rn(r, rc, q0);
+}
+
+__device__ __forceinline__ float pcm_to_float_generic(const int16_t *s, int nChan)
 {
   float tmp = (float)s[0];
   for (int c = 1; c < nChan; c++) tmp = __fadd_rn(tmp, (float)s[c]);
+  if (nChan == 1) return div32767(tmp);
+  if (nChan == 2) return div32767(tmp * 0.5f);          // tmp / 2.0f is exact
   return __fdiv_rn(__fdiv_rn(tmp, (float)nChan), 32767.0f);
 }
-__device__ __forceinline__ float pcm1_to_float(int v) { return __fdiv_rn((float)v, 32767.0f); }
+
+// ------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA unit, SASS UBLKCP) wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// geometry of one tile (all warp-uniform)
+struct TileGeom {
+  int nf;            // frames in this tile
+  int count;         // sample frames the tile covers
+  int lead;          // sample frames fetched before the tile start (0 at the utterance start)
+  int mis;           // bytes between the 16-byte aligned fetch address and the first wanted byte
+  uint32_t bytes;    // bulk copy size
+  const char *src;   // 16-byte aligned fetch address
+  long long row0;    // first output row
+};
+
+template <int F>
+__device__ __forceinline__ TileGeom tile_geom(const LldParams &p, int tile)
+{
+  TileGeom g;
+  const TileRef tr = p.tiles[tile];
+  const long long uo = p.uttOff[tr.utt];
+  const long long Ls = p.uttOff[tr.utt + 1] - uo;
+  const int T = (int)((Ls - p.frameSize) / p.frameStep + 1);
+  g.nf = min(F, T - tr.f0);
+  const long long s0 = (long long)tr.f0 * p.frameStep;
+  g.count = (g.nf - 1) * p.frameStep + p.frameSize;
+  g.lead = (s0 > 0) ? kLeadFrames : 0;
+  const char *a = reinterpret_cast<const char *>(p.pcm + (uo + s0 - g.lead) * p.nChan);
+  g.mis = (int)(reinterpret_cast<uintptr_t>(a) & 15);
+  g.src = a - g.mis;
+  g.bytes = (uint32_t)align_up(g.mis + (g.lead + g.count) * p.nChan * 2, 16);
+  g.row0 = p.rowOff[tr.utt] + tr.f0;
+  return g;
+}
 
 // ------------------------------------------------------------------------------------------
 // one in-place DIF stage.  Virtual warp vw (of NVW) handles butterflies t = vw, vw+NVW, ...
 // ------------------------------------------------------------------------------------------
-template <int M, int F, int NVW, int R, int MS, bool FIRST, bool LAST>
+template <int M, int F, int NVW, int R, int MS, bool FIRST, bool LAST, bool VEC2>
 __device__ __forceinline__ void fft_stage(float2 *__restrict__ Z, const float *__restrict__ sampF,
                                           const float *__restrict__ raw,
-                                          const float2 *__restrict__ winPairs,
-                                          const int *__restrict__ lut, const float2 *__restrict__ tw,
+                                          const float4 *__restrict__ winLut,
+                                          const float2 *__restrict__ tw,
                                           const LldParams &p, int vw, int f)
 {
   constexpr int stride = MS / R;
@@ -100,14 +180,19 @@ __device__ __forceinline__ void fft_stage(float2 *__restrict__ Z, const float *_
         const int n = 2 * e;
         float2 x = make_float2(0.f, 0.f);
         if (n < p.frameSize) {          // warp-uniform
-          const int off = lut[e];
-          x.x = sampF[off];
-          if (n + 1 < p.frameSize) x.y = sampF[off + 1];
+          const float4 wl = winLut[e];  // (w[2e], w[2e+1], smem offset of sample 2e, -)
+          const int off = __float_as_int(wl.z);
+          if (VEC2) {
+            x = *reinterpret_cast<const float2 *>(sampF + off);
+          } else {
+            x.x = sampF[off];
+            x.y = sampF[off + 1];
+          }
           if (e == 0 && p.preemph) x.x = __fmul_rn(p.oneMinusK, raw[f]);   // vectorPreemphasis.cpp:94
-          const float2 w = winPairs[e];
-          // windower.cpp:226 : src * (float)w + (float)offset (two roundings)
-          x.x = __fmul_rn(x.x, w.x);
-          x.y = __fmul_rn(x.y, w.y);
+          // windower.cpp:226 : src * (float)w + (float)offset (two roundings); the table holds
+          // w = 0 for the phantom sample of an odd frame size
+          x.x = __fmul_rn(x.x, wl.x);
+          x.y = __fmul_rn(x.y, wl.y);
           if (p.hasWinOffset) {
             x.x = __fadd_rn(x.x, p.winOffset);
             if (n + 1 < p.frameSize) x.y = __fadd_rn(x.y, p.winOffset);
@@ -133,7 +218,7 @@ __device__ __forceinline__ void fft_stage(float2 *__restrict__ Z, const float *_
 // ------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------
-template <int M, int F, int NT, int MINB>
+template <int M, int F, int NT, int MINB, bool VEC2>
 __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 {
   constexpr int NW = NT / 32, G = 32 / F, NVW = NW * G;
@@ -148,8 +233,9 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   float *P = reinterpret_cast<float *>(smem + L.zbuf);   // aliases Z (used after the split)
   float *samp = reinterpret_cast<float *>(smem + L.samp);
   float *raw = reinterpret_cast<float *>(smem + L.raw);
-  float2 *sWin = reinterpret_cast<float2 *>(smem + L.winPairs);
-  int *sLut = reinterpret_cast<int *>(smem + L.sampLut);
+  unsigned char *rawPcm = smem + L.rawPcm;
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem + L.mbar);
+  float4 *sWinLut = reinterpret_cast<float4 *>(smem + L.winLut);
   float2 *sTw = reinterpret_cast<float2 *>(smem + L.tw);
   float2 *sSplit = reinterpret_cast<float2 *>(smem + L.splitTw);
   float *sMelCoef = reinterpret_cast<float *>(smem + L.melCoef);
@@ -164,85 +250,125 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   const int f = lane & (F - 1);
   const int vw = warp * G + lane / F;
 
-  // ---- constant tables -> smem (once per CTA) ----
-  for (int i = tid; i < M; i += NT) { sWin[i] = p.winPairs[i]; sLut[i] = p.sampLut[i]; }
+  // ---- one-time setup: barrier, constant tables -> smem, zero the sample tile ----
+  if (tid == 0) mbar_init(mbar, 1);
+  for (int i = tid; i < M; i += NT) sWinLut[i] = p.winLut[i];
   for (int i = tid; i < p.twCount; i += NT) sTw[i] = p.twiddles[i];
   for (int i = tid; i < NPAIR; i += NT) sSplit[i] = p.splitTw[i];
   for (int i = tid; i < NBINS; i += NT) sMelCoef[i] = p.melCoef[i];
   for (int i = tid; i < p.nBands + 2; i += NT) sMelRange[i] = p.melRange[i];
   for (int i = tid; i < p.nMfcc * p.nBands; i += NT) sDct[i] = p.dctCos[i];
   for (int i = tid; i < p.nMfcc; i += NT) sLift[i] = p.dctLift[i];
+  for (int i = tid; i < L.sampFloats; i += NT) samp[i] = 0.f;   // lanes beyond a short tile read finite data
   __syncthreads();
 
-  const int hop = p.frameStep, size = p.frameSize, nChan = p.nChan;
+  const int hop = p.frameStep, nChan = p.nChan;
   const int S = hop + p.sPad;
+  uint32_t phase = 0;
 
-  for (int tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x) {
-    const TileRef tr = p.tiles[tile];
-    const long long uo = p.uttOff[tr.utt];
-    const long long Ls = p.uttOff[tr.utt + 1] - uo;
-    const int T = (int)((Ls - size) / hop + 1);
-    const int nf = min(F, T - tr.f0);
-    const long long s0 = (long long)tr.f0 * hop;
-    const int count = (nf - 1) * hop + size;
-    const int16_t *src = p.pcm + (uo + s0) * nChan;
+  int tile = blockIdx.x;
+  if (tile < p.nTiles && tid == 0) {
+    const TileGeom g0 = tile_geom<F>(p, tile);
+    mbar_expect_tx(mbar, g0.bytes);
+    bulk_g2s(rawPcm, g0.src, g0.bytes, mbar);
+  }
 
-    // ================= stage: PCM -> float -> pre-emphasis -> smem =================
+  for (; tile < p.nTiles; tile += gridDim.x) {
+    const TileGeom tg = tile_geom<F>(p, tile);
+    const int nf = tg.nf, count = tg.count;
+
+    // ================= stage: PCM (smem, prefetched by the bulk copy) -> float -> pre-emphasis -> smem =================
+    mbar_wait(mbar, phase);
+    phase ^= 1;
     {
-      const bool vecOk = (nChan == 1) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+      const int16_t *rp = reinterpret_cast<const int16_t *>(rawPcm + tg.mis) + tg.lead * nChan;   // sample frame 0 of the tile
+      const bool fastLoad = (tg.mis == 0) && (nChan <= 2);
+      const bool fastStore = (p.sPad == 0) || (hop % 8 == 0);
       for (int c = tid; c * 8 < count; c += NT) {
         const int i = c * 8;
-        float x[8];
-        float xprev = 0.f;
         const int nvalid = min(8, count - i);
-        if (vecOk && nvalid == 8) {
-          const int4 raw4 = __ldg(reinterpret_cast<const int4 *>(src + i));
-          const int wds[4] = {raw4.x, raw4.y, raw4.z, raw4.w};
+        float x[8];
+        if (fastLoad && nvalid == 8) {
+          if (nChan == 1) {
+            const int4 w4 = *reinterpret_cast<const int4 *>(rp + i);
+            const int wds[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            x[2 * j] = pcm1_to_float((int)(short)(wds[j] & 0xffff));
-            x[2 * j + 1] = pcm1_to_float(wds[j] >> 16);
+            for (int j = 0; j < 4; j++) {
+              x[2 * j] = div32767((float)(short)(wds[j] & 0xffff));
+              x[2 * j + 1] = div32767((float)(wds[j] >> 16));
+            }
+          } else {
+            const int4 a4 = *reinterpret_cast<const int4 *>(rp + 2 * i);
+            const int4 b4 = *reinterpret_cast<const int4 *>(rp + 2 * i + 8);
+            const int wds[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float l = (float)(short)(wds[j] & 0xffff), r = (float)(wds[j] >> 16);
+              x[j] = div32767(__fadd_rn(l, r) * 0.5f);
+            }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; j++) x[j] = (j < nvalid) ? pcm_to_float(src + (long long)(i + j) * nChan, nChan) : 0.f;
+          for (int j = 0; j < 8; j++) x[j] = (j < nvalid) ? pcm_to_float_generic(rp + (i + j) * nChan, nChan) : 0.f;
         }
-        if (p.preemph && (s0 + i) > 0) xprev = pcm_to_float(src + (long long)(i - 1) * nChan, nChan);
-        int q = i / hop;
-        int r = i - q * hop;
-        float *dst = samp + i + q * p.sPad;
+        float y[8];
+        if (p.preemph) {
+          // vectorPreemphasis.cpp:96-104 : x[n] -/+ k * x[n-1], two roundings
+          float xprev = 0.f;
+          if (i > 0 || tg.lead > 0) xprev = pcm_to_float_generic(rp + (i - 1) * nChan, nChan);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          if (j < nvalid) {
-            float y = x[j];
-            if (p.preemph) {
-              // vectorPreemphasis.cpp:96-104 : x[n] -/+ k * x[n-1], two roundings
-              const float kx = __fmul_rn(p.preK, (j == 0) ? xprev : x[j - 1]);
-              y = p.preDe ? __fadd_rn(x[j], kx) : __fsub_rn(x[j], kx);
+          for (int j = 0; j < 8; j++) {
+            const float kx = __fmul_rn(p.preK, (j == 0) ? xprev : x[j - 1]);
+            y[j] = p.preDe ? __fadd_rn(x[j], kx) : __fsub_rn(x[j], kx);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; j++) y[j] = x[j];
+        }
+        const int q = i / hop;
+        const int r = i - q * hop;
+        float *dst = samp + i + q * p.sPad;
+        if (fastStore && nvalid == 8 && r + 8 <= hop) {
+          // the 8 samples lie inside one frame step: no pad crossing, at most one frame start
+          if (r == 0 && q < F) raw[q] = x[0];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) *reinterpret_cast<float2 *>(dst + j) = make_float2(y[j], y[j + 1]);
+        } else {
+          int qq = q, rr = r;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (j < nvalid) {
+              if (rr == 0 && qq < F) raw[qq] = x[j];
+              dst[j] = y[j];
+              rr++;
+              if (rr == hop) { rr = 0; qq++; dst += p.sPad; }
             }
-            if (r == 0) {
-              if (q < F) raw[q] = x[j];
-            }
-            dst[j] = y;
-            r++;
-            if (r == hop) { r = 0; q++; dst += p.sPad; }
           }
         }
       }
     }
     __syncthreads();
+    // the landing zone is free again: fetch the next tile's PCM while this one is processed
+    {
+      const int next = tile + gridDim.x;
+      if (next < p.nTiles && tid == 0) {
+        const TileGeom gn = tile_geom<F>(p, next);
+        mbar_expect_tx(mbar, gn.bytes);
+        bulk_g2s(rawPcm, gn.src, gn.bytes, mbar);
+      }
+    }
 
     // ================= FFT =================
     {
       const float *sampF = samp + f * S;
-      fft_stage<M, F, NVW, Fc::R0, M, true, false>(Z, sampF, raw, sWin, sLut, sTw + p.twOff[0], p, vw, f);
+      fft_stage<M, F, NVW, Fc::R0, M, true, false, VEC2>(Z, sampF, raw, sWinLut, sTw + p.twOff[0], p, vw, f);
       __syncthreads();
       if constexpr (Fc::NS == 2) {
-        fft_stage<M, F, NVW, Fc::R1, M / Fc::R0, false, true>(Z, nullptr, nullptr, nullptr, nullptr, nullptr, p, vw, f);
+        fft_stage<M, F, NVW, Fc::R1, M / Fc::R0, false, true, VEC2>(Z, nullptr, nullptr, nullptr, nullptr, p, vw, f);
       } else {
-        fft_stage<M, F, NVW, Fc::R1, M / Fc::R0, false, false>(Z, nullptr, nullptr, nullptr, nullptr, sTw + p.twOff[1], p, vw, f);
+        fft_stage<M, F, NVW, Fc::R1, M / Fc::R0, false, false, VEC2>(Z, nullptr, nullptr, nullptr, sTw + p.twOff[1], p, vw, f);
         __syncthreads();
-        fft_stage<M, F, NVW, Fc::R2, M / (Fc::R0 * Fc::R1), false, true>(Z, nullptr, nullptr, nullptr, nullptr, nullptr, p, vw, f);
+        fft_stage<M, F, NVW, Fc::R2, M / (Fc::R0 * Fc::R1), false, true, VEC2>(Z, nullptr, nullptr, nullptr, nullptr, p, vw, f);
       }
       __syncthreads();
     }
@@ -289,25 +415,35 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     __syncthreads();
 
     // ================= mel filterbank (melspec.cpp:543-569) + log (mfcc.cpp:239-243) =================
+    // range r holds the bins whose lower band is r-1: band[r-1] += a ; band[r] += p - a, visited
+    // in ascending bin order exactly like the reference loop, so each band's float sum has the
+    // reference's summation order.
     {
       const int bs = p.melSplit[vw], be = p.melSplit[vw + 1];
       if (bs < be) {
-        float cur = 0.f, nxt = 0.f;
-        for (int r = bs; r <= be; r++) {
-          const int n0 = sMelRange[r], n1 = sMelRange[r + 1];
-          for (int n = n0; n < n1; n++) {
+        float cur = 0.f;
+        {   // range bs only feeds band bs (its rising slope)
+          const int n1 = sMelRange[bs + 1];
+#pragma unroll 4
+          for (int n = sMelRange[bs]; n < n1; n++) {
+            const float pw = P[n * F + f];
+            cur = __fadd_rn(cur, __fsub_rn(pw, __fmul_rn(pw, sMelCoef[n])));
+          }
+        }
+        for (int r = bs + 1; r <= be; r++) {
+          float nxt = 0.f;
+          const int n1 = sMelRange[r + 1];
+#pragma unroll 4
+          for (int n = sMelRange[r]; n < n1; n++) {
             const float pw = P[n * F + f];
             const float a = __fmul_rn(pw, sMelCoef[n]);    // (float)((double)p*(double)w) == fl(p*w)
-            if (r > bs) cur = __fadd_rn(cur, a);
+            cur = __fadd_rn(cur, a);
             nxt = __fadd_rn(nxt, __fsub_rn(pw, a));
           }
-          if (r > bs) {
-            float mval = __fmul_rn(cur, p.melScale);
-            if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);
-            melS[(r - 1) * F + f] = mval;
-          }
+          float mval = __fmul_rn(cur, p.melScale);
+          if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);
+          melS[(r - 1) * F + f] = mval;
           cur = nxt;
-          nxt = 0.f;
         }
       }
     }
@@ -317,6 +453,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     for (int i = vw; i < p.nMfcc; i += NVW) {
       const float *ct = sDct + i * p.nBands;
       float acc = 0.f;
+#pragma unroll 2
       for (int m = 0; m < p.nBands; m++) acc = __fadd_rn(acc, __fmul_rn(melS[m * F + f], ct[m]));
       mfccS[i * F + f] = __fmul_rn(acc, sLift[i]);
     }
@@ -324,11 +461,10 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 
     // ================= store =================
     {
-      const long long row0 = p.rowOff[tr.utt] + tr.f0;
       const int tot = nf * p.nMfcc;
       for (int idx = tid; idx < tot; idx += NT) {
         const int ff = idx / p.nMfcc, c = idx - ff * p.nMfcc;
-        p.out[(row0 + ff) * p.outStride + p.outCol + c] = mfccS[c * F + ff];
+        p.out[(tg.row0 + ff) * p.outStride + p.outCol + c] = mfccS[c * F + ff];
       }
     }
     // no barrier needed here: the next tile's staging only writes samp/raw, which no thread
@@ -339,12 +475,6 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 // ------------------------------------------------------------------------------------------
 // temporal post-processing
 // ------------------------------------------------------------------------------------------
-struct PostCtx {
-  const float *base;     // static rows of this utterance
-  int stride;
-  int T;                 // static frames
-};
-
 // Tick-order model of chained window processors (cWindowProcessor with blocksize=1, components
 // ticking in data-flow order; core/windowProcessor.cpp:85-119,167-230, core/componentManager.cpp:
 // 1233-1262).  For the level produced by stage s:  final_s = final_{s-1} + W_s frames in total,
@@ -356,99 +486,134 @@ struct PostCtx {
 // from the zero-initialised, not yet written level buffer (0.0).  For c0_{s-1} >= W_s this is the
 // plain "clamp to [0, final-1]" rule; the rest only triggers for utterances shorter than the
 // summed window lengths and is reproduced because the reference does it.
-template <int LVL>
-__device__ float post_eval(const PostCtx &cx, const PostGroup &g, int t, int c);
+//
+// post_kernel: one CTA per tile of kPostRows output rows of one utterance.  The static rows the
+// tile depends on (halo = summed half windows) are staged in shared memory once, every stage of
+// every group is then evaluated level by level in shared memory (O(window) per element) and
+// the finished rows are written out.
+constexpr int kPostRows = 64;
+constexpr int kPostMaxHalo = 12;
+constexpr int kPostThreads = 256;
 
-template <>
-__device__ __forceinline__ float post_eval<0>(const PostCtx &cx, const PostGroup &g, int t, int c)
+__device__ __forceinline__ float post_read(const float *lvl, int n, int rowBase, int t, int W, int navail, int i, int c)
 {
-  return cx.base[(long long)t * cx.stride + c];
-}
-
-template <int LVL>
-__device__ __forceinline__ float post_read(const PostCtx &cx, const PostGroup &g, int t, int W, int navail, int i, int c)
-{
+  // lvl: smem rows of the input level, row index (absolute frame - rowBase), n columns
   if (t - W < 0) {
-    if (i < 0) return post_eval<LVL - 1>(cx, g, 0, c);
-    if (i >= navail) return 0.f;
-    return post_eval<LVL - 1>(cx, g, i, c);
+    if (i < 0) i = 0;
+    else if (i >= navail) return 0.f;
+  } else if (i > navail - 1) {
+    i = navail - 1;
   }
-  return post_eval<LVL - 1>(cx, g, min(i, navail - 1), c);
+  return lvl[(i - rowBase) * n + c];
 }
 
-template <int LVL>
-__device__ float post_eval(const PostCtx &cx, const PostGroup &g, int t, int c)
+__global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
 {
-  int Tprev = cx.T, n0 = cx.T;          // input level: final frame count, frames before EOI
-#pragma unroll
-  for (int i = 0; i < LVL - 1; i++) { Tprev += g.win[i]; n0 = max(n0 - g.win[i], 0); }
-  const int W = g.win[LVL - 1];
-  const int c0 = max(n0 - W, 0);
-  const int navail = (t < c0) ? Tprev : min(n0 + (t - c0) + 1, Tprev);
-  if (g.kind[LVL - 1] == 0) {
-    // deltaRegression.cpp:139-146 : num = sum_i i*(x[t+i]-x[t-i]) ; y = num / (2 sum i^2)
-    float norm = 0.f;
-    for (int i = 1; i <= W; i++) norm = __fadd_rn(norm, __fmul_rn((float)i, (float)i));
-    norm = __fmul_rn(norm, 2.0f);
-    float num = 0.f;
-    for (int i = 1; i <= W; i++) {
-      const float later = post_read<LVL>(cx, g, t, W, navail, t + i, c);
-      const float prior = post_read<LVL>(cx, g, t, W, navail, t - i, c);
-      num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));
-    }
-    return __fdiv_rn(num, norm);
-  } else {
-    // contourSmoother.cpp:84-117 : y = x[n]; y += x[n-w]; y += x[n+w]; y /= smaWin
-    const int noZero = g.flags[LVL - 1];
-    const float x0 = post_read<LVL>(cx, g, t, W, navail, t, c);
-    if (noZero && x0 == 0.f) return 0.f;
-    float y = x0;
-    int cnt = 1;
-    for (int w = 1; w <= W; w++) {
-      const float a = post_read<LVL>(cx, g, t, W, navail, t - w, c);
-      const float b = post_read<LVL>(cx, g, t, W, navail, t + w, c);
-      if (!noZero || a != 0.f) { y = __fadd_rn(y, a); cnt++; }
-      if (!noZero || b != 0.f) { y = __fadd_rn(y, b); cnt++; }
-    }
-    return __fdiv_rn(y, noZero ? (float)cnt : (float)(2 * W + 1));
-  }
-}
+  extern __shared__ float psm[];
+  const TileRef tr = p.tiles[blockIdx.x];
+  const int u = tr.utt, r0 = tr.f0;
+  const long long Ls = p.uttOff[u + 1] - p.uttOff[u];
+  const int T = (int)((Ls - p.frameSize) / p.frameStep + 1);
+  const int Tout = (int)(p.rowOff[u + 1] - p.rowOff[u]);
+  const int r1 = min(r0 + kPostRows, Tout);
+  const int H = p.halo;
+  const int rowBase = r0 - H;                       // absolute frame of smem row 0 (may be < 0)
+  const int nRowsBuf = kPostRows + 2 * H;
+  float *S0 = psm;                                  // [nRowsBuf][nStat]
+  float *A = S0 + nRowsBuf * p.nStat;               // [nRowsBuf][maxN]
+  float *B = A + nRowsBuf * p.maxN;
+  const int tid = threadIdx.x;
 
-__global__ void __launch_bounds__(256) post_kernel(const PostParams p)
-{
-  // one thread per (output row, column of a staged group); rows are found by binary search
-  // over the per-utterance row offsets.
-  int colsTotal = 0;
-  for (int g = 0; g < p.nGroups; g++) colsTotal += p.groups[g].n;
-  const long long total = p.totalRows * colsTotal;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long row = idx / colsTotal;
-    int col = (int)(idx - row * colsTotal);
-    int gi = 0;
-    while (col >= p.groups[gi].n) { col -= p.groups[gi].n; gi++; }
+  // ---- static rows [r0-H, r1+H) /\ [0, T) -> smem ----
+  {
+    const int lo = max(rowBase, 0), hi = min(r1 + H, T);
+    const float *src = p.stat + p.statOff[u] * (long long)p.statStride;
+    const int tot = (hi - lo) * p.nStat;
+    for (int idx = tid; idx < tot; idx += kPostThreads) {
+      const int rr = idx / p.nStat, c = idx - rr * p.nStat;
+      S0[(lo + rr - rowBase) * p.nStat + c] = src[(long long)(lo + rr) * p.statStride + c];
+    }
+  }
+  __syncthreads();
+
+  for (int gi = 0; gi < p.nGroups; gi++) {
     const PostGroup &g = p.groups[gi];
-    // utterance of this row
-    int lo = 0, hi = p.nUtt;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (p.rowOff[mid] <= row) lo = mid; else hi = mid;
+    const int n = g.n;
+    // level 0 view of this group: copy its columns so that every level has row stride n
+    const float *cur;
+    {
+      const int lo = max(rowBase, 0), hi = min(r1 + H, T);
+      const int tot = (hi - lo) * n;
+      for (int idx = tid; idx < tot; idx += kPostThreads) {
+        const int rr = idx / n, c = idx - rr * n;
+        A[(lo + rr - rowBase) * n + c] = S0[(lo + rr - rowBase) * p.nStat + g.srcCol + c];
+      }
+      cur = A;
     }
-    const int u = lo;
-    const int t = (int)(row - p.rowOff[u]);
-    const long long Ls = p.uttOff[u + 1] - p.uttOff[u];
-    PostCtx cx;
-    cx.T = (int)((Ls - p.frameSize) / p.frameStep + 1);
-    cx.stride = p.statStride;
-    cx.base = p.stat + p.statOff[u] * (long long)p.statStride + g.srcCol;
-    float v;
-    switch (g.nStages) {
-      case 1: v = post_eval<1>(cx, g, t, col); break;
-      case 2: v = post_eval<2>(cx, g, t, col); break;
-      case 3: v = post_eval<3>(cx, g, t, col); break;
-      default: v = post_eval<0>(cx, g, min(t, cx.T - 1), col); break;
+    __syncthreads();
+    int Tprev = T, n0 = T;                          // input level: total frames, frames before EOI
+    int Hrem = 0;
+    for (int s = 0; s < g.nStages; s++) Hrem += g.win[s];
+    for (int s = 0; s < g.nStages; s++) {
+      const int W = g.win[s];
+      Hrem -= W;
+      const int c0 = max(n0 - W, 0);
+      const int Tcur = Tprev + W;
+      float *dst = (cur == A) ? B : A;
+      const int lo = max(r0 - Hrem, 0), hi = min(r1 + Hrem, Tcur);   // rows of this level needed
+      const int tot = (hi - lo) * n;
+      float norm = 0.f;
+      for (int i = 1; i <= W; i++) norm = __fadd_rn(norm, __fmul_rn((float)i, (float)i));
+      norm = __fmul_rn(norm, 2.0f);                 // deltaRegression.cpp:77-80
+      for (int idx = tid; idx < tot; idx += kPostThreads) {
+        const int rr = idx / n, c = idx - rr * n;
+        const int t = lo + rr;
+        const int navail = (t < c0) ? Tprev : min(n0 + (t - c0) + 1, Tprev);
+        float y;
+        if (g.kind[s] == 0) {
+          // deltaRegression.cpp:139-146 : num = sum_i i*(x[t+i]-x[t-i]) ; y = num / norm
+          float num = 0.f;
+          for (int i = 1; i <= W; i++) {
+            const float later = post_read(cur, n, rowBase, t, W, navail, t + i, c);
+            const float prior = post_read(cur, n, rowBase, t, W, navail, t - i, c);
+            num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));
+          }
+          y = __fdiv_rn(num, norm);
+        } else {
+          // contourSmoother.cpp:84-117 : y = x[n]; y += x[n-w]; y += x[n+w]; y /= smaWin
+          const int noZero = g.flags[s];
+          const float x0 = post_read(cur, n, rowBase, t, W, navail, t, c);
+          if (noZero && x0 == 0.f) {
+            y = 0.f;
+          } else {
+            y = x0;
+            int cnt = 1;
+            for (int w = 1; w <= W; w++) {
+              const float a = post_read(cur, n, rowBase, t, W, navail, t - w, c);
+              const float b = post_read(cur, n, rowBase, t, W, navail, t + w, c);
+              if (!noZero || a != 0.f) { y = __fadd_rn(y, a); cnt++; }
+              if (!noZero || b != 0.f) { y = __fadd_rn(y, b); cnt++; }
+            }
+            y = __fdiv_rn(y, noZero ? (float)cnt : (float)(2 * W + 1));
+          }
+        }
+        dst[(t - rowBase) * n + c] = y;
+      }
+      __syncthreads();
+      cur = dst;
+      n0 = c0;
+      Tprev = Tcur;
     }
-    p.out[row * p.outStride + g.outCol + col] = v;
+    // ---- write rows [r0, r1) of this group ----
+    {
+      float *o = p.out + (p.rowOff[u] + r0) * (long long)p.outStride + g.outCol;
+      const int tot = (r1 - r0) * n;
+      for (int idx = tid; idx < tot; idx += kPostThreads) {
+        const int rr = idx / n, c = idx - rr * n;
+        o[(long long)rr * p.outStride + c] = cur[(r0 + rr - rowBase) * n + c];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -464,11 +629,11 @@ size_t lld_smem_bytes(const LldParams &p, int nfft)
   return (size_t)make_layout(p, nfft / 2, lld_tile_frames(nfft)).total;
 }
 
-template <int M, int F, int NT, int MINB>
+template <int M, int F, int NT, int MINB, bool VEC2>
 static cudaError_t launch_t(const LldParams &p, int numSMs, cudaStream_t st, LldLaunchInfo *info)
 {
   const size_t smem = (size_t)make_layout(p, M, F).total;
-  auto kern = lld_kernel<M, F, NT, MINB>;
+  auto kern = lld_kernel<M, F, NT, MINB, VEC2>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -485,23 +650,26 @@ static cudaError_t launch_t(const LldParams &p, int numSMs, cudaStream_t st, Lld
 
 cudaError_t launch_lld(const LldParams &p, int nfft, int numSMs, cudaStream_t st, LldLaunchInfo *info)
 {
+  // VEC2: 64-bit sample-pair loads need an even per-lane stride (frameStep + sPad)
+  const bool vec2 = ((p.frameStep + p.sPad) % 2) == 0;
   switch (nfft) {
-    case 512:  return launch_t<256, 32, 256, 2>(p, numSMs, st, info);
-    case 1024: return launch_t<512, 32, 512, 1>(p, numSMs, st, info);
-    case 2048: return launch_t<1024, 16, 512, 1>(p, numSMs, st, info);
+    case 512:  return vec2 ? launch_t<256, 32, 256, 2, true>(p, numSMs, st, info) : launch_t<256, 32, 256, 2, false>(p, numSMs, st, info);
+    case 1024: return vec2 ? launch_t<512, 32, 512, 1, true>(p, numSMs, st, info) : launch_t<512, 32, 512, 1, false>(p, numSMs, st, info);
+    case 2048: return vec2 ? launch_t<1024, 16, 512, 1, true>(p, numSMs, st, info) : launch_t<1024, 16, 512, 1, false>(p, numSMs, st, info);
     default:   return cudaErrorInvalidValue;
   }
 }
 
+int post_tile_rows() { return kPostRows; }
+
 cudaError_t launch_post(const PostParams &p, cudaStream_t st)
 {
-  int colsTotal = 0;
-  for (int g = 0; g < p.nGroups; g++) colsTotal += p.groups[g].n;
-  const long long total = p.totalRows * colsTotal;
-  if (total <= 0) return cudaSuccess;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 16) blocks = 148LL * 16;
-  post_kernel<<<(int)blocks, 256, 0, st>>>(p);
+  if (p.nTiles <= 0 || p.nGroups <= 0) return cudaSuccess;
+  if (p.halo > kPostMaxHalo) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(kPostRows + 2 * p.halo) * (p.nStat + 2 * p.maxN) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  post_kernel<<<p.nTiles, kPostThreads, smem, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -25,8 +25,7 @@ struct LldParams {
   float preK, oneMinusK;
   int hasWinOffset;
   float winOffset;
-  const float2 *winPairs;        // [M] (w[2e], w[2e+1]), zero beyond frameSize
-  const int *sampLut;            // [M] smem offset of sample 2e relative to the frame base
+  const float4 *winLut;          // [M] (w[2e], w[2e+1], smem offset of sample 2e as int bits, 0)
   const float2 *twiddles;        // per-stage tables, concatenated
   int twOff[4];                  // offset (in float2) of each stage's table
   int twCount;                   // total float2 in twiddles
@@ -69,7 +68,11 @@ struct PostParams {
   int nUtt;
   int nGroups;
   PostGroup groups[kMaxPostGroups];
-  long long totalRows;
+  const TileRef *tiles;          // (utt, first output row) per CTA, post_tile_rows() rows each
+  int nTiles;
+  int nStat;                     // static columns staged per row
+  int maxN;                      // widest group
+  int halo;                      // max over groups of the summed half windows
 };
 
 struct LldLaunchInfo { int grid, block; size_t smem; };
@@ -77,6 +80,7 @@ struct LldLaunchInfo { int grid, block; size_t smem; };
 // returns cudaSuccess or the launch error; fills `info`
 cudaError_t launch_lld(const LldParams &p, int nfft, int numSMs, cudaStream_t st, LldLaunchInfo *info);
 cudaError_t launch_post(const PostParams &p, cudaStream_t st);
+int post_tile_rows();
 // smem bytes the fused kernel needs for a given geometry (host helper, used for diagnostics)
 size_t lld_smem_bytes(const LldParams &p, int nfft);
 // frames per tile / virtual warps per CTA for a given FFT size

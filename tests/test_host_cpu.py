@@ -91,3 +91,33 @@ def test_fft_butterflies_host_build():
     subprocess.check_call(["nvcc", "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-o", exe,
                            os.path.join(ROOT, "tests", "native", "test_fft_radix.cu")])
     subprocess.check_call([exe])
+
+
+def test_div32767_trick():
+    """kernels.cu::div32767 (reciprocal multiply + two FMAs) must equal IEEE x / 32767.0f for
+    every value the PCM conversion can produce: all int16 (mono) and all half-integers k/2,
+    |k| <= 65536 (stereo mixdown).  Exact rational arithmetic, no GPU needed."""
+    import struct
+    from fractions import Fraction
+
+    def f32(fr):
+        if fr == 0:
+            return 0.0
+        y = np.float32(float(fr))
+        c = [np.nextafter(y, np.float32(-np.inf)), y, np.nextafter(y, np.float32(np.inf))]
+        ds = sorted(c, key=lambda v: abs(Fraction(float(v)) - fr))
+        if abs(Fraction(float(ds[0])) - fr) == abs(Fraction(float(ds[1])) - fr):
+            for v in ds[:2]:
+                if (struct.unpack("I", struct.pack("f", float(v)))[0] & 1) == 0:
+                    return float(v)
+        return float(ds[0])
+
+    D = Fraction(32767)
+    rc = f32(Fraction(1) / D)
+    assert rc == float(np.float32(3.0518509447574615e-05))
+    for k in list(range(-65536, 65535, 7)) + list(range(-65536, -65400)) + list(range(65400, 65535)) + list(range(-64, 64)):
+        x = Fraction(k, 2)
+        q0 = f32(x * Fraction(rc))
+        r = f32(x - Fraction(q0) * D)
+        q1 = f32(Fraction(q0) + Fraction(r) * Fraction(rc))
+        assert q1 == f32(x / D), k
