@@ -265,8 +265,9 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     const int n = 2 * e;
     if (n < fe.frameSize) winLut[e].x = fe.window[n];
     if (n + 1 < fe.frameSize) winLut[e].y = fe.window[n + 1];
-    const int off = n + (n / fe.frameStep) * kp.sPad;
+    const int off = (n < fe.frameSize) ? n + (n / fe.frameStep) * kp.sPad : 0;
     memcpy(&winLut[e].z, &off, sizeof(int));
+    winLut[e].w = (n + 1 < fe.frameSize) ? 2.f : ((n < fe.frameSize) ? 1.f : 0.f);
   }
   std::vector<float2> tw;
   build_twiddles(M, tw, kp.twOff);
@@ -276,7 +277,11 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     const double ang = -2.0 * M_PI * (double)k / (double)fe.nfft;
     split[k] = make_float2((float)cos(ang), (float)sin(ang));
   }
-  kp.nBands = mb.nBands; kp.melScale = mb.outScale; kp.melUsePower = mb.usePower;
+  kp.nBands = mb.nBands; kp.melUsePower = mb.usePower;
+  // the kernel keeps 2X (4|X|^2) out of the real-FFT split; the exact factor 1/4 of the power
+  // path is folded into the band scale (power-of-two scaling commutes with rounding)
+  kp.melScale = mb.usePower ? mb.outScale * 0.25f : mb.outScale;
+  kp.dctStride = (mb.nBands + 3) / 4 * 4;
   kp.nMfcc = mf.nMfcc; kp.melfloor = mf.melfloor; kp.logMelfloor = mf.logMelfloor; kp.doLog = mf.doLog;
   // split the bands over the virtual warps, balancing visited bins (ranges bs..be)
   {
@@ -301,7 +306,10 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   const size_t oSplit = o; o = up16(o + split.size() * sizeof(float2));
   const size_t oCoef = o; o = up16(o + mb.coef.size() * sizeof(float));
   const size_t oRange = o; o = up16(o + mb.rangeBegin.size() * sizeof(int));
-  const size_t oDct = o; o = up16(o + mf.cosT.size() * sizeof(float));
+  std::vector<float> dctPad((size_t)mf.nMfcc * kp.dctStride, 0.f);
+  for (int i = 0; i < mf.nMfcc; i++)
+    memcpy(&dctPad[(size_t)i * kp.dctStride], &mf.cosT[(size_t)i * mb.nBands], sizeof(float) * mb.nBands);
+  const size_t oDct = o; o = up16(o + dctPad.size() * sizeof(float));
   const size_t oLift = o; o = up16(o + mf.liftFactor.size() * sizeof(float));
   std::vector<unsigned char> blob(o, 0);
   memcpy(&blob[oWin], winLut.data(), winLut.size() * sizeof(float4));
@@ -309,7 +317,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   memcpy(&blob[oSplit], split.data(), split.size() * sizeof(float2));
   memcpy(&blob[oCoef], mb.coef.data(), mb.coef.size() * sizeof(float));
   memcpy(&blob[oRange], mb.rangeBegin.data(), mb.rangeBegin.size() * sizeof(int));
-  memcpy(&blob[oDct], mf.cosT.data(), mf.cosT.size() * sizeof(float));
+  memcpy(&blob[oDct], dctPad.data(), dctPad.size() * sizeof(float));
   memcpy(&blob[oLift], mf.liftFactor.data(), mf.liftFactor.size() * sizeof(float));
   CUP(cudaMalloc(&pl->dConst, o));
   CUP(cudaMemcpy(pl->dConst, blob.data(), o, cudaMemcpyHostToDevice));

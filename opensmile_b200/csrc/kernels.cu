@@ -63,7 +63,7 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
   L.melCoef = o; o += (M + 1) * 4;
   L.melRange = o; o += (p.nBands + 2) * 4;
   o = align_up(o, 16);
-  L.dctCos = o; o += p.nMfcc * p.nBands * 4;
+  L.dctCos = o; o += p.nMfcc * p.dctStride * 4;
   L.dctLift = o; o += p.nMfcc * 4;
   o = align_up(o, 16);
   L.melS = o; o += p.nBands * F * 4;
@@ -174,31 +174,33 @@ __device__ __forceinline__ void fft_stage(float2 *__restrict__ Z, const float *_
     const int base = blk * MS + j;
     float2 v[R];
     if (FIRST) {
+      // Elements beyond the frame (zero padding) have table weight 0 and offset 0: they load a
+      // finite sample and multiply it by 0 -> no per-element branch (the sample tile only ever
+      // holds finite floats, it is zero-filled at kernel start).
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        const int e = base + stride * r;
-        const int n = 2 * e;
-        float2 x = make_float2(0.f, 0.f);
-        if (n < p.frameSize) {          // warp-uniform
-          const float4 wl = winLut[e];  // (w[2e], w[2e+1], smem offset of sample 2e, -)
-          const int off = __float_as_int(wl.z);
-          if (VEC2) {
-            x = *reinterpret_cast<const float2 *>(sampF + off);
-          } else {
-            x.x = sampF[off];
-            x.y = sampF[off + 1];
-          }
-          if (e == 0 && p.preemph) x.x = __fmul_rn(p.oneMinusK, raw[f]);   // vectorPreemphasis.cpp:94
-          // windower.cpp:226 : src * (float)w + (float)offset (two roundings); the table holds
-          // w = 0 for the phantom sample of an odd frame size
-          x.x = __fmul_rn(x.x, wl.x);
-          x.y = __fmul_rn(x.y, wl.y);
-          if (p.hasWinOffset) {
-            x.x = __fadd_rn(x.x, p.winOffset);
-            if (n + 1 < p.frameSize) x.y = __fadd_rn(x.y, p.winOffset);
-          }
+        const float4 wl = winLut[base + stride * r];   // (w[2e], w[2e+1], offset, #valid)
+        const int off = __float_as_int(wl.z);
+        float2 x;
+        if (VEC2) {
+          x = *reinterpret_cast<const float2 *>(sampF + off);
+        } else {
+          x.x = sampF[off];
+          x.y = sampF[off + 1];
         }
-        v[r] = x;
+        // windower.cpp:226 : src * (float)w (+ (float)offset below), separate roundings
+        v[r] = make_float2(__fmul_rn(x.x, wl.x), __fmul_rn(x.y, wl.y));
+      }
+      if (base == 0 && p.preemph)      // first sample of the frame, vectorPreemphasis.cpp:94
+        v[0].x = __fmul_rn(__fmul_rn(p.oneMinusK, raw[f]), winLut[0].x);
+      if (p.hasWinOffset) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          // #valid: 0 = padding, 1 = only the first sample of the pair exists, 2 = both
+          const float nv = winLut[base + stride * r].w;
+          if (nv >= 1.f) v[r].x = __fadd_rn(v[r].x, p.winOffset);
+          if (nv >= 2.f) v[r].y = __fadd_rn(v[r].y, p.winOffset);
+        }
       }
     } else {
 #pragma unroll
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   for (int i = tid; i < NPAIR; i += NT) sSplit[i] = p.splitTw[i];
   for (int i = tid; i < NBINS; i += NT) sMelCoef[i] = p.melCoef[i];
   for (int i = tid; i < p.nBands + 2; i += NT) sMelRange[i] = p.melRange[i];
-  for (int i = tid; i < p.nMfcc * p.nBands; i += NT) sDct[i] = p.dctCos[i];
+  for (int i = tid; i < p.nMfcc * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
   for (int i = tid; i < p.nMfcc; i += NT) sLift[i] = p.dctLift[i];
   for (int i = tid; i < L.sampFloats; i += NT) samp[i] = 0.f;   // lanes beyond a short tile read finite data
   __syncthreads();
@@ -389,16 +391,18 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           const float2 o2 = make_float2(a.x - b.x, a.y + b.y);         // 2O
           const float2 t2 = cmul(o2, w);                               // 2 W^k O
           // 2 X[k] = e2 - i t2 ; 2 conj(X[M-k]) = e2 + i t2
-          const float xr = 0.5f * (e2.x + t2.y), xi = 0.5f * (e2.y - t2.x);
-          const float yr = 0.5f * (e2.x - t2.y), yi = 0.5f * (e2.y + t2.x);
+          const float xr = e2.x + t2.y, xi = e2.y - t2.x;
+          const float yr = e2.x - t2.y, yi = e2.y + t2.x;
           // fftmagphase.cpp:215-221 computes sqrt(re*re+im*im), melspec.cpp:524 squares it
-          // again; we keep re*re+im*im (<= 1.5 ulp apart, below the FFT's own noise floor)
+          // again; we keep re*re+im*im (<= 1.5 ulp apart, below the FFT's own noise floor).
+          // The factor 1/2 of X (1/4 of the power) is an exact power-of-two scaling that commutes
+          // with every rounding downstream; it is folded into melScale on the host.
           if (p.melUsePower) {
             pk[i] = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
             pm[i] = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
           } else {
-            pk[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
-            pm[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi)));
+            pk[i] = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
+            pm[i] = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi)));
           }
         }
       }
@@ -422,21 +426,24 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       const int bs = p.melSplit[vw], be = p.melSplit[vw + 1];
       if (bs < be) {
         float cur = 0.f;
+        int n = sMelRange[bs];
+        const float *pp = P + n * F + f;
+        const float *cp = sMelCoef + n;
         {   // range bs only feeds band bs (its rising slope)
           const int n1 = sMelRange[bs + 1];
 #pragma unroll 4
-          for (int n = sMelRange[bs]; n < n1; n++) {
-            const float pw = P[n * F + f];
-            cur = __fadd_rn(cur, __fsub_rn(pw, __fmul_rn(pw, sMelCoef[n])));
+          for (; n < n1; n++, pp += F, cp++) {
+            const float pw = *pp;
+            cur = __fadd_rn(cur, __fsub_rn(pw, __fmul_rn(pw, *cp)));
           }
         }
         for (int r = bs + 1; r <= be; r++) {
           float nxt = 0.f;
           const int n1 = sMelRange[r + 1];
 #pragma unroll 4
-          for (int n = sMelRange[r]; n < n1; n++) {
-            const float pw = P[n * F + f];
-            const float a = __fmul_rn(pw, sMelCoef[n]);    // (float)((double)p*(double)w) == fl(p*w)
+          for (; n < n1; n++, pp += F, cp++) {
+            const float pw = *pp;
+            const float a = __fmul_rn(pw, *cp);            // (float)((double)p*(double)w) == fl(p*w)
             cur = __fadd_rn(cur, a);
             nxt = __fadd_rn(nxt, __fsub_rn(pw, a));
           }
@@ -450,12 +457,33 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     __syncthreads();
 
     // ================= DCT-II + lifter (mfcc.cpp:251-272) =================
-    for (int i = vw; i < p.nMfcc; i += NVW) {
-      const float *ct = sDct + i * p.nBands;
-      float acc = 0.f;
-#pragma unroll 2
-      for (int m = 0; m < p.nBands; m++) acc = __fadd_rn(acc, __fmul_rn(melS[m * F + f], ct[m]));
-      mfccS[i * F + f] = __fmul_rn(acc, sLift[i]);
+    // each virtual warp owns coefficients i, i+NVW, ... and evaluates them two at a time so
+    // that one read of the log-mel column feeds two dot products; the cosine rows are read as
+    // float4 (row stride padded to 4).  Each dot product keeps the reference's m = 0..nBands-1
+    // accumulation order.
+    for (int i = vw; i < p.nMfcc; i += 2 * NVW) {
+      const int i1 = i + NVW;
+      const bool two = i1 < p.nMfcc;
+      const float4 *c0 = reinterpret_cast<const float4 *>(sDct + i * p.dctStride);
+      const float4 *c1 = reinterpret_cast<const float4 *>(sDct + (two ? i1 : i) * p.dctStride);
+      const float *lp = melS + f;
+      float a0 = 0.f, a1 = 0.f;
+      int m = 0;
+      for (; m + 4 <= p.nBands; m += 4, lp += 4 * F) {
+        const float4 w0 = *c0++, w1 = *c1++;
+        const float l0 = lp[0], l1 = lp[F], l2 = lp[2 * F], l3 = lp[3 * F];
+        a0 = __fadd_rn(a0, __fmul_rn(l0, w0.x)); a1 = __fadd_rn(a1, __fmul_rn(l0, w1.x));
+        a0 = __fadd_rn(a0, __fmul_rn(l1, w0.y)); a1 = __fadd_rn(a1, __fmul_rn(l1, w1.y));
+        a0 = __fadd_rn(a0, __fmul_rn(l2, w0.z)); a1 = __fadd_rn(a1, __fmul_rn(l2, w1.z));
+        a0 = __fadd_rn(a0, __fmul_rn(l3, w0.w)); a1 = __fadd_rn(a1, __fmul_rn(l3, w1.w));
+      }
+      const float *r0 = reinterpret_cast<const float *>(c0), *r1 = reinterpret_cast<const float *>(c1);
+      for (int k = 0; m < p.nBands; m++, k++, lp += F) {
+        const float l0 = lp[0];
+        a0 = __fadd_rn(a0, __fmul_rn(l0, r0[k])); a1 = __fadd_rn(a1, __fmul_rn(l0, r1[k]));
+      }
+      mfccS[i * F + f] = __fmul_rn(a0, sLift[i]);
+      if (two) mfccS[i1 * F + f] = __fmul_rn(a1, sLift[i1]);
     }
     __syncthreads();
 

@@ -25,7 +25,7 @@ struct LldParams {
   float preK, oneMinusK;
   int hasWinOffset;
   float winOffset;
-  const float4 *winLut;          // [M] (w[2e], w[2e+1], smem offset of sample 2e as int bits, 0)
+  const float4 *winLut;          // [M] (w[2e], w[2e+1], smem offset of sample 2e as int bits, #valid samples of the pair)
   const float2 *twiddles;        // per-stage tables, concatenated
   int twOff[4];                  // offset (in float2) of each stage's table
   int twCount;                   // total float2 in twiddles
@@ -37,7 +37,8 @@ struct LldParams {
   float melScale;
   int melUsePower;
   int melSplit[kMaxVW + 1];      // virtual warp w computes bands [melSplit[w], melSplit[w+1])
-  const float *dctCos;           // [nMfcc][nBands], output order
+  const float *dctCos;           // [nMfcc][dctStride], output order, rows zero padded
+  int dctStride;                 // nBands rounded up to a multiple of 4
   const float *dctLift;          // [nMfcc]
   int nMfcc;
   float melfloor, logMelfloor;
