@@ -3,8 +3,10 @@
 // compute entry point fails with OSM_B200_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -87,8 +89,12 @@ struct osm_b200_plan {
   // batch bookkeeping
   std::vector<int64_t> cachedUttOff;
   PinBuf<long long> hMeta;     // uttOff | rowOff | statOff
-  PinBuf<TileRef> hTiles;      // lld tiles | post tiles
+  PinBuf<TileRef> hTiles;      // post_kernel tiles
   size_t nPostTiles = 0;
+  PinBuf<ChunkRef> hChunks;    // lld_kernel work units
+  DevBuf<ChunkRef> dChunks;
+  size_t nChunks = 0;
+  bool fused = false;          // delta / delta-delta evaluated inside lld_kernel
   DevBuf<long long> dMeta;
   DevBuf<TileRef> dTiles;
   DevBuf<float> dStat;
@@ -348,6 +354,25 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     pg.srcCol = g.srcCol; pg.n = g.n; pg.outCol = g.outCol; pg.nStages = (int)g.stages.size();
     for (size_t i = 0; i < g.stages.size(); i++) { pg.kind[i] = g.stages[i].kind; pg.win[i] = g.stages[i].win; pg.flags[i] = g.stages[i].flags; }
   }
+  // fused pattern: [static | delta(W1) | delta(W1,W2)] over the whole static vector
+  pl->fused = false;
+  kp.fused = 0; kp.halo = 0; kp.fW1 = kp.fW2 = 0; kp.fNorm1 = kp.fNorm2 = 1.f;
+  if (pl->staticDirect && pl->identityOutCol == 0 && d.groups.size() == 3 && d.nOut == 3 * d.nStatic) {
+    const auto &g1 = d.groups[1], &g2 = d.groups[2];
+    const bool shape = d.groups[0].stages.empty() && g1.stages.size() == 1 && g2.stages.size() == 2 &&
+                       g1.srcCol == 0 && g2.srcCol == 0 && g1.n == d.nStatic && g2.n == d.nStatic &&
+                       g1.outCol == d.nStatic && g2.outCol == 2 * d.nStatic &&
+                       g1.stages[0].kind == ST_DELTA && g2.stages[0].kind == ST_DELTA && g2.stages[1].kind == ST_DELTA &&
+                       g1.stages[0].win == g2.stages[0].win;
+    // OSM_B200_NO_FUSE=1 forces the two-kernel path (used by the tests to cross-check both)
+    const char *nf = getenv("OSM_B200_NO_FUSE");
+    if (shape && g1.stages[0].win + g2.stages[1].win <= 8 && !(nf && nf[0] == '1')) {
+      pl->fused = true;
+      kp.fused = 1; kp.fW1 = g1.stages[0].win; kp.fW2 = g2.stages[1].win; kp.halo = kp.fW1 + kp.fW2;
+      auto normOf = [](int W) { float n = 0.f; for (int i = 1; i <= W; i++) n += (float)i * (float)i; return n * 2.0f; };
+      kp.fNorm1 = normOf(kp.fW1); kp.fNorm2 = normOf(kp.fW2);    // deltaRegression.cpp:77-80
+    }
+  }
   pp.frameSize = fe.frameSize; pp.frameStep = fe.frameStep;
   pp.nStat = d.nStatic; pp.maxN = 1; pp.halo = 0;
   for (int g = 0; g < pp.nGroups; g++) {
@@ -376,6 +401,7 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
   cudaDeviceSynchronize();
   if (pl->dConst) cudaFree(pl->dConst);
   pl->hMeta.release(); pl->hTiles.release(); pl->dMeta.release(); pl->dTiles.release(); pl->dStat.release();
+  pl->hChunks.release(); pl->dChunks.release();
   pl->dPcm.release(); pl->dOut.release();
   if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
   if (pl->evK0) cudaEventDestroy(pl->evK0);
@@ -423,8 +449,10 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
     const size_t nm = (size_t)(nUtt + 1);
     CU(pl->hMeta.reserve(3 * nm));
     long long *hU = pl->hMeta.p, *hR = hU + nm, *hS = hR + nm;
-    size_t nTiles = 0, nPost = 0;
+    size_t nPost = 0;
     const int PR = post_tile_rows();
+    const int F = pl->tileF, H = pl->kp.halo, KT = lld_max_chunk_tiles();
+    std::vector<ChunkRef> chunks;
     hR[0] = 0; hS[0] = 0;
     for (int u = 0; u < nUtt; u++) {
       if (uttOff[u + 1] < uttOff[u]) return fail(OSM_B200_ERR_INVALID, "utt_offsets must be non-decreasing");
@@ -433,29 +461,38 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
       hU[u] = uttOff[u];
       hR[u + 1] = hR[u] + desc_num_frames(d, L);
       hS[u + 1] = hS[u] + T;
-      nTiles += (size_t)((T + pl->tileF - 1) / pl->tileF);
-      nPost += (size_t)((hR[u + 1] - hR[u] + PR - 1) / PR);
+      if (!pl->fused) nPost += (size_t)((hR[u + 1] - hR[u] + PR - 1) / PR);
+      // chunks: output rows [a,b) whose static range [a-H, b+H) /\ [0,T) is a whole number of
+      // tiles (except at the utterance end), at most KT tiles each
+      for (int64_t a = 0; a < T;) {
+        const int64_t s0 = std::max<int64_t>(a - H, 0);
+        const int64_t maxEnd = s0 + (int64_t)F * KT;
+        const int64_t b2 = (maxEnd >= T) ? T : maxEnd - H;
+        chunks.push_back(ChunkRef{u, (int32_t)a, (int32_t)b2});
+        a = b2;
+      }
     }
     hU[nUtt] = uttOff[nUtt];
-    CU(pl->hTiles.reserve(nTiles + nPost + 1));
+    CU(pl->hTiles.reserve(nPost + 1));
     size_t ti = 0;
-    for (int u = 0; u < nUtt; u++) {
-      const int64_t T = hS[u + 1] - hS[u];
-      for (int64_t f0 = 0; f0 < T; f0 += pl->tileF) pl->hTiles.p[ti++] = TileRef{u, (int32_t)f0};
-    }
-    for (int u = 0; u < nUtt; u++) {
-      const int64_t To = hR[u + 1] - hR[u];
-      for (int64_t r0 = 0; r0 < To; r0 += PR) pl->hTiles.p[ti++] = TileRef{u, (int32_t)r0};
-    }
-    pl->nTiles = nTiles;
+    if (!pl->fused)
+      for (int u = 0; u < nUtt; u++) {
+        const int64_t To = hR[u + 1] - hR[u];
+        for (int64_t r0 = 0; r0 < To; r0 += PR) pl->hTiles.p[ti++] = TileRef{u, (int32_t)r0};
+      }
     pl->nPostTiles = nPost;
+    pl->nChunks = chunks.size();
+    CU(pl->hChunks.reserve(chunks.size() + 1));
+    if (!chunks.empty()) memcpy(pl->hChunks.p, chunks.data(), chunks.size() * sizeof(ChunkRef));
     pl->totalRows = hR[nUtt];
     pl->totalStat = hS[nUtt];
     pl->totalSamples = uttOff[nUtt];
     CU(pl->dMeta.reserve(3 * nm));
-    CU(pl->dTiles.reserve(nTiles + nPost + 1));
+    CU(pl->dTiles.reserve(nPost + 1));
+    CU(pl->dChunks.reserve(pl->nChunks + 1));
     CU(cudaMemcpyAsync(pl->dMeta.p, pl->hMeta.p, 3 * nm * sizeof(long long), cudaMemcpyHostToDevice, st));
-    if (nTiles + nPost) CU(cudaMemcpyAsync(pl->dTiles.p, pl->hTiles.p, (nTiles + nPost) * sizeof(TileRef), cudaMemcpyHostToDevice, st));
+    if (nPost) CU(cudaMemcpyAsync(pl->dTiles.p, pl->hTiles.p, nPost * sizeof(TileRef), cudaMemcpyHostToDevice, st));
+    if (pl->nChunks) CU(cudaMemcpyAsync(pl->dChunks.p, pl->hChunks.p, pl->nChunks * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(pl->evMetaDone, st));
     pl->metaPending = true;
     pl->cachedUttOff.assign(uttOff, uttOff + nUtt + 1);
@@ -481,7 +518,7 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
   pl->timed = false;
   osm_b200_status s = prepare_batch(pl, utt_offsets, n_utt, frame_offsets, st);
   if (s != OSM_B200_OK) return s;
-  if (pl->totalRows == 0 || pl->nTiles == 0) return OSM_B200_OK;
+  if (pl->totalRows == 0 || pl->nChunks == 0) return OSM_B200_OK;
   if (!d_pcm || !d_out) return fail(OSM_B200_ERR_INVALID, "null device buffer");
 
   const size_t nm = (size_t)(n_utt + 1);
@@ -489,8 +526,8 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
   LldParams kp = pl->kp;
   kp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
   kp.uttOff = dU;
-  kp.tiles = pl->dTiles.p;
-  kp.nTiles = (int)pl->nTiles;
+  kp.chunks = pl->dChunks.p;
+  kp.nChunks = (int)pl->nChunks;
   PostParams pp = pl->pp;
   if (pl->staticDirect) {
     kp.out = d_out; kp.outStride = pl->d.nOut; kp.outCol = pl->identityOutCol; kp.rowOff = dR;
@@ -501,13 +538,13 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
     pp.stat = pl->dStat.p; pp.statStride = pl->d.nStatic; pp.statOff = dS;
   }
   pp.out = d_out; pp.outStride = pl->d.nOut; pp.rowOff = dR; pp.uttOff = dU; pp.nUtt = n_utt;
-  pp.tiles = pl->dTiles.p + pl->nTiles; pp.nTiles = (int)pl->nPostTiles;
+  pp.tiles = pl->dTiles.p; pp.nTiles = (int)pl->nPostTiles;
 
   CU(cudaEventRecord(pl->evK0, st));
   CU(launch_lld(kp, pl->d.fe.nfft, pl->numSMs, st, &pl->lastInfo));
   pl->lastLaunches++;
   CU(cudaEventRecord(pl->evKm, st));
-  if (pp.nGroups > 0) {
+  if (pp.nGroups > 0 && !pl->fused) {
     CU(launch_post(pp, st));
     pl->lastLaunches++;
   }

@@ -32,7 +32,7 @@ namespace osm {
 // shared memory layout (identical computation on host and device)
 // ------------------------------------------------------------------------------------------
 struct SmemLayout {
-  int zbuf, samp, raw, rawPcm, mbar, winLut, tw, splitTw, melCoef, melRange, dctCos, dctLift, melS, mfccS;
+  int zbuf, samp, raw, rawPcm, mbar, winLut, tw, splitTw, melCoef, melRange, dctCos, dctLift, melS, ring;
   int total;
   int sampFloats, rawPcmBytes;
 };
@@ -67,7 +67,7 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
   L.dctLift = o; o += p.nMfcc * 4;
   o = align_up(o, 16);
   L.melS = o; o += p.nBands * F * 4;
-  L.mfccS = o; o += p.nMfcc * F * 4;
+  L.ring = o; o += p.nMfcc * 2 * F * 4;     // static features of the last two tiles
   L.total = align_up(o, 16);
   return L;
 }
@@ -127,35 +127,67 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// A chunk = output rows [a, b) of one utterance, processed by ONE CTA as consecutive tiles of F
+// frames.  With a temporal halo H (fused delta stages) the chunk computes the static features of
+// frames [max(a-H,0), min(b+H,T)); the host picks b so that this range is a whole number of
+// tiles, i.e. the halo costs no extra tile.
+struct ChunkCtx {
+  int utt, a, b;     // output rows [a,b) of utterance utt
+  int T;             // static frames of the utterance
+  int s0;            // first static frame computed by this chunk
+  int sEnd;          // one past the last static frame computed
+  int nT;            // tiles in this chunk
+  long long uo;      // sample-frame offset of the utterance
+  long long row0;    // output row of frame 0 of the utterance
+};
+
+template <int F>
+__device__ __forceinline__ ChunkCtx load_chunk(const LldParams &p, int chunk)
+{
+  ChunkCtx c;
+  const ChunkRef cr = p.chunks[chunk];
+  c.utt = cr.utt; c.a = cr.a; c.b = cr.b;
+  c.uo = p.uttOff[cr.utt];
+  const long long Ls = p.uttOff[cr.utt + 1] - c.uo;
+  c.T = (int)((Ls - p.frameSize) / p.frameStep + 1);
+  c.s0 = max(cr.a - p.halo, 0);
+  c.sEnd = min(cr.b + p.halo, c.T);
+  c.nT = (c.sEnd - c.s0 + F - 1) / F;
+  c.row0 = p.rowOff[cr.utt];
+  return c;
+}
+
 // geometry of one tile (all warp-uniform)
 struct TileGeom {
+  int fs;            // first static frame of the tile
   int nf;            // frames in this tile
   int count;         // sample frames the tile covers
   int lead;          // sample frames fetched before the tile start (0 at the utterance start)
   int mis;           // bytes between the 16-byte aligned fetch address and the first wanted byte
   uint32_t bytes;    // bulk copy size
   const char *src;   // 16-byte aligned fetch address
-  long long row0;    // first output row
 };
 
 template <int F>
-__device__ __forceinline__ TileGeom tile_geom(const LldParams &p, int tile)
+__device__ __forceinline__ TileGeom tile_geom(const LldParams &p, const ChunkCtx &c, int j)
 {
   TileGeom g;
-  const TileRef tr = p.tiles[tile];
-  const long long uo = p.uttOff[tr.utt];
-  const long long Ls = p.uttOff[tr.utt + 1] - uo;
-  const int T = (int)((Ls - p.frameSize) / p.frameStep + 1);
-  g.nf = min(F, T - tr.f0);
-  const long long s0 = (long long)tr.f0 * p.frameStep;
+  g.fs = c.s0 + j * F;
+  g.nf = min(F, c.sEnd - g.fs);
+  const long long s0 = (long long)g.fs * p.frameStep;
   g.count = (g.nf - 1) * p.frameStep + p.frameSize;
   g.lead = (s0 > 0) ? kLeadFrames : 0;
-  const char *a = reinterpret_cast<const char *>(p.pcm + (uo + s0 - g.lead) * p.nChan);
+  const char *a = reinterpret_cast<const char *>(p.pcm + (c.uo + s0 - g.lead) * p.nChan);
   g.mis = (int)(reinterpret_cast<uintptr_t>(a) & 15);
   g.src = a - g.mis;
   g.bytes = (uint32_t)align_up(g.mis + (g.lead + g.count) * p.nChan * 2, 16);
-  g.row0 = p.rowOff[tr.utt] + tr.f0;
   return g;
+}
+
+// reads of a window processor's input level under the tick-order model (see post_kernel)
+__device__ __forceinline__ int win_navail(int t, int n0, int c0, int Tprev)
+{
+  return (t < c0) ? Tprev : min(n0 + (t - c0) + 1, Tprev);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -245,7 +277,8 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   float *sDct = reinterpret_cast<float *>(smem + L.dctCos);
   float *sLift = reinterpret_cast<float *>(smem + L.dctLift);
   float *melS = reinterpret_cast<float *>(smem + L.melS);
-  float *mfccS = reinterpret_cast<float *>(smem + L.mfccS);
+  float *ring = reinterpret_cast<float *>(smem + L.ring);   // [nMfcc][2F], slot = (frame - chunk.s0) & (2F-1)
+  float *Dbuf = reinterpret_cast<float *>(smem + L.zbuf);  // delta level rows (aliases Z, dead after mel)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -268,15 +301,19 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   const int S = hop + p.sPad;
   uint32_t phase = 0;
 
-  int tile = blockIdx.x;
-  if (tile < p.nTiles && tid == 0) {
-    const TileGeom g0 = tile_geom<F>(p, tile);
+  int chunk = blockIdx.x;
+  if (chunk >= p.nChunks) return;
+  ChunkCtx cx = load_chunk<F>(p, chunk);
+  int j = 0;
+  int emitted = cx.a;                 // next output row of the current chunk to be written
+  if (tid == 0) {
+    const TileGeom g0 = tile_geom<F>(p, cx, 0);
     mbar_expect_tx(mbar, g0.bytes);
     bulk_g2s(rawPcm, g0.src, g0.bytes, mbar);
   }
 
-  for (; tile < p.nTiles; tile += gridDim.x) {
-    const TileGeom tg = tile_geom<F>(p, tile);
+  while (chunk < p.nChunks) {
+    const TileGeom tg = tile_geom<F>(p, cx, j);
     const int nf = tg.nf, count = tg.count;
 
     // ================= stage: PCM (smem, prefetched by the bulk copy) -> float -> pre-emphasis -> smem =================
@@ -295,23 +332,23 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
             const int4 w4 = *reinterpret_cast<const int4 *>(rp + i);
             const int wds[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              x[2 * j] = div32767((float)(short)(wds[j] & 0xffff));
-              x[2 * j + 1] = div32767((float)(wds[j] >> 16));
+            for (int jj = 0; jj < 4; jj++) {
+              x[2 * jj] = div32767((float)(short)(wds[jj] & 0xffff));
+              x[2 * jj + 1] = div32767((float)(wds[jj] >> 16));
             }
           } else {
             const int4 a4 = *reinterpret_cast<const int4 *>(rp + 2 * i);
             const int4 b4 = *reinterpret_cast<const int4 *>(rp + 2 * i + 8);
             const int wds[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const float l = (float)(short)(wds[j] & 0xffff), r = (float)(wds[j] >> 16);
-              x[j] = div32767(__fadd_rn(l, r) * 0.5f);
+            for (int jj = 0; jj < 8; jj++) {
+              const float l = (float)(short)(wds[jj] & 0xffff), r = (float)(wds[jj] >> 16);
+              x[jj] = div32767(__fadd_rn(l, r) * 0.5f);
             }
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; j++) x[j] = (j < nvalid) ? pcm_to_float_generic(rp + (i + j) * nChan, nChan) : 0.f;
+          for (int jj = 0; jj < 8; jj++) x[jj] = (jj < nvalid) ? pcm_to_float_generic(rp + (i + jj) * nChan, nChan) : 0.f;
         }
         float y[8];
         if (p.preemph) {
@@ -319,13 +356,13 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           float xprev = 0.f;
           if (i > 0 || tg.lead > 0) xprev = pcm_to_float_generic(rp + (i - 1) * nChan, nChan);
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float kx = __fmul_rn(p.preK, (j == 0) ? xprev : x[j - 1]);
-            y[j] = p.preDe ? __fadd_rn(x[j], kx) : __fsub_rn(x[j], kx);
+          for (int jj = 0; jj < 8; jj++) {
+            const float kx = __fmul_rn(p.preK, (jj == 0) ? xprev : x[jj - 1]);
+            y[jj] = p.preDe ? __fadd_rn(x[jj], kx) : __fsub_rn(x[jj], kx);
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 8; j++) y[j] = x[j];
+          for (int jj = 0; jj < 8; jj++) y[jj] = x[jj];
         }
         const int q = i / hop;
         const int r = i - q * hop;
@@ -334,14 +371,14 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           // the 8 samples lie inside one frame step: no pad crossing, at most one frame start
           if (r == 0 && q < F) raw[q] = x[0];
 #pragma unroll
-          for (int j = 0; j < 8; j += 2) *reinterpret_cast<float2 *>(dst + j) = make_float2(y[j], y[j + 1]);
+          for (int jj = 0; jj < 8; jj += 2) *reinterpret_cast<float2 *>(dst + jj) = make_float2(y[jj], y[jj + 1]);
         } else {
           int qq = q, rr = r;
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            if (j < nvalid) {
-              if (rr == 0 && qq < F) raw[qq] = x[j];
-              dst[j] = y[j];
+          for (int jj = 0; jj < 8; jj++) {
+            if (jj < nvalid) {
+              if (rr == 0 && qq < F) raw[qq] = x[jj];
+              dst[jj] = y[jj];
               rr++;
               if (rr == hop) { rr = 0; qq++; dst += p.sPad; }
             }
@@ -351,10 +388,14 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     }
     __syncthreads();
     // the landing zone is free again: fetch the next tile's PCM while this one is processed
-    {
-      const int next = tile + gridDim.x;
-      if (next < p.nTiles && tid == 0) {
-        const TileGeom gn = tile_geom<F>(p, next);
+    if (tid == 0) {
+      if (j + 1 < cx.nT) {
+        const TileGeom gn = tile_geom<F>(p, cx, j + 1);
+        mbar_expect_tx(mbar, gn.bytes);
+        bulk_g2s(rawPcm, gn.src, gn.bytes, mbar);
+      } else if (chunk + (int)gridDim.x < p.nChunks) {
+        const ChunkCtx cn = load_chunk<F>(p, chunk + gridDim.x);
+        const TileGeom gn = tile_geom<F>(p, cn, 0);
         mbar_expect_tx(mbar, gn.bytes);
         bulk_g2s(rawPcm, gn.src, gn.bytes, mbar);
       }
@@ -457,6 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     __syncthreads();
 
     // ================= DCT-II + lifter (mfcc.cpp:251-272) =================
+    const int ringBase = (j & 1) * F;   // tiles of a chunk alternate between the two ring halves
     // each virtual warp owns coefficients i, i+NVW, ... and evaluates them two at a time so
     // that one read of the log-mel column feeds two dot products; the cosine rows are read as
     // float4 (row stride padded to 4).  Each dot product keeps the reference's m = 0..nBands-1
@@ -482,21 +524,101 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
         const float l0 = lp[0];
         a0 = __fadd_rn(a0, __fmul_rn(l0, r0[k])); a1 = __fadd_rn(a1, __fmul_rn(l0, r1[k]));
       }
-      mfccS[i * F + f] = __fmul_rn(a0, sLift[i]);
-      if (two) mfccS[i1 * F + f] = __fmul_rn(a1, sLift[i1]);
+      ring[i * (2 * F) + ringBase + f] = __fmul_rn(a0, sLift[i]);
+      if (two) ring[i1 * (2 * F) + ringBase + f] = __fmul_rn(a1, sLift[i1]);
     }
     __syncthreads();
 
     // ================= store =================
-    {
+    if (!p.fused) {
+      // static rows only (the temporal stages, if any, run in post_kernel)
       const int tot = nf * p.nMfcc;
       for (int idx = tid; idx < tot; idx += NT) {
         const int ff = idx / p.nMfcc, c = idx - ff * p.nMfcc;
-        p.out[(tg.row0 + ff) * p.outStride + p.outCol + c] = mfccS[c * F + ff];
+        p.out[(cx.row0 + tg.fs + ff) * p.outStride + p.outCol + c] = ring[c * (2 * F) + ringBase + ff];
       }
+    } else {
+      // Fused delta / delta-delta (cDeltaRegression x2 + cVectorConcat): output row t needs the
+      // statics of frames t-H..t+H.  After tile j all rows up to (tile end - H) are computable
+      // (up to b on the chunk's last tile); their statics live in the two ring halves.
+      const int K = p.nMfcc, W1 = p.fW1, W2 = p.fW2, H = W1 + W2;
+      const int T = cx.T;
+      const int r0 = emitted;
+      const int r1 = (j + 1 == cx.nT) ? cx.b : min(tg.fs + F - H, cx.b);
+      // tick-order model (see post_kernel): level 1 (delta) has T+W1 frames, c0_1 = max(T-W1,0) of
+      // them before EOI; level 2 reads it with n0 = c0_1
+      const int T1 = T + W1, c01 = max(T - W1, 0), c02 = max(c01 - W2, 0);
+      const float norm1 = p.fNorm1, norm2 = p.fNorm2;
+      // ---- delta rows [r0-W2, r1+W2) /\ [0, T1) -> Dbuf[K][dRows] ----
+      const int d0 = max(r0 - W2, 0), d1 = min(r1 + W2, T1);
+      const int dRows = F + 24;             // row stride of Dbuf: >= (F + H) + 2 W2 rows, H <= 8
+      for (int idx = tid; idx < (d1 - d0) * K; idx += NT) {
+        const int tt = idx / K, c = idx - tt * K;
+        const int t = d0 + tt;
+        // level-0 reads: navail = T (the static level is complete at EOI)
+        const float *rc = ring + c * (2 * F);
+        float num = 0.f;
+        for (int i = 1; i <= W1; i++) {
+          int hi = t + i, lo = t - i;
+          float later, prior;
+          if (t - W1 < 0) {
+            later = (hi >= T) ? 0.f : rc[(hi - cx.s0) & (2 * F - 1)];
+            prior = rc[(max(lo, 0) - cx.s0) & (2 * F - 1)];
+          } else {
+            later = rc[(min(hi, T - 1) - cx.s0) & (2 * F - 1)];
+            prior = rc[(min(lo, T - 1) - cx.s0) & (2 * F - 1)];
+          }
+          num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));   // deltaRegression.cpp:139-146
+        }
+        Dbuf[c * dRows + tt] = __fdiv_rn(num, norm1);
+      }
+      __syncthreads();
+      // ---- rows [r0, r1): static | delta | delta-delta, 8 threads per row ----
+      {
+        float *o = p.out + (cx.row0 + r0) * (long long)p.outStride;
+        const int l8 = tid & 7;
+        for (int rr = tid >> 3; rr < r1 - r0; rr += NT / 8) {
+          const int t = r0 + rr;
+          const int navail2 = win_navail(t, c01, c02, T1);
+          for (int col = l8; col < 3 * K; col += 8) {
+            float v;
+            if (col < K) {
+              v = ring[col * (2 * F) + ((t - cx.s0) & (2 * F - 1))];
+            } else if (col < 2 * K) {
+              v = Dbuf[(col - K) * dRows + (t - d0)];
+            } else {
+              const float *dc = Dbuf + (col - 2 * K) * dRows - d0;
+              float num = 0.f;
+              for (int i = 1; i <= W2; i++) {
+                int hi = t + i, lo = t - i;
+                float later, prior;
+                if (t - W2 < 0) {
+                  later = (hi >= navail2) ? 0.f : dc[hi];
+                  prior = dc[max(lo, 0)];
+                } else {
+                  later = dc[min(hi, navail2 - 1)];
+                  prior = dc[min(lo, navail2 - 1)];
+                }
+                num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));
+              }
+              v = __fdiv_rn(num, norm2);
+            }
+            o[(long long)rr * p.outStride + col] = v;
+          }
+        }
+      }
+      emitted = r1;
+      // Dbuf aliases Z: the next tile's first FFT stage writes Z only after the barrier that
+      // follows its staging phase, which every thread reaches after finishing this block.
     }
-    // no barrier needed here: the next tile's staging only writes samp/raw, which no thread
-    // reads after the FFT's first stage; the barrier after staging orders everything else.
+
+    // ---- advance to the next tile / chunk ----
+    j++;
+    if (j == cx.nT) {
+      chunk += gridDim.x;
+      j = 0;
+      if (chunk < p.nChunks) { cx = load_chunk<F>(p, chunk); emitted = cx.a; }
+    }
   }
 }
 
@@ -650,6 +772,7 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
 // ------------------------------------------------------------------------------------------
 int lld_tile_frames(int nfft) { return nfft == 2048 ? 16 : 32; }
 int lld_virtual_warps(int nfft) { return nfft == 512 ? 8 : (nfft == 1024 ? 16 : 32); }
+int lld_max_chunk_tiles() { return 16; }
 bool lld_supported_fft(int nfft) { return nfft == 512 || nfft == 1024 || nfft == 2048; }
 
 size_t lld_smem_bytes(const LldParams &p, int nfft)
@@ -669,7 +792,7 @@ static cudaError_t launch_t(const LldParams &p, int numSMs, cudaStream_t st, Lld
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
   int grid = numSMs * occ;
-  if (grid > p.nTiles) grid = p.nTiles;
+  if (grid > p.nChunks) grid = p.nChunks;
   if (grid < 1) grid = 1;
   if (info) { info->grid = grid; info->block = NT; info->smem = smem; }
   kern<<<grid, NT, smem, st>>>(p);

@@ -7,7 +7,8 @@ namespace osm {
 
 constexpr int kMaxVW = 32;   // virtual warps (F-lane groups) per CTA
 
-struct TileRef { int32_t utt; int32_t f0; };   // <= F consecutive frames of one utterance
+struct TileRef { int32_t utt; int32_t f0; };   // (utterance, first row) of a post_kernel tile
+struct ChunkRef { int32_t utt; int32_t a; int32_t b; };   // output rows [a,b) of one utterance = one CTA work unit
 
 // Everything the fused per-frame kernel needs.  Pointers are device pointers; the table
 // pointers reference one packed constant blob uploaded at plan creation.
@@ -16,9 +17,12 @@ struct LldParams {
   const int16_t *pcm;
   const long long *uttOff;       // [nUtt+1] sample-frame offsets
   const long long *rowOff;       // [nUtt+1] first output row of each utterance
-  const TileRef *tiles;
-  int nTiles;
+  const ChunkRef *chunks;
+  int nChunks;
   int nChan;
+  // fused temporal stages (static | delta(W1) | delta(W1,W2)); halo = W1 + W2, 0 when not fused
+  int fused, halo, fW1, fW2;
+  float fNorm1, fNorm2;
   // ---- front end ----
   int frameSize, frameStep, sPad;
   int preemph, preDe;
@@ -87,6 +91,7 @@ size_t lld_smem_bytes(const LldParams &p, int nfft);
 // frames per tile / virtual warps per CTA for a given FFT size
 int lld_tile_frames(int nfft);
 int lld_virtual_warps(int nfft);
+int lld_max_chunk_tiles();
 bool lld_supported_fft(int nfft);
 
 }  // namespace osm

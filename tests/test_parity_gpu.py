@@ -128,3 +128,25 @@ def test_full_size_properties(plan16):
     assert np.array_equal(blk[0], blk[-1]) and np.array_equal(blk[0], blk[len(blk) // 2])
     single = plan16.run_host(base[:L], np.array([0, L], np.int64))
     assert np.array_equal(single, out[:500])
+
+
+def test_fused_and_two_kernel_paths_agree(plan16, monkeypatch):
+    """The delta stages run fused inside lld_kernel by default; OSM_B200_NO_FUSE=1 selects the
+    generic post_kernel path.  Both must give bit-identical rows (same float arithmetic), on
+    ragged batches including 1-3 frame utterances (tick-order edge model) and long utterances
+    that are split into several chunks."""
+    lens = [400, 560, 720, 880, 1040, 16000, 400 + 160 * 600, 400 + 160 * 1100, 399, 5000]
+    utts = [voiced_pcm(n, 16000, seed=400 + i) for i, n in enumerate(lens)]
+    pcm, off = pack_utterances(utts)
+    fused = plan16.run_host(pcm, off)
+    monkeypatch.setenv("OSM_B200_NO_FUSE", "1")
+    p2 = Plan(components_mfcc12_0_d_a(16000.0), "lld", device=0)
+    two = p2.run_host(pcm, off)
+    assert p2.last_launch_count() == 2 and plan16.last_launch_count() == 1
+    p2.close()
+    assert np.array_equal(fused, two)
+    fo = plan16.frame_offsets(off)
+    for u, x in enumerate(utts):
+        ref = oracle.mfcc_d_a(x, 16000.0)
+        if ref.shape[0]:
+            assert rel_to_frame_scale(fused[fo[u]:fo[u + 1]], ref) < TOL
