@@ -371,6 +371,9 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       kp.fused = 1; kp.fW1 = g1.stages[0].win; kp.fW2 = g2.stages[1].win; kp.halo = kp.fW1 + kp.fW2;
       auto normOf = [](int W) { float n = 0.f; for (int i = 1; i <= W; i++) n += (float)i * (float)i; return n * 2.0f; };
       kp.fNorm1 = normOf(kp.fW1); kp.fNorm2 = normOf(kp.fW2);    // deltaRegression.cpp:77-80
+      // divisors with an exhaustively verified exact reciprocal+FMA division (kernels.cu div_exact)
+      auto rcpOf = [](float n) { return (n == 2.f || n == 10.f || n == 28.f || n == 60.f) ? 1.0f / n : 0.f; };
+      kp.fRcp1 = rcpOf(kp.fNorm1); kp.fRcp2 = rcpOf(kp.fNorm2);
     }
   }
   pp.frameSize = fe.frameSize; pp.frameStep = fe.frameStep;

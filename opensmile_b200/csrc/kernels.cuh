@@ -23,6 +23,7 @@ struct LldParams {
   // fused temporal stages (static | delta(W1) | delta(W1,W2)); halo = W1 + W2, 0 when not fused
   int fused, halo, fW1, fW2;
   float fNorm1, fNorm2;
+  float fRcp1, fRcp2;            // 1/norm when the reciprocal+FMA division is proven exact for it, else 0
   // ---- front end ----
   int frameSize, frameStep, sPad;
   int preemph, preDe;
