@@ -105,7 +105,9 @@ struct osm_b200_plan {
   // run_host buffers
   DevBuf<int16_t> dPcm;
   DevBuf<float> dOut;
-  cudaStream_t hostStream = nullptr;
+  cudaStream_t hostStream = nullptr, h2dStream = nullptr, d2hStream = nullptr;
+  std::vector<cudaEvent_t> evPiece;   // 2 per pipeline piece: PCM landed / rows computed
+  std::vector<int32_t> uttChunk0, uttPost0;   // first chunk / post tile of each utterance (+ sentinel)
   int lastLaunches = 0;
   LldLaunchInfo lastInfo{};
 };
@@ -401,6 +403,9 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
   if (pl->device < 0) { delete pl; return; }
   cudaSetDevice(pl->device);
   if (pl->hostStream) { cudaStreamSynchronize(pl->hostStream); cudaStreamDestroy(pl->hostStream); }
+  if (pl->h2dStream) cudaStreamDestroy(pl->h2dStream);
+  if (pl->d2hStream) cudaStreamDestroy(pl->d2hStream);
+  for (cudaEvent_t e : pl->evPiece) cudaEventDestroy(e);
   cudaDeviceSynchronize();
   if (pl->dConst) cudaFree(pl->dConst);
   pl->hMeta.release(); pl->hTiles.release(); pl->dMeta.release(); pl->dTiles.release(); pl->dStat.release();
@@ -456,6 +461,7 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
     const int PR = post_tile_rows();
     const int F = pl->tileF, H = pl->kp.halo, KT = lld_max_chunk_tiles();
     std::vector<ChunkRef> chunks;
+    pl->uttChunk0.assign(nm, 0); pl->uttPost0.assign(nm, 0);
     hR[0] = 0; hS[0] = 0;
     for (int u = 0; u < nUtt; u++) {
       if (uttOff[u + 1] < uttOff[u]) return fail(OSM_B200_ERR_INVALID, "utt_offsets must be non-decreasing");
@@ -464,6 +470,8 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
       hU[u] = uttOff[u];
       hR[u + 1] = hR[u] + desc_num_frames(d, L);
       hS[u + 1] = hS[u] + T;
+      pl->uttChunk0[u] = (int32_t)chunks.size();
+      pl->uttPost0[u] = (int32_t)nPost;
       if (!pl->fused) nPost += (size_t)((hR[u + 1] - hR[u] + PR - 1) / PR);
       // chunks: output rows [a,b) whose static range [a-H, b+H) /\ [0,T) is a whole number of
       // tiles (except at the utterance end), at most KT tiles each
@@ -476,6 +484,8 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
       }
     }
     hU[nUtt] = uttOff[nUtt];
+    pl->uttChunk0[nUtt] = (int32_t)chunks.size();
+    pl->uttPost0[nUtt] = (int32_t)nPost;
     CU(pl->hTiles.reserve(nPost + 1));
     size_t ti = 0;
     if (!pl->fused)
@@ -510,6 +520,40 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
   return OSM_B200_OK;
 }
 
+// launch the kernels for utterances [u0, u1) of the prepared batch
+static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float *d_out, int n_utt, int u0, int u1,
+                                    cudaStream_t st)
+{
+  const int c0 = pl->uttChunk0[u0], c1 = pl->uttChunk0[u1];
+  if (c1 <= c0) return OSM_B200_OK;
+  const size_t nm = (size_t)(n_utt + 1);
+  const long long *dU = pl->dMeta.p, *dR = dU + nm, *dS = dR + nm;
+  LldParams kp = pl->kp;
+  kp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
+  kp.uttOff = dU;
+  kp.chunks = pl->dChunks.p + c0;
+  kp.nChunks = c1 - c0;
+  PostParams pp = pl->pp;
+  if (pl->staticDirect) {
+    kp.out = d_out; kp.outStride = pl->d.nOut; kp.outCol = pl->identityOutCol; kp.rowOff = dR;
+    pp.stat = d_out + pl->identityOutCol; pp.statStride = pl->d.nOut; pp.statOff = dR;
+  } else {
+    kp.out = pl->dStat.p; kp.outStride = pl->d.nStatic; kp.outCol = 0; kp.rowOff = dS;
+    pp.stat = pl->dStat.p; pp.statStride = pl->d.nStatic; pp.statOff = dS;
+  }
+  pp.out = d_out; pp.outStride = pl->d.nOut; pp.rowOff = dR; pp.uttOff = dU; pp.nUtt = n_utt;
+  pp.tiles = pl->dTiles.p + pl->uttPost0[u0]; pp.nTiles = pl->uttPost0[u1] - pl->uttPost0[u0];
+
+  CU(launch_lld(kp, pl->d.fe.nfft, pl->numSMs, st, &pl->lastInfo));
+  pl->lastLaunches++;
+  if (u0 == 0) CU(cudaEventRecord(pl->evKm, st));
+  if (pp.nGroups > 0 && !pl->fused) {
+    CU(launch_post(pp, st));
+    pl->lastLaunches++;
+  }
+  return OSM_B200_OK;
+}
+
 osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, const int64_t *utt_offsets,
                                          int32_t n_utt, const int64_t *frame_offsets, float *d_out, void *stream)
 {
@@ -523,64 +567,80 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
   if (s != OSM_B200_OK) return s;
   if (pl->totalRows == 0 || pl->nChunks == 0) return OSM_B200_OK;
   if (!d_pcm || !d_out) return fail(OSM_B200_ERR_INVALID, "null device buffer");
-
-  const size_t nm = (size_t)(n_utt + 1);
-  const long long *dU = pl->dMeta.p, *dR = dU + nm, *dS = dR + nm;
-  LldParams kp = pl->kp;
-  kp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
-  kp.uttOff = dU;
-  kp.chunks = pl->dChunks.p;
-  kp.nChunks = (int)pl->nChunks;
-  PostParams pp = pl->pp;
-  if (pl->staticDirect) {
-    kp.out = d_out; kp.outStride = pl->d.nOut; kp.outCol = pl->identityOutCol; kp.rowOff = dR;
-    pp.stat = d_out + pl->identityOutCol; pp.statStride = pl->d.nOut; pp.statOff = dR;
-  } else {
-    CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic));
-    kp.out = pl->dStat.p; kp.outStride = pl->d.nStatic; kp.outCol = 0; kp.rowOff = dS;
-    pp.stat = pl->dStat.p; pp.statStride = pl->d.nStatic; pp.statOff = dS;
-  }
-  pp.out = d_out; pp.outStride = pl->d.nOut; pp.rowOff = dR; pp.uttOff = dU; pp.nUtt = n_utt;
-  pp.tiles = pl->dTiles.p; pp.nTiles = (int)pl->nPostTiles;
-
+  if (!pl->staticDirect) CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic));
   CU(cudaEventRecord(pl->evK0, st));
-  CU(launch_lld(kp, pl->d.fe.nfft, pl->numSMs, st, &pl->lastInfo));
-  pl->lastLaunches++;
-  CU(cudaEventRecord(pl->evKm, st));
-  if (pp.nGroups > 0 && !pl->fused) {
-    CU(launch_post(pp, st));
-    pl->lastLaunches++;
-  }
+  s = launch_range(pl, d_pcm, d_out, n_utt, 0, n_utt, st);
+  if (s != OSM_B200_OK) return s;
   CU(cudaEventRecord(pl->evK1, st));
   pl->timed = true;
   return OSM_B200_OK;
 }
 
+// Host buffers.  The batch is cut into pieces of whole utterances and pipelined over three
+// streams: H2D of piece k+1, kernels of piece k and D2H of piece k-1 overlap (the two copy
+// directions use separate copy engines).  Host memory should be pinned (cudaHostAlloc /
+// torch pin_memory) for the copies to be asynchronous; pageable memory works but serialises.
 osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const int64_t *utt_offsets, int32_t n_utt,
                                        const int64_t *frame_offsets, float *out)
 {
   if (!pl || !utt_offsets || n_utt < 0) return fail(OSM_B200_ERR_INVALID, "null argument");
   if (pl->device < 0) return fail(OSM_B200_ERR_CUDA, "description-only plan (device < 0) cannot run; no CPU fallback");
   CU(cudaSetDevice(pl->device));
-  if (!pl->hostStream) CU(cudaStreamCreateWithFlags(&pl->hostStream, cudaStreamNonBlocking));
-  cudaStream_t st = pl->hostStream;
-  const int64_t nSamp = utt_offsets[n_utt] * pl->d.fe.nChan;
-  std::vector<int64_t> fo;
-  if (!frame_offsets) {
-    fo.resize(n_utt + 1);
-    osm_b200_status s = osm_b200_plan_frame_offsets(pl, utt_offsets, n_utt, fo.data());
-    if (s != OSM_B200_OK) return s;
-    frame_offsets = fo.data();
+  if (!pl->hostStream) {
+    CU(cudaStreamCreateWithFlags(&pl->hostStream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&pl->h2dStream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&pl->d2hStream, cudaStreamNonBlocking));
   }
-  const int64_t rows = frame_offsets[n_utt];
-  if (rows == 0) return OSM_B200_OK;
-  if (!pcm || !out) return fail(OSM_B200_ERR_INVALID, "null host buffer");
-  CU(pl->dPcm.reserve((size_t)nSamp + 8));
-  CU(pl->dOut.reserve((size_t)rows * pl->d.nOut));
-  CU(cudaMemcpyAsync(pl->dPcm.p, pcm, (size_t)nSamp * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-  osm_b200_status s = osm_b200_plan_run_device(pl, pl->dPcm.p, utt_offsets, n_utt, frame_offsets, pl->dOut.p, st);
+  cudaStream_t st = pl->hostStream;
+  pl->lastLaunches = 0;
+  pl->timed = false;
+  osm_b200_status s = prepare_batch(pl, utt_offsets, n_utt, frame_offsets, st);
   if (s != OSM_B200_OK) return s;
-  CU(cudaMemcpyAsync(out, pl->dOut.p, (size_t)rows * pl->d.nOut * sizeof(float), cudaMemcpyDeviceToHost, st));
+  const long long rows = pl->totalRows;
+  if (rows == 0 || pl->nChunks == 0) return OSM_B200_OK;
+  if (!pcm || !out) return fail(OSM_B200_ERR_INVALID, "null host buffer");
+  const int nChan = pl->d.fe.nChan, nOut = pl->d.nOut;
+  const int64_t nSamp = utt_offsets[n_utt] * nChan;
+  CU(pl->dPcm.reserve((size_t)nSamp + 16));
+  CU(pl->dOut.reserve((size_t)rows * nOut));
+  if (!pl->staticDirect) CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic));
+  const long long *hR = pl->hMeta.p + (size_t)(n_utt + 1);
+
+  // pieces of ~24 MB of PCM, at most 16, cut at utterance boundaries
+  const int64_t totalBytes = nSamp * 2;
+  int nPieces = (int)std::min<int64_t>(16, std::max<int64_t>(1, totalBytes / (24 << 20)));
+  if (nPieces > n_utt) nPieces = n_utt;
+  while ((int)pl->evPiece.size() < 2 * nPieces) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    pl->evPiece.push_back(e);
+  }
+  CU(cudaEventRecord(pl->evK0, st));
+  int u0 = 0;
+  for (int k = 0; k < nPieces; k++) {
+    int u1 = u0;
+    const int64_t target = utt_offsets[n_utt] * (int64_t)(k + 1) / nPieces;
+    while (u1 < n_utt && (utt_offsets[u1 + 1] <= target || u1 == u0)) u1++;
+    if (k == nPieces - 1) u1 = n_utt;
+    if (u1 == u0) continue;
+    const int64_t sa = utt_offsets[u0] * nChan, sb = utt_offsets[u1] * nChan;
+    CU(cudaMemcpyAsync(pl->dPcm.p + sa, reinterpret_cast<const int16_t *>(pcm) + sa, (size_t)(sb - sa) * sizeof(int16_t),
+                       cudaMemcpyHostToDevice, pl->h2dStream));
+    CU(cudaEventRecord(pl->evPiece[2 * k], pl->h2dStream));
+    CU(cudaStreamWaitEvent(st, pl->evPiece[2 * k], 0));
+    s = launch_range(pl, pl->dPcm.p, pl->dOut.p, n_utt, u0, u1, st);
+    if (s != OSM_B200_OK) return s;
+    CU(cudaEventRecord(pl->evPiece[2 * k + 1], st));
+    CU(cudaStreamWaitEvent(pl->d2hStream, pl->evPiece[2 * k + 1], 0));
+    const long long ra = hR[u0], rb = hR[u1];
+    if (rb > ra)
+      CU(cudaMemcpyAsync(out + ra * nOut, pl->dOut.p + ra * nOut, (size_t)(rb - ra) * nOut * sizeof(float),
+                         cudaMemcpyDeviceToHost, pl->d2hStream));
+    u0 = u1;
+  }
+  CU(cudaEventRecord(pl->evK1, st));
+  pl->timed = true;
+  CU(cudaStreamSynchronize(pl->d2hStream));
   CU(cudaStreamSynchronize(st));
   return OSM_B200_OK;
 }

@@ -150,3 +150,22 @@ def test_fused_and_two_kernel_paths_agree(plan16, monkeypatch):
         ref = oracle.mfcc_d_a(x, 16000.0)
         if ref.shape[0]:
             assert rel_to_frame_scale(fused[fo[u]:fo[u + 1]], ref) < TOL
+
+
+def test_pipelined_host_path_matches_device_path(plan16):
+    """run_host cuts large batches into pieces that overlap H2D / kernels / D2H on three streams;
+    rows must be bit-identical to the single-launch device path (112 MB of PCM -> 4 pieces)."""
+    import torch
+    n_utt, L = 700, 80240
+    base = np.concatenate([voiced_pcm(L, 16000, seed=500 + i) for i in range(7)])
+    pcm = np.tile(base, n_utt // 7)
+    off = np.arange(n_utt + 1, dtype=np.int64) * L
+    h_pcm = torch.from_numpy(pcm).pin_memory()
+    h_out = torch.empty((n_utt * 500, 39), dtype=torch.float32).pin_memory()
+    plan16.run_host(h_pcm, off, out=h_out)
+    dev = plan16.run_device(h_pcm.cuda(), off)
+    torch.cuda.synchronize()
+    assert torch.equal(dev.cpu(), h_out)
+    ref = oracle.mfcc_d_a(base[:L], 16000.0)
+    assert rel_to_frame_scale(h_out[:500].numpy(), ref) < TOL
+    assert rel_to_frame_scale(h_out[-3500:-3000].numpy(), ref) < TOL
