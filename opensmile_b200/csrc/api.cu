@@ -226,7 +226,8 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     delete pl;
     return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(d.fe.nfft) + " not supported (512, 1024, 2048)");
   }
-  if (d.ops.size() != 1 || d.ops[0].kind != SOP_MFCC) { delete pl; return fail(OSM_B200_ERR_UNSUPPORTED, "only a single cMfcc static producer is supported"); }
+  if (d.ops.size() != 1 || (d.ops[0].kind != SOP_MFCC && d.ops[0].kind != SOP_PLP)) { delete pl; return fail(OSM_B200_ERR_UNSUPPORTED, "exactly one cMfcc or cPlp static producer is supported"); }
+  if (d.ops[0].kind == SOP_PLP && d.ops[0].plp.doLpToCeps && d.ops[0].plp.firstCC > 1) { delete pl; return fail(OSM_B200_ERR_UNSUPPORTED, "cPlp: firstCC > 1 is not supported"); }
 
   if (device < 0) {
     // description-only plan: geometry, names and frame-count rules without touching CUDA
@@ -253,8 +254,10 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   // ---- pack constant tables ----
   const FrontEnd &fe = d.fe;
   const int M = fe.nfft / 2;
-  const MelBank &mb = d.mels[d.ops[0].mfcc.melIdx];
+  const bool isPlp = d.ops[0].kind == SOP_PLP;
+  const MelBank &mb = d.mels[isPlp ? d.ops[0].plp.melIdx : d.ops[0].mfcc.melIdx];
   const MfccOp &mf = d.ops[0].mfcc;
+  const PlpOp &po = d.ops[0].plp;
   pl->tileF = lld_tile_frames(fe.nfft);
 
   LldParams &kp = pl->kp;
@@ -289,8 +292,17 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   // the kernel keeps 2X (4|X|^2) out of the real-FFT split; the exact factor 1/4 of the power
   // path is folded into the band scale (power-of-two scaling commutes with rounding)
   kp.melScale = mb.usePower ? mb.outScale * 0.25f : mb.outScale;
-  kp.dctStride = (mb.nBands + 3) / 4 * 4;
-  kp.nMfcc = mf.nMfcc; kp.melfloor = mf.melfloor; kp.logMelfloor = mf.logMelfloor; kp.doLog = mf.doLog;
+  if (!isPlp) { kp.dctStride = (mb.nBands + 3) / 4 * 4; kp.dctRows = mf.nMfcc; }
+  else { kp.dctStride = po.nFreq; kp.dctRows = po.nAuto; }
+  kp.opKind = isPlp ? 1 : 0;
+  if (!isPlp) {
+    kp.nStat = mf.nMfcc; kp.melfloor = mf.melfloor; kp.logMelfloor = mf.logMelfloor; kp.doLog = mf.doLog;
+  } else {
+    kp.nStat = po.nOut; kp.melfloor = po.melfloor; kp.logMelfloor = po.logMelfloor; kp.doLog = po.doLog;
+    kp.plpAud = po.doAud; kp.plpInvLog = po.doInvLog; kp.plpIDFT = po.doIDFT; kp.plpLP = po.doLP; kp.plpCeps = po.doLpToCeps;
+    kp.plpHtk = po.htk; kp.plpLifter = po.lifter; kp.plpOrder = po.lpOrder; kp.plpNAuto = po.nAuto; kp.plpNFreq = po.nFreq;
+    kp.plpFirstCC = po.firstCC; kp.plpLastCC = po.lastCC; kp.plpCompression = po.compression;
+  }
   // split the bands over the virtual warps, balancing visited bins (ranges bs..be)
   {
     const int nvw = lld_virtual_warps(fe.nfft);
@@ -314,11 +326,18 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   const size_t oSplit = o; o = up16(o + split.size() * sizeof(float2));
   const size_t oCoef = o; o = up16(o + mb.coef.size() * sizeof(float));
   const size_t oRange = o; o = up16(o + mb.rangeBegin.size() * sizeof(int));
-  std::vector<float> dctPad((size_t)mf.nMfcc * kp.dctStride, 0.f);
-  for (int i = 0; i < mf.nMfcc; i++)
-    memcpy(&dctPad[(size_t)i * kp.dctStride], &mf.cosT[(size_t)i * mb.nBands], sizeof(float) * mb.nBands);
+  std::vector<float> dctPad((size_t)kp.dctRows * kp.dctStride, 0.f);
+  if (!isPlp) {
+    for (int i = 0; i < mf.nMfcc; i++)
+      memcpy(&dctPad[(size_t)i * kp.dctStride], &mf.cosT[(size_t)i * mb.nBands], sizeof(float) * mb.nBands);
+  } else {
+    memcpy(dctPad.data(), po.cosT.data(), sizeof(float) * po.cosT.size());
+  }
+  const std::vector<float> &liftV = isPlp ? po.lift : mf.liftFactor;
+  std::vector<float> eqlV = isPlp ? po.eql : std::vector<float>(1, 0.f);
   const size_t oDct = o; o = up16(o + dctPad.size() * sizeof(float));
-  const size_t oLift = o; o = up16(o + mf.liftFactor.size() * sizeof(float));
+  const size_t oLift = o; o = up16(o + liftV.size() * sizeof(float));
+  const size_t oEql = o; o = up16(o + eqlV.size() * sizeof(float));
   std::vector<unsigned char> blob(o, 0);
   memcpy(&blob[oWin], winLut.data(), winLut.size() * sizeof(float4));
   if (!tw.empty()) memcpy(&blob[oTw], tw.data(), tw.size() * sizeof(float2));
@@ -326,7 +345,8 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   memcpy(&blob[oCoef], mb.coef.data(), mb.coef.size() * sizeof(float));
   memcpy(&blob[oRange], mb.rangeBegin.data(), mb.rangeBegin.size() * sizeof(int));
   memcpy(&blob[oDct], dctPad.data(), dctPad.size() * sizeof(float));
-  memcpy(&blob[oLift], mf.liftFactor.data(), mf.liftFactor.size() * sizeof(float));
+  memcpy(&blob[oLift], liftV.data(), liftV.size() * sizeof(float));
+  memcpy(&blob[oEql], eqlV.data(), eqlV.size() * sizeof(float));
   CUP(cudaMalloc(&pl->dConst, o));
   CUP(cudaMemcpy(pl->dConst, blob.data(), o, cudaMemcpyHostToDevice));
   kp.winLut = reinterpret_cast<const float4 *>(pl->dConst + oWin);
@@ -336,6 +356,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   kp.melRange = reinterpret_cast<const int *>(pl->dConst + oRange);
   kp.dctCos = reinterpret_cast<const float *>(pl->dConst + oDct);
   kp.dctLift = reinterpret_cast<const float *>(pl->dConst + oLift);
+  kp.plpEql = reinterpret_cast<const float *>(pl->dConst + oEql);
 
   const size_t smemNeed = lld_smem_bytes(kp, fe.nfft);
   if (smemNeed > (size_t)prop.sharedMemPerBlockOptin) {

@@ -144,12 +144,12 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     if (it != staticOpOf.end()) {
       opIdx = it->second;
     } else {
-      if (c->type != OSM_B200_C_MFCC) {
+      if (c->type != OSM_B200_C_MFCC && c->type != OSM_B200_C_PLP) {
         snprintf(buf, sizeof buf, "component '%s' (%s) is not a supported static LLD producer", c->name, type_name(c->type));
         err = buf; return OSM_B200_ERR_UNSUPPORTED;
       }
       const osm_b200_component *mel = single_input(c);
-      if (!mel || mel->type != OSM_B200_C_MELSPEC) { err = "cMfcc must read a cMelspec level"; return OSM_B200_ERR_UNSUPPORTED; }
+      if (!mel || mel->type != OSM_B200_C_MELSPEC) { err = "cMfcc / cPlp must read a cMelspec level"; return OSM_B200_ERR_UNSUPPORTED; }
       const osm_b200_component *mag = single_input(mel);
       if (!mag || mag->type != OSM_B200_C_FFTMAGPHASE) { err = "cMelspec must read a cFFTmagphase level"; return OSM_B200_ERR_UNSUPPORTED; }
       if (feTail && feTail != mag) { err = "all static LLDs must share one framer/FFT chain"; return OSM_B200_ERR_UNSUPPORTED; }
@@ -232,18 +232,32 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       build_mel(melp, d.fe.nBins, d.fe.fftFrameSizeSec, mb);
       d.mels.push_back(mb);
       StaticOp op;
-      op.kind = SOP_MFCC;
-      const auto &mfp = c->u.mfcc;
-      if (mfp.lastMfcc < mfp.firstMfcc || mfp.firstMfcc < 0 || mfp.lastMfcc >= melp.nBands) { err = "cMfcc: bad firstMfcc/lastMfcc"; return OSM_B200_ERR_INVALID; }
-      build_mfcc(mfp, melp.nBands, op.mfcc);
-      op.mfcc.melIdx = (int)d.mels.size() - 1;
+      std::string opName;
+      if (c->type == OSM_B200_C_MFCC) {
+        op.kind = SOP_MFCC;
+        const auto &mfp = c->u.mfcc;
+        if (mfp.lastMfcc < mfp.firstMfcc || mfp.firstMfcc < 0 || mfp.lastMfcc >= melp.nBands) { err = "cMfcc: bad firstMfcc/lastMfcc"; return OSM_B200_ERR_INVALID; }
+        build_mfcc(mfp, melp.nBands, op.mfcc);
+        op.mfcc.melIdx = (int)d.mels.size() - 1;
+        op.nOut = op.mfcc.nMfcc;
+        op.arrNameOffset = op.mfcc.first;                              // lldcore/mfcc.cpp:125
+        opName = name_append_auto(*c, base, nullptr);                  // lldcore/mfcc.cpp:120-128
+      } else {
+        op.kind = SOP_PLP;
+        if (!build_plp(c->u.plp, d.mels.back(), op.plp, err)) return OSM_B200_ERR_UNSUPPORTED;
+        op.plp.melIdx = (int)d.mels.size() - 1;
+        op.nOut = op.plp.nOut;
+        op.arrNameOffset = 0;
+        // lldcore/plp.cpp:232-267 replaces the field name, then cVectorProcessor appends nameAppend
+        const char *fixed = op.plp.doLpToCeps ? "PlpCC" : (op.plp.doLP ? "Plpc" : (op.plp.doIDFT ? "audAutoCor" : "audSpec"));
+        opName = name_append_auto(*c, fixed, nullptr);
+      }
       op.outCol = d.nStatic;
-      op.nOut = op.mfcc.nMfcc;
       d.nStatic += op.nOut;
       d.ops.push_back(op);
       opIdx = (int)d.ops.size() - 1;
       staticOpOf[c] = opIdx;
-      staticBaseName.push_back(name_append_auto(*c, base, nullptr));  // lldcore/mfcc.cpp:120-128
+      staticBaseName.push_back(opName);
     }
 
     // ---- group ----
@@ -274,7 +288,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     d.groups.push_back(g);
     // element names: name[idx + arrNameOffset] (core/dataMemoryLevel.cpp:1158-1169);
     // cMfcc passes firstMfcc as arrNameOffset (lldcore/mfcc.cpp:125)
-    const int off = d.ops[opIdx].mfcc.first;
+    const int off = d.ops[opIdx].arrNameOffset;
     for (int i = 0; i < g.n; i++) {
       snprintf(buf, sizeof buf, "%s[%d]", nm.c_str(), i + off);
       d.names.push_back(buf);

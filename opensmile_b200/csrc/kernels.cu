@@ -32,7 +32,7 @@ namespace osm {
 // shared memory layout (identical computation on host and device)
 // ------------------------------------------------------------------------------------------
 struct SmemLayout {
-  int zbuf, samp, raw, rawPcm, mbar, winLut, tw, splitTw, melCoef, melRange, dctCos, dctLift, melS, ring;
+  int zbuf, samp, raw, rawPcm, mbar, winLut, tw, splitTw, melCoef, melRange, dctCos, dctLift, eql, melS, ring;
   int total;
   int sampFloats, rawPcmBytes;
 };
@@ -63,11 +63,12 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
   L.melCoef = o; o += (M + 1) * 4;
   L.melRange = o; o += (p.nBands + 2) * 4;
   o = align_up(o, 16);
-  L.dctCos = o; o += p.nMfcc * p.dctStride * 4;
-  L.dctLift = o; o += p.nMfcc * 4;
+  L.dctCos = o; o += p.dctRows * p.dctStride * 4;
+  L.dctLift = o; o += p.nStat * 4;
+  L.eql = o; o += (p.opKind == 1 ? p.nBands : 0) * 4;
   o = align_up(o, 16);
   L.melS = o; o += p.nBands * F * 4;
-  L.ring = o; o += p.nMfcc * 2 * F * 4;     // static features of the last two tiles
+  L.ring = o; o += p.nStat * 2 * F * 4;     // static features of the last two tiles
   L.total = align_up(o, 16);
   return L;
 }
@@ -265,6 +266,107 @@ __device__ __forceinline__ void fft_stage(float2 *__restrict__ Z, const float *_
 }
 
 // ------------------------------------------------------------------------------------------
+// cPlp back end for one tile, lane = frame (lldcore/plp.cpp:520-590):
+//   IDFT of the compressed auditory spectrum -> autocorrelation (double accumulation, :522-532)
+//   Durbin recursion (smileutil/smileUtil.c:1572-1627), lp -> cepstrum (HTK eq. 5.11, :1532-1556),
+//   c0 = -log(1/gain), lifter.  melS holds the nBands processed band values per frame; acfS is
+//   scratch [nAuto][F] (aliases the dead FFT tile); dst = ring slot base, row stride 2F.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxLp = 8;
+
+template <int F, int NVW>
+__device__ __forceinline__ void plp_backend(const LldParams &p, const float *melS, const float *sCos,
+                                            const float *sLift, float *acfS, float *dst, int vw, int f)
+{
+  const int nB = p.nBands, nFreq = p.plpNFreq, nAuto = p.plpNAuto;
+  if (!p.plpIDFT) {   // audSpec output: the processed bands themselves
+    for (int i = vw; i < nB; i += NVW) dst[i * (2 * F) + f] = melS[i * F + f];
+    return;
+  }
+  for (int i = vw; i < nAuto; i += NVW) {
+    const float *ct = sCos + i * p.dctStride;
+    double tmp = 0.0;
+    if (p.plpHtk) tmp = (double)ct[0] * (double)melS[f];
+    for (int m = 1; m < nFreq - 1; m++) tmp = __dadd_rn(tmp, (double)ct[m] * (double)melS[(m - 1) * F + f]);
+    tmp = __dadd_rn(tmp, (double)ct[nFreq - 1] * (double)melS[(nFreq - 3) * F + f]);
+    const float a = (float)(tmp / (2.0 * (double)(nFreq - 1)));
+    if (!p.plpLP) dst[i * (2 * F) + f] = a;
+    else acfS[i * F + f] = a;
+  }
+  if (!p.plpLP) return;
+  __syncthreads();
+  if (vw == 0) {
+    const int P = p.plpOrder;
+    float r[kMaxLp + 1], a[kMaxLp], cc[kMaxLp + 1];
+#pragma unroll
+    for (int i = 0; i <= kMaxLp; i++) r[i] = (i <= P) ? acfS[i * F + f] : 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxLp; i++) a[i] = 0.f;
+    float gain = 0.f;
+    if (r[0] != 0.f) {
+      float e = r[0];
+#pragma unroll
+      for (int m = 1; m <= kMaxLp; m++) {
+        if (m <= P && e != 0.f) {
+          float sum = r[m];                                            // 1.0f * r[m]
+#pragma unroll
+          for (int i = 1; i < m; i++) sum = __fadd_rn(sum, __fmul_rn(a[i - 1], r[m - i]));
+          const float km = __fmul_rn(__fdiv_rn(-1.0f, e), sum);
+          a[m - 1] = km;
+#pragma unroll
+          for (int i = 1; i <= m / 2; i++) {
+            const float x = a[i - 1];
+            a[i - 1] = __fadd_rn(a[i - 1], __fmul_rn(km, a[m - i - 1]));
+            if ((i < (m / 2)) || ((m & 1) == 1)) a[m - i - 1] = __fadd_rn(a[m - i - 1], __fmul_rn(km, x));
+          }
+          e = __fmul_rn(e, __fsub_rn(1.0f, __fmul_rn(km, km)));
+        }
+      }
+      gain = e;
+    }
+    if (!p.plpCeps) {
+#pragma unroll
+      for (int i = 0; i < kMaxLp; i++) if (i < P) dst[i * (2 * F) + f] = a[i];
+      return;
+    }
+    if (gain <= 0.f) gain = 1.0f;                                      // plp.cpp:541-544
+    // lp -> cepstrum: ceps[n-1] = -(lp[n-1] + (float)(sum_{i<n} (n-i) lp[i-1] ceps[n-i-1] / n)),
+    // products in float, sum in double (smileUtil.c:1545-1551)
+    int first = p.plpFirstCC < 1 ? 1 : p.plpFirstCC;
+    const int last = p.plpLastCC > P ? P : p.plpLastCC;
+    // NOTE (reference indexing): ceps[] is written at n - firstCC but read at n - i - 1; the two
+    // agree only for firstCC <= 1, which is what every shipped config uses (checked on the host)
+#pragma unroll
+    for (int n = 1; n <= kMaxLp; n++) {
+      if (n >= first && n <= last) {
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 1; i < n; i++)
+          sum = __dadd_rn(sum, (double)__fmul_rn(__fmul_rn((float)(n - i), a[i - 1]), cc[n - i - 1]));
+        cc[n - first] = -__fadd_rn(a[n - first], (float)(sum / (double)n));
+      }
+    }
+    const float zeroth = (float)(-log(1.0 / (double)gain));
+    const int nC = p.nStat;
+    // output order (plp.cpp:549-553): firstCC == 0 puts c0 first, or last when htkcompatible
+#pragma unroll
+    for (int i = 0; i <= kMaxLp; i++) {
+      if (i < nC) {
+        float v;
+        if (p.plpFirstCC == 0) {
+          if (p.plpHtk) v = (i == nC - 1) ? zeroth : cc[i];
+          else v = (i == 0) ? zeroth : cc[i - 1];
+        } else {
+          v = cc[i];
+        }
+        if (p.plpLifter) v = __fmul_rn(v, sLift[i]);
+        dst[i * (2 * F) + f] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------
 template <int M, int F, int NT, int MINB, bool VEC2>
@@ -291,6 +393,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   int *sMelRange = reinterpret_cast<int *>(smem + L.melRange);
   float *sDct = reinterpret_cast<float *>(smem + L.dctCos);
   float *sLift = reinterpret_cast<float *>(smem + L.dctLift);
+  float *sEql = reinterpret_cast<float *>(smem + L.eql);
   float *melS = reinterpret_cast<float *>(smem + L.melS);
   float *ring = reinterpret_cast<float *>(smem + L.ring);   // [nMfcc][2F], slot = (frame - chunk.s0) & (2F-1)
   float *Dbuf = reinterpret_cast<float *>(smem + L.zbuf);  // delta level rows (aliases Z, dead after mel)
@@ -307,8 +410,9 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   for (int i = tid; i < NPAIR; i += NT) sSplit[i] = p.splitTw[i];
   for (int i = tid; i < NBINS; i += NT) sMelCoef[i] = p.melCoef[i];
   for (int i = tid; i < p.nBands + 2; i += NT) sMelRange[i] = p.melRange[i];
-  for (int i = tid; i < p.nMfcc * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
-  for (int i = tid; i < p.nMfcc; i += NT) sLift[i] = p.dctLift[i];
+  for (int i = tid; i < p.dctRows * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
+  if (p.opKind == 1) for (int i = tid; i < p.nBands; i += NT) sEql[i] = p.plpEql[i];
+  for (int i = tid; i < p.nStat; i += NT) sLift[i] = p.dctLift[i];
   for (int i = tid; i < L.sampFloats; i += NT) samp[i] = 0.f;   // lanes beyond a short tile read finite data
   __syncthreads();
 
@@ -504,7 +608,18 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
             nxt = __fadd_rn(nxt, __fsub_rn(pw, a));
           }
           float mval = __fmul_rn(cur, p.melScale);
-          if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);
+          if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);   // mfcc.cpp:239-243 / plp.cpp:434-440
+          if (p.opKind == 1 && p.plpAud) {
+            // auditory weighting + loudness compression (plp.cpp:488-510)
+            if (p.doLog) {
+              mval = __fmul_rn(__fadd_rn(mval, sEql[r - 1]), p.plpCompression);
+            } else {
+              if (mval < p.melfloor) mval = p.melfloor;
+              mval = __fmul_rn(mval, sEql[r - 1]);
+              mval = (float)pow((double)mval, (double)p.plpCompression);
+            }
+          }
+          if (p.opKind == 1 && p.plpInvLog) mval = expf(mval);                    // plp.cpp:513-518
           melS[(r - 1) * F + f] = mval;
           cur = nxt;
         }
@@ -512,15 +627,16 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     }
     __syncthreads();
 
-    // ================= DCT-II + lifter (mfcc.cpp:251-272) =================
+    // ================= DCT-II + lifter (mfcc.cpp:251-272) / PLP back end (plp.cpp:520-590) =================
     const int ringBase = (j & 1) * F;   // tiles of a chunk alternate between the two ring halves
+    if (p.opKind == 0) {
     // each virtual warp owns coefficients i, i+NVW, ... and evaluates them two at a time so
     // that one read of the log-mel column feeds two dot products; the cosine rows are read as
     // float4 (row stride padded to 4).  Each dot product keeps the reference's m = 0..nBands-1
     // accumulation order.
-    for (int i = vw; i < p.nMfcc; i += 2 * NVW) {
+    for (int i = vw; i < p.nStat; i += 2 * NVW) {
       const int i1 = i + NVW;
-      const bool two = i1 < p.nMfcc;
+      const bool two = i1 < p.nStat;
       const float4 *c0 = reinterpret_cast<const float4 *>(sDct + i * p.dctStride);
       const float4 *c1 = reinterpret_cast<const float4 *>(sDct + (two ? i1 : i) * p.dctStride);
       const float *lp = melS + f;
@@ -542,21 +658,24 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       ring[i * (2 * F) + ringBase + f] = __fmul_rn(a0, sLift[i]);
       if (two) ring[i1 * (2 * F) + ringBase + f] = __fmul_rn(a1, sLift[i1]);
     }
+    } else {
+      plp_backend<F, NVW>(p, melS, sDct, sLift, reinterpret_cast<float *>(smem + L.zbuf), ring + ringBase, vw, f);
+    }
     __syncthreads();
 
     // ================= store =================
     if (!p.fused) {
       // static rows only (the temporal stages, if any, run in post_kernel)
-      const int tot = nf * p.nMfcc;
+      const int tot = nf * p.nStat;
       for (int idx = tid; idx < tot; idx += NT) {
-        const int ff = idx / p.nMfcc, c = idx - ff * p.nMfcc;
+        const int ff = idx / p.nStat, c = idx - ff * p.nStat;
         p.out[(cx.row0 + tg.fs + ff) * p.outStride + p.outCol + c] = ring[c * (2 * F) + ringBase + ff];
       }
     } else {
       // Fused delta / delta-delta (cDeltaRegression x2 + cVectorConcat): output row t needs the
       // statics of frames t-H..t+H.  After tile j all rows up to (tile end - H) are computable
       // (up to b on the chunk's last tile); their statics live in the two ring halves.
-      const int K = p.nMfcc, W1 = p.fW1, W2 = p.fW2, H = W1 + W2;
+      const int K = p.nStat, W1 = p.fW1, W2 = p.fW2, H = W1 + W2;
       const int T = cx.T;
       const int r0 = emitted;
       const int r1 = (j + 1 == cx.nT) ? cx.b : min(tg.fs + F - H, cx.b);

@@ -42,12 +42,20 @@ struct LldParams {
   float melScale;
   int melUsePower;
   int melSplit[kMaxVW + 1];      // virtual warp w computes bands [melSplit[w], melSplit[w+1])
-  const float *dctCos;           // [nMfcc][dctStride], output order, rows zero padded
-  int dctStride;                 // nBands rounded up to a multiple of 4
-  const float *dctLift;          // [nMfcc]
-  int nMfcc;
+  // ---- static LLD op on the mel bands: 0 = cMfcc (log, DCT-II, lifter), 1 = cPlp ----
+  int opKind;
+  int nStat;                     // static outputs per frame (nMfcc / nCeps / ...)
+  const float *dctCos;           // MFCC: [nStat][dctStride] DCT rows (output order, zero padded)
+                                 // PLP : [nAuto][dctStride = nFreq] IDFT table
+  int dctRows, dctStride;
+  const float *dctLift;          // [nStat] MFCC: lifter * sqrt(2/N) ; PLP: lifter per output slot
   float melfloor, logMelfloor;
   int doLog;
+  // cPlp (lldcore/plp.cpp:416-593)
+  const float *plpEql;           // [nBands]
+  int plpAud, plpInvLog, plpIDFT, plpLP, plpCeps, plpHtk, plpLifter;
+  int plpOrder, plpNAuto, plpNFreq, plpFirstCC, plpLastCC;
+  float plpCompression;
   // ---- output ----
   float *out;
   int outStride, outCol;

@@ -55,10 +55,25 @@ struct MfccOp {
   std::vector<float> liftFactor;   // [nMfcc] = sintable[i0] * factor, output order
 };
 
+struct PlpOp {
+  int melIdx = 0;
+  int lpOrder = 0, nAuto = 0, nFreq = 0, nCeps = 0, firstCC = 0, lastCC = 0;
+  bool doLog = false, doAud = true, doInvLog = false, doIDFT = true, doLP = true, doLpToCeps = true;
+  bool htk = true;
+  float melfloor = 1.f, logMelfloor = 0.f, compression = 0.33f;
+  bool lifter = false;
+  std::vector<float> eql;          // [nBands] equal loudness weights (log of them when doLog)
+  std::vector<float> cosT;         // [nAuto][nFreq] IDFT table (plp.cpp:298-306)
+  std::vector<float> lift;         // [nCeps] lifter per OUTPUT slot (plp.cpp:560-573)
+  int nOut = 0;
+};
+
 struct StaticOp {
   StaticOpKind kind;
   int outCol = 0, nOut = 0;
+  int arrNameOffset = 0;
   MfccOp mfcc;
+  PlpOp plp;
 };
 
 // temporal stage applied to a static column range (cWindowProcessor family)
@@ -92,5 +107,6 @@ int64_t desc_num_static_frames(const PlanDesc &d, int64_t nSampleFrames);
 void build_window(int winFunc, int N, double sigma, double gain, std::vector<float> &w);
 void build_mel(const osm_b200_melspec &cfg, int nBins, double frameSizeSec, MelBank &mb);
 void build_mfcc(const osm_b200_mfcc &cfg, int nBands, MfccOp &op);
+bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, PlpOp &op, std::string &err);
 
 }  // namespace osm

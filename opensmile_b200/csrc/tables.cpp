@@ -179,4 +179,86 @@ void build_mfcc(const osm_b200_mfcc &cfg, int nBands, MfccOp &op)
   }
 }
 
+// smileDsp_equalLoudnessWeight(_htk), smileutil/smileUtil.c:1041-1061
+static double eql_htk(double f)
+{
+  const double f2 = f * f, fs = f2 / (f2 + 1.6e5);
+  return fs * fs * ((f2 + 1.44e6) / (f2 + 9.61e6));
+}
+static double eql_hermansky(double f)
+{
+  const double w = 2.0 * M_PI * f, w2 = w * w, c = w2 + 6300000.0;
+  if (c > 0.0) return (1e32 * ((w2 + 56.8e6) * w2 * w2) / (c * c * (w2 + 0.38e9) * (w2 * w2 * w2 * w + 1.7e31)));
+  return 0.0;
+}
+
+// cPlp::myFetchConfig (lldcore/plp.cpp:88-171) + cPlp::initTables (:276-341).
+// RASTA / newRASTA (a recurrence over frames) is not fused yet.
+bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, PlpOp &op, std::string &err)
+{
+  if (cfg.RASTA || cfg.newRASTA) { err = "cPlp: RASTA / newRASTA are not supported yet"; return false; }
+  int lpOrder = cfg.lpOrder;
+  bool doLP = cfg.doLP != 0, doLpToCeps = cfg.doLpToCeps != 0, doIDFT = cfg.doIDFT != 0;
+  if (lpOrder <= 0) { lpOrder = 0; doLP = false; doLpToCeps = false; }                 // :103-106
+  int nCeps = cfg.nCeps, firstCC = cfg.firstCC, lastCC = cfg.lastCC;
+  if (firstCC > lpOrder) { firstCC = lpOrder; nCeps = 1; lastCC = lpOrder; }           // :111-112
+  else if (firstCC < 0) firstCC = 0;
+  if (nCeps < 0) nCeps = lpOrder - firstCC + 1;                                         // :114-116
+  if (lastCC < 0) lastCC = firstCC + nCeps - 1;                                         // :118-121
+  else if (lastCC >= firstCC) nCeps = lastCC - firstCC + 1;
+  if (lastCC > lpOrder) { lastCC = lpOrder; nCeps = lastCC - firstCC + 1; }             // :122-126
+  if (nCeps == 0) doLpToCeps = false;                                                   // :132
+  if (doLpToCeps) doLP = true;                                                          // :134-136
+  if (doLP) doIDFT = true;                                                              // :137-139
+  if (lpOrder > 8) { err = "cPlp: lpOrder > 8 is not supported"; return false; }
+  op.lpOrder = lpOrder; op.nCeps = nCeps; op.firstCC = firstCC; op.lastCC = lastCC;
+  op.doLP = doLP; op.doLpToCeps = doLpToCeps; op.doIDFT = doIDFT;
+  float compression = (float)cfg.compression;                                           // :142-143
+  if (compression < 0.0) compression = 0.0;
+  op.compression = compression;
+  float cepLifter = (float)(int)cfg.cepLifter;                                          // :146 getInt
+  if (cepLifter < 0) cepLifter = 0;
+  op.melfloor = (float)cfg.melfloor;
+  op.doLog = cfg.doLog != 0; op.doAud = cfg.doAud != 0; op.doInvLog = cfg.doInvLog != 0;
+  op.htk = cfg.htkcompatible != 0;
+  if (op.htk) { op.melfloor = 1.0f; op.doAud = true; op.doLog = false; op.doInvLog = false; }   // :152-163
+  op.logMelfloor = std::log(op.melfloor);
+  const int nBands = mb.nBands;
+  op.nFreq = nBands + 2;                                                                // :288
+  op.nAuto = lpOrder + 1;
+  op.cosT.assign((size_t)op.nAuto * op.nFreq, 0.f);
+  {
+    const float a = (float)M_PI / (float)(op.nFreq - 1);                                // :298
+    for (int i = 0; i < op.nAuto; i++) {
+      const int ib = i * op.nFreq;
+      int m;
+      op.cosT[ib] = 1.0;
+      for (m = 1; m < (op.nFreq - 1); m++) op.cosT[m + ib] = (float)(2.0 * cos(a * (double)i * (double)m));
+      op.cosT[m + ib] = (float)(cos(a * (double)i * (double)m));
+    }
+  }
+  op.lifter = cepLifter > 0.0;
+  std::vector<float> sint(nCeps > 0 ? nCeps : 1, 1.f);
+  for (int i = firstCC; i <= lastCC; i++) {                                             // :320-327
+    if (cepLifter > 0.0)
+      sint[i - firstCC] = ((float)1.0 + cepLifter / (float)2.0 * std::sin((float)M_PI * ((float)(i)) / cepLifter));
+    else
+      sint[i - firstCC] = 1.0;
+  }
+  op.lift.assign(nCeps > 0 ? nCeps : 1, 1.f);
+  for (int i = firstCC; i <= lastCC; i++) {                                             // :560-573 output slot -> table index
+    const int i0 = i - firstCC;
+    int i1 = i0;
+    if (op.htk && firstCC == 0) i1 = (i == lastCC) ? 0 : i1 + 1;
+    op.lift[i0] = sint[i1];
+  }
+  op.eql.assign(nBands, 1.f);
+  for (int i = 0; i < nBands; i++) {                                                    // :345-357 (band centres = melspec field info)
+    op.eql[i] = op.htk ? (float)eql_htk(mb.bandHz[i]) : (float)eql_hermansky(mb.bandHz[i]);
+    if (op.doLog) op.eql[i] = std::log(op.eql[i]);
+  }
+  op.nOut = doLpToCeps ? nCeps : (doLP ? lpOrder : (doIDFT ? op.nAuto : nBands));        // :232-267
+  return true;
+}
+
 }  // namespace osm

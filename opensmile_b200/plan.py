@@ -59,6 +59,27 @@ def components_mfcc12_0_d_a(sample_rate=16000.0, n_channels=1):
     ]
 
 
+def components_plp_0_d_a(sample_rate=16000.0, n_channels=1):
+    """config/plp/PLP_0_D_A.conf (+ shared/standard_wave_input.conf.inc) as a component list."""
+    T = capi
+    return [
+        _comp(T.C_WAVESOURCE, "waveIn", "", "wave", sampleRate=float(sample_rate),
+              nChannels=n_channels, monoMixdown=1),
+        _comp(T.C_FRAMER, "frame", "wave", "frames", frameSize=0.025, frameStep=0.010),
+        _comp(T.C_VECTORPREEMPHASIS, "pe", "frames", "framespe", k=0.97, de=0),
+        _comp(T.C_WINDOWER, "win", "framespe", "winframes", winFunc=T.WIN_BY_NAME["ham"], gain=1.0, offset=0.0),
+        _comp(T.C_TRANSFORMFFT, "fft", "winframes", "fft", zeroPadSymmetric=0),
+        _comp(T.C_FFTMAGPHASE, "fftmag", "fft", "fftmag"),
+        _comp(T.C_MELSPEC, "melspec", "fftmag", "melspec", htkcompatible=1, nBands=26, usePower=1,
+              lofreq=0.0, hifreq=8000.0),
+        _comp(T.C_PLP, "plp", "melspec", "plp", firstCC=0, lpOrder=5, cepLifter=22.0, compression=0.33,
+              htkcompatible=1, doIDFT=1, doLpToCeps=1, doLP=1, doInvLog=0, doAud=1, doLog=0),
+        _comp(T.C_DELTAREGRESSION, "delta", "plp", "plpde", deltawin=2),
+        _comp(T.C_DELTAREGRESSION, "accel", "plpde", "plpdede", deltawin=2),
+        _comp(T.C_VECTORCONCAT, "audspec_lldconcat", "plp;plpde;plpdede", "lld"),
+    ]
+
+
 class Plan:
     """A compiled LLD plan bound to one CUDA device."""
 

@@ -112,6 +112,29 @@ def mfcc_d_a(pcm, sample_rate, n_chan=1, taps=False, cfg=None, delta_win=2, acce
     return (out, tap_mag, tap_mel) if taps else out
 
 
+def plp_0_d_a(sample_rate):
+    """config/plp/PLP_0_D_A.conf"""
+    fe = Frontend(sample_rate, 0.025, 0.010, 1, 0.97, WIN["ham"], 0.4, 1.0, 0.0, 0)
+    ms = Melspec(26, 0.0, 8000.0, 1, 1)
+    pl = Plp(5, 0, -1, 0, 1, 0, 1, 1, 1, 0, 0, 29.0, 1.0, 22.0, 0.33, 9.3e-10, 1)
+    return fe, ms, pl
+
+
+def plp_d_a(pcm, sample_rate, n_chan=1, cfg=None, delta_win=2, accel_win=2):
+    """int16 PCM -> float32 [T, 3*nCeps] (PlpCC static | delta | accel)."""
+    fe, ms, pl = cfg if cfg is not None else plp_0_d_a(sample_rate)
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nS = pcm.size // n_chan
+    N, H, nfft, T = geometry(fe, nS)
+    K = lib().osm_or_plp_num_out(C.byref(pl), C.c_int(ms.n_bands))
+    out = np.zeros((max(T, 0), 3 * K), np.float32)
+    r = lib().osm_or_plp_d_a(C.byref(fe), C.byref(ms), C.byref(pl), C.c_int(delta_win), C.c_int(accel_win),
+                             pcm.ctypes.data_as(C.POINTER(C.c_int16)), C.c_long(nS), C.c_int(n_chan),
+                             _fp(out), None)
+    assert r == max(T, 0), (r, T)
+    return out
+
+
 def delta(x, win):
     x = np.ascontiguousarray(x, np.float32)
     T, K = x.shape

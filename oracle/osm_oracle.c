@@ -522,10 +522,191 @@ long osm_or_mfcc_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const 
   return T;
 }
 
+/* ------------------------------------------------------------------ a-9 PLP */
+
+/* smileutil/smileUtil.c:1053-1059 (HTK equal loudness) and :1041-1051 (Hermansky) */
+static double eql_htk(double f) { double f2 = f * f; double fs = f2 / (f2 + 1.6e5); return fs * fs * ((f2 + 1.44e6) / (f2 + 9.61e6)); }
+static double eql_herm(double f)
+{
+  double w = 2.0 * M_PI * f, w2 = w * w, c = w2 + 6300000.0;
+  if (c > 0.0) return (1e32 * ((w2 + 56.8e6) * w2 * w2) / (c * c * (w2 + 0.38e9) * (w2 * w2 * w2 * w + 1.7e31)));
+  return 0.0;
+}
+
+/* smileutil/smileUtil.c:1572-1627 (Durbin recursion, float) */
+static int lpc_acf(const float *r, float *a, int p, float *gain)
+{
+  int i, m;
+  float e, k_m;
+  if (r[0] == 0.0f) { for (i = 0; i < p; i++) a[i] = 0.0f; return 0; }
+  e = r[0];
+  for (m = 1; m <= p; m++) {
+    float sum = (float)1.0 * r[m];
+    for (i = 1; i < m; i++) sum += a[i - 1] * r[m - i];
+    k_m = ((float)-1.0 / e) * sum;
+    a[m - 1] = k_m;
+    for (i = 1; i <= m / 2; i++) {
+      float x = a[i - 1];
+      a[i - 1] += k_m * a[m - i - 1];
+      if ((i < (m / 2)) || ((m & 1) == 1)) a[m - i - 1] += k_m * x;
+    }
+    e *= ((float)1.0 - k_m * k_m);
+    if (e == 0.0f) { for (i = m; i < p; i++) a[i] = 0.0f; break; }
+  }
+  *gain = e;
+  return 1;
+}
+
+/* smileutil/smileUtil.c:1532-1556 (HTK book eq. 5.11) */
+static float lp_to_ceps(const float *lp, int nLp, float lpGain, float *ceps, int firstCC, int lastCC)
+{
+  if (firstCC < 1) firstCC = 1;
+  if (lastCC > nLp) lastCC = nLp;
+  for (int n = firstCC; n <= lastCC; n++) {
+    double sum = 0;
+    for (int i = 1; i < n; i++) sum += (n - i) * lp[i - 1] * ceps[n - i - 1];
+    ceps[n - firstCC] = -(lp[n - firstCC] + (float)(sum / (double)n));
+  }
+  if (lpGain <= 0.0) lpGain = (float)1.0;
+  return (float)(-log(1.0 / (double)lpGain));
+}
+
+typedef struct {
+  const osm_or_melspec *ms; const osm_or_plp *pl; mel_bank mb; float *mel; float *tap_mel; long t;
+  int nFreq, nAuto, nCeps, firstCC, lastCC;
+  float *cost, *sint, *eql;
+  float melfloor, compression, cepLifter;
+  int doLog, doAud, doInvLog;
+} plp_ctx;
+
+/* lldcore/plp.cpp:88-171 (config resolution) + :276-341 (tables) */
+static void plp_init(plp_ctx *c, int nBands)
+{
+  const osm_or_plp *pl = c->pl;
+  int lpOrder = pl->lp_order;
+  c->firstCC = pl->first_cc; c->lastCC = pl->last_cc;
+  int nCeps = -1;
+  if (c->firstCC > lpOrder) { c->firstCC = lpOrder; nCeps = 1; c->lastCC = lpOrder; }
+  else if (c->firstCC < 0) c->firstCC = 0;
+  if (nCeps < 0) nCeps = lpOrder - c->firstCC + 1;            /* :116-118 */
+  if (c->lastCC < 0) c->lastCC = c->firstCC + nCeps - 1;      /* :120 */
+  else if (c->lastCC >= c->firstCC) nCeps = c->lastCC - c->firstCC + 1;
+  if (c->lastCC > lpOrder) { c->lastCC = lpOrder; nCeps = c->lastCC - c->firstCC + 1; }
+  c->nCeps = nCeps;
+  c->compression = (float)pl->compression; if (c->compression < 0.0) c->compression = 0.0;   /* :141-142 */
+  c->cepLifter = (float)(int)pl->cep_lifter; if (c->cepLifter < 0) c->cepLifter = 0;          /* :145 getInt */
+  c->melfloor = (float)pl->melfloor;
+  c->doLog = pl->do_log; c->doAud = pl->do_aud; c->doInvLog = pl->do_inv_log;
+  if (pl->htkcompatible) { c->melfloor = 1.0f; c->doAud = 1; c->doLog = 0; c->doInvLog = 0; }   /* :152-163 */
+  c->nFreq = nBands + 2; c->nAuto = lpOrder + 1;               /* :288-290 */
+  c->cost = (float *)malloc(sizeof(float) * c->nAuto * c->nFreq);
+  float a = (float)M_PI / (float)(c->nFreq - 1);               /* :298 */
+  for (int i = 0; i < c->nAuto; i++) {
+    int ib = i * c->nFreq, m;
+    c->cost[ib] = 1.0;
+    for (m = 1; m < (c->nFreq - 1); m++) c->cost[m + ib] = (float)(2.0 * cos(a * (double)i * (double)m));
+    c->cost[m + ib] = (float)(cos(a * (double)i * (double)m));
+  }
+  c->sint = (float *)malloc(sizeof(float) * nCeps);
+  for (int i = c->firstCC; i <= c->lastCC; i++) {              /* :320-327 */
+    if (c->cepLifter > 0.0) c->sint[i - c->firstCC] = ((float)1.0 + c->cepLifter / (float)2.0 * sinf((float)M_PI * ((float)(i)) / c->cepLifter));
+    else c->sint[i - c->firstCC] = 1.0;
+  }
+  c->eql = (float *)malloc(sizeof(float) * nBands);
+  for (int i = 0; i < nBands; i++) {                           /* :345-357: band centres from the melspec field info */
+    c->eql[i] = pl->htkcompatible ? (float)eql_htk(c->mb.band_hz[i]) : (float)eql_herm(c->mb.band_hz[i]);
+    if (c->doLog) c->eql[i] = logf(c->eql[i]);
+  }
+}
+
+/* lldcore/plp.cpp:416-593 without RASTA (RASTA=newRASTA=0 in PLP_0_D_A.conf) */
+static void plp_apply(plp_ctx *c, const float *src, int Nsrc, float *dst)
+{
+  const osm_or_plp *pl = c->pl;
+  int lpOrder = pl->lp_order, nFreq = c->nFreq, nAuto = c->nAuto, i, m;
+  float s[128], acf[32], lpc[32], ceps[32];
+  for (i = 0; i < Nsrc; i++) {
+    if (c->doLog) s[i] = (src[i] < c->melfloor) ? logf(c->melfloor) : logf(src[i]);   /* :434-440 */
+    else s[i] = src[i];
+  }
+  if (c->doAud) {
+    if (c->doLog) {
+      for (i = 0; i < Nsrc; i++) s[i] += c->eql[i];
+      for (i = 0; i < Nsrc; i++) s[i] *= c->compression;
+    } else {
+      for (i = 0; i < Nsrc; i++) { if (s[i] < c->melfloor) s[i] = c->melfloor; s[i] *= c->eql[i]; }   /* :501-504 */
+      for (i = 0; i < Nsrc; i++) s[i] = (float)pow((double)s[i], (double)c->compression);              /* :506-508 */
+    }
+  }
+  if (c->doInvLog) for (i = 0; i < Nsrc; i++) s[i] = expf(s[i]);
+  if (!pl->do_idft) { memcpy(dst, s, sizeof(float) * Nsrc); return; }
+  for (i = 0; i < nAuto; i++) {                                 /* :522-532 */
+    double tmp = 0;
+    if (pl->htkcompatible) tmp = (double)c->cost[i * nFreq] * (double)s[0];
+    for (m = 1; m < nFreq - 1; m++) tmp += (double)c->cost[m + i * nFreq] * (double)s[m - 1];
+    tmp += (double)c->cost[m + i * nFreq] * (double)s[nFreq - 3];
+    acf[i] = (float)(tmp / (2.0 * (nFreq - 1)));
+  }
+  if (!pl->do_lp) { memcpy(dst, acf, sizeof(float) * nAuto); return; }
+  float lpGain = 0.0f;
+  lpc_acf(acf, lpc, lpOrder, &lpGain);                          /* :537 */
+  if (!pl->do_lp_to_ceps) { memcpy(dst, lpc, sizeof(float) * lpOrder); return; }
+  if (lpGain <= 0) lpGain = (float)1.0;                         /* :541-544 */
+  float *cc = ceps;
+  if (!pl->htkcompatible && (c->firstCC == 0)) cc++;
+  float zeroth = lp_to_ceps(lpc, lpOrder, lpGain, cc, c->firstCC, c->lastCC);
+  if (c->firstCC == 0) { if (!pl->htkcompatible) ceps[0] = zeroth; else ceps[c->nCeps - 1] = zeroth; }
+  for (i = c->firstCC; i <= c->lastCC; i++) {                   /* :560-573 */
+    int i0 = i - c->firstCC, i1 = i0;
+    if (pl->htkcompatible && (c->firstCC == 0)) { if (i == c->lastCC) i1 = 0; else i1 += 1; }
+    dst[i0] = (c->cepLifter > 0.0) ? ceps[i0] * c->sint[i1] : ceps[i0];
+  }
+}
+
+static void plp_frame(void *vctx, const float *mag, long nb, float *dst)
+{
+  plp_ctx *c = (plp_ctx *)vctx;
+  (void)nb;
+  mel_apply(c->ms, &c->mb, mag, c->mel);
+  if (c->tap_mel) memcpy(c->tap_mel + c->t * c->ms->n_bands, c->mel, sizeof(float) * c->ms->n_bands);
+  plp_apply(c, c->mel, c->ms->n_bands, dst);
+  c->t++;
+}
+
+/* number of output elements of the cPlp instance (lldcore/plp.cpp:232-267) */
+int osm_or_plp_num_out(const osm_or_plp *pl, int n_bands)
+{
+  plp_ctx c; memset(&c, 0, sizeof c);
+  if (pl->do_lp_to_ceps) {
+    int lpOrder = pl->lp_order, first = pl->first_cc, last = pl->last_cc, nCeps = -1;
+    if (first > lpOrder) { first = lpOrder; nCeps = 1; last = lpOrder; } else if (first < 0) first = 0;
+    if (nCeps < 0) nCeps = lpOrder - first + 1;
+    if (last < 0) last = first + nCeps - 1; else if (last >= first) nCeps = last - first + 1;
+    if (last > lpOrder) { last = lpOrder; nCeps = last - first + 1; }
+    return nCeps;
+  }
+  if (pl->do_lp) return pl->lp_order;
+  if (pl->do_idft) return pl->lp_order + 1;
+  return n_bands;
+}
+
 long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const osm_or_plp *pl,
                     int dW, int aW, const int16_t *pcm, long L, int n_chan,
                     float *out, float *tap_mel)
 {
-  (void)fe; (void)ms; (void)pl; (void)dW; (void)aW; (void)pcm; (void)L; (void)n_chan; (void)out; (void)tap_mel;
-  return -1; /* filled in with the PLP row (a-9) */
+  long N = osm_or_frame_size_samples(fe), H = osm_or_frame_step_samples(fe);
+  long nfft = osm_or_fft_size(N);
+  long T = osm_or_num_frames(L, N, H);
+  if (T <= 0) return 0;
+  plp_ctx c; memset(&c, 0, sizeof c);
+  c.ms = ms; c.pl = pl; c.tap_mel = tap_mel; c.t = 0;
+  mel_design(ms, nfft / 2 + 1, osm_or_fft_frame_size_sec(fe), &c.mb);
+  plp_init(&c, ms->n_bands);
+  int K = osm_or_plp_num_out(pl, ms->n_bands);
+  c.mel = (float *)malloc(sizeof(float) * ms->n_bands);
+  float *stat = (float *)malloc(sizeof(float) * T * K);
+  run_frames(fe, pcm, L, n_chan, plp_frame, &c, K, stat, NULL);
+  add_deltas(stat, T, K, dW, aW, out);
+  free(stat); free(c.mel); free(c.cost); free(c.sint); free(c.eql); mel_free(&c.mb);
+  return T;
 }

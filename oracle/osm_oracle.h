@@ -99,6 +99,8 @@ long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const o
                     const int16_t *pcm, long n_samples, int n_chan,
                     float *out, float *tap_mel);
 
+int osm_or_plp_num_out(const osm_or_plp *pl, int n_bands);
+
 /* cDeltaRegression with the reference's edge/phantom-frame semantics.
  * in: T x K ; out: (T + win) x K.  Returns T + win. */
 long osm_or_delta(const float *in, long T, int K, int win, float *out);

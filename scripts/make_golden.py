@@ -8,6 +8,8 @@ Fixtures (all small):
   mfcc_synth16k_s0.npz    MFCC12_0_D_A on the seeded synthetic 16 kHz signal (seed 0, 80000
                           samples -> [498, 39]); only the OUTPUT is stored, the input is
                           regenerated from opensmile_b200.synth.voiced_pcm(80000, 16000, seed=0)
+  plp_goldens.npz         config/plp/PLP_0_D_A.conf on the example wav ([202, 18]) and on a seeded
+                          44.1 kHz stereo signal (voiced_pcm(44100, 44100, seed=2, n_chan=2) -> [98, 18])
   mfcc_taps16k_s1.npz     intermediate levels (fftmag, melspec, ft0) of the first 20 frames for
                           seed 1, 16 kHz, dumped with extra cHtkSink instances
 """
@@ -56,6 +58,15 @@ def main():
     lld = refrun.extract("mfcc/MFCC12_0_D_A.conf", pcm, 16000)
     np.savez_compressed(os.path.join(GOLD, "mfcc_synth16k_s0.npz"), lld=lld, crc=np.int64(pcm.astype(np.int64).sum()))
     print("synth16k", lld.shape)
+
+    # PLP_0_D_A (config/plp/PLP_0_D_A.conf): example wav + 44.1 kHz STEREO synthetic (BASELINE cfg 5 shape)
+    pcm, sr, nch = refrun.read_wav("/root/reference/example-audio/opensmile.wav")
+    lld = refrun.extract("plp/PLP_0_D_A.conf", pcm, sr, nch)
+    pcm2 = voiced_pcm(44100, 44100, seed=2, n_chan=2)
+    lld2 = refrun.extract("plp/PLP_0_D_A.conf", pcm2, 44100, 2)
+    np.savez_compressed(os.path.join(GOLD, "plp_goldens.npz"), example_lld=lld, stereo44k1_lld=lld2,
+                        stereo_crc=np.int64(pcm2.astype(np.int64).sum()))
+    print("plp", lld.shape, lld2.shape)
 
     # intermediate taps through extra sinks (first 20 frames kept)
     import tempfile

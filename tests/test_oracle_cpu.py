@@ -81,3 +81,26 @@ def test_oracle_vs_live_reference_stereo():
     out = oracle.mfcc_d_a(pcm, 16000.0, n_chan=2)
     assert out.shape == ref.shape
     assert rel_to_frame_scale(out, ref) < TOL
+
+
+def test_plp_oracle_vs_golden():
+    g = np.load(os.path.join(GOLD, "plp_goldens.npz"))
+    ex = np.load(os.path.join(GOLD, "mfcc_example_44k1.npz"))
+    out = oracle.plp_d_a(ex["pcm"], float(ex["sample_rate"]))
+    assert out.shape == g["example_lld"].shape == (202, 18)
+    assert rel_to_frame_scale(out, g["example_lld"]) < TOL
+    pcm2 = voiced_pcm(44100, 44100, seed=2, n_chan=2)
+    assert int(pcm2.astype(np.int64).sum()) == int(g["stereo_crc"])
+    out2 = oracle.plp_d_a(pcm2, 44100.0, n_chan=2)
+    assert out2.shape == g["stereo44k1_lld"].shape
+    assert rel_to_frame_scale(out2, g["stereo44k1_lld"]) < TOL
+
+
+@pytest.mark.skipif(not refrun.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("sr,n,seed,nch", [(16000, 30000, 11, 1), (44100, 20000, 12, 2), (16000, 560, 13, 1)])
+def test_plp_oracle_vs_live_reference(sr, n, seed, nch):
+    pcm = voiced_pcm(n, sr, seed=seed, n_chan=nch)
+    ref = refrun.extract("plp/PLP_0_D_A.conf", pcm, sr, n_chan=nch)
+    out = oracle.plp_d_a(pcm, float(sr), n_chan=nch)
+    assert out.shape == ref.shape
+    assert rel_to_frame_scale(out, ref) < TOL

@@ -169,3 +169,46 @@ def test_pipelined_host_path_matches_device_path(plan16):
     ref = oracle.mfcc_d_a(base[:L], 16000.0)
     assert rel_to_frame_scale(h_out[:500].numpy(), ref) < TOL
     assert rel_to_frame_scale(h_out[-3500:-3000].numpy(), ref) < TOL
+
+
+# ---------------------------------------------------------------- PLP_0_D_A (BASELINE cfg 5)
+def test_plp_goldens_and_oracle():
+    from opensmile_b200 import components_plp_0_d_a
+    g = np.load(os.path.join(GOLD, "plp_goldens.npz"))
+    ex = np.load(os.path.join(GOLD, "mfcc_example_44k1.npz"))
+    p = Plan(components_plp_0_d_a(44100.0), "lld", device=0)
+    assert p.num_elements == 18
+    out = p.run_host(ex["pcm"], np.array([0, ex["pcm"].size], np.int64))
+    assert out.shape == (202, 18)
+    assert rel_to_frame_scale(out, g["example_lld"]) < TOL
+    p.close()
+    # 44.1 kHz stereo (monoMixdown), ragged batch, vs the reference golden and the oracle
+    p2 = Plan(components_plp_0_d_a(44100.0, n_channels=2), "lld", device=0)
+    a = voiced_pcm(44100, 44100, seed=2, n_chan=2)
+    others = [voiced_pcm(n, 44100, seed=600 + i, n_chan=2) for i, n in enumerate([1103, 30011, 1102, 9000])]
+    pcm, off = pack_utterances([a] + others, n_chan=2)
+    out2 = p2.run_host(pcm, off)
+    fo = p2.frame_offsets(off)
+    assert rel_to_frame_scale(out2[fo[0]:fo[1]], g["stereo44k1_lld"]) < TOL
+    for u, x in enumerate([a] + others):
+        ref = oracle.plp_d_a(x, 44100.0, n_chan=2)
+        assert out2[fo[u]:fo[u + 1]].shape == ref.shape
+        if ref.shape[0]:
+            assert rel_to_frame_scale(out2[fo[u]:fo[u + 1]], ref) < TOL
+    p2.close()
+
+
+def test_plp_16k_batch_vs_oracle():
+    from opensmile_b200 import components_plp_0_d_a
+    p = Plan(components_plp_0_d_a(16000.0), "lld", device=0)
+    lens = [16000, 400, 560, 80240, 5000]
+    utts = [voiced_pcm(n, 16000, seed=700 + i) for i, n in enumerate(lens)]
+    pcm, off = pack_utterances(utts)
+    out = p.run_host(pcm, off)
+    fo = p.frame_offsets(off)
+    assert np.isfinite(out).all()
+    for u, x in enumerate(utts):
+        ref = oracle.plp_d_a(x, 16000.0)
+        assert rel_to_frame_scale(out[fo[u]:fo[u + 1]], ref) < TOL
+    assert p.element_names[0] == "PlpCC[0]" and p.element_names[6] == "PlpCC_de[0]"
+    p.close()
