@@ -311,15 +311,15 @@ def run_ours(args, rank, world, local_rank):
     checksum = float(h_out[::997].double().abs().sum())
     assert np.isfinite(checksum)
 
-    times = torch.tensor([dt_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)     # max over ranks
-    dt_ms, e2e_ms = float(times[0]), float(times[1])
+    # the only communication of the job: SUM of frame counters, MAX of times over ranks (NCCL)
+    from opensmile_b200.dist import reduce_counters
+    frames_all, dt_s = reduce_counters(rows * args.steps, dt_ms * 1e-3, dist, dev)
+    frames_e2e, e2e_s = reduce_counters(rows * e2e_steps, e2e_s, dist, dev)
+    dt_ms, e2e_ms = dt_s * 1e3, e2e_s * 1e3
 
     if rank == 0:
-        total_frames = rows * world * args.steps
-        value = total_frames / (dt_ms * 1e-3)
-        e2e_value = rows * world * e2e_steps / (e2e_ms * 1e-3)
+        value = frames_all / (dt_ms * 1e-3)
+        e2e_value = frames_e2e / (e2e_ms * 1e-3)
         peak, peak_src = measured_peak_hbm()
         k_ms = statistics.mean(lld_ms)
         achieved = rows * BYTES_PER_FRAME / (k_ms * 1e-3) / 1e9
