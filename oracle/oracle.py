@@ -42,6 +42,101 @@ class Plp(C.Structure):
                 ("htkcompatible", C.c_int)]
 
 
+MAX_LIST = 16
+
+
+class Spectral(C.Structure):
+    _fields_ = [("squareInput", C.c_int),
+                ("nBands", C.c_int), ("bandLo", C.c_double * MAX_LIST), ("bandHi", C.c_double * MAX_LIST),
+                ("nSlopes", C.c_int), ("slopeLo", C.c_double * MAX_LIST), ("slopeHi", C.c_double * MAX_LIST),
+                ("nRollOff", C.c_int), ("rollOff", C.c_double * MAX_LIST),
+                ("flux", C.c_int), ("centroid", C.c_int), ("maxPos", C.c_int), ("minPos", C.c_int),
+                ("entropy", C.c_int), ("standardDeviation", C.c_int), ("variance", C.c_int),
+                ("skewness", C.c_int), ("kurtosis", C.c_int), ("slope", C.c_int), ("alphaRatio", C.c_int),
+                ("hammarbergIndex", C.c_int), ("sharpness", C.c_int), ("harmonicity", C.c_int),
+                ("flatness", C.c_int), ("normBandEnergies", C.c_int), ("buggyRollOff", C.c_int),
+                ("oldSlopeScale", C.c_int), ("useLogSpectrum", C.c_int),
+                ("freqRangeLo", C.c_double), ("freqRangeHi", C.c_double), ("specFloor", C.c_double),
+                ("logFlatness", C.c_int)]
+
+
+class Energy(C.Structure):
+    _fields_ = [("htkcompatible", C.c_int), ("rms", C.c_int), ("energy2", C.c_int), ("log", C.c_int),
+                ("escaleLog", C.c_double), ("escaleRms", C.c_double), ("escaleSquare", C.c_double),
+                ("ebiasLog", C.c_double), ("ebiasRms", C.c_double), ("ebiasSquare", C.c_double)]
+
+
+class MZcr(C.Structure):
+    _fields_ = [("zcr", C.c_int), ("mcr", C.c_int), ("amax", C.c_int), ("maxmin", C.c_int), ("dc", C.c_int)]
+
+
+def spectral_cfg(bands=(), slopes=(), rolloff=(), **kw):
+    """cSpectral defaults + overrides."""
+    sp = Spectral()
+    sp.squareInput = 1; sp.flux = 1; sp.centroid = 1; sp.maxPos = 1; sp.minPos = 1
+    sp.oldSlopeScale = 1; sp.specFloor = 1e-7
+    sp.nBands = len(bands)
+    for i, (a, b) in enumerate(bands):
+        sp.bandLo[i], sp.bandHi[i] = a, b
+    sp.nSlopes = len(slopes)
+    for i, (a, b) in enumerate(slopes):
+        sp.slopeLo[i], sp.slopeHi[i] = a, b
+    sp.nRollOff = len(rolloff)
+    for i, r in enumerate(rolloff):
+        sp.rollOff[i] = r
+    for k, v in kw.items():
+        assert hasattr(sp, k), k
+        setattr(sp, k, v)
+    return sp
+
+
+def compare16_spectral():
+    """[is13_spectral:cSpectral] of config/compare16/ComParE_2016_core.lld.conf.inc:283-302"""
+    return spectral_cfg(bands=[(250, 650), (1000, 4000)], rolloff=[0.25, 0.50, 0.75, 0.90], flux=1, centroid=1,
+                        maxPos=0, minPos=0, entropy=1, variance=1, skewness=1, kurtosis=1, slope=1,
+                        harmonicity=1, sharpness=1)
+
+
+def gemaps_logspectral():
+    """[gemapsv01b_logSpectral:cSpectral] of config/gemaps/v01b/GeMAPSv01b_core.lld.conf.inc:321-346"""
+    return spectral_cfg(slopes=[(0, 500), (500, 1500)], flux=0, centroid=0, maxPos=0, minPos=0, alphaRatio=1,
+                        hammarbergIndex=1, normBandEnergies=1, squareInput=1, useLogSpectrum=1,
+                        freqRangeLo=0, freqRangeHi=5000, oldSlopeScale=0)
+
+
+def frontend(sample_rate, frame_size, frame_step, win="ham", preemph=None, sigma=0.4, zero_pad_symmetric=1):
+    return Frontend(sample_rate, frame_size, frame_step, 1 if preemph is not None else 0,
+                    preemph if preemph is not None else 0.97, WIN[win], sigma, 1.0, 0.0, zero_pad_symmetric)
+
+
+def _run_static(fn_name, nout_name, fe, cfg, pcm, n_chan, extra=()):
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nS = pcm.size // n_chan
+    N, H, nfft, T = geometry(fe, nS)
+    L = lib()
+    getattr(L, fn_name).restype = C.c_long
+    K = getattr(L, nout_name)(C.byref(cfg))
+    out = np.zeros((max(T, 0), K), np.float32)
+    r = getattr(L, fn_name)(C.byref(fe), C.byref(cfg), *extra, pcm.ctypes.data_as(C.POINTER(C.c_int16)),
+                            C.c_long(nS), C.c_int(n_chan), _fp(out))
+    assert r == max(T, 0), (r, T)
+    return out
+
+
+def spectral(pcm, fe, cfg, n_chan=1):
+    return _run_static("osm_or_spectral", "osm_or_spectral_num_out", fe, cfg, pcm, n_chan)
+
+
+def energy(pcm, fe, cfg=None, windowed=0, n_chan=1):
+    cfg = cfg or Energy(0, 1, 0, 1, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0)
+    return _run_static("osm_or_energy", "osm_or_energy_num_out", fe, cfg, pcm, n_chan, (C.c_int(windowed),))
+
+
+def mzcr(pcm, fe, cfg=None, windowed=0, n_chan=1):
+    cfg = cfg or MZcr(1, 1, 1, 1, 0)
+    return _run_static("osm_or_mzcr", "osm_or_mzcr_num_out", fe, cfg, pcm, n_chan, (C.c_int(windowed),))
+
+
 def build(force=False):
     """Compile liboracle.so with gcc (oracle/Makefile)."""
     so = os.path.join(_HERE, "liboracle.so")

@@ -710,3 +710,460 @@ long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const o
   free(stat); free(c.mel); free(c.cost); free(c.sint); free(c.eql); mel_free(&c.mb);
   return T;
 }
+
+
+/* ------------------------------------------------------------------ a-12 cEnergy / cMZcr */
+
+int osm_or_energy_num_out(const osm_or_energy_cfg *en)
+{
+  int rms = en->rms, lg = en->log;
+  if (en->htkcompatible) { lg = 1; rms = 0; }                /* lldcore/energy.cpp:67 */
+  return (rms ? 1 : 0) + (en->energy2 ? 1 : 0) + (lg ? 1 : 0);
+}
+
+/* lldcore/energy.cpp:152-187 */
+static void energy_frame(const osm_or_energy_cfg *en, const float *src, long N, float *dst)
+{
+  int rms = en->rms, lg = en->log, n = 0;
+  if (en->htkcompatible) { lg = 1; rms = 0; }
+  double d = 0.0;
+  for (long i = 0; i < N; i++) { float tmp = src[i]; d += tmp * tmp; }   /* float product, double sum */
+  if (rms) dst[n++] = (float)sqrt(d / (float)N) * (float)en->escaleRms + (float)en->ebiasRms;
+  if (en->energy2) dst[n++] = (float)(d / (double)N) * (float)en->escaleSquare + (float)en->ebiasSquare;
+  if (lg) {
+    const double minE = 8.674676e-019;                        /* :19 */
+    if (!en->htkcompatible) {
+      d /= (float)N;
+      if (d < minE) d = minE;
+      dst[n++] = (float)log(d) * (float)en->escaleLog + (float)en->ebiasLog;
+    } else {
+      d *= 32767.0 * 32767.0;
+      if (d <= 1.0) d = 1.0;
+      dst[n++] = (float)log(d) * (float)en->escaleLog + (float)en->ebiasLog;
+    }
+  }
+}
+
+int osm_or_mzcr_num_out(const osm_or_mzcr_cfg *mz)
+{
+  return (mz->zcr ? 1 : 0) + (mz->mcr ? 1 : 0) + (mz->amax ? 1 : 0) + (mz->maxmin ? 2 : 0) + (mz->dc ? 1 : 0);
+}
+
+/* lldcore/mzcr.cpp:109-157 (note the loop bounds 1..N-2 and nmc starting at 4.0) */
+static void mzcr_frame(const osm_or_mzcr_cfg *mz, const float *src, long N, float *dst)
+{
+  float mean = src[0], nzc = 0.0f, nmc = 4.0f, max = 0, min = 0, absmax = 0;
+  long i;
+  if (mz->zcr || mz->mcr || mz->dc) {
+    for (i = 1; i < N - 1; i++) {
+      mean += src[i];
+      if (((src[i - 1] * src[i + 1] <= 0.0) && (src[i] == 0.0)) || (src[i - 1] * src[i] < 0.0)) nzc += 1.0;
+    }
+    nzc /= (float)N;
+    mean /= (float)N;
+  }
+  if (mz->mcr) {
+    for (i = 1; i < N - 1; i++) {
+      if ((((src[i - 1] - mean) * (src[i + 1] - mean) <= 0.0) && ((src[i] - mean) == 0.0)) || ((src[i - 1] - mean) * (src[i] - mean) < 0.0)) nmc++;
+    }
+    nmc /= (float)N;
+  }
+  if (mz->amax || mz->maxmin) {
+    max = min = src[0];
+    for (i = 1; i < N; i++) { if (src[i] < min) min = src[i]; if (src[i] > max) max = src[i]; }
+    if (fabs(min) > fabs(max)) absmax = fabsf(min); else absmax = fabsf(max);
+  }
+  int n = 0;
+  if (mz->zcr) dst[n++] = nzc;
+  if (mz->mcr) dst[n++] = nmc;
+  if (mz->amax) dst[n++] = absmax;
+  if (mz->maxmin) { dst[n++] = max; dst[n++] = min; }
+  if (mz->dc) dst[n++] = mean;
+}
+
+/* time-domain frames: framer output, optionally through pre-emphasis + window */
+typedef void (*tframe_fn)(const void *cfg, const float *x, long N, float *dst);
+static long run_time_frames(const osm_or_frontend *fe, int windowed, const int16_t *pcm, long L, int n_chan,
+                            tframe_fn fn, const void *cfg, int K, float *out)
+{
+  long N = osm_or_frame_size_samples(fe), H = osm_or_frame_step_samples(fe);
+  long T = osm_or_num_frames(L, N, H);
+  if (T <= 0) return 0;
+  float *x = (float *)malloc(sizeof(float) * L);
+  osm_or_pcm16_to_float(pcm, L, n_chan, x);
+  double *win = (double *)malloc(sizeof(double) * N);
+  osm_or_window_table(fe->win_func, N, fe->win_sigma, fe->win_gain, win);
+  float *y = (float *)malloc(sizeof(float) * N);
+  for (long t = 0; t < T; t++) {
+    const float *fx = x + t * H;
+    if (windowed) {
+      if (fe->preemph_on) {
+        float k = (float)fe->preemph_k;
+        y[0] = (1 - k) * fx[0];
+        for (long n = 1; n < N; n++) y[n] = fx[n] - k * fx[n - 1];
+      } else memcpy(y, fx, sizeof(float) * N);
+      float off = (float)fe->win_offset;
+      for (long n = 0; n < N; n++) y[n] = y[n] * (float)win[n] + off;
+      fn(cfg, y, N, out + t * K);
+    } else {
+      fn(cfg, fx, N, out + t * K);
+    }
+  }
+  free(x); free(win); free(y);
+  return T;
+}
+
+static void energy_tf(const void *c, const float *x, long N, float *d) { energy_frame((const osm_or_energy_cfg *)c, x, N, d); }
+static void mzcr_tf(const void *c, const float *x, long N, float *d) { mzcr_frame((const osm_or_mzcr_cfg *)c, x, N, d); }
+
+long osm_or_energy(const osm_or_frontend *fe, const osm_or_energy_cfg *en, int windowed,
+                   const int16_t *pcm, long L, int n_chan, float *out)
+{
+  return run_time_frames(fe, windowed, pcm, L, n_chan, energy_tf, en, osm_or_energy_num_out(en), out);
+}
+long osm_or_mzcr(const osm_or_frontend *fe, const osm_or_mzcr_cfg *mz, int windowed,
+                 const int16_t *pcm, long L, int n_chan, float *out)
+{
+  return run_time_frames(fe, windowed, pcm, L, n_chan, mzcr_tf, mz, osm_or_mzcr_num_out(mz), out);
+}
+
+/* ------------------------------------------------------------------ a-11 cSpectral */
+
+int osm_or_spectral_num_out(const osm_or_spectral_cfg *sp)
+{
+  int n = 0;
+  for (int i = 0; i < sp->nBands; i++) if (sp->bandLo[i] >= 0 && sp->bandHi[i] > 0) n++;
+  for (int i = 0; i < sp->nSlopes; i++) if (sp->slopeLo[i] >= 0 && sp->slopeHi[i] > 0) n++;
+  n += (sp->alphaRatio ? 1 : 0) + (sp->hammarbergIndex ? 1 : 0) + sp->nRollOff + (sp->flux ? 1 : 0);
+  n += (sp->centroid ? 1 : 0) + (sp->maxPos ? 1 : 0) + (sp->minPos ? 1 : 0) + (sp->entropy ? 1 : 0);
+  n += (sp->standardDeviation ? 1 : 0) + (sp->variance ? 1 : 0) + (sp->skewness ? 1 : 0) + (sp->kurtosis ? 1 : 0);
+  n += (sp->slope ? 1 : 0) + (sp->sharpness ? 1 : 0) + (sp->harmonicity ? 1 : 0) + (sp->flatness ? 1 : 0);
+  return n;
+}
+
+/* Traunmueller bark, smileutil/smileUtil.c:1113-1128 */
+static double bark_fwd(double x)
+{
+  if (x > 0) {
+    double zz = (26.81 / (1.0 + 1960.0 / x)) - 0.53;
+    if (zz < 2) return (0.85 * zz + 0.3);
+    else if (zz > 20.1) return (1.22 * zz - 0.22 * 20.1);
+    else return zz;
+  }
+  return 0.0;
+}
+/* smileutil/smileUtil.c:1064-1079 with frqScale == BARK */
+static double sharp_g(double z) { return z <= 16.0 ? 1.0 : pow((z - 16.0) / 4.0, 1.5849625) + 1.0; }
+
+/* smileutil/smileUtil.c:2082-2124 */
+static float stat_entropy(const float *vals, long N)
+{
+  const double entropy_floor = 0.0000001;
+  double e = 0.0, dn = 0.0, l2 = log(2.0);
+  float min = 0.0f;
+  long i;
+  for (i = 0; i < N; i++) { dn += (double)vals[i]; if (vals[i] < min) min = vals[i]; }
+  if (min < 0.0) {
+    double mf = entropy_floor + min;
+    for (i = 0; i < N; i++) { if (vals[i] <= mf) dn += mf - vals[i]; dn -= (double)min; }
+  } else min = 0.0f;
+  if (dn < (float)entropy_floor) dn = (float)entropy_floor;
+  for (i = 0; i < N; i++) {
+    double v = vals[i] - min, ln;
+    if (v <= entropy_floor) v = entropy_floor;
+    ln = v / dn;
+    if (ln > 0.0) e += ln * log(ln) / l2;
+  }
+  return (float)(-e);
+}
+
+typedef struct {
+  const osm_or_spectral_cfg *sp;
+  double fsSec;            /* frameSizeSec of the fftmag level (transformFft.cpp:78-85) */
+  double *frq;             /* bin frequencies, field info (transformFft.cpp:102-117) */
+  long Nsrc;
+  float *prev; int havePrev;
+  double *sharpW;
+  long loBin, hiBin;
+} spec_ctx;
+
+/* band edge -> (bin index, weight) with the frequency axis from the field info
+ * (lldcore/spectral.cpp:781-795 lower, :808-825 upper) */
+static void edge_lo(const spec_ctx *c, double f, double *idx, double *w)
+{
+  long ii, nScale = c->Nsrc;
+  for (ii = 0; ii < nScale; ii++) if (c->frq[ii] > f) break;
+  if ((ii < nScale) && (ii > 0)) *w = (c->frq[ii] - f) / (c->frq[ii] - c->frq[ii - 1]); else *w = 1.0;
+  *idx = (double)ii - 1.0;
+  if (*idx < 0) *idx = 0;
+  if (*idx >= c->Nsrc) *idx = c->Nsrc;
+}
+static void edge_hi(const spec_ctx *c, double f, double *idx, double *w)
+{
+  long ii, nScale = c->Nsrc;
+  for (ii = 0; ii < nScale; ii++) if (c->frq[ii] >= (float)f) break;
+  if ((ii < nScale) && (ii > 0)) *w = (f - c->frq[ii - 1]) / (c->frq[ii] - c->frq[ii - 1]); else *w = 1.0;
+  if ((ii < nScale) && (c->frq[ii] == (float)f)) *idx = (double)ii; else *idx = (double)ii - 1.0;
+  if (*idx >= c->Nsrc) *idx = c->Nsrc - 1;
+}
+
+/* lldcore/spectral.cpp:586-1555 for magnitude input with bin-frequency info, linear scale */
+static void spectral_frame(spec_ctx *c, const float *src, float *dst)
+{
+  const osm_or_spectral_cfg *sp = c->sp;
+  long Nsrc = c->Nsrc, i, j, n = 0;
+  const double *frq = c->frq;
+  int useLog = sp->useLogSpectrum;
+  /* requirements, :219-376 */
+  int reqMag = sp->flux, reqPow = 0, reqLog = 0;
+#define LORP() do { if (useLog) reqLog = 1; else reqPow = 1; } while (0)
+  if (sp->centroid) LORP(); if (sp->maxPos) LORP(); if (sp->minPos) LORP(); if (sp->entropy) LORP();
+  if (sp->standardDeviation) LORP(); if (sp->variance) LORP(); if (sp->skewness) LORP(); if (sp->kurtosis) LORP();
+  if (sp->slope) LORP();
+  if (sp->alphaRatio) reqPow = 1; if (sp->hammarbergIndex) reqPow = 1;
+  if (sp->nBands > 0) reqPow = 1; if (sp->nSlopes > 0) LORP(); if (sp->nRollOff > 0) reqPow = 1;
+  if (sp->sharpness) reqPow = 1; if (sp->harmonicity) LORP(); if (sp->flatness) LORP();
+  float specFloor = 0, logSpecFloor = 0;
+  if (useLog) {                                                /* :228-237 */
+    specFloor = (float)sp->specFloor;
+    specFloor = specFloor * specFloor;
+    logSpecFloor = (float)(10.0 * log(specFloor) / log(10.0));
+  }
+  long loBin = c->loBin, hiBin = c->hiBin, nBins = hiBin - loBin + 1;
+  float *srcM = NULL, *srcP = NULL, *srcL = NULL;
+  const float *srcLP;
+  if (reqMag) {
+    srcM = (float *)malloc(sizeof(float) * Nsrc);
+    for (i = 0; i < Nsrc; i++) srcM[i] = sp->squareInput ? src[i] : (src[i] > 0.0 ? sqrtf(src[i]) : 0.0f);
+  }
+  if (reqPow) {
+    srcP = (float *)malloc(sizeof(float) * Nsrc);
+    for (i = 0; i < Nsrc; i++) srcP[i] = sp->squareInput ? src[i] * src[i] : src[i];
+  }
+  if (reqLog) {                                                /* :700-729 */
+    float logSpecFactor = (float)(10.0 / log(10.0));
+    float myF = logSpecFactor;
+    const float *mySrc;
+    if (reqPow) mySrc = srcP;
+    else if (reqMag) { mySrc = srcM; logSpecFactor *= 2.0; }
+    else { mySrc = src; if (sp->squareInput) logSpecFactor *= 2.0; }
+    srcL = (float *)malloc(sizeof(float) * Nsrc);
+    for (i = 0; i < Nsrc; i++) srcL[i] = (mySrc[i] <= specFloor) ? logSpecFloor : myF * logf(mySrc[i]);
+  }
+  srcLP = useLog ? srcL : srcP;
+
+  double frameSum = 0.0;                                       /* :766-771 */
+  if (sp->normBandEnergies || sp->sharpness || sp->nRollOff > 0)
+    for (i = loBin; i <= hiBin; i++) frameSum += srcP[i];
+
+  for (i = 0; i < sp->nBands; i++) {                           /* :775-870 */
+    long bL = (long)sp->bandLo[i], bH = (long)sp->bandHi[i];
+    if (!(bL >= 0 && bH > 0)) continue;
+    double idxL, wL, idxR, wR;
+    edge_lo(c, (double)bL, &idxL, &wL); if (wL == 0.0) wL = 1.0;
+    edge_hi(c, (double)bH, &idxR, &wR); if (wR == 0.0) wR = 1.0;
+    long iL = (long)floor(idxL), iR = (long)floor(idxR);
+    if (iL >= Nsrc) { iL = iR = Nsrc - 1; wR = 0.0; wL = 0.0; }
+    if (iR >= Nsrc) { iR = Nsrc - 1; wR = 1.0; }
+    if (iL < 0) iL = 0; if (iR < 0) iR = 0;
+    double sum = (double)srcP[iL] * wL;
+    for (j = iL + 1; j < iR; j++) sum += (double)srcP[j];
+    sum += (double)srcP[iR] * wR;
+    if (sp->normBandEnergies) dst[n++] = frameSum > 0.0 ? (float)(sum / frameSum) : 0.0f;
+    else if (nBins > 0) dst[n++] = useLog ? (float)(10.0 * log(sum / (double)nBins) / log(10.0)) : (float)(sum / (double)nBins);
+    else dst[n++] = 0.0f;
+  }
+  for (i = 0; i < sp->nSlopes; i++) {                          /* :873-993 */
+    long bL = (long)sp->slopeLo[i], bH = (long)sp->slopeHi[i];
+    if (!(bL >= 0 && bH > 0)) continue;
+    double idxL, wL, idxR, wR;
+    edge_lo(c, (double)bL, &idxL, &wL); if (wL == 0.0) wL = 1.0;
+    edge_hi(c, (double)bH, &idxR, &wR); if (wR == 0.0) wR = 1.0;
+    long iL = (long)floor(idxL), iR = (long)floor(idxR);
+    if (iL >= Nsrc) { iL = iR = Nsrc - 1; wR = 0.0; wL = 0.0; }
+    if (iR >= Nsrc) { iR = Nsrc - 1; wR = 1.0; }
+    if (iL < 0) iL = 0; if (iR < 0) iR = 0;
+    double Nind = idxR - idxL;
+    double Sf = (double)frq[iL] * wL, S2f = Sf * Sf;
+    double sumA = (double)frq[iL] * wL * (double)srcLP[iL], sumB = wL * srcLP[iL];
+    for (long ii = iL + 1; ii < iR && ii < Nsrc; ii++) {
+      S2f += (double)frq[ii] * (double)frq[ii];
+      Sf += (double)frq[ii];
+      sumA += (double)frq[ii] * (double)srcLP[ii];
+      sumB += (double)srcLP[ii];
+    }
+    S2f += (double)frq[iR] * wR * (double)frq[iR] * wR;
+    Sf += (double)frq[iR] * wR;
+    sumA += (double)frq[iR] * wR * (double)srcLP[iR];
+    sumB += wR * (double)srcLP[iR];
+    double deno = (Nind * S2f - Sf * Sf), slope = 0.0;
+    if (deno != 0.0) slope = (Nind * sumA - Sf * sumB) / deno;
+    dst[n++] = sp->oldSlopeScale ? (float)(slope * (Nind - 1.0)) : (float)slope;
+  }
+  if (sp->alphaRatio) {                                        /* :996-1037 */
+    float sum01 = 0.0f, sum15 = 0.0f;
+    for (j = 0; j < Nsrc; j++) {
+      if (frq[j] > 5000.0) break;
+      if (frq[j] < 1000.0) sum01 += srcP[j]; else sum15 += srcP[j];
+    }
+    if (sum01 > 0.0) {
+      if (useLog) dst[n++] = (sum15 > specFloor) ? (float)(10.0 * log(sum15 / sum01) / log(10.0))
+                                                : (float)(10.0 * (log(specFloor) - log(sum01)) / log(10.0));
+      else dst[n++] = sum15 / sum01;
+    } else dst[n++] = 0.0f;
+  }
+  if (sp->hammarbergIndex) {                                   /* :1040-1089 */
+    float max02 = 0.0f, max25 = 0.0f;
+    for (j = 0; j < Nsrc; j++) {
+      if (frq[j] > 5000.0) break;
+      if (frq[j] < 2000.0) { if (srcP[j] > max02) max02 = srcP[j]; } else { if (srcP[j] > max25) max25 = srcP[j]; }
+    }
+    if (max25 > 0.0) {
+      if (useLog) dst[n++] = (max02 > specFloor) ? (float)(10.0 * log(max02 / max25) / log(10.0))
+                                                : (float)(10.0 * (log(specFloor) - log(max25)) / log(10.0));
+      else dst[n++] = max02 / max25;
+    } else dst[n++] = 0.0f;
+  }
+  double sumB = 0.0, sumC = 0.0;                               /* :1092-1099 */
+  if (sp->normBandEnergies && !useLog) sumB = frameSum;
+  else for (j = loBin; j <= hiBin; j++) sumB += (double)srcLP[j];
+  {                                                            /* roll-off :1103-1122 */
+    float ro[OSM_OR_MAX_LIST];
+    for (i = 0; i < sp->nRollOff; i++) ro[i] = 0.0f;
+    for (j = loBin; j <= hiBin; j++) {
+      sumC += (double)srcP[j];
+      for (i = 0; i < sp->nRollOff; i++) {
+        if (sp->buggyRollOff == 1 && i > 0) sumC += (double)srcP[j];
+        if ((ro[i] == 0.0) && (sumC >= sp->rollOff[i] * frameSum)) ro[i] = (float)frq[j];
+      }
+    }
+    for (i = 0; i < sp->nRollOff; i++) dst[n++] = ro[i];
+  }
+  if (sp->flux) {                                              /* :1125-1254 */
+    if (!c->havePrev) { dst[n++] = 0.0f; c->havePrev = 1; }
+    else {
+      double myA = 0.0;
+      for (j = loBin; j <= hiBin; j++) {
+        double myB = ((double)srcM[j] / 1.0 - (double)c->prev[j - loBin] / 1.0);
+        myA += myB * myB;
+      }
+      double fl = nBins > 0 ? myA / (double)nBins : 0.0;
+      dst[n++] = fl > 0.0 ? (float)sqrt(fl) : 0.0f;
+    }
+    for (j = loBin; j <= hiBin; j++) c->prev[j - loBin] = srcM[j];
+  }
+  float ctr = 0.0f;                                            /* centroid :1257-1312 */
+  double sumA = 0.0;
+  if (sp->centroid || sp->standardDeviation || sp->variance || sp->skewness || sp->kurtosis || sp->slope) {
+    for (j = loBin; j <= hiBin; j++) sumA += (double)frq[j] * (double)srcLP[j];
+    if (sumB != 0.0) ctr = (float)(sumA / sumB);
+    if (sp->centroid) dst[n++] = ctr;
+  }
+  if (sp->maxPos || sp->minPos) {                              /* :1314-1330 */
+    long maP = loBin, miP = loBin;
+    float mx = srcLP[loBin], mn = srcLP[loBin];
+    for (j = loBin + 1; j < hiBin; j++) {
+      if (srcLP[j] < mn) { mn = srcLP[j]; miP = j; }
+      if (srcLP[j] > mx) { mx = srcLP[j]; maP = j; }
+    }
+    if (sp->maxPos) dst[n++] = (float)frq[maP];
+    if (sp->minPos) dst[n++] = (float)frq[miP];
+  }
+  if (sp->entropy) dst[n++] = stat_entropy(srcLP + loBin, hiBin - loBin + 1);   /* :1333-1336 */
+  if (sp->standardDeviation || sp->variance || sp->skewness || sp->kurtosis) { /* :1338-1397 */
+    double u = ctr, m2 = 0.0, m3 = 0.0, m4 = 0.0;
+    for (i = loBin; i <= hiBin; i++) {
+      double t1 = ((double)frq[i] - u);
+      double m = t1 * t1 * (double)srcLP[i];
+      m2 += m; m *= t1; m3 += m; m4 += m * t1;
+    }
+    double sigma2 = 0.0;
+    if (sumB != 0.0) sigma2 = m2 / sumB;
+    if (sp->standardDeviation) dst[n++] = sigma2 > 0.0 ? (float)sqrt(sigma2) : 0.0f;
+    if (sp->variance) dst[n++] = (float)sigma2;
+    if (sp->skewness) dst[n++] = sigma2 <= 0.0 ? 0.0f : (float)(m3 / (sumB * sigma2 * sqrt(sigma2)));
+    if (sp->kurtosis) dst[n++] = sigma2 == 0.0 ? 0.0f : (float)(m4 / (sumB * sigma2 * sigma2));
+  }
+  if (sp->slope) {                                             /* :1400-1427 */
+    double Sf = 0.0, S2f = 0.0, Nind = (double)nBins;
+    for (i = loBin; i <= hiBin && i < Nsrc; i++) { S2f += (double)frq[i] * (double)frq[i]; Sf += (double)frq[i]; }
+    double deno = (Nind * S2f - Sf * Sf), slope = 0.0;
+    if (deno != 0.0) slope = (Nind * sumA - Sf * sumB) / deno;
+    dst[n++] = sp->oldSlopeScale ? (float)(slope * (Nind - 1.0)) : (float)slope;
+  }
+  if (sp->sharpness) {                                         /* :1429-1478 */
+    float sumAA = 0.0f, c2 = 0.0f;
+    for (j = loBin; j <= hiBin && j < Nsrc; j++) sumAA += (float)(c->sharpW[j - loBin] * (double)srcP[j]);
+    if (frameSum != 0.0) c2 = (float)(sumAA / frameSum);
+    dst[n++] = (float)(0.11 * c2);
+  }
+  if (sp->harmonicity) {                                       /* :1484-1513 */
+    float ptpSum = 0.0f, lastPeak = -99.0f;
+    for (j = loBin + 2; j < hiBin - 1; j++) {
+      if ((srcLP[j - 2] < srcLP[j] && srcLP[j - 1] < srcLP[j] && srcLP[j] > srcLP[j + 1] && srcLP[j] > srcLP[j + 2]) ||
+          (srcLP[j - 2] > srcLP[j] && srcLP[j - 1] > srcLP[j] && srcLP[j] < srcLP[j + 1] && srcLP[j] < srcLP[j + 2])) {
+        if (lastPeak != -99.0) ptpSum += fabs(srcLP[j] - lastPeak);
+        lastPeak = srcLP[j];
+      }
+    }
+    ptpSum /= 2.0;
+    if (sp->normBandEnergies && sumB != 0.0) {
+      if (useLog) ptpSum /= (float)fabs(sumB); else ptpSum /= (float)(frameSum);
+    } else ptpSum /= (float)nBins;
+    dst[n++] = ptpSum;
+  }
+  if (sp->flatness) {                                          /* :1515-1544 */
+    float sf = 0.0f, gmean = 0.0f;
+    int nGm = 0;
+    if (sumB != 0.0) {
+      for (j = loBin; j <= hiBin; j++) if (srcLP[j] != 0.0) { gmean += log(fabs(srcLP[j])); nGm++; }
+      if (nGm > 0) gmean /= (float)nGm;
+      gmean = exp(gmean);
+      sf = gmean / (float)fabs(sumB / (double)nBins);
+    }
+    if (sp->logFlatness) dst[n++] = sf > 0.0 ? (float)log(sf) : 0.0f; else dst[n++] = sf;
+  }
+  free(srcM); free(srcP); free(srcL);
+}
+
+static void spec_mag_frame(void *vctx, const float *mag, long nb, float *dst)
+{
+  (void)nb;
+  spectral_frame((spec_ctx *)vctx, mag, dst);
+}
+
+long osm_or_spectral(const osm_or_frontend *fe, const osm_or_spectral_cfg *sp,
+                     const int16_t *pcm, long L, int n_chan, float *out)
+{
+  long N = osm_or_frame_size_samples(fe), H = osm_or_frame_step_samples(fe);
+  long nfft = osm_or_fft_size(N), Nsrc = nfft / 2 + 1;
+  long T = osm_or_num_frames(L, N, H);
+  if (T <= 0) return 0;
+  spec_ctx c; memset(&c, 0, sizeof c);
+  c.sp = sp; c.Nsrc = Nsrc; c.fsSec = osm_or_fft_frame_size_sec(fe);
+  c.frq = (double *)malloc(sizeof(double) * Nsrc);
+  double F0 = (double)(1.0) / (double)c.fsSec;                 /* transformFft.cpp:111-115 */
+  for (long i = 0; i < Nsrc; i++) c.frq[i] = F0 * (double)i;
+  /* spectral range :625-647 */
+  long lo = (long)sp->freqRangeLo, hi = (long)sp->freqRangeHi;
+  if (lo == hi && hi == 0) { c.loBin = 1; c.hiBin = Nsrc - 1; }
+  else {
+    c.loBin = -1; c.hiBin = -1;
+    for (long i = 0; i < Nsrc; i++) {
+      if ((double)lo >= c.frq[i]) c.loBin = i;
+      if ((double)hi > c.frq[i]) c.hiBin = i;
+    }
+    if (c.hiBin == -1 || c.hiBin >= Nsrc) c.hiBin = Nsrc - 1;
+    if (c.loBin < 0) c.loBin = 0;
+  }
+  c.prev = (float *)calloc(Nsrc, sizeof(float));
+  c.sharpW = (double *)calloc(Nsrc, sizeof(double));
+  for (long j = c.loBin; j <= c.hiBin; j++) {                  /* :1443-1453 (linear scale -> bark) */
+    double fb = bark_fwd(c.frq[j]);
+    c.sharpW[j - c.loBin] = fb * sharp_g(fb);
+  }
+  int K = osm_or_spectral_num_out(sp);
+  run_frames(fe, pcm, L, n_chan, spec_mag_frame, &c, K, out, NULL);
+  free(c.frq); free(c.prev); free(c.sharpW);
+  return T;
+}

@@ -71,6 +71,27 @@ typedef struct {
   int    htkcompatible;
 } osm_or_plp;
 
+#define OSM_OR_MAX_LIST 16
+typedef struct {            /* cSpectral (lldcore/spectral.cpp), same fields as osm_b200_spectral */
+  int squareInput;
+  int nBands;  double bandLo[OSM_OR_MAX_LIST], bandHi[OSM_OR_MAX_LIST];
+  int nSlopes; double slopeLo[OSM_OR_MAX_LIST], slopeHi[OSM_OR_MAX_LIST];
+  int nRollOff; double rollOff[OSM_OR_MAX_LIST];
+  int flux, centroid, maxPos, minPos, entropy, standardDeviation, variance, skewness,
+      kurtosis, slope, alphaRatio, hammarbergIndex, sharpness, harmonicity, flatness;
+  int normBandEnergies, buggyRollOff, oldSlopeScale, useLogSpectrum;
+  double freqRangeLo, freqRangeHi;
+  double specFloor;
+  int logFlatness;
+} osm_or_spectral_cfg;
+
+typedef struct {            /* cEnergy (lldcore/energy.cpp) */
+  int htkcompatible, rms, energy2, log;
+  double escaleLog, escaleRms, escaleSquare, ebiasLog, ebiasRms, ebiasSquare;
+} osm_or_energy_cfg;
+
+typedef struct { int zcr, mcr, amax, maxmin, dc; } osm_or_mzcr_cfg;   /* cMZcr (lldcore/mzcr.cpp) */
+
 /* ---- geometry (integer work, must be bit exact) ---- */
 long osm_or_frame_size_samples(const osm_or_frontend *fe);
 long osm_or_frame_step_samples(const osm_or_frontend *fe);
@@ -100,6 +121,18 @@ long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const o
                     float *out, float *tap_mel);
 
 int osm_or_plp_num_out(const osm_or_plp *pl, int n_bands);
+
+/* static (per-frame) LLDs other than the cepstral chains.  `windowed` selects whether the
+ * time-domain component reads the framer level (0) or the windower level (1). */
+int  osm_or_spectral_num_out(const osm_or_spectral_cfg *sp);
+long osm_or_spectral(const osm_or_frontend *fe, const osm_or_spectral_cfg *sp,
+                     const int16_t *pcm, long n_samples, int n_chan, float *out);
+int  osm_or_energy_num_out(const osm_or_energy_cfg *en);
+long osm_or_energy(const osm_or_frontend *fe, const osm_or_energy_cfg *en, int windowed,
+                   const int16_t *pcm, long n_samples, int n_chan, float *out);
+int  osm_or_mzcr_num_out(const osm_or_mzcr_cfg *mz);
+long osm_or_mzcr(const osm_or_frontend *fe, const osm_or_mzcr_cfg *mz, int windowed,
+                 const int16_t *pcm, long n_samples, int n_chan, float *out);
 
 /* cDeltaRegression with the reference's edge/phantom-frame semantics.
  * in: T x K ; out: (T + win) x K.  Returns T + win. */
