@@ -162,6 +162,7 @@ typedef struct {            /* cSpectral (subset of switches used by eGeMAPS / C
   int32_t normBandEnergies, buggyRollOff, oldSlopeScale, useLogSpectrum;
   double  freqRangeLo, freqRangeHi;  /* freqRange = lo-hi, 0-0 = full */
   double  specFloor;        /* 1e-7 */
+  int32_t logFlatness;      /* 0 */
 } osm_b200_spectral;
 
 typedef struct {            /* cEnergy */

@@ -5,6 +5,7 @@ include/osm_b200.h; importing this package does not load it, the first use of
 `opensmile_b200.plan.Plan` does (and fails loudly if it has not been built).
 """
 from . import capi  # noqa: F401
-from .plan import Plan, components_mfcc12_0_d_a, components_plp_0_d_a, pack_utterances  # noqa: F401
+from .plan import (Plan, comp, components_frontend, components_mfcc12_0_d_a,  # noqa: F401
+                   components_plp_0_d_a, pack_utterances)
 
 __all__ = ["Plan", "components_mfcc12_0_d_a", "components_plp_0_d_a", "pack_utterances", "capi"]

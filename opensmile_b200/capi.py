@@ -92,7 +92,7 @@ class Spectral(C.Structure):
                 ("harmonicity", i32), ("flatness", i32),
                 ("normBandEnergies", i32), ("buggyRollOff", i32), ("oldSlopeScale", i32),
                 ("useLogSpectrum", i32),
-                ("freqRangeLo", f64), ("freqRangeHi", f64), ("specFloor", f64)]
+                ("freqRangeLo", f64), ("freqRangeHi", f64), ("specFloor", f64), ("logFlatness", i32)]
 
 
 class Energy(C.Structure):

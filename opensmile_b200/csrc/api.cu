@@ -75,31 +75,47 @@ struct PinBuf {
 
 }  // namespace
 
+
+// per-stream runtime state (one framer / FFT chain)
+struct StreamRt {
+  unsigned char *dConst = nullptr;
+  LldParams kp;                  // template filled at create
+  int tileF = 32;
+  bool runLld = false;           // lld_kernel is launched for this stream
+  bool needTiles = false;        // standalone ops read this stream tile by tile
+  const float *dWindow = nullptr;   // [frameSize] window floats (time-domain ops)
+  std::vector<int32_t> uttChunk0, uttTile0;
+  PinBuf<ChunkRef> hChunks; DevBuf<ChunkRef> dChunks; size_t nChunks = 0;
+  PinBuf<OpTile> hTiles; DevBuf<OpTile> dTiles; size_t nTiles = 0;
+  DevBuf<float> dMag;
+};
+
+struct OpRt {
+  int kind = 0, stream = 0;
+  SpectralParams sp;
+  TimeOpParams tp;
+  double *dSharpW = nullptr;
+};
+
 struct osm_b200_plan {
   PlanDesc d;
   int device = 0;
   int numSMs = 0;
-  // constant tables on the device (one blob)
-  unsigned char *dConst = nullptr;
-  LldParams kp;            // template: table pointers + geometry filled at create
+  std::vector<StreamRt> st;
+  std::vector<OpRt> ops;         // standalone ops (not fused into lld_kernel)
   PostParams pp;
-  int tileF = 32;
-  bool staticDirect = false;   // static rows are written straight into the output rows
+  bool staticDirect = false;     // static rows are written straight into the output rows
   int identityOutCol = 0;
+  bool fused = false;            // delta / delta-delta evaluated inside lld_kernel
   // batch bookkeeping
   std::vector<int64_t> cachedUttOff;
-  PinBuf<long long> hMeta;     // uttOff | rowOff | statOff
-  PinBuf<TileRef> hTiles;      // post_kernel tiles
-  size_t nPostTiles = 0;
-  PinBuf<ChunkRef> hChunks;    // lld_kernel work units
-  DevBuf<ChunkRef> dChunks;
-  size_t nChunks = 0;
-  bool fused = false;          // delta / delta-delta evaluated inside lld_kernel
+  PinBuf<long long> hMeta;       // uttOff | rowOff | statOff
   DevBuf<long long> dMeta;
-  DevBuf<TileRef> dTiles;
+  PinBuf<TileRef> hPost; DevBuf<TileRef> dPost; size_t nPostTiles = 0;
+  std::vector<int32_t> uttPost0;
   DevBuf<float> dStat;
-  size_t nTiles = 0;
   long long totalRows = 0, totalStat = 0, totalSamples = 0;
+  size_t totalWork = 0;
   cudaEvent_t evMetaDone = nullptr, evK0 = nullptr, evKm = nullptr, evK1 = nullptr;
   bool metaPending = false, timed = false;
   // run_host buffers
@@ -107,11 +123,9 @@ struct osm_b200_plan {
   DevBuf<float> dOut;
   cudaStream_t hostStream = nullptr, h2dStream = nullptr, d2hStream = nullptr;
   std::vector<cudaEvent_t> evPiece;   // 2 per pipeline piece: PCM landed / rows computed
-  std::vector<int32_t> uttChunk0, uttPost0;   // first chunk / post tile of each utterance (+ sentinel)
   int lastLaunches = 0;
   LldLaunchInfo lastInfo{};
 };
-
 extern "C" {
 
 int32_t osm_b200_abi_version(void) { return OSM_B200_ABI_VERSION; }
@@ -211,6 +225,131 @@ static void build_twiddles(int M, std::vector<float2> &tw, int twOff[4])
   }
 }
 
+
+// pack the constant tables of one stream (front end + optional fused band op) and fill its LldParams
+static osm_b200_status setup_stream(osm_b200_plan *pl, int si, const cudaDeviceProp &prop)
+{
+  const PlanDesc &d = pl->d;
+  const Stream &sd = d.streams[si];
+  StreamRt &rt = pl->st[si];
+  const FrontEnd &fe = sd.fe;
+  rt.runLld = sd.hasFft && (sd.fusedOp >= 0 || sd.dumpMag);
+  rt.tileF = lld_supported_fft(fe.nfft) ? lld_tile_frames(fe.nfft) : 32;
+  LldParams &kp = rt.kp;
+  memset(&kp, 0, sizeof kp);
+  kp.opKind = -1;
+  kp.nChan = fe.nChan;
+  kp.frameSize = fe.frameSize; kp.frameStep = fe.frameStep;
+  // per-lane stride S = frameStep + sPad of the shared-memory sample tile: odd S (scalar loads)
+  // or even S with S/2 odd (64-bit sample-pair loads) is bank-conflict free across the lanes
+  kp.sPad = (fe.frameStep % 2 != 0) ? 0 : (((fe.frameStep / 2) % 2 != 0) ? 0 : 2);
+  kp.preemph = fe.preemph; kp.preDe = fe.preDe; kp.preK = fe.preK;
+  kp.oneMinusK = 1 - fe.preK;                     // (1-k), float arithmetic (vectorPreemphasis.cpp:94)
+  kp.winOffset = fe.winOffset; kp.hasWinOffset = fe.winOffset != 0.f;
+
+  auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+  size_t o = 0;
+  std::vector<unsigned char> blob;
+  auto put = [&](const void *src, size_t bytes) { const size_t at = o; blob.resize(up16(o + bytes), 0); if (bytes) memcpy(&blob[at], src, bytes); o = up16(o + bytes); return at; };
+  const size_t oWindow = put(fe.window.data(), fe.window.size() * sizeof(float));
+  size_t oWin = 0, oTw = 0, oSplit = 0, oCoef = 0, oRange = 0, oDct = 0, oLift = 0, oEql = 0;
+  if (rt.runLld) {
+    if (!lld_supported_fft(fe.nfft))
+      return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(fe.nfft) + " not supported (512, 1024, 2048)");
+    const int M = fe.nfft / 2;
+    std::vector<float4> winLut(M, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int e = 0; e < M; e++) {
+      const int n = 2 * e;
+      if (n < fe.frameSize) winLut[e].x = fe.window[n];
+      if (n + 1 < fe.frameSize) winLut[e].y = fe.window[n + 1];
+      const int off = (n < fe.frameSize) ? n + (n / fe.frameStep) * kp.sPad : 0;
+      memcpy(&winLut[e].z, &off, sizeof(int));
+      winLut[e].w = (n + 1 < fe.frameSize) ? 2.f : ((n < fe.frameSize) ? 1.f : 0.f);
+    }
+    std::vector<float2> tw;
+    build_twiddles(M, tw, kp.twOff);
+    kp.twCount = (int)tw.size();
+    std::vector<float2> split(M / 2 + 1);
+    for (int k = 0; k <= M / 2; k++) {
+      const double ang = -2.0 * M_PI * (double)k / (double)fe.nfft;
+      split[k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    oWin = put(winLut.data(), winLut.size() * sizeof(float4));
+    tw.push_back(make_float2(0.f, 0.f));
+    oTw = put(tw.data(), tw.size() * sizeof(float2));
+    oSplit = put(split.data(), split.size() * sizeof(float2));
+    if (sd.fusedOp >= 0) {
+      const StaticOp &op = d.ops[sd.fusedOp];
+      const bool isPlp = op.kind == SOP_PLP;
+      const MelBank &mb = d.mels[isPlp ? op.plp.melIdx : op.mfcc.melIdx];
+      const MfccOp &mf = op.mfcc;
+      const PlpOp &po = op.plp;
+      if (isPlp && po.doLpToCeps && po.firstCC > 1) return fail(OSM_B200_ERR_UNSUPPORTED, "cPlp: firstCC > 1 is not supported");
+      kp.opKind = isPlp ? 1 : 0;
+      kp.nBands = mb.nBands; kp.melUsePower = mb.usePower;
+      // without a magnitude dump the kernel keeps 2X (4|X|^2) out of the real-FFT split and the
+      // exact factor 1/4 of the power path is folded into the band scale
+      kp.melScale = (mb.usePower && !sd.dumpMag) ? mb.outScale * 0.25f : mb.outScale;
+      if (!isPlp) {
+        kp.nStat = mf.nMfcc; kp.melfloor = mf.melfloor; kp.logMelfloor = mf.logMelfloor; kp.doLog = mf.doLog;
+        kp.dctStride = (mb.nBands + 3) / 4 * 4; kp.dctRows = mf.nMfcc;
+      } else {
+        kp.nStat = po.nOut; kp.melfloor = po.melfloor; kp.logMelfloor = po.logMelfloor; kp.doLog = po.doLog;
+        kp.plpAud = po.doAud; kp.plpInvLog = po.doInvLog; kp.plpIDFT = po.doIDFT; kp.plpLP = po.doLP; kp.plpCeps = po.doLpToCeps;
+        kp.plpHtk = po.htk; kp.plpLifter = po.lifter; kp.plpOrder = po.lpOrder; kp.plpNAuto = po.nAuto; kp.plpNFreq = po.nFreq;
+        kp.plpFirstCC = po.firstCC; kp.plpLastCC = po.lastCC; kp.plpCompression = po.compression;
+        kp.dctStride = po.nFreq; kp.dctRows = po.nAuto;
+      }
+      // split the bands over the virtual warps, balancing visited bins (ranges bs..be)
+      {
+        const int nvw = lld_virtual_warps(fe.nfft);
+        const int totalBins = mb.rangeBegin[mb.nBands + 1] - mb.rangeBegin[0];
+        int b = 0;
+        kp.melSplit[0] = 0;
+        for (int w = 1; w <= nvw; w++) {
+          const double target = (double)totalBins * w / nvw;
+          while (b < mb.nBands && (mb.rangeBegin[b + 1] - mb.rangeBegin[0]) < target) b++;
+          if (w == nvw) b = mb.nBands;
+          kp.melSplit[w] = b;
+        }
+        for (int w = nvw + 1; w <= kMaxVW; w++) kp.melSplit[w] = mb.nBands;
+      }
+      std::vector<float> dctPad((size_t)kp.dctRows * kp.dctStride, 0.f);
+      if (!isPlp) {
+        for (int i = 0; i < mf.nMfcc; i++)
+          memcpy(&dctPad[(size_t)i * kp.dctStride], &mf.cosT[(size_t)i * mb.nBands], sizeof(float) * mb.nBands);
+      } else {
+        memcpy(dctPad.data(), po.cosT.data(), sizeof(float) * po.cosT.size());
+      }
+      const std::vector<float> &liftV = isPlp ? po.lift : mf.liftFactor;
+      std::vector<float> eqlV = isPlp ? po.eql : std::vector<float>(1, 0.f);
+      oCoef = put(mb.coef.data(), mb.coef.size() * sizeof(float));
+      oRange = put(mb.rangeBegin.data(), mb.rangeBegin.size() * sizeof(int));
+      oDct = put(dctPad.data(), dctPad.size() * sizeof(float));
+      oLift = put(liftV.data(), liftV.size() * sizeof(float));
+      oEql = put(eqlV.data(), eqlV.size() * sizeof(float));
+    }
+  }
+  CU(cudaMalloc(&rt.dConst, blob.size()));
+  CU(cudaMemcpy(rt.dConst, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  rt.dWindow = reinterpret_cast<const float *>(rt.dConst + oWindow);
+  if (rt.runLld) {
+    kp.winLut = reinterpret_cast<const float4 *>(rt.dConst + oWin);
+    kp.twiddles = reinterpret_cast<const float2 *>(rt.dConst + oTw);
+    kp.splitTw = reinterpret_cast<const float2 *>(rt.dConst + oSplit);
+    if (sd.fusedOp >= 0) {
+      kp.melCoef = reinterpret_cast<const float *>(rt.dConst + oCoef);
+      kp.melRange = reinterpret_cast<const int *>(rt.dConst + oRange);
+      kp.dctCos = reinterpret_cast<const float *>(rt.dConst + oDct);
+      kp.dctLift = reinterpret_cast<const float *>(rt.dConst + oLift);
+      kp.plpEql = reinterpret_cast<const float *>(rt.dConst + oEql);
+    }
+    if (lld_smem_bytes(kp, fe.nfft) > (size_t)prop.sharedMemPerBlockOptin)
+      return fail(OSM_B200_ERR_UNSUPPORTED, "configuration needs more shared memory than the device offers");
+  }
+  return OSM_B200_OK;
+}
+
 osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_comps,
                                      const char *output_level, int32_t device, osm_b200_plan **out)
 {
@@ -222,13 +361,12 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   osm_b200_status st = compile_graph(comps, n_comps, output_level, pl->d, err);
   if (st != OSM_B200_OK) { delete pl; return fail(st, err); }
   const PlanDesc &d = pl->d;
-  if (!lld_supported_fft(d.fe.nfft)) {
-    delete pl;
-    return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(d.fe.nfft) + " not supported (512, 1024, 2048)");
-  }
-  if (d.ops.size() != 1 || (d.ops[0].kind != SOP_MFCC && d.ops[0].kind != SOP_PLP)) { delete pl; return fail(OSM_B200_ERR_UNSUPPORTED, "exactly one cMfcc or cPlp static producer is supported"); }
-  if (d.ops[0].kind == SOP_PLP && d.ops[0].plp.doLpToCeps && d.ops[0].plp.firstCC > 1) { delete pl; return fail(OSM_B200_ERR_UNSUPPORTED, "cPlp: firstCC > 1 is not supported"); }
-
+  for (const Stream &sd : d.streams)
+    if (sd.hasFft && (sd.fusedOp >= 0 || sd.dumpMag) && !lld_supported_fft(sd.fe.nfft)) {
+      const int nf = sd.fe.nfft;
+      delete pl;
+      return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(nf) + " not supported (512, 1024, 2048)");
+    }
   if (device < 0) {
     // description-only plan: geometry, names and frame-count rules without touching CUDA
     // (used by host-side tooling and CPU-only tests); it can never run.
@@ -243,163 +381,61 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     delete pl;
     return fail(OSM_B200_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
   }
-  if (device < 0 || device >= ndev) { delete pl; return fail(OSM_B200_ERR_INVALID, "bad device index"); }
+  if (device >= ndev) { delete pl; return fail(OSM_B200_ERR_INVALID, "bad device index"); }
   pl->device = device;
 #define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { osm_b200_plan_destroy(pl); return cuda_fail(e_, #call); } } while (0)
+#define STP(call) do { osm_b200_status s_ = (call); if (s_ != OSM_B200_OK) { osm_b200_plan_destroy(pl); return s_; } } while (0)
   CUP(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUP(cudaGetDeviceProperties(&prop, device));
   pl->numSMs = prop.multiProcessorCount;
 
-  // ---- pack constant tables ----
-  const FrontEnd &fe = d.fe;
-  const int M = fe.nfft / 2;
-  const bool isPlp = d.ops[0].kind == SOP_PLP;
-  const MelBank &mb = d.mels[isPlp ? d.ops[0].plp.melIdx : d.ops[0].mfcc.melIdx];
-  const MfccOp &mf = d.ops[0].mfcc;
-  const PlpOp &po = d.ops[0].plp;
-  pl->tileF = lld_tile_frames(fe.nfft);
+  pl->st.resize(d.streams.size());
+  for (size_t s = 0; s < d.streams.size(); s++) STP(setup_stream(pl, (int)s, prop));
 
-  LldParams &kp = pl->kp;
-  memset(&kp, 0, sizeof kp);
-  kp.nChan = fe.nChan;
-  kp.frameSize = fe.frameSize; kp.frameStep = fe.frameStep;
-  // per-lane stride S = frameStep + sPad of the shared-memory sample tile: odd S (scalar loads)
-  // or even S with S/2 odd (64-bit sample-pair loads) is bank-conflict free across the lanes
-  kp.sPad = (fe.frameStep % 2 != 0) ? 0 : (((fe.frameStep / 2) % 2 != 0) ? 0 : 2);
-  kp.preemph = fe.preemph; kp.preDe = fe.preDe; kp.preK = fe.preK;
-  kp.oneMinusK = 1 - fe.preK;                     // (1-k), float arithmetic (vectorPreemphasis.cpp:94)
-  kp.winOffset = fe.winOffset; kp.hasWinOffset = fe.winOffset != 0.f;
-
-  std::vector<float4> winLut(M, make_float4(0.f, 0.f, 0.f, 0.f));
-  for (int e = 0; e < M; e++) {
-    const int n = 2 * e;
-    if (n < fe.frameSize) winLut[e].x = fe.window[n];
-    if (n + 1 < fe.frameSize) winLut[e].y = fe.window[n + 1];
-    const int off = (n < fe.frameSize) ? n + (n / fe.frameStep) * kp.sPad : 0;
-    memcpy(&winLut[e].z, &off, sizeof(int));
-    winLut[e].w = (n + 1 < fe.frameSize) ? 2.f : ((n < fe.frameSize) ? 1.f : 0.f);
-  }
-  std::vector<float2> tw;
-  build_twiddles(M, tw, kp.twOff);
-  kp.twCount = (int)tw.size();
-  std::vector<float2> split(M / 2 + 1);
-  for (int k = 0; k <= M / 2; k++) {
-    const double ang = -2.0 * M_PI * (double)k / (double)fe.nfft;
-    split[k] = make_float2((float)cos(ang), (float)sin(ang));
-  }
-  kp.nBands = mb.nBands; kp.melUsePower = mb.usePower;
-  // the kernel keeps 2X (4|X|^2) out of the real-FFT split; the exact factor 1/4 of the power
-  // path is folded into the band scale (power-of-two scaling commutes with rounding)
-  kp.melScale = mb.usePower ? mb.outScale * 0.25f : mb.outScale;
-  if (!isPlp) { kp.dctStride = (mb.nBands + 3) / 4 * 4; kp.dctRows = mf.nMfcc; }
-  else { kp.dctStride = po.nFreq; kp.dctRows = po.nAuto; }
-  kp.opKind = isPlp ? 1 : 0;
-  if (!isPlp) {
-    kp.nStat = mf.nMfcc; kp.melfloor = mf.melfloor; kp.logMelfloor = mf.logMelfloor; kp.doLog = mf.doLog;
-  } else {
-    kp.nStat = po.nOut; kp.melfloor = po.melfloor; kp.logMelfloor = po.logMelfloor; kp.doLog = po.doLog;
-    kp.plpAud = po.doAud; kp.plpInvLog = po.doInvLog; kp.plpIDFT = po.doIDFT; kp.plpLP = po.doLP; kp.plpCeps = po.doLpToCeps;
-    kp.plpHtk = po.htk; kp.plpLifter = po.lifter; kp.plpOrder = po.lpOrder; kp.plpNAuto = po.nAuto; kp.plpNFreq = po.nFreq;
-    kp.plpFirstCC = po.firstCC; kp.plpLastCC = po.lastCC; kp.plpCompression = po.compression;
-  }
-  // split the bands over the virtual warps, balancing visited bins (ranges bs..be)
-  {
-    const int nvw = lld_virtual_warps(fe.nfft);
-    const int totalBins = mb.rangeBegin[mb.nBands + 1] - mb.rangeBegin[0];
-    int b = 0;
-    kp.melSplit[0] = 0;
-    for (int w = 1; w <= nvw; w++) {
-      // advance b until the cumulative bin count reaches w/nvw of the total
-      const double target = (double)totalBins * w / nvw;
-      while (b < mb.nBands && (mb.rangeBegin[b + 1] - mb.rangeBegin[0]) < target) b++;
-      if (w == nvw) b = mb.nBands;
-      kp.melSplit[w] = b;
-    }
-    for (int w = nvw + 1; w <= kMaxVW; w++) kp.melSplit[w] = mb.nBands;
-  }
-
-  auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
-  size_t o = 0;
-  const size_t oWin = o; o = up16(o + winLut.size() * sizeof(float4));
-  const size_t oTw = o; o = up16(o + (tw.size() + 1) * sizeof(float2));
-  const size_t oSplit = o; o = up16(o + split.size() * sizeof(float2));
-  const size_t oCoef = o; o = up16(o + mb.coef.size() * sizeof(float));
-  const size_t oRange = o; o = up16(o + mb.rangeBegin.size() * sizeof(int));
-  std::vector<float> dctPad((size_t)kp.dctRows * kp.dctStride, 0.f);
-  if (!isPlp) {
-    for (int i = 0; i < mf.nMfcc; i++)
-      memcpy(&dctPad[(size_t)i * kp.dctStride], &mf.cosT[(size_t)i * mb.nBands], sizeof(float) * mb.nBands);
-  } else {
-    memcpy(dctPad.data(), po.cosT.data(), sizeof(float) * po.cosT.size());
-  }
-  const std::vector<float> &liftV = isPlp ? po.lift : mf.liftFactor;
-  std::vector<float> eqlV = isPlp ? po.eql : std::vector<float>(1, 0.f);
-  const size_t oDct = o; o = up16(o + dctPad.size() * sizeof(float));
-  const size_t oLift = o; o = up16(o + liftV.size() * sizeof(float));
-  const size_t oEql = o; o = up16(o + eqlV.size() * sizeof(float));
-  std::vector<unsigned char> blob(o, 0);
-  memcpy(&blob[oWin], winLut.data(), winLut.size() * sizeof(float4));
-  if (!tw.empty()) memcpy(&blob[oTw], tw.data(), tw.size() * sizeof(float2));
-  memcpy(&blob[oSplit], split.data(), split.size() * sizeof(float2));
-  memcpy(&blob[oCoef], mb.coef.data(), mb.coef.size() * sizeof(float));
-  memcpy(&blob[oRange], mb.rangeBegin.data(), mb.rangeBegin.size() * sizeof(int));
-  memcpy(&blob[oDct], dctPad.data(), dctPad.size() * sizeof(float));
-  memcpy(&blob[oLift], liftV.data(), liftV.size() * sizeof(float));
-  memcpy(&blob[oEql], eqlV.data(), eqlV.size() * sizeof(float));
-  CUP(cudaMalloc(&pl->dConst, o));
-  CUP(cudaMemcpy(pl->dConst, blob.data(), o, cudaMemcpyHostToDevice));
-  kp.winLut = reinterpret_cast<const float4 *>(pl->dConst + oWin);
-  kp.twiddles = reinterpret_cast<const float2 *>(pl->dConst + oTw);
-  kp.splitTw = reinterpret_cast<const float2 *>(pl->dConst + oSplit);
-  kp.melCoef = reinterpret_cast<const float *>(pl->dConst + oCoef);
-  kp.melRange = reinterpret_cast<const int *>(pl->dConst + oRange);
-  kp.dctCos = reinterpret_cast<const float *>(pl->dConst + oDct);
-  kp.dctLift = reinterpret_cast<const float *>(pl->dConst + oLift);
-  kp.plpEql = reinterpret_cast<const float *>(pl->dConst + oEql);
-
-  const size_t smemNeed = lld_smem_bytes(kp, fe.nfft);
-  if (smemNeed > (size_t)prop.sharedMemPerBlockOptin) {
-    osm_b200_plan_destroy(pl);
-    return fail(OSM_B200_ERR_UNSUPPORTED, "configuration needs more shared memory than the device offers");
-  }
-
-  // ---- output groups ----
+  // ---- output groups / execution mode ----
   PostParams &pp = pl->pp;
   memset(&pp, 0, sizeof pp);
+  // "simple" plans: one stream, one fused band op, nothing else.  Their static rows go straight
+  // into the output rows; delta / delta-delta can then be fused into lld_kernel as well.
+  const bool simple = d.streams.size() == 1 && d.ops.size() == 1 && d.streams[0].fusedOp == 0 && !d.streams[0].dumpMag;
   pl->staticDirect = false;
-  for (const auto &g : d.groups)
-    if (g.stages.empty() && g.srcCol == 0 && g.n == d.nStatic) { pl->staticDirect = true; pl->identityOutCol = g.outCol; break; }
+  if (simple)
+    for (const auto &g : d.groups)
+      if (g.stages.empty() && g.srcCol == 0 && g.n == d.nStatic) { pl->staticDirect = true; pl->identityOutCol = g.outCol; break; }
   for (const auto &g : d.groups) {
     if (g.stages.empty() && pl->staticDirect && g.srcCol == 0 && g.n == d.nStatic && g.outCol == pl->identityOutCol) continue;
     if (pp.nGroups >= kMaxPostGroups) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many output groups"); }
     PostGroup &pg = pp.groups[pp.nGroups++];
     pg.srcCol = g.srcCol; pg.n = g.n; pg.outCol = g.outCol; pg.nStages = (int)g.stages.size();
+    pg.frameSize = d.streams[g.stream].fe.frameSize; pg.frameStep = d.streams[g.stream].fe.frameStep;
     for (size_t i = 0; i < g.stages.size(); i++) { pg.kind[i] = g.stages[i].kind; pg.win[i] = g.stages[i].win; pg.flags[i] = g.stages[i].flags; }
   }
   // fused pattern: [static | delta(W1) | delta(W1,W2)] over the whole static vector
   pl->fused = false;
-  kp.fused = 0; kp.halo = 0; kp.fW1 = kp.fW2 = 0; kp.fNorm1 = kp.fNorm2 = 1.f;
-  if (pl->staticDirect && pl->identityOutCol == 0 && d.groups.size() == 3 && d.nOut == 3 * d.nStatic) {
-    const auto &g1 = d.groups[1], &g2 = d.groups[2];
-    const bool shape = d.groups[0].stages.empty() && g1.stages.size() == 1 && g2.stages.size() == 2 &&
-                       g1.srcCol == 0 && g2.srcCol == 0 && g1.n == d.nStatic && g2.n == d.nStatic &&
-                       g1.outCol == d.nStatic && g2.outCol == 2 * d.nStatic &&
-                       g1.stages[0].kind == ST_DELTA && g2.stages[0].kind == ST_DELTA && g2.stages[1].kind == ST_DELTA &&
-                       g1.stages[0].win == g2.stages[0].win;
-    // OSM_B200_NO_FUSE=1 forces the two-kernel path (used by the tests to cross-check both)
-    const char *nf = getenv("OSM_B200_NO_FUSE");
-    if (shape && g1.stages[0].win + g2.stages[1].win <= 8 && !(nf && nf[0] == '1')) {
-      pl->fused = true;
-      kp.fused = 1; kp.fW1 = g1.stages[0].win; kp.fW2 = g2.stages[1].win; kp.halo = kp.fW1 + kp.fW2;
-      auto normOf = [](int W) { float n = 0.f; for (int i = 1; i <= W; i++) n += (float)i * (float)i; return n * 2.0f; };
-      kp.fNorm1 = normOf(kp.fW1); kp.fNorm2 = normOf(kp.fW2);    // deltaRegression.cpp:77-80
-      // divisors with an exhaustively verified exact reciprocal+FMA division (kernels.cu div_exact)
-      auto rcpOf = [](float n) { return (n == 2.f || n == 10.f || n == 28.f || n == 60.f) ? 1.0f / n : 0.f; };
-      kp.fRcp1 = rcpOf(kp.fNorm1); kp.fRcp2 = rcpOf(kp.fNorm2);
+  {
+    LldParams &kp = pl->st[0].kp;
+    kp.fused = 0; kp.halo = 0; kp.fW1 = kp.fW2 = 0; kp.fNorm1 = kp.fNorm2 = 1.f;
+    if (simple && pl->staticDirect && pl->identityOutCol == 0 && d.groups.size() == 3 && d.nOut == 3 * d.nStatic) {
+      const auto &g1 = d.groups[1], &g2 = d.groups[2];
+      const bool shape = d.groups[0].stages.empty() && g1.stages.size() == 1 && g2.stages.size() == 2 &&
+                         g1.srcCol == 0 && g2.srcCol == 0 && g1.n == d.nStatic && g2.n == d.nStatic &&
+                         g1.outCol == d.nStatic && g2.outCol == 2 * d.nStatic &&
+                         g1.stages[0].kind == ST_DELTA && g2.stages[0].kind == ST_DELTA && g2.stages[1].kind == ST_DELTA &&
+                         g1.stages[0].win == g2.stages[0].win;
+      // OSM_B200_NO_FUSE=1 forces the two-kernel path (used by the tests to cross-check both)
+      const char *nf = getenv("OSM_B200_NO_FUSE");
+      if (shape && g1.stages[0].win + g2.stages[1].win <= 8 && !(nf && nf[0] == '1')) {
+        pl->fused = true;
+        kp.fused = 1; kp.fW1 = g1.stages[0].win; kp.fW2 = g2.stages[1].win; kp.halo = kp.fW1 + kp.fW2;
+        auto normOf = [](int W) { float n = 0.f; for (int i = 1; i <= W; i++) n += (float)i * (float)i; return n * 2.0f; };
+        kp.fNorm1 = normOf(kp.fW1); kp.fNorm2 = normOf(kp.fW2);    // deltaRegression.cpp:77-80
+        // divisors with an exhaustively verified exact reciprocal+FMA division (kernels.cu div_exact)
+        auto rcpOf = [](float n) { return (n == 2.f || n == 10.f || n == 28.f || n == 60.f) ? 1.0f / n : 0.f; };
+        kp.fRcp1 = rcpOf(kp.fNorm1); kp.fRcp2 = rcpOf(kp.fNorm2);
+      }
     }
   }
-  pp.frameSize = fe.frameSize; pp.frameStep = fe.frameStep;
   pp.nStat = d.nStatic; pp.maxN = 1; pp.halo = 0;
   for (int g = 0; g < pp.nGroups; g++) {
     int h = 0;
@@ -409,11 +445,63 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   }
   if (pp.halo > 12) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "summed temporal half windows exceed 12 frames"); }
 
+  // ---- standalone ops ----
+  for (size_t oi = 0; oi < d.ops.size(); oi++) {
+    const StaticOp &op = d.ops[oi];
+    if (op.kind == SOP_MFCC || op.kind == SOP_PLP) continue;      // fused into its stream's lld_kernel
+    OpRt rt;
+    rt.kind = op.kind; rt.stream = op.stream;
+    const FrontEnd &fe = d.streams[op.stream].fe;
+    StreamRt &srt = pl->st[op.stream];
+    srt.needTiles = true;
+    if (op.kind == SOP_SPECTRAL) {
+      const SpectralOp &so = op.spectral;
+      SpectralParams &sp = rt.sp;
+      memset(&sp, 0, sizeof sp);
+      sp.F = srt.tileF; sp.statStride = d.nStatic; sp.outCol = op.outCol;
+      sp.nSrc = so.nSrc; sp.loBin = so.loBin; sp.hiBin = so.hiBin; sp.F0 = so.F0;
+      sp.squareInput = so.squareInput; sp.useLog = so.useLog; sp.normBand = so.normBand; sp.buggyRollOff = so.buggyRollOff;
+      sp.oldSlopeScale = so.oldSlopeScale; sp.reqMag = so.reqMag; sp.reqPow = so.reqPow; sp.reqLog = so.reqLog;
+      sp.specFloor = so.specFloor; sp.logSpecFloor = so.logSpecFloor;
+      sp.nBands = (int)so.bandIL.size();
+      for (int i = 0; i < sp.nBands; i++) { sp.bandIL[i] = so.bandIL[i]; sp.bandIR[i] = so.bandIR[i]; sp.bandWL[i] = so.bandWL[i]; sp.bandWR[i] = so.bandWR[i]; }
+      sp.nSlopes = (int)so.slopeIL.size();
+      for (int i = 0; i < sp.nSlopes; i++) { sp.slopeIL[i] = so.slopeIL[i]; sp.slopeIR[i] = so.slopeIR[i]; sp.slopeWL[i] = so.slopeWL[i]; sp.slopeWR[i] = so.slopeWR[i]; sp.slopeNind[i] = so.slopeNind[i]; }
+      sp.nRollOff = (int)so.rollOff.size();
+      for (int i = 0; i < sp.nRollOff; i++) sp.rollOff[i] = so.rollOff[i];
+      sp.alphaRatio = so.alphaRatio; sp.hammarberg = so.hammarberg; sp.flux = so.flux; sp.centroid = so.centroid;
+      sp.maxPos = so.maxPos; sp.minPos = so.minPos; sp.entropy = so.entropy; sp.stddev = so.stddev; sp.variance = so.variance;
+      sp.skewness = so.skewness; sp.kurtosis = so.kurtosis; sp.slope = so.slope; sp.sharpness = so.sharpness;
+      sp.harmonicity = so.harmonicity; sp.flatness = so.flatness; sp.logFlatness = so.logFlatness;
+      CUP(cudaMalloc(&rt.dSharpW, so.sharpW.size() * sizeof(double)));
+      CUP(cudaMemcpy(rt.dSharpW, so.sharpW.data(), so.sharpW.size() * sizeof(double), cudaMemcpyHostToDevice));
+      sp.sharpW = rt.dSharpW;
+    } else {
+      TimeOpParams &tp = rt.tp;
+      memset(&tp, 0, sizeof tp);
+      tp.nChan = fe.nChan; tp.F = srt.tileF; tp.statStride = d.nStatic; tp.outCol = op.outCol;
+      tp.frameSize = fe.frameSize; tp.frameStep = fe.frameStep;
+      tp.windowed = op.windowed; tp.preemph = op.windowed && fe.preemph; tp.preDe = fe.preDe; tp.preK = fe.preK;
+      tp.oneMinusK = 1 - fe.preK; tp.winOffset = fe.winOffset; tp.window = srt.dWindow;
+      if (op.kind == SOP_ENERGY) {
+        const EnergyOp &e = op.energy;
+        tp.eHtk = e.htk; tp.eRms = e.rms; tp.eEnergy2 = e.energy2; tp.eLog = e.lg;
+        tp.escaleLog = e.escaleLog; tp.escaleRms = e.escaleRms; tp.escaleSquare = e.escaleSquare;
+        tp.ebiasLog = e.ebiasLog; tp.ebiasRms = e.ebiasRms; tp.ebiasSquare = e.ebiasSquare;
+      } else {
+        const MzcrOp &z = op.mzcr;
+        tp.zZcr = z.zcr; tp.zMcr = z.mcr; tp.zAmax = z.amax; tp.zMaxmin = z.maxmin; tp.zDc = z.dc;
+      }
+    }
+    pl->ops.push_back(rt);
+  }
+
   CUP(cudaEventCreateWithFlags(&pl->evMetaDone, cudaEventDisableTiming));
   CUP(cudaEventCreate(&pl->evK0));
   CUP(cudaEventCreate(&pl->evK1));
   CUP(cudaEventCreate(&pl->evKm));
 #undef CUP
+#undef STP
   *out = pl;
   return OSM_B200_OK;
 }
@@ -428,9 +516,12 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
   if (pl->d2hStream) cudaStreamDestroy(pl->d2hStream);
   for (cudaEvent_t e : pl->evPiece) cudaEventDestroy(e);
   cudaDeviceSynchronize();
-  if (pl->dConst) cudaFree(pl->dConst);
-  pl->hMeta.release(); pl->hTiles.release(); pl->dMeta.release(); pl->dTiles.release(); pl->dStat.release();
-  pl->hChunks.release(); pl->dChunks.release();
+  for (StreamRt &s : pl->st) {
+    if (s.dConst) cudaFree(s.dConst);
+    s.hChunks.release(); s.dChunks.release(); s.hTiles.release(); s.dTiles.release(); s.dMag.release();
+  }
+  for (OpRt &o : pl->ops) if (o.dSharpW) cudaFree(o.dSharpW);
+  pl->hMeta.release(); pl->dMeta.release(); pl->hPost.release(); pl->dPost.release(); pl->dStat.release();
   pl->dPcm.release(); pl->dOut.release();
   if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
   if (pl->evK0) cudaEventDestroy(pl->evK0);
@@ -447,10 +538,10 @@ const char *osm_b200_plan_element_name(const osm_b200_plan *pl, int32_t idx)
   return pl->d.names[idx].c_str();
 }
 
-double osm_b200_plan_frame_period(const osm_b200_plan *pl) { return pl ? pl->d.fe.frameStepSec : 0.0; }
-int32_t osm_b200_plan_frame_size_samples(const osm_b200_plan *pl) { return pl ? pl->d.fe.frameSize : 0; }
-int32_t osm_b200_plan_frame_step_samples(const osm_b200_plan *pl) { return pl ? pl->d.fe.frameStep : 0; }
-int32_t osm_b200_plan_fft_size(const osm_b200_plan *pl) { return pl ? pl->d.fe.nfft : 0; }
+double osm_b200_plan_frame_period(const osm_b200_plan *pl) { return pl ? pl->d.fe0().frameStepSec : 0.0; }
+int32_t osm_b200_plan_frame_size_samples(const osm_b200_plan *pl) { return pl ? pl->d.fe0().frameSize : 0; }
+int32_t osm_b200_plan_frame_step_samples(const osm_b200_plan *pl) { return pl ? pl->d.fe0().frameStep : 0; }
+int32_t osm_b200_plan_fft_size(const osm_b200_plan *pl) { return pl ? pl->d.fe0().nfft : 0; }
 
 int64_t osm_b200_plan_num_frames(const osm_b200_plan *pl, int64_t n) { return pl ? desc_num_frames(pl->d, n) : 0; }
 
@@ -478,55 +569,88 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
     const size_t nm = (size_t)(nUtt + 1);
     CU(pl->hMeta.reserve(3 * nm));
     long long *hU = pl->hMeta.p, *hR = hU + nm, *hS = hR + nm;
-    size_t nPost = 0;
     const int PR = post_tile_rows();
-    const int F = pl->tileF, H = pl->kp.halo, KT = lld_max_chunk_tiles();
-    std::vector<ChunkRef> chunks;
-    pl->uttChunk0.assign(nm, 0); pl->uttPost0.assign(nm, 0);
+    const int KT = lld_max_chunk_tiles();
+    const bool needPost = pl->pp.nGroups > 0 && !pl->fused;
+    size_t nPost = 0;
+    pl->uttPost0.assign(nm, 0);
     hR[0] = 0; hS[0] = 0;
     for (int u = 0; u < nUtt; u++) {
       if (uttOff[u + 1] < uttOff[u]) return fail(OSM_B200_ERR_INVALID, "utt_offsets must be non-decreasing");
       const int64_t L = uttOff[u + 1] - uttOff[u];
-      const int64_t T = desc_num_static_frames(d, L);
       hU[u] = uttOff[u];
       hR[u + 1] = hR[u] + desc_num_frames(d, L);
-      hS[u + 1] = hS[u] + T;
-      pl->uttChunk0[u] = (int32_t)chunks.size();
+      hS[u + 1] = hS[u] + desc_max_static_frames(d, L);
       pl->uttPost0[u] = (int32_t)nPost;
-      if (!pl->fused) nPost += (size_t)((hR[u + 1] - hR[u] + PR - 1) / PR);
-      // chunks: output rows [a,b) whose static range [a-H, b+H) /\ [0,T) is a whole number of
-      // tiles (except at the utterance end), at most KT tiles each
-      for (int64_t a = 0; a < T;) {
-        const int64_t s0 = std::max<int64_t>(a - H, 0);
-        const int64_t maxEnd = s0 + (int64_t)F * KT;
-        const int64_t b2 = (maxEnd >= T) ? T : maxEnd - H;
-        chunks.push_back(ChunkRef{u, (int32_t)a, (int32_t)b2});
-        a = b2;
-      }
+      if (needPost) nPost += (size_t)((hR[u + 1] - hR[u] + PR - 1) / PR);
     }
     hU[nUtt] = uttOff[nUtt];
-    pl->uttChunk0[nUtt] = (int32_t)chunks.size();
     pl->uttPost0[nUtt] = (int32_t)nPost;
-    CU(pl->hTiles.reserve(nPost + 1));
-    size_t ti = 0;
-    if (!pl->fused)
-      for (int u = 0; u < nUtt; u++) {
-        const int64_t To = hR[u + 1] - hR[u];
-        for (int64_t r0 = 0; r0 < To; r0 += PR) pl->hTiles.p[ti++] = TileRef{u, (int32_t)r0};
-      }
+    CU(pl->hPost.reserve(nPost + 1));
+    {
+      size_t ti = 0;
+      if (needPost)
+        for (int u = 0; u < nUtt; u++) {
+          const int64_t To = hR[u + 1] - hR[u];
+          for (int64_t r0 = 0; r0 < To; r0 += PR) pl->hPost.p[ti++] = TileRef{u, (int32_t)r0};
+        }
+    }
     pl->nPostTiles = nPost;
-    pl->nChunks = chunks.size();
-    CU(pl->hChunks.reserve(chunks.size() + 1));
-    if (!chunks.empty()) memcpy(pl->hChunks.p, chunks.data(), chunks.size() * sizeof(ChunkRef));
+    pl->totalWork = 0;
+    // per stream: chunks for lld_kernel, tiles for the standalone ops
+    for (size_t si = 0; si < pl->st.size(); si++) {
+      StreamRt &rt = pl->st[si];
+      const int F = rt.tileF, H = rt.kp.halo;
+      std::vector<ChunkRef> chunks;
+      std::vector<OpTile> tiles;
+      rt.uttChunk0.assign(nm, 0); rt.uttTile0.assign(nm, 0);
+      int64_t tileCount = 0;
+      for (int u = 0; u < nUtt; u++) {
+        const int64_t L = uttOff[u + 1] - uttOff[u];
+        const int64_t T = desc_num_static_frames(d, (int)si, L);
+        rt.uttChunk0[u] = (int32_t)chunks.size();
+        rt.uttTile0[u] = (int32_t)tileCount;
+        // chunks: output rows [a,b) whose static range [a-H, b+H) /\ [0,T) is a whole number of
+        // tiles (except at the utterance end), at most KT tiles each
+        for (int64_t a = 0; a < T;) {
+          const int64_t s0 = std::max<int64_t>(a - H, 0);
+          const int64_t maxEnd = s0 + (int64_t)F * KT;
+          const int64_t b2 = (maxEnd >= T) ? T : maxEnd - H;
+          chunks.push_back(ChunkRef{u, (int32_t)a, (int32_t)b2, (int32_t)(tileCount + s0 / F)});
+          a = b2;
+        }
+        if (rt.needTiles)
+          for (int64_t f0 = 0; f0 < T; f0 += F)
+            tiles.push_back(OpTile{u, (int32_t)f0, (int32_t)std::min<int64_t>(F, T - f0), f0 > 0 ? 1 : 0});
+        tileCount += (T + F - 1) / F;
+      }
+      rt.uttChunk0[nUtt] = (int32_t)chunks.size();
+      rt.uttTile0[nUtt] = (int32_t)tileCount;
+      rt.nChunks = rt.runLld ? chunks.size() : 0;
+      rt.nTiles = tiles.size();
+      pl->totalWork += rt.nChunks + rt.nTiles;
+      if (rt.runLld) {
+        CU(rt.hChunks.reserve(chunks.size() + 1));
+        if (!chunks.empty()) memcpy(rt.hChunks.p, chunks.data(), chunks.size() * sizeof(ChunkRef));
+        CU(rt.dChunks.reserve(chunks.size() + 1));
+        if (!chunks.empty()) CU(cudaMemcpyAsync(rt.dChunks.p, rt.hChunks.p, chunks.size() * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
+        if (rt.kp.opKind < 0 || d.streams[si].dumpMag)
+          CU(rt.dMag.reserve((size_t)tileCount * d.streams[si].fe.nBins * F + 64));
+      }
+      if (rt.needTiles) {
+        CU(rt.hTiles.reserve(tiles.size() + 1));
+        if (!tiles.empty()) memcpy(rt.hTiles.p, tiles.data(), tiles.size() * sizeof(OpTile));
+        CU(rt.dTiles.reserve(tiles.size() + 1));
+        if (!tiles.empty()) CU(cudaMemcpyAsync(rt.dTiles.p, rt.hTiles.p, tiles.size() * sizeof(OpTile), cudaMemcpyHostToDevice, st));
+      }
+    }
     pl->totalRows = hR[nUtt];
     pl->totalStat = hS[nUtt];
     pl->totalSamples = uttOff[nUtt];
     CU(pl->dMeta.reserve(3 * nm));
-    CU(pl->dTiles.reserve(nPost + 1));
-    CU(pl->dChunks.reserve(pl->nChunks + 1));
+    CU(pl->dPost.reserve(nPost + 1));
     CU(cudaMemcpyAsync(pl->dMeta.p, pl->hMeta.p, 3 * nm * sizeof(long long), cudaMemcpyHostToDevice, st));
-    if (nPost) CU(cudaMemcpyAsync(pl->dTiles.p, pl->hTiles.p, nPost * sizeof(TileRef), cudaMemcpyHostToDevice, st));
-    if (pl->nChunks) CU(cudaMemcpyAsync(pl->dChunks.p, pl->hChunks.p, pl->nChunks * sizeof(ChunkRef), cudaMemcpyHostToDevice, st));
+    if (nPost) CU(cudaMemcpyAsync(pl->dPost.p, pl->hPost.p, nPost * sizeof(TileRef), cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(pl->evMetaDone, st));
     pl->metaPending = true;
     pl->cachedUttOff.assign(uttOff, uttOff + nUtt + 1);
@@ -545,32 +669,63 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
 static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float *d_out, int n_utt, int u0, int u1,
                                     cudaStream_t st)
 {
-  const int c0 = pl->uttChunk0[u0], c1 = pl->uttChunk0[u1];
-  if (c1 <= c0) return OSM_B200_OK;
+  const PlanDesc &d = pl->d;
   const size_t nm = (size_t)(n_utt + 1);
   const long long *dU = pl->dMeta.p, *dR = dU + nm, *dS = dR + nm;
-  LldParams kp = pl->kp;
-  kp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
-  kp.uttOff = dU;
-  kp.chunks = pl->dChunks.p + c0;
-  kp.nChunks = c1 - c0;
-  PostParams pp = pl->pp;
-  if (pl->staticDirect) {
-    kp.out = d_out; kp.outStride = pl->d.nOut; kp.outCol = pl->identityOutCol; kp.rowOff = dR;
-    pp.stat = d_out + pl->identityOutCol; pp.statStride = pl->d.nOut; pp.statOff = dR;
-  } else {
-    kp.out = pl->dStat.p; kp.outStride = pl->d.nStatic; kp.outCol = 0; kp.rowOff = dS;
-    pp.stat = pl->dStat.p; pp.statStride = pl->d.nStatic; pp.statOff = dS;
-  }
-  pp.out = d_out; pp.outStride = pl->d.nOut; pp.rowOff = dR; pp.uttOff = dU; pp.nUtt = n_utt;
-  pp.tiles = pl->dTiles.p + pl->uttPost0[u0]; pp.nTiles = pl->uttPost0[u1] - pl->uttPost0[u0];
-
-  CU(launch_lld(kp, pl->d.fe.nfft, pl->numSMs, st, &pl->lastInfo));
-  pl->lastLaunches++;
-  if (u0 == 0) CU(cudaEventRecord(pl->evKm, st));
-  if (pp.nGroups > 0 && !pl->fused) {
-    CU(launch_post(pp, st));
+  // 1. per stream: FFT front end (+ fused band op / magnitude dump)
+  for (size_t si = 0; si < pl->st.size(); si++) {
+    StreamRt &rt = pl->st[si];
+    if (!rt.runLld) continue;
+    const int c0 = rt.uttChunk0[u0], c1 = rt.uttChunk0[u1];
+    if (c1 <= c0) continue;
+    LldParams kp = rt.kp;
+    kp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
+    kp.uttOff = dU;
+    kp.chunks = rt.dChunks.p + c0;
+    kp.nChunks = c1 - c0;
+    kp.magOut = d.streams[si].dumpMag ? rt.dMag.p : nullptr;
+    if (pl->staticDirect) {
+      kp.out = d_out; kp.outStride = d.nOut; kp.outCol = pl->identityOutCol; kp.rowOff = dR;
+    } else {
+      kp.out = pl->dStat.p; kp.outStride = d.nStatic; kp.rowOff = dS;
+      kp.outCol = d.streams[si].fusedOp >= 0 ? d.ops[d.streams[si].fusedOp].outCol : 0;
+    }
+    CU(launch_lld(kp, d.streams[si].fe.nfft, pl->numSMs, st, &pl->lastInfo));
     pl->lastLaunches++;
+  }
+  if (u0 == 0) CU(cudaEventRecord(pl->evKm, st));
+  // 2. standalone ops
+  for (OpRt &o : pl->ops) {
+    StreamRt &rt = pl->st[o.stream];
+    const int t0 = rt.uttTile0[u0], t1 = rt.uttTile0[u1];
+    if (t1 <= t0) continue;
+    if (o.kind == SOP_SPECTRAL) {
+      SpectralParams sp = o.sp;
+      sp.mag = rt.dMag.p + (size_t)t0 * sp.nSrc * sp.F;
+      sp.tiles = rt.dTiles.p + t0; sp.nTiles = t1 - t0;
+      sp.statOff = dS; sp.stat = pl->dStat.p;
+      CU(launch_spectral(sp, st));
+    } else {
+      TimeOpParams tp = o.tp;
+      tp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
+      tp.uttOff = dU; tp.statOff = dS;
+      tp.tiles = rt.dTiles.p + t0; tp.nTiles = t1 - t0;
+      tp.stat = pl->dStat.p;
+      CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : launch_mzcr(tp, st));
+    }
+    pl->lastLaunches++;
+  }
+  // 3. temporal stages + assembly of the output rows
+  if (pl->pp.nGroups > 0 && !pl->fused) {
+    PostParams pp = pl->pp;
+    if (pl->staticDirect) { pp.stat = d_out + pl->identityOutCol; pp.statStride = d.nOut; pp.statOff = dR; }
+    else { pp.stat = pl->dStat.p; pp.statStride = d.nStatic; pp.statOff = dS; }
+    pp.out = d_out; pp.outStride = d.nOut; pp.rowOff = dR; pp.uttOff = dU; pp.nUtt = n_utt;
+    pp.tiles = pl->dPost.p + pl->uttPost0[u0]; pp.nTiles = pl->uttPost0[u1] - pl->uttPost0[u0];
+    if (pp.nTiles > 0) {
+      CU(launch_post(pp, st));
+      pl->lastLaunches++;
+    }
   }
   return OSM_B200_OK;
 }
@@ -586,9 +741,9 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
   pl->timed = false;
   osm_b200_status s = prepare_batch(pl, utt_offsets, n_utt, frame_offsets, st);
   if (s != OSM_B200_OK) return s;
-  if (pl->totalRows == 0 || pl->nChunks == 0) return OSM_B200_OK;
+  if (pl->totalRows == 0 || pl->totalWork == 0) return OSM_B200_OK;
   if (!d_pcm || !d_out) return fail(OSM_B200_ERR_INVALID, "null device buffer");
-  if (!pl->staticDirect) CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic));
+  if (!pl->staticDirect) CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic + 64));
   CU(cudaEventRecord(pl->evK0, st));
   s = launch_range(pl, d_pcm, d_out, n_utt, 0, n_utt, st);
   if (s != OSM_B200_OK) return s;
@@ -618,13 +773,13 @@ osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const
   osm_b200_status s = prepare_batch(pl, utt_offsets, n_utt, frame_offsets, st);
   if (s != OSM_B200_OK) return s;
   const long long rows = pl->totalRows;
-  if (rows == 0 || pl->nChunks == 0) return OSM_B200_OK;
+  if (rows == 0 || pl->totalWork == 0) return OSM_B200_OK;
   if (!pcm || !out) return fail(OSM_B200_ERR_INVALID, "null host buffer");
-  const int nChan = pl->d.fe.nChan, nOut = pl->d.nOut;
+  const int nChan = pl->d.fe0().nChan, nOut = pl->d.nOut;
   const int64_t nSamp = utt_offsets[n_utt] * nChan;
   CU(pl->dPcm.reserve((size_t)nSamp + 16));
   CU(pl->dOut.reserve((size_t)rows * nOut));
-  if (!pl->staticDirect) CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic));
+  if (!pl->staticDirect) CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic + 64));
   const long long *hR = pl->hMeta.p + (size_t)(n_utt + 1);
 
   // pieces of ~24 MB of PCM, at most 16, cut at utterance boundaries

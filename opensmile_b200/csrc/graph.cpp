@@ -4,6 +4,7 @@
 // sub-graph: it follows reader.dmLevel / writer.dmLevel wiring, applies the per-component
 // geometry rules (frame size rounding, FFT size, frameSizeSec rescale, frame counts, field
 // names) and emits tables.  Citations relative to /root/reference/src.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -67,10 +68,18 @@ std::string name_append_auto(const osm_b200_component &c, const std::string &bas
 
 // core/winToVecProcessor.cpp:868-877 (noPostEOIprocessing=1, frameCenterSpecial=left):
 // only complete frames => T = floor((L - size)/step) + 1
-int64_t desc_num_static_frames(const PlanDesc &d, int64_t L)
+int64_t desc_num_static_frames(const PlanDesc &d, int stream, int64_t L)
 {
-  if (L < d.fe.frameSize || d.fe.frameSize <= 0) return 0;
-  return (L - d.fe.frameSize) / d.fe.frameStep + 1;
+  const FrontEnd &fe = d.streams[stream].fe;
+  if (L < fe.frameSize || fe.frameSize <= 0) return 0;
+  return (L - fe.frameSize) / fe.frameStep + 1;
+}
+
+int64_t desc_max_static_frames(const PlanDesc &d, int64_t L)
+{
+  int64_t m = 0;
+  for (size_t s = 0; s < d.streams.size(); s++) m = std::max<int64_t>(m, desc_num_static_frames(d, (int)s, L));
+  return m;
 }
 
 // window processors emit T + W frames at EOI (core/dataMemoryLevel.cpp:1022-1026 via
@@ -78,16 +87,23 @@ int64_t desc_num_static_frames(const PlanDesc &d, int64_t L)
 // (core/dataReader.cpp:375-380).
 int64_t desc_num_frames(const PlanDesc &d, int64_t L)
 {
-  const int64_t T = desc_num_static_frames(d, L);
-  if (T <= 0) return 0;
   int64_t best = -1;
   for (const auto &g : d.groups) {
-    int64_t t = T;
+    int64_t t = desc_num_static_frames(d, g.stream, L);
+    if (t <= 0) return 0;
     for (const auto &s : g.stages) t += s.win;
     if (best < 0 || t < best) best = t;
   }
   return best < 0 ? 0 : best;
 }
+
+namespace {
+
+struct ChainInfo {               // resolved front-end chain below a static producer
+  const osm_b200_component *wav = nullptr, *frm = nullptr, *pe = nullptr, *win = nullptr, *fft = nullptr, *mag = nullptr;
+};
+
+}  // namespace
 
 osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char *outputLevel,
                               PlanDesc &d, std::string &err)
@@ -118,15 +134,98 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
   }
 
   auto single_input = [&](const osm_b200_component *c) -> const osm_b200_component * {
-    if (c->n_inputs != 1) return nullptr;
+    if (!c || c->n_inputs != 1) return nullptr;
     return R.prod(c->reader_dmLevel[0]);
   };
 
-  std::map<const osm_b200_component *, int> staticOpOf;   // static producer -> op index
-  const osm_b200_component *feTail = nullptr;              // the cFFTmagphase all ops hang off
-  std::vector<std::string> staticBaseName;                 // per op: field base name
+  // walk from a time-domain level (framer / pre-emphasis / windower output) down to the wave source
+  auto resolve_time_chain = [&](const osm_b200_component *x, ChainInfo &ci) -> bool {
+    if (x && x->type == OSM_B200_C_WINDOWER) { ci.win = x; x = single_input(x); }
+    if (x && x->type == OSM_B200_C_VECTORPREEMPHASIS) { ci.pe = x; x = single_input(x); }
+    if (!x || x->type != OSM_B200_C_FRAMER) { err = "expected cFramer [-> cVectorPreemphasis] [-> cWindower] below this component"; return false; }
+    ci.frm = x;
+    ci.wav = single_input(x);
+    if (!ci.wav || ci.wav->type != OSM_B200_C_WAVESOURCE) { err = "cFramer must read the cWaveSource level"; return false; }
+    return true;
+  };
+  auto resolve_mag_chain = [&](const osm_b200_component *mag, ChainInfo &ci) -> bool {
+    if (!mag || mag->type != OSM_B200_C_FFTMAGPHASE) { err = "expected a cFFTmagphase level"; return false; }
+    ci.mag = mag;
+    const auto &mp = mag->u.fftmagphase;
+    if (!mp.magnitude || mp.phase || mp.normalise || mp.power || mp.dBpsd) {
+      err = "cFFTmagphase: only magnitude=1 (no phase/normalise/power/dBpsd) is supported"; return false;
+    }
+    ci.fft = single_input(mag);
+    if (!ci.fft || ci.fft->type != OSM_B200_C_TRANSFORMFFT) { err = "cFFTmagphase must read a cTransformFFT level"; return false; }
+    if (ci.fft->u.transformfft.inverse) { err = "cTransformFFT.inverse=1 is not supported"; return false; }
+    const osm_b200_component *w = single_input(ci.fft);
+    if (!w || w->type != OSM_B200_C_WINDOWER) { err = "cTransformFFT must read a cWindower level"; return false; }
+    return resolve_time_chain(w, ci);
+  };
 
   d = PlanDesc();
+  // find or create the stream of a chain; needFft extends an existing time-only stream
+  auto get_stream = [&](const ChainInfo &ci, bool needFft, int &idx) -> osm_b200_status {
+    for (size_t s = 0; s < d.streams.size(); s++) {
+      Stream &st = d.streams[s];
+      if (st.keyFramer == ci.frm && st.keyPe == ci.pe && (st.keyWin == ci.win || !ci.win || !st.keyWin)) {
+        if (ci.win && !st.keyWin) continue;      // a windowed chain cannot reuse a window-less stream
+        if (!ci.win && st.keyWin) { /* framer-level reader on a windowed stream: fine, same geometry */ }
+        if (needFft && !st.hasFft) continue;
+        idx = (int)s;
+        return OSM_B200_OK;
+      }
+    }
+    Stream st;
+    FrontEnd &fe = st.fe;
+    const auto &wp = ci.wav->u.wavesource;
+    if (wp.sampleRate <= 0 || wp.nChannels < 1) { err = "cWaveSource: bad sampleRate/nChannels"; return OSM_B200_ERR_INVALID; }
+    if (wp.nChannels > 1 && !wp.monoMixdown) { err = "multi-channel without monoMixdown is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+    if (wp.format != OSM_B200_PCM_S16) { err = "only 16-bit integer PCM is supported"; return OSM_B200_ERR_UNSUPPORTED; }
+    fe.sampleRate = wp.sampleRate; fe.nChan = wp.nChannels; fe.format = wp.format; fe.mixdown = true;
+    // cWinToVecProcessor::configureWriter (core/winToVecProcessor.cpp:435-456)
+    const auto &fp = ci.frm->u.framer;
+    if (!fp.frameCenterSpecialLeft) { err = "cFramer: only frameCenterSpecial=left is supported"; return OSM_B200_ERR_UNSUPPORTED; }
+    if (!fp.noPostEOIprocessing) { err = "cFramer: only noPostEOIprocessing=1 is supported"; return OSM_B200_ERR_UNSUPPORTED; }
+    const double T = 1.0 / wp.sampleRate;
+    double frameSize = fp.frameSize, frameStep = fp.frameStep;
+    long fsf = (long)round(frameSize / T);
+    if (frameStep == 0.0) frameStep = frameSize;
+    long fstf = (long)round(frameStep / T);
+    if (fstf == 0) fstf = fsf;
+    if (fsf < 2) { err = "cFramer: frame too short"; return OSM_B200_ERR_INVALID; }
+    fe.frameSize = (int)fsf; fe.frameStep = (int)fstf;
+    fe.frameSizeSec = frameSize; fe.frameStepSec = frameStep;
+    if (ci.pe) {
+      fe.preemph = true;
+      fe.preK = (float)ci.pe->u.vectorpreemphasis.k;     // dspcore/vectorPreemphasis.cpp:55
+      fe.preDe = ci.pe->u.vectorpreemphasis.de;
+    }
+    if (ci.win) {
+      const auto &wnp = ci.win->u.windower;
+      build_window(wnp.winFunc, fe.frameSize, wnp.sigma, wnp.gain, fe.window);
+      fe.winOffset = (float)wnp.offset;
+      st.hasWindow = true;
+    } else {
+      fe.window.assign(fe.frameSize, 1.0f);
+    }
+    // cTransformFFT: next power of two >= frame size, >= 4 (dspcore/transformFft.cpp:124-129);
+    // frameSizeSec *= nfft/frameSize (:78-85)
+    int nfft = 4;
+    while (nfft < fe.frameSize) nfft <<= 1;
+    fe.nfft = nfft; fe.nBins = nfft / 2 + 1;
+    fe.fftFrameSizeSec = frameSize;
+    if (nfft != fe.frameSize) fe.fftFrameSizeSec *= (double)nfft / (double)fe.frameSize;
+    if (ci.fft) fe.zeroPadSymmetric = ci.fft->u.transformfft.zeroPadSymmetric != 0;
+    st.hasFft = needFft;
+    st.keyFramer = ci.frm; st.keyPe = ci.pe; st.keyWin = ci.win;
+    d.streams.push_back(st);
+    idx = (int)d.streams.size() - 1;
+    return OSM_B200_OK;
+  };
+
+  std::map<const osm_b200_component *, int> staticOpOf;   // static producer -> op index
+
   for (const std::string &lvl : chainLevels) {
     // walk back through temporal stages
     const osm_b200_component *c = R.prod(lvl.c_str());
@@ -136,7 +235,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       stageComps.insert(stageComps.begin(), c);
       c = single_input(c);
     }
-    if (!c) { err = "broken temporal chain below level '" + lvl + "'"; return OSM_B200_ERR_INVALID; }
+    if (!c) { err = "broken temporal chain below level '" + lvl + "' (temporal stages must read exactly one level)"; return OSM_B200_ERR_UNSUPPORTED; }
 
     // static feature producer
     int opIdx;
@@ -144,128 +243,126 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     if (it != staticOpOf.end()) {
       opIdx = it->second;
     } else {
-      if (c->type != OSM_B200_C_MFCC && c->type != OSM_B200_C_PLP) {
+      StaticOp op;
+      ChainInfo ci;
+      std::string base;
+      auto wave_name = [&]() { return std::string(ci.wav->u.wavesource.outFieldName[0] ? ci.wav->u.wavesource.outFieldName : "pcm"); };
+      if (c->type == OSM_B200_C_MFCC || c->type == OSM_B200_C_PLP) {
+        const osm_b200_component *mel = single_input(c);
+        if (!mel || mel->type != OSM_B200_C_MELSPEC) { err = "cMfcc / cPlp must read a cMelspec level"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (!resolve_mag_chain(single_input(mel), ci)) return OSM_B200_ERR_UNSUPPORTED;
+        osm_b200_status s2 = get_stream(ci, true, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        const FrontEnd &fe = d.streams[op.stream].fe;
+        // field base name: outFieldName -> (pe/win/fft keep) -> fftMag -> melspec keeps
+        base = name_append_auto(*ci.mag, wave_name(), "fftMag");        // dspcore/fftmagphase.cpp:154
+        base = name_append_auto(*mel, base, nullptr);
+        const auto &melp = mel->u.melspec;
+        if (melp.nBands < 1 || melp.nBands > 64 || melp.nBands >= fe.nBins) { err = "cMelspec.nBands out of range"; return OSM_B200_ERR_UNSUPPORTED; }
+        MelBank mb;
+        build_mel(melp, fe.nBins, fe.fftFrameSizeSec, mb);
+        d.mels.push_back(mb);
+        FieldName fn;
+        if (c->type == OSM_B200_C_MFCC) {
+          op.kind = SOP_MFCC;
+          const auto &mfp = c->u.mfcc;
+          if (mfp.lastMfcc < mfp.firstMfcc || mfp.firstMfcc < 0 || mfp.lastMfcc >= melp.nBands) { err = "cMfcc: bad firstMfcc/lastMfcc"; return OSM_B200_ERR_INVALID; }
+          build_mfcc(mfp, melp.nBands, op.mfcc);
+          op.mfcc.melIdx = (int)d.mels.size() - 1;
+          op.nOut = op.mfcc.nMfcc;
+          fn.name = name_append_auto(*c, base, nullptr);                // lldcore/mfcc.cpp:120-128
+          fn.n = op.nOut; fn.arrNameOffset = op.mfcc.first;             // lldcore/mfcc.cpp:125
+        } else {
+          op.kind = SOP_PLP;
+          if (!build_plp(c->u.plp, d.mels.back(), op.plp, err)) return OSM_B200_ERR_UNSUPPORTED;
+          op.plp.melIdx = (int)d.mels.size() - 1;
+          op.nOut = op.plp.nOut;
+          // lldcore/plp.cpp:232-267 replaces the field name, then cVectorProcessor appends nameAppend
+          const char *fixed = op.plp.doLpToCeps ? "PlpCC" : (op.plp.doLP ? "Plpc" : (op.plp.doIDFT ? "audAutoCor" : "audSpec"));
+          fn.name = name_append_auto(*c, fixed, nullptr);
+          fn.n = op.nOut; fn.arrNameOffset = 0;
+        }
+        op.fields.push_back(fn);
+      } else if (c->type == OSM_B200_C_SPECTRAL) {
+        if (!resolve_mag_chain(single_input(c), ci)) return OSM_B200_ERR_UNSUPPORTED;
+        osm_b200_status s2 = get_stream(ci, true, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        const FrontEnd &fe = d.streams[op.stream].fe;
+        op.kind = SOP_SPECTRAL;
+        if (!build_spectral(c->u.spectral, fe.nBins, fe.fftFrameSizeSec, op.spectral, err)) return OSM_B200_ERR_UNSUPPORTED;
+        op.nOut = op.spectral.nOut;
+        base = name_append_auto(*ci.mag, wave_name(), "fftMag");
+        // element names, lldcore/spectral.cpp:378-584
+        const auto &sc = c->u.spectral;
+        const bool lg = sc.useLogSpectrum != 0;
+        auto add = [&](const std::string &suffix) { FieldName f; f.name = base + "_" + suffix; op.fields.push_back(f); };
+        for (int i = 0; i < sc.nBands; i++)
+          if ((long)sc.bandLo[i] >= 0 && (long)sc.bandHi[i] > 0) { snprintf(buf, sizeof buf, "%s%ld-%ld", lg ? "logFband" : "fband", (long)sc.bandLo[i], (long)sc.bandHi[i]); add(buf); }
+        for (int i = 0; i < sc.nSlopes; i++)
+          if ((long)sc.slopeLo[i] >= 0 && (long)sc.slopeHi[i] > 0) { snprintf(buf, sizeof buf, "%s%ld-%ld", lg ? "logSpectralSlopeOfBand" : "spectralSlopeOfBand", (long)sc.slopeLo[i], (long)sc.slopeHi[i]); add(buf); }
+        if (sc.alphaRatio) add(lg ? "alphaRatioDB" : "alphaRatio");
+        if (sc.hammarbergIndex) add(lg ? "hammarbergIndexDB" : "hammarbergIndex");
+        for (size_t i = 0; i < op.spectral.rollOff.size(); i++) { snprintf(buf, sizeof buf, "spectralRollOff%.1f", op.spectral.rollOff[i] * 100.0); add(buf); }
+        if (sc.flux) add("spectralFlux");
+        if (sc.centroid) add(lg ? "logSpectralCentroid" : "spectralCentroid");
+        if (sc.maxPos) add("spectralMaxPos");
+        if (sc.minPos) add("spectralMinPos");
+        if (sc.entropy) add(lg ? "logSpectralEntropy" : "spectralEntropy");
+        if (sc.standardDeviation) add(lg ? "logSpectralStdDev" : "spectralStdDev");
+        if (sc.variance) add(lg ? "logSpectralVariance" : "spectralVariance");
+        if (sc.skewness) add(lg ? "logSpectralSkewness" : "spectralSkewness");
+        if (sc.kurtosis) add(lg ? "logSpectralKurtosis" : "spectralKurtosis");
+        if (sc.slope) add(lg ? "logSpectralSlope" : "spectralSlope");
+        if (sc.sharpness) add("psySharpness");
+        if (sc.harmonicity) add(lg ? "logSpectralHarmonicity" : "spectralHarmonicity");
+        if (sc.flatness) add(lg ? "logSpectralFlatness" : "spectralFlatness");
+        if ((int)op.fields.size() != op.nOut) { err = "internal: cSpectral name/element mismatch"; return OSM_B200_ERR_INVALID; }
+      } else if (c->type == OSM_B200_C_ENERGY || c->type == OSM_B200_C_MZCR) {
+        const osm_b200_component *in = single_input(c);
+        if (!resolve_time_chain(in, ci)) return OSM_B200_ERR_UNSUPPORTED;
+        op.windowed = ci.win != nullptr;
+        if (ci.pe && !ci.win) { err = "cEnergy / cMZcr reading a pre-emphasised, un-windowed level is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        osm_b200_status s2 = get_stream(ci, false, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        base = wave_name();
+        if (c->type == OSM_B200_C_ENERGY) {
+          op.kind = SOP_ENERGY;
+          build_energy(c->u.energy, op.energy);
+          op.nOut = op.energy.nOut;
+          // lldcore/energy.cpp:97-125: addNameAppendFieldAuto(name, "RMS"|"SQUARED"|"LOG")
+          if (op.energy.rms) { FieldName f; f.name = name_append_auto(*c, base, "RMS"); op.fields.push_back(f); }
+          if (op.energy.energy2) { FieldName f; f.name = name_append_auto(*c, base, "SQUARED"); op.fields.push_back(f); }
+          if (op.energy.lg) { FieldName f; f.name = name_append_auto(*c, base, "LOG"); op.fields.push_back(f); }
+        } else {
+          op.kind = SOP_MZCR;
+          build_mzcr(c->u.mzcr, op.mzcr);
+          op.nOut = op.mzcr.nOut;
+          auto add = [&](const char *suffix) { FieldName f; f.name = base + "_" + suffix; op.fields.push_back(f); };   // lldcore/mzcr.cpp:68-100
+          if (op.mzcr.zcr) add("zcr");
+          if (op.mzcr.mcr) add("mcr");
+          if (op.mzcr.amax) add("absmax");
+          if (op.mzcr.maxmin) { add("max"); add("min"); }
+          if (op.mzcr.dc) add("dc");
+        }
+        if (op.nOut < 1) { err = "component produces no output"; return OSM_B200_ERR_INVALID; }
+      } else {
         snprintf(buf, sizeof buf, "component '%s' (%s) is not a supported static LLD producer", c->name, type_name(c->type));
         err = buf; return OSM_B200_ERR_UNSUPPORTED;
-      }
-      const osm_b200_component *mel = single_input(c);
-      if (!mel || mel->type != OSM_B200_C_MELSPEC) { err = "cMfcc / cPlp must read a cMelspec level"; return OSM_B200_ERR_UNSUPPORTED; }
-      const osm_b200_component *mag = single_input(mel);
-      if (!mag || mag->type != OSM_B200_C_FFTMAGPHASE) { err = "cMelspec must read a cFFTmagphase level"; return OSM_B200_ERR_UNSUPPORTED; }
-      if (feTail && feTail != mag) { err = "all static LLDs must share one framer/FFT chain"; return OSM_B200_ERR_UNSUPPORTED; }
-
-      if (!feTail) {
-        // ---- resolve the front end once: fftmag <- fft <- win <- [pe] <- frame <- wave ----
-        feTail = mag;
-        const auto &mp = mag->u.fftmagphase;
-        if (!mp.magnitude || mp.phase || mp.normalise || mp.power || mp.dBpsd) {
-          err = "cFFTmagphase: only magnitude=1 (no phase/normalise/power/dBpsd) is supported"; return OSM_B200_ERR_UNSUPPORTED;
-        }
-        const osm_b200_component *fft = single_input(mag);
-        if (!fft || fft->type != OSM_B200_C_TRANSFORMFFT) { err = "cFFTmagphase must read a cTransformFFT level"; return OSM_B200_ERR_UNSUPPORTED; }
-        if (fft->u.transformfft.inverse) { err = "cTransformFFT.inverse=1 is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
-        const osm_b200_component *win = single_input(fft);
-        if (!win || win->type != OSM_B200_C_WINDOWER) { err = "cTransformFFT must read a cWindower level"; return OSM_B200_ERR_UNSUPPORTED; }
-        const osm_b200_component *x = single_input(win);
-        const osm_b200_component *pe = nullptr;
-        if (x && x->type == OSM_B200_C_VECTORPREEMPHASIS) { pe = x; x = single_input(x); }
-        if (!x || x->type != OSM_B200_C_FRAMER) { err = "cWindower must read a cFramer (optionally via cVectorPreemphasis)"; return OSM_B200_ERR_UNSUPPORTED; }
-        const osm_b200_component *frm = x;
-        const osm_b200_component *wav = single_input(frm);
-        if (!wav || wav->type != OSM_B200_C_WAVESOURCE) { err = "cFramer must read the cWaveSource level"; return OSM_B200_ERR_UNSUPPORTED; }
-
-        FrontEnd &fe = d.fe;
-        const auto &wp = wav->u.wavesource;
-        if (wp.sampleRate <= 0 || wp.nChannels < 1) { err = "cWaveSource: bad sampleRate/nChannels"; return OSM_B200_ERR_INVALID; }
-        if (wp.nChannels > 1 && !wp.monoMixdown) { err = "multi-channel without monoMixdown is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
-        if (wp.format != OSM_B200_PCM_S16) { err = "only 16-bit integer PCM is supported"; return OSM_B200_ERR_UNSUPPORTED; }
-        fe.sampleRate = wp.sampleRate; fe.nChan = wp.nChannels; fe.format = wp.format; fe.mixdown = true;
-
-        // cWinToVecProcessor::configureWriter (core/winToVecProcessor.cpp:435-456)
-        const auto &fp = frm->u.framer;
-        if (!fp.frameCenterSpecialLeft) { err = "cFramer: only frameCenterSpecial=left is supported"; return OSM_B200_ERR_UNSUPPORTED; }
-        if (!fp.noPostEOIprocessing) { err = "cFramer: only noPostEOIprocessing=1 is supported"; return OSM_B200_ERR_UNSUPPORTED; }
-        const double T = 1.0 / wp.sampleRate;
-        double frameSize = fp.frameSize, frameStep = fp.frameStep;
-        long fsf = (long)round(frameSize / T);
-        if (frameStep == 0.0) frameStep = frameSize;
-        long fstf = (long)round(frameStep / T);
-        if (fstf == 0) fstf = fsf;
-        if (fsf < 2) { err = "cFramer: frame too short"; return OSM_B200_ERR_INVALID; }
-        fe.frameSize = (int)fsf; fe.frameStep = (int)fstf;
-        fe.frameSizeSec = frameSize; fe.frameStepSec = frameStep;
-
-        if (pe) {
-          fe.preemph = true;
-          fe.preK = (float)pe->u.vectorpreemphasis.k;     // dspcore/vectorPreemphasis.cpp:55
-          fe.preDe = pe->u.vectorpreemphasis.de;
-        }
-        const auto &wnp = win->u.windower;
-        build_window(wnp.winFunc, fe.frameSize, wnp.sigma, wnp.gain, fe.window);
-        fe.winOffset = (float)wnp.offset;
-
-        // cTransformFFT: next power of two >= frame size, >= 4 (dspcore/transformFft.cpp:124-129);
-        // frameSizeSec *= nfft/frameSize (:78-85)
-        int nfft = 4;
-        while (nfft < fe.frameSize) nfft <<= 1;
-        fe.nfft = nfft; fe.nBins = nfft / 2 + 1;
-        fe.fftFrameSizeSec = frameSize;
-        if (nfft != fe.frameSize) fe.fftFrameSizeSec *= (double)nfft / (double)fe.frameSize;
-        fe.zeroPadSymmetric = fft->u.transformfft.zeroPadSymmetric != 0;
-        if (nfft < 64 || nfft > 4096) { err = "FFT size out of the supported range 64..4096"; return OSM_B200_ERR_UNSUPPORTED; }
-      }
-
-      // field base name along the chain: outFieldName -> (pe/win/fft keep) -> fftMag -> melspec keeps
-      const osm_b200_component *fft = single_input(mag);
-      const osm_b200_component *win = single_input(fft);
-      const osm_b200_component *x = single_input(win);
-      if (x->type == OSM_B200_C_VECTORPREEMPHASIS) x = single_input(x);
-      const osm_b200_component *wav = single_input(x);
-      std::string base = wav->u.wavesource.outFieldName[0] ? wav->u.wavesource.outFieldName : "pcm";
-      base = name_append_auto(*mag, base, "fftMag");         // dspcore/fftmagphase.cpp:154
-      base = name_append_auto(*mel, base, nullptr);          // melspec keeps the name
-
-      // mel bank + mfcc op
-      const auto &melp = mel->u.melspec;
-      if (melp.nBands < 1 || melp.nBands > 64 || melp.nBands >= d.fe.nBins) { err = "cMelspec.nBands out of range"; return OSM_B200_ERR_UNSUPPORTED; }
-      MelBank mb;
-      build_mel(melp, d.fe.nBins, d.fe.fftFrameSizeSec, mb);
-      d.mels.push_back(mb);
-      StaticOp op;
-      std::string opName;
-      if (c->type == OSM_B200_C_MFCC) {
-        op.kind = SOP_MFCC;
-        const auto &mfp = c->u.mfcc;
-        if (mfp.lastMfcc < mfp.firstMfcc || mfp.firstMfcc < 0 || mfp.lastMfcc >= melp.nBands) { err = "cMfcc: bad firstMfcc/lastMfcc"; return OSM_B200_ERR_INVALID; }
-        build_mfcc(mfp, melp.nBands, op.mfcc);
-        op.mfcc.melIdx = (int)d.mels.size() - 1;
-        op.nOut = op.mfcc.nMfcc;
-        op.arrNameOffset = op.mfcc.first;                              // lldcore/mfcc.cpp:125
-        opName = name_append_auto(*c, base, nullptr);                  // lldcore/mfcc.cpp:120-128
-      } else {
-        op.kind = SOP_PLP;
-        if (!build_plp(c->u.plp, d.mels.back(), op.plp, err)) return OSM_B200_ERR_UNSUPPORTED;
-        op.plp.melIdx = (int)d.mels.size() - 1;
-        op.nOut = op.plp.nOut;
-        op.arrNameOffset = 0;
-        // lldcore/plp.cpp:232-267 replaces the field name, then cVectorProcessor appends nameAppend
-        const char *fixed = op.plp.doLpToCeps ? "PlpCC" : (op.plp.doLP ? "Plpc" : (op.plp.doIDFT ? "audAutoCor" : "audSpec"));
-        opName = name_append_auto(*c, fixed, nullptr);
       }
       op.outCol = d.nStatic;
       d.nStatic += op.nOut;
       d.ops.push_back(op);
       opIdx = (int)d.ops.size() - 1;
       staticOpOf[c] = opIdx;
-      staticBaseName.push_back(opName);
     }
 
     // ---- group ----
     OutGroup g;
     g.srcCol = d.ops[opIdx].outCol;
     g.n = d.ops[opIdx].nOut;
+    g.stream = d.ops[opIdx].stream;
     g.outCol = d.nOut;
-    std::string nm = staticBaseName[opIdx];
+    std::vector<FieldName> fields = d.ops[opIdx].fields;
     for (const osm_b200_component *s : stageComps) {
       Stage st;
       if (s->type == OSM_B200_C_DELTAREGRESSION) {
@@ -281,20 +378,38 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         st = Stage{ST_SMA, (p.smaWin - 1) / 2, p.noZeroSma};
       }
       g.stages.push_back(st);
-      nm = name_append_auto(*s, nm, nullptr);
+      for (auto &f : fields) f.name = name_append_auto(*s, f.name, nullptr);
     }
     if (g.stages.size() > 3) { err = "more than 3 chained temporal stages"; return OSM_B200_ERR_UNSUPPORTED; }
     d.nOut += g.n;
     d.groups.push_back(g);
-    // element names: name[idx + arrNameOffset] (core/dataMemoryLevel.cpp:1158-1169);
-    // cMfcc passes firstMfcc as arrNameOffset (lldcore/mfcc.cpp:125)
-    const int off = d.ops[opIdx].arrNameOffset;
-    for (int i = 0; i < g.n; i++) {
-      snprintf(buf, sizeof buf, "%s[%d]", nm.c_str(), i + off);
-      d.names.push_back(buf);
+    // element names: name (single element fields) or name[idx + arrNameOffset]
+    // (core/dataMemoryLevel.cpp:1158-1169)
+    for (const auto &f : fields) {
+      if (f.n == 1) { d.names.push_back(f.name); continue; }
+      for (int i = 0; i < f.n; i++) {
+        snprintf(buf, sizeof buf, "%s[%d]", f.name.c_str(), i + f.arrNameOffset);
+        d.names.push_back(buf);
+      }
     }
   }
   if (d.ops.empty()) { err = "empty plan"; return OSM_B200_ERR_INVALID; }
+
+  // ---- execution strategy per stream ----
+  // A stream with exactly one band op (MFCC / PLP) and no other spectral consumer evaluates it
+  // inside lld_kernel; any other spectral consumer reads the magnitude level from HBM.
+  for (size_t s = 0; s < d.streams.size(); s++) {
+    int nBand = 0, nSpec = 0, band = -1;
+    for (size_t o = 0; o < d.ops.size(); o++) {
+      if (d.ops[o].stream != (int)s) continue;
+      if (d.ops[o].kind == SOP_MFCC || d.ops[o].kind == SOP_PLP) { nBand++; band = (int)o; }
+      if (d.ops[o].kind == SOP_SPECTRAL) nSpec++;
+    }
+    if (nBand > 1) { err = "more than one cMfcc / cPlp on one FFT chain is not supported yet"; return OSM_B200_ERR_UNSUPPORTED; }
+    d.streams[s].fusedOp = band;
+    d.streams[s].dumpMag = nSpec > 0;
+    if ((nBand || nSpec) && (d.streams[s].fe.nfft < 64 || d.streams[s].fe.nfft > 4096)) { err = "FFT size out of the supported range"; return OSM_B200_ERR_UNSUPPORTED; }
+  }
   return OSM_B200_OK;
 }
 

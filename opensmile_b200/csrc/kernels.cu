@@ -138,6 +138,7 @@ struct ChunkCtx {
   int s0;            // first static frame computed by this chunk
   int sEnd;          // one past the last static frame computed
   int nT;            // tiles in this chunk
+  int tile0;         // global index of the chunk's first tile
   long long uo;      // sample-frame offset of the utterance
   long long row0;    // output row of frame 0 of the utterance
 };
@@ -147,7 +148,7 @@ __device__ __forceinline__ ChunkCtx load_chunk(const LldParams &p, int chunk)
 {
   ChunkCtx c;
   const ChunkRef cr = p.chunks[chunk];
-  c.utt = cr.utt; c.a = cr.a; c.b = cr.b;
+  c.utt = cr.utt; c.a = cr.a; c.b = cr.b; c.tile0 = cr.tile0;
   c.uo = p.uttOff[cr.utt];
   const long long Ls = p.uttOff[cr.utt + 1] - c.uo;
   c.T = (int)((Ls - p.frameSize) / p.frameStep + 1);
@@ -408,11 +409,13 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   for (int i = tid; i < M; i += NT) sWinLut[i] = p.winLut[i];
   for (int i = tid; i < p.twCount; i += NT) sTw[i] = p.twiddles[i];
   for (int i = tid; i < NPAIR; i += NT) sSplit[i] = p.splitTw[i];
-  for (int i = tid; i < NBINS; i += NT) sMelCoef[i] = p.melCoef[i];
-  for (int i = tid; i < p.nBands + 2; i += NT) sMelRange[i] = p.melRange[i];
-  for (int i = tid; i < p.dctRows * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
-  if (p.opKind == 1) for (int i = tid; i < p.nBands; i += NT) sEql[i] = p.plpEql[i];
-  for (int i = tid; i < p.nStat; i += NT) sLift[i] = p.dctLift[i];
+  if (p.opKind >= 0) {
+    for (int i = tid; i < NBINS; i += NT) sMelCoef[i] = p.melCoef[i];
+    for (int i = tid; i < p.nBands + 2; i += NT) sMelRange[i] = p.melRange[i];
+    for (int i = tid; i < p.dctRows * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
+    if (p.opKind == 1) for (int i = tid; i < p.nBands; i += NT) sEql[i] = p.plpEql[i];
+    for (int i = tid; i < p.nStat; i += NT) sLift[i] = p.dctLift[i];
+  }
   for (int i = tid; i < L.sampFloats; i += NT) samp[i] = 0.f;   // lanes beyond a short tile read finite data
   __syncthreads();
 
@@ -557,7 +560,18 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           // again; we keep re*re+im*im (<= 1.5 ulp apart, below the FFT's own noise floor).
           // The factor 1/2 of X (1/4 of the power) is an exact power-of-two scaling that commutes
           // with every rounding downstream; it is folded into melScale on the host.
-          if (p.melUsePower) {
+          if (p.magOut != nullptr) {
+            // a non-fused consumer needs the magnitude level (fftmagphase.cpp:215-221):
+            // |X| = 0.5 * sqrt(a^2+b^2) is exact scaling; the band op then squares it like
+            // melspec.cpp:524 does (melScale carries no 1/4 in this mode)
+            const float mk = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
+            const float mm = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi)));
+            float *mo = p.magOut + ((size_t)(cx.tile0 + j) * NBINS) * F + f;
+            mo[(size_t)k * F] = mk;
+            if (k != M - k) mo[(size_t)(M - k) * F] = mm;
+            pk[i] = p.melUsePower ? __fmul_rn(mk, mk) : mk;
+            pm[i] = p.melUsePower ? __fmul_rn(mm, mm) : mm;
+          } else if (p.melUsePower) {
             pk[i] = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
             pm[i] = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
           } else {
@@ -578,6 +592,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     }
     __syncthreads();
 
+    if (p.opKind >= 0) {
     // ================= mel filterbank (melspec.cpp:543-569) + log (mfcc.cpp:239-243) =================
     // range r holds the bins whose lower band is r-1: band[r-1] += a ; band[r] += p - a, visited
     // in ascending bin order exactly like the reference loop, so each band's float sum has the
@@ -786,6 +801,8 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       // follows its staging phase, which every thread reaches after finishing this block.
     }
 
+    }   // opKind >= 0
+
     // ---- advance to the next tile / chunk ----
     j++;
     if (j == cx.nT) {
@@ -837,7 +854,6 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
   const TileRef tr = p.tiles[blockIdx.x];
   const int u = tr.utt, r0 = tr.f0;
   const long long Ls = p.uttOff[u + 1] - p.uttOff[u];
-  const int T = (int)((Ls - p.frameSize) / p.frameStep + 1);
   const int Tout = (int)(p.rowOff[u + 1] - p.rowOff[u]);
   const int r1 = min(r0 + kPostRows, Tout);
   const int H = p.halo;
@@ -848,9 +864,10 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
   float *B = A + nRowsBuf * p.maxN;
   const int tid = threadIdx.x;
 
-  // ---- static rows [r0-H, r1+H) /\ [0, T) -> smem ----
+  // ---- static rows [r0-H, r1+H) /\ [0, Tmax) -> smem (Tmax = rows of the static buffer) ----
   {
-    const int lo = max(rowBase, 0), hi = min(r1 + H, T);
+    const int Tmax = (int)(p.statOff[u + 1] - p.statOff[u]);
+    const int lo = max(rowBase, 0), hi = min(r1 + H, Tmax);
     const float *src = p.stat + p.statOff[u] * (long long)p.statStride;
     const int tot = (hi - lo) * p.nStat;
     for (int idx = tid; idx < tot; idx += kPostThreads) {
@@ -863,6 +880,7 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
   for (int gi = 0; gi < p.nGroups; gi++) {
     const PostGroup &g = p.groups[gi];
     const int n = g.n;
+    const int T = (Ls >= g.frameSize) ? (int)((Ls - g.frameSize) / g.frameStep + 1) : 0;   // frames of this group's source level
     // level 0 view of this group: copy its columns so that every level has row stride n
     const float *cur;
     {

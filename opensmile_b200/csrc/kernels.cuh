@@ -8,7 +8,7 @@ namespace osm {
 constexpr int kMaxVW = 32;   // virtual warps (F-lane groups) per CTA
 
 struct TileRef { int32_t utt; int32_t f0; };   // (utterance, first row) of a post_kernel tile
-struct ChunkRef { int32_t utt; int32_t a; int32_t b; };   // output rows [a,b) of one utterance = one CTA work unit
+struct ChunkRef { int32_t utt; int32_t a; int32_t b; int32_t tile0; };   // output rows [a,b) of one utterance = one CTA work unit; tile0 = global index of its first tile
 
 // Everything the fused per-frame kernel needs.  Pointers are device pointers; the table
 // pointers reference one packed constant blob uploaded at plan creation.
@@ -42,8 +42,10 @@ struct LldParams {
   float melScale;
   int melUsePower;
   int melSplit[kMaxVW + 1];      // virtual warp w computes bands [melSplit[w], melSplit[w+1])
-  // ---- static LLD op on the mel bands: 0 = cMfcc (log, DCT-II, lifter), 1 = cPlp ----
+  // ---- static LLD op on the mel bands: 0 = cMfcc (log, DCT-II, lifter), 1 = cPlp, -1 = none ----
   int opKind;
+  // magnitude level for non-fused consumers (cSpectral ...): tile-major [tile][bin][F] floats, or null
+  float *magOut;
   int nStat;                     // static outputs per frame (nMfcc / nCeps / ...)
   const float *dctCos;           // MFCC: [nStat][dctStride] DCT rows (output order, zero padded)
                                  // PLP : [nAuto][dctStride = nFreq] IDFT table
@@ -64,6 +66,7 @@ struct LldParams {
 // temporal post-processing (cDeltaRegression / cContourSmoother chains)
 struct PostGroup {
   int srcCol, n, outCol;
+  int frameSize, frameStep;      // geometry of the stream the source level belongs to (defines its T)
   int nStages;
   int kind[3];                   // 0 = delta, 1 = sma
   int win[3];
@@ -78,7 +81,6 @@ struct PostParams {
   int outStride;
   const long long *rowOff;       // [nUtt+1] output row offsets
   const long long *uttOff;       // [nUtt+1] sample-frame offsets (to derive T)
-  int frameSize, frameStep;
   int nUtt;
   int nGroups;
   PostGroup groups[kMaxPostGroups];
@@ -102,5 +104,46 @@ int lld_tile_frames(int nfft);
 int lld_virtual_warps(int nfft);
 int lld_max_chunk_tiles();
 bool lld_supported_fft(int nfft);
+
+// ------------------------------------------------------------------------------------------
+// standalone per-frame ops (ops.cu): lane = frame kernels used when an op is not fused into
+// lld_kernel.  One tile = up to F consecutive frames of one utterance.
+// ------------------------------------------------------------------------------------------
+struct OpTile { int32_t utt; int32_t f0; int32_t nf; int32_t prev; };   // prev = 1 if frame f0-1 exists in tile-1
+
+struct SpectralParams {
+  const float *mag;              // tile-major magnitude level [tile][nSrc][F]
+  const OpTile *tiles; int nTiles; int F;
+  const long long *statOff;      // static row offsets
+  float *stat; int statStride, outCol;
+  int nSrc, loBin, hiBin;
+  double F0;
+  int squareInput, useLog, normBand, buggyRollOff, oldSlopeScale, reqMag, reqPow, reqLog;
+  float specFloor, logSpecFloor;
+  int nBands; int bandIL[16], bandIR[16]; double bandWL[16], bandWR[16];
+  int nSlopes; int slopeIL[16], slopeIR[16]; double slopeWL[16], slopeWR[16], slopeNind[16];
+  int nRollOff; double rollOff[16];
+  int alphaRatio, hammarberg, flux, centroid, maxPos, minPos, entropy, stddev, variance, skewness, kurtosis,
+      slope, sharpness, harmonicity, flatness, logFlatness;
+  const double *sharpW;          // [hiBin-loBin+1] (device)
+};
+
+struct TimeOpParams {            // cEnergy / cMZcr on the framer or windower level
+  const int16_t *pcm; int nChan;
+  const long long *uttOff, *statOff;
+  const OpTile *tiles; int nTiles; int F;
+  float *stat; int statStride, outCol;
+  int frameSize, frameStep;
+  int windowed, preemph, preDe; float preK, oneMinusK, winOffset;
+  const float *window;           // [frameSize] (device), only when windowed
+  // cEnergy
+  int eHtk, eRms, eEnergy2, eLog; float escaleLog, escaleRms, escaleSquare, ebiasLog, ebiasRms, ebiasSquare;
+  // cMZcr
+  int zZcr, zMcr, zAmax, zMaxmin, zDc;
+};
+
+cudaError_t launch_spectral(const SpectralParams &p, cudaStream_t st);
+cudaError_t launch_energy(const TimeOpParams &p, cudaStream_t st);
+cudaError_t launch_mzcr(const TimeOpParams &p, cudaStream_t st);
 
 }  // namespace osm

@@ -68,12 +68,47 @@ struct PlpOp {
   int nOut = 0;
 };
 
+// cSpectral resolved against the bin-frequency axis of its input level (lldcore/spectral.cpp)
+struct SpectralOp {
+  int nSrc = 0;                    // input bins
+  int loBin = 1, hiBin = 0;        // specRange (spectral.cpp:625-647)
+  double F0 = 0;                   // bin spacing in Hz (field info, transformFft.cpp:111-115)
+  bool squareInput = true, useLog = false, normBand = false, buggyRollOff = false, oldSlopeScale = true;
+  bool reqMag = false, reqPow = false, reqLog = false;
+  float specFloor = 0.f, logSpecFloor = 0.f;
+  // bands / slopes: resolved edges
+  std::vector<int> bandIL, bandIR; std::vector<double> bandWL, bandWR;
+  std::vector<int> slopeIL, slopeIR; std::vector<double> slopeWL, slopeWR, slopeNind;
+  std::vector<double> rollOff;
+  bool alphaRatio = false, hammarberg = false, flux = false, centroid = false, maxPos = false, minPos = false,
+       entropy = false, stddev = false, variance = false, skewness = false, kurtosis = false, slope = false,
+       sharpness = false, harmonicity = false, flatness = false, logFlatness = false;
+  std::vector<double> sharpW;      // [hiBin-loBin+1]
+  int nOut = 0;
+};
+
+struct EnergyOp {
+  bool htk = false, rms = true, energy2 = false, lg = true;
+  float escaleLog = 1, escaleRms = 1, escaleSquare = 1, ebiasLog = 0, ebiasRms = 0, ebiasSquare = 0;
+  int nOut = 0;
+};
+
+struct MzcrOp { bool zcr = true, mcr = true, amax = true, maxmin = true, dc = false; int nOut = 0; };
+
+// one field of a level: `n` elements named name (n == 1) or name[i + arrNameOffset]
+struct FieldName { std::string name; int n = 1; int arrNameOffset = 0; };
+
 struct StaticOp {
   StaticOpKind kind;
+  int stream = 0;                  // index into PlanDesc::streams
+  bool windowed = false;           // time-domain ops: reads the windower level instead of the framer level
   int outCol = 0, nOut = 0;
-  int arrNameOffset = 0;
+  std::vector<FieldName> fields;   // names of the produced level
   MfccOp mfcc;
   PlpOp plp;
+  SpectralOp spectral;
+  EnergyOp energy;
+  MzcrOp mzcr;
 };
 
 // temporal stage applied to a static column range (cWindowProcessor family)
@@ -83,30 +118,45 @@ struct Stage { StageKind kind; int win; int flags; };
 // one contiguous block of output columns
 struct OutGroup {
   int srcCol = 0, n = 0;           // columns of the static vector
+  int stream = 0;                  // stream whose frame geometry defines T of the source level
   std::vector<Stage> stages;       // applied in order
   int outCol = 0;
 };
 
-struct PlanDesc {
+// one framer -> [pre-emphasis] -> [window] -> [FFT -> magnitude] chain
+struct Stream {
   FrontEnd fe;
+  bool hasWindow = false, hasFft = false;
+  bool dumpMag = false;            // a non-fused consumer reads the magnitude level from HBM
+  int fusedOp = -1;                // band op (MFCC / PLP) evaluated inside lld_kernel, -1 = none
+  const void *keyFramer = nullptr, *keyPe = nullptr, *keyWin = nullptr;
+};
+
+struct PlanDesc {
+  std::vector<Stream> streams;
   std::vector<MelBank> mels;
   std::vector<StaticOp> ops;
   int nStatic = 0;
   std::vector<OutGroup> groups;
   int nOut = 0;
   std::vector<std::string> names;  // output element names
+  const FrontEnd &fe0() const { return streams[0].fe; }
 };
 
 // graph.cpp
 osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char *outputLevel,
                               PlanDesc &out, std::string &err);
 int64_t desc_num_frames(const PlanDesc &d, int64_t nSampleFrames);
-int64_t desc_num_static_frames(const PlanDesc &d, int64_t nSampleFrames);
+int64_t desc_num_static_frames(const PlanDesc &d, int stream, int64_t nSampleFrames);
+int64_t desc_max_static_frames(const PlanDesc &d, int64_t nSampleFrames);
 
 // tables.cpp
 void build_window(int winFunc, int N, double sigma, double gain, std::vector<float> &w);
 void build_mel(const osm_b200_melspec &cfg, int nBins, double frameSizeSec, MelBank &mb);
 void build_mfcc(const osm_b200_mfcc &cfg, int nBands, MfccOp &op);
 bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, PlpOp &op, std::string &err);
+bool build_spectral(const osm_b200_spectral &cfg, int nSrc, double fftFrameSizeSec, SpectralOp &op, std::string &err);
+void build_energy(const osm_b200_energy &cfg, EnergyOp &op);
+void build_mzcr(const osm_b200_mzcr &cfg, MzcrOp &op);
 
 }  // namespace osm

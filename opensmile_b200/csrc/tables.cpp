@@ -261,4 +261,134 @@ bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, PlpOp &op, std::strin
   return true;
 }
 
+// Traunmueller bark (smileutil/smileUtil.c:1113-1128) and Zwicker's g(z) (:1064-1079)
+static double bark_fwd(double x)
+{
+  if (x > 0) {
+    const double zz = (26.81 / (1.0 + 1960.0 / x)) - 0.53;
+    if (zz < 2) return (0.85 * zz + 0.3);
+    if (zz > 20.1) return (1.22 * zz - 0.22 * 20.1);
+    return zz;
+  }
+  return 0.0;
+}
+static double sharp_g(double z) { return z <= 16.0 ? 1.0 : pow((z - 16.0) / 4.0, 1.5849625) + 1.0; }
+
+// cSpectral::myFetchConfig (lldcore/spectral.cpp:219-376) + the lazily computed, frame
+// independent parts of processVector: spectral range (:625-647), band / slope edges
+// (:781-825, :879-925), sharpness weights (:1443-1453).  Input = magnitude bins with the
+// bin-frequency field info written by cTransformFFT (linear scale).
+bool build_spectral(const osm_b200_spectral &cfg, int nSrc, double fftFrameSizeSec, SpectralOp &op, std::string &err)
+{
+  op = SpectralOp();
+  op.nSrc = nSrc;
+  op.F0 = (double)(1.0) / (double)fftFrameSizeSec;           // transformFft.cpp:111
+  std::vector<double> frq(nSrc);
+  for (int i = 0; i < nSrc; i++) frq[i] = op.F0 * (double)i;
+  op.squareInput = cfg.squareInput != 0; op.useLog = cfg.useLogSpectrum != 0; op.normBand = cfg.normBandEnergies != 0;
+  op.buggyRollOff = cfg.buggyRollOff != 0; op.oldSlopeScale = cfg.oldSlopeScale != 0;
+  if (op.useLog) {                                            // :228-237
+    float sf = (float)cfg.specFloor;
+    sf = sf * sf;
+    op.specFloor = sf;
+    op.logSpecFloor = (float)(10.0 * log(sf) / log(10.0));
+  }
+  op.flux = cfg.flux != 0; op.centroid = cfg.centroid != 0; op.maxPos = cfg.maxPos != 0; op.minPos = cfg.minPos != 0;
+  op.entropy = cfg.entropy != 0; op.stddev = cfg.standardDeviation != 0; op.variance = cfg.variance != 0;
+  op.skewness = cfg.skewness != 0; op.kurtosis = cfg.kurtosis != 0; op.slope = cfg.slope != 0;
+  op.alphaRatio = cfg.alphaRatio != 0; op.hammarberg = cfg.hammarbergIndex != 0; op.sharpness = cfg.sharpness != 0;
+  op.harmonicity = cfg.harmonicity != 0; op.flatness = cfg.flatness != 0; op.logFlatness = false;
+  auto lorp = [&]() { if (op.useLog) op.reqLog = true; else op.reqPow = true; };
+  op.reqMag = op.flux;
+  if (op.centroid) lorp(); if (op.maxPos) lorp(); if (op.minPos) lorp(); if (op.entropy) lorp();
+  if (op.stddev) lorp(); if (op.variance) lorp(); if (op.skewness) lorp(); if (op.kurtosis) lorp(); if (op.slope) lorp();
+  if (op.alphaRatio) op.reqPow = true; if (op.hammarberg) op.reqPow = true;
+  if (cfg.nBands > 0) op.reqPow = true; if (cfg.nSlopes > 0) lorp(); if (cfg.nRollOff > 0) op.reqPow = true;
+  if (op.sharpness) op.reqPow = true; if (op.harmonicity) lorp(); if (op.flatness) lorp();
+  if (!op.reqPow && !op.reqLog) { err = "cSpectral: no descriptor that needs a spectrum is enabled"; return false; }
+  if (op.useLog && !op.reqLog) op.reqLog = true;
+
+  const long lo = (long)cfg.freqRangeLo, hi = (long)cfg.freqRangeHi;      // :625-647
+  if (lo == hi && hi == 0) { op.loBin = 1; op.hiBin = nSrc - 1; }
+  else {
+    int lb = -1, hb = -1;
+    for (int i = 0; i < nSrc; i++) {
+      if ((double)lo >= frq[i]) lb = i;
+      if ((double)hi > frq[i]) hb = i;
+    }
+    if (hb == -1 || hb >= nSrc) hb = nSrc - 1;
+    if (lb < 0) lb = 0;
+    op.loBin = lb; op.hiBin = hb;
+  }
+  auto edgeLo = [&](double f, double &idx, double &w) {       // :781-795
+    int ii;
+    for (ii = 0; ii < nSrc; ii++) if (frq[ii] > f) break;
+    if ((ii < nSrc) && (ii > 0)) w = (frq[ii] - f) / (frq[ii] - frq[ii - 1]); else w = 1.0;
+    idx = (double)ii - 1.0;
+    if (idx < 0) idx = 0;
+    if (idx >= nSrc) idx = nSrc;
+  };
+  auto edgeHi = [&](double f, double &idx, double &w) {       // :808-825
+    int ii;
+    for (ii = 0; ii < nSrc; ii++) if (frq[ii] >= (float)f) break;
+    if ((ii < nSrc) && (ii > 0)) w = (f - frq[ii - 1]) / (frq[ii] - frq[ii - 1]); else w = 1.0;
+    if ((ii < nSrc) && (frq[ii] == (float)f)) idx = (double)ii; else idx = (double)ii - 1.0;
+    if (idx >= nSrc) idx = nSrc - 1;
+  };
+  auto resolve = [&](double fl, double fh, int &iL, int &iR, double &wL, double &wR, double &nind) {
+    double idxL, idxR;
+    edgeLo((double)(long)fl, idxL, wL); if (wL == 0.0) wL = 1.0;
+    edgeHi((double)(long)fh, idxR, wR); if (wR == 0.0) wR = 1.0;
+    long l = (long)floor(idxL), r = (long)floor(idxR);          // :833-839
+    if (l >= nSrc) { l = r = nSrc - 1; wR = 0.0; wL = 0.0; }
+    if (r >= nSrc) { r = nSrc - 1; wR = 1.0; }
+    if (l < 0) l = 0; if (r < 0) r = 0;
+    iL = (int)l; iR = (int)r; nind = idxR - idxL;
+  };
+  for (int i = 0; i < cfg.nBands && i < OSM_B200_MAX_LIST; i++) {
+    if (!((long)cfg.bandLo[i] >= 0 && (long)cfg.bandHi[i] > 0)) continue;   // isBandValid, spectral.hpp:64-68
+    int iL, iR; double wL, wR, nind;
+    resolve(cfg.bandLo[i], cfg.bandHi[i], iL, iR, wL, wR, nind);
+    op.bandIL.push_back(iL); op.bandIR.push_back(iR); op.bandWL.push_back(wL); op.bandWR.push_back(wR);
+  }
+  for (int i = 0; i < cfg.nSlopes && i < OSM_B200_MAX_LIST; i++) {
+    if (!((long)cfg.slopeLo[i] >= 0 && (long)cfg.slopeHi[i] > 0)) continue;
+    int iL, iR; double wL, wR, nind;
+    resolve(cfg.slopeLo[i], cfg.slopeHi[i], iL, iR, wL, wR, nind);
+    op.slopeIL.push_back(iL); op.slopeIR.push_back(iR); op.slopeWL.push_back(wL); op.slopeWR.push_back(wR);
+    op.slopeNind.push_back(nind);
+  }
+  for (int i = 0; i < cfg.nRollOff && i < OSM_B200_MAX_LIST; i++) {
+    double r = cfg.rollOff[i];
+    if (r < 0.0) r = 0.0; else if (r > 1.0) r = 1.0;           // :340-347
+    op.rollOff.push_back(r);
+  }
+  op.sharpW.assign(op.hiBin - op.loBin + 1, 0.0);
+  for (int j = op.loBin; j <= op.hiBin; j++) {                 // :1443-1453 (linear axis -> bark)
+    const double fb = bark_fwd(frq[j]);
+    op.sharpW[j - op.loBin] = fb * sharp_g(fb);
+  }
+  op.nOut = (int)(op.bandIL.size() + op.slopeIL.size() + op.rollOff.size()) + op.alphaRatio + op.hammarberg + op.flux +
+            op.centroid + op.maxPos + op.minPos + op.entropy + op.stddev + op.variance + op.skewness + op.kurtosis +
+            op.slope + op.sharpness + op.harmonicity + op.flatness;
+  if (op.hiBin - op.loBin < 4) { err = "cSpectral: spectral range too narrow"; return false; }
+  return true;
+}
+
+// cEnergy::myFetchConfig (lldcore/energy.cpp:60-80)
+void build_energy(const osm_b200_energy &cfg, EnergyOp &op)
+{
+  op.htk = cfg.htkcompatible != 0; op.rms = cfg.rms != 0; op.energy2 = cfg.energy2 != 0; op.lg = cfg.log != 0;
+  if (op.htk) { op.lg = true; op.rms = false; }
+  op.escaleLog = (float)cfg.escaleLog; op.escaleRms = (float)cfg.escaleRms; op.escaleSquare = (float)cfg.escaleSquare;
+  op.ebiasLog = (float)cfg.ebiasLog; op.ebiasRms = (float)cfg.ebiasRms; op.ebiasSquare = (float)cfg.ebiasSquare;
+  op.nOut = (int)op.rms + (int)op.energy2 + (int)op.lg;
+}
+
+void build_mzcr(const osm_b200_mzcr &cfg, MzcrOp &op)
+{
+  op.zcr = cfg.zcr != 0; op.mcr = cfg.mcr != 0; op.amax = cfg.amax != 0; op.maxmin = cfg.maxmin != 0; op.dc = cfg.dc != 0;
+  op.nOut = (int)op.zcr + (int)op.mcr + (int)op.amax + 2 * (int)op.maxmin + (int)op.dc;
+}
+
 }  // namespace osm

@@ -80,6 +80,52 @@ def components_plp_0_d_a(sample_rate=16000.0, n_channels=1):
     ]
 
 
+def comp(type_name, name, reader, writer, **fields):
+    """One `[name:cType]` section -> osm_b200_component (type by the reference's component name).
+    List-valued cSpectral options: bands=[(lo,hi),...], slopes=[...], rollOff=[...]."""
+    ctype = capi.TYPE_BY_NAME[type_name]
+    bands = fields.pop("bands", None)
+    slopes = fields.pop("slopes", None)
+    rolloff = fields.pop("rollOff", None)
+    freq_range = fields.pop("freqRange", None)
+    c = _comp(ctype, name, reader, writer, **fields)
+    if ctype == capi.C_SPECTRAL:
+        sp = c.u.spectral
+        if bands is not None:
+            sp.nBands = len(bands)
+            for i, (a, b) in enumerate(bands):
+                sp.bandLo[i], sp.bandHi[i] = a, b
+        if slopes is not None:
+            sp.nSlopes = len(slopes)
+            for i, (a, b) in enumerate(slopes):
+                sp.slopeLo[i], sp.slopeHi[i] = a, b
+        if rolloff is not None:
+            sp.nRollOff = len(rolloff)
+            for i, r in enumerate(rolloff):
+                sp.rollOff[i] = r
+        if freq_range is not None:
+            sp.freqRangeLo, sp.freqRangeHi = freq_range
+    return c
+
+
+def components_frontend(sample_rate, frame_size, frame_step=0.010, win="ham", sigma=0.4, preemph=None,
+                        n_channels=1, prefix="", with_fft=True, zero_pad_symmetric=1):
+    """wave -> framer [-> pre-emphasis] -> windower [-> FFT -> magnitude] with level names
+    <prefix>frame / <prefix>pe / <prefix>win / <prefix>fft / <prefix>mag."""
+    T = capi
+    cs = [_comp(T.C_WAVESOURCE, "waveIn", "", "wave", sampleRate=float(sample_rate), nChannels=n_channels, monoMixdown=1),
+          _comp(T.C_FRAMER, prefix + "frame", "wave", prefix + "frame", frameSize=frame_size, frameStep=frame_step)]
+    last = prefix + "frame"
+    if preemph is not None:
+        cs.append(_comp(T.C_VECTORPREEMPHASIS, prefix + "pe", last, prefix + "pe", k=preemph))
+        last = prefix + "pe"
+    cs.append(_comp(T.C_WINDOWER, prefix + "win", last, prefix + "win", winFunc=T.WIN_BY_NAME[win], sigma=sigma))
+    if with_fft:
+        cs.append(_comp(T.C_TRANSFORMFFT, prefix + "fft", prefix + "win", prefix + "fft", zeroPadSymmetric=zero_pad_symmetric))
+        cs.append(_comp(T.C_FFTMAGPHASE, prefix + "mag", prefix + "fft", prefix + "mag"))
+    return cs
+
+
 class Plan:
     """A compiled LLD plan bound to one CUDA device."""
 

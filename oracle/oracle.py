@@ -249,6 +249,16 @@ def delta_chained(x, win, n0):
     return out[:r], c0.value
 
 
+def sma_chained(x, sma_win, n0, no_zero_sma=0):
+    x = np.ascontiguousarray(x, np.float32)
+    T, K = x.shape
+    out = np.zeros((T + sma_win // 2, K), np.float32)
+    c0 = C.c_long(0)
+    r = lib().osm_or_sma_chained(_fp(x), C.c_long(T), C.c_long(n0), C.c_int(K), C.c_int(sma_win), C.c_int(no_zero_sma),
+                                 _fp(out), C.byref(c0))
+    return out[:r], c0.value
+
+
 def sma(x, sma_win=3, no_zero_sma=0):
     x = np.ascontiguousarray(x, np.float32)
     T, K = x.shape

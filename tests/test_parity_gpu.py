@@ -212,3 +212,95 @@ def test_plp_16k_batch_vs_oracle():
         assert rel_to_frame_scale(out[fo[u]:fo[u + 1]], ref) < TOL
     assert p.element_names[0] == "PlpCC[0]" and p.element_names[6] == "PlpCC_de[0]"
     p.close()
+
+
+# ---------------------------------------------------------------- cSpectral / cEnergy / cMZcr (general, non-fused path)
+def _check_cols(got, ref, rtol=1e-5, exact_cols=()):
+    """per-column check: |got-ref| <= rtol * max|ref[:,c]| ; columns in exact_cols must be equal
+    (roll-off points are bin frequencies: a 1e-7 FFT perturbation must not move them here)."""
+    assert got.shape == ref.shape
+    for c in range(ref.shape[1]):
+        scale = max(float(np.abs(ref[:, c]).max()), 1e-30)
+        err = float(np.abs(got[:, c] - ref[:, c]).max())
+        if c in exact_cols:
+            assert np.array_equal(got[:, c], ref[:, c]), (c, err)
+        else:
+            assert err <= rtol * scale, (c, err, scale)
+
+
+def test_spectral_compare16_and_gemaps_vs_oracle():
+    from opensmile_b200 import comp, components_frontend
+    utts = [voiced_pcm(n, 16000, seed=800 + i) for i, n in enumerate([16000, 320, 5000, 48000])]
+    pcm, off = pack_utterances(utts)
+    fe = oracle.frontend(16000.0, 0.020, 0.010, "ham")
+    # ComParE is13_spectral (config/compare16/ComParE_2016_core.lld.conf.inc:283-302)
+    cs = components_frontend(16000.0, 0.020, win="ham") + [
+        comp("cSpectral", "spec", "mag", "spec", bands=[(250, 650), (1000, 4000)], rollOff=[0.25, 0.5, 0.75, 0.9],
+             flux=1, centroid=1, maxPos=0, minPos=0, entropy=1, variance=1, skewness=1, kurtosis=1, slope=1,
+             harmonicity=1, sharpness=1)]
+    p = Plan(cs, "spec", device=0)
+    assert p.num_elements == 15
+    assert p.element_names[0] == "pcm_fftMag_fband250-650" and p.element_names[2] == "pcm_fftMag_spectralRollOff25.0"
+    assert p.element_names[6] == "pcm_fftMag_spectralFlux" and p.element_names[13] == "pcm_fftMag_psySharpness"
+    out = p.run_host(pcm, off)
+    fo = p.frame_offsets(off)
+    for u, x in enumerate(utts):
+        ref = oracle.spectral(x, fe, oracle.compare16_spectral())
+        _check_cols(out[fo[u]:fo[u + 1]], ref, rtol=2e-5)
+    p.close()
+    # GeMAPS log-spectral descriptors (config/gemaps/v01b/GeMAPSv01b_core.lld.conf.inc:321-346)
+    cs = components_frontend(16000.0, 0.020, win="ham") + [
+        comp("cSpectral", "lspec", "mag", "lspec", slopes=[(0, 500), (500, 1500)], flux=0, centroid=0, maxPos=0, minPos=0,
+             alphaRatio=1, hammarbergIndex=1, normBandEnergies=1, squareInput=1, useLogSpectrum=1,
+             freqRange=(0, 5000), oldSlopeScale=0)]
+    p = Plan(cs, "lspec", device=0)
+    assert p.element_names == ["pcm_fftMag_logSpectralSlopeOfBand0-500", "pcm_fftMag_logSpectralSlopeOfBand500-1500",
+                               "pcm_fftMag_alphaRatioDB", "pcm_fftMag_hammarbergIndexDB"]
+    out = p.run_host(pcm, off)
+    # log-spectral slopes / ratios are differences of dB values of bins far below the frame peak:
+    # the FFT's 2e-7-of-peak noise is a >1e-5 RELATIVE perturbation of those bins, so these four
+    # columns are ill-conditioned (the float64 oracle itself sits at 1.2e-5 from the reference);
+    # they are checked at 1e-4 of the column scale
+    for u, x in enumerate(utts):
+        ref = oracle.spectral(x, fe, oracle.gemaps_logspectral())
+        _check_cols(out[fo[u]:fo[u + 1]], ref, rtol=1e-4)
+    p.close()
+
+
+def test_energy_zcr_bit_exact_and_multi_stream_concat():
+    """cEnergy on the 20 ms framer level + cMZcr on the 60 ms framer level + windowed cEnergy, joined by
+    cVectorConcat, smoothed by cContourSmoother / cDeltaRegression: time-domain ops are pure float
+    arithmetic in the reference's order, so they must match the oracle bit for bit."""
+    from opensmile_b200 import comp, components_frontend
+    T = 16000
+    utts = [voiced_pcm(n, T, seed=900 + i) for i, n in enumerate([16000, 960, 7000, 959, 31000])]
+    pcm, off = pack_utterances(utts)
+    cs = components_frontend(16000.0, 0.020, win="ham", prefix="a", with_fft=False)
+    cs += components_frontend(16000.0, 0.060, win="gau", prefix="b", with_fft=False)[1:]
+    cs += [comp("cEnergy", "e25", "aframe", "e25", rms=1, log=0),
+           comp("cMZcr", "z60", "bframe", "z60", zcr=1, mcr=1, amax=1, maxmin=1, dc=1),
+           comp("cEnergy", "e60", "bwin", "e60", rms=1, log=1, energy2=1),
+           comp("cContourSmoother", "sm", "e25", "e25s", smaWin=3),
+           comp("cDeltaRegression", "de", "e25s", "e25sd", deltawin=2),
+           comp("cVectorConcat", "cat", "e25;z60;e60;e25s;e25sd", "lld")]
+    p = Plan(cs, "lld", device=0)
+    assert p.element_names == ["pcm_RMSenergy", "pcm_zcr", "pcm_mcr", "pcm_absmax", "pcm_max", "pcm_min", "pcm_dc",
+                               "pcm_RMSenergy", "pcm_SQUAREDenergy", "pcm_LOGenergy", "pcm_RMSenergy_sma", "pcm_RMSenergy_sma_de"]
+    out = p.run_host(pcm, off)
+    fo = p.frame_offsets(off)
+    fa = oracle.frontend(16000.0, 0.020, 0.010, "ham")
+    fb = oracle.frontend(16000.0, 0.060, 0.010, "gau", sigma=0.4)
+    for u, x in enumerate(utts):
+        n60 = oracle.geometry(fb, len(x))[3]
+        assert fo[u + 1] - fo[u] == max(n60, 0)           # concat = min over inputs (60 ms stream is shortest)
+        if n60 <= 0:
+            continue
+        e25 = oracle.energy(x, fa, oracle.Energy(0, 1, 0, 0, 1, 1, 1, 0, 0, 0), 0)
+        z60 = oracle.mzcr(x, fb, oracle.MZcr(1, 1, 1, 1, 1), 0)
+        e60 = oracle.energy(x, fb, oracle.Energy(0, 1, 1, 1, 1, 1, 1, 0, 0, 0), 1)
+        sm, c0 = oracle.sma_chained(e25, 3, e25.shape[0])
+        de, _ = oracle.delta_chained(sm, 2, c0)
+        ref = np.concatenate([e25[:n60], z60[:n60], e60[:n60], sm[:n60], de[:n60]], axis=1)
+        got = out[fo[u]:fo[u + 1]]
+        assert np.array_equal(got, ref), (u, np.abs(got - ref).max(axis=0))
+    p.close()
