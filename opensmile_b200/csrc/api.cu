@@ -94,7 +94,10 @@ struct OpRt {
   int kind = 0, stream = 0;
   SpectralParams sp;
   TimeOpParams tp;
+  AcfPitchParams ap;
   double *dSharpW = nullptr;
+  float2 *dTw = nullptr;
+  DevBuf<PitchRaw> dRaw;
 };
 
 struct osm_b200_plan {
@@ -476,6 +479,25 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       CUP(cudaMalloc(&rt.dSharpW, so.sharpW.size() * sizeof(double)));
       CUP(cudaMemcpy(rt.dSharpW, so.sharpW.data(), so.sharpW.size() * sizeof(double), cudaMemcpyHostToDevice));
       sp.sharpW = rt.dSharpW;
+    } else if (op.kind == SOP_PITCHACF) {
+      if (!acf_pitch_supported_fft(fe.nfft)) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cAcf / cPitchACF: FFT size must be 512 or 1024"); }
+      const PitchAcfOp &po = op.pitch;
+      AcfPitchParams &ap = rt.ap;
+      memset(&ap, 0, sizeof ap);
+      ap.F = srt.tileF;     // width of the magnitude level's tiles
+      ap.nfft = fe.nfft; ap.nSrc = fe.nBins;
+      ap.acfUsePower = po.acfUsePower; ap.cepUsePower = po.cepUsePower; ap.absCepstrum = po.absCepstrum; ap.normOutput = po.normOutput;
+      ap.maxPitch = po.maxPitch; ap.voicingCutoff = po.voicingCutoff; ap.fsSec = po.fsSec;
+      ap.voiceProb = po.voiceProb; ap.voiceQual = po.voiceQual; ap.HNR = po.HNR; ap.HNRdB = po.HNRdB; ap.linHNR = po.linHNR;
+      ap.F0 = po.F0; ap.F0raw = po.F0raw; ap.F0env = po.F0env;
+      ap.statStride = d.nStatic; ap.outCol = op.outCol; ap.frameSize = fe.frameSize; ap.frameStep = fe.frameStep;
+      // complex FFT of size nfft: same factorisation tables as lld_kernel's M = nfft
+      std::vector<float2> tw;
+      build_twiddles(fe.nfft, tw, ap.twOff);
+      ap.twCount = (int)tw.size();
+      CUP(cudaMalloc(&rt.dTw, (tw.size() + 1) * sizeof(float2)));
+      CUP(cudaMemcpy(rt.dTw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+      ap.twiddles = rt.dTw;
     } else {
       TimeOpParams &tp = rt.tp;
       memset(&tp, 0, sizeof tp);
@@ -520,7 +542,7 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
     if (s.dConst) cudaFree(s.dConst);
     s.hChunks.release(); s.dChunks.release(); s.hTiles.release(); s.dTiles.release(); s.dMag.release();
   }
-  for (OpRt &o : pl->ops) if (o.dSharpW) cudaFree(o.dSharpW);
+  for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); }
   pl->hMeta.release(); pl->dMeta.release(); pl->hPost.release(); pl->dPost.release(); pl->dStat.release();
   pl->dPcm.release(); pl->dOut.release();
   if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
@@ -705,6 +727,15 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       sp.tiles = rt.dTiles.p + t0; sp.nTiles = t1 - t0;
       sp.statOff = dS; sp.stat = pl->dStat.p;
       CU(launch_spectral(sp, st));
+    } else if (o.kind == SOP_PITCHACF) {
+      AcfPitchParams ap = o.ap;
+      CU(o.dRaw.reserve((size_t)pl->totalStat + 64));
+      ap.mag = rt.dMag.p + (size_t)t0 * ap.nSrc * ap.F;
+      ap.tiles = rt.dTiles.p + t0; ap.nTiles = t1 - t0;
+      ap.statOff = dS; ap.uttOff = dU; ap.raw = o.dRaw.p; ap.stat = pl->dStat.p; ap.nUtt = n_utt;
+      CU(launch_acf_pitch(ap, st));
+      CU(launch_pitch_smooth(ap, u0, u1, st));
+      pl->lastLaunches++;
     } else {
       TimeOpParams tp = o.tp;
       tp.pcm = reinterpret_cast<const int16_t *>(d_pcm);

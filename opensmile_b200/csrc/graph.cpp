@@ -317,6 +317,46 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         if (sc.harmonicity) add(lg ? "logSpectralHarmonicity" : "spectralHarmonicity");
         if (sc.flatness) add(lg ? "logSpectralFlatness" : "spectralFlatness");
         if ((int)op.fields.size() != op.nOut) { err = "internal: cSpectral name/element mismatch"; return OSM_B200_ERR_INVALID; }
+      } else if (c->type == OSM_B200_C_PITCHACF) {
+        // reader.dmLevel = <acf level>;<cepstrum level> (lldcore/pitchACF.cpp:148-152), both cAcf
+        // instances on the same magnitude level
+        if (c->n_inputs != 2) { err = "cPitchACF must read two levels: acf;cepstrum"; return OSM_B200_ERR_UNSUPPORTED; }
+        const osm_b200_component *a = R.prod(c->reader_dmLevel[0]), *b = R.prod(c->reader_dmLevel[1]);
+        if (!a || !b || a->type != OSM_B200_C_ACF || b->type != OSM_B200_C_ACF) { err = "cPitchACF inputs must be cAcf levels"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (a->u.acf.cepstrum || !b->u.acf.cepstrum) { err = "cPitchACF expects [acf ; cepstrum] in this order"; return OSM_B200_ERR_UNSUPPORTED; }
+        for (const osm_b200_component *x : {a, b}) {
+          const auto &q = x->u.acf;
+          if (q.inverse || q.cosLifterCepstrum || q.oldCompatCepstrum || !q.symmetricData) { err = "cAcf: inverse / cosLifterCepstrum / oldCompatCepstrum / symmetricData=0 are not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        }
+        if (single_input(a) != single_input(b)) { err = "both cAcf instances must read the same cFFTmagphase level"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (!resolve_mag_chain(single_input(a), ci)) return OSM_B200_ERR_UNSUPPORTED;
+        osm_b200_status s2 = get_stream(ci, true, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        const FrontEnd &fe = d.streams[op.stream].fe;
+        op.kind = SOP_PITCHACF;
+        PitchAcfOp &po = op.pitch;
+        po.acfUsePower = a->u.acf.usePower != 0; po.cepUsePower = b->u.acf.usePower != 0;
+        po.absCepstrum = b->u.acf.absCepstrum != 0;
+        po.normOutput = a->u.acf.acfCepsNormOutput != 0;
+        if ((b->u.acf.acfCepsNormOutput != 0) != po.normOutput) { err = "cAcf.acfCepsNormOutput must agree on both instances"; return OSM_B200_ERR_UNSUPPORTED; }
+        const auto &pp = c->u.pitchacf;
+        po.maxPitch = pp.maxPitch < 0.0 ? 0.0 : pp.maxPitch;                       // lldcore/pitchACF.cpp:101-102
+        po.voicingCutoff = pp.voicingCutoff > 1.0 ? 1.0 : (pp.voicingCutoff < 0.0 ? 0.0 : pp.voicingCutoff);
+        po.fsSec = (float)fe.fftFrameSizeSec;                                       // :107-110
+        po.voiceProb = pp.voiceProb != 0; po.voiceQual = pp.voiceQual != 0; po.HNR = pp.HNR != 0; po.HNRdB = pp.HNRdB != 0;
+        po.linHNR = pp.linHNR != 0; po.F0 = pp.F0 != 0; po.F0raw = pp.F0raw != 0; po.F0env = pp.F0env != 0;
+        auto add = [&](const char *nm) { FieldName f; f.name = nm; op.fields.push_back(f); };   // :112-121
+        if (po.voiceProb) add("voiceProb");
+        if (po.HNR) add("HNR");
+        if (po.HNRdB) add("HNRdBacf");
+        if (po.linHNR) add("linearHNRacf");
+        if (po.voiceQual) add("voiceQual");
+        if (po.F0) add("F0");
+        if (po.F0raw) add("F0raw");
+        if (po.F0env) add("F0env");
+        po.nOut = (int)op.fields.size();
+        op.nOut = po.nOut;
+        if (op.nOut < 1) { err = "cPitchACF produces no output"; return OSM_B200_ERR_INVALID; }
       } else if (c->type == OSM_B200_C_ENERGY || c->type == OSM_B200_C_MZCR) {
         const osm_b200_component *in = single_input(c);
         if (!resolve_time_chain(in, ci)) return OSM_B200_ERR_UNSUPPORTED;
@@ -403,7 +443,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     for (size_t o = 0; o < d.ops.size(); o++) {
       if (d.ops[o].stream != (int)s) continue;
       if (d.ops[o].kind == SOP_MFCC || d.ops[o].kind == SOP_PLP) { nBand++; band = (int)o; }
-      if (d.ops[o].kind == SOP_SPECTRAL) nSpec++;
+      if (d.ops[o].kind == SOP_SPECTRAL || d.ops[o].kind == SOP_PITCHACF) nSpec++;
     }
     if (nBand > 1) { err = "more than one cMfcc / cPlp on one FFT chain is not supported yet"; return OSM_B200_ERR_UNSUPPORTED; }
     d.streams[s].fusedOp = band;

@@ -960,6 +960,207 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
 }
 
 // ------------------------------------------------------------------------------------------
+// cAcf (ACF + cepstrum) + cPitchACF, per-frame part.
+//   dspcore/acf.cpp:250-345: both levels are the inverse real FFT of a real, even spectrum
+//   (power resp. log(1+x)), i.e. cosine transforms.  With z[n] = Pfull[n] + i*Cfull[n] over the
+//   symmetric extension n = 0..N-1, ONE complex FFT of size N gives both at once:
+//   Re Z[j] = 2*acf_ooura[j], Im Z[j] = 2*cep_ooura[j]  (real even input -> real even output).
+//   lldcore/pitchACF.cpp:137-361 then scans the two arrays per frame.
+// One CTA per tile, lane = frame, same batched in-place FFT as lld_kernel.
+// ------------------------------------------------------------------------------------------
+template <int N, int F, int NT>
+__global__ void __launch_bounds__(NT, 1) acf_pitch_kernel(const AcfPitchParams p)
+{
+  constexpr int NW = NT / 32, G = 32 / F, NVW = NW * G;
+  using Fc = Fact<N>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  float2 *Z = reinterpret_cast<float2 *>(smem);
+  float2 *sTw = reinterpret_cast<float2 *>(smem + (size_t)N * F * 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f = lane & (F - 1);
+  const int vw = warp * G + lane / F;
+  // the magnitude level is stored in tiles of p.F frames; this CTA handles F of them (sub-tile)
+  const int SUB = p.F / F;
+  const int tileIdx = blockIdx.x / SUB, sub = blockIdx.x - tileIdx * SUB;
+  OpTile tl = p.tiles[tileIdx];
+  tl.f0 += sub * F;
+  tl.nf = min(max(tl.nf - sub * F, 0), F);
+  const int nSrc = p.nSrc;
+  for (int i = tid; i < p.twCount; i += NT) sTw[i] = p.twiddles[i];
+  // ---- spectrum -> symmetric complex input ----
+  {
+    const float *mg = p.mag + (size_t)tileIdx * nSrc * p.F + sub * F;
+    for (int idx = tid; idx < nSrc * F; idx += NT) {
+      const int k = idx / F, ff = idx - k * F;
+      const float m = mg[(size_t)k * p.F + ff];
+      const float pw = p.acfUsePower ? __fmul_rn(m, m) : m;                       // acf.cpp:253-261
+      const float cs = p.cepUsePower ? __fmul_rn(m, m) : m;
+      const float cv = (cs > 0.0f) ? (float)log((double)cs + 1.0) : 0.0f;         // acf.cpp:289-305
+      const float2 v = make_float2(pw, cv);
+      Z[k * F + ff] = v;
+      if (k > 0 && k < N / 2) Z[(N - k) * F + ff] = v;
+    }
+  }
+  __syncthreads();
+  {
+    LldParams dummy;     // fft_stage only reads it in its FIRST (sample loading) specialisation
+    fft_stage<N, F, NVW, Fc::R0, N, false, false, false>(Z, nullptr, nullptr, nullptr, sTw + p.twOff[0], dummy, vw, f);
+    __syncthreads();
+    fft_stage<N, F, NVW, Fc::R1, N / Fc::R0, false, false, false>(Z, nullptr, nullptr, nullptr, sTw + p.twOff[1], dummy, vw, f);
+    __syncthreads();
+    fft_stage<N, F, NVW, Fc::R2, N / (Fc::R0 * Fc::R1), false, true, false>(Z, nullptr, nullptr, nullptr, nullptr, dummy, vw, f);
+  }
+  __syncthreads();
+  // ---- per-frame analysis (lldcore/pitchACF.cpp:137-183), one lane per frame ----
+  if (vw == 0 && f < tl.nf) {
+    const int n = N / 2;                                   // length of each cAcf level (Ndst = Nsrc - 1)
+    const float fNsrc = (float)nSrc;
+    auto acf = [&](int j) {
+      float d = 0.5f * Z[fft_pos<N>(j) * F + f].x;
+      if (p.normOutput) d = __fdiv_rn(d, fNsrc);           // acf.cpp:321-325
+      return fabsf(d);                                     // :342-344
+    };
+    auto cep = [&](int j) {
+      float d = 0.5f * Z[fft_pos<N>(j) * F + f].y;
+      if (p.normOutput) d = __fdiv_rn(d, fNsrc);
+      return p.absCepstrum ? fabsf(d) : d;                 // :327-341
+    };
+    const double Nd = (double)(2 * n);
+    const double Tsamp = (double)p.fsSec / Nd;
+    const int preskip = (p.maxPitch <= 0.0) ? 0 : (int)(1.0 / (p.maxPitch * Tsamp));
+    // voicingProb (:249-284)
+    int zcr = 0, mcr = 0;
+    double mx = acf(n - 1), mean = acf(preskip);
+    {
+      float a0 = acf(0);
+      for (int i = 1; i < n; i++) {
+        const float a1 = acf(i);
+        if (__fmul_rn(a0, a1) < 0.0f) zcr++;
+        if (i >= preskip) {
+          if (((double)a1 > mx) && (a0 < a1)) mx = a1;
+          mean += (double)a1;
+        }
+        a0 = a1;
+      }
+    }
+    mean /= (double)(n - preskip + 1);
+    {
+      float a0 = acf(0);
+      for (int i = 1; i < n; i++) {
+        const float a1 = acf(i);
+        if (((double)a0 - mean) * ((double)a1 - mean) < 0.0) mcr++;
+        a0 = a1;
+      }
+    }
+    const double acfZcr = (mcr > zcr) ? (double)mcr / (double)n : (double)zcr / (double)n;
+    const float acf0 = acf(0);
+    const double voicing = (acf0 > 0.0f) ? mx / (double)acf0 : 0.0;
+    // pitchPeak on the cepstrum (:286-310), skip = preskip + 1
+    const int skip = preskip + 1;
+    double cmax = cep(n - 1), csum = 0.0;
+    for (int i = n - 1; i >= 0; i--) {
+      const double buf = cep(i);
+      csum += fabs(buf);
+      if (i >= skip && buf > cmax) cmax = buf;
+    }
+    csum /= (double)n;
+    int maxIdx = 0;
+    {
+      const double thr = (cmax + csum) * 0.6;
+      float cm = cep(skip), c0 = cep(skip + 1);
+      for (int i = skip + 1; i < n - 1; i++) {
+        const float c1 = cep(i + 1);
+        if ((double)c0 > thr && (cm < c0) && (c0 > c1)) { maxIdx = i; break; }
+        cm = c0; c0 = c1;
+      }
+    }
+    PitchRaw r;
+    r.voicing = voicing; r.acfZcr = acfZcr; r.maxIdx = maxIdx;
+    const float aI = acf(maxIdx);
+    r.hnr = 0.f; r.hnrDB = 0.f; r.hnrLin = 0.f;
+    if (p.HNR) {                                           // :312-326
+      const float dd = __fsub_rn(acf0, aI);
+      const double buf = (dd == 0.0f) ? 100000000000000000000.0 : (double)__fdiv_rn(aI, dd);
+      r.hnr = (float)((buf > 0.00000000001) ? 10.0 * log(buf) : 10.0 * log(0.00000000001));
+    }
+    if (p.HNRdB) {                                         // :329-343
+      double buf = (double)__fsub_rn(acf0, aI);
+      buf = (buf == 0.0) ? 10e10 : (double)aI / buf;
+      r.hnrDB = (float)((buf <= 10e-10) ? -100.0 : ((buf >= 10e10) ? +100.0 : 10.0 * log(buf) / log(10.0)));
+    }
+    if (p.linHNR) {                                        // :346-360
+      double buf = (double)__fsub_rn(acf0, aI);
+      buf = (buf == 0.0) ? 10e3 : (double)aI / buf;
+      r.hnrLin = (float)((buf <= 10e-3) ? 10e-3 : ((buf >= 10e3) ? 10e3 : buf));
+    }
+    p.raw[p.statOff[tl.utt] + tl.f0 + f] = r;
+  }
+}
+
+// per-utterance pitch contour smoothing state machine (lldcore/pitchACF.cpp:184-245): sequential in
+// time, one thread per utterance
+__global__ void pitch_smooth_kernel(const AcfPitchParams p, int u0, int u1)
+{
+  const int u = u0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= u1) return;
+  const long long Ls = p.uttOff[u + 1] - p.uttOff[u];
+  const int T = (Ls >= p.frameSize) ? (int)((Ls - p.frameSize) / p.frameStep + 1) : 0;
+  const int n = p.nfft / 2;
+  const double Tsamp = (double)p.fsSec / (double)(2 * n);
+  float lastPitch = 0.f, lastlastPitch = 0.f, glMeanPitch = 0.f, pitchEnv = 0.f;
+  int onsFlag = 0;
+  const double maxPitch = p.maxPitch;
+  for (int t = 0; t < T; t++) {
+    const PitchRaw r = p.raw[p.statOff[u] + t];
+    float *dst = p.stat + (p.statOff[u] + t) * (long long)p.statStride + p.outCol;
+    int k = 0;
+    if (p.voiceProb) dst[k++] = (float)r.voicing;
+    if (p.HNR) dst[k++] = r.hnr;
+    if (p.HNRdB) dst[k++] = r.hnrDB;
+    if (p.linHNR) dst[k++] = r.hnrLin;
+    if (p.F0 || p.F0env || p.voiceQual || p.F0raw) {
+      int maxIdx = r.maxIdx;
+      const float invT = __fdiv_rn(1.0f, __fmul_rn((float)maxIdx, (float)Tsamp));
+      float vq = __fmul_rn(__fsub_rn((float)maxPitch, (float)fabs((r.acfZcr * maxPitch) - (double)invT)), (float)r.voicing);
+      if (maxIdx == 0) vq = 0.0f;
+      if (p.voiceQual) dst[k++] = vq;
+      float pitch = 0.0f, rawF0 = 0.0f;
+      if (maxIdx > 0) { pitch = invT; rawF0 = pitch; }
+      if (r.voicing < p.voicingCutoff) { maxIdx = 0; pitch = 0.0f; }
+      if ((lastPitch == 0.0f) && (pitch > 0.0f)) onsFlag = 1;
+      if ((lastPitch > 0.0f) && (pitch == 0.0f) && (onsFlag == 0)) onsFlag = -1;
+      if ((lastPitch > 0.0f) && (pitch > 0.0f)) onsFlag = 0;
+      if ((lastPitch == 0.0f) && (pitch == 0.0f)) onsFlag = 0;
+      if ((pitch == 0.0f) && (onsFlag == 1)) lastPitch = 0.0f;
+      const float oPitch = pitch;
+      const float tol = 0.4f;
+      float alpha = 0.3f;
+      if (pitch > 0.0f) {
+        if (glMeanPitch == 0.0f) glMeanPitch = pitch;
+        if (!((pitch < __fmul_rn(__fadd_rn(1.0f, tol), glMeanPitch)) && (pitch > __fmul_rn(__fsub_rn(1.0f, tol), glMeanPitch)))) {
+          pitch = glMeanPitch;
+          alpha = __fdiv_rn(alpha, 3.0f);
+        }
+        if (onsFlag && (lastPitch > pitch)) lastPitch = __fmul_rn(lastPitch, 0.85f);
+      }
+      if ((pitch > 0.0f) && (onsFlag == -1)) lastPitch = pitch;
+      if (oPitch > 0.0f) glMeanPitch = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, alpha), glMeanPitch), __fmul_rn(alpha, oPitch));
+      float out;
+      if ((lastlastPitch != 0.0f) && (lastPitch != 0.0f)) out = __fmul_rn(0.5f, __fadd_rn(lastlastPitch, lastPitch));
+      else out = lastPitch;
+      if (p.F0) dst[k++] = out;
+      if (p.F0raw) dst[k++] = rawF0;
+      lastlastPitch = lastPitch;
+      lastPitch = pitch;
+      if (p.F0env) {
+        if (out > 0.0f) pitchEnv = __fadd_rn(__fmul_rn(0.75f, pitchEnv), __fmul_rn(0.25f, out));
+        dst[k++] = pitchEnv;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 int lld_tile_frames(int nfft) { return nfft == 2048 ? 16 : 32; }
@@ -1013,6 +1214,37 @@ cudaError_t launch_post(const PostParams &p, cudaStream_t st)
   cudaError_t e = cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   post_kernel<<<p.nTiles, kPostThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+bool acf_pitch_supported_fft(int nfft) { return nfft == 512 || nfft == 1024; }
+
+template <int N, int F, int NT>
+static cudaError_t launch_acf_t(const AcfPitchParams &p, cudaStream_t st)
+{
+  const size_t smem = (size_t)N * F * 8 + (size_t)p.twCount * 8 + 16;
+  auto kern = acf_pitch_kernel<N, F, NT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<p.nTiles * (p.F / F), NT, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_acf_pitch(const AcfPitchParams &p, cudaStream_t st)
+{
+  if (p.nTiles <= 0) return cudaSuccess;
+  switch (p.nfft) {
+    case 512:  return launch_acf_t<512, 32, 512>(p, st);
+    case 1024: return launch_acf_t<1024, 16, 512>(p, st);
+    default:   return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_pitch_smooth(const AcfPitchParams &p, int u0, int u1, cudaStream_t st)
+{
+  if (u1 <= u0) return cudaSuccess;
+  const int bs = 64;
+  pitch_smooth_kernel<<<(u1 - u0 + bs - 1) / bs, bs, 0, st>>>(p, u0, u1);
   return cudaGetLastError();
 }
 

@@ -142,6 +142,28 @@ struct TimeOpParams {            // cEnergy / cMZcr on the framer or windower le
   int zZcr, zMcr, zAmax, zMaxmin, zDc;
 };
 
+// cAcf (ACF) + cAcf (cepstrum) + cPitchACF: per-frame part (one CTA per tile, batched complex FFT of
+// size nfft over the symmetric power / log spectrum) and the per-utterance smoothing pass
+struct PitchRaw { double voicing, acfZcr; int maxIdx; float hnr, hnrDB, hnrLin; };
+struct AcfPitchParams {
+  const float *mag;              // tile-major magnitude level [tile][nSrc][F]
+  const OpTile *tiles; int nTiles; int F;
+  int nfft, nSrc;
+  const long long *statOff, *uttOff;
+  PitchRaw *raw;                 // [static rows]
+  const float2 *twiddles; int twOff[4]; int twCount;
+  int acfUsePower, cepUsePower, absCepstrum, normOutput;
+  double maxPitch, voicingCutoff;
+  float fsSec;
+  int voiceProb, voiceQual, HNR, HNRdB, linHNR, F0, F0raw, F0env;
+  // smoothing pass
+  float *stat; int statStride, outCol;
+  int frameSize, frameStep, nUtt;
+};
+cudaError_t launch_acf_pitch(const AcfPitchParams &p, cudaStream_t st);     // per-frame analysis -> raw
+cudaError_t launch_pitch_smooth(const AcfPitchParams &p, int u0, int u1, cudaStream_t st);   // raw -> static columns
+bool acf_pitch_supported_fft(int nfft);
+
 cudaError_t launch_spectral(const SpectralParams &p, cudaStream_t st);
 cudaError_t launch_energy(const TimeOpParams &p, cudaStream_t st);
 cudaError_t launch_mzcr(const TimeOpParams &p, cudaStream_t st);

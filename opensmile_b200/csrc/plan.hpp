@@ -43,7 +43,7 @@ struct FrontEnd {
   bool zeroPadSymmetric = false;   // phase only; magnitude consumers are unaffected
 };
 
-enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR };
+enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF };
 
 struct MfccOp {
   int melIdx = 0;
@@ -93,6 +93,15 @@ struct EnergyOp {
   int nOut = 0;
 };
 
+// cAcf (ACF) + cAcf (cepstrum) -> cPitchACF (dspcore/acf.cpp, lldcore/pitchACF.cpp)
+struct PitchAcfOp {
+  bool acfUsePower = true, cepUsePower = false, absCepstrum = false, normOutput = true;
+  double maxPitch = 500, voicingCutoff = 0.55;
+  float fsSec = 0.f;
+  bool voiceProb = true, voiceQual = false, HNR = false, HNRdB = false, linHNR = false, F0 = false, F0raw = false, F0env = false;
+  int nOut = 0;
+};
+
 struct MzcrOp { bool zcr = true, mcr = true, amax = true, maxmin = true, dc = false; int nOut = 0; };
 
 // one field of a level: `n` elements named name (n == 1) or name[i + arrNameOffset]
@@ -109,6 +118,7 @@ struct StaticOp {
   SpectralOp spectral;
   EnergyOp energy;
   MzcrOp mzcr;
+  PitchAcfOp pitch;
 };
 
 // temporal stage applied to a static column range (cWindowProcessor family)

@@ -70,6 +70,39 @@ class MZcr(C.Structure):
     _fields_ = [("zcr", C.c_int), ("mcr", C.c_int), ("amax", C.c_int), ("maxmin", C.c_int), ("dc", C.c_int)]
 
 
+class PitchAcf(C.Structure):
+    _fields_ = [("acfUsePower", C.c_int), ("cepUsePower", C.c_int), ("absCepstrum", C.c_int),
+                ("acfCepsNormOutput", C.c_int), ("maxPitch", C.c_double),
+                ("voiceProb", C.c_int), ("voiceQual", C.c_int), ("HNR", C.c_int), ("HNRdB", C.c_int),
+                ("linHNR", C.c_int), ("F0", C.c_int), ("F0raw", C.c_int), ("F0env", C.c_int),
+                ("voicingCutoff", C.c_double)]
+
+
+def pitchacf_cfg(**kw):
+    """cAcf / cPitchACF defaults + overrides."""
+    pc = PitchAcf(1, 0, 0, 1, 500.0, 1, 0, 0, 0, 0, 0, 0, 0, 0.55)
+    for k, v in kw.items():
+        assert hasattr(pc, k), k
+        setattr(pc, k, v)
+    return pc
+
+
+def pitchacf(pcm, fe, cfg, n_chan=1, taps=False):
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nS = pcm.size // n_chan
+    N, H, nfft, T = geometry(fe, nS)
+    L = lib()
+    L.osm_or_pitchacf.restype = C.c_long
+    K = L.osm_or_pitchacf_num_out(C.byref(cfg))
+    out = np.zeros((max(T, 0), K), np.float32)
+    ta = np.zeros((max(T, 0), nfft // 2), np.float32) if taps else None
+    tc = np.zeros((max(T, 0), nfft // 2), np.float32) if taps else None
+    r = L.osm_or_pitchacf(C.byref(fe), C.byref(cfg), pcm.ctypes.data_as(C.POINTER(C.c_int16)), C.c_long(nS),
+                          C.c_int(n_chan), _fp(out), _fp(ta), _fp(tc))
+    assert r == max(T, 0)
+    return (out, ta, tc) if taps else out
+
+
 def spectral_cfg(bands=(), slopes=(), rolloff=(), **kw):
     """cSpectral defaults + overrides."""
     sp = Spectral()

@@ -1167,3 +1167,185 @@ long osm_or_spectral(const osm_or_frontend *fe, const osm_or_spectral_cfg *sp,
   free(c.frq); free(c.prev); free(c.sharpW);
   return T;
 }
+
+
+/* ------------------------------------------------------------------ a-10 cAcf + cPitchACF */
+
+int osm_or_pitchacf_num_out(const osm_or_pitchacf_cfg *pc)
+{
+  return (pc->voiceProb ? 1 : 0) + (pc->HNR ? 1 : 0) + (pc->HNRdB ? 1 : 0) + (pc->linHNR ? 1 : 0) +
+         (pc->voiceQual ? 1 : 0) + (pc->F0 ? 1 : 0) + (pc->F0raw ? 1 : 0) + (pc->F0env ? 1 : 0);
+}
+
+typedef struct {
+  const osm_or_pitchacf_cfg *pc;
+  long Nsrc, N;             /* magnitude bins, FFT size */
+  double *costab;           /* cos(2 pi i / N) */
+  float *acf, *cep;         /* N/2 each */
+  float fsSec;              /* (float) frameSizeSec of the acf level (pitchACF.cpp:107-110) */
+  float lastPitch, lastlastPitch, glMeanPitch, pitchEnv;
+  int onsFlag;
+  float *tap_acf, *tap_cep; long t;
+} pacf_ctx;
+
+/* dspcore/acf.cpp:250-345 (non-inverse): inverse rdft of the (power / log) spectrum.
+ * Ooura's rdft(n,-1,a): x[j] = (R0 + R_{n/2} (-1)^j)/2 + sum_{k=1}^{n/2-1} R_k cos(2 pi j k/n)
+ * (dspcore/fftsg.c:104-122; the imaginary parts are zero here). */
+static void acf_level(const pacf_ctx *c, const float *src, int usePower, int cepstrum, int absCeps, float *dst)
+{
+  long Nsrc = c->Nsrc, N = c->N, Ndst = Nsrc - 1;    /* symmetricData=1: nOutEl = nEl - 1 (acf.cpp:123-128) */
+  float *r = (float *)malloc(sizeof(float) * Nsrc);
+  for (long k = 0; k < Nsrc; k++) {
+    float v = usePower ? src[k] * src[k] : src[k];    /* :253-261 */
+    if (cepstrum) v = (v > 0.0) ? (float)log(v + 1.0) : 0.0f;   /* :289-305 */
+    r[k] = v;
+  }
+  for (long j = 0; j < Ndst; j++) {
+    double x = ((double)r[0] + (double)r[N / 2] * ((j & 1) ? -1.0 : 1.0)) / 2.0;
+    for (long k = 1; k < N / 2; k++) x += (double)r[k] * c->costab[(j * k) % N];
+    float d = (float)x;
+    if (c->pc->acfCepsNormOutput) d = d / (float)Nsrc;  /* :321-325 */
+    if (cepstrum) { if (absCeps) d = fabsf(d); }         /* :327-341 */
+    else d = fabsf(d);                                   /* :342-344 */
+    dst[j] = d;
+  }
+  free(r);
+}
+
+/* lldcore/pitchACF.cpp:249-284 */
+static double voicing_prob(const float *a, int n, int skip, double *Zcr)
+{
+  int zcr = 0, mcr = 0;
+  double mean, max;
+  max = a[n - 1];
+  mean = a[skip];
+  for (int i = 1; i < n; i++) {
+    if (a[i - 1] * a[i] < 0) zcr++;
+    if (i >= skip) {
+      if ((a[i] > max) && (a[i - 1] < a[i])) max = a[i];
+      mean += a[i];
+    }
+  }
+  mean /= (double)(n - skip + 1);
+  for (int i = 1; i < n; i++) if ((a[i - 1] - mean) * (a[i] - mean) < 0) mcr++;
+  if (mcr > zcr) *Zcr = (double)mcr / (double)n; else *Zcr = (double)zcr / (double)n;
+  if (a[0] > 0) return max / a[0];
+  return 0.0;
+}
+
+/* lldcore/pitchACF.cpp:286-310 */
+static long pitch_peak(const float *a, long n, long skip)
+{
+  double max, buf, sum = 0.0;
+  max = a[n - 1];
+  for (int i = (int)n - 1; i >= 0; i--) {
+    buf = a[i];
+    sum += fabs(buf);
+    if (i >= skip) if (buf > max) max = buf;
+  }
+  sum /= n;
+  for (int i = (int)skip + 1; i < n - 1; i++)
+    if (a[i] > (max + sum) * 0.6)
+      if ((a[i - 1] < a[i]) && (a[i] > a[i + 1])) return i;
+  return 0;
+}
+
+/* lldcore/pitchACF.cpp:137-247 */
+static void pitchacf_frame(void *vctx, const float *mag, long nb, float *dst)
+{
+  pacf_ctx *c = (pacf_ctx *)vctx;
+  const osm_or_pitchacf_cfg *pc = c->pc;
+  (void)nb;
+  long N = c->Nsrc - 1;                       /* length of each cAcf level */
+  acf_level(c, mag, pc->acfUsePower, 0, 0, c->acf);
+  acf_level(c, mag, pc->cepUsePower, 1, pc->absCepstrum, c->cep);
+  if (c->tap_acf) memcpy(c->tap_acf + c->t * N, c->acf, sizeof(float) * N);
+  if (c->tap_cep) memcpy(c->tap_cep + c->t * N, c->cep, sizeof(float) * N);
+  c->t++;
+  const float *src = c->acf;                  /* the reader concatenates [acf ; cepstrum], Nsrc = 2N */
+  long NsrcCat = 2 * N;
+  double Nd = (double)NsrcCat;
+  double Tsamp = c->fsSec / Nd;
+  double maxPitch = pc->maxPitch < 0.0 ? 0.0 : pc->maxPitch;
+  double voicingCutoff = pc->voicingCutoff > 1.0 ? 1.0 : (pc->voicingCutoff < 0.0 ? 0.0 : pc->voicingCutoff);
+  int preskip = (maxPitch <= 0.0) ? 0 : (int)(1.0 / (maxPitch * Tsamp));
+  double acfZcr = 0.0;
+  double voicing = voicing_prob(src, (int)N, preskip, &acfZcr);
+  long maxIdx = pitch_peak(c->cep, N, preskip + 1);
+  double hnr = 0.0, hnrDB = 0.0, hnrLin = 0.0;
+  if (pc->HNR) {                              /* :312-326 */
+    double buf = ((src[0] - src[maxIdx]) == 0.0) ? 100000000000000000000.0 : src[maxIdx] / (src[0] - src[maxIdx]);
+    hnr = (buf > 0.00000000001) ? 10.0 * log(buf) : 10.0 * log(0.00000000001);
+  }
+  if (pc->HNRdB) {                            /* :329-343 */
+    double buf = src[0] - src[maxIdx];
+    buf = (buf == 0.0) ? 10e10 : src[maxIdx] / buf;
+    hnrDB = (buf <= 10e-10) ? -100.0 : ((buf >= 10e10) ? +100.0 : 10.0 * log(buf) / log(10.0));
+  }
+  if (pc->linHNR) {                           /* :346-360 */
+    double buf = src[0] - src[maxIdx];
+    buf = (buf == 0.0) ? 10e3 : src[maxIdx] / buf;
+    hnrLin = (buf <= 10e-3) ? 10e-3 : ((buf >= 10e3) ? 10e3 : buf);
+  }
+  int n = 0;
+  if (pc->voiceProb) dst[n++] = (float)voicing;
+  if (pc->HNR) dst[n++] = (float)hnr;
+  if (pc->HNRdB) dst[n++] = (float)hnrDB;
+  if (pc->linHNR) dst[n++] = (float)hnrLin;
+  if (pc->F0 || pc->F0env || pc->voiceQual || pc->F0raw) {   /* :181-245 */
+    float vq = ((float)maxPitch - (float)fabs((acfZcr * maxPitch) - ((float)1.0 / ((float)(maxIdx) * (float)Tsamp)))) * (float)voicing;
+    if (maxIdx == 0.0) vq = 0.0;
+    if (pc->voiceQual) dst[n++] = vq;
+    float pitch = 0.0f, rawF0 = 0.0f;
+    if (maxIdx > 0) { pitch = (float)1.0 / ((float)(maxIdx) * (float)Tsamp); rawF0 = pitch; }
+    if (voicing < voicingCutoff) { maxIdx = 0; pitch = 0.0; }
+    if ((c->lastPitch == 0.0) && (pitch > 0.0)) c->onsFlag = 1;
+    if ((c->lastPitch > 0.0) && (pitch == 0.0) && (c->onsFlag == 0)) c->onsFlag = -1;
+    if ((c->lastPitch > 0.0) && (pitch > 0.0)) c->onsFlag = 0;
+    if ((c->lastPitch == 0.0) && (pitch == 0.0)) c->onsFlag = 0;
+    if ((pitch == 0.0) && (c->onsFlag == 1)) c->lastPitch = 0.0;
+    float oPitch = pitch, tol = (float)0.4, alpha = (float)0.3;
+    if (pitch > 0.0) {
+      if (c->glMeanPitch == 0.0) c->glMeanPitch = pitch;
+      if (!((pitch < ((float)1.0 + tol) * c->glMeanPitch) && (pitch > ((float)1.0 - tol) * c->glMeanPitch))) {
+        pitch = c->glMeanPitch;
+        alpha /= (float)3.0;
+      }
+      if (c->onsFlag && (c->lastPitch > pitch)) c->lastPitch *= (float)0.85;
+    }
+    if ((pitch > 0.0) && (c->onsFlag == -1)) c->lastPitch = pitch;
+    if (oPitch > (float)0.0) c->glMeanPitch = ((float)1.0 - alpha) * c->glMeanPitch + alpha * oPitch;
+    float out;
+    if ((c->lastlastPitch != (float)0.0) && (c->lastPitch != 0.0)) out = (float)0.5 * (c->lastlastPitch + c->lastPitch);
+    else out = c->lastPitch;
+    if (pc->F0) dst[n++] = out;
+    if (pc->F0raw) dst[n++] = rawF0;
+    c->lastlastPitch = c->lastPitch;
+    c->lastPitch = pitch;
+    if (pc->F0env) {
+      if (out > 0.0) c->pitchEnv = (float)0.75 * c->pitchEnv + (float)0.25 * out;
+      dst[n++] = c->pitchEnv;
+    }
+  }
+}
+
+long osm_or_pitchacf(const osm_or_frontend *fe, const osm_or_pitchacf_cfg *pc,
+                     const int16_t *pcm, long L, int n_chan, float *out, float *tap_acf, float *tap_cep)
+{
+  long N0 = osm_or_frame_size_samples(fe), H = osm_or_frame_step_samples(fe);
+  long nfft = osm_or_fft_size(N0), Nsrc = nfft / 2 + 1;
+  long T = osm_or_num_frames(L, N0, H);
+  if (T <= 0) return 0;
+  pacf_ctx c; memset(&c, 0, sizeof c);
+  c.pc = pc; c.Nsrc = Nsrc; c.N = nfft;
+  c.costab = (double *)malloc(sizeof(double) * nfft);
+  for (long i = 0; i < nfft; i++) c.costab[i] = cos(2.0 * M_PI * (double)i / (double)nfft);
+  c.acf = (float *)malloc(sizeof(float) * Nsrc);
+  c.cep = (float *)malloc(sizeof(float) * Nsrc);
+  c.fsSec = (float)osm_or_fft_frame_size_sec(fe);      /* cAcf keeps the level's frameSizeSec */
+  c.tap_acf = tap_acf; c.tap_cep = tap_cep;
+  int K = osm_or_pitchacf_num_out(pc);
+  run_frames(fe, pcm, L, n_chan, pitchacf_frame, &c, K, out, NULL);
+  free(c.costab); free(c.acf); free(c.cep);
+  return T;
+}

@@ -92,6 +92,16 @@ typedef struct {            /* cEnergy (lldcore/energy.cpp) */
 
 typedef struct { int zcr, mcr, amax, maxmin, dc; } osm_or_mzcr_cfg;   /* cMZcr (lldcore/mzcr.cpp) */
 
+typedef struct {            /* cAcf x2 + cPitchACF (dspcore/acf.cpp, lldcore/pitchACF.cpp) */
+  int acfUsePower;          /* [acf] usePower (1) */
+  int cepUsePower;          /* [cep] usePower (0 when cepstrum=1 and not set) */
+  int absCepstrum;          /* [cep] absCepstrum (0) */
+  int acfCepsNormOutput;    /* 1 */
+  double maxPitch;          /* 500 */
+  int voiceProb, voiceQual, HNR, HNRdB, linHNR, F0, F0raw, F0env;
+  double voicingCutoff;     /* 0.55 */
+} osm_or_pitchacf_cfg;
+
 /* ---- geometry (integer work, must be bit exact) ---- */
 long osm_or_frame_size_samples(const osm_or_frontend *fe);
 long osm_or_frame_step_samples(const osm_or_frontend *fe);
@@ -130,6 +140,12 @@ long osm_or_spectral(const osm_or_frontend *fe, const osm_or_spectral_cfg *sp,
 int  osm_or_energy_num_out(const osm_or_energy_cfg *en);
 long osm_or_energy(const osm_or_frontend *fe, const osm_or_energy_cfg *en, int windowed,
                    const int16_t *pcm, long n_samples, int n_chan, float *out);
+int  osm_or_pitchacf_num_out(const osm_or_pitchacf_cfg *pc);
+/* fftmag -> cAcf (ACF) + cAcf (cepstrum) -> cPitchACF, including its per-utterance smoothing
+ * state.  tap_acf / tap_cep (optional): [T x nfft/2] dumps of the two cAcf levels. */
+long osm_or_pitchacf(const osm_or_frontend *fe, const osm_or_pitchacf_cfg *pc,
+                     const int16_t *pcm, long n_samples, int n_chan, float *out,
+                     float *tap_acf, float *tap_cep);
 int  osm_or_mzcr_num_out(const osm_or_mzcr_cfg *mz);
 long osm_or_mzcr(const osm_or_frontend *fe, const osm_or_mzcr_cfg *mz, int windowed,
                  const int16_t *pcm, long n_samples, int n_chan, float *out);

@@ -304,3 +304,39 @@ def test_energy_zcr_bit_exact_and_multi_stream_concat():
         got = out[fo[u]:fo[u + 1]]
         assert np.array_equal(got, ref), (u, np.abs(got - ref).max(axis=0))
     p.close()
+
+
+def test_acf_pitchacf_vs_oracle():
+    """cAcf (ACF) + cAcf (cepstrum) -> cPitchACF (config/prosody/prosodyAcf.conf shape): per-frame
+    voicing / HNR and the per-utterance F0 smoothing state machine.  F0 candidates are lags
+    (integers): the F0 / F0raw / F0env columns must match the oracle exactly unless a peak decision
+    flips, which is counted and bounded."""
+    from opensmile_b200 import comp, components_frontend
+    for fs, sr in ((0.050, 16000), (0.025, 16000)):
+        utts = [voiced_pcm(n, sr, seed=950 + i) for i, n in enumerate([32000, 900, 12000, 799])]
+        pcm, off = pack_utterances(utts)
+        cs = components_frontend(float(sr), fs, win="gau", sigma=0.4, zero_pad_symmetric=0) + [
+            comp("cAcf", "acf", "mag", "acf"),
+            comp("cAcf", "cep", "mag", "cepstrum", cepstrum=1, usePower=0),
+            comp("cPitchACF", "pitch", "acf;cepstrum", "pitch", maxPitch=500.0, voiceProb=1, voiceQual=1, HNR=1, HNRdB=1,
+                 linHNR=1, F0=1, F0raw=1, F0env=1, voicingCutoff=0.55)]
+        p = Plan(cs, "pitch", device=0)
+        assert p.element_names == ["voiceProb", "HNR", "HNRdBacf", "linearHNRacf", "voiceQual", "F0", "F0raw", "F0env"]
+        out = p.run_host(pcm, off)
+        fo = p.frame_offsets(off)
+        fe = oracle.frontend(float(sr), fs, 0.010, "gau", sigma=0.4, zero_pad_symmetric=0)
+        cfg = oracle.pitchacf_cfg(voiceProb=1, voiceQual=1, HNR=1, HNRdB=1, linHNR=1, F0=1, F0raw=1, F0env=1)
+        for u, x in enumerate(utts):
+            ref = oracle.pitchacf(x, fe, cfg)
+            got = out[fo[u]:fo[u + 1]]
+            assert got.shape == ref.shape
+            if not ref.shape[0]:
+                continue
+            flips = int((got[:, 6] != ref[:, 6]).sum())            # F0raw = 1/(lag*Ts): differs only if the peak lag flips
+            assert flips <= max(1, ref.shape[0] // 100), flips
+            if flips == 0:
+                assert np.array_equal(got[:, 5:8], ref[:, 5:8])
+                for c in range(5):
+                    scale = max(float(np.abs(ref[:, c]).max()), 1e-6)
+                    assert float(np.abs(got[:, c] - ref[:, c]).max()) <= 1e-4 * scale, c
+        p.close()
