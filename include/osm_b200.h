@@ -192,6 +192,11 @@ typedef struct { int32_t smaWin; int32_t noZeroSma; } osm_b200_contoursmoother; 
 
 typedef struct { int32_t operation; } osm_b200_vectoroperation; /* 0 = ll1 (L1 norm / sum) */
 
+/* cVectorConcat: the cVectorProcessor field selection (src/core/vectorProcessor.cpp:37-39,196-243).
+ * processArrayFields = 1 passes array fields only (single-element fields are dropped unless
+ * includeSingleElementFields = 1); processArrayFields = 0 passes the whole frame, field names kept. */
+typedef struct { int32_t processArrayFields, includeSingleElementFields; } osm_b200_vectorconcat; /* 1, 0 */
+
 /* one `[name:cType]` section */
 typedef struct {
   int32_t type;                                  /* osm_b200_component_type */
@@ -221,6 +226,7 @@ typedef struct {
     osm_b200_deltaregression deltaregression;
     osm_b200_contoursmoother contoursmoother;
     osm_b200_vectoroperation vectoroperation;
+    osm_b200_vectorconcat vectorconcat;
   } u;
 } osm_b200_component;
 

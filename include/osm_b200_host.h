@@ -1,0 +1,88 @@
+/*
+ * osm_b200_host.h -- host-side front end of libosm_b200.so: reads the reference's own .conf
+ * files, resolves the LLD sub-graph into an osm_b200_plan (include/osm_b200.h) and moves
+ * utterances between WAV files / PCM buffers and HTK / CSV files / row buffers.
+ *
+ * It mirrors, for the LLD path only, what SMILExtract / SMILEapi do around the component graph
+ * (reference: progsrc/smilextract/SMILExtract.cpp:42-174, progsrc/include/smileapi/SMILEapi.h):
+ *
+ *   osm_b200_session_open          ~ smile_new + smile_initialize(configFile, options...)
+ *                                    (cConfigManager: ini sections, \{include}, \cm[opt(short){dflt}:help],
+ *                                     src/core/configManager.cpp:1632-1645,1747-2146; unknown fields are an
+ *                                     error like CONF_PARSER_ERR, :2599)
+ *   osm_b200_session_extract_files ~ one SMILExtract run per input file (-I wav -O htk -csvoutput csv),
+ *                                    all files of the call batched through ONE plan run
+ *   osm_b200_session_extract_pcm   ~ smile_extaudiosource_write_data + smile_run + cExternalSink rows
+ *   osm_b200_session_num_elements / element_name ~ smile_extsink_get_num_elements / _get_element_name
+ *
+ * Component types understood in a .conf: the LLD components of include/osm_b200.h plus the host
+ * edges cDataMemory, cWaveSource / cExternalAudioSource, cHtkSink, cCsvSink, cArffSink (parsed,
+ * ARFF output not written) and cExternalSink.  Anything else on the path to the sink's level
+ * makes session_open fail with OSM_B200_ERR_UNSUPPORTED; there is no CPU fallback.
+ */
+#ifndef OSM_B200_HOST_H
+#define OSM_B200_HOST_H
+
+#include "osm_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct osm_b200_session osm_b200_session;
+
+/* conf_path: an openSMILE configuration file.  opt_names/opt_values: command line options the
+ * config declares through \cm[...] (e.g. "csvoutput" -> "x.csv"; names without the leading '-').
+ * output_level: level to extract, NULL = the level the active file sinks read (normally "lld").
+ * device: CUDA device, < 0 = description only (parsing / validation without a GPU). */
+OSM_B200_API osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts,
+                                                   const char *const *opt_names, const char *const *opt_values,
+                                                   const char *output_level, int32_t device,
+                                                   osm_b200_session **session);
+OSM_B200_API void osm_b200_session_close(osm_b200_session *session);
+
+/* number / names of the elements of the output level for the given input format (compiles the
+ * plan for that format on first use) */
+OSM_B200_API int32_t osm_b200_session_num_elements(osm_b200_session *session, double sample_rate, int32_t n_channels);
+OSM_B200_API const char *osm_b200_session_element_name(osm_b200_session *session, int32_t idx);
+
+/* Extract n WAV files (16-bit PCM) in one batch.  htk_paths / csv_paths may be NULL or hold NULL
+ * entries; files are written in the reference's formats (src/iocore/htkSink.cpp:90-106,183-206,
+ * src/iocore/csvSink.cpp:150-235).  frames_out (optional): rows written per file. */
+OSM_B200_API osm_b200_status osm_b200_session_extract_files(osm_b200_session *session, int32_t n,
+                                                            const char *const *wav_paths,
+                                                            const char *const *htk_paths,
+                                                            const char *const *csv_paths,
+                                                            int64_t *frames_out);
+
+/* Extract from packed PCM (layout of osm_b200_plan_run_host).  frame_offsets_out: n_utt+1 entries;
+ * out: caller buffer of at least max_rows * num_elements floats, or NULL to only get the offsets. */
+OSM_B200_API osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *session, const int16_t *pcm,
+                                                          const int64_t *utt_offsets, int32_t n_utt,
+                                                          double sample_rate, int32_t n_channels,
+                                                          int64_t *frame_offsets_out, float *out, int64_t max_rows);
+
+/* the component list the session resolved (for diagnostics / tests): number of osm_b200_component
+ * entries and a pointer to them (owned by the session, valid until close) */
+OSM_B200_API int32_t osm_b200_session_components(osm_b200_session *session, double sample_rate, int32_t n_channels,
+                                                 const osm_b200_component **comps, const char **output_level);
+
+/* message of the last failed osm_b200_session_* call on this thread (falls back to osm_b200_last_error) */
+OSM_B200_API const char *osm_b200_host_last_error(void);
+
+/* the file writers on their own (rows -> file), 0 on success.  HTK: 12-byte big-endian header
+ * {nSamples, samplePeriod = round(period * 1e7), sampleSize = 4 * n_elements, parmKind} followed by
+ * big-endian float32 rows (src/iocore/htkSink.cpp:90-106,183-206).  CSV: cCsvSink's format --
+ * header "[name;][frameIndex;][frameTime;]<elements>", rows "['<instance>';][<index>;][<%f time>;]<values>"
+ * with integer-valued floats printed as %.0f and the rest as %e, ';' as delimiter
+ * (src/iocore/csvSink.cpp:150-235); instance_name NULL = no name column. */
+OSM_B200_API int32_t osm_b200_write_htk(const char *path, const float *rows, int64_t n_rows, int32_t n_elements,
+                                        double period, int32_t parm_kind);
+OSM_B200_API int32_t osm_b200_write_csv(const char *path, const float *rows, int64_t n_rows, int32_t n_elements,
+                                        const char *const *names, double period, const char *instance_name,
+                                        int32_t frame_index, int32_t frame_time);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -130,6 +130,10 @@ class VectorOperation(C.Structure):
     _fields_ = [("operation", i32)]
 
 
+class VectorConcat(C.Structure):
+    _fields_ = [("processArrayFields", i32), ("includeSingleElementFields", i32)]
+
+
 class _U(C.Union):
     _fields_ = [("wavesource", WaveSource), ("framer", Framer),
                 ("vectorpreemphasis", VectorPreemphasis), ("windower", Windower),
@@ -137,7 +141,7 @@ class _U(C.Union):
                 ("melspec", Melspec), ("mfcc", Mfcc), ("plp", Plp), ("spectral", Spectral),
                 ("energy", Energy), ("mzcr", MZcr), ("acf", Acf), ("pitchacf", PitchACF),
                 ("deltaregression", DeltaRegression), ("contoursmoother", ContourSmoother),
-                ("vectoroperation", VectorOperation)]
+                ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat)]
 
 
 class Component(C.Structure):
@@ -153,7 +157,7 @@ UNION_FIELD = {
     C_MELSPEC: "melspec", C_MFCC: "mfcc", C_PLP: "plp", C_SPECTRAL: "spectral",
     C_ENERGY: "energy", C_MZCR: "mzcr", C_ACF: "acf", C_PITCHACF: "pitchacf",
     C_DELTAREGRESSION: "deltaregression", C_CONTOURSMOOTHER: "contoursmoother",
-    C_VECTOROPERATION: "vectoroperation",
+    C_VECTOROPERATION: "vectoroperation", C_VECTORCONCAT: "vectorconcat",
 }
 
 # every symbol include/osm_b200.h declares (tests assert the library exports all of them)
@@ -166,6 +170,11 @@ EXPORTS = [
     "osm_b200_plan_frame_offsets", "osm_b200_plan_run_device", "osm_b200_plan_run_host",
     "osm_b200_plan_last_launch_count", "osm_b200_plan_last_kernel_ms",
     "osm_b200_plan_last_kernel_times",
+    # include/osm_b200_host.h
+    "osm_b200_session_open", "osm_b200_session_close", "osm_b200_session_num_elements",
+    "osm_b200_session_element_name", "osm_b200_session_extract_files",
+    "osm_b200_session_extract_pcm", "osm_b200_session_components", "osm_b200_host_last_error",
+    "osm_b200_write_htk", "osm_b200_write_csv",
 ]
 
 _lib = None
@@ -210,6 +219,20 @@ def lib():
     L.osm_b200_plan_last_kernel_ms.argtypes = [vp]
     L.osm_b200_plan_last_kernel_ms.restype = C.c_float
     L.osm_b200_plan_last_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    # host front end (include/osm_b200_host.h)
+    cpp = C.POINTER(C.c_char_p)
+    L.osm_b200_session_open.argtypes = [C.c_char_p, i32, cpp, cpp, C.c_char_p, i32, C.POINTER(vp)]
+    L.osm_b200_session_close.argtypes = [vp]
+    L.osm_b200_session_close.restype = None
+    L.osm_b200_session_num_elements.argtypes = [vp, f64, i32]
+    L.osm_b200_session_element_name.argtypes = [vp, i32]
+    L.osm_b200_session_element_name.restype = C.c_char_p
+    L.osm_b200_session_extract_files.argtypes = [vp, i32, cpp, cpp, cpp, i64p]
+    L.osm_b200_session_extract_pcm.argtypes = [vp, vp, i64p, i32, f64, i32, i64p, vp, C.c_int64]
+    L.osm_b200_session_components.argtypes = [vp, f64, i32, C.POINTER(C.POINTER(Component)), cpp]
+    L.osm_b200_host_last_error.restype = C.c_char_p
+    L.osm_b200_write_htk.argtypes = [C.c_char_p, vp, C.c_int64, i32, f64, i32]
+    L.osm_b200_write_csv.argtypes = [C.c_char_p, vp, C.c_int64, i32, cpp, f64, C.c_char_p, i32, i32]
     if L.osm_b200_sizeof_component() != C.sizeof(Component):
         raise RuntimeError("ABI mismatch: sizeof(osm_b200_component) = %d, ctypes mirror = %d"
                            % (L.osm_b200_sizeof_component(), C.sizeof(Component)))

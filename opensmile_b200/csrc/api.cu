@@ -201,6 +201,7 @@ osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
     case OSM_B200_C_PITCHACF: c->u.pitchacf.maxPitch = 500; c->u.pitchacf.voiceProb = 1; c->u.pitchacf.voicingCutoff = 0.55; break;
     case OSM_B200_C_DELTAREGRESSION: c->u.deltaregression.deltawin = 2; c->u.deltaregression.zeroSegBound = 1; break;
     case OSM_B200_C_CONTOURSMOOTHER: c->u.contoursmoother.smaWin = 3; break;
+    case OSM_B200_C_VECTORCONCAT: c->u.vectorconcat.processArrayFields = 1; c->u.vectorconcat.includeSingleElementFields = 0; break;
     default: break;
   }
   return OSM_B200_OK;

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 
 #include "plan.hpp"
@@ -124,15 +125,6 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
   if (nWave != 1) { err = "graph must contain exactly one cWaveSource"; return OSM_B200_ERR_INVALID; }
   if (!outputLevel || !R.prod(outputLevel)) { err = "output level has no writer"; return OSM_B200_ERR_INVALID; }
 
-  // ---- output level: a cVectorConcat of chains, or a single chain ----
-  std::vector<std::string> chainLevels;
-  const osm_b200_component *outc = R.prod(outputLevel);
-  if (outc->type == OSM_B200_C_VECTORCONCAT) {
-    for (int i = 0; i < outc->n_inputs; i++) chainLevels.push_back(outc->reader_dmLevel[i]);
-  } else {
-    chainLevels.push_back(outputLevel);
-  }
-
   auto single_input = [&](const osm_b200_component *c) -> const osm_b200_component * {
     if (!c || c->n_inputs != 1) return nullptr;
     return R.prod(c->reader_dmLevel[0]);
@@ -226,16 +218,58 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
 
   std::map<const osm_b200_component *, int> staticOpOf;   // static producer -> op index
 
-  for (const std::string &lvl : chainLevels) {
-    // walk back through temporal stages
+  // ---- leaves of the output level ----
+  // The output level is a tree: temporal stages (cDeltaRegression / cContourSmoother, one input
+  // level each) and cVectorConcat nodes over static producers.  Temporal stages work element by
+  // element, so stage(concat(a, b)) = concat(stage(a), stage(b)) as long as concat does not
+  // truncate (all inputs equally long); every leaf becomes one output group carrying the stages
+  // between it and the output level.
+  struct Leaf { const osm_b200_component *c; std::vector<const osm_b200_component *> stages; bool arraysOnly; };
+  std::vector<Leaf> leaves;
+  struct ConcatCheck { size_t g0, g1; };          // leaves [g0, g1) sit below a concat that has stages above it
+  std::vector<std::pair<size_t, size_t>> leafGroups;   // leaf -> its groups [first, last)
+  std::vector<ConcatCheck> concatChecks;
+  std::function<osm_b200_status(const std::string &, std::vector<const osm_b200_component *>, int, bool)> expand =
+    [&](const std::string &lvl, std::vector<const osm_b200_component *> above, int depth, bool arraysOnly) -> osm_b200_status {
+    if (depth > 8) { err = "level graph nested too deeply (cycle?)"; return OSM_B200_ERR_INVALID; }
     const osm_b200_component *c = R.prod(lvl.c_str());
     if (!c) { err = "level '" + lvl + "' has no writer"; return OSM_B200_ERR_INVALID; }
     std::vector<const osm_b200_component *> stageComps;
+    // a temporal stage reading several levels (reader.dmLevel = a;b) sees their implicit concat
+    // (core/dataReader.cpp:360-444), i.e. it behaves like stage(cVectorConcat(a, b))
+    bool multi = false;
     while (c && (c->type == OSM_B200_C_DELTAREGRESSION || c->type == OSM_B200_C_CONTOURSMOOTHER)) {
       stageComps.insert(stageComps.begin(), c);
+      if (c->n_inputs > 1) { multi = true; break; }
       c = single_input(c);
     }
-    if (!c) { err = "broken temporal chain below level '" + lvl + "' (temporal stages must read exactly one level)"; return OSM_B200_ERR_UNSUPPORTED; }
+    if (!c) { err = "broken temporal chain below level '" + lvl + "'"; return OSM_B200_ERR_INVALID; }
+    stageComps.insert(stageComps.end(), above.begin(), above.end());
+    if (c->type == OSM_B200_C_VECTORCONCAT || multi) {
+      if (c->n_inputs < 1) { err = "cVectorConcat without inputs"; return OSM_B200_ERR_INVALID; }
+      // a real cVectorConcat is a cVectorProcessor: with processArrayFields=1 it drops single-element
+      // fields unless includeSingleElementFields=1 (core/vectorProcessor.cpp:196-243)
+      if (!multi && c->u.vectorconcat.processArrayFields == 1 && !c->u.vectorconcat.includeSingleElementFields) arraysOnly = true;
+      if (!multi && c->u.vectorconcat.processArrayFields == 2) { err = "cVectorConcat.processArrayFields=2 is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+      const size_t g0 = leaves.size();
+      for (int i = 0; i < c->n_inputs; i++) {
+        osm_b200_status s2 = expand(c->reader_dmLevel[i], stageComps, depth + 1, arraysOnly);
+        if (s2 != OSM_B200_OK) return s2;
+      }
+      if (!stageComps.empty()) concatChecks.push_back({g0, leaves.size()});
+      return OSM_B200_OK;
+    }
+    leaves.push_back(Leaf{c, stageComps, arraysOnly});
+    return OSM_B200_OK;
+  };
+  {
+    osm_b200_status s0 = expand(outputLevel, {}, 0, false);
+    if (s0 != OSM_B200_OK) return s0;
+  }
+
+  for (const Leaf &leaf : leaves) {
+    const osm_b200_component *c = leaf.c;
+    const std::vector<const osm_b200_component *> &stageComps = leaf.stages;
 
     // static feature producer
     int opIdx;
@@ -396,12 +430,8 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       staticOpOf[c] = opIdx;
     }
 
-    // ---- group ----
-    OutGroup g;
-    g.srcCol = d.ops[opIdx].outCol;
-    g.n = d.ops[opIdx].nOut;
-    g.stream = d.ops[opIdx].stream;
-    g.outCol = d.nOut;
+    // ---- groups: one per run of consecutive fields that survive the concat's field selection ----
+    std::vector<Stage> stages;
     std::vector<FieldName> fields = d.ops[opIdx].fields;
     for (const osm_b200_component *s : stageComps) {
       Stage st;
@@ -417,23 +447,58 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         if (p.smaWin < 1 || (p.smaWin & 1) == 0 || p.smaWin > 9) { err = "cContourSmoother.smaWin must be odd, 1..9"; return OSM_B200_ERR_UNSUPPORTED; }
         st = Stage{ST_SMA, (p.smaWin - 1) / 2, p.noZeroSma};
       }
-      g.stages.push_back(st);
+      stages.push_back(st);
       for (auto &f : fields) f.name = name_append_auto(*s, f.name, nullptr);
     }
-    if (g.stages.size() > 3) { err = "more than 3 chained temporal stages"; return OSM_B200_ERR_UNSUPPORTED; }
-    d.nOut += g.n;
-    d.groups.push_back(g);
-    // element names: name (single element fields) or name[idx + arrNameOffset]
-    // (core/dataMemoryLevel.cpp:1158-1169)
+    if (stages.size() > 3) { err = "more than 3 chained temporal stages"; return OSM_B200_ERR_UNSUPPORTED; }
+    const size_t firstGroup = d.groups.size();
+    int col = d.ops[opIdx].outCol;
+    bool open = false;
     for (const auto &f : fields) {
-      if (f.n == 1) { d.names.push_back(f.name); continue; }
-      for (int i = 0; i < f.n; i++) {
-        snprintf(buf, sizeof buf, "%s[%d]", f.name.c_str(), i + f.arrNameOffset);
-        d.names.push_back(buf);
+      const bool keep = !(leaf.arraysOnly && f.n == 1);
+      if (keep) {
+        if (!open) {
+          OutGroup g;
+          g.srcCol = col; g.n = 0; g.stream = d.ops[opIdx].stream; g.outCol = d.nOut; g.stages = stages;
+          d.groups.push_back(g);
+          open = true;
+        }
+        d.groups.back().n += f.n;
+        d.nOut += f.n;
+        // element names: name (single element fields) or name[idx + arrNameOffset]
+        // (core/dataMemoryLevel.cpp:1158-1169)
+        if (f.n == 1) d.names.push_back(f.name);
+        else for (int i = 0; i < f.n; i++) {
+          snprintf(buf, sizeof buf, "%s[%d]", f.name.c_str(), i + f.arrNameOffset);
+          d.names.push_back(buf);
+        }
+      } else {
+        open = false;
       }
+      col += f.n;
     }
+    leafGroups.push_back({firstGroup, d.groups.size()});
   }
-  if (d.ops.empty()) { err = "empty plan"; return OSM_B200_ERR_INVALID; }
+  if (d.ops.empty() || d.groups.empty()) { err = "the output level has no elements (cVectorConcat drops single-element fields unless includeSingleElementFields=1)"; return OSM_B200_ERR_INVALID; }
+  // a concat below temporal stages must not truncate: same frame geometry and the same number of
+  // EOI padding frames on every input (core/dataReader.cpp:375-380 takes the minimum otherwise)
+  for (const ConcatCheck &cc : concatChecks) {
+    auto geom = [&](const OutGroup &g, int &fs, int &fst, int &w) {
+      fs = d.streams[g.stream].fe.frameSize; fst = d.streams[g.stream].fe.frameStep; w = 0;
+      for (const auto &st : g.stages) w += st.win;
+    };
+    int fs0 = -1, fst0 = 0, w0 = 0;
+    for (size_t l = cc.g0; l < cc.g1; l++)
+      for (size_t g = leafGroups[l].first; g < leafGroups[l].second; g++) {
+        int fs, fst, w;
+        geom(d.groups[g], fs, fst, w);
+        if (fs0 < 0) { fs0 = fs; fst0 = fst; w0 = w; }
+        if (fs != fs0 || fst != fst0 || w != w0) {
+          err = "cVectorConcat of unequally long levels below a temporal stage is not supported";
+          return OSM_B200_ERR_UNSUPPORTED;
+        }
+      }
+  }
 
   // ---- execution strategy per stream ----
   // A stream with exactly one band op (MFCC / PLP) and no other spectral consumer evaluates it

@@ -1,0 +1,743 @@
+// front.cpp -- host front end: openSMILE .conf parsing -> osm_b200_component[] -> plan, WAV in,
+// HTK / CSV out (include/osm_b200_host.h).  Pure host C++; all numerics happen in the CUDA plan.
+// Citations relative to /root/reference/src.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/osm_b200_host.h"
+
+namespace {
+
+thread_local std::string g_herr;
+osm_b200_status hfail(osm_b200_status s, const std::string &m) { g_herr = m; return s; }
+
+// ------------------------------------------------------------------------------------------
+// ini-style config reader (core/configManager.cpp:1632-1645 format, :2180-2300 line rules)
+// ------------------------------------------------------------------------------------------
+struct Section {
+  std::string name, type;
+  std::vector<std::pair<std::string, std::string>> kv;   // field -> value, in file order
+  const std::string *get(const std::string &k) const
+  {
+    const std::string *r = nullptr;
+    for (const auto &p : kv) if (p.first == k) r = &p.second;    // last assignment wins
+    return r;
+  }
+};
+
+struct Conf {
+  std::vector<Section> sections;
+  std::vector<std::pair<std::string, std::string>> instances;   // instance name -> type, in order
+  std::map<std::string, std::string> cmOpts;                    // declared \cm options -> value
+};
+
+std::string trim(const std::string &s)
+{
+  size_t a = 0, b = s.size();
+  while (a < b && (s[a] == ' ' || s[a] == '\t' || s[a] == '\r' || s[a] == '\n')) a++;
+  while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\t' || s[b - 1] == '\r' || s[b - 1] == '\n')) b--;
+  return s.substr(a, b - a);
+}
+
+std::string dir_of(const std::string &p)
+{
+  const size_t i = p.find_last_of('/');
+  return i == std::string::npos ? std::string(".") : p.substr(0, i);
+}
+
+// \cm[long(short){default}:description] -> value (configManager.cpp:2012-2070).  The first
+// occurrence declares the option and its default; later \cm[long] references reuse it.
+bool substitute_cm(std::string &value, Conf &cf, const std::map<std::string, std::string> &given, std::string &err)
+{
+  for (;;) {
+    const size_t a = value.find("\\cm[");
+    if (a == std::string::npos) return true;
+    const size_t b = value.find(']', a);
+    if (b == std::string::npos) { err = "unterminated \\cm[...] in '" + value + "'"; return false; }
+    std::string body = value.substr(a + 4, b - a - 4);
+    const size_t colon = body.find(':');
+    if (colon != std::string::npos) body = body.substr(0, colon);
+    std::string name = body, dflt;
+    bool hasDflt = false;
+    const size_t br = body.find('{');
+    if (br != std::string::npos) {
+      const size_t be = body.find('}', br);
+      dflt = body.substr(br + 1, (be == std::string::npos ? body.size() : be) - br - 1);
+      hasDflt = true;
+      name = body.substr(0, br);
+    }
+    const size_t par = name.find('(');
+    std::string shortName;
+    if (par != std::string::npos) {
+      const size_t pe = name.find(')', par);
+      shortName = name.substr(par + 1, (pe == std::string::npos ? name.size() : pe) - par - 1);
+      name = name.substr(0, par);
+    }
+    name = trim(name);
+    std::string v;
+    auto g = given.find(name);
+    if (g == given.end() && !shortName.empty()) g = given.find(shortName);
+    if (g != given.end()) v = g->second;
+    else if (cf.cmOpts.count(name)) v = cf.cmOpts[name];
+    else if (hasDflt) v = dflt;
+    else { err = "command line option '" + name + "' referenced by the config has no value"; return false; }
+    cf.cmOpts[name] = v;
+    value = value.substr(0, a) + v + value.substr(b + 1);
+  }
+}
+
+bool parse_file(const std::string &path, Conf &cf, const std::map<std::string, std::string> &given,
+                std::string &err, int &cur, int depth = 0)
+{
+  if (depth > 16) { err = "config includes nested too deeply"; return false; }
+  std::ifstream in(path);
+  if (!in) { err = "cannot open config file '" + path + "'"; return false; }
+  std::stringstream ss;
+  ss << in.rdbuf();
+  std::string text = ss.str();
+  // block comments /* ... */
+  for (;;) {
+    const size_t a = text.find("/*");
+    if (a == std::string::npos) break;
+    const size_t b = text.find("*/", a + 2);
+    text.erase(a, (b == std::string::npos ? text.size() : b + 2) - a);
+  }
+  std::istringstream ls(text);
+  std::string line;
+  int lineNr = 0;
+  while (std::getline(ls, line)) {
+    lineNr++;
+    line = trim(line);
+    if (line.empty()) continue;
+    if (line[0] == '%' || line[0] == '#' || line[0] == ';' || (line.size() > 1 && line[0] == '/' && line[1] == '/')) continue;
+    const size_t cc = line.find("//");                         // EOL comments (configManager.cpp:2226-2232)
+    if (cc != std::string::npos) line = trim(line.substr(0, cc));
+    if (line.empty()) continue;
+    if (line.compare(0, 2, "\\{") == 0) {                       // include (configManager.cpp:1757-1791)
+      const size_t e = line.rfind('}');
+      std::string inc = trim(line.substr(2, (e == std::string::npos || e < 2 ? line.size() : e) - 2));
+      if (!substitute_cm(inc, cf, given, err)) return false;
+      std::string full = inc;
+      if (!inc.empty() && inc[0] != '/') full = dir_of(path) + "/" + inc;
+      // an include inside a section continues that section (e.g. arff_targets.conf.inc)
+      if (!parse_file(full, cf, given, err, cur, depth + 1)) {
+        std::string err2;
+        if (!(inc[0] != '/' && parse_file(inc, cf, given, err2, cur, depth + 1))) return false;   // also relative to cwd
+        err.clear();
+      }
+      continue;
+    }
+    if (line[0] == '[') {
+      const size_t e = line.find(']');
+      const std::string head = line.substr(1, (e == std::string::npos ? line.size() : e) - 1);
+      const size_t c = head.find(':');
+      if (c == std::string::npos) { err = path + ":" + std::to_string(lineNr) + ": section header without ':type'"; return false; }
+      cf.sections.push_back(Section{trim(head.substr(0, c)), trim(head.substr(c + 1)), {}});
+      cur = (int)cf.sections.size() - 1;
+      continue;
+    }
+    if (cur < 0) { err = path + ":" + std::to_string(lineNr) + ": assignment outside of a section"; return false; }
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos) { err = path + ":" + std::to_string(lineNr) + ": missing '='"; return false; }
+    std::string field = trim(line.substr(0, eq)), value = trim(line.substr(eq + 1));
+    Section &sec = cf.sections[cur];
+    if (field.compare(0, sec.name.size() + 1, sec.name + ".") == 0) field = field.substr(sec.name.size() + 1);
+    if (!substitute_cm(value, cf, given, err)) return false;
+    if (sec.type == "cComponentManager") {
+      // instance[NAME].type = TYPE (core/componentManager.cpp:840-957)
+      if (field.compare(0, 9, "instance[") == 0) {
+        const size_t e = field.find(']');
+        const std::string nm = field.substr(9, e - 9);
+        if (field.find(".type", e) != std::string::npos) cf.instances.push_back({nm, value});
+      }
+      continue;   // nThreads, printLevelStats, ... : runtime options of the reference's tick loop
+    }
+    sec.kv.push_back({field, value});
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// component registry: accepted fields per type (the reference's ConfigType schemas, SURVEY.md
+// Appendix A).  Unknown fields are an error, like CONF_PARSER_ERR (configManager.cpp:2599).
+// ------------------------------------------------------------------------------------------
+const char *kCommonFields[] = {"reader.dmLevel", "writer.dmLevel", "reader.dmInstance", "writer.dmInstance",
+  "reader.forceAsyncMerge", "reader.errorOnFullInputIncomplete", "nameAppend", "copyInputName", "EOIlevel",
+  "processArrayFields", "includeSingleElementFields", "preserveFieldNames", "buffersize", "buffersize_sec",
+  "blocksize", "blocksizeR", "blocksizeW", "blocksize_sec", "blocksizeR_sec", "blocksizeW_sec",
+  "writer.levelconf.isRb", "writer.levelconf.nT", "writer.levelconf.T", "writer.levelconf.lenSec",
+  "writer.levelconf.frameSizeSec", "writer.levelconf.growDyn", "writer.levelconf.noHang", "writer.levelconf.type"};
+
+bool is_common(const std::string &f)
+{
+  for (const char *c : kCommonFields) if (f == c) return true;
+  return false;
+}
+
+double num(const std::string &v) { return atof(v.c_str()); }
+int inum(const std::string &v) { return (int)lround(atof(v.c_str())); }
+
+int win_func(const std::string &s)
+{
+  // cWindower::winFuncToInt (dspcore/windower.cpp:60-80): prefix match, case-insensitive
+  std::string l;
+  for (char c : s) l.push_back((char)tolower(c));
+  if (l.compare(0, 3, "han") == 0) return OSM_B200_WIN_HANNING;
+  if (l.compare(0, 3, "ham") == 0) return OSM_B200_WIN_HAMMING;
+  if (l.compare(0, 3, "rec") == 0) return OSM_B200_WIN_RECTANGLE;
+  if (l.compare(0, 3, "gau") == 0) return OSM_B200_WIN_GAUSS;
+  if (l.compare(0, 3, "sin") == 0 || l.compare(0, 3, "cos") == 0) return OSM_B200_WIN_SINE;
+  if (l.compare(0, 3, "tri") == 0) return OSM_B200_WIN_TRIANGLE;
+  if (l.compare(0, 3, "bar") == 0) return OSM_B200_WIN_BARTLETT;
+  return -1;
+}
+
+bool parse_range(const std::string &v, double &lo, double &hi)   // "250-650" (lldcore/spectral.cpp:142-200)
+{
+  const size_t d = v.find('-', 1);
+  if (d == std::string::npos) return false;
+  lo = (double)strtol(v.substr(0, d).c_str(), nullptr, 10);
+  hi = (double)strtol(v.substr(d + 1).c_str(), nullptr, 10);
+  return true;
+}
+
+struct TypeInfo { const char *name; int type; };
+const TypeInfo kTypes[] = {
+  {"cWaveSource", OSM_B200_C_WAVESOURCE}, {"cExternalAudioSource", OSM_B200_C_WAVESOURCE}, {"cFramer", OSM_B200_C_FRAMER},
+  {"cVectorPreemphasis", OSM_B200_C_VECTORPREEMPHASIS}, {"cWindower", OSM_B200_C_WINDOWER},
+  {"cTransformFFT", OSM_B200_C_TRANSFORMFFT}, {"cFFTmagphase", OSM_B200_C_FFTMAGPHASE}, {"cMelspec", OSM_B200_C_MELSPEC},
+  {"cMfcc", OSM_B200_C_MFCC}, {"cPlp", OSM_B200_C_PLP}, {"cSpectral", OSM_B200_C_SPECTRAL}, {"cEnergy", OSM_B200_C_ENERGY},
+  {"cMZcr", OSM_B200_C_MZCR}, {"cAcf", OSM_B200_C_ACF}, {"cPitchACF", OSM_B200_C_PITCHACF},
+  {"cDeltaRegression", OSM_B200_C_DELTAREGRESSION}, {"cContourSmoother", OSM_B200_C_CONTOURSMOOTHER},
+  {"cVectorConcat", OSM_B200_C_VECTORCONCAT}, {"cVectorOperation", OSM_B200_C_VECTOROPERATION}};
+
+int type_of(const std::string &t)
+{
+  for (const auto &ti : kTypes) if (t == ti.name) return ti.type;
+  return -1;
+}
+
+#define SETI(field, member) if (f == field) { member = inum(v); continue; }
+#define SETD(field, member) if (f == field) { member = num(v); continue; }
+
+// one [name:cType] section -> osm_b200_component
+bool to_component(const Section &s, osm_b200_component &c, std::string &err)
+{
+  const int t = type_of(s.type);
+  if (t < 0) { err = "component type '" + s.type + "' (instance '" + s.name + "') is not on the supported LLD path"; return false; }
+  if (osm_b200_component_defaults(t, &c) != OSM_B200_OK) { err = osm_b200_last_error(); return false; }
+  snprintf(c.name, sizeof c.name, "%s", s.name.c_str());
+  bool usePowerSet = false;
+  for (const auto &kv : s.kv) {
+    const std::string &f = kv.first, &v = kv.second;
+    if (f == "reader.dmLevel") {
+      std::stringstream ss(v);
+      std::string lv;
+      c.n_inputs = 0;
+      while (std::getline(ss, lv, ';')) {
+        lv = trim(lv);
+        if (lv.empty()) continue;
+        if (c.n_inputs >= OSM_B200_MAX_INPUTS) { err = "too many input levels for '" + s.name + "'"; return false; }
+        snprintf(c.reader_dmLevel[c.n_inputs++], OSM_B200_NAME_LEN, "%s", lv.c_str());
+      }
+      continue;
+    }
+    if (f == "writer.dmLevel") { snprintf(c.writer_dmLevel, sizeof c.writer_dmLevel, "%s", v.c_str()); continue; }
+    if (f == "nameAppend") { snprintf(c.nameAppend, sizeof c.nameAppend, "%s", v.c_str()); continue; }
+    if (f == "copyInputName") { c.copyInputName = inum(v); continue; }
+    if (t == OSM_B200_C_VECTORCONCAT) {
+      SETI("processArrayFields", c.u.vectorconcat.processArrayFields)
+      SETI("includeSingleElementFields", c.u.vectorconcat.includeSingleElementFields)
+      if (f == "preserveFieldNames") { if (!inum(v)) { err = "cVectorConcat.preserveFieldNames=0 is not supported"; return false; } continue; }
+    }
+    if (is_common(f)) continue;
+    switch (t) {
+      case OSM_B200_C_WAVESOURCE:
+        SETI("monoMixdown", c.u.wavesource.monoMixdown)
+        if (f == "outFieldName") { snprintf(c.u.wavesource.outFieldName, OSM_B200_NAME_LEN, "%s", v.c_str()); continue; }
+        if (f == "filename" || f == "start" || f == "end" || f == "endrel" || f == "startSamples" || f == "endSamples" ||
+            f == "endrelSamples" || f == "noHeader" || f == "properTimestamps" || f == "period" || f == "sampleRate" ||
+            f == "channels" || f == "nBits" || f == "nBPS" || f == "fieldName") continue;
+        break;
+      case OSM_B200_C_FRAMER:
+        SETD("frameSize", c.u.framer.frameSize) SETD("frameStep", c.u.framer.frameStep)
+        SETI("noPostEOIprocessing", c.u.framer.noPostEOIprocessing)
+        if (f == "frameCenterSpecial") { c.u.framer.frameCenterSpecialLeft = (v.compare(0, 2, "le") == 0) ? 1 : 0; continue; }
+        if (f == "frameMode") { if (v != "fixed") { err = "cFramer.frameMode=" + v + " is not supported"; return false; } continue; }
+        if (f == "allowLastFrameIncomplete") { if (inum(v)) { err = "cFramer.allowLastFrameIncomplete=1 is not supported"; return false; } continue; }
+        break;
+      case OSM_B200_C_VECTORPREEMPHASIS:
+        SETD("k", c.u.vectorpreemphasis.k) SETI("de", c.u.vectorpreemphasis.de)
+        break;
+      case OSM_B200_C_WINDOWER:
+        SETD("gain", c.u.windower.gain) SETD("offset", c.u.windower.offset) SETD("sigma", c.u.windower.sigma)
+        if (f == "winFunc") { c.u.windower.winFunc = win_func(v); if (c.u.windower.winFunc < 0) { err = "cWindower.winFunc=" + v + " is not supported"; return false; } continue; }
+        if (f == "xscale" || f == "xshift" || f == "fade" || f == "squareRoot" || f == "alpha") {
+          const double d = num(v);
+          const bool dflt = (f == "xscale" && d == 1.0) || (f == "alpha" && d == 0.16) || ((f == "xshift" || f == "fade" || f == "squareRoot") && d == 0.0);
+          if (!dflt && f != "alpha") { err = "cWindower." + f + " is not supported"; return false; }
+          continue;
+        }
+        break;
+      case OSM_B200_C_TRANSFORMFFT:
+        SETI("inverse", c.u.transformfft.inverse) SETI("zeroPadSymmetric", c.u.transformfft.zeroPadSymmetric)
+        break;
+      case OSM_B200_C_FFTMAGPHASE:
+        SETI("magnitude", c.u.fftmagphase.magnitude) SETI("phase", c.u.fftmagphase.phase) SETI("normalise", c.u.fftmagphase.normalise)
+        SETI("power", c.u.fftmagphase.power) SETI("dBpsd", c.u.fftmagphase.dBpsd)
+        if (f == "inverse" || f == "joinMagphase") { if (inum(v)) { err = "cFFTmagphase." + f + " is not supported"; return false; } continue; }
+        if (f == "dBpnorm" || f == "mindBp") continue;
+        break;
+      case OSM_B200_C_MELSPEC:
+        SETI("nBands", c.u.melspec.nBands) SETD("lofreq", c.u.melspec.lofreq) SETD("hifreq", c.u.melspec.hifreq)
+        SETI("usePower", c.u.melspec.usePower) SETI("htkcompatible", c.u.melspec.htkcompatible)
+        if (f == "specScale") { if (v != "mel") { err = "cMelspec.specScale=" + v + " is not supported"; return false; } continue; }
+        if (f == "bwMethod") { if (v.compare(0, 2, "lr") != 0) { err = "cMelspec.bwMethod=" + v + " is not supported"; return false; } continue; }
+        if (f == "inverse") { if (inum(v)) { err = "cMelspec.inverse is not supported"; return false; } continue; }
+        if (f == "showFbank" || f == "halfBwTarg" || f == "logScaleBase" || f == "firstNote") continue;
+        break;
+      case OSM_B200_C_MFCC:
+        SETI("firstMfcc", c.u.mfcc.firstMfcc) SETI("lastMfcc", c.u.mfcc.lastMfcc) SETD("melfloor", c.u.mfcc.melfloor)
+        SETI("doLog", c.u.mfcc.doLog) SETD("cepLifter", c.u.mfcc.cepLifter) SETI("htkcompatible", c.u.mfcc.htkcompatible)
+        if (f == "nMfcc") { if (!s.get("lastMfcc")) c.u.mfcc.lastMfcc = -1000 - inum(v); continue; }   // resolved below
+        if (f == "inverse") { if (inum(v)) { err = "cMfcc.inverse is not supported"; return false; } continue; }
+        if (f == "nBands" || f == "printDctBaseFunctions") continue;
+        break;
+      case OSM_B200_C_PLP:
+        SETI("lpOrder", c.u.plp.lpOrder) SETI("nCeps", c.u.plp.nCeps) SETI("firstCC", c.u.plp.firstCC) SETI("lastCC", c.u.plp.lastCC)
+        SETI("doLog", c.u.plp.doLog) SETI("doAud", c.u.plp.doAud) SETI("RASTA", c.u.plp.RASTA) SETI("newRASTA", c.u.plp.newRASTA)
+        SETI("doInvLog", c.u.plp.doInvLog) SETI("doIDFT", c.u.plp.doIDFT) SETI("doLP", c.u.plp.doLP) SETI("doLpToCeps", c.u.plp.doLpToCeps)
+        SETD("rastaUpperCutoff", c.u.plp.rastaUpperCutoff) SETD("rastaLowerCutoff", c.u.plp.rastaLowerCutoff)
+        SETD("cepLifter", c.u.plp.cepLifter) SETD("compression", c.u.plp.compression) SETD("melfloor", c.u.plp.melfloor)
+        SETI("htkcompatible", c.u.plp.htkcompatible)
+        break;
+      case OSM_B200_C_SPECTRAL: {
+        auto &sp = c.u.spectral;
+        SETI("squareInput", sp.squareInput) SETI("flux", sp.flux) SETI("centroid", sp.centroid) SETI("maxPos", sp.maxPos)
+        SETI("minPos", sp.minPos) SETI("entropy", sp.entropy) SETI("standardDeviation", sp.standardDeviation)
+        SETI("variance", sp.variance) SETI("skewness", sp.skewness) SETI("kurtosis", sp.kurtosis) SETI("slope", sp.slope)
+        SETI("alphaRatio", sp.alphaRatio) SETI("hammarbergIndex", sp.hammarbergIndex) SETI("sharpness", sp.sharpness)
+        SETI("harmonicity", sp.harmonicity) SETI("flatness", sp.flatness) SETI("logFlatness", sp.logFlatness)
+        SETI("normBandEnergies", sp.normBandEnergies) SETI("buggyRollOff", sp.buggyRollOff) SETI("oldSlopeScale", sp.oldSlopeScale)
+        SETI("useLogSpectrum", sp.useLogSpectrum) SETD("specFloor", sp.specFloor)
+        if (f == "freqRange") { if (!parse_range(v, sp.freqRangeLo, sp.freqRangeHi)) { err = "cSpectral.freqRange: bad value '" + v + "'"; return false; } continue; }
+        auto arr = [&](const char *base, int &n, double *lo, double *hi) -> int {
+          const std::string b = std::string(base) + "[";
+          if (f.compare(0, b.size(), b) != 0) return 0;
+          const int idx = atoi(f.c_str() + b.size());
+          if (idx < 0 || idx >= OSM_B200_MAX_LIST) return -1;
+          if (hi) { if (!parse_range(v, lo[idx], hi[idx])) return -1; } else lo[idx] = num(v);
+          n = std::max(n, idx + 1);
+          return 1;
+        };
+        int r = arr("bands", sp.nBands, sp.bandLo, sp.bandHi);
+        if (!r) r = arr("slopes", sp.nSlopes, sp.slopeLo, sp.slopeHi);
+        if (!r) r = arr("rollOff", sp.nRollOff, sp.rollOff, nullptr);
+        if (r < 0) { err = "cSpectral: bad array entry '" + f + " = " + v + "'"; return false; }
+        if (r > 0) continue;
+        if (f == "specDiff" || f == "specPosDiff" || f == "fluxCentroid" || f == "fluxAtFluxCentroid" || f == "tonality") {
+          if (inum(v)) { err = "cSpectral." + f + " is not supported"; return false; }
+          continue;
+        }
+        break;
+      }
+      case OSM_B200_C_ENERGY:
+        SETI("htkcompatible", c.u.energy.htkcompatible) SETI("rms", c.u.energy.rms) SETI("energy2", c.u.energy.energy2)
+        SETI("log", c.u.energy.log) SETD("escaleLog", c.u.energy.escaleLog) SETD("escaleRms", c.u.energy.escaleRms)
+        SETD("escaleSquare", c.u.energy.escaleSquare) SETD("ebiasLog", c.u.energy.ebiasLog) SETD("ebiasRms", c.u.energy.ebiasRms)
+        SETD("ebiasSquare", c.u.energy.ebiasSquare)
+        break;
+      case OSM_B200_C_MZCR:
+        SETI("zcr", c.u.mzcr.zcr) SETI("mcr", c.u.mzcr.mcr) SETI("amax", c.u.mzcr.amax) SETI("maxmin", c.u.mzcr.maxmin) SETI("dc", c.u.mzcr.dc)
+        break;
+      case OSM_B200_C_ACF:
+        if (f == "usePower") { c.u.acf.usePower = inum(v); usePowerSet = true; continue; }
+        SETI("cepstrum", c.u.acf.cepstrum) SETI("inverse", c.u.acf.inverse) SETI("cosLifterCepstrum", c.u.acf.cosLifterCepstrum)
+        SETI("expBeforeAbs", c.u.acf.expBeforeAbs) SETI("symmetricData", c.u.acf.symmetricData)
+        SETI("acfCepsNormOutput", c.u.acf.acfCepsNormOutput) SETI("oldCompatCepstrum", c.u.acf.oldCompatCepstrum)
+        SETI("absCepstrum", c.u.acf.absCepstrum)
+        break;
+      case OSM_B200_C_PITCHACF:
+        SETD("maxPitch", c.u.pitchacf.maxPitch) SETI("voiceProb", c.u.pitchacf.voiceProb) SETI("voiceQual", c.u.pitchacf.voiceQual)
+        SETI("HNR", c.u.pitchacf.HNR) SETI("HNRdB", c.u.pitchacf.HNRdB) SETI("linHNR", c.u.pitchacf.linHNR) SETI("F0", c.u.pitchacf.F0)
+        SETI("F0raw", c.u.pitchacf.F0raw) SETI("F0env", c.u.pitchacf.F0env) SETD("voicingCutoff", c.u.pitchacf.voicingCutoff)
+        break;
+      case OSM_B200_C_DELTAREGRESSION:
+        SETI("deltawin", c.u.deltaregression.deltawin) SETI("absOutput", c.u.deltaregression.absOutput)
+        SETI("halfWaveRect", c.u.deltaregression.halfWaveRect) SETI("onlyInSegments", c.u.deltaregression.onlyInSegments)
+        SETI("zeroSegBound", c.u.deltaregression.zeroSegBound) SETI("relativeDelta", c.u.deltaregression.relativeDelta)
+        if (f == "noPostEOIprocessing") { if (inum(v)) { err = "cDeltaRegression.noPostEOIprocessing=1 is not supported"; return false; } continue; }
+        break;
+      case OSM_B200_C_CONTOURSMOOTHER:
+        SETI("smaWin", c.u.contoursmoother.smaWin) SETI("noZeroSma", c.u.contoursmoother.noZeroSma)
+        if (f == "noPostEOIprocessing") { if (inum(v)) { err = "cContourSmoother.noPostEOIprocessing=1 is not supported"; return false; } continue; }
+        break;
+      case OSM_B200_C_VECTORCONCAT:
+        break;
+      default: break;
+    }
+    // same behaviour as the reference: an unknown field aborts configuration (configManager.cpp:2599)
+    err = "unknown field '" + f + "' in section [" + s.name + ":" + s.type + "]";
+    return false;
+  }
+  if (t == OSM_B200_C_MFCC && c.u.mfcc.lastMfcc <= -1000)          // lastMfcc = firstMfcc + nMfcc - 1 (lldcore/mfcc.cpp:77-82)
+    c.u.mfcc.lastMfcc = c.u.mfcc.firstMfcc + (-1000 - c.u.mfcc.lastMfcc) - 1;
+  if (t == OSM_B200_C_ACF && c.u.acf.cepstrum && !usePowerSet) c.u.acf.usePower = 0;   // dspcore/acf.cpp:91-99
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// WAV in, HTK / CSV out
+// ------------------------------------------------------------------------------------------
+struct Wav { int sampleRate = 0, nChan = 0; std::vector<int16_t> pcm; };
+
+bool read_wav(const char *path, Wav &w, std::string &err)    // 16-bit PCM RIFF (iocore/waveSource.cpp, smileUtil.c:2390-2495)
+{
+  FILE *f = fopen(path, "rb");
+  if (!f) { err = std::string("cannot open '") + path + "'"; return false; }
+  unsigned char h[12];
+  if (fread(h, 1, 12, f) != 12 || memcmp(h, "RIFF", 4) || memcmp(h + 8, "WAVE", 4)) { fclose(f); err = std::string(path) + ": not a RIFF/WAVE file"; return false; }
+  bool fmtOk = false;
+  int bits = 0, fmtTag = 0;
+  for (;;) {
+    unsigned char ch[8];
+    if (fread(ch, 1, 8, f) != 8) break;
+    const uint32_t sz = ch[4] | (ch[5] << 8) | (ch[6] << 16) | ((uint32_t)ch[7] << 24);
+    if (!memcmp(ch, "fmt ", 4)) {
+      std::vector<unsigned char> b(sz);
+      if (fread(b.data(), 1, sz, f) != sz || sz < 16) break;
+      fmtTag = b[0] | (b[1] << 8); w.nChan = b[2] | (b[3] << 8);
+      w.sampleRate = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+      bits = b[14] | (b[15] << 8);
+      fmtOk = true;
+      if (sz & 1) fseek(f, 1, SEEK_CUR);
+    } else if (!memcmp(ch, "data", 4)) {
+      if (!fmtOk) break;
+      if (!(fmtTag == 1 || fmtTag == 0xFFFE) || bits != 16) { fclose(f); err = std::string(path) + ": only 16-bit integer PCM is supported"; return false; }
+      w.pcm.resize(sz / 2);
+      const size_t got = fread(w.pcm.data(), 2, sz / 2, f);
+      w.pcm.resize(got - got % (size_t)std::max(w.nChan, 1));
+      fclose(f);
+      return true;
+    } else {
+      fseek(f, sz + (sz & 1), SEEK_CUR);
+    }
+  }
+  fclose(f);
+  err = std::string(path) + ": malformed WAV file";
+  return false;
+}
+
+// HTK parameter file (iocore/htkSink.cpp:90-106 header, :183-206 rows): big-endian
+bool write_htk(const char *path, const float *rows, int64_t n, int K, double period, int parmKind, std::string &err)
+{
+  FILE *f = fopen(path, "wb");
+  if (!f) { err = std::string("cannot write '") + path + "'"; return false; }
+  auto be32 = [&](uint32_t v) { unsigned char b[4] = {(unsigned char)(v >> 24), (unsigned char)(v >> 16), (unsigned char)(v >> 8), (unsigned char)v}; fwrite(b, 1, 4, f); };
+  auto be16 = [&](uint16_t v) { unsigned char b[2] = {(unsigned char)(v >> 8), (unsigned char)v}; fwrite(b, 1, 2, f); };
+  be32((uint32_t)n);
+  be32(period <= 0.0 ? 100000u : (uint32_t)round(period * 10000000.0));
+  be16((uint16_t)(sizeof(float) * K));
+  be16((uint16_t)parmKind);
+  std::vector<unsigned char> buf((size_t)K * 4);
+  for (int64_t r = 0; r < n; r++) {
+    for (int k = 0; k < K; k++) {
+      uint32_t u;
+      memcpy(&u, &rows[r * K + k], 4);
+      buf[4 * k] = (unsigned char)(u >> 24); buf[4 * k + 1] = (unsigned char)(u >> 16);
+      buf[4 * k + 2] = (unsigned char)(u >> 8); buf[4 * k + 3] = (unsigned char)u;
+    }
+    fwrite(buf.data(), 1, buf.size(), f);
+  }
+  fclose(f);
+  return true;
+}
+
+// cCsvSink options with the component's defaults (iocore/csvSink.cpp:40-54,78-110)
+struct CsvOpts { bool printHeader = true, timestamp = true, number = true; int prname = 0; char delim = ';'; std::string instName; };
+
+// iocore/csvSink.cpp:150-235
+bool write_csv(const char *path, const float *rows, int64_t n, int K, const std::vector<std::string> &names, double period,
+               const CsvOpts &o, std::string &err)
+{
+  FILE *f = fopen(path, "w");
+  if (!f) { err = std::string("cannot write '") + path + "'"; return false; }
+  if (o.printHeader) {
+    if (o.prname) fprintf(f, "name%c", o.delim);
+    if (o.number) fprintf(f, "frameIndex%c", o.delim);
+    if (o.timestamp) fprintf(f, "frameTime%c", o.delim);
+    for (int k = 0; k < K - 1; k++) fprintf(f, "%s%c", names[k].c_str(), o.delim);
+    fprintf(f, "%s\n", names[K - 1].c_str());
+  }
+  for (int64_t r = 0; r < n; r++) {
+    if (o.prname == 1) fprintf(f, "'%s'%c", o.instName.c_str(), o.delim);
+    else if (o.prname == 2) fprintf(f, "'%s_%ld'%c", o.instName.c_str(), (long)r, o.delim);
+    if (o.number) fprintf(f, "%ld%c", (long)r, o.delim);
+    if (o.timestamp) fprintf(f, "%f%c", (double)r * period, o.delim);
+    for (int k = 0; k < K; k++) {
+      const float v = rows[r * K + k];
+      const bool last = k == K - 1;
+      if (v == floorf(v)) fprintf(f, "%.0f", v); else fprintf(f, "%e", v);
+      if (last) fputc('\n', f); else fputc(o.delim, f);
+    }
+  }
+  fclose(f);
+  return true;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+struct osm_b200_session {
+  Conf conf;
+  std::vector<osm_b200_component> comps;     // everything except the wave source parameters
+  int waveIdx = -1;
+  std::string outputLevel;
+  int device = 0;
+  int parmKind = 9;
+  CsvOpts csv;
+  // plan cache keyed by (sample rate, channels)
+  std::map<std::pair<long, int>, osm_b200_plan *> plans;
+  osm_b200_plan *cur = nullptr;
+  std::vector<osm_b200_component> curComps;
+};
+
+static osm_b200_status get_plan(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan **out)
+{
+  const auto key = std::make_pair((long)lround(sampleRate * 1000.0), nChan);
+  auto it = s->plans.find(key);
+  if (it == s->plans.end()) {
+    std::vector<osm_b200_component> cs = s->comps;
+    cs[s->waveIdx].u.wavesource.sampleRate = sampleRate;
+    cs[s->waveIdx].u.wavesource.nChannels = nChan;
+    osm_b200_plan *p = nullptr;
+    osm_b200_status st = osm_b200_plan_create(cs.data(), (int)cs.size(), s->outputLevel.c_str(), s->device, &p);
+    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    it = s->plans.insert({key, p}).first;
+    s->curComps = cs;
+  }
+  s->cur = it->second;
+  *out = it->second;
+  return OSM_B200_OK;
+}
+
+extern "C" {
+
+osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, const char *const *opt_names,
+                                      const char *const *opt_values, const char *output_level, int32_t device,
+                                      osm_b200_session **session)
+{
+  if (!conf_path || !session) return hfail(OSM_B200_ERR_INVALID, "null argument");
+  *session = nullptr;
+  std::map<std::string, std::string> given;
+  for (int i = 0; i < n_opts; i++) if (opt_names && opt_names[i]) given[opt_names[i]] = (opt_values && opt_values[i]) ? opt_values[i] : "";
+  osm_b200_session *s = new osm_b200_session();
+  s->device = device;
+  std::string err;
+  int curSec = -1;
+  g_herr.clear();
+  if (!parse_file(conf_path, s->conf, given, err, curSec)) { delete s; return hfail(OSM_B200_ERR_INVALID, err); }
+  // instances listed in [componentInstances:cComponentManager] (core/componentManager.cpp:840-957)
+  std::map<std::string, const Section *> secOf;
+  for (const auto &sec : s->conf.sections) if (sec.type != "cComponentManager") secOf[sec.name] = &sec;
+  std::vector<std::string> sinkLevels;
+  std::set<std::string> hostTypes = {"cDataMemory", "cHtkSink", "cCsvSink", "cArffSink", "cExternalSink", "cNullSink", "cDatadumpSink"};
+  for (const auto &inst : s->conf.instances) {
+    const std::string &name = inst.first, &type = inst.second;
+    const Section *sec = secOf.count(name) ? secOf[name] : nullptr;
+    if (sec && sec->type != type) { delete s; return hfail(OSM_B200_ERR_INVALID, "instance '" + name + "' is declared as " + type + " but configured as " + sec->type); }
+    if (hostTypes.count(type)) {
+      if (!sec) continue;
+      if (type == "cHtkSink" || type == "cCsvSink" || type == "cArffSink" || type == "cExternalSink") {
+        const std::string *fn = sec->get("filename");
+        const bool active = type == "cExternalSink" || (fn && *fn != "?" && !fn->empty());
+        const std::string *lv = sec->get("reader.dmLevel");
+        if (active && lv && type != "cArffSink") sinkLevels.push_back(*lv);
+        if (type == "cHtkSink") { if (const std::string *pk = sec->get("parmKind")) s->parmKind = inum(*pk); }
+        if (type == "cCsvSink") {
+          if (const std::string *x = sec->get("printHeader")) s->csv.printHeader = inum(*x) != 0;
+          if (const std::string *x = sec->get("timestamp")) s->csv.timestamp = inum(*x) == 1;
+          if (const std::string *x = sec->get("frameTime")) s->csv.timestamp = inum(*x) == 1;
+          if (const std::string *x = sec->get("number")) s->csv.number = inum(*x) == 1;
+          if (const std::string *x = sec->get("frameIndex")) s->csv.number = inum(*x) == 1;
+          if (const std::string *x = sec->get("instanceBase")) { s->csv.instName = *x; s->csv.prname = 2; }
+          if (const std::string *x = sec->get("instanceName")) { s->csv.instName = *x; s->csv.prname = 1; }
+          if (const std::string *x = sec->get("frameLength")) if (inum(*x) == 1) { delete s; return hfail(OSM_B200_ERR_UNSUPPORTED, "cCsvSink.frameLength=1 is not supported"); }
+          if (const std::string *x = sec->get("delimChar")) if (!x->empty()) s->csv.delim = *x == "<space>" ? ' ' : (*x == "<tab>" ? '\t' : (*x)[0]);
+        }
+      }
+      continue;
+    }
+    if (!sec) { delete s; return hfail(OSM_B200_ERR_INVALID, "instance '" + name + "' (" + type + ") has no configuration section"); }
+    osm_b200_component c;
+    if (!to_component(*sec, c, err)) {
+      const bool unknownType = type_of(type) < 0;
+      delete s;
+      return hfail(unknownType ? OSM_B200_ERR_UNSUPPORTED : OSM_B200_ERR_INVALID, err);
+    }
+    if (c.type == OSM_B200_C_WAVESOURCE) s->waveIdx = (int)s->comps.size();
+    s->comps.push_back(c);
+  }
+  if (s->waveIdx < 0) { delete s; return hfail(OSM_B200_ERR_INVALID, "the configuration has no cWaveSource / cExternalAudioSource"); }
+  // output level: explicit, or the level the active sinks read; a multi-level sink reader is an
+  // implicit concat (core/dataReader.cpp:360-444)
+  std::string lvl = output_level ? output_level : "";
+  if (lvl.empty()) {
+    if (sinkLevels.empty()) { delete s; return hfail(OSM_B200_ERR_INVALID, "no active sink: pass output_level or enable a sink (-O / -csvoutput)"); }
+    lvl = sinkLevels[0];
+  }
+  if (lvl.find(';') != std::string::npos) {
+    osm_b200_component c;
+    osm_b200_component_defaults(OSM_B200_C_VECTORCONCAT, &c);
+    snprintf(c.name, sizeof c.name, "%s", "_sinkconcat");
+    std::stringstream ss(lvl);
+    std::string one;
+    while (std::getline(ss, one, ';')) {
+      one = trim(one);
+      if (!one.empty() && c.n_inputs < OSM_B200_MAX_INPUTS) snprintf(c.reader_dmLevel[c.n_inputs++], OSM_B200_NAME_LEN, "%s", one.c_str());
+    }
+    snprintf(c.writer_dmLevel, sizeof c.writer_dmLevel, "%s", "_sinkconcat");
+    c.u.vectorconcat.processArrayFields = 0;     // a reader's level concatenation keeps every field
+    s->comps.push_back(c);
+    lvl = "_sinkconcat";
+  }
+  s->outputLevel = lvl;
+  // validate the graph now (description-only plan at a nominal format) so that errors surface at open
+  {
+    std::vector<osm_b200_component> cs = s->comps;
+    cs[s->waveIdx].u.wavesource.sampleRate = 16000;
+    cs[s->waveIdx].u.wavesource.nChannels = 1;
+    osm_b200_plan *p = nullptr;
+    osm_b200_status st = osm_b200_plan_create(cs.data(), (int)cs.size(), s->outputLevel.c_str(), -1, &p);
+    if (st != OSM_B200_OK) { const std::string m = osm_b200_last_error(); delete s; return hfail(st, m); }
+    osm_b200_plan_destroy(p);
+  }
+  *session = s;
+  return OSM_B200_OK;
+}
+
+void osm_b200_session_close(osm_b200_session *s)
+{
+  if (!s) return;
+  for (auto &kv : s->plans) osm_b200_plan_destroy(kv.second);
+  delete s;
+}
+
+int32_t osm_b200_session_num_elements(osm_b200_session *s, double sampleRate, int32_t nChan)
+{
+  if (!s) return 0;
+  osm_b200_plan *p;
+  if (get_plan(s, sampleRate, nChan, &p) != OSM_B200_OK) return 0;
+  return osm_b200_plan_num_elements(p);
+}
+
+const char *osm_b200_session_element_name(osm_b200_session *s, int32_t idx)
+{
+  return (s && s->cur) ? osm_b200_plan_element_name(s->cur, idx) : nullptr;
+}
+
+int32_t osm_b200_session_components(osm_b200_session *s, double sampleRate, int32_t nChan, const osm_b200_component **comps,
+                                    const char **outputLevel)
+{
+  if (!s) return 0;
+  s->curComps = s->comps;
+  s->curComps[s->waveIdx].u.wavesource.sampleRate = sampleRate;
+  s->curComps[s->waveIdx].u.wavesource.nChannels = nChan;
+  if (comps) *comps = s->curComps.data();
+  if (outputLevel) *outputLevel = s->outputLevel.c_str();
+  return (int32_t)s->curComps.size();
+}
+
+osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t *pcm, const int64_t *uttOff, int32_t nUtt,
+                                             double sampleRate, int32_t nChan, int64_t *frameOff, float *out, int64_t maxRows)
+{
+  if (!s || !uttOff || !frameOff) return hfail(OSM_B200_ERR_INVALID, "null argument");
+  osm_b200_plan *p;
+  osm_b200_status st = get_plan(s, sampleRate, nChan, &p);
+  if (st != OSM_B200_OK) return st;
+  st = osm_b200_plan_frame_offsets(p, uttOff, nUtt, frameOff);
+  if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+  if (!out) return OSM_B200_OK;
+  if (frameOff[nUtt] > maxRows) return hfail(OSM_B200_ERR_INVALID, "output buffer too small");
+  st = osm_b200_plan_run_host(p, pcm, uttOff, nUtt, frameOff, out);
+  if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+  return OSM_B200_OK;
+}
+
+osm_b200_status osm_b200_session_extract_files(osm_b200_session *s, int32_t n, const char *const *wavPaths,
+                                               const char *const *htkPaths, const char *const *csvPaths, int64_t *framesOut)
+{
+  if (!s || !wavPaths || n < 0) return hfail(OSM_B200_ERR_INVALID, "null argument");
+  // files of one call are grouped by (sample rate, channels); each group is one batched plan run
+  std::vector<Wav> wavs(n);
+  std::string err;
+  for (int i = 0; i < n; i++) if (!read_wav(wavPaths[i], wavs[i], err)) return hfail(OSM_B200_ERR_INVALID, err);
+  std::map<std::pair<int, int>, std::vector<int>> groups;
+  for (int i = 0; i < n; i++) groups[{wavs[i].sampleRate, wavs[i].nChan}].push_back(i);
+  for (auto &g : groups) {
+    const int sr = g.first.first, nc = g.first.second;
+    std::vector<int64_t> off(g.second.size() + 1, 0), fo(g.second.size() + 1, 0);
+    size_t total = 0;
+    for (size_t k = 0; k < g.second.size(); k++) { total += wavs[g.second[k]].pcm.size(); off[k + 1] = off[k] + (int64_t)(wavs[g.second[k]].pcm.size() / nc); }
+    std::vector<int16_t> pcm(total + 8);
+    size_t at = 0;
+    for (int idx : g.second) { memcpy(pcm.data() + at, wavs[idx].pcm.data(), wavs[idx].pcm.size() * 2); at += wavs[idx].pcm.size(); }
+    osm_b200_plan *p;
+    osm_b200_status st = get_plan(s, sr, nc, &p);
+    if (st != OSM_B200_OK) return st;
+    st = osm_b200_plan_frame_offsets(p, off.data(), (int)g.second.size(), fo.data());
+    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    const int K = osm_b200_plan_num_elements(p);
+    std::vector<float> rows((size_t)fo.back() * K + 1);
+    st = osm_b200_plan_run_host(p, pcm.data(), off.data(), (int)g.second.size(), fo.data(), rows.data());
+    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    std::vector<std::string> names(K);
+    for (int k = 0; k < K; k++) names[k] = osm_b200_plan_element_name(p, k);
+    const double period = osm_b200_plan_frame_period(p);
+    for (size_t k = 0; k < g.second.size(); k++) {
+      const int idx = g.second[k];
+      const float *r = rows.data() + (size_t)fo[k] * K;
+      const int64_t nr = fo[k + 1] - fo[k];
+      if (framesOut) framesOut[idx] = nr;
+      if (htkPaths && htkPaths[idx] && !write_htk(htkPaths[idx], r, nr, K, period, s->parmKind, err)) return hfail(OSM_B200_ERR_INVALID, err);
+      if (csvPaths && csvPaths[idx] && !write_csv(csvPaths[idx], r, nr, K, names, period, s->csv, err)) return hfail(OSM_B200_ERR_INVALID, err);
+    }
+  }
+  return OSM_B200_OK;
+}
+
+const char *osm_b200_host_last_error(void) { return g_herr.empty() ? osm_b200_last_error() : g_herr.c_str(); }
+
+int32_t osm_b200_write_htk(const char *path, const float *rows, int64_t n, int32_t K, double period, int32_t parmKind)
+{
+  std::string err;
+  if (write_htk(path, rows, n, K, period, parmKind, err)) return 0;
+  g_herr = err;
+  return 1;
+}
+
+int32_t osm_b200_write_csv(const char *path, const float *rows, int64_t n, int32_t K, const char *const *names, double period,
+                           const char *instName, int32_t frameIndex, int32_t frameTime)
+{
+  std::string err;
+  std::vector<std::string> nm(K);
+  for (int k = 0; k < K; k++) nm[k] = names[k];
+  CsvOpts o;
+  if (instName) { o.instName = instName; o.prname = 1; }
+  o.number = frameIndex != 0;
+  o.timestamp = frameTime != 0;
+  if (write_csv(path, rows, n, K, nm, period, o, err)) return 0;
+  g_herr = err;
+  return 1;
+}
+
+}  // extern "C"

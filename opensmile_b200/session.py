@@ -1,0 +1,109 @@
+"""Session: extract with one of the reference's own .conf files (include/osm_b200_host.h).
+
+Mirrors, for the LLD path, what `SMILExtract -C conf -I wav -O htk -csvoutput csv` and the
+SMILEapi external source / sink pair do (progsrc/smilextract/SMILExtract.cpp:42-174,
+progsrc/include/smileapi/SMILEapi.h); config parsing, WAV / HTK / CSV I/O are host C++ inside
+libosm_b200.so, the numerics are the CUDA plan.  No CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class SessionError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(msg)
+        self.status = status
+
+
+def _strs(items):
+    arr = (C.c_char_p * max(len(items), 1))()
+    for i, x in enumerate(items):
+        arr[i] = None if x is None else str(x).encode()
+    return arr
+
+
+class Session:
+    def __init__(self, conf_path, options=None, output_level=None, device=0):
+        self._L = capi.lib()
+        self._h = C.c_void_p()
+        options = dict(options or {})
+        st = self._L.osm_b200_session_open(
+            str(conf_path).encode(), len(options), _strs(list(options.keys())), _strs(list(options.values())),
+            output_level.encode() if output_level else None, device, C.byref(self._h))
+        if st != capi.OK:
+            self._h = C.c_void_p()
+            raise SessionError(st, self._L.osm_b200_host_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self._L.osm_b200_session_close(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, st):
+        if st != capi.OK:
+            raise SessionError(st, self._L.osm_b200_host_last_error().decode())
+
+    def element_names(self, sample_rate=16000.0, n_channels=1):
+        n = self._L.osm_b200_session_num_elements(self._h, float(sample_rate), n_channels)
+        if n <= 0:
+            raise SessionError(capi.ERR_INVALID, self._L.osm_b200_host_last_error().decode())
+        return [self._L.osm_b200_session_element_name(self._h, i).decode() for i in range(n)]
+
+    def components(self, sample_rate=16000.0, n_channels=1):
+        """the osm_b200_component list the config resolved to, and the output level"""
+        p = C.POINTER(capi.Component)()
+        lvl = C.c_char_p()
+        n = self._L.osm_b200_session_components(self._h, float(sample_rate), n_channels, C.byref(p), C.byref(lvl))
+        arr = (capi.Component * n)()
+        for i in range(n):
+            C.memmove(C.byref(arr[i]), C.byref(p[i]), C.sizeof(capi.Component))
+        return arr, lvl.value.decode()
+
+    def frame_offsets(self, utt_offsets, sample_rate, n_channels=1):
+        off = np.ascontiguousarray(utt_offsets, dtype=np.int64)
+        fo = np.zeros(len(off), dtype=np.int64)
+        i64p = C.POINTER(C.c_int64)
+        self._check(self._L.osm_b200_session_extract_pcm(
+            self._h, None, off.ctypes.data_as(i64p), len(off) - 1, float(sample_rate), n_channels,
+            fo.ctypes.data_as(i64p), None, 0))
+        return fo
+
+    def extract_pcm(self, pcm, utt_offsets, sample_rate, n_channels=1):
+        """packed int16 PCM (layout of Plan.run_host) -> (rows [sum frames, n_elements], frame_offsets)"""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        off = np.ascontiguousarray(utt_offsets, dtype=np.int64)
+        fo = self.frame_offsets(off, sample_rate, n_channels)
+        n_el = self._L.osm_b200_session_num_elements(self._h, float(sample_rate), n_channels)
+        out = np.empty((int(fo[-1]), n_el), dtype=np.float32)
+        i64p = C.POINTER(C.c_int64)
+        self._check(self._L.osm_b200_session_extract_pcm(
+            self._h, pcm.ctypes.data, off.ctypes.data_as(i64p), len(off) - 1, float(sample_rate), n_channels,
+            fo.ctypes.data_as(i64p), out.ctypes.data, out.shape[0]))
+        return out, fo
+
+    def extract_files(self, wav_paths, htk_paths=None, csv_paths=None):
+        n = len(wav_paths)
+        frames = np.zeros(n, dtype=np.int64)
+        self._check(self._L.osm_b200_session_extract_files(
+            self._h, n, _strs(wav_paths), _strs(htk_paths) if htk_paths else None,
+            _strs(csv_paths) if csv_paths else None, frames.ctypes.data_as(C.POINTER(C.c_int64))))
+        return frames
+
+
+def write_htk(path, rows, period, parm_kind=9):
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    if capi.lib().osm_b200_write_htk(str(path).encode(), rows.ctypes.data, rows.shape[0], rows.shape[1], float(period), parm_kind):
+        raise IOError(capi.lib().osm_b200_host_last_error().decode())
+
+
+def write_csv(path, rows, names, period, instance_name=None, frame_index=True, frame_time=True):
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    if capi.lib().osm_b200_write_csv(str(path).encode(), rows.ctypes.data, rows.shape[0], rows.shape[1], _strs(names),
+                                     float(period), instance_name.encode() if instance_name is not None else None,
+                                     int(frame_index), int(frame_time)):
+        raise IOError(capi.lib().osm_b200_host_last_error().decode())

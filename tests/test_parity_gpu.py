@@ -282,7 +282,7 @@ def test_energy_zcr_bit_exact_and_multi_stream_concat():
            comp("cEnergy", "e60", "bwin", "e60", rms=1, log=1, energy2=1),
            comp("cContourSmoother", "sm", "e25", "e25s", smaWin=3),
            comp("cDeltaRegression", "de", "e25s", "e25sd", deltawin=2),
-           comp("cVectorConcat", "cat", "e25;z60;e60;e25s;e25sd", "lld")]
+           comp("cVectorConcat", "cat", "e25;z60;e60;e25s;e25sd", "lld", includeSingleElementFields=1)]
     p = Plan(cs, "lld", device=0)
     assert p.element_names == ["pcm_RMSenergy", "pcm_zcr", "pcm_mcr", "pcm_absmax", "pcm_max", "pcm_min", "pcm_dc",
                                "pcm_RMSenergy", "pcm_SQUAREDenergy", "pcm_LOGenergy", "pcm_RMSenergy_sma", "pcm_RMSenergy_sma_de"]

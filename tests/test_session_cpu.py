@@ -1,0 +1,120 @@
+"""CPU tests of the host front end (include/osm_b200_host.h): the reference's .conf syntax is parsed
+into the same component graph, element names and frame counts as the reference produces (golden
+vectors from the unmodified reference, scripts/make_golden_conf.py), and the HTK / CSV writers are
+byte-identical to the reference's sinks.  Description-only sessions (device = -1): no compute."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from opensmile_b200 import Session, SessionError, capi, write_csv, write_htk
+
+CONF = os.path.join(ROOT, "tests", "configs")
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "conf_goldens.npz"))
+REF_CONF = os.path.join(ROOT, "oracle", "_ref", "config")
+
+
+@pytest.mark.parametrize("conf,key", [("lld_mix.conf", "mix"), ("mfcc_e_d_a.conf", "mfcc_e"), ("plp_e_d_a.conf", "plp_e")])
+def test_element_names_match_reference_csv_header(conf, key):
+    s = Session(os.path.join(CONF, conf), device=-1)
+    assert s.element_names(16000, 1) == [str(x) for x in GOLD["names_" + key]]
+
+
+def test_frame_counts_match_reference():
+    s = Session(os.path.join(CONF, "mfcc_e_d_a.conf"), device=-1)
+    lens = [12000, 400, 560, 720, 880, 399, 0]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    fo = s.frame_offsets(off, 16000, 1)
+    want = [GOLD["mfcc_e"].shape[0]] + [GOLD["mfcc_e_short_%d" % n].shape[0] for n in (400, 560, 720, 880)] + [0, 0]
+    assert list(np.diff(fo)) == want
+    m = Session(os.path.join(CONF, "lld_mix.conf"), device=-1)
+    assert m.frame_offsets([0, 16000], 16000, 1)[-1] == GOLD["mix16k"].shape[0]          # min over the three levels
+    assert m.frame_offsets([0, 16000], 32000, 2)[-1] == GOLD["mix32k_stereo"].shape[0]
+
+
+def test_parsed_components_carry_config_values():
+    s = Session(os.path.join(CONF, "lld_mix.conf"), device=-1)
+    comps, level = s.components(16000, 1)
+    by = {c.name.decode(): c for c in comps}
+    assert level == "_sinkconcat"                        # the sink reads three levels -> implicit concat
+    assert [by["_sinkconcat"].reader_dmLevel[i].value.decode() for i in range(3)] == ["lld", "lld_de", "pitch_sma"]
+    assert by["waveIn"].u.wavesource.sampleRate == 16000 and by["waveIn"].u.wavesource.monoMixdown == 1
+    assert (by["fr25"].u.framer.frameSize, by["fr25"].u.framer.frameStep) == (0.025, 0.010)
+    assert by["fr50"].u.framer.frameSize == 0.050
+    assert by["win25"].u.windower.winFunc == capi.WIN_BY_NAME["ham"] and by["win50"].u.windower.winFunc == capi.WIN_BY_NAME["gau"]
+    sp = by["spec"].u.spectral
+    assert (sp.nBands, sp.bandLo[0], sp.bandHi[0], sp.bandLo[1], sp.bandHi[1]) == (2, 250, 650, 1000, 4000)
+    assert (sp.nRollOff, sp.rollOff[0], sp.rollOff[1]) == (2, 0.25, 0.90)
+    assert by["cep"].u.acf.cepstrum == 1 and by["cep"].u.acf.usePower == 0      # dspcore/acf.cpp:91-99
+    assert by["acf"].u.acf.usePower == 1
+    assert by["cat"].u.vectorconcat.includeSingleElementFields == 1
+    assert by["pitch"].n_inputs == 2 and by["sm"].u.contoursmoother.smaWin == 3
+
+
+def test_command_line_options_substitute():
+    s = Session(os.path.join(CONF, "lld_mix.conf"), options={"step": "0.020"}, device=-1)
+    comps, _ = s.components(16000, 1)
+    by = {c.name.decode(): c for c in comps}
+    assert by["fr25"].u.framer.frameStep == 0.020 and by["fr50"].u.framer.frameStep == 0.020   # \cm[step] reuse
+    assert s.frame_offsets([0, 16000], 16000, 1)[-1] == (16000 - 800) // 320 + 1 + 1
+
+
+def test_concat_drops_single_element_fields_by_default(tmp_path):
+    # cVectorProcessor's processArrayFields=1 default (core/vectorProcessor.cpp:196-243): the
+    # reference writes 36 columns for this variant (energy dropped), cf. tests/configs/inc/ft0_d_a_out.conf.inc
+    inc = open(os.path.join(CONF, "inc", "ft0_d_a_out.conf.inc")).read().replace("includeSingleElementFields = 1", "")
+    os.makedirs(tmp_path / "inc")
+    (tmp_path / "inc" / "ft0_d_a_out.conf.inc").write_text(inc)
+    (tmp_path / "inc" / "htk_frontend.conf.inc").write_text(open(os.path.join(CONF, "inc", "htk_frontend.conf.inc")).read())
+    (tmp_path / "c.conf").write_text(open(os.path.join(CONF, "mfcc_e_d_a.conf")).read())
+    names = Session(str(tmp_path / "c.conf"), device=-1).element_names()
+    assert len(names) == 36 and not any("energy" in n for n in names)
+
+
+@pytest.mark.parametrize("text,status,needle", [
+    ("[frame:cFramer]\nreader.dmLevel=wave\nwriter.dmLevel=frames\nframeSizee = 0.025\n", capi.ERR_INVALID, "unknown field"),
+    ("[x:cFunctionals]\nreader.dmLevel=wave\nwriter.dmLevel=func\n", capi.ERR_UNSUPPORTED, "cFunctionals"),
+    ("[frame:cFramer]\nreader.dmLevel=wave\nwriter.dmLevel=frames\nframeSize = \\cm[fs:frame size]\n", capi.ERR_INVALID, "no value"),
+    ("\\{does_not_exist.conf.inc}\n", capi.ERR_INVALID, "cannot open"),
+    ("[frame:cFramer]\nreader.dmLevel=wave\nwriter.dmLevel=frames\nframeMode = list\n", capi.ERR_INVALID, "frameMode"),
+])
+def test_config_errors_are_loud(tmp_path, text, status, needle):
+    head = ("[componentInstances:cComponentManager]\ninstance[dataMemory].type=cDataMemory\ninstance[waveIn].type=cWaveSource\n"
+            "instance[frame].type=cFramer\ninstance[x].type=cFunctionals\n[waveIn:cWaveSource]\nwriter.dmLevel=wave\n")
+    if "cFunctionals" not in text:
+        head = head.replace("instance[x].type=cFunctionals\n", "")
+    if "[frame:" not in text:
+        head = head.replace("instance[frame].type=cFramer\n", "")
+    (tmp_path / "bad.conf").write_text(head + text)
+    with pytest.raises(SessionError) as e:
+        Session(str(tmp_path / "bad.conf"), output_level="frames", device=-1)
+    assert e.value.status == status and needle in str(e.value), str(e.value)
+
+
+def test_writers_are_byte_identical_to_reference_sinks(tmp_path):
+    rows, names = GOLD["mfcc_e"], [str(x) for x in GOLD["names_mfcc_e"]]
+    write_htk(tmp_path / "a.htk", rows, 0.01, 9)
+    assert (tmp_path / "a.htk").read_bytes() == GOLD["htk_bytes"].tobytes()
+    write_csv(tmp_path / "a.csv", rows, names, 0.01, instance_name="utt7", frame_index=False)
+    assert (tmp_path / "a.csv").read_bytes() == GOLD["csv_bytes"].tobytes()
+
+
+def test_description_only_session_refuses_to_compute():
+    s = Session(os.path.join(CONF, "mfcc_e_d_a.conf"), device=-1)
+    with pytest.raises(SessionError) as e:
+        s.extract_pcm(np.zeros(16000, np.int16), [0, 16000], 16000, 1)
+    assert e.value.status == capi.ERR_CUDA            # no CPU fallback
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONF), reason="reference configs not built into oracle/_ref")
+@pytest.mark.parametrize("conf,n", [("mfcc/MFCC12_0_D_A.conf", 39), ("mfcc/MFCC12_E_D_A.conf", 39),
+                                    ("plp/PLP_0_D_A.conf", 18), ("plp/PLP_E_D_A.conf", 18)])
+def test_reference_standard_configs_parse(conf, n):
+    s = Session(os.path.join(REF_CONF, conf), device=-1)
+    names = s.element_names(16000, 1)
+    assert len(names) == n
+    if conf.endswith("MFCC12_E_D_A.conf"):
+        assert names == [str(x) for x in GOLD["names_mfcc_e"]]
+    if conf.endswith("PLP_E_D_A.conf"):
+        assert names == [str(x) for x in GOLD["names_plp_e"]]

@@ -1,0 +1,124 @@
+"""GPU tests of the conf front end: whole configuration files through libosm_b200.so (parser ->
+plan -> CUDA kernels -> HTK / CSV writers) against outputs of the UNMODIFIED reference for the same
+files (tests/golden/conf_goldens.npz, scripts/make_golden_conf.py).
+
+Tolerance: float32 path, |got - ref| <= 1e-5 * (largest magnitude of that element over the
+utterance) per element -- BASELINE's 1e-5 relative bound taken per output column, because one row
+mixes quantities of very different scale (spectral variance ~1e6 Hz^2 next to a zero-crossing rate)."""
+import os
+import struct
+import subprocess
+import wave
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from opensmile_b200 import Session, pack_utterances
+from opensmile_b200.synth import voiced_pcm
+
+pytestmark = pytest.mark.gpu
+CONF = os.path.join(ROOT, "tests", "configs")
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "conf_goldens.npz"))
+
+
+def col_err(got, ref):
+    scale = np.maximum(np.abs(ref).max(axis=0), 1e-30)
+    return (np.abs(got.astype(np.float64) - ref) / scale).max(axis=0)
+
+
+def write_wav(path, pcm, sr, nch=1):
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(nch)
+        w.setsampwidth(2)
+        w.setframerate(sr)
+        w.writeframes(np.ascontiguousarray(pcm, dtype="<i2").tobytes())
+
+
+def read_htk(path):
+    raw = open(path, "rb").read()
+    n, period, size, kind = struct.unpack(">iihh", raw[:12])
+    return np.frombuffer(raw[12:], dtype=">f4").astype(np.float32).reshape(n, size // 4), period, kind
+
+
+def test_mfcc_e_d_a_conf_batch_with_short_utterances():
+    pcm = voiced_pcm(12000, 16000, seed=5)
+    utts = [pcm, pcm[:400], pcm[:560], pcm[:720], pcm[:880]]
+    packed, off = pack_utterances(utts)
+    s = Session(os.path.join(CONF, "mfcc_e_d_a.conf"))
+    rows, fo = s.extract_pcm(packed, off, 16000, 1)
+    refs = [GOLD["mfcc_e"]] + [GOLD["mfcc_e_short_%d" % n] for n in (400, 560, 720, 880)]
+    assert list(np.diff(fo)) == [r.shape[0] for r in refs]
+    for u, ref in enumerate(refs):
+        got = rows[fo[u]:fo[u + 1]]
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(got - ref) / scale).max() < 1e-5, u
+
+
+def test_plp_e_d_a_conf():
+    pcm = voiced_pcm(12000, 16000, seed=6)
+    s = Session(os.path.join(CONF, "plp_e_d_a.conf"))
+    rows, fo = s.extract_pcm(pcm, [0, 12000], 16000, 1)
+    ref = GOLD["plp_e"]
+    assert rows.shape == ref.shape
+    assert (np.abs(rows - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
+
+
+@pytest.mark.parametrize("key,n,sr,nch,seed", [("mix16k", 16000, 16000, 1, 3), ("mix32k_stereo", 16000, 32000, 2, 4)])
+def test_mixed_lld_conf_two_streams(key, n, sr, nch, seed):
+    pcm = voiced_pcm(n, sr, seed=seed, n_chan=nch)
+    s = Session(os.path.join(CONF, "lld_mix.conf"))
+    names = s.element_names(sr, nch)
+    rows, fo = s.extract_pcm(pcm, [0, n], sr, nch)
+    ref = GOLD[key]
+    assert rows.shape == ref.shape
+    err = col_err(rows, ref)
+    # F0 / F0env follow an arg-max over ACF lags: exact lag or a different peak, never "close"
+    lagcols = [i for i, nm in enumerate(names) if nm.startswith("F0")]
+    others = [i for i in range(len(names)) if i not in lagcols]
+    bad = [(names[i], float(err[i])) for i in others if err[i] > 1e-5]
+    assert not bad, bad
+    for i in lagcols:
+        assert (np.abs(rows[:, i] - ref[:, i]) <= 1e-5 * np.abs(ref[:, i]).max()).mean() > 0.98, names[i]
+
+
+def test_extract_files_writes_reference_formats(tmp_path):
+    pcm = voiced_pcm(12000, 16000, seed=5)
+    write_wav(tmp_path / "a.wav", pcm, 16000)
+    write_wav(tmp_path / "b.wav", pcm[:880], 16000)
+    s = Session(os.path.join(CONF, "mfcc_e_d_a.conf"), options={"instname": "utt7"})
+    frames = s.extract_files([str(tmp_path / "a.wav"), str(tmp_path / "b.wav")],
+                             [str(tmp_path / "a.htk"), str(tmp_path / "b.htk")], [str(tmp_path / "a.csv"), None])
+    assert list(frames) == [73, 4]
+    got, period, kind = read_htk(tmp_path / "a.htk")
+    assert (period, kind) == (100000, 9)
+    ref = GOLD["mfcc_e"]
+    assert (np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
+    gotb, _, _ = read_htk(tmp_path / "b.htk")
+    assert np.abs(gotb - GOLD["mfcc_e_short_880"]).max() < 1e-5 * np.abs(GOLD["mfcc_e_short_880"]).max()
+    lines = (tmp_path / "a.csv").read_text().splitlines()
+    ref_lines = GOLD["csv_bytes"].tobytes().decode().splitlines()
+    assert lines[0] == ref_lines[0] and len(lines) == len(ref_lines)
+    for a, b in zip(lines[1:], ref_lines[1:]):
+        fa, fb = a.split(";"), b.split(";")
+        assert fa[:2] == fb[:2]                      # 'utt7' and the %f time stamp
+        va, vb = np.array(fa[2:], float), np.array(fb[2:], float)
+        assert np.abs(va - vb).max() <= 2e-5 * np.abs(vb).max()
+    assert not (tmp_path / "b.csv").exists()
+
+
+def test_command_line_front_end(tmp_path):
+    exe = os.path.join(ROOT, "opensmile_b200", "SMILExtract_b200")
+    pcm = voiced_pcm(12000, 16000, seed=6)
+    write_wav(tmp_path / "in.wav", pcm, 16000)
+    r = subprocess.run([exe, "-C", os.path.join(CONF, "plp_e_d_a.conf"), "-I", str(tmp_path / "in.wav"),
+                        "-O", str(tmp_path / "out.htk"), "-csvoutput", str(tmp_path / "out.csv")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got, _, _ = read_htk(tmp_path / "out.htk")
+    ref = GOLD["plp_e"]
+    assert (np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
+    hdr = (tmp_path / "out.csv").read_text().splitlines()[0].split(";")
+    assert hdr[:2] == ["name", "frameTime"] and hdr[2:] == [str(x) for x in GOLD["names_plp_e"]]
+    # errors are loud and non-zero
+    r = subprocess.run([exe, "-C", os.path.join(CONF, "does_not_exist.conf"), "-I", str(tmp_path / "in.wav")], capture_output=True, text=True)
+    assert r.returncode != 0 and "cannot open" in r.stderr
