@@ -213,7 +213,8 @@ static void build_twiddles(int M, std::vector<float2> &tw, int twOff[4])
   int R[3] = {0, 0, 0}, ns = 0;
   if (M == 256) { R[0] = 16; R[1] = 16; ns = 2; }
   else if (M == 512) { R[0] = 8; R[1] = 8; R[2] = 8; ns = 3; }
-  else { R[0] = 16; R[1] = 16; R[2] = 4; ns = 3; }
+  else if (M == 1024) { R[0] = 16; R[1] = 16; R[2] = 4; ns = 3; }
+  else { R[0] = 16; R[1] = 16; R[2] = 8; ns = 3; }
   int MS = M;
   tw.clear();
   for (int s = 0; s < 4; s++) twOff[s] = 0;
@@ -259,7 +260,7 @@ static osm_b200_status setup_stream(osm_b200_plan *pl, int si, const cudaDeviceP
   size_t oWin = 0, oTw = 0, oSplit = 0, oCoef = 0, oRange = 0, oDct = 0, oLift = 0, oEql = 0;
   if (rt.runLld) {
     if (!lld_supported_fft(fe.nfft))
-      return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(fe.nfft) + " not supported (512, 1024, 2048)");
+      return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(fe.nfft) + " not supported (512, 1024, 2048, 4096)");
     const int M = fe.nfft / 2;
     std::vector<float4> winLut(M, make_float4(0.f, 0.f, 0.f, 0.f));
     for (int e = 0; e < M; e++) {
@@ -348,6 +349,10 @@ static osm_b200_status setup_stream(osm_b200_plan *pl, int si, const cudaDeviceP
       kp.dctLift = reinterpret_cast<const float *>(rt.dConst + oLift);
       kp.plpEql = reinterpret_cast<const float *>(rt.dConst + oEql);
     }
+    if (lld_smem_bytes(kp, fe.nfft) > (size_t)prop.sharedMemPerBlockOptin && fe.nfft >= 1024) {
+      kp.narrow = 1;                                   // long stereo strides: half-width tiles
+      rt.tileF = lld_tile_frames(fe.nfft, true);
+    }
     if (lld_smem_bytes(kp, fe.nfft) > (size_t)prop.sharedMemPerBlockOptin)
       return fail(OSM_B200_ERR_UNSUPPORTED, "configuration needs more shared memory than the device offers");
   }
@@ -369,7 +374,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     if (sd.hasFft && (sd.fusedOp >= 0 || sd.dumpMag) && !lld_supported_fft(sd.fe.nfft)) {
       const int nf = sd.fe.nfft;
       delete pl;
-      return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(nf) + " not supported (512, 1024, 2048)");
+      return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(nf) + " not supported (512, 1024, 2048, 4096)");
     }
   if (device < 0) {
     // description-only plan: geometry, names and frame-count rules without touching CUDA
@@ -429,7 +434,9 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
                          g1.stages[0].win == g2.stages[0].win;
       // OSM_B200_NO_FUSE=1 forces the two-kernel path (used by the tests to cross-check both)
       const char *nf = getenv("OSM_B200_NO_FUSE");
-      if (shape && g1.stages[0].win + g2.stages[1].win <= 8 && !(nf && nf[0] == '1')) {
+      // the kernel keeps the statics of two tiles (2F frames): a row needs 2*halo+1 of them
+      const int hl = g1.stages[0].win + g2.stages[1].win, tF = pl->st[0].tileF;
+      if (shape && hl <= 8 && 2 * hl + 1 <= 2 * tF && !(nf && nf[0] == '1')) {
         pl->fused = true;
         kp.fused = 1; kp.fW1 = g1.stages[0].win; kp.fW2 = g2.stages[1].win; kp.halo = kp.fW1 + kp.fW2;
         auto normOf = [](int W) { float n = 0.f; for (int i = 1; i <= W; i++) n += (float)i * (float)i; return n * 2.0f; };
@@ -481,7 +488,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       CUP(cudaMemcpy(rt.dSharpW, so.sharpW.data(), so.sharpW.size() * sizeof(double), cudaMemcpyHostToDevice));
       sp.sharpW = rt.dSharpW;
     } else if (op.kind == SOP_PITCHACF) {
-      if (!acf_pitch_supported_fft(fe.nfft)) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cAcf / cPitchACF: FFT size must be 512 or 1024"); }
+      if (!acf_pitch_supported_fft(fe.nfft)) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cAcf / cPitchACF: FFT size must be 512, 1024 or 2048"); }
       const PitchAcfOp &po = op.pitch;
       AcfPitchParams &ap = rt.ap;
       memset(&ap, 0, sizeof ap);

@@ -98,6 +98,7 @@ template <int M> struct Fact;
 template <> struct Fact<256>  { static constexpr int NS = 2, R0 = 16, R1 = 16, R2 = 1; };
 template <> struct Fact<512>  { static constexpr int NS = 3, R0 = 8,  R1 = 8,  R2 = 8; };
 template <> struct Fact<1024> { static constexpr int NS = 3, R0 = 16, R1 = 16, R2 = 4; };
+template <> struct Fact<2048> { static constexpr int NS = 3, R0 = 16, R1 = 16, R2 = 8; };
 
 // position of X[k] after the in-place DIF passes (digit reversal)
 template <int M>

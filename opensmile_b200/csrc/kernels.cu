@@ -370,9 +370,13 @@ __device__ __forceinline__ void plp_backend(const LldParams &p, const float *mel
 // ------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------
-template <int M, int F, int NT, int MINB, bool VEC2>
+// GEN = false: the MFCC-only instance (band op = cMfcc, no magnitude level dump); the PLP back end and
+// the magnitude dump compile away.  GEN = true: band op and dump selected at run time.
+template <int M, int F, int NT, int MINB, bool VEC2, bool GEN>
 __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 {
+  const int opKind = GEN ? p.opKind : 0;
+  float *const magOut = GEN ? p.magOut : nullptr;
   constexpr int NW = NT / 32, G = 32 / F, NVW = NW * G;
   constexpr int NBINS = M + 1;
   constexpr int NPAIR = M / 2 + 1;                 // pairs (k, M-k), k = 0..M/2
@@ -409,11 +413,11 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   for (int i = tid; i < M; i += NT) sWinLut[i] = p.winLut[i];
   for (int i = tid; i < p.twCount; i += NT) sTw[i] = p.twiddles[i];
   for (int i = tid; i < NPAIR; i += NT) sSplit[i] = p.splitTw[i];
-  if (p.opKind >= 0) {
+  if (opKind >= 0) {
     for (int i = tid; i < NBINS; i += NT) sMelCoef[i] = p.melCoef[i];
     for (int i = tid; i < p.nBands + 2; i += NT) sMelRange[i] = p.melRange[i];
     for (int i = tid; i < p.dctRows * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
-    if (p.opKind == 1) for (int i = tid; i < p.nBands; i += NT) sEql[i] = p.plpEql[i];
+    if (opKind == 1) for (int i = tid; i < p.nBands; i += NT) sEql[i] = p.plpEql[i];
     for (int i = tid; i < p.nStat; i += NT) sLift[i] = p.dctLift[i];
   }
   for (int i = tid; i < L.sampFloats; i += NT) samp[i] = 0.f;   // lanes beyond a short tile read finite data
@@ -560,13 +564,13 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           // again; we keep re*re+im*im (<= 1.5 ulp apart, below the FFT's own noise floor).
           // The factor 1/2 of X (1/4 of the power) is an exact power-of-two scaling that commutes
           // with every rounding downstream; it is folded into melScale on the host.
-          if (p.magOut != nullptr) {
+          if (magOut != nullptr) {
             // a non-fused consumer needs the magnitude level (fftmagphase.cpp:215-221):
             // |X| = 0.5 * sqrt(a^2+b^2) is exact scaling; the band op then squares it like
             // melspec.cpp:524 does (melScale carries no 1/4 in this mode)
             const float mk = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
             const float mm = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi)));
-            float *mo = p.magOut + ((size_t)(cx.tile0 + j) * NBINS) * F + f;
+            float *mo = magOut + ((size_t)(cx.tile0 + j) * NBINS) * F + f;
             mo[(size_t)k * F] = mk;
             if (k != M - k) mo[(size_t)(M - k) * F] = mm;
             pk[i] = p.melUsePower ? __fmul_rn(mk, mk) : mk;
@@ -592,7 +596,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     }
     __syncthreads();
 
-    if (p.opKind >= 0) {
+    if (opKind >= 0) {
     // ================= mel filterbank (melspec.cpp:543-569) + log (mfcc.cpp:239-243) =================
     // range r holds the bins whose lower band is r-1: band[r-1] += a ; band[r] += p - a, visited
     // in ascending bin order exactly like the reference loop, so each band's float sum has the
@@ -624,7 +628,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           }
           float mval = __fmul_rn(cur, p.melScale);
           if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);   // mfcc.cpp:239-243 / plp.cpp:434-440
-          if (p.opKind == 1 && p.plpAud) {
+          if (opKind == 1 && p.plpAud) {
             // auditory weighting + loudness compression (plp.cpp:488-510)
             if (p.doLog) {
               mval = __fmul_rn(__fadd_rn(mval, sEql[r - 1]), p.plpCompression);
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
               mval = (float)pow((double)mval, (double)p.plpCompression);
             }
           }
-          if (p.opKind == 1 && p.plpInvLog) mval = expf(mval);                    // plp.cpp:513-518
+          if (opKind == 1 && p.plpInvLog) mval = expf(mval);                    // plp.cpp:513-518
           melS[(r - 1) * F + f] = mval;
           cur = nxt;
         }
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 
     // ================= DCT-II + lifter (mfcc.cpp:251-272) / PLP back end (plp.cpp:520-590) =================
     const int ringBase = (j & 1) * F;   // tiles of a chunk alternate between the two ring halves
-    if (p.opKind == 0) {
+    if (opKind == 0) {
     // each virtual warp owns coefficients i, i+NVW, ... and evaluates them two at a time so
     // that one read of the log-mel column feeds two dot products; the cosine rows are read as
     // float4 (row stride padded to 4).  Each dot product keeps the reference's m = 0..nBands-1
@@ -1163,21 +1167,25 @@ __global__ void pitch_smooth_kernel(const AcfPitchParams p, int u0, int u1)
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-int lld_tile_frames(int nfft) { return nfft == 2048 ? 16 : 32; }
+int lld_tile_frames(int nfft, bool narrow)
+{
+  const int F = nfft == 4096 ? 8 : (nfft == 2048 ? 16 : 32);
+  return (narrow && nfft >= 1024) ? F / 2 : F;
+}
 int lld_virtual_warps(int nfft) { return nfft == 512 ? 8 : (nfft == 1024 ? 16 : 32); }
 int lld_max_chunk_tiles() { return 16; }
-bool lld_supported_fft(int nfft) { return nfft == 512 || nfft == 1024 || nfft == 2048; }
+bool lld_supported_fft(int nfft) { return nfft == 512 || nfft == 1024 || nfft == 2048 || nfft == 4096; }
 
 size_t lld_smem_bytes(const LldParams &p, int nfft)
 {
-  return (size_t)make_layout(p, nfft / 2, lld_tile_frames(nfft)).total;
+  return (size_t)make_layout(p, nfft / 2, lld_tile_frames(nfft, p.narrow != 0)).total;
 }
 
-template <int M, int F, int NT, int MINB, bool VEC2>
-static cudaError_t launch_t(const LldParams &p, int numSMs, cudaStream_t st, LldLaunchInfo *info)
+template <int M, int F, int NT, int MINB, bool VEC2, bool GEN>
+static cudaError_t launch_g(const LldParams &p, int numSMs, cudaStream_t st, LldLaunchInfo *info)
 {
   const size_t smem = (size_t)make_layout(p, M, F).total;
-  auto kern = lld_kernel<M, F, NT, MINB, VEC2>;
+  auto kern = lld_kernel<M, F, NT, MINB, VEC2, GEN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -1192,14 +1200,26 @@ static cudaError_t launch_t(const LldParams &p, int numSMs, cudaStream_t st, Lld
   return cudaGetLastError();
 }
 
+template <int M, int F, int NT, int MINB, bool VEC2>
+static cudaError_t launch_t(const LldParams &p, int numSMs, cudaStream_t st, LldLaunchInfo *info)
+{
+  if (p.opKind == 0 && p.magOut == nullptr) return launch_g<M, F, NT, MINB, VEC2, false>(p, numSMs, st, info);
+  return launch_g<M, F, NT, MINB, VEC2, true>(p, numSMs, st, info);
+}
+
 cudaError_t launch_lld(const LldParams &p, int nfft, int numSMs, cudaStream_t st, LldLaunchInfo *info)
 {
   // VEC2: 64-bit sample-pair loads need an even per-lane stride (frameStep + sPad)
   const bool vec2 = ((p.frameStep + p.sPad) % 2) == 0;
+  // narrow tiles: half the frames per tile with half the threads (same number of virtual warps)
+  if (p.narrow && nfft == 1024) return vec2 ? launch_t<512, 16, 256, 1, true>(p, numSMs, st, info) : launch_t<512, 16, 256, 1, false>(p, numSMs, st, info);
+  if (p.narrow && nfft == 2048) return vec2 ? launch_t<1024, 8, 256, 1, true>(p, numSMs, st, info) : launch_t<1024, 8, 256, 1, false>(p, numSMs, st, info);
+  if (p.narrow && nfft == 4096) return vec2 ? launch_t<2048, 4, 128, 1, true>(p, numSMs, st, info) : launch_t<2048, 4, 128, 1, false>(p, numSMs, st, info);
   switch (nfft) {
     case 512:  return vec2 ? launch_t<256, 32, 256, 2, true>(p, numSMs, st, info) : launch_t<256, 32, 256, 2, false>(p, numSMs, st, info);
     case 1024: return vec2 ? launch_t<512, 32, 512, 1, true>(p, numSMs, st, info) : launch_t<512, 32, 512, 1, false>(p, numSMs, st, info);
     case 2048: return vec2 ? launch_t<1024, 16, 512, 1, true>(p, numSMs, st, info) : launch_t<1024, 16, 512, 1, false>(p, numSMs, st, info);
+    case 4096: return vec2 ? launch_t<2048, 8, 256, 1, true>(p, numSMs, st, info) : launch_t<2048, 8, 256, 1, false>(p, numSMs, st, info);
     default:   return cudaErrorInvalidValue;
   }
 }
@@ -1217,7 +1237,7 @@ cudaError_t launch_post(const PostParams &p, cudaStream_t st)
   return cudaGetLastError();
 }
 
-bool acf_pitch_supported_fft(int nfft) { return nfft == 512 || nfft == 1024; }
+bool acf_pitch_supported_fft(int nfft) { return nfft == 512 || nfft == 1024 || nfft == 2048; }
 
 template <int N, int F, int NT>
 static cudaError_t launch_acf_t(const AcfPitchParams &p, cudaStream_t st)
@@ -1236,6 +1256,7 @@ cudaError_t launch_acf_pitch(const AcfPitchParams &p, cudaStream_t st)
   switch (p.nfft) {
     case 512:  return launch_acf_t<512, 32, 512>(p, st);
     case 1024: return launch_acf_t<1024, 16, 512>(p, st);
+    case 2048: return launch_acf_t<2048, 8, 256>(p, st);
     default:   return cudaErrorInvalidValue;
   }
 }

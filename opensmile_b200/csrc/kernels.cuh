@@ -21,6 +21,7 @@ struct LldParams {
   int nChunks;
   int nChan;
   // fused temporal stages (static | delta(W1) | delta(W1,W2)); halo = W1 + W2, 0 when not fused
+  int narrow;                    // 1: half-width tiles (F/2 frames), used when the full tile does not fit shared memory
   int fused, halo, fW1, fW2;
   float fNorm1, fNorm2;
   float fRcp1, fRcp2;            // 1/norm when the reciprocal+FMA division is proven exact for it, else 0
@@ -100,7 +101,7 @@ int post_tile_rows();
 // smem bytes the fused kernel needs for a given geometry (host helper, used for diagnostics)
 size_t lld_smem_bytes(const LldParams &p, int nfft);
 // frames per tile / virtual warps per CTA for a given FFT size
-int lld_tile_frames(int nfft);
+int lld_tile_frames(int nfft, bool narrow = false);
 int lld_virtual_warps(int nfft);
 int lld_max_chunk_tiles();
 bool lld_supported_fft(int nfft);

@@ -83,7 +83,7 @@ int main()
   printf("butterflies max err %.3g\n", maxerr);
   if (maxerr > 2e-6) return 1;
   maxerr = 0;
-  check_fft<256>(); check_fft<512>(); check_fft<1024>();
+  check_fft<256>(); check_fft<512>(); check_fft<1024>(); check_fft<2048>();
   printf("fft max err / sqrt(M) %.3g\n", maxerr);
   return maxerr > 2e-6 ? 1 : 0;
 }

@@ -83,6 +83,38 @@ def test_batch_vs_oracle_44k1_stereo():
     p.close()
 
 
+def test_batch_vs_oracle_48k_stereo_narrow_tiles():
+    """48 kHz stereo: 1200-sample frames (FFT 2048) with a 480-sample stride do not fit the full
+    16-frame tile into shared memory -> the half-width (8-frame) kernel instance runs."""
+    comps = components_mfcc12_0_d_a(48000.0, n_channels=2)
+    p = Plan(comps, "lld", device=0)
+    utts = [voiced_pcm(n, 48000, seed=300 + i, n_chan=2) for i, n in enumerate([24000, 1200, 1679, 9000])]
+    pcm, off = pack_utterances(utts, n_chan=2)
+    out = p.run_host(pcm, off)
+    fo = p.frame_offsets(off)
+    for u, x in enumerate(utts):
+        ref = oracle.mfcc_d_a(x, 48000.0, n_chan=2)
+        got = out[fo[u]:fo[u + 1]]
+        assert got.shape == ref.shape
+        assert rel_to_frame_scale(got, ref) < TOL
+    p.close()
+
+
+def test_batch_vs_oracle_96k_fft4096():
+    """96 kHz: 2400-sample frames -> FFT 4096 (8-frame tiles, radix 16 x 16 x 8)."""
+    p = Plan(components_mfcc12_0_d_a(96000.0), "lld", device=0)
+    utts = [voiced_pcm(n, 96000, seed=400 + i) for i, n in enumerate([48000, 2400, 5000])]
+    pcm, off = pack_utterances(utts)
+    out = p.run_host(pcm, off)
+    fo = p.frame_offsets(off)
+    for u, x in enumerate(utts):
+        ref = oracle.mfcc_d_a(x, 96000.0)
+        got = out[fo[u]:fo[u + 1]]
+        assert got.shape == ref.shape
+        assert rel_to_frame_scale(got, ref) < TOL
+    p.close()
+
+
 def test_extreme_inputs(plan16):
     # silence (log floor path), full-scale square wave, single impulse
     n = 400 + 160 * 40
