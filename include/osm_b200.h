@@ -190,7 +190,10 @@ typedef struct {            /* cDeltaRegression */
 
 typedef struct { int32_t smaWin; int32_t noZeroSma; } osm_b200_contoursmoother; /* 3, 0 */
 
-typedef struct { int32_t operation; } osm_b200_vectoroperation; /* 0 = ll1 (L1 norm / sum) */
+typedef struct {            /* cVectorOperation, n -> 1 operations only (src/other/vectorOperation.cpp:475-481) */
+  int32_t operation;        /* 0 = ll1: sum of the input vector / number of elements */
+  char    nameBase[OSM_B200_NAME_LEN]; /* replaces the input field name when set (:246-248) */
+} osm_b200_vectoroperation;
 
 /* cVectorConcat: the cVectorProcessor field selection (src/core/vectorProcessor.cpp:37-39,196-243).
  * processArrayFields = 1 passes array fields only (single-element fields are dropped unless

@@ -127,7 +127,7 @@ class ContourSmoother(C.Structure):
 
 
 class VectorOperation(C.Structure):
-    _fields_ = [("operation", i32)]
+    _fields_ = [("operation", i32), ("nameBase", C.c_char * NAME_LEN)]
 
 
 class VectorConcat(C.Structure):

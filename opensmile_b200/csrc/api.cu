@@ -77,11 +77,25 @@ struct PinBuf {
 
 
 // per-stream runtime state (one framer / FFT chain)
+// one lld_kernel launch of a stream: the FFT front end + one band op (or none: magnitude dump only)
+struct PassRt {
+  LldParams kp;
+  unsigned char *dConst = nullptr;
+  int op = -1;                   // index into PlanDesc::ops, -1 = no band op
+  bool rasta = false;            // cPlp with RASTA: kp stops at the band level, tail = the rest of cPlp
+  LldParams tail;
+  RastaParams rp;
+  DevBuf<float> dBand;           // [static rows][nBands]
+};
+
 struct StreamRt {
   unsigned char *dConst = nullptr;
-  LldParams kp;                  // template filled at create
+  LldParams kp;                  // pass 0 (the only pass of fused plans)
+  std::vector<PassRt> extra;     // passes 1.. (further band ops on the same FFT chain)
+  PassRt pass0x;                 // RASTA state of pass 0 (kp / dConst of pass 0 live above)
   int tileF = 32;
   bool runLld = false;           // lld_kernel is launched for this stream
+  bool forceNarrow = false;
   bool needTiles = false;        // standalone ops read this stream tile by tile
   const float *dWindow = nullptr;   // [frameSize] window floats (time-domain ops)
   std::vector<int32_t> uttChunk0, uttTile0;
@@ -92,6 +106,7 @@ struct StreamRt {
 
 struct OpRt {
   int kind = 0, stream = 0;
+  int vSrcCol = 0, vN = 0, vOutCol = 0;     // SOP_VECOP
   SpectralParams sp;
   TimeOpParams tp;
   AcfPitchParams ap;
@@ -231,8 +246,10 @@ static void build_twiddles(int M, std::vector<float2> &tw, int twOff[4])
 }
 
 
-// pack the constant tables of one stream (front end + optional fused band op) and fill its LldParams
-static osm_b200_status setup_stream(osm_b200_plan *pl, int si, const cudaDeviceProp &prop)
+// pack the constant tables of one lld_kernel pass of a stream (front end + optional band op `opIdx`)
+// and fill its LldParams.  `dumps`: this pass writes the magnitude level.
+static osm_b200_status build_pass(osm_b200_plan *pl, int si, int opIdx, bool dumps, const cudaDeviceProp &prop,
+                                  LldParams &kp, unsigned char *&dConstOut, PassRt &pr)
 {
   const PlanDesc &d = pl->d;
   const Stream &sd = d.streams[si];
@@ -240,7 +257,7 @@ static osm_b200_status setup_stream(osm_b200_plan *pl, int si, const cudaDeviceP
   const FrontEnd &fe = sd.fe;
   rt.runLld = sd.hasFft && (sd.fusedOp >= 0 || sd.dumpMag);
   rt.tileF = lld_supported_fft(fe.nfft) ? lld_tile_frames(fe.nfft) : 32;
-  LldParams &kp = rt.kp;
+  pr.op = opIdx;
   memset(&kp, 0, sizeof kp);
   kp.opKind = -1;
   kp.nChan = fe.nChan;
@@ -283,8 +300,8 @@ static osm_b200_status setup_stream(osm_b200_plan *pl, int si, const cudaDeviceP
     tw.push_back(make_float2(0.f, 0.f));
     oTw = put(tw.data(), tw.size() * sizeof(float2));
     oSplit = put(split.data(), split.size() * sizeof(float2));
-    if (sd.fusedOp >= 0) {
-      const StaticOp &op = d.ops[sd.fusedOp];
+    if (opIdx >= 0) {
+      const StaticOp &op = d.ops[opIdx];
       const bool isPlp = op.kind == SOP_PLP;
       const MelBank &mb = d.mels[isPlp ? op.plp.melIdx : op.mfcc.melIdx];
       const MfccOp &mf = op.mfcc;
@@ -294,7 +311,7 @@ static osm_b200_status setup_stream(osm_b200_plan *pl, int si, const cudaDeviceP
       kp.nBands = mb.nBands; kp.melUsePower = mb.usePower;
       // without a magnitude dump the kernel keeps 2X (4|X|^2) out of the real-FFT split and the
       // exact factor 1/4 of the power path is folded into the band scale
-      kp.melScale = (mb.usePower && !sd.dumpMag) ? mb.outScale * 0.25f : mb.outScale;
+      kp.melScale = (mb.usePower && !dumps) ? mb.outScale * 0.25f : mb.outScale;
       if (!isPlp) {
         kp.nStat = mf.nMfcc; kp.melfloor = mf.melfloor; kp.logMelfloor = mf.logMelfloor; kp.doLog = mf.doLog;
         kp.dctStride = (mb.nBands + 3) / 4 * 4; kp.dctRows = mf.nMfcc;
@@ -335,23 +352,39 @@ static osm_b200_status setup_stream(osm_b200_plan *pl, int si, const cudaDeviceP
       oEql = put(eqlV.data(), eqlV.size() * sizeof(float));
     }
   }
-  CU(cudaMalloc(&rt.dConst, blob.size()));
-  CU(cudaMemcpy(rt.dConst, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-  rt.dWindow = reinterpret_cast<const float *>(rt.dConst + oWindow);
+  unsigned char *dC = nullptr;
+  CU(cudaMalloc(&dC, blob.size()));
+  dConstOut = dC;
+  CU(cudaMemcpy(dC, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  if (!rt.dWindow) rt.dWindow = reinterpret_cast<const float *>(dC + oWindow);
   if (rt.runLld) {
-    kp.winLut = reinterpret_cast<const float4 *>(rt.dConst + oWin);
-    kp.twiddles = reinterpret_cast<const float2 *>(rt.dConst + oTw);
-    kp.splitTw = reinterpret_cast<const float2 *>(rt.dConst + oSplit);
-    if (sd.fusedOp >= 0) {
-      kp.melCoef = reinterpret_cast<const float *>(rt.dConst + oCoef);
-      kp.melRange = reinterpret_cast<const int *>(rt.dConst + oRange);
-      kp.dctCos = reinterpret_cast<const float *>(rt.dConst + oDct);
-      kp.dctLift = reinterpret_cast<const float *>(rt.dConst + oLift);
-      kp.plpEql = reinterpret_cast<const float *>(rt.dConst + oEql);
+    kp.winLut = reinterpret_cast<const float4 *>(dC + oWin);
+    kp.twiddles = reinterpret_cast<const float2 *>(dC + oTw);
+    kp.splitTw = reinterpret_cast<const float2 *>(dC + oSplit);
+    if (opIdx >= 0) {
+      kp.melCoef = reinterpret_cast<const float *>(dC + oCoef);
+      kp.melRange = reinterpret_cast<const int *>(dC + oRange);
+      kp.dctCos = reinterpret_cast<const float *>(dC + oDct);
+      kp.dctLift = reinterpret_cast<const float *>(dC + oLift);
+      kp.plpEql = reinterpret_cast<const float *>(dC + oEql);
+      const StaticOp &op = d.ops[opIdx];
+      if (op.kind == SOP_PLP && op.plp.rasta) {
+        // RASTA sits in the middle of cPlp: the kernel pass stops at the (log) band level, a
+        // sequential filter runs over time, plp_tail_kernel finishes the op
+        pr.rasta = true;
+        pr.tail = kp;
+        kp.plpAud = 0; kp.plpInvLog = 0; kp.plpIDFT = 0; kp.plpLP = 0; kp.plpCeps = 0; kp.plpLifter = 0;
+        kp.nStat = kp.nBands;
+        memset(&pr.rp, 0, sizeof pr.rp);
+        pr.rp.nBands = kp.nBands; pr.rp.frameSize = fe.frameSize; pr.rp.frameStep = fe.frameStep;
+        pr.rp.mode = op.plp.rasta; pr.rp.iir = op.plp.rastaIir;
+        for (int i = 0; i < 5; i++) pr.rp.fir[i] = op.plp.rastaFir[i];
+      }
     }
-    if (lld_smem_bytes(kp, fe.nfft) > (size_t)prop.sharedMemPerBlockOptin && fe.nfft >= 1024) {
+    if (rt.forceNarrow || (lld_smem_bytes(kp, fe.nfft) > (size_t)prop.sharedMemPerBlockOptin && fe.nfft >= 1024)) {
       kp.narrow = 1;                                   // long stereo strides: half-width tiles
       rt.tileF = lld_tile_frames(fe.nfft, true);
+      rt.forceNarrow = true;                           // every pass of a stream uses the same tile width
     }
     if (lld_smem_bytes(kp, fe.nfft) > (size_t)prop.sharedMemPerBlockOptin)
       return fail(OSM_B200_ERR_UNSUPPORTED, "configuration needs more shared memory than the device offers");
@@ -400,14 +433,29 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   pl->numSMs = prop.multiProcessorCount;
 
   pl->st.resize(d.streams.size());
-  for (size_t s = 0; s < d.streams.size(); s++) STP(setup_stream(pl, (int)s, prop));
+  for (size_t s = 0; s < d.streams.size(); s++) {
+    StreamRt &rt = pl->st[s];
+    const std::vector<int> &bo = d.streams[s].bandOps;
+    // pass 0: first band op (or none) + the magnitude dump; passes 1..: the other band ops
+    STP(build_pass(pl, (int)s, bo.empty() ? -1 : bo[0], d.streams[s].dumpMag, prop, rt.kp, rt.dConst, rt.pass0x));
+    rt.extra.resize(bo.size() > 1 ? bo.size() - 1 : 0);
+    for (size_t j = 1; j < bo.size(); j++) {
+      PassRt &pr = rt.extra[j - 1];
+      STP(build_pass(pl, (int)s, bo[j], false, prop, pr.kp, pr.dConst, pr));
+    }
+    if (rt.forceNarrow) {                              // a later pass switched to half-width tiles: all must agree
+      rt.kp.narrow = 1;
+      for (PassRt &pr : rt.extra) pr.kp.narrow = 1;
+    }
+  }
 
   // ---- output groups / execution mode ----
   PostParams &pp = pl->pp;
   memset(&pp, 0, sizeof pp);
   // "simple" plans: one stream, one fused band op, nothing else.  Their static rows go straight
   // into the output rows; delta / delta-delta can then be fused into lld_kernel as well.
-  const bool simple = d.streams.size() == 1 && d.ops.size() == 1 && d.streams[0].fusedOp == 0 && !d.streams[0].dumpMag;
+  const bool simple = d.streams.size() == 1 && d.ops.size() == 1 && d.streams[0].fusedOp == 0 && !d.streams[0].dumpMag &&
+                      !(d.ops[0].kind == SOP_PLP && d.ops[0].plp.rasta);
   pl->staticDirect = false;
   if (simple)
     for (const auto &g : d.groups)
@@ -418,6 +466,8 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     PostGroup &pg = pp.groups[pp.nGroups++];
     pg.srcCol = g.srcCol; pg.n = g.n; pg.outCol = g.outCol; pg.nStages = (int)g.stages.size();
     pg.frameSize = d.streams[g.stream].fe.frameSize; pg.frameStep = d.streams[g.stream].fe.frameStep;
+    pg.nLim = 0;
+    for (int ls : g.limitStreams) if (pg.nLim < 3) { pg.limSize[pg.nLim] = d.streams[ls].fe.frameSize; pg.limStep[pg.nLim] = d.streams[ls].fe.frameStep; pg.nLim++; }
     for (size_t i = 0; i < g.stages.size(); i++) { pg.kind[i] = g.stages[i].kind; pg.win[i] = g.stages[i].win; pg.flags[i] = g.stages[i].flags; }
   }
   // fused pattern: [static | delta(W1) | delta(W1,W2)] over the whole static vector
@@ -462,6 +512,13 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     if (op.kind == SOP_MFCC || op.kind == SOP_PLP) continue;      // fused into its stream's lld_kernel
     OpRt rt;
     rt.kind = op.kind; rt.stream = op.stream;
+    if (op.kind == SOP_VECOP) {
+      const StaticOp &src = d.ops[op.srcOp];
+      if (src.kind != SOP_MFCC && src.kind != SOP_PLP) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cVectorOperation: the input must be a cMfcc / cPlp level"); }
+      rt.vSrcCol = src.outCol; rt.vN = src.nOut; rt.vOutCol = op.outCol;
+      pl->ops.push_back(rt);
+      continue;
+    }
     const FrontEnd &fe = d.streams[op.stream].fe;
     StreamRt &srt = pl->st[op.stream];
     srt.needTiles = true;
@@ -548,6 +605,8 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
   cudaDeviceSynchronize();
   for (StreamRt &s : pl->st) {
     if (s.dConst) cudaFree(s.dConst);
+    s.pass0x.dBand.release();
+    for (PassRt &pr : s.extra) { if (pr.dConst) cudaFree(pr.dConst); pr.dBand.release(); }
     s.hChunks.release(); s.dChunks.release(); s.hTiles.release(); s.dTiles.release(); s.dMag.release();
   }
   for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); }
@@ -708,25 +767,47 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
     if (!rt.runLld) continue;
     const int c0 = rt.uttChunk0[u0], c1 = rt.uttChunk0[u1];
     if (c1 <= c0) continue;
-    LldParams kp = rt.kp;
-    kp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
-    kp.uttOff = dU;
-    kp.chunks = rt.dChunks.p + c0;
-    kp.nChunks = c1 - c0;
-    kp.magOut = d.streams[si].dumpMag ? rt.dMag.p : nullptr;
-    if (pl->staticDirect) {
-      kp.out = d_out; kp.outStride = d.nOut; kp.outCol = pl->identityOutCol; kp.rowOff = dR;
-    } else {
-      kp.out = pl->dStat.p; kp.outStride = d.nStatic; kp.rowOff = dS;
-      kp.outCol = d.streams[si].fusedOp >= 0 ? d.ops[d.streams[si].fusedOp].outCol : 0;
+    const long long *hS = pl->hMeta.p + 2 * nm;
+    const long long row0 = hS[u0], row1 = hS[u1];
+    for (size_t j = 0; j <= rt.extra.size(); j++) {
+      PassRt &pr = j == 0 ? rt.pass0x : rt.extra[j - 1];
+      LldParams kp = j == 0 ? rt.kp : pr.kp;
+      kp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
+      kp.uttOff = dU;
+      kp.chunks = rt.dChunks.p + c0;
+      kp.nChunks = c1 - c0;
+      kp.magOut = (j == 0 && d.streams[si].dumpMag) ? rt.dMag.p : nullptr;
+      if (pl->staticDirect) {
+        kp.out = d_out; kp.outStride = d.nOut; kp.outCol = pl->identityOutCol; kp.rowOff = dR;
+      } else {
+        kp.out = pl->dStat.p; kp.outStride = d.nStatic; kp.rowOff = dS;
+        kp.outCol = pr.op >= 0 ? d.ops[pr.op].outCol : 0;
+      }
+      if (pr.rasta) {
+        CU(pr.dBand.reserve((size_t)pl->totalStat * kp.nBands + 64));
+        kp.out = pr.dBand.p; kp.outStride = kp.nBands; kp.outCol = 0; kp.rowOff = dS;
+      }
+      CU(launch_lld(kp, d.streams[si].fe.nfft, pl->numSMs, st, &pl->lastInfo));
+      pl->lastLaunches++;
+      if (pr.rasta) {
+        RastaParams rp = pr.rp;
+        rp.band = pr.dBand.p; rp.uttOff = dU; rp.statOff = dS;
+        CU(launch_rasta(rp, u0, u1, st));
+        CU(launch_plp_tail(pr.tail, pr.dBand.p, pl->dStat.p, d.nStatic, d.ops[pr.op].outCol, row0, row1, st));
+        pl->lastLaunches += 2;
+      }
     }
-    CU(launch_lld(kp, d.streams[si].fe.nfft, pl->numSMs, st, &pl->lastInfo));
-    pl->lastLaunches++;
   }
   if (u0 == 0) CU(cudaEventRecord(pl->evKm, st));
   // 2. standalone ops
   for (OpRt &o : pl->ops) {
     StreamRt &rt = pl->st[o.stream];
+    if (o.kind == SOP_VECOP) {
+      const long long *hS = pl->hMeta.p + 2 * nm;
+      CU(launch_vecop_ll1(pl->dStat.p, d.nStatic, o.vSrcCol, o.vN, o.vOutCol, hS[u0], hS[u1], st));
+      pl->lastLaunches++;
+      continue;
+    }
     const int t0 = rt.uttTile0[u0], t1 = rt.uttTile0[u1];
     if (t1 <= t0) continue;
     if (o.kind == SOP_SPECTRAL) {

@@ -91,6 +91,7 @@ int64_t desc_num_frames(const PlanDesc &d, int64_t L)
   int64_t best = -1;
   for (const auto &g : d.groups) {
     int64_t t = desc_num_static_frames(d, g.stream, L);
+    for (int ls : g.limitStreams) t = std::min<int64_t>(t, desc_num_static_frames(d, ls, L));
     if (t <= 0) return 0;
     for (const auto &s : g.stages) t += s.win;
     if (best < 0 || t < best) best = t;
@@ -226,7 +227,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
   // between it and the output level.
   struct Leaf { const osm_b200_component *c; std::vector<const osm_b200_component *> stages; bool arraysOnly; };
   std::vector<Leaf> leaves;
-  struct ConcatCheck { size_t g0, g1; };          // leaves [g0, g1) sit below a concat that has stages above it
+  struct ConcatCheck { size_t g0, g1, above; };          // leaves [g0, g1) sit below a concat that has stages above it
   std::vector<std::pair<size_t, size_t>> leafGroups;   // leaf -> its groups [first, last)
   std::vector<ConcatCheck> concatChecks;
   std::function<osm_b200_status(const std::string &, std::vector<const osm_b200_component *>, int, bool)> expand =
@@ -256,7 +257,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         osm_b200_status s2 = expand(c->reader_dmLevel[i], stageComps, depth + 1, arraysOnly);
         if (s2 != OSM_B200_OK) return s2;
       }
-      if (!stageComps.empty()) concatChecks.push_back({g0, leaves.size()});
+      if (!stageComps.empty()) concatChecks.push_back({g0, leaves.size(), stageComps.size()});
       return OSM_B200_OK;
     }
     leaves.push_back(Leaf{c, stageComps, arraysOnly});
@@ -267,16 +268,12 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     if (s0 != OSM_B200_OK) return s0;
   }
 
-  for (const Leaf &leaf : leaves) {
-    const osm_b200_component *c = leaf.c;
-    const std::vector<const osm_b200_component *> &stageComps = leaf.stages;
-
-    // static feature producer
-    int opIdx;
-    auto it = staticOpOf.find(c);
-    if (it != staticOpOf.end()) {
-      opIdx = it->second;
-    } else {
+  // static feature producer of component c (created on first use)
+  std::function<osm_b200_status(const osm_b200_component *, int &)> get_op =
+    [&](const osm_b200_component *c, int &opIdx) -> osm_b200_status {
+    {
+      auto it = staticOpOf.find(c);
+      if (it != staticOpOf.end()) { opIdx = it->second; return OSM_B200_OK; }
       StaticOp op;
       ChainInfo ci;
       std::string base;
@@ -308,11 +305,14 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
           fn.n = op.nOut; fn.arrNameOffset = op.mfcc.first;             // lldcore/mfcc.cpp:125
         } else {
           op.kind = SOP_PLP;
-          if (!build_plp(c->u.plp, d.mels.back(), op.plp, err)) return OSM_B200_ERR_UNSUPPORTED;
+          if (!build_plp(c->u.plp, d.mels.back(), fe.frameStepSec, op.plp, err)) return OSM_B200_ERR_UNSUPPORTED;
           op.plp.melIdx = (int)d.mels.size() - 1;
           op.nOut = op.plp.nOut;
           // lldcore/plp.cpp:232-267 replaces the field name, then cVectorProcessor appends nameAppend
-          const char *fixed = op.plp.doLpToCeps ? "PlpCC" : (op.plp.doLP ? "Plpc" : (op.plp.doIDFT ? "audAutoCor" : "audSpec"));
+          const int ra = op.plp.rasta;
+          const char *fixed = op.plp.doLpToCeps ? (ra ? "RASTAPlpCC" : "PlpCC")
+                            : (op.plp.doLP ? (ra == 1 ? "RASTAPlpc" : (ra == 2 ? "newRASTAPlpc" : "Plpc"))
+                            : (op.plp.doIDFT ? "audAutoCor" : "audSpec"));
           fn.name = name_append_auto(*c, fixed, nullptr);
           fn.n = op.nOut; fn.arrNameOffset = 0;
         }
@@ -419,6 +419,25 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
           if (op.mzcr.dc) add("dc");
         }
         if (op.nOut < 1) { err = "component produces no output"; return OSM_B200_ERR_INVALID; }
+      } else if (c->type == OSM_B200_C_VECTOROPERATION) {
+        // n -> 1 reduction of another static level (other/vectorOperation.cpp:475-481, names :226-249)
+        if (c->u.vectoroperation.operation != 0) { err = "cVectorOperation: only operation=ll1 is supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        const osm_b200_component *in = single_input(c);
+        if (!in) { err = "cVectorOperation must read exactly one level"; return OSM_B200_ERR_UNSUPPORTED; }
+        int src = -1;
+        osm_b200_status s2 = get_op(in, src);
+        if (s2 != OSM_B200_OK) return s2;
+        if (d.ops[src].fields.size() != 1) { err = "cVectorOperation: the input level must hold exactly one field"; return OSM_B200_ERR_UNSUPPORTED; }
+        op.kind = SOP_VECOP;
+        op.srcOp = src;
+        op.stream = d.ops[src].stream;
+        op.nOut = 1;
+        FieldName fn;
+        osm_b200_component named = *c;
+        if (!named.nameAppend[0]) snprintf(named.nameAppend, sizeof named.nameAppend, "%s", "lengthL1norm");
+        const std::string inName = c->u.vectoroperation.nameBase[0] ? std::string(c->u.vectoroperation.nameBase) : d.ops[src].fields[0].name;
+        fn.name = name_append_auto(named, inName, nullptr);
+        op.fields.push_back(fn);
       } else {
         snprintf(buf, sizeof buf, "component '%s' (%s) is not a supported static LLD producer", c->name, type_name(c->type));
         err = buf; return OSM_B200_ERR_UNSUPPORTED;
@@ -428,6 +447,17 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       d.ops.push_back(op);
       opIdx = (int)d.ops.size() - 1;
       staticOpOf[c] = opIdx;
+    }
+    return OSM_B200_OK;
+  };
+
+  for (const Leaf &leaf : leaves) {
+    const osm_b200_component *c = leaf.c;
+    const std::vector<const osm_b200_component *> &stageComps = leaf.stages;
+    int opIdx = -1;
+    {
+      osm_b200_status so = get_op(c, opIdx);
+      if (so != OSM_B200_OK) return so;
     }
 
     // ---- groups: one per run of consecutive fields that survive the concat's field selection ----
@@ -480,38 +510,53 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     leafGroups.push_back({firstGroup, d.groups.size()});
   }
   if (d.ops.empty() || d.groups.empty()) { err = "the output level has no elements (cVectorConcat drops single-element fields unless includeSingleElementFields=1)"; return OSM_B200_ERR_INVALID; }
-  // a concat below temporal stages must not truncate: same frame geometry and the same number of
-  // EOI padding frames on every input (core/dataReader.cpp:375-380 takes the minimum otherwise)
+  // A concat (or multi-level reader) below temporal stages delivers min over its inputs
+  // (core/dataReader.cpp:375-380).  Inputs of different frame geometry are supported when they are
+  // static levels (no stage below the concat): every group then carries the other streams as limits.
   for (const ConcatCheck &cc : concatChecks) {
-    auto geom = [&](const OutGroup &g, int &fs, int &fst, int &w) {
-      fs = d.streams[g.stream].fe.frameSize; fst = d.streams[g.stream].fe.frameStep; w = 0;
-      for (const auto &st : g.stages) w += st.win;
-    };
-    int fs0 = -1, fst0 = 0, w0 = 0;
+    std::vector<int> streams;
+    int w0 = -1;
+    bool sameW = true;
     for (size_t l = cc.g0; l < cc.g1; l++)
       for (size_t g = leafGroups[l].first; g < leafGroups[l].second; g++) {
-        int fs, fst, w;
-        geom(d.groups[g], fs, fst, w);
-        if (fs0 < 0) { fs0 = fs; fst0 = fst; w0 = w; }
-        if (fs != fs0 || fst != fst0 || w != w0) {
-          err = "cVectorConcat of unequally long levels below a temporal stage is not supported";
-          return OSM_B200_ERR_UNSUPPORTED;
-        }
+        int w = 0;
+        for (const auto &st : d.groups[g].stages) w += st.win;
+        if (w0 < 0) w0 = w;
+        if (w != w0) sameW = false;
+        const FrontEnd &fe = d.streams[d.groups[g].stream].fe;
+        bool known = false;
+        for (int sidx : streams) known = known || (d.streams[sidx].fe.frameSize == fe.frameSize && d.streams[sidx].fe.frameStep == fe.frameStep);
+        if (!known) streams.push_back(d.groups[g].stream);
       }
+    if (streams.size() <= 1 && sameW) continue;          // nothing truncates
+    bool ok = sameW;
+    // the stages every leaf carries must all sit above the concat (i.e. the leaves are statics)
+    for (size_t l = cc.g0; l < cc.g1 && ok; l++) ok = leaves[l].stages.size() == cc.above;
+    if (!ok) { err = "cVectorConcat of unequally long, already smoothed levels below a temporal stage is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+    if (streams.size() > 4) { err = "more than 4 frame geometries below one cVectorConcat"; return OSM_B200_ERR_UNSUPPORTED; }
+    for (size_t l = cc.g0; l < cc.g1; l++)
+      for (size_t g = leafGroups[l].first; g < leafGroups[l].second; g++)
+        for (int sidx : streams) {
+          const FrontEnd &a = d.streams[sidx].fe, &b = d.streams[d.groups[g].stream].fe;
+          if (a.frameSize == b.frameSize && a.frameStep == b.frameStep) continue;
+          if (std::find(d.groups[g].limitStreams.begin(), d.groups[g].limitStreams.end(), sidx) == d.groups[g].limitStreams.end())
+            d.groups[g].limitStreams.push_back(sidx);
+        }
   }
 
   // ---- execution strategy per stream ----
   // A stream with exactly one band op (MFCC / PLP) and no other spectral consumer evaluates it
   // inside lld_kernel; any other spectral consumer reads the magnitude level from HBM.
   for (size_t s = 0; s < d.streams.size(); s++) {
-    int nBand = 0, nSpec = 0, band = -1;
+    int nSpec = 0;
+    d.streams[s].bandOps.clear();
     for (size_t o = 0; o < d.ops.size(); o++) {
       if (d.ops[o].stream != (int)s) continue;
-      if (d.ops[o].kind == SOP_MFCC || d.ops[o].kind == SOP_PLP) { nBand++; band = (int)o; }
+      if (d.ops[o].kind == SOP_MFCC || d.ops[o].kind == SOP_PLP) d.streams[s].bandOps.push_back((int)o);
       if (d.ops[o].kind == SOP_SPECTRAL || d.ops[o].kind == SOP_PITCHACF) nSpec++;
     }
-    if (nBand > 1) { err = "more than one cMfcc / cPlp on one FFT chain is not supported yet"; return OSM_B200_ERR_UNSUPPORTED; }
-    d.streams[s].fusedOp = band;
+    const int nBand = (int)d.streams[s].bandOps.size();
+    d.streams[s].fusedOp = nBand ? d.streams[s].bandOps[0] : -1;
     d.streams[s].dumpMag = nSpec > 0;
     if ((nBand || nSpec) && (d.streams[s].fe.nfft < 64 || d.streams[s].fe.nfft > 4096)) { err = "FFT size out of the supported range"; return OSM_B200_ERR_UNSUPPORTED; }
   }

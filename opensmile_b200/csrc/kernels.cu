@@ -885,6 +885,10 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
     const PostGroup &g = p.groups[gi];
     const int n = g.n;
     const int T = (Ls >= g.frameSize) ? (int)((Ls - g.frameSize) / g.frameStep + 1) : 0;   // frames of this group's source level
+    // a multi-level reader delivers min over its levels: that bounds how many frames the first stage
+    // produces (before EOI and in total), while reads of THIS level still clamp at its own end
+    int Tlim = T;
+    for (int k = 0; k < g.nLim; k++) Tlim = min(Tlim, (Ls >= g.limSize[k]) ? (int)((Ls - g.limSize[k]) / g.limStep[k] + 1) : 0);
     // level 0 view of this group: copy its columns so that every level has row stride n
     const float *cur;
     {
@@ -898,13 +902,14 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
     }
     __syncthreads();
     int Tprev = T, n0 = T;                          // input level: total frames, frames before EOI
+    int Tcnt = Tlim, n0cnt = Tlim;                  // the same as seen through the reader (min over its levels)
     int Hrem = 0;
     for (int s = 0; s < g.nStages; s++) Hrem += g.win[s];
     for (int s = 0; s < g.nStages; s++) {
       const int W = g.win[s];
       Hrem -= W;
-      const int c0 = max(n0 - W, 0);
-      const int Tcur = Tprev + W;
+      const int c0 = max(n0cnt - W, 0);
+      const int Tcur = Tcnt + W;
       float *dst = (cur == A) ? B : A;
       const int lo = max(r0 - Hrem, 0), hi = min(r1 + Hrem, Tcur);   // rows of this level needed
       const int tot = (hi - lo) * n;
@@ -947,8 +952,8 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
       }
       __syncthreads();
       cur = dst;
-      n0 = c0;
-      Tprev = Tcur;
+      n0 = c0; n0cnt = c0;
+      Tprev = Tcur; Tcnt = Tcur;
     }
     // ---- write rows [r0, r1) of this group ----
     {
@@ -1259,6 +1264,131 @@ cudaError_t launch_acf_pitch(const AcfPitchParams &p, cudaStream_t st)
     case 2048: return launch_acf_t<2048, 8, 256>(p, st);
     default:   return cudaErrorInvalidValue;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// cPlp RASTA filter (lldcore/plp.cpp:446-483): a 5-tap FIR + one-pole IIR along time on every band,
+// state reset per utterance; the first 5 outputs are forced to 0.  Sequential in time by
+// construction -> one thread per (utterance, band); float operations in the reference's order.
+// ------------------------------------------------------------------------------------------
+__global__ void rasta_kernel(const RastaParams p, int u0, int u1)
+{
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nB = p.nBands;
+  const int u = u0 + (int)(idx / nB), b = (int)(idx % nB);
+  if (u >= u1) return;
+  const long long L = p.uttOff[u + 1] - p.uttOff[u];
+  const long long T = (L < p.frameSize) ? 0 : (L - p.frameSize) / p.frameStep + 1;
+  float *x = p.band + p.statOff[u] * nB + b;
+  if (p.mode == 1) {
+    float fir[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // circular input history, slot ptr = newest
+    float iir = 0.f;
+    int ptr = 0;
+    for (long long t = 0; t < T; t++) {
+      const float s = x[t * nB];
+      fir[ptr] = s;
+      float sum = __fmul_rn(p.fir[0], s);
+#pragma unroll
+      for (int m = 1; m < 5; m++) sum = __fadd_rn(sum, __fmul_rn(p.fir[m], fir[(5 - m + ptr) % 5]));
+      sum = __fadd_rn(sum, __fmul_rn(p.iir, iir));
+      iir = sum;
+      x[t * nB] = (t >= 5) ? sum : 0.f;
+      ptr = (ptr + 1) % 5;
+    }
+  } else {
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    for (long long t = 0; t < T; t++) {
+      const float s = x[t * nB];
+      const float out = __fadd_rn(__fmul_rn(p.fir[0], s), b0);
+      const float fb = (t >= 5) ? __fmul_rn(p.iir, out) : __fmul_rn(__fmul_rn(0.f, p.iir), out);   // (init>=5) * iir * out
+      b0 = __fadd_rn(__fadd_rn(__fmul_rn(p.fir[1], s), b1), fb);
+      b1 = __fadd_rn(__fmul_rn(p.fir[2], s), b2);
+      b2 = __fadd_rn(__fmul_rn(p.fir[3], s), b3);
+      b3 = __fmul_rn(p.fir[4], s);
+      x[t * nB] = (t >= 5) ? out : 0.f;
+    }
+  }
+}
+
+cudaError_t launch_rasta(const RastaParams &p, int u0, int u1, cudaStream_t st)
+{
+  const long long n = (long long)(u1 - u0) * p.nBands;
+  if (n <= 0) return cudaSuccess;
+  const int bs = 128;
+  rasta_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, st>>>(p, u0, u1);
+  return cudaGetLastError();
+}
+
+// rest of cPlp after the RASTA filter (plp.cpp:486-590) for 32 static rows per CTA, lane = frame
+constexpr int kTailF = 32, kTailWarps = 4;
+__global__ void __launch_bounds__(kTailF * kTailWarps) plp_tail_kernel(const LldParams p, const float *band, float *stat,
+                                                                       int statStride, int outCol, long long row0, long long row1)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int nB = p.nBands;
+  float *melS = reinterpret_cast<float *>(smem);                    // [nB][F]
+  float *acfS = melS + nB * kTailF;                                 // [nAuto][F]
+  float *outS = acfS + (kMaxLp + 1) * kTailF;                       // [nStat][2F]
+  const int tid = threadIdx.x, f = tid & 31, vw = tid >> 5;
+  const long long r0 = row0 + (long long)blockIdx.x * kTailF;
+  const int nf = (int)min((long long)kTailF, row1 - r0);
+  for (int idx = tid; idx < nB * kTailF; idx += blockDim.x) {
+    const int ff = idx / nB, b = idx - ff * nB;
+    float v = 0.f;
+    if (ff < nf) {
+      v = band[(r0 + ff) * nB + b];
+      if (p.plpAud) {                                               // plp.cpp:488-510
+        if (p.doLog) {
+          v = __fmul_rn(__fadd_rn(v, p.plpEql[b]), p.plpCompression);
+        } else {
+          if (v < p.melfloor) v = p.melfloor;
+          v = __fmul_rn(v, p.plpEql[b]);
+          v = (float)pow((double)v, (double)p.plpCompression);
+        }
+      }
+      if (p.plpInvLog) v = expf(v);                                 // :513-518
+    }
+    melS[b * kTailF + ff] = v;
+  }
+  __syncthreads();
+  plp_backend<kTailF, kTailWarps>(p, melS, p.dctCos, p.dctLift, acfS, outS, vw, f);
+  __syncthreads();
+  for (int idx = tid; idx < nf * p.nStat; idx += blockDim.x) {
+    const int ff = idx / p.nStat, c = idx - ff * p.nStat;
+    stat[(r0 + ff) * statStride + outCol + c] = outS[c * (2 * kTailF) + ff];
+  }
+}
+
+cudaError_t launch_plp_tail(const LldParams &op, const float *band, float *stat, int statStride, int outCol,
+                            long long row0, long long row1, cudaStream_t st)
+{
+  if (row1 <= row0) return cudaSuccess;
+  const size_t smem = (size_t)(op.nBands + kMaxLp + 1 + 2 * op.nStat) * kTailF * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(plp_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long nb = (row1 - row0 + kTailF - 1) / kTailF;
+  plp_tail_kernel<<<(unsigned)nb, kTailF * kTailWarps, smem, st>>>(op, band, stat, statStride, outCol, row0, row1);
+  return cudaGetLastError();
+}
+
+__global__ void vecop_ll1_kernel(float *stat, int statStride, int srcCol, int n, int outCol, long long row0, long long row1)
+{
+  const long long r = row0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= row1) return;
+  const float *x = stat + r * statStride + srcCol;
+  float d = 0.f;
+  for (int i = 0; i < n; i++) d = __fadd_rn(d, x[i]);               // vectorOperation.cpp:475-481
+  if (n > 0) d = __fdiv_rn(d, (float)n);
+  stat[r * statStride + outCol] = d;
+}
+
+cudaError_t launch_vecop_ll1(float *stat, int statStride, int srcCol, int n, int outCol, long long row0, long long row1,
+                             cudaStream_t st)
+{
+  if (row1 <= row0) return cudaSuccess;
+  const int bs = 128;
+  vecop_ll1_kernel<<<(unsigned)((row1 - row0 + bs - 1) / bs), bs, 0, st>>>(stat, statStride, srcCol, n, outCol, row0, row1);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pitch_smooth(const AcfPitchParams &p, int u0, int u1, cudaStream_t st)

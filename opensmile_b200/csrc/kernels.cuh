@@ -68,6 +68,9 @@ struct LldParams {
 struct PostGroup {
   int srcCol, n, outCol;
   int frameSize, frameStep;      // geometry of the stream the source level belongs to (defines its T)
+  // the source sits in a multi-level reader / concat together with levels of other streams: the
+  // reader only delivers min over them (core/dataReader.cpp:375-380) -> T = min(T, T of these)
+  int nLim; int limSize[3], limStep[3];
   int nStages;
   int kind[3];                   // 0 = delta, 1 = sma
   int win[3];
@@ -164,6 +167,24 @@ struct AcfPitchParams {
 cudaError_t launch_acf_pitch(const AcfPitchParams &p, cudaStream_t st);     // per-frame analysis -> raw
 cudaError_t launch_pitch_smooth(const AcfPitchParams &p, int u0, int u1, cudaStream_t st);   // raw -> static columns
 bool acf_pitch_supported_fft(int nfft);
+
+// cPlp with RASTA: lld_kernel leaves the (log) band level in `band`, rasta_kernel filters it in place
+// along time (one thread per utterance x band, lldcore/plp.cpp:446-483), plp_tail_kernel applies the
+// rest of cPlp (auditory weighting ... cepstrum, :486-590) and writes the op's static columns.
+struct RastaParams {
+  float *band; int nBands;       // [static rows][nBands]
+  const long long *uttOff, *statOff;
+  int frameSize, frameStep;
+  int mode;                      // 1 RASTA, 2 newRASTA
+  float fir[5], iir;
+};
+cudaError_t launch_rasta(const RastaParams &p, int u0, int u1, cudaStream_t st);
+// op = the cPlp op's LldParams (tables + plp* switches); rows [row0, row1) of the static level
+cudaError_t launch_plp_tail(const LldParams &op, const float *band, float *stat, int statStride, int outCol,
+                            long long row0, long long row1, cudaStream_t st);
+// cVectorOperation ll1: stat[row][outCol] = (sum_i stat[row][srcCol + i]) / n, float, in order
+cudaError_t launch_vecop_ll1(float *stat, int statStride, int srcCol, int n, int outCol, long long row0, long long row1,
+                             cudaStream_t st);
 
 cudaError_t launch_spectral(const SpectralParams &p, cudaStream_t st);
 cudaError_t launch_energy(const TimeOpParams &p, cudaStream_t st);

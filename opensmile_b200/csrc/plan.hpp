@@ -43,7 +43,7 @@ struct FrontEnd {
   bool zeroPadSymmetric = false;   // phase only; magnitude consumers are unaffected
 };
 
-enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF };
+enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP };
 
 struct MfccOp {
   int melIdx = 0;
@@ -65,6 +65,8 @@ struct PlpOp {
   std::vector<float> eql;          // [nBands] equal loudness weights (log of them when doLog)
   std::vector<float> cosT;         // [nAuto][nFreq] IDFT table (plp.cpp:298-306)
   std::vector<float> lift;         // [nCeps] lifter per OUTPUT slot (plp.cpp:560-573)
+  int rasta = 0;                   // 0 none, 1 RASTA, 2 newRASTA: temporal band filter (plp.cpp:361-397,446-483)
+  float rastaFir[5] = {0, 0, 0, 0, 0}, rastaIir = 0.f;
   int nOut = 0;
 };
 
@@ -113,6 +115,7 @@ struct StaticOp {
   bool windowed = false;           // time-domain ops: reads the windower level instead of the framer level
   int outCol = 0, nOut = 0;
   std::vector<FieldName> fields;   // names of the produced level
+  int srcOp = -1;                  // SOP_VECOP: op whose columns of the static level are reduced (ll1)
   MfccOp mfcc;
   PlpOp plp;
   SpectralOp spectral;
@@ -130,6 +133,7 @@ struct OutGroup {
   int srcCol = 0, n = 0;           // columns of the static vector
   int stream = 0;                  // stream whose frame geometry defines T of the source level
   std::vector<Stage> stages;       // applied in order
+  std::vector<int> limitStreams;   // truncating concat / multi-level reader: source length = min over these streams too
   int outCol = 0;
 };
 
@@ -138,7 +142,8 @@ struct Stream {
   FrontEnd fe;
   bool hasWindow = false, hasFft = false;
   bool dumpMag = false;            // a non-fused consumer reads the magnitude level from HBM
-  int fusedOp = -1;                // band op (MFCC / PLP) evaluated inside lld_kernel, -1 = none
+  int fusedOp = -1;                // first band op (MFCC / PLP) evaluated inside lld_kernel, -1 = none
+  std::vector<int> bandOps;        // all band ops of this FFT chain, one lld_kernel pass each
   const void *keyFramer = nullptr, *keyPe = nullptr, *keyWin = nullptr;
 };
 
@@ -164,7 +169,7 @@ int64_t desc_max_static_frames(const PlanDesc &d, int64_t nSampleFrames);
 void build_window(int winFunc, int N, double sigma, double gain, std::vector<float> &w);
 void build_mel(const osm_b200_melspec &cfg, int nBins, double frameSizeSec, MelBank &mb);
 void build_mfcc(const osm_b200_mfcc &cfg, int nBands, MfccOp &op);
-bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, PlpOp &op, std::string &err);
+bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, double levelPeriod, PlpOp &op, std::string &err);
 bool build_spectral(const osm_b200_spectral &cfg, int nSrc, double fftFrameSizeSec, SpectralOp &op, std::string &err);
 void build_energy(const osm_b200_energy &cfg, EnergyOp &op);
 void build_mzcr(const osm_b200_mzcr &cfg, MzcrOp &op);

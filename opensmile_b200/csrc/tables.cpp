@@ -194,9 +194,20 @@ static double eql_hermansky(double f)
 
 // cPlp::myFetchConfig (lldcore/plp.cpp:88-171) + cPlp::initTables (:276-341).
 // RASTA / newRASTA (a recurrence over frames) is not fused yet.
-bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, PlpOp &op, std::string &err)
+bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, double levelPeriod, PlpOp &op, std::string &err)
 {
-  if (cfg.RASTA || cfg.newRASTA) { err = "cPlp: RASTA / newRASTA are not supported yet"; return false; }
+  op.rasta = cfg.newRASTA ? 2 : (cfg.RASTA ? 1 : 0);                                      // :176 newRASTA disables RASTA
+  if (op.rasta) {                                                                       // :361-397, T = reader level period
+    const float upper = (float)cfg.rastaUpperCutoff, lower = (float)cfg.rastaLowerCutoff;   // :171-173 (FLOAT_DMEM)
+    op.rastaIir = (float)(1.0 - sin(2.0 * M_PI * lower * levelPeriod));
+    const float om = (float)cos(2.0 * M_PI * upper * levelPeriod);
+    const float norm = (float)sqrt(10.0 * (32.0 * om * om + 8.0));
+    op.rastaFir[0] = (float)(2.0 / norm);
+    op.rastaFir[1] = (float)(-4.0 * om / norm);
+    op.rastaFir[2] = 0.0;
+    op.rastaFir[3] = -op.rastaFir[1];
+    op.rastaFir[4] = -op.rastaFir[0];
+  }
   int lpOrder = cfg.lpOrder;
   bool doLP = cfg.doLP != 0, doLpToCeps = cfg.doLpToCeps != 0, doIDFT = cfg.doIDFT != 0;
   if (lpOrder <= 0) { lpOrder = 0; doLP = false; doLpToCeps = false; }                 // :103-106
@@ -222,6 +233,7 @@ bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, PlpOp &op, std::strin
   op.doLog = cfg.doLog != 0; op.doAud = cfg.doAud != 0; op.doInvLog = cfg.doInvLog != 0;
   op.htk = cfg.htkcompatible != 0;
   if (op.htk) { op.melfloor = 1.0f; op.doAud = true; op.doLog = false; op.doInvLog = false; }   // :152-163
+  if (op.rasta) { op.doLog = true; op.doInvLog = true; }                                     // :169-170 RASTA works in the log domain
   op.logMelfloor = std::log(op.melfloor);
   const int nBands = mb.nBands;
   op.nFreq = nBands + 2;                                                                // :288

@@ -237,6 +237,7 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
   if (osm_b200_component_defaults(t, &c) != OSM_B200_OK) { err = osm_b200_last_error(); return false; }
   snprintf(c.name, sizeof c.name, "%s", s.name.c_str());
   bool usePowerSet = false;
+  if (t == OSM_B200_C_VECTOROPERATION) c.u.vectoroperation.operation = -1;   // the reference's default is "norm"
   for (const auto &kv : s.kv) {
     const std::string &f = kv.first, &v = kv.second;
     if (f == "reader.dmLevel") {
@@ -383,6 +384,15 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         break;
       case OSM_B200_C_VECTORCONCAT:
         break;
+      case OSM_B200_C_VECTOROPERATION:
+        if (f == "operation") {
+          if (v.compare(0, 3, "ll1") != 0) { err = "cVectorOperation.operation=" + v + " is not supported (ll1 only)"; return false; }
+          c.u.vectoroperation.operation = 0;
+          continue;
+        }
+        if (f == "nameBase") { snprintf(c.u.vectoroperation.nameBase, OSM_B200_NAME_LEN, "%s", v.c_str()); continue; }
+        if (f == "param1" || f == "param2" || f == "logfloor" || f == "powOnlyPos") continue;
+        break;
       default: break;
     }
     // same behaviour as the reference: an unknown field aborts configuration (configManager.cpp:2599)
@@ -392,6 +402,7 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
   if (t == OSM_B200_C_MFCC && c.u.mfcc.lastMfcc <= -1000)          // lastMfcc = firstMfcc + nMfcc - 1 (lldcore/mfcc.cpp:77-82)
     c.u.mfcc.lastMfcc = c.u.mfcc.firstMfcc + (-1000 - c.u.mfcc.lastMfcc) - 1;
   if (t == OSM_B200_C_ACF && c.u.acf.cepstrum && !usePowerSet) c.u.acf.usePower = 0;   // dspcore/acf.cpp:91-99
+  if (t == OSM_B200_C_VECTOROPERATION && c.u.vectoroperation.operation < 0) { err = "cVectorOperation.operation=norm (the default) is not supported (ll1 only)"; return false; }
   return true;
 }
 

@@ -263,6 +263,29 @@ def plp_d_a(pcm, sample_rate, n_chan=1, cfg=None, delta_win=2, accel_win=2):
     return out
 
 
+def plp_static(pcm, sample_rate, cfg, n_chan=1):
+    """cPlp static level only (with RASTA / newRASTA when configured): int16 PCM -> float32 [T, nOut]."""
+    fe, ms, pl = cfg
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nS = pcm.size // n_chan
+    N, H, nfft, T = geometry(fe, nS)
+    K = lib().osm_or_plp_num_out(C.byref(pl), C.c_int(ms.n_bands))
+    out = np.zeros((max(T, 0), K), np.float32)
+    lib().osm_or_plp_static.restype = C.c_long
+    r = lib().osm_or_plp_static(C.byref(fe), C.byref(ms), C.byref(pl), pcm.ctypes.data_as(C.POINTER(C.c_int16)),
+                                C.c_long(nS), C.c_int(n_chan), _fp(out))
+    assert r == max(T, 0), (r, T)
+    return out
+
+
+def ll1(x):
+    """cVectorOperation operation=ll1: per-row float sum / K."""
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.shape[0], np.float32)
+    lib().osm_or_ll1(_fp(x), C.c_long(x.shape[0]), C.c_int(x.shape[1]), _fp(out))
+    return out
+
+
 def delta(x, win):
     x = np.ascontiguousarray(x, np.float32)
     T, K = x.shape

@@ -577,6 +577,10 @@ typedef struct {
   float *cost, *sint, *eql;
   float melfloor, compression, cepLifter;
   int doLog, doAud, doInvLog;
+  /* RASTA (temporal) filter state, lldcore/plp.cpp:361-397,446-483 */
+  double period;            /* reader_->getLevelT(): frame period of the band level */
+  int rasta, newRasta, rInit, rPtr;
+  float rFir[5], rIir, *rBufFir, *rBufIir;
 } plp_ctx;
 
 /* lldcore/plp.cpp:88-171 (config resolution) + :276-341 (tables) */
@@ -598,6 +602,7 @@ static void plp_init(plp_ctx *c, int nBands)
   c->melfloor = (float)pl->melfloor;
   c->doLog = pl->do_log; c->doAud = pl->do_aud; c->doInvLog = pl->do_inv_log;
   if (pl->htkcompatible) { c->melfloor = 1.0f; c->doAud = 1; c->doLog = 0; c->doInvLog = 0; }   /* :152-163 */
+  if (pl->rasta || pl->new_rasta) { c->doLog = 1; c->doInvLog = 1; }                            /* :169-170 */
   c->nFreq = nBands + 2; c->nAuto = lpOrder + 1;               /* :288-290 */
   c->cost = (float *)malloc(sizeof(float) * c->nAuto * c->nFreq);
   float a = (float)M_PI / (float)(c->nFreq - 1);               /* :298 */
@@ -612,6 +617,22 @@ static void plp_init(plp_ctx *c, int nBands)
     if (c->cepLifter > 0.0) c->sint[i - c->firstCC] = ((float)1.0 + c->cepLifter / (float)2.0 * sinf((float)M_PI * ((float)(i)) / c->cepLifter));
     else c->sint[i - c->firstCC] = 1.0;
   }
+  c->rasta = pl->rasta; c->newRasta = pl->new_rasta;
+  if (c->newRasta) c->rasta = 0;                               /* :176 */
+  if (c->rasta || c->newRasta) {                               /* :361-397 */
+    float upper = (float)pl->rasta_upper, lower = (float)pl->rasta_lower;   /* :171-173 (FLOAT_DMEM) */
+    c->rIir = (float)(1.0 - sin(2.0 * M_PI * lower * c->period));
+    float om = (float)cos(2.0 * M_PI * upper * c->period);
+    float norm = (float)sqrt(10.0 * (32.0 * om * om + 8.0));
+    c->rFir[0] = (float)(2.0 / norm);
+    c->rFir[1] = (float)(-4.0 * om / norm);
+    c->rFir[2] = 0.0;
+    c->rFir[3] = -c->rFir[1];
+    c->rFir[4] = -c->rFir[0];
+    c->rBufIir = (float *)calloc(nBands, sizeof(float));
+    c->rBufFir = (float *)calloc((size_t)nBands * 5, sizeof(float));
+    c->rPtr = 0; c->rInit = 0;
+  }
   c->eql = (float *)malloc(sizeof(float) * nBands);
   for (int i = 0; i < nBands; i++) {                           /* :345-357: band centres from the melspec field info */
     c->eql[i] = pl->htkcompatible ? (float)eql_htk(c->mb.band_hz[i]) : (float)eql_herm(c->mb.band_hz[i]);
@@ -619,7 +640,7 @@ static void plp_init(plp_ctx *c, int nBands)
   }
 }
 
-/* lldcore/plp.cpp:416-593 without RASTA (RASTA=newRASTA=0 in PLP_0_D_A.conf) */
+/* lldcore/plp.cpp:416-593 */
 static void plp_apply(plp_ctx *c, const float *src, int Nsrc, float *dst)
 {
   const osm_or_plp *pl = c->pl;
@@ -628,6 +649,32 @@ static void plp_apply(plp_ctx *c, const float *src, int Nsrc, float *dst)
   for (i = 0; i < Nsrc; i++) {
     if (c->doLog) s[i] = (src[i] < c->melfloor) ? logf(c->melfloor) : logf(src[i]);   /* :434-440 */
     else s[i] = src[i];
+  }
+  if (c->rasta) {                                               /* :447-467 */
+    for (i = 0; i < Nsrc; i++) {
+      float sum;
+      c->rBufFir[i * 5 + c->rPtr] = s[i];
+      sum = c->rFir[0] * s[i];
+      for (m = 1; m < 5; m++) sum += c->rFir[m] * c->rBufFir[i * 5 + ((5 - m + c->rPtr) % 5)];
+      sum += c->rIir * c->rBufIir[i];
+      c->rBufIir[i] = sum;
+      if (c->rInit >= 5) s[i] = sum; else s[i] = 0;
+    }
+    if (c->rInit < 5) c->rInit++;
+    c->rPtr = (c->rPtr + 1) % 5;
+  }
+  if (c->newRasta) {                                            /* :468-483 */
+    float *b = c->rBufFir;
+    for (i = 0; i < Nsrc; i++) {
+      float out;
+      out = c->rFir[0] * s[i] + b[i * 4 + 0];
+      b[i * 4 + 0] = c->rFir[1] * s[i] + b[i * 4 + 1] + (c->rInit >= 5) * c->rIir * out;
+      b[i * 4 + 1] = c->rFir[2] * s[i] + b[i * 4 + 2];
+      b[i * 4 + 2] = c->rFir[3] * s[i] + b[i * 4 + 3];
+      b[i * 4 + 3] = c->rFir[4] * s[i];
+      if (c->rInit >= 5) s[i] = out; else s[i] = 0;
+    }
+    if (c->rInit < 5) c->rInit++;
   }
   if (c->doAud) {
     if (c->doLog) {
@@ -690,6 +737,37 @@ int osm_or_plp_num_out(const osm_or_plp *pl, int n_bands)
   return n_bands;
 }
 
+/* cPlp static level only (no temporal stages): out = [T][num_out] */
+long osm_or_plp_static(const osm_or_frontend *fe, const osm_or_melspec *ms, const osm_or_plp *pl,
+                       const int16_t *pcm, long L, int n_chan, float *out)
+{
+  long N = osm_or_frame_size_samples(fe), H = osm_or_frame_step_samples(fe);
+  long nfft = osm_or_fft_size(N);
+  long T = osm_or_num_frames(L, N, H);
+  if (T <= 0) return 0;
+  plp_ctx c; memset(&c, 0, sizeof c);
+  c.ms = ms; c.pl = pl; c.t = 0;
+  c.period = (fe->frame_step_sec != 0.0) ? fe->frame_step_sec : fe->frame_size_sec;   /* level period = cFramer.frameStep */
+  mel_design(ms, nfft / 2 + 1, osm_or_fft_frame_size_sec(fe), &c.mb);
+  plp_init(&c, ms->n_bands);
+  int K = osm_or_plp_num_out(pl, ms->n_bands);
+  c.mel = (float *)malloc(sizeof(float) * ms->n_bands);
+  run_frames(fe, pcm, L, n_chan, plp_frame, &c, K, out, NULL);
+  free(c.mel); free(c.cost); free(c.sint); free(c.eql); free(c.rBufFir); free(c.rBufIir); mel_free(&c.mb);
+  return T;
+}
+
+/* cVectorOperation operation=ll1 (other/vectorOperation.cpp:475-481): float sum / N per row */
+void osm_or_ll1(const float *x, long T, int K, float *out)
+{
+  for (long t = 0; t < T; t++) {
+    float d = 0.0;
+    for (int i = 0; i < K; i++) d += x[t * K + i];
+    if (K > 0) d /= (float)K;
+    out[t] = d;
+  }
+}
+
 long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const osm_or_plp *pl,
                     int dW, int aW, const int16_t *pcm, long L, int n_chan,
                     float *out, float *tap_mel)
@@ -700,6 +778,7 @@ long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const o
   if (T <= 0) return 0;
   plp_ctx c; memset(&c, 0, sizeof c);
   c.ms = ms; c.pl = pl; c.tap_mel = tap_mel; c.t = 0;
+  c.period = (fe->frame_step_sec != 0.0) ? fe->frame_step_sec : fe->frame_size_sec;   /* level period = cFramer.frameStep */
   mel_design(ms, nfft / 2 + 1, osm_or_fft_frame_size_sec(fe), &c.mb);
   plp_init(&c, ms->n_bands);
   int K = osm_or_plp_num_out(pl, ms->n_bands);
@@ -707,7 +786,7 @@ long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const o
   float *stat = (float *)malloc(sizeof(float) * T * K);
   run_frames(fe, pcm, L, n_chan, plp_frame, &c, K, stat, NULL);
   add_deltas(stat, T, K, dW, aW, out);
-  free(stat); free(c.mel); free(c.cost); free(c.sint); free(c.eql); mel_free(&c.mb);
+  free(stat); free(c.mel); free(c.cost); free(c.sint); free(c.eql); free(c.rBufFir); free(c.rBufIir); mel_free(&c.mb);
   return T;
 }
 

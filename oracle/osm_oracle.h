@@ -131,6 +131,11 @@ long osm_or_plp_d_a(const osm_or_frontend *fe, const osm_or_melspec *ms, const o
                     float *out, float *tap_mel);
 
 int osm_or_plp_num_out(const osm_or_plp *pl, int n_bands);
+/* cPlp static level only, with RASTA / newRASTA if configured: out = [T][num_out] */
+long osm_or_plp_static(const osm_or_frontend *fe, const osm_or_melspec *ms, const osm_or_plp *pl,
+                       const int16_t *pcm, long n_samples, int n_chan, float *out);
+/* cVectorOperation operation=ll1: per-row sum / K (other/vectorOperation.cpp:475-481) */
+void osm_or_ll1(const float *x, long T, int K, float *out);
 
 /* static (per-frame) LLDs other than the cepstral chains.  `windowed` selects whether the
  * time-domain component reads the framer level (0) or the windower level (1). */

@@ -9,6 +9,11 @@ Contents (inputs are regenerated in the tests from opensmile_b200.synth.voiced_p
   mfcc_e            config/mfcc/MFCC12_E_D_A.conf, voiced_pcm(12000, 16000, seed=5)
   mfcc_e_short_<n>  the same config on the first n samples of seed 5, n = 400, 560, 720, 880 (1..4 frames)
   plp_e             config/plp/PLP_E_D_A.conf, voiced_pcm(12000, 16000, seed=6)
+  cmp_ns            tests/configs/compare_ns.conf (ComParE_2016's LLD-path columns, 59 + 59 deltas),
+                    voiced_pcm(16000, 16000, seed=7); cmp_ns_short_<n>: its first n samples, n = 960, 1100, 1300, 2000;
+                    cmp_ns_44k: voiced_pcm(30000, 44100, seed=8)
+  cmp_taps          static levels audR (26) | audSum | audRSum of compare_ns.conf for the same input (oracle pin)
+  rasta_plp         tests/configs/rasta_plp.conf (RASTA-PLP cepstra 0..8 + delta), voiced_pcm(16000, 16000, seed=9)
   names_<case>      the CSV header's element names
   htk_bytes / csv_bytes   the reference's HTK and CSV files for case mfcc_e (instance name 'utt7')
 """
@@ -25,14 +30,16 @@ from oracle import refrun  # noqa: E402
 from opensmile_b200.synth import voiced_pcm  # noqa: E402
 
 
-def run(conf, pcm, sr, nch, keep_files=False):
+def run(conf, pcm, sr, nch, keep_files=False, csv_out=True):
     with tempfile.TemporaryDirectory() as d:
         wav, htk, csv = (os.path.join(d, x) for x in ("in.wav", "out.htk", "out.csv"))
         refrun.write_wav(wav, pcm, sr, nch)
-        subprocess.run([refrun.SMILEXTRACT, "-C", conf, "-I", wav, "-O", htk, "-csvoutput", csv, "-instname", "utt7", "-l", "0"],
+        extra = ["-csvoutput", csv, "-instname", "utt7"] if csv_out else []
+        subprocess.run([refrun.SMILEXTRACT, "-C", conf, "-I", wav, "-O", htk, "-l", "0"] + extra,
                        check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         rows, _ = refrun.read_htk(htk)
-        names = open(csv).readline().strip().split(";")[2:]
+        hdr = open(csv).readline().strip().split(";") if csv_out else []
+        names = [h for h in hdr if h not in ("name", "frameIndex", "frameTime")]
         files = (open(htk, "rb").read(), open(csv, "rb").read()) if keep_files else None
     return rows, np.array(names), files
 
@@ -52,6 +59,20 @@ def main():
         out["mfcc_e_short_%d" % n], _, _ = run(mfe, pcm[:n], 16000, 1)
     out["plp_e"], out["names_plp_e"], _ = run(os.path.join(refrun.CONFIG_DIR, "plp", "PLP_E_D_A.conf"),
                                               voiced_pcm(12000, 16000, seed=6), 16000, 1)
+    cns = os.path.join(ROOT, "tests", "configs", "compare_ns.conf")
+    pcm = voiced_pcm(16000, 16000, seed=7)
+    out["cmp_ns"], out["names_cmp_ns"], _ = run(cns, pcm, 16000, 1)
+    for n in (960, 1100, 1300, 2000):
+        out["cmp_ns_short_%d" % n], _, _ = run(cns, pcm[:n], 16000, 1)
+    out["cmp_ns_44k"], _, _ = run(cns, voiced_pcm(30000, 44100, seed=8), 44100, 1)
+    out["rasta_plp"], _, _ = run(os.path.join(ROOT, "tests", "configs", "rasta_plp.conf"), voiced_pcm(16000, 16000, seed=9), 16000, 1,
+                                 csv_out=False)
+    # taps of compare_ns.conf (the same graph with the HTK sink moved): RASTA-filtered bands and the two sums
+    tap = os.path.join(ROOT, "tests", "configs", "_cmp_taps.conf")
+    with open(tap, "w") as f:
+        f.write(open(cns).read().replace("reader.dmLevel = lld;lld_de\nfilename = \\cm[output(O)", "reader.dmLevel = audR;audSum;audRSum\nfilename = \\cm[output(O)"))
+    out["cmp_taps"], _, _ = run(tap, pcm, 16000, 1, csv_out=False)
+    os.remove(tap)
     for k, v in out.items():
         print(k, v.shape)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "conf_goldens.npz"), **out)

@@ -104,3 +104,30 @@ def test_plp_oracle_vs_live_reference(sr, n, seed, nch):
     out = oracle.plp_d_a(pcm, float(sr), n_chan=nch)
     assert out.shape == ref.shape
     assert rel_to_frame_scale(out, ref) < TOL
+
+
+def test_rasta_oracle_vs_golden():
+    """cPlp with RASTA / newRASTA and cVectorOperation(ll1): oracle restatement against outputs of the
+    unmodified reference (tests/golden/conf_goldens.npz, scripts/make_golden_conf.py)."""
+    g = np.load(os.path.join(GOLD, "conf_goldens.npz"))
+    # tests/configs/rasta_plp.conf: RASTA-PLP cepstra 0..8 on the HTK-style front end
+    fe = oracle.Frontend(16000.0, 0.025, 0.010, 1, 0.97, oracle.WIN["ham"], 0.4, 1.0, 0.0, 0)
+    ms = oracle.Melspec(26, 0.0, 8000.0, 1, 1)
+    pl = oracle.Plp(8, 0, -1, 1, 1, 1, 1, 1, 1, 1, 0, 29.0, 1.0, 22.0, 0.33, 1e-6, 0)
+    st = oracle.plp_static(voiced_pcm(16000, 16000, seed=9), 16000.0, (fe, ms, pl))
+    ref = g["rasta_plp"]
+    assert st.shape == (ref.shape[0], 9)
+    assert rel_to_frame_scale(st, ref[:, :9]) < TOL
+    assert np.array_equal(oracle.delta(ref[:, :9], 2)[:ref.shape[0]], ref[:, 9:])
+    # tests/configs/compare_ns.conf taps: newRASTA-filtered auditory bands and the two band sums
+    fe = oracle.Frontend(16000.0, 0.020, 0.010, 0, 0.0, oracle.WIN["ham"], 0.4, 1.0, 0.0, 1)
+    ms = oracle.Melspec(26, 20.0, 8000.0, 1, 0)
+    pcm = voiced_pcm(16000, 16000, seed=7)
+    aud, audR = (oracle.plp_static(pcm, 16000.0, (fe, ms, oracle.Plp(5, 0, -1, 0, 1, 0, 0, 0, 0, 0, nr, 29.0, 1.0, 22.0, 0.33, 9.3e-10, 0)))
+                 for nr in (0, 1))
+    tap = g["cmp_taps"]
+    assert tap.shape == (aud.shape[0], 28)
+    assert rel_to_frame_scale(audR, tap[:, :26]) < TOL
+    assert np.abs(oracle.ll1(aud) - tap[:, 26]).max() < TOL * np.abs(tap[:, 26]).max()
+    assert np.abs(oracle.ll1(audR) - tap[:, 27]).max() < TOL * np.abs(tap[:, 27]).max()
+    assert np.array_equal(oracle.ll1(tap[:, :26]), tap[:, 27])       # ll1 itself is bit-exact given its input

@@ -15,7 +15,8 @@ GOLD = np.load(os.path.join(ROOT, "tests", "golden", "conf_goldens.npz"))
 REF_CONF = os.path.join(ROOT, "oracle", "_ref", "config")
 
 
-@pytest.mark.parametrize("conf,key", [("lld_mix.conf", "mix"), ("mfcc_e_d_a.conf", "mfcc_e"), ("plp_e_d_a.conf", "plp_e")])
+@pytest.mark.parametrize("conf,key", [("lld_mix.conf", "mix"), ("mfcc_e_d_a.conf", "mfcc_e"), ("plp_e_d_a.conf", "plp_e"),
+                                      ("compare_ns.conf", "cmp_ns")])
 def test_element_names_match_reference_csv_header(conf, key):
     s = Session(os.path.join(CONF, conf), device=-1)
     assert s.element_names(16000, 1) == [str(x) for x in GOLD["names_" + key]]
@@ -31,6 +32,20 @@ def test_frame_counts_match_reference():
     m = Session(os.path.join(CONF, "lld_mix.conf"), device=-1)
     assert m.frame_offsets([0, 16000], 16000, 1)[-1] == GOLD["mix16k"].shape[0]          # min over the three levels
     assert m.frame_offsets([0, 16000], 32000, 2)[-1] == GOLD["mix32k_stereo"].shape[0]
+
+
+def test_truncating_multi_level_reader_frame_counts():
+    # compare_ns.conf: cContourSmoother reads levels of the 20 ms and the 60 ms stream at once -> the
+    # reader delivers min over them (core/dataReader.cpp:375-380); the reference's row counts:
+    s = Session(os.path.join(CONF, "compare_ns.conf"), device=-1)
+    lens = [16000, 960, 1100, 1300, 2000, 959]
+    fo = s.frame_offsets(np.concatenate([[0], np.cumsum(lens)]), 16000, 1)
+    want = [GOLD["cmp_ns"].shape[0]] + [GOLD["cmp_ns_short_%d" % n].shape[0] for n in (960, 1100, 1300, 2000)] + [0]
+    assert list(np.diff(fo)) == want
+    assert s.frame_offsets([0, 30000], 44100, 1)[-1] == GOLD["cmp_ns_44k"].shape[0]
+    names = s.element_names()
+    assert names[:4] == ["audspec_lengthL1norm_sma", "audspecRasta_lengthL1norm_sma", "pcm_RMSenergy_sma", "pcm_zcr_sma"]
+    assert names[4] == "audSpec_Rfilt_sma[0]" and names[59] == "audspec_lengthL1norm_sma_de"
 
 
 def test_parsed_components_carry_config_values():

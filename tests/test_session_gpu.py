@@ -122,3 +122,45 @@ def test_command_line_front_end(tmp_path):
     # errors are loud and non-zero
     r = subprocess.run([exe, "-C", os.path.join(CONF, "does_not_exist.conf"), "-I", str(tmp_path / "in.wav")], capture_output=True, text=True)
     assert r.returncode != 0 and "cannot open" in r.stderr
+
+
+def _check_columns(rows, ref, names, tol=1e-5):
+    assert rows.shape == ref.shape
+    err = col_err(rows, ref)
+    bad = [(names[i], float(err[i])) for i in range(len(names)) if err[i] > tol]
+    assert not bad, bad
+
+
+def test_compare_ns_conf_three_band_ops_rasta_and_truncating_reader():
+    """ComParE_2016's LLD-path columns: three band ops on one FFT chain (auditory spectrum, its
+    newRASTA-filtered variant, MFCC 1-14), band sums (ll1), cSpectral, RMS energy, a 60 ms zcr stream,
+    sma3 over multi-level readers that truncate to the shorter stream, delta regression."""
+    s = Session(os.path.join(CONF, "compare_ns.conf"))
+    pcm = voiced_pcm(16000, 16000, seed=7)
+    utts = [pcm, pcm[:960], pcm[:1100], pcm[:1300], pcm[:2000]]
+    packed, off = pack_utterances(utts)
+    names = s.element_names(16000, 1)
+    rows, fo = s.extract_pcm(packed, off, 16000, 1)
+    refs = [GOLD["cmp_ns"]] + [GOLD["cmp_ns_short_%d" % n] for n in (960, 1100, 1300, 2000)]
+    assert list(np.diff(fo)) == [r.shape[0] for r in refs]
+    _check_columns(rows[fo[0]:fo[1]], refs[0], names)
+    for u in range(1, 5):     # 2..8-row utterances: per-column scales are not meaningful, use the long utterance's
+        scale = np.abs(refs[0]).max(axis=0)
+        assert (np.abs(rows[fo[u]:fo[u + 1]] - refs[u]) <= 1e-5 * scale).all(), u
+
+
+def test_compare_ns_conf_44k():
+    s = Session(os.path.join(CONF, "compare_ns.conf"))
+    pcm = voiced_pcm(30000, 44100, seed=8)
+    rows, fo = s.extract_pcm(pcm, [0, 30000], 44100, 1)
+    _check_columns(rows, GOLD["cmp_ns_44k"], s.element_names(44100, 1))
+
+
+def test_rasta_plp_conf():
+    s = Session(os.path.join(CONF, "rasta_plp.conf"))
+    pcm = voiced_pcm(16000, 16000, seed=9)
+    rows, fo = s.extract_pcm(pcm, [0, 16000], 16000, 1)
+    ref = GOLD["rasta_plp"]
+    assert rows.shape == ref.shape
+    assert (np.abs(rows - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
+    assert s.element_names()[:2] == ["RASTAPlpCC[0]", "RASTAPlpCC[1]"]
