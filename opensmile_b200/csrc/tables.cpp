@@ -317,7 +317,7 @@ bool build_spectral(const osm_b200_spectral &cfg, int nSrc, double fftFrameSizeS
   if (op.alphaRatio) op.reqPow = true; if (op.hammarberg) op.reqPow = true;
   if (cfg.nBands > 0) op.reqPow = true; if (cfg.nSlopes > 0) lorp(); if (cfg.nRollOff > 0) op.reqPow = true;
   if (op.sharpness) op.reqPow = true; if (op.harmonicity) lorp(); if (op.flatness) lorp();
-  if (!op.reqPow && !op.reqLog) { err = "cSpectral: no descriptor that needs a spectrum is enabled"; return false; }
+  if (!op.reqPow && !op.reqLog && !op.reqMag) { err = "cSpectral: no descriptor is enabled"; return false; }
   if (op.useLog && !op.reqLog) op.reqLog = true;
 
   const long lo = (long)cfg.freqRangeLo, hi = (long)cfg.freqRangeHi;      // :625-647

@@ -12,6 +12,7 @@ Contents (inputs are regenerated in the tests from opensmile_b200.synth.voiced_p
   cmp_ns            tests/configs/compare_ns.conf (ComParE_2016's LLD-path columns, 59 + 59 deltas),
                     voiced_pcm(16000, 16000, seed=7); cmp_ns_short_<n>: its first n samples, n = 960, 1100, 1300, 2000;
                     cmp_ns_44k: voiced_pcm(30000, 44100, seed=8)
+  gemaps_ns         tests/configs/gemaps_ns.conf (eGeMAPSv02's LLD-path columns), voiced_pcm(16000, 16000, seed=10)
   cmp_taps          static levels audR (26) | audSum | audRSum of compare_ns.conf for the same input (oracle pin)
   rasta_plp         tests/configs/rasta_plp.conf (RASTA-PLP cepstra 0..8 + delta), voiced_pcm(16000, 16000, seed=9)
   names_<case>      the CSV header's element names
@@ -67,6 +68,8 @@ def main():
     out["cmp_ns_44k"], _, _ = run(cns, voiced_pcm(30000, 44100, seed=8), 44100, 1)
     out["rasta_plp"], _, _ = run(os.path.join(ROOT, "tests", "configs", "rasta_plp.conf"), voiced_pcm(16000, 16000, seed=9), 16000, 1,
                                  csv_out=False)
+    gns = os.path.join(ROOT, "tests", "configs", "gemaps_ns.conf")
+    out["gemaps_ns"], out["names_gemaps_ns"], _ = run(gns, voiced_pcm(16000, 16000, seed=10), 16000, 1)
     # taps of compare_ns.conf (the same graph with the HTK sink moved): RASTA-filtered bands and the two sums
     tap = os.path.join(ROOT, "tests", "configs", "_cmp_taps.conf")
     with open(tap, "w") as f:

@@ -16,7 +16,7 @@ REF_CONF = os.path.join(ROOT, "oracle", "_ref", "config")
 
 
 @pytest.mark.parametrize("conf,key", [("lld_mix.conf", "mix"), ("mfcc_e_d_a.conf", "mfcc_e"), ("plp_e_d_a.conf", "plp_e"),
-                                      ("compare_ns.conf", "cmp_ns")])
+                                      ("compare_ns.conf", "cmp_ns"), ("gemaps_ns.conf", "gemaps_ns")])
 def test_element_names_match_reference_csv_header(conf, key):
     s = Session(os.path.join(CONF, conf), device=-1)
     assert s.element_names(16000, 1) == [str(x) for x in GOLD["names_" + key]]

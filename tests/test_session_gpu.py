@@ -164,3 +164,19 @@ def test_rasta_plp_conf():
     assert rows.shape == ref.shape
     assert (np.abs(rows - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
     assert s.element_names()[:2] == ["RASTAPlpCC[0]", "RASTAPlpCC[1]"]
+
+
+def test_gemaps_ns_conf():
+    """eGeMAPSv02's LLD-path columns: loudness, log-spectral slopes / alpha ratio / Hammarberg index,
+    flux, MFCC 1-4, sma3.  The two log-spectral slopes are least-squares fits over a handful of dB
+    values of low-energy bins -> ill-conditioned, checked at 1e-4 of the column scale (see
+    test_spectral_compare16_and_gemaps_vs_oracle)."""
+    s = Session(os.path.join(CONF, "gemaps_ns.conf"))
+    pcm = voiced_pcm(16000, 16000, seed=10)
+    rows, fo = s.extract_pcm(pcm, [0, 16000], 16000, 1)
+    ref = GOLD["gemaps_ns"]
+    names = s.element_names()
+    assert rows.shape == ref.shape and names == [str(x) for x in GOLD["names_gemaps_ns"]]
+    err = col_err(rows, ref)
+    for i, nm in enumerate(names):
+        assert err[i] < (1e-4 if "Slope" in nm else 1e-5), (nm, float(err[i]))
