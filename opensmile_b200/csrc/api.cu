@@ -322,19 +322,30 @@ static osm_b200_status build_pass(osm_b200_plan *pl, int si, int opIdx, bool dum
         kp.plpFirstCC = po.firstCC; kp.plpLastCC = po.lastCC; kp.plpCompression = po.compression;
         kp.dctStride = po.nFreq; kp.dctRows = po.nAuto;
       }
-      // split the bands over the virtual warps, balancing visited bins (ranges bs..be)
+      // split the bands over the virtual warps: contiguous band groups, minimising the most expensive
+      // group (cost model from the kernel's SASS: ~6 instructions per visited bin, ~50 per band for
+      // scale / floor / log / store, ~12 per group) -- all warps meet at a barrier after this phase
       {
         const int nvw = lld_virtual_warps(fe.nfft);
-        const int totalBins = mb.rangeBegin[mb.nBands + 1] - mb.rangeBegin[0];
-        int b = 0;
-        kp.melSplit[0] = 0;
-        for (int w = 1; w <= nvw; w++) {
-          const double target = (double)totalBins * w / nvw;
-          while (b < mb.nBands && (mb.rangeBegin[b + 1] - mb.rangeBegin[0]) < target) b++;
-          if (w == nvw) b = mb.nBands;
-          kp.melSplit[w] = b;
-        }
-        for (int w = nvw + 1; w <= kMaxVW; w++) kp.melSplit[w] = mb.nBands;
+        const int nB = mb.nBands;
+        auto cost = [&](int bs, int be) -> double {          // bands [bs, be) visit ranges bs..be
+          if (be <= bs) return 0.0;
+          return 6.0 * (mb.rangeBegin[be + 1] - mb.rangeBegin[bs]) + 50.0 * (be - bs) + 12.0;
+        };
+        // best[w][b] = minimal max-cost of covering bands [0, b) with w groups
+        std::vector<std::vector<double>> best(nvw + 1, std::vector<double>(nB + 1, 1e30));
+        std::vector<std::vector<int>> from(nvw + 1, std::vector<int>(nB + 1, 0));
+        best[0][0] = 0.0;
+        for (int w = 1; w <= nvw; w++)
+          for (int b = 0; b <= nB; b++)
+            for (int a = 0; a <= b; a++) {
+              const double c = std::max(best[w - 1][a], cost(a, b));
+              if (c < best[w][b]) { best[w][b] = c; from[w][b] = a; }
+            }
+        int b = nB;
+        kp.melSplit[nvw] = nB;
+        for (int w = nvw; w >= 1; w--) { b = from[w][b]; kp.melSplit[w - 1] = b; }
+        for (int w = nvw + 1; w <= kMaxVW; w++) kp.melSplit[w] = nB;
       }
       std::vector<float> dctPad((size_t)kp.dctRows * kp.dctStride, 0.f);
       if (!isPlp) {

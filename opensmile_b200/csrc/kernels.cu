@@ -60,7 +60,7 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
   L.tw = o; o += p.twCount * 8;
   L.splitTw = o; o += (M / 2 + 1) * 8;
   o = align_up(o, 16);
-  L.melCoef = o; o += (M + 1) * 4;
+  L.melCoef = o; o += (M + 1) * 8;          // (w, 1-w) per bin
   L.melRange = o; o += (p.nBands + 2) * 4;
   o = align_up(o, 16);
   L.dctCos = o; o += p.dctRows * p.dctStride * 4;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   float4 *sWinLut = reinterpret_cast<float4 *>(smem + L.winLut);
   float2 *sTw = reinterpret_cast<float2 *>(smem + L.tw);
   float2 *sSplit = reinterpret_cast<float2 *>(smem + L.splitTw);
-  float *sMelCoef = reinterpret_cast<float *>(smem + L.melCoef);
+  float2 *sMelCoef = reinterpret_cast<float2 *>(smem + L.melCoef);
   int *sMelRange = reinterpret_cast<int *>(smem + L.melRange);
   float *sDct = reinterpret_cast<float *>(smem + L.dctCos);
   float *sLift = reinterpret_cast<float *>(smem + L.dctLift);
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   for (int i = tid; i < p.twCount; i += NT) sTw[i] = p.twiddles[i];
   for (int i = tid; i < NPAIR; i += NT) sSplit[i] = p.splitTw[i];
   if (opKind >= 0) {
-    for (int i = tid; i < NBINS; i += NT) sMelCoef[i] = p.melCoef[i];
+    for (int i = tid; i < NBINS; i += NT) { const float w = p.melCoef[i]; sMelCoef[i] = make_float2(w, __fsub_rn(1.0f, w)); }
     for (int i = tid; i < p.nBands + 2; i += NT) sMelRange[i] = p.melRange[i];
     for (int i = tid; i < p.dctRows * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
     if (opKind == 1) for (int i = tid; i < p.nBands; i += NT) sEql[i] = p.plpEql[i];
@@ -598,23 +598,20 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 
     if (opKind >= 0) {
     // ================= mel filterbank (melspec.cpp:543-569) + log (mfcc.cpp:239-243) =================
-    // range r holds the bins whose lower band is r-1: band[r-1] += a ; band[r] += p - a, visited
-    // in ascending bin order exactly like the reference loop, so each band's float sum has the
-    // reference's summation order.
+    // range r holds the bins whose lower band is r-1: band[r-1] += p*w ; band[r] += p*(1-w), visited
+    // in ascending bin order like the reference loop (same summation order per band; the products
+    // are fused into the sums, which only removes roundings).
     {
       const int bs = p.melSplit[vw], be = p.melSplit[vw + 1];
       if (bs < be) {
         float cur = 0.f;
         int n = sMelRange[bs];
         const float *pp = P + n * F + f;
-        const float *cp = sMelCoef + n;
+        const float2 *cp = sMelCoef + n;
         {   // range bs only feeds band bs (its rising slope)
           const int n1 = sMelRange[bs + 1];
 #pragma unroll 4
-          for (; n < n1; n++, pp += F, cp++) {
-            const float pw = *pp;
-            cur = __fadd_rn(cur, __fsub_rn(pw, __fmul_rn(pw, *cp)));
-          }
+          for (; n < n1; n++, pp += F, cp++) cur = __fmaf_rn(*pp, cp->y, cur);
         }
         for (int r = bs + 1; r <= be; r++) {
           float nxt = 0.f;
@@ -622,9 +619,9 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 #pragma unroll 4
           for (; n < n1; n++, pp += F, cp++) {
             const float pw = *pp;
-            const float a = __fmul_rn(pw, *cp);            // (float)((double)p*(double)w) == fl(p*w)
-            cur = __fadd_rn(cur, a);
-            nxt = __fadd_rn(nxt, __fsub_rn(pw, a));
+            const float2 w = *cp;
+            cur = __fmaf_rn(pw, w.x, cur);
+            nxt = __fmaf_rn(pw, w.y, nxt);
           }
           float mval = __fmul_rn(cur, p.melScale);
           if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);   // mfcc.cpp:239-243 / plp.cpp:434-440
@@ -664,15 +661,15 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       for (; m + 4 <= p.nBands; m += 4, lp += 4 * F) {
         const float4 w0 = *c0++, w1 = *c1++;
         const float l0 = lp[0], l1 = lp[F], l2 = lp[2 * F], l3 = lp[3 * F];
-        a0 = __fadd_rn(a0, __fmul_rn(l0, w0.x)); a1 = __fadd_rn(a1, __fmul_rn(l0, w1.x));
-        a0 = __fadd_rn(a0, __fmul_rn(l1, w0.y)); a1 = __fadd_rn(a1, __fmul_rn(l1, w1.y));
-        a0 = __fadd_rn(a0, __fmul_rn(l2, w0.z)); a1 = __fadd_rn(a1, __fmul_rn(l2, w1.z));
-        a0 = __fadd_rn(a0, __fmul_rn(l3, w0.w)); a1 = __fadd_rn(a1, __fmul_rn(l3, w1.w));
+        a0 = __fmaf_rn(l0, w0.x, a0); a1 = __fmaf_rn(l0, w1.x, a1);
+        a0 = __fmaf_rn(l1, w0.y, a0); a1 = __fmaf_rn(l1, w1.y, a1);
+        a0 = __fmaf_rn(l2, w0.z, a0); a1 = __fmaf_rn(l2, w1.z, a1);
+        a0 = __fmaf_rn(l3, w0.w, a0); a1 = __fmaf_rn(l3, w1.w, a1);
       }
       const float *r0 = reinterpret_cast<const float *>(c0), *r1 = reinterpret_cast<const float *>(c1);
       for (int k = 0; m < p.nBands; m++, k++, lp += F) {
         const float l0 = lp[0];
-        a0 = __fadd_rn(a0, __fmul_rn(l0, r0[k])); a1 = __fadd_rn(a1, __fmul_rn(l0, r1[k]));
+        a0 = __fmaf_rn(l0, r0[k], a0); a1 = __fmaf_rn(l0, r1[k], a1);
       }
       ring[i * (2 * F) + ringBase + f] = __fmul_rn(a0, sLift[i]);
       if (two) ring[i1 * (2 * F) + ringBase + f] = __fmul_rn(a1, sLift[i1]);
