@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libosm_b200.so")
+LIB_PATH = os.environ.get("OSM_B200_LIB") or os.path.join(_HERE, "libosm_b200.so")   # override: A/B builds of the same library
 
 NAME_LEN = 64
 MAX_INPUTS = 8

@@ -262,6 +262,7 @@ static osm_b200_status build_pass(osm_b200_plan *pl, int si, int opIdx, bool dum
   kp.opKind = -1;
   kp.nChan = fe.nChan;
   kp.frameSize = fe.frameSize; kp.frameStep = fe.frameStep;
+  kp.hopMagic = (unsigned)((0x100000000ull + (unsigned long long)fe.frameStep - 1) / (unsigned long long)fe.frameStep);
   // per-lane stride S = frameStep + sPad of the shared-memory sample tile: odd S (scalar loads)
   // or even S with S/2 odd (64-bit sample-pair loads) is bank-conflict free across the lanes
   kp.sPad = (fe.frameStep % 2 != 0) ? 0 : (((fe.frameStep / 2) % 2 != 0) ? 0 : 2);
@@ -274,7 +275,7 @@ static osm_b200_status build_pass(osm_b200_plan *pl, int si, int opIdx, bool dum
   std::vector<unsigned char> blob;
   auto put = [&](const void *src, size_t bytes) { const size_t at = o; blob.resize(up16(o + bytes), 0); if (bytes) memcpy(&blob[at], src, bytes); o = up16(o + bytes); return at; };
   const size_t oWindow = put(fe.window.data(), fe.window.size() * sizeof(float));
-  size_t oWin = 0, oTw = 0, oSplit = 0, oCoef = 0, oRange = 0, oDct = 0, oLift = 0, oEql = 0;
+  size_t oWin = 0, oTw = 0, oSplit = 0, oCoef = 0, oRange = 0, oDct = 0, oLift = 0, oEql = 0, oVisit = 0, oVB = 0;
   if (rt.runLld) {
     if (!lld_supported_fft(fe.nfft))
       return fail(OSM_B200_ERR_UNSUPPORTED, "FFT size " + std::to_string(fe.nfft) + " not supported (512, 1024, 2048, 4096)");
@@ -358,6 +359,20 @@ static osm_b200_status build_pass(osm_b200_plan *pl, int si, int opIdx, bool dum
       std::vector<float> eqlV = isPlp ? po.eql : std::vector<float>(1, 0.f);
       oCoef = put(mb.coef.data(), mb.coef.size() * sizeof(float));
       oRange = put(mb.rangeBegin.data(), mb.rangeBegin.size() * sizeof(int));
+      {
+        std::vector<float2> visit;
+        std::vector<int> vb(mb.nBands + 2, 0);
+        for (int r = 0; r <= mb.nBands; r++) {
+          vb[r] = (int)visit.size();
+          for (int n = mb.rangeBegin[r]; n < mb.rangeBegin[r + 1]; n++) visit.push_back(make_float2(mb.coef[n], 1.0f - mb.coef[n]));
+          while (visit.size() % 4) visit.push_back(make_float2(0.f, 0.f));
+        }
+        vb[mb.nBands + 1] = (int)visit.size();
+        kp.melVCount = (int)visit.size();
+        visit.push_back(make_float2(0.f, 0.f));
+        oVisit = put(visit.data(), visit.size() * sizeof(float2));
+        oVB = put(vb.data(), vb.size() * sizeof(int));
+      }
       oDct = put(dctPad.data(), dctPad.size() * sizeof(float));
       oLift = put(liftV.data(), liftV.size() * sizeof(float));
       oEql = put(eqlV.data(), eqlV.size() * sizeof(float));
@@ -375,6 +390,8 @@ static osm_b200_status build_pass(osm_b200_plan *pl, int si, int opIdx, bool dum
     if (opIdx >= 0) {
       kp.melCoef = reinterpret_cast<const float *>(dC + oCoef);
       kp.melRange = reinterpret_cast<const int *>(dC + oRange);
+      kp.melVisit = reinterpret_cast<const float2 *>(dC + oVisit);
+      kp.melVB = reinterpret_cast<const int *>(dC + oVB);
       kp.dctCos = reinterpret_cast<const float *>(dC + oDct);
       kp.dctLift = reinterpret_cast<const float *>(dC + oLift);
       kp.plpEql = reinterpret_cast<const float *>(dC + oEql);

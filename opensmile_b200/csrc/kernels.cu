@@ -26,7 +26,32 @@
 #include "fft_radix.cuh"
 #include "kernels.cuh"
 
+// experiment switches (A/B builds): -DOSM_OPT_MELV=0 etc.
+#ifndef OSM_OPT_MELV
+#define OSM_OPT_MELV 0
+#endif
+#ifndef OSM_OPT_EMIT
+#define OSM_OPT_EMIT 0
+#endif
+#ifndef OSM_OPT_STAGE
+#define OSM_OPT_STAGE 1
+#endif
+#ifndef OSM_UNROLL_MEL
+#define OSM_UNROLL_MEL 4
+#endif
+#ifndef OSM_UNROLL_DCT
+#define OSM_UNROLL_DCT 2
+#endif
+#ifndef OSM_OPT_COLD
+#define OSM_OPT_COLD 1        // rarely executed paths out of line (instruction cache footprint)
+#endif
+#ifndef OSM_OPT_MELS_ALIAS
+#define OSM_OPT_MELS_ALIAS 1
+#endif
+
 namespace osm {
+
+constexpr int kUnrollMel = OSM_UNROLL_MEL, kUnrollDct = OSM_UNROLL_DCT;
 
 // ------------------------------------------------------------------------------------------
 // shared memory layout (identical computation on host and device)
@@ -60,14 +85,17 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
   L.tw = o; o += p.twCount * 8;
   L.splitTw = o; o += (M / 2 + 1) * 8;
   o = align_up(o, 16);
-  L.melCoef = o; o += (M + 1) * 8;          // (w, 1-w) per bin
-  L.melRange = o; o += (p.nBands + 2) * 4;
+  L.melCoef = o; o += (p.melVCount + 4) * 8;   // visit list: (w, 1-w) per visited bin, ranges padded to x4
+  L.melRange = o; o += 2 * (p.nBands + 2) * 4;  // first bin / first visit entry of every range
   o = align_up(o, 16);
   L.dctCos = o; o += p.dctRows * p.dctStride * 4;
   L.dctLift = o; o += p.nStat * 4;
   L.eql = o; o += (p.opKind == 1 ? p.nBands : 0) * 4;
   o = align_up(o, 16);
-  L.melS = o; o += p.nBands * F * 4;
+  // the band values live only between the mel phase and the DCT / PLP back end of the same tile: the
+  // sample tile is dead then (it is rewritten by the next tile's staging), so they share its space
+  if (OSM_OPT_MELS_ALIAS && L.sampFloats >= p.nBands * F) L.melS = L.samp;
+  else { L.melS = o; o += p.nBands * F * 4; }
   L.ring = o; o += p.nStat * 2 * F * 4;     // static features of the last two tiles
   L.total = align_up(o, 16);
   return L;
@@ -87,6 +115,11 @@ __device__ __forceinline__ float div32767(float x)
   return __fmaf_rn(r, rc, q0);
 }
 
+#if OSM_OPT_COLD
+#define OSM_COLD __noinline__
+#else
+#define OSM_COLD __forceinline__
+#endif
 __device__ __forceinline__ float pcm_to_float_generic(const int16_t *s, int nChan)
 {
   float tmp = (float)s[0];
@@ -95,6 +128,8 @@ __device__ __forceinline__ float pcm_to_float_generic(const int16_t *s, int nCha
   if (nChan == 2) return div32767(tmp * 0.5f);          // tmp / 2.0f is exact
   return __fdiv_rn(__fdiv_rn(tmp, (float)nChan), 32767.0f);
 }
+// out-of-line copy for the rarely taken staging paths (unaligned / partial chunks, >2 channels)
+__device__ OSM_COLD float pcm_to_float_slow(const int16_t *s, int nChan) { return pcm_to_float_generic(s, nChan); }
 
 // ------------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (TMA unit, SASS UBLKCP) wrappers
@@ -368,6 +403,107 @@ __device__ __forceinline__ void plp_backend(const LldParams &p, const float *mel
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused delta / delta-delta emission of one interior tile (deltawin = 2 for both stages, no
+// clamping, all rows before EOI): F output rows = statics | delta | delta-delta -> outS laid out
+// like the global rows.  num = 1*(x[t+1]-x[t-1]) + 2*(x[t+2]-x[t-2]) in the reference's order:
+// (0 + 1*d1) + 2*d2 == d1 + 2*d2 exactly (deltaRegression.cpp:139-146).  KC > 0: K known at
+// compile time.
+// ------------------------------------------------------------------------------------------
+template <int F, int NT, int KC>
+__device__ __forceinline__ void emit_interior(const float *__restrict__ ring, float *__restrict__ Dbuf,
+                                              float *__restrict__ outS, int Krt, int dRows, int slot0, int rslot0,
+                                              float norm1, float rcp1, float norm2, float rcp2, int tid)
+{
+  const int K = KC > 0 ? KC : Krt;
+  const int K3 = 3 * K;
+  constexpr int DR = F + 4;                                    // delta rows of this tile
+  for (int item = tid; item < K * DR; item += NT) {
+    const int c = item / DR, tt = item - c * DR;
+    const float *rc = ring + c * (2 * F);
+    const int sl = slot0 + tt;
+    const float dA = __fsub_rn(rc[(sl + 1) & (2 * F - 1)], rc[(sl - 1) & (2 * F - 1)]);
+    const float dB = __fsub_rn(rc[(sl + 2) & (2 * F - 1)], rc[(sl - 2) & (2 * F - 1)]);
+    const float dv = div_exact(__fadd_rn(dA, __fmul_rn(2.0f, dB)), norm1, rcp1);
+    Dbuf[c * dRows + tt] = dv;
+    const int rr = tt - 2;
+    if (rr >= 0 && rr < F) outS[rr * K3 + K + c] = dv;
+  }
+  for (int item = tid; item < K * F; item += NT) {             // statics -> outS
+    const int c = item / F, rr = item - c * F;
+    outS[rr * K3 + c] = ring[c * (2 * F) + ((rslot0 + rr) & (2 * F - 1))];
+  }
+  __syncthreads();
+  for (int item = tid; item < K * F; item += NT) {             // delta-delta rows
+    const int c = item / F, rr = item - c * F;
+    const float *dt = Dbuf + c * dRows + rr + 2;               // row t = r0 + rr sits at tt = rr + 2
+    const float dA = __fsub_rn(dt[1], dt[-1]);
+    const float dB = __fsub_rn(dt[2], dt[-2]);
+    outS[rr * K3 + 2 * K + c] = div_exact(__fadd_rn(dA, __fmul_rn(2.0f, dB)), norm2, rcp2);
+  }
+  __syncthreads();
+}
+
+// Fused delta / delta-delta emission, general path (utterance edges, deltawin != 2): lane = row, warps
+// take the coefficients; clamping and the tick-order model of post_kernel decide what a read past
+// either end of a level returns.  Out of line: it runs on the first / last tiles of an utterance only.
+template <int F, int NW>
+__device__ OSM_COLD void emit_edge(const float *__restrict__ ring, float *__restrict__ Dbuf, float *__restrict__ outS,
+                               int K, int W1, int W2, int T, int T1, int c01, int c02, int s0, int r0, int r1,
+                               int d0, int d1, int dRows, float norm1, float rcp1, float norm2, float rcp2,
+                               int warp, int lane)
+{
+  const int K3 = 3 * K, nr = r1 - r0;
+  for (int c = warp; c < K; c += NW) {
+    const float *rc = ring + c * (2 * F);
+    for (int tt = lane; tt < d1 - d0; tt += 32) {
+      const int t = d0 + tt;
+      // level-0 reads: navail = T (the static level is complete when EOI is raised)
+      float num = 0.f;
+      for (int i = 1; i <= W1; i++) {
+        const int hi = t + i, lo = t - i;
+        float later, prior;
+        if (t - W1 < 0) {
+          later = (hi >= T) ? 0.f : rc[(hi - s0) & (2 * F - 1)];
+          prior = rc[(max(lo, 0) - s0) & (2 * F - 1)];
+        } else {
+          later = rc[(min(hi, T - 1) - s0) & (2 * F - 1)];
+          prior = rc[(min(lo, T - 1) - s0) & (2 * F - 1)];
+        }
+        num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));   // deltaRegression.cpp:139-146
+      }
+      const float dv = div_exact(num, norm1, rcp1);
+      Dbuf[c * dRows + tt] = dv;
+      if (t >= r0 && t < r1) outS[(t - r0) * K3 + K + c] = dv;
+    }
+    for (int rr = lane; rr < nr; rr += 32) outS[rr * K3 + c] = rc[(r0 + rr - s0) & (2 * F - 1)];
+  }
+  __syncthreads();
+  // ---- delta-delta rows [r0, r1) -> outS ----
+  for (int c = warp; c < K; c += NW) {
+    const float *dc = Dbuf + c * dRows - d0;
+    for (int rr = lane; rr < nr; rr += 32) {
+      const int t = r0 + rr;
+      const int navail2 = win_navail(t, c01, c02, T1);
+      float num = 0.f;
+      for (int i = 1; i <= W2; i++) {
+        const int hi = t + i, lo = t - i;
+        float later, prior;
+        if (t - W2 < 0) {
+          later = (hi >= navail2) ? 0.f : dc[hi];
+          prior = dc[max(lo, 0)];
+        } else {
+          later = dc[min(hi, navail2 - 1)];
+          prior = dc[min(lo, navail2 - 1)];
+        }
+        num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));
+      }
+      outS[rr * K3 + 2 * K + c] = div_exact(num, norm2, rcp2);
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
 // the fused kernel
 // ------------------------------------------------------------------------------------------
 // GEN = false: the MFCC-only instance (band op = cMfcc, no magnitude level dump); the PLP back end and
@@ -414,8 +550,8 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
   for (int i = tid; i < p.twCount; i += NT) sTw[i] = p.twiddles[i];
   for (int i = tid; i < NPAIR; i += NT) sSplit[i] = p.splitTw[i];
   if (opKind >= 0) {
-    for (int i = tid; i < NBINS; i += NT) { const float w = p.melCoef[i]; sMelCoef[i] = make_float2(w, __fsub_rn(1.0f, w)); }
-    for (int i = tid; i < p.nBands + 2; i += NT) sMelRange[i] = p.melRange[i];
+    for (int i = tid; i < p.melVCount; i += NT) sMelCoef[i] = p.melVisit[i];
+    for (int i = tid; i < p.nBands + 2; i += NT) { sMelRange[i] = p.melRange[i]; sMelRange[p.nBands + 2 + i] = p.melVB[i]; }
     for (int i = tid; i < p.dctRows * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
     if (opKind == 1) for (int i = tid; i < p.nBands; i += NT) sEql[i] = p.plpEql[i];
     for (int i = tid; i < p.nStat; i += NT) sLift[i] = p.dctLift[i];
@@ -474,23 +610,25 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           }
         } else {
 #pragma unroll
-          for (int jj = 0; jj < 8; jj++) x[jj] = (jj < nvalid) ? pcm_to_float_generic(rp + (i + jj) * nChan, nChan) : 0.f;
+          for (int jj = 0; jj < 8; jj++) x[jj] = (jj < nvalid) ? pcm_to_float_slow(rp + (i + jj) * nChan, nChan) : 0.f;
         }
         float y[8];
         if (p.preemph) {
           // vectorPreemphasis.cpp:96-104 : x[n] -/+ k * x[n-1], two roundings
           float xprev = 0.f;
-          if (i > 0 || tg.lead > 0) xprev = pcm_to_float_generic(rp + (i - 1) * nChan, nChan);
-#pragma unroll
-          for (int jj = 0; jj < 8; jj++) {
-            const float kx = __fmul_rn(p.preK, (jj == 0) ? xprev : x[jj - 1]);
-            y[jj] = p.preDe ? __fadd_rn(x[jj], kx) : __fsub_rn(x[jj], kx);
+          if (i > 0 || tg.lead > 0) {
+            if (OSM_OPT_STAGE && nChan == 1) xprev = div32767((float)rp[i - 1]);
+            else xprev = pcm_to_float_slow(rp + (i - 1) * nChan, nChan);
           }
+          // x - k*xp == x + (-k)*xp exactly: one signed coefficient instead of a per-sample select
+          const float ks = p.preDe ? p.preK : -p.preK;
+#pragma unroll
+          for (int jj = 0; jj < 8; jj++) y[jj] = __fadd_rn(x[jj], __fmul_rn(ks, (jj == 0) ? xprev : x[jj - 1]));
         } else {
 #pragma unroll
           for (int jj = 0; jj < 8; jj++) y[jj] = x[jj];
         }
-        const int q = i / hop;
+        const int q = OSM_OPT_STAGE ? (int)__umulhi((unsigned)i, p.hopMagic) : i / hop;
         const int r = i - q * hop;
         float *dst = samp + i + q * p.sPad;
         if (fastStore && nvalid == 8 && r + 8 <= hop) {
@@ -560,27 +698,33 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           // 2 X[k] = e2 - i t2 ; 2 conj(X[M-k]) = e2 + i t2
           const float xr = e2.x + t2.y, xi = e2.y - t2.x;
           const float yr = e2.x - t2.y, yi = e2.y + t2.x;
-          // fftmagphase.cpp:215-221 computes sqrt(re*re+im*im), melspec.cpp:524 squares it
-          // again; we keep re*re+im*im (<= 1.5 ulp apart, below the FFT's own noise floor).
-          // The factor 1/2 of X (1/4 of the power) is an exact power-of-two scaling that commutes
-          // with every rounding downstream; it is folded into melScale on the host.
-          if (magOut != nullptr) {
-            // a non-fused consumer needs the magnitude level (fftmagphase.cpp:215-221):
-            // |X| = 0.5 * sqrt(a^2+b^2) is exact scaling; the band op then squares it like
-            // melspec.cpp:524 does (melScale carries no 1/4 in this mode)
-            const float mk = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
-            const float mm = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi)));
-            float *mo = magOut + ((size_t)(cx.tile0 + j) * NBINS) * F + f;
-            mo[(size_t)k * F] = mk;
-            if (k != M - k) mo[(size_t)(M - k) * F] = mm;
-            pk[i] = p.melUsePower ? __fmul_rn(mk, mk) : mk;
-            pm[i] = p.melUsePower ? __fmul_rn(mm, mm) : mm;
-          } else if (p.melUsePower) {
-            pk[i] = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
-            pm[i] = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
-          } else {
-            pk[i] = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi)));
-            pm[i] = 0.5f * __fsqrt_rn(__fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi)));
+          // 4 |X|^2: fftmagphase.cpp:215-221 computes sqrt(re*re+im*im), melspec.cpp:524 squares it
+          // again; the power path keeps re*re+im*im (<= 1.5 ulp apart, below the FFT's own noise
+          // floor).  The factor 1/2 of X (1/4 of the power) is an exact power-of-two scaling that
+          // commutes with every rounding downstream; it is folded into melScale on the host.
+          pk[i] = __fadd_rn(__fmul_rn(xr, xr), __fmul_rn(xi, xi));
+          pm[i] = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+        }
+      }
+      if (magOut != nullptr || !p.melUsePower) {
+        // magnitude needed (kept out of the loop above: this is the rarely used variant).  A
+        // non-fused consumer reads the magnitude level |X| = 0.5 * sqrt(a^2+b^2) (exact scaling,
+        // fftmagphase.cpp:215-221); the band op then squares it like melspec.cpp:524 does (melScale
+        // carries no 1/4 in this mode)
+        float *mo = (magOut != nullptr) ? magOut + ((size_t)(cx.tile0 + j) * NBINS) * F + f : nullptr;
+#pragma unroll
+        for (int i = 0; i < PAIRS_PER_VW; i++) {
+          const int k = vw + i * NVW;
+          if (k < NPAIR) {
+            const float mk = 0.5f * __fsqrt_rn(pk[i]);
+            const float mm = 0.5f * __fsqrt_rn(pm[i]);
+            if (mo != nullptr) {
+              mo[(size_t)k * F] = mk;
+              if (k != M - k) mo[(size_t)(M - k) * F] = mm;
+            }
+            const bool sq = (mo != nullptr) && p.melUsePower;
+            pk[i] = sq ? __fmul_rn(mk, mk) : mk;
+            pm[i] = sq ? __fmul_rn(mm, mm) : mm;
           }
         }
       }
@@ -604,25 +748,56 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     {
       const int bs = p.melSplit[vw], be = p.melSplit[vw + 1];
       if (bs < be) {
+#if OSM_OPT_MELV
+        // every range is walked in groups of 4 visit entries (zero-weight padding at its end), so
+        // the loops have no remainder and all addresses inside a group are immediates
+        const int *sVB = sMelRange + p.nBands + 2;
+        float cur = 0.f;
+        {   // range bs only feeds band bs (its rising slope)
+          const float *pp = P + sMelRange[bs] * F + f;
+          const float2 *cp = sMelCoef + sVB[bs];
+          for (int q = (sVB[bs + 1] - sVB[bs]) >> 2; q > 0; q--, pp += 4 * F, cp += 4) {
+            cur = __fmaf_rn(pp[0], cp[0].y, cur);
+            cur = __fmaf_rn(pp[F], cp[1].y, cur);
+            cur = __fmaf_rn(pp[2 * F], cp[2].y, cur);
+            cur = __fmaf_rn(pp[3 * F], cp[3].y, cur);
+          }
+        }
+        for (int r = bs + 1; r <= be; r++) {
+          float nxt = 0.f;
+          const float *pp = P + sMelRange[r] * F + f;
+          const float2 *cp = sMelCoef + sVB[r];
+          for (int q = (sVB[r + 1] - sVB[r]) >> 2; q > 0; q--, pp += 4 * F, cp += 4) {
+            const float p0 = pp[0], p1 = pp[F], p2 = pp[2 * F], p3 = pp[3 * F];
+            const float2 w0 = cp[0], w1 = cp[1], w2 = cp[2], w3 = cp[3];
+            cur = __fmaf_rn(p0, w0.x, cur); nxt = __fmaf_rn(p0, w0.y, nxt);
+            cur = __fmaf_rn(p1, w1.x, cur); nxt = __fmaf_rn(p1, w1.y, nxt);
+            cur = __fmaf_rn(p2, w2.x, cur); nxt = __fmaf_rn(p2, w2.y, nxt);
+            cur = __fmaf_rn(p3, w3.x, cur); nxt = __fmaf_rn(p3, w3.y, nxt);
+          }
+#else
+        const int *sVB = sMelRange + p.nBands + 2;
         float cur = 0.f;
         int n = sMelRange[bs];
         const float *pp = P + n * F + f;
-        const float2 *cp = sMelCoef + n;
-        {   // range bs only feeds band bs (its rising slope)
+        const float2 *cp = sMelCoef + sVB[bs];
+        {
           const int n1 = sMelRange[bs + 1];
-#pragma unroll 4
+#pragma unroll kUnrollMel
           for (; n < n1; n++, pp += F, cp++) cur = __fmaf_rn(*pp, cp->y, cur);
         }
         for (int r = bs + 1; r <= be; r++) {
           float nxt = 0.f;
           const int n1 = sMelRange[r + 1];
-#pragma unroll 4
+          cp = sMelCoef + sVB[r];
+#pragma unroll kUnrollMel
           for (; n < n1; n++, pp += F, cp++) {
             const float pw = *pp;
             const float2 w = *cp;
             cur = __fmaf_rn(pw, w.x, cur);
             nxt = __fmaf_rn(pw, w.y, nxt);
           }
+#endif
           float mval = __fmul_rn(cur, p.melScale);
           if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);   // mfcc.cpp:239-243 / plp.cpp:434-440
           if (opKind == 1 && p.plpAud) {
@@ -658,6 +833,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       const float *lp = melS + f;
       float a0 = 0.f, a1 = 0.f;
       int m = 0;
+#pragma unroll kUnrollDct
       for (; m + 4 <= p.nBands; m += 4, lp += 4 * F) {
         const float4 w0 = *c0++, w1 = *c1++;
         const float l0 = lp[0], l1 = lp[F], l2 = lp[2 * F], l3 = lp[3 * F];
@@ -705,7 +881,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       // bank conflicts and then copied to HBM as one contiguous, fully coalesced block.
       const int d0 = max(r0 - W2, 0), d1 = min(r1 + W2, T1);
       const int dRows = F + 24;             // row stride of Dbuf: >= (F + H) + 2 W2 rows, H <= 8
-      float *outS = Dbuf + K * dRows;       // [(r1-r0)][3K], aliases Z like Dbuf
+      float *outS = Dbuf + ((K * dRows + 3) & ~3);   // [(r1-r0)][3K], aliases Z like Dbuf; 16-byte aligned
       const int K3 = 3 * K;
       const int nr = r1 - r0;
       // ---- delta rows [r0-W2, r1+W2) /\ [0, T1) -> Dbuf[K][dRows] (+ outS), statics -> outS ----
@@ -713,89 +889,23 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       const bool interior2 = (r0 >= W2) && (r1 <= c02);           // all rows computed before EOI
       if (interior1 && interior2 && W1 == 2 && W2 == 2 && nr == F) {
         // ---- common case (deltawin = 2 twice, interior tile): straight-line code, work items
-        // spread evenly over all threads.  num = 1*(x[t+1]-x[t-1]) + 2*(x[t+2]-x[t-2]) in the
-        // reference's order: (0 + 1*d1) + 2*d2 == d1 + 2*d2 exactly.
-        constexpr int DR = F + 4;                                  // delta rows of this tile
-        const int slot0 = d0 - cx.s0;
-        for (int item = tid; item < K * DR; item += NT) {
-          const int c = item / DR, tt = item - c * DR;
-          const float *rc = ring + c * (2 * F);
-          const int sl = slot0 + tt;
-          const float dA = __fsub_rn(rc[(sl + 1) & (2 * F - 1)], rc[(sl - 1) & (2 * F - 1)]);
-          const float dB = __fsub_rn(rc[(sl + 2) & (2 * F - 1)], rc[(sl - 2) & (2 * F - 1)]);
-          const float dv = div_exact(__fadd_rn(dA, __fmul_rn(2.0f, dB)), norm1, p.fRcp1);
-          Dbuf[c * dRows + tt] = dv;
-          const int rr = tt - 2;
-          if (rr >= 0 && rr < F) outS[rr * K3 + K + c] = dv;
-        }
-        for (int item = tid; item < K * F; item += NT) {           // statics -> outS
-          const int c = item / F, rr = item - c * F;
-          outS[rr * K3 + c] = ring[c * (2 * F) + ((r0 + rr - cx.s0) & (2 * F - 1))];
-        }
-        __syncthreads();
-        for (int item = tid; item < K * F; item += NT) {           // delta-delta rows
-          const int c = item / F, rr = item - c * F;
-          const float *dt = Dbuf + c * dRows + rr + 2;             // row t = r0 + rr sits at tt = rr + 2
-          const float dA = __fsub_rn(dt[1], dt[-1]);
-          const float dB = __fsub_rn(dt[2], dt[-2]);
-          outS[rr * K3 + 2 * K + c] = div_exact(__fadd_rn(dA, __fmul_rn(2.0f, dB)), norm2, p.fRcp2);
-        }
-        __syncthreads();
+        // spread evenly over all threads; K = 13 (MFCC12_0_D_A) gets compile-time trip counts
+        if (OSM_OPT_EMIT && K == 13) emit_interior<F, NT, 13>(ring, Dbuf, outS, K, dRows, d0 - cx.s0, r0 - cx.s0, norm1, p.fRcp1, norm2, p.fRcp2, tid);
+        else emit_interior<F, NT, 0>(ring, Dbuf, outS, K, dRows, d0 - cx.s0, r0 - cx.s0, norm1, p.fRcp1, norm2, p.fRcp2, tid);
       } else {
-      for (int c = warp; c < K; c += NW) {
-        const float *rc = ring + c * (2 * F);
-        for (int tt = lane; tt < d1 - d0; tt += 32) {
-          const int t = d0 + tt;
-          // level-0 reads: navail = T (the static level is complete when EOI is raised)
-          float num = 0.f;
-          for (int i = 1; i <= W1; i++) {
-            const int hi = t + i, lo = t - i;
-            float later, prior;
-            if (t - W1 < 0) {
-              later = (hi >= T) ? 0.f : rc[(hi - cx.s0) & (2 * F - 1)];
-              prior = rc[(max(lo, 0) - cx.s0) & (2 * F - 1)];
-            } else {
-              later = rc[(min(hi, T - 1) - cx.s0) & (2 * F - 1)];
-              prior = rc[(min(lo, T - 1) - cx.s0) & (2 * F - 1)];
-            }
-            num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));   // deltaRegression.cpp:139-146
-          }
-          const float dv = div_exact(num, norm1, p.fRcp1);
-          Dbuf[c * dRows + tt] = dv;
-          if (t >= r0 && t < r1) outS[(t - r0) * K3 + K + c] = dv;
-        }
-        for (int rr = lane; rr < nr; rr += 32) outS[rr * K3 + c] = rc[(r0 + rr - cx.s0) & (2 * F - 1)];
-      }
-      __syncthreads();
-      // ---- delta-delta rows [r0, r1) -> outS ----
-      for (int c = warp; c < K; c += NW) {
-        const float *dc = Dbuf + c * dRows - d0;
-        for (int rr = lane; rr < nr; rr += 32) {
-          const int t = r0 + rr;
-          const int navail2 = win_navail(t, c01, c02, T1);
-          float num = 0.f;
-          for (int i = 1; i <= W2; i++) {
-            const int hi = t + i, lo = t - i;
-            float later, prior;
-            if (t - W2 < 0) {
-              later = (hi >= navail2) ? 0.f : dc[hi];
-              prior = dc[max(lo, 0)];
-            } else {
-              later = dc[min(hi, navail2 - 1)];
-              prior = dc[min(lo, navail2 - 1)];
-            }
-            num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));
-          }
-          outS[rr * K3 + 2 * K + c] = div_exact(num, norm2, p.fRcp2);
-        }
-      }
-      __syncthreads();
+        emit_edge<F, NW>(ring, Dbuf, outS, K, W1, W2, T, T1, c01, c02, cx.s0, r0, r1, d0, d1, dRows, norm1, p.fRcp1, norm2, p.fRcp2, warp, lane);
       }
       // ---- rows [r0, r1) -> HBM, one contiguous block ----
       {
         float *o = p.out + (cx.row0 + r0) * (long long)K3;
         const int n = nr * K3;
-        for (int i = tid; i < n; i += NT) o[i] = outS[i];
+        if (OSM_OPT_EMIT && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && (n & 3) == 0) {   // 16-byte aligned block: vector stores
+          const float4 *s4 = reinterpret_cast<const float4 *>(outS);
+          float4 *o4 = reinterpret_cast<float4 *>(o);
+          for (int i = tid; i < (n >> 2); i += NT) o4[i] = s4[i];
+        } else {
+          for (int i = tid; i < n; i += NT) o[i] = outS[i];
+        }
       }
       emitted = r1;
       // Dbuf aliases Z: the next tile's first FFT stage writes Z only after the barrier that

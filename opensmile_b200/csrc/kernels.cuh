@@ -21,6 +21,7 @@ struct LldParams {
   int nChunks;
   int nChan;
   // fused temporal stages (static | delta(W1) | delta(W1,W2)); halo = W1 + W2, 0 when not fused
+  unsigned hopMagic;             // ceil(2^32 / frameStep): i / frameStep == __umulhi(i, hopMagic) for i * frameStep < 2^32
   int narrow;                    // 1: half-width tiles (F/2 frames), used when the full tile does not fit shared memory
   int fused, halo, fW1, fW2;
   float fNorm1, fNorm2;
@@ -39,6 +40,9 @@ struct LldParams {
   // ---- mel + mfcc op ----
   const float *melCoef;          // [nBins]
   const int *melRange;           // [nBands+2]
+  // visit list of the mel phase: per range r the (w, 1-w) pairs of its bins, zero-padded to a multiple
+  // of 4 entries (the padding multiplies the next bins by 0): melVisit[melVB[r] .. melVB[r+1])
+  const float2 *melVisit; const int *melVB; int melVCount;
   int nBands;
   float melScale;
   int melUsePower;

@@ -7,13 +7,21 @@ import ncu_lines as nl
 rep, ksub = sys.argv[1], sys.argv[2]
 line = int(sys.argv[sys.argv.index("--line") + 1]) if "--line" in sys.argv else None
 frames = float(sys.argv[sys.argv.index("--frames") + 1]) if "--frames" in sys.argv else 1e6
-table = nl.line_table(os.path.join(nl.ROOT, "opensmile_b200", "libosm_b200.so"), ksub)
+so = os.path.join(nl.ROOT, "opensmile_b200", "libosm_b200.so")
+for a in sys.argv[3:]:
+    if a.endswith(".so"):
+        so = a
+table = nl.line_table(so, ksub)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "Address" in r and "Source" in r)
 hdr, body = rows[hi], rows[hi + 1:]
 iI = hdr.index("Instructions Executed")
-fn = list({k[0] for k in table})[0]
+fns = {k[0] for k in table}
+fn = next((f for f in fns if sum(1 for k in table if k[0] == f) == len(body)), None)   # the instance that was profiled
+if fn is None:
+    fn = list(fns)[0]
+    print("warning: no instance with %d instructions, using %s" % (len(body), fn), file=sys.stderr)
 offs = sorted(k[1] for k in table if k[0] == fn)
 marks = []
 for i, ln in enumerate(open(os.path.join(nl.ROOT, "opensmile_b200", "csrc", "kernels.cu")).read().splitlines(), 1):
