@@ -26,27 +26,13 @@
 #include "fft_radix.cuh"
 #include "kernels.cuh"
 
-// experiment switches (A/B builds): -DOSM_OPT_MELV=0 etc.
-#ifndef OSM_OPT_MELV
-#define OSM_OPT_MELV 0
-#endif
-#ifndef OSM_OPT_EMIT
-#define OSM_OPT_EMIT 0
-#endif
-#ifndef OSM_OPT_STAGE
-#define OSM_OPT_STAGE 1
-#endif
+// A/B builds: scripts/ab_variants.py times library variants compiled with different -D switches; the
+// only switches left are the two unroll factors below.
 #ifndef OSM_UNROLL_MEL
 #define OSM_UNROLL_MEL 4
 #endif
 #ifndef OSM_UNROLL_DCT
 #define OSM_UNROLL_DCT 2
-#endif
-#ifndef OSM_OPT_COLD
-#define OSM_OPT_COLD 1        // rarely executed paths out of line (instruction cache footprint)
-#endif
-#ifndef OSM_OPT_MELS_ALIAS
-#define OSM_OPT_MELS_ALIAS 1
 #endif
 
 namespace osm {
@@ -94,7 +80,7 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
   o = align_up(o, 16);
   // the band values live only between the mel phase and the DCT / PLP back end of the same tile: the
   // sample tile is dead then (it is rewritten by the next tile's staging), so they share its space
-  if (OSM_OPT_MELS_ALIAS && L.sampFloats >= p.nBands * F) L.melS = L.samp;
+  if (L.sampFloats >= p.nBands * F) L.melS = L.samp;
   else { L.melS = o; o += p.nBands * F * 4; }
   L.ring = o; o += p.nStat * 2 * F * 4;     // static features of the last two tiles
   L.total = align_up(o, 16);
@@ -115,11 +101,7 @@ __device__ __forceinline__ float div32767(float x)
   return __fmaf_rn(r, rc, q0);
 }
 
-#if OSM_OPT_COLD
-#define OSM_COLD __noinline__
-#else
-#define OSM_COLD __forceinline__
-#endif
+#define OSM_COLD __noinline__     // rarely executed paths stay out of the hot instruction stream
 __device__ __forceinline__ float pcm_to_float_generic(const int16_t *s, int nChan)
 {
   float tmp = (float)s[0];
@@ -617,7 +599,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           // vectorPreemphasis.cpp:96-104 : x[n] -/+ k * x[n-1], two roundings
           float xprev = 0.f;
           if (i > 0 || tg.lead > 0) {
-            if (OSM_OPT_STAGE && nChan == 1) xprev = div32767((float)rp[i - 1]);
+            if (nChan == 1) xprev = div32767((float)rp[i - 1]);
             else xprev = pcm_to_float_slow(rp + (i - 1) * nChan, nChan);
           }
           // x - k*xp == x + (-k)*xp exactly: one signed coefficient instead of a per-sample select
@@ -628,7 +610,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 #pragma unroll
           for (int jj = 0; jj < 8; jj++) y[jj] = x[jj];
         }
-        const int q = OSM_OPT_STAGE ? (int)__umulhi((unsigned)i, p.hopMagic) : i / hop;
+        const int q = (int)__umulhi((unsigned)i, p.hopMagic);      // i / hop
         const int r = i - q * hop;
         float *dst = samp + i + q * p.sPad;
         if (fastStore && nvalid == 8 && r + 8 <= hop) {
@@ -748,34 +730,6 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     {
       const int bs = p.melSplit[vw], be = p.melSplit[vw + 1];
       if (bs < be) {
-#if OSM_OPT_MELV
-        // every range is walked in groups of 4 visit entries (zero-weight padding at its end), so
-        // the loops have no remainder and all addresses inside a group are immediates
-        const int *sVB = sMelRange + p.nBands + 2;
-        float cur = 0.f;
-        {   // range bs only feeds band bs (its rising slope)
-          const float *pp = P + sMelRange[bs] * F + f;
-          const float2 *cp = sMelCoef + sVB[bs];
-          for (int q = (sVB[bs + 1] - sVB[bs]) >> 2; q > 0; q--, pp += 4 * F, cp += 4) {
-            cur = __fmaf_rn(pp[0], cp[0].y, cur);
-            cur = __fmaf_rn(pp[F], cp[1].y, cur);
-            cur = __fmaf_rn(pp[2 * F], cp[2].y, cur);
-            cur = __fmaf_rn(pp[3 * F], cp[3].y, cur);
-          }
-        }
-        for (int r = bs + 1; r <= be; r++) {
-          float nxt = 0.f;
-          const float *pp = P + sMelRange[r] * F + f;
-          const float2 *cp = sMelCoef + sVB[r];
-          for (int q = (sVB[r + 1] - sVB[r]) >> 2; q > 0; q--, pp += 4 * F, cp += 4) {
-            const float p0 = pp[0], p1 = pp[F], p2 = pp[2 * F], p3 = pp[3 * F];
-            const float2 w0 = cp[0], w1 = cp[1], w2 = cp[2], w3 = cp[3];
-            cur = __fmaf_rn(p0, w0.x, cur); nxt = __fmaf_rn(p0, w0.y, nxt);
-            cur = __fmaf_rn(p1, w1.x, cur); nxt = __fmaf_rn(p1, w1.y, nxt);
-            cur = __fmaf_rn(p2, w2.x, cur); nxt = __fmaf_rn(p2, w2.y, nxt);
-            cur = __fmaf_rn(p3, w3.x, cur); nxt = __fmaf_rn(p3, w3.y, nxt);
-          }
-#else
         const int *sVB = sMelRange + p.nBands + 2;
         float cur = 0.f;
         int n = sMelRange[bs];
@@ -797,7 +751,6 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
             cur = __fmaf_rn(pw, w.x, cur);
             nxt = __fmaf_rn(pw, w.y, nxt);
           }
-#endif
           float mval = __fmul_rn(cur, p.melScale);
           if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);   // mfcc.cpp:239-243 / plp.cpp:434-440
           if (opKind == 1 && p.plpAud) {
@@ -889,9 +842,8 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       const bool interior2 = (r0 >= W2) && (r1 <= c02);           // all rows computed before EOI
       if (interior1 && interior2 && W1 == 2 && W2 == 2 && nr == F) {
         // ---- common case (deltawin = 2 twice, interior tile): straight-line code, work items
-        // spread evenly over all threads; K = 13 (MFCC12_0_D_A) gets compile-time trip counts
-        if (OSM_OPT_EMIT && K == 13) emit_interior<F, NT, 13>(ring, Dbuf, outS, K, dRows, d0 - cx.s0, r0 - cx.s0, norm1, p.fRcp1, norm2, p.fRcp2, tid);
-        else emit_interior<F, NT, 0>(ring, Dbuf, outS, K, dRows, d0 - cx.s0, r0 - cx.s0, norm1, p.fRcp1, norm2, p.fRcp2, tid);
+        // spread evenly over all threads
+        emit_interior<F, NT, 0>(ring, Dbuf, outS, K, dRows, d0 - cx.s0, r0 - cx.s0, norm1, p.fRcp1, norm2, p.fRcp2, tid);
       } else {
         emit_edge<F, NW>(ring, Dbuf, outS, K, W1, W2, T, T1, c01, c02, cx.s0, r0, r1, d0, d1, dRows, norm1, p.fRcp1, norm2, p.fRcp2, warp, lane);
       }
@@ -899,13 +851,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       {
         float *o = p.out + (cx.row0 + r0) * (long long)K3;
         const int n = nr * K3;
-        if (OSM_OPT_EMIT && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && (n & 3) == 0) {   // 16-byte aligned block: vector stores
-          const float4 *s4 = reinterpret_cast<const float4 *>(outS);
-          float4 *o4 = reinterpret_cast<float4 *>(o);
-          for (int i = tid; i < (n >> 2); i += NT) o4[i] = s4[i];
-        } else {
-          for (int i = tid; i < n; i += NT) o[i] = outS[i];
-        }
+        for (int i = tid; i < n; i += NT) o[i] = outS[i];
       }
       emitted = r1;
       // Dbuf aliases Z: the next tile's first FFT stage writes Z only after the barrier that

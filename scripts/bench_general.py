@@ -1,0 +1,31 @@
+"""Device-resident throughput of a general (multi-kernel) plan built from a .conf file.
+usage: bench_general.py [conf] [n_utt] [n_samples]   (default: tests/configs/compare_ns.conf, 1000 x 48000 @16 kHz)"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from opensmile_b200 import Plan, Session
+import bench
+
+conf = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "configs", "compare_ns.conf")
+n_utt = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+n_samp = int(sys.argv[3]) if len(sys.argv) > 3 else 48000
+s = Session(conf, device=-1)
+comps, level = s.components(16000, 1)
+plan = Plan(list(comps), level, 0)
+pcm = bench.synth_batch_torch(n_utt, n_samp, torch.device("cuda", 0), 0)
+off = np.arange(n_utt + 1, dtype=np.int64) * n_samp
+out = plan.run_device(pcm, off)
+torch.cuda.synchronize()
+for _ in range(3):
+    out = plan.run_device(pcm, off, d_out=out)
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record()
+K = 10
+for _ in range(K):
+    out = plan.run_device(pcm, off, d_out=out)
+ev1.record()
+torch.cuda.synchronize()
+ms = ev0.elapsed_time(ev1) / K
+rows = out.shape[0]
+print("%s: %d rows x %d cols, %.3f ms/step, %.1f M rows/s, launches %d" % (os.path.basename(conf), rows, out.shape[1], ms, rows / ms / 1e3, plan.last_launch_count()))
