@@ -134,6 +134,7 @@ struct SpectralParams {
   int alphaRatio, hammarberg, flux, centroid, maxPos, minPos, entropy, stddev, variance, skewness, kurtosis,
       slope, sharpness, harmonicity, flatness, logFlatness;
   const double *sharpW;          // [hiBin-loBin+1] (device)
+  int stageMag;                  // set by the launcher: magnitude tile staged in shared memory
 };
 
 struct TimeOpParams {            // cEnergy / cMZcr on the framer or windower level

@@ -10,14 +10,16 @@ namespace osm {
 // ------------------------------------------------------------------------------------------
 // cSpectral (lldcore/spectral.cpp:586-1555), magnitude input with a linear bin-frequency axis
 // ------------------------------------------------------------------------------------------
-constexpr int kSpecThreads = 32;     // one warp = one tile
+constexpr int kSpecWarps = 4;
+constexpr int kSpecThreads = 32 * kSpecWarps;   // one CTA = one tile; lane = frame, warps split the descriptors
 
 struct SpecView {
-  const float *mag;     // this frame's bin k at mag[k * F]
+  const float *mag;     // magnitudes of this frame: bin k at mag[k * mstride] (shared-memory tile, stride 32,
+                        // or -- when both tiles do not fit -- the global tile, stride F)
   const float *logS;    // shared-memory log spectrum of this frame, bin k at logS[k * 32] (or null)
-  int F;
+  int mstride;
   int squareInput, useLog;
-  __device__ __forceinline__ float m(int k) const { return mag[(size_t)k * F]; }
+  __device__ __forceinline__ float m(int k) const { return mag[(size_t)k * mstride]; }
   __device__ __forceinline__ float M(int k) const   // srcM (:677-690)
   {
     const float v = m(k);
@@ -32,18 +34,34 @@ struct SpecView {
   __device__ __forceinline__ float LP(int k) const { return useLog ? L(k) : P(k); }
 };
 
+// The tile's magnitudes (and, when needed, its log spectrum) are staged in shared memory once;
+// the descriptors are then distributed over the four warps of the CTA.  Every descriptor is still
+// evaluated by ONE thread per frame in the reference's loop order and accumulator types; a warp
+// that needs a shared prerequisite (frame sum, sum of the spectrum, centroid) recomputes it with the
+// same loop, so the split does not change any result.
 __global__ void __launch_bounds__(kSpecThreads) spectral_kernel(const SpectralParams p)
 {
-  extern __shared__ float slog[];      // [nSrc][32] when reqLog
+  extern __shared__ float ssm[];       // [nSrc][32] magnitudes | [nSrc][32] log spectrum (when reqLog) | [32] previous frame's column is read from global
   const OpTile tl = p.tiles[blockIdx.x];
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool active = lane < tl.nf;
   const int F = p.F, Nsrc = p.nSrc;
   const int fl = active ? lane : 0;    // inactive lanes shadow frame 0 (results discarded)
+  const bool staged = p.stageMag != 0;
+  float *smag = ssm, *slog = ssm + (staged ? (size_t)Nsrc * 32 : 0);
+  const float *gmag = p.mag + ((size_t)blockIdx.x * Nsrc) * F;
+  if (staged) {
+    for (int idx = tid; idx < Nsrc * 32; idx += kSpecThreads) {
+      const int k = idx >> 5, ff = idx & 31;
+      smag[idx] = gmag[(size_t)k * F + (ff < F ? ff : 0)];
+    }
+    __syncthreads();
+  }
   SpecView v;
-  v.mag = p.mag + ((size_t)blockIdx.x * Nsrc) * F + fl;
-  v.logS = slog + lane;
-  v.F = F; v.squareInput = p.squareInput; v.useLog = p.useLog;
+  v.mag = staged ? (smag + fl) : (gmag + fl);
+  v.mstride = staged ? 32 : F;
+  v.logS = slog + fl;
+  v.squareInput = p.squareInput; v.useLog = p.useLog;
   const double F0 = p.F0;
   const int lo = p.loBin, hi = p.hiBin, nBins = hi - lo + 1;
   const float specFloor = p.specFloor;
@@ -54,217 +72,272 @@ __global__ void __launch_bounds__(kSpecThreads) spectral_kernel(const SpectralPa
     if (p.reqPow) src = 0;
     else if (p.reqMag) src = 1;
     else src = 2;
-    for (int k = 0; k < Nsrc; k++) {
-      const float x = (src == 0) ? v.P(k) : ((src == 1) ? v.M(k) : v.m(k));
+    SpecView vl = v;     // inactive lanes compute the shadow column too: every slog column is defined
+    for (int k = warp; k < Nsrc; k += kSpecWarps) {
+      const float x = (src == 0) ? vl.P(k) : ((src == 1) ? vl.M(k) : vl.m(k));
       slog[k * 32 + lane] = (x <= specFloor) ? p.logSpecFloor : __fmul_rn(fac, logf(x));
     }
+    __syncthreads();
   }
-  __syncwarp();
 
   float *dst = p.stat + (p.statOff[tl.utt] + tl.f0 + fl) * (long long)p.statStride + p.outCol;
-  int n = 0;
-  auto put = [&](float x) { if (active) dst[n] = x; n++; };
   auto frq = [&](int k) { return F0 * (double)k; };
+  // output columns, in the order of spectral.cpp:378-584
+  int col = 0;
+  const int cBands = col; col += p.nBands;
+  const int cSlopes = col; col += p.nSlopes;
+  const int cAlpha = col; col += p.alphaRatio ? 1 : 0;
+  const int cHamm = col; col += p.hammarberg ? 1 : 0;
+  const int cRoll = col; col += p.nRollOff;
+  const int cFlux = col; col += p.flux ? 1 : 0;
+  const int cCentroid = col; col += p.centroid ? 1 : 0;
+  const int cMaxPos = col; col += p.maxPos ? 1 : 0;
+  const int cMinPos = col; col += p.minPos ? 1 : 0;
+  const int cEntropy = col; col += p.entropy ? 1 : 0;
+  const int cStd = col; col += p.stddev ? 1 : 0;
+  const int cVar = col; col += p.variance ? 1 : 0;
+  const int cSkew = col; col += p.skewness ? 1 : 0;
+  const int cKurt = col; col += p.kurtosis ? 1 : 0;
+  const int cSlope = col; col += p.slope ? 1 : 0;
+  const int cSharp = col; col += p.sharpness ? 1 : 0;
+  const int cHarm = col; col += p.harmonicity ? 1 : 0;
+  const int cFlat = col;
+  auto put = [&](int c, float x) { if (active) dst[c] = x; };
 
-  double frameSum = 0.0;                                                // :766-771
-  if (p.normBand || p.sharpness || p.nRollOff > 0)
-    for (int i = lo; i <= hi; i++) frameSum += v.P(i);
+  auto frame_sum = [&]() {                                              // :766-771
+    double fs = 0.0;
+    for (int i = lo; i <= hi; i++) fs += v.P(i);
+    return fs;
+  };
+  auto sum_b = [&](double frameSum) {                                   // :1092-1099
+    double sb = 0.0;
+    if (p.normBand && !p.useLog) sb = frameSum;
+    else for (int j = lo; j <= hi; j++) sb += (double)v.LP(j);
+    return sb;
+  };
+  auto sum_a = [&]() {                                                  // :1257-1312
+    double sa = 0.0;
+    for (int j = lo; j <= hi; j++) sa += frq(j) * (double)v.LP(j);
+    return sa;
+  };
 
-  for (int b = 0; b < p.nBands; b++) {                                  // :775-870
-    const int iL = p.bandIL[b], iR = p.bandIR[b];
-    double sum = (double)v.P(iL) * p.bandWL[b];
-    for (int j = iL + 1; j < iR; j++) sum += (double)v.P(j);
-    sum += (double)v.P(iR) * p.bandWR[b];
-    if (p.normBand) put(frameSum > 0.0 ? (float)(sum / frameSum) : 0.0f);
-    else if (nBins > 0) put(p.useLog ? (float)(10.0 * log(sum / (double)nBins) / log(10.0)) : (float)(sum / (double)nBins));
-    else put(0.0f);
-  }
-  for (int b = 0; b < p.nSlopes; b++) {                                 // :873-993
-    const int iL = p.slopeIL[b], iR = p.slopeIR[b];
-    const double wL = p.slopeWL[b], wR = p.slopeWR[b], Nind = p.slopeNind[b];
-    double Sf = frq(iL) * wL, S2f = Sf * Sf;
-    double sumA = frq(iL) * wL * (double)v.LP(iL), sumB = wL * v.LP(iL);
-    for (int ii = iL + 1; ii < iR && ii < Nsrc; ii++) {
-      const double f = frq(ii), x = (double)v.LP(ii);
-      S2f += f * f; Sf += f; sumA += f * x; sumB += x;
+  if (warp == 0) {
+    // ---- frame sum -> band energies, roll-off points, sharpness ----
+    double frameSum = 0.0;
+    if (p.normBand || p.sharpness || p.nRollOff > 0) frameSum = frame_sum();
+    for (int b = 0; b < p.nBands; b++) {                                // :775-870
+      const int iL = p.bandIL[b], iR = p.bandIR[b];
+      double sum = (double)v.P(iL) * p.bandWL[b];
+      for (int j = iL + 1; j < iR; j++) sum += (double)v.P(j);
+      sum += (double)v.P(iR) * p.bandWR[b];
+      if (p.normBand) put(cBands + b, frameSum > 0.0 ? (float)(sum / frameSum) : 0.0f);
+      else if (nBins > 0) put(cBands + b, p.useLog ? (float)(10.0 * log(sum / (double)nBins) / log(10.0)) : (float)(sum / (double)nBins));
+      else put(cBands + b, 0.0f);
     }
-    S2f += frq(iR) * wR * frq(iR) * wR;
-    Sf += frq(iR) * wR;
-    sumA += frq(iR) * wR * (double)v.LP(iR);
-    sumB += wR * (double)v.LP(iR);
-    const double deno = (Nind * S2f - Sf * Sf);
-    double slope = 0.0;
-    if (deno != 0.0) slope = (Nind * sumA - Sf * sumB) / deno;
-    put(p.oldSlopeScale ? (float)(slope * (Nind - 1.0)) : (float)slope);
-  }
-  if (p.alphaRatio) {                                                   // :996-1037 (float sums)
-    float sum01 = 0.0f, sum15 = 0.0f;
-    for (int j = 0; j < Nsrc; j++) {
-      const double f = frq(j);
-      if (f > 5000.0) break;
-      if (f < 1000.0) sum01 = __fadd_rn(sum01, v.P(j)); else sum15 = __fadd_rn(sum15, v.P(j));
-    }
-    if (sum01 > 0.0f) {
-      if (p.useLog) put((sum15 > specFloor) ? (float)(10.0 * log((double)__fdiv_rn(sum15, sum01)) / log(10.0))
-                                           : (float)(10.0 * (log((double)specFloor) - log((double)sum01)) / log(10.0)));
-      else put(__fdiv_rn(sum15, sum01));
-    } else put(0.0f);
-  }
-  if (p.hammarberg) {                                                   // :1040-1089
-    float max02 = 0.0f, max25 = 0.0f;
-    for (int j = 0; j < Nsrc; j++) {
-      const double f = frq(j);
-      if (f > 5000.0) break;
-      const float x = v.P(j);
-      if (f < 2000.0) { if (x > max02) max02 = x; } else { if (x > max25) max25 = x; }
-    }
-    if (max25 > 0.0f) {
-      if (p.useLog) put((max02 > specFloor) ? (float)(10.0 * log((double)__fdiv_rn(max02, max25)) / log(10.0))
-                                           : (float)(10.0 * (log((double)specFloor) - log((double)max25)) / log(10.0)));
-      else put(__fdiv_rn(max02, max25));
-    } else put(0.0f);
-  }
-  double sumB = 0.0, sumC = 0.0;                                        // :1092-1099
-  if (p.normBand && !p.useLog) sumB = frameSum;
-  else for (int j = lo; j <= hi; j++) sumB += (double)v.LP(j);
-  if (p.nRollOff > 0) {                                                 // :1103-1122
-    float ro[16];
+    if (p.nRollOff > 0) {                                               // :1103-1122
+      double sumC = 0.0;
+      float ro[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) ro[i] = 0.0f;
-    for (int j = lo; j <= hi; j++) {
-      sumC += (double)v.P(j);
+      for (int i = 0; i < 16; i++) ro[i] = 0.0f;
+      for (int j = lo; j <= hi; j++) {
+        sumC += (double)v.P(j);
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        if (i < p.nRollOff) {
-          if (p.buggyRollOff == 1 && i > 0) sumC += (double)v.P(j);
-          if ((ro[i] == 0.0f) && (sumC >= p.rollOff[i] * frameSum)) ro[i] = (float)frq(j);
+        for (int i = 0; i < 16; i++) {
+          if (i < p.nRollOff) {
+            if (p.buggyRollOff == 1 && i > 0) sumC += (double)v.P(j);
+            if ((ro[i] == 0.0f) && (sumC >= p.rollOff[i] * frameSum)) ro[i] = (float)frq(j);
+          }
         }
       }
-    }
 #pragma unroll
-    for (int i = 0; i < 16; i++) if (i < p.nRollOff) put(ro[i]);
-  }
-  if (p.flux) {                                                         // :1125-1254
-    const bool first = (tl.f0 + fl) == 0;
-    if (first) put(0.0f);
-    else {
-      const float *prev = (fl > 0) ? (v.mag - 1) : (p.mag + ((size_t)(blockIdx.x - 1) * Nsrc) * F + (F - 1));
-      double myA = 0.0;
-      for (int j = lo; j <= hi; j++) {
-        const float pm = prev[(size_t)j * F];
-        const float pM = p.squareInput ? pm : (pm > 0.0f ? __fsqrt_rn(pm) : 0.0f);
-        const double myB = ((double)v.M(j) - (double)pM);
-        myA += myB * myB;
-      }
-      const double fx = nBins > 0 ? myA / (double)nBins : 0.0;
-      put(fx > 0.0 ? (float)sqrt(fx) : 0.0f);
+      for (int i = 0; i < 16; i++) if (i < p.nRollOff) put(cRoll + i, ro[i]);
     }
-  }
-  float ctr = 0.0f;                                                     // :1257-1312
-  double sumA = 0.0;
-  if (p.centroid || p.stddev || p.variance || p.skewness || p.kurtosis || p.slope) {
-    for (int j = lo; j <= hi; j++) sumA += frq(j) * (double)v.LP(j);
-    if (sumB != 0.0) ctr = (float)(sumA / sumB);
-    if (p.centroid) put(ctr);
-  }
-  if (p.maxPos || p.minPos) {                                           // :1314-1330
-    int maP = lo, miP = lo;
-    float mx = v.LP(lo), mn = mx;
-    for (int j = lo + 1; j < hi; j++) {
-      const float x = v.LP(j);
-      if (x < mn) { mn = x; miP = j; }
-      if (x > mx) { mx = x; maP = j; }
+    if (p.sharpness) {                                                  // :1429-1478 (float accumulation)
+      float sumAA = 0.0f, c2 = 0.0f;
+      for (int j = lo; j <= hi && j < Nsrc; j++) sumAA = __fadd_rn(sumAA, (float)(p.sharpW[j - lo] * (double)v.P(j)));
+      if (frameSum != 0.0) c2 = (float)((double)sumAA / frameSum);
+      put(cSharp, (float)(0.11 * (double)c2));
     }
-    if (p.maxPos) put((float)frq(maP));
-    if (p.minPos) put((float)frq(miP));
-  }
-  if (p.entropy) {                                                      // smileutil/smileUtil.c:2082-2124
-    const double entropy_floor = 0.0000001;
-    double e = 0.0, dn = 0.0;
-    const double l2 = log(2.0);
-    float mn = 0.0f;
-    for (int i = lo; i <= hi; i++) { const float x = v.LP(i); dn += (double)x; if (x < mn) mn = x; }
-    if (mn < 0.0f) {
-      const double mf = entropy_floor + mn;
-      for (int i = lo; i <= hi; i++) { const float x = v.LP(i); if (x <= mf) dn += mf - x; dn -= (double)mn; }
-    } else mn = 0.0f;
-    if (dn < (float)entropy_floor) dn = (float)entropy_floor;
-    for (int i = lo; i <= hi; i++) {
-      double vv = __fsub_rn(v.LP(i), mn);
-      if (vv <= entropy_floor) vv = entropy_floor;
-      const double ln = vv / dn;
-      if (ln > 0.0) e += ln * log(ln) / l2;
-    }
-    put((float)(-e));
-  }
-  if (p.stddev || p.variance || p.skewness || p.kurtosis) {             // :1338-1397
-    const double u = ctr;
-    double m2 = 0.0, m3 = 0.0, m4 = 0.0;
-    for (int i = lo; i <= hi; i++) {
-      const double t1 = (frq(i) - u);
-      double m = t1 * t1 * (double)v.LP(i);
-      m2 += m; m *= t1; m3 += m; m4 += m * t1;
-    }
-    double sigma2 = 0.0;
-    if (sumB != 0.0) sigma2 = m2 / sumB;
-    if (p.stddev) put(sigma2 > 0.0 ? (float)sqrt(sigma2) : 0.0f);
-    if (p.variance) put((float)sigma2);
-    if (p.skewness) put(sigma2 <= 0.0 ? 0.0f : (float)(m3 / (sumB * sigma2 * sqrt(sigma2))));
-    if (p.kurtosis) put(sigma2 == 0.0 ? 0.0f : (float)(m4 / (sumB * sigma2 * sigma2)));
-  }
-  if (p.slope) {                                                        // :1400-1427
-    double Sf = 0.0, S2f = 0.0;
-    const double Nind = (double)nBins;
-    for (int i = lo; i <= hi && i < Nsrc; i++) { const double f = frq(i); S2f += f * f; Sf += f; }
-    const double deno = (Nind * S2f - Sf * Sf);
-    double slope = 0.0;
-    if (deno != 0.0) slope = (Nind * sumA - Sf * sumB) / deno;
-    put(p.oldSlopeScale ? (float)(slope * (Nind - 1.0)) : (float)slope);
-  }
-  if (p.sharpness) {                                                    // :1429-1478 (float accumulation)
-    float sumAA = 0.0f, c2 = 0.0f;
-    for (int j = lo; j <= hi && j < Nsrc; j++) sumAA = __fadd_rn(sumAA, (float)(p.sharpW[j - lo] * (double)v.P(j)));
-    if (frameSum != 0.0) c2 = (float)((double)sumAA / frameSum);
-    put((float)(0.11 * (double)c2));
-  }
-  if (p.harmonicity) {                                                  // :1484-1513
-    float ptpSum = 0.0f, lastPeak = -99.0f;
-    for (int j = lo + 2; j < hi - 1; j++) {
-      const float a = v.LP(j - 2), b = v.LP(j - 1), c = v.LP(j), d = v.LP(j + 1), e = v.LP(j + 2);
-      if ((a < c && b < c && c > d && c > e) || (a > c && b > c && c < d && c < e)) {
-        if (lastPeak != -99.0f) ptpSum = __fadd_rn(ptpSum, fabsf(__fsub_rn(c, lastPeak)));
-        lastPeak = c;
+  } else if (warp == 1) {
+    // ---- flux, entropy ----
+    if (p.flux) {                                                       // :1125-1254
+      const bool first = (tl.f0 + fl) == 0;
+      if (first) put(cFlux, 0.0f);
+      else {
+        // previous frame: the neighbouring column of this tile, or the last column of the tile before
+        const float *prev = (fl > 0) ? (v.mag - 1) : (p.mag + ((size_t)(blockIdx.x - 1) * Nsrc) * F + (F - 1));
+        const int pstride = (fl > 0) ? v.mstride : F;
+        double myA = 0.0;
+        for (int j = lo; j <= hi; j++) {
+          const float pm = prev[(size_t)j * pstride];
+          const float pM = p.squareInput ? pm : (pm > 0.0f ? __fsqrt_rn(pm) : 0.0f);
+          const double myB = ((double)v.M(j) - (double)pM);
+          myA += myB * myB;
+        }
+        const double fx = nBins > 0 ? myA / (double)nBins : 0.0;
+        put(cFlux, fx > 0.0 ? (float)sqrt(fx) : 0.0f);
       }
     }
-    ptpSum = __fdiv_rn(ptpSum, 2.0f);
-    if (p.normBand && sumB != 0.0) {
-      if (p.useLog) ptpSum = __fdiv_rn(ptpSum, (float)fabs(sumB)); else ptpSum = __fdiv_rn(ptpSum, (float)frameSum);
-    } else ptpSum = __fdiv_rn(ptpSum, (float)nBins);
-    put(ptpSum);
-  }
-  if (p.flatness) {                                                     // :1515-1544
-    float sf = 0.0f, gmean = 0.0f;
-    int nGm = 0;
-    if (sumB != 0.0) {
-      for (int j = lo; j <= hi; j++) {
+    if (p.entropy) {                                                    // smileutil/smileUtil.c:2082-2124
+      const double entropy_floor = 0.0000001;
+      double e = 0.0, dn = 0.0;
+      const double l2 = log(2.0);
+      float mn = 0.0f;
+      for (int i = lo; i <= hi; i++) { const float x = v.LP(i); dn += (double)x; if (x < mn) mn = x; }
+      if (mn < 0.0f) {
+        const double mf = entropy_floor + mn;
+        for (int i = lo; i <= hi; i++) { const float x = v.LP(i); if (x <= mf) dn += mf - x; dn -= (double)mn; }
+      } else mn = 0.0f;
+      if (dn < (float)entropy_floor) dn = (float)entropy_floor;
+      for (int i = lo; i <= hi; i++) {
+        double vv = __fsub_rn(v.LP(i), mn);
+        if (vv <= entropy_floor) vv = entropy_floor;
+        const double ln = vv / dn;
+        if (ln > 0.0) e += ln * log(ln) / l2;
+      }
+      put(cEntropy, (float)(-e));
+    }
+  } else if (warp == 2) {
+    // ---- centroid, moments, overall slope ----
+    if (p.centroid || p.stddev || p.variance || p.skewness || p.kurtosis || p.slope) {
+      const double frameSum = (p.normBand && !p.useLog) ? frame_sum() : 0.0;
+      const double sumB = sum_b(frameSum);
+      const double sumA = sum_a();
+      float ctr = 0.0f;
+      if (sumB != 0.0) ctr = (float)(sumA / sumB);
+      if (p.centroid) put(cCentroid, ctr);
+      if (p.stddev || p.variance || p.skewness || p.kurtosis) {         // :1338-1397
+        const double u = ctr;
+        double m2 = 0.0, m3 = 0.0, m4 = 0.0;
+        for (int i = lo; i <= hi; i++) {
+          const double t1 = (frq(i) - u);
+          double m = t1 * t1 * (double)v.LP(i);
+          m2 += m; m *= t1; m3 += m; m4 += m * t1;
+        }
+        double sigma2 = 0.0;
+        if (sumB != 0.0) sigma2 = m2 / sumB;
+        if (p.stddev) put(cStd, sigma2 > 0.0 ? (float)sqrt(sigma2) : 0.0f);
+        if (p.variance) put(cVar, (float)sigma2);
+        if (p.skewness) put(cSkew, sigma2 <= 0.0 ? 0.0f : (float)(m3 / (sumB * sigma2 * sqrt(sigma2))));
+        if (p.kurtosis) put(cKurt, sigma2 == 0.0 ? 0.0f : (float)(m4 / (sumB * sigma2 * sigma2)));
+      }
+      if (p.slope) {                                                    // :1400-1427
+        double Sf = 0.0, S2f = 0.0;
+        const double Nind = (double)nBins;
+        for (int i = lo; i <= hi && i < Nsrc; i++) { const double f = frq(i); S2f += f * f; Sf += f; }
+        const double deno = (Nind * S2f - Sf * Sf);
+        double slope = 0.0;
+        if (deno != 0.0) slope = (Nind * sumA - Sf * sumB) / deno;
+        put(cSlope, p.oldSlopeScale ? (float)(slope * (Nind - 1.0)) : (float)slope);
+      }
+    }
+  } else {
+    // ---- band slopes, alpha ratio, Hammarberg index, extrema, harmonicity, flatness ----
+    for (int b = 0; b < p.nSlopes; b++) {                               // :873-993
+      const int iL = p.slopeIL[b], iR = p.slopeIR[b];
+      const double wL = p.slopeWL[b], wR = p.slopeWR[b], Nind = p.slopeNind[b];
+      double Sf = frq(iL) * wL, S2f = Sf * Sf;
+      double sumA = frq(iL) * wL * (double)v.LP(iL), sumB = wL * v.LP(iL);
+      for (int ii = iL + 1; ii < iR && ii < Nsrc; ii++) {
+        const double f = frq(ii), x = (double)v.LP(ii);
+        S2f += f * f; Sf += f; sumA += f * x; sumB += x;
+      }
+      S2f += frq(iR) * wR * frq(iR) * wR;
+      Sf += frq(iR) * wR;
+      sumA += frq(iR) * wR * (double)v.LP(iR);
+      sumB += wR * (double)v.LP(iR);
+      const double deno = (Nind * S2f - Sf * Sf);
+      double slope = 0.0;
+      if (deno != 0.0) slope = (Nind * sumA - Sf * sumB) / deno;
+      put(cSlopes + b, p.oldSlopeScale ? (float)(slope * (Nind - 1.0)) : (float)slope);
+    }
+    if (p.alphaRatio) {                                                 // :996-1037 (float sums)
+      float sum01 = 0.0f, sum15 = 0.0f;
+      for (int j = 0; j < Nsrc; j++) {
+        const double f = frq(j);
+        if (f > 5000.0) break;
+        if (f < 1000.0) sum01 = __fadd_rn(sum01, v.P(j)); else sum15 = __fadd_rn(sum15, v.P(j));
+      }
+      if (sum01 > 0.0f) {
+        if (p.useLog) put(cAlpha, (sum15 > specFloor) ? (float)(10.0 * log((double)__fdiv_rn(sum15, sum01)) / log(10.0))
+                                                      : (float)(10.0 * (log((double)specFloor) - log((double)sum01)) / log(10.0)));
+        else put(cAlpha, __fdiv_rn(sum15, sum01));
+      } else put(cAlpha, 0.0f);
+    }
+    if (p.hammarberg) {                                                 // :1040-1089
+      float max02 = 0.0f, max25 = 0.0f;
+      for (int j = 0; j < Nsrc; j++) {
+        const double f = frq(j);
+        if (f > 5000.0) break;
+        const float x = v.P(j);
+        if (f < 2000.0) { if (x > max02) max02 = x; } else { if (x > max25) max25 = x; }
+      }
+      if (max25 > 0.0f) {
+        if (p.useLog) put(cHamm, (max02 > specFloor) ? (float)(10.0 * log((double)__fdiv_rn(max02, max25)) / log(10.0))
+                                                     : (float)(10.0 * (log((double)specFloor) - log((double)max25)) / log(10.0)));
+        else put(cHamm, __fdiv_rn(max02, max25));
+      } else put(cHamm, 0.0f);
+    }
+    if (p.maxPos || p.minPos) {                                         // :1314-1330
+      int maP = lo, miP = lo;
+      float mx = v.LP(lo), mn = mx;
+      for (int j = lo + 1; j < hi; j++) {
         const float x = v.LP(j);
-        if (x != 0.0f) { gmean = (float)((double)gmean + log((double)fabsf(x))); nGm++; }
+        if (x < mn) { mn = x; miP = j; }
+        if (x > mx) { mx = x; maP = j; }
       }
-      if (nGm > 0) gmean = __fdiv_rn(gmean, (float)nGm);
-      gmean = (float)exp((double)gmean);
-      sf = __fdiv_rn(gmean, (float)fabs(sumB / (double)nBins));
+      if (p.maxPos) put(cMaxPos, (float)frq(maP));
+      if (p.minPos) put(cMinPos, (float)frq(miP));
     }
-    if (p.logFlatness) put(sf > 0.0f ? (float)log((double)sf) : 0.0f); else put(sf);
+    if (p.harmonicity || p.flatness) {
+      const double frameSum = (p.normBand && !p.useLog) || (p.harmonicity && p.normBand) ? frame_sum() : 0.0;
+      const double sumB = sum_b(frameSum);
+      if (p.harmonicity) {                                              // :1484-1513
+        float ptpSum = 0.0f, lastPeak = -99.0f;
+        for (int j = lo + 2; j < hi - 1; j++) {
+          const float a = v.LP(j - 2), b = v.LP(j - 1), c = v.LP(j), d = v.LP(j + 1), e = v.LP(j + 2);
+          if ((a < c && b < c && c > d && c > e) || (a > c && b > c && c < d && c < e)) {
+            if (lastPeak != -99.0f) ptpSum = __fadd_rn(ptpSum, fabsf(__fsub_rn(c, lastPeak)));
+            lastPeak = c;
+          }
+        }
+        ptpSum = __fdiv_rn(ptpSum, 2.0f);
+        if (p.normBand && sumB != 0.0) {
+          if (p.useLog) ptpSum = __fdiv_rn(ptpSum, (float)fabs(sumB)); else ptpSum = __fdiv_rn(ptpSum, (float)frameSum);
+        } else ptpSum = __fdiv_rn(ptpSum, (float)nBins);
+        put(cHarm, ptpSum);
+      }
+      if (p.flatness) {                                                 // :1515-1544
+        float sf = 0.0f, gmean = 0.0f;
+        int nGm = 0;
+        if (sumB != 0.0) {
+          for (int j = lo; j <= hi; j++) {
+            const float x = v.LP(j);
+            if (x != 0.0f) { gmean = (float)((double)gmean + log((double)fabsf(x))); nGm++; }
+          }
+          if (nGm > 0) gmean = __fdiv_rn(gmean, (float)nGm);
+          gmean = (float)exp((double)gmean);
+          sf = __fdiv_rn(gmean, (float)fabs(sumB / (double)nBins));
+        }
+        if (p.logFlatness) put(cFlat, sf > 0.0f ? (float)log((double)sf) : 0.0f); else put(cFlat, sf);
+      }
+    }
   }
 }
 
 cudaError_t launch_spectral(const SpectralParams &p, cudaStream_t st)
 {
   if (p.nTiles <= 0) return cudaSuccess;
-  const size_t smem = p.reqLog ? (size_t)p.nSrc * 32 * sizeof(float) : 0;
+  // Stage the magnitude tile in shared memory only together with a log spectrum (measured: without
+  // one, the extra shared memory costs more occupancy than the cached global reads cost time), and
+  // only when both tiles fit (they do up to FFT 1024)
+  const size_t tile = (size_t)p.nSrc * 32 * sizeof(float);
+  SpectralParams q = p;
+  q.stageMag = (p.reqLog && tile * 2 <= 200 * 1024) ? 1 : 0;
+  const size_t smem = tile * ((p.reqLog ? 1 : 0) + q.stageMag);
   cudaError_t e = cudaFuncSetAttribute(spectral_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  spectral_kernel<<<p.nTiles, kSpecThreads, smem, st>>>(p);
+  spectral_kernel<<<p.nTiles, kSpecThreads, smem, st>>>(q);
   return cudaGetLastError();
 }
 
@@ -276,6 +349,14 @@ __device__ __forceinline__ float td_pcm(const TimeOpParams &p, const int16_t *s)
   // smileutil/smileUtil.c:2520-2534 : ((sum_c (float)x_c) / nChan) / 32767
   float tmp = (float)s[0];
   for (int c = 1; c < p.nChan; c++) tmp = __fadd_rn(tmp, (float)s[c]);
+  // x / 32767 through a reciprocal multiply + two FMAs: bit-identical to IEEE division for every
+  // int16 and every half-integer mean of two (see kernels.cu div32767 / tests/test_host_cpu.py)
+  if (p.nChan <= 2) {
+    const float x = (p.nChan == 2) ? tmp * 0.5f : tmp;
+    const float rc = 3.0518509447574615e-05f;
+    const float q0 = __fmul_rn(x, rc);
+    return __fmaf_rn(__fmaf_rn(-q0, 32767.0f, x), rc, q0);
+  }
   return __fdiv_rn(__fdiv_rn(tmp, (float)p.nChan), 32767.0f);
 }
 
