@@ -180,3 +180,22 @@ def test_gemaps_ns_conf():
     err = col_err(rows, ref)
     for i, nm in enumerate(names):
         assert err[i] < (1e-4 if "Slope" in nm else 1e-5), (nm, float(err[i]))
+
+
+def test_mfcc_and_plp_0_d_a_confs_match_reference_goldens():
+    """tests/configs/{mfcc,plp}_0_d_a.conf carry the parameters of the reference's MFCC12_0_D_A / PLP_0_D_A
+    configurations: their output must equal the goldens the reference produced with its own files."""
+    ex = np.load(os.path.join(ROOT, "tests", "golden", "mfcc_example_44k1.npz"))
+    pcm, sr = ex["pcm"], int(ex["sample_rate"])
+    s = Session(os.path.join(CONF, "mfcc_0_d_a.conf"))
+    rows, _ = s.extract_pcm(pcm, [0, len(pcm)], sr, 1)
+    ref = ex["lld"]
+    assert rows.shape == ref.shape == (202, 39)
+    assert (np.abs(rows - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
+    assert s.element_names(sr, 1)[0] == "pcm_fftMag_mfcc[0]"
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plp_goldens.npz"))
+    s = Session(os.path.join(CONF, "plp_0_d_a.conf"))
+    rows, _ = s.extract_pcm(pcm, [0, len(pcm)], sr, 1)
+    ref = g["example_lld"]
+    assert rows.shape == ref.shape == (202, 18)
+    assert (np.abs(rows - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
