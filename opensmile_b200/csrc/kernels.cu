@@ -1073,69 +1073,99 @@ __global__ void __launch_bounds__(NT, 1) acf_pitch_kernel(const AcfPitchParams p
     fft_stage<N, F, NVW, Fc::R2, N / (Fc::R0 * Fc::R1), false, true, false>(Z, nullptr, nullptr, nullptr, nullptr, dummy, vw, f);
   }
   __syncthreads();
-  // ---- per-frame analysis (lldcore/pitchACF.cpp:137-183), one lane per frame ----
-  if (vw == 0 && f < tl.nf) {
-    const int n = N / 2;                                   // length of each cAcf level (Ndst = Nsrc - 1)
-    const float fNsrc = (float)nSrc;
-    auto acf = [&](int j) {
-      float d = 0.5f * Z[fft_pos<N>(j) * F + f].x;
-      if (p.normOutput) d = __fdiv_rn(d, fNsrc);           // acf.cpp:321-325
-      return fabsf(d);                                     // :342-344
-    };
-    auto cep = [&](int j) {
-      float d = 0.5f * Z[fft_pos<N>(j) * F + f].y;
-      if (p.normOutput) d = __fdiv_rn(d, fNsrc);
-      return p.absCepstrum ? fabsf(d) : d;                 // :327-341
-    };
-    const double Nd = (double)(2 * n);
-    const double Tsamp = (double)p.fsSec / Nd;
-    const int preskip = (p.maxPitch <= 0.0) ? 0 : (int)(1.0 / (p.maxPitch * Tsamp));
-    // voicingProb (:249-284)
-    int zcr = 0, mcr = 0;
-    double mx = acf(n - 1), mean = acf(preskip);
-    {
-      float a0 = acf(0);
-      for (int i = 1; i < n; i++) {
-        const float a1 = acf(i);
-        if (__fmul_rn(a0, a1) < 0.0f) zcr++;
-        if (i >= preskip) {
-          if (((double)a1 > mx) && (a0 < a1)) mx = a1;
-          mean += (double)a1;
-        }
-        a0 = a1;
+  // ---- per-frame analysis (lldcore/pitchACF.cpp:137-183) ----
+  // lane = frame as everywhere; the lag range [0, n) is cut into NVW slices, one per virtual warp.
+  // Counts, maxima and the first-peak index combine exactly; the two double sums (mean of the ACF,
+  // mean |cepstrum|) are added slice by slice instead of lag by lag (differences at the 1e-16 level).
+  const int n = N / 2;                                     // length of each cAcf level (Ndst = Nsrc - 1)
+  const float fNsrc = (float)nSrc;
+  auto acf = [&](int j) {
+    float d = 0.5f * Z[fft_pos<N>(j) * F + f].x;
+    if (p.normOutput) d = __fdiv_rn(d, fNsrc);             // acf.cpp:321-325
+    return fabsf(d);                                       // :342-344
+  };
+  auto cep = [&](int j) {
+    float d = 0.5f * Z[fft_pos<N>(j) * F + f].y;
+    if (p.normOutput) d = __fdiv_rn(d, fNsrc);
+    return p.absCepstrum ? fabsf(d) : d;                   // :327-341
+  };
+  // per-slice partial results, [NVW][F] each, behind the twiddles
+  double *sD = reinterpret_cast<double *>(smem + (((size_t)N * F * 8 + (size_t)p.twCount * 8 + 15) & ~(size_t)15));
+  double *sMx = sD, *sMean = sD + NVW * F, *sCmax = sD + 2 * NVW * F, *sCsum = sD + 3 * NVW * F;
+  int *sI = reinterpret_cast<int *>(sD + 4 * NVW * F);
+  int *sZcr = sI, *sMcr = sI + NVW * F, *sIdx = sI + 2 * NVW * F;
+  const double Nd = (double)(2 * n);
+  const double Tsamp = (double)p.fsSec / Nd;
+  const int preskip = (p.maxPitch <= 0.0) ? 0 : (int)(1.0 / (p.maxPitch * Tsamp));
+  const int skip = preskip + 1;
+  const int j0 = (int)(((long long)n * vw) / NVW), j1 = (int)(((long long)n * (vw + 1)) / NVW);
+  {
+    // voicingProb pass (:249-284): sign changes, rising maximum, sum; cepstrum maximum and |.| sum (:286-297)
+    int zcr = 0;
+    double mx = -1.0, mean = 0.0;                          // ACF values are >= 0
+    const int i0 = max(j0, 1);
+    float a0 = acf(i0 - 1);
+    for (int i = i0; i < j1; i++) {
+      const float a1 = acf(i);
+      if (__fmul_rn(a0, a1) < 0.0f) zcr++;
+      if (i >= preskip) {
+        if (((double)a1 > mx) && (a0 < a1)) mx = a1;
+        mean += (double)a1;
       }
+      a0 = a1;
     }
-    mean /= (double)(n - preskip + 1);
-    {
-      float a0 = acf(0);
-      for (int i = 1; i < n; i++) {
-        const float a1 = acf(i);
-        if (((double)a0 - mean) * ((double)a1 - mean) < 0.0) mcr++;
-        a0 = a1;
-      }
-    }
-    const double acfZcr = (mcr > zcr) ? (double)mcr / (double)n : (double)zcr / (double)n;
-    const float acf0 = acf(0);
-    const double voicing = (acf0 > 0.0f) ? mx / (double)acf0 : 0.0;
-    // pitchPeak on the cepstrum (:286-310), skip = preskip + 1
-    const int skip = preskip + 1;
-    double cmax = cep(n - 1), csum = 0.0;
-    for (int i = n - 1; i >= 0; i--) {
+    double cmax = -1e300, csum = 0.0;
+    for (int i = j1 - 1; i >= j0; i--) {
       const double buf = cep(i);
       csum += fabs(buf);
       if (i >= skip && buf > cmax) cmax = buf;
     }
-    csum /= (double)n;
-    int maxIdx = 0;
-    {
-      const double thr = (cmax + csum) * 0.6;
-      float cm = cep(skip), c0 = cep(skip + 1);
-      for (int i = skip + 1; i < n - 1; i++) {
+    sZcr[vw * F + f] = zcr; sMx[vw * F + f] = mx; sMean[vw * F + f] = mean;
+    sCmax[vw * F + f] = cmax; sCsum[vw * F + f] = csum;
+  }
+  __syncthreads();
+  double mean = acf(preskip), mx = acf(n - 1), cmax = cep(n - 1), csum = 0.0;
+  int zcr = 0;
+  for (int w = 0; w < NVW; w++) {
+    zcr += sZcr[w * F + f];
+    mean += sMean[w * F + f];
+    if (sMx[w * F + f] > mx) mx = sMx[w * F + f];
+    if (sCmax[w * F + f] > cmax) cmax = sCmax[w * F + f];
+  }
+  for (int w = NVW - 1; w >= 0; w--) csum += sCsum[w * F + f];     // the reference walks the lags downwards
+  mean /= (double)(n - preskip + 1);
+  csum /= (double)n;
+  {
+    // mean crossings (:266-273) and the first cepstral peak above the threshold (:299-310)
+    int mcr = 0;
+    const int i0 = max(j0, 1);
+    float a0 = acf(i0 - 1);
+    for (int i = i0; i < j1; i++) {
+      const float a1 = acf(i);
+      if (((double)a0 - mean) * ((double)a1 - mean) < 0.0) mcr++;
+      a0 = a1;
+    }
+    int first = 0x7fffffff;
+    const double thr = (cmax + csum) * 0.6;
+    const int lo = max(j0, skip + 1), hi = min(j1, n - 1);
+    if (lo < hi) {
+      float cm = cep(lo - 1), c0 = cep(lo);
+      for (int i = lo; i < hi; i++) {
         const float c1 = cep(i + 1);
-        if ((double)c0 > thr && (cm < c0) && (c0 > c1)) { maxIdx = i; break; }
+        if ((double)c0 > thr && (cm < c0) && (c0 > c1)) { first = i; break; }
         cm = c0; c0 = c1;
       }
     }
+    sMcr[vw * F + f] = mcr; sIdx[vw * F + f] = first;
+  }
+  __syncthreads();
+  if (vw == 0 && f < tl.nf) {
+    int mcr = 0, maxIdx = 0x7fffffff;
+    for (int w = 0; w < NVW; w++) { mcr += sMcr[w * F + f]; maxIdx = min(maxIdx, sIdx[w * F + f]); }
+    if (maxIdx == 0x7fffffff) maxIdx = 0;
+    const double acfZcr = (mcr > zcr) ? (double)mcr / (double)n : (double)zcr / (double)n;
+    const float acf0 = acf(0);
+    const double voicing = (acf0 > 0.0f) ? mx / (double)acf0 : 0.0;
     PitchRaw r;
     r.voicing = voicing; r.acfZcr = acfZcr; r.maxIdx = maxIdx;
     const float aI = acf(maxIdx);
@@ -1300,7 +1330,9 @@ bool acf_pitch_supported_fft(int nfft) { return nfft == 512 || nfft == 1024 || n
 template <int N, int F, int NT>
 static cudaError_t launch_acf_t(const AcfPitchParams &p, cudaStream_t st)
 {
-  const size_t smem = (size_t)N * F * 8 + (size_t)p.twCount * 8 + 16;
+  constexpr int NVW = (NT / 32) * (32 / F);
+  // FFT tile | twiddles | per-slice partials of the analysis (4 doubles + 3 ints per slice and frame)
+  const size_t smem = (((size_t)N * F * 8 + (size_t)p.twCount * 8 + 15) & ~(size_t)15) + (size_t)NVW * F * (4 * 8 + 3 * 4) + 16;
   auto kern = acf_pitch_kernel<N, F, NT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

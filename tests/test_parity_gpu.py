@@ -162,6 +162,19 @@ def test_full_size_properties(plan16):
     assert np.array_equal(single, out[:500])
 
 
+def test_one_long_utterance_600s(plan16):
+    """SURVEY.md 8(a') known answer: 600 s at 16 kHz -> 59 998 MFCC rows.  One utterance spanning many
+    chunks of many tiles: compared with the oracle on the whole signal."""
+    L = 9_600_000
+    pcm = np.tile(voiced_pcm(160_000, 16000, seed=77), L // 160_000)
+    off = np.array([0, L], np.int64)
+    assert int(plan16.frame_offsets(off)[-1]) == 59_998
+    out = plan16.run_host(pcm, off)
+    ref = oracle.mfcc_d_a(pcm, 16000.0)
+    assert out.shape == ref.shape == (59_998, 39)
+    assert rel_to_frame_scale(out, ref) < TOL
+
+
 def test_fused_and_two_kernel_paths_agree(plan16, monkeypatch):
     """The delta stages run fused inside lld_kernel by default; OSM_B200_NO_FUSE=1 selects the
     generic post_kernel path.  Both must give bit-identical rows (same float arithmetic), on
