@@ -83,6 +83,7 @@ typedef enum {
   OSM_B200_C_CONTOURSMOOTHER,    /* cContourSmoother    src/dspcore/contourSmoother.cpp:84-117    */
   OSM_B200_C_VECTORCONCAT,       /* cVectorConcat       src/other/vectorConcat.cpp:48-53          */
   OSM_B200_C_VECTOROPERATION,    /* cVectorOperation    src/other/vectorOperation.cpp:130 (ll1)   */
+  OSM_B200_C_FULLINPUTMEAN,      /* cFullinputMean      src/dspcore/fullinputMean.cpp:484-548     */
   OSM_B200_C_COUNT_
 } osm_b200_component_type;
 
@@ -200,6 +201,10 @@ typedef struct {            /* cVectorOperation, n -> 1 operations only (src/oth
  * includeSingleElementFields = 1); processArrayFields = 0 passes the whole frame, field names kept. */
 typedef struct { int32_t processArrayFields, includeSingleElementFields; } osm_b200_vectorconcat; /* 1, 0 */
 
+/* cFullinputMean: per-utterance mean subtraction (cepstral mean subtraction of the *_Z configurations).
+ * Only the default mode is supported: arithmetic mean, single EOI loop (src/dspcore/fullinputMean.cpp:484-548) */
+typedef struct { int32_t mvn, meanNorm /* 0 = amean */, symmSubtract, subtractClipToZero, specEnorm, htkLogEnorm, excludeZeros, multiLoopMode; } osm_b200_fullinputmean;
+
 /* one `[name:cType]` section */
 typedef struct {
   int32_t type;                                  /* osm_b200_component_type */
@@ -230,6 +235,7 @@ typedef struct {
     osm_b200_contoursmoother contoursmoother;
     osm_b200_vectoroperation vectoroperation;
     osm_b200_vectorconcat vectorconcat;
+    osm_b200_fullinputmean fullinputmean;
   } u;
 } osm_b200_component;
 

@@ -20,7 +20,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = range(5)
 # component types (osm_b200_component_type)
 (C_WAVESOURCE, C_FRAMER, C_VECTORPREEMPHASIS, C_WINDOWER, C_TRANSFORMFFT, C_FFTMAGPHASE,
  C_MELSPEC, C_MFCC, C_PLP, C_SPECTRAL, C_ENERGY, C_MZCR, C_ACF, C_PITCHACF,
- C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION) = range(18)
+ C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION, C_FULLINPUTMEAN) = range(19)
 
 TYPE_BY_NAME = {
     "cWaveSource": C_WAVESOURCE, "cExternalAudioSource": C_WAVESOURCE, "cFramer": C_FRAMER,
@@ -30,6 +30,7 @@ TYPE_BY_NAME = {
     "cMZcr": C_MZCR, "cAcf": C_ACF, "cPitchACF": C_PITCHACF,
     "cDeltaRegression": C_DELTAREGRESSION, "cContourSmoother": C_CONTOURSMOOTHER,
     "cVectorConcat": C_VECTORCONCAT, "cVectorOperation": C_VECTOROPERATION,
+    "cFullinputMean": C_FULLINPUTMEAN,
 }
 
 WIN_BY_NAME = {"rec": 0, "han": 1, "ham": 2, "gau": 3, "sin": 4, "tri": 5, "bar": 6}
@@ -134,6 +135,11 @@ class VectorConcat(C.Structure):
     _fields_ = [("processArrayFields", i32), ("includeSingleElementFields", i32)]
 
 
+class FullinputMean(C.Structure):
+    _fields_ = [("mvn", i32), ("meanNorm", i32), ("symmSubtract", i32), ("subtractClipToZero", i32),
+                ("specEnorm", i32), ("htkLogEnorm", i32), ("excludeZeros", i32), ("multiLoopMode", i32)]
+
+
 class _U(C.Union):
     _fields_ = [("wavesource", WaveSource), ("framer", Framer),
                 ("vectorpreemphasis", VectorPreemphasis), ("windower", Windower),
@@ -141,7 +147,7 @@ class _U(C.Union):
                 ("melspec", Melspec), ("mfcc", Mfcc), ("plp", Plp), ("spectral", Spectral),
                 ("energy", Energy), ("mzcr", MZcr), ("acf", Acf), ("pitchacf", PitchACF),
                 ("deltaregression", DeltaRegression), ("contoursmoother", ContourSmoother),
-                ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat)]
+                ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat), ("fullinputmean", FullinputMean)]
 
 
 class Component(C.Structure):
@@ -158,6 +164,7 @@ UNION_FIELD = {
     C_ENERGY: "energy", C_MZCR: "mzcr", C_ACF: "acf", C_PITCHACF: "pitchacf",
     C_DELTAREGRESSION: "deltaregression", C_CONTOURSMOOTHER: "contoursmoother",
     C_VECTOROPERATION: "vectoroperation", C_VECTORCONCAT: "vectorconcat",
+    C_FULLINPUTMEAN: "fullinputmean",
 }
 
 # every symbol include/osm_b200.h declares (tests assert the library exports all of them)

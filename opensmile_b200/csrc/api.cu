@@ -132,6 +132,8 @@ struct osm_b200_plan {
   PinBuf<TileRef> hPost; DevBuf<TileRef> dPost; size_t nPostTiles = 0;
   std::vector<int32_t> uttPost0;
   DevBuf<float> dStat;
+  DevBuf<float> dMeans;          // [nUtt][nStatic] column means for cFullinputMean groups
+  bool needMeans = false;
   long long totalRows = 0, totalStat = 0, totalSamples = 0;
   size_t totalWork = 0;
   cudaEvent_t evMetaDone = nullptr, evK0 = nullptr, evKm = nullptr, evK1 = nullptr;
@@ -496,7 +498,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     pg.frameSize = d.streams[g.stream].fe.frameSize; pg.frameStep = d.streams[g.stream].fe.frameStep;
     pg.nLim = 0;
     for (int ls : g.limitStreams) if (pg.nLim < 3) { pg.limSize[pg.nLim] = d.streams[ls].fe.frameSize; pg.limStep[pg.nLim] = d.streams[ls].fe.frameStep; pg.nLim++; }
-    for (size_t i = 0; i < g.stages.size(); i++) { pg.kind[i] = g.stages[i].kind; pg.win[i] = g.stages[i].win; pg.flags[i] = g.stages[i].flags; }
+    for (size_t i = 0; i < g.stages.size(); i++) { pg.kind[i] = g.stages[i].kind; pg.win[i] = g.stages[i].win; pg.flags[i] = g.stages[i].flags; if (g.stages[i].kind == ST_CMS) pl->needMeans = true; }
   }
   // fused pattern: [static | delta(W1) | delta(W1,W2)] over the whole static vector
   pl->fused = false;
@@ -638,7 +640,7 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
     s.hChunks.release(); s.dChunks.release(); s.hTiles.release(); s.dTiles.release(); s.dMag.release();
   }
   for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); }
-  pl->hMeta.release(); pl->dMeta.release(); pl->hPost.release(); pl->dPost.release(); pl->dStat.release();
+  pl->hMeta.release(); pl->dMeta.release(); pl->hPost.release(); pl->dPost.release(); pl->dStat.release(); pl->dMeans.release();
   pl->dPcm.release(); pl->dOut.release();
   if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
   if (pl->evK0) cudaEventDestroy(pl->evK0);
@@ -870,6 +872,13 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
     else { pp.stat = pl->dStat.p; pp.statStride = d.nStatic; pp.statOff = dS; }
     pp.out = d_out; pp.outStride = d.nOut; pp.rowOff = dR; pp.uttOff = dU; pp.nUtt = n_utt;
     pp.tiles = pl->dPost.p + pl->uttPost0[u0]; pp.nTiles = pl->uttPost0[u1] - pl->uttPost0[u0];
+    pp.means = nullptr;
+    if (pl->needMeans) {
+      CU(pl->dMeans.reserve((size_t)n_utt * d.nStatic + 64));
+      CU(launch_cms_means(pp, pl->dMeans.p, u0, u1, st));
+      pl->lastLaunches++;
+      pp.means = pl->dMeans.p;
+    }
     if (pp.nTiles > 0) {
       CU(launch_post(pp, st));
       pl->lastLaunches++;

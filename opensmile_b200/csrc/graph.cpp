@@ -34,7 +34,7 @@ const char *type_name(int t)
   static const char *names[] = {"cWaveSource", "cFramer", "cVectorPreemphasis", "cWindower",
     "cTransformFFT", "cFFTmagphase", "cMelspec", "cMfcc", "cPlp", "cSpectral", "cEnergy",
     "cMZcr", "cAcf", "cPitchACF", "cDeltaRegression", "cContourSmoother", "cVectorConcat",
-    "cVectorOperation"};
+    "cVectorOperation", "cFullinputMean"};
   return (t >= 0 && t < OSM_B200_C_COUNT_) ? names[t] : "?";
 }
 
@@ -239,7 +239,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     // a temporal stage reading several levels (reader.dmLevel = a;b) sees their implicit concat
     // (core/dataReader.cpp:360-444), i.e. it behaves like stage(cVectorConcat(a, b))
     bool multi = false;
-    while (c && (c->type == OSM_B200_C_DELTAREGRESSION || c->type == OSM_B200_C_CONTOURSMOOTHER)) {
+    while (c && (c->type == OSM_B200_C_DELTAREGRESSION || c->type == OSM_B200_C_CONTOURSMOOTHER || c->type == OSM_B200_C_FULLINPUTMEAN)) {
       stageComps.insert(stageComps.begin(), c);
       if (c->n_inputs > 1) { multi = true; break; }
       c = single_input(c);
@@ -472,6 +472,16 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         }
         if (p.deltawin < 1 || p.deltawin > 8) { err = "cDeltaRegression.deltawin must be 1..8"; return OSM_B200_ERR_UNSUPPORTED; }
         st = Stage{ST_DELTA, p.deltawin, 0};
+      } else if (s->type == OSM_B200_C_FULLINPUTMEAN) {
+        // dspcore/fullinputMean.cpp:484-548 (single EOI loop): all frames are read before EOI, the
+        // arithmetic mean is subtracted from every frame at EOI -> same number of frames, and the
+        // level is complete only after EOI, so nothing may be chained behind it here
+        const auto &p = s->u.fullinputmean;
+        if (p.mvn || p.meanNorm != 0 || p.symmSubtract || p.subtractClipToZero || p.specEnorm || p.htkLogEnorm || p.excludeZeros || p.multiLoopMode) {
+          err = "cFullinputMean: only plain arithmetic mean subtraction (the defaults) is supported"; return OSM_B200_ERR_UNSUPPORTED;
+        }
+        if (s != stageComps.back()) { err = "a temporal stage reading a cFullinputMean level is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        st = Stage{ST_CMS, 0, 0};
       } else {
         const auto &p = s->u.contoursmoother;
         if (p.smaWin < 1 || (p.smaWin & 1) == 0 || p.smaWin > 9) { err = "cContourSmoother.smaWin must be odd, 1..9"; return OSM_B200_ERR_UNSUPPORTED; }

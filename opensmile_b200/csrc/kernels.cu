@@ -974,7 +974,10 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
         const int t = lo + rr;
         const int navail = (t < c0) ? Tprev : min(n0 + (t - c0) + 1, Tprev);
         float y;
-        if (g.kind[s] == 0) {
+        if (g.kind[s] == 2) {
+          // fullinputMean.cpp:516-522 : vec->data[i] -= means[i]
+          y = __fsub_rn(post_read(cur, n, rowBase, t, 0, navail, t, c), p.means[(long long)u * p.nStat + g.srcCol + c]);
+        } else if (g.kind[s] == 0) {
           // deltaRegression.cpp:139-146 : num = sum_i i*(x[t+i]-x[t-i]) ; y = num / norm
           float num = 0.f;
           for (int i = 1; i <= W; i++) {
@@ -1453,6 +1456,39 @@ cudaError_t launch_plp_tail(const LldParams &op, const float *band, float *stat,
   if (e != cudaSuccess) return e;
   const long long nb = (row1 - row0 + kTailF - 1) / kTailF;
   plp_tail_kernel<<<(unsigned)nb, kTailF * kTailWarps, smem, st>>>(op, band, stat, statStride, outCol, row0, row1);
+  return cudaGetLastError();
+}
+
+// cFullinputMean, single-loop mode (dspcore/fullinputMean.cpp:526-546): means = first frame, += every
+// further frame (float, frame order), /= (float)n at EOI.  One thread per (utterance, column of a group
+// that ends in a mean subtraction); T follows the group's reader (min over its levels' streams).
+__global__ void cms_mean_kernel(const PostParams p, float *means, int u0, int u1)
+{
+  const int u = u0 + blockIdx.x;
+  if (u >= u1) return;
+  const long long Ls = p.uttOff[u + 1] - p.uttOff[u];
+  const float *src = p.stat + p.statOff[u] * (long long)p.statStride;
+  for (int gi = 0; gi < p.nGroups; gi++) {
+    const PostGroup &g = p.groups[gi];
+    if (g.nStages < 1 || g.kind[g.nStages - 1] != 2) continue;
+    int T = (Ls >= g.frameSize) ? (int)((Ls - g.frameSize) / g.frameStep + 1) : 0;
+    for (int k = 0; k < g.nLim; k++) T = min(T, (Ls >= g.limSize[k]) ? (int)((Ls - g.limSize[k]) / g.limStep[k] + 1) : 0);
+    for (int c = threadIdx.x; c < g.n; c += blockDim.x) {
+      float m = 0.f;
+      if (T > 0) {
+        m = src[g.srcCol + c];
+        for (int t = 1; t < T; t++) m = __fadd_rn(m, src[(long long)t * p.statStride + g.srcCol + c]);
+        m = __fdiv_rn(m, (float)T);
+      }
+      means[(long long)u * p.nStat + g.srcCol + c] = m;
+    }
+  }
+}
+
+cudaError_t launch_cms_means(const PostParams &p, float *means, int u0, int u1, cudaStream_t st)
+{
+  if (u1 <= u0) return cudaSuccess;
+  cms_mean_kernel<<<u1 - u0, 64, 0, st>>>(p, means, u0, u1);
   return cudaGetLastError();
 }
 

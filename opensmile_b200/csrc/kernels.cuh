@@ -76,7 +76,7 @@ struct PostGroup {
   // reader only delivers min over them (core/dataReader.cpp:375-380) -> T = min(T, T of these)
   int nLim; int limSize[3], limStep[3];
   int nStages;
-  int kind[3];                   // 0 = delta, 1 = sma
+  int kind[3];                   // 0 = delta, 1 = sma, 2 = utterance mean subtraction (cFullinputMean)
   int win[3];
   int flags[3];
 };
@@ -97,6 +97,7 @@ struct PostParams {
   int nStat;                     // static columns staged per row
   int maxN;                      // widest group
   int halo;                      // max over groups of the summed half windows
+  const float *means;            // [nUtt][nStat] per-utterance column means (groups with a kind-2 stage), or null
 };
 
 struct LldLaunchInfo { int grid, block; size_t smem; };
@@ -188,6 +189,9 @@ cudaError_t launch_rasta(const RastaParams &p, int u0, int u1, cudaStream_t st);
 cudaError_t launch_plp_tail(const LldParams &op, const float *band, float *stat, int statStride, int outCol,
                             long long row0, long long row1, cudaStream_t st);
 // cVectorOperation ll1: stat[row][outCol] = (sum_i stat[row][srcCol + i]) / n, float, in order
+// cFullinputMean: means[u][srcCol + c] = (float sum over the utterance's T frames, in frame order) / (float)T
+// for the columns of every output group that ends in a mean subtraction (dspcore/fullinputMean.cpp:526-546)
+cudaError_t launch_cms_means(const PostParams &p, float *means, int u0, int u1, cudaStream_t st);
 cudaError_t launch_vecop_ll1(float *stat, int statStride, int srcCol, int n, int outCol, long long row0, long long row1,
                              cudaStream_t st);
 

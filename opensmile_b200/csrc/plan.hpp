@@ -125,7 +125,7 @@ struct StaticOp {
 };
 
 // temporal stage applied to a static column range (cWindowProcessor family)
-enum StageKind { ST_DELTA = 0, ST_SMA = 1 };
+enum StageKind { ST_DELTA = 0, ST_SMA = 1, ST_CMS = 2 };   // ST_CMS: cFullinputMean, x - mean over the utterance (win 0)
 struct Stage { StageKind kind; int win; int flags; };
 
 // one contiguous block of output columns

@@ -218,7 +218,8 @@ const TypeInfo kTypes[] = {
   {"cMfcc", OSM_B200_C_MFCC}, {"cPlp", OSM_B200_C_PLP}, {"cSpectral", OSM_B200_C_SPECTRAL}, {"cEnergy", OSM_B200_C_ENERGY},
   {"cMZcr", OSM_B200_C_MZCR}, {"cAcf", OSM_B200_C_ACF}, {"cPitchACF", OSM_B200_C_PITCHACF},
   {"cDeltaRegression", OSM_B200_C_DELTAREGRESSION}, {"cContourSmoother", OSM_B200_C_CONTOURSMOOTHER},
-  {"cVectorConcat", OSM_B200_C_VECTORCONCAT}, {"cVectorOperation", OSM_B200_C_VECTOROPERATION}};
+  {"cVectorConcat", OSM_B200_C_VECTORCONCAT}, {"cVectorOperation", OSM_B200_C_VECTOROPERATION},
+  {"cFullinputMean", OSM_B200_C_FULLINPUTMEAN}};
 
 int type_of(const std::string &t)
 {
@@ -383,6 +384,14 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         if (f == "noPostEOIprocessing") { if (inum(v)) { err = "cContourSmoother.noPostEOIprocessing=1 is not supported"; return false; } continue; }
         break;
       case OSM_B200_C_VECTORCONCAT:
+        break;
+      case OSM_B200_C_FULLINPUTMEAN:
+        SETI("mvn", c.u.fullinputmean.mvn) SETI("symmSubtract", c.u.fullinputmean.symmSubtract)
+        SETI("subtractClipToZero", c.u.fullinputmean.subtractClipToZero) SETI("specEnorm", c.u.fullinputmean.specEnorm)
+        SETI("htkLogEnorm", c.u.fullinputmean.htkLogEnorm) SETI("excludeZeros", c.u.fullinputmean.excludeZeros)
+        SETI("multiLoopMode", c.u.fullinputmean.multiLoopMode)
+        if (f == "meanNorm") { c.u.fullinputmean.meanNorm = (v.compare(0, 3, "ame") == 0) ? 0 : 1; continue; }
+        if (f == "printMeans" || f == "printStddevs") continue;
         break;
       case OSM_B200_C_VECTOROPERATION:
         if (f == "operation") {

@@ -278,6 +278,14 @@ def plp_static(pcm, sample_rate, cfg, n_chan=1):
     return out
 
 
+def cms(x):
+    """cFullinputMean (default mode): subtract the per-column mean over all frames (float, frame order)."""
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros_like(x)
+    lib().osm_or_cms(_fp(x), C.c_long(x.shape[0]), C.c_int(x.shape[1]), _fp(out))
+    return out
+
+
 def ll1(x):
     """cVectorOperation operation=ll1: per-row float sum / K."""
     x = np.ascontiguousarray(x, np.float32)

@@ -757,6 +757,20 @@ long osm_or_plp_static(const osm_or_frontend *fe, const osm_or_melspec *ms, cons
   return T;
 }
 
+/* cFullinputMean, default mode (dspcore/fullinputMean.cpp:526-546 accumulate, :506-522 subtract):
+ * means = frame 0, += every further frame (float), /= (float)n, then x - mean for every frame */
+void osm_or_cms(const float *x, long T, int K, float *out)
+{
+  if (T <= 0) return;
+  float *m = (float *)malloc(sizeof(float) * K);
+  for (int i = 0; i < K; i++) m[i] = x[i];
+  for (long t = 1; t < T; t++) for (int i = 0; i < K; i++) m[i] += x[t * K + i];
+  float nM = (float)T;
+  for (int i = 0; i < K; i++) m[i] /= nM;
+  for (long t = 0; t < T; t++) for (int i = 0; i < K; i++) { float v = x[t * K + i]; v -= m[i]; out[t * K + i] = v; }
+  free(m);
+}
+
 /* cVectorOperation operation=ll1 (other/vectorOperation.cpp:475-481): float sum / N per row */
 void osm_or_ll1(const float *x, long T, int K, float *out)
 {

@@ -134,6 +134,8 @@ int osm_or_plp_num_out(const osm_or_plp *pl, int n_bands);
 /* cPlp static level only, with RASTA / newRASTA if configured: out = [T][num_out] */
 long osm_or_plp_static(const osm_or_frontend *fe, const osm_or_melspec *ms, const osm_or_plp *pl,
                        const int16_t *pcm, long n_samples, int n_chan, float *out);
+/* cFullinputMean (default mode): per-column mean over all T frames subtracted (dspcore/fullinputMean.cpp:484-548) */
+void osm_or_cms(const float *x, long T, int K, float *out);
 /* cVectorOperation operation=ll1: per-row sum / K (other/vectorOperation.cpp:475-481) */
 void osm_or_ll1(const float *x, long T, int K, float *out);
 

@@ -13,6 +13,9 @@ Contents (inputs are regenerated in the tests from opensmile_b200.synth.voiced_p
                     voiced_pcm(16000, 16000, seed=7); cmp_ns_short_<n>: its first n samples, n = 960, 1100, 1300, 2000;
                     cmp_ns_44k: voiced_pcm(30000, 44100, seed=8)
   gemaps_ns         tests/configs/gemaps_ns.conf (eGeMAPSv02's LLD-path columns), voiced_pcm(16000, 16000, seed=10)
+  mfcc_z            tests/configs/mfcc_0_d_a_z.conf (cFullinputMean on the statics), voiced_pcm(12000, 16000, seed=11);
+                    mfcc_z_plain: tests/configs/mfcc_0_d_a.conf on the same input (statics before the mean subtraction);
+                    ref_mfcc_0_z / ref_mfcc_e_z / ref_plp_0_z / ref_plp_e_z: the reference's shipped *_Z configurations, same input
   cmp_taps          static levels audR (26) | audSum | audRSum of compare_ns.conf for the same input (oracle pin)
   rasta_plp         tests/configs/rasta_plp.conf (RASTA-PLP cepstra 0..8 + delta), voiced_pcm(16000, 16000, seed=9)
   names_<case>      the CSV header's element names
@@ -70,6 +73,13 @@ def main():
                                  csv_out=False)
     gns = os.path.join(ROOT, "tests", "configs", "gemaps_ns.conf")
     out["gemaps_ns"], out["names_gemaps_ns"], _ = run(gns, voiced_pcm(16000, 16000, seed=10), 16000, 1)
+    # cepstral mean subtraction (cFullinputMean): own config + the reference's shipped *_Z configurations
+    pz = voiced_pcm(12000, 16000, seed=11)
+    out["mfcc_z"], out["names_mfcc_z"], _ = run(os.path.join(ROOT, "tests", "configs", "mfcc_0_d_a_z.conf"), pz, 16000, 1)
+    out["mfcc_z_plain"], _, _ = run(os.path.join(ROOT, "tests", "configs", "mfcc_0_d_a.conf"), pz, 16000, 1, csv_out=False)
+    for key, rel in (("ref_mfcc_0_z", "mfcc/MFCC12_0_D_A_Z.conf"), ("ref_mfcc_e_z", "mfcc/MFCC12_E_D_A_Z.conf"),
+                     ("ref_plp_0_z", "plp/PLP_0_D_A_Z.conf"), ("ref_plp_e_z", "plp/PLP_E_D_A_Z.conf")):
+        out[key], _, _ = run(os.path.join(refrun.CONFIG_DIR, rel), pz, 16000, 1, csv_out=False)
     # taps of compare_ns.conf (the same graph with the HTK sink moved): RASTA-filtered bands and the two sums
     tap = os.path.join(ROOT, "tests", "configs", "_cmp_taps.conf")
     with open(tap, "w") as f:

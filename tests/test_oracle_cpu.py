@@ -131,3 +131,14 @@ def test_rasta_oracle_vs_golden():
     assert np.abs(oracle.ll1(aud) - tap[:, 26]).max() < TOL * np.abs(tap[:, 26]).max()
     assert np.abs(oracle.ll1(audR) - tap[:, 27]).max() < TOL * np.abs(tap[:, 27]).max()
     assert np.array_equal(oracle.ll1(tap[:, :26]), tap[:, 27])       # ll1 itself is bit-exact given its input
+
+
+def test_cms_oracle_bit_exact_given_reference_statics():
+    """cFullinputMean (cepstral mean subtraction): float sum in frame order / (float)T, subtracted --
+    bit-exact against the reference given the reference's own statics; deltas are taken from the
+    un-normalised coefficients and stay untouched."""
+    g = np.load(os.path.join(GOLD, "conf_goldens.npz"))
+    z, plain = g["mfcc_z"], g["mfcc_z_plain"]
+    assert z.shape == plain.shape == (73, 39)
+    assert np.array_equal(oracle.cms(plain[:, :13]), z[:, :13])
+    assert np.array_equal(plain[:, 13:], z[:, 13:])

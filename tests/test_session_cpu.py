@@ -16,7 +16,8 @@ REF_CONF = os.path.join(ROOT, "oracle", "_ref", "config")
 
 
 @pytest.mark.parametrize("conf,key", [("lld_mix.conf", "mix"), ("mfcc_e_d_a.conf", "mfcc_e"), ("plp_e_d_a.conf", "plp_e"),
-                                      ("compare_ns.conf", "cmp_ns"), ("gemaps_ns.conf", "gemaps_ns")])
+                                      ("compare_ns.conf", "cmp_ns"), ("gemaps_ns.conf", "gemaps_ns"),
+                                      ("mfcc_0_d_a_z.conf", "mfcc_z")])
 def test_element_names_match_reference_csv_header(conf, key):
     s = Session(os.path.join(CONF, conf), device=-1)
     assert s.element_names(16000, 1) == [str(x) for x in GOLD["names_" + key]]
@@ -124,7 +125,9 @@ def test_description_only_session_refuses_to_compute():
 
 @pytest.mark.skipif(not os.path.isdir(REF_CONF), reason="reference configs not built into oracle/_ref")
 @pytest.mark.parametrize("conf,n", [("mfcc/MFCC12_0_D_A.conf", 39), ("mfcc/MFCC12_E_D_A.conf", 39),
-                                    ("plp/PLP_0_D_A.conf", 18), ("plp/PLP_E_D_A.conf", 18)])
+                                    ("plp/PLP_0_D_A.conf", 18), ("plp/PLP_E_D_A.conf", 18),
+                                    ("mfcc/MFCC12_0_D_A_Z.conf", 39), ("mfcc/MFCC12_E_D_A_Z.conf", 39),
+                                    ("plp/PLP_0_D_A_Z.conf", 18), ("plp/PLP_E_D_A_Z.conf", 18)])
 def test_reference_standard_configs_parse(conf, n):
     s = Session(os.path.join(REF_CONF, conf), device=-1)
     names = s.element_names(16000, 1)

@@ -199,3 +199,29 @@ def test_mfcc_and_plp_0_d_a_confs_match_reference_goldens():
     ref = g["example_lld"]
     assert rows.shape == ref.shape == (202, 18)
     assert (np.abs(rows - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
+
+
+def test_cepstral_mean_subtraction_confs():
+    """cFullinputMean: per-utterance mean of the static coefficients (float sum in frame order) subtracted;
+    own configuration and -- when the build copied them -- the reference's four shipped *_Z files."""
+    pcm = voiced_pcm(12000, 16000, seed=11)
+    utts = [pcm, pcm[:4000], pcm]                    # the mean is per utterance: neighbours must not leak
+    packed, off = pack_utterances(utts)
+    s = Session(os.path.join(CONF, "mfcc_0_d_a_z.conf"))
+    rows, fo = s.extract_pcm(packed, off, 16000, 1)
+    ref = GOLD["mfcc_z"]
+    for u in (0, 2):
+        got = rows[fo[u]:fo[u + 1]]
+        assert got.shape == ref.shape
+        assert (np.abs(got - ref) / np.abs(GOLD["mfcc_z_plain"]).max(axis=1, keepdims=True)).max() < 1e-5
+    assert np.array_equal(rows[fo[0]:fo[1]], rows[fo[2]:fo[3]])
+    refdir = os.path.join(ROOT, "oracle", "_ref", "config")
+    if os.path.isdir(refdir):
+        for key, rel in (("ref_mfcc_0_z", "mfcc/MFCC12_0_D_A_Z.conf"), ("ref_mfcc_e_z", "mfcc/MFCC12_E_D_A_Z.conf"),
+                         ("ref_plp_0_z", "plp/PLP_0_D_A_Z.conf"), ("ref_plp_e_z", "plp/PLP_E_D_A_Z.conf")):
+            s = Session(os.path.join(refdir, rel))
+            got, _ = s.extract_pcm(pcm, [0, 12000], 16000, 1)
+            ref = GOLD[key]
+            assert got.shape == ref.shape, key
+            # scale: the un-normalised statics are ~1e1, mean-subtracted columns can be ~0 in a whole row
+            assert np.abs(got - ref).max() < 1e-5 * np.abs(ref).max(), key
