@@ -535,6 +535,11 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     if (pp.groups[g].n > pp.maxN) pp.maxN = pp.groups[g].n;
   }
   if (pp.halo > 12) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "summed temporal half windows exceed 12 frames"); }
+  pp.rows = post_tile_rows(pp.nStat, pp.maxN, pp.halo);
+  if ((size_t)(pp.rows + 2 * pp.halo) * (pp.nStat + 2 * pp.maxN) * sizeof(float) > 200 * 1024) {
+    osm_b200_plan_destroy(pl);
+    return fail(OSM_B200_ERR_UNSUPPORTED, "the static level is too wide for the row assembly kernel");
+  }
 
   // ---- standalone ops ----
   for (size_t oi = 0; oi < d.ops.size(); oi++) {
@@ -542,6 +547,12 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     if (op.kind == SOP_MFCC || op.kind == SOP_PLP) continue;      // fused into its stream's lld_kernel
     OpRt rt;
     rt.kind = op.kind; rt.stream = op.stream;
+    if (op.kind == SOP_MAG) {
+      pl->st[op.stream].needTiles = true;
+      rt.vN = d.streams[op.stream].fe.nBins; rt.vOutCol = op.outCol;
+      pl->ops.push_back(rt);
+      continue;
+    }
     if (op.kind == SOP_VECOP) {
       const StaticOp &src = d.ops[op.srcOp];
       if (src.kind != SOP_MFCC && src.kind != SOP_PLP) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cVectorOperation: the input must be a cMfcc / cPlp level"); }
@@ -688,7 +699,7 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
     const size_t nm = (size_t)(nUtt + 1);
     CU(pl->hMeta.reserve(3 * nm));
     long long *hU = pl->hMeta.p, *hR = hU + nm, *hS = hR + nm;
-    const int PR = post_tile_rows();
+    const int PR = pl->pp.rows;
     const int KT = lld_max_chunk_tiles();
     const bool needPost = pl->pp.nGroups > 0 && !pl->fused;
     size_t nPost = 0;
@@ -840,6 +851,12 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
     }
     const int t0 = rt.uttTile0[u0], t1 = rt.uttTile0[u1];
     if (t1 <= t0) continue;
+    if (o.kind == SOP_MAG) {
+      CU(launch_mag_rows(rt.dMag.p + (size_t)t0 * o.vN * rt.tileF, rt.dTiles.p + t0, t1 - t0, rt.tileF, o.vN, dS,
+                         pl->dStat.p, d.nStatic, o.vOutCol, st));
+      pl->lastLaunches++;
+      continue;
+    }
     if (o.kind == SOP_SPECTRAL) {
       SpectralParams sp = o.sp;
       sp.mag = rt.dMag.p + (size_t)t0 * sp.nSrc * sp.F;

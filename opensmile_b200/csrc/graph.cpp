@@ -419,6 +419,17 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
           if (op.mzcr.dc) add("dc");
         }
         if (op.nOut < 1) { err = "component produces no output"; return OSM_B200_ERR_INVALID; }
+      } else if (c->type == OSM_B200_C_FFTMAGPHASE) {
+        // the magnitude level itself as an output (config/spectrum/spectrogram.conf): nBins elements
+        if (!resolve_mag_chain(c, ci)) return OSM_B200_ERR_UNSUPPORTED;
+        osm_b200_status s2 = get_stream(ci, true, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        op.kind = SOP_MAG;
+        op.nOut = d.streams[op.stream].fe.nBins;
+        FieldName fn;
+        fn.name = name_append_auto(*c, wave_name(), "fftMag");              // dspcore/fftmagphase.cpp:154
+        fn.n = op.nOut; fn.arrNameOffset = 0;
+        op.fields.push_back(fn);
       } else if (c->type == OSM_B200_C_VECTOROPERATION) {
         // n -> 1 reduction of another static level (other/vectorOperation.cpp:475-481, names :226-249)
         if (c->u.vectoroperation.operation != 0) { err = "cVectorOperation: only operation=ll1 is supported"; return OSM_B200_ERR_UNSUPPORTED; }
@@ -563,7 +574,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     for (size_t o = 0; o < d.ops.size(); o++) {
       if (d.ops[o].stream != (int)s) continue;
       if (d.ops[o].kind == SOP_MFCC || d.ops[o].kind == SOP_PLP) d.streams[s].bandOps.push_back((int)o);
-      if (d.ops[o].kind == SOP_SPECTRAL || d.ops[o].kind == SOP_PITCHACF) nSpec++;
+      if (d.ops[o].kind == SOP_SPECTRAL || d.ops[o].kind == SOP_PITCHACF || d.ops[o].kind == SOP_MAG) nSpec++;
     }
     const int nBand = (int)d.streams[s].bandOps.size();
     d.streams[s].fusedOp = nBand ? d.streams[s].bandOps[0] : -1;

@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
 // tile depends on (halo = summed half windows) are staged in shared memory once, every stage of
 // every group is then evaluated level by level in shared memory (O(window) per element) and
 // the finished rows are written out.
-constexpr int kPostRows = 64;
+constexpr int kPostRows = 64;      // at most; see post_tile_rows()
 constexpr int kPostMaxHalo = 12;
 constexpr int kPostThreads = 256;
 
@@ -912,10 +912,10 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
   const int u = tr.utt, r0 = tr.f0;
   const long long Ls = p.uttOff[u + 1] - p.uttOff[u];
   const int Tout = (int)(p.rowOff[u + 1] - p.rowOff[u]);
-  const int r1 = min(r0 + kPostRows, Tout);
+  const int r1 = min(r0 + p.rows, Tout);
   const int H = p.halo;
   const int rowBase = r0 - H;                       // absolute frame of smem row 0 (may be < 0)
-  const int nRowsBuf = kPostRows + 2 * H;
+  const int nRowsBuf = p.rows + 2 * H;
   float *S0 = psm;                                  // [nRowsBuf][nStat]
   float *A = S0 + nRowsBuf * p.nStat;               // [nRowsBuf][maxN]
   float *B = A + nRowsBuf * p.maxN;
@@ -1315,13 +1315,18 @@ cudaError_t launch_lld(const LldParams &p, int nfft, int numSMs, cudaStream_t st
   }
 }
 
-int post_tile_rows() { return kPostRows; }
+int post_tile_rows(int nStat, int maxN, int halo)
+{
+  int rows = kPostRows;
+  while (rows > 4 && (size_t)(rows + 2 * halo) * (nStat + 2 * maxN) * sizeof(float) > 160 * 1024) rows /= 2;
+  return rows;
+}
 
 cudaError_t launch_post(const PostParams &p, cudaStream_t st)
 {
   if (p.nTiles <= 0 || p.nGroups <= 0) return cudaSuccess;
   if (p.halo > kPostMaxHalo) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)(kPostRows + 2 * p.halo) * (p.nStat + 2 * p.maxN) * sizeof(float);
+  const size_t smem = (size_t)(p.rows + 2 * p.halo) * (p.nStat + 2 * p.maxN) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   post_kernel<<<p.nTiles, kPostThreads, smem, st>>>(p);

@@ -92,7 +92,8 @@ struct PostParams {
   int nUtt;
   int nGroups;
   PostGroup groups[kMaxPostGroups];
-  const TileRef *tiles;          // (utt, first output row) per CTA, post_tile_rows() rows each
+  const TileRef *tiles;          // (utt, first output row) per CTA, `rows` output rows each
+  int rows;                      // output rows per CTA: post_tile_rows(nStat, maxN, halo)
   int nTiles;
   int nStat;                     // static columns staged per row
   int maxN;                      // widest group
@@ -105,7 +106,8 @@ struct LldLaunchInfo { int grid, block; size_t smem; };
 // returns cudaSuccess or the launch error; fills `info`
 cudaError_t launch_lld(const LldParams &p, int nfft, int numSMs, cudaStream_t st, LldLaunchInfo *info);
 cudaError_t launch_post(const PostParams &p, cudaStream_t st);
-int post_tile_rows();
+// output rows per post_kernel CTA: 64, or fewer when a wide static level would not fit shared memory
+int post_tile_rows(int nStat, int maxN, int halo);
 // smem bytes the fused kernel needs for a given geometry (host helper, used for diagnostics)
 size_t lld_smem_bytes(const LldParams &p, int nfft);
 // frames per tile / virtual warps per CTA for a given FFT size
@@ -196,6 +198,9 @@ cudaError_t launch_vecop_ll1(float *stat, int statStride, int srcCol, int n, int
                              cudaStream_t st);
 
 cudaError_t launch_spectral(const SpectralParams &p, cudaStream_t st);
+// cFFTmagphase as an output level: tile-major magnitude level [tile][nSrc][F] -> columns of the static rows
+cudaError_t launch_mag_rows(const float *mag, const OpTile *tiles, int nTiles, int F, int nSrc, const long long *statOff,
+                            float *stat, int statStride, int outCol, cudaStream_t st);
 cudaError_t launch_energy(const TimeOpParams &p, cudaStream_t st);
 cudaError_t launch_mzcr(const TimeOpParams &p, cudaStream_t st);
 

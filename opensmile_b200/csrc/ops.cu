@@ -341,6 +341,34 @@ cudaError_t launch_spectral(const SpectralParams &p, cudaStream_t st)
   return cudaGetLastError();
 }
 
+// cFFTmagphase as an output level (spectrogram): transposes a magnitude tile [nSrc][F] into rows of the
+// static level, 32 bins at a time through shared memory so that both sides are coalesced
+__global__ void __launch_bounds__(256) mag_rows_kernel(const float *mag, const OpTile *tiles, int F, int nSrc,
+                                                       const long long *statOff, float *stat, int statStride, int outCol)
+{
+  __shared__ float t[32][33];
+  const OpTile tl = tiles[blockIdx.x];
+  const float *src = mag + ((size_t)blockIdx.x * nSrc) * F;
+  float *dst = stat + (statOff[tl.utt] + tl.f0) * (long long)statStride + outCol;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+  for (int k0 = 0; k0 < nSrc; k0 += 32) {
+    for (int kk = ty; kk < 32; kk += 8)
+      t[kk][tx] = (k0 + kk < nSrc && tx < F) ? src[(size_t)(k0 + kk) * F + tx] : 0.f;
+    __syncthreads();
+    for (int ff = ty; ff < tl.nf; ff += 8)
+      if (k0 + tx < nSrc) dst[(long long)ff * statStride + k0 + tx] = t[tx][ff];
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_mag_rows(const float *mag, const OpTile *tiles, int nTiles, int F, int nSrc, const long long *statOff,
+                            float *stat, int statStride, int outCol, cudaStream_t st)
+{
+  if (nTiles <= 0) return cudaSuccess;
+  mag_rows_kernel<<<nTiles, 256, 0, st>>>(mag, tiles, F, nSrc, statOff, stat, statStride, outCol);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // time-domain frames: sample n of frame t, as the framer (or the windower) level holds it
 // ------------------------------------------------------------------------------------------

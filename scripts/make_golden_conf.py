@@ -16,6 +16,8 @@ Contents (inputs are regenerated in the tests from opensmile_b200.synth.voiced_p
   mfcc_z            tests/configs/mfcc_0_d_a_z.conf (cFullinputMean on the statics), voiced_pcm(12000, 16000, seed=11);
                     mfcc_z_plain: tests/configs/mfcc_0_d_a.conf on the same input (statics before the mean subtraction);
                     ref_mfcc_0_z / ref_mfcc_e_z / ref_plp_0_z / ref_plp_e_z: the reference's shipped *_Z configurations, same input
+  ref_audspec / ref_audspec_compat / ref_spectrogram / ref_demo1_energy_csv: the reference's config/audspec/*.conf,
+                    config/spectrum/spectrogram.conf (first 4000 samples) and config/demo/demo1_energy.conf (its CSV file) on seed 11
   cmp_taps          static levels audR (26) | audSum | audRSum of compare_ns.conf for the same input (oracle pin)
   rasta_plp         tests/configs/rasta_plp.conf (RASTA-PLP cepstra 0..8 + delta), voiced_pcm(16000, 16000, seed=9)
   names_<case>      the CSV header's element names
@@ -80,6 +82,16 @@ def main():
     for key, rel in (("ref_mfcc_0_z", "mfcc/MFCC12_0_D_A_Z.conf"), ("ref_mfcc_e_z", "mfcc/MFCC12_E_D_A_Z.conf"),
                      ("ref_plp_0_z", "plp/PLP_0_D_A_Z.conf"), ("ref_plp_e_z", "plp/PLP_E_D_A_Z.conf")):
         out[key], _, _ = run(os.path.join(refrun.CONFIG_DIR, rel), pz, 16000, 1, csv_out=False)
+    # further shipped configurations made of LLD-path components only
+    out["ref_audspec"], _, _ = run(os.path.join(refrun.CONFIG_DIR, "audspec", "audspec.conf"), pz, 16000, 1, csv_out=False)
+    out["ref_audspec_compat"], _, _ = run(os.path.join(refrun.CONFIG_DIR, "audspec", "audspec_compat.conf"), pz, 16000, 1, csv_out=False)
+    out["ref_spectrogram"], _, _ = run(os.path.join(refrun.CONFIG_DIR, "spectrum", "spectrogram.conf"), pz[:4000], 16000, 1, csv_out=False)
+    with tempfile.TemporaryDirectory() as d:           # demo1_energy.conf writes CSV only (-O names the csv file)
+        wav, csv = os.path.join(d, "in.wav"), os.path.join(d, "out.csv")
+        refrun.write_wav(wav, pz, 16000, 1)
+        subprocess.run([refrun.SMILEXTRACT, "-C", os.path.join(refrun.CONFIG_DIR, "demo", "demo1_energy.conf"), "-I", wav, "-O", csv, "-l", "0"],
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out["ref_demo1_energy_csv"] = np.frombuffer(open(csv, "rb").read(), dtype=np.uint8)
     # taps of compare_ns.conf (the same graph with the HTK sink moved): RASTA-filtered bands and the two sums
     tap = os.path.join(ROOT, "tests", "configs", "_cmp_taps.conf")
     with open(tap, "w") as f:

@@ -225,3 +225,34 @@ def test_cepstral_mean_subtraction_confs():
             assert got.shape == ref.shape, key
             # scale: the un-normalised statics are ~1e1, mean-subtracted columns can be ~0 in a whole row
             assert np.abs(got - ref).max() < 1e-5 * np.abs(ref).max(), key
+
+
+REFCONF = os.path.join(ROOT, "oracle", "_ref", "config")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "audspec")), reason="reference configs not built into oracle/_ref")
+def test_more_shipped_configs_audspec_spectrogram_demo1(tmp_path):
+    """config/audspec/*.conf (auditory spectrum + deltas), config/spectrum/spectrogram.conf (the magnitude
+    level itself as output) and config/demo/demo1_energy.conf (CSV sink with a frame index column), unchanged."""
+    pcm = voiced_pcm(12000, 16000, seed=11)
+    for key, rel in (("ref_audspec", "audspec/audspec.conf"), ("ref_audspec_compat", "audspec/audspec_compat.conf")):
+        got, _ = Session(os.path.join(REFCONF, rel)).extract_pcm(pcm, [0, 12000], 16000, 1)
+        ref = GOLD[key]
+        assert got.shape == ref.shape, key
+        assert (np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5, key
+    s = Session(os.path.join(REFCONF, "spectrum", "spectrogram.conf"))
+    got, _ = s.extract_pcm(pcm[:4000], [0, 4000], 16000, 1)
+    ref = GOLD["ref_spectrogram"]
+    assert got.shape == ref.shape == (23, 257)
+    assert (np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
+    assert s.element_names()[256] == "pcm_fftMag[256]"
+    # demo1: the csv file is named by -O (the config's own option), one row per frame: index;time;value
+    write_wav(tmp_path / "in.wav", pcm, 16000)
+    s = Session(os.path.join(REFCONF, "demo", "demo1_energy.conf"), options={"O": str(tmp_path / "unused.csv")})
+    s.extract_files([str(tmp_path / "in.wav")], None, [str(tmp_path / "out.csv")])
+    lines = (tmp_path / "out.csv").read_text().splitlines()
+    ref_lines = GOLD["ref_demo1_energy_csv"].tobytes().decode().splitlines()
+    assert lines[0] == ref_lines[0] == "frameIndex;frameTime;pcm_LOGenergy" and len(lines) == len(ref_lines)
+    for a, b in zip(lines[1:], ref_lines[1:]):
+        fa, fb = a.split(";"), b.split(";")
+        assert fa[:2] == fb[:2] and abs(float(fa[2]) - float(fb[2])) <= 2e-6 * abs(float(fb[2]))
