@@ -138,3 +138,23 @@ def test_reference_standard_configs_parse(conf, n):
         assert names == [str(x) for x in GOLD["names_mfcc_e"]]
     if conf.endswith("PLP_E_D_A.conf"):
         assert names == [str(x) for x in GOLD["names_plp_e"]]
+
+
+def test_cli_fails_loudly_without_a_gpu(tmp_path):
+    """No CPU fallback anywhere: on a box without a CUDA device the command line front end parses the
+    configuration, then refuses to compute (non-zero exit, no output file)."""
+    import subprocess
+    import wave
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    exe = os.path.join(ROOT, "opensmile_b200", "SMILExtract_b200")
+    pcm = (np.random.default_rng(0).standard_normal(8000) * 1000).astype("<i2")
+    with wave.open(str(tmp_path / "t.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000); w.writeframes(pcm.tobytes())
+    r = subprocess.run([exe, "-C", os.path.join(CONF, "mfcc_e_d_a.conf"), "-I", str(tmp_path / "t.wav"), "-O", str(tmp_path / "o.htk")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "CUDA" in r.stderr and not (tmp_path / "o.htk").exists()
