@@ -28,6 +28,12 @@
 
 // A/B builds: scripts/ab_variants.py times library variants compiled with different -D switches; the
 // only switches left are the two unroll factors below.
+#ifndef OSM_EMIT_LANES
+#define OSM_EMIT_LANES 0
+#endif
+#ifndef OSM_MEL_COMPACT
+#define OSM_MEL_COMPACT 1
+#endif
 #ifndef OSM_UNROLL_MEL
 #define OSM_UNROLL_MEL 4
 #endif
@@ -399,6 +405,35 @@ __device__ __forceinline__ void emit_interior(const float *__restrict__ ring, fl
   const int K = KC > 0 ? KC : Krt;
   const int K3 = 3 * K;
   constexpr int DR = F + 4;                                    // delta rows of this tile
+#if OSM_EMIT_LANES
+  // lane = row, warps take the coefficients: no index arithmetic per item (13 coefficients over 8 warps
+  // leave some warps idle in the second round, which costs less than a division per item)
+  constexpr int NW = NT / 32;
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int c = warp; c < K; c += NW) {
+    const float *rc = ring + c * (2 * F);
+    for (int tt = lane; tt < DR; tt += 32) {
+      const int sl = slot0 + tt;
+      const float dA = __fsub_rn(rc[(sl + 1) & (2 * F - 1)], rc[(sl - 1) & (2 * F - 1)]);
+      const float dB = __fsub_rn(rc[(sl + 2) & (2 * F - 1)], rc[(sl - 2) & (2 * F - 1)]);
+      const float dv = div_exact(__fadd_rn(dA, __fmul_rn(2.0f, dB)), norm1, rcp1);
+      Dbuf[c * dRows + tt] = dv;
+      const int rr = tt - 2;
+      if (rr >= 0 && rr < F) outS[rr * K3 + K + c] = dv;
+    }
+    for (int rr = lane; rr < F; rr += 32) outS[rr * K3 + c] = rc[(rslot0 + rr) & (2 * F - 1)];
+  }
+  __syncthreads();
+  for (int c = warp; c < K; c += NW) {
+    for (int rr = lane; rr < F; rr += 32) {
+      const float *dt = Dbuf + c * dRows + rr + 2;             // row t = r0 + rr sits at tt = rr + 2
+      const float dA = __fsub_rn(dt[1], dt[-1]);
+      const float dB = __fsub_rn(dt[2], dt[-2]);
+      outS[rr * K3 + 2 * K + c] = div_exact(__fadd_rn(dA, __fmul_rn(2.0f, dB)), norm2, rcp2);
+    }
+  }
+  __syncthreads();
+#else
   for (int item = tid; item < K * DR; item += NT) {
     const int c = item / DR, tt = item - c * DR;
     const float *rc = ring + c * (2 * F);
@@ -423,6 +458,7 @@ __device__ __forceinline__ void emit_interior(const float *__restrict__ ring, fl
     outS[rr * K3 + 2 * K + c] = div_exact(__fadd_rn(dA, __fmul_rn(2.0f, dB)), norm2, rcp2);
   }
   __syncthreads();
+#endif
 }
 
 // Fused delta / delta-delta emission, general path (utterance edges, deltawin != 2): lane = row, warps
@@ -732,6 +768,26 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
       if (bs < be) {
         const int *sVB = sMelRange + p.nBands + 2;
         float cur = 0.f;
+#if OSM_MEL_COMPACT
+        // One loop for all ranges: every range is walked in groups of 4 visit entries (zero-weight
+        // padding at its end multiplies the following bins by 0), so there is no remainder code and the
+        // addresses inside a group are immediates.  Range bs only feeds band bs: its "current band"
+        // sum is a throw-away and no value is stored after it.
+        for (int r = bs; r <= be; r++) {
+          float nxt = 0.f;
+          const float *pp = P + sMelRange[r] * F + f;
+          const float2 *cp = sMelCoef + sVB[r];
+#pragma unroll 1
+          for (int q = (sVB[r + 1] - sVB[r]) >> 2; q > 0; q--, pp += 4 * F, cp += 4) {
+            const float p0 = pp[0], p1 = pp[F], p2 = pp[2 * F], p3 = pp[3 * F];
+            const float2 w0 = cp[0], w1 = cp[1], w2 = cp[2], w3 = cp[3];
+            cur = __fmaf_rn(p0, w0.x, cur); nxt = __fmaf_rn(p0, w0.y, nxt);
+            cur = __fmaf_rn(p1, w1.x, cur); nxt = __fmaf_rn(p1, w1.y, nxt);
+            cur = __fmaf_rn(p2, w2.x, cur); nxt = __fmaf_rn(p2, w2.y, nxt);
+            cur = __fmaf_rn(p3, w3.x, cur); nxt = __fmaf_rn(p3, w3.y, nxt);
+          }
+          if (r == bs) { cur = nxt; continue; }
+#else
         int n = sMelRange[bs];
         const float *pp = P + n * F + f;
         const float2 *cp = sMelCoef + sVB[bs];
@@ -751,6 +807,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
             cur = __fmaf_rn(pw, w.x, cur);
             nxt = __fmaf_rn(pw, w.y, nxt);
           }
+#endif
           float mval = __fmul_rn(cur, p.melScale);
           if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);   // mfcc.cpp:239-243 / plp.cpp:434-440
           if (opKind == 1 && p.plpAud) {

@@ -158,3 +158,47 @@ def test_cli_fails_loudly_without_a_gpu(tmp_path):
     r = subprocess.run([exe, "-C", os.path.join(CONF, "mfcc_e_d_a.conf"), "-I", str(tmp_path / "t.wav"), "-O", str(tmp_path / "o.htk")],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "CUDA" in r.stderr and not (tmp_path / "o.htk").exists()
+
+
+def _conf_with(tmp_path, extra_instances, extra_sections, level):
+    """htk front end + extra sections, HTK sink on `level`"""
+    inc = tmp_path / "inc"
+    inc.mkdir(exist_ok=True)
+    (inc / "htk_frontend.conf.inc").write_text(open(os.path.join(CONF, "inc", "htk_frontend.conf.inc")).read())
+    text = "\\{inc/htk_frontend.conf.inc}\n[componentInstances:cComponentManager]\n"
+    text += "".join("instance[%s].type = %s\n" % kv for kv in extra_instances) + "instance[out].type = cHtkSink\n"
+    text += extra_sections + "\n[out:cHtkSink]\nreader.dmLevel = %s\nfilename = o.htk\n" % level
+    (tmp_path / "c.conf").write_text(text)
+    return str(tmp_path / "c.conf")
+
+
+def test_graph_rules_of_the_wider_component_set(tmp_path):
+    # the magnitude level itself as output (spectrogram): one array field of nBins elements
+    c = _conf_with(tmp_path, [], "", "fftmag")
+    names = Session(c, device=-1).element_names(16000, 1)
+    assert len(names) == 257 and names[0] == "pcm_fftMag[0]"
+    assert len(Session(c, device=-1).element_names(44100, 1)) == 1025          # 1103-sample frames -> FFT 2048
+    # mean subtraction must be the last stage of its branch
+    secs = ("[mfcc:cMfcc]\nreader.dmLevel = melspec\nwriter.dmLevel = mfcc\n[cms:cFullinputMean]\nreader.dmLevel = mfcc\nwriter.dmLevel = mfccM\n"
+            "[de:cDeltaRegression]\nreader.dmLevel = mfccM\nwriter.dmLevel = mfccMde\n")
+    c = _conf_with(tmp_path, [("mfcc", "cMfcc"), ("cms", "cFullinputMean"), ("de", "cDeltaRegression")], secs, "mfccMde")
+    with pytest.raises(SessionError) as e:
+        Session(c, device=-1)
+    assert e.value.status == capi.ERR_UNSUPPORTED and "cFullinputMean" in str(e.value)
+    c = _conf_with(tmp_path, [("mfcc", "cMfcc"), ("cms", "cFullinputMean")], secs.split("[de:")[0], "mfccM")
+    assert Session(c, device=-1).element_names()[0] == "pcm_fftMag_mfcc[1]"
+    # cVectorOperation: only the n -> 1 mean (ll1) is on the path
+    secs = ("[mfcc:cMfcc]\nreader.dmLevel = melspec\nwriter.dmLevel = mfcc\n[vo:cVectorOperation]\nreader.dmLevel = mfcc\nwriter.dmLevel = vo\n"
+            "operation = %s\nnameBase = cepsum\n")
+    c = _conf_with(tmp_path, [("mfcc", "cMfcc"), ("vo", "cVectorOperation")], secs % "ll1", "vo")
+    assert Session(c, device=-1).element_names() == ["cepsum_lengthL1norm"]
+    c = _conf_with(tmp_path, [("mfcc", "cMfcc"), ("vo", "cVectorOperation")], secs % "norm", "vo")
+    with pytest.raises(SessionError) as e:
+        Session(c, device=-1)
+    assert "ll1" in str(e.value)
+    # two cepstral ops on one FFT chain + RASTA naming
+    secs = ("[mfcc:cMfcc]\nreader.dmLevel = melspec\nwriter.dmLevel = mfcc\n[rp:cPlp]\nreader.dmLevel = melspec\nwriter.dmLevel = rp\n"
+            "RASTA = 1\nhtkcompatible = 0\n[cat:cVectorConcat]\nreader.dmLevel = mfcc;rp\nwriter.dmLevel = both\n")
+    c = _conf_with(tmp_path, [("mfcc", "cMfcc"), ("rp", "cPlp"), ("cat", "cVectorConcat")], secs, "both")
+    names = Session(c, device=-1).element_names()
+    assert names[0] == "pcm_fftMag_mfcc[1]" and names[12] == "RASTAPlpCC[0]" and len(names) == 12 + 5   # cPlp defaults: firstCC = 1, lpOrder = 5
