@@ -84,6 +84,7 @@ typedef enum {
   OSM_B200_C_VECTORCONCAT,       /* cVectorConcat       src/other/vectorConcat.cpp:48-53          */
   OSM_B200_C_VECTOROPERATION,    /* cVectorOperation    src/other/vectorOperation.cpp:130 (ll1)   */
   OSM_B200_C_FULLINPUTMEAN,      /* cFullinputMean      src/dspcore/fullinputMean.cpp:484-548     */
+  OSM_B200_C_INTENSITY,          /* cIntensity          src/lldcore/intensity.cpp:124-146         */
   OSM_B200_C_COUNT_
 } osm_b200_component_type;
 
@@ -205,6 +206,8 @@ typedef struct { int32_t processArrayFields, includeSingleElementFields; } osm_b
  * Only the default mode is supported: arithmetic mean, single EOI loop (src/dspcore/fullinputMean.cpp:484-548) */
 typedef struct { int32_t mvn, meanNorm /* 0 = amean */, symmSubtract, subtractClipToZero, specEnorm, htkLogEnorm, excludeZeros, multiLoopMode; } osm_b200_fullinputmean;
 
+typedef struct { int32_t intensity, loudness; } osm_b200_intensity;   /* cIntensity: 1, 0 */
+
 /* one `[name:cType]` section */
 typedef struct {
   int32_t type;                                  /* osm_b200_component_type */
@@ -236,6 +239,7 @@ typedef struct {
     osm_b200_vectoroperation vectoroperation;
     osm_b200_vectorconcat vectorconcat;
     osm_b200_fullinputmean fullinputmean;
+    osm_b200_intensity intensity;
   } u;
 } osm_b200_component;
 

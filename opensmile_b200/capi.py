@@ -20,7 +20,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = range(5)
 # component types (osm_b200_component_type)
 (C_WAVESOURCE, C_FRAMER, C_VECTORPREEMPHASIS, C_WINDOWER, C_TRANSFORMFFT, C_FFTMAGPHASE,
  C_MELSPEC, C_MFCC, C_PLP, C_SPECTRAL, C_ENERGY, C_MZCR, C_ACF, C_PITCHACF,
- C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION, C_FULLINPUTMEAN) = range(19)
+ C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION, C_FULLINPUTMEAN, C_INTENSITY) = range(20)
 
 TYPE_BY_NAME = {
     "cWaveSource": C_WAVESOURCE, "cExternalAudioSource": C_WAVESOURCE, "cFramer": C_FRAMER,
@@ -30,7 +30,7 @@ TYPE_BY_NAME = {
     "cMZcr": C_MZCR, "cAcf": C_ACF, "cPitchACF": C_PITCHACF,
     "cDeltaRegression": C_DELTAREGRESSION, "cContourSmoother": C_CONTOURSMOOTHER,
     "cVectorConcat": C_VECTORCONCAT, "cVectorOperation": C_VECTOROPERATION,
-    "cFullinputMean": C_FULLINPUTMEAN,
+    "cFullinputMean": C_FULLINPUTMEAN, "cIntensity": C_INTENSITY,
 }
 
 WIN_BY_NAME = {"rec": 0, "han": 1, "ham": 2, "gau": 3, "sin": 4, "tri": 5, "bar": 6}
@@ -140,6 +140,10 @@ class FullinputMean(C.Structure):
                 ("specEnorm", i32), ("htkLogEnorm", i32), ("excludeZeros", i32), ("multiLoopMode", i32)]
 
 
+class Intensity(C.Structure):
+    _fields_ = [("intensity", i32), ("loudness", i32)]
+
+
 class _U(C.Union):
     _fields_ = [("wavesource", WaveSource), ("framer", Framer),
                 ("vectorpreemphasis", VectorPreemphasis), ("windower", Windower),
@@ -147,7 +151,7 @@ class _U(C.Union):
                 ("melspec", Melspec), ("mfcc", Mfcc), ("plp", Plp), ("spectral", Spectral),
                 ("energy", Energy), ("mzcr", MZcr), ("acf", Acf), ("pitchacf", PitchACF),
                 ("deltaregression", DeltaRegression), ("contoursmoother", ContourSmoother),
-                ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat), ("fullinputmean", FullinputMean)]
+                ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat), ("fullinputmean", FullinputMean), ("intensity", Intensity)]
 
 
 class Component(C.Structure):
@@ -164,7 +168,7 @@ UNION_FIELD = {
     C_ENERGY: "energy", C_MZCR: "mzcr", C_ACF: "acf", C_PITCHACF: "pitchacf",
     C_DELTAREGRESSION: "deltaregression", C_CONTOURSMOOTHER: "contoursmoother",
     C_VECTOROPERATION: "vectoroperation", C_VECTORCONCAT: "vectorconcat",
-    C_FULLINPUTMEAN: "fullinputmean",
+    C_FULLINPUTMEAN: "fullinputmean", C_INTENSITY: "intensity",
 }
 
 # every symbol include/osm_b200.h declares (tests assert the library exports all of them)

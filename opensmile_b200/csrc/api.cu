@@ -218,6 +218,7 @@ osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
     case OSM_B200_C_PITCHACF: c->u.pitchacf.maxPitch = 500; c->u.pitchacf.voiceProb = 1; c->u.pitchacf.voicingCutoff = 0.55; break;
     case OSM_B200_C_DELTAREGRESSION: c->u.deltaregression.deltawin = 2; c->u.deltaregression.zeroSegBound = 1; break;
     case OSM_B200_C_CONTOURSMOOTHER: c->u.contoursmoother.smaWin = 3; break;
+    case OSM_B200_C_INTENSITY: c->u.intensity.intensity = 1; c->u.intensity.loudness = 0; break;
     case OSM_B200_C_VECTORCONCAT: c->u.vectorconcat.processArrayFields = 1; c->u.vectorconcat.includeSingleElementFields = 0; break;
     default: break;
   }
@@ -611,7 +612,10 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       tp.frameSize = fe.frameSize; tp.frameStep = fe.frameStep;
       tp.windowed = op.windowed; tp.preemph = op.windowed && fe.preemph; tp.preDe = fe.preDe; tp.preK = fe.preK;
       tp.oneMinusK = 1 - fe.preK; tp.winOffset = fe.winOffset; tp.window = srt.dWindow;
-      if (op.kind == SOP_ENERGY) {
+      if (op.kind == SOP_INTENSITY) {
+        tp.iIntensity = op.intensity.intensity; tp.iLoudness = op.intensity.loudness;
+        tp.iW0 = op.intensity.w[0]; tp.iW1 = op.intensity.w[1]; tp.iWinSum = op.intensity.winSum;
+      } else if (op.kind == SOP_ENERGY) {
         const EnergyOp &e = op.energy;
         tp.eHtk = e.htk; tp.eRms = e.rms; tp.eEnergy2 = e.energy2; tp.eLog = e.lg;
         tp.escaleLog = e.escaleLog; tp.escaleRms = e.escaleRms; tp.escaleSquare = e.escaleSquare;
@@ -878,7 +882,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       tp.uttOff = dU; tp.statOff = dS;
       tp.tiles = rt.dTiles.p + t0; tp.nTiles = t1 - t0;
       tp.stat = pl->dStat.p;
-      CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : launch_mzcr(tp, st));
+      CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : (o.kind == SOP_INTENSITY ? launch_intensity(tp, st) : launch_mzcr(tp, st)));
     }
     pl->lastLaunches++;
   }

@@ -34,7 +34,7 @@ const char *type_name(int t)
   static const char *names[] = {"cWaveSource", "cFramer", "cVectorPreemphasis", "cWindower",
     "cTransformFFT", "cFFTmagphase", "cMelspec", "cMfcc", "cPlp", "cSpectral", "cEnergy",
     "cMZcr", "cAcf", "cPitchACF", "cDeltaRegression", "cContourSmoother", "cVectorConcat",
-    "cVectorOperation", "cFullinputMean"};
+    "cVectorOperation", "cFullinputMean", "cIntensity"};
   return (t >= 0 && t < OSM_B200_C_COUNT_) ? names[t] : "?";
 }
 
@@ -391,7 +391,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         po.nOut = (int)op.fields.size();
         op.nOut = po.nOut;
         if (op.nOut < 1) { err = "cPitchACF produces no output"; return OSM_B200_ERR_INVALID; }
-      } else if (c->type == OSM_B200_C_ENERGY || c->type == OSM_B200_C_MZCR) {
+      } else if (c->type == OSM_B200_C_ENERGY || c->type == OSM_B200_C_MZCR || c->type == OSM_B200_C_INTENSITY) {
         const osm_b200_component *in = single_input(c);
         if (!resolve_time_chain(in, ci)) return OSM_B200_ERR_UNSUPPORTED;
         op.windowed = ci.win != nullptr;
@@ -407,6 +407,23 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
           if (op.energy.rms) { FieldName f; f.name = name_append_auto(*c, base, "RMS"); op.fields.push_back(f); }
           if (op.energy.energy2) { FieldName f; f.name = name_append_auto(*c, base, "SQUARED"); op.fields.push_back(f); }
           if (op.energy.lg) { FieldName f; f.name = name_append_auto(*c, base, "LOG"); op.fields.push_back(f); }
+        } else if (c->type == OSM_B200_C_INTENSITY) {
+          op.kind = SOP_INTENSITY;
+          IntensityOp &io = op.intensity;
+          io.intensity = c->u.intensity.intensity != 0; io.loudness = c->u.intensity.loudness != 0;
+          io.nOut = (io.intensity ? 1 : 0) + (io.loudness ? 1 : 0);
+          op.nOut = io.nOut;
+          // Hamming window of the frame length (smileutil/smileUtil.c:1291-1303), summed in index order
+          const int N = d.streams[op.stream].fe.frameSize;
+          io.winSum = 0.0;
+          for (int j = 0; j < N; j++) {
+            const double w = 0.54 - 0.46 * cos((2.0 * M_PI * (double)j) / ((double)N - 1.0));
+            if (j < 2) io.w[j] = w;
+            io.winSum += w;
+          }
+          if (io.winSum <= 0.0) io.winSum = 1.0;
+          if (io.intensity) { FieldName f; f.name = name_append_auto(*c, base, "intensity"); op.fields.push_back(f); }   // lldcore/intensity.cpp:91-92
+          if (io.loudness) { FieldName f; f.name = name_append_auto(*c, base, "loudness"); op.fields.push_back(f); }
         } else {
           op.kind = SOP_MZCR;
           build_mzcr(c->u.mzcr, op.mzcr);

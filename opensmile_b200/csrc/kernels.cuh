@@ -152,6 +152,8 @@ struct TimeOpParams {            // cEnergy / cMZcr on the framer or windower le
   int eHtk, eRms, eEnergy2, eLog; float escaleLog, escaleRms, escaleSquare, ebiasLog, ebiasRms, ebiasSquare;
   // cMZcr
   int zZcr, zMcr, zAmax, zMaxmin, zDc;
+  // cIntensity
+  int iIntensity, iLoudness; double iW0, iW1, iWinSum;
 };
 
 // cAcf (ACF) + cAcf (cepstrum) + cPitchACF: per-frame part (one CTA per tile, batched complex FFT of
@@ -203,5 +205,6 @@ cudaError_t launch_mag_rows(const float *mag, const OpTile *tiles, int nTiles, i
                             float *stat, int statStride, int outCol, cudaStream_t st);
 cudaError_t launch_energy(const TimeOpParams &p, cudaStream_t st);
 cudaError_t launch_mzcr(const TimeOpParams &p, cudaStream_t st);
+cudaError_t launch_intensity(const TimeOpParams &p, cudaStream_t st);
 
 }  // namespace osm

@@ -477,6 +477,35 @@ __global__ void __launch_bounds__(32) mzcr_kernel(const TimeOpParams p)
   if (p.zDc) dst[n++] = mean;
 }
 
+// cIntensity (lldcore/intensity.cpp:124-146).  The reference bounds its summation loop by
+// MIN(Nsrc, MIN(nWin, Ndst)) with Ndst = number of OUTPUT values (1 or 2), i.e. only the first one or
+// two samples of the frame enter the "mean": reproduced as is, this is what the shipped configs emit.
+__global__ void __launch_bounds__(32) intensity_kernel(const TimeOpParams p)
+{
+  const OpTile tl = p.tiles[blockIdx.x];
+  const int lane = threadIdx.x;
+  if (lane >= tl.nf) return;
+  const long long uo = p.uttOff[tl.utt];
+  FrameReader fr{p, p.pcm + (uo + (long long)(tl.f0 + lane) * p.frameStep) * p.nChan};
+  const int nOut = (p.iIntensity ? 1 : 0) + (p.iLoudness ? 1 : 0);
+  const int safeN = min(p.frameSize, nOut);
+  double Im = 0.0;
+  if (safeN > 0) { const float x = fr.at(0); Im += p.iW0 * (double)x * (double)x; }
+  if (safeN > 1) { const float x = fr.at(1); Im += p.iW1 * (double)x * (double)x; }
+  Im /= p.iWinSum;
+  float *dst = p.stat + (p.statOff[tl.utt] + tl.f0 + lane) * (long long)p.statStride + p.outCol;
+  int n = 0;
+  if (p.iIntensity) dst[n++] = (float)Im;
+  if (p.iLoudness) dst[n++] = (float)pow(Im / 0.000001, 0.3);
+}
+
+cudaError_t launch_intensity(const TimeOpParams &p, cudaStream_t st)
+{
+  if (p.nTiles <= 0) return cudaSuccess;
+  intensity_kernel<<<p.nTiles, 32, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_energy(const TimeOpParams &p, cudaStream_t st)
 {
   if (p.nTiles <= 0) return cudaSuccess;

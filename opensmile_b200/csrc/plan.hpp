@@ -43,7 +43,7 @@ struct FrontEnd {
   bool zeroPadSymmetric = false;   // phase only; magnitude consumers are unaffected
 };
 
-enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP, SOP_MAG };
+enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP, SOP_MAG, SOP_INTENSITY };
 
 struct MfccOp {
   int melIdx = 0;
@@ -104,6 +104,10 @@ struct PitchAcfOp {
   int nOut = 0;
 };
 
+// cIntensity (lldcore/intensity.cpp:86-146): Hamming-weighted mean square of the first min(N, nOut) samples
+// (the reference bounds its loop by the OUTPUT size, reproduced as is), loudness = (I / 1e-6)^0.3
+struct IntensityOp { bool intensity = true, loudness = false; double w[2] = {0, 0}; double winSum = 1.0; int nOut = 0; };
+
 struct MzcrOp { bool zcr = true, mcr = true, amax = true, maxmin = true, dc = false; int nOut = 0; };
 
 // one field of a level: `n` elements named name (n == 1) or name[i + arrNameOffset]
@@ -121,6 +125,7 @@ struct StaticOp {
   SpectralOp spectral;
   EnergyOp energy;
   MzcrOp mzcr;
+  IntensityOp intensity;
   PitchAcfOp pitch;
 };
 

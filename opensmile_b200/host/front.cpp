@@ -219,7 +219,7 @@ const TypeInfo kTypes[] = {
   {"cMZcr", OSM_B200_C_MZCR}, {"cAcf", OSM_B200_C_ACF}, {"cPitchACF", OSM_B200_C_PITCHACF},
   {"cDeltaRegression", OSM_B200_C_DELTAREGRESSION}, {"cContourSmoother", OSM_B200_C_CONTOURSMOOTHER},
   {"cVectorConcat", OSM_B200_C_VECTORCONCAT}, {"cVectorOperation", OSM_B200_C_VECTOROPERATION},
-  {"cFullinputMean", OSM_B200_C_FULLINPUTMEAN}};
+  {"cFullinputMean", OSM_B200_C_FULLINPUTMEAN}, {"cIntensity", OSM_B200_C_INTENSITY}};
 
 int type_of(const std::string &t)
 {
@@ -384,6 +384,9 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         if (f == "noPostEOIprocessing") { if (inum(v)) { err = "cContourSmoother.noPostEOIprocessing=1 is not supported"; return false; } continue; }
         break;
       case OSM_B200_C_VECTORCONCAT:
+        break;
+      case OSM_B200_C_INTENSITY:
+        SETI("intensity", c.u.intensity.intensity) SETI("loudness", c.u.intensity.loudness)
         break;
       case OSM_B200_C_FULLINPUTMEAN:
         SETI("mvn", c.u.fullinputmean.mvn) SETI("symmSubtract", c.u.fullinputmean.symmSubtract)

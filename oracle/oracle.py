@@ -170,6 +170,15 @@ def mzcr(pcm, fe, cfg=None, windowed=0, n_chan=1):
     return _run_static("osm_or_mzcr", "osm_or_mzcr_num_out", fe, cfg, pcm, n_chan, (C.c_int(windowed),))
 
 
+class Intensity(C.Structure):
+    _fields_ = [("intensity", C.c_int), ("loudness", C.c_int)]
+
+
+def intensity(pcm, fe, cfg=None, windowed=0, n_chan=1):
+    cfg = cfg or Intensity(1, 0)
+    return _run_static("osm_or_intensity", "osm_or_intensity_num_out", fe, cfg, pcm, n_chan, (C.c_int(windowed),))
+
+
 def build(force=False):
     """Compile liboracle.so with gcc (oracle/Makefile)."""
     so = os.path.join(_HERE, "liboracle.so")

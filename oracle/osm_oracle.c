@@ -906,6 +906,33 @@ static long run_time_frames(const osm_or_frontend *fe, int windowed, const int16
   return T;
 }
 
+/* cIntensity (lldcore/intensity.cpp:86-146).  NOTE the loop bound MIN(Nsrc, MIN(nWin, Ndst)): Ndst is the
+ * number of OUTPUT values of the field (1 or 2), so only the first one or two samples enter the sum --
+ * restated as the reference computes it. */
+int osm_or_intensity_num_out(const osm_or_intensity_cfg *in) { return (in->intensity ? 1 : 0) + (in->loudness ? 1 : 0); }
+static void intensity_tf(const void *c, const float *src, long Nsrc, float *dst)
+{
+  const osm_or_intensity_cfg *in = (const osm_or_intensity_cfg *)c;
+  long Ndst = osm_or_intensity_num_out(in), nWin = Nsrc;
+  double winSum = 0.0, NN = (double)Nsrc;
+  double *hamWin = (double *)malloc(sizeof(double) * Nsrc);               /* smileDsp_winHam, smileUtil.c:1291-1303 */
+  for (long j = 0; j < Nsrc; j++) { hamWin[j] = 0.54 - 0.46 * cos((2.0 * M_PI * (double)j) / (NN - 1.0)); winSum += hamWin[j]; }
+  if (winSum <= 0.0) winSum = 1.0;
+  double Im = 0.0, I0 = (double)0.000001;
+  long safeN = Nsrc < (nWin < Ndst ? nWin : Ndst) ? Nsrc : (nWin < Ndst ? nWin : Ndst);
+  for (long i = 0; i < safeN; i++) Im += hamWin[i] * (double)src[i] * (double)src[i];
+  Im /= winSum;
+  long n = 0;
+  if (in->intensity) dst[n++] = (float)Im;
+  if (in->loudness) dst[n++] = (float)pow(Im / I0, 0.3);
+  free(hamWin);
+}
+long osm_or_intensity(const osm_or_frontend *fe, const osm_or_intensity_cfg *in, int windowed,
+                      const int16_t *pcm, long L, int n_chan, float *out)
+{
+  return run_time_frames(fe, windowed, pcm, L, n_chan, intensity_tf, in, osm_or_intensity_num_out(in), out);
+}
+
 static void energy_tf(const void *c, const float *x, long N, float *d) { energy_frame((const osm_or_energy_cfg *)c, x, N, d); }
 static void mzcr_tf(const void *c, const float *x, long N, float *d) { mzcr_frame((const osm_or_mzcr_cfg *)c, x, N, d); }
 

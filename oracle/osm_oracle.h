@@ -91,6 +91,7 @@ typedef struct {            /* cEnergy (lldcore/energy.cpp) */
 } osm_or_energy_cfg;
 
 typedef struct { int zcr, mcr, amax, maxmin, dc; } osm_or_mzcr_cfg;   /* cMZcr (lldcore/mzcr.cpp) */
+typedef struct { int intensity, loudness; } osm_or_intensity_cfg;        /* cIntensity (lldcore/intensity.cpp) */
 
 typedef struct {            /* cAcf x2 + cPitchACF (dspcore/acf.cpp, lldcore/pitchACF.cpp) */
   int acfUsePower;          /* [acf] usePower (1) */
@@ -154,6 +155,10 @@ long osm_or_pitchacf(const osm_or_frontend *fe, const osm_or_pitchacf_cfg *pc,
                      const int16_t *pcm, long n_samples, int n_chan, float *out,
                      float *tap_acf, float *tap_cep);
 int  osm_or_mzcr_num_out(const osm_or_mzcr_cfg *mz);
+int  osm_or_intensity_num_out(const osm_or_intensity_cfg *in);
+/* cIntensity on the framer level: out = [T][num_out] (lldcore/intensity.cpp:86-146) */
+long osm_or_intensity(const osm_or_frontend *fe, const osm_or_intensity_cfg *in, int windowed,
+                      const int16_t *pcm, long n_samples, int n_chan, float *out);
 long osm_or_mzcr(const osm_or_frontend *fe, const osm_or_mzcr_cfg *mz, int windowed,
                  const int16_t *pcm, long n_samples, int n_chan, float *out);
 

@@ -16,6 +16,7 @@ Contents (inputs are regenerated in the tests from opensmile_b200.synth.voiced_p
   mfcc_z            tests/configs/mfcc_0_d_a_z.conf (cFullinputMean on the statics), voiced_pcm(12000, 16000, seed=11);
                     mfcc_z_plain: tests/configs/mfcc_0_d_a.conf on the same input (statics before the mean subtraction);
                     ref_mfcc_0_z / ref_mfcc_e_z / ref_plp_0_z / ref_plp_e_z: the reference's shipped *_Z configurations, same input
+  ref_prosody_acf   config/prosody/prosodyAcf.conf (cPitchACF + cIntensity loudness, sma3) on seed 11
   ref_audspec / ref_audspec_compat / ref_spectrogram / ref_demo1_energy_csv: the reference's config/audspec/*.conf,
                     config/spectrum/spectrogram.conf (first 4000 samples) and config/demo/demo1_energy.conf (its CSV file) on seed 11
   cmp_taps          static levels audR (26) | audSum | audRSum of compare_ns.conf for the same input (oracle pin)
@@ -86,6 +87,7 @@ def main():
     out["ref_audspec"], _, _ = run(os.path.join(refrun.CONFIG_DIR, "audspec", "audspec.conf"), pz, 16000, 1, csv_out=False)
     out["ref_audspec_compat"], _, _ = run(os.path.join(refrun.CONFIG_DIR, "audspec", "audspec_compat.conf"), pz, 16000, 1, csv_out=False)
     out["ref_spectrogram"], _, _ = run(os.path.join(refrun.CONFIG_DIR, "spectrum", "spectrogram.conf"), pz[:4000], 16000, 1, csv_out=False)
+    out["ref_prosody_acf"], out["names_ref_prosody_acf"], _ = run(os.path.join(refrun.CONFIG_DIR, "prosody", "prosodyAcf.conf"), pz, 16000, 1)
     with tempfile.TemporaryDirectory() as d:           # demo1_energy.conf writes CSV only (-O names the csv file)
         wav, csv = os.path.join(d, "in.wav"), os.path.join(d, "out.csv")
         refrun.write_wav(wav, pz, 16000, 1)

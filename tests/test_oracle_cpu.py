@@ -142,3 +142,13 @@ def test_cms_oracle_bit_exact_given_reference_statics():
     assert z.shape == plain.shape == (73, 39)
     assert np.array_equal(oracle.cms(plain[:, :13]), z[:, :13])
     assert np.array_equal(plain[:, 13:], z[:, 13:])
+
+
+def test_intensity_oracle_bit_exact_vs_reference():
+    """cIntensity loudness of config/prosody/prosodyAcf.conf (third column of its lld level, after sma3):
+    restated with the reference's own loop bound (only the first sample(s) of a frame enter the sum)."""
+    g = np.load(os.path.join(GOLD, "conf_goldens.npz"))
+    ref = g["ref_prosody_acf"]
+    fe = oracle.Frontend(16000.0, 0.050, 0.010, 0, 0.0, oracle.WIN["gau"], 0.4, 1.0, 0.0, 0)
+    loud = oracle.intensity(voiced_pcm(12000, 16000, seed=11), fe, oracle.Intensity(0, 1))
+    assert np.array_equal(oracle.sma(loud, 3)[:ref.shape[0], 0], ref[:, 2])

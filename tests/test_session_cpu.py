@@ -129,7 +129,8 @@ def test_description_only_session_refuses_to_compute():
                                     ("mfcc/MFCC12_0_D_A_Z.conf", 39), ("mfcc/MFCC12_E_D_A_Z.conf", 39),
                                     ("plp/PLP_0_D_A_Z.conf", 18), ("plp/PLP_E_D_A_Z.conf", 18),
                                     ("audspec/audspec.conf", 78), ("audspec/audspec_compat.conf", 78),
-                                    ("spectrum/spectrogram.conf", 257), ("demo/demo1_energy.conf", 1)])
+                                    ("spectrum/spectrogram.conf", 257), ("demo/demo1_energy.conf", 1),
+                                    ("prosody/prosodyAcf.conf", 3)])
 def test_reference_standard_configs_parse(conf, n):
     s = Session(os.path.join(REF_CONF, conf), device=-1)
     names = s.element_names(16000, 1)

@@ -246,6 +246,13 @@ def test_more_shipped_configs_audspec_spectrogram_demo1(tmp_path):
     assert got.shape == ref.shape == (23, 257)
     assert (np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-5
     assert s.element_names()[256] == "pcm_fftMag[256]"
+    # prosodyAcf: ACF / cepstrum pitch + cIntensity loudness, smoothed
+    s = Session(os.path.join(REFCONF, "prosody", "prosodyAcf.conf"))
+    got, _ = s.extract_pcm(pcm, [0, 12000], 16000, 1)
+    ref = GOLD["ref_prosody_acf"]
+    assert got.shape == ref.shape and s.element_names() == [str(x) for x in GOLD["names_ref_prosody_acf"]]
+    assert np.abs(got[:, 0] - ref[:, 0]).max() < 1e-5 and np.abs(got[:, 2] - ref[:, 2]).max() <= 1e-6 * np.abs(ref[:, 2]).max()
+    assert (np.abs(got[:, 1] - ref[:, 1]) <= 1e-5 * np.abs(ref[:, 1]).max()).mean() > 0.98      # F0: lag-valued
     # demo1: the csv file is named by -O (the config's own option), one row per frame: index;time;value
     write_wav(tmp_path / "in.wav", pcm, 16000)
     s = Session(os.path.join(REFCONF, "demo", "demo1_energy.conf"), options={"O": str(tmp_path / "unused.csv")})
