@@ -15,8 +15,8 @@
  *   osm_b200_session_extract_pcm   ~ smile_extaudiosource_write_data + smile_run + cExternalSink rows
  *   osm_b200_session_num_elements / element_name ~ smile_extsink_get_num_elements / _get_element_name
  *
- * Component types understood in a .conf: the LLD components of include/osm_b200.h (incl. cFullinputMean
- * and cVectorOperation ll1) plus the host
+ * Component types understood in a .conf: the LLD components of include/osm_b200.h (incl. cFullinputMean,
+ * cIntensity and cVectorOperation ll1) plus the host
  * edges cDataMemory, cWaveSource / cExternalAudioSource, cHtkSink, cCsvSink, cArffSink (parsed,
  * ARFF output not written) and cExternalSink.  Anything else on the path to the sink's level
  * makes session_open fail with OSM_B200_ERR_UNSUPPORTED; there is no CPU fallback.
