@@ -182,7 +182,7 @@ def intensity(pcm, fe, cfg=None, windowed=0, n_chan=1):
 def build(force=False):
     """Compile liboracle.so with gcc (oracle/Makefile)."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = [os.path.join(_HERE, f) for f in ("osm_oracle.c", "osm_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("osm_oracle.c", "osm_oracle.h", "osm_oracle_pitch.c", "osm_oracle_pitch.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
     return so
@@ -338,3 +338,184 @@ def sma(x, sma_win=3, no_zero_sma=0):
     out = np.zeros((T + (sma_win - 1) // 2, K), np.float32)
     r = lib().osm_or_sma(_fp(x), C.c_long(T), C.c_int(K), C.c_int(sma_win), C.c_int(no_zero_sma), _fp(out))
     return out[:r]
+
+
+# ---- SHS pitch chain (oracle/osm_oracle_pitch.c): cSpecScale -> cPitchShs -> cPitchSmootherViterbi ->
+# cValbasedSelector -> cPitchJitter, values of config/compare16/ComParE_2016_core.lld.conf.inc ----
+
+class SpecScale(C.Structure):
+    _fields_ = [("minF", C.c_double), ("maxF", C.c_double), ("nPointsTarget", C.c_int), ("specSmooth", C.c_int),
+                ("specEnhance", C.c_int), ("auditoryWeighting", C.c_int)]
+
+
+class PitchShs(C.Structure):
+    _fields_ = [("maxPitch", C.c_double), ("minPitch", C.c_double), ("nCandidates", C.c_int), ("scores", C.c_int),
+                ("voicing", C.c_int), ("F0C1", C.c_int), ("voicingC1", C.c_int), ("F0raw", C.c_int), ("voicingClip", C.c_int),
+                ("voicingCutoff", C.c_double), ("octaveCorrection", C.c_int), ("nHarmonics", C.c_int),
+                ("compressionFactor", C.c_double), ("greedyPeakAlgo", C.c_int), ("lfCut", C.c_double)]
+
+
+class Viterbi(C.Structure):
+    _fields_ = [("bufferLength", C.c_int), ("F0final", C.c_int), ("F0finalLog", C.c_int), ("F0finalEnv", C.c_int),
+                ("F0finalEnvLog", C.c_int), ("voicingFinalClipped", C.c_int), ("voicingFinalUnclipped", C.c_int),
+                ("wLocal", C.c_double), ("wTvv", C.c_double), ("wTvvd", C.c_double), ("wTvuv", C.c_double),
+                ("wThr", C.c_double), ("wRange", C.c_double), ("wTuu", C.c_double)]
+
+
+class Jitter(C.Structure):
+    _fields_ = [("searchRangeRel", C.c_double), ("jitterLocal", C.c_int), ("jitterDDP", C.c_int), ("jitterLocalEnv", C.c_int),
+                ("jitterDDPEnv", C.c_int), ("shimmerLocal", C.c_int), ("shimmerLocalDB", C.c_int), ("shimmerLocalEnv", C.c_int),
+                ("shimmerLocalDBEnv", C.c_int), ("harmonicERMS", C.c_int), ("noiseERMS", C.c_int), ("linearHNR", C.c_int),
+                ("logHNR", C.c_int), ("lgHNRfloor", C.c_double), ("shimmerUseRmsAmplitude", C.c_int), ("minNumPeriods", C.c_int),
+                ("minCC", C.c_double), ("refinedF0", C.c_int), ("sourceQualityRange", C.c_int), ("sourceQualityMean", C.c_int),
+                ("usePeakToPeakPeriodLength", C.c_int), ("useBrokenJitterThresh", C.c_int), ("onlyVoiced", C.c_int)]
+
+
+def compare16_pitch_cfg():
+    """(frontend, SpecScale, PitchShs, Viterbi, Jitter) of ComParE_2016_core.lld.conf.inc:16-46,62-190"""
+    fe = frontend(16000.0, 0.060, 0.010, win="gau", sigma=0.4, zero_pad_symmetric=1)
+    sc = SpecScale(25.0, -1.0, 0, 1, 1, 1)
+    ps = PitchShs(620.0, 52.0, 6, 1, 1, 0, 0, 1, 1, 0.70, 0, 15, 0.85, 1, 0.0)
+    vc = Viterbi(30, 1, 0, 0, 0, 0, 1, 2.0, 10.0, 5.0, 10.0, 4.0, 1.0, 0.0)
+    jc = Jitter(0.25, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, -100.0, 0, 2, 0.5, 0, 0, 0, 0, 0, 0)
+    return fe, sc, ps, vc, jc
+
+
+def pitch_shs(pcm, fe, sc, ps, n_chan=1, tap=False):
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nS = pcm.size // n_chan
+    N, H, nfft, T = geometry(fe, nS)
+    L = lib()
+    L.osm_or_pitch_shs.restype = C.c_long
+    K = L.osm_or_pitchshs_num_out(C.byref(ps))
+    out = np.zeros((max(T, 0), K), np.float32)
+    npts = sc.nPointsTarget if sc.nPointsTarget > 0 else nfft // 2 + 1
+    hps = np.zeros((max(T, 0), npts), np.float32) if tap else None
+    r = L.osm_or_pitch_shs(C.byref(fe), C.byref(sc), C.byref(ps), pcm.ctypes.data_as(C.POINTER(C.c_int16)), C.c_long(nS),
+                           C.c_int(n_chan), _fp(out), _fp(hps))
+    assert r == max(T, 0), (r, T)
+    return (out, hps) if tap else out
+
+
+def viterbi(shs, ps, vc, with_lag=False):
+    """-> [T, K] (and V = frames the level holds before the end-of-input flush when with_lag)"""
+    shs = np.ascontiguousarray(shs, np.float32)
+    L = lib()
+    L.osm_or_viterbi.restype = C.c_long
+    K = L.osm_or_viterbi_num_out(C.byref(vc))
+    out = np.zeros((shs.shape[0], K), np.float32)
+    v = C.c_long(0)
+    r = L.osm_or_viterbi(C.byref(ps), C.byref(vc), _fp(shs), C.c_long(shs.shape[0]), _fp(out), C.byref(v))
+    assert r == shs.shape[0], (r, shs.shape)
+    return (out, v.value) if with_lag else out
+
+
+def sma_nz_lagged(x, V, lag_cols):
+    """cContourSmoother (smaWin=3, noZeroSma=1) over a multi-level reader whose `lag_cols` come from a level
+    that holds only V frames during the reference's first end-of-input pass (cPitchJitter does not run while
+    EOI is set, lld/pitchJitter.cpp:593): output rows V-1 and V see that level padded with its row V-1
+    (core/dataMemoryLevel.cpp:1020-1027,1698-1708); every other row is the plain clamp-at-the-ends result.
+    Verified against oracle/_ref (scripts/make_golden_pitch.py)."""
+    x = np.asarray(x, np.float32)
+    T, K = x.shape
+    out = np.zeros((T + 1, K), np.float32)
+    for n in range(T + 1):
+        for k in range(K):
+            def g(i):
+                i = min(max(i, 0), T - 1)
+                if k in lag_cols and n in (V - 1, V) and i > V - 1:
+                    i = max(V - 1, 0)
+                return x[i, k]
+            x0 = g(n)
+            if x0 != 0:
+                y, N = np.float32(x0), 1
+                for v in (g(n - 1), g(n + 1)):
+                    if v != 0:
+                        y = np.float32(y + v)
+                        N += 1
+                out[n, k] = np.float32(y / np.float32(N))
+    return out
+
+
+def delta_segments_lagged(x, V, win=2):
+    """cDeltaRegression (onlyInSegments=1) behind sma_nz_lagged: x = [T+1, K].  Rows V-1..V+2 are computed
+    during the first end-of-input pass, when the input level ends at row V; row V+3 (if T-5 <= V <= T-2) is
+    computed in the first tick of the second pass, when it ends at row T-1; the accumulating norm
+    (dspcore/deltaRegression.cpp:123-141) runs through all rows in order."""
+    x = np.asarray(x, np.float32)
+    T1, K = x.shape
+    T = T1 - 1
+    out = np.zeros((T1 + win, K), np.float32)
+    norm = np.float32(0)
+    for i in range(1, win + 1):
+        norm = np.float32(norm + np.float32(i) * np.float32(i))
+    norm = np.float32(norm * 2)
+    for n in range(T1 + win):
+        last = T1 - 1
+        if V - 1 <= n <= V + 2:
+            last = min(last, max(V, 0))
+        elif n == V + 3 and T - 5 <= V <= T - 2:
+            last = T - 1
+        for k in range(K):
+            num = np.float32(0)
+            for i in range(1, win + 1):
+                a = x[min(max(n - i, 0), last), k]
+                b = x[min(max(n + i, 0), last), k]
+                if a != 0 and b != 0 and a == a and b == b:
+                    num = np.float32(num + np.float32(i) * np.float32(b - a))
+                    norm = np.float32(norm + np.float32(i) * np.float32(i))
+            out[n, k] = np.float32(num / norm) if norm != 0 else np.float32(0)
+    return out
+
+
+def valbased_select(sel, x, threshold, output_val=0.0):
+    sel = np.ascontiguousarray(sel, np.float32).reshape(-1)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros_like(x)
+    lib().osm_or_valbased_select(_fp(sel), _fp(x), C.c_long(x.shape[0]), C.c_int(x.shape[1]), C.c_double(threshold),
+                                 C.c_double(output_val), _fp(out))
+    return out
+
+
+def pitch_jitter(pcm, fe, jc, f0, n_chan=1):
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nS = pcm.size // n_chan
+    f0 = np.ascontiguousarray(f0, np.float32).reshape(-1)
+    L = lib()
+    L.osm_or_pitch_jitter.restype = C.c_long
+    K = L.osm_or_jitter_num_out(C.byref(jc))
+    out = np.zeros((f0.size, K), np.float32)
+    r = L.osm_or_pitch_jitter(C.byref(fe), C.byref(jc), pcm.ctypes.data_as(C.POINTER(C.c_int16)), C.c_long(nS), C.c_int(n_chan),
+                              _fp(f0), C.c_long(f0.size), _fp(out))
+    return out[:r]
+
+
+def delta_segments(x, win, n0=None):
+    x = np.ascontiguousarray(x, np.float32)
+    T, K = x.shape
+    out = np.zeros((T + win, K), np.float32)
+    L = lib()
+    L.osm_or_delta_segments.restype = C.c_long
+    r = L.osm_or_delta_segments(_fp(x), C.c_long(T), C.c_long(T if n0 is None else n0), C.c_int(K), C.c_int(win), _fp(out))
+    return out[:r]
+
+
+def compare16_pitch(pcm, n_chan=1, sample_rate=16000.0, with_lag=False):
+    """The six `nz` columns of ComParE_2016 before smoothing: F0final, voicingFinalUnclipped, jitterLocal,
+    jitterDDP, shimmerLocal, logHNR -> [T, 6]"""
+    fe, sc, ps, vc, jc = compare16_pitch_cfg()
+    fe.sample_rate = sample_rate
+    shs = pitch_shs(pcm, fe, sc, ps, n_chan)
+    vit, lag = viterbi(shs, ps, vc, with_lag=True)
+    e60 = energy(pcm, fe, Energy(0, 1, 0, 0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0), windowed=1, n_chan=n_chan)
+    sel = valbased_select(e60[:, 0], vit, 0.001)
+    jit = pitch_jitter(pcm, fe, jc, sel[:, 0], n_chan)
+    nz = np.concatenate([sel, jit], axis=1)
+    return (nz, lag) if with_lag else nz
+
+
+def compare16_nz_lld(pcm, n_chan=1, sample_rate=16000.0):
+    """ComParE_2016 levels is13_lld_nzsmo [T+1, 6] and is13_lld_nzsmo_de [T+3, 6] (ComParE_2016_core.lld.conf.inc:331-341,392-398)"""
+    nz, lag = compare16_pitch(pcm, n_chan, sample_rate, with_lag=True)
+    sm = sma_nz_lagged(nz, lag, {2, 3, 4, 5})
+    return sm, delta_segments_lagged(sm, lag, 2)

@@ -391,6 +391,36 @@ static long delta_stage(const float *in, long T, long n0, int K, int W, float *o
   return To;
 }
 
+/* cDeltaRegression with onlyInSegments=1 (dspcore/deltaRegression.cpp:123-141, hpp:41-45): a pair
+ * enters the sum only when neither value is 0 / NaN, and the member `norm` (initialised to
+ * 2*sum i^2, :77-79) GROWS by i^2 for every accepted pair and is never reset, in
+ * processing order: frame by frame (one frame per tick), element by element
+ * (core/windowProcessor.cpp:190-212), i = 1..W. */
+long osm_or_delta_segments(const float *in, long T, long n0, int K, int W, float *out)
+{
+  long c0 = n0 - W > 0 ? n0 - W : 0;
+  if (T <= 0) return 0;
+  float norm = 0.0f;
+  for (int i = 1; i <= W; i++) norm += (float)i * (float)i;
+  norm *= 2.0;
+  long To = T + W;
+  for (long t = 0; t < To; t++) {
+    long na = win_navail(t, n0, c0, T);
+    for (int k = 0; k < K; k++) {
+      float num = 0.0f;
+      for (int i = 1; i <= W; i++) {
+        float a = row_win(in, na, K, t, W, t - i)[k], b = row_win(in, na, K, t, W, t + i)[k];
+        if (!(b == 0.0f || b != b || a == 0.0f || a != a)) {
+          num += (float)i * (b - a);
+          norm += (float)i * (float)i;
+        }
+      }
+      out[t * K + k] = norm != 0.0f ? num / norm : 0.0f;
+    }
+  }
+  return To;
+}
+
 /* dspcore/contourSmoother.cpp:84-117: y = x[n]; y += x[n-w]; y += x[n+w] (w = 1..smaWin/2);
  * y /= smaWin  (noZeroSma: zeros are skipped and the divisor is the count) */
 static long sma_stage(const float *in, long T, long n0, int K, int smaWin, int noZeroSma, float *out, long *c0_out)
