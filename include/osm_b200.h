@@ -85,6 +85,11 @@ typedef enum {
   OSM_B200_C_VECTOROPERATION,    /* cVectorOperation    src/other/vectorOperation.cpp:130 (ll1)   */
   OSM_B200_C_FULLINPUTMEAN,      /* cFullinputMean      src/dspcore/fullinputMean.cpp:484-548     */
   OSM_B200_C_INTENSITY,          /* cIntensity          src/lldcore/intensity.cpp:124-146         */
+  OSM_B200_C_SPECSCALE,          /* cSpecScale          src/dsp/specScale.cpp:318-371             */
+  OSM_B200_C_PITCHSHS,           /* cPitchShs           src/lld/pitchShs.cpp:220-358, lldcore/pitchBase.cpp:173-300 */
+  OSM_B200_C_PITCHSMOOTHERVITERBI, /* cPitchSmootherViterbi src/lld/pitchSmootherViterbi.cpp:79-545 */
+  OSM_B200_C_VALBASEDSELECTOR,   /* cValbasedSelector   src/other/valbasedSelector.cpp:130-233    */
+  OSM_B200_C_PITCHJITTER,        /* cPitchJitter        src/lld/pitchJitter.cpp:591-1107          */
   OSM_B200_C_COUNT_
 } osm_b200_component_type;
 
@@ -208,6 +213,53 @@ typedef struct { int32_t mvn, meanNorm /* 0 = amean */, symmSubtract, subtractCl
 
 typedef struct { int32_t intensity, loudness; } osm_b200_intensity;   /* cIntensity: 1, 0 */
 
+/* ---- sub-harmonic-summation pitch chain ---- */
+typedef struct {            /* cSpecScale: scale=octave, sourceScale=lin, interpMethod=spline only */
+  int32_t scaleOctave, sourceLin, splineInterp;  /* 1 when the section selects exactly these (else the plan is rejected) */
+  double  minF, maxF;       /* 25, -1 */
+  int32_t nPointsTarget;    /* 0 = number of magnitude bins */
+  int32_t specSmooth, specEnhance, auditoryWeighting;  /* 0, 0, 0 */
+} osm_b200_specscale;
+
+typedef struct {            /* cPitchShs (cPitchBase options + its own) */
+  double  maxPitch, minPitch;   /* 620, 52 */
+  int32_t nCandidates;      /* 3 */
+  int32_t scores, voicing, F0C1, voicingC1, F0raw, voicingClip;  /* 1,1,0,0,0,0 */
+  double  voicingCutoff;    /* 0.70 */
+  int32_t octaveCorrection; /* 0 */
+  int32_t nHarmonics;       /* 15 */
+  double  compressionFactor;/* 0.85 */
+  int32_t greedyPeakAlgo;   /* 0 */
+  double  lfCut;            /* 0 */
+} osm_b200_pitchshs;
+
+typedef struct {            /* cPitchSmootherViterbi */
+  int32_t bufferLength;     /* 30 */
+  int32_t F0final, F0finalLog, F0finalEnv, F0finalEnvLog, voicingFinalClipped, voicingFinalUnclipped; /* 1,0,0,0,0,0 */
+  int32_t F0raw, voicingC1, voicingClip;  /* 0,0,0 (copies of input fields: not supported when set) */
+  double  wLocal, wTvv, wTvvd, wTvuv, wThr, wRange, wTuu;  /* 2, 10, 5, 10, 4, 1, 0 */
+} osm_b200_pitchsmootherviterbi;
+
+typedef struct {            /* cValbasedSelector: reader.dmLevel = <selector level>;<data level> */
+  double  threshold;        /* 1.0 */
+  int32_t idx, invert, allowEqual, removeIdx, zeroVec, adaptiveThreshold;  /* 0,0,0,0,0,0 */
+  double  outputVal;        /* 0 */
+} osm_b200_valbasedselector;
+
+typedef struct {            /* cPitchJitter: reader.dmLevel = wave level, F0reader.dmLevel = pitch level */
+  char    F0reader_dmLevel[OSM_B200_NAME_LEN];
+  char    F0field[OSM_B200_NAME_LEN];   /* "F0final" */
+  double  searchRangeRel;   /* 0.10 */
+  int32_t jitterLocal, jitterDDP, jitterLocalEnv, jitterDDPEnv;           /* 0,0,0,0 */
+  int32_t shimmerLocal, shimmerLocalDB, shimmerLocalEnv, shimmerLocalDBEnv; /* 0,0,0,0 */
+  int32_t harmonicERMS, noiseERMS, linearHNR, logHNR;                     /* 0,0,0,0 */
+  double  lgHNRfloor;       /* -100 */
+  int32_t shimmerUseRmsAmplitude, minNumPeriods;  /* 0, 2 */
+  double  minCC;            /* 0.5 */
+  int32_t refinedF0, sourceQualityRange, sourceQualityMean;  /* 0,0,0 */
+  int32_t usePeakToPeakPeriodLength, useBrokenJitterThresh, onlyVoiced;  /* 0, 1, 0 */
+} osm_b200_pitchjitter;
+
 /* one `[name:cType]` section */
 typedef struct {
   int32_t type;                                  /* osm_b200_component_type */
@@ -240,6 +292,11 @@ typedef struct {
     osm_b200_vectorconcat vectorconcat;
     osm_b200_fullinputmean fullinputmean;
     osm_b200_intensity intensity;
+    osm_b200_specscale specscale;
+    osm_b200_pitchshs pitchshs;
+    osm_b200_pitchsmootherviterbi pitchsmootherviterbi;
+    osm_b200_valbasedselector valbasedselector;
+    osm_b200_pitchjitter pitchjitter;
   } u;
 } osm_b200_component;
 

@@ -20,7 +20,8 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = range(5)
 # component types (osm_b200_component_type)
 (C_WAVESOURCE, C_FRAMER, C_VECTORPREEMPHASIS, C_WINDOWER, C_TRANSFORMFFT, C_FFTMAGPHASE,
  C_MELSPEC, C_MFCC, C_PLP, C_SPECTRAL, C_ENERGY, C_MZCR, C_ACF, C_PITCHACF,
- C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION, C_FULLINPUTMEAN, C_INTENSITY) = range(20)
+ C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION, C_FULLINPUTMEAN, C_INTENSITY,
+ C_SPECSCALE, C_PITCHSHS, C_PITCHSMOOTHERVITERBI, C_VALBASEDSELECTOR, C_PITCHJITTER) = range(25)
 
 TYPE_BY_NAME = {
     "cWaveSource": C_WAVESOURCE, "cExternalAudioSource": C_WAVESOURCE, "cFramer": C_FRAMER,
@@ -31,6 +32,8 @@ TYPE_BY_NAME = {
     "cDeltaRegression": C_DELTAREGRESSION, "cContourSmoother": C_CONTOURSMOOTHER,
     "cVectorConcat": C_VECTORCONCAT, "cVectorOperation": C_VECTOROPERATION,
     "cFullinputMean": C_FULLINPUTMEAN, "cIntensity": C_INTENSITY,
+    "cSpecScale": C_SPECSCALE, "cPitchShs": C_PITCHSHS, "cPitchSmootherViterbi": C_PITCHSMOOTHERVITERBI,
+    "cValbasedSelector": C_VALBASEDSELECTOR, "cPitchJitter": C_PITCHJITTER,
 }
 
 WIN_BY_NAME = {"rec": 0, "han": 1, "ham": 2, "gau": 3, "sin": 4, "tri": 5, "bar": 6}
@@ -144,6 +147,40 @@ class Intensity(C.Structure):
     _fields_ = [("intensity", i32), ("loudness", i32)]
 
 
+class SpecScale(C.Structure):
+    _fields_ = [("scaleOctave", i32), ("sourceLin", i32), ("splineInterp", i32), ("minF", f64), ("maxF", f64),
+                ("nPointsTarget", i32), ("specSmooth", i32), ("specEnhance", i32), ("auditoryWeighting", i32)]
+
+
+class PitchShs(C.Structure):
+    _fields_ = [("maxPitch", f64), ("minPitch", f64), ("nCandidates", i32), ("scores", i32), ("voicing", i32),
+                ("F0C1", i32), ("voicingC1", i32), ("F0raw", i32), ("voicingClip", i32), ("voicingCutoff", f64),
+                ("octaveCorrection", i32), ("nHarmonics", i32), ("compressionFactor", f64), ("greedyPeakAlgo", i32),
+                ("lfCut", f64)]
+
+
+class PitchSmootherViterbi(C.Structure):
+    _fields_ = [("bufferLength", i32), ("F0final", i32), ("F0finalLog", i32), ("F0finalEnv", i32), ("F0finalEnvLog", i32),
+                ("voicingFinalClipped", i32), ("voicingFinalUnclipped", i32), ("F0raw", i32), ("voicingC1", i32),
+                ("voicingClip", i32), ("wLocal", f64), ("wTvv", f64), ("wTvvd", f64), ("wTvuv", f64), ("wThr", f64),
+                ("wRange", f64), ("wTuu", f64)]
+
+
+class ValbasedSelector(C.Structure):
+    _fields_ = [("threshold", f64), ("idx", i32), ("invert", i32), ("allowEqual", i32), ("removeIdx", i32),
+                ("zeroVec", i32), ("adaptiveThreshold", i32), ("outputVal", f64)]
+
+
+class PitchJitter(C.Structure):
+    _fields_ = [("F0reader_dmLevel", C.c_char * NAME_LEN), ("F0field", C.c_char * NAME_LEN), ("searchRangeRel", f64),
+                ("jitterLocal", i32), ("jitterDDP", i32), ("jitterLocalEnv", i32), ("jitterDDPEnv", i32),
+                ("shimmerLocal", i32), ("shimmerLocalDB", i32), ("shimmerLocalEnv", i32), ("shimmerLocalDBEnv", i32),
+                ("harmonicERMS", i32), ("noiseERMS", i32), ("linearHNR", i32), ("logHNR", i32), ("lgHNRfloor", f64),
+                ("shimmerUseRmsAmplitude", i32), ("minNumPeriods", i32), ("minCC", f64), ("refinedF0", i32),
+                ("sourceQualityRange", i32), ("sourceQualityMean", i32), ("usePeakToPeakPeriodLength", i32),
+                ("useBrokenJitterThresh", i32), ("onlyVoiced", i32)]
+
+
 class _U(C.Union):
     _fields_ = [("wavesource", WaveSource), ("framer", Framer),
                 ("vectorpreemphasis", VectorPreemphasis), ("windower", Windower),
@@ -151,7 +188,9 @@ class _U(C.Union):
                 ("melspec", Melspec), ("mfcc", Mfcc), ("plp", Plp), ("spectral", Spectral),
                 ("energy", Energy), ("mzcr", MZcr), ("acf", Acf), ("pitchacf", PitchACF),
                 ("deltaregression", DeltaRegression), ("contoursmoother", ContourSmoother),
-                ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat), ("fullinputmean", FullinputMean), ("intensity", Intensity)]
+                ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat), ("fullinputmean", FullinputMean), ("intensity", Intensity),
+                ("specscale", SpecScale), ("pitchshs", PitchShs), ("pitchsmootherviterbi", PitchSmootherViterbi),
+                ("valbasedselector", ValbasedSelector), ("pitchjitter", PitchJitter)]
 
 
 class Component(C.Structure):
@@ -169,6 +208,8 @@ UNION_FIELD = {
     C_DELTAREGRESSION: "deltaregression", C_CONTOURSMOOTHER: "contoursmoother",
     C_VECTOROPERATION: "vectoroperation", C_VECTORCONCAT: "vectorconcat",
     C_FULLINPUTMEAN: "fullinputmean", C_INTENSITY: "intensity",
+    C_SPECSCALE: "specscale", C_PITCHSHS: "pitchshs", C_PITCHSMOOTHERVITERBI: "pitchsmootherviterbi",
+    C_VALBASEDSELECTOR: "valbasedselector", C_PITCHJITTER: "pitchjitter",
 }
 
 # every symbol include/osm_b200.h declares (tests assert the library exports all of them)

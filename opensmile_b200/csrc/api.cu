@@ -113,6 +113,14 @@ struct OpRt {
   double *dSharpW = nullptr;
   float2 *dTw = nullptr;
   DevBuf<PitchRaw> dRaw;
+  // SHS pitch chain (SOP_PITCH) / cPitchJitter (SOP_JITTER)
+  ShsParams shs;
+  ViterbiParams vit;
+  JitterParams jit;
+  unsigned char *dPitchTab = nullptr;   // spline / interpolation / harmonic tables of the chain
+  DevBuf<float> dShs;                   // [static rows][nShsCols] cPitchShs level
+  DevBuf<int> dLag;                     // [nUtt] frames of the Viterbi level before the end-of-input flush
+  int descOp = -1;                      // index into PlanDesc::ops
 };
 
 struct osm_b200_plan {
@@ -122,6 +130,9 @@ struct osm_b200_plan {
   std::vector<StreamRt> st;
   std::vector<OpRt> ops;         // standalone ops (not fused into lld_kernel)
   PostParams pp;
+  SeqPostParams sp;              // groups behind a Viterbi-smoothed pitch level (seq_post_kernel)
+  int seqLagOp = -1;             // index into `ops` of the pitch chain whose lag they follow
+  int *dErr = nullptr;           // device flag: a kernel left its supported geometry (checked after run_host)
   bool staticDirect = false;     // static rows are written straight into the output rows
   int identityOutCol = 0;
   bool fused = false;            // delta / delta-delta evaluated inside lld_kernel
@@ -220,6 +231,30 @@ osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
     case OSM_B200_C_CONTOURSMOOTHER: c->u.contoursmoother.smaWin = 3; break;
     case OSM_B200_C_INTENSITY: c->u.intensity.intensity = 1; c->u.intensity.loudness = 0; break;
     case OSM_B200_C_VECTORCONCAT: c->u.vectorconcat.processArrayFields = 1; c->u.vectorconcat.includeSingleElementFields = 0; break;
+    case OSM_B200_C_SPECSCALE: {           // dsp/specScale.cpp:38-62 (scale "log" with logScaleBase 2 == octave)
+      auto &q = c->u.specscale;
+      q.scaleOctave = 1; q.sourceLin = 1; q.splineInterp = 1; q.minF = 25.0; q.maxF = -1.0;
+      break;
+    }
+    case OSM_B200_C_PITCHSHS: {            // lldcore/pitchBase.cpp:41-62, lld/pitchShs.cpp:56-64
+      auto &q = c->u.pitchshs;
+      q.maxPitch = 620.0; q.minPitch = 52.0; q.nCandidates = 3; q.scores = 1; q.voicing = 1; q.voicingCutoff = 0.70;
+      q.nHarmonics = 15; q.compressionFactor = 0.85;
+      break;
+    }
+    case OSM_B200_C_PITCHSMOOTHERVITERBI: { // lld/pitchSmootherViterbi.cpp:45-68
+      auto &q = c->u.pitchsmootherviterbi;
+      q.bufferLength = 30; q.F0final = 1; q.wLocal = 2.0; q.wTvv = 10.0; q.wTvvd = 5.0; q.wTvuv = 10.0; q.wThr = 4.0;
+      q.wRange = 1.0; q.wTuu = 0.0;
+      break;
+    }
+    case OSM_B200_C_VALBASEDSELECTOR: c->u.valbasedselector.threshold = 1.0; break;   // other/valbasedSelector.cpp:35-49
+    case OSM_B200_C_PITCHJITTER: {         // lld/pitchJitter.cpp:45-78
+      auto &q = c->u.pitchjitter;
+      snprintf(q.F0field, sizeof q.F0field, "%s", "F0final");
+      q.searchRangeRel = 0.10; q.lgHNRfloor = -100.0; q.minNumPeriods = 2; q.minCC = 0.5; q.useBrokenJitterThresh = 1;
+      break;
+    }
     default: break;
   }
   return OSM_B200_OK;
@@ -491,8 +526,25 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
   if (simple)
     for (const auto &g : d.groups)
       if (g.stages.empty() && g.srcCol == 0 && g.n == d.nStatic) { pl->staticDirect = true; pl->identityOutCol = g.outCol; break; }
+  memset(&pl->sp, 0, sizeof pl->sp);
+  int seqLagDescOp = -1;
   for (const auto &g : d.groups) {
     if (g.stages.empty() && pl->staticDirect && g.srcCol == 0 && g.n == d.nStatic && g.outCol == pl->identityOutCol) continue;
+    if (g.lagKind != 0 && !g.stages.empty()) {
+      SeqPostParams &sq = pl->sp;
+      if (sq.nGroups >= kMaxSeqGroups) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many output groups behind the pitch chain"); }
+      if (seqLagDescOp >= 0 && seqLagDescOp != g.lagOp) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "more than one SHS pitch chain per graph is not supported"); }
+      seqLagDescOp = g.lagOp;
+      SeqGroup &G = sq.groups[sq.nGroups++];
+      G.srcCol = g.srcCol; G.n = g.n; G.outCol = g.outCol; G.lagKind = g.lagKind; G.nStages = (int)g.stages.size();
+      G.noZero = g.stages[0].flags & 1;
+      G.deltaWin = g.stages.size() > 1 ? g.stages[1].win : 0;
+      G.segId = g.segId;
+      if (G.nStages == 2 && G.deltaWin != 2) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cDeltaRegression(onlyInSegments) behind the pitch chain: deltawin must be 2"); }
+      if (G.segId >= kMaxSeqGroups) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many onlyInSegments delta components"); }
+      sq.frameSize = d.streams[g.stream].fe.frameSize; sq.frameStep = d.streams[g.stream].fe.frameStep;
+      continue;
+    }
     if (pp.nGroups >= kMaxPostGroups) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many output groups"); }
     PostGroup &pg = pp.groups[pp.nGroups++];
     pg.srcCol = g.srcCol; pg.n = g.n; pg.outCol = g.outCol; pg.nStages = (int)g.stages.size();
@@ -547,7 +599,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     const StaticOp &op = d.ops[oi];
     if (op.kind == SOP_MFCC || op.kind == SOP_PLP) continue;      // fused into its stream's lld_kernel
     OpRt rt;
-    rt.kind = op.kind; rt.stream = op.stream;
+    rt.kind = op.kind; rt.stream = op.stream; rt.descOp = (int)oi;
     if (op.kind == SOP_MAG) {
       pl->st[op.stream].needTiles = true;
       rt.vN = d.streams[op.stream].fe.nBins; rt.vOutCol = op.outCol;
@@ -586,6 +638,69 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       CUP(cudaMalloc(&rt.dSharpW, so.sharpW.size() * sizeof(double)));
       CUP(cudaMemcpy(rt.dSharpW, so.sharpW.data(), so.sharpW.size() * sizeof(double), cudaMemcpyHostToDevice));
       sp.sharpW = rt.dSharpW;
+    } else if (op.kind == SOP_PITCH) {
+      const PitchChainOp &pc = op.chain;
+      // one blob: fwdA | fwdP6 | r1 | r2 | bwdD (double[nMag]) | ia | ic | id | audW (double[nPts]) | ik (int[nPts]) | shift (int) | hscale (float)
+      const size_t nM = (size_t)pc.nMag, nP = (size_t)pc.nPts, nH = pc.shift.size();
+      std::vector<unsigned char> blob((5 * nM + 4 * nP) * sizeof(double) + nP * sizeof(int) + nH * (sizeof(int) + sizeof(float)) + 64);
+      double *bd = reinterpret_cast<double *>(blob.data());
+      memcpy(bd, pc.fwdA.data(), nM * 8); memcpy(bd + nM, pc.fwdP6.data(), nM * 8); memcpy(bd + 2 * nM, pc.r1.data(), nM * 8);
+      memcpy(bd + 3 * nM, pc.r2.data(), nM * 8); memcpy(bd + 4 * nM, pc.bwdD.data(), nM * 8);
+      double *bp = bd + 5 * nM;
+      memcpy(bp, pc.ia.data(), nP * 8); memcpy(bp + nP, pc.ic.data(), nP * 8); memcpy(bp + 2 * nP, pc.id.data(), nP * 8);
+      if (!pc.audW.empty()) memcpy(bp + 3 * nP, pc.audW.data(), nP * 8);
+      int *bi = reinterpret_cast<int *>(bp + 4 * nP);
+      memcpy(bi, pc.ik.data(), nP * sizeof(int));
+      memcpy(bi + nP, pc.shift.data(), nH * sizeof(int));
+      memcpy(bi + nP + nH, pc.hscale.data(), nH * sizeof(float));
+      CUP(cudaMalloc(&rt.dPitchTab, blob.size()));
+      CUP(cudaMemcpy(rt.dPitchTab, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+      const double *dd = reinterpret_cast<const double *>(rt.dPitchTab);
+      ShsParams &sh = rt.shs;
+      memset(&sh, 0, sizeof sh);
+      sh.F = srt.tileF; sh.nShsCols = pc.nShsCols; sh.nMag = pc.nMag; sh.nPts = pc.nPts; sh.blk = (pc.nMag + 31) / 32;
+      sh.enhance = pc.enhance; sh.smooth = pc.smooth; sh.hasAudW = !pc.audW.empty();
+      sh.fwdA = dd; sh.fwdP6 = dd + nM; sh.r1 = dd + 2 * nM; sh.r2 = dd + 3 * nM; sh.bwdD = dd + 4 * nM;
+      const double *dp = dd + 5 * nM;
+      sh.ia = dp; sh.ic = dp + nP; sh.id = dp + 2 * nP; sh.audW = dp + 3 * nP;
+      const int *di = reinterpret_cast<const int *>(dp + 4 * nP);
+      sh.ik = di; sh.shift = di + nP; sh.hscale = reinterpret_cast<const float *>(di + nP + nH);
+      sh.nCand = pc.nCand; sh.nHarm = pc.nHarm; sh.Fmint = pc.Fmint; sh.Fstept = pc.Fstept; sh.logBase = pc.logBase;
+      sh.maxPitch = pc.maxPitch; sh.minPitch = pc.minPitch; sh.voicingCutoff = pc.voicingCutoff; sh.lfCutBin = pc.lfCutBin;
+      sh.greedy = pc.greedy; sh.octaveCorr = pc.octaveCorr; sh.scores = pc.scores; sh.voicing = pc.voicing; sh.F0C1 = pc.F0C1;
+      sh.voicingC1 = pc.voicingC1; sh.F0raw = pc.F0raw; sh.voicingClip = pc.voicingClip;
+      if ((size_t)8 * ((size_t)2 * (pc.nMag + 2) * sizeof(double) + (size_t)2 * pc.nPts * sizeof(float) + 128) > (size_t)prop.sharedMemPerBlockOptin) {
+        osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cSpecScale: spectrum too long for the SHS kernel's workspace");
+      }
+      ViterbiParams &vp = rt.vit;
+      memset(&vp, 0, sizeof vp);
+      vp.nShsCols = pc.nShsCols; vp.nCand = pc.nCand; vp.frameSize = fe.frameSize; vp.frameStep = fe.frameStep;
+      vp.statStride = d.nStatic; vp.outCol = op.outCol; vp.bufLen = pc.bufLen;
+      vp.oF0final = pc.oF0final; vp.oF0finalLog = pc.oF0finalLog; vp.oF0finalEnv = pc.oF0finalEnv; vp.oF0finalEnvLog = pc.oF0finalEnvLog;
+      vp.oVClipped = pc.oVClipped; vp.oVUnclipped = pc.oVUnclipped;
+      vp.wLocal = pc.wLocal; vp.wTvv = pc.wTvv; vp.wTvvd = pc.wTvvd; vp.wTvuv = pc.wTvuv; vp.wThr = pc.wThr; vp.wRange = pc.wRange; vp.wTuu = pc.wTuu;
+      vp.voiceThresh = pc.voicingCutoff;                       // level meta data of cPitchShs (lldcore/pitchBase.cpp:150-153)
+      vp.hasSel = pc.hasSel; vp.selCol = pc.hasSel ? d.ops[pc.selOp].outCol : 0; vp.selInvert = pc.selInvert; vp.selAllowEqual = pc.selAllowEqual;
+      vp.selThreshold = pc.selThreshold; vp.selOutputVal = pc.selOutputVal;
+      if (pc.nCand + 1 > 9) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cPitchShs.nCandidates > 8 is not supported"); }
+    } else if (op.kind == SOP_JITTER) {
+      const JitterOp &jo = op.jitter;
+      JitterParams &jp = rt.jit;
+      memset(&jp, 0, sizeof jp);
+      jp.nChan = fe.nChan; jp.frameSize = fe.frameSize; jp.frameStep = fe.frameStep;
+      jp.Ts = 1.0 / fe.sampleRate;                               // period of the wave level
+      jp.pitchT = fe.frameStepSec;                               // period of the F0 level (core/winToVecProcessor.cpp:563)
+      jp.statStride = d.nStatic; jp.f0Col = d.ops[jo.pitchOp].outCol + jo.f0Col; jp.outCol = op.outCol;
+      jp.searchRangeRel = jo.searchRangeRel; jp.lgHNRfloor = (float)jo.lgHNRfloor; jp.minNumPeriods = jo.minNumPeriods;
+      float thr = (float)jo.minCC;                               // lld/pitchJitter.cpp:150-158
+      if (thr < 0.01f) thr = 0.01f;
+      if (thr > 0.99f) thr = 0.99f;
+      jp.threshCC = thr;
+      jp.jitterLocal = jo.jitterLocal; jp.jitterDDP = jo.jitterDDP; jp.jitterLocalEnv = jo.jitterLocalEnv; jp.jitterDDPEnv = jo.jitterDDPEnv;
+      jp.shimmerLocal = jo.shimmerLocal; jp.shimmerLocalDB = jo.shimmerLocalDB; jp.shimmerLocalEnv = jo.shimmerLocalEnv;
+      jp.shimmerLocalDBEnv = jo.shimmerLocalDBEnv; jp.harmonicERMS = jo.harmonicERMS; jp.noiseERMS = jo.noiseERMS; jp.linearHNR = jo.linearHNR;
+      jp.logHNR = jo.logHNR; jp.shimmerUseRms = jo.shimmerUseRms; jp.refinedF0 = jo.refinedF0; jp.srcQualRange = jo.srcQualRange;
+      jp.srcQualMean = jo.srcQualMean; jp.peakToPeak = jo.peakToPeak; jp.brokenThresh = jo.brokenThresh;
     } else if (op.kind == SOP_PITCHACF) {
       if (!acf_pitch_supported_fft(fe.nfft)) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cAcf / cPitchACF: FFT size must be 512, 1024 or 2048"); }
       const PitchAcfOp &po = op.pitch;
@@ -628,6 +743,10 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     pl->ops.push_back(rt);
   }
 
+  CUP(cudaMalloc(&pl->dErr, sizeof(int)));
+  CUP(cudaMemset(pl->dErr, 0, sizeof(int)));
+  if (seqLagDescOp >= 0)
+    for (size_t i = 0; i < pl->ops.size(); i++) if (pl->ops[i].descOp == seqLagDescOp) pl->seqLagOp = (int)i;
   CUP(cudaEventCreateWithFlags(&pl->evMetaDone, cudaEventDisableTiming));
   CUP(cudaEventCreate(&pl->evK0));
   CUP(cudaEventCreate(&pl->evK1));
@@ -654,7 +773,8 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
     for (PassRt &pr : s.extra) { if (pr.dConst) cudaFree(pr.dConst); pr.dBand.release(); }
     s.hChunks.release(); s.dChunks.release(); s.hTiles.release(); s.dTiles.release(); s.dMag.release();
   }
-  for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); }
+  for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); if (o.dPitchTab) cudaFree(o.dPitchTab); o.dShs.release(); o.dLag.release(); }
+  if (pl->dErr) cudaFree(pl->dErr);
   pl->hMeta.release(); pl->dMeta.release(); pl->hPost.release(); pl->dPost.release(); pl->dStat.release(); pl->dMeans.release();
   pl->dPcm.release(); pl->dOut.release();
   if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
@@ -867,6 +987,23 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       sp.tiles = rt.dTiles.p + t0; sp.nTiles = t1 - t0;
       sp.statOff = dS; sp.stat = pl->dStat.p;
       CU(launch_spectral(sp, st));
+    } else if (o.kind == SOP_PITCH) {
+      ShsParams sh = o.shs;
+      CU(o.dShs.reserve((size_t)pl->totalStat * sh.nShsCols + 64));
+      CU(o.dLag.reserve((size_t)n_utt + 64));
+      sh.mag = rt.dMag.p + (size_t)t0 * sh.nMag * sh.F;
+      sh.tiles = rt.dTiles.p + t0; sh.nTiles = t1 - t0;
+      sh.statOff = dS; sh.shs = o.dShs.p;
+      CU(launch_shs(sh, st));
+      ViterbiParams vp = o.vit;
+      vp.shs = o.dShs.p; vp.uttOff = dU; vp.statOff = dS; vp.stat = pl->dStat.p; vp.lag = o.dLag.p;
+      CU(launch_viterbi(vp, u0, u1, st));
+      pl->lastLaunches++;
+    } else if (o.kind == SOP_JITTER) {
+      JitterParams jp = o.jit;
+      jp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
+      jp.uttOff = dU; jp.statOff = dS; jp.stat = pl->dStat.p; jp.errFlag = pl->dErr;
+      CU(launch_jitter(jp, u0, u1, st));
     } else if (o.kind == SOP_PITCHACF) {
       AcfPitchParams ap = o.ap;
       CU(o.dRaw.reserve((size_t)pl->totalStat + 64));
@@ -904,6 +1041,14 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       CU(launch_post(pp, st));
       pl->lastLaunches++;
     }
+  }
+  // 4. levels behind the Viterbi-smoothed pitch chain
+  if (pl->sp.nGroups > 0 && pl->seqLagOp >= 0) {
+    SeqPostParams sq = pl->sp;
+    sq.stat = pl->dStat.p; sq.statStride = d.nStatic; sq.statOff = dS; sq.rowOff = dR; sq.uttOff = dU;
+    sq.out = d_out; sq.outStride = d.nOut; sq.lag = pl->ops[pl->seqLagOp].dLag.p;
+    CU(launch_seq_post(sq, u0, u1, st));
+    pl->lastLaunches++;
   }
   return OSM_B200_OK;
 }
@@ -996,6 +1141,14 @@ osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const
   pl->timed = true;
   CU(cudaStreamSynchronize(pl->d2hStream));
   CU(cudaStreamSynchronize(st));
+  if (pl->dErr && pl->sp.nGroups + (int)pl->ops.size() > 0) {
+    int flag = 0;
+    CU(cudaMemcpy(&flag, pl->dErr, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) {
+      CU(cudaMemset(pl->dErr, 0, sizeof(int)));
+      return fail(OSM_B200_ERR_UNSUPPORTED, "cPitchJitter: a frame left the supported geometry (F0 period / read window too long for the kernel's workspace, or a read past the end of the utterance); its rows were zeroed");
+    }
+  }
   return OSM_B200_OK;
 }
 

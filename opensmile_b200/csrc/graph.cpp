@@ -34,7 +34,8 @@ const char *type_name(int t)
   static const char *names[] = {"cWaveSource", "cFramer", "cVectorPreemphasis", "cWindower",
     "cTransformFFT", "cFFTmagphase", "cMelspec", "cMfcc", "cPlp", "cSpectral", "cEnergy",
     "cMZcr", "cAcf", "cPitchACF", "cDeltaRegression", "cContourSmoother", "cVectorConcat",
-    "cVectorOperation", "cFullinputMean", "cIntensity"};
+    "cVectorOperation", "cFullinputMean", "cIntensity", "cSpecScale", "cPitchShs", "cPitchSmootherViterbi",
+    "cValbasedSelector", "cPitchJitter"};
   return (t >= 0 && t < OSM_B200_C_COUNT_) ? names[t] : "?";
 }
 
@@ -466,6 +467,102 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         const std::string inName = c->u.vectoroperation.nameBase[0] ? std::string(c->u.vectoroperation.nameBase) : d.ops[src].fields[0].name;
         fn.name = name_append_auto(named, inName, nullptr);
         op.fields.push_back(fn);
+      } else if (c->type == OSM_B200_C_VALBASEDSELECTOR || c->type == OSM_B200_C_PITCHSMOOTHERVITERBI) {
+        // [cValbasedSelector <-] cPitchSmootherViterbi <- cPitchShs <- cSpecScale <- cFFTmagphase chain
+        const osm_b200_component *vit = c, *selSrc = nullptr;
+        if (c->type == OSM_B200_C_VALBASEDSELECTOR) {
+          const auto &q = c->u.valbasedselector;
+          if (c->n_inputs != 2) { err = "cValbasedSelector must read two levels: selector;data"; return OSM_B200_ERR_UNSUPPORTED; }
+          if (q.idx != 0 || !q.removeIdx || !q.zeroVec || q.adaptiveThreshold) { err = "cValbasedSelector: only idx=0, removeIdx=1, zeroVec=1, adaptiveThreshold=0 are supported"; return OSM_B200_ERR_UNSUPPORTED; }
+          selSrc = R.prod(c->reader_dmLevel[0]);
+          vit = R.prod(c->reader_dmLevel[1]);
+          if (!selSrc || !vit || vit->type != OSM_B200_C_PITCHSMOOTHERVITERBI) { err = "cValbasedSelector: the data level must come from cPitchSmootherViterbi"; return OSM_B200_ERR_UNSUPPORTED; }
+        }
+        const osm_b200_component *shs = single_input(vit);
+        if (!shs || shs->type != OSM_B200_C_PITCHSHS) { err = "cPitchSmootherViterbi must read a cPitchShs level"; return OSM_B200_ERR_UNSUPPORTED; }
+        const osm_b200_component *scl = single_input(shs);
+        if (!scl || scl->type != OSM_B200_C_SPECSCALE) { err = "cPitchShs must read a cSpecScale level"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (!resolve_mag_chain(single_input(scl), ci)) return OSM_B200_ERR_UNSUPPORTED;
+        int selOp = -1;
+        if (selSrc) {
+          osm_b200_status s3 = get_op(selSrc, selOp);                   // e.g. cEnergy (rms) on the same frames
+          if (s3 != OSM_B200_OK) return s3;
+          if (d.ops[selOp].nOut != 1) { err = "cValbasedSelector: the selector level must hold exactly one element"; return OSM_B200_ERR_UNSUPPORTED; }
+        }
+        osm_b200_status s2 = get_stream(ci, true, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        const FrontEnd &fe = d.streams[op.stream].fe;
+        if (selOp >= 0) {
+          const FrontEnd &fs = d.streams[d.ops[selOp].stream].fe;
+          if (fs.frameSize != fe.frameSize || fs.frameStep != fe.frameStep) { err = "cValbasedSelector: selector and data levels must share the frame geometry"; return OSM_B200_ERR_UNSUPPORTED; }
+        }
+        op.kind = SOP_PITCH;
+        if (!build_pitch_chain(scl->u.specscale, shs->u.pitchshs, vit->u.pitchsmootherviterbi, fe.nBins, fe.fftFrameSizeSec, op.chain, err))
+          return OSM_B200_ERR_UNSUPPORTED;
+        PitchChainOp &pc = op.chain;
+        if (selOp >= 0) {
+          const auto &q = c->u.valbasedselector;
+          pc.hasSel = true; pc.selOp = selOp; pc.selThreshold = (float)q.threshold; pc.selOutputVal = (float)q.outputVal;
+          pc.selInvert = q.invert != 0; pc.selAllowEqual = q.allowEqual != 0;
+        }
+        op.nOut = pc.nOut;
+        // field names: lld/pitchSmootherViterbi.cpp:297-316; the selector keeps them (valbasedSelector.cpp:105-118)
+        auto add = [&](const char *nm) {
+          FieldName f; f.name = nm;
+          if (c->type == OSM_B200_C_VALBASEDSELECTOR) f.name = name_append_auto(*c, f.name, nullptr);
+          op.fields.push_back(f);
+        };
+        if (pc.oF0final) add("F0final");
+        if (pc.oF0finalLog) add("F0finalLog");
+        if (pc.oF0finalEnv) add("F0finEnv");
+        if (pc.oF0finalEnvLog) add("F0finEnvLog");
+        if (pc.oVClipped) add("voicingFinalClipped");
+        if (pc.oVUnclipped) add("voicingFinalUnclipped");
+      } else if (c->type == OSM_B200_C_PITCHJITTER) {
+        const auto &q = c->u.pitchjitter;
+        const osm_b200_component *wv = single_input(c);
+        if (!wv || wv->type != OSM_B200_C_WAVESOURCE) { err = "cPitchJitter must read the cWaveSource level"; return OSM_B200_ERR_UNSUPPORTED; }
+        const osm_b200_component *f0c = R.prod(q.F0reader_dmLevel);
+        if (!f0c) { err = "cPitchJitter: F0reader.dmLevel has no writer"; return OSM_B200_ERR_INVALID; }
+        int pOp = -1;
+        osm_b200_status s2 = get_op(f0c, pOp);
+        if (s2 != OSM_B200_OK) return s2;
+        if (d.ops[pOp].kind != SOP_PITCH) { err = "cPitchJitter: the F0 level must come from cPitchSmootherViterbi (optionally through cValbasedSelector)"; return OSM_B200_ERR_UNSUPPORTED; }
+        op.kind = SOP_JITTER;
+        op.stream = d.ops[pOp].stream;
+        JitterOp &jo = op.jitter;
+        jo.pitchOp = pOp; jo.f0Col = 0;                                   // lld/pitchJitter.cpp:271-280: unknown field -> element 0
+        { int col = 0; for (const auto &f : d.ops[pOp].fields) { if (f.name == q.F0field) { jo.f0Col = col; break; } col += f.n; } }
+        jo.searchRangeRel = q.searchRangeRel; jo.lgHNRfloor = q.lgHNRfloor;
+        jo.minNumPeriods = q.minNumPeriods < 2 ? 2 : q.minNumPeriods;      // :145-149
+        jo.minCC = q.minCC;
+        jo.jitterLocal = q.jitterLocal != 0; jo.jitterDDP = q.jitterDDP != 0; jo.jitterLocalEnv = q.jitterLocalEnv != 0; jo.jitterDDPEnv = q.jitterDDPEnv != 0;
+        jo.shimmerLocal = q.shimmerLocal != 0; jo.shimmerLocalDB = q.shimmerLocalDB != 0; jo.shimmerLocalEnv = q.shimmerLocalEnv != 0;
+        jo.shimmerLocalDBEnv = q.shimmerLocalDBEnv != 0; jo.harmonicERMS = q.harmonicERMS != 0; jo.noiseERMS = q.noiseERMS != 0;
+        jo.linearHNR = q.linearHNR != 0; jo.logHNR = q.logHNR != 0; jo.shimmerUseRms = q.shimmerUseRmsAmplitude != 0;
+        jo.refinedF0 = q.refinedF0 != 0; jo.srcQualRange = q.sourceQualityRange != 0; jo.srcQualMean = q.sourceQualityMean != 0;
+        jo.peakToPeak = q.usePeakToPeakPeriodLength != 0; jo.brokenThresh = q.useBrokenJitterThresh != 0;
+        if (q.onlyVoiced) { err = "cPitchJitter.onlyVoiced=1 (variable frame count) is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (wv->u.wavesource.nChannels > 1 && !wv->u.wavesource.monoMixdown) { err = "cPitchJitter needs mono input"; return OSM_B200_ERR_UNSUPPORTED; }
+        auto add = [&](const std::string &nm) { FieldName f; f.name = nm; op.fields.push_back(f); };   // :283-312
+        if (jo.jitterLocal) add("jitterLocal");
+        if (jo.jitterDDP) add("jitterDDP");
+        if (jo.jitterLocalEnv) add("jitterLocEnv");
+        if (jo.jitterDDPEnv) add("jitterDEnv");
+        if (jo.shimmerLocal) add("shimmerLocal");
+        if (jo.shimmerLocalDB) add("shimmerLocalDB");
+        if (jo.shimmerLocalEnv) add("shimmerLocEnv");
+        if (jo.shimmerLocalDBEnv) add("shimmerLocDBEnv");
+        if (jo.harmonicERMS) add("harmonicERMS");
+        if (jo.noiseERMS) add("noiseERMS");
+        if (jo.linearHNR) add("linearHNR");
+        if (jo.logHNR) add("logHNR");
+        if (jo.refinedF0) add(q.F0field[0] ? q.F0field : "F0final");
+        if (jo.srcQualMean) add("sourceQualityMean");
+        if (jo.srcQualRange) add("sourceQualityRange");
+        jo.nOut = (int)op.fields.size();
+        op.nOut = jo.nOut;
+        if (op.nOut < 1) { err = "cPitchJitter produces no output"; return OSM_B200_ERR_INVALID; }
       } else {
         snprintf(buf, sizeof buf, "component '%s' (%s) is not a supported static LLD producer", c->name, type_name(c->type));
         err = buf; return OSM_B200_ERR_UNSUPPORTED;
@@ -479,6 +576,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     return OSM_B200_OK;
   };
 
+  std::vector<const osm_b200_component *> segComps;     // cDeltaRegression instances with onlyInSegments=1
   for (const Leaf &leaf : leaves) {
     const osm_b200_component *c = leaf.c;
     const std::vector<const osm_b200_component *> &stageComps = leaf.stages;
@@ -491,15 +589,21 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     // ---- groups: one per run of consecutive fields that survive the concat's field selection ----
     std::vector<Stage> stages;
     std::vector<FieldName> fields = d.ops[opIdx].fields;
+    int segId = -1;
     for (const osm_b200_component *s : stageComps) {
       Stage st;
       if (s->type == OSM_B200_C_DELTAREGRESSION) {
         const auto &p = s->u.deltaregression;
-        if (p.absOutput || p.halfWaveRect || p.onlyInSegments || p.relativeDelta) {
-          err = "cDeltaRegression: absOutput/halfWaveRect/onlyInSegments/relativeDelta are not supported"; return OSM_B200_ERR_UNSUPPORTED;
+        if (p.absOutput || p.halfWaveRect || p.relativeDelta) {
+          err = "cDeltaRegression: absOutput/halfWaveRect/relativeDelta are not supported"; return OSM_B200_ERR_UNSUPPORTED;
         }
         if (p.deltawin < 1 || p.deltawin > 8) { err = "cDeltaRegression.deltawin must be 1..8"; return OSM_B200_ERR_UNSUPPORTED; }
-        st = Stage{ST_DELTA, p.deltawin, 0};
+        st = Stage{ST_DELTA, p.deltawin, p.onlyInSegments ? 1 : 0};
+        if (p.onlyInSegments) {
+          segId = -1;
+          for (size_t q = 0; q < segComps.size(); q++) if (segComps[q] == s) segId = (int)q;
+          if (segId < 0) { segComps.push_back(s); segId = (int)segComps.size() - 1; }
+        }
       } else if (s->type == OSM_B200_C_FULLINPUTMEAN) {
         // dspcore/fullinputMean.cpp:484-548 (single EOI loop): all frames are read before EOI, the
         // arithmetic mean is subtracted from every frame at EOI -> same number of frames, and the
@@ -528,6 +632,9 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         if (!open) {
           OutGroup g;
           g.srcCol = col; g.n = 0; g.stream = d.ops[opIdx].stream; g.outCol = d.nOut; g.stages = stages;
+          if (d.ops[opIdx].kind == SOP_PITCH) { g.lagKind = 1; g.lagOp = opIdx; }
+          if (d.ops[opIdx].kind == SOP_JITTER) { g.lagKind = 2; g.lagOp = d.ops[opIdx].jitter.pitchOp; }
+          g.segId = segId;
           d.groups.push_back(g);
           open = true;
         }
@@ -582,6 +689,20 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         }
   }
 
+  // ---- groups behind a Viterbi-smoothed pitch level (seq_post_kernel) ----
+  // Supported shapes (the ones the shipped feature sets use): [cContourSmoother(3)] and
+  // [cContourSmoother(3), cDeltaRegression(onlyInSegments)], no truncating concat in between.
+  for (const OutGroup &g : d.groups) {
+    const bool seg = g.segId >= 0;
+    if (!seg && g.lagKind == 0) continue;
+    if (g.lagKind == 0) { err = "cDeltaRegression.onlyInSegments=1 is only supported behind the SHS pitch chain (cPitchSmootherViterbi / cPitchJitter levels)"; return OSM_B200_ERR_UNSUPPORTED; }
+    const size_t ns = g.stages.size();
+    bool ok = ns >= 1 && ns <= 2 && g.stages[0].kind == ST_SMA && g.stages[0].win == 1;
+    if (ok && ns == 2) ok = g.stages[1].kind == ST_DELTA && (g.stages[1].flags & 1) && g.stages[1].win >= 1 && g.stages[1].win <= 4;
+    if (!ok) { err = "levels behind cPitchSmootherViterbi / cPitchJitter support cContourSmoother(smaWin=3) optionally followed by cDeltaRegression(onlyInSegments=1) only"; return OSM_B200_ERR_UNSUPPORTED; }
+    if (!g.limitStreams.empty()) { err = "a truncating concat below the temporal stages of a pitch level is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+  }
+
   // ---- execution strategy per stream ----
   // A stream with exactly one band op (MFCC / PLP) and no other spectral consumer evaluates it
   // inside lld_kernel; any other spectral consumer reads the magnitude level from HBM.
@@ -591,7 +712,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     for (size_t o = 0; o < d.ops.size(); o++) {
       if (d.ops[o].stream != (int)s) continue;
       if (d.ops[o].kind == SOP_MFCC || d.ops[o].kind == SOP_PLP) d.streams[s].bandOps.push_back((int)o);
-      if (d.ops[o].kind == SOP_SPECTRAL || d.ops[o].kind == SOP_PITCHACF || d.ops[o].kind == SOP_MAG) nSpec++;
+      if (d.ops[o].kind == SOP_SPECTRAL || d.ops[o].kind == SOP_PITCHACF || d.ops[o].kind == SOP_MAG || d.ops[o].kind == SOP_PITCH) nSpec++;
     }
     const int nBand = (int)d.streams[s].bandOps.size();
     d.streams[s].fusedOp = nBand ? d.streams[s].bandOps[0] : -1;

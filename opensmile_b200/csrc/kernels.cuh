@@ -207,4 +207,66 @@ cudaError_t launch_energy(const TimeOpParams &p, cudaStream_t st);
 cudaError_t launch_mzcr(const TimeOpParams &p, cudaStream_t st);
 cudaError_t launch_intensity(const TimeOpParams &p, cudaStream_t st);
 
+// ------------------------------------------------------------------------------------------
+// SHS pitch chain (pitch.cu): cSpecScale + cPitchShs per frame (one warp per frame), cPitchSmootherViterbi
+// [+ cValbasedSelector] per utterance (one thread), cPitchJitter per utterance (one warp), and the temporal
+// stages of the levels behind them (one thread per utterance, seq_post_kernel).
+// ------------------------------------------------------------------------------------------
+struct ShsParams {
+  const float *mag;              // tile-major magnitude level [tile][nMag][F]
+  const OpTile *tiles; int nTiles; int F;
+  const long long *statOff;      // static row offsets
+  float *shs; int nShsCols;      // [static rows][nShsCols] cPitchShs level
+  int nMag, nPts, blk;           // blk = ceil(nMag / 32)
+  int enhance, smooth, hasAudW;
+  const double *fwdA, *fwdP6, *r1, *r2, *bwdD;   // [nMag]
+  const int *ik; const double *ia, *ic, *id;     // [nPts]
+  const double *audW;                            // [nPts]
+  int nCand, nHarm;
+  const int *shift; const float *hscale;         // [nHarm-1]
+  float Fmint, Fstept; double logBase, maxPitch, minPitch; float voicingCutoff;
+  int lfCutBin, greedy, octaveCorr, scores, voicing, F0C1, voicingC1, F0raw, voicingClip;
+};
+cudaError_t launch_shs(const ShsParams &p, cudaStream_t st);
+
+struct ViterbiParams {
+  const float *shs; int nShsCols, nCand;
+  const long long *uttOff, *statOff;
+  int frameSize, frameStep;
+  float *stat; int statStride, outCol;
+  int *lag;                      // [nUtt] frames the level holds before the end-of-input flush
+  int bufLen;
+  int oF0final, oF0finalLog, oF0finalEnv, oF0finalEnvLog, oVClipped, oVUnclipped;
+  double wLocal, wTvv, wTvvd, wTvuv, wThr, wRange, wTuu;
+  float voiceThresh;
+  int hasSel, selCol, selInvert, selAllowEqual; float selThreshold, selOutputVal;
+};
+cudaError_t launch_viterbi(const ViterbiParams &p, int u0, int u1, cudaStream_t st);
+
+struct JitterParams {
+  const int16_t *pcm; int nChan;
+  const long long *uttOff, *statOff;
+  int frameSize, frameStep;
+  double Ts, pitchT;             // wave sample period, period of the F0 level
+  float *stat; int statStride, f0Col, outCol;
+  double searchRangeRel; float threshCC, lgHNRfloor; int minNumPeriods;
+  int jitterLocal, jitterDDP, jitterLocalEnv, jitterDDPEnv, shimmerLocal, shimmerLocalDB, shimmerLocalEnv, shimmerLocalDBEnv,
+      harmonicERMS, noiseERMS, linearHNR, logHNR, shimmerUseRms, refinedF0, srcQualRange, srcQualMean, peakToPeak, brokenThresh;
+  int *errFlag;                  // set when a frame exceeds the kernel's workspace (reported by the host)
+};
+cudaError_t launch_jitter(const JitterParams &p, int u0, int u1, cudaStream_t st);
+
+struct SeqGroup { int srcCol, n, outCol, lagKind, nStages, deltaWin, noZero, segId; };
+constexpr int kMaxSeqGroups = 8;
+struct SeqPostParams {
+  const float *stat; int statStride;
+  const long long *statOff, *rowOff, *uttOff;
+  float *out; int outStride;
+  const int *lag;
+  int frameSize, frameStep;
+  int nGroups;
+  SeqGroup groups[kMaxSeqGroups];
+};
+cudaError_t launch_seq_post(const SeqPostParams &p, int u0, int u1, cudaStream_t st);
+
 }  // namespace osm

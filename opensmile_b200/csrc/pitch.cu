@@ -1,0 +1,830 @@
+// pitch.cu -- the sub-harmonic-summation pitch chain of the ComParE / GeMAPS graphs, sm_100a:
+//   shs_kernel       cSpecScale + cPitchShs (+ cPitchBase output logic), one WARP per frame
+//   viterbi_kernel   cPitchSmootherViterbi [+ cValbasedSelector], one THREAD per utterance (sequential in time)
+//   jitter_kernel    cPitchJitter, one WARP per utterance (sequential over frames and pitch periods, lanes =
+//                    candidate period lengths of the waveform matching)
+//   seq_post_kernel  cContourSmoother / cDeltaRegression(onlyInSegments) of the levels behind them, one thread
+//                    per utterance (the delta's norm is a running sum over the whole level)
+// Citations are relative to /root/reference/src.  Compiled with -fmad=false: the reference's x86-64 build has
+// no FMA contraction, and the discrete decisions below (peak picking, path costs, period matching) should see
+// the same roundings.
+#include <cfloat>
+#include <climits>
+#include <cmath>
+
+#include "kernels.cuh"
+
+namespace osm {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kShsWarps = 8;
+
+__device__ __forceinline__ int frames_of(long long L, int frameSize, int frameStep)
+{
+  return L < frameSize ? 0 : (int)((L - frameSize) / frameStep) + 1;      // core/winToVecProcessor.cpp:868-877
+}
+
+// smileutil/smileUtil.c:1009-1034: vertex of the parabola through three points
+__device__ double quad3(double x1, double y1, double x2, double y2, double x3, double y3, double *y, double *aOut)
+{
+  const double den = x1 * x1 * x2 + x2 * x2 * x3 + x3 * x3 * x1 - x3 * x3 * x2 - x2 * x2 * x1 - x1 * x1 * x3;
+  if (den != 0.0) {
+    const double a = (y1 * x2 + y2 * x3 + y3 * x1 - y3 * x2 - y2 * x1 - y1 * x3) / den;
+    const double b = (x1 * x1 * y2 + x2 * x2 * y3 + x3 * x3 * y1 - x3 * x3 * y2 - x2 * x2 * y1 - x1 * x1 * y3) / den;
+    const double c = (x1 * x1 * x2 * y3 + x2 * x2 * x3 * y1 + x3 * x3 * x1 * y2 - x3 * x3 * x2 * y1 - x2 * x2 * x1 * y3 - x1 * x1 * x3 * y2) / den;
+    if (a != 0.0) {
+      if (aOut) *aOut = a;
+      const double x = -b / (2.0 * a);
+      if (y) *y = c - a * x * x;
+      return x;
+    }
+  }
+  if (aOut) *aOut = 0.0;
+  if (y1 > y2 && y1 > y3) { if (y) *y = y1; return x1; }
+  else if (y2 > y1 && y2 > y3) { if (y) *y = y2; return x2; }
+  else if (y3 > y1 && y3 > y2) { if (y) *y = y3; return x3; }
+  if (y) *y = y1;
+  return x1;
+}
+
+// ------------------------------------------------------------------------------------------ shs_kernel
+
+// warp-wide (value, index) maximum; ties keep the lower index; idx < 0 = no entry
+__device__ __forceinline__ void warp_argmax(float &v, int &idx)
+{
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float ov = __shfl_xor_sync(kFull, v, d);
+    const int oi = __shfl_xor_sync(kFull, idx, d);
+    if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+  }
+}
+
+__global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.nMag, M = p.nPts;
+  const size_t perWarp = (size_t)2 * (N + 2) * sizeof(double) + (size_t)2 * M * sizeof(float) + 128;
+  unsigned char *ws = smemRaw + warp * perWarp;
+  double *yS = reinterpret_cast<double *>(ws);
+  double *uS = yS + (N + 2);
+  float *hps = reinterpret_cast<float *>(uS + (N + 2));
+  float *SS = hps + M;
+  float *cand = SS + M;                       // [3][8]: f0 | voicing | score
+  const OpTile tl = p.tiles[blockIdx.x];
+  const long long rowBase = p.statOff[tl.utt] + tl.f0;
+  const int lo = lane * p.blk, hi = min(N, lo + p.blk);
+
+  for (int f = warp; f < tl.nf; f += kShsWarps) {
+    const float *mg = p.mag + ((size_t)blockIdx.x * N) * p.F + f;
+    for (int j = lane; j < N; j += 32) yS[j] = (double)mg[(size_t)j * p.F];      // dsp/specScale.cpp:329-331
+    __syncwarp();
+    if (p.enhance) {                                                             // smileUtil.c:1965-2003
+      unsigned char *fl = reinterpret_cast<unsigned char *>(uS);
+      int cnt = 0, fmin = INT_MAX, fmax = -1;
+      for (int j = lane; j < N; j += 32) {
+        bool m;
+        if (j == 0) m = yS[0] > yS[1];
+        else if (j == N - 1) m = yS[N - 1] > yS[N - 2];
+        else m = yS[j] > yS[j - 1] && yS[j] >= yS[j + 1];
+        fl[j] = m;
+        if (m) { cnt++; fmin = min(fmin, j); fmax = max(fmax, j); }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        cnt += __shfl_xor_sync(kFull, cnt, d);
+        fmin = min(fmin, __shfl_xor_sync(kFull, fmin, d));
+        fmax = max(fmax, __shfl_xor_sync(kFull, fmax, d));
+      }
+      __syncwarp();
+      for (int j = lane; j < N; j += 32) {
+        bool zero;
+        if (cnt == 1) zero = j >= 3;            // the reference reads posmax[1] == 0 here
+        else zero = j > fmin && j < fmax &&
+                    !(fl[j] || (j >= 1 && fl[j - 1]) || (j >= 2 && fl[j - 2]) || (j + 1 < N && fl[j + 1]) || (j + 2 < N && fl[j + 2]));
+        if (zero) yS[j] = 0.0;
+      }
+      __syncwarp();
+    }
+    if (p.smooth) {                                                              // smileUtil.c:2006-2016
+      for (int j = lane; j < N; j += 32)
+        uS[j] = j < N - 1 ? ((j > 0 ? yS[j - 1] : 0.0) + 2.0 * yS[j] + yS[j + 1]) / 4.0 : yS[j];
+      __syncwarp();
+      double *t = yS; yS = uS; uS = t;
+    }
+    // natural cubic spline: second derivatives by two first-order recurrences (smileUtilSpline.c:142-190);
+    // lane l owns points [lo, hi), the carries cross the lanes through a scan of affine maps
+    {
+      double A = 1.0, B = 0.0;
+      for (int i = lo; i < hi; i++) {
+        double a = 0.0, b = 0.0;
+        if (i >= 1 && i <= N - 2) { a = p.fwdA[i]; b = p.fwdP6[i] * ((yS[i + 1] - yS[i]) * p.r1[i] - (yS[i] - yS[i - 1]) * p.r2[i]); }
+        B = a * B + b; A = a * A;
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double A2 = __shfl_up_sync(kFull, A, d), B2 = __shfl_up_sync(kFull, B, d);
+        if (lane >= d) { B = A * B2 + B; A = A * A2; }
+      }
+      double u = __shfl_up_sync(kFull, B, 1);
+      if (lane == 0) u = 0.0;
+      for (int i = lo; i < hi; i++) {
+        double a = 0.0, b = 0.0;
+        if (i >= 1 && i <= N - 2) { a = p.fwdA[i]; b = p.fwdP6[i] * ((yS[i + 1] - yS[i]) * p.r1[i] - (yS[i] - yS[i - 1]) * p.r2[i]); }
+        u = a * u + b;
+        uS[i] = u;
+      }
+      __syncwarp();
+      A = 1.0; B = 0.0;
+      for (int j = hi - 1; j >= lo; j--) {
+        const double a = j <= N - 2 ? p.bwdD[j] : 0.0, b = j <= N - 2 ? uS[j] : 0.0;
+        B = a * B + b; A = a * A;
+      }
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double A2 = __shfl_down_sync(kFull, A, d), B2 = __shfl_down_sync(kFull, B, d);
+        if (lane + d < 32) { B = A * B2 + B; A = A * A2; }
+      }
+      double v = __shfl_down_sync(kFull, B, 1);
+      if (lane == 31) v = 0.0;
+      for (int j = hi - 1; j >= lo; j--) {
+        const double a = j <= N - 2 ? p.bwdD[j] : 0.0, b = j <= N - 2 ? uS[j] : 0.0;
+        v = a * v + b;
+        uS[j] = v;
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < M; i += 32) {                                         // smileUtilSpline.c:355-368, specScale.cpp:343-368
+      const int k = p.ik[i];
+      const double a = p.ia[i], b = 1.0 - a;
+      const double o = a * yS[k] + b * yS[k + 1] + p.ic[i] * uS[k] + p.id[i] * uS[k + 1];
+      float of = (float)o;
+      if (p.hasAudW) of = of > 0.0f ? (float)((double)of * p.audW[i]) : 0.0f;
+      if (i <= p.lfCutBin) of = 0.0f;                                            // lld/pitchShs.cpp:230-236
+      hps[i] = of;
+    }
+    __syncwarp();
+    // sub-harmonic summation (lld/pitchShs.cpp:238-258)
+    double part = 0.0;
+    for (int j = lane; j < M; j += 32) {
+      float s = hps[j];
+      for (int h = 0; h < p.nHarm - 1; h++) {
+        const int q = j + p.shift[h];
+        if (q < M) s = s + hps[q] * p.hscale[h];
+      }
+      s = s / (float)p.nHarm;
+      if (s < 0) s = 0.0f;
+      SS[j] = s;
+      part += (double)s;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(kFull, part, d);
+    const double ssMean = part / (double)M;                                      // :271,320
+    __syncwarp();
+    // peak candidates (:271-318)
+    const int nC = p.nCand;
+    if (lane < 8) { cand[lane] = 0.0f; cand[8 + lane] = 0.0f; cand[16 + lane] = 0.0f; }
+    __syncwarp();
+    int nCand = 0;
+    if (p.greedy) {
+      float lastS = FLT_MAX; int lastI = -1;
+      for (int r = 0; r < nC; r++) {
+        float bs = -1.0f; int bi = -1;
+        for (int i = 1 + lane; i < M - 1; i += 32) {
+          const float s = SS[i];
+          if (SS[i - 1] < s && s > SS[i + 1] && (s < lastS || (s == lastS && i > lastI)) && s > bs) { bs = s; bi = i; }
+        }
+        warp_argmax(bs, bi);
+        if (bi < 0) break;
+        if (lane == 0) { cand[r] = (float)bi; cand[16 + r] = bs; }
+        lastS = bs; lastI = bi; nCand++;
+      }
+    } else {
+      if (lane == 0) {
+        for (int i = 1; i < M - 1; i++) {
+          if (SS[i - 1] < SS[i] && SS[i] > SS[i + 1] && (SS[i] > cand[16] || cand[16] == 0.0f)) {
+            for (int j = nC - 1; j > 0; j--) { cand[16 + j] = cand[16 + j - 1]; cand[j] = cand[j - 1]; }
+            cand[0] = (float)i; cand[16] = SS[i];
+            if (nCand < nC) nCand++;
+          }
+        }
+      }
+      nCand = __shfl_sync(kFull, nCand, 0);
+    }
+    __syncwarp();
+    if (lane < nCand) {                                                          // :323-343
+      const float fc = cand[lane];
+      const int jx = (int)fc;
+      const float f1 = fc * p.Fstept + p.Fmint;
+      const float f2 = (fc + 1.0f) * p.Fstept + p.Fmint;
+      const float f0 = (fc - 1.0f) * p.Fstept + p.Fmint;
+      double sc = 0;
+      const double fx = quad3((double)f0, (double)SS[jx - 1], (double)f1, (double)SS[jx], (double)f2, (double)SS[jx + 1], &sc, nullptr);
+      cand[lane] = (float)exp(fx * p.logBase);
+      cand[16 + lane] = (float)sc;
+      cand[8 + lane] = (sc > 0.0 && sc > ssMean) ? (float)(1.0 - ssMean / sc) : 0.0f;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      float *cf = cand, *cv = cand + 8, *cs = cand + 16;
+      if (p.octaveCorr) {                                                        // :346-358
+        for (int i = 1; i < nCand; i++) {
+          if (cf[i] < cf[0] && cf[i] > 0 && (cv[i] > p.voicingCutoff || cv[i] >= 0.9 * p.voicingCutoff) &&
+              cs[i] > ((1.0 / (float)(p.nHarm - 1) * p.hscale[0])) * cs[0]) {
+            float t;
+            t = cf[0]; cf[0] = cf[i]; cf[i] = t;
+            t = cv[0]; cv[0] = cv[i]; cv[i] = t;
+            t = cs[0]; cs[0] = cs[i]; cs[i] = t;
+          }
+        }
+      }
+      // cPitchBase::processVector (lldcore/pitchBase.cpp:196-290)
+      int nc = nCand;
+      if (nc > 0) {
+        for (int i = 0; i < nC && nc > 0; i++) {
+          if ((double)cf[i] > p.maxPitch || (double)cf[i] < p.minPitch) {
+            const float origF = cf[i];
+            int j;
+            for (j = i + 1; j < nC; j++) { cf[j - 1] = cf[j]; cv[j - 1] = cv[j]; cs[j - 1] = cs[j]; }
+            cf[j - 1] = 0; cv[j - 1] = 0; cs[j - 1] = 0;
+            if (origF > 0.0f) { nc--; i--; }
+          }
+        }
+      }
+      float *dst = p.shs + (size_t)(rowBase + f) * p.nShsCols;
+      int n = 0;
+      dst[n++] = (float)nc;
+      int maxI = 0;
+      if (!p.octaveCorr) {
+        float mx = cs[0];
+        for (int i = 1; i < nC; i++) if (cs[i] > mx) { mx = cs[i]; maxI = i; }
+      }
+      if (maxI > 0) {
+        float t;
+        t = cf[0]; cf[0] = cf[maxI]; cf[maxI] = t;
+        t = cv[0]; cv[0] = cv[maxI]; cv[maxI] = t;
+        t = cs[0]; cs[0] = cs[maxI]; cs[maxI] = t;
+      }
+      for (int i = 0; i < nC; i++) dst[n++] = cf[i];
+      if (p.voicing) for (int i = 0; i < nC; i++) dst[n++] = cv[i];
+      if (p.scores) for (int i = 0; i < nC; i++) dst[n++] = cs[i];
+      if (p.F0C1) dst[n++] = cf[0];
+      if (p.voicingC1) dst[n++] = cv[0];
+      if (p.F0raw) dst[n++] = cv[0] <= p.voicingCutoff ? 0.0f : cf[0];
+      if (p.voicingClip) dst[n++] = cv[0] <= p.voicingCutoff ? 0.0f : cv[0];
+    }
+    __syncwarp();
+    if (p.smooth) { double *t = yS; yS = uS; uS = t; }      // undo the swap: same buffers for the next frame
+  }
+}
+
+// ------------------------------------------------------------------------------------------ viterbi_kernel
+
+constexpr int kVitStates = 9, kVitBuf = 64;
+
+// include/lld/pitchSmootherViterbi.hpp:167-197
+__device__ __forceinline__ double vit_fweight(float f)
+{
+  if (f > 0.0 && f < 100.0) return -(1.0 / 100.0) * f + 1.0;
+  else if (f >= 100.0 && f < 350.0) return 0.0;
+  else if (f >= 350.0 && f < 600.0) return ((f - 350.0) / 250.0);
+  else if (f >= 600.0) return 1.2;
+  else if (f <= 0) return 2.0;
+  return 0.0;
+}
+
+__global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int u0, int u1)
+{
+  const int u = u0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= u1) return;
+  const int T = frames_of(p.uttOff[u + 1] - p.uttOff[u], p.frameSize, p.frameStep);
+  if (T <= 0) { p.lag[u] = 0; return; }
+  const long long row0 = p.statOff[u];
+  const int nC = p.nCand, nS = nC + 1, last = nC, bl = p.bufLen;
+  double costA[kVitStates], costB[kVitStates];
+  unsigned char paths[2][kVitStates][kVitBuf], bestPath[kVitBuf];
+  double *pathCosts = costA, *pathCostsNew = costB;
+  double lastChange = 1.0;
+  int pathBuf = 0, pathIdx = 0, convIdx = -1, rdIdx = 0;
+  float lastValidf0 = 0.0f;
+  const double thrD = (double)p.voiceThresh;
+
+  auto local_cost = [&](int i, const float *fr) -> double {              // hpp:202-221; fr[1+k] = F0, fr[1+nC+k] = voicing
+    if (i < last) {
+      double pv = (double)fr[1 + nC + i];
+      double thr = 0.0;
+      if (pv < 0.01) pv = 0.01;
+      if (pv > 1.00) pv = 1.00;
+      if (pv < thrD) thr = p.wThr;
+      return (-log(pv) + thr) * p.wLocal + vit_fweight(fr[1 + i]) * p.wRange;
+    }
+    double flag = 0.0;
+    for (int j = 0; j < nC; j++) if (fr[1 + nC + j] >= p.voiceThresh) { flag = p.wThr; break; }
+    return p.wLocal * flag;
+  };
+  auto drain = [&]() {                                                       // lld/pitchSmootherViterbi.cpp:470-545
+    while (rdIdx <= convIdx) {
+      const int state = bestPath[rdIdx % bl];
+      const float *b = p.shs + (size_t)(row0 + rdIdx) * p.nShsCols;
+      float f0 = state < last ? b[1 + state] : 0.0f;
+      const float vp = state < nC ? b[1 + nC + state] : b[1 + nC];
+      float *o = p.stat + (size_t)(row0 + rdIdx) * p.statStride + p.outCol;
+      bool copy = true;
+      if (p.hasSel) {                                                         // other/valbasedSelector.cpp:153-233
+        const float val = p.stat[(size_t)(row0 + rdIdx) * p.statStride + p.selCol];
+        copy = (!p.selInvert && val > p.selThreshold) || (p.selInvert && val < p.selThreshold) || (p.selAllowEqual && val == p.selThreshold);
+      }
+      int n = 0;
+      if (p.oF0final) o[n++] = copy ? f0 : p.selOutputVal;
+      if (p.oF0finalEnv) {
+        if (f0 <= 0.0) f0 = lastValidf0; else lastValidf0 = f0;
+        o[n++] = copy ? f0 : p.selOutputVal;
+      }
+      if (p.oVClipped) o[n++] = copy ? (vp >= p.voiceThresh ? vp : 0.0f) : p.selOutputVal;
+      if (p.oVUnclipped) o[n++] = copy ? vp : p.selOutputVal;
+      rdIdx++;
+    }
+  };
+
+  for (int t = 0; t < T; t++) {                                               // lld/pitchSmootherViterbi.cpp:79-183
+    const float *cur = p.shs + (size_t)(row0 + t) * p.nShsCols;
+    const float *prv = cur - p.nShsCols;
+    if (pathIdx == 0) {
+      convIdx = -1;
+      for (int i = 0; i < nS; i++) { pathCosts[i] = local_cost(i, cur); paths[pathBuf][i][0] = (unsigned char)i; }
+    } else {
+      const int nb = pathBuf ^ 1;
+      for (int i = 0; i < nS; i++) {
+        int minState = 0;
+        double minCost = 0.0;
+        for (int j = 0; j < nS; j++) {
+          double tc;                                                          // hpp:224-252 (i = current state, j = previous state)
+          if ((int)(i == j) == last) tc = p.wTuu;                             // the reference's `i == j == nStates-1`
+          else if (i < last && j < last) {
+            const float f0 = prv[1 + j], f1 = cur[1 + i];
+            if (f0 == 0 || f1 == 0) tc = 999.0;
+            else {
+              const double r = log((double)(f1 / f0));
+              tc = p.wTvv * fabs(r) + p.wTvvd * fabs(r - lastChange);
+              lastChange = r;
+            }
+          } else if ((i == last && j < last) || (i < last && j == last)) { lastChange = 0.0; tc = p.wTvuv; }
+          else tc = 1.0;
+          const double c = tc + pathCosts[j];
+          if (j == 0 || c < minCost) { minState = j; minCost = c; }
+        }
+        pathCostsNew[i] = minCost + local_cost(i, cur);
+        for (int k = 0; k < bl; k++) paths[nb][i][k] = paths[pathBuf][minState][k];
+        paths[nb][i][pathIdx % bl] = (unsigned char)i;
+      }
+      double *tmp = pathCosts; pathCosts = pathCostsNew; pathCostsNew = tmp;
+      pathBuf = nb;
+    }
+    pathIdx++;
+    if (pathIdx - convIdx > bl) {
+      int minState = 0;
+      for (int i = 1; i < nS; i++) if (pathCosts[i] < pathCosts[minState]) minState = i;
+      convIdx++;
+      bestPath[convIdx % bl] = paths[pathBuf][minState][convIdx % bl];
+    } else {
+      for (int n = convIdx + 1; n < pathIdx; n++) {
+        const unsigned char x = paths[pathBuf][0][n % bl];
+        bool match = true;
+        for (int i = 1; i < nS; i++) if (x != paths[pathBuf][i][n % bl]) { match = false; break; }
+        if (!match) break;
+        convIdx++;
+        bestPath[convIdx % bl] = x;
+      }
+    }
+    drain();
+  }
+  p.lag[u] = rdIdx;                       // frames written before the end of input is signalled
+  {                                       // flushTrellis (hpp:105-125)
+    int minState = 0;
+    for (int i = 1; i < nS; i++) if (pathCosts[i] < pathCosts[minState]) minState = i;
+    // at most bufLen entries are pending (forced decisions keep pathIdx - convIdx <= bufLen), so the ring is intact
+    while (convIdx + 1 < pathIdx) {
+      convIdx++;
+      bestPath[convIdx % bl] = paths[pathBuf][minState][convIdx % bl];
+      drain();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ jitter_kernel
+
+constexpr int kJitWarps = 4, kJitWav = 6144, kJitCC = 512, kJitAvg = 1024, kJitPb = 128;
+
+__device__ __forceinline__ float jit_pcm(const int16_t *s, int nChan)       // smileutil/smileUtil.c:2520-2534
+{
+  float tmp = (float)s[0];
+  for (int c = 1; c < nChan; c++) tmp = tmp + (float)s[c];
+  if (nChan > 1) tmp = tmp / (float)nChan;
+  return tmp / 32767.0f;
+}
+
+// lld/pitchJitter.cpp:339-413, one lag per lane
+__device__ double jit_cross_corr(const float *x, const float *y, int N)
+{
+  double cc = 0.0, mx = 0.0, my = 0.0, nx = 0.0, ny = 0.0;
+  for (int i = 0; i < N; i++) { mx += x[i]; my += y[i]; }
+  mx /= (double)N; my /= (double)N;
+  for (int i = 0; i < N; i++) {
+    const double dx = x[i] - mx, dy = y[i] - my;
+    cc += dx * dy;
+    nx += dx * dx;
+    ny += dy * dy;
+  }
+  cc /= sqrt(nx) * sqrt(ny);
+  return cc;
+}
+
+// first maximum / minimum of x[1 .. N-2] (lld/pitchJitter.cpp:424-431), all lanes get the result
+__device__ void jit_extrema(const float *x, int N, int lane, float &mx, int &mI, float &mn)
+{
+  float bv = -FLT_MAX, lo = FLT_MAX; int bi = -1;
+  for (int i = 1 + lane; i < N - 1; i += 32) {
+    const float v = x[i];
+    if (bi < 0 || v > bv) { bv = v; bi = i; }
+    lo = fminf(lo, v);
+  }
+  warp_argmax(bv, bi);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) lo = fminf(lo, __shfl_xor_sync(kFull, lo, d));
+  if (bi < 0) { mx = x[1]; mI = 1; mn = x[1]; }
+  else { mx = bv; mI = bi; mn = lo; }
+}
+
+__global__ void __launch_bounds__(kJitWarps * 32) jitter_kernel(const JitterParams p, int u0, int u1)
+{
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = u0 + blockIdx.x * kJitWarps + warp;
+  if (u >= u1) return;
+  const size_t perWarp = (size_t)kJitCC * sizeof(double) + (size_t)(kJitWav + kJitAvg) * sizeof(float) + (size_t)kJitPb * sizeof(int);
+  unsigned char *ws = smemRaw + warp * perWarp;
+  double *cc = reinterpret_cast<double *>(ws);
+  float *wav = reinterpret_cast<float *>(cc + kJitCC);
+  float *avgWf = wav + kJitWav;
+  int *pb = reinterpret_cast<int *>(avgWf + kJitAvg);
+
+  const long long L = p.uttOff[u + 1] - p.uttOff[u];
+  const int T = frames_of(L, p.frameSize, p.frameStep);
+  const int16_t *pcm = p.pcm + p.uttOff[u] * p.nChan;
+  const long long row0 = p.statOff[u];
+  const double Ts = p.Ts;
+  // state (lld/pitchJitter.cpp:88-93), identical in every lane
+  long long lastIdx = 0, lastMis = 0;
+  float lastT0 = 0.0f, lastDiff = 0.0f, lastJitterLocal = 0.0f, lastJitterDDP = 0.0f, lastShimmerLocal = 0.0f;
+  float lastJitterLocal_b = 0.0f, lastJitterDDP_b = 0.0f, lastShimmerLocal_b = 0.0f;
+  float threshCC = p.threshCC;
+  const int nOutCols = p.jitterLocal + p.jitterDDP + p.jitterLocalEnv + p.jitterDDPEnv + p.shimmerLocal + p.shimmerLocalDB +
+                       p.shimmerLocalEnv + p.shimmerLocalDBEnv + p.harmonicERMS + p.noiseERMS + p.linearHNR + p.logHNR +
+                       p.refinedF0 + p.srcQualMean + p.srcQualRange;
+
+  for (int t = 0; t < T; t++) {
+    float *o = p.stat + (size_t)(row0 + t) * p.statStride + p.outCol;
+    const float F0 = p.stat[(size_t)(row0 + t) * p.statStride + p.f0Col];
+    // time meta of frame t (core/dataMemoryLevel.cpp:617-625: lengthSec spans the source samples)
+    const long long s0 = (long long)t * p.frameStep;
+    const double time = (double)s0 * Ts;
+    const double lengthSec = (double)(s0 + p.frameSize - 1) * Ts - (double)s0 * Ts + Ts;
+    long long lenF = (long long)ceil(lengthSec / Ts);                         // :609
+    const long long startVidx = (long long)round(time / Ts);                   // :612
+    const long long ppLen = (long long)ceil(p.pitchT / Ts);                    // :616
+    const long long toRead0 = ppLen + lastMis;
+    long long toRead = toRead0;
+    double Tf = 0.0;
+    long long T0f = 0, T0minF = 0, T0maxF = 0;
+    if (F0 > 0.0) {                                                            // :635-648
+      const double T0 = 1.0 / F0;
+      Tf = T0 / Ts;
+      T0f = (long long)round(Tf);
+      T0minF = (long long)floor((1.0 - p.searchRangeRel) * Tf);
+      T0maxF = (long long)ceil((1.0 + p.searchRangeRel) * Tf);
+      const long long two_pp = p.minNumPeriods * T0maxF + p.minNumPeriods;
+      if (toRead < two_pp) toRead = two_pp;
+    }
+    long long maxRead = lastMis + lenF;
+    if (toRead > maxRead) toRead = maxRead;
+    if (startVidx - lastMis != lastIdx) {                                      // :658-663
+      lastIdx = startVidx;
+      if (toRead > lenF) toRead = lenF;
+      if (maxRead > lenF) maxRead = lenF;
+    }
+    bool bad = lastIdx + toRead > L || toRead > kJitWav || toRead < 1;
+    if (F0 > 0.0 && (T0maxF - T0minF + 1 > kJitCC || T0f + 1 > kJitAvg || T0minF < 1 || maxRead / T0minF + 4 > kJitPb)) bad = true;
+    if (bad) {               // the reference drops such a frame (:668-673) or leaves the supported geometry: flagged
+      if (lane == 0) { atomicOr(p.errFlag, 1); for (int k = 0; k < nOutCols; k++) o[k] = 0.0f; }
+      lastIdx += toRead0;
+      continue;
+    }
+    const int nT = (int)toRead;
+    __syncwarp();
+    for (int i = lane; i < nT; i += 32) wav[i] = jit_pcm(pcm + (lastIdx + i) * p.nChan, p.nChan);
+    __syncwarp();
+
+    float nPeriodsLocal = 0, nPeriodsDDP = 0, nPeriods = 0, avgPeriod = 0.0f, JitterDDP = 0.0f, JitterLocal = 0.0f;
+    float avgAmp = 0.0f, avgAmpDiff = 0.0f, eH = 0.0f, eN = 0.0f, HNR = 0.0f, lgHNR = 0.0f, sumCC = 0.0f, maxCC = -2.0f, minCC = -2.0f;
+    long long lastPeriod = 0;
+    if (F0 > 0.0) {
+      const int t0f = (int)T0f, tmin = (int)T0minF, tmax = (int)T0maxF, nLag = tmax - tmin + 1;
+      int numPeriods = 0, start = 0, pp = 0;
+      for (int i = lane; i <= t0f; i += 32) avgWf[i] = 0.0f;
+      for (int i = lane; i < kJitPb; i += 32) pb[i] = 0;
+      __syncwarp();
+      while (start < nT - 2 * tmax - 1) {                                      // :728
+        for (int k = lane; k < nLag; k += 32) cc[k] = jit_cross_corr(wav + start, wav + start + tmin + k, tmin + k);
+        __syncwarp();
+        int maxI = -1;                                                         // :743-754 (first of the highest peaks)
+        {
+          double bd = 0.0;
+          for (int i = 1 + lane; i < nLag - 2; i += 32)
+            if (cc[i - 1] < cc[i] && cc[i] > cc[i + 1] && (maxI < 0 || cc[i] > bd)) { bd = cc[i]; maxI = i; }
+          // reduce on the double value: ties keep the lower index
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            const double od = __shfl_xor_sync(kFull, bd, d);
+            const int oi = __shfl_xor_sync(kFull, maxI, d);
+            if (oi >= 0 && (maxI < 0 || od > bd || (od == bd && oi < maxI))) { bd = od; maxI = oi; }
+          }
+        }
+        pp = maxI == -1 ? t0f : tmin + maxI;
+        const int os = start;
+        if (maxI >= 0) {
+          start += pp;
+          float max0, min0, max1, min1; int mI0, mI1;
+          double pk0 = 0.0, pk1 = 0.0;
+          float a0, a1, ad;
+          if (p.shimmerUseRms) {                                               // :461-513 (sequential float sums, every lane alike)
+            const float *x = wav + os, *y = wav + start;
+            int i, mI = 1; float mxv = x[1];
+            float rmsX = x[0] * x[0];
+            for (i = 1; i < pp - 1; i++) { if (x[i] > mxv) { mxv = x[i]; mI = i; } rmsX += x[i] * x[i]; }
+            rmsX = sqrtf((rmsX + x[i] * x[i]) / (float)pp);
+            pk0 = quad3((double)(mI - 1), x[mI - 1], (double)mI, x[mI], (double)(mI + 1), x[mI + 1], nullptr, nullptr);
+            mI = 1; mxv = y[1];
+            float rmsY = y[0] * y[0];
+            for (i = 1; i < pp - 1; i++) { if (y[i] > mxv) { mxv = y[i]; mI = i; } rmsY += y[i] * y[i]; }
+            rmsY = sqrtf((rmsY + y[i] * y[i]) / (float)pp);
+            pk1 = quad3((double)(mI - 1), y[mI - 1], (double)mI, y[mI], (double)(mI + 1), y[mI + 1], nullptr, nullptr);
+            a0 = rmsX; a1 = rmsY; ad = fabsf(rmsX - rmsY);
+          } else {                                                             // :418-456
+            jit_extrema(wav + os, pp, lane, max0, mI0, min0);
+            jit_extrema(wav + start, pp, lane, max1, mI1, min1);
+            if (p.peakToPeak) {
+              const float *x = wav + os, *y = wav + start;
+              pk0 = quad3((double)(mI0 - 1), x[mI0 - 1], (double)mI0, x[mI0], (double)(mI0 + 1), x[mI0 + 1], nullptr, nullptr);
+              pk1 = quad3((double)(mI1 - 1), y[mI1 - 1], (double)mI1, y[mI1], (double)(mI1 + 1), y[mI1 + 1], nullptr, nullptr);
+            }
+            a0 = max0 - min0; a1 = max1 - min1;
+            ad = (float)fabs((double)((max0 - min0) - (max1 - min1)));
+          }
+          if (lane == 0) pb[numPeriods] = os;
+          numPeriods++;
+          for (int i = lane; i < t0f; i += 32) avgWf[i] += wav[os + i];
+          double conf = 0.0, ccI = 0.0;
+          const double maxId = fabs(((double)tmin + quad3((double)(maxI - 1), cc[maxI - 1], (double)maxI, cc[maxI],
+                                                          (double)(maxI + 1), cc[maxI + 1], &ccI, &conf))) * Ts;
+          sumCC += (float)ccI;
+          if (minCC == -2.0f || minCC > (float)ccI) minCC = (float)ccI;
+          if (maxCC == -2.0f || maxCC < (float)ccI) maxCC = (float)ccI;
+          if (p.brokenThresh) threshCC = minCC;                                // :811-816
+          if (ccI > threshCC) {
+            float period;
+            if (p.peakToPeak) period = (float)(((double)start + pk1 - (double)os - pk0) * Ts);
+            else period = (float)maxId;
+            avgPeriod += period;
+            nPeriods += 1.0f;
+            if (lastT0 > 0.0) {
+              const float diff = fabsf(lastT0 - period);
+              JitterLocal += diff;
+              nPeriodsLocal += 1.0f;
+              if (lastDiff > 0.0) { JitterDDP += fabsf(lastDiff - diff); nPeriodsDDP += 1.0f; }
+              lastDiff = diff;
+            }
+            lastT0 = period;
+            avgAmp += (a0 + a1) / 2.0f;
+            avgAmpDiff += ad;
+          }
+        } else {
+          start += t0f;
+        }
+        if (start < toRead0 - 1) lastPeriod = start;                           // :856-858
+        __syncwarp();
+      }
+      if (lane == 0) { pb[numPeriods] = start; if (pp > 0) pb[numPeriods + 1] = start + pp; }
+      numPeriods++;
+      for (int i = lane; i < t0f && start + i < nT; i += 32) {                 // :865-870
+        avgWf[i] += wav[start + i];
+        avgWf[i] /= (float)numPeriods;
+      }
+      __syncwarp();
+      float Eh = 0.0f;
+      for (int i = 3; i < t0f - 2 && start + i < nT; i++) Eh += avgWf[i] * avgWf[i];
+      if (t0f - 4 > 0) Eh /= (float)(t0f - 4);
+      Eh = sqrtf(Eh);
+      float En = 0.0f; int nEn = 0;
+      for (int i = 0; i < numPeriods; i++) {                                   // :882-889
+        int n = 2;
+        const int hiJ = min(pb[i + 1], pb[i] + t0f);
+        for (int j = pb[i] + 2; j < hiJ - 2; j++) {
+          const float delta = wav[j] - avgWf[n++];
+          En += delta * delta;
+          nEn++;
+        }
+      }
+      if (nEn > 0) En /= (float)nEn;
+      En = sqrtf(En);
+      eH = Eh; eN = En;
+      if (En > 0.0) {
+        HNR = Eh / En;
+        if (HNR > 0.0) lgHNR = (float)(20.0 * log((double)HNR) / log(10.0));
+        else lgHNR = p.lgHNRfloor;
+      }
+      if (numPeriods > 0) sumCC /= (float)numPeriods;
+      lastMis = toRead0 - lastPeriod;
+    } else {                                                                   // :918-943
+      lastPeriod = toRead0; lastMis = 0;
+      lastT0 = 0.0f; lastDiff = 0.0f; lastJitterDDP = 0.0f; lastJitterLocal = 0.0f; lastShimmerLocal = 0.0f;
+      if (p.noiseERMS || p.linearHNR || p.logHNR) {
+        double E = 0.0;
+        for (int i = 0; i < nT; i++) E += wav[i] * wav[i];
+        E /= (double)nT;
+        eH = 0.0f; HNR = 0.0f; eN = (float)sqrt(E); lgHNR = p.lgHNRfloor;
+      }
+    }
+    lastIdx += lastPeriod;
+    // output vector (:950-1080)
+    int n = 0;
+    float ov[16];
+    const bool okL = nPeriods > 0.0 && nPeriodsLocal > 0.0 && F0 > 0.0;
+    if (okL) { JitterLocal /= nPeriodsLocal; lastJitterLocal_b = lastJitterLocal = JitterLocal / (avgPeriod / nPeriods); }
+    if (p.jitterLocal) {
+      if (okL || (nPeriods == 0.0 && F0 > 0.0)) { if (lastJitterLocal > 1.0) lastJitterLocal = 1.0f; ov[n] = lastJitterLocal; }
+      else ov[n] = 0.0f;
+      n++;
+    }
+    if (p.jitterLocalEnv) { if (lastJitterLocal_b > 1.0) lastJitterLocal_b = 1.0f; ov[n++] = lastJitterLocal_b; }
+    const bool okD = nPeriods > 0.0 && nPeriodsDDP > 0.0 && F0 > 0.0;
+    if (okD) { JitterDDP /= nPeriodsDDP; lastJitterDDP_b = lastJitterDDP = JitterDDP / (avgPeriod / nPeriods); }
+    if (p.jitterDDP) {
+      if (okD || (nPeriods == 0.0 && F0 > 0.0)) { if (lastJitterDDP > 1.0) lastJitterDDP = 1.0f; ov[n] = lastJitterDDP; }
+      else ov[n] = 0.0f;
+      n++;
+    }
+    if (p.jitterDDPEnv) { if (lastJitterDDP_b > 1.0) lastJitterDDP_b = 1.0f; ov[n++] = lastJitterDDP_b; }
+    if (nPeriods > 0.0 && F0 > 0.0) {
+      if (avgAmp > 0.0) lastShimmerLocal_b = lastShimmerLocal = (avgAmpDiff / avgAmp);
+      else lastShimmerLocal = 0.0f;
+    }
+    if (p.shimmerLocal || p.shimmerLocalDB) {
+      if (F0 > 0.0) {
+        if (lastShimmerLocal > 1.0) lastShimmerLocal = 1.0f;
+        if (p.shimmerLocal) ov[n++] = lastShimmerLocal;
+        if (p.shimmerLocalDB) { const double a = lastShimmerLocal + 1.0; ov[n++] = (float)(a > 10e-50 ? 20.0 * log(a) / log(10.0) : -1000.0); }
+      } else {
+        if (p.shimmerLocal) ov[n++] = 0.0f;
+        if (p.shimmerLocalDB) ov[n++] = 0.0f;
+      }
+    }
+    if (p.shimmerLocalEnv) { if (lastShimmerLocal_b > 1.0) lastShimmerLocal_b = 1.0f; ov[n++] = lastShimmerLocal_b; }
+    if (p.harmonicERMS) ov[n++] = eH;
+    if (p.noiseERMS) ov[n++] = eN;
+    if (p.linearHNR) ov[n++] = HNR;
+    if (p.logHNR) { if (lgHNR < p.lgHNRfloor) lgHNR = p.lgHNRfloor; ov[n++] = lgHNR; }
+    if (p.refinedF0) ov[n++] = (nPeriods > 0.0 && F0 > 0.0) ? 1.0f / (avgPeriod / nPeriods) : 0.0f;
+    if (p.srcQualMean) ov[n++] = sumCC;
+    if (p.srcQualRange) ov[n++] = fabsf(maxCC - minCC);
+    if (lane == 0) for (int k = 0; k < n; k++) o[k] = ov[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ seq_post_kernel
+
+struct SeqCtx { const float *x; int stride; int T; int V; };
+
+// cContourSmoother (smaWin = 3) value of row m, column c (dspcore/contourSmoother.cpp:84-117) with the
+// end-of-input behaviour of a reader over [pitch level ; jitter level]: rows V-1 and V are produced during the
+// reference's first EOI pass, when the jitter level (lagKind 2) still ends at its row V-1
+__device__ float seq_sma(const SeqCtx &c, int col, int m, int lagKind, int noZero)
+{
+  const bool lagged = lagKind == 2 && (m == c.V - 1 || m == c.V);
+  auto g = [&](int i) -> float {
+    i = min(max(i, 0), c.T - 1);
+    if (lagged && i > c.V - 1) i = max(c.V - 1, 0);
+    return c.x[(size_t)i * c.stride + col];
+  };
+  const float x0 = g(m);
+  if (noZero) {
+    if (x0 == 0.0f) return 0.0f;
+    float y = x0; int N = 1;
+    const float a = g(m - 1), b = g(m + 1);
+    if (a != 0.0f) { y += a; N++; }
+    if (b != 0.0f) { y += b; N++; }
+    return y / (float)N;
+  }
+  float y = x0;
+  y += g(m - 1);
+  y += g(m + 1);
+  return y / 3.0f;
+}
+
+__global__ void __launch_bounds__(64) seq_post_kernel(const SeqPostParams p, int u0, int u1)
+{
+  const int u = u0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= u1) return;
+  SeqCtx c;
+  c.T = frames_of(p.uttOff[u + 1] - p.uttOff[u], p.frameSize, p.frameStep);
+  if (c.T <= 0) return;
+  c.V = p.lag[u];
+  c.x = p.stat + (size_t)p.statOff[u] * p.statStride;
+  c.stride = p.statStride;
+  const long long R = p.rowOff[u + 1] - p.rowOff[u];
+  float *out = p.out + (size_t)p.rowOff[u] * p.outStride;
+  const int T = c.T, V = c.V;
+  // 1. smoothed levels
+  for (int g = 0; g < p.nGroups; g++) {
+    const SeqGroup &G = p.groups[g];
+    if (G.nStages != 1) continue;
+    for (int m = 0; m <= T && m < R; m++)
+      for (int k = 0; k < G.n; k++) out[(size_t)m * p.outStride + G.outCol + k] = seq_sma(c, G.srcCol + k, m, G.lagKind, G.noZero);
+  }
+  // 2. deltas with onlyInSegments: one running norm per delta component (dspcore/deltaRegression.cpp:77-79,123-141),
+  //    rows in order, elements in column order.  Rows V-1..V+2 are produced during the first EOI pass, when the
+  //    smoothed level ends at its row V; row V+3 (for T-5 <= V <= T-2) in the first tick of the second pass,
+  //    when it ends at row T-1 (core/dataMemoryLevel.cpp:1020-1027,1698-1708).
+  for (int seg = 0; seg < kMaxSeqGroups; seg++) {
+    int W = 0;
+    for (int g = 0; g < p.nGroups; g++) if (p.groups[g].nStages == 2 && p.groups[g].segId == seg) W = p.groups[g].deltaWin;
+    if (W == 0) continue;
+    float norm = 0.0f;
+    for (int i = 1; i <= W; i++) norm += (float)i * (float)i;
+    norm *= 2.0f;
+    for (int n = 0; n <= T + W; n++) {
+      int last = T;
+      if (n >= V - 1 && n <= V + 2) last = min(T, max(V, 0));
+      else if (n == V + 3 && V >= T - 5 && V <= T - 2) last = T - 1;
+      for (int g = 0; g < p.nGroups; g++) {
+        const SeqGroup &G = p.groups[g];
+        if (G.nStages != 2 || G.segId != seg) continue;
+        for (int k = 0; k < G.n; k++) {
+          float num = 0.0f;
+          for (int i = 1; i <= W; i++) {
+            const float a = seq_sma(c, G.srcCol + k, min(max(n - i, 0), last), G.lagKind, G.noZero);
+            const float b = seq_sma(c, G.srcCol + k, min(max(n + i, 0), last), G.lagKind, G.noZero);
+            if (!(a == 0.0f || a != a || b == 0.0f || b != b)) {
+              num += (float)i * (b - a);
+              norm += (float)i * (float)i;
+            }
+          }
+          if (n < R) out[(size_t)n * p.outStride + G.outCol + k] = norm != 0.0f ? num / norm : 0.0f;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_shs(const ShsParams &p, cudaStream_t st)
+{
+  if (p.nTiles <= 0) return cudaSuccess;
+  const size_t perWarp = (size_t)2 * (p.nMag + 2) * sizeof(double) + (size_t)2 * p.nPts * sizeof(float) + 128;
+  const size_t smem = perWarp * kShsWarps;
+  cudaError_t e = cudaFuncSetAttribute(shs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  shs_kernel<<<p.nTiles, kShsWarps * 32, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_viterbi(const ViterbiParams &p, int u0, int u1, cudaStream_t st)
+{
+  if (u1 <= u0) return cudaSuccess;
+  if (p.nCand + 1 > kVitStates || p.bufLen > kVitBuf) return cudaErrorInvalidValue;
+  viterbi_kernel<<<(u1 - u0 + 63) / 64, 64, 0, st>>>(p, u0, u1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_jitter(const JitterParams &p, int u0, int u1, cudaStream_t st)
+{
+  if (u1 <= u0) return cudaSuccess;
+  const size_t perWarp = (size_t)kJitCC * sizeof(double) + (size_t)(kJitWav + kJitAvg) * sizeof(float) + (size_t)kJitPb * sizeof(int);
+  const size_t smem = perWarp * kJitWarps;
+  cudaError_t e = cudaFuncSetAttribute(jitter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  jitter_kernel<<<(u1 - u0 + kJitWarps - 1) / kJitWarps, kJitWarps * 32, smem, st>>>(p, u0, u1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seq_post(const SeqPostParams &p, int u0, int u1, cudaStream_t st)
+{
+  if (u1 <= u0 || p.nGroups <= 0) return cudaSuccess;
+  seq_post_kernel<<<(u1 - u0 + 63) / 64, 64, 0, st>>>(p, u0, u1);
+  return cudaGetLastError();
+}
+
+}  // namespace osm

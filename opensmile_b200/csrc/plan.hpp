@@ -43,7 +43,7 @@ struct FrontEnd {
   bool zeroPadSymmetric = false;   // phase only; magnitude consumers are unaffected
 };
 
-enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP, SOP_MAG, SOP_INTENSITY };
+enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP, SOP_MAG, SOP_INTENSITY, SOP_PITCH, SOP_JITTER };
 
 struct MfccOp {
   int melIdx = 0;
@@ -110,6 +110,51 @@ struct IntensityOp { bool intensity = true, loudness = false; double w[2] = {0, 
 
 struct MzcrOp { bool zcr = true, mcr = true, amax = true, maxmin = true, dc = false; int nOut = 0; };
 
+// cSpecScale -> cPitchShs -> cPitchSmootherViterbi [-> cValbasedSelector] (dsp/specScale.cpp, lld/pitchShs.cpp,
+// lldcore/pitchBase.cpp, lld/pitchSmootherViterbi.cpp, other/valbasedSelector.cpp): one static producer
+struct PitchChainOp {
+  // --- cSpecScale: natural cubic spline from the linear bins onto an octave axis.  The abscissa terms are
+  // constants, so the tridiagonal solve is two first-order recurrences with fixed coefficients:
+  //   u[i]  = fwdA[i] * u[i-1] + fwdP6[i] * ((y[i+1]-y[i]) * r1[i] - (y[i]-y[i-1]) * r2[i])      (smileUtilSpline.c:159-165)
+  //   y2[j] = bwdD[j] * y2[j+1] + u[j]                                                             (:178-180)
+  int nMag = 0, nPts = 0;
+  bool enhance = false, smooth = false;
+  std::vector<double> fwdA, fwdP6, r1, r2, bwdD;
+  std::vector<int> ik; std::vector<double> ia, ic, id;     // interpolation cache (smileUtilSpline.c:301-352)
+  std::vector<double> audW;                                 // empty = no auditory weighting
+  // --- cPitchShs
+  int nCand = 3, nHarm = 15;
+  std::vector<int> shift; std::vector<float> hscale;        // per harmonic 2..nHarm: bin shift, compression^(h-1) (float products)
+  float Fmint = 0, Fstept = 0;
+  double logBase = 0;                                        // log(base)
+  double maxPitch = 620, minPitch = 52;
+  float voicingCutoff = 0.7f;
+  int lfCutBin = -1;
+  bool greedy = false, octaveCorr = false, scores = true, voicing = true, F0C1 = false, voicingC1 = false, F0raw = false, voicingClip = false;
+  int nShsCols = 0;
+  // --- cPitchSmootherViterbi
+  int bufLen = 30;
+  bool oF0final = true, oF0finalLog = false, oF0finalEnv = false, oF0finalEnvLog = false, oVClipped = false, oVUnclipped = false;
+  double wLocal = 2, wTvv = 10, wTvvd = 10, wTvuv = 10, wThr = 4, wRange = 1, wTuu = 0;
+  // --- cValbasedSelector (optional)
+  bool hasSel = false;
+  int selOp = -1;                                            // static op whose first column is the selector value
+  float selThreshold = 0, selOutputVal = 0;
+  bool selInvert = false, selAllowEqual = false;
+  int nOut = 0;
+};
+
+// cPitchJitter (lld/pitchJitter.cpp:591-1107): waveform matching around the F0 of a pitch chain op
+struct JitterOp {
+  int pitchOp = -1, f0Col = 0;         // F0 = column f0Col of static op pitchOp
+  double searchRangeRel = 0.1, minCC = 0.5, lgHNRfloor = -100;
+  int minNumPeriods = 2;
+  bool jitterLocal = false, jitterDDP = false, jitterLocalEnv = false, jitterDDPEnv = false, shimmerLocal = false, shimmerLocalDB = false,
+       shimmerLocalEnv = false, shimmerLocalDBEnv = false, harmonicERMS = false, noiseERMS = false, linearHNR = false, logHNR = false,
+       shimmerUseRms = false, refinedF0 = false, srcQualRange = false, srcQualMean = false, peakToPeak = false, brokenThresh = false;
+  int nOut = 0;
+};
+
 // one field of a level: `n` elements named name (n == 1) or name[i + arrNameOffset]
 struct FieldName { std::string name; int n = 1; int arrNameOffset = 0; };
 
@@ -127,10 +172,13 @@ struct StaticOp {
   MzcrOp mzcr;
   IntensityOp intensity;
   PitchAcfOp pitch;
+  PitchChainOp chain;
+  JitterOp jitter;
 };
 
 // temporal stage applied to a static column range (cWindowProcessor family)
 enum StageKind { ST_DELTA = 0, ST_SMA = 1, ST_CMS = 2 };   // ST_CMS: cFullinputMean, x - mean over the utterance (win 0)
+// flags: ST_SMA bit0 = noZeroSma; ST_DELTA bit0 = onlyInSegments (the norm accumulates over the whole level)
 struct Stage { StageKind kind; int win; int flags; };
 
 // one contiguous block of output columns
@@ -140,6 +188,11 @@ struct OutGroup {
   std::vector<Stage> stages;       // applied in order
   std::vector<int> limitStreams;   // truncating concat / multi-level reader: source length = min over these streams too
   int outCol = 0;
+  // Groups behind a Viterbi-smoothed pitch level are evaluated by seq_post_kernel (one thread per utterance):
+  // lagKind 1 = columns of the pitch chain op, 2 = columns of a cPitchJitter op (its level lags during the
+  // reference's first end-of-input pass), lagOp = the pitch chain op that supplies the per-utterance lag,
+  // segId >= 0 = groups sharing one onlyInSegments delta component (one running norm, in column order)
+  int lagKind = 0, lagOp = -1, segId = -1;
 };
 
 // one framer -> [pre-emphasis] -> [window] -> [FFT -> magnitude] chain
@@ -178,5 +231,7 @@ bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, double levelPeriod, P
 bool build_spectral(const osm_b200_spectral &cfg, int nSrc, double fftFrameSizeSec, SpectralOp &op, std::string &err);
 void build_energy(const osm_b200_energy &cfg, EnergyOp &op);
 void build_mzcr(const osm_b200_mzcr &cfg, MzcrOp &op);
+bool build_pitch_chain(const osm_b200_specscale &sc, const osm_b200_pitchshs &ps, const osm_b200_pitchsmootherviterbi &vc,
+                       int nMag, double fftFrameSizeSec, PitchChainOp &op, std::string &err);
 
 }  // namespace osm

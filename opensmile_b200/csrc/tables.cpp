@@ -403,4 +403,105 @@ void build_mzcr(const osm_b200_mzcr &cfg, MzcrOp &op)
   op.nOut = (int)op.zcr + (int)op.mcr + (int)op.amax + 2 * (int)op.maxmin + (int)op.dc;
 }
 
+// cSpecScale::dataProcessorCustomFinalise (dsp/specScale.cpp:236-313), cPitchShs::setupNewNames
+// (lld/pitchShs.cpp:160-215), cPitchBase / cPitchSmootherViterbi configuration.  The spline's abscissa
+// terms (smileUtilSpline.c:124-140) are folded into recurrence coefficients, see PitchChainOp.
+bool build_pitch_chain(const osm_b200_specscale &sc, const osm_b200_pitchshs &ps, const osm_b200_pitchsmootherviterbi &vc,
+                       int nMag, double fftFrameSizeSec, PitchChainOp &op, std::string &err)
+{
+  if (!(sc.scaleOctave && sc.sourceLin && sc.splineInterp)) { err = "cSpecScale: only scale=octave (log base 2), sourceScale=lin, interpMethod=spline are supported"; return false; }
+  op.nMag = nMag;
+  op.nPts = sc.nPointsTarget > 0 ? sc.nPointsTarget : nMag;
+  if (nMag < 8 || op.nPts < 8 || op.nPts > 4096) { err = "cSpecScale: unsupported number of points"; return false; }
+  op.enhance = sc.specEnhance != 0; op.smooth = sc.specSmooth != 0;
+  const double fsSec = (double)(float)fftFrameSizeSec;              // specScale.cpp:184-187
+  const double deltaF = 1.0 / fsSec;
+  double minF = sc.minF < 1.0 ? 1.0 : sc.minF, maxF = sc.maxF;
+  const double samplF = deltaF * (double)(nMag - 1);
+  if (maxF <= minF || maxF > samplF) maxF = samplF;
+  const double fmin_t = log(minF) / log(2.0), fmax_t = log(maxF) / log(2.0);
+  const double deltaF_t = (fmax_t - fmin_t) / (double)(op.nPts - 1);
+  std::vector<double> x(nMag);
+  for (int i = 1; i < nMag; i++) x[i] = log((double)i * deltaF) / log(2.0);
+  x[0] = 2.0 * x[1] - x[2];
+  op.fwdA.assign(nMag, 0.0); op.fwdP6.assign(nMag, 0.0); op.r1.assign(nMag, 0.0); op.r2.assign(nMag, 0.0); op.bwdD.assign(nMag, 0.0);
+  double dPrev = 0.0;                                               // y2[0] = 0 (natural boundary, y1p = 1e30)
+  for (int i = 1; i < nMag - 1; i++) {
+    const double sigma = (x[i] - x[i - 1]) / (x[i + 1] - x[i - 1]);
+    const double diff1 = (x[i + 1] - x[i]) * (x[i + 1] - x[i - 1]);
+    const double diff2 = (x[i] - x[i - 1]) * (x[i + 1] - x[i - 1]);
+    const double p = 1.0 / (sigma * dPrev + 2.0);
+    dPrev = (sigma - 1.0) * p;
+    op.bwdD[i] = dPrev;
+    op.fwdA[i] = -p * sigma;
+    op.fwdP6[i] = 6.0 * p;
+    op.r1[i] = 1.0 / diff1;
+    op.r2[i] = 1.0 / diff2;
+  }
+  op.ik.resize(op.nPts); op.ia.resize(op.nPts); op.ic.resize(op.nPts); op.id.resize(op.nPts);
+  long kupper = 1;
+  for (int i = 0; i < op.nPts; i++) {                               // smileUtilSpline.c:301-352
+    const double xi = fmin_t + (double)i * deltaF_t;
+    if (i == 0 && xi < x[0]) { err = "cSpecScale: minF below the source axis"; return false; }
+    while (kupper < nMag && x[kupper] < xi) kupper++;
+    if (kupper == nMag) { err = "cSpecScale: target axis exceeds the source axis"; return false; }
+    const long klower = kupper - 1;
+    const double range = x[kupper] - x[klower];
+    if (range == 0.0) { err = "cSpecScale: degenerate source axis"; return false; }
+    const double a = (x[kupper] - xi) / range, b = 1.0 - a, range2 = range * range / 6.0;
+    op.ik[i] = (int)klower; op.ia[i] = a; op.ic[i] = (a * a * a - a) * range2; op.id[i] = (b * b * b - b) * range2;
+  }
+  const double nOct = log(maxF / minF) / log(2.0);
+  const double ppo = (double)op.nPts / nOct;
+  op.audW.clear();
+  if (sc.auditoryWeighting) {                                       // specScale.cpp:289-297
+    const double atan_s = ppo * (log(65.0 / 50.0) / log(2.0)) - 1.0;
+    op.audW.resize(op.nPts);
+    for (int i = 0; i < op.nPts; i++) op.audW[i] = 0.5 + atan(3.0 * ((double)(i + 1) - atan_s) / ppo) / M_PI;
+  }
+  // level meta data is stored as float (specScale.cpp:299-311) and read back by cPitchShs (pitchShs.cpp:166-194)
+  const float fMinF = (float)minF, fNOct = (float)nOct, fPpo = (float)ppo, fFminT = (float)fmin_t, fFmaxT = (float)fmax_t;
+  if (fNOct == 0.0f) { err = "cSpecScale: zero octaves"; return false; }
+  double base = exp(log((double)fMinF) / (double)fFminT);
+  if (fabs(base - 2.0) < 0.00001) base = 2.0;
+  op.logBase = log(base);
+  op.Fmint = fFminT;
+  op.Fstept = (fFmaxT - fFminT) / (float)(op.nPts - 1);
+  // cPitchBase (lldcore/pitchBase.cpp:80-118)
+  op.maxPitch = ps.maxPitch < 0.0 ? 0.0 : ps.maxPitch;
+  op.minPitch = ps.minPitch < 0.0 ? 0.0 : ps.minPitch;
+  if (op.minPitch > op.maxPitch) op.minPitch = op.maxPitch;
+  op.nCand = ps.nCandidates < 1 ? 1 : (ps.nCandidates > 20 ? 20 : ps.nCandidates);
+  if (op.nCand > 8) { err = "cPitchShs.nCandidates > 8 is not supported"; return false; }
+  op.scores = ps.scores != 0; op.voicing = ps.voicing != 0; op.F0C1 = ps.F0C1 != 0; op.voicingC1 = ps.voicingC1 != 0;
+  op.F0raw = ps.F0raw != 0; op.voicingClip = ps.voicingClip != 0;
+  if (!op.voicing) { err = "cPitchShs.voicing=0 below cPitchSmootherViterbi is not supported"; return false; }
+  op.voicingCutoff = (float)ps.voicingCutoff;
+  op.octaveCorr = ps.octaveCorrection != 0; op.greedy = ps.greedyPeakAlgo != 0;
+  op.nHarm = ps.nHarmonics;
+  if (op.nHarm < 1 || op.nHarm > 32) { err = "cPitchShs.nHarmonics out of range"; return false; }
+  op.shift.clear(); op.hscale.clear();
+  const float comp = (float)ps.compressionFactor;
+  float scale = comp;
+  for (int i = 2; i < op.nHarm + 1; i++) {                          // pitchShs.cpp:246-254
+    op.shift.push_back((int)(long)floor((double)fPpo * (log((double)i) / log(2.0))));
+    op.hscale.push_back(scale);
+    scale *= comp;
+  }
+  op.lfCutBin = -1;
+  if (ps.lfCut > 0.0) op.lfCutBin = (int)((ceil(log(ps.lfCut) / log(base)) - op.Fmint) / op.Fstept);   // :230-236
+  op.nShsCols = 1 + op.nCand * (1 + (int)op.voicing + (int)op.scores) + (int)op.F0C1 + (int)op.voicingC1 + (int)op.F0raw + (int)op.voicingClip;
+  // cPitchSmootherViterbi (lld/pitchSmootherViterbi.cpp:260-292; setWeights stores tvv in wTvvd, hpp:291-299)
+  op.bufLen = vc.bufferLength;
+  if (op.bufLen < 2 || op.bufLen > 64) { err = "cPitchSmootherViterbi.bufferLength must be 2..64"; return false; }
+  if (vc.F0raw || vc.voicingC1 || vc.voicingClip) { err = "cPitchSmootherViterbi: the copied fields F0raw / voicingC1 / voicingClip are not supported"; return false; }
+  if (vc.F0finalLog || vc.F0finalEnvLog) { err = "cPitchSmootherViterbi: F0finalLog / F0finalEnvLog are not supported yet"; return false; }
+  op.oF0final = vc.F0final != 0; op.oF0finalLog = vc.F0finalLog != 0; op.oF0finalEnv = vc.F0finalEnv != 0; op.oF0finalEnvLog = vc.F0finalEnvLog != 0;
+  op.oVClipped = vc.voicingFinalClipped != 0; op.oVUnclipped = vc.voicingFinalUnclipped != 0;
+  op.wLocal = vc.wLocal; op.wTvv = vc.wTvv; op.wTvvd = vc.wTvv; op.wTvuv = vc.wTvuv; op.wThr = vc.wThr; op.wRange = vc.wRange; op.wTuu = vc.wTuu;
+  op.nOut = (int)op.oF0final + (int)op.oF0finalLog + (int)op.oF0finalEnv + (int)op.oF0finalEnvLog + (int)op.oVClipped + (int)op.oVUnclipped;
+  if (op.nOut < 1) { err = "cPitchSmootherViterbi produces no output"; return false; }
+  return true;
+}
+
 }  // namespace osm

@@ -219,7 +219,10 @@ const TypeInfo kTypes[] = {
   {"cMZcr", OSM_B200_C_MZCR}, {"cAcf", OSM_B200_C_ACF}, {"cPitchACF", OSM_B200_C_PITCHACF},
   {"cDeltaRegression", OSM_B200_C_DELTAREGRESSION}, {"cContourSmoother", OSM_B200_C_CONTOURSMOOTHER},
   {"cVectorConcat", OSM_B200_C_VECTORCONCAT}, {"cVectorOperation", OSM_B200_C_VECTOROPERATION},
-  {"cFullinputMean", OSM_B200_C_FULLINPUTMEAN}, {"cIntensity", OSM_B200_C_INTENSITY}};
+  {"cFullinputMean", OSM_B200_C_FULLINPUTMEAN}, {"cIntensity", OSM_B200_C_INTENSITY},
+  {"cSpecScale", OSM_B200_C_SPECSCALE}, {"cPitchShs", OSM_B200_C_PITCHSHS},
+  {"cPitchSmootherViterbi", OSM_B200_C_PITCHSMOOTHERVITERBI}, {"cValbasedSelector", OSM_B200_C_VALBASEDSELECTOR},
+  {"cPitchJitter", OSM_B200_C_PITCHJITTER}};
 
 int type_of(const std::string &t)
 {
@@ -405,6 +408,72 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         if (f == "nameBase") { snprintf(c.u.vectoroperation.nameBase, OSM_B200_NAME_LEN, "%s", v.c_str()); continue; }
         if (f == "param1" || f == "param2" || f == "logfloor" || f == "powOnlyPos") continue;
         break;
+      case OSM_B200_C_SPECSCALE: {          // dsp/specScale.cpp:38-62,104-176
+        auto &q = c.u.specscale;
+        SETD("minF", q.minF) SETD("maxF", q.maxF) SETI("nPointsTarget", q.nPointsTarget) SETI("specSmooth", q.specSmooth)
+        SETI("specEnhance", q.specEnhance) SETI("auditoryWeighting", q.auditoryWeighting)
+        if (f == "scale") {
+          std::string l = v; for (auto &ch : l) ch = (char)tolower(ch);
+          q.scaleOctave = (l.compare(0, 3, "oct") == 0) ? 1 : ((l.compare(0, 3, "log") == 0) ? 2 : 0);   // 2: needs logScaleBase == 2
+          continue;
+        }
+        if (f == "logScaleBase") { if (num(v) != 2.0) q.scaleOctave = 0; continue; }
+        if (f == "sourceScale") { std::string l = v; for (auto &ch : l) ch = (char)tolower(ch); q.sourceLin = l.compare(0, 3, "lin") == 0; continue; }
+        if (f == "interpMethod") { q.splineInterp = v == "spline"; continue; }
+        if (f == "logSourceScaleBase" || f == "firstNote") continue;
+        break;
+      }
+      case OSM_B200_C_PITCHSHS: {           // lldcore/pitchBase.cpp:41-62, lld/pitchShs.cpp:56-64
+        auto &q = c.u.pitchshs;
+        SETD("maxPitch", q.maxPitch) SETD("minPitch", q.minPitch) SETI("nCandidates", q.nCandidates) SETI("scores", q.scores)
+        SETI("voicing", q.voicing) SETI("F0C1", q.F0C1) SETI("voicingC1", q.voicingC1) SETI("F0raw", q.F0raw)
+        SETI("voicingClip", q.voicingClip) SETD("voicingCutoff", q.voicingCutoff) SETI("octaveCorrection", q.octaveCorrection)
+        SETI("nHarmonics", q.nHarmonics) SETD("compressionFactor", q.compressionFactor) SETI("greedyPeakAlgo", q.greedyPeakAlgo)
+        SETD("lfCut", q.lfCut)
+        if (f == "shsSpectrumOutput") { if (inum(v)) { err = "cPitchShs.shsSpectrumOutput=1 is not supported"; return false; } continue; }
+        if (f == "inputFieldSearch" || f.compare(0, 10, "shsWriter.") == 0) continue;
+        break;
+      }
+      case OSM_B200_C_PITCHSMOOTHERVITERBI: {   // lld/pitchSmootherViterbi.cpp:45-68
+        auto &q = c.u.pitchsmootherviterbi;
+        SETI("bufferLength", q.bufferLength) SETI("F0final", q.F0final) SETI("F0finalLog", q.F0finalLog) SETI("F0finalEnv", q.F0finalEnv)
+        SETI("F0finalEnvLog", q.F0finalEnvLog) SETI("voicingFinalClipped", q.voicingFinalClipped)
+        SETI("voicingFinalUnclipped", q.voicingFinalUnclipped) SETI("F0raw", q.F0raw) SETI("voicingC1", q.voicingC1)
+        SETI("voicingClip", q.voicingClip) SETD("wLocal", q.wLocal) SETD("wTvv", q.wTvv) SETD("wTvvd", q.wTvvd) SETD("wTvuv", q.wTvuv)
+        SETD("wThr", q.wThr) SETD("wRange", q.wRange) SETD("wTuu", q.wTuu)
+        if (f == "no0f0") continue;
+        if (f == "reader2.dmLevel") {        // the second reader only fetches time stamps; it must name the same level
+          const std::string *r1 = s.get("reader.dmLevel");
+          if (!r1 || *r1 != v) { err = "cPitchSmootherViterbi: reader2.dmLevel must equal reader.dmLevel"; return false; }
+          continue;
+        }
+        if (f.compare(0, 8, "reader2.") == 0) continue;
+        break;
+      }
+      case OSM_B200_C_VALBASEDSELECTOR: {   // other/valbasedSelector.cpp:35-49
+        auto &q = c.u.valbasedselector;
+        SETD("threshold", q.threshold) SETI("idx", q.idx) SETI("invert", q.invert) SETI("allowEqual", q.allowEqual)
+        SETI("removeIdx", q.removeIdx) SETI("zeroVec", q.zeroVec) SETD("outputVal", q.outputVal)
+        SETI("adaptiveThreshold", q.adaptiveThreshold)
+        if (f == "adaptationLengthSec" || f == "adaptationLength" || f == "debugAdaptiveThreshold") continue;
+        break;
+      }
+      case OSM_B200_C_PITCHJITTER: {        // lld/pitchJitter.cpp:45-78
+        auto &q = c.u.pitchjitter;
+        if (f == "F0reader.dmLevel") { snprintf(q.F0reader_dmLevel, OSM_B200_NAME_LEN, "%s", v.c_str()); continue; }
+        if (f == "F0field") { snprintf(q.F0field, OSM_B200_NAME_LEN, "%s", v.c_str()); continue; }
+        SETD("searchRangeRel", q.searchRangeRel) SETI("jitterLocal", q.jitterLocal) SETI("jitterDDP", q.jitterDDP)
+        SETI("jitterLocalEnv", q.jitterLocalEnv) SETI("jitterDDPEnv", q.jitterDDPEnv) SETI("shimmerLocal", q.shimmerLocal)
+        SETI("shimmerLocalDB", q.shimmerLocalDB) SETI("shimmerLocalEnv", q.shimmerLocalEnv) SETI("shimmerLocalDBEnv", q.shimmerLocalDBEnv)
+        SETI("harmonicERMS", q.harmonicERMS) SETI("noiseERMS", q.noiseERMS) SETI("linearHNR", q.linearHNR) SETI("logHNR", q.logHNR)
+        SETD("lgHNRfloor", q.lgHNRfloor) SETI("shimmerUseRmsAmplitude", q.shimmerUseRmsAmplitude) SETI("minNumPeriods", q.minNumPeriods)
+        SETD("minCC", q.minCC) SETI("refinedF0", q.refinedF0) SETI("sourceQualityRange", q.sourceQualityRange)
+        SETI("sourceQualityMean", q.sourceQualityMean) SETI("usePeakToPeakPeriodLength", q.usePeakToPeakPeriodLength)
+        SETI("useBrokenJitterThresh", q.useBrokenJitterThresh) SETI("onlyVoiced", q.onlyVoiced)
+        if (f == "periodOutputFile") { if (!v.empty()) { err = "cPitchJitter.periodOutputFile is not supported"; return false; } continue; }
+        if (f == "inputMaxDelaySec" || f.compare(0, 9, "F0reader.") == 0) continue;
+        break;
+      }
       default: break;
     }
     // same behaviour as the reference: an unknown field aborts configuration (configManager.cpp:2599)
@@ -573,6 +642,7 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
   std::map<std::string, const Section *> secOf;
   for (const auto &sec : s->conf.sections) if (sec.type != "cComponentManager") secOf[sec.name] = &sec;
   std::vector<std::string> sinkLevels;
+  std::vector<const Section *> compute;
   std::set<std::string> hostTypes = {"cDataMemory", "cHtkSink", "cCsvSink", "cArffSink", "cExternalSink", "cNullSink", "cDatadumpSink"};
   for (const auto &inst : s->conf.instances) {
     const std::string &name = inst.first, &type = inst.second;
@@ -601,16 +671,8 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
       continue;
     }
     if (!sec) { delete s; return hfail(OSM_B200_ERR_INVALID, "instance '" + name + "' (" + type + ") has no configuration section"); }
-    osm_b200_component c;
-    if (!to_component(*sec, c, err)) {
-      const bool unknownType = type_of(type) < 0;
-      delete s;
-      return hfail(unknownType ? OSM_B200_ERR_UNSUPPORTED : OSM_B200_ERR_INVALID, err);
-    }
-    if (c.type == OSM_B200_C_WAVESOURCE) s->waveIdx = (int)s->comps.size();
-    s->comps.push_back(c);
+    compute.push_back(sec);
   }
-  if (s->waveIdx < 0) { delete s; return hfail(OSM_B200_ERR_INVALID, "the configuration has no cWaveSource / cExternalAudioSource"); }
   // output level: explicit, or the level the active sinks read; a multi-level sink reader is an
   // implicit concat (core/dataReader.cpp:360-444)
   std::string lvl = output_level ? output_level : "";
@@ -618,6 +680,43 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
     if (sinkLevels.empty()) { delete s; return hfail(OSM_B200_ERR_INVALID, "no active sink: pass output_level or enable a sink (-O / -csvoutput)"); }
     lvl = sinkLevels[0];
   }
+  // Only the components the output level depends on are part of the plan: the shipped feature-set
+  // configurations carry sinks and summaries (cFunctionals ...) that stay idle when their output file is
+  // not requested (filename = ?), exactly like the reference leaves those sinks unwritten.
+  {
+    std::map<std::string, const Section *> writerOf;
+    for (const Section *sec : compute) if (const std::string *w = sec->get("writer.dmLevel")) writerOf[*w] = sec;
+    std::set<const Section *> need;
+    std::vector<std::string> todo;
+    auto push_levels = [&](const std::string &v) {
+      std::stringstream ss(v);
+      std::string one;
+      while (std::getline(ss, one, ';')) { one = trim(one); if (!one.empty()) todo.push_back(one); }
+    };
+    push_levels(lvl);
+    while (!todo.empty()) {
+      const std::string l = todo.back();
+      todo.pop_back();
+      auto it = writerOf.find(l);
+      if (it == writerOf.end() || need.count(it->second)) continue;
+      need.insert(it->second);
+      for (const char *key : {"reader.dmLevel", "reader2.dmLevel", "F0reader.dmLevel"})
+        if (const std::string *r = it->second->get(key)) push_levels(*r);
+    }
+    for (const Section *sec : compute) {
+      const bool isWave = sec->type == "cWaveSource" || sec->type == "cExternalAudioSource";
+      if (!isWave && !need.count(sec)) continue;
+      osm_b200_component c;
+      if (!to_component(*sec, c, err)) {
+        const bool unknownType = type_of(sec->type) < 0;
+        delete s;
+        return hfail(unknownType ? OSM_B200_ERR_UNSUPPORTED : OSM_B200_ERR_INVALID, err);
+      }
+      if (c.type == OSM_B200_C_WAVESOURCE) s->waveIdx = (int)s->comps.size();
+      s->comps.push_back(c);
+    }
+  }
+  if (s->waveIdx < 0) { delete s; return hfail(OSM_B200_ERR_INVALID, "the configuration has no cWaveSource / cExternalAudioSource"); }
   if (lvl.find(';') != std::string::npos) {
     osm_b200_component c;
     osm_b200_component_defaults(OSM_B200_C_VECTORCONCAT, &c);

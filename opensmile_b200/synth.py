@@ -21,3 +21,24 @@ def voiced_pcm(n_samples, sample_rate=16000, seed=0, n_chan=1):
         chans.append(np.clip(y, -1.0, 1.0))
     y = np.stack(chans, axis=1).reshape(-1) if n_chan > 1 else chans[0]
     return np.round(y * 32767.0).astype(np.int16)
+
+
+def mixed_pcm(n_samples, sample_rate=16000, seed=0):
+    """voiced_pcm with stretches replaced by loud noise (unvoiced) and near silence: exercises the
+    voiced / unvoiced decisions of the pitch chain (segments of 50..375 ms, kinds cycle voiced, noise,
+    voiced, silence)."""
+    rng = np.random.default_rng(seed)
+    x = voiced_pcm(n_samples, sample_rate, seed=seed).astype(np.float64)
+    seg = 0
+    pos = 0
+    while pos < n_samples:
+        ln = int(rng.integers(sample_rate // 20, sample_rate * 3 // 8))
+        kind = seg % 4
+        m = min(ln, n_samples - pos)
+        if kind == 1:
+            x[pos:pos + m] = rng.normal(0, 600, size=m)
+        if kind == 3:
+            x[pos:pos + m] = rng.normal(0, 3, size=m)
+        pos += ln
+        seg += 1
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)

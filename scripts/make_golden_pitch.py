@@ -1,0 +1,70 @@
+"""Generate tests/golden/pitch_goldens.npz with the UNMODIFIED reference (oracle/_ref/SMILExtract):
+
+    python scripts/make_golden_pitch.py        # needs `make -C oracle ref` (build container only)
+
+For each case (inputs are regenerated in the tests from opensmile_b200.synth):
+  <case>_lld      config/compare16/ComParE_2016.conf -lldhtkoutput: the full ComParE_2016 LLD set [rows, 130]
+                  (level lld ; lld_de, float32 exact)
+  <case>_shs/_vit/_sel/_jit/_nz/_nzde/_e60   level taps of tests/configs/compare_pitch_taps.conf (cPitchShs,
+                  cPitchSmootherViterbi, cValbasedSelector, cPitchJitter, smoothed level and its delta, rms energy)
+  names_lld       element names of the LLD CSV header
+Cases: v32k = voiced_pcm(32000, seed=7); m48k = mixed_pcm(48000, seed=2) (Viterbi lag 1); m30k = mixed_pcm(30000, seed=4);
+       m64k = mixed_pcm(64000, seed=3); short_<n> = voiced_pcm(n, seed=7) for n = 960, 1120, 1600, 2400 (1, 2, 5, 10 frames of 60 ms)
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refrun  # noqa: E402
+from opensmile_b200.synth import mixed_pcm, voiced_pcm  # noqa: E402
+
+CASES = {
+    "v32k": lambda: voiced_pcm(32000, 16000, seed=7),
+    "m48k": lambda: mixed_pcm(48000, 16000, seed=2),
+    "m30k": lambda: mixed_pcm(30000, 16000, seed=4),
+    "m64k": lambda: mixed_pcm(64000, 16000, seed=3),
+    "short_960": lambda: voiced_pcm(960, 16000, seed=7),
+    "short_1120": lambda: voiced_pcm(1120, 16000, seed=7),
+    "short_1600": lambda: voiced_pcm(1600, 16000, seed=7),
+    "short_2400": lambda: voiced_pcm(2400, 16000, seed=7),
+}
+
+
+def main():
+    assert refrun.available(), "build the reference first: make -C oracle ref"
+    out = {}
+    taps_src = open(os.path.join(ROOT, "tests", "configs", "compare_pitch_taps.conf")).read().replace("REFCONF", refrun.CONFIG_DIR)
+    full = os.path.join(refrun.CONFIG_DIR, "compare16", "ComParE_2016.conf")
+    for name, gen in CASES.items():
+        pcm = gen()
+        with tempfile.TemporaryDirectory() as d:
+            wav = os.path.join(d, "in.wav")
+            refrun.write_wav(wav, pcm, 16000, 1)
+            with open(os.path.join(d, "taps.conf"), "w") as f:
+                f.write(taps_src)
+            subprocess.run([refrun.SMILEXTRACT, "-C", "taps.conf", "-I", "in.wav", "-l", "0"], cwd=d, check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            for k in ("shs", "vit", "sel", "jit", "nz", "nzde", "e60"):
+                p = os.path.join(d, k + ".htk")
+                if os.path.exists(p) and os.path.getsize(p) > 12:
+                    out["%s_%s" % (name, k)] = refrun.read_htk(p)[0]
+            subprocess.run([refrun.SMILEXTRACT, "-C", full, "-I", wav, "-lldhtkoutput", os.path.join(d, "lld.htk"),
+                            "-lldcsvoutput", os.path.join(d, "lld.csv"), "-l", "0"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            p = os.path.join(d, "lld.htk")
+            if os.path.exists(p) and os.path.getsize(p) > 12:
+                out["%s_lld" % name] = refrun.read_htk(p)[0]
+            if "names_lld" not in out and os.path.exists(os.path.join(d, "lld.csv")):
+                hdr = open(os.path.join(d, "lld.csv")).readline().strip().split(";")
+                out["names_lld"] = np.array([h for h in hdr if h not in ("name", "frameIndex", "frameTime")])
+        print(name, {k[len(name) + 1:]: v.shape for k, v in out.items() if k.startswith(name + "_")})
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pitch_goldens.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,88 @@
+"""SHS pitch chain: the CPU restatement (oracle/osm_oracle_pitch.c + the end-of-input lag
+model in oracle/oracle.py) against level taps of the UNMODIFIED reference (tests/golden/pitch_goldens.npz,
+scripts/make_golden_pitch.py), and the description-only view of the shipped ComParE_2016 configuration."""
+import os
+
+import numpy as np
+import pytest
+
+from opensmile_b200.synth import mixed_pcm, voiced_pcm
+from oracle import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "pitch_goldens.npz"))
+
+CASES = {
+    "v32k": lambda: voiced_pcm(32000, 16000, seed=7),
+    "m48k": lambda: mixed_pcm(48000, 16000, seed=2),
+    "m30k": lambda: mixed_pcm(30000, 16000, seed=4),
+    "m64k": lambda: mixed_pcm(64000, 16000, seed=3),
+}
+
+
+def _rel(a, b):
+    sc = np.abs(b).max(axis=0) + 1e-30
+    return float((np.abs(a - b) / sc).max())
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_shs_level(case):
+    fe, sc, ps, vc, jc = oracle.compare16_pitch_cfg()
+    shs = oracle.pitch_shs(CASES[case](), fe, sc, ps)
+    ref = G[case + "_shs"]
+    assert shs.shape == ref.shape
+    assert np.array_equal(shs[:, 0], ref[:, 0])                 # number of candidates
+    assert _rel(shs, ref) < 2e-6
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_viterbi_selector_jitter_exact_given_inputs(case):
+    """Given the reference's own input levels the sequential stages reproduce it bit for bit."""
+    fe, sc, ps, vc, jc = oracle.compare16_pitch_cfg()
+    vit = oracle.viterbi(G[case + "_shs"], ps, vc)
+    assert np.array_equal(vit, G[case + "_vit"])
+    sel = oracle.valbased_select(G[case + "_e60"][:, 0], G[case + "_vit"], 0.001)
+    assert np.array_equal(sel, G[case + "_sel"])
+    jit = oracle.pitch_jitter(CASES[case](), fe, jc, G[case + "_sel"][:, 0])
+    assert np.array_equal(jit, G[case + "_jit"])
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_whole_chain_and_eoi_lag_model(case):
+    """PCM -> smoothed level and its onlyInSegments delta, including the rows the reference computes
+    while its jitter level lags behind the flushed Viterbi level."""
+    pcm = CASES[case]()
+    nz, lag = oracle.compare16_pitch(pcm, with_lag=True)
+    ref = np.concatenate([G[case + "_sel"], G[case + "_jit"]], axis=1)
+    assert nz.shape == ref.shape
+    assert _rel(nz, ref) < 2e-6
+    sm, de = oracle.compare16_nz_lld(pcm)
+    assert sm.shape == G[case + "_nz"].shape and de.shape == G[case + "_nzde"].shape
+    assert _rel(sm, G[case + "_nz"]) < 2e-6
+    assert _rel(de, G[case + "_nzde"]) < 1e-5
+    # the lag model is exact on the reference's own statics
+    assert np.array_equal(oracle.sma_nz_lagged(ref, lag, {2, 3, 4, 5}), G[case + "_nz"])
+    assert np.array_equal(oracle.delta_segments_lagged(G[case + "_nz"], lag, 2), G[case + "_nzde"])
+
+
+def test_lagged_cases_cover_both_lags():
+    fe, sc, ps, vc, jc = oracle.compare16_pitch_cfg()
+    lags = {c: oracle.viterbi(G[c + "_shs"], ps, vc, with_lag=True)[1] - G[c + "_shs"].shape[0] for c in CASES}
+    assert set(lags.values()) >= {-1, -2}, lags
+
+
+def test_compare16_conf_description():
+    """The shipped ComParE_2016.conf opens unchanged (sinks without a file name and the functionals they feed
+    stay idle); element names and row counts equal the reference's LLD file."""
+    from opensmile_b200.session import Session
+    conf = os.path.join(HERE, "configs", "ref", "compare16", "ComParE_2016.conf")
+    if not os.path.exists(conf):
+        from oracle import refrun
+        if not refrun.available():
+            pytest.skip("reference configuration files not available")
+        conf = os.path.join(refrun.CONFIG_DIR, "compare16", "ComParE_2016.conf")
+    s = Session(conf, options={"lldcsvoutput": "x.csv"}, device=-1)
+    assert list(s.element_names(16000.0, 1)) == [str(x) for x in G["names_lld"]]
+    off = s.frame_offsets(np.array([0, 32000, 32000 + 48000, 32000 + 48000 + 960]), 16000.0)
+    assert list(np.diff(off)) == [G["v32k_lld"].shape[0], G["m48k_lld"].shape[0], G["short_960_lld"].shape[0]]
+    s.close()

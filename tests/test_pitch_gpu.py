@@ -1,0 +1,64 @@
+"""ComParE_2016 full LLD set (BASELINE configs[3]) on the GPU: the shipped configuration file runs unchanged
+through the C ABI (session layer) and is compared with the UNMODIFIED reference's LLD output
+(tests/golden/pitch_goldens.npz, scripts/make_golden_pitch.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from opensmile_b200.synth import mixed_pcm, voiced_pcm
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "pitch_goldens.npz"))
+CONF = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "config", "compare16", "ComParE_2016.conf")
+
+CASES = {
+    "v32k": lambda: voiced_pcm(32000, 16000, seed=7),
+    "m48k": lambda: mixed_pcm(48000, 16000, seed=2),
+    "m30k": lambda: mixed_pcm(30000, 16000, seed=4),
+    "m64k": lambda: mixed_pcm(64000, 16000, seed=3),
+    "short_960": lambda: voiced_pcm(960, 16000, seed=7),
+    "short_1600": lambda: voiced_pcm(1600, 16000, seed=7),
+    "short_2400": lambda: voiced_pcm(2400, 16000, seed=7),
+}
+
+
+@pytest.fixture(scope="module")
+def session():
+    from opensmile_b200.session import Session
+    if not os.path.exists(CONF):
+        pytest.skip("reference configuration files not built (make -C oracle ref)")
+    s = Session(CONF, options={"lldcsvoutput": "x.csv"}, device=0)
+    yield s
+    s.close()
+
+
+def _check(got, ref, names):
+    assert got.shape == ref.shape
+    # tolerance: 1e-5 of each column's largest magnitude (columns mix Hz, ratios and dB)
+    sc = np.abs(ref).max(axis=0) + 1e-30
+    err = np.abs(got - ref) / sc
+    bad = np.argwhere(err > 1e-5)
+    assert bad.size == 0, [(names[c], int(r), float(got[r, c]), float(ref[r, c])) for r, c in bad[:8]]
+
+
+def test_compare16_full_lld_batch(session):
+    """all cases as ONE ragged batch"""
+    keys = sorted(CASES)
+    pcms = [CASES[k]() for k in keys]
+    off = np.cumsum([0] + [p.size for p in pcms]).astype(np.int64)
+    rows, fo = session.extract_pcm(np.concatenate(pcms), off, 16000.0, 1)
+    names = session.element_names(16000.0, 1)
+    assert list(names) == [str(x) for x in G["names_lld"]]
+    for i, k in enumerate(keys):
+        _check(rows[fo[i]:fo[i + 1]], G[k + "_lld"], names)
+
+
+def test_compare16_single_and_repeatable(session):
+    pcm = CASES["m30k"]()
+    off = np.array([0, pcm.size], np.int64)
+    a, _ = session.extract_pcm(pcm, off, 16000.0, 1)
+    b, _ = session.extract_pcm(pcm, off, 16000.0, 1)
+    assert np.array_equal(a, b)
+    _check(a, G["m30k_lld"], session.element_names(16000.0, 1))
