@@ -15,7 +15,10 @@ n_utt = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 n_samp = int(sys.argv[3]) if len(sys.argv) > 3 else 48000
 sr = float(sys.argv[4]) if len(sys.argv) > 4 else 16000.0
 nch = int(sys.argv[5]) if len(sys.argv) > 5 else 1
-s = Session(conf, device=-1)
+# OSM_BENCH_OPTS="lldcsvoutput=x.csv,other=value": command line options of the configuration file (e.g. the shipped
+# ComParE_2016.conf only has an LLD sink when -lldcsvoutput is given)
+opts = dict(kv.split("=", 1) for kv in os.environ.get("OSM_BENCH_OPTS", "").split(",") if "=" in kv)
+s = Session(conf, options=opts or None, device=-1)
 comps, level = s.components(sr, nch)
 plan = Plan(list(comps), level, 0)
 pcm = bench.synth_batch_torch(n_utt, n_samp * nch, torch.device("cuda", 0), 0)
