@@ -541,6 +541,11 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       G.deltaWin = g.stages.size() > 1 ? g.stages[1].win : 0;
       G.segId = g.segId;
       if (G.nStages == 2 && G.deltaWin != 2) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cDeltaRegression(onlyInSegments) behind the pitch chain: deltawin must be 2"); }
+      if (G.nStages == 2) {
+        int segCols = 0;
+        for (int q = 0; q < sq.nGroups; q++) if (sq.groups[q].nStages == 2 && sq.groups[q].segId == G.segId) segCols += sq.groups[q].n;
+        if (segCols > 16) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cDeltaRegression(onlyInSegments): more than 16 elements"); }
+      }
       if (G.segId >= kMaxSeqGroups) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many onlyInSegments delta components"); }
       sq.frameSize = d.streams[g.stream].fe.frameSize; sq.frameStep = d.streams[g.stream].fe.frameStep;
       continue;
@@ -701,6 +706,26 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       jp.shimmerLocalDBEnv = jo.shimmerLocalDBEnv; jp.harmonicERMS = jo.harmonicERMS; jp.noiseERMS = jo.noiseERMS; jp.linearHNR = jo.linearHNR;
       jp.logHNR = jo.logHNR; jp.shimmerUseRms = jo.shimmerUseRms; jp.refinedF0 = jo.refinedF0; jp.srcQualRange = jo.srcQualRange;
       jp.srcQualMean = jo.srcQualMean; jp.peakToPeak = jo.peakToPeak; jp.brokenThresh = jo.brokenThresh;
+      {
+        // F0 comes out of the pitch chain within [minPitch, maxPitch]: longest / shortest period in samples
+        const PitchChainOp &pc = d.ops[jo.pitchOp].chain;
+        const double fs = fe.sampleRate, fLo = pc.minPitch > 1.0 ? pc.minPitch : 1.0, fHi = pc.maxPitch > fLo ? pc.maxPitch : fLo;
+        const double tMax = fs / fLo, tMin = fs / fHi;
+        const long maxPer = (long)ceil((1.0 + jo.searchRangeRel) * tMax) + 2;
+        long minPer = (long)floor((1.0 - jo.searchRangeRel) * tMin);
+        if (minPer < 1) minPer = 1;
+        const long ppLen = (long)ceil(fe.frameStepSec * fs) + 1;
+        long capWav = fe.frameSize + 2 + ppLen + maxPer + 16;
+        const long twoPp = jo.minNumPeriods * maxPer + jo.minNumPeriods + ppLen + 16;
+        if (capWav < twoPp) capWav = twoPp;
+        jp.capWav = (int)((capWav + 3) & ~3L);
+        jp.capCC = (int)(((long)ceil(2.0 * jo.searchRangeRel * tMax) + 8 + 1) & ~1L);
+        jp.capAvg = (int)(((long)ceil(tMax) + 8 + 3) & ~3L);
+        jp.capPb = (int)((capWav / minPer + 8 + 3) & ~3L);
+        if (pc.minPitch < 1.0 || (size_t)4 * ((size_t)jp.capCC * 8 + (size_t)(jp.capWav + jp.capAvg) * 4 + (size_t)jp.capPb * 4) > 200 * 1024) {
+          osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cPitchJitter: frame size / pitch range need more workspace than the kernel has");
+        }
+      }
     } else if (op.kind == SOP_PITCHACF) {
       if (!acf_pitch_supported_fft(fe.nfft)) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cAcf / cPitchACF: FFT size must be 512, 1024 or 2048"); }
       const PitchAcfOp &po = op.pitch;

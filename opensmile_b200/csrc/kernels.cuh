@@ -253,6 +253,9 @@ struct JitterParams {
   int jitterLocal, jitterDDP, jitterLocalEnv, jitterDDPEnv, shimmerLocal, shimmerLocalDB, shimmerLocalEnv, shimmerLocalDBEnv,
       harmonicERMS, noiseERMS, linearHNR, logHNR, shimmerUseRms, refinedF0, srcQualRange, srcQualMean, peakToPeak, brokenThresh;
   int *errFlag;                  // set when a frame exceeds the kernel's workspace (reported by the host)
+  // per-warp workspace (elements): staged wave window, cross correlations per candidate period length, averaged
+  // period waveform, period starts -- sized from the frame geometry and the pitch range of the F0 level
+  int capWav, capCC, capAvg, capPb;
 };
 cudaError_t launch_jitter(const JitterParams &p, int u0, int u1, cudaStream_t st);
 

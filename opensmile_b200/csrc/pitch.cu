@@ -305,7 +305,16 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
   const long long row0 = p.statOff[u];
   const int nC = p.nCand, nS = nC + 1, last = nC, bl = p.bufLen;
   double costA[kVitStates], costB[kVitStates];
-  unsigned char paths[2][kVitStates][kVitBuf], bestPath[kVitBuf];
+  // best path per state as packed bytes (entry k = byte k%4 of word k/4): copying a path moves bufLen/4 words
+  unsigned int paths[2][kVitStates][kVitBuf / 4];
+  unsigned char bestPath[kVitBuf];
+  const int nW = (bl + 3) >> 2;
+  auto path_get = [&](int b, int s, int k) -> int { return (paths[b][s][k >> 2] >> ((k & 3) * 8)) & 0xff; };
+  auto path_set = [&](int b, int s, int k, int v) {
+    const unsigned int sh = (k & 3) * 8;
+    paths[b][s][k >> 2] = (paths[b][s][k >> 2] & ~(0xffu << sh)) | ((unsigned int)v << sh);
+  };
+  double rr[kVitStates][kVitStates];          // log(f1_i / f0_j) of the current frame pair (NaN = empty candidate)
   double *pathCosts = costA, *pathCostsNew = costB;
   double lastChange = 1.0;
   int pathBuf = 0, pathIdx = 0, convIdx = -1, rdIdx = 0;
@@ -354,9 +363,22 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
     const float *prv = cur - p.nShsCols;
     if (pathIdx == 0) {
       convIdx = -1;
-      for (int i = 0; i < nS; i++) { pathCosts[i] = local_cost(i, cur); paths[pathBuf][i][0] = (unsigned char)i; }
+      for (int i = 0; i < nS; i++) {
+        pathCosts[i] = local_cost(i, cur);
+        for (int w = 0; w < nW; w++) paths[pathBuf][i][w] = 0;
+        path_set(pathBuf, i, 0, i);
+      }
     } else {
       const int nb = pathBuf ^ 1;
+      // the logarithms do not depend on the running `lastChange`: evaluate them up front (independent, pipelined),
+      // then walk the (i, j) pairs in the reference's order
+      for (int i = 0; i < nC; i++)
+        for (int j = 0; j < nC; j++) {
+          const float f0 = prv[1 + j], f1 = cur[1 + i];
+          rr[i][j] = (f0 == 0 || f1 == 0) ? nan("") : log((double)(f1 / f0));
+        }
+      double lc[kVitStates];
+      for (int i = 0; i < nS; i++) lc[i] = local_cost(i, cur);
       for (int i = 0; i < nS; i++) {
         int minState = 0;
         double minCost = 0.0;
@@ -364,10 +386,9 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
           double tc;                                                          // hpp:224-252 (i = current state, j = previous state)
           if ((int)(i == j) == last) tc = p.wTuu;                             // the reference's `i == j == nStates-1`
           else if (i < last && j < last) {
-            const float f0 = prv[1 + j], f1 = cur[1 + i];
-            if (f0 == 0 || f1 == 0) tc = 999.0;
+            const double r = rr[i][j];
+            if (r != r) tc = 999.0;
             else {
-              const double r = log((double)(f1 / f0));
               tc = p.wTvv * fabs(r) + p.wTvvd * fabs(r - lastChange);
               lastChange = r;
             }
@@ -376,9 +397,9 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
           const double c = tc + pathCosts[j];
           if (j == 0 || c < minCost) { minState = j; minCost = c; }
         }
-        pathCostsNew[i] = minCost + local_cost(i, cur);
-        for (int k = 0; k < bl; k++) paths[nb][i][k] = paths[pathBuf][minState][k];
-        paths[nb][i][pathIdx % bl] = (unsigned char)i;
+        pathCostsNew[i] = minCost + lc[i];
+        for (int w = 0; w < nW; w++) paths[nb][i][w] = paths[pathBuf][minState][w];
+        path_set(nb, i, pathIdx % bl, i);
       }
       double *tmp = pathCosts; pathCosts = pathCostsNew; pathCostsNew = tmp;
       pathBuf = nb;
@@ -388,15 +409,15 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
       int minState = 0;
       for (int i = 1; i < nS; i++) if (pathCosts[i] < pathCosts[minState]) minState = i;
       convIdx++;
-      bestPath[convIdx % bl] = paths[pathBuf][minState][convIdx % bl];
+      bestPath[convIdx % bl] = (unsigned char)path_get(pathBuf, minState, convIdx % bl);
     } else {
       for (int n = convIdx + 1; n < pathIdx; n++) {
-        const unsigned char x = paths[pathBuf][0][n % bl];
+        const int x = path_get(pathBuf, 0, n % bl);
         bool match = true;
-        for (int i = 1; i < nS; i++) if (x != paths[pathBuf][i][n % bl]) { match = false; break; }
+        for (int i = 1; i < nS; i++) if (x != path_get(pathBuf, i, n % bl)) { match = false; break; }
         if (!match) break;
         convIdx++;
-        bestPath[convIdx % bl] = x;
+        bestPath[convIdx % bl] = (unsigned char)x;
       }
     }
     drain();
@@ -408,7 +429,7 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
     // at most bufLen entries are pending (forced decisions keep pathIdx - convIdx <= bufLen), so the ring is intact
     while (convIdx + 1 < pathIdx) {
       convIdx++;
-      bestPath[convIdx % bl] = paths[pathBuf][minState][convIdx % bl];
+      bestPath[convIdx % bl] = (unsigned char)path_get(pathBuf, minState, convIdx % bl);
       drain();
     }
   }
@@ -416,7 +437,7 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
 
 // ------------------------------------------------------------------------------------------ jitter_kernel
 
-constexpr int kJitWarps = 4, kJitWav = 6144, kJitCC = 512, kJitAvg = 1024, kJitPb = 128;
+constexpr int kJitWarps = 4;
 
 __device__ __forceinline__ float jit_pcm(const int16_t *s, int nChan)       // smileutil/smileUtil.c:2520-2534
 {
@@ -464,6 +485,8 @@ __global__ void __launch_bounds__(kJitWarps * 32) jitter_kernel(const JitterPara
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = u0 + blockIdx.x * kJitWarps + warp;
   if (u >= u1) return;
+  // workspace per warp, sized by the host from the frame geometry and the pitch range (launch_jitter)
+  const int kJitCC = p.capCC, kJitWav = p.capWav, kJitAvg = p.capAvg, kJitPb = p.capPb;
   const size_t perWarp = (size_t)kJitCC * sizeof(double) + (size_t)(kJitWav + kJitAvg) * sizeof(float) + (size_t)kJitPb * sizeof(int);
   unsigned char *ws = smemRaw + warp * perWarp;
   double *cc = reinterpret_cast<double *>(ws);
@@ -733,9 +756,13 @@ __device__ float seq_sma(const SeqCtx &c, int col, int m, int lagKind, int noZer
   return y / 3.0f;
 }
 
-__global__ void __launch_bounds__(64) seq_post_kernel(const SeqPostParams p, int u0, int u1)
+constexpr int kSeqWarps = 4, kMaxSegCols = 16;
+
+// one warp per utterance, lane = row of a 32-row chunk
+__global__ void __launch_bounds__(kSeqWarps * 32) seq_post_kernel(const SeqPostParams p, int u0, int u1)
 {
-  const int u = u0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int u = u0 + blockIdx.x * kSeqWarps + (threadIdx.x >> 5);
   if (u >= u1) return;
   SeqCtx c;
   c.T = frames_of(p.uttOff[u + 1] - p.uttOff[u], p.frameSize, p.frameStep);
@@ -750,38 +777,59 @@ __global__ void __launch_bounds__(64) seq_post_kernel(const SeqPostParams p, int
   for (int g = 0; g < p.nGroups; g++) {
     const SeqGroup &G = p.groups[g];
     if (G.nStages != 1) continue;
-    for (int m = 0; m <= T && m < R; m++)
+    for (int m = lane; m <= T && m < R; m += 32)
       for (int k = 0; k < G.n; k++) out[(size_t)m * p.outStride + G.outCol + k] = seq_sma(c, G.srcCol + k, m, G.lagKind, G.noZero);
   }
   // 2. deltas with onlyInSegments: one running norm per delta component (dspcore/deltaRegression.cpp:77-79,123-141),
-  //    rows in order, elements in column order.  Rows V-1..V+2 are produced during the first EOI pass, when the
-  //    smoothed level ends at its row V; row V+3 (for T-5 <= V <= T-2) in the first tick of the second pass,
-  //    when it ends at row T-1 (core/dataMemoryLevel.cpp:1020-1027,1698-1708).
+  //    rows in order, elements in column order: norm(n, k) = 2*sum i^2 + (i^2 of every accepted pair before and
+  //    including element (n, k)) -- integers, exact in float below 2^24 -- so the running sum is a prefix sum.
+  //    Rows V-1..V+2 are produced during the reference's first EOI pass, when the smoothed level ends at its row V;
+  //    row V+3 (for T-5 <= V <= T-2) in the first tick of the second pass, when it ends at row T-1
+  //    (core/dataMemoryLevel.cpp:1020-1027,1698-1708).
   for (int seg = 0; seg < kMaxSeqGroups; seg++) {
     int W = 0;
     for (int g = 0; g < p.nGroups; g++) if (p.groups[g].nStages == 2 && p.groups[g].segId == seg) W = p.groups[g].deltaWin;
     if (W == 0) continue;
-    float norm = 0.0f;
-    for (int i = 1; i <= W; i++) norm += (float)i * (float)i;
-    norm *= 2.0f;
-    for (int n = 0; n <= T + W; n++) {
+    int normInit = 0;
+    for (int i = 1; i <= W; i++) normInit += i * i;
+    normInit *= 2;
+    int base = 0;
+    for (int n0 = 0; n0 <= T + W; n0 += 32) {
+      const int n = n0 + lane;
+      const bool live = n <= T + W;
       int last = T;
       if (n >= V - 1 && n <= V + 2) last = min(T, max(V, 0));
       else if (n == V + 3 && V >= T - 5 && V <= T - 2) last = T - 1;
+      float num[kMaxSegCols];
+      int cnt[kMaxSegCols];
+      int col = 0, rowTot = 0;
       for (int g = 0; g < p.nGroups; g++) {
         const SeqGroup &G = p.groups[g];
         if (G.nStages != 2 || G.segId != seg) continue;
-        for (int k = 0; k < G.n; k++) {
-          float num = 0.0f;
-          for (int i = 1; i <= W; i++) {
-            const float a = seq_sma(c, G.srcCol + k, min(max(n - i, 0), last), G.lagKind, G.noZero);
-            const float b = seq_sma(c, G.srcCol + k, min(max(n + i, 0), last), G.lagKind, G.noZero);
-            if (!(a == 0.0f || a != a || b == 0.0f || b != b)) {
-              num += (float)i * (b - a);
-              norm += (float)i * (float)i;
+        for (int k = 0; k < G.n && col < kMaxSegCols; k++, col++) {
+          float nm = 0.0f; int ct = 0;
+          if (live) {
+            for (int i = 1; i <= W; i++) {
+              const float a = seq_sma(c, G.srcCol + k, min(max(n - i, 0), last), G.lagKind, G.noZero);
+              const float b = seq_sma(c, G.srcCol + k, min(max(n + i, 0), last), G.lagKind, G.noZero);
+              if (!(a == 0.0f || a != a || b == 0.0f || b != b)) { nm += (float)i * (b - a); ct += i * i; }
             }
           }
-          if (n < R) out[(size_t)n * p.outStride + G.outCol + k] = norm != 0.0f ? num / norm : 0.0f;
+          num[col] = nm; cnt[col] = ct; rowTot += ct;
+        }
+      }
+      int incl = rowTot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFull, incl, d); if (lane >= d) incl += o; }
+      int running = base + incl - rowTot;
+      base += __shfl_sync(kFull, incl, 31);
+      col = 0;
+      for (int g = 0; g < p.nGroups; g++) {
+        const SeqGroup &G = p.groups[g];
+        if (G.nStages != 2 || G.segId != seg) continue;
+        for (int k = 0; k < G.n && col < kMaxSegCols; k++, col++) {
+          running += cnt[col];
+          if (live && n < R) out[(size_t)n * p.outStride + G.outCol + k] = num[col] / (float)(normInit + running);
         }
       }
     }
@@ -812,8 +860,9 @@ cudaError_t launch_viterbi(const ViterbiParams &p, int u0, int u1, cudaStream_t 
 cudaError_t launch_jitter(const JitterParams &p, int u0, int u1, cudaStream_t st)
 {
   if (u1 <= u0) return cudaSuccess;
-  const size_t perWarp = (size_t)kJitCC * sizeof(double) + (size_t)(kJitWav + kJitAvg) * sizeof(float) + (size_t)kJitPb * sizeof(int);
+  const size_t perWarp = (size_t)p.capCC * sizeof(double) + (size_t)(p.capWav + p.capAvg) * sizeof(float) + (size_t)p.capPb * sizeof(int);
   const size_t smem = perWarp * kJitWarps;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(jitter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   jitter_kernel<<<(u1 - u0 + kJitWarps - 1) / kJitWarps, kJitWarps * 32, smem, st>>>(p, u0, u1);
@@ -823,7 +872,7 @@ cudaError_t launch_jitter(const JitterParams &p, int u0, int u1, cudaStream_t st
 cudaError_t launch_seq_post(const SeqPostParams &p, int u0, int u1, cudaStream_t st)
 {
   if (u1 <= u0 || p.nGroups <= 0) return cudaSuccess;
-  seq_post_kernel<<<(u1 - u0 + 63) / 64, 64, 0, st>>>(p, u0, u1);
+  seq_post_kernel<<<(u1 - u0 + kSeqWarps - 1) / kSeqWarps, kSeqWarps * 32, 0, st>>>(p, u0, u1);
   return cudaGetLastError();
 }
 
