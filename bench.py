@@ -40,6 +40,29 @@ FRAMES_PER_UTT = 500
 SAMPLE_RATE = 16000
 BYTES_PER_FRAME = 160 * 2 + 39 * 4   # algorithmic: each PCM sample read once, each LLD value written once
 WORKLOAD = "MFCC12_0_D_A, synthetic 16 kHz mono int16, 2000 utterances x 500 frames = 1M frames per GPU"
+WORKLOAD_KEY = "mfcc12"
+REF_CONF = "mfcc/MFCC12_0_D_A.conf"
+REF_OUT_OPT = "-O"
+N_COLS = 39
+
+
+def select_workload(name):
+    """--workload compare16: BASELINE configs[3], the shipped config/compare16/ComParE_2016.conf (full LLD set,
+    65 + 65 columns incl. the SHS pitch chain) on 3.0 s utterances: 296 LLD rows each."""
+    global N_UTT, UTT_LEN, FRAMES_PER_UTT, BYTES_PER_FRAME, WORKLOAD, WORKLOAD_KEY, REF_CONF, REF_OUT_OPT, N_COLS
+    if name == "mfcc12":
+        return
+    assert name == "compare16"
+    WORKLOAD_KEY = name
+    N_UTT = int(os.environ.get("OSM_BENCH_N_UTT", "10000"))
+    UTT_LEN = 48000
+    FRAMES_PER_UTT = 296                 # min(295 + 1, 299 + 1) rows of the lld level (SURVEY.md 8a')
+    N_COLS = 130
+    BYTES_PER_FRAME = 160 * 2 + N_COLS * 4
+    REF_CONF = "compare16/ComParE_2016.conf"
+    REF_OUT_OPT = "-lldhtkoutput"
+    WORKLOAD = ("ComParE_2016 full LLD set (config/compare16/ComParE_2016.conf unchanged, 130 columns), synthetic 16 kHz mono "
+                "int16, %d utterances x 3.0 s = %d rows per GPU" % (N_UTT, N_UTT * FRAMES_PER_UTT))
 
 
 # ------------------------------------------------------------------------------------------
@@ -146,11 +169,13 @@ def profile_traffic():
 # ------------------------------------------------------------------------------------------
 def _ref_worker(args):
     from oracle import refrun
-    files, outdir = args
+    files, outdir, key = args
+    select_workload(key)
     n = 0
     for wav in files:
         out = os.path.join(outdir, "%s.%d.htk" % (os.path.basename(wav), os.getpid()))
-        refrun.run_config("mfcc/MFCC12_0_D_A.conf", wav, out)
+        subprocess.run([refrun.SMILEXTRACT, "-C", os.path.join(refrun.CONFIG_DIR, REF_CONF), "-I", wav, REF_OUT_OPT, out,
+                        "-l", "0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         n += refrun.read_htk(out)[1]["n"]
         os.remove(out)
     return n
@@ -171,9 +196,9 @@ def reference_sample(n_files, workers, tmpdir, seed=0):
     shards = [files[i::workers] for i in range(workers)]
     shards = [s for s in shards if s]
     with ProcessPoolExecutor(max_workers=len(shards)) as ex:
-        list(ex.map(_ref_worker, [([files[0]], tmpdir)] * len(shards)))       # warm the page cache / binaries
+        list(ex.map(_ref_worker, [([files[0]], tmpdir, WORKLOAD_KEY)] * len(shards)))       # warm the page cache / binaries
         t0 = time.perf_counter()
-        frames = sum(ex.map(_ref_worker, [(s, tmpdir) for s in shards]))
+        frames = sum(ex.map(_ref_worker, [(s, tmpdir, WORKLOAD_KEY) for s in shards]))
         dt = time.perf_counter() - t0
     for w in files:
         os.remove(w)
@@ -188,11 +213,13 @@ def cpu_baseline(n_files=None):
         if refrun.available():
             if n_files is None:
                 n_files = max(64, min(2000, 48 * cores))   # ~13 ms of CPU work per file
+                if WORKLOAD_KEY == "compare16":
+                    n_files = max(16, 4 * cores)           # ~55 ms of CPU work per 3 s file
             frames, dt = reference_sample(n_files, cores, tmp)
             return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
-                    "sample": "%d of the 2000 utterances (%d frames) through oracle/_ref/SMILExtract -C "
-                              "mfcc/MFCC12_0_D_A.conf, one process per core, WAV in /dev/shm -> HTK out, %.2f s"
-                              % (n_files, frames, dt)}
+                    "sample": "%d of the %d utterances (%d frames) through oracle/_ref/SMILExtract -C "
+                              "%s, one process per core, WAV in /dev/shm -> HTK out, %.2f s"
+                              % (n_files, N_UTT, frames, REF_CONF, dt)}
         # the reference binary did not travel: time the C restatement instead (single thread)
         from opensmile_b200.synth import voiced_pcm
         from oracle import oracle
@@ -215,6 +242,8 @@ def run_reference(args, rank, world):
     from oracle import refrun
     cores = os.cpu_count() or 1
     n_files = max(64, min(2000, 48 * cores))
+    if WORKLOAD_KEY == "compare16":
+        n_files = max(16, 4 * cores)
     tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
         if not refrun.available():
@@ -232,8 +261,8 @@ def run_reference(args, rank, world):
             v = tot_f / tot_t
             ms = tot_t / args.steps * 1e3
             cb = {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference",
-                  "sample": "per step %d of the 2000 utterances (%d frames) through oracle/_ref/SMILExtract, "
-                            "one process per host core" % (n_files, n_files * FRAMES_PER_UTT)}
+                  "sample": "per step %d of the %d utterances (%d frames) through oracle/_ref/SMILExtract, "
+                            "one process per host core" % (n_files, N_UTT, n_files * FRAMES_PER_UTT)}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     print(json.dumps({
@@ -257,7 +286,14 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    plan = Plan(components_mfcc12_0_d_a(float(SAMPLE_RATE)), "lld", device=local_rank)
+    if WORKLOAD_KEY == "compare16":
+        from opensmile_b200 import Session
+        conf = os.path.join(ROOT, "oracle", "_ref", "config", "compare16", "ComParE_2016.conf")
+        sess = Session(conf, options={"lldhtkoutput": "x.htk"}, device=-1)     # conf front end only; the plan below computes
+        comps, level = sess.components(float(SAMPLE_RATE), 1)
+        plan = Plan(list(comps), level, device=local_rank)
+    else:
+        plan = Plan(components_mfcc12_0_d_a(float(SAMPLE_RATE)), "lld", device=local_rank)
     off = np.arange(N_UTT + 1, dtype=np.int64) * UTT_LEN
     fo = plan.frame_offsets(off)
     rows = int(fo[-1])
@@ -331,7 +367,8 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": rows,
-                       "l2": "no flush needed: per step 321 MB PCM in + 156 MB rows out exceed the 126 MB L2",
+                       "l2": "no flush needed: per step %d MB PCM in + %d MB rows out exceed the 126 MB L2"
+                             % (N_UTT * UTT_LEN * 2 // 1000000, rows * plan.num_elements * 4 // 1000000),
                        "parallelism": "utterance shards, one rank per GPU, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h_pcm.numel() * 2),
@@ -339,7 +376,8 @@ def run_ours(args, rank, world, local_rank):
                     "api": "osm_b200_plan_run_host (pinned host buffers)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": profile_traffic(), "kernel": "lld_kernel<256,32,256,2,VEC2,MFCC>",
+                         "frac": achieved / peak, "traffic": profile_traffic() if WORKLOAD_KEY == "mfcc12" else None,
+                         "kernel": "lld_kernel<256,32,256,2,VEC2,MFCC>" if WORKLOAD_KEY == "mfcc12" else "FFT front-end passes (lld_kernel) of the %d launches of a step" % (launches // max(args.steps, 1)),
                          "kernel_ms": k_ms, "post_kernel_ms": statistics.mean(post_ms),
                          "algorithmic_bytes_per_launch": rows * BYTES_PER_FRAME, "peak_source": peak_src},
         }
@@ -358,7 +396,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mfcc12", choices=["mfcc12", "compare16"],
+                    help="mfcc12 = BASELINE configs[1] (default, the quoted metric); compare16 = configs[3], full ComParE_2016 LLD set")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
