@@ -19,7 +19,7 @@ namespace osm {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kShsWarps = 8;
+constexpr int kShsWarps = 8;      // warps per CTA (fewer when a long spectrum needs more workspace per warp)
 
 __device__ __forceinline__ int frames_of(long long L, int frameSize, int frameStep)
 {
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
   const long long rowBase = p.statOff[tl.utt] + tl.f0;
   const int lo = lane * p.blk, hi = min(N, lo + p.blk);
 
-  for (int f = warp; f < tl.nf; f += kShsWarps) {
+  const int nWarps = blockDim.x >> 5;
+  for (int f = warp; f < tl.nf; f += nWarps) {
     const float *mg = p.mag + ((size_t)blockIdx.x * N) * p.F + f;
     for (int j = lane; j < N; j += 32) yS[j] = (double)mg[(size_t)j * p.F];      // dsp/specScale.cpp:329-331
     __syncwarp();
@@ -842,10 +843,13 @@ cudaError_t launch_shs(const ShsParams &p, cudaStream_t st)
 {
   if (p.nTiles <= 0) return cudaSuccess;
   const size_t perWarp = (size_t)2 * (p.nMag + 2) * sizeof(double) + (size_t)2 * p.nPts * sizeof(float) + 128;
-  const size_t smem = perWarp * kShsWarps;
+  int warps = kShsWarps;
+  while (warps > 1 && perWarp * warps > 100 * 1024) warps >>= 1;      // two CTAs per SM where possible
+  const size_t smem = perWarp * warps;
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(shs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  shs_kernel<<<p.nTiles, kShsWarps * 32, smem, st>>>(p);
+  shs_kernel<<<p.nTiles, warps * 32, smem, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -656,7 +656,7 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
         const std::string *lv = sec->get("reader.dmLevel");
         if (active && lv && type != "cArffSink") sinkLevels.push_back(*lv);
         if (type == "cHtkSink") { if (const std::string *pk = sec->get("parmKind")) s->parmKind = inum(*pk); }
-        if (type == "cCsvSink") {
+        if (type == "cCsvSink" && active) {
           if (const std::string *x = sec->get("printHeader")) s->csv.printHeader = inum(*x) != 0;
           if (const std::string *x = sec->get("timestamp")) s->csv.timestamp = inum(*x) == 1;
           if (const std::string *x = sec->get("frameTime")) s->csv.timestamp = inum(*x) == 1;

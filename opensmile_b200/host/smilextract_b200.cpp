@@ -51,8 +51,10 @@ int main(int argc, char **argv)
     else if (a.size() > 1 && a[0] == '-') {
       const std::string n = a.substr(1), v = val();
       optN.push_back(n); optV.push_back(v);
-      if (n == "O" || n == "output") outHtk = v;
-      if (n == "csvoutput") outCsv = v;
+      // the feature-set configurations name their LLD sinks' files -lldhtkoutput / -lldcsvoutput
+      // (config/shared/standard_data_output.conf.inc:23,33)
+      if (n == "O" || n == "output" || n == "lldhtkoutput") outHtk = v;
+      if (n == "csvoutput" || n == "lldcsvoutput") outCsv = v;
     }
   }
   if (conf.empty() || wavs.empty()) { fprintf(stderr, "SMILExtract_b200: -C <config> and -I <wav> are required (-h for help)\n"); return 2; }

@@ -9,7 +9,8 @@ For each case (inputs are regenerated in the tests from opensmile_b200.synth):
                   cPitchSmootherViterbi, cValbasedSelector, cPitchJitter, smoothed level and its delta, rms energy)
   names_lld       element names of the LLD CSV header
 Cases: v32k = voiced_pcm(32000, seed=7); m48k = mixed_pcm(48000, seed=2) (Viterbi lag 1); m30k = mixed_pcm(30000, seed=4);
-       m64k = mixed_pcm(64000, seed=3); short_<n> = voiced_pcm(n, seed=7) for n = 960, 1120, 1600, 2400 (1, 2, 5, 10 frames of 60 ms)
+       m64k = mixed_pcm(64000, seed=3); m60k_44k = mixed_pcm(60000, seed=5) written as a 44.1 kHz file (FFT 4096 / 1024,
+       _lld only); short_<n> = voiced_pcm(n, seed=7) for n = 960, 1120, 1600, 2400 (1, 2, 5, 10 frames of 60 ms)
 """
 import os
 import subprocess
@@ -63,6 +64,12 @@ def main():
                 hdr = open(os.path.join(d, "lld.csv")).readline().strip().split(";")
                 out["names_lld"] = np.array([h for h in hdr if h not in ("name", "frameIndex", "frameTime")])
         print(name, {k[len(name) + 1:]: v.shape for k, v in out.items() if k.startswith(name + "_")})
+    with tempfile.TemporaryDirectory() as d:            # the same configuration at 44.1 kHz
+        wav = os.path.join(d, "in.wav")
+        refrun.write_wav(wav, mixed_pcm(60000, 16000, seed=5), 44100, 1)
+        subprocess.run([refrun.SMILEXTRACT, "-C", full, "-I", wav, "-lldhtkoutput", os.path.join(d, "lld.htk"), "-l", "0"],
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out["m60k_44k_lld"] = refrun.read_htk(os.path.join(d, "lld.htk"))[0]
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pitch_goldens.npz"), **out)
 
 

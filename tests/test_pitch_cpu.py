@@ -65,6 +65,17 @@ def test_whole_chain_and_eoi_lag_model(case):
     assert np.array_equal(oracle.delta_segments_lagged(G[case + "_nz"], lag, 2), G[case + "_nzde"])
 
 
+def test_whole_chain_44k():
+    """same graph at 44.1 kHz (FFT 4096: 2049-point spline) against the reference's LLD file"""
+    pcm = mixed_pcm(60000, 16000, seed=5)
+    sm, de = oracle.compare16_nz_lld(pcm, sample_rate=44100.0)
+    ref = G["m60k_44k_lld"]
+    R = ref.shape[0]
+    sc = np.abs(ref).max(axis=0) + 1e-30
+    assert (np.abs(sm[:R] - ref[:, :6]) / sc[:6]).max() < 2e-6
+    assert (np.abs(de[:R] - ref[:, 65:71]) / sc[65:71]).max() < 1e-5
+
+
 def test_lagged_cases_cover_both_lags():
     fe, sc, ps, vc, jc = oracle.compare16_pitch_cfg()
     lags = {c: oracle.viterbi(G[c + "_shs"], ps, vc, with_lag=True)[1] - G[c + "_shs"].shape[0] for c in CASES}

@@ -56,6 +56,19 @@ def test_compare16_full_lld_batch(session):
         _check(rows[fo[i]:fo[i + 1]], G[k + "_lld"], names)
 
 
+def test_compare16_44k(session):
+    """the same configuration file at 44.1 kHz: 2646-sample frames, FFT 4096 (2049-point spline), 882-sample frames, FFT 1024"""
+    pcm = mixed_pcm(60000, 16000, seed=5)
+    rows, _ = session.extract_pcm(pcm, np.array([0, pcm.size], np.int64), 44100.0, 1)
+    ref = G["m60k_44k_lld"]
+    assert rows.shape == ref.shape
+    sc = np.abs(ref).max(axis=0) + 1e-30
+    err = np.abs(rows - ref) / sc
+    names = session.element_names(44100.0, 1)
+    bad = np.argwhere(err > 1e-5)
+    assert bad.size == 0, [(names[c], int(r), float(rows[r, c]), float(ref[r, c])) for r, c in bad[:8]]
+
+
 def test_compare16_single_and_repeatable(session):
     pcm = CASES["m30k"]()
     off = np.array([0, pcm.size], np.int64)
