@@ -519,3 +519,48 @@ def compare16_nz_lld(pcm, n_chan=1, sample_rate=16000.0):
     nz, lag = compare16_pitch(pcm, n_chan, sample_rate, with_lag=True)
     sm = sma_nz_lagged(nz, lag, {2, 3, 4, 5})
     return sm, delta_segments_lagged(sm, lag, 2)
+
+
+def pitch_variants_cfg():
+    """tests/configs/pitch_variants.conf"""
+    fe = frontend(16000.0, 0.050, 0.010, win="ham", zero_pad_symmetric=1)
+    sc = SpecScale(30.0, 4000.0, 400, 1, 0, 0)
+    ps = PitchShs(500.0, 60.0, 3, 1, 1, 1, 1, 1, 1, 0.65, 1, 10, 0.8, 0, 0.0)
+    vc = Viterbi(8, 1, 0, 1, 0, 1, 1, 1.5, 8.0, 3.0, 6.0, 3.0, 2.0, 0.5)
+    jc = Jitter(0.15, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, -100.0, 0, 2, 0.4, 1, 1, 1, 0, 1, 0)
+    return fe, sc, ps, vc, jc
+
+
+def pitch_variants_lld(pcm, n_chan=1):
+    """levels smo ; smo_de of tests/configs/pitch_variants.conf -> [T+1, 36] (no energy gate, plain smoother)"""
+    fe, sc, ps, vc, jc = pitch_variants_cfg()
+    shs = pitch_shs(pcm, fe, sc, ps, n_chan)
+    vit, lag = viterbi(shs, ps, vc, with_lag=True)
+    jit = pitch_jitter(pcm, fe, jc, vit[:, 0], n_chan)
+    x = np.concatenate([vit, jit], axis=1)
+    nv = vit.shape[1]
+    sm = sma_lagged(x, lag, set(range(nv, x.shape[1])), no_zero=False)
+    de = delta_segments_lagged(sm, lag, 2)
+    R = sm.shape[0]
+    return np.concatenate([sm, de[:R]], axis=1), lag
+
+
+def sma_lagged(x, V, lag_cols, no_zero):
+    """sma_nz_lagged with the noZeroSma switch (dspcore/contourSmoother.cpp:84-117)"""
+    if no_zero:
+        return sma_nz_lagged(x, V, lag_cols)
+    x = np.asarray(x, np.float32)
+    T, K = x.shape
+    out = np.zeros((T + 1, K), np.float32)
+    for n in range(T + 1):
+        for k in range(K):
+            def g(i):
+                i = min(max(i, 0), T - 1)
+                if k in lag_cols and n in (V - 1, V) and i > V - 1:
+                    i = max(V - 1, 0)
+                return x[i, k]
+            y = np.float32(g(n))
+            y = np.float32(y + g(n - 1))
+            y = np.float32(y + g(n + 1))
+            out[n, k] = np.float32(y / np.float32(3.0))
+    return out

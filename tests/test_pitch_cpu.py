@@ -97,3 +97,23 @@ def test_compare16_conf_description():
     off = s.frame_offsets(np.array([0, 32000, 32000 + 48000, 32000 + 48000 + 960]), 16000.0)
     assert list(np.diff(off)) == [G["v32k_lld"].shape[0], G["m48k_lld"].shape[0], G["short_960_lld"].shape[0]]
     s.close()
+
+
+@pytest.mark.parametrize("case,seed,n", [("var_m48k", 6, 48000), ("var_m40k", 8, 40000)])
+def test_variant_switches(case, seed, n):
+    """tests/configs/pitch_variants.conf: non-greedy peak picker, octave correction, forced Viterbi decisions,
+    envelope / clipped outputs, every cPitchJitter output incl. the 2.2-compatible threshold, plain smoother
+    (the 40 000-sample case ends with a Viterbi lag of 7 frames)"""
+    got, lag = oracle.pitch_variants_lld(mixed_pcm(n, 16000, seed=seed))
+    ref = G[case + "_lld"]
+    assert got.shape == ref.shape
+    assert _rel(got, ref) < 1e-5
+
+
+def test_variant_conf_description():
+    from opensmile_b200.session import Session
+    s = Session(os.path.join(HERE, "configs", "pitch_variants.conf"), options={"O": "x.htk"}, device=-1)
+    assert list(s.element_names(16000.0, 1)) == [str(x) for x in G["names_var"]]
+    off = s.frame_offsets(np.array([0, 48000, 88000]), 16000.0)
+    assert list(np.diff(off)) == [G["var_m48k_lld"].shape[0], G["var_m40k_lld"].shape[0]]
+    s.close()

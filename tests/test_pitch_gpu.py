@@ -76,3 +76,20 @@ def test_compare16_single_and_repeatable(session):
     b, _ = session.extract_pcm(pcm, off, 16000.0, 1)
     assert np.array_equal(a, b)
     _check(a, G["m30k_lld"], session.element_names(16000.0, 1))
+
+
+def test_pitch_variant_switches():
+    """tests/configs/pitch_variants.conf (see tests/test_pitch_cpu.py::test_variant_switches) vs the reference"""
+    from opensmile_b200.session import Session
+    s = Session(os.path.join(HERE, "configs", "pitch_variants.conf"), options={"O": "x.htk"}, device=0)
+    pcms = [mixed_pcm(48000, 16000, seed=6), mixed_pcm(40000, 16000, seed=8)]
+    off = np.cumsum([0] + [p.size for p in pcms]).astype(np.int64)
+    rows, fo = s.extract_pcm(np.concatenate(pcms), off, 16000.0, 1)
+    names = s.element_names(16000.0, 1)
+    for i, case in enumerate(("var_m48k", "var_m40k")):
+        got, ref = rows[fo[i]:fo[i + 1]], G[case + "_lld"]
+        assert got.shape == ref.shape
+        sc = np.abs(ref).max(axis=0) + 1e-30
+        bad = np.argwhere(np.abs(got - ref) / sc > 1e-5)
+        assert bad.size == 0, [(names[c], int(r), float(got[r, c]), float(ref[r, c])) for r, c in bad[:8]]
+    s.close()
