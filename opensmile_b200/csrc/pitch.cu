@@ -736,10 +736,10 @@ struct SeqCtx { const float *x; int stride; int T; int V; };
 // reference's first EOI pass, when the jitter level (lagKind 2) still ends at its row V-1
 __device__ float seq_sma(const SeqCtx &c, int col, int m, int lagKind, int noZero)
 {
-  const bool lagged = lagKind == 2 && (m == c.V - 1 || m == c.V);
+  const bool lagged = lagKind == 2 && c.V >= 1 && (m == c.V - 1 || m == c.V);   // V == 0: nothing runs in the first pass
   auto g = [&](int i) -> float {
     i = min(max(i, 0), c.T - 1);
-    if (lagged && i > c.V - 1) i = max(c.V - 1, 0);
+    if (lagged && i > c.V - 1) i = c.V - 1;
     return c.x[(size_t)i * c.stride + col];
   };
   const float x0 = g(m);
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) seq_post_kernel(const SeqPostP
       const int n = n0 + lane;
       const bool live = n <= T + W;
       int last = T;
-      if (n >= V - 1 && n <= V + 2) last = min(T, max(V, 0));
+      if (V >= 1 && n >= V - 1 && n <= V + 2) last = min(T, V);
       else if (n == V + 3 && V >= T - 5 && V <= T - 2) last = T - 1;
       float num[kMaxSegCols];
       int cnt[kMaxSegCols];

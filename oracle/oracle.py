@@ -423,8 +423,8 @@ def sma_nz_lagged(x, V, lag_cols):
         for k in range(K):
             def g(i):
                 i = min(max(i, 0), T - 1)
-                if k in lag_cols and n in (V - 1, V) and i > V - 1:
-                    i = max(V - 1, 0)
+                if V >= 1 and k in lag_cols and n in (V - 1, V) and i > V - 1:     # V == 0: the lagging level is
+                    i = V - 1                                                      # empty, nothing runs in the first pass
                 return x[i, k]
             x0 = g(n)
             if x0 != 0:
@@ -452,8 +452,8 @@ def delta_segments_lagged(x, V, win=2):
     norm = np.float32(norm * 2)
     for n in range(T1 + win):
         last = T1 - 1
-        if V - 1 <= n <= V + 2:
-            last = min(last, max(V, 0))
+        if V >= 1 and V - 1 <= n <= V + 2:
+            last = min(last, V)
         elif n == V + 3 and T - 5 <= V <= T - 2:
             last = T - 1
         for k in range(K):
@@ -556,8 +556,8 @@ def sma_lagged(x, V, lag_cols, no_zero):
         for k in range(K):
             def g(i):
                 i = min(max(i, 0), T - 1)
-                if k in lag_cols and n in (V - 1, V) and i > V - 1:
-                    i = max(V - 1, 0)
+                if V >= 1 and k in lag_cols and n in (V - 1, V) and i > V - 1:
+                    i = V - 1
                 return x[i, k]
             y = np.float32(g(n))
             y = np.float32(y + g(n - 1))
