@@ -544,7 +544,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       if (G.nStages == 2) {
         int segCols = 0;
         for (int q = 0; q < sq.nGroups; q++) if (sq.groups[q].nStages == 2 && sq.groups[q].segId == G.segId) segCols += sq.groups[q].n;
-        if (segCols > 16) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cDeltaRegression(onlyInSegments): more than 16 elements"); }
+        if (segCols > 32) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cDeltaRegression(onlyInSegments): more than 32 elements"); }
       }
       if (G.segId >= kMaxSeqGroups) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many onlyInSegments delta components"); }
       sq.frameSize = d.streams[g.stream].fe.frameSize; sq.frameStep = d.streams[g.stream].fe.frameStep;
@@ -646,11 +646,19 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     } else if (op.kind == SOP_PITCH) {
       const PitchChainOp &pc = op.chain;
       // one blob: fwdA | fwdP6 | r1 | r2 | bwdD (double[nMag]) | ia | ic | id | audW (double[nPts]) | ik (int[nPts]) | shift (int) | hscale (float)
-      const size_t nM = (size_t)pc.nMag, nP = (size_t)pc.nPts, nH = pc.shift.size();
+      // the five recurrence tables are stored lane-interleaved for the blocked scan of shs_kernel (lane l owns points
+      // [l * blk, (l+1) * blk)): entry of (lane, step k) at [k * 32 + lane], so a warp reads 32 consecutive doubles
+      const int blk = (pc.nMag + 31) / 32;
+      const size_t nM = (size_t)blk * 32, nP = (size_t)pc.nPts, nH = pc.shift.size();
       std::vector<unsigned char> blob((5 * nM + 4 * nP) * sizeof(double) + nP * sizeof(int) + nH * (sizeof(int) + sizeof(float)) + 64);
       double *bd = reinterpret_cast<double *>(blob.data());
-      memcpy(bd, pc.fwdA.data(), nM * 8); memcpy(bd + nM, pc.fwdP6.data(), nM * 8); memcpy(bd + 2 * nM, pc.r1.data(), nM * 8);
-      memcpy(bd + 3 * nM, pc.r2.data(), nM * 8); memcpy(bd + 4 * nM, pc.bwdD.data(), nM * 8);
+      const std::vector<double> *tabs[5] = {&pc.fwdA, &pc.fwdP6, &pc.r1, &pc.r2, &pc.bwdD};
+      for (int t = 0; t < 5; t++)
+        for (int l = 0; l < 32; l++)
+          for (int k = 0; k < blk; k++) {
+            const int i = l * blk + k;
+            bd[(size_t)t * nM + (size_t)k * 32 + l] = i < pc.nMag ? (*tabs[t])[i] : 0.0;
+          }
       double *bp = bd + 5 * nM;
       memcpy(bp, pc.ia.data(), nP * 8); memcpy(bp + nP, pc.ic.data(), nP * 8); memcpy(bp + 2 * nP, pc.id.data(), nP * 8);
       if (!pc.audW.empty()) memcpy(bp + 3 * nP, pc.audW.data(), nP * 8);
@@ -1132,7 +1140,10 @@ osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const
 
   // pieces of ~24 MB of PCM, at most 16, cut at utterance boundaries
   const int64_t totalBytes = nSamp * 2;
-  int nPieces = (int)std::min<int64_t>(16, std::max<int64_t>(1, totalBytes / (24 << 20)));
+  // (plans with per-utterance sequential kernels -- Viterbi, jitter -- get their parallelism from the number of
+  // utterances in flight: fewer, larger pieces)
+  const int64_t maxPieces = pl->sp.nGroups > 0 ? 4 : 16;
+  int nPieces = (int)std::min<int64_t>(maxPieces, std::max<int64_t>(1, totalBytes / (24 << 20)));
   if (nPieces > n_utt) nPieces = n_utt;
   while ((int)pl->evPiece.size() < 2 * nPieces) {
     cudaEvent_t e;

@@ -120,9 +120,11 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
     // lane l owns points [lo, hi), the carries cross the lanes through a scan of affine maps
     {
       double A = 1.0, B = 0.0;
+      // (coefficient tables are stored lane-interleaved: entry of (lane, step k) at [k * 32 + lane] -> coalesced)
       for (int i = lo; i < hi; i++) {
         double a = 0.0, b = 0.0;
-        if (i >= 1 && i <= N - 2) { a = p.fwdA[i]; b = p.fwdP6[i] * ((yS[i + 1] - yS[i]) * p.r1[i] - (yS[i] - yS[i - 1]) * p.r2[i]); }
+        const int q = (i - lo) * 32 + lane;
+        if (i >= 1 && i <= N - 2) { a = p.fwdA[q]; b = p.fwdP6[q] * ((yS[i + 1] - yS[i]) * p.r1[q] - (yS[i] - yS[i - 1]) * p.r2[q]); }
         B = a * B + b; A = a * A;
       }
 #pragma unroll
@@ -134,14 +136,15 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
       if (lane == 0) u = 0.0;
       for (int i = lo; i < hi; i++) {
         double a = 0.0, b = 0.0;
-        if (i >= 1 && i <= N - 2) { a = p.fwdA[i]; b = p.fwdP6[i] * ((yS[i + 1] - yS[i]) * p.r1[i] - (yS[i] - yS[i - 1]) * p.r2[i]); }
+        const int q = (i - lo) * 32 + lane;
+        if (i >= 1 && i <= N - 2) { a = p.fwdA[q]; b = p.fwdP6[q] * ((yS[i + 1] - yS[i]) * p.r1[q] - (yS[i] - yS[i - 1]) * p.r2[q]); }
         u = a * u + b;
         uS[i] = u;
       }
       __syncwarp();
       A = 1.0; B = 0.0;
       for (int j = hi - 1; j >= lo; j--) {
-        const double a = j <= N - 2 ? p.bwdD[j] : 0.0, b = j <= N - 2 ? uS[j] : 0.0;
+        const double a = j <= N - 2 ? p.bwdD[(j - lo) * 32 + lane] : 0.0, b = j <= N - 2 ? uS[j] : 0.0;
         B = a * B + b; A = a * A;
       }
 #pragma unroll
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
       double v = __shfl_down_sync(kFull, B, 1);
       if (lane == 31) v = 0.0;
       for (int j = hi - 1; j >= lo; j--) {
-        const double a = j <= N - 2 ? p.bwdD[j] : 0.0, b = j <= N - 2 ? uS[j] : 0.0;
+        const double a = j <= N - 2 ? p.bwdD[(j - lo) * 32 + lane] : 0.0, b = j <= N - 2 ? uS[j] : 0.0;
         v = a * v + b;
         uS[j] = v;
       }
@@ -191,12 +194,19 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
     __syncwarp();
     int nCand = 0;
     if (p.greedy) {
+      // the lane's local maxima (positions 1 + lane + 32 k) as a bit mask, found once
+      unsigned long long pk = 0;
+      for (int i = 1 + lane, k = 0; i < M - 1; i += 32, k++) {
+        const float s = SS[i];
+        if (SS[i - 1] < s && s > SS[i + 1]) pk |= 1ull << k;
+      }
       float lastS = FLT_MAX; int lastI = -1;
       for (int r = 0; r < nC; r++) {
         float bs = -1.0f; int bi = -1;
-        for (int i = 1 + lane; i < M - 1; i += 32) {
+        for (unsigned long long m = pk; m; m &= m - 1) {
+          const int i = 1 + lane + 32 * (__ffsll((long long)m) - 1);
           const float s = SS[i];
-          if (SS[i - 1] < s && s > SS[i + 1] && (s < lastS || (s == lastS && i > lastI)) && s > bs) { bs = s; bi = i; }
+          if ((s < lastS || (s == lastS && i > lastI)) && s > bs) { bs = s; bi = i; }
         }
         warp_argmax(bs, bi);
         if (bi < 0) break;
@@ -452,8 +462,10 @@ __device__ __forceinline__ float jit_pcm(const int16_t *s, int nChan)       // s
 __device__ double jit_cross_corr(const float *x, const float *y, int N)
 {
   double cc = 0.0, mx = 0.0, my = 0.0, nx = 0.0, ny = 0.0;
+#pragma unroll 4
   for (int i = 0; i < N; i++) { mx += x[i]; my += y[i]; }
   mx /= (double)N; my /= (double)N;
+#pragma unroll 4
   for (int i = 0; i < N; i++) {
     const double dx = x[i] - mx, dy = y[i] - my;
     cc += dx * dy;
@@ -757,7 +769,7 @@ __device__ float seq_sma(const SeqCtx &c, int col, int m, int lagKind, int noZer
   return y / 3.0f;
 }
 
-constexpr int kSeqWarps = 4, kMaxSegCols = 16;
+constexpr int kSeqWarps = 4, kMaxSegCols = 32;
 
 // one warp per utterance, lane = row of a 32-row chunk
 __global__ void __launch_bounds__(kSeqWarps * 32) seq_post_kernel(const SeqPostParams p, int u0, int u1)
