@@ -133,6 +133,10 @@ struct osm_b200_plan {
   SeqPostParams sp;              // groups behind a Viterbi-smoothed pitch level (seq_post_kernel)
   int seqLagOp = -1;             // index into `ops` of the pitch chain whose lag they follow
   int *dErr = nullptr;           // device flag: a kernel left its supported geometry (checked after run_host)
+  // the pitch chain (shs -> viterbi -> jitter: latency-bound, low occupancy) runs on its own stream next to the
+  // other standalone ops of a step
+  cudaStream_t auxStream = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   bool staticDirect = false;     // static rows are written straight into the output rows
   int identityOutCol = 0;
   bool fused = false;            // delta / delta-delta evaluated inside lld_kernel
@@ -677,7 +681,8 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       const double *dp = dd + 5 * nM;
       sh.ia = dp; sh.ic = dp + nP; sh.id = dp + 2 * nP; sh.audW = dp + 3 * nP;
       const int *di = reinterpret_cast<const int *>(dp + 4 * nP);
-      sh.ik = di; sh.shift = di + nP; sh.hscale = reinterpret_cast<const float *>(di + nP + nH);
+      sh.ik = di;
+      for (size_t h = 0; h < nH && h < 32; h++) { sh.shift[h] = pc.shift[h]; sh.hscale[h] = pc.hscale[h]; }
       sh.nCand = pc.nCand; sh.nHarm = pc.nHarm; sh.Fmint = pc.Fmint; sh.Fstept = pc.Fstept; sh.logBase = pc.logBase;
       sh.maxPitch = pc.maxPitch; sh.minPitch = pc.minPitch; sh.voicingCutoff = pc.voicingCutoff; sh.lfCutBin = pc.lfCutBin;
       sh.greedy = pc.greedy; sh.octaveCorr = pc.octaveCorr; sh.scores = pc.scores; sh.voicing = pc.voicing; sh.F0C1 = pc.F0C1;
@@ -776,6 +781,11 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     pl->ops.push_back(rt);
   }
 
+  if (seqLagDescOp >= 0) {
+    CUP(cudaStreamCreateWithFlags(&pl->auxStream, cudaStreamNonBlocking));
+    CUP(cudaEventCreateWithFlags(&pl->evFork, cudaEventDisableTiming));
+    CUP(cudaEventCreateWithFlags(&pl->evJoin, cudaEventDisableTiming));
+  }
   CUP(cudaMalloc(&pl->dErr, sizeof(int)));
   CUP(cudaMemset(pl->dErr, 0, sizeof(int)));
   if (seqLagDescOp >= 0)
@@ -808,6 +818,9 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
   }
   for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); if (o.dPitchTab) cudaFree(o.dPitchTab); o.dShs.release(); o.dLag.release(); }
   if (pl->dErr) cudaFree(pl->dErr);
+  if (pl->auxStream) cudaStreamDestroy(pl->auxStream);
+  if (pl->evFork) cudaEventDestroy(pl->evFork);
+  if (pl->evJoin) cudaEventDestroy(pl->evJoin);
   pl->hMeta.release(); pl->dMeta.release(); pl->hPost.release(); pl->dPost.release(); pl->dStat.release(); pl->dMeans.release();
   pl->dPcm.release(); pl->dOut.release();
   if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
@@ -998,8 +1011,16 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
   }
   if (u0 == 0) CU(cudaEventRecord(pl->evKm, st));
   // 2. standalone ops
+  bool forked = false;
   for (OpRt &o : pl->ops) {
     StreamRt &rt = pl->st[o.stream];
+    if ((o.kind == SOP_PITCH || o.kind == SOP_JITTER) && pl->auxStream && !forked) {
+      // everything the chain reads (magnitude level, selector energy) has been launched on `st` by now
+      CU(cudaEventRecord(pl->evFork, st));
+      CU(cudaStreamWaitEvent(pl->auxStream, pl->evFork, 0));
+      forked = true;
+    }
+    cudaStream_t ks = (forked && (o.kind == SOP_PITCH || o.kind == SOP_JITTER)) ? pl->auxStream : st;
     if (o.kind == SOP_VECOP) {
       const long long *hS = pl->hMeta.p + 2 * nm;
       CU(launch_vecop_ll1(pl->dStat.p, d.nStatic, o.vSrcCol, o.vN, o.vOutCol, hS[u0], hS[u1], st));
@@ -1027,16 +1048,16 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       sh.mag = rt.dMag.p + (size_t)t0 * sh.nMag * sh.F;
       sh.tiles = rt.dTiles.p + t0; sh.nTiles = t1 - t0;
       sh.statOff = dS; sh.shs = o.dShs.p;
-      CU(launch_shs(sh, st));
+      CU(launch_shs(sh, ks));
       ViterbiParams vp = o.vit;
       vp.shs = o.dShs.p; vp.uttOff = dU; vp.statOff = dS; vp.stat = pl->dStat.p; vp.lag = o.dLag.p;
-      CU(launch_viterbi(vp, u0, u1, st));
+      CU(launch_viterbi(vp, u0, u1, ks));
       pl->lastLaunches++;
     } else if (o.kind == SOP_JITTER) {
       JitterParams jp = o.jit;
       jp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
       jp.uttOff = dU; jp.statOff = dS; jp.stat = pl->dStat.p; jp.errFlag = pl->dErr;
-      CU(launch_jitter(jp, u0, u1, st));
+      CU(launch_jitter(jp, u0, u1, ks));
     } else if (o.kind == SOP_PITCHACF) {
       AcfPitchParams ap = o.ap;
       CU(o.dRaw.reserve((size_t)pl->totalStat + 64));
@@ -1055,6 +1076,10 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : (o.kind == SOP_INTENSITY ? launch_intensity(tp, st) : launch_mzcr(tp, st)));
     }
     pl->lastLaunches++;
+  }
+  if (forked) {
+    CU(cudaEventRecord(pl->evJoin, pl->auxStream));
+    CU(cudaStreamWaitEvent(st, pl->evJoin, 0));
   }
   // 3. temporal stages + assembly of the output rows
   if (pl->pp.nGroups > 0 && !pl->fused) {

@@ -223,7 +223,7 @@ struct ShsParams {
   const int *ik; const double *ia, *ic, *id;     // [nPts]
   const double *audW;                            // [nPts]
   int nCand, nHarm;
-  const int *shift; const float *hscale;         // [nHarm-1]
+  int shift[32]; float hscale[32];               // [nHarm-1] per harmonic 2..nHarm: bin shift, compression^(h-1) (kernel parameters = constant bank)
   float Fmint, Fstept; double logBase, maxPitch, minPitch; float voicingCutoff;
   int lfCutBin, greedy, octaveCorr, scores, voicing, F0C1, voicingC1, F0raw, voicingClip;
 };

@@ -84,28 +84,43 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
     for (int j = lane; j < N; j += 32) yS[j] = (double)mg[(size_t)j * p.F];      // dsp/specScale.cpp:329-331
     __syncwarp();
     if (p.enhance) {                                                             // smileUtil.c:1965-2003
-      unsigned char *fl = reinterpret_cast<unsigned char *>(uS);
+      // local maxima as bits: position j = 32 k + lane -> bit `lane` of the k-th ballot word (kept in shared memory,
+      // 65 words at most); "a maximum within two bins" is a 5-bit window of the concatenated words
+      unsigned int *mw = reinterpret_cast<unsigned int *>(uS);
+      const int nWords = (N + 31) >> 5;
       int cnt = 0, fmin = INT_MAX, fmax = -1;
-      for (int j = lane; j < N; j += 32) {
-        bool m;
-        if (j == 0) m = yS[0] > yS[1];
-        else if (j == N - 1) m = yS[N - 1] > yS[N - 2];
-        else m = yS[j] > yS[j - 1] && yS[j] >= yS[j + 1];
-        fl[j] = m;
-        if (m) { cnt++; fmin = min(fmin, j); fmax = max(fmax, j); }
+      for (int k = 0; k < nWords; k++) {
+        const int j = (k << 5) + lane;
+        bool m = false;
+        if (j < N) {
+          if (j == 0) m = yS[0] > yS[1];
+          else if (j == N - 1) m = yS[N - 1] > yS[N - 2];
+          else m = yS[j] > yS[j - 1] && yS[j] >= yS[j + 1];
+        }
+        const unsigned int w = __ballot_sync(kFull, m);
+        if (lane == 0) mw[k + 1] = w;
+        if (w) {
+          cnt += __popc(w);
+          if (fmin == INT_MAX) fmin = (k << 5) + __ffs(w) - 1;
+          fmax = (k << 5) + 31 - __clz(w);
+        }
       }
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        cnt += __shfl_xor_sync(kFull, cnt, d);
-        fmin = min(fmin, __shfl_xor_sync(kFull, fmin, d));
-        fmax = max(fmax, __shfl_xor_sync(kFull, fmax, d));
-      }
+      if (lane == 0) { mw[0] = 0; mw[nWords + 1] = 0; }
       __syncwarp();
-      for (int j = lane; j < N; j += 32) {
+      for (int k = 0; k < nWords; k++) {
+        const int j = (k << 5) + lane;
+        if (j >= N) break;
         bool zero;
         if (cnt == 1) zero = j >= 3;            // the reference reads posmax[1] == 0 here
-        else zero = j > fmin && j < fmax &&
-                    !(fl[j] || (j >= 1 && fl[j - 1]) || (j >= 2 && fl[j - 2]) || (j + 1 < N && fl[j + 1]) || (j + 2 < N && fl[j + 2]));
+        else {
+          // bits of positions 32k-32 .. 32k+63 ; position j sits at bit 32 + lane
+          const unsigned long long lo64 = ((unsigned long long)mw[k + 1] << 32) | mw[k];
+          const unsigned int hiw = mw[k + 2];
+          const int b = 32 + lane;                                       // window bits b-2 .. b+2
+          unsigned long long win = lo64 >> (b - 2);
+          if (b + 2 >= 64) win |= (unsigned long long)hiw << (64 - (b - 2));
+          zero = j > fmin && j < fmax && (win & 0x1full) == 0;
+        }
         if (zero) yS[j] = 0.0;
       }
       __syncwarp();

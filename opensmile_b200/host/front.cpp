@@ -643,6 +643,7 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
   for (const auto &sec : s->conf.sections) if (sec.type != "cComponentManager") secOf[sec.name] = &sec;
   std::vector<std::string> sinkLevels;
   std::vector<const Section *> compute;
+  bool csvLocked = false;
   std::set<std::string> hostTypes = {"cDataMemory", "cHtkSink", "cCsvSink", "cArffSink", "cExternalSink", "cNullSink", "cDatadumpSink"};
   for (const auto &inst : s->conf.instances) {
     const std::string &name = inst.first, &type = inst.second;
@@ -656,7 +657,11 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
         const std::string *lv = sec->get("reader.dmLevel");
         if (active && lv && type != "cArffSink") sinkLevels.push_back(*lv);
         if (type == "cHtkSink") { if (const std::string *pk = sec->get("parmKind")) s->parmKind = inum(*pk); }
-        if (type == "cCsvSink" && active) {
+        // CSV formatting options: those of the active CSV sink; without one (explicit csv paths over the API),
+        // those of the last cCsvSink section
+        if (type == "cCsvSink" && !csvLocked) {
+          s->csv = CsvOpts();
+          csvLocked = active;
           if (const std::string *x = sec->get("printHeader")) s->csv.printHeader = inum(*x) != 0;
           if (const std::string *x = sec->get("timestamp")) s->csv.timestamp = inum(*x) == 1;
           if (const std::string *x = sec->get("frameTime")) s->csv.timestamp = inum(*x) == 1;
