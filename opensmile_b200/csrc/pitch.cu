@@ -2,7 +2,8 @@
 //   shs_kernel       cSpecScale + cPitchShs (+ cPitchBase output logic), one WARP per frame
 //   viterbi_kernel   cPitchSmootherViterbi [+ cValbasedSelector], one THREAD per utterance (sequential in time)
 //   jitter_kernel    cPitchJitter, one WARP per utterance (sequential over frames and pitch periods, lanes =
-//                    candidate period lengths of the waveform matching)
+//                    candidate period lengths of the waveform matching; -DOSM_JITTER_EXACT_CC selects the reference's
+//                    two-pass cross correlation instead of the one-pass form)
 //   seq_post_kernel  cContourSmoother / cDeltaRegression(onlyInSegments) of the levels behind them, one thread
 //                    per utterance (the delta's norm is a running sum over the whole level)
 // Citations are relative to /root/reference/src.  Compiled with -fmad=false: the reference's x86-64 build has
@@ -473,6 +474,7 @@ __device__ __forceinline__ float jit_pcm(const int16_t *s, int nChan)       // s
   return tmp / 32767.0f;
 }
 
+#ifdef OSM_JITTER_EXACT_CC
 // lld/pitchJitter.cpp:339-413, one lag per lane
 __device__ double jit_cross_corr(const float *x, const float *y, int N)
 {
@@ -490,6 +492,7 @@ __device__ double jit_cross_corr(const float *x, const float *y, int N)
   cc /= sqrt(nx) * sqrt(ny);
   return cc;
 }
+#endif
 
 // first maximum / minimum of x[1 .. N-2] (lld/pitchJitter.cpp:424-431), all lanes get the result
 __device__ void jit_extrema(const float *x, int N, int lane, float &mx, int &mI, float &mn)
@@ -588,7 +591,60 @@ __global__ void __launch_bounds__(kJitWarps * 32) jitter_kernel(const JitterPara
       for (int i = lane; i < kJitPb; i += 32) pb[i] = 0;
       __syncwarp();
       while (start < nT - 2 * tmax - 1) {                                      // :728
+#ifdef OSM_JITTER_EXACT_CC
+        // the reference's two-pass form, bit-identical cc (lld/pitchJitter.cpp:339-413); ~3.7x the instructions
         for (int k = lane; k < nLag; k += 32) cc[k] = jit_cross_corr(wav + start, wav + start + tmin + k, tmin + k);
+#else
+        // One-pass form of the same normalised cross correlation:
+        //   cc = (Sxy - Sx Sy / N) / (sqrt(Sxx - Sx^2 / N) sqrt(Syy - Sy^2 / N)),
+        // x = w[start .. start+tf), y = w[start+tf .. start+2tf).  The window sums of all candidate lengths are prefix
+        // sums P(t) = sum_{i<t} w[start+i] (and of squares): Sx = P(tf), Sy = P(2 tf) - P(tf).  Per round of 32
+        // consecutive tf they come from two warp scans; only Sxy needs a loop per lane.  Products of floats are
+        // exact in double, so the result differs from the two-pass value by a few 1e-16 (relative to the sums).
+        {
+          const float *w = wav + start;
+          double PA1 = 0.0, PA2 = 0.0, PB1 = 0.0, PB2 = 0.0;            // P(t0), P(2 t0) -- uniform over the warp
+          for (int i = lane; i < 2 * tmin; i += 32) {
+            const double v = (double)w[i], v2 = v * v;
+            PB1 += v; PB2 += v2;
+            if (i < tmin) { PA1 += v; PA2 += v2; }
+          }
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            PA1 += __shfl_xor_sync(kFull, PA1, d); PA2 += __shfl_xor_sync(kFull, PA2, d);
+            PB1 += __shfl_xor_sync(kFull, PB1, d); PB2 += __shfl_xor_sync(kFull, PB2, d);
+          }
+          for (int t0 = tmin; t0 <= tmax; t0 += 32) {
+            const int tf = t0 + lane;
+            // elements entering the prefixes between this lane's tf and the next one
+            double e1 = 0.0, e2 = 0.0, g1 = 0.0, g2 = 0.0;
+            if (start + tf < nT) { const double v = (double)w[tf]; e1 = v; e2 = v * v; }
+            if (start + 2 * tf + 1 < nT) {
+              const double a = (double)w[2 * tf], b = (double)w[2 * tf + 1];
+              g1 = a + b; g2 = a * a + b * b;
+            }
+            double s1 = e1, s2 = e2, q1 = g1, q2 = g2;                  // inclusive scans
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+              const double a1 = __shfl_up_sync(kFull, s1, d), a2 = __shfl_up_sync(kFull, s2, d);
+              const double b1 = __shfl_up_sync(kFull, q1, d), b2 = __shfl_up_sync(kFull, q2, d);
+              if (lane >= d) { s1 += a1; s2 += a2; q1 += b1; q2 += b2; }
+            }
+            const double Sx = PA1 + (s1 - e1), Sxx = PA2 + (s2 - e2);   // P(tf)
+            const double P2a = PB1 + (q1 - g1), P2b = PB2 + (q2 - g2);  // P(2 tf)
+            if (tf <= tmax) {
+              const float *x = w, *y = w + tf;
+              double Sxy = 0.0;
+#pragma unroll 4
+              for (int i = 0; i < tf; i++) Sxy += (double)x[i] * (double)y[i];
+              const double N = (double)tf, Sy = P2a - Sx, Syy = P2b - Sxx;
+              cc[tf - tmin] = (Sxy - Sx * Sy / N) / (sqrt(Sxx - Sx * Sx / N) * sqrt(Syy - Sy * Sy / N));
+            }
+            PA1 += __shfl_sync(kFull, s1, 31); PA2 += __shfl_sync(kFull, s2, 31);
+            PB1 += __shfl_sync(kFull, q1, 31); PB2 += __shfl_sync(kFull, q2, 31);
+          }
+        }
+#endif
         __syncwarp();
         int maxI = -1;                                                         // :743-754 (first of the highest peaks)
         {
