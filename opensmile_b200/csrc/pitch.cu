@@ -374,10 +374,14 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
         copy = (!p.selInvert && val > p.selThreshold) || (p.selInvert && val < p.selThreshold) || (p.selAllowEqual && val == p.selThreshold);
       }
       int n = 0;
+      // semitones above 27.5 Hz, float arithmetic like the reference's log(float) overload (:490-500,512-522)
+      auto semitone = [](float f) -> float { return f > 29.136 ? 12.0f * logf(f / 27.5f) / logf(2.0f) : (f > 0.0 ? 1.0f : 0.0f); };
       if (p.oF0final) o[n++] = copy ? f0 : p.selOutputVal;
-      if (p.oF0finalEnv) {
+      if (p.oF0finalLog) o[n++] = copy ? semitone(f0) : p.selOutputVal;
+      if (p.oF0finalEnv || p.oF0finalEnvLog) {
         if (f0 <= 0.0) f0 = lastValidf0; else lastValidf0 = f0;
-        o[n++] = copy ? f0 : p.selOutputVal;
+        if (p.oF0finalEnv) o[n++] = copy ? f0 : p.selOutputVal;
+        if (p.oF0finalEnvLog) o[n++] = copy ? semitone(f0) : p.selOutputVal;
       }
       if (p.oVClipped) o[n++] = copy ? (vp >= p.voiceThresh ? vp : 0.0f) : p.selOutputVal;
       if (p.oVUnclipped) o[n++] = copy ? vp : p.selOutputVal;

@@ -495,7 +495,6 @@ bool build_pitch_chain(const osm_b200_specscale &sc, const osm_b200_pitchshs &ps
   op.bufLen = vc.bufferLength;
   if (op.bufLen < 2 || op.bufLen > 64) { err = "cPitchSmootherViterbi.bufferLength must be 2..64"; return false; }
   if (vc.F0raw || vc.voicingC1 || vc.voicingClip) { err = "cPitchSmootherViterbi: the copied fields F0raw / voicingC1 / voicingClip are not supported"; return false; }
-  if (vc.F0finalLog || vc.F0finalEnvLog) { err = "cPitchSmootherViterbi: F0finalLog / F0finalEnvLog are not supported yet"; return false; }
   op.oF0final = vc.F0final != 0; op.oF0finalLog = vc.F0finalLog != 0; op.oF0finalEnv = vc.F0finalEnv != 0; op.oF0finalEnvLog = vc.F0finalEnvLog != 0;
   op.oVClipped = vc.voicingFinalClipped != 0; op.oVUnclipped = vc.voicingFinalUnclipped != 0;
   op.wLocal = vc.wLocal; op.wTvv = vc.wTvv; op.wTvvd = vc.wTvv; op.wTvuv = vc.wTvuv; op.wThr = vc.wThr; op.wRange = vc.wRange; op.wTuu = vc.wTuu;

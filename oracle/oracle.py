@@ -526,7 +526,7 @@ def pitch_variants_cfg():
     fe = frontend(16000.0, 0.050, 0.010, win="ham", zero_pad_symmetric=1)
     sc = SpecScale(30.0, 4000.0, 400, 1, 0, 0)
     ps = PitchShs(500.0, 60.0, 3, 1, 1, 1, 1, 1, 1, 0.65, 1, 10, 0.8, 0, 0.0)
-    vc = Viterbi(8, 1, 0, 1, 0, 1, 1, 1.5, 8.0, 3.0, 6.0, 3.0, 2.0, 0.5)
+    vc = Viterbi(8, 1, 1, 1, 1, 1, 1, 1.5, 8.0, 3.0, 6.0, 3.0, 2.0, 0.5)
     jc = Jitter(0.15, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, -100.0, 0, 2, 0.4, 1, 1, 1, 0, 1, 0)
     return fe, sc, ps, vc, jc
 

@@ -504,7 +504,9 @@ static void vit_drain(vit *v, vit_sink *s)
     if (vc->F0final) o[n++] = f0;
     if (vc->F0finalLog) {
       float fs = 0.0f;
-      if (f0 > 29.136) fs = (float)12.0 * log(f0 / (float)27.5) / log((float)2.0);
+      /* the reference's C++ resolves log(float) to the float overload: 12 * logf(f0 / 27.5f) / logf(2) in float
+       * (verified against oracle/_ref: the double form differs in 1/3 of the frames) */
+      if (f0 > 29.136) fs = (float)12.0 * logf(f0 / (float)27.5) / logf((float)2.0);
       else if (f0 > 0.0) fs = 1.0f;
       o[n++] = fs;
     }
@@ -513,7 +515,7 @@ static void vit_drain(vit *v, vit_sink *s)
       if (vc->F0finalEnv) o[n++] = f0;
       if (vc->F0finalEnvLog) {
         float fs = 0.0f;
-        if (f0 > 29.136) fs = (float)12.0 * log(f0 / (float)27.5) / log((float)2.0);
+        if (f0 > 29.136) fs = (float)12.0 * logf(f0 / (float)27.5) / logf((float)2.0);
         else if (f0 > 0.0) fs = 1.0f;
         o[n++] = fs;
       }
