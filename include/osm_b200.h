@@ -44,7 +44,8 @@
 extern "C" {
 #endif
 
-#define OSM_B200_ABI_VERSION 1
+/* 2: component types cSpecScale .. cPitchJitter appended (existing values and struct layouts unchanged) */
+#define OSM_B200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define OSM_B200_API __attribute__((visibility("default")))
 #else
