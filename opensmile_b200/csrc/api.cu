@@ -687,7 +687,8 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       sh.maxPitch = pc.maxPitch; sh.minPitch = pc.minPitch; sh.voicingCutoff = pc.voicingCutoff; sh.lfCutBin = pc.lfCutBin;
       sh.greedy = pc.greedy; sh.octaveCorr = pc.octaveCorr; sh.scores = pc.scores; sh.voicing = pc.voicing; sh.F0C1 = pc.F0C1;
       sh.voicingC1 = pc.voicingC1; sh.F0raw = pc.F0raw; sh.voicingClip = pc.voicingClip;
-      if (((size_t)2 * (pc.nMag + 2) * sizeof(double) + (size_t)2 * pc.nPts * sizeof(float) + 128) > (size_t)prop.sharedMemPerBlockOptin) {
+      if (((size_t)2 * (pc.nMag + 2) * sizeof(double) + (size_t)pc.nPts * sizeof(float) + 128) > (size_t)prop.sharedMemPerBlockOptin ||
+          (size_t)pc.nPts * sizeof(float) > (size_t)(pc.nMag + 2) * sizeof(double)) {
         osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cSpecScale: spectrum too long for the SHS kernel's workspace");
       }
       ViterbiParams &vp = rt.vit;

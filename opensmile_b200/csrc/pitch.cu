@@ -68,13 +68,14 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.nMag, M = p.nPts;
-  const size_t perWarp = (size_t)2 * (N + 2) * sizeof(double) + (size_t)2 * M * sizeof(float) + 128;
+  // per warp: spectrum yS | second derivatives uS (doubles), scaled spectrum hps (float), 24 candidate floats; the
+  // summed spectrum SS reuses the second-derivative buffer, which is dead once the interpolation has run
+  const size_t perWarp = (size_t)2 * (N + 2) * sizeof(double) + (size_t)M * sizeof(float) + 128;
   unsigned char *ws = smemRaw + warp * perWarp;
   double *yS = reinterpret_cast<double *>(ws);
   double *uS = yS + (N + 2);
-  float *hps = reinterpret_cast<float *>(uS + (N + 2));
-  float *SS = hps + M;
-  float *cand = SS + M;                       // [3][8]: f0 | voicing | score
+  float *hps = reinterpret_cast<float *>(yS + 2 * (N + 2));
+  float *cand = hps + M;                      // [3][8]: f0 | voicing | score
   const OpTile tl = p.tiles[blockIdx.x];
   const long long rowBase = p.statOff[tl.utt] + tl.f0;
   const int lo = lane * p.blk, hi = min(N, lo + p.blk);
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
     }
     __syncwarp();
     // sub-harmonic summation (lld/pitchShs.cpp:238-258)
+    float *SS = reinterpret_cast<float *>(uS);
     double part = 0.0;
     for (int j = lane; j < M; j += 32) {
       float s = hps[j];
@@ -514,7 +516,8 @@ __device__ void jit_extrema(const float *x, int N, int lane, float &mx, int &mI,
   else { mx = bv; mI = bi; mn = lo; }
 }
 
-__global__ void __launch_bounds__(kJitWarps * 32) jitter_kernel(const JitterParams p, int u0, int u1)
+// 5 CTAs / SM: 96 registers per thread (a few spilled words outside the loops) -> 20 warps / SM instead of 16
+__global__ void __launch_bounds__(kJitWarps * 32, 5) jitter_kernel(const JitterParams p, int u0, int u1)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -929,9 +932,10 @@ __global__ void __launch_bounds__(kSeqWarps * 32) seq_post_kernel(const SeqPostP
 cudaError_t launch_shs(const ShsParams &p, cudaStream_t st)
 {
   if (p.nTiles <= 0) return cudaSuccess;
-  const size_t perWarp = (size_t)2 * (p.nMag + 2) * sizeof(double) + (size_t)2 * p.nPts * sizeof(float) + 128;
+  const size_t perWarp = (size_t)2 * (p.nMag + 2) * sizeof(double) + (size_t)p.nPts * sizeof(float) + 128;
   int warps = kShsWarps;
-  while (warps > 1 && perWarp * warps > 100 * 1024) warps >>= 1;      // two CTAs per SM where possible
+  while (warps > 1 && (perWarp * warps + 1024) * 3 > 227 * 1024) warps--;   // three CTAs per SM (7 warps each for 513 bins)
+  if ((size_t)p.nPts * sizeof(float) > (size_t)(p.nMag + 2) * sizeof(double)) return cudaErrorInvalidValue;   // SS must fit the buffer it reuses
   const size_t smem = perWarp * warps;
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(shs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
