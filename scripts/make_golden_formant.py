@@ -1,0 +1,37 @@
+"""Generate tests/golden/formant_goldens.npz with the UNMODIFIED reference (oracle/_ref/SMILExtract):
+
+    python scripts/make_golden_formant.py        # needs `make -C oracle ref` (build container only)
+
+Level taps of tests/configs/formant_taps.conf (the GeMAPS formant chain) on mixed_pcm(24000, seed=3):
+  res [T, 220]  cSpecResample output (11 kHz frames)      lpc [T, 11]  cLpc coefficients
+  fmt [T, 10]   cFormantLpc: formantFreqLpc[1..5] | formantBandwidthLpc[1..5]
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refrun  # noqa: E402
+from opensmile_b200.synth import mixed_pcm  # noqa: E402
+
+
+def main():
+    assert refrun.available(), "build the reference first: make -C oracle ref"
+    pcm = mixed_pcm(24000, 16000, seed=3)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        refrun.write_wav(os.path.join(d, "in.wav"), pcm, 16000, 1)
+        subprocess.run([refrun.SMILEXTRACT, "-C", os.path.join(ROOT, "tests", "configs", "formant_taps.conf"), "-I", "in.wav", "-l", "0"],
+                       cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for k in ("res", "lpc", "fmt"):
+            out[k] = refrun.read_htk(os.path.join(d, k + ".htk"))[0]
+    print({k: v.shape for k, v in out.items()})
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "formant_goldens.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,35 @@
+"""Formant chain of the GeMAPS graphs (SURVEY.md 8f-2, next scope row): the numpy restatement
+(oracle/formant_oracle.py) against level taps of the UNMODIFIED reference (tests/golden/formant_goldens.npz,
+scripts/make_golden_formant.py).  No product code yet -- this pins the checker the GPU path will be held to."""
+import os
+
+import numpy as np
+
+from opensmile_b200.synth import mixed_pcm
+from oracle import formant_oracle as fo
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "formant_goldens.npz"))
+
+
+def test_resampled_frames():
+    fmt, res, lpcs = fo.gemaps_formant_chain(mixed_pcm(24000, 16000, seed=3), taps=True)
+    assert res.shape == G["res"].shape
+    scale = np.abs(G["res"]).max(axis=1, keepdims=True) + 1e-30
+    assert (np.abs(res - G["res"]) / scale).max() < 2e-6          # own FFT vs Ooura's float FFT
+
+
+def test_lpc_and_formants_exact_given_inputs():
+    """float autocorrelation + Durbin and the root -> formant mapping reproduce the reference bit for bit"""
+    a = np.stack([fo.lpc_acf(fo.autocorr(x, 12), 11)[0] for x in G["res"]])
+    assert np.array_equal(a, G["lpc"])
+    f = np.stack([np.concatenate(fo.formants_from_lpc(x, 1.0 / 11000.0, 5, 50.0, 5450.0)) for x in G["lpc"]])
+    assert (np.abs(f - G["fmt"]) / (np.abs(G["fmt"]) + 1.0)).max() < 1e-6
+
+
+def test_conditioning_of_the_chain_is_documented():
+    """Order-11 LPC in float amplifies a 2e-7 perturbation of the frame (own FFT vs Ooura) to percent-level
+    changes of the coefficients on strongly harmonic frames: end-to-end parity of the formant columns needs a
+    bit-identical FFT + resampler in front of cLpc."""
+    fmt, res, lpcs = fo.gemaps_formant_chain(mixed_pcm(24000, 16000, seed=3), taps=True)
+    err = np.abs(lpcs - G["lpc"]).max(axis=1)
+    assert np.median(err) < 1e-2 and err.max() > 1e-3
