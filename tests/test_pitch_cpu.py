@@ -117,3 +117,36 @@ def test_variant_conf_description():
     off = s.frame_offsets(np.array([0, 48000, 88000]), 16000.0)
     assert list(np.diff(off)) == [G["var_m48k_lld"].shape[0], G["var_m40k_lld"].shape[0]]
     s.close()
+
+
+def _compare16_conf():
+    conf = os.path.join(HERE, "configs", "ref", "compare16", "ComParE_2016.conf")
+    if os.path.exists(conf):
+        return conf
+    from oracle import refrun
+    if not refrun.available():
+        pytest.skip("reference configuration files not available")
+    return os.path.join(refrun.CONFIG_DIR, "compare16", "ComParE_2016.conf")
+
+
+def test_compare16_sink_selection():
+    """Which sink is active decides the plan: the LLD sinks read lld;lld_de (130 columns, both give the same
+    plan); the summary sinks (-O / -csvoutput) read the cFunctionals level, which is off the supported path and
+    is rejected by naming the component; without any file name there is nothing to compute."""
+    from opensmile_b200 import capi
+    from opensmile_b200.session import Session, SessionError
+    conf = _compare16_conf()
+    a = Session(conf, options={"lldcsvoutput": "x.csv"}, device=-1)
+    b = Session(conf, options={"lldhtkoutput": "x.htk"}, device=-1)
+    assert list(a.element_names(16000.0, 1)) == list(b.element_names(16000.0, 1))
+    assert len(a.element_names(16000.0, 1)) == 130
+    # the same level at 44.1 kHz: frame geometry changes, names and columns do not
+    assert list(a.element_names(44100.0, 1)) == list(a.element_names(16000.0, 1))
+    a.close(); b.close()
+    with pytest.raises(SessionError) as e:               # summaries: cDataSelector / cFunctionals are upstream of `func`
+        Session(conf, options={"csvoutput": "x.csv"}, device=-1)
+    assert e.value.status == capi.ERR_UNSUPPORTED and "not on the supported LLD path" in str(e.value), str(e.value)
+    for opts in ({"O": "x.arff"}, None):                 # ARFF summaries only / nothing requested
+        with pytest.raises(SessionError) as e:
+            Session(conf, options=opts, device=-1)
+        assert "no active sink" in str(e.value)
