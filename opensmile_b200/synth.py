@@ -42,3 +42,14 @@ def mixed_pcm(n_samples, sample_rate=16000, seed=0):
         pos += ln
         seg += 1
     return np.clip(np.round(x), -32768, 32767).astype(np.int16)
+
+
+def stereo_mixed_pcm(n_samples, sample_rate=16000, seed=0):
+    """interleaved stereo: left = mixed_pcm, right = the same signal 37 samples earlier, scaled by 0.8, plus
+    its own noise (the mono mixdown therefore differs from either channel)"""
+    a = mixed_pcm(n_samples + 64, sample_rate, seed=seed).astype(np.float64)
+    rng = np.random.default_rng(seed + 100)
+    left = a[64:]
+    right = 0.8 * a[27:27 + n_samples] + rng.normal(0, 40, size=n_samples)
+    x = np.stack([left, right], axis=1)
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16).reshape(-1)

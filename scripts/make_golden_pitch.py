@@ -10,7 +10,7 @@ For each case (inputs are regenerated in the tests from opensmile_b200.synth):
   names_lld       element names of the LLD CSV header
 Cases: v32k = voiced_pcm(32000, seed=7); m48k = mixed_pcm(48000, seed=2) (Viterbi lag 1); m30k = mixed_pcm(30000, seed=4);
        m64k = mixed_pcm(64000, seed=3); m60k_44k = mixed_pcm(60000, seed=5) written as a 44.1 kHz file (FFT 4096 / 1024,
-       _lld only); var_m48k / var_m40k = tests/configs/pitch_variants.conf on mixed_pcm(48000, seed=6) / mixed_pcm(40000, seed=8)
+       _lld only); m40k_stereo = stereo_mixed_pcm(40000, seed=9), 16 kHz, 2 channels (_lld only); var_m48k / var_m40k = tests/configs/pitch_variants.conf on mixed_pcm(48000, seed=6) / mixed_pcm(40000, seed=8)
        (Viterbi lags 1 and 7), names_var its element names; short_<n> = voiced_pcm(n, seed=7) for n = 960, 1120, 1600, 2400 (1, 2, 5, 10 frames of 60 ms)
 """
 import os
@@ -71,6 +71,13 @@ def main():
         subprocess.run([refrun.SMILEXTRACT, "-C", full, "-I", wav, "-lldhtkoutput", os.path.join(d, "lld.htk"), "-l", "0"],
                        check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         out["m60k_44k_lld"] = refrun.read_htk(os.path.join(d, "lld.htk"))[0]
+    with tempfile.TemporaryDirectory() as d:            # stereo input (mono mixdown in the wave source)
+        from opensmile_b200.synth import stereo_mixed_pcm
+        wav = os.path.join(d, "in.wav")
+        refrun.write_wav(wav, stereo_mixed_pcm(40000, 16000, seed=9), 16000, 2)
+        subprocess.run([refrun.SMILEXTRACT, "-C", full, "-I", wav, "-lldhtkoutput", os.path.join(d, "lld.htk"), "-l", "0"],
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out["m40k_stereo_lld"] = refrun.read_htk(os.path.join(d, "lld.htk"))[0]
     var = os.path.join(ROOT, "tests", "configs", "pitch_variants.conf")     # the chain's other switches
     for name, pcm in (("var_m48k", mixed_pcm(48000, 16000, seed=6)), ("var_m40k", mixed_pcm(40000, 16000, seed=8))):
         with tempfile.TemporaryDirectory() as d:

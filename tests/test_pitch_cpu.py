@@ -76,6 +76,16 @@ def test_whole_chain_44k():
     assert (np.abs(de[:R] - ref[:, 65:71]) / sc[65:71]).max() < 1e-5
 
 
+def test_whole_chain_stereo():
+    from opensmile_b200.synth import stereo_mixed_pcm
+    sm, de = oracle.compare16_nz_lld(stereo_mixed_pcm(40000, 16000, seed=9), n_chan=2)
+    ref = G["m40k_stereo_lld"]
+    R = ref.shape[0]
+    sc = np.abs(ref).max(axis=0) + 1e-30
+    assert (np.abs(sm[:R] - ref[:, :6]) / sc[:6]).max() < 2e-6
+    assert (np.abs(de[:R] - ref[:, 65:71]) / sc[65:71]).max() < 1e-5
+
+
 def test_lagged_cases_cover_both_lags():
     fe, sc, ps, vc, jc = oracle.compare16_pitch_cfg()
     lags = {c: oracle.viterbi(G[c + "_shs"], ps, vc, with_lag=True)[1] - G[c + "_shs"].shape[0] for c in CASES}

@@ -69,6 +69,14 @@ def test_compare16_44k(session):
     assert bad.size == 0, [(names[c], int(r), float(rows[r, c]), float(ref[r, c])) for r, c in bad[:8]]
 
 
+def test_compare16_stereo(session):
+    """two channels, mono mixdown in the wave source (every kernel that reads PCM averages the channels itself)"""
+    from opensmile_b200.synth import stereo_mixed_pcm
+    pcm = stereo_mixed_pcm(40000, 16000, seed=9)
+    rows, _ = session.extract_pcm(pcm, np.array([0, 40000], np.int64), 16000.0, 2)
+    _check(rows, G["m40k_stereo_lld"], session.element_names(16000.0, 2))
+
+
 def test_compare16_single_and_repeatable(session):
     pcm = CASES["m30k"]()
     off = np.array([0, pcm.size], np.int64)
