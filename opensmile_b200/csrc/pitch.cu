@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
   const int N = p.nMag, M = p.nPts;
   // per warp: spectrum yS | second derivatives uS (doubles), scaled spectrum hps (float), 24 candidate floats; the
   // summed spectrum SS reuses the second-derivative buffer, which is dead once the interpolation has run
-  const size_t perWarp = (size_t)2 * (N + 2) * sizeof(double) + (size_t)M * sizeof(float) + 128;
+  const size_t perWarp = ((size_t)2 * (N + 2) * sizeof(double) + (size_t)M * sizeof(float) + 128 + 15) & ~(size_t)15;   // keeps the doubles aligned
   unsigned char *ws = smemRaw + warp * perWarp;
   double *yS = reinterpret_cast<double *>(ws);
   double *uS = yS + (N + 2);
@@ -932,7 +932,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) seq_post_kernel(const SeqPostP
 cudaError_t launch_shs(const ShsParams &p, cudaStream_t st)
 {
   if (p.nTiles <= 0) return cudaSuccess;
-  const size_t perWarp = (size_t)2 * (p.nMag + 2) * sizeof(double) + (size_t)p.nPts * sizeof(float) + 128;
+  const size_t perWarp = ((size_t)2 * (p.nMag + 2) * sizeof(double) + (size_t)p.nPts * sizeof(float) + 128 + 15) & ~(size_t)15;
   int warps = kShsWarps;
   while (warps > 1 && (perWarp * warps + 1024) * 3 > 227 * 1024) warps--;   // three CTAs per SM (7 warps each for 513 bins)
   if ((size_t)p.nPts * sizeof(float) > (size_t)(p.nMag + 2) * sizeof(double)) return cudaErrorInvalidValue;   // SS must fit the buffer it reuses
