@@ -101,3 +101,15 @@ def test_pitch_variant_switches():
         bad = np.argwhere(np.abs(got - ref) / sc > 1e-5)
         assert bad.size == 0, [(names[c], int(r), float(got[r, c]), float(ref[r, c])) for r, c in bad[:8]]
     s.close()
+
+
+def test_compare16_empty_and_too_short_utterances(session):
+    """utterances with no 60 ms frame (0 and 500 samples) inside a batch yield no rows and leave their neighbours alone"""
+    a, b = CASES["m30k"](), CASES["short_2400"]()
+    pcm = np.concatenate([a, np.zeros(0, np.int16), voiced_pcm(500, 16000, seed=1), b])
+    off = np.cumsum([0, a.size, 0, 500, b.size]).astype(np.int64)
+    rows, fo = session.extract_pcm(pcm, off, 16000.0, 1)
+    assert list(np.diff(fo)) == [G["m30k_lld"].shape[0], 0, 0, G["short_2400_lld"].shape[0]]
+    names = session.element_names(16000.0, 1)
+    _check(rows[fo[0]:fo[1]], G["m30k_lld"], names)
+    _check(rows[fo[3]:fo[4]], G["short_2400_lld"], names)
