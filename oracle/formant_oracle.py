@@ -167,3 +167,204 @@ def gemaps_formant_chain(pcm, sample_rate=16000.0, taps=False):
         f, b = formants_from_lpc(a, rs.base_period_out, 5, 50.0, 5450.0)
         fmt[t, :5], fmt[t, 5:] = f, b
     return (fmt, res, lpcs) if taps else fmt
+
+
+# ------------------------------------------------------------------------------------------------------------
+# cHarmonics (lld/harmonics.cpp): harmonic peaks of the 60 ms magnitude spectrum around multiples of F0, their
+# log magnitudes relative to the fundamental, harmonic differences (H1-H2, H1-A3), formant amplitudes, HNR from
+# the autocorrelation (inverse FFT of the power spectrum).  Restated for the switch set of the GeMAPS graphs
+# (config/gemaps/v01b/GeMAPSv01b_core.lld.conf.inc:289-318); `frq` is the bin-frequency axis of the spectrum.
+
+def _is_peak(x, n):                                                          # harmonics.cpp:369-390
+    N = len(x)
+    if n >= N or n < 0:
+        return False
+    if n + 1 < N:
+        if n > 0:
+            return x[n] > x[n - 1] and x[n] > x[n + 1]
+        return x[0] > x[1]
+    return n > 0 and x[n] > x[n - 1]
+
+
+def _freq_to_bin(frq, freq, start):                                          # :403-415
+    for b in range(start, len(frq)):
+        if frq[b] > freq:
+            return b - 1 if frq[b] - freq > freq - frq[b - 1] else b
+    return 0
+
+
+def _quad3(x1, y1, x2, y2, x3, y3):                                          # smileutil/smileUtil.c:1009-1034 -> (x, y)
+    den = x1 * x1 * x2 + x2 * x2 * x3 + x3 * x3 * x1 - x3 * x3 * x2 - x2 * x2 * x1 - x1 * x1 * x3
+    if den != 0.0:
+        a = (y1 * x2 + y2 * x3 + y3 * x1 - y3 * x2 - y2 * x1 - y1 * x3) / den
+        b = (x1 * x1 * y2 + x2 * x2 * y3 + x3 * x3 * y1 - x3 * x3 * y2 - x2 * x2 * y1 - x1 * x1 * y3) / den
+        c = (x1 * x1 * x2 * y3 + x2 * x2 * x3 * y1 + x3 * x3 * x1 * y2 - x3 * x3 * x2 * y1 - x2 * x2 * x1 * y3 - x1 * x1 * x3 * y2) / den
+        if a != 0.0:
+            x = -b / (2.0 * a)
+            return x, c - a * x * x
+    if y1 > y2 and y1 > y3:
+        return x1, y1
+    if y2 > y1 and y2 > y3:
+        return x2, y2
+    if y3 > y1 and y3 > y2:
+        return x3, y3
+    return x1, y1
+
+
+def find_harmonics(pitch, mag, frq, n_harm):
+    """findHarmonicPeaks, branch with a frequency axis (:476-545) + postProcessHarmonics (:550-588)
+    -> list of dicts (bin, freqInterpolated, magnitude, magnitudeInterpolated, magnitudeLogRelF0)"""
+    nb = len(mag)
+    pitch = f32(pitch)
+    H = []
+    last = _freq_to_bin(frq, f32(0.5) * pitch, 1)
+    first = _freq_to_bin(frq, f32(0.5) * pitch, last)
+    for i in range(n_harm):
+        h = dict(bin=-1, fi=f32(0), mag=f32(0), magi=f32(0), lr=f32(-201.0), fe=f32(0))
+        cand = _freq_to_bin(frq, f32(f32(i + 1) * pitch), last)
+        if cand >= nb:
+            H.append(h)
+            continue
+        peak = -1
+        if _is_peak(mag, cand):
+            peak = cand
+        else:
+            cl, cr = cand - 1, cand + 1
+            lo = _freq_to_bin(frq, f32((f32(i) + f32(0.5)) * pitch), last)
+            hi = _freq_to_bin(frq, f32((f32(i) + f32(1.5)) * pitch), cand)
+            while (cl >= lo or cr <= hi) and peak == -1:
+                if cr <= hi:
+                    if _is_peak(mag, cr):
+                        peak = cr
+                        break
+                    cr += 1
+                if cl >= lo:
+                    if _is_peak(mag, cl):
+                        peak = cl
+                        break
+                    cl -= 1
+        h["fe"] = f32(f32(i + 1) * pitch)
+        if first <= peak < nb - 1:
+            h["bin"] = peak
+            h["mag"] = f32(mag[peak])
+            x, y = _quad3(frq[peak - 1], float(mag[peak - 1]), frq[peak], float(mag[peak]), frq[peak + 1], float(mag[peak + 1]))
+            h["fi"], h["magi"] = f32(x), f32(y)
+        else:
+            h["bin"] = cand
+        last = cand
+        H.append(h)
+    # post processing, logRelMagnitude = true
+    log_rel = True
+    m0 = H[0]["mag"]
+    if m0 == 0.0:
+        log_rel = False
+    else:
+        m0 = f32(np.log10(m0))                   # float magnitudeF0 = log10(float)
+        H[0]["lr"] = f32(0.0)
+    if log_rel is False:
+        pass
+    for i in range(1, n_harm):
+        if log_rel:
+            if H[i]["magi"] > 0.0:
+                tmp = np.log10(np.float64(H[i]["magi"]))
+                v = f32(20.0 * (tmp - np.float64(m0)))
+                H[i]["lr"] = v if v >= -200.0 else f32(-200.0)
+            else:
+                H[i]["lr"] = f32(-200.0)
+        else:
+            H[i]["lr"] = f32(-201.0)
+        if H[i]["bin"] == H[i - 1]["bin"]:
+            H[i] = dict(bin=0, fi=f32(0), mag=f32(0), magi=f32(0), lr=f32(-201.0), fe=f32(0))
+    return H
+
+
+def acf_hnr_db(mag, F0, frq):
+    """computeAcf (:590-630, inverse FFT of the power spectrum; numpy's FFT instead of Ooura's) +
+    getClosestPeak (:632-665) + computeAcfHnr_dB (:690-712)"""
+    nb = len(mag)
+    N = (nb - 1) * 2
+    p = (np.asarray(mag, f32) * np.asarray(mag, f32)).astype(f32)
+    spec = np.zeros(N // 2 + 1, np.complex128)
+    spec[:] = p[:N // 2 + 1]
+    # rdft(N, -1, a): a[j] = R_0/2 .. the Ooura inverse without the 2/N factor: x[j] = a0/2 + sum_k a_k cos + .. + aN/2 cos(pi j)/2
+    k = np.arange(1, N // 2)
+    j = np.arange(nb)[:, None]
+    full = 0.5 * p[0] + 0.5 * p[N // 2] * np.cos(np.pi * j[:, 0]) + (p[k][None, :] * np.cos(2 * np.pi * j * k[None, :] / N)).sum(axis=1)
+    acf = (np.abs(full).astype(f32) / f32(nb)).astype(f32)
+    fs = frq[-1] * 2.0
+    F0 = f32(F0)
+    f0bin = int(np.floor(fs / F0)) if F0 > 0.0 else 0                       # freqToAcfBinLin (:393-401)
+    ref = 0
+    if f0bin > 0:
+        ref = _closest_peak(acf, f0bin)
+    if ref <= 0:
+        return f32(0.0), acf
+    hnr = float(acf[0]) - float(acf[ref])
+    hnr = 10e10 if hnr == 0.0 else float(acf[ref]) / hnr
+    if hnr > 10e10:
+        ret = 10.0 * np.log10(10e10)
+    elif hnr < 10e-10:
+        ret = 10.0 * np.log10(10e-10)
+    else:
+        ret = 10.0 * np.log10(hnr)
+    return f32(ret), acf
+
+
+def _closest_peak(x, idx):
+    N = len(x)
+    if _is_peak(x, idx):
+        return idx
+    o = 1
+    while idx - o > 0 or idx + o < N - 1:
+        if idx - o > 0 and _is_peak(x, idx - o):
+            return idx - o
+        if idx + o < N - 1 and _is_peak(x, idx + o):
+            return idx + o
+        o += 1
+    if x[0] > x[idx] and x[N - 1] <= x[idx]:
+        return 0
+    if x[0] <= x[idx] and x[N - 1] > x[idx]:
+        return N - 1
+    if x[0] > x[idx] and x[N - 1] > x[idx]:
+        return 0 if idx < N // 2 else N - 1
+    return idx
+
+
+def harmonics_gemaps(F0, formant_freq, mag, frq, n_harm=100, floor_unvoiced=-201.0):
+    """cHarmonics::processVector for the GeMAPS switch set -> [HNRdBACF, H1-H2, H1-A3, F1amp, F2amp, F3amp] (log rel. F0).
+    Differences are parsed like the reference: "H1" is element 1 of the harmonics array whose element 0 is the
+    fundamental (:98-104), "A3" the strongest harmonic within +-20 % of the third formant (:714-741)."""
+    out = []
+    hnr, _ = acf_hnr_db(mag, F0, frq)
+    out.append(hnr)
+    if F0 > 0.0:
+        H = find_harmonics(F0, mag, frq, n_harm)
+        fa = []
+        for f in formant_freq:
+            lo, hi = f32(0.8) * f32(f), f32(1.2) * f32(f)
+            best, bm = -1, f32(0.0)
+            for h, hh in enumerate(H):
+                if lo <= hh["fi"] <= hi and hh["mag"] > bm:
+                    best, bm = h, hh["mag"]
+            fa.append(best)
+        for (h1f, h1i, h2f, h2i) in ((-1, 1, -1, 2), (-1, 1, 3, -1)):       # H1-H2, H1-A3
+            if h1f > 0:
+                h1i = fa[h1f - 1]
+            if h2f > 0:
+                h2i = fa[h2f - 1]
+            ok1, ok2 = 0 <= h1i < n_harm, 0 <= h2i < n_harm
+            if ok1 and ok2:
+                v = f32(H[h1i]["lr"] - H[h2i]["lr"])
+            elif ok1:
+                v = f32(H[h1i]["lr"] - f32(201.0))
+            elif ok2:
+                v = f32(-201.0 - np.float64(H[h2i]["lr"]))
+            else:
+                out.append(f32(0.0))
+                continue
+            out.append(f32(min(max(v, f32(-201.0)), f32(201.0))))
+        for i in (1, 2, 3):                                                   # formantAmplitudesStart..End, log rel.
+            out.append(H[fa[i - 1]]["lr"] if fa[i - 1] >= 0 else f32(0.0))
+    else:
+        out += [f32(0.0), f32(0.0)] + [f32(floor_unvoiced)] * 3
+    return np.array(out, f32)

@@ -5,6 +5,8 @@
 Level taps of tests/configs/formant_taps.conf (the GeMAPS formant chain) on mixed_pcm(24000, seed=3):
   res [T, 220]  cSpecResample output (11 kHz frames)      lpc [T, 11]  cLpc coefficients
   fmt [T, 10]   cFormantLpc: formantFreqLpc[1..5] | formantBandwidthLpc[1..5]
+and of tests/configs/harmonics_taps.conf (same input): h_f0 [T60, 3] Viterbi level (F0final first), h_fmt, h_mag [T60, 513]
+60 ms magnitude spectrum, h_harm [T60, 6] cHarmonics: HNRdBACF, H1-H2, H1-A3, F1..F3 amplitude (log rel. F0)
 """
 import os
 import subprocess
@@ -29,6 +31,13 @@ def main():
                        cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         for k in ("res", "lpc", "fmt"):
             out[k] = refrun.read_htk(os.path.join(d, k + ".htk"))[0]
+    with tempfile.TemporaryDirectory() as d:            # cHarmonics with its three input levels
+        refrun.write_wav(os.path.join(d, "in.wav"), pcm, 16000, 1)
+        subprocess.run([refrun.SMILEXTRACT, "-C", os.path.join(ROOT, "tests", "configs", "harmonics_taps.conf"), "-I", "in.wav", "-l", "0"],
+                       cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for k in ("f0", "mag", "harm"):
+            out["h_" + k] = refrun.read_htk(os.path.join(d, k + ".htk"))[0]
+        out["h_fmt"] = refrun.read_htk(os.path.join(d, "fmt.htk"))[0]
     print({k: v.shape for k, v in out.items()})
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "formant_goldens.npz"), **out)
 

@@ -33,3 +33,14 @@ def test_conditioning_of_the_chain_is_documented():
     fmt, res, lpcs = fo.gemaps_formant_chain(mixed_pcm(24000, 16000, seed=3), taps=True)
     err = np.abs(lpcs - G["lpc"]).max(axis=1)
     assert np.median(err) < 1e-2 and err.max() > 1e-3
+
+
+def test_harmonics_exact_given_inputs():
+    """cHarmonics (HNR from the ACF, H1-H2, H1-A3, formant amplitudes) on the reference's own F0 / formant / magnitude
+    levels: every decision (harmonic peak search, formant-range maximum) and value reproduced"""
+    T = G["h_harm"].shape[0]
+    frq = np.arange(513, dtype=np.float64) * (1.0 / 0.064)          # bin k -> k / frameSizeSec (dspcore/transformFft.cpp:111-115)
+    got = np.stack([fo.harmonics_gemaps(G["h_f0"][t, 0], G["h_fmt"][t, :5], G["h_mag"][t], frq) for t in range(T)])
+    assert np.abs(got - G["h_harm"][:T]).max() < 1e-4
+    voiced = G["h_f0"][:T, 0] > 0
+    assert voiced.sum() > 20 and (~voiced).sum() > 20
