@@ -160,3 +160,40 @@ def test_compare16_sink_selection():
         with pytest.raises(SessionError) as e:
             Session(conf, options=opts, device=-1)
         assert "no active sink" in str(e.value)
+
+
+def test_compare16_component_mapping_and_baseline_geometry():
+    """the conf front end hands the pitch chain's sections over with the reference's values
+    (ComParE_2016_core.lld.conf.inc:62-190), and BASELINE configs[3]'s shard (125 000 utterances x 3.0 s) has the
+    row counts of SURVEY.md 8a' (296 per utterance) -- description only, no device"""
+    from opensmile_b200 import capi
+    from opensmile_b200.session import Session
+    s = Session(_compare16_conf(), options={"lldcsvoutput": "x.csv"}, device=-1)
+    comps, level = s.components(16000.0, 1)
+    by_type = {}
+    for c in comps:
+        by_type.setdefault(c.type, []).append(c)
+    assert not by_type.get(-1)
+    sc = by_type[capi.C_SPECSCALE][0].u.specscale
+    assert (sc.scaleOctave, sc.sourceLin, sc.splineInterp, sc.specSmooth, sc.specEnhance, sc.auditoryWeighting) == (1, 1, 1, 1, 1, 1)
+    assert (sc.minF, sc.maxF, sc.nPointsTarget) == (25.0, -1.0, 0)
+    ps = by_type[capi.C_PITCHSHS][0].u.pitchshs
+    assert (ps.nCandidates, ps.greedyPeakAlgo, ps.nHarmonics, ps.F0raw, ps.voicingClip) == (6, 1, 15, 1, 1)
+    assert (ps.maxPitch, ps.minPitch) == (620.0, 52.0) and abs(ps.voicingCutoff - 0.7) < 1e-12 and abs(ps.compressionFactor - 0.85) < 1e-12
+    vt = by_type[capi.C_PITCHSMOOTHERVITERBI][0].u.pitchsmootherviterbi
+    assert (vt.bufferLength, vt.F0final, vt.voicingFinalUnclipped, vt.voicingFinalClipped) == (30, 1, 1, 0)
+    assert (vt.wTvv, vt.wTvvd, vt.wTvuv, vt.wThr, vt.wLocal, vt.wRange, vt.wTuu) == (10.0, 5.0, 10.0, 4.0, 2.0, 1.0, 0.0)
+    vs = by_type[capi.C_VALBASEDSELECTOR][0]
+    assert (vs.u.valbasedselector.idx, vs.u.valbasedselector.removeIdx, vs.u.valbasedselector.zeroVec) == (0, 1, 1)
+    assert abs(vs.u.valbasedselector.threshold - 0.001) < 1e-12 and vs.n_inputs == 2
+    pj = by_type[capi.C_PITCHJITTER][0].u.pitchjitter
+    assert pj.F0reader_dmLevel == b"is13_pitchG60" and pj.F0field == b"F0final"
+    assert (pj.jitterLocal, pj.jitterDDP, pj.shimmerLocal, pj.logHNR, pj.useBrokenJitterThresh) == (1, 1, 1, 1, 0)
+    assert abs(pj.searchRangeRel - 0.25) < 1e-12
+    # functionals and their sinks are not part of the plan
+    assert capi.C_VECTORCONCAT in by_type and len(comps) < 50
+    n = 1000                                            # (frame_offsets is linear in the number of utterances)
+    off = np.arange(n + 1, dtype=np.int64) * 48000
+    fo = s.frame_offsets(off, 16000.0)
+    assert int(fo[-1]) == 296 * n and set(np.diff(fo)) == {296}
+    s.close()
