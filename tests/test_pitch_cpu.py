@@ -197,3 +197,56 @@ def test_compare16_component_mapping_and_baseline_geometry():
     fo = s.frame_offsets(off, 16000.0)
     assert int(fo[-1]) == 296 * n and set(np.diff(fo)) == {296}
     s.close()
+
+
+def test_one_pass_cross_correlation_matches_the_two_pass_form():
+    """jitter_kernel evaluates the normalised cross correlation of a candidate period in its one-pass form
+    (window sums from prefix sums); the reference's two-pass loop (lld/pitchJitter.cpp:339-413)
+    gives the same value to ~1e-15 and the same peak decision on every window tried"""
+    rng = np.random.default_rng(0)
+
+    def two_pass(x, y):
+        n = len(x)
+        mx = my = 0.0
+        for a, b in zip(x, y):
+            mx += float(a)
+            my += float(b)
+        mx /= n
+        my /= n
+        cc = nx = ny = 0.0
+        for a, b in zip(x, y):
+            dx, dy = float(a) - mx, float(b) - my
+            cc += dx * dy
+            nx += dx * dx
+            ny += dy * dy
+        return cc / (np.sqrt(nx) * np.sqrt(ny))
+
+    def one_pass(w, tf):
+        x, y = w[:tf].astype(np.float64), w[tf:2 * tf].astype(np.float64)
+        n = float(tf)
+        sx, sy = x.sum(), y.sum()
+        return ((x * y).sum() - sx * sy / n) / (np.sqrt((x * x).sum() - sx * sx / n) * np.sqrt((y * y).sum() - sy * sy / n))
+
+    def pick(c):
+        best, mx = -1, None
+        for i in range(1, len(c) - 2):
+            if c[i - 1] < c[i] and c[i] > c[i + 1] and (best == -1 or c[i] > mx):
+                best, mx = i, c[i]
+        return best
+
+    worst, n_win = 0.0, 0
+    for seed in range(4):
+        pcm = (mixed_pcm(24000, 16000, seed=seed) if seed % 2 else voiced_pcm(24000, 16000, seed=seed)).astype(np.float32) / np.float32(32767.0)
+        for _ in range(12):
+            start, tf0 = int(rng.integers(0, 22000)), int(rng.integers(60, 300))
+            tmin, tmax = int(0.75 * tf0), int(np.ceil(1.25 * tf0))
+            if start + 2 * tmax + 1 >= len(pcm):
+                continue
+            w = pcm[start:]
+            a = np.array([two_pass(w[:tf], w[tf:2 * tf]) for tf in range(tmin, tmax + 1)])
+            b = np.array([one_pass(w, tf) for tf in range(tmin, tmax + 1)])
+            ok = np.isfinite(a) & np.isfinite(b)
+            worst = max(worst, float(np.abs(a[ok] - b[ok]).max()))
+            assert pick(a) == pick(b)
+            n_win += 1
+    assert n_win > 30 and worst < 1e-12
