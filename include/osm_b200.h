@@ -341,6 +341,12 @@ OSM_B200_API int32_t     osm_b200_plan_fft_size(const osm_b200_plan *plan);
  * concat = min over inputs) */
 OSM_B200_API int64_t     osm_b200_plan_num_frames(const osm_b200_plan *plan, int64_t n_sample_frames);
 
+/* number of distinct time stamps of those rows: frames of the level the first output field comes from, before its
+ * window processors.  The rows a window processor appends at the end of input repeat the time stamp of the last
+ * real frame (their tmeta is a copy, src/core/dataMemoryLevel.cpp:1698-1708), so row r of a sink's file carries the
+ * time min(r, n - 1) * period */
+OSM_B200_API int64_t     osm_b200_plan_num_time_frames(const osm_b200_plan *plan, int64_t n_sample_frames);
+
 /* exclusive prefix sums over utterances: frame_offsets[0..n_utt] (host arrays) */
 OSM_B200_API osm_b200_status osm_b200_plan_frame_offsets(const osm_b200_plan *plan,
                                             const int64_t *utt_offsets, int32_t n_utt,

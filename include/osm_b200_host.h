@@ -83,6 +83,12 @@ OSM_B200_API int32_t osm_b200_write_csv(const char *path, const float *rows, int
                                         const char *const *names, double period, const char *instance_name,
                                         int32_t frame_index, int32_t frame_time);
 
+/* same, with the time stamp of row r = min(r, n_time_frames - 1) * period (osm_b200_plan_num_time_frames);
+ * n_time_frames <= 0: every row has its own time stamp */
+OSM_B200_API int32_t osm_b200_write_csv_timed(const char *path, const float *rows, int64_t n_rows, int32_t n_elements,
+                                              const char *const *names, double period, const char *instance_name,
+                                              int32_t frame_index, int32_t frame_time, int64_t n_time_frames);
+
 #ifdef __cplusplus
 }
 #endif

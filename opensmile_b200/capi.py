@@ -218,7 +218,7 @@ EXPORTS = [
     "osm_b200_device_count", "osm_b200_component_defaults", "osm_b200_plan_create",
     "osm_b200_plan_destroy", "osm_b200_plan_num_elements", "osm_b200_plan_element_name",
     "osm_b200_plan_frame_period", "osm_b200_plan_frame_size_samples",
-    "osm_b200_plan_frame_step_samples", "osm_b200_plan_fft_size", "osm_b200_plan_num_frames",
+    "osm_b200_plan_frame_step_samples", "osm_b200_plan_fft_size", "osm_b200_plan_num_frames", "osm_b200_plan_num_time_frames",
     "osm_b200_plan_frame_offsets", "osm_b200_plan_run_device", "osm_b200_plan_run_host",
     "osm_b200_plan_last_launch_count", "osm_b200_plan_last_kernel_ms",
     "osm_b200_plan_last_kernel_times",
@@ -226,7 +226,7 @@ EXPORTS = [
     "osm_b200_session_open", "osm_b200_session_close", "osm_b200_session_num_elements",
     "osm_b200_session_element_name", "osm_b200_session_extract_files",
     "osm_b200_session_extract_pcm", "osm_b200_session_components", "osm_b200_host_last_error",
-    "osm_b200_write_htk", "osm_b200_write_csv",
+    "osm_b200_write_htk", "osm_b200_write_csv", "osm_b200_write_csv_timed",
 ]
 
 _lib = None
@@ -265,6 +265,8 @@ def lib():
         getattr(L, "osm_b200_plan_" + fn).restype = i32
     L.osm_b200_plan_num_frames.argtypes = [vp, C.c_int64]
     L.osm_b200_plan_num_frames.restype = C.c_int64
+    L.osm_b200_plan_num_time_frames.argtypes = [vp, C.c_int64]
+    L.osm_b200_plan_num_time_frames.restype = C.c_int64
     L.osm_b200_plan_frame_offsets.argtypes = [vp, i64p, i32, i64p]
     L.osm_b200_plan_run_device.argtypes = [vp, vp, i64p, i32, i64p, vp, vp]
     L.osm_b200_plan_run_host.argtypes = [vp, vp, i64p, i32, i64p, vp]

@@ -846,6 +846,15 @@ int32_t osm_b200_plan_fft_size(const osm_b200_plan *pl) { return pl ? pl->d.fe0(
 
 int64_t osm_b200_plan_num_frames(const osm_b200_plan *pl, int64_t n) { return pl ? desc_num_frames(pl->d, n) : 0; }
 
+int64_t osm_b200_plan_num_time_frames(const osm_b200_plan *pl, int64_t n)
+{
+  if (!pl || pl->d.groups.empty()) return 0;
+  const OutGroup &g = pl->d.groups[0];
+  int64_t t = desc_num_static_frames(pl->d, g.stream, n);
+  for (int ls : g.limitStreams) t = std::min<int64_t>(t, desc_num_static_frames(pl->d, ls, n));
+  return t < 0 ? 0 : t;
+}
+
 osm_b200_status osm_b200_plan_frame_offsets(const osm_b200_plan *pl, const int64_t *utt_offsets, int32_t n_utt,
                                             int64_t *frame_offsets)
 {

@@ -559,7 +559,7 @@ struct CsvOpts { bool printHeader = true, timestamp = true, number = true; int p
 
 // iocore/csvSink.cpp:150-235
 bool write_csv(const char *path, const float *rows, int64_t n, int K, const std::vector<std::string> &names, double period,
-               const CsvOpts &o, std::string &err)
+               const CsvOpts &o, std::string &err, int64_t nTimeFrames = 0)
 {
   FILE *f = fopen(path, "w");
   if (!f) { err = std::string("cannot write '") + path + "'"; return false; }
@@ -574,7 +574,8 @@ bool write_csv(const char *path, const float *rows, int64_t n, int K, const std:
     if (o.prname == 1) fprintf(f, "'%s'%c", o.instName.c_str(), o.delim);
     else if (o.prname == 2) fprintf(f, "'%s_%ld'%c", o.instName.c_str(), (long)r, o.delim);
     if (o.number) fprintf(f, "%ld%c", (long)r, o.delim);
-    if (o.timestamp) fprintf(f, "%f%c", (double)r * period, o.delim);
+    // rows appended by a window processor at the end of input carry a copy of the last frame's time stamp
+    if (o.timestamp) fprintf(f, "%f%c", (double)((nTimeFrames > 0 && r > nTimeFrames - 1) ? nTimeFrames - 1 : r) * period, o.delim);
     for (int k = 0; k < K; k++) {
       const float v = rows[r * K + k];
       const bool last = k == K - 1;
@@ -836,7 +837,9 @@ osm_b200_status osm_b200_session_extract_files(osm_b200_session *s, int32_t n, c
       const int64_t nr = fo[k + 1] - fo[k];
       if (framesOut) framesOut[idx] = nr;
       if (htkPaths && htkPaths[idx] && !write_htk(htkPaths[idx], r, nr, K, period, s->parmKind, err)) return hfail(OSM_B200_ERR_INVALID, err);
-      if (csvPaths && csvPaths[idx] && !write_csv(csvPaths[idx], r, nr, K, names, period, s->csv, err)) return hfail(OSM_B200_ERR_INVALID, err);
+      if (csvPaths && csvPaths[idx] &&
+          !write_csv(csvPaths[idx], r, nr, K, names, period, s->csv, err, osm_b200_plan_num_time_frames(p, off[k + 1] - off[k])))
+        return hfail(OSM_B200_ERR_INVALID, err);
     }
   }
   return OSM_B200_OK;
@@ -863,6 +866,21 @@ int32_t osm_b200_write_csv(const char *path, const float *rows, int64_t n, int32
   o.number = frameIndex != 0;
   o.timestamp = frameTime != 0;
   if (write_csv(path, rows, n, K, nm, period, o, err)) return 0;
+  g_herr = err;
+  return 1;
+}
+
+int32_t osm_b200_write_csv_timed(const char *path, const float *rows, int64_t n, int32_t K, const char *const *names, double period,
+                                 const char *instName, int32_t frameIndex, int32_t frameTime, int64_t nTimeFrames)
+{
+  std::string err;
+  std::vector<std::string> nm(K);
+  for (int k = 0; k < K; k++) nm[k] = names[k];
+  CsvOpts o;
+  if (instName) { o.instName = instName; o.prname = 1; }
+  o.number = frameIndex != 0;
+  o.timestamp = frameTime != 0;
+  if (write_csv(path, rows, n, K, nm, period, o, err, nTimeFrames)) return 0;
   g_herr = err;
   return 1;
 }

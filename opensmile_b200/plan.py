@@ -162,6 +162,10 @@ class Plan:
     def num_frames(self, n_sample_frames):
         return int(self._L.osm_b200_plan_num_frames(self._h, int(n_sample_frames)))
 
+    def num_time_frames(self, n_sample_frames):
+        """distinct time stamps of those rows (see osm_b200_plan_num_time_frames)"""
+        return int(self._L.osm_b200_plan_num_time_frames(self._h, int(n_sample_frames)))
+
     def frame_offsets(self, utt_offsets):
         utt = np.ascontiguousarray(utt_offsets, dtype=np.int64)
         fo = np.zeros(utt.size, np.int64)

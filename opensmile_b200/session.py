@@ -101,9 +101,14 @@ def write_htk(path, rows, period, parm_kind=9):
         raise IOError(capi.lib().osm_b200_host_last_error().decode())
 
 
-def write_csv(path, rows, names, period, instance_name=None, frame_index=True, frame_time=True):
+def write_csv(path, rows, names, period, instance_name=None, frame_index=True, frame_time=True, n_time_frames=0):
+    """cCsvSink's file format.  n_time_frames (Plan.num_time_frames) > 0: rows past that index repeat the last time stamp,
+    as the rows a window processor appends at the end of input do in the reference"""
     rows = np.ascontiguousarray(rows, dtype=np.float32)
-    if capi.lib().osm_b200_write_csv(str(path).encode(), rows.ctypes.data, rows.shape[0], rows.shape[1], _strs(names),
-                                     float(period), instance_name.encode() if instance_name is not None else None,
-                                     int(frame_index), int(frame_time)):
-        raise IOError(capi.lib().osm_b200_host_last_error().decode())
+    L = capi.lib()
+    L.osm_b200_write_csv_timed.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), C.c_double,
+                                           C.c_char_p, C.c_int32, C.c_int32, C.c_int64]
+    if L.osm_b200_write_csv_timed(str(path).encode(), rows.ctypes.data, rows.shape[0], rows.shape[1], _strs(names),
+                                  float(period), instance_name.encode() if instance_name is not None else None,
+                                  int(frame_index), int(frame_time), int(n_time_frames)):
+        raise IOError(L.osm_b200_host_last_error().decode())

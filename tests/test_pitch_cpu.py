@@ -250,3 +250,23 @@ def test_one_pass_cross_correlation_matches_the_two_pass_form():
             assert pick(a) == pick(b)
             n_win += 1
     assert n_win > 30 and worst < 1e-12
+
+
+def test_compare16_lld_csv_file_is_byte_identical():
+    """cCsvSink file of the lld;lld_de reader (instance name, frameTime, 130 values per row): written from the
+    reference's rows it equals the reference's file byte for byte -- including the last row, which a window
+    processor appended at the end of input and which repeats the time stamp of the last real frame"""
+    import tempfile
+    from opensmile_b200 import Plan, write_csv
+    from opensmile_b200.session import Session
+    s = Session(_compare16_conf(), options={"lldcsvoutput": "x.csv"}, device=-1)
+    comps, level = s.components(16000.0, 1)
+    p = Plan(list(comps), level, device=-1)
+    assert (p.num_frames(32000), p.num_time_frames(32000)) == (196, 195)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "lld.csv")
+        write_csv(path, G["v32k_lld"], [str(x) for x in G["names_lld"]], 0.01, instance_name="utt7", frame_index=False,
+                  frame_time=True, n_time_frames=p.num_time_frames(32000))
+        assert open(path, "rb").read() == G["v32k_lld_csv"].tobytes()
+    p.close()
+    s.close()
