@@ -369,6 +369,11 @@ OSM_B200_API osm_b200_status osm_b200_plan_run_host(osm_b200_plan *plan, const v
 
 /* number of CUDA kernels the last run_* call launched (for bench.py's gpu_launches) */
 OSM_B200_API int32_t     osm_b200_plan_last_launch_count(const osm_b200_plan *plan);
+/* Device-side condition flags of the runs since the last call (synchronises the device, then clears them).
+ * bit 0: a cPitchJitter frame left the supported geometry (wave window past the end of the utterance or beyond the
+ * kernel's workspace) and its row was zeroed.  osm_b200_plan_run_host checks this itself and fails with
+ * OSM_B200_ERR_UNSUPPORTED; callers of the asynchronous osm_b200_plan_run_device ask here after their own sync. */
+OSM_B200_API int32_t     osm_b200_plan_take_device_flags(osm_b200_plan *plan);
 /* device time in ms of the fused LLD kernel(s) of the last run_* call, measured with CUDA
  * events on the run's stream; blocks until the run has finished.  <0 if unavailable. */
 OSM_B200_API float       osm_b200_plan_last_kernel_ms(osm_b200_plan *plan);

@@ -220,7 +220,7 @@ EXPORTS = [
     "osm_b200_plan_frame_period", "osm_b200_plan_frame_size_samples",
     "osm_b200_plan_frame_step_samples", "osm_b200_plan_fft_size", "osm_b200_plan_num_frames", "osm_b200_plan_num_time_frames",
     "osm_b200_plan_frame_offsets", "osm_b200_plan_run_device", "osm_b200_plan_run_host",
-    "osm_b200_plan_last_launch_count", "osm_b200_plan_last_kernel_ms",
+    "osm_b200_plan_last_launch_count", "osm_b200_plan_take_device_flags", "osm_b200_plan_last_kernel_ms",
     "osm_b200_plan_last_kernel_times",
     # include/osm_b200_host.h
     "osm_b200_session_open", "osm_b200_session_close", "osm_b200_session_num_elements",

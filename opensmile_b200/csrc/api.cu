@@ -1225,6 +1225,16 @@ osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const
 
 int32_t osm_b200_plan_last_launch_count(const osm_b200_plan *pl) { return pl ? pl->lastLaunches : 0; }
 
+int32_t osm_b200_plan_take_device_flags(osm_b200_plan *pl)
+{
+  if (!pl || pl->device < 0 || !pl->dErr) return 0;
+  int flag = 0;
+  if (cudaSetDevice(pl->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(&flag, pl->dErr, sizeof flag, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (flag && cudaMemset(pl->dErr, 0, sizeof(int)) != cudaSuccess) return -1;
+  return flag;
+}
+
 float osm_b200_plan_last_kernel_ms(osm_b200_plan *pl)
 {
   if (!pl || !pl->timed) return -1.f;

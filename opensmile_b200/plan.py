@@ -212,6 +212,11 @@ class Plan:
     def last_launch_count(self):
         return int(self._L.osm_b200_plan_last_launch_count(self._h))
 
+    def take_device_flags(self):
+        """condition flags of the runs since the last call (bit 0: a cPitchJitter row was zeroed); synchronises the device"""
+        self._L.osm_b200_plan_take_device_flags.argtypes = [C.c_void_p]
+        return int(self._L.osm_b200_plan_take_device_flags(self._h))
+
     def last_kernel_ms(self):
         return float(self._L.osm_b200_plan_last_kernel_ms(self._h))
 
