@@ -56,6 +56,15 @@ OSM_B200_API osm_b200_status osm_b200_session_extract_files(osm_b200_session *se
                                                             const char *const *csv_paths,
                                                             int64_t *frames_out);
 
+/* same, additionally writing WEKA ARFF files like cArffSink (src/iocore/arffSink.cpp:225-440) with the options of the
+ * configuration's active ARFF sink (relation, instance name, class[] / target[].all from the included targets file) */
+OSM_B200_API osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *session, int32_t n,
+                                                                 const char *const *wav_paths,
+                                                                 const char *const *htk_paths,
+                                                                 const char *const *csv_paths,
+                                                                 const char *const *arff_paths,
+                                                                 int64_t *frames_out);
+
 /* Extract from packed PCM (layout of osm_b200_plan_run_host).  frame_offsets_out: n_utt+1 entries;
  * out: caller buffer of at least max_rows * num_elements floats, or NULL to only get the offsets. */
 OSM_B200_API osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *session, const int16_t *pcm,
@@ -88,6 +97,14 @@ OSM_B200_API int32_t osm_b200_write_csv(const char *path, const float *rows, int
 OSM_B200_API int32_t osm_b200_write_csv_timed(const char *path, const float *rows, int64_t n_rows, int32_t n_elements,
                                               const char *const *names, double period, const char *instance_name,
                                               int32_t frame_index, int32_t frame_time, int64_t n_time_frames);
+
+/* cArffSink's file format for rows already in host memory; targets[c] = value of class attribute c for every row
+ * ("?" = unknown); append: add rows to an existing file without repeating the header */
+OSM_B200_API int32_t osm_b200_write_arff(const char *path, const float *rows, int64_t n_rows, int32_t n_elements,
+                                         const char *const *names, double period, const char *relation,
+                                         const char *instance_name, int32_t frame_index, int32_t frame_time,
+                                         int32_t n_classes, const char *const *class_names, const char *const *class_types,
+                                         const char *const *targets, int32_t append, int64_t n_time_frames);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,6 @@ from . import capi  # noqa: F401
 from .plan import (Plan, comp, components_frontend, components_mfcc12_0_d_a,  # noqa: F401
                    components_plp_0_d_a, pack_utterances)
 
-from .session import Session, SessionError, write_csv, write_htk  # noqa: F401
+from .session import Session, SessionError, write_arff, write_csv, write_htk  # noqa: F401
 
 __all__ = ["Session", "SessionError", "Plan", "components_mfcc12_0_d_a", "components_plp_0_d_a", "pack_utterances", "capi"]

@@ -224,9 +224,9 @@ EXPORTS = [
     "osm_b200_plan_last_kernel_times",
     # include/osm_b200_host.h
     "osm_b200_session_open", "osm_b200_session_close", "osm_b200_session_num_elements",
-    "osm_b200_session_element_name", "osm_b200_session_extract_files",
+    "osm_b200_session_element_name", "osm_b200_session_extract_files", "osm_b200_session_extract_files_arff",
     "osm_b200_session_extract_pcm", "osm_b200_session_components", "osm_b200_host_last_error",
-    "osm_b200_write_htk", "osm_b200_write_csv", "osm_b200_write_csv_timed",
+    "osm_b200_write_htk", "osm_b200_write_csv", "osm_b200_write_csv_timed", "osm_b200_write_arff",
 ]
 
 _lib = None
@@ -282,6 +282,7 @@ def lib():
     L.osm_b200_session_element_name.argtypes = [vp, i32]
     L.osm_b200_session_element_name.restype = C.c_char_p
     L.osm_b200_session_extract_files.argtypes = [vp, i32, cpp, cpp, cpp, i64p]
+    L.osm_b200_session_extract_files_arff.argtypes = [vp, i32, cpp, cpp, cpp, cpp, i64p]
     L.osm_b200_session_extract_pcm.argtypes = [vp, vp, i64p, i32, f64, i32, i64p, vp, C.c_int64]
     L.osm_b200_session_components.argtypes = [vp, f64, i32, C.POINTER(C.POINTER(Component)), cpp]
     L.osm_b200_host_last_error.restype = C.c_char_p

@@ -587,6 +587,78 @@ bool write_csv(const char *path, const float *rows, int64_t n, int K, const std:
   return true;
 }
 
+// cArffSink options (iocore/arffSink.cpp:40-100) and writer (:225-330 header, :337-440 rows)
+struct ArffOpts {
+  std::string relation = "smile", instName;
+  int prname = 0;                      // 1 instanceName, 2 instanceBase_<index>
+  bool number = true, timestamp = true, append = false, dummyClass = true;
+  double frameTimeAdd = 0.0;
+  std::vector<std::pair<std::string, std::string>> classes;   // (name, type); type "" = numeric
+  std::vector<std::string> targetAll;                         // per class, already escaped; "" -> NULL
+};
+
+std::string arff_escape(const std::string &str)               // iocore/arffSink.cpp:189-232
+{
+  if (str.empty()) return "''";
+  bool quote = false;
+  std::string e;
+  for (char c : str) {
+    switch (c) {
+      case '"': case '\'': case '%': case '\\': e += '\\'; e += c; quote = true; break;
+      case '\r': e += "\\r"; quote = true; break;
+      case '\n': e += "\\n"; quote = true; break;
+      case '\t': e += "\\t"; quote = true; break;
+      case ' ': case ',': case '{': case '}': e += c; quote = true; break;
+      default: e += c;
+    }
+  }
+  return quote ? "'" + e + "'" : e;
+}
+
+bool write_arff(const char *path, const float *rows, int64_t n, int K, const std::vector<std::string> &names, double period,
+                const ArffOpts &o, std::string &err, int64_t nTimeFrames = 0)
+{
+  bool header = true;
+  if (o.append) {                                             // :244-256: append to an existing file without a header
+    FILE *t = fopen(path, "r");
+    if (t) { fclose(t); header = false; }
+  }
+  FILE *f = fopen(path, header ? "w" : "a");
+  if (!f) { err = std::string("cannot write '") + path + "'"; return false; }
+  if (header) {
+    fprintf(f, "@relation %s\n\n", arff_escape(o.relation).c_str());
+    if (o.prname) fprintf(f, "@attribute name string\n");
+    if (o.number) fprintf(f, "@attribute frameIndex numeric\n");
+    if (o.timestamp) fprintf(f, "@attribute frameTime numeric\n");
+    for (int k = 0; k < K; k++) fprintf(f, "@attribute %s numeric\n", arff_escape(names[k]).c_str());
+    if (!o.classes.empty()) {
+      for (const auto &c : o.classes) fprintf(f, "@attribute %s %s\n", c.first.c_str(), c.second.empty() ? "numeric" : c.second.c_str());
+    } else if (o.dummyClass) {
+      fprintf(f, "@attribute class {0,1,2,3}\n");
+    }
+    fprintf(f, "\n@data\n\n");
+  }
+  for (int64_t r = 0; r < n; r++) {
+    if (o.prname == 1) fprintf(f, "%s,", arff_escape(o.instName).c_str());
+    else if (o.prname == 2) { char b[512]; snprintf(b, sizeof b, "%s_%ld", o.instName.c_str(), (long)r); fprintf(f, "%s,", arff_escape(b).c_str()); }
+    if (o.number) fprintf(f, "%ld,", (long)r);
+    if (o.timestamp) fprintf(f, "%f,", (double)((nTimeFrames > 0 && r > nTimeFrames - 1) ? nTimeFrames - 1 : r) * period + o.frameTimeAdd);
+    fprintf(f, "%e", rows[r * K]);
+    for (int k = 1; k < K; k++) fprintf(f, ",%e", rows[r * K + k]);
+    if (!o.classes.empty()) {
+      for (size_t c = 0; c < o.classes.size(); c++) {
+        if (c < o.targetAll.size() && !o.targetAll[c].empty()) fprintf(f, ",%s", o.targetAll[c].c_str());
+        else fprintf(f, ",NULL");
+      }
+    } else if (o.dummyClass) {
+      fprintf(f, ",0");
+    }
+    fputc('\n', f);
+  }
+  fclose(f);
+  return true;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -598,6 +670,7 @@ struct osm_b200_session {
   int device = 0;
   int parmKind = 9;
   CsvOpts csv;
+  ArffOpts arff;
   // plan cache keyed by (sample rate, channels)
   std::map<std::pair<long, int>, osm_b200_plan *> plans;
   osm_b200_plan *cur = nullptr;
@@ -644,7 +717,7 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
   for (const auto &sec : s->conf.sections) if (sec.type != "cComponentManager") secOf[sec.name] = &sec;
   std::vector<std::string> sinkLevels;
   std::vector<const Section *> compute;
-  bool csvLocked = false;
+  bool csvLocked = false, arffLocked = false;
   std::set<std::string> hostTypes = {"cDataMemory", "cHtkSink", "cCsvSink", "cArffSink", "cExternalSink", "cNullSink", "cDatadumpSink"};
   for (const auto &inst : s->conf.instances) {
     const std::string &name = inst.first, &type = inst.second;
@@ -656,7 +729,37 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
         const std::string *fn = sec->get("filename");
         const bool active = type == "cExternalSink" || (fn && *fn != "?" && !fn->empty());
         const std::string *lv = sec->get("reader.dmLevel");
-        if (active && lv && type != "cArffSink") sinkLevels.push_back(*lv);
+        if (active && lv) sinkLevels.push_back(*lv);
+        if (type == "cArffSink" && active && !arffLocked) {
+          arffLocked = true;
+          ArffOpts &a = s->arff;
+          a = ArffOpts();
+          if (const std::string *x = sec->get("relation")) a.relation = *x;
+          if (const std::string *x = sec->get("append")) a.append = inum(*x) != 0;
+          if (const std::string *x = sec->get("number")) a.number = inum(*x) == 1;
+          if (const std::string *x = sec->get("frameIndex")) a.number = inum(*x) == 1;
+          if (const std::string *x = sec->get("timestamp")) a.timestamp = inum(*x) == 1;
+          if (const std::string *x = sec->get("frameTime")) a.timestamp = inum(*x) == 1;
+          if (const std::string *x = sec->get("frameTimeAdd")) a.frameTimeAdd = num(*x);
+          if (const std::string *x = sec->get("printDefaultClassDummyAttribute")) a.dummyClass = inum(*x) != 0;
+          if (const std::string *x = sec->get("frameLength")) if (inum(*x) == 1) { delete s; return hfail(OSM_B200_ERR_UNSUPPORTED, "cArffSink.frameLength=1 is not supported"); }
+          if (const std::string *x = sec->get("instanceBase")) if (!x->empty() && *x != "-") { a.instName = *x; a.prname = 2; }
+          if (const std::string *x = sec->get("instanceName")) if (!x->empty() && *x != "-") { a.instName = *x; a.prname = 1; }
+          for (int c = 0; c < 64; c++) {                       // class[c].name / class[c].type, target[c].all (:112-170)
+            char key[64];
+            snprintf(key, sizeof key, "class[%d].name", c);
+            const std::string *nm = sec->get(key);
+            snprintf(key, sizeof key, "class[%d].type", c);
+            const std::string *ty = sec->get(key);
+            if (!nm && !ty) break;
+            a.classes.push_back({nm ? *nm : std::string("class"), ty ? *ty : std::string("numeric")});
+            snprintf(key, sizeof key, "target[%d].all", c);
+            const std::string *tg = sec->get(key);
+            a.targetAll.push_back(tg ? (*tg == "?" ? *tg : arff_escape(*tg)) : std::string());
+            snprintf(key, sizeof key, "target[%d].instance[0]", c);
+            if (sec->get(key)) { delete s; return hfail(OSM_B200_ERR_UNSUPPORTED, "cArffSink.target[].instance[] is not supported"); }
+          }
+        }
         if (type == "cHtkSink") { if (const std::string *pk = sec->get("parmKind")) s->parmKind = inum(*pk); }
         // CSV formatting options: those of the active CSV sink; without one (explicit csv paths over the API),
         // those of the last cCsvSink section
@@ -804,6 +907,13 @@ osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t 
 osm_b200_status osm_b200_session_extract_files(osm_b200_session *s, int32_t n, const char *const *wavPaths,
                                                const char *const *htkPaths, const char *const *csvPaths, int64_t *framesOut)
 {
+  return osm_b200_session_extract_files_arff(s, n, wavPaths, htkPaths, csvPaths, nullptr, framesOut);
+}
+
+osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t n, const char *const *wavPaths,
+                                                    const char *const *htkPaths, const char *const *csvPaths,
+                                                    const char *const *arffPaths, int64_t *framesOut)
+{
   if (!s || !wavPaths || n < 0) return hfail(OSM_B200_ERR_INVALID, "null argument");
   // files of one call are grouped by (sample rate, channels); each group is one batched plan run
   std::vector<Wav> wavs(n);
@@ -839,6 +949,9 @@ osm_b200_status osm_b200_session_extract_files(osm_b200_session *s, int32_t n, c
       if (htkPaths && htkPaths[idx] && !write_htk(htkPaths[idx], r, nr, K, period, s->parmKind, err)) return hfail(OSM_B200_ERR_INVALID, err);
       if (csvPaths && csvPaths[idx] &&
           !write_csv(csvPaths[idx], r, nr, K, names, period, s->csv, err, osm_b200_plan_num_time_frames(p, off[k + 1] - off[k])))
+        return hfail(OSM_B200_ERR_INVALID, err);
+      if (arffPaths && arffPaths[idx] &&
+          !write_arff(arffPaths[idx], r, nr, K, names, period, s->arff, err, osm_b200_plan_num_time_frames(p, off[k + 1] - off[k])))
         return hfail(OSM_B200_ERR_INVALID, err);
     }
   }
@@ -881,6 +994,30 @@ int32_t osm_b200_write_csv_timed(const char *path, const float *rows, int64_t n,
   o.number = frameIndex != 0;
   o.timestamp = frameTime != 0;
   if (write_csv(path, rows, n, K, nm, period, o, err, nTimeFrames)) return 0;
+  g_herr = err;
+  return 1;
+}
+
+int32_t osm_b200_write_arff(const char *path, const float *rows, int64_t n, int32_t K, const char *const *names, double period,
+                            const char *relation, const char *instName, int32_t frameIndex, int32_t frameTime,
+                            int32_t nClasses, const char *const *classNames, const char *const *classTypes,
+                            const char *const *targets, int32_t append, int64_t nTimeFrames)
+{
+  std::string err;
+  std::vector<std::string> nm(K);
+  for (int k = 0; k < K; k++) nm[k] = names[k];
+  ArffOpts o;
+  if (relation) o.relation = relation;
+  if (instName && instName[0] && strcmp(instName, "-")) { o.instName = instName; o.prname = 1; }
+  o.number = frameIndex != 0;
+  o.timestamp = frameTime != 0;
+  o.append = append != 0;
+  for (int c = 0; c < nClasses; c++) {
+    o.classes.push_back({classNames && classNames[c] ? classNames[c] : "class", classTypes && classTypes[c] ? classTypes[c] : "numeric"});
+    const char *t = targets ? targets[c] : nullptr;
+    o.targetAll.push_back(t ? (strcmp(t, "?") ? arff_escape(t) : std::string("?")) : std::string());
+  }
+  if (write_arff(path, rows, n, K, nm, period, o, err, nTimeFrames)) return 0;
   g_herr = err;
   return 1;
 }

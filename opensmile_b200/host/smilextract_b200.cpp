@@ -21,8 +21,8 @@ static std::string replace_ext(const std::string &p, const char *ext)
 int main(int argc, char **argv)
 {
   std::string conf, level;
-  std::vector<std::string> wavs, htks, csvs, optN, optV;
-  std::string outHtk, outCsv, htkDir, csvDir;
+  std::vector<std::string> wavs, htks, csvs, arffs, optN, optV;
+  std::string outHtk, outCsv, outArff, htkDir, csvDir;
   int device = 0;
   for (int i = 1; i < argc; i++) {
     const std::string a = argv[i];
@@ -44,7 +44,7 @@ int main(int argc, char **argv)
       }
     }
     else if (a == "-h" || a == "-help") {
-      printf("usage: SMILExtract_b200 -C <config> -I <in.wav> [-I ...] [-O out.htk] [-csvoutput out.csv]\n"
+      printf("usage: SMILExtract_b200 -C <config> -I <in.wav> [-I ...] [-O out.htk] [-csvoutput out.csv] [-lldarffoutput out.arff]\n"
              "       [-filelist list.txt] [-device N] [-level lld] [-<config option> value ...]\n");
       return 0;
     }
@@ -55,22 +55,26 @@ int main(int argc, char **argv)
       // (config/shared/standard_data_output.conf.inc:23,33)
       if (n == "O" || n == "output" || n == "lldhtkoutput") outHtk = v;
       if (n == "csvoutput" || n == "lldcsvoutput") outCsv = v;
+      if (n == "lldarffoutput") outArff = v;
     }
   }
   if (conf.empty() || wavs.empty()) { fprintf(stderr, "SMILExtract_b200: -C <config> and -I <wav> are required (-h for help)\n"); return 2; }
-  htks.resize(wavs.size()); csvs.resize(wavs.size());
+  htks.resize(wavs.size()); csvs.resize(wavs.size()); arffs.resize(wavs.size());
   // single-file form: -O / -csvoutput name that file's outputs; with several inputs they name a
   // directory-less prefix -> per-file names derived from the input name
   for (size_t k = 0; k < wavs.size(); k++) {
     if (htks[k].empty() && !outHtk.empty()) htks[k] = wavs.size() == 1 ? outHtk : replace_ext(wavs[k], ".htk");
     if (csvs[k].empty() && !outCsv.empty()) csvs[k] = wavs.size() == 1 ? outCsv : replace_ext(wavs[k], ".csv");
+    // cArffSink appends when its `append` option says so: every input may go to the same file
+    if (!outArff.empty()) arffs[k] = outArff;
   }
-  std::vector<const char *> on, ov, pw, ph, pc;
+  std::vector<const char *> on, ov, pw, ph, pc, pa;
   for (size_t k = 0; k < optN.size(); k++) { on.push_back(optN[k].c_str()); ov.push_back(optV[k].c_str()); }
   for (size_t k = 0; k < wavs.size(); k++) {
     pw.push_back(wavs[k].c_str());
     ph.push_back(htks[k].empty() ? nullptr : htks[k].c_str());
     pc.push_back(csvs[k].empty() ? nullptr : csvs[k].c_str());
+    pa.push_back(arffs[k].empty() ? nullptr : arffs[k].c_str());
   }
   osm_b200_session *s = nullptr;
   if (osm_b200_session_open(conf.c_str(), (int)on.size(), on.data(), ov.data(), level.empty() ? nullptr : level.c_str(), device, &s) != OSM_B200_OK) {
@@ -78,7 +82,7 @@ int main(int argc, char **argv)
     return 1;
   }
   std::vector<int64_t> frames(wavs.size(), 0);
-  const osm_b200_status st = osm_b200_session_extract_files(s, (int)wavs.size(), pw.data(), ph.data(), pc.data(), frames.data());
+  const osm_b200_status st = osm_b200_session_extract_files_arff(s, (int)wavs.size(), pw.data(), ph.data(), pc.data(), pa.data(), frames.data());
   if (st != OSM_B200_OK) { fprintf(stderr, "SMILExtract_b200: %s\n", osm_b200_host_last_error()); osm_b200_session_close(s); return 1; }
   for (size_t k = 0; k < wavs.size(); k++) fprintf(stderr, "%s: %ld frames\n", wavs[k].c_str(), (long)frames[k]);
   osm_b200_session_close(s);

@@ -86,12 +86,13 @@ class Session:
             fo.ctypes.data_as(i64p), out.ctypes.data, out.shape[0]))
         return out, fo
 
-    def extract_files(self, wav_paths, htk_paths=None, csv_paths=None):
+    def extract_files(self, wav_paths, htk_paths=None, csv_paths=None, arff_paths=None):
         n = len(wav_paths)
         frames = np.zeros(n, dtype=np.int64)
-        self._check(self._L.osm_b200_session_extract_files(
+        self._check(self._L.osm_b200_session_extract_files_arff(
             self._h, n, _strs(wav_paths), _strs(htk_paths) if htk_paths else None,
-            _strs(csv_paths) if csv_paths else None, frames.ctypes.data_as(C.POINTER(C.c_int64))))
+            _strs(csv_paths) if csv_paths else None, _strs(arff_paths) if arff_paths else None,
+            frames.ctypes.data_as(C.POINTER(C.c_int64))))
         return frames
 
 
@@ -111,4 +112,19 @@ def write_csv(path, rows, names, period, instance_name=None, frame_index=True, f
     if L.osm_b200_write_csv_timed(str(path).encode(), rows.ctypes.data, rows.shape[0], rows.shape[1], _strs(names),
                                   float(period), instance_name.encode() if instance_name is not None else None,
                                   int(frame_index), int(frame_time), int(n_time_frames)):
+        raise IOError(L.osm_b200_host_last_error().decode())
+
+
+def write_arff(path, rows, names, period, relation="smile", instance_name=None, frame_index=True, frame_time=True,
+               classes=(("class", "numeric", "?"),), append=False, n_time_frames=0):
+    """cArffSink's file format; classes = (name, type, value for every row) per class attribute"""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    L = capi.lib()
+    cpp = C.POINTER(C.c_char_p)
+    L.osm_b200_write_arff.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, cpp, C.c_double, C.c_char_p, C.c_char_p,
+                                      C.c_int32, C.c_int32, C.c_int32, cpp, cpp, cpp, C.c_int32, C.c_int64]
+    if L.osm_b200_write_arff(str(path).encode(), rows.ctypes.data, rows.shape[0], rows.shape[1], _strs(names), float(period),
+                             relation.encode(), instance_name.encode() if instance_name is not None else None,
+                             int(frame_index), int(frame_time), len(classes), _strs([c[0] for c in classes]),
+                             _strs([c[1] for c in classes]), _strs([c[2] for c in classes]), int(append), int(n_time_frames)):
         raise IOError(L.osm_b200_host_last_error().decode())

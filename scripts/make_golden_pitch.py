@@ -7,7 +7,7 @@ For each case (inputs are regenerated in the tests from opensmile_b200.synth):
                   (level lld ; lld_de, float32 exact)
   <case>_shs/_vit/_sel/_jit/_nz/_nzde/_e60   level taps of tests/configs/compare_pitch_taps.conf (cPitchShs,
                   cPitchSmootherViterbi, cValbasedSelector, cPitchJitter, smoothed level and its delta, rms energy)
-  names_lld       element names of the LLD CSV header; v32k_lld_csv = the reference's -lldcsvoutput file (-instname utt7) as bytes
+  names_lld       element names of the LLD CSV header; v32k_lld_csv / v32k_lld_arff = the reference's -lldcsvoutput / -lldarffoutput files (-instname utt7) as bytes
 Cases: v32k = voiced_pcm(32000, seed=7); m48k = mixed_pcm(48000, seed=2) (Viterbi lag 1); m30k = mixed_pcm(30000, seed=4);
        m64k = mixed_pcm(64000, seed=3); m60k_44k = mixed_pcm(60000, seed=5) written as a 44.1 kHz file (FFT 4096 / 1024,
        _lld only); m40k_stereo = stereo_mixed_pcm(40000, seed=9), 16 kHz, 2 channels (_lld only); var_m48k / var_m40k = tests/configs/pitch_variants.conf on mixed_pcm(48000, seed=6) / mixed_pcm(40000, seed=8)
@@ -65,6 +65,9 @@ def main():
                 subprocess.run([refrun.SMILEXTRACT, "-C", full, "-I", wav, "-lldcsvoutput", os.path.join(d, "utt7.csv"),
                                 "-instname", "utt7", "-l", "0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
                 out["v32k_lld_csv"] = np.frombuffer(open(os.path.join(d, "utt7.csv"), "rb").read(), dtype=np.uint8)
+                subprocess.run([refrun.SMILEXTRACT, "-C", full, "-I", wav, "-lldarffoutput", os.path.join(d, "utt7.arff"),
+                                "-instname", "utt7", "-l", "0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                out["v32k_lld_arff"] = np.frombuffer(open(os.path.join(d, "utt7.arff"), "rb").read(), dtype=np.uint8)
             if "names_lld" not in out and os.path.exists(os.path.join(d, "lld.csv")):
                 hdr = open(os.path.join(d, "lld.csv")).readline().strip().split(";")
                 out["names_lld"] = np.array([h for h in hdr if h not in ("name", "frameIndex", "frameTime")])

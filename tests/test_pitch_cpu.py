@@ -152,14 +152,18 @@ def test_compare16_sink_selection():
     assert len(a.element_names(16000.0, 1)) == 130
     # the same level at 44.1 kHz: frame geometry changes, names and columns do not
     assert list(a.element_names(44100.0, 1)) == list(a.element_names(16000.0, 1))
-    a.close(); b.close()
-    with pytest.raises(SessionError) as e:               # summaries: cDataSelector / cFunctionals are upstream of `func`
-        Session(conf, options={"csvoutput": "x.csv"}, device=-1)
-    assert e.value.status == capi.ERR_UNSUPPORTED and "not on the supported LLD path" in str(e.value), str(e.value)
-    for opts in ({"O": "x.arff"}, None):                 # ARFF summaries only / nothing requested
+    a.close()
+    b.close()
+    c = Session(conf, options={"lldarffoutput": "x.arff"}, device=-1)      # the LLD ARFF sink reads the same levels
+    assert len(c.element_names(16000.0, 1)) == 130
+    c.close()
+    for opts in ({"csvoutput": "x.csv"}, {"O": "x.arff"}):   # summaries: cDataSelector / cFunctionals are upstream of `func`
         with pytest.raises(SessionError) as e:
             Session(conf, options=opts, device=-1)
-        assert "no active sink" in str(e.value)
+        assert e.value.status == capi.ERR_UNSUPPORTED and "not on the supported LLD path" in str(e.value), str(e.value)
+    with pytest.raises(SessionError) as e:               # nothing requested
+        Session(conf, device=-1)
+    assert "no active sink" in str(e.value)
 
 
 def test_compare16_component_mapping_and_baseline_geometry():
@@ -270,3 +274,20 @@ def test_compare16_lld_csv_file_is_byte_identical():
         assert open(path, "rb").read() == G["v32k_lld_csv"].tobytes()
     p.close()
     s.close()
+
+
+def test_compare16_lld_arff_file_is_byte_identical(tmp_path):
+    """cArffSink file of the LLD reader (-lldarffoutput, -instname utt7; relation, attributes, the class attribute of
+    the included targets file, %e values, '?' target): written from the reference's rows it equals the reference's
+    file byte for byte; with append=1 a second call adds rows without repeating the header (iocore/arffSink.cpp:244-256)"""
+    from opensmile_b200 import write_arff
+    names = [str(x) for x in G["names_lld"]]
+    p = tmp_path / "lld.arff"
+    write_arff(p, G["v32k_lld"], names, 0.01, relation="openSMILE_features", instance_name="utt7", frame_index=False,
+               frame_time=True, classes=(("class", "numeric", "?"),), n_time_frames=195)
+    ref = G["v32k_lld_arff"].tobytes()
+    assert p.read_bytes() == ref
+    write_arff(p, G["v32k_lld"][:3], names, 0.01, relation="openSMILE_features", instance_name="utt8", frame_index=False,
+               frame_time=True, classes=(("class", "numeric", "?"),), append=True)
+    lines = p.read_bytes().split(b"\n")
+    assert lines[: len(ref.split(b"\n")) - 1] == ref.split(b"\n")[:-1] and lines[-2].startswith(b"utt8,0.020000,") and lines.count(b"@data") == 1
