@@ -65,6 +65,10 @@ OSM_B200_API osm_b200_status osm_b200_session_extract_files_arff(osm_b200_sessio
                                                                  const char *const *arff_paths,
                                                                  int64_t *frames_out);
 
+/* the sink formatting options taken from the configuration (active CSV / HTK / ARFF sinks), as text; for bindings
+ * and tests.  The string is owned by the library (thread-local). */
+OSM_B200_API const char *osm_b200_session_sink_options(osm_b200_session *session);
+
 /* Extract from packed PCM (layout of osm_b200_plan_run_host).  frame_offsets_out: n_utt+1 entries;
  * out: caller buffer of at least max_rows * num_elements floats, or NULL to only get the offsets. */
 OSM_B200_API osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *session, const int16_t *pcm,

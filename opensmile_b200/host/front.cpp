@@ -958,6 +958,27 @@ osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t
   return OSM_B200_OK;
 }
 
+// introspection for bindings and tests: the sink formatting options the session took from the configuration
+const char *osm_b200_session_sink_options(osm_b200_session *s)
+{
+  static thread_local std::string out;
+  out.clear();
+  if (!s) return "";
+  char b[1024];
+  snprintf(b, sizeof b, "csv: header=%d time=%d index=%d name=%d:'%s' delim=%c\n", (int)s->csv.printHeader, (int)s->csv.timestamp,
+           (int)s->csv.number, s->csv.prname, s->csv.instName.c_str(), s->csv.delim);
+  out += b;
+  snprintf(b, sizeof b, "htk: parmKind=%d\n", s->parmKind);
+  out += b;
+  snprintf(b, sizeof b, "arff: relation='%s' time=%d index=%d name=%d:'%s' append=%d dummy=%d classes=", s->arff.relation.c_str(),
+           (int)s->arff.timestamp, (int)s->arff.number, s->arff.prname, s->arff.instName.c_str(), (int)s->arff.append, (int)s->arff.dummyClass);
+  out += b;
+  for (size_t c = 0; c < s->arff.classes.size(); c++)
+    out += (c ? "," : "") + s->arff.classes[c].first + ":" + s->arff.classes[c].second + ":" + (c < s->arff.targetAll.size() ? s->arff.targetAll[c] : "");
+  out += "\n";
+  return out.c_str();
+}
+
 const char *osm_b200_host_last_error(void) { return g_herr.empty() ? osm_b200_last_error() : g_herr.c_str(); }
 
 int32_t osm_b200_write_htk(const char *path, const float *rows, int64_t n, int32_t K, double period, int32_t parmKind)

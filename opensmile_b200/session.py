@@ -86,6 +86,12 @@ class Session:
             fo.ctypes.data_as(i64p), out.ctypes.data, out.shape[0]))
         return out, fo
 
+    def sink_options(self):
+        """formatting options of the configuration's active sinks, as text (osm_b200_session_sink_options)"""
+        self._L.osm_b200_session_sink_options.restype = C.c_char_p
+        self._L.osm_b200_session_sink_options.argtypes = [C.c_void_p]
+        return self._L.osm_b200_session_sink_options(self._h).decode()
+
     def extract_files(self, wav_paths, htk_paths=None, csv_paths=None, arff_paths=None):
         n = len(wav_paths)
         frames = np.zeros(n, dtype=np.int64)

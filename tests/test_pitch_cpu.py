@@ -291,3 +291,20 @@ def test_compare16_lld_arff_file_is_byte_identical(tmp_path):
                frame_time=True, classes=(("class", "numeric", "?"),), append=True)
     lines = p.read_bytes().split(b"\n")
     assert lines[: len(ref.split(b"\n")) - 1] == ref.split(b"\n")[:-1] and lines[-2].startswith(b"utt8,0.020000,") and lines.count(b"@data") == 1
+
+
+def test_compare16_sink_options_from_the_configuration():
+    """formatting options of the active sinks as the session took them from the shipped configuration: CSV without
+    frame index, instance name from -instname; ARFF relation / class attribute / target of the included targets file
+    (config/shared/arff_targets.conf.inc) incl. its command line options, append = 1 for the LLD ARFF sink"""
+    from opensmile_b200.session import Session
+    conf = _compare16_conf()
+    s = Session(conf, options={"lldcsvoutput": "x.csv", "lldarffoutput": "x.arff", "lldhtkoutput": "x.htk", "instname": "utt7"}, device=-1)
+    o = s.sink_options().splitlines()
+    assert o[0] == "csv: header=1 time=1 index=0 name=1:'utt7' delim=;"
+    assert o[1] == "htk: parmKind=9"
+    assert o[2] == "arff: relation='openSMILE_features' time=1 index=0 name=1:'utt7' append=1 dummy=1 classes=class:numeric:?"
+    s.close()
+    s = Session(conf, options={"lldarffoutput": "x.arff", "class": "happy", "classtype": "{happy,sad}", "relation": "my set"}, device=-1)
+    assert s.sink_options().splitlines()[2] == "arff: relation='my set' time=1 index=0 name=1:'unknown' append=1 dummy=1 classes=class:{happy,sad}:happy"
+    s.close()
