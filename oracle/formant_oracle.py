@@ -18,6 +18,54 @@ from . import oracle
 f32 = np.float32
 
 
+_FFT = None
+
+
+def ref_fft_available():
+    import os
+    return os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libfftsg.so"))
+
+
+def _ref_rdft(frames_padded):
+    """rdft() of the reference's own FFT source (oracle/_ref/libfftsg.so, built by `make -C oracle ref` from
+    src/dspcore/fftsg.c where it lies), forward transform in place on every row, work arrays sized like
+    cTransformFFT (dspcore/transformFft.cpp:197-207)"""
+    global _FFT
+    import os
+    if _FFT is None:
+        _FFT = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libfftsg.so"))
+        _FFT.rdft.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float)]
+    a = np.ascontiguousarray(frames_padded, np.float32).copy()
+    n = a.shape[1]
+    ip = np.zeros(3 + int(np.ceil(np.sqrt(np.float32(n)))), np.int32)
+    w = np.zeros(n // 2 + 1, np.float32)
+    for row in a:
+        _FFT.rdft(n, 1, row.ctypes.data_as(C.POINTER(C.c_float)), ip.ctypes.data_as(C.POINTER(C.c_int)),
+                  w.ctypes.data_as(C.POINTER(C.c_float)))
+    return a
+
+
+def fft_frames_exact(pcm, fe, n_chan=1):
+    """like fft_frames, but through the reference's FFT: bit-identical to the cTransformFFT level.  Windowing as in
+    dspcore/windower.cpp:221-229 (float product with the float-cast double table), zero padding as in
+    dspcore/transformFft.cpp:175-196"""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    nS = pcm.size // n_chan
+    N, H, nfft, T = oracle.geometry(fe, nS)
+    L = oracle.lib()
+    x = np.zeros(nS, np.float32)
+    L.osm_or_pcm16_to_float(pcm.ctypes.data_as(C.POINTER(C.c_int16)), C.c_long(nS), C.c_int(n_chan), oracle._fp(x))
+    win = np.zeros(N, np.float64)
+    L.osm_or_window_table(C.c_int(fe.win_func), C.c_long(N), C.c_double(fe.win_sigma), C.c_double(fe.win_gain),
+                          win.ctypes.data_as(C.POINTER(C.c_double)))
+    wf = win.astype(np.float32)
+    pad = (nfft - N) // 2 if fe.zero_pad_symmetric else 0
+    z = np.zeros((max(T, 0), nfft), np.float32)
+    for t in range(max(T, 0)):
+        z[t, pad:pad + N] = (x[t * H:t * H + N] * wf + np.float32(fe.win_offset)).astype(np.float32)
+    return _ref_rdft(z)
+
+
 def fft_frames(pcm, fe, n_chan=1):
     """packed real FFT of every frame (dspcore/transformFft.cpp:165-223, packing dspcore/fftsg.c:104-122) -> [T, nfft]"""
     pcm = np.ascontiguousarray(pcm, dtype=np.int16)
@@ -151,10 +199,11 @@ def formants_from_lpc(a, T, n_formants, min_f, max_f):
     return freq.astype(f32), bw.astype(f32)
 
 
-def gemaps_formant_chain(pcm, sample_rate=16000.0, taps=False):
-    """config/gemaps/v01b/GeMAPSv01b_core.lld.conf.inc:43-58,250-286 -> [T, 10] = formantFreqLpc[1..5] | formantBandwidthLpc[1..5]"""
+def gemaps_formant_chain(pcm, sample_rate=16000.0, taps=False, exact_fft=False):
+    """config/gemaps/v01b/GeMAPSv01b_core.lld.conf.inc:43-58,250-286 -> [T, 10] = formantFreqLpc[1..5] | formantBandwidthLpc[1..5];
+    exact_fft: the FFT level through the reference's own FFT (bit-identical front end, needs oracle/_ref/libfftsg.so)"""
     fe = oracle.frontend(sample_rate, 0.020, 0.010, win="ham", zero_pad_symmetric=1)
-    spec = fft_frames(pcm, fe)
+    spec = fft_frames_exact(pcm, fe) if exact_fft else fft_frames(pcm, fe)
     N, H, nfft, T = oracle.geometry(fe, len(pcm))
     fs_sec = oracle.lib().osm_or_fft_frame_size_sec(C.byref(fe))
     rs = SpecResample(nfft, sample_rate, 11000.0, fs_sec, 0.020)

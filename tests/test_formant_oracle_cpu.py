@@ -44,3 +44,16 @@ def test_harmonics_exact_given_inputs():
     assert np.abs(got - G["h_harm"][:T]).max() < 1e-4
     voiced = G["h_f0"][:T, 0] > 0
     assert voiced.sum() > 20 and (~voiced).sum() > 20
+
+
+def test_whole_chain_bit_identical_with_the_reference_fft():
+    """With the reference's own FFT (oracle/_ref/libfftsg.so = src/dspcore/fftsg.c compiled where it lies) in front, the
+    restated chain PCM -> window -> FFT -> cSpecResample -> cLpc -> cFormantLpc is bit-identical to the reference end
+    to end: everything behind the FFT is exact, so the FFT's butterfly order is what the product has to reproduce."""
+    import pytest
+    if not fo.ref_fft_available():
+        pytest.skip("oracle/_ref/libfftsg.so not built (make -C oracle ref)")
+    fmt, res, lpcs = fo.gemaps_formant_chain(mixed_pcm(24000, 16000, seed=3), taps=True, exact_fft=True)
+    assert np.array_equal(res, G["res"])
+    assert np.array_equal(lpcs, G["lpc"])
+    assert (np.abs(fmt - G["fmt"]) / (np.abs(G["fmt"]) + 1.0)).max() < 1e-6
