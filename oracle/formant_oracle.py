@@ -417,3 +417,36 @@ def harmonics_gemaps(F0, formant_freq, mag, frq, n_harm=100, floor_unvoiced=-201
     else:
         out += [f32(0.0), f32(0.0)] + [f32(floor_unvoiced)] * 3
     return np.array(out, f32)
+
+
+def gemaps_vq_levels(pcm, sample_rate=16000.0, exact_fft=False):
+    """The four voice-quality levels of the shipped GeMAPS graph (config/gemaps/v01b/GeMAPSv01b_core.lld.conf.inc),
+    end to end from PCM:
+      logPitch  [T60, 3]  F0final, F0finalLog, voicingFinalUnclipped, gated by the 60 ms rms energy (:62-171)
+      jitter    [T60, 2]  jitterLocal, shimmerLocalDB (:174-195)
+      formants  [T25, 10] formantFreqLpc[1..5] | formantBandwidthLpc[1..5] (:250-286)
+      harmonics [T60, 6]  HNRdBACF, H1-H2, H1-A3, F1..F3 amplitude (:289-318; frame t of the three input levels)"""
+    fe60 = oracle.frontend(sample_rate, 0.060, 0.010, win="gau", sigma=0.4, zero_pad_symmetric=1)
+    sc = oracle.SpecScale(25.0, -1.0, 0, 1, 1, 1)
+    ps = oracle.PitchShs(1000.0, 55.0, 6, 1, 1, 0, 0, 1, 1, 0.70, 0, 15, 0.85, 1, 0.0)
+    vc = oracle.Viterbi(40, 1, 1, 0, 0, 0, 1, 2.0, 10.0, 5.0, 10.0, 4.0, 1.0, 0.0)
+    jc = oracle.Jitter(0.10, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, -100.0, 0, 2, 0.5, 0, 0, 0, 0, 0, 0)
+    shs = oracle.pitch_shs(pcm, fe60, sc, ps)
+    vit = oracle.viterbi(shs, ps, vc)
+    e60 = oracle.energy(pcm, fe60, oracle.Energy(0, 1, 0, 0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0), windowed=1)
+    pitch = oracle.valbased_select(e60[:, 0], vit, 0.001)
+    jit = oracle.pitch_jitter(pcm, fe60, jc, pitch[:, 0])
+    fmt = gemaps_formant_chain(pcm, sample_rate, exact_fft=exact_fft)
+    # 60 ms magnitude spectrum and its bin axis (dspcore/transformFft.cpp:111-115)
+    N, H, nfft, T = oracle.geometry(fe60, len(pcm))
+    spec = fft_frames_exact(pcm, fe60) if exact_fft else fft_frames(pcm, fe60)
+    mag = np.zeros((spec.shape[0], nfft // 2 + 1), f32)
+    mag[:, 0] = np.abs(spec[:, 0])
+    mag[:, -1] = np.abs(spec[:, 1])
+    re, im = spec[:, 2::2], spec[:, 3::2]
+    mag[:, 1:-1] = np.sqrt((re * re + im * im).astype(f32)).astype(f32)
+    fs_sec = oracle.lib().osm_or_fft_frame_size_sec(C.byref(fe60))
+    frq = np.arange(nfft // 2 + 1, dtype=np.float64) * (1.0 / fs_sec)
+    Th = min(pitch.shape[0], fmt.shape[0], mag.shape[0])
+    harm = np.stack([harmonics_gemaps(pitch[t, 0], fmt[t, :5], mag[t], frq) for t in range(Th)]) if Th > 0 else np.zeros((0, 6), f32)
+    return pitch, jit, fmt, harm

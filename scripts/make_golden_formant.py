@@ -7,6 +7,8 @@ Level taps of tests/configs/formant_taps.conf (the GeMAPS formant chain) on mixe
   fmt [T, 10]   cFormantLpc: formantFreqLpc[1..5] | formantBandwidthLpc[1..5]
 and of tests/configs/harmonics_taps.conf (same input): h_f0 [T60, 3] Viterbi level (F0final first), h_fmt, h_mag [T60, 513]
 60 ms magnitude spectrum, h_harm [T60, 6] cHarmonics: HNRdBACF, H1-H2, H1-A3, F1..F3 amplitude (log rel. F0)
+and of tests/configs/gemaps_vq_taps.conf (the shipped GeMAPSv01b_core.lld.conf.inc unchanged): g_f0 = gemapsv01b_logPitch
+[T60, 3], g_jit = gemapsv01b_jitterShimmer [T60, 2], g_fmt = gemapsv01b_formants [T25, 10], g_harm = gemapsv01b_harmonics [T60, 6]
 """
 import os
 import subprocess
@@ -38,6 +40,14 @@ def main():
         for k in ("f0", "mag", "harm"):
             out["h_" + k] = refrun.read_htk(os.path.join(d, k + ".htk"))[0]
         out["h_fmt"] = refrun.read_htk(os.path.join(d, "fmt.htk"))[0]
+    taps = open(os.path.join(ROOT, "tests", "configs", "gemaps_vq_taps.conf")).read().replace("REFCONF", refrun.CONFIG_DIR)
+    with tempfile.TemporaryDirectory() as d:            # the shipped GeMAPS graph itself, its four voice-quality levels
+        refrun.write_wav(os.path.join(d, "in.wav"), pcm, 16000, 1)
+        open(os.path.join(d, "t.conf"), "w").write(taps)
+        subprocess.run([refrun.SMILEXTRACT, "-C", "t.conf", "-I", "in.wav", "-l", "0"], cwd=d, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for k in ("f0", "jit", "fmt", "harm"):
+            out["g_" + k] = refrun.read_htk(os.path.join(d, k + ".htk"))[0]
     print({k: v.shape for k, v in out.items()})
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "formant_goldens.npz"), **out)
 

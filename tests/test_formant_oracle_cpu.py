@@ -57,3 +57,22 @@ def test_whole_chain_bit_identical_with_the_reference_fft():
     assert np.array_equal(res, G["res"])
     assert np.array_equal(lpcs, G["lpc"])
     assert (np.abs(fmt - G["fmt"]) / (np.abs(G["fmt"]) + 1.0)).max() < 1e-6
+
+
+def test_gemaps_voice_quality_levels_end_to_end():
+    """PCM -> the four voice-quality levels of the shipped GeMAPS graph (pitch with semitone scale, jitter / shimmer dB,
+    formants, harmonics): pitch and jitter match with the oracle's own FFT; formants and the harmonic columns that read
+    them need the bit-identical FFT in front of cLpc (then everything matches)"""
+    import pytest
+    pcm = mixed_pcm(24000, 16000, seed=3)
+
+    def rel(a, b):
+        return float((np.abs(a - b) / (np.abs(b).max(axis=0) + 1e-30)).max())
+
+    pitch, jit, fmt, harm = fo.gemaps_vq_levels(pcm, exact_fft=False)
+    assert rel(pitch, G["g_f0"]) < 2e-6 and np.array_equal(jit, G["g_jit"])
+    assert rel(harm[:, :2], G["g_harm"][:, :2]) < 1e-5            # HNR from the ACF and H1-H2 do not read the formants
+    if not fo.ref_fft_available():
+        pytest.skip("oracle/_ref/libfftsg.so not built (make -C oracle ref)")
+    pitch, jit, fmt, harm = fo.gemaps_vq_levels(pcm, exact_fft=True)
+    assert rel(fmt, G["g_fmt"]) < 1e-6 and rel(harm, G["g_harm"]) < 1e-5 and rel(pitch, G["g_f0"]) < 2e-6
