@@ -450,3 +450,35 @@ def gemaps_vq_levels(pcm, sample_rate=16000.0, exact_fft=False):
     Th = min(pitch.shape[0], fmt.shape[0], mag.shape[0])
     harm = np.stack([harmonics_gemaps(pitch[t, 0], fmt[t, :5], mag[t], frq) for t in range(Th)]) if Th > 0 else np.zeros((0, 6), f32)
     return pitch, jit, fmt, harm
+
+
+def gemaps_lld(pcm, sample_rate=16000.0, exact_fft=False):
+    """Level `lld` of the shipped config/gemaps/v01b/GeMAPSv01b.conf (18 columns, T60 + 1 rows):
+      lldsetE_smo: Loudness, alphaRatio, hammarbergIndex, slope0-500, slope500-1500 (sma3)
+      lldsetF_smo: F0semitone, jitterLocal, shimmerLocaldB, HNRdBACF, logRelF0-H1-H2, logRelF0-H1-A3, F1 frequency /
+                   bandwidth / amplitude, F2 frequency / amplitude, F3 frequency / amplitude (sma3nz)
+    cDataSelector picks the elements in the order of its `selected` list (core/dataSelector.cpp:388-470).  The selector
+    in front of the second smoother waits for the jitter level, which does not advance during the reference's first
+    end-of-input pass: rows V-1 and V of ALL its columns are smoothed with the level padded at row V-1."""
+    pitch, jit, fmt, harm = gemaps_vq_levels(pcm, sample_rate, exact_fft)
+    fe60 = oracle.frontend(sample_rate, 0.060, 0.010, win="gau", sigma=0.4, zero_pad_symmetric=1)
+    sc = oracle.SpecScale(25.0, -1.0, 0, 1, 1, 1)
+    ps = oracle.PitchShs(1000.0, 55.0, 6, 1, 1, 0, 0, 1, 1, 0.70, 0, 15, 0.85, 1, 0.0)
+    vc = oracle.Viterbi(40, 1, 1, 0, 0, 0, 1, 2.0, 10.0, 5.0, 10.0, 4.0, 1.0, 0.0)
+    _, lag = oracle.viterbi(oracle.pitch_shs(pcm, fe60, sc, ps), ps, vc, with_lag=True)
+    T = min(pitch.shape[0], jit.shape[0], harm.shape[0], fmt.shape[0])
+    F = np.stack([pitch[:T, 1], jit[:T, 0], jit[:T, 1], harm[:T, 0], harm[:T, 1], harm[:T, 2], fmt[:T, 0], fmt[:T, 5], harm[:T, 3],
+                  fmt[:T, 1], harm[:T, 4], fmt[:T, 2], harm[:T, 5]], axis=1).astype(f32)
+    Fs = oracle.sma_nz_lagged(F, lag, set(range(F.shape[1])))
+    # energy-related part on the 20 ms frames
+    fe25 = oracle.Frontend(sample_rate, 0.020, 0.010, 0, 0.0, oracle.WIN["ham"], 0.4, 1.0, 0.0, 1)
+    aud = oracle.plp_static(pcm, sample_rate, (fe25, oracle.Melspec(26, 20.0, 8000.0, 1, 0),
+                                                oracle.Plp(5, 0, -1, 0, 1, 0, 0, 0, 0, 0, 0, 29.0, 1.0, 22.0, 0.33, 9.3e-10, 0)))
+    loud = oracle.ll1(aud)
+    spec = oracle.spectral(pcm, fe25, oracle.gemaps_logspectral())
+    # cSpectral emits slopes before alphaRatio / hammarbergIndex (lldcore/spectral.cpp:378-584); the selector's order is
+    # loudness, alphaRatioDB, hammarbergIndexDB, slope 0-500, slope 500-1500 (GeMAPSv01b_core.lld.conf.inc:177-181)
+    E = np.stack([loud, spec[:, 2], spec[:, 3], spec[:, 0], spec[:, 1]], axis=1).astype(f32)
+    Es = oracle.sma(E, 3, 0)
+    R = min(Es.shape[0], Fs.shape[0])
+    return np.concatenate([Es[:R], Fs[:R]], axis=1)

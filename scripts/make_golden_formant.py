@@ -9,6 +9,8 @@ and of tests/configs/harmonics_taps.conf (same input): h_f0 [T60, 3] Viterbi lev
 60 ms magnitude spectrum, h_harm [T60, 6] cHarmonics: HNRdBACF, H1-H2, H1-A3, F1..F3 amplitude (log rel. F0)
 and of tests/configs/gemaps_vq_taps.conf (the shipped GeMAPSv01b_core.lld.conf.inc unchanged): g_f0 = gemapsv01b_logPitch
 [T60, 3], g_jit = gemapsv01b_jitterShimmer [T60, 2], g_fmt = gemapsv01b_formants [T25, 10], g_harm = gemapsv01b_harmonics [T60, 6]
+and the LLD file of the shipped config/gemaps/v01b/GeMAPSv01b.conf (-lldhtkoutput, 18 columns): gemaps_lld_m24k (same input),
+gemaps_lld_m40k = mixed_pcm(40000, seed=5)
 """
 import os
 import subprocess
@@ -48,6 +50,14 @@ def main():
                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         for k in ("f0", "jit", "fmt", "harm"):
             out["g_" + k] = refrun.read_htk(os.path.join(d, k + ".htk"))[0]
+    full = os.path.join(refrun.CONFIG_DIR, "gemaps", "v01b", "GeMAPSv01b.conf")      # the shipped feature set, LLD sink
+    for name, x in (("gemaps_lld_m24k", pcm), ("gemaps_lld_m40k", mixed_pcm(40000, 16000, seed=5))):
+        with tempfile.TemporaryDirectory() as d:
+            wav = os.path.join(d, "in.wav")
+            refrun.write_wav(wav, x, 16000, 1)
+            subprocess.run([refrun.SMILEXTRACT, "-C", full, "-I", wav, "-lldhtkoutput", os.path.join(d, "l.htk"), "-l", "0"],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out[name] = refrun.read_htk(os.path.join(d, "l.htk"))[0]
     print({k: v.shape for k, v in out.items()})
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "formant_goldens.npz"), **out)
 

@@ -76,3 +76,16 @@ def test_gemaps_voice_quality_levels_end_to_end():
         pytest.skip("oracle/_ref/libfftsg.so not built (make -C oracle ref)")
     pitch, jit, fmt, harm = fo.gemaps_vq_levels(pcm, exact_fft=True)
     assert rel(fmt, G["g_fmt"]) < 1e-6 and rel(harm, G["g_harm"]) < 1e-5 and rel(pitch, G["g_f0"]) < 2e-6
+
+
+def test_shipped_gemaps_lld_level_end_to_end():
+    """The complete `lld` level of the shipped config/gemaps/v01b/GeMAPSv01b.conf (18 columns incl. the selectors' element
+    order, sma3 / sma3nz smoothing and the rows smoothed while the jitter level lags at the end of input), PCM to rows,
+    against the reference's -lldhtkoutput file"""
+    import pytest
+    if not fo.ref_fft_available():
+        pytest.skip("oracle/_ref/libfftsg.so not built (make -C oracle ref)")
+    for key, pcm in (("gemaps_lld_m24k", mixed_pcm(24000, 16000, seed=3)), ("gemaps_lld_m40k", mixed_pcm(40000, 16000, seed=5))):
+        got, ref = fo.gemaps_lld(pcm, exact_fft=True), G[key]
+        assert got.shape == ref.shape == (ref.shape[0], 18)
+        assert (np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)).max() < 5e-6
