@@ -482,3 +482,41 @@ def gemaps_lld(pcm, sample_rate=16000.0, exact_fft=False):
     Es = oracle.sma(E, 3, 0)
     R = min(Es.shape[0], Fs.shape[0])
     return np.concatenate([Es[:R], Fs[:R]], axis=1)
+
+
+EGEMAPS_LLD_NAMES = (["Loudness_sma3", "alphaRatio_sma3", "hammarbergIndex_sma3", "slope0-500_sma3", "slope500-1500_sma3",
+                      "spectralFlux_sma3"] + ["mfcc%d_sma3" % i for i in range(1, 5)]
+                     + ["F0semitoneFrom27.5Hz_sma3nz", "jitterLocal_sma3nz", "shimmerLocaldB_sma3nz", "HNRdBACF_sma3nz",
+                        "logRelF0-H1-H2_sma3nz", "logRelF0-H1-A3_sma3nz"]
+                     + ["F%d%s_sma3nz" % (k, w) for k in (1, 2, 3) for w in ("frequency", "bandwidth", "amplitudeLogRelF0")])
+
+
+def egemaps_lld(pcm, sample_rate=16000.0, exact_fft=False):
+    """Level `lld` of the shipped config/egemaps/v02/eGeMAPSv02.conf -- BASELINE configs[2] -- 25 columns, T60 + 1 rows:
+      lldsetE_smo (sma3):   Loudness, alphaRatio, hammarbergIndex, slope0-500, slope500-1500, spectralFlux, mfcc1..4
+      lldsetF_smo (sma3nz): F0semitone, jitterLocal, shimmerLocaldB, HNRdBACF, logRelF0-H1-H2, logRelF0-H1-A3,
+                            F1 / F2 / F3 frequency, bandwidth, amplitude
+    (eGeMAPSv02_core.lld.conf.inc:13-60,79-89 on top of the GeMAPS levels, see gemaps_lld)"""
+    pitch, jit, fmt, harm = gemaps_vq_levels(pcm, sample_rate, exact_fft)
+    fe60 = oracle.frontend(sample_rate, 0.060, 0.010, win="gau", sigma=0.4, zero_pad_symmetric=1)
+    sc = oracle.SpecScale(25.0, -1.0, 0, 1, 1, 1)
+    ps = oracle.PitchShs(1000.0, 55.0, 6, 1, 1, 0, 0, 1, 1, 0.70, 0, 15, 0.85, 1, 0.0)
+    vc = oracle.Viterbi(40, 1, 1, 0, 0, 0, 1, 2.0, 10.0, 5.0, 10.0, 4.0, 1.0, 0.0)
+    _, lag = oracle.viterbi(oracle.pitch_shs(pcm, fe60, sc, ps), ps, vc, with_lag=True)
+    T = min(pitch.shape[0], jit.shape[0], harm.shape[0], fmt.shape[0])
+    cols = [pitch[:T, 1], jit[:T, 0], jit[:T, 1], harm[:T, 0], harm[:T, 1], harm[:T, 2]]
+    for k in range(3):
+        cols += [fmt[:T, k], fmt[:T, 5 + k], harm[:T, 3 + k]]
+    F = np.stack(cols, axis=1).astype(f32)
+    Fs = oracle.sma_nz_lagged(F, lag, set(range(F.shape[1])))
+    fe25 = oracle.Frontend(sample_rate, 0.020, 0.010, 0, 0.0, oracle.WIN["ham"], 0.4, 1.0, 0.0, 1)
+    aud = oracle.plp_static(pcm, sample_rate, (fe25, oracle.Melspec(26, 20.0, 8000.0, 1, 0),
+                                                oracle.Plp(5, 0, -1, 0, 1, 0, 0, 0, 0, 0, 0, 29.0, 1.0, 22.0, 0.33, 9.3e-10, 0)))
+    spec = oracle.spectral(pcm, fe25, oracle.gemaps_logspectral())
+    flux = oracle.spectral(pcm, fe25, oracle.spectral_cfg(flux=1, centroid=0, maxPos=0, minPos=0, normBandEnergies=1, squareInput=1,
+                                                          useLogSpectrum=1, freqRangeLo=0, freqRangeHi=5000, oldSlopeScale=0))
+    mf = oracle.mfcc_d_a(pcm, sample_rate, cfg=(fe25, oracle.Melspec(26, 20.0, 8000.0, 1, 1), oracle.Mfcc(1, 4, 22.0, 1e-8, 1)))[:, :4]
+    E = np.concatenate([np.stack([oracle.ll1(aud), spec[:, 2], spec[:, 3], spec[:, 0], spec[:, 1], flux[:, 0]], axis=1), mf], axis=1).astype(f32)
+    Es = oracle.sma(E, 3, 0)
+    R = min(Es.shape[0], Fs.shape[0])
+    return np.concatenate([Es[:R], Fs[:R]], axis=1)

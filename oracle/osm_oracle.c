@@ -1103,7 +1103,7 @@ static void spectral_frame(spec_ctx *c, const float *src, float *dst)
   srcLP = useLog ? srcL : srcP;
 
   double frameSum = 0.0;                                       /* :766-771 */
-  if (sp->normBandEnergies || sp->sharpness || sp->nRollOff > 0)
+  if ((sp->normBandEnergies || sp->sharpness || sp->nRollOff > 0) && srcP)   /* no power spectrum requested (flux only): nothing reads frameSum */
     for (i = loBin; i <= hiBin; i++) frameSum += srcP[i];
 
   for (i = 0; i < sp->nBands; i++) {                           /* :775-870 */
@@ -1176,8 +1176,8 @@ static void spectral_frame(spec_ctx *c, const float *src, float *dst)
   }
   double sumB = 0.0, sumC = 0.0;                               /* :1092-1099 */
   if (sp->normBandEnergies && !useLog) sumB = frameSum;
-  else for (j = loBin; j <= hiBin; j++) sumB += (double)srcLP[j];
-  {                                                            /* roll-off :1103-1122 */
+  else if (srcLP) for (j = loBin; j <= hiBin; j++) sumB += (double)srcLP[j];   /* (flux only: no log / power spectrum, nothing reads sumB) */
+  if (sp->nRollOff > 0) {                                      /* roll-off :1103-1122 */
     float ro[OSM_OR_MAX_LIST];
     for (i = 0; i < sp->nRollOff; i++) ro[i] = 0.0f;
     for (j = loBin; j <= hiBin; j++) {

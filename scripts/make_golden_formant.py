@@ -10,7 +10,8 @@ and of tests/configs/harmonics_taps.conf (same input): h_f0 [T60, 3] Viterbi lev
 and of tests/configs/gemaps_vq_taps.conf (the shipped GeMAPSv01b_core.lld.conf.inc unchanged): g_f0 = gemapsv01b_logPitch
 [T60, 3], g_jit = gemapsv01b_jitterShimmer [T60, 2], g_fmt = gemapsv01b_formants [T25, 10], g_harm = gemapsv01b_harmonics [T60, 6]
 and the LLD file of the shipped config/gemaps/v01b/GeMAPSv01b.conf (-lldhtkoutput, 18 columns): gemaps_lld_m24k (same input),
-gemaps_lld_m40k = mixed_pcm(40000, seed=5)
+gemaps_lld_m40k = mixed_pcm(40000, seed=5); the same two inputs through config/egemaps/v02/eGeMAPSv02.conf (25 columns):
+egemaps_lld_m24k, egemaps_lld_m40k, and the column names of that file (names_egemaps_lld, from its -lldcsvoutput header)
 """
 import os
 import subprocess
@@ -58,6 +59,16 @@ def main():
             subprocess.run([refrun.SMILEXTRACT, "-C", full, "-I", wav, "-lldhtkoutput", os.path.join(d, "l.htk"), "-l", "0"],
                            check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
             out[name] = refrun.read_htk(os.path.join(d, "l.htk"))[0]
+    efull = os.path.join(refrun.CONFIG_DIR, "egemaps", "v02", "eGeMAPSv02.conf")
+    for name, x in (("egemaps_lld_m24k", pcm), ("egemaps_lld_m40k", mixed_pcm(40000, 16000, seed=5))):
+        with tempfile.TemporaryDirectory() as d:
+            wav = os.path.join(d, "in.wav")
+            refrun.write_wav(wav, x, 16000, 1)
+            subprocess.run([refrun.SMILEXTRACT, "-C", efull, "-I", wav, "-lldhtkoutput", os.path.join(d, "l.htk"),
+                            "-lldcsvoutput", os.path.join(d, "l.csv"), "-l", "0"],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out[name] = refrun.read_htk(os.path.join(d, "l.htk"))[0]
+            out["names_egemaps_lld"] = np.array(open(os.path.join(d, "l.csv")).readline().strip().split(";")[2:])
     print({k: v.shape for k, v in out.items()})
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "formant_goldens.npz"), **out)
 

@@ -89,3 +89,27 @@ def test_shipped_gemaps_lld_level_end_to_end():
         got, ref = fo.gemaps_lld(pcm, exact_fft=True), G[key]
         assert got.shape == ref.shape == (ref.shape[0], 18)
         assert (np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)).max() < 5e-6
+
+
+def test_shipped_egemaps_lld_level_end_to_end():
+    """The `lld` level of the shipped config/egemaps/v02/eGeMAPSv02.conf (25 columns: GeMAPS plus spectral flux from the
+    flux-only cSpectral instance, MFCC 1-4 and the F2 / F3 bandwidths; every voice-quality column lags behind the selector in
+    front of the smoother) against the reference's -lldhtkoutput file, column names against its CSV header"""
+    import pytest
+    if not fo.ref_fft_available():
+        pytest.skip("oracle/_ref/libfftsg.so not built (make -C oracle ref)")
+    assert list(G["names_egemaps_lld"]) == fo.EGEMAPS_LLD_NAMES
+    for key, pcm in (("egemaps_lld_m24k", mixed_pcm(24000, 16000, seed=3)), ("egemaps_lld_m40k", mixed_pcm(40000, 16000, seed=5))):
+        got, ref = fo.egemaps_lld(pcm, exact_fft=True), G[key]
+        assert got.shape == ref.shape == (ref.shape[0], 25)
+        assert (np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)).max() < 5e-6
+
+
+def test_flux_only_spectral_instance():
+    """[egemapsv02_spectral_flux] requests nothing but the magnitude spectrum: one column, first frame 0"""
+    from oracle import oracle
+    pcm = mixed_pcm(8000, 16000, seed=1)
+    fe = oracle.frontend(16000, 0.020, 0.010, win="ham")
+    x = oracle.spectral(pcm, fe, oracle.spectral_cfg(flux=1, centroid=0, maxPos=0, minPos=0, normBandEnergies=1, squareInput=1,
+                                                      useLogSpectrum=1, freqRangeLo=0, freqRangeHi=5000, oldSlopeScale=0))
+    assert x.shape[1] == 1 and x[0, 0] == 0.0 and np.all(x[1:, 0] > 0)
