@@ -44,8 +44,9 @@
 extern "C" {
 #endif
 
-/* 2: component types cSpecScale .. cPitchJitter appended (existing values and struct layouts unchanged) */
-#define OSM_B200_ABI_VERSION 2
+/* 2: component types cSpecScale .. cPitchJitter appended (existing values and struct layouts unchanged)
+ * 3: cSpecResample, cLpc, cFormantLpc appended (same rule) */
+#define OSM_B200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define OSM_B200_API __attribute__((visibility("default")))
 #else
@@ -91,6 +92,9 @@ typedef enum {
   OSM_B200_C_PITCHSMOOTHERVITERBI, /* cPitchSmootherViterbi src/lld/pitchSmootherViterbi.cpp:79-545 */
   OSM_B200_C_VALBASEDSELECTOR,   /* cValbasedSelector   src/other/valbasedSelector.cpp:130-233    */
   OSM_B200_C_PITCHJITTER,        /* cPitchJitter        src/lld/pitchJitter.cpp:591-1107          */
+  OSM_B200_C_SPECRESAMPLE,       /* cSpecResample       src/dsp/specResample.cpp:97-185           */
+  OSM_B200_C_LPC,                /* cLpc                src/lld/lpc.cpp:156-215 (method acf)      */
+  OSM_B200_C_FORMANTLPC,         /* cFormantLpc         src/lld/formantLpc.cpp:192-394 (root solving branch) */
   OSM_B200_C_COUNT_
 } osm_b200_component_type;
 
@@ -261,6 +265,24 @@ typedef struct {            /* cPitchJitter: reader.dmLevel = wave level, F0read
   int32_t usePeakToPeakPeriodLength, useBrokenJitterThresh, onlyVoiced;  /* 0, 1, 0 */
 } osm_b200_pitchjitter;
 
+typedef struct {            /* cSpecResample: reads a cTransformFFT level (complex spectrum) */
+  double  targetFs;         /* 16000 */
+  double  resampleRatio;    /* <= 0: derive from targetFs (the reference's "not set") */
+} osm_b200_specresample;
+
+typedef struct {            /* cLpc */
+  int32_t method;           /* 0 = acf (the only supported one), 1 = burg */
+  int32_t p;                /* 8 */
+  int32_t saveLPCoeff, lpGain, saveRefCoeff, residual, residualGainScale, forwardFilter, lpSpectrum;  /* 1,0,0,0,0,0,0 */
+} osm_b200_lpc;
+
+typedef struct {            /* cFormantLpc */
+  int32_t nFormants;        /* -1 = p - 1 */
+  int32_t saveFormants, saveIntensity, saveNumberOfValidFormants, saveBandwidths;  /* 1,0,0,0 */
+  double  minF, maxF;       /* 50, 5500 */
+  int32_t useLpSpec, medianFilter, octaveCorrection;   /* 0,0,0 (only these values are supported) */
+} osm_b200_formantlpc;
+
 /* one `[name:cType]` section */
 typedef struct {
   int32_t type;                                  /* osm_b200_component_type */
@@ -298,6 +320,9 @@ typedef struct {
     osm_b200_pitchsmootherviterbi pitchsmootherviterbi;
     osm_b200_valbasedselector valbasedselector;
     osm_b200_pitchjitter pitchjitter;
+    osm_b200_specresample specresample;
+    osm_b200_lpc lpc;
+    osm_b200_formantlpc formantlpc;
   } u;
 } osm_b200_component;
 

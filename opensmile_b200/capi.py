@@ -21,7 +21,8 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = range(5)
 (C_WAVESOURCE, C_FRAMER, C_VECTORPREEMPHASIS, C_WINDOWER, C_TRANSFORMFFT, C_FFTMAGPHASE,
  C_MELSPEC, C_MFCC, C_PLP, C_SPECTRAL, C_ENERGY, C_MZCR, C_ACF, C_PITCHACF,
  C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION, C_FULLINPUTMEAN, C_INTENSITY,
- C_SPECSCALE, C_PITCHSHS, C_PITCHSMOOTHERVITERBI, C_VALBASEDSELECTOR, C_PITCHJITTER) = range(25)
+ C_SPECSCALE, C_PITCHSHS, C_PITCHSMOOTHERVITERBI, C_VALBASEDSELECTOR, C_PITCHJITTER,
+ C_SPECRESAMPLE, C_LPC, C_FORMANTLPC) = range(28)
 
 TYPE_BY_NAME = {
     "cWaveSource": C_WAVESOURCE, "cExternalAudioSource": C_WAVESOURCE, "cFramer": C_FRAMER,
@@ -34,6 +35,7 @@ TYPE_BY_NAME = {
     "cFullinputMean": C_FULLINPUTMEAN, "cIntensity": C_INTENSITY,
     "cSpecScale": C_SPECSCALE, "cPitchShs": C_PITCHSHS, "cPitchSmootherViterbi": C_PITCHSMOOTHERVITERBI,
     "cValbasedSelector": C_VALBASEDSELECTOR, "cPitchJitter": C_PITCHJITTER,
+    "cSpecResample": C_SPECRESAMPLE, "cLpc": C_LPC, "cFormantLpc": C_FORMANTLPC,
 }
 
 WIN_BY_NAME = {"rec": 0, "han": 1, "ham": 2, "gau": 3, "sin": 4, "tri": 5, "bar": 6}
@@ -181,6 +183,21 @@ class PitchJitter(C.Structure):
                 ("useBrokenJitterThresh", i32), ("onlyVoiced", i32)]
 
 
+class SpecResample(C.Structure):
+    _fields_ = [("targetFs", f64), ("resampleRatio", f64)]
+
+
+class Lpc(C.Structure):
+    _fields_ = [("method", i32), ("p", i32), ("saveLPCoeff", i32), ("lpGain", i32), ("saveRefCoeff", i32), ("residual", i32),
+                ("residualGainScale", i32), ("forwardFilter", i32), ("lpSpectrum", i32)]
+
+
+class FormantLpc(C.Structure):
+    _fields_ = [("nFormants", i32), ("saveFormants", i32), ("saveIntensity", i32), ("saveNumberOfValidFormants", i32),
+                ("saveBandwidths", i32), ("minF", f64), ("maxF", f64), ("useLpSpec", i32), ("medianFilter", i32),
+                ("octaveCorrection", i32)]
+
+
 class _U(C.Union):
     _fields_ = [("wavesource", WaveSource), ("framer", Framer),
                 ("vectorpreemphasis", VectorPreemphasis), ("windower", Windower),
@@ -190,7 +207,8 @@ class _U(C.Union):
                 ("deltaregression", DeltaRegression), ("contoursmoother", ContourSmoother),
                 ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat), ("fullinputmean", FullinputMean), ("intensity", Intensity),
                 ("specscale", SpecScale), ("pitchshs", PitchShs), ("pitchsmootherviterbi", PitchSmootherViterbi),
-                ("valbasedselector", ValbasedSelector), ("pitchjitter", PitchJitter)]
+                ("valbasedselector", ValbasedSelector), ("pitchjitter", PitchJitter),
+                ("specresample", SpecResample), ("lpc", Lpc), ("formantlpc", FormantLpc)]
 
 
 class Component(C.Structure):

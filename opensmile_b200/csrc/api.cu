@@ -117,6 +117,8 @@ struct OpRt {
   ShsParams shs;
   ViterbiParams vit;
   JitterParams jit;
+  FormantParams fmt;                    // SOP_FORMANT
+  float *dFmtD = nullptr;               // its resampling table
   unsigned char *dPitchTab = nullptr;   // spline / interpolation / harmonic tables of the chain
   DevBuf<float> dShs;                   // [static rows][nShsCols] cPitchShs level
   DevBuf<int> dLag;                     // [nUtt] frames of the Viterbi level before the end-of-input flush
@@ -257,6 +259,13 @@ osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
       auto &q = c->u.pitchjitter;
       snprintf(q.F0field, sizeof q.F0field, "%s", "F0final");
       q.searchRangeRel = 0.10; q.lgHNRfloor = -100.0; q.minNumPeriods = 2; q.minCC = 0.5; q.useBrokenJitterThresh = 1;
+      break;
+    }
+    case OSM_B200_C_SPECRESAMPLE: c->u.specresample.targetFs = 16000.0; c->u.specresample.resampleRatio = -1.0; break;   // dsp/specResample.cpp:40-41
+    case OSM_B200_C_LPC: c->u.lpc.p = 8; c->u.lpc.saveLPCoeff = 1; break;                                               // lld/lpc.cpp:33-45
+    case OSM_B200_C_FORMANTLPC: {          // lld/formantLpc.cpp:40-52
+      auto &q = c->u.formantlpc;
+      q.nFormants = -1; q.saveFormants = 1; q.minF = 50.0; q.maxF = 5500.0;
       break;
     }
     default: break;
@@ -769,6 +778,16 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       if (op.kind == SOP_INTENSITY) {
         tp.iIntensity = op.intensity.intensity; tp.iLoudness = op.intensity.loudness;
         tp.iW0 = op.intensity.w[0]; tp.iW1 = op.intensity.w[1]; tp.iWinSum = op.intensity.winSum;
+      } else if (op.kind == SOP_FORMANT) {
+        const FormantOp &fo = op.formant;
+        FormantParams &fp = rt.fmt;
+        memset(&fp, 0, sizeof fp);
+        CUP(cudaMalloc(&rt.dFmtD, fo.D.size() * sizeof(float)));
+        CUP(cudaMemcpy(rt.dFmtD, fo.D.data(), fo.D.size() * sizeof(float), cudaMemcpyHostToDevice));
+        fp.tp = tp; fp.D = rt.dFmtD; fp.nRes = fo.nRes; fp.nResPad = fo.nResPad; fp.p = fo.p; fp.nFormants = fo.nFormants;
+        fp.T = fo.T; fp.minF = fo.minF; fp.maxF = fo.maxF;
+        fp.saveFormants = fo.saveFormants; fp.saveBandwidths = fo.saveBandwidths; fp.saveNValid = fo.saveNValid;
+        if (formant_smem_bytes(fp) > 200 * 1024) { pl->ops.push_back(rt); osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cSpecResample: frame too long for the formant kernel"); }
       } else if (op.kind == SOP_ENERGY) {
         const EnergyOp &e = op.energy;
         tp.eHtk = e.htk; tp.eRms = e.rms; tp.eEnergy2 = e.energy2; tp.eLog = e.lg;
@@ -817,7 +836,7 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
     for (PassRt &pr : s.extra) { if (pr.dConst) cudaFree(pr.dConst); pr.dBand.release(); }
     s.hChunks.release(); s.dChunks.release(); s.hTiles.release(); s.dTiles.release(); s.dMag.release();
   }
-  for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); if (o.dPitchTab) cudaFree(o.dPitchTab); o.dShs.release(); o.dLag.release(); }
+  for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); if (o.dPitchTab) cudaFree(o.dPitchTab); if (o.dFmtD) cudaFree(o.dFmtD); o.dShs.release(); o.dLag.release(); }
   if (pl->dErr) cudaFree(pl->dErr);
   if (pl->auxStream) cudaStreamDestroy(pl->auxStream);
   if (pl->evFork) cudaEventDestroy(pl->evFork);
@@ -1083,7 +1102,8 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       tp.uttOff = dU; tp.statOff = dS;
       tp.tiles = rt.dTiles.p + t0; tp.nTiles = t1 - t0;
       tp.stat = pl->dStat.p;
-      CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : (o.kind == SOP_INTENSITY ? launch_intensity(tp, st) : launch_mzcr(tp, st)));
+      if (o.kind == SOP_FORMANT) { FormantParams fp = o.fmt; fp.tp = tp; CU(launch_formant(fp, st)); }
+      else CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : (o.kind == SOP_INTENSITY ? launch_intensity(tp, st) : launch_mzcr(tp, st)));
     }
     pl->lastLaunches++;
   }

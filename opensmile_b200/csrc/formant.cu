@@ -1,0 +1,157 @@
+// formant.cu -- the formant chain of the GeMAPS graphs as one kernel (sm_100a):
+//   cWindower level -> [cTransformFFT -> cSpecResample] -> cLpc (acf) -> cFormantLpc        
+//
+// The reference transforms every windowed frame (zero padded to the FFT size), and cSpecResample evaluates an
+// inverse DFT of the low bins on a coarser time grid (dsp/specResample.cpp:175-185, smileDsp_irdft
+// smileutil/smileUtil.c:1800-1820).  Both steps are linear and no other component reads that FFT level's
+// resampled copy, so the kernel applies their composition directly: res[i] = sum_m xw[m] * D[m][i] with the
+// table D built in double on the host (tables.cpp build_formant).  That is one dense [frames x N] * [N x I]
+// product per tile -- fp32 FMA on purpose: order-11 LPC amplifies input noise of 1e-7 to ~1e-2 in the formants
+// (DESIGN.md), so reduced-precision tensor-core formats are not an option here.
+// Then one warp per frame: autocorrelation (one lane per lag, the reference's float summation order), Levinson-
+// Durbin on lane 0, the roots of the predictor polynomial with one lane per root (formant_math.cuh), and the
+// formant frequencies / bandwidths of the roots in the upper half plane.
+// Compiled with -fmad=false: the float recursions keep the reference's statement order.
+#include "kernels.cuh"
+#include "frame_reader.cuh"
+#include "formant_math.cuh"
+
+namespace osm {
+
+namespace {
+
+constexpr int kFmtWarps = 8;               // frames in flight per CTA (one warp each in the per-frame phase)
+constexpr int kFmtThreads = kFmtWarps * 32;
+
+struct FmtWarpWs {                          // per-warp scratch of the per-frame phase
+  double c[fm::kMaxLpcOrder];               // polynomial, ascending powers (monic)
+  double zr[fm::kMaxLpcOrder], zi[fm::kMaxLpcOrder];
+  double f[fm::kMaxLpcOrder], b[fm::kMaxLpcOrder];
+  float r[fm::kMaxLpcOrder + 1];
+  float a[fm::kMaxLpcOrder];
+  int ok[fm::kMaxLpcOrder];
+  int n, z0;
+};
+
+__global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParams p)
+{
+  extern __shared__ __align__(16) unsigned char fmtSmem[];
+  const TimeOpParams &tp = p.tp;
+  const int N = tp.frameSize, I = p.nRes, IP = p.nResPad;
+  FmtWarpWs *ws = reinterpret_cast<FmtWarpWs *>(fmtSmem);
+  float *xw = reinterpret_cast<float *>(ws + kFmtWarps);        // [kFmtWarps][N]
+  float *res = xw + (size_t)kFmtWarps * N;                      // [kFmtWarps][IP]
+  const OpTile tl = tp.tiles[blockIdx.x];
+  const long long uo = tp.uttOff[tl.utt];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int fb = 0; fb < tl.nf; fb += kFmtWarps) {
+    const int nb = min(kFmtWarps, tl.nf - fb);
+    // 1. windowed frames (dspcore/windower.cpp:226) into shared memory
+    for (int f = 0; f < nb; f++) {
+      FrameReader fr{tp, tp.pcm + (uo + (long long)(tl.f0 + fb + f) * tp.frameStep) * tp.nChan};
+      for (int m = tid; m < N; m += kFmtThreads) xw[f * N + m] = fr.at(m);
+    }
+    __syncthreads();
+    // 2. resampled frames: thread i owns output sample i of all frames of the batch
+    for (int i = tid; i < I; i += kFmtThreads) {
+      float acc[kFmtWarps];
+#pragma unroll
+      for (int f = 0; f < kFmtWarps; f++) acc[f] = 0.0f;
+      const float *dcol = p.D + i;
+      for (int m = 0; m < N; m++) {
+        const float dv = __ldg(dcol + (size_t)m * IP);
+#pragma unroll
+        for (int f = 0; f < kFmtWarps; f++) acc[f] = __fmaf_rn(xw[f * N + m], dv, acc[f]);
+      }
+#pragma unroll
+      for (int f = 0; f < kFmtWarps; f++) res[f * IP + i] = acc[f];
+    }
+    __syncthreads();
+    // 3. one warp per frame
+    if (warp < nb) {
+      FmtWarpWs &w = ws[warp];
+      const float *x = res + warp * IP;
+      const int P = p.p;
+      if (lane <= P) w.r[lane] = fm::acf_lag(x, I, lane);            // lld/lpc.cpp:156-215 (method acf)
+      __syncwarp();
+      if (lane == 0) {
+        fm::durbin(w.r, P, w.a);
+        for (int i = 0; i < P; i++) w.c[i] = -(double)w.a[P - 1 - i];  // lld/formantLpc.cpp:258-262
+        int z0 = 0;
+        while (z0 < P && w.c[z0] == 0.0) z0++;                         // roots at the origin yield no candidate
+        w.z0 = z0; w.n = P - z0;
+      }
+      __syncwarp();
+      const int n = w.n;
+      const double *c = w.c + w.z0;
+      double zr = 0.0, zi = 0.0, prev = 1e300;
+      if (lane < n) { fm::aberth_init(c, n, lane, &zr, &zi); w.zr[lane] = zr; w.zi[lane] = zi; }
+      __syncwarp();
+      bool last = false;
+      for (int it = 0; it < fm::kAberthMaxIter && n > 0; it++) {
+        bool done = true;
+        if (lane < n) {
+          const double c2 = fm::aberth_step(c, n, w.zr, w.zi, lane, &zr, &zi);
+          done = fm::aberth_done(c2, prev, zr, zi);
+          prev = c2;
+        }
+        __syncwarp();
+        if (lane < n) { w.zr[lane] = zr; w.zi[lane] = zi; }
+        const bool all = __all_sync(0xffffffffu, done);
+        __syncwarp();
+        if (last) break;
+        last = all;
+      }
+      if (lane < n) {
+        double f = 0.0, b = 0.0;
+        w.ok[lane] = fm::root_to_formant(zr, zi, p.T, p.minF, p.maxF, &f, &b) ? 1 : 0;
+        w.f[lane] = f; w.b[lane] = b;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        // smileDsp_lpcrootsToFormants (smileutil/smileUtil.c:2019-2054): candidates in root order, then the
+        // ascending sort of lld/formantLpc.cpp:277-296 over the leading non-zero entries
+        double f[fm::kMaxLpcOrder], b[fm::kMaxLpcOrder];
+        const int nF = p.nFormants;
+        int nv = 0;
+        for (int k = 0; k < n && nv < nF; k++) if (w.ok[k]) { f[nv] = w.f[k]; b[nv] = w.b[k]; nv++; }
+        for (int i = nv; i < nF; i++) { f[i] = 0.0; b[i] = 0.0; }
+        int nz = 0;
+        while (nz < nF && f[nz] != 0.0) nz++;
+        for (int i = 0; i < nz; i++)
+          for (int j = i + 1; j < nz; j++)
+            if (f[j] < f[i]) { double t = f[j]; f[j] = f[i]; f[i] = t; t = b[j]; b[j] = b[i]; b[i] = t; }
+        float *dst = tp.stat + (tp.statOff[tl.utt] + tl.f0 + fb + warp) * (long long)tp.statStride + tp.outCol;
+        int o = 0;
+        if (p.saveNValid) dst[o++] = (float)nv;                        // lld/formantLpc.cpp:376-392
+        if (p.saveFormants) for (int i = 0; i < nF; i++) dst[o++] = (float)f[i];
+        if (p.saveBandwidths) for (int i = 0; i < nF; i++) dst[o++] = (float)b[i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+size_t formant_smem_bytes(const FormantParams &p)
+{
+  return sizeof(FmtWarpWs) * kFmtWarps + (size_t)kFmtWarps * ((size_t)p.tp.frameSize + p.nResPad) * sizeof(float);
+}
+
+cudaError_t launch_formant(const FormantParams &p, cudaStream_t st)
+{
+  if (p.tp.nTiles <= 0) return cudaSuccess;
+  const size_t smem = formant_smem_bytes(p);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(formant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  formant_kernel<<<p.tp.nTiles, kFmtThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace osm

@@ -35,7 +35,7 @@ const char *type_name(int t)
     "cTransformFFT", "cFFTmagphase", "cMelspec", "cMfcc", "cPlp", "cSpectral", "cEnergy",
     "cMZcr", "cAcf", "cPitchACF", "cDeltaRegression", "cContourSmoother", "cVectorConcat",
     "cVectorOperation", "cFullinputMean", "cIntensity", "cSpecScale", "cPitchShs", "cPitchSmootherViterbi",
-    "cValbasedSelector", "cPitchJitter"};
+    "cValbasedSelector", "cPitchJitter", "cSpecResample", "cLpc", "cFormantLpc"};
   return (t >= 0 && t < OSM_B200_C_COUNT_) ? names[t] : "?";
 }
 
@@ -467,6 +467,28 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         const std::string inName = c->u.vectoroperation.nameBase[0] ? std::string(c->u.vectoroperation.nameBase) : d.ops[src].fields[0].name;
         fn.name = name_append_auto(named, inName, nullptr);
         op.fields.push_back(fn);
+      } else if (c->type == OSM_B200_C_FORMANTLPC) {
+        // cFormantLpc <- cLpc <- cSpecResample <- cTransformFFT <- cWindower chain (GeMAPSv01b_core.lld.conf.inc:250-286)
+        const osm_b200_component *lpc = single_input(c);
+        if (!lpc || lpc->type != OSM_B200_C_LPC) { err = "cFormantLpc must read a cLpc level"; return OSM_B200_ERR_UNSUPPORTED; }
+        const osm_b200_component *rsm = single_input(lpc);
+        if (!rsm || rsm->type != OSM_B200_C_SPECRESAMPLE) { err = "cLpc must read a cSpecResample level"; return OSM_B200_ERR_UNSUPPORTED; }
+        const osm_b200_component *fft = single_input(rsm);
+        if (!fft || fft->type != OSM_B200_C_TRANSFORMFFT || fft->u.transformfft.inverse) { err = "cSpecResample must read a (forward) cTransformFFT level"; return OSM_B200_ERR_UNSUPPORTED; }
+        const osm_b200_component *w = single_input(fft);
+        if (!w || w->type != OSM_B200_C_WINDOWER) { err = "cTransformFFT must read a cWindower level"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (!resolve_time_chain(w, ci)) return OSM_B200_ERR_UNSUPPORTED;
+        op.windowed = true;
+        osm_b200_status s2 = get_stream(ci, false, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        op.kind = SOP_FORMANT;
+        if (!build_formant(rsm->u.specresample, lpc->u.lpc, c->u.formantlpc, d.streams[op.stream].fe,
+                           fft->u.transformfft.zeroPadSymmetric != 0, op.formant, err)) return OSM_B200_ERR_UNSUPPORTED;
+        op.nOut = op.formant.nOut;
+        // lld/formantLpc.cpp:113-136: fixed field names, array indices start at 1
+        if (op.formant.saveNValid) { FieldName f; f.name = "nFormants"; op.fields.push_back(f); }
+        if (op.formant.saveFormants) { FieldName f; f.name = "formantFreqLpc"; f.n = op.formant.nFormants; f.arrNameOffset = 1; op.fields.push_back(f); }
+        if (op.formant.saveBandwidths) { FieldName f; f.name = "formantBandwidthLpc"; f.n = op.formant.nFormants; f.arrNameOffset = 1; op.fields.push_back(f); }
       } else if (c->type == OSM_B200_C_VALBASEDSELECTOR || c->type == OSM_B200_C_PITCHSMOOTHERVITERBI) {
         // [cValbasedSelector <-] cPitchSmootherViterbi <- cPitchShs <- cSpecScale <- cFFTmagphase chain
         const osm_b200_component *vit = c, *selSrc = nullptr;

@@ -208,6 +208,22 @@ cudaError_t launch_mzcr(const TimeOpParams &p, cudaStream_t st);
 cudaError_t launch_intensity(const TimeOpParams &p, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
+// formant chain (formant.cu): windower level -> [cTransformFFT -> cSpecResample] -> cLpc -> cFormantLpc, one CTA
+// per tile of frames: dense resampling product, then one warp per frame (ACF, Durbin, polynomial roots)
+// ------------------------------------------------------------------------------------------
+struct FormantParams {
+  TimeOpParams tp;               // frame geometry, tiles, static rows (windowed = 1)
+  const float *D;                // [frameSize][nResPad] composition of zero padding, FFT and the resampling inverse DFT
+  int nRes, nResPad;             // samples of the resampled frame, row pitch of D
+  int p;                         // predictor order
+  int nFormants;
+  double T, minF, maxF;          // sample period of the cLpc level, search range
+  int saveFormants, saveBandwidths, saveNValid;
+};
+cudaError_t launch_formant(const FormantParams &p, cudaStream_t st);
+size_t formant_smem_bytes(const FormantParams &p);
+
+// ------------------------------------------------------------------------------------------
 // SHS pitch chain (pitch.cu): cSpecScale + cPitchShs per frame (one warp per frame), cPitchSmootherViterbi
 // [+ cValbasedSelector] per utterance (one thread), cPitchJitter per utterance (one warp), and the temporal
 // stages of the levels behind them (one thread per utterance, seq_post_kernel).

@@ -4,6 +4,7 @@
 // reference's accumulator types (double sums), so results differ from the CPU only through the
 // FFT that produced the magnitudes.  Citations relative to /root/reference/src.
 #include "kernels.cuh"
+#include "frame_reader.cuh"
 
 namespace osm {
 
@@ -368,44 +369,6 @@ cudaError_t launch_mag_rows(const float *mag, const OpTile *tiles, int nTiles, i
   mag_rows_kernel<<<nTiles, 256, 0, st>>>(mag, tiles, F, nSrc, statOff, stat, statStride, outCol);
   return cudaGetLastError();
 }
-
-// ------------------------------------------------------------------------------------------
-// time-domain frames: sample n of frame t, as the framer (or the windower) level holds it
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float td_pcm(const TimeOpParams &p, const int16_t *s)
-{
-  // smileutil/smileUtil.c:2520-2534 : ((sum_c (float)x_c) / nChan) / 32767
-  float tmp = (float)s[0];
-  for (int c = 1; c < p.nChan; c++) tmp = __fadd_rn(tmp, (float)s[c]);
-  // x / 32767 through a reciprocal multiply + two FMAs: bit-identical to IEEE division for every
-  // int16 and every half-integer mean of two (see kernels.cu div32767 / tests/test_host_cpu.py)
-  if (p.nChan <= 2) {
-    const float x = (p.nChan == 2) ? tmp * 0.5f : tmp;
-    const float rc = 3.0518509447574615e-05f;
-    const float q0 = __fmul_rn(x, rc);
-    return __fmaf_rn(__fmaf_rn(-q0, 32767.0f, x), rc, q0);
-  }
-  return __fdiv_rn(__fdiv_rn(tmp, (float)p.nChan), 32767.0f);
-}
-
-struct FrameReader {
-  const TimeOpParams &p;
-  const int16_t *base;     // first sample frame of this frame
-  __device__ __forceinline__ float raw(int n) const { return td_pcm(p, base + (long long)n * p.nChan); }
-  __device__ __forceinline__ float at(int n) const
-  {
-    float x = raw(n);
-    if (!p.windowed) return x;
-    if (p.preemph) {                                  // vectorPreemphasis.cpp:89-108
-      if (n == 0) x = __fmul_rn(p.oneMinusK, x);
-      else {
-        const float kx = __fmul_rn(p.preK, raw(n - 1));
-        x = p.preDe ? __fadd_rn(x, kx) : __fsub_rn(x, kx);
-      }
-    }
-    return __fadd_rn(__fmul_rn(x, p.window[n]), p.winOffset);    // windower.cpp:226
-  }
-};
 
 __global__ void __launch_bounds__(32) energy_kernel(const TimeOpParams p)
 {

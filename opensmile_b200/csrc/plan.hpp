@@ -43,7 +43,7 @@ struct FrontEnd {
   bool zeroPadSymmetric = false;   // phase only; magnitude consumers are unaffected
 };
 
-enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP, SOP_MAG, SOP_INTENSITY, SOP_PITCH, SOP_JITTER };
+enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP, SOP_MAG, SOP_INTENSITY, SOP_PITCH, SOP_JITTER, SOP_FORMANT };
 
 struct MfccOp {
   int melIdx = 0;
@@ -155,6 +155,20 @@ struct JitterOp {
   int nOut = 0;
 };
 
+// cTransformFFT -> cSpecResample -> cLpc -> cFormantLpc on a windower level (dsp/specResample.cpp, lld/lpc.cpp,
+// lld/formantLpc.cpp): one static producer
+struct FormantOp {
+  int nIn = 0;                     // samples of the windowed frame
+  int nRes = 0, nResPad = 0;       // samples of the resampled frame (cSpecResample output), row pitch of D
+  std::vector<float> D;            // [nIn][nResPad]: res[i] = sum_m xw[m] * D[m][i]
+  int p = 8;                       // cLpc.p
+  double T = 0;                    // base period of the cLpc level = 1 / targetFs
+  int nFormants = 0;
+  double minF = 50, maxF = 5500;
+  bool saveFormants = true, saveBandwidths = false, saveNValid = false;
+  int nOut = 0;
+};
+
 // one field of a level: `n` elements named name (n == 1) or name[i + arrNameOffset]
 struct FieldName { std::string name; int n = 1; int arrNameOffset = 0; };
 
@@ -174,6 +188,7 @@ struct StaticOp {
   PitchAcfOp pitch;
   PitchChainOp chain;
   JitterOp jitter;
+  FormantOp formant;
 };
 
 // temporal stage applied to a static column range (cWindowProcessor family)
@@ -233,5 +248,9 @@ void build_energy(const osm_b200_energy &cfg, EnergyOp &op);
 void build_mzcr(const osm_b200_mzcr &cfg, MzcrOp &op);
 bool build_pitch_chain(const osm_b200_specscale &sc, const osm_b200_pitchshs &ps, const osm_b200_pitchsmootherviterbi &vc,
                        int nMag, double fftFrameSizeSec, PitchChainOp &op, std::string &err);
+
+// fe = front end of the windower level the chain's cTransformFFT reads; zeroPadSymmetric = that cTransformFFT's switch
+bool build_formant(const osm_b200_specresample &rs, const osm_b200_lpc &lp, const osm_b200_formantlpc &fl, const FrontEnd &fe,
+                   bool zeroPadSymmetric, FormantOp &op, std::string &err);
 
 }  // namespace osm

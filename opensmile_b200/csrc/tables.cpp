@@ -4,6 +4,7 @@
 // per plan on the CPU exactly as the reference runs them once per component instance, with
 // the same float/double casting order so that the tables are bit-identical.
 // Citations are relative to /root/reference/src.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -500,6 +501,95 @@ bool build_pitch_chain(const osm_b200_specscale &sc, const osm_b200_pitchshs &ps
   op.wLocal = vc.wLocal; op.wTvv = vc.wTvv; op.wTvvd = vc.wTvv; op.wTvuv = vc.wTvuv; op.wThr = vc.wThr; op.wRange = vc.wRange; op.wTuu = vc.wTuu;
   op.nOut = (int)op.oF0final + (int)op.oF0finalLog + (int)op.oF0finalEnv + (int)op.oF0finalEnvLog + (int)op.oVClipped + (int)op.oVUnclipped;
   if (op.nOut < 1) { err = "cPitchSmootherViterbi produces no output"; return false; }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// cTransformFFT -> cSpecResample -> cLpc -> cFormantLpc.
+//
+// cSpecResample (dsp/specResample.cpp:97-185) reads the packed real FFT a[0..K) of the zero-padded windowed frame
+// (K = FFT size; a[0] = R0, a[1] = R(K/2), a[2k] = Rk, a[2k+1] = Ik with X_k = sum_n x[n] exp(+2 pi i nk / K),
+// dspcore/fftsg.c:104-122) and evaluates, for i = 0 .. I-1 (smileDsp_initIrdft / smileDsp_irdft,
+// smileutil/smileUtil.c:1752-1820):
+//   out[i] = ( a[0] + [I >= K] a[1] cos(2 pi (K/2) i / nd) + sum_{k=1}^{kMax/2-1} ( Rk cos(2 pi k i / nd) + Ik sin(2 pi k i / nd) ) ) / (K/2)
+// with kMax = min(K, I) rounded down to even (antiAlias) and nd, I from the rounding rules of :150-172.
+// Substituting the forward transform gives out[i] = sum_n x[n] D(n, i),
+//   D(n, i) = ( 1 + [I >= K] (-1)^n cos(pi K i / nd) + sum_{k=1}^{kMax/2-1} cos(2 pi k (n / K - i / nd)) ) / (K/2),
+// evaluated here in double for the samples n = pad .. pad+N-1 the frame occupies in the padded buffer
+// (dspcore/transformFft.cpp:175-196).  The reference rounds to float after the FFT and again in the inverse sum; the
+// table path rounds once per product -- same quantity, not the same bits (formant chain).
+// ---------------------------------------------------------------------------------------
+bool build_formant(const osm_b200_specresample &rs, const osm_b200_lpc &lp, const osm_b200_formantlpc &fl, const FrontEnd &fe,
+                   bool zeroPadSymmetric, FormantOp &op, std::string &err)
+{
+  if (lp.method != 0) { err = "cLpc: only method=acf is supported"; return false; }
+  if (!lp.saveLPCoeff || lp.saveRefCoeff || lp.residual || lp.lpSpectrum) { err = "cLpc: only saveLPCoeff=1 without saveRefCoeff / residual / lpSpectrum is supported"; return false; }
+  if (lp.p < 1 || lp.p > 16) { err = "cLpc.p must be in 1..16"; return false; }
+  if (fl.useLpSpec || fl.medianFilter || fl.octaveCorrection) { err = "cFormantLpc: useLpSpec / medianFilter / octaveCorrection are not supported"; return false; }
+  if (fl.saveIntensity) { err = "cFormantLpc.saveIntensity is not supported"; return false; }
+  const int K = fe.nfft, N = fe.frameSize;
+  const double bT = 1.0 / fe.sampleRate, sr = 1.0 / bT;
+  double ratio, targetFs;
+  if (rs.resampleRatio > 0.0) { ratio = rs.resampleRatio; targetFs = ratio * sr; }     // specResample.cpp:72-88,107-115
+  else {
+    targetFs = rs.targetFs;
+    if (targetFs <= 0.0) targetFs = 1.0;
+    ratio = targetFs / sr;
+  }
+  op.T = 1.0 / targetFs;                                                                // :117 (before the adjustment below)
+  const double fsSec = fe.fftFrameSizeSec, lastFsSec = fe.frameSizeSec;                 // level frameSizeSec / lastFrameSizeSec
+  double nd, nOut0;
+  if (fsSec != lastFsSec && lastFsSec != 0.0 && lastFsSec != bT) {                      // :150-160 zero-padded FFT input
+    nOut0 = round((double)K * ratio * lastFsSec / fsSec);
+    const double nr = nOut0 / ((double)K * (lastFsSec / fsSec));
+    if (nr != ratio) ratio = nr;
+    nd = (double)K * ratio;
+  } else {                                                                              // :161-171
+    nOut0 = round((double)K * ratio);
+    const double nr = nOut0 / (double)K;
+    if (nr != ratio) ratio = nr;
+    nd = nOut0;
+  }
+  const int I = (int)nOut0;
+  if (I < lp.p + 2 || I > 4096) { err = "cSpecResample: resampled frame size out of range"; return false; }
+  int kMax = std::min(K, I);
+  if (kMax & 1) kMax--;
+  const int J = kMax / 2 - 1;                                                           // harmonics k = 1 .. J
+  const int pad = zeroPadSymmetric ? (K - N) / 2 : 0;
+  op.nIn = N; op.nRes = I; op.nResPad = (I + 31) / 32 * 32;
+  op.D.assign((size_t)N * op.nResPad, 0.0f);
+  const double twoPi = 2.0 * M_PI, scale = 1.0 / (double)(K / 2);
+  for (int m = 0; m < N; m++) {
+    const int n = pad + m;
+    for (int i = 0; i < I; i++) {
+      const double th = twoPi * ((double)n / (double)K - (double)i / nd);
+      double acc = 1.0;
+      if (I >= K) acc += ((n & 1) ? -1.0 : 1.0) * cos(twoPi * (double)(K / 2) * (double)i / nd);
+      // sum_{k=1}^{J} cos(k th) by the Chebyshev recurrence c_{k+1} = 2 cos(th) c_k - c_{k-1}, restarted from libm
+      // every 16 terms so the recurrence error stays at the rounding level of the direct sum
+      for (int k0 = 1; k0 <= J; k0 += 16) {
+        double cm = cos((double)(k0 - 1) * th), c0 = cos((double)k0 * th);
+        const double t2 = 2.0 * cos(th);
+        const int k1 = std::min(J, k0 + 15);
+        for (int k = k0; k <= k1; k++) { acc += c0; const double cn = t2 * c0 - cm; cm = c0; c0 = cn; }
+      }
+      op.D[(size_t)m * op.nResPad + i] = (float)(acc * scale);
+    }
+  }
+  op.p = lp.p;
+  int nF = fl.nFormants;                                                                // formantLpc.cpp:160-167
+  if (nF > lp.p - 1) nF = lp.p - 1;
+  if (nF <= 0) nF = lp.p - 1;
+  if (nF < lp.p / 2) {
+    // more roots in the upper half plane than slots: the reference keeps the first nFormants in the order its QR
+    // iteration lists them, which no other solver reproduces
+    err = "cFormantLpc: nFormants < p/2 (the result would depend on the reference's root order) is not supported"; return false;
+  }
+  op.nFormants = nF;
+  op.minF = fl.minF; op.maxF = fl.maxF;
+  op.saveFormants = fl.saveFormants != 0; op.saveBandwidths = fl.saveBandwidths != 0; op.saveNValid = fl.saveNumberOfValidFormants != 0;
+  op.nOut = (op.saveNValid ? 1 : 0) + (op.saveFormants ? nF : 0) + (op.saveBandwidths ? nF : 0);
+  if (op.nOut < 1) { err = "cFormantLpc produces no output"; return false; }
   return true;
 }
 

@@ -222,7 +222,8 @@ const TypeInfo kTypes[] = {
   {"cFullinputMean", OSM_B200_C_FULLINPUTMEAN}, {"cIntensity", OSM_B200_C_INTENSITY},
   {"cSpecScale", OSM_B200_C_SPECSCALE}, {"cPitchShs", OSM_B200_C_PITCHSHS},
   {"cPitchSmootherViterbi", OSM_B200_C_PITCHSMOOTHERVITERBI}, {"cValbasedSelector", OSM_B200_C_VALBASEDSELECTOR},
-  {"cPitchJitter", OSM_B200_C_PITCHJITTER}};
+  {"cPitchJitter", OSM_B200_C_PITCHJITTER}, {"cSpecResample", OSM_B200_C_SPECRESAMPLE}, {"cLpc", OSM_B200_C_LPC},
+  {"cFormantLpc", OSM_B200_C_FORMANTLPC}};
 
 int type_of(const std::string &t)
 {
@@ -472,6 +473,29 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         SETI("useBrokenJitterThresh", q.useBrokenJitterThresh) SETI("onlyVoiced", q.onlyVoiced)
         if (f == "periodOutputFile") { if (!v.empty()) { err = "cPitchJitter.periodOutputFile is not supported"; return false; } continue; }
         if (f == "inputMaxDelaySec" || f.compare(0, 9, "F0reader.") == 0) continue;
+        break;
+      }
+      case OSM_B200_C_SPECRESAMPLE: {       // dsp/specResample.cpp:36-46
+        auto &q = c.u.specresample;
+        SETD("targetFs", q.targetFs) SETD("resampleRatio", q.resampleRatio)
+        if (f == "inputFieldPartial") { if (!v.empty()) { err = "cSpecResample.inputFieldPartial is not supported"; return false; } continue; }
+        break;
+      }
+      case OSM_B200_C_LPC: {                // lld/lpc.cpp:33-45
+        auto &q = c.u.lpc;
+        if (f == "method") { q.method = (v == "acf") ? 0 : 1; continue; }
+        SETI("p", q.p) SETI("saveLPCoeff", q.saveLPCoeff) SETI("lpGain", q.lpGain) SETI("saveRefCoeff", q.saveRefCoeff)
+        SETI("residual", q.residual) SETI("residualGainScale", q.residualGainScale) SETI("forwardFilter", q.forwardFilter)
+        SETI("lpSpectrum", q.lpSpectrum)
+        if (f == "forwardLPspec" || f == "forwardLPspecFloor" || f == "lpSpecDeltaF" || f == "lpSpecBins") continue;   // only read with lpSpectrum=1
+        break;
+      }
+      case OSM_B200_C_FORMANTLPC: {         // lld/formantLpc.cpp:40-52
+        auto &q = c.u.formantlpc;
+        SETI("nFormants", q.nFormants) SETI("saveFormants", q.saveFormants) SETI("saveIntensity", q.saveIntensity)
+        SETI("saveNumberOfValidFormants", q.saveNumberOfValidFormants) SETI("saveBandwidths", q.saveBandwidths)
+        SETD("minF", q.minF) SETD("maxF", q.maxF) SETI("useLpSpec", q.useLpSpec) SETI("medianFilter", q.medianFilter)
+        SETI("octaveCorrection", q.octaveCorrection)
         break;
       }
       default: break;

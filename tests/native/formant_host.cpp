@@ -1,0 +1,99 @@
+// formant_host.cpp -- host build of opensmile_b200/csrc/formant_math.cuh (test infrastructure).
+// The CUDA kernel (opensmile_b200/csrc/formant.cu) runs these statements with one lane per lag / per root; here the
+// lanes are loops, so the CPU tests can hold the arithmetic against the reference's level taps without a GPU.
+//   g++ -O2 -ffp-contract=off -shared -fPIC -o formant_host.so formant_host.cpp
+#include "../../opensmile_b200/csrc/formant_math.cuh"
+
+using namespace osm::fm;
+
+extern "C" {
+
+// x[n] -> a[p] (predictor coefficients), returns the gain
+float fmh_lpc(const float *x, int n, int p, float *a)
+{
+  float r[kMaxLpcOrder + 1];
+  for (int l = 0; l <= p; l++) r[l] = acf_lag(x, n, l);
+  return durbin(r, p, a);
+}
+
+// roots of z^n + c[n-1] z^(n-1) + .. + c[0]; returns the number of sweeps
+int fmh_roots(const double *c, int n, double *zr, double *zi)
+{
+  double nr[kMaxLpcOrder], ni[kMaxLpcOrder], prev[kMaxLpcOrder];
+  for (int k = 0; k < n; k++) prev[k] = 1e300;
+  for (int k = 0; k < n; k++) aberth_init(c, n, k, &zr[k], &zi[k]);
+  int it = 0;
+  bool last = false;
+  for (; it < kAberthMaxIter; it++) {
+    bool all = true;
+    for (int k = 0; k < n; k++) {
+      const double c2 = aberth_step(c, n, zr, zi, k, &nr[k], &ni[k]);
+      all = all && aberth_done(c2, prev[k], nr[k], ni[k]);
+      prev[k] = c2;
+    }
+    for (int k = 0; k < n; k++) { zr[k] = nr[k]; zi[k] = ni[k]; }
+    if (last) { it++; break; }          // the polishing sweep after every root met the test
+    last = all;
+  }
+  return it;
+}
+
+// a[p] (cLpc level) -> freq[nF] | bw[nF] as cFormantLpc writes them (lld/formantLpc.cpp:255-301,379-392)
+int fmh_formants(const float *a, int p, double T, int nF, double minF, double maxF, float *freq, float *bw)
+{
+  double c[kMaxLpcOrder], zr[kMaxLpcOrder], zi[kMaxLpcOrder], f[kMaxLpcOrder], b[kMaxLpcOrder];
+  for (int i = 0; i < p; i++) c[i] = -(double)a[p - 1 - i];
+  int n = p, z0 = 0;
+  while (z0 < n && c[z0] == 0.0) z0++;               // roots at the origin: no candidates
+  int nv = 0;
+  if (z0 < n) {
+    const int m = n - z0;
+    fmh_roots(c + z0, m, zr, zi);
+    for (int k = 0; k < m && nv < nF; k++)
+      if (root_to_formant(zr[k], zi[k], T, minF, maxF, &f[nv], &b[nv])) nv++;
+  }
+  for (int i = nv; i < nF; i++) { f[i] = 0.0; b[i] = 0.0; }
+  int nz = 0;
+  while (nz < nF && f[nz] != 0.0) nz++;
+  for (int i = 0; i < nz; i++)
+    for (int j = i + 1; j < nz; j++)
+      if (f[j] < f[i]) { double t = f[j]; f[j] = f[i]; f[i] = t; t = b[j]; b[j] = b[i]; b[i] = t; }
+  for (int i = 0; i < nF; i++) { freq[i] = (float)f[i]; bw[i] = (float)b[i]; }
+  return nv;
+}
+
+}
+
+// ---- the product's table builder (opensmile_b200/csrc/tables.cpp, linked into this harness) + the kernel's
+// resampling loop: xw[T][N] windowed frames -> res[T][I] (fmaf in sample order, as formant_kernel phase 2) ----
+#include <cmath>
+#include <string>
+#include "../../opensmile_b200/csrc/plan.hpp"
+
+extern "C" {
+
+// returns I (resampled samples per frame) or -1; *Tper = base period of the cLpc level; res may be null (query)
+int fmh_resample(double sampleRate, int N, int nfft, double frameSizeSec, int zeroPadSymmetric, double targetFs,
+                 int p, int nFormants, const float *xw, int T, float *res, double *Tper)
+{
+  osm::FrontEnd fe;
+  fe.sampleRate = sampleRate; fe.frameSize = N; fe.nfft = nfft; fe.frameSizeSec = frameSizeSec;
+  fe.fftFrameSizeSec = frameSizeSec * (double)nfft / (double)N;
+  osm_b200_specresample rs{targetFs, -1.0};
+  osm_b200_lpc lp{}; lp.p = p; lp.saveLPCoeff = 1;
+  osm_b200_formantlpc fl{}; fl.nFormants = nFormants; fl.saveFormants = 1; fl.saveBandwidths = 1; fl.minF = 50; fl.maxF = 5450;
+  osm::FormantOp op;
+  std::string err;
+  if (!osm::build_formant(rs, lp, fl, fe, zeroPadSymmetric != 0, op, err)) return -1;
+  if (Tper) *Tper = op.T;
+  if (res)
+    for (int t = 0; t < T; t++)
+      for (int i = 0; i < op.nRes; i++) {
+        float acc = 0.0f;
+        for (int m = 0; m < N; m++) acc = fmaf(xw[(size_t)t * N + m], op.D[(size_t)m * op.nResPad + i], acc);
+        res[(size_t)t * op.nRes + i] = acc;
+      }
+  return op.nRes;
+}
+
+}

@@ -1,0 +1,93 @@
+"""The arithmetic of the formant kernel (opensmile_b200/csrc/formant.cu) held against level taps of the UNMODIFIED
+reference without a GPU: formant_math.cuh and the table builder are compiled for the host (tests/formant_harness.py),
+the lanes of a warp become loops.  Stage by stage, each on the reference's own input level:
+  cSpecResample level -> cLpc coefficients      bit-identical
+  cLpc level -> cFormantLpc frequencies / bandwidths   bit-identical
+  windower level -> cSpecResample level         within 2e-6 of the frame scale (one rounding per product instead of the
+                                                reference's float FFT + float inverse sum)
+and the graph side: element names, defaults, refusals."""
+import os
+
+import numpy as np
+import pytest
+
+import formant_harness as fh
+from opensmile_b200.session import Session, SessionError
+from opensmile_b200.synth import mixed_pcm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "formant_goldens.npz"))
+CONF = os.path.join(HERE, "configs", "formant_taps.conf")
+
+
+def test_lpc_bit_identical_on_the_reference_resampled_level():
+    a = np.stack([fh.lpc(x, 11) for x in G["res"]])
+    assert np.array_equal(a, G["lpc"])
+
+
+def test_formants_bit_identical_on_the_reference_lpc_level():
+    f = np.stack([fh.formants(a, 1.0 / 11000.0, 5, 50.0, 5450.0) for a in G["lpc"]])
+    assert np.array_equal(f, G["fmt"])
+
+
+def test_root_finder_against_lapack():
+    """simultaneous iteration vs numpy (companion matrix eigenvalues) on LPC-like polynomials incl. poles next to the
+    unit circle; bounded sweep count"""
+    rng = np.random.default_rng(0)
+    worst, sweeps = 0.0, 0
+    for _ in range(400):
+        r = []
+        for k in range(5):
+            m, th = rng.uniform(0.3, 0.9999), rng.uniform(0.01, 3.13)
+            r += [m * np.exp(1j * th), m * np.exp(-1j * th)]
+        r.append(rng.uniform(-0.99, 0.99))
+        c = np.poly(r).real[::-1][:11].copy()
+        z, it = fh.roots(c)
+        ref = np.roots(np.concatenate([c, [1.0]])[::-1])
+        worst = max(worst, np.abs(z[:, None] - ref[None, :]).min(axis=1).max())
+        sweeps = max(sweeps, it)
+    assert worst < 1e-8 and sweeps < 40
+
+
+def test_degenerate_frames():
+    assert not fh.lpc(np.zeros(220, np.float32), 11).any()                        # silence: r[0] == 0 -> a = 0
+    assert not fh.formants(np.zeros(11, np.float32), 1.0 / 11000.0, 5, 50.0, 5450.0).any()   # all roots at the origin
+    a = np.zeros(11, np.float32)
+    a[0] = -0.9                                                                   # one real pole, ten roots at the origin
+    assert not fh.formants(a, 1.0 / 11000.0, 5, 50.0, 5450.0).any()
+    a[:2] = [-1.2, -0.81]                                                         # a conjugate pair: radius 0.9, angle acos(-2/3)
+    f = fh.formants(a, 1.0 / 11000.0, 5, 50.0, 5450.0)
+    ang = np.arccos(-1.2 / (2 * 0.9))
+    assert abs(f[0] - ang / (2 * np.pi) * 11000.0) < 1e-2 and abs(f[5] - (-np.log(0.9) * 11000.0 / np.pi)) < 1e-2 and not f[1:5].any()
+
+
+def test_resampling_table_against_the_reference_level():
+    pcm = mixed_pcm(24000, 16000, seed=3)
+    xw, nfft = fh.windowed_frames(pcm)
+    res, per = fh.resample(xw, 16000.0, nfft, 0.020, 11000.0)
+    assert res.shape == G["res"].shape and per == 1.0 / 11000.0
+    assert np.abs(res - G["res"]).max() / np.abs(G["res"]).max() < 2e-6
+
+
+def test_end_to_end_deviation_is_the_conditioning_of_lpc():
+    """The 1e-6 difference of the resampled frames (above) reaches the formants through an order-11 float Durbin recursion:
+    typical rows agree to 1e-5, rows with poles next to each other move by percents (the same happens between two builds of
+    the reference with different FFT rounding).  Recorded here so a change of the table path shows up."""
+    got = fh.formant_chain(mixed_pcm(24000, 16000, seed=3))
+    ref = G["fmt"]
+    err = np.abs(got - ref) / np.abs(ref).max(axis=0)
+    assert np.median(err) < 1e-4
+    assert (err.max(axis=1) > 1e-3).mean() < 0.25
+
+
+def test_graph_names_and_refusals(tmp_path):
+    s = Session(CONF, output_level="formants", device=-1)
+    assert s.element_names() == ["formantFreqLpc[%d]" % i for i in range(1, 6)] + ["formantBandwidthLpc[%d]" % i for i in range(1, 6)]
+    text = open(CONF).read()
+    for old, new, needle in (("method=acf", "method=burg", "method=acf"), ("nFormants=5", "nFormants=3", "nFormants < p/2"),
+                             ("medianFilter=0", "medianFilter=5", "medianFilter"), ("residual=0", "residual=1", "residual")):
+        assert old in text
+        p = tmp_path / "c.conf"
+        p.write_text(text.replace(old, new))
+        with pytest.raises(SessionError, match=needle):
+            Session(str(p), output_level="formants", device=-1)

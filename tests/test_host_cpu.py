@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(capi.LIB_PATH)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert capi.lib().osm_b200_abi_version() == 2
+    assert capi.lib().osm_b200_abi_version() == 3
 
 
 def test_struct_mirror_matches_library():
