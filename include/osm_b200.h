@@ -45,7 +45,7 @@ extern "C" {
 #endif
 
 /* 2: component types cSpecScale .. cPitchJitter appended (existing values and struct layouts unchanged)
- * 3: cSpecResample, cLpc, cFormantLpc appended (same rule) */
+ * 3: cSpecResample, cLpc, cFormantLpc, cDataSelector appended (same rule; sizeof(osm_b200_component) grows) */
 #define OSM_B200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define OSM_B200_API __attribute__((visibility("default")))
@@ -55,6 +55,7 @@ extern "C" {
 #define OSM_B200_NAME_LEN 64
 #define OSM_B200_MAX_INPUTS 8
 #define OSM_B200_MAX_LIST 16
+#define OSM_B200_MAX_SELECTED 32
 
 typedef enum {
   OSM_B200_OK = 0,
@@ -95,6 +96,7 @@ typedef enum {
   OSM_B200_C_SPECRESAMPLE,       /* cSpecResample       src/dsp/specResample.cpp:97-185           */
   OSM_B200_C_LPC,                /* cLpc                src/lld/lpc.cpp:156-215 (method acf)      */
   OSM_B200_C_FORMANTLPC,         /* cFormantLpc         src/lld/formantLpc.cpp:192-394 (root solving branch) */
+  OSM_B200_C_DATASELECTOR,       /* cDataSelector       src/core/dataSelector.cpp:296-366 (elementMode=1)    */
   OSM_B200_C_COUNT_
 } osm_b200_component_type;
 
@@ -283,6 +285,13 @@ typedef struct {            /* cFormantLpc */
   int32_t useLpSpec, medianFilter, octaveCorrection;   /* 0,0,0 (only these values are supported) */
 } osm_b200_formantlpc;
 
+typedef struct {            /* cDataSelector, elementMode = 1: exact element names, output in the order of `selected` */
+  int32_t nSelected;
+  int32_t elementMode;      /* 1 */
+  char    selected[OSM_B200_MAX_SELECTED][OSM_B200_NAME_LEN];
+  char    newNames[OSM_B200_MAX_SELECTED][OSM_B200_NAME_LEN];   /* "" = keep the name (+ "_" nameAppend) */
+} osm_b200_dataselector;
+
 /* one `[name:cType]` section */
 typedef struct {
   int32_t type;                                  /* osm_b200_component_type */
@@ -323,6 +332,7 @@ typedef struct {
     osm_b200_specresample specresample;
     osm_b200_lpc lpc;
     osm_b200_formantlpc formantlpc;
+    osm_b200_dataselector dataselector;
   } u;
 } osm_b200_component;
 

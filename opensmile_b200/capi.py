@@ -22,7 +22,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = range(5)
  C_MELSPEC, C_MFCC, C_PLP, C_SPECTRAL, C_ENERGY, C_MZCR, C_ACF, C_PITCHACF,
  C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION, C_FULLINPUTMEAN, C_INTENSITY,
  C_SPECSCALE, C_PITCHSHS, C_PITCHSMOOTHERVITERBI, C_VALBASEDSELECTOR, C_PITCHJITTER,
- C_SPECRESAMPLE, C_LPC, C_FORMANTLPC) = range(28)
+ C_SPECRESAMPLE, C_LPC, C_FORMANTLPC, C_DATASELECTOR) = range(29)
 
 TYPE_BY_NAME = {
     "cWaveSource": C_WAVESOURCE, "cExternalAudioSource": C_WAVESOURCE, "cFramer": C_FRAMER,
@@ -36,6 +36,7 @@ TYPE_BY_NAME = {
     "cSpecScale": C_SPECSCALE, "cPitchShs": C_PITCHSHS, "cPitchSmootherViterbi": C_PITCHSMOOTHERVITERBI,
     "cValbasedSelector": C_VALBASEDSELECTOR, "cPitchJitter": C_PITCHJITTER,
     "cSpecResample": C_SPECRESAMPLE, "cLpc": C_LPC, "cFormantLpc": C_FORMANTLPC,
+    "cDataSelector": C_DATASELECTOR,
 }
 
 WIN_BY_NAME = {"rec": 0, "han": 1, "ham": 2, "gau": 3, "sin": 4, "tri": 5, "bar": 6}
@@ -198,6 +199,11 @@ class FormantLpc(C.Structure):
                 ("octaveCorrection", i32)]
 
 
+class DataSelector(C.Structure):
+    _fields_ = [("nSelected", i32), ("elementMode", i32), ("selected", (C.c_char * NAME_LEN) * 32),
+                ("newNames", (C.c_char * NAME_LEN) * 32)]
+
+
 class _U(C.Union):
     _fields_ = [("wavesource", WaveSource), ("framer", Framer),
                 ("vectorpreemphasis", VectorPreemphasis), ("windower", Windower),
@@ -208,7 +214,8 @@ class _U(C.Union):
                 ("vectoroperation", VectorOperation), ("vectorconcat", VectorConcat), ("fullinputmean", FullinputMean), ("intensity", Intensity),
                 ("specscale", SpecScale), ("pitchshs", PitchShs), ("pitchsmootherviterbi", PitchSmootherViterbi),
                 ("valbasedselector", ValbasedSelector), ("pitchjitter", PitchJitter),
-                ("specresample", SpecResample), ("lpc", Lpc), ("formantlpc", FormantLpc)]
+                ("specresample", SpecResample), ("lpc", Lpc), ("formantlpc", FormantLpc),
+                ("dataselector", DataSelector)]
 
 
 class Component(C.Structure):

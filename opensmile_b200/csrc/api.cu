@@ -263,6 +263,7 @@ osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
     }
     case OSM_B200_C_SPECRESAMPLE: c->u.specresample.targetFs = 16000.0; c->u.specresample.resampleRatio = -1.0; break;   // dsp/specResample.cpp:40-41
     case OSM_B200_C_LPC: c->u.lpc.p = 8; c->u.lpc.saveLPCoeff = 1; break;                                               // lld/lpc.cpp:33-45
+    case OSM_B200_C_DATASELECTOR: c->u.dataselector.elementMode = 1; break;                                              // core/dataSelector.cpp:39
     case OSM_B200_C_FORMANTLPC: {          // lld/formantLpc.cpp:40-52
       auto &q = c->u.formantlpc;
       q.nFormants = -1; q.saveFormants = 1; q.minF = 50.0; q.maxF = 5500.0;

@@ -35,7 +35,7 @@ const char *type_name(int t)
     "cTransformFFT", "cFFTmagphase", "cMelspec", "cMfcc", "cPlp", "cSpectral", "cEnergy",
     "cMZcr", "cAcf", "cPitchACF", "cDeltaRegression", "cContourSmoother", "cVectorConcat",
     "cVectorOperation", "cFullinputMean", "cIntensity", "cSpecScale", "cPitchShs", "cPitchSmootherViterbi",
-    "cValbasedSelector", "cPitchJitter", "cSpecResample", "cLpc", "cFormantLpc"};
+    "cValbasedSelector", "cPitchJitter", "cSpecResample", "cLpc", "cFormantLpc", "cDataSelector"};
   return (t >= 0 && t < OSM_B200_C_COUNT_) ? names[t] : "?";
 }
 
@@ -231,6 +231,10 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
   struct ConcatCheck { size_t g0, g1, above; };          // leaves [g0, g1) sit below a concat that has stages above it
   std::vector<std::pair<size_t, size_t>> leafGroups;   // leaf -> its groups [first, last)
   std::vector<ConcatCheck> concatChecks;
+  struct SelScope { const osm_b200_component *c; size_t l0, l1, above; };   // leaves [l0, l1) sit below selector c, `above` stages above it
+  std::vector<SelScope> selScopes;
+  bool inSelector = false;
+  std::vector<std::vector<std::string>> leafSelNames;   // per leaf: element names as a selector above it sees them
   std::function<osm_b200_status(const std::string &, std::vector<const osm_b200_component *>, int, bool)> expand =
     [&](const std::string &lvl, std::vector<const osm_b200_component *> above, int depth, bool arraysOnly) -> osm_b200_status {
     if (depth > 8) { err = "level graph nested too deeply (cycle?)"; return OSM_B200_ERR_INVALID; }
@@ -247,6 +251,28 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     }
     if (!c) { err = "broken temporal chain below level '" + lvl + "'"; return OSM_B200_ERR_INVALID; }
     stageComps.insert(stageComps.end(), above.begin(), above.end());
+    if (c->type == OSM_B200_C_DATASELECTOR && !multi) {
+      // cDataSelector (core/dataSelector.cpp:296-366): picks elements of its (implicitly concatenated) input levels by
+      // exact name, in the order of `selected`, each as a single-element field.  Element-wise like the temporal
+      // stages, so stage(select(x)) = select(stage(x)): the leaves below carry the stages, the selection is applied
+      // to the output groups afterwards (selector scopes).
+      const auto &q = c->u.dataselector;
+      if (!q.elementMode) { err = "cDataSelector.elementMode=0 is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+      if (q.nSelected < 1) { err = "cDataSelector: no elements selected"; return OSM_B200_ERR_INVALID; }
+      if (arraysOnly) { err = "cDataSelector below a cVectorConcat that drops single-element fields is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+      if (inSelector) { err = "nested cDataSelector levels are not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+      if (c->n_inputs < 1) { err = "cDataSelector without inputs"; return OSM_B200_ERR_INVALID; }
+      const size_t l0 = leaves.size();
+      inSelector = true;
+      for (int i = 0; i < c->n_inputs; i++) {
+        osm_b200_status s2 = expand(c->reader_dmLevel[i], stageComps, depth + 1, false);
+        if (s2 != OSM_B200_OK) { inSelector = false; return s2; }
+      }
+      inSelector = false;
+      if (!stageComps.empty() && c->n_inputs > 1) concatChecks.push_back({l0, leaves.size(), stageComps.size()});
+      selScopes.push_back(SelScope{c, l0, leaves.size(), stageComps.size()});
+      return OSM_B200_OK;
+    }
     if (c->type == OSM_B200_C_VECTORCONCAT || multi) {
       if (c->n_inputs < 1) { err = "cVectorConcat without inputs"; return OSM_B200_ERR_INVALID; }
       // a real cVectorConcat is a cVectorProcessor: with processArrayFields=1 it drops single-element
@@ -612,6 +638,20 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     std::vector<Stage> stages;
     std::vector<FieldName> fields = d.ops[opIdx].fields;
     int segId = -1;
+    const size_t leafIdx = (size_t)(&leaf - &leaves[0]);
+    long selAbove = -1;                                  // stages above the selector this leaf sits below, -1 = none
+    for (const SelScope &sc : selScopes) if (leafIdx >= sc.l0 && leafIdx < sc.l1) selAbove = (long)sc.above;
+    auto element_names = [&](const std::vector<FieldName> &fs) {
+      std::vector<std::string> out;
+      for (const auto &f : fs) {
+        if (f.n == 1) out.push_back(f.name);
+        else for (int i = 0; i < f.n; i++) { snprintf(buf, sizeof buf, "%s[%d]", f.name.c_str(), i + f.arrNameOffset); out.push_back(buf); }
+      }
+      return out;
+    };
+    leafSelNames.push_back({});
+    if (selAbove >= 0 && (long)stageComps.size() == selAbove) leafSelNames.back() = element_names(fields);
+    size_t stageNo = 0;
     for (const osm_b200_component *s : stageComps) {
       Stage st;
       if (s->type == OSM_B200_C_DELTAREGRESSION) {
@@ -643,6 +683,8 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       }
       stages.push_back(st);
       for (auto &f : fields) f.name = name_append_auto(*s, f.name, nullptr);
+      stageNo++;
+      if (selAbove >= 0 && (long)(stageComps.size() - stageNo) == selAbove) leafSelNames.back() = element_names(fields);
     }
     if (stages.size() > 3) { err = "more than 3 chained temporal stages"; return OSM_B200_ERR_UNSUPPORTED; }
     const size_t firstGroup = d.groups.size();
@@ -709,6 +751,70 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
           if (std::find(d.groups[g].limitStreams.begin(), d.groups[g].limitStreams.end(), sidx) == d.groups[g].limitStreams.end())
             d.groups[g].limitStreams.push_back(sidx);
         }
+  }
+
+  // ---- cDataSelector scopes: replace the groups of the leaves below a selector by the selected elements ----
+  if (!selScopes.empty()) {
+    std::vector<OutGroup> ng;
+    std::vector<std::string> nn;
+    int outCol = 0;
+    for (size_t l = 0; l < leaves.size();) {
+      const SelScope *sc = nullptr;
+      for (const SelScope &x : selScopes) if (x.l0 == l) sc = &x;
+      if (!sc) {
+        for (size_t g = leafGroups[l].first; g < leafGroups[l].second; g++) {
+          OutGroup x = d.groups[g];
+          for (int i = 0; i < x.n; i++) nn.push_back(d.names[x.outCol + i]);
+          x.outCol = outCol; outCol += x.n;
+          ng.push_back(x);
+        }
+        l++;
+        continue;
+      }
+      struct El { size_t g; int off; const std::string *name; };
+      std::vector<El> els;                                // the elements of the selector's input, in reader order
+      for (size_t ll = sc->l0; ll < sc->l1; ll++) {
+        size_t e = 0;
+        for (size_t g = leafGroups[ll].first; g < leafGroups[ll].second; g++)
+          for (int i = 0; i < d.groups[g].n; i++, e++) {
+            if (e >= leafSelNames[ll].size()) { err = "internal: cDataSelector element bookkeeping"; return OSM_B200_ERR_INVALID; }
+            els.push_back(El{g, i, &leafSelNames[ll][e]});
+          }
+      }
+      const auto &q = sc->c->u.dataselector;
+      const std::vector<const osm_b200_component *> &lst = leaves[sc->l0].stages;
+      // A selector that reads a cPitchJitter level waits for it: during the reference's first end-of-input pass that
+      // level does not advance (lld/pitchJitter.cpp:593), so EVERY element of the selector's output lags like the jitter
+      // columns do (oracle/formant_oracle.py:gemaps_lld, pinned on the shipped GeMAPS configurations)
+      bool scopeLags = false;
+      for (const El &e : els) scopeLags = scopeLags || d.groups[e.g].lagKind == 2;
+      long prevG = -1;
+      for (int k = 0; k < q.nSelected; k++) {
+        for (int k2 = 0; k2 < k; k2++)
+          if (!strcmp(q.selected[k], q.selected[k2])) { err = std::string("cDataSelector: element selected twice: ") + q.selected[k]; return OSM_B200_ERR_UNSUPPORTED; }
+        const El *hit = nullptr;
+        for (const El &e : els) if (*e.name == q.selected[k]) { hit = &e; break; }
+        if (!hit) {                                       // core/dataSelector.cpp:330-343 aborts as well
+          err = std::string("cDataSelector '") + sc->c->name + "': element '" + q.selected[k] + "' not found in its input levels";
+          return OSM_B200_ERR_INVALID;
+        }
+        OutGroup x = d.groups[hit->g];
+        x.srcCol += hit->off; x.n = 1; x.outCol = outCol++;
+        if (scopeLags && x.lagKind == 1) x.lagKind = 2;
+        if (scopeLags && x.lagKind == 0) { err = "cDataSelector reading a cPitchJitter level together with levels outside the pitch chain is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (prevG == (long)hit->g && !ng.empty() && ng.back().srcCol + ng.back().n == x.srcCol) ng.back().n++;
+        else ng.push_back(x);
+        prevG = (long)hit->g;
+        std::string nm = q.newNames[k][0] ? std::string(q.newNames[k])                                  // :344-356
+                         : (sc->c->nameAppend[0] ? std::string(q.selected[k]) + "_" + sc->c->nameAppend : std::string(q.selected[k]));
+        for (size_t a = lst.size() - sc->above; a < lst.size(); a++) nm = name_append_auto(*lst[a], nm, nullptr);
+        nn.push_back(nm);
+      }
+      l = sc->l1;
+    }
+    d.groups.swap(ng);
+    d.names.swap(nn);
+    d.nOut = outCol;
   }
 
   // ---- groups behind a Viterbi-smoothed pitch level (seq_post_kernel) ----

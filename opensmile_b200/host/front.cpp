@@ -223,7 +223,7 @@ const TypeInfo kTypes[] = {
   {"cSpecScale", OSM_B200_C_SPECSCALE}, {"cPitchShs", OSM_B200_C_PITCHSHS},
   {"cPitchSmootherViterbi", OSM_B200_C_PITCHSMOOTHERVITERBI}, {"cValbasedSelector", OSM_B200_C_VALBASEDSELECTOR},
   {"cPitchJitter", OSM_B200_C_PITCHJITTER}, {"cSpecResample", OSM_B200_C_SPECRESAMPLE}, {"cLpc", OSM_B200_C_LPC},
-  {"cFormantLpc", OSM_B200_C_FORMANTLPC}};
+  {"cFormantLpc", OSM_B200_C_FORMANTLPC}, {"cDataSelector", OSM_B200_C_DATASELECTOR}};
 
 int type_of(const std::string &t)
 {
@@ -488,6 +488,32 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         SETI("residual", q.residual) SETI("residualGainScale", q.residualGainScale) SETI("forwardFilter", q.forwardFilter)
         SETI("lpSpectrum", q.lpSpectrum)
         if (f == "forwardLPspec" || f == "forwardLPspecFloor" || f == "lpSpecDeltaF" || f == "lpSpecBins") continue;   // only read with lpSpectrum=1
+        break;
+      }
+      case OSM_B200_C_DATASELECTOR: {       // core/dataSelector.cpp:35-41
+        auto &q = c.u.dataselector;
+        if (f == "selected" || f == "newNames") {          // array fields: a;b;c (configManager array syntax)
+          int k = 0;
+          size_t a = 0;
+          while (a <= v.size()) {
+            size_t b = v.find(';', a);
+            if (b == std::string::npos) b = v.size();
+            std::string item = v.substr(a, b - a);
+            while (!item.empty() && (item.back() == ' ' || item.back() == '\t')) item.pop_back();
+            while (!item.empty() && (item.front() == ' ' || item.front() == '\t')) item.erase(item.begin());
+            if (b == v.size() && item.empty()) break;       // trailing ';'
+            if (k >= OSM_B200_MAX_SELECTED) { err = "cDataSelector: more than 32 selected elements"; return false; }
+            if (item.size() >= OSM_B200_NAME_LEN) { err = "cDataSelector: element name too long: " + item; return false; }
+            snprintf(f == "selected" ? q.selected[k] : q.newNames[k], OSM_B200_NAME_LEN, "%s", item.c_str());
+            k++;
+            a = b + 1;
+          }
+          if (f == "selected") q.nSelected = k;
+          continue;
+        }
+        SETI("elementMode", q.elementMode)
+        if (f == "selFile" || f == "selectedRange" || f == "outputSingleField") { if (!v.empty()) { err = "cDataSelector." + f + " is not supported"; return false; } continue; }
+        if (f == "dummyMode") { if (inum(v)) { err = "cDataSelector.dummyMode is not supported"; return false; } continue; }
         break;
       }
       case OSM_B200_C_FORMANTLPC: {         // lld/formantLpc.cpp:40-52

@@ -484,6 +484,32 @@ def gemaps_lld(pcm, sample_rate=16000.0, exact_fft=False):
     return np.concatenate([Es[:R], Fs[:R]], axis=1)
 
 
+def gemaps_sel_lld(pcm, sample_rate=16000.0):
+    """Level `lld` of tests/configs/gemaps_sel.conf: the shipped gemapsv01b_lldsetE (5 columns, sma3) next to a cDataSelector
+    over the pitch and jitter / shimmer levels (shimmerLocalDB, F0finalLog, jitterLocal in this order; sma3nz, every column
+    lagging with the jitter level).  No FFT-sensitive branch: none of the columns reads the formant chain."""
+    fe60 = oracle.frontend(sample_rate, 0.060, 0.010, win="gau", sigma=0.4, zero_pad_symmetric=1)
+    sc = oracle.SpecScale(25.0, -1.0, 0, 1, 1, 1)
+    ps = oracle.PitchShs(1000.0, 55.0, 6, 1, 1, 0, 0, 1, 1, 0.70, 0, 15, 0.85, 1, 0.0)
+    vc = oracle.Viterbi(40, 1, 1, 0, 0, 0, 1, 2.0, 10.0, 5.0, 10.0, 4.0, 1.0, 0.0)
+    jc = oracle.Jitter(0.10, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, -100.0, 0, 2, 0.5, 0, 0, 0, 0, 0, 0)
+    vit, lag = oracle.viterbi(oracle.pitch_shs(pcm, fe60, sc, ps), ps, vc, with_lag=True)
+    e60 = oracle.energy(pcm, fe60, oracle.Energy(0, 1, 0, 0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0), windowed=1)
+    pitch = oracle.valbased_select(e60[:, 0], vit, 0.001)
+    jit = oracle.pitch_jitter(pcm, fe60, jc, pitch[:, 0])
+    T = min(pitch.shape[0], jit.shape[0])
+    F = np.stack([jit[:T, 1], pitch[:T, 1], jit[:T, 0]], axis=1).astype(f32)
+    Fs = oracle.sma_nz_lagged(F, lag, set(range(F.shape[1])))
+    fe25 = oracle.Frontend(sample_rate, 0.020, 0.010, 0, 0.0, oracle.WIN["ham"], 0.4, 1.0, 0.0, 1)
+    aud = oracle.plp_static(pcm, sample_rate, (fe25, oracle.Melspec(26, 20.0, 8000.0, 1, 0),
+                                                oracle.Plp(5, 0, -1, 0, 1, 0, 0, 0, 0, 0, 0, 29.0, 1.0, 22.0, 0.33, 9.3e-10, 0)))
+    spec = oracle.spectral(pcm, fe25, oracle.gemaps_logspectral())
+    E = np.stack([oracle.ll1(aud), spec[:, 2], spec[:, 3], spec[:, 0], spec[:, 1]], axis=1).astype(f32)
+    Es = oracle.sma(E, 3, 0)
+    R = min(Es.shape[0], Fs.shape[0])
+    return np.concatenate([Es[:R], Fs[:R]], axis=1)
+
+
 EGEMAPS_LLD_NAMES = (["Loudness_sma3", "alphaRatio_sma3", "hammarbergIndex_sma3", "slope0-500_sma3", "slope500-1500_sma3",
                       "spectralFlux_sma3"] + ["mfcc%d_sma3" % i for i in range(1, 5)]
                      + ["F0semitoneFrom27.5Hz_sma3nz", "jitterLocal_sma3nz", "shimmerLocaldB_sma3nz", "HNRdBACF_sma3nz",

@@ -1,0 +1,62 @@
+"""cDataSelector (core/dataSelector.cpp, elementMode = 1) in the graph compiler: tests/configs/gemaps_sel.conf puts a selector
+on top of the reference's shipped GeMAPS graph (pitch + jitter / shimmer levels) next to the shipped selector
+gemapsv01b_lldsetE.  Element names, order and frame counts against the reference's CSV file
+(tests/golden/select_goldens.npz, scripts/make_golden_select.py); the oracle's rows (incl. the rule that every column of a
+selector reading the cPitchJitter level lags at the end of input) against the same file; refusals."""
+import os
+
+import numpy as np
+import pytest
+
+from opensmile_b200.session import Session, SessionError
+from opensmile_b200.synth import mixed_pcm, voiced_pcm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+G = np.load(os.path.join(HERE, "golden", "select_goldens.npz"))
+REFCONF = os.path.join(ROOT, "oracle", "_ref", "config")
+
+
+def _conf(tmp_path, edit=None):
+    if not os.path.isdir(REFCONF):
+        pytest.skip("reference configuration files not built (make -C oracle ref)")
+    text = open(os.path.join(HERE, "configs", "gemaps_sel.conf")).read().replace("REFCONF", REFCONF)
+    if edit:
+        assert edit[0] in text
+        text = text.replace(edit[0], edit[1])
+    p = tmp_path / "gsel.conf"
+    p.write_text(text)
+    return str(p)
+
+
+def test_names_order_and_frame_counts(tmp_path):
+    s = Session(_conf(tmp_path), device=-1)
+    assert s.element_names() == list(G["gsel_names"])
+    fo = s.frame_offsets(np.array([0, 24000, 56000], np.int64), 16000.0, 1)
+    assert list(np.diff(fo)) == [G["gsel_m24k"].shape[0], G["gsel_v32k"].shape[0]]
+
+
+def test_oracle_rows_of_the_selector_configuration():
+    from oracle import formant_oracle as fo
+    for key, pcm in (("gsel_m24k", mixed_pcm(24000, 16000, seed=3)), ("gsel_v32k", voiced_pcm(32000, 16000, seed=7))):
+        got, ref = fo.gemaps_sel_lld(pcm), G[key]
+        assert got.shape == ref.shape
+        assert (np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)).max() < 5e-6     # the CSV file holds 7 digits
+
+
+@pytest.mark.parametrize("edit,needle", [
+    (("selected = shimmerLocalDB;F0finalLog;jitterLocal", "selected = shimmerLocalDB;F0finalLogX;jitterLocal"), "not found"),
+    (("selected = shimmerLocalDB;F0finalLog;jitterLocal", "selected = jitterLocal;F0finalLog;jitterLocal"), "selected twice"),
+    (("newNames = shimmerLocaldB;F0semitoneFrom27.5Hz", "elementMode = 0"), "elementMode"),
+    (("[smoF:cContourSmoother]\nreader.dmLevel = selF\n",
+      "[componentInstances:cComponentManager]\ninstance[selF2].type=cDataSelector\n[selF2:cDataSelector]\nreader.dmLevel = selF\n"
+      "writer.dmLevel = selF2\nselected = jitterLocal\n[smoF:cContourSmoother]\nreader.dmLevel = selF2\n"), "nested"),
+])
+def test_refusals(tmp_path, edit, needle):
+    with pytest.raises(SessionError, match=needle):
+        Session(_conf(tmp_path, edit), device=-1)
+
+
+def test_names_without_new_names(tmp_path):
+    s = Session(_conf(tmp_path, ("newNames = shimmerLocaldB;F0semitoneFrom27.5Hz", "nameAppend = sel")), device=-1)
+    assert s.element_names()[5:] == ["shimmerLocalDB_sel_sma3nz", "F0finalLog_sel_sma3nz", "jitterLocal_sel_sma3nz"]
