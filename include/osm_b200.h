@@ -45,7 +45,7 @@ extern "C" {
 #endif
 
 /* 2: component types cSpecScale .. cPitchJitter appended (existing values and struct layouts unchanged)
- * 3: cSpecResample, cLpc, cFormantLpc, cDataSelector appended (same rule; sizeof(osm_b200_component) grows) */
+ * 3: cSpecResample, cLpc, cFormantLpc, cDataSelector, cHarmonics appended (same rule; sizeof(osm_b200_component) grows) */
 #define OSM_B200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define OSM_B200_API __attribute__((visibility("default")))
@@ -97,6 +97,7 @@ typedef enum {
   OSM_B200_C_LPC,                /* cLpc                src/lld/lpc.cpp:156-215 (method acf)      */
   OSM_B200_C_FORMANTLPC,         /* cFormantLpc         src/lld/formantLpc.cpp:192-394 (root solving branch) */
   OSM_B200_C_DATASELECTOR,       /* cDataSelector       src/core/dataSelector.cpp:296-366 (elementMode=1)    */
+  OSM_B200_C_HARMONICS,          /* cHarmonics          src/lld/harmonics.cpp:743-935 (GeMAPS switch set)    */
   OSM_B200_C_COUNT_
 } osm_b200_component_type;
 
@@ -292,6 +293,21 @@ typedef struct {            /* cDataSelector, elementMode = 1: exact element nam
   char    newNames[OSM_B200_MAX_SELECTED][OSM_B200_NAME_LEN];   /* "" = keep the name (+ "_" nameAppend) */
 } osm_b200_dataselector;
 
+typedef struct {            /* cHarmonics: reader.dmLevel = <pitch level>;<formant level>;<cFFTmagphase level> (any order) */
+  char    f0ElementName[OSM_B200_NAME_LEN];             /* "F0final" */
+  char    magSpecFieldName[OSM_B200_NAME_LEN];          /* "pcm_fftMag" */
+  char    formantFrequencyFieldName[OSM_B200_NAME_LEN]; /* "" */
+  char    formantBandwidthFieldName[OSM_B200_NAME_LEN]; /* "" */
+  int32_t f0ElementNameIsFull, magSpecFieldNameIsFull, formantFrequencyFieldNameIsFull, formantBandwidthFieldNameIsFull; /* 1,0,1,1 */
+  int32_t nHarmonics, firstHarmonicMagnitude, nHarmonicMagnitudes, outputLogRelMagnitudes, outputLinearMagnitudes;       /* 100,1,0,1,0 */
+  int32_t nHarmonicDifferences;                          /* entries of harmonicDifferences */
+  char    harmonicDifferences[4][16];                    /* "H1-H2", "H1-A3", ... */
+  int32_t harmonicDifferencesLog, harmonicDifferencesRatioLinear;    /* 1, 0 */
+  int32_t formantAmplitudes, formantAmplitudesLinear, formantAmplitudesLogRel, formantAmplitudesStart, formantAmplitudesEnd; /* 0,0,1,1,-1 */
+  int32_t computeAcfHnrLogdB, computeAcfHnrLinear;       /* 0, 0 */
+  double  logRelValueFloorUnvoiced;                      /* -201 */
+} osm_b200_harmonics;
+
 /* one `[name:cType]` section */
 typedef struct {
   int32_t type;                                  /* osm_b200_component_type */
@@ -333,6 +349,7 @@ typedef struct {
     osm_b200_lpc lpc;
     osm_b200_formantlpc formantlpc;
     osm_b200_dataselector dataselector;
+    osm_b200_harmonics harmonics;
   } u;
 } osm_b200_component;
 

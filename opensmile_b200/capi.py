@@ -22,7 +22,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NOMEM = range(5)
  C_MELSPEC, C_MFCC, C_PLP, C_SPECTRAL, C_ENERGY, C_MZCR, C_ACF, C_PITCHACF,
  C_DELTAREGRESSION, C_CONTOURSMOOTHER, C_VECTORCONCAT, C_VECTOROPERATION, C_FULLINPUTMEAN, C_INTENSITY,
  C_SPECSCALE, C_PITCHSHS, C_PITCHSMOOTHERVITERBI, C_VALBASEDSELECTOR, C_PITCHJITTER,
- C_SPECRESAMPLE, C_LPC, C_FORMANTLPC, C_DATASELECTOR) = range(29)
+ C_SPECRESAMPLE, C_LPC, C_FORMANTLPC, C_DATASELECTOR, C_HARMONICS) = range(30)
 
 TYPE_BY_NAME = {
     "cWaveSource": C_WAVESOURCE, "cExternalAudioSource": C_WAVESOURCE, "cFramer": C_FRAMER,
@@ -36,7 +36,7 @@ TYPE_BY_NAME = {
     "cSpecScale": C_SPECSCALE, "cPitchShs": C_PITCHSHS, "cPitchSmootherViterbi": C_PITCHSMOOTHERVITERBI,
     "cValbasedSelector": C_VALBASEDSELECTOR, "cPitchJitter": C_PITCHJITTER,
     "cSpecResample": C_SPECRESAMPLE, "cLpc": C_LPC, "cFormantLpc": C_FORMANTLPC,
-    "cDataSelector": C_DATASELECTOR,
+    "cDataSelector": C_DATASELECTOR, "cHarmonics": C_HARMONICS,
 }
 
 WIN_BY_NAME = {"rec": 0, "han": 1, "ham": 2, "gau": 3, "sin": 4, "tri": 5, "bar": 6}
@@ -204,6 +204,18 @@ class DataSelector(C.Structure):
                 ("newNames", (C.c_char * NAME_LEN) * 32)]
 
 
+class Harmonics(C.Structure):
+    _fields_ = [("f0ElementName", C.c_char * NAME_LEN), ("magSpecFieldName", C.c_char * NAME_LEN),
+                ("formantFrequencyFieldName", C.c_char * NAME_LEN), ("formantBandwidthFieldName", C.c_char * NAME_LEN),
+                ("f0ElementNameIsFull", i32), ("magSpecFieldNameIsFull", i32), ("formantFrequencyFieldNameIsFull", i32),
+                ("formantBandwidthFieldNameIsFull", i32), ("nHarmonics", i32), ("firstHarmonicMagnitude", i32),
+                ("nHarmonicMagnitudes", i32), ("outputLogRelMagnitudes", i32), ("outputLinearMagnitudes", i32),
+                ("nHarmonicDifferences", i32), ("harmonicDifferences", (C.c_char * 16) * 4), ("harmonicDifferencesLog", i32),
+                ("harmonicDifferencesRatioLinear", i32), ("formantAmplitudes", i32), ("formantAmplitudesLinear", i32),
+                ("formantAmplitudesLogRel", i32), ("formantAmplitudesStart", i32), ("formantAmplitudesEnd", i32),
+                ("computeAcfHnrLogdB", i32), ("computeAcfHnrLinear", i32), ("logRelValueFloorUnvoiced", f64)]
+
+
 class _U(C.Union):
     _fields_ = [("wavesource", WaveSource), ("framer", Framer),
                 ("vectorpreemphasis", VectorPreemphasis), ("windower", Windower),
@@ -215,7 +227,7 @@ class _U(C.Union):
                 ("specscale", SpecScale), ("pitchshs", PitchShs), ("pitchsmootherviterbi", PitchSmootherViterbi),
                 ("valbasedselector", ValbasedSelector), ("pitchjitter", PitchJitter),
                 ("specresample", SpecResample), ("lpc", Lpc), ("formantlpc", FormantLpc),
-                ("dataselector", DataSelector)]
+                ("dataselector", DataSelector), ("harmonics", Harmonics)]
 
 
 class Component(C.Structure):

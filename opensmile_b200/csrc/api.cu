@@ -117,6 +117,8 @@ struct OpRt {
   ShsParams shs;
   ViterbiParams vit;
   JitterParams jit;
+  HarmonicsParams hrm;                  // SOP_HARMONICS
+  double *dCosTab = nullptr;            // its cos(2 pi m / N) table
   FormantParams fmt;                    // SOP_FORMANT
   float *dFmtD = nullptr;               // its resampling table
   unsigned char *dPitchTab = nullptr;   // spline / interpolation / harmonic tables of the chain
@@ -264,6 +266,15 @@ osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
     case OSM_B200_C_SPECRESAMPLE: c->u.specresample.targetFs = 16000.0; c->u.specresample.resampleRatio = -1.0; break;   // dsp/specResample.cpp:40-41
     case OSM_B200_C_LPC: c->u.lpc.p = 8; c->u.lpc.saveLPCoeff = 1; break;                                               // lld/lpc.cpp:33-45
     case OSM_B200_C_DATASELECTOR: c->u.dataselector.elementMode = 1; break;                                              // core/dataSelector.cpp:39
+    case OSM_B200_C_HARMONICS: {           // lld/harmonics.cpp:28-56
+      auto &q = c->u.harmonics;
+      snprintf(q.f0ElementName, sizeof q.f0ElementName, "%s", "F0final");
+      snprintf(q.magSpecFieldName, sizeof q.magSpecFieldName, "%s", "pcm_fftMag");
+      q.f0ElementNameIsFull = 1; q.formantFrequencyFieldNameIsFull = 1; q.formantBandwidthFieldNameIsFull = 1;
+      q.nHarmonics = 100; q.firstHarmonicMagnitude = 1; q.outputLogRelMagnitudes = 1; q.harmonicDifferencesLog = 1;
+      q.formantAmplitudesLogRel = 1; q.formantAmplitudesStart = 1; q.formantAmplitudesEnd = -1; q.logRelValueFloorUnvoiced = -201.0;
+      break;
+    }
     case OSM_B200_C_FORMANTLPC: {          // lld/formantLpc.cpp:40-52
       auto &q = c->u.formantlpc;
       q.nFormants = -1; q.saveFormants = 1; q.minF = 50.0; q.maxF = 5500.0;
@@ -657,6 +668,21 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       CUP(cudaMalloc(&rt.dSharpW, so.sharpW.size() * sizeof(double)));
       CUP(cudaMemcpy(rt.dSharpW, so.sharpW.data(), so.sharpW.size() * sizeof(double), cudaMemcpyHostToDevice));
       sp.sharpW = rt.dSharpW;
+    } else if (op.kind == SOP_HARMONICS) {
+      const HarmonicsOp &ho = op.harmonics;
+      HarmonicsParams &hp = rt.hrm;
+      memset(&hp, 0, sizeof hp);
+      const int N = (ho.nb - 1) * 2;
+      std::vector<double> ct(N);
+      for (int m = 0; m < N; m++) ct[m] = cos(2.0 * M_PI * (double)m / (double)N);
+      CUP(cudaMalloc(&rt.dCosTab, ct.size() * sizeof(double)));
+      CUP(cudaMemcpy(rt.dCosTab, ct.data(), ct.size() * sizeof(double), cudaMemcpyHostToDevice));
+      hp.F = srt.tileF; hp.nb = ho.nb; hp.binHz = ho.binHz; hp.statStride = d.nStatic; hp.outCol = op.outCol;
+      hp.f0Col = ho.f0Col; hp.fmtCol = ho.fmtCol; hp.nFmt = ho.nFmt; hp.cosTab = rt.dCosTab;
+      hp.nHarm = ho.nHarm; hp.doHnr = ho.hnr; hp.nDiffs = (int)ho.diffs.size() / 4;
+      for (size_t i = 0; i < ho.diffs.size() && i < 16; i++) hp.diffs[i] = ho.diffs[i];
+      hp.doFa = ho.fa; hp.faStart = ho.faStart; hp.faEnd = ho.faEnd; hp.floorUnvoiced = ho.floorUnvoiced;
+      if (harmonics_smem_bytes(hp) > 200 * 1024) { pl->ops.push_back(rt); osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cHarmonics: spectrum too long for the kernel"); }
     } else if (op.kind == SOP_PITCH) {
       const PitchChainOp &pc = op.chain;
       // one blob: fwdA | fwdP6 | r1 | r2 | bwdD (double[nMag]) | ia | ic | id | audW (double[nPts]) | ik (int[nPts]) | shift (int) | hscale (float)
@@ -837,7 +863,7 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
     for (PassRt &pr : s.extra) { if (pr.dConst) cudaFree(pr.dConst); pr.dBand.release(); }
     s.hChunks.release(); s.dChunks.release(); s.hTiles.release(); s.dTiles.release(); s.dMag.release();
   }
-  for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); if (o.dPitchTab) cudaFree(o.dPitchTab); if (o.dFmtD) cudaFree(o.dFmtD); o.dShs.release(); o.dLag.release(); }
+  for (OpRt &o : pl->ops) { if (o.dSharpW) cudaFree(o.dSharpW); if (o.dTw) cudaFree(o.dTw); o.dRaw.release(); if (o.dPitchTab) cudaFree(o.dPitchTab); if (o.dFmtD) cudaFree(o.dFmtD); if (o.dCosTab) cudaFree(o.dCosTab); o.dShs.release(); o.dLag.release(); }
   if (pl->dErr) cudaFree(pl->dErr);
   if (pl->auxStream) cudaStreamDestroy(pl->auxStream);
   if (pl->evFork) cudaEventDestroy(pl->evFork);
@@ -1050,6 +1076,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       CU(cudaStreamWaitEvent(pl->auxStream, pl->evFork, 0));
       forked = true;
     }
+    if (o.kind == SOP_HARMONICS) continue;              // reads the pitch and formant columns: launched after the join below
     cudaStream_t ks = (forked && (o.kind == SOP_PITCH || o.kind == SOP_JITTER)) ? pl->auxStream : st;
     if (o.kind == SOP_VECOP) {
       const long long *hS = pl->hMeta.p + 2 * nm;
@@ -1111,6 +1138,18 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
   if (forked) {
     CU(cudaEventRecord(pl->evJoin, pl->auxStream));
     CU(cudaStreamWaitEvent(st, pl->evJoin, 0));
+  }
+  for (OpRt &o : pl->ops) {
+    if (o.kind != SOP_HARMONICS) continue;
+    StreamRt &rt = pl->st[o.stream];
+    const int t0 = rt.uttTile0[u0], t1 = rt.uttTile0[u1];
+    if (t1 <= t0) continue;
+    HarmonicsParams hp = o.hrm;
+    hp.mag = rt.dMag.p + (size_t)t0 * hp.nb * hp.F;
+    hp.tiles = rt.dTiles.p + t0; hp.nTiles = t1 - t0;
+    hp.statOff = dS; hp.stat = pl->dStat.p;
+    CU(launch_harmonics(hp, st));
+    pl->lastLaunches++;
   }
   // 3. temporal stages + assembly of the output rows
   if (pl->pp.nGroups > 0 && !pl->fused) {

@@ -35,7 +35,7 @@ const char *type_name(int t)
     "cTransformFFT", "cFFTmagphase", "cMelspec", "cMfcc", "cPlp", "cSpectral", "cEnergy",
     "cMZcr", "cAcf", "cPitchACF", "cDeltaRegression", "cContourSmoother", "cVectorConcat",
     "cVectorOperation", "cFullinputMean", "cIntensity", "cSpecScale", "cPitchShs", "cPitchSmootherViterbi",
-    "cValbasedSelector", "cPitchJitter", "cSpecResample", "cLpc", "cFormantLpc", "cDataSelector"};
+    "cValbasedSelector", "cPitchJitter", "cSpecResample", "cLpc", "cFormantLpc", "cDataSelector", "cHarmonics"};
   return (t >= 0 && t < OSM_B200_C_COUNT_) ? names[t] : "?";
 }
 
@@ -515,6 +515,111 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         if (op.formant.saveNValid) { FieldName f; f.name = "nFormants"; op.fields.push_back(f); }
         if (op.formant.saveFormants) { FieldName f; f.name = "formantFreqLpc"; f.n = op.formant.nFormants; f.arrNameOffset = 1; op.fields.push_back(f); }
         if (op.formant.saveBandwidths) { FieldName f; f.name = "formantBandwidthLpc"; f.n = op.formant.nFormants; f.arrNameOffset = 1; op.fields.push_back(f); }
+      } else if (c->type == OSM_B200_C_HARMONICS) {
+        // cHarmonics reads [pitch level ; formant level ; magnitude level] through one multi-level reader
+        // (GeMAPSv01b_core.lld.conf.inc:289-318) and looks its inputs up by name (lld/harmonics.cpp:258-300)
+        const auto &q = c->u.harmonics;
+        const osm_b200_component *pit = nullptr, *fmt = nullptr, *mg = nullptr;
+        for (int i = 0; i < c->n_inputs; i++) {
+          const osm_b200_component *x = R.prod(c->reader_dmLevel[i]);
+          if (!x) { err = std::string("level '") + c->reader_dmLevel[i] + "' has no writer"; return OSM_B200_ERR_INVALID; }
+          if (x->type == OSM_B200_C_VALBASEDSELECTOR || x->type == OSM_B200_C_PITCHSMOOTHERVITERBI) pit = x;
+          else if (x->type == OSM_B200_C_FORMANTLPC) fmt = x;
+          else if (x->type == OSM_B200_C_FFTMAGPHASE) mg = x;
+          else { err = "cHarmonics: inputs must be a Viterbi-smoothed pitch level, a cFormantLpc level and a cFFTmagphase level"; return OSM_B200_ERR_UNSUPPORTED; }
+        }
+        if (!pit || !mg || c->n_inputs > 3) { err = "cHarmonics needs a pitch level and a magnitude level (and optionally a formant level)"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (q.nHarmonicMagnitudes > 0 || q.outputLinearMagnitudes || q.harmonicDifferencesRatioLinear || q.formantAmplitudesLinear || q.computeAcfHnrLinear) {
+          err = "cHarmonics: harmonic magnitudes / linear outputs are not supported (log differences, log formant amplitudes, HNR in dB only)"; return OSM_B200_ERR_UNSUPPORTED;
+        }
+        if (!resolve_mag_chain(mg, ci)) return OSM_B200_ERR_UNSUPPORTED;
+        HarmonicsOp &ho = op.harmonics;
+        osm_b200_status s3 = get_op(pit, ho.pitchOp);
+        if (s3 != OSM_B200_OK) return s3;
+        if (fmt) { s3 = get_op(fmt, ho.formantOp); if (s3 != OSM_B200_OK) return s3; }
+        osm_b200_status s2 = get_stream(ci, true, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        const FrontEnd &fe = d.streams[op.stream].fe;
+        {
+          const FrontEnd &fp = d.streams[d.ops[ho.pitchOp].stream].fe;
+          if (fp.frameSize != fe.frameSize || fp.frameStep != fe.frameStep) { err = "cHarmonics: the pitch level and the magnitude level must share the frame geometry"; return OSM_B200_ERR_UNSUPPORTED; }
+          if (fmt) {
+            const FrontEnd &ff = d.streams[d.ops[ho.formantOp].stream].fe;
+            if (ff.frameStep != fe.frameStep || ff.frameSize > fe.frameSize) { err = "cHarmonics: the formant level must have the same frame step and frames no longer than the magnitude level's"; return OSM_B200_ERR_UNSUPPORTED; }
+          }
+        }
+        // the magnitude field (name of the cFFTmagphase level, dspcore/fftmagphase.cpp:154)
+        {
+          const std::string magName = name_append_auto(*mg, wave_name(), "fftMag");
+          const bool ok = q.magSpecFieldNameIsFull ? magName == q.magSpecFieldName : magName.find(q.magSpecFieldName) != std::string::npos;
+          if (!ok) { err = "cHarmonics: magSpecFieldName '" + std::string(q.magSpecFieldName) + "' does not match the magnitude level's field '" + magName + "'"; return OSM_B200_ERR_INVALID; }
+        }
+        auto find_field = [&](int opI, const char *name, bool full, int &colOut, int &nOutF) -> bool {
+          int col = d.ops[opI].outCol;
+          for (const FieldName &f : d.ops[opI].fields) {
+            if (full ? f.name == name : f.name.find(name) != std::string::npos) { colOut = col; nOutF = f.n; return true; }
+            col += f.n;
+          }
+          return false;
+        };
+        int nF0 = 0;
+        if (!find_field(ho.pitchOp, q.f0ElementName, q.f0ElementNameIsFull != 0, ho.f0Col, nF0) || nF0 != 1) {
+          err = "cHarmonics: f0ElementName '" + std::string(q.f0ElementName) + "' not found in the pitch level"; return OSM_B200_ERR_INVALID;
+        }
+        bool fa = q.formantAmplitudes != 0 && q.formantAmplitudesLogRel != 0;
+        bool haveFormantDiff = false;
+        if (fmt && q.formantFrequencyFieldName[0]) {
+          if (!find_field(ho.formantOp, q.formantFrequencyFieldName, q.formantFrequencyFieldNameIsFull != 0, ho.fmtCol, ho.nFmt)) {
+            err = "cHarmonics: formantFrequencyFieldName '" + std::string(q.formantFrequencyFieldName) + "' not found in the formant level"; return OSM_B200_ERR_INVALID;
+          }
+          int bc = 0, bn = 0;
+          if (!q.formantBandwidthFieldName[0] || !find_field(ho.formantOp, q.formantBandwidthFieldName, q.formantBandwidthFieldNameIsFull != 0, bc, bn) || bn != ho.nFmt) {
+            err = "cHarmonics: formantBandwidthFieldName must name the bandwidth field of the formant level (lld/harmonics.cpp:270-296)"; return OSM_B200_ERR_UNSUPPORTED;
+          }
+          if (ho.nFmt > 8) { err = "cHarmonics: more than 8 formants"; return OSM_B200_ERR_UNSUPPORTED; }
+        } else fa = false;
+        // harmonicDifferences: "H<i>-H<j>", "H<i>-A<k>", ... (:84-160); A0 = the fundamental
+        int maxHarm = 0;
+        for (int i = 0; i < q.nHarmonicDifferences && q.harmonicDifferencesLog; i++) {
+          const char *t = q.harmonicDifferences[i];
+          const char *dash = strchr(t, '-');
+          if (!dash || dash == t) { err = std::string("cHarmonics: cannot parse harmonic difference '") + t + "'"; return OSM_B200_ERR_INVALID; }
+          int part[2][2];                                            // {formant, idx}
+          const char *ps[2] = {t, dash + 1};
+          for (int k = 0; k < 2; k++) {
+            char *ep = nullptr;
+            const long r = strtol(ps[k] + 1, &ep, 10);
+            if (ep == ps[k] + 1 || (ps[k][0] != 'H' && ps[k][0] != 'A')) { err = std::string("cHarmonics: cannot parse harmonic difference '") + t + "'"; return OSM_B200_ERR_INVALID; }
+            if (ps[k][0] == 'H') { part[k][0] = -1; part[k][1] = (int)r; if (r > maxHarm) maxHarm = (int)r; }
+            else if (r == 0) { part[k][0] = -1; part[k][1] = 0; }
+            else { part[k][0] = (int)r; part[k][1] = -1; haveFormantDiff = true; }
+          }
+          ho.diffs.insert(ho.diffs.end(), {part[0][0], part[0][1], part[1][0], part[1][1]});
+        }
+        if (haveFormantDiff && ho.nFmt == 0) ho.diffs.clear();       // :296-300: disabled without a formant level
+        ho.nHarm = q.nHarmonics;
+        if (ho.nHarm < q.nHarmonicMagnitudes + q.firstHarmonicMagnitude + 1) ho.nHarm = q.nHarmonicMagnitudes + q.firstHarmonicMagnitude + 1;   // :212-217
+        if (ho.nHarm < maxHarm + 1) ho.nHarm = maxHarm + 1;
+        if (ho.nHarm < 2 || ho.nHarm > 128) { err = "cHarmonics.nHarmonics must be in 2..128"; return OSM_B200_ERR_UNSUPPORTED; }
+        ho.hnr = q.computeAcfHnrLogdB != 0;
+        ho.fa = fa;
+        if (fa) {                                                    // :341-352
+          ho.faStart = q.formantAmplitudesStart < 0 ? 0 : q.formantAmplitudesStart;
+          ho.faEnd = q.formantAmplitudesEnd == -1 ? ho.nFmt : std::min(q.formantAmplitudesEnd, ho.nFmt);
+          if (ho.faEnd < ho.faStart) ho.fa = false;
+          else if (ho.faStart < 1) { err = "cHarmonics.formantAmplitudesStart=0 is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        }
+        ho.floorUnvoiced = (float)q.logRelValueFloorUnvoiced;
+        ho.nb = fe.nBins;
+        ho.binHz = 1.0 / fe.fftFrameSizeSec;                         // dspcore/transformFft.cpp:111-115
+        op.kind = SOP_HARMONICS;
+        if (ho.hnr) { FieldName f; f.name = "HarmonicsToNoiseRatioACFLogdB"; op.fields.push_back(f); }   // :236-240
+        for (size_t i = 0; i < ho.diffs.size() / 4; i++) { FieldName f; f.name = std::string("HarmonicDifferenceLogRel") + q.harmonicDifferences[i]; op.fields.push_back(f); }
+        if (ho.fa) { FieldName f; f.name = "FormantAmplitudeByMaxHarmonicLogRelF0"; f.n = ho.faEnd - ho.faStart + 1; f.arrNameOffset = ho.faStart; op.fields.push_back(f); }
+        ho.nOut = 0;
+        for (const FieldName &f : op.fields) ho.nOut += f.n;
+        op.nOut = ho.nOut;
+        if (op.nOut < 1) { err = "cHarmonics produces no output"; return OSM_B200_ERR_INVALID; }
       } else if (c->type == OSM_B200_C_VALBASEDSELECTOR || c->type == OSM_B200_C_PITCHSMOOTHERVITERBI) {
         // [cValbasedSelector <-] cPitchSmootherViterbi <- cPitchShs <- cSpecScale <- cFFTmagphase chain
         const osm_b200_component *vit = c, *selSrc = nullptr;
@@ -698,6 +803,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
           g.srcCol = col; g.n = 0; g.stream = d.ops[opIdx].stream; g.outCol = d.nOut; g.stages = stages;
           if (d.ops[opIdx].kind == SOP_PITCH) { g.lagKind = 1; g.lagOp = opIdx; }
           if (d.ops[opIdx].kind == SOP_JITTER) { g.lagKind = 2; g.lagOp = d.ops[opIdx].jitter.pitchOp; }
+          if (d.ops[opIdx].kind == SOP_HARMONICS) { g.lagKind = 1; g.lagOp = d.ops[opIdx].harmonics.pitchOp; }
           g.segId = segId;
           d.groups.push_back(g);
           open = true;
@@ -787,7 +893,8 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       // level does not advance (lld/pitchJitter.cpp:593), so EVERY element of the selector's output lags like the jitter
       // columns do (oracle/formant_oracle.py:gemaps_lld, pinned on the shipped GeMAPS configurations)
       bool scopeLags = false;
-      for (const El &e : els) scopeLags = scopeLags || d.groups[e.g].lagKind == 2;
+      int scopeLagOp = -1;
+      for (const El &e : els) if (d.groups[e.g].lagKind == 2) { scopeLags = true; scopeLagOp = d.groups[e.g].lagOp; }
       long prevG = -1;
       for (int k = 0; k < q.nSelected; k++) {
         for (int k2 = 0; k2 < k; k2++)
@@ -800,8 +907,22 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         }
         OutGroup x = d.groups[hit->g];
         x.srcCol += hit->off; x.n = 1; x.outCol = outCol++;
-        if (scopeLags && x.lagKind == 1) x.lagKind = 2;
-        if (scopeLags && x.lagKind == 0) { err = "cDataSelector reading a cPitchJitter level together with levels outside the pitch chain is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        if (scopeLags) {
+          // every input level of a lagging selector must deliver at least the rows of the pitch level (same step, frames
+          // not longer): the selector's output then has the pitch level's length and the limits of the truncating reader
+          // are redundant.  A per-frame level routed through it (e.g. the formants of the 20 ms frames) lags like the rest.
+          const FrontEnd &fp = d.streams[d.ops[scopeLagOp].stream].fe;
+          std::vector<int> chk = x.limitStreams;
+          chk.push_back(x.stream);
+          for (int sidx : chk) {
+            const FrontEnd &fx = d.streams[sidx].fe;
+            if (fx.frameStep != fp.frameStep || fx.frameSize > fp.frameSize) {
+              err = "cDataSelector reading a cPitchJitter level together with a level of another frame step / longer frames is not supported"; return OSM_B200_ERR_UNSUPPORTED;
+            }
+          }
+          x.limitStreams.clear();
+          x.lagKind = 2; x.lagOp = scopeLagOp; x.stream = d.ops[scopeLagOp].stream;
+        }
         if (prevG == (long)hit->g && !ng.empty() && ng.back().srcCol + ng.back().n == x.srcCol) ng.back().n++;
         else ng.push_back(x);
         prevG = (long)hit->g;
@@ -840,7 +961,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     for (size_t o = 0; o < d.ops.size(); o++) {
       if (d.ops[o].stream != (int)s) continue;
       if (d.ops[o].kind == SOP_MFCC || d.ops[o].kind == SOP_PLP) d.streams[s].bandOps.push_back((int)o);
-      if (d.ops[o].kind == SOP_SPECTRAL || d.ops[o].kind == SOP_PITCHACF || d.ops[o].kind == SOP_MAG || d.ops[o].kind == SOP_PITCH) nSpec++;
+      if (d.ops[o].kind == SOP_SPECTRAL || d.ops[o].kind == SOP_PITCHACF || d.ops[o].kind == SOP_MAG || d.ops[o].kind == SOP_PITCH || d.ops[o].kind == SOP_HARMONICS) nSpec++;
     }
     const int nBand = (int)d.streams[s].bandOps.size();
     d.streams[s].fusedOp = nBand ? d.streams[s].bandOps[0] : -1;

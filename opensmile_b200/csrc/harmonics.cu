@@ -1,0 +1,118 @@
+// harmonics.cu -- cHarmonics (lld/harmonics.cpp:743-900) for the switch set of the GeMAPS graphs (sm_100a):
+// reads, per frame t, the F0 of the Viterbi-smoothed pitch level, the formant frequencies of the cFormantLpc level
+// (static rows of this plan) and the 60 ms magnitude spectrum (tile-major level in HBM), writes
+//   [HarmonicsToNoiseRatioACFLogdB] | HarmonicDifferenceLogRel* | FormantAmplitudeByMaxHarmonicLogRelF0[start..end].
+// One warp per frame (CTA = one tile of the magnitude level, 8 frames at a time):
+//   - the frame's magnitudes are transposed into shared memory once;
+//   - HNR: the reference takes an inverse FFT of the whole power spectrum and then looks at a handful of lags around
+//     fs / F0 (getClosestPeak).  Only those lags are evaluated here, each as a cosine sum over the bins with the lanes
+//     of the warp striding the bins (double accumulation, table of cos(2 pi m / N)); every lane holds the reduced
+//     value, so the peak search runs uniformly on all lanes;
+//   - the harmonic peak search is inherently sequential (each harmonic starts where the previous one ended): lane 0,
+//     on the shared-memory copy, statements of harmonics_math.cuh.
+// Compiled with -fmad=false.  Status: built, first device run pending.
+#include "kernels.cuh"
+#include "harmonics_math.cuh"
+
+namespace osm {
+
+namespace {
+
+constexpr int kHmWarps = 8;
+constexpr int kHmThreads = kHmWarps * 32;
+
+struct MagS { const float *m; __device__ __forceinline__ float operator()(int b) const { return m[b]; } };
+
+// warp-collective autocorrelation lag j of the power spectrum (computeAcf, lld/harmonics.cpp:590-630, as a cosine sum):
+// |p0/2 + p(N/2)/2 (-1)^j + sum_{k=1}^{N/2-1} p_k cos(2 pi j k / N)| / nb, p_k = mag_k^2 (float product)
+struct AcfWarp {
+  const float *m; int nb, N; const double *cosTab; int lane;
+  __device__ __forceinline__ float operator()(int j) const
+  {
+    double s = 0.0;
+    for (int k = 1 + lane; k < N / 2; k += 32) s += (double)(m[k] * m[k]) * cosTab[(j * k) & (N - 1)];
+    if (lane == 0) s += 0.5 * (double)(m[0] * m[0]) + 0.5 * (double)(m[N / 2] * m[N / 2]) * ((j & 1) ? -1.0 : 1.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return (float)fabs(s) / (float)nb;
+  }
+};
+
+__global__ void __launch_bounds__(kHmThreads) harmonics_kernel(const HarmonicsParams p)
+{
+  extern __shared__ __align__(16) unsigned char hmSmem[];
+  const int nb = p.nb, N = (nb - 1) * 2;
+  const int nbP = nb + 1;                                      // odd pitch: the transposing stores spread over the banks
+  float *magS = reinterpret_cast<float *>(hmSmem);             // [kHmWarps][nbP]
+  hm::Harm *HS = reinterpret_cast<hm::Harm *>(magS + (size_t)kHmWarps * nbP);   // [kHmWarps][nHarm]
+  const OpTile tl = p.tiles[blockIdx.x];
+  const float *tile = p.mag + (size_t)blockIdx.x * nb * p.F;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  for (int fb = 0; fb < tl.nf; fb += kHmWarps) {
+    const int nf = min(kHmWarps, tl.nf - fb);
+    for (int idx = tid; idx < nb * kHmWarps; idx += kHmThreads) {
+      const int b = idx / kHmWarps, f = idx % kHmWarps;
+      if (f < nf) magS[f * nbP + b] = tile[(size_t)b * p.F + fb + f];
+    }
+    __syncthreads();
+    if (warp < nf) {
+      const float *m = magS + warp * nbP;
+      const long long row = p.statOff[tl.utt] + tl.f0 + fb + warp;
+      float *srow = p.stat + row * (long long)p.statStride;
+      const float F0 = srow[p.f0Col];
+      float *dst = srow + p.outCol;
+      int o = 0;
+      if (p.doHnr) {
+        AcfWarp A{m, nb, N, p.cosTab, lane};
+        const double fs = (double)(nb - 1) * p.binHz * 2.0;
+        const int f0bin = F0 > 0.0f ? (int)floor(fs / (double)F0) : 0;       // freqToAcfBinLin (:393-401)
+        int ref = 0;
+        if (f0bin > 0) ref = hm::closest_peak(A, nb, f0bin);
+        float v = 0.0f;
+        if (ref > 0) { const float a0 = A(0), ar = A(ref); v = hm::hnr_db(a0, ar); }
+        if (lane == 0) dst[o] = v;
+        o++;
+      }
+      if (lane == 0) {
+        if (F0 > 0.0f) {
+          hm::Harm *H = HS + (size_t)warp * p.nHarm;
+          MagS M{m};
+          hm::find_harmonics(F0, M, nb, p.binHz, p.nHarm, H);
+          int fa[hm::kMaxFormants];
+          for (int k = 0; k < p.nFmt; k++) fa[k] = hm::formant_harmonic(H, p.nHarm, srow[p.fmtCol + k]);
+          for (int i = 0; i < p.nDiffs; i++)
+            dst[o++] = hm::harmonic_difference(H, p.nHarm, fa, p.nFmt, hm::Diff{p.diffs[4 * i], p.diffs[4 * i + 1], p.diffs[4 * i + 2], p.diffs[4 * i + 3]});
+          if (p.doFa) for (int k = p.faStart; k <= p.faEnd; k++) dst[o++] = (k >= 1 && k <= p.nFmt && fa[k - 1] >= 0) ? H[fa[k - 1]].lr : 0.0f;
+        } else {
+          for (int i = 0; i < p.nDiffs; i++) dst[o++] = 0.0f;
+          if (p.doFa) for (int k = p.faStart; k <= p.faEnd; k++) dst[o++] = p.floorUnvoiced;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+size_t harmonics_smem_bytes(const HarmonicsParams &p)
+{
+  return (size_t)kHmWarps * (p.nb + 1) * sizeof(float) + (size_t)kHmWarps * p.nHarm * sizeof(hm::Harm);
+}
+
+cudaError_t launch_harmonics(const HarmonicsParams &p, cudaStream_t st)
+{
+  if (p.nTiles <= 0) return cudaSuccess;
+  const size_t smem = harmonics_smem_bytes(p);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(harmonics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  harmonics_kernel<<<p.nTiles, kHmThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace osm

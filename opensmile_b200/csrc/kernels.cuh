@@ -223,6 +223,23 @@ struct FormantParams {
 cudaError_t launch_formant(const FormantParams &p, cudaStream_t st);
 size_t formant_smem_bytes(const FormantParams &p);
 
+// cHarmonics (harmonics.cu): one warp per frame on the magnitude level + F0 / formant columns of the static rows
+struct HarmonicsParams {
+  const float *mag;              // tile-major magnitude level [tile][nb][F]
+  const OpTile *tiles; int nTiles; int F;
+  int nb; double binHz;          // bins, bin spacing in Hz (frequency axis of the level, transformFft.cpp:111-115)
+  const long long *statOff;
+  float *stat; int statStride, outCol;
+  int f0Col, fmtCol, nFmt;       // columns of the static rows: F0, formant frequencies
+  const double *cosTab;          // [2 (nb - 1)] cos(2 pi m / N)
+  int nHarm, doHnr, nDiffs;
+  int diffs[16];                 // per difference: h1formant, h1idx, h2formant, h2idx
+  int doFa, faStart, faEnd;
+  float floorUnvoiced;
+};
+cudaError_t launch_harmonics(const HarmonicsParams &p, cudaStream_t st);
+size_t harmonics_smem_bytes(const HarmonicsParams &p);
+
 // ------------------------------------------------------------------------------------------
 // SHS pitch chain (pitch.cu): cSpecScale + cPitchShs per frame (one warp per frame), cPitchSmootherViterbi
 // [+ cValbasedSelector] per utterance (one thread), cPitchJitter per utterance (one warp), and the temporal
@@ -276,7 +293,7 @@ struct JitterParams {
 cudaError_t launch_jitter(const JitterParams &p, int u0, int u1, cudaStream_t st);
 
 struct SeqGroup { int srcCol, n, outCol, lagKind, nStages, deltaWin, noZero, segId; };
-constexpr int kMaxSeqGroups = 8;
+constexpr int kMaxSeqGroups = 16;
 struct SeqPostParams {
   const float *stat; int statStride;
   const long long *statOff, *rowOff, *uttOff;

@@ -43,7 +43,7 @@ struct FrontEnd {
   bool zeroPadSymmetric = false;   // phase only; magnitude consumers are unaffected
 };
 
-enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP, SOP_MAG, SOP_INTENSITY, SOP_PITCH, SOP_JITTER, SOP_FORMANT };
+enum StaticOpKind { SOP_MFCC = 0, SOP_PLP, SOP_MELSPEC, SOP_SPECTRAL, SOP_ENERGY, SOP_MZCR, SOP_PITCHACF, SOP_VECOP, SOP_MAG, SOP_INTENSITY, SOP_PITCH, SOP_JITTER, SOP_FORMANT, SOP_HARMONICS };
 
 struct MfccOp {
   int melIdx = 0;
@@ -169,6 +169,19 @@ struct FormantOp {
   int nOut = 0;
 };
 
+// cHarmonics (lld/harmonics.cpp) on [pitch level ; formant level ; magnitude level]
+struct HarmonicsOp {
+  int pitchOp = -1, f0Col = 0;        // F0 = column f0Col of the static rows (absolute)
+  int formantOp = -1, fmtCol = 0, nFmt = 0;   // formant frequencies = columns fmtCol .. fmtCol + nFmt - 1 (absolute)
+  int nb = 0; double binHz = 0;
+  int nHarm = 100;
+  bool hnr = false;
+  std::vector<int> diffs;             // 4 ints per difference: h1formant, h1idx, h2formant, h2idx
+  bool fa = false; int faStart = 1, faEnd = 0;
+  float floorUnvoiced = -201.f;
+  int nOut = 0;
+};
+
 // one field of a level: `n` elements named name (n == 1) or name[i + arrNameOffset]
 struct FieldName { std::string name; int n = 1; int arrNameOffset = 0; };
 
@@ -189,6 +202,7 @@ struct StaticOp {
   PitchChainOp chain;
   JitterOp jitter;
   FormantOp formant;
+  HarmonicsOp harmonics;
 };
 
 // temporal stage applied to a static column range (cWindowProcessor family)

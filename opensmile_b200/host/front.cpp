@@ -223,7 +223,8 @@ const TypeInfo kTypes[] = {
   {"cSpecScale", OSM_B200_C_SPECSCALE}, {"cPitchShs", OSM_B200_C_PITCHSHS},
   {"cPitchSmootherViterbi", OSM_B200_C_PITCHSMOOTHERVITERBI}, {"cValbasedSelector", OSM_B200_C_VALBASEDSELECTOR},
   {"cPitchJitter", OSM_B200_C_PITCHJITTER}, {"cSpecResample", OSM_B200_C_SPECRESAMPLE}, {"cLpc", OSM_B200_C_LPC},
-  {"cFormantLpc", OSM_B200_C_FORMANTLPC}, {"cDataSelector", OSM_B200_C_DATASELECTOR}};
+  {"cFormantLpc", OSM_B200_C_FORMANTLPC}, {"cDataSelector", OSM_B200_C_DATASELECTOR},
+  {"cHarmonics", OSM_B200_C_HARMONICS}};
 
 int type_of(const std::string &t)
 {
@@ -514,6 +515,40 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         SETI("elementMode", q.elementMode)
         if (f == "selFile" || f == "selectedRange" || f == "outputSingleField") { if (!v.empty()) { err = "cDataSelector." + f + " is not supported"; return false; } continue; }
         if (f == "dummyMode") { if (inum(v)) { err = "cDataSelector.dummyMode is not supported"; return false; } continue; }
+        break;
+      }
+      case OSM_B200_C_HARMONICS: {          // lld/harmonics.cpp:28-56
+        auto &q = c.u.harmonics;
+#define SETS(field, member) if (f == field) { if (v.size() >= sizeof(member)) { err = "cHarmonics." + f + ": name too long"; return false; } snprintf(member, sizeof(member), "%s", v.c_str()); continue; }
+        SETS("f0ElementName", q.f0ElementName) SETS("magSpecFieldName", q.magSpecFieldName)
+        SETS("formantFrequencyFieldName", q.formantFrequencyFieldName) SETS("formantBandwidthFieldName", q.formantBandwidthFieldName)
+#undef SETS
+        SETI("f0ElementNameIsFull", q.f0ElementNameIsFull) SETI("magSpecFieldNameIsFull", q.magSpecFieldNameIsFull)
+        SETI("formantFrequencyFieldNameIsFull", q.formantFrequencyFieldNameIsFull) SETI("formantBandwidthFieldNameIsFull", q.formantBandwidthFieldNameIsFull)
+        SETI("nHarmonics", q.nHarmonics) SETI("firstHarmonicMagnitude", q.firstHarmonicMagnitude) SETI("nHarmonicMagnitudes", q.nHarmonicMagnitudes)
+        SETI("outputLogRelMagnitudes", q.outputLogRelMagnitudes) SETI("outputLinearMagnitudes", q.outputLinearMagnitudes)
+        SETI("harmonicDifferencesLog", q.harmonicDifferencesLog) SETI("harmonicDifferencesRatioLinear", q.harmonicDifferencesRatioLinear)
+        SETI("formantAmplitudes", q.formantAmplitudes) SETI("formantAmplitudesLinear", q.formantAmplitudesLinear)
+        SETI("formantAmplitudesLogRel", q.formantAmplitudesLogRel) SETI("formantAmplitudesStart", q.formantAmplitudesStart)
+        SETI("formantAmplitudesEnd", q.formantAmplitudesEnd) SETI("computeAcfHnrLogdB", q.computeAcfHnrLogdB)
+        SETI("computeAcfHnrLinear", q.computeAcfHnrLinear) SETD("logRelValueFloorUnvoiced", q.logRelValueFloorUnvoiced)
+        if (f == "harmonicDifferences") {                   // array field: H1-H2;H1-A3
+          int k = 0;
+          size_t a = 0;
+          while (a <= v.size()) {
+            size_t b = v.find(';', a);
+            if (b == std::string::npos) b = v.size();
+            std::string item = v.substr(a, b - a);
+            while (!item.empty() && item.back() == ' ') item.pop_back();
+            while (!item.empty() && item.front() == ' ') item.erase(item.begin());
+            if (b == v.size() && item.empty()) break;
+            if (k >= 4 || item.size() >= 16) { err = "cHarmonics.harmonicDifferences: at most 4 entries of < 16 characters"; return false; }
+            snprintf(q.harmonicDifferences[k++], 16, "%s", item.c_str());
+            a = b + 1;
+          }
+          q.nHarmonicDifferences = k;
+          continue;
+        }
         break;
       }
       case OSM_B200_C_FORMANTLPC: {         // lld/formantLpc.cpp:40-52

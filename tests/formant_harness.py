@@ -85,3 +85,14 @@ def formant_chain(pcm, sample_rate=16000.0, target_fs=11000.0, p=11, n_formants=
     xw, nfft = windowed_frames(pcm, sample_rate)
     res, per = resample(xw, sample_rate, nfft, 0.020, target_fs, p, n_formants)
     return np.stack([formants(lpc(x, p), per, n_formants, min_f, max_f) for x in res]) if len(res) else np.zeros((0, 2 * n_formants), np.float32)
+
+
+def harmonics(F0, formants, mag, bin_hz, n_harm=100, diffs=((-1, 1, -1, 2), (-1, 1, 3, -1)), fa=(1, 3), floor_unvoiced=-201.0, hnr=True):
+    """one frame of cHarmonics -> [HNRdBACF] + differences + formant amplitudes (GeMAPS switch set by default)"""
+    mag = np.ascontiguousarray(mag, np.float32)
+    fm = np.ascontiguousarray(formants, np.float32)
+    d = np.ascontiguousarray(np.array(diffs, np.int32).reshape(-1))
+    out = np.zeros(1 + len(diffs) + fa[1] - fa[0] + 1, np.float32)
+    n = lib().fmh_harmonics(C.c_float(F0), _fp(fm), fm.size, _fp(mag), mag.size, C.c_double(bin_hz), n_harm, len(diffs),
+                            d.ctypes.data_as(C.POINTER(C.c_int)), fa[0], fa[1], C.c_float(floor_unvoiced), 1 if hnr else 0, _fp(out))
+    return out[:n]

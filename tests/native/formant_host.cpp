@@ -3,6 +3,8 @@
 // lanes are loops, so the CPU tests can hold the arithmetic against the reference's level taps without a GPU.
 //   g++ -O2 -ffp-contract=off -shared -fPIC -o formant_host.so formant_host.cpp
 #include "../../opensmile_b200/csrc/formant_math.cuh"
+#include "../../opensmile_b200/csrc/harmonics_math.cuh"
+#include <vector>
 
 using namespace osm::fm;
 
@@ -94,6 +96,59 @@ int fmh_resample(double sampleRate, int N, int nfft, double frameSizeSec, int ze
         res[(size_t)t * op.nRes + i] = acc;
       }
   return op.nRes;
+}
+
+}
+
+// ---- cHarmonics (harmonics_math.cuh): one frame.  The kernel evaluates the autocorrelation lags it needs with the lanes of
+// a warp over the bins; here the same cosine sum runs sequentially. ----
+namespace {
+struct AcfHost {
+  const float *mag; int nb, N; const double *cosTab;
+  float operator()(int j) const
+  {
+    auto p = [&](int k) { return (double)(mag[k] * mag[k]); };
+    double s = 0.5 * p(0) + 0.5 * p(N / 2) * ((j & 1) ? -1.0 : 1.0);
+    for (int k = 1; k < N / 2; k++) s += p(k) * cosTab[(j * k) & (N - 1)];
+    return (float)fabs(s) / (float)nb;
+  }
+};
+struct MagHost { const float *m; float operator()(int b) const { return m[b]; } };
+}
+
+extern "C" {
+
+// out = [HNRdB if doHnr] | nDiffs differences | formant amplitudes faStart..faEnd (log rel. F0); returns the count
+int fmh_harmonics(float F0, const float *formants, int nFmt, const float *mag, int nb, double binHz, int nHarm, int nDiffs,
+                  const int *diffs, int faStart, int faEnd, float floorUnvoiced, int doHnr, float *out)
+{
+  using namespace osm::hm;
+  int o = 0;
+  const int N = (nb - 1) * 2;
+  if (doHnr) {
+    std::vector<double> cosTab(N);
+    for (int m = 0; m < N; m++) cosTab[m] = cos(2.0 * M_PI * (double)m / (double)N);
+    AcfHost A{mag, nb, N, cosTab.data()};
+    const double fs = (double)(nb - 1) * binHz * 2.0;
+    const int f0bin = F0 > 0.0f ? (int)floor(fs / (double)F0) : 0;                 // freqToAcfBinLin (:393-401)
+    int ref = 0;
+    if (f0bin > 0) ref = closest_peak(A, nb, f0bin);
+    out[o++] = ref <= 0 ? 0.0f : hnr_db(A(0), A(ref));
+  }
+  if (F0 > 0.0f) {
+    std::vector<Harm> H(nHarm);
+    MagHost M{mag};
+    find_harmonics(F0, M, nb, binHz, nHarm, H.data());
+    int fa[kMaxFormants];
+    for (int k = 0; k < nFmt; k++) fa[k] = formant_harmonic(H.data(), nHarm, formants[k]);
+    for (int i = 0; i < nDiffs; i++)
+      out[o++] = harmonic_difference(H.data(), nHarm, fa, nFmt, Diff{diffs[4 * i], diffs[4 * i + 1], diffs[4 * i + 2], diffs[4 * i + 3]});
+    for (int k = faStart; k <= faEnd; k++) out[o++] = (k >= 1 && k <= nFmt && fa[k - 1] >= 0) ? H[fa[k - 1]].lr : 0.0f;
+  } else {
+    for (int i = 0; i < nDiffs; i++) out[o++] = 0.0f;
+    for (int k = faStart; k <= faEnd; k++) out[o++] = floorUnvoiced;
+  }
+  return o;
 }
 
 }

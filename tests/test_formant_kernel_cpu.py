@@ -91,3 +91,50 @@ def test_graph_names_and_refusals(tmp_path):
         p.write_text(text.replace(old, new))
         with pytest.raises(SessionError, match=needle):
             Session(str(p), output_level="formants", device=-1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# cHarmonics (opensmile_b200/csrc/harmonics_math.cuh, kernel harmonics.cu) and the shipped GeMAPS graphs
+
+def test_harmonics_on_the_reference_input_levels():
+    """host build of the kernel's statements on the reference's own F0 / formant / magnitude levels
+    (tests/configs/harmonics_taps.conf): every decision (harmonic peaks, formant-range maxima, ACF peak) reproduced,
+    values within 1e-5 dB (log10f / log10 of another libm)"""
+    f0, fmt, mag, harm = G["h_f0"], G["h_fmt"], G["h_mag"], G["h_harm"]
+    T = min(len(f0), len(fmt), len(mag), len(harm))
+    nfft = (mag.shape[1] - 1) * 2
+    bin_hz = 1.0 / (0.060 * nfft / 960)
+    out = np.stack([fh.harmonics(f0[t, 0], fmt[t, :5], mag[t], bin_hz) for t in range(T)])
+    assert (f0[:T, 0] > 0).sum() > 50
+    assert np.abs(out - harm[:T]).max() < 1e-5
+
+
+def test_harmonics_unvoiced_and_edge_frames():
+    mag = np.abs(np.random.default_rng(0).standard_normal(513)).astype(np.float32)
+    out = fh.harmonics(0.0, [500.0, 1500.0, 2500.0], mag, 16000.0 / 1024)
+    assert list(out) == [0.0, 0.0, 0.0, -201.0, -201.0, -201.0]                  # F0 = 0: HNR 0, differences 0, amplitudes at the floor
+    out = fh.harmonics(7900.0, [500.0, 1500.0, 2500.0], mag, 16000.0 / 1024)    # first harmonic next to Nyquist
+    assert np.isfinite(out).all()
+    out = fh.harmonics(120.0, [500.0, 1500.0, 2500.0], np.zeros(513, np.float32), 16000.0 / 1024)   # silence
+    assert np.isfinite(out).all()
+
+
+@pytest.mark.parametrize("conf,opts,key,n", [("gemaps/v01b/GeMAPSv01b.conf", {"lldhtkoutput": "x.htk"}, "gemaps_lld", 18),
+                                             ("egemaps/v02/eGeMAPSv02.conf", {"lldcsvoutput": "x.csv"}, "egemaps_lld", 25)])
+def test_shipped_gemaps_configurations_open(conf, opts, key, n):
+    """the shipped GeMAPSv01b.conf / eGeMAPSv02.conf (BASELINE configs[2]) compile unchanged: cDataSelector scopes, cHarmonics
+    field lookup by name, the lagging selector over pitch / jitter / harmonics / formant levels; element names and frame
+    counts against the reference's LLD files"""
+    ref = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "config")
+    if not os.path.isdir(ref):
+        pytest.skip("reference configuration files not built (make -C oracle ref)")
+    from oracle import formant_oracle as fo
+    s = Session(os.path.join(ref, conf), options=opts, device=-1)
+    names = s.element_names()
+    assert len(names) == n
+    if key == "egemaps_lld":
+        assert names == list(G["names_egemaps_lld"]) == fo.EGEMAPS_LLD_NAMES
+    else:
+        assert names[:5] == fo.EGEMAPS_LLD_NAMES[:5] and names[5] == "F0semitoneFrom27.5Hz_sma3nz" and names[-1] == "F3amplitudeLogRelF0_sma3nz"
+    fo_ = s.frame_offsets(np.array([0, 24000, 64000], np.int64), 16000.0, 1)
+    assert list(np.diff(fo_)) == [G[key + "_m24k"].shape[0], G[key + "_m40k"].shape[0]]
