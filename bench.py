@@ -52,17 +52,25 @@ def select_workload(name):
     global N_UTT, UTT_LEN, FRAMES_PER_UTT, BYTES_PER_FRAME, WORKLOAD, WORKLOAD_KEY, REF_CONF, REF_OUT_OPT, N_COLS
     if name == "mfcc12":
         return
-    assert name == "compare16"
+    assert name in ("compare16", "egemaps")
     WORKLOAD_KEY = name
     N_UTT = int(os.environ.get("OSM_BENCH_N_UTT", "10000"))
     UTT_LEN = 48000
     FRAMES_PER_UTT = 296                 # min(295 + 1, 299 + 1) rows of the lld level (SURVEY.md 8a')
-    N_COLS = 130
-    BYTES_PER_FRAME = 160 * 2 + N_COLS * 4
-    REF_CONF = "compare16/ComParE_2016.conf"
     REF_OUT_OPT = "-lldhtkoutput"
-    WORKLOAD = ("ComParE_2016 full LLD set (config/compare16/ComParE_2016.conf unchanged, 130 columns), synthetic 16 kHz mono "
-                "int16, %d utterances x 3.0 s = %d rows per GPU" % (N_UTT, N_UTT * FRAMES_PER_UTT))
+    if name == "egemaps":
+        # BASELINE configs[2]: the shipped config/egemaps/v02/eGeMAPSv02.conf, 25 LLD columns incl. the formant / harmonics
+        # chain.  Its kernels have not run on a device yet: use this workload only to measure them.
+        N_COLS = 25
+        REF_CONF = "egemaps/v02/eGeMAPSv02.conf"
+        WORKLOAD = ("eGeMAPSv02 LLD set (config/egemaps/v02/eGeMAPSv02.conf unchanged, 25 columns), synthetic 16 kHz mono "
+                    "int16, %d utterances x 3.0 s = %d rows per GPU" % (N_UTT, N_UTT * FRAMES_PER_UTT))
+    else:
+        N_COLS = 130
+        REF_CONF = "compare16/ComParE_2016.conf"
+        WORKLOAD = ("ComParE_2016 full LLD set (config/compare16/ComParE_2016.conf unchanged, 130 columns), synthetic 16 kHz mono "
+                    "int16, %d utterances x 3.0 s = %d rows per GPU" % (N_UTT, N_UTT * FRAMES_PER_UTT))
+    BYTES_PER_FRAME = 160 * 2 + N_COLS * 4
 
 
 # ------------------------------------------------------------------------------------------
@@ -213,7 +221,7 @@ def cpu_baseline(n_files=None):
         if refrun.available():
             if n_files is None:
                 n_files = max(64, min(2000, 48 * cores))   # ~13 ms of CPU work per file
-                if WORKLOAD_KEY == "compare16":
+                if WORKLOAD_KEY in ("compare16", "egemaps"):
                     n_files = max(16, 4 * cores)           # ~55 ms of CPU work per 3 s file
             frames, dt = reference_sample(n_files, cores, tmp)
             return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
@@ -242,7 +250,7 @@ def run_reference(args, rank, world):
     from oracle import refrun
     cores = os.cpu_count() or 1
     n_files = max(64, min(2000, 48 * cores))
-    if WORKLOAD_KEY == "compare16":
+    if WORKLOAD_KEY in ("compare16", "egemaps"):
         n_files = max(16, 4 * cores)
     tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
@@ -286,9 +294,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    if WORKLOAD_KEY == "compare16":
+    if WORKLOAD_KEY in ("compare16", "egemaps"):
         from opensmile_b200 import Session
-        conf = os.path.join(ROOT, "oracle", "_ref", "config", "compare16", "ComParE_2016.conf")
+        conf = os.path.join(ROOT, "oracle", "_ref", "config", *REF_CONF.split("/"))
         sess = Session(conf, options={"lldhtkoutput": "x.htk"}, device=-1)     # conf front end only; the plan below computes
         comps, level = sess.components(float(SAMPLE_RATE), 1)
         plan = Plan(list(comps), level, device=local_rank)
@@ -396,8 +404,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mfcc12", choices=["mfcc12", "compare16"],
-                    help="mfcc12 = BASELINE configs[1] (default, the quoted metric); compare16 = configs[3], full ComParE_2016 LLD set")
+    ap.add_argument("--workload", default="mfcc12", choices=["mfcc12", "compare16", "egemaps"],
+                    help="mfcc12 = BASELINE configs[1] (default, the quoted metric); compare16 = configs[3], full ComParE_2016 LLD set; "
+                         "egemaps = configs[2], eGeMAPSv02 LLD set (kernels pending their first device run)")
     args = ap.parse_args()
     select_workload(args.workload)
     if args.warmup < 3 and args.impl == "ours":
