@@ -1,6 +1,7 @@
-"""Formant chain of the GeMAPS graphs (SURVEY.md 8f-2, next scope row): the numpy restatement
-(oracle/formant_oracle.py) against level taps of the UNMODIFIED reference (tests/golden/formant_goldens.npz,
-scripts/make_golden_formant.py).  No product code yet -- this pins the checker the GPU path will be held to."""
+"""Formant / harmonics chain of the GeMAPS graphs: the numpy restatement (oracle/formant_oracle.py)
+against level taps and LLD files of the UNMODIFIED reference (tests/golden/formant_goldens.npz,
+scripts/make_golden_formant.py).  This pins the checker; the product's kernels (formant.cu, harmonics.cu) are held to the same
+taps through a host build of their statements in tests/test_formant_kernel_cpu.py."""
 import os
 
 import numpy as np
