@@ -33,14 +33,23 @@ OSM_HM_HD bool is_peak(const X &x, int N, int n)
   return n > 0 && x(n) > x(n - 1);
 }
 
-// freqToBin (:403-415) on the linear axis frq[b] = b * binHz
+// freqToBin (:403-415) on the linear axis frq[b] = b * binHz.  The reference walks b = start, start+1, .. until
+// frq[b] > freq and then picks the closer of b-1 and b (0 if it runs off the axis).  On a linear axis the first such b is
+// found in closed form; the two fix-up loops re-establish the reference's exact predicate (double product, strict >)
+// where the division rounds the other way.
 OSM_HM_HD int freq_to_bin(double binHz, int nb, float freq, int start)
 {
-  for (int b = start; b < nb; b++) {
-    const double fb = (double)b * binHz;
-    if (fb > (double)freq) return (fb - (double)freq > (double)freq - (double)(b - 1) * binHz) ? b - 1 : b;
-  }
-  return 0;
+  const double fr = (double)freq;
+  long b0 = (long)floor(fr / binHz);                       // last bin with frq[b0] <= freq, up to rounding
+  if (b0 < -1) b0 = -1;
+  if (b0 > (long)nb) b0 = (long)nb;
+  while (b0 >= 0 && (double)b0 * binHz > fr) b0--;
+  while (b0 + 1 <= (long)nb && (double)(b0 + 1) * binHz <= fr) b0++;
+  long b = b0 + 1;
+  if (b < (long)start) b = (long)start;
+  if (b >= (long)nb) return 0;
+  const double fb = (double)b * binHz;
+  return (fb - fr > fr - (double)(b - 1) * binHz) ? (int)b - 1 : (int)b;
 }
 
 // smileMath_quadFrom3pts (smileutil/smileUtil.c:1009-1034): vertex (x, y) of the parabola through three points
