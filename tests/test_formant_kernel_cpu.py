@@ -138,3 +138,21 @@ def test_shipped_gemaps_configurations_open(conf, opts, key, n):
         assert names[:5] == fo.EGEMAPS_LLD_NAMES[:5] and names[5] == "F0semitoneFrom27.5Hz_sma3nz" and names[-1] == "F3amplitudeLogRelF0_sma3nz"
     fo_ = s.frame_offsets(np.array([0, 24000, 64000], np.int64), 16000.0, 1)
     assert list(np.diff(fo_)) == [G[key + "_m24k"].shape[0], G[key + "_m40k"].shape[0]]
+
+
+@pytest.mark.parametrize("sr,target", [(44100.0, 11000.0), (8000.0, 11000.0), (8000.0, 16000.0), (16000.0, 32000.0), (22050.0, 22050.0)])
+def test_resampling_table_other_rates(sr, target):
+    """the composed table (zero padding + FFT + inverse DFT of the low bins in one matrix) against the literal restatement
+    FFT -> cSpecResample of the oracle at other sample rates, incl. up-sampling (the branch with the Nyquist term, I >= K)"""
+    import ctypes as C
+    from oracle import oracle, formant_oracle as fo
+    pcm = mixed_pcm(int(sr * 0.3), int(sr), seed=4)
+    fe = oracle.frontend(sr, 0.020, 0.010, win="ham", zero_pad_symmetric=1)
+    spec = fo.fft_frames(pcm, fe)
+    N, H, nfft, T = oracle.geometry(fe, len(pcm))
+    rs = fo.SpecResample(nfft, sr, target, oracle.lib().osm_or_fft_frame_size_sec(C.byref(fe)), 0.020)
+    ref = np.stack([rs(a) for a in spec])
+    xw, nfft2 = fh.windowed_frames(pcm, sr)
+    res, per = fh.resample(xw, sr, nfft2, 0.020, target)
+    assert nfft2 == nfft and res.shape == ref.shape and per == rs.base_period_out
+    assert np.abs(res - ref).max() / np.abs(ref).max() < 3e-6
