@@ -60,3 +60,74 @@ def test_refusals(tmp_path, edit, needle):
 def test_names_without_new_names(tmp_path):
     s = Session(_conf(tmp_path, ("newNames = shimmerLocaldB;F0semitoneFrom27.5Hz", "nameAppend = sel")), device=-1)
     assert s.element_names()[5:] == ["shimmerLocalDB_sel_sma3nz", "F0finalLog_sel_sma3nz", "jitterLocal_sel_sma3nz"]
+
+
+_BASE = """[componentInstances:cComponentManager]
+instance[dataMemory].type=cDataMemory
+instance[waveIn].type=cWaveSource
+instance[fr].type=cFramer
+instance[win].type=cWindower
+instance[fft].type=cTransformFFT
+instance[mag].type=cFFTmagphase
+instance[mel].type=cMelspec
+instance[mfcc].type=cMfcc
+instance[en].type=cEnergy
+instance[sel].type=cDataSelector
+instance[sink].type=cCsvSink
+[waveIn:cWaveSource]
+writer.dmLevel=wave
+filename=\\cm[inputfile(I){in.wav}:input]
+monoMixdown=1
+[fr:cFramer]
+reader.dmLevel=wave
+writer.dmLevel=frames
+frameSize=0.025
+frameStep=0.010
+frameCenterSpecial=left
+[win:cWindower]
+reader.dmLevel=frames
+writer.dmLevel=win
+winFunc=ham
+[fft:cTransformFFT]
+reader.dmLevel=win
+writer.dmLevel=fft
+[mag:cFFTmagphase]
+reader.dmLevel=fft
+writer.dmLevel=mag
+[mel:cMelspec]
+reader.dmLevel=mag
+writer.dmLevel=mel
+nBands=26
+[mfcc:cMfcc]
+reader.dmLevel=mel
+writer.dmLevel=mfcc
+firstMfcc=0
+lastMfcc=12
+[en:cEnergy]
+reader.dmLevel=frames
+writer.dmLevel=energy
+rms=1
+log=1
+[sel:cDataSelector]
+reader.dmLevel=mfcc;energy
+writer.dmLevel=out
+SELECTED
+[sink:cCsvSink]
+reader.dmLevel=out
+filename=\\cm[outputfile(O){out.csv}:output]
+"""
+
+
+def test_selector_on_array_elements_and_plain_fields(tmp_path):
+    """elements of an array field (mfcc[3]) and single-element fields (pcm_LOGenergy) through one selector at the top of the
+    graph: order of `selected`, contiguous elements merged into one group, nameAppend when no new name is given"""
+    p = tmp_path / "s.conf"
+    p.write_text(_BASE.replace("SELECTED", "selected = pcm_LOGenergy;pcm_fftMag_mfcc[3];pcm_fftMag_mfcc[4];pcm_fftMag_mfcc[1]\nnewNames = E;c3"))
+    s = Session(str(p), device=-1)
+    assert s.element_names() == ["E", "c3", "pcm_fftMag_mfcc[4]", "pcm_fftMag_mfcc[1]"]
+    assert int(s.frame_offsets(np.array([0, 16000], np.int64), 16000.0, 1)[-1]) == 98
+    p.write_text(_BASE.replace("SELECTED", "selected = pcm_fftMag_mfcc[12];pcm_RMSenergy\nnameAppend = x"))
+    assert Session(str(p), device=-1).element_names() == ["pcm_fftMag_mfcc[12]_x", "pcm_RMSenergy_x"]
+    p.write_text(_BASE.replace("SELECTED", "selected = pcm_fftMag_mfcc"))          # a field name is not an element name (elementMode = 1)
+    with pytest.raises(SessionError, match="not found"):
+        Session(str(p), device=-1)
