@@ -3,6 +3,7 @@
 // Citations relative to /root/reference/src.
 #include <algorithm>
 #include <cmath>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -639,6 +640,47 @@ bool write_htk(const char *path, const float *rows, int64_t n, int K, double per
   return true;
 }
 
+// ---- number formatting of the text sinks -------------------------------------------------------------------
+// The reference prints every value with fprintf("%e") (iocore/csvSink.cpp:216-233, arffSink.cpp:400-420).  At GPU
+// rates the sink is the bottleneck, so rows are formatted into a buffer with std::to_chars: for finite values the
+// scientific / fixed conversions with an explicit precision produce the correctly rounded decimal expansion of the
+// same real number printf sees (float -> double is exact), i.e. the same bytes (tests/test_host_cpu.py checks
+// millions of values against printf).  Non-finite values take the printf path.
+struct TextBuf {
+  FILE *f;
+  std::vector<char> b;
+  size_t n = 0;
+  explicit TextBuf(FILE *fp) : f(fp), b(1 << 20) {}
+  void room(size_t need) { if (n + need > b.size()) flush(); if (need > b.size()) b.resize(need * 2); }
+  void flush() { if (n) fwrite(b.data(), 1, n, f); n = 0; }
+  void ch(char c) { room(1); b[n++] = c; }
+  void str(const char *s, size_t len) { room(len); memcpy(b.data() + n, s, len); n += len; }
+  void str(const std::string &s) { str(s.data(), s.size()); }
+  void fmt_e(float v)                       // == fprintf("%e", v)
+  {
+    room(64);
+    if (std::isfinite(v)) {
+      auto r = std::to_chars(b.data() + n, b.data() + n + 48, v, std::chars_format::scientific, 6);
+      n = (size_t)(r.ptr - b.data());
+    } else n += (size_t)snprintf(b.data() + n, 48, "%e", (double)v);
+  }
+  void fmt_f0(float v)                      // == fprintf("%.0f", v)
+  {
+    room(64);
+    if (std::isfinite(v) && fabsf(v) < 1e15f) {
+      auto r = std::to_chars(b.data() + n, b.data() + n + 48, v, std::chars_format::fixed, 0);
+      n = (size_t)(r.ptr - b.data());
+    } else { char t[400]; const int l = snprintf(t, sizeof t, "%.0f", (double)v); str(t, (size_t)l); }
+  }
+  void fmt_f6(double v)                     // == fprintf("%f", v)
+  {
+    char t[400];
+    const int l = snprintf(t, sizeof t, "%f", v);
+    str(t, (size_t)l);
+  }
+  void fmt_ld(long v) { room(32); auto r = std::to_chars(b.data() + n, b.data() + n + 24, v); n = (size_t)(r.ptr - b.data()); }
+};
+
 // cCsvSink options with the component's defaults (iocore/csvSink.cpp:40-54,78-110)
 struct CsvOpts { bool printHeader = true, timestamp = true, number = true; int prname = 0; char delim = ';'; std::string instName; };
 
@@ -655,19 +697,23 @@ bool write_csv(const char *path, const float *rows, int64_t n, int K, const std:
     for (int k = 0; k < K - 1; k++) fprintf(f, "%s%c", names[k].c_str(), o.delim);
     fprintf(f, "%s\n", names[K - 1].c_str());
   }
+  TextBuf tb(f);
   for (int64_t r = 0; r < n; r++) {
-    if (o.prname == 1) fprintf(f, "'%s'%c", o.instName.c_str(), o.delim);
-    else if (o.prname == 2) fprintf(f, "'%s_%ld'%c", o.instName.c_str(), (long)r, o.delim);
-    if (o.number) fprintf(f, "%ld%c", (long)r, o.delim);
+    if (o.prname) {
+      tb.ch('\''); tb.str(o.instName);
+      if (o.prname == 2) { tb.ch('_'); tb.fmt_ld((long)r); }
+      tb.ch('\''); tb.ch(o.delim);
+    }
+    if (o.number) { tb.fmt_ld((long)r); tb.ch(o.delim); }
     // rows appended by a window processor at the end of input carry a copy of the last frame's time stamp
-    if (o.timestamp) fprintf(f, "%f%c", (double)((nTimeFrames > 0 && r > nTimeFrames - 1) ? nTimeFrames - 1 : r) * period, o.delim);
+    if (o.timestamp) { tb.fmt_f6((double)((nTimeFrames > 0 && r > nTimeFrames - 1) ? nTimeFrames - 1 : r) * period); tb.ch(o.delim); }
     for (int k = 0; k < K; k++) {
       const float v = rows[r * K + k];
-      const bool last = k == K - 1;
-      if (v == floorf(v)) fprintf(f, "%.0f", v); else fprintf(f, "%e", v);
-      if (last) fputc('\n', f); else fputc(o.delim, f);
+      if (v == floorf(v)) tb.fmt_f0(v); else tb.fmt_e(v);
+      tb.ch(k == K - 1 ? '\n' : o.delim);
     }
   }
+  tb.flush();
   fclose(f);
   return true;
 }
@@ -723,13 +769,15 @@ bool write_arff(const char *path, const float *rows, int64_t n, int K, const std
     }
     fprintf(f, "\n@data\n\n");
   }
+  TextBuf tb(f);
   for (int64_t r = 0; r < n; r++) {
     if (o.prname == 1) fprintf(f, "%s,", arff_escape(o.instName).c_str());
     else if (o.prname == 2) { char b[512]; snprintf(b, sizeof b, "%s_%ld", o.instName.c_str(), (long)r); fprintf(f, "%s,", arff_escape(b).c_str()); }
     if (o.number) fprintf(f, "%ld,", (long)r);
     if (o.timestamp) fprintf(f, "%f,", (double)((nTimeFrames > 0 && r > nTimeFrames - 1) ? nTimeFrames - 1 : r) * period + o.frameTimeAdd);
-    fprintf(f, "%e", rows[r * K]);
-    for (int k = 1; k < K; k++) fprintf(f, ",%e", rows[r * K + k]);
+    tb.fmt_e(rows[r * K]);
+    for (int k = 1; k < K; k++) { tb.ch(','); tb.fmt_e(rows[r * K + k]); }
+    tb.flush();                          // keeps the order with the fprintf calls around it (both end in the FILE buffer)
     if (!o.classes.empty()) {
       for (size_t c = 0; c < o.classes.size(); c++) {
         if (c < o.targetAll.size() && !o.targetAll[c].empty()) fprintf(f, ",%s", o.targetAll[c].c_str());

@@ -121,3 +121,11 @@ def test_div32767_trick():
         r = f32(x - Fraction(q0) * D)
         q1 = f32(Fraction(q0) + Fraction(r) * Fraction(rc))
         assert q1 == f32(x / D), k
+
+
+def test_text_sink_number_formatting_equals_printf():
+    """the text sinks format values with std::to_chars into a buffer (opensmile_b200/host/front.cpp TextBuf); for finite
+    floats that is byte-identical to the reference's fprintf("%e") / ("%.0f"): 40 M values incl. random bit patterns"""
+    exe = "/tmp/osm_test_fmt_check"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "native", "fmt_check.cpp")])
+    subprocess.check_call([exe], stdout=subprocess.DEVNULL)
