@@ -513,6 +513,16 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
           if (f == "selected") q.nSelected = k;
           continue;
         }
+        {                                                   // indexed form: selected[2] = name
+          const bool isSel = f.compare(0, 9, "selected[") == 0, isNew = f.compare(0, 9, "newNames[") == 0;
+          if (isSel || isNew) {
+            const int idx = atoi(f.c_str() + 9);
+            if (idx < 0 || idx >= OSM_B200_MAX_SELECTED || v.size() >= OSM_B200_NAME_LEN) { err = "cDataSelector: bad array index / name too long in '" + f + "'"; return false; }
+            snprintf(isSel ? q.selected[idx] : q.newNames[idx], OSM_B200_NAME_LEN, "%s", v.c_str());
+            if (isSel) q.nSelected = std::max(q.nSelected, idx + 1);
+            continue;
+          }
+        }
         SETI("elementMode", q.elementMode)
         if (f == "selFile" || f == "selectedRange" || f == "outputSingleField") { if (!v.empty()) { err = "cDataSelector." + f + " is not supported"; return false; } continue; }
         if (f == "dummyMode") { if (inum(v)) { err = "cDataSelector.dummyMode is not supported"; return false; } continue; }
@@ -533,6 +543,13 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         SETI("formantAmplitudesLogRel", q.formantAmplitudesLogRel) SETI("formantAmplitudesStart", q.formantAmplitudesStart)
         SETI("formantAmplitudesEnd", q.formantAmplitudesEnd) SETI("computeAcfHnrLogdB", q.computeAcfHnrLogdB)
         SETI("computeAcfHnrLinear", q.computeAcfHnrLinear) SETD("logRelValueFloorUnvoiced", q.logRelValueFloorUnvoiced)
+        if (f.compare(0, 20, "harmonicDifferences[") == 0) {   // indexed form
+          const int idx = atoi(f.c_str() + 20);
+          if (idx < 0 || idx >= 4 || v.size() >= 16) { err = "cHarmonics.harmonicDifferences: at most 4 entries of < 16 characters"; return false; }
+          snprintf(q.harmonicDifferences[idx], 16, "%s", v.c_str());
+          q.nHarmonicDifferences = std::max(q.nHarmonicDifferences, idx + 1);
+          continue;
+        }
         if (f == "harmonicDifferences") {                   // array field: H1-H2;H1-A3
           int k = 0;
           size_t a = 0;

@@ -128,6 +128,8 @@ def test_selector_on_array_elements_and_plain_fields(tmp_path):
     assert int(s.frame_offsets(np.array([0, 16000], np.int64), 16000.0, 1)[-1]) == 98
     p.write_text(_BASE.replace("SELECTED", "selected = pcm_fftMag_mfcc[12];pcm_RMSenergy\nnameAppend = x"))
     assert Session(str(p), device=-1).element_names() == ["pcm_fftMag_mfcc[12]_x", "pcm_RMSenergy_x"]
+    p.write_text(_BASE.replace("SELECTED", "selected[0] = pcm_RMSenergy\nselected[1] = pcm_fftMag_mfcc[0]\nnewNames[1] = c0"))   # indexed array syntax
+    assert Session(str(p), device=-1).element_names() == ["pcm_RMSenergy", "c0"]
     p.write_text(_BASE.replace("SELECTED", "selected = pcm_fftMag_mfcc"))          # a field name is not an element name (elementMode = 1)
     with pytest.raises(SessionError, match="not found"):
         Session(str(p), device=-1)
