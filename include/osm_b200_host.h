@@ -65,6 +65,16 @@ OSM_B200_API osm_b200_status osm_b200_session_extract_files_arff(osm_b200_sessio
                                                                  const char *const *arff_paths,
                                                                  int64_t *frames_out);
 
+/* The sink half of osm_b200_session_extract_files_arff for rows the caller already holds (osm_b200_session_extract_pcm):
+ * file i gets rows [frame_offsets[i], frame_offsets[i+1]) of `rows`; n_samples[i] = sample frames of utterance i (time stamps
+ * of the rows a window processor appends at the end of input), may be NULL.  Files are formatted on host threads in parallel
+ * (OSM_B200_IO_THREADS overrides the count).  Replaces cHtkSink / cCsvSink / cArffSink (src/iocore/htkSink.cpp:120-190,
+ * csvSink.cpp:150-235, arffSink.cpp:225-440); needs no device. */
+OSM_B200_API osm_b200_status osm_b200_session_write_files(osm_b200_session *session, double sample_rate, int32_t n_channels,
+                                                          int32_t n, const int64_t *frame_offsets, const int64_t *n_samples,
+                                                          const float *rows, const char *const *htk_paths,
+                                                          const char *const *csv_paths, const char *const *arff_paths);
+
 /* the sink formatting options taken from the configuration (active CSV / HTK / ARFF sinks), as text; for bindings
  * and tests.  The string is owned by the library (thread-local). */
 OSM_B200_API const char *osm_b200_session_sink_options(osm_b200_session *session);

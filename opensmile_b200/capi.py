@@ -262,6 +262,7 @@ EXPORTS = [
     # include/osm_b200_host.h
     "osm_b200_session_open", "osm_b200_session_close", "osm_b200_session_num_elements",
     "osm_b200_session_element_name", "osm_b200_session_extract_files", "osm_b200_session_extract_files_arff", "osm_b200_session_sink_options",
+    "osm_b200_session_write_files",
     "osm_b200_session_extract_pcm", "osm_b200_session_components", "osm_b200_host_last_error",
     "osm_b200_write_htk", "osm_b200_write_csv", "osm_b200_write_csv_timed", "osm_b200_write_arff",
 ]
@@ -320,6 +321,8 @@ def lib():
     L.osm_b200_session_element_name.restype = C.c_char_p
     L.osm_b200_session_extract_files.argtypes = [vp, i32, cpp, cpp, cpp, i64p]
     L.osm_b200_session_extract_files_arff.argtypes = [vp, i32, cpp, cpp, cpp, cpp, i64p]
+    L.osm_b200_session_write_files.argtypes = [vp, C.c_double, i32, i32, i64p, i64p, C.c_void_p, cpp, cpp, cpp]
+    L.osm_b200_session_write_files.restype = i32
     L.osm_b200_session_extract_pcm.argtypes = [vp, vp, i64p, i32, f64, i32, i64p, vp, C.c_int64]
     L.osm_b200_session_components.argtypes = [vp, f64, i32, C.POINTER(C.POINTER(Component)), cpp]
     L.osm_b200_host_last_error.restype = C.c_char_p

@@ -8,7 +8,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <atomic>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <set>
 #include <sstream>
 #include <string>
@@ -1060,6 +1063,52 @@ osm_b200_status osm_b200_session_extract_files(osm_b200_session *s, int32_t n, c
   return osm_b200_session_extract_files_arff(s, n, wavPaths, htkPaths, csvPaths, nullptr, framesOut);
 }
 
+extern "C++" {
+// run fn(i) for i = 0 .. n-1 on up to `maxThreads` host threads (file reading / formatting: at GPU rates the sinks are the
+// bottleneck of a file-based run); returns the first error
+template <class Fn>
+static bool parallel_files(int n, Fn fn, std::string &err)
+{
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = (int)std::min<unsigned>(hw ? hw : 4u, 32u);
+  if (const char *e = getenv("OSM_B200_IO_THREADS")) nt = std::max(1, atoi(e));
+  nt = std::min(nt, n);
+  std::atomic<int> next(0);
+  std::atomic<bool> failed(false);
+  std::mutex mu;
+  auto worker = [&]() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n || failed.load()) return;
+      std::string e;
+      if (!fn(i, e)) { std::lock_guard<std::mutex> lk(mu); if (!failed.exchange(true)) err = e; return; }
+    }
+  };
+  if (nt <= 1) { worker(); return !failed.load(); }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++) th.emplace_back(worker);
+  for (auto &t : th) t.join();
+  return !failed.load();
+}
+
+// the sinks of one batch: rows [fo[k], fo[k+1]) of file idx[k] -> its HTK / CSV / ARFF files, files in parallel
+static bool write_batch(osm_b200_session *s, const std::vector<int> &idx, const int64_t *fo, const int64_t *nTime, const float *rows, int K,
+                        const std::vector<std::string> &names, double period, const char *const *htkPaths, const char *const *csvPaths,
+                        const char *const *arffPaths, int64_t *framesOut, std::string &err)
+{
+  return parallel_files((int)idx.size(), [&](int k, std::string &e) -> bool {
+    const int i = idx[k];
+    const float *r = rows + (size_t)fo[k] * K;
+    const int64_t nr = fo[k + 1] - fo[k];
+    if (framesOut) framesOut[i] = nr;
+    if (htkPaths && htkPaths[i] && !write_htk(htkPaths[i], r, nr, K, period, s->parmKind, e)) return false;
+    if (csvPaths && csvPaths[i] && !write_csv(csvPaths[i], r, nr, K, names, period, s->csv, e, nTime[k])) return false;
+    if (arffPaths && arffPaths[i] && !write_arff(arffPaths[i], r, nr, K, names, period, s->arff, e, nTime[k])) return false;
+    return true;
+  }, err);
+}
+}  // extern "C++"
+
 osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t n, const char *const *wavPaths,
                                                     const char *const *htkPaths, const char *const *csvPaths,
                                                     const char *const *arffPaths, int64_t *framesOut)
@@ -1068,12 +1117,12 @@ osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t
   // files of one call are grouped by (sample rate, channels); each group is one batched plan run
   std::vector<Wav> wavs(n);
   std::string err;
-  for (int i = 0; i < n; i++) if (!read_wav(wavPaths[i], wavs[i], err)) return hfail(OSM_B200_ERR_INVALID, err);
+  if (!parallel_files(n, [&](int i, std::string &e) { return read_wav(wavPaths[i], wavs[i], e); }, err)) return hfail(OSM_B200_ERR_INVALID, err);
   std::map<std::pair<int, int>, std::vector<int>> groups;
   for (int i = 0; i < n; i++) groups[{wavs[i].sampleRate, wavs[i].nChan}].push_back(i);
   for (auto &g : groups) {
     const int sr = g.first.first, nc = g.first.second;
-    std::vector<int64_t> off(g.second.size() + 1, 0), fo(g.second.size() + 1, 0);
+    std::vector<int64_t> off(g.second.size() + 1, 0), fo(g.second.size() + 1, 0), nTime(g.second.size(), 0);
     size_t total = 0;
     for (size_t k = 0; k < g.second.size(); k++) { total += wavs[g.second[k]].pcm.size(); off[k + 1] = off[k] + (int64_t)(wavs[g.second[k]].pcm.size() / nc); }
     std::vector<int16_t> pcm(total + 8);
@@ -1090,21 +1139,34 @@ osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t
     if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
     std::vector<std::string> names(K);
     for (int k = 0; k < K; k++) names[k] = osm_b200_plan_element_name(p, k);
-    const double period = osm_b200_plan_frame_period(p);
-    for (size_t k = 0; k < g.second.size(); k++) {
-      const int idx = g.second[k];
-      const float *r = rows.data() + (size_t)fo[k] * K;
-      const int64_t nr = fo[k + 1] - fo[k];
-      if (framesOut) framesOut[idx] = nr;
-      if (htkPaths && htkPaths[idx] && !write_htk(htkPaths[idx], r, nr, K, period, s->parmKind, err)) return hfail(OSM_B200_ERR_INVALID, err);
-      if (csvPaths && csvPaths[idx] &&
-          !write_csv(csvPaths[idx], r, nr, K, names, period, s->csv, err, osm_b200_plan_num_time_frames(p, off[k + 1] - off[k])))
-        return hfail(OSM_B200_ERR_INVALID, err);
-      if (arffPaths && arffPaths[idx] &&
-          !write_arff(arffPaths[idx], r, nr, K, names, period, s->arff, err, osm_b200_plan_num_time_frames(p, off[k + 1] - off[k])))
-        return hfail(OSM_B200_ERR_INVALID, err);
-    }
+    for (size_t k = 0; k < g.second.size(); k++) nTime[k] = osm_b200_plan_num_time_frames(p, off[k + 1] - off[k]);
+    if (!write_batch(s, g.second, fo.data(), nTime.data(), rows.data(), K, names, osm_b200_plan_frame_period(p), htkPaths, csvPaths, arffPaths, framesOut, err))
+      return hfail(OSM_B200_ERR_INVALID, err);
   }
+  return OSM_B200_OK;
+}
+
+// The sink half of osm_b200_session_extract_files_arff on rows the caller already holds (e.g. from
+// osm_b200_session_extract_pcm): file i gets rows [frame_offsets[i], frame_offsets[i+1]) of `rows` ([.., num_elements]);
+// n_samples[i] = sample frames of utterance i (for the time stamps of rows appended at the end of input).  Files are
+// formatted in parallel on host threads.  Needs no device: it works on description-only sessions as well.
+osm_b200_status osm_b200_session_write_files(osm_b200_session *s, double sampleRate, int32_t nChan, int32_t n, const int64_t *frameOff,
+                                             const int64_t *nSamples, const float *rows, const char *const *htkPaths,
+                                             const char *const *csvPaths, const char *const *arffPaths)
+{
+  if (!s || !frameOff || !rows || n < 0) return hfail(OSM_B200_ERR_INVALID, "null argument");
+  osm_b200_plan *p;
+  osm_b200_status st = get_plan(s, sampleRate, nChan, &p);
+  if (st != OSM_B200_OK) return st;
+  const int K = osm_b200_plan_num_elements(p);
+  std::vector<std::string> names(K);
+  for (int k = 0; k < K; k++) names[k] = osm_b200_plan_element_name(p, k);
+  std::vector<int> idx(n);
+  std::vector<int64_t> nTime(n, 0);
+  for (int i = 0; i < n; i++) { idx[i] = i; nTime[i] = nSamples ? osm_b200_plan_num_time_frames(p, nSamples[i]) : 0; }
+  std::string err;
+  if (!write_batch(s, idx, frameOff, nTime.data(), rows, K, names, osm_b200_plan_frame_period(p), htkPaths, csvPaths, arffPaths, nullptr, err))
+    return hfail(OSM_B200_ERR_INVALID, err);
   return OSM_B200_OK;
 }
 

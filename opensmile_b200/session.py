@@ -92,6 +92,18 @@ class Session:
         self._L.osm_b200_session_sink_options.argtypes = [C.c_void_p]
         return self._L.osm_b200_session_sink_options(self._h).decode()
 
+    def write_files(self, rows, frame_offsets, sample_rate, n_channels=1, n_samples=None, htk_paths=None, csv_paths=None, arff_paths=None):
+        """the sinks for rows already in host memory (osm_b200_session_write_files): file i gets rows
+        [frame_offsets[i], frame_offsets[i+1]); files are formatted on host threads in parallel"""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        fo = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+        ns = None if n_samples is None else np.ascontiguousarray(n_samples, dtype=np.int64)
+        i64p = C.POINTER(C.c_int64)
+        self._check(self._L.osm_b200_session_write_files(
+            self._h, float(sample_rate), n_channels, len(fo) - 1, fo.ctypes.data_as(i64p),
+            ns.ctypes.data_as(i64p) if ns is not None else None, rows.ctypes.data,
+            _strs(htk_paths) if htk_paths else None, _strs(csv_paths) if csv_paths else None, _strs(arff_paths) if arff_paths else None))
+
     def extract_files(self, wav_paths, htk_paths=None, csv_paths=None, arff_paths=None):
         n = len(wav_paths)
         frames = np.zeros(n, dtype=np.int64)

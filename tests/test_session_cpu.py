@@ -205,3 +205,42 @@ def test_graph_rules_of_the_wider_component_set(tmp_path):
     c = _conf_with(tmp_path, [("mfcc", "cMfcc"), ("rp", "cPlp"), ("cat", "cVectorConcat")], secs, "both")
     names = Session(c, device=-1).element_names()
     assert names[0] == "pcm_fftMag_mfcc[1]" and names[12] == "RASTAPlpCC[0]" and len(names) == 12 + 5   # cPlp defaults: firstCC = 1, lpOrder = 5
+
+
+def test_parallel_file_sinks_equal_the_single_file_writers(tmp_path):
+    """osm_b200_session_write_files (the sink half of extract_files: files formatted on host threads) against the single-file
+    writers that are pinned byte for byte to the reference's sinks; incl. an empty file and the repeated time stamp of rows a
+    window processor appends at the end of input"""
+    from opensmile_b200 import write_csv, write_htk
+    s = Session(os.path.join(CONF, "mfcc_e_d_a.conf"), device=-1)
+    names = s.element_names()
+    K = len(names)
+    n_samples = np.array([16000, 400, 0, 48000] + [8000 + 160 * i for i in range(36)], np.int64)
+    off = np.concatenate([[0], np.cumsum(n_samples)])
+    fo = s.frame_offsets(off, 16000.0, 1)
+    rows = np.random.default_rng(0).standard_normal((int(fo[-1]), K)).astype(np.float32)
+    rows[::7, 3] = 0.0
+    rows[5, 1] = 42.0
+    assert "index=0 name=1:'unknown'" in s.sink_options()
+    n = len(n_samples)
+    htk = [str(tmp_path / ("p%d.htk" % i)) for i in range(n)]
+    csv = [str(tmp_path / ("p%d.csv" % i)) for i in range(n)]
+    s.write_files(rows, fo, 16000.0, 1, n_samples=n_samples, htk_paths=htk, csv_paths=csv)
+    comps, level = s.components(16000.0, 1)
+    from opensmile_b200 import Plan
+    plan = Plan(list(comps), level, device=-1)
+    for i in range(n):
+        r = rows[fo[i]:fo[i + 1]]
+        write_htk(str(tmp_path / "a.htk"), r, 0.01)
+        write_csv(str(tmp_path / "a.csv"), r, names, 0.01, instance_name="unknown", frame_index=False,      # the configuration's sink options
+                  n_time_frames=plan.num_time_frames(int(n_samples[i])))
+        assert open(htk[i], "rb").read() == open(tmp_path / "a.htk", "rb").read()
+        assert open(csv[i], "rb").read() == open(tmp_path / "a.csv", "rb").read()
+    os.environ["OSM_B200_IO_THREADS"] = "1"                       # serial path
+    try:
+        s.write_files(rows, fo, 16000.0, 1, n_samples=n_samples, csv_paths=[str(tmp_path / ("q%d.csv" % i)) for i in range(n)])
+    finally:
+        del os.environ["OSM_B200_IO_THREADS"]
+    assert all(open(csv[i], "rb").read() == open(tmp_path / ("q%d.csv" % i), "rb").read() for i in range(n))
+    with pytest.raises(Exception, match="cannot write"):
+        s.write_files(rows, fo, 16000.0, 1, csv_paths=[str(tmp_path / "nodir" / "x.csv")] * n)
