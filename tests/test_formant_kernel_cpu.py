@@ -156,3 +156,19 @@ def test_resampling_table_other_rates(sr, target):
     res, per = fh.resample(xw, sr, nfft2, 0.020, target)
     assert nfft2 == nfft and res.shape == ref.shape and per == rs.base_period_out
     assert np.abs(res - ref).max() / np.abs(ref).max() < 3e-6
+
+
+def test_all_shipped_gemaps_family_configurations_compile_unchanged():
+    """the five shipped feature-set files of the GeMAPS family (-lldcsvoutput): element names and row counts equal the
+    reference's CSV files (tests/golden/gemaps_headers.json, written by running oracle/_ref/SMILExtract on
+    mixed_pcm(24000, seed=3))"""
+    import json
+    ref = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "config")
+    if not os.path.isdir(ref):
+        pytest.skip("reference configuration files not built (make -C oracle ref)")
+    gold = json.load(open(os.path.join(HERE, "golden", "gemaps_headers.json")))
+    assert len(gold) == 5
+    for conf, g in gold.items():
+        s = Session(os.path.join(ref, conf), options={"lldcsvoutput": "x.csv"}, device=-1)
+        assert s.element_names() == g["names"]
+        assert int(s.frame_offsets(np.array([0, 24000], np.int64), 16000.0, 1)[-1]) == g["rows_m24k"]
