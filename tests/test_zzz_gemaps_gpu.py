@@ -39,3 +39,26 @@ def test_shipped_configuration_rows(conf, opts, key):
         err = np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)
         assert err[:, rest].max() < 1e-5
         assert np.median(err[:, fdep]) < 1e-4 and (err[:, fdep].max(axis=1) > 1e-3).mean() < 0.25
+
+
+def test_all_shipped_gemaps_family_rows():
+    """the five shipped feature-set files (v01a / v01b / v02) against the reference's LLD rows (tests/golden/gemaps_family.npz)"""
+    import json
+    from opensmile_b200.session import Session
+    if not os.path.isdir(REF):
+        pytest.skip("reference configuration files not built (make -C oracle ref)")
+    gold = json.load(open(os.path.join(HERE, "golden", "gemaps_headers.json")))
+    R = np.load(os.path.join(HERE, "golden", "gemaps_family.npz"))
+    pcm = mixed_pcm(24000, 16000, seed=3)
+    for conf, g in gold.items():
+        s = Session(os.path.join(REF, conf), options={"lldcsvoutput": "x.csv"}, device=0)
+        names = s.element_names()
+        rows, fo = s.extract_pcm(np.concatenate([pcm, np.zeros(8, np.int16)]), np.array([0, len(pcm)], np.int64), 16000.0, 1)
+        s.close()
+        ref = R[os.path.splitext(os.path.basename(conf))[0]]
+        assert names == g["names"] and rows.shape == ref.shape
+        fdep = [i for i, n in enumerate(names) if n.startswith(("F1", "F2", "F3")) or "H1-A3" in n]
+        rest = [i for i in range(len(names)) if i not in fdep]
+        err = np.abs(rows - ref) / (np.abs(ref).max(axis=0) + 1e-30)
+        assert err[:, rest].max() < 1e-5
+        assert np.median(err[:, fdep]) < 1e-4 and (err[:, fdep].max(axis=1) > 1e-3).mean() < 0.25
