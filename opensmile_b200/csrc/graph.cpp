@@ -895,6 +895,13 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       bool scopeLags = false;
       int scopeLagOp = -1;
       for (const El &e : els) if (d.groups[e.g].lagKind == 2) { scopeLags = true; scopeLagOp = d.groups[e.g].lagOp; }
+      if (scopeLags)
+        for (size_t ll = sc->l0; ll < sc->l1; ll++)
+          if (leaves[ll].stages.size() != sc->above) {
+            // pinned only for a selector directly on the per-frame levels (the shipped graphs); a selector over levels
+            // that were smoothed first sees another tick order
+            err = "cDataSelector reading a cPitchJitter level: temporal stages below the selector are not supported"; return OSM_B200_ERR_UNSUPPORTED;
+          }
       long prevG = -1;
       for (int k = 0; k < q.nSelected; k++) {
         for (int k2 = 0; k2 < k; k2++)
