@@ -199,10 +199,12 @@ def formants_from_lpc(a, T, n_formants, min_f, max_f):
     return freq.astype(f32), bw.astype(f32)
 
 
-def gemaps_formant_chain(pcm, sample_rate=16000.0, taps=False, exact_fft=False):
+def gemaps_formant_chain(pcm, sample_rate=16000.0, taps=False, exact_fft=False, v01a=False):
     """config/gemaps/v01b/GeMAPSv01b_core.lld.conf.inc:43-58,250-286 -> [T, 10] = formantFreqLpc[1..5] | formantBandwidthLpc[1..5];
     exact_fft: the FFT level through the reference's own FFT (bit-identical front end, needs oracle/_ref/libfftsg.so)"""
-    fe = oracle.frontend(sample_rate, 0.020, 0.010, win="ham", zero_pad_symmetric=1)
+    # v01a (config/gemaps/v01a/GeMAPSv01a_core.lld.conf.inc): zeroPadSymmetric = 0 on both FFTs, maxF = 5500,
+    # useBrokenJitterThresh = 1 -- otherwise the v01b graph
+    fe = oracle.frontend(sample_rate, 0.020, 0.010, win="ham", zero_pad_symmetric=0 if v01a else 1)
     spec = fft_frames_exact(pcm, fe) if exact_fft else fft_frames(pcm, fe)
     N, H, nfft, T = oracle.geometry(fe, len(pcm))
     fs_sec = oracle.lib().osm_or_fft_frame_size_sec(C.byref(fe))
@@ -213,7 +215,7 @@ def gemaps_formant_chain(pcm, sample_rate=16000.0, taps=False, exact_fft=False):
     for t, x in enumerate(res):
         a, _ = lpc_acf(autocorr(x, 12), 11)
         lpcs[t] = a
-        f, b = formants_from_lpc(a, rs.base_period_out, 5, 50.0, 5450.0)
+        f, b = formants_from_lpc(a, rs.base_period_out, 5, 50.0, 5500.0 if v01a else 5450.0)
         fmt[t, :5], fmt[t, 5:] = f, b
     return (fmt, res, lpcs) if taps else fmt
 
@@ -419,24 +421,24 @@ def harmonics_gemaps(F0, formant_freq, mag, frq, n_harm=100, floor_unvoiced=-201
     return np.array(out, f32)
 
 
-def gemaps_vq_levels(pcm, sample_rate=16000.0, exact_fft=False):
+def gemaps_vq_levels(pcm, sample_rate=16000.0, exact_fft=False, v01a=False):
     """The four voice-quality levels of the shipped GeMAPS graph (config/gemaps/v01b/GeMAPSv01b_core.lld.conf.inc),
     end to end from PCM:
       logPitch  [T60, 3]  F0final, F0finalLog, voicingFinalUnclipped, gated by the 60 ms rms energy (:62-171)
       jitter    [T60, 2]  jitterLocal, shimmerLocalDB (:174-195)
       formants  [T25, 10] formantFreqLpc[1..5] | formantBandwidthLpc[1..5] (:250-286)
       harmonics [T60, 6]  HNRdBACF, H1-H2, H1-A3, F1..F3 amplitude (:289-318; frame t of the three input levels)"""
-    fe60 = oracle.frontend(sample_rate, 0.060, 0.010, win="gau", sigma=0.4, zero_pad_symmetric=1)
+    fe60 = oracle.frontend(sample_rate, 0.060, 0.010, win="gau", sigma=0.4, zero_pad_symmetric=0 if v01a else 1)
     sc = oracle.SpecScale(25.0, -1.0, 0, 1, 1, 1)
     ps = oracle.PitchShs(1000.0, 55.0, 6, 1, 1, 0, 0, 1, 1, 0.70, 0, 15, 0.85, 1, 0.0)
     vc = oracle.Viterbi(40, 1, 1, 0, 0, 0, 1, 2.0, 10.0, 5.0, 10.0, 4.0, 1.0, 0.0)
-    jc = oracle.Jitter(0.10, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, -100.0, 0, 2, 0.5, 0, 0, 0, 0, 0, 0)
+    jc = oracle.Jitter(0.10, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, -100.0, 0, 2, 0.5, 0, 0, 0, 0, 1 if v01a else 0, 0)
     shs = oracle.pitch_shs(pcm, fe60, sc, ps)
     vit = oracle.viterbi(shs, ps, vc)
     e60 = oracle.energy(pcm, fe60, oracle.Energy(0, 1, 0, 0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0), windowed=1)
     pitch = oracle.valbased_select(e60[:, 0], vit, 0.001)
     jit = oracle.pitch_jitter(pcm, fe60, jc, pitch[:, 0])
-    fmt = gemaps_formant_chain(pcm, sample_rate, exact_fft=exact_fft)
+    fmt = gemaps_formant_chain(pcm, sample_rate, exact_fft=exact_fft, v01a=v01a)
     # 60 ms magnitude spectrum and its bin axis (dspcore/transformFft.cpp:111-115)
     N, H, nfft, T = oracle.geometry(fe60, len(pcm))
     spec = fft_frames_exact(pcm, fe60) if exact_fft else fft_frames(pcm, fe60)
@@ -452,7 +454,7 @@ def gemaps_vq_levels(pcm, sample_rate=16000.0, exact_fft=False):
     return pitch, jit, fmt, harm
 
 
-def gemaps_lld(pcm, sample_rate=16000.0, exact_fft=False):
+def gemaps_lld(pcm, sample_rate=16000.0, exact_fft=False, v01a=False):
     """Level `lld` of the shipped config/gemaps/v01b/GeMAPSv01b.conf (18 columns, T60 + 1 rows):
       lldsetE_smo: Loudness, alphaRatio, hammarbergIndex, slope0-500, slope500-1500 (sma3)
       lldsetF_smo: F0semitone, jitterLocal, shimmerLocaldB, HNRdBACF, logRelF0-H1-H2, logRelF0-H1-A3, F1 frequency /
@@ -460,7 +462,7 @@ def gemaps_lld(pcm, sample_rate=16000.0, exact_fft=False):
     cDataSelector picks the elements in the order of its `selected` list (core/dataSelector.cpp:388-470).  The selector
     in front of the second smoother waits for the jitter level, which does not advance during the reference's first
     end-of-input pass: rows V-1 and V of ALL its columns are smoothed with the level padded at row V-1."""
-    pitch, jit, fmt, harm = gemaps_vq_levels(pcm, sample_rate, exact_fft)
+    pitch, jit, fmt, harm = gemaps_vq_levels(pcm, sample_rate, exact_fft, v01a)
     fe60 = oracle.frontend(sample_rate, 0.060, 0.010, win="gau", sigma=0.4, zero_pad_symmetric=1)
     sc = oracle.SpecScale(25.0, -1.0, 0, 1, 1, 1)
     ps = oracle.PitchShs(1000.0, 55.0, 6, 1, 1, 0, 0, 1, 1, 0.70, 0, 15, 0.85, 1, 0.0)

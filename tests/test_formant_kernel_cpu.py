@@ -172,3 +172,15 @@ def test_all_shipped_gemaps_family_configurations_compile_unchanged():
         s = Session(os.path.join(ref, conf), options={"lldcsvoutput": "x.csv"}, device=-1)
         assert s.element_names() == g["names"]
         assert int(s.frame_offsets(np.array([0, 24000], np.int64), 16000.0, 1)[-1]) == g["rows_m24k"]
+
+
+def test_formants_at_the_nyquist_edge():
+    """GeMAPSv01a searches up to maxF = 5500 Hz = the Nyquist frequency of the resampled frames, where real negative roots
+    sit: the kernel statements (roots with rounding-noise imaginary parts snapped to the real axis) take the same decisions
+    as the oracle's LAPACK roots on every frame"""
+    from oracle import formant_oracle as fo
+    if not fo.ref_fft_available():
+        pytest.skip("oracle/_ref/libfftsg.so not built (make -C oracle ref)")
+    fmt, res, lpcs = fo.gemaps_formant_chain(mixed_pcm(24000, 16000, seed=3), taps=True, exact_fft=True, v01a=True)
+    got = np.stack([fh.formants(a, 1.0 / 11000.0, 5, 50.0, 5500.0) for a in lpcs])
+    assert np.abs(got - fmt).max() < 1e-2

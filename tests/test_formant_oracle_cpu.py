@@ -129,3 +129,19 @@ def test_end_to_end_bound_of_the_formant_dependent_columns():
     err = np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)
     assert err[:, rest].max() < 5e-6
     assert np.median(err[:, fdep]) < 5e-5 and (err[:, fdep].max(axis=1) > 1e-3).mean() < 0.15
+
+
+def test_shipped_gemaps_v01a_lld_level():
+    """config/gemaps/v01a/GeMAPSv01a.conf differs from v01b in zeroPadSymmetric = 0 on both FFTs (the formant branch sees
+    another phase), maxF = 5500 (= Nyquist of the 11 kHz frames) and useBrokenJitterThresh = 1: same oracle, three
+    switches, against the reference's rows (tests/golden/gemaps_family.npz)"""
+    import pytest
+    if not fo.ref_fft_available():
+        pytest.skip("oracle/_ref/libfftsg.so not built (make -C oracle ref)")
+    R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemaps_family.npz"))
+    pcm = mixed_pcm(24000, 16000, seed=3)
+    for key, v in (("GeMAPSv01a", True), ("GeMAPSv01b", False)):
+        got, ref = fo.gemaps_lld(pcm, exact_fft=True, v01a=v), R[key]
+        assert got.shape == ref.shape
+        assert (np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)).max() < 5e-6
+    assert not np.array_equal(R["GeMAPSv01a"], R["GeMAPSv01b"])
