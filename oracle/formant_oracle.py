@@ -548,3 +548,14 @@ def egemaps_lld(pcm, sample_rate=16000.0, exact_fft=False):
     Es = oracle.sma(E, 3, 0)
     R = min(Es.shape[0], Fs.shape[0])
     return np.concatenate([Es[:R], Fs[:R]], axis=1)
+
+
+def egemaps_v01_lld(pcm, sample_rate=16000.0, exact_fft=False, v01a=False):
+    """Level `lld` of the shipped config/egemaps/v01a|v01b/eGeMAPSv01*.conf (23 columns): the ten sma3 columns of eGeMAPS
+    (loudness, four log-spectral descriptors, spectral flux, MFCC 1-4) next to the thirteen sma3nz columns of the GeMAPS
+    selector (v01a: the GeMAPSv01a switches in the voice-quality branch; the magnitude-based columns do not see
+    zeroPadSymmetric)"""
+    E = egemaps_lld(pcm, sample_rate, exact_fft)[:, :10]
+    F = gemaps_lld(pcm, sample_rate, exact_fft, v01a)[:, 5:]
+    R = min(len(E), len(F))
+    return np.concatenate([E[:R], F[:R]], axis=1)

@@ -145,3 +145,17 @@ def test_shipped_gemaps_v01a_lld_level():
         assert got.shape == ref.shape
         assert (np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)).max() < 5e-6
     assert not np.array_equal(R["GeMAPSv01a"], R["GeMAPSv01b"])
+
+
+def test_shipped_egemaps_v01_lld_levels():
+    """eGeMAPSv01a.conf / eGeMAPSv01b.conf (23 columns) -- with GeMAPSv01a/b and eGeMAPSv02 the oracle now reproduces the LLD
+    level of all five shipped feature-set files of the family"""
+    import pytest
+    if not fo.ref_fft_available():
+        pytest.skip("oracle/_ref/libfftsg.so not built (make -C oracle ref)")
+    R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gemaps_family.npz"))
+    pcm = mixed_pcm(24000, 16000, seed=3)
+    for key, v in (("eGeMAPSv01a", True), ("eGeMAPSv01b", False)):
+        got, ref = fo.egemaps_v01_lld(pcm, exact_fft=True, v01a=v), R[key]
+        assert got.shape == ref.shape == (ref.shape[0], 23)
+        assert (np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)).max() < 5e-6
