@@ -149,6 +149,12 @@ OSM_HM_HD float harmonic_difference(const Harm *H, int nHarm, const int *fa, int
 template <class A>
 OSM_HM_HD int closest_peak(const A &x, int N, int idx)
 {
+  if (idx >= N) {
+    // a lag beyond the sequence (F0 below fs / N, never produced by the pitch chain's range): the reference's outward walk
+    // then only ever finds peaks below N, highest first, and ends in an out-of-bounds read when there is none; bounded here
+    for (int j = N - 1; j > 0; j--) if (is_peak(x, N, j)) return j;
+    return 0;
+  }
   if (is_peak(x, N, idx)) return idx;
   int o = 1;
   while (idx - o > 0 || idx + o < N - 1) {

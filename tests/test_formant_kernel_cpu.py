@@ -117,6 +117,8 @@ def test_harmonics_unvoiced_and_edge_frames():
     assert np.isfinite(out).all()
     out = fh.harmonics(120.0, [500.0, 1500.0, 2500.0], np.zeros(513, np.float32), 16000.0 / 1024)   # silence
     assert np.isfinite(out).all()
+    out = fh.harmonics(1e-3, [500.0, 1500.0, 2500.0], mag, 16000.0 / 1024)      # F0 far below the pitch range: lag beyond the ACF, bounded search
+    assert np.isfinite(out).all()
 
 
 @pytest.mark.parametrize("conf,opts,key,n", [("gemaps/v01b/GeMAPSv01b.conf", {"lldhtkoutput": "x.htk"}, "gemaps_lld", 18),
