@@ -24,3 +24,9 @@ OSM_BENCH_N_UTT=2000 timeout 900 ncu --metrics gpu__time_duration.sum --clock-co
   python bench.py --workload egemaps --steps 2 --warmup 3 > gpurun_out/nr_egemaps_ncu.log 2>&1
 # 6. the default bench line, unchanged path
 timeout 600 python bench.py 2>&1 | tail -1 | tee gpurun_out/nr_bench.json
+# 7. one ncu --set full capture each of the two new kernels (small batch), summaries -> profiles/ by scripts/ncu_summary.py
+for K in formant_kernel harmonics_kernel; do
+  OSM_BENCH_N_UTT=500 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -o gpurun_out/nr_$K \
+    python bench.py --workload egemaps --steps 1 --warmup 3 > gpurun_out/nr_${K}_ncu.log 2>&1
+done
+ls -la gpurun_out | tail -20
