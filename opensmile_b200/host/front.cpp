@@ -1067,12 +1067,13 @@ extern "C++" {
 // run fn(i) for i = 0 .. n-1 on up to `maxThreads` host threads (file reading / formatting: at GPU rates the sinks are the
 // bottleneck of a file-based run); returns the first error
 template <class Fn>
-static bool parallel_files(int n, Fn fn, std::string &err)
+static bool parallel_files(int n, Fn fn, std::string &err, bool serial = false)
 {
   unsigned hw = std::thread::hardware_concurrency();
   int nt = (int)std::min<unsigned>(hw ? hw : 4u, 32u);
   if (const char *e = getenv("OSM_B200_IO_THREADS")) nt = std::max(1, atoi(e));
   nt = std::min(nt, n);
+  if (serial) nt = 1;
   std::atomic<int> next(0);
   std::atomic<bool> failed(false);
   std::mutex mu;
@@ -1096,6 +1097,16 @@ static bool write_batch(osm_b200_session *s, const std::vector<int> &idx, const 
                         const std::vector<std::string> &names, double period, const char *const *htkPaths, const char *const *csvPaths,
                         const char *const *arffPaths, int64_t *framesOut, std::string &err)
 {
+  // several inputs may name the same output file (cArffSink / cCsvSink with append=1 collect every input in one file):
+  // those files must be written one after the other, in input order
+  bool shared = false;
+  {
+    std::set<std::string> seen;
+    for (const char *const *paths : {htkPaths, csvPaths, arffPaths})
+      if (paths)
+        for (int i : idx)
+          if (paths[i] && !seen.insert(std::string(paths[i])).second) shared = true;
+  }
   return parallel_files((int)idx.size(), [&](int k, std::string &e) -> bool {
     const int i = idx[k];
     const float *r = rows + (size_t)fo[k] * K;
@@ -1105,7 +1116,7 @@ static bool write_batch(osm_b200_session *s, const std::vector<int> &idx, const 
     if (csvPaths && csvPaths[i] && !write_csv(csvPaths[i], r, nr, K, names, period, s->csv, e, nTime[k])) return false;
     if (arffPaths && arffPaths[i] && !write_arff(arffPaths[i], r, nr, K, names, period, s->arff, e, nTime[k])) return false;
     return true;
-  }, err);
+  }, err, shared);
 }
 }  // extern "C++"
 

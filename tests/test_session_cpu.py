@@ -244,3 +244,25 @@ def test_parallel_file_sinks_equal_the_single_file_writers(tmp_path):
     assert all(open(csv[i], "rb").read() == open(tmp_path / ("q%d.csv" % i), "rb").read() for i in range(n))
     with pytest.raises(Exception, match="cannot write"):
         s.write_files(rows, fo, 16000.0, 1, csv_paths=[str(tmp_path / "nodir" / "x.csv")] * n)
+
+
+def test_inputs_sharing_one_output_file_are_written_in_order(tmp_path):
+    """the LLD ARFF sink of the feature-set configurations appends (append = 1): several inputs naming the same file must be
+    written one after the other in input order, not by the parallel writers"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "config", "compare16", "ComParE_2016.conf")
+    if not os.path.exists(ref):
+        pytest.skip("reference configuration files not built (make -C oracle ref)")
+    s = Session(ref, options={"lldarffoutput": "x.arff", "instname": "u"}, device=-1)
+    assert "append=1" in s.sink_options()
+    K = len(s.element_names())
+    n_samples = np.array([16000 + 1600 * i for i in range(12)], np.int64)
+    fo = s.frame_offsets(np.concatenate([[0], np.cumsum(n_samples)]), 16000.0, 1)
+    rows = np.zeros((int(fo[-1]), K), np.float32)
+    for i in range(len(n_samples)):
+        rows[fo[i]:fo[i + 1], 0] = i + 1                            # first column = 1-based file index
+    out = str(tmp_path / "all.arff")
+    s.write_files(rows, fo, 16000.0, 1, n_samples=n_samples, arff_paths=[out] * len(n_samples))
+    data = open(out).read().split("@data")[1].strip().splitlines()
+    assert len(data) == int(fo[-1])
+    first = [int(float(ln.split(",")[2])) for ln in data]          # name, frameTime, then the values
+    assert first == sorted(first) and first[0] == 1 and first[-1] == len(n_samples)
