@@ -11,6 +11,12 @@ if ROOT not in sys.path:
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
+def pytest_report_header(config):
+    on = os.environ.get("OSM_B200_RUN_UNVERIFIED") == "1"
+    return ("opensmile_b200: GPU tests of code that has not run on a device yet (formant / harmonics kernels, selector grouping, "
+            "ARFF session path) are opt-in: OSM_B200_RUN_UNVERIFIED=1 -- currently %s (scripts/next_round_gpu.sh)" % ("ON" if on else "off, they are skipped"))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
