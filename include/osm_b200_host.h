@@ -91,6 +91,11 @@ OSM_B200_API osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *sess
 OSM_B200_API int32_t osm_b200_session_components(osm_b200_session *session, double sample_rate, int32_t n_channels,
                                                  const osm_b200_component **comps, const char **output_level);
 
+/* the plan the session compiled for this input format (owned by the session, valid until close): geometry / row-count /
+ * time-stamp queries of include/osm_b200.h for callers that embed the session in a host runtime (plugin/lldBlockB200.cpp) */
+OSM_B200_API osm_b200_status osm_b200_session_plan(osm_b200_session *session, double sample_rate, int32_t n_channels,
+                                                   osm_b200_plan **plan);
+
 /* message of the last failed osm_b200_session_* call on this thread (falls back to osm_b200_last_error) */
 OSM_B200_API const char *osm_b200_host_last_error(void);
 

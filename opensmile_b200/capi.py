@@ -263,7 +263,7 @@ EXPORTS = [
     "osm_b200_session_open", "osm_b200_session_close", "osm_b200_session_num_elements",
     "osm_b200_session_element_name", "osm_b200_session_extract_files", "osm_b200_session_extract_files_arff", "osm_b200_session_sink_options",
     "osm_b200_session_write_files",
-    "osm_b200_session_extract_pcm", "osm_b200_session_components", "osm_b200_host_last_error",
+    "osm_b200_session_extract_pcm", "osm_b200_session_components", "osm_b200_session_plan", "osm_b200_host_last_error",
     "osm_b200_write_htk", "osm_b200_write_csv", "osm_b200_write_csv_timed", "osm_b200_write_arff",
 ]
 

@@ -144,11 +144,9 @@ cudaError_t launch_formant(const FormantParams &p, cudaStream_t st)
 {
   if (p.tp.nTiles <= 0) return cudaSuccess;
   const size_t smem = formant_smem_bytes(p);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {   // per device / context attribute: set on every launch like the other launchers
     cudaError_t e = cudaFuncSetAttribute(formant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   formant_kernel<<<p.tp.nTiles, kFmtThreads, smem, st>>>(p);
   return cudaGetLastError();

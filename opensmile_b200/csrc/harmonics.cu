@@ -105,11 +105,9 @@ cudaError_t launch_harmonics(const HarmonicsParams &p, cudaStream_t st)
 {
   if (p.nTiles <= 0) return cudaSuccess;
   const size_t smem = harmonics_smem_bytes(p);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {   // per device / context attribute: set on every launch like the other launchers
     cudaError_t e = cudaFuncSetAttribute(harmonics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   harmonics_kernel<<<p.nTiles, kHmThreads, smem, st>>>(p);
   return cudaGetLastError();

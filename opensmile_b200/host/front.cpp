@@ -1041,6 +1041,12 @@ int32_t osm_b200_session_components(osm_b200_session *s, double sampleRate, int3
   return (int32_t)s->curComps.size();
 }
 
+osm_b200_status osm_b200_session_plan(osm_b200_session *s, double sampleRate, int32_t nChan, osm_b200_plan **plan)
+{
+  if (!s || !plan) return hfail(OSM_B200_ERR_INVALID, "null argument");
+  return get_plan(s, sampleRate, nChan, plan);
+}
+
 osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t *pcm, const int64_t *uttOff, int32_t nUtt,
                                              double sampleRate, int32_t nChan, int64_t *frameOff, float *out, int64_t maxRows)
 {

@@ -10,6 +10,8 @@ timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/
 # 2. the opt-in tests: selector grouping, formant kernel vs its host build, shipped GeMAPS / eGeMAPS end to end
 export OSM_B200_RUN_UNVERIFIED=1
 timeout 900 python -m pytest tests/test_zz_lld_sinks_gpu.py tests/test_zz_select_gpu.py tests/test_zzz_formant_gpu.py tests/test_zzz_gemaps_gpu.py -q 2>&1 | tail -30 | tee gpurun_out/nr_unverified.txt
+# 2b. per-column parity table (eGeMAPS / GeMAPS vs the reference's rows)
+timeout 300 python scripts/parity_report.py gpurun_out/nr_parity_report.md 2>&1 | tail -30
 # 3. memcheck over the new kernels (small inputs)
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_zzz_formant_gpu.py tests/test_zzz_gemaps_gpu.py -x -q \
   > gpurun_out/nr_memcheck.txt 2>&1; echo "memcheck exit $?" | tee -a gpurun_out/nr_memcheck.txt
