@@ -813,6 +813,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
         CUP(cudaMemcpy(rt.dFmtD, fo.D.data(), fo.D.size() * sizeof(float), cudaMemcpyHostToDevice));
         fp.tp = tp; fp.D = rt.dFmtD; fp.nRes = fo.nRes; fp.nResPad = fo.nResPad; fp.p = fo.p; fp.nFormants = fo.nFormants;
         fp.T = fo.T; fp.minF = fo.minF; fp.maxF = fo.maxF;
+        fp.refOrder = fo.refOrder ? 1 : 0; fp.kHalf = fo.kHalf; fp.padLeft = fo.padLeft; fp.halfK = fo.halfK;
         fp.saveFormants = fo.saveFormants; fp.saveBandwidths = fo.saveBandwidths; fp.saveNValid = fo.saveNValid;
         if (formant_smem_bytes(fp) > 200 * 1024) { pl->ops.push_back(rt); osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cSpecResample: frame too long for the formant kernel"); }
       } else if (op.kind == SOP_ENERGY) {

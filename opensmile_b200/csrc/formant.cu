@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "frame_reader.cuh"
 #include "formant_math.cuh"
+#include "fft_ref_order.cuh"
 
 namespace osm {
 
@@ -40,13 +41,58 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
   const int N = tp.frameSize, I = p.nRes, IP = p.nResPad;
   FmtWarpWs *ws = reinterpret_cast<FmtWarpWs *>(fmtSmem);
   float *xw = reinterpret_cast<float *>(ws + kFmtWarps);        // [kFmtWarps][N]
-  float *res = xw + (size_t)kFmtWarps * N;                      // [kFmtWarps][IP]
+  float *res = xw + (size_t)kFmtWarps * (p.refOrder ? 4 * ro::kPlane : N);   // [kFmtWarps][IP]
   const OpTile tl = tp.tiles[blockIdx.x];
   const long long uo = tp.uttOff[tl.utt];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int fb = 0; fb < tl.nf; fb += kFmtWarps) {
     const int nb = min(kFmtWarps, tl.nf - fb);
+    if (p.refOrder) {
+      // Reference-order path (fft_ref_order.cuh): the zero padded windowed frame goes through a 512-point real FFT with the
+      // reference's rounding sequence; then cSpecResample's inverse sum over the reference's float tables, in its order.
+      float *planes = xw;                                        // [kFmtWarps][4][kPlane]: in / out, real / imaginary
+      const float *wc = p.D, *cosT = p.D + ro::kNw + ro::kNc, *sinT = cosT + (size_t)p.kHalf * IP;
+      for (int f = 0; f < nb; f++) {
+        FrameReader fr{tp, tp.pcm + (uo + (long long)(tl.f0 + fb + f) * tp.frameStep) * tp.nChan};
+        float *re = planes + (size_t)f * 4 * ro::kPlane, *im = re + ro::kPlane;
+        for (int n = tid; n < ro::kN; n += kFmtThreads) {
+          const int m = n - p.padLeft;
+          const float v = (m >= 0 && m < N) ? fr.at(m) : 0.0f;
+          ((n & 1) ? im : re)[ro::phys(n >> 1)] = v;
+        }
+      }
+      __syncthreads();
+      auto frame_planes = [&](int f, int which) { float *b = planes + ((size_t)f * 4 + 2 * which) * ro::kPlane; return ro::Planes{b, b + ro::kPlane}; };
+      for (int it = tid; it < ro::kItemsA * nb; it += kFmtThreads) ro::phase_a(frame_planes(it / ro::kItemsA, 0), wc, it % ro::kItemsA);
+      __syncthreads();
+      for (int it = tid; it < ro::kItemsB * nb; it += kFmtThreads) ro::phase_b(frame_planes(it / ro::kItemsB, 0), wc, it % ro::kItemsB);
+      __syncthreads();
+      for (int it = tid; it < ro::kItemsC * nb; it += kFmtThreads) ro::phase_c(frame_planes(it / ro::kItemsC, 0), wc, it % ro::kItemsC);
+      __syncthreads();
+      for (int it = tid; it < ro::kItemsD * nb; it += kFmtThreads)
+        ro::phase_d(frame_planes(it / ro::kItemsD, 0), frame_planes(it / ro::kItemsD, 1), wc + ro::kNw, it % ro::kItemsD);
+      __syncthreads();
+      // smileDsp_irdft (smileutil/smileUtil.c:1800-1820): out = DC; out += Re_k cos; out += Im_k sin (k ascending); out /= K/2
+      for (int i = tid; i < I; i += kFmtThreads) {
+        float acc[kFmtWarps];
+#pragma unroll
+        for (int f = 0; f < kFmtWarps; f++) acc[f] = planes[((size_t)f * 4 + 2) * ro::kPlane];
+        for (int k2 = 1; k2 < p.kHalf; k2++) {
+          const float cv = __ldg(cosT + (size_t)k2 * IP + i), sv = __ldg(sinT + (size_t)k2 * IP + i);
+          const int ph = ro::phys(k2);
+#pragma unroll
+          for (int f = 0; f < kFmtWarps; f++) {
+            const float *b = planes + ((size_t)f * 4 + 2) * ro::kPlane;
+            acc[f] = __fadd_rn(acc[f], __fmul_rn(b[ph], cv));
+            acc[f] = __fadd_rn(acc[f], __fmul_rn(b[ro::kPlane + ph], sv));
+          }
+        }
+#pragma unroll
+        for (int f = 0; f < kFmtWarps; f++) res[f * IP + i] = __fdiv_rn(acc[f], p.halfK);
+      }
+      __syncthreads();
+    } else {
     // 1. windowed frames (dspcore/windower.cpp:226) into shared memory
     for (int f = 0; f < nb; f++) {
       FrameReader fr{tp, tp.pcm + (uo + (long long)(tl.f0 + fb + f) * tp.frameStep) * tp.nChan};
@@ -68,6 +114,7 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
       for (int f = 0; f < kFmtWarps; f++) res[f * IP + i] = acc[f];
     }
     __syncthreads();
+    }
     // 3. one warp per frame
     if (warp < nb) {
       FmtWarpWs &w = ws[warp];
@@ -137,7 +184,8 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
 
 size_t formant_smem_bytes(const FormantParams &p)
 {
-  return sizeof(FmtWarpWs) * kFmtWarps + (size_t)kFmtWarps * ((size_t)p.tp.frameSize + p.nResPad) * sizeof(float);
+  const size_t perFrame = p.refOrder ? (size_t)4 * ro::kPlane : (size_t)p.tp.frameSize;
+  return sizeof(FmtWarpWs) * kFmtWarps + (size_t)kFmtWarps * (perFrame + p.nResPad) * sizeof(float);
 }
 
 cudaError_t launch_formant(const FormantParams &p, cudaStream_t st)

@@ -215,6 +215,8 @@ struct FormantParams {
   TimeOpParams tp;               // frame geometry, tiles, static rows (windowed = 1)
   const float *D;                // [frameSize][nResPad] composition of zero padding, FFT and the resampling inverse DFT
   int nRes, nResPad;             // samples of the resampled frame, row pitch of D
+  int refOrder, kHalf, padLeft;  // reference-order path: D = [wc | cos | sin] (plan.hpp FormantOp)
+  float halfK;
   int p;                         // predictor order
   int nFormants;
   double T, minF, maxF;          // sample period of the cLpc level, search range

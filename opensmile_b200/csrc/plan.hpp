@@ -160,7 +160,13 @@ struct JitterOp {
 struct FormantOp {
   int nIn = 0;                     // samples of the windowed frame
   int nRes = 0, nResPad = 0;       // samples of the resampled frame (cSpecResample output), row pitch of D
-  std::vector<float> D;            // [nIn][nResPad]: res[i] = sum_m xw[m] * D[m][i]
+  std::vector<float> D;            // [nIn][nResPad]: res[i] = sum_m xw[m] * D[m][i]   (composition path)
+  // reference-order path (FFT size 512, fft_ref_order.cuh): the frame is transformed with the reference's rounding sequence
+  // and resampled by the reference's float inverse-DFT sum; D then holds [wc (256) | cos [kHalf][nResPad] | sin [kHalf][nResPad]]
+  bool refOrder = false;
+  int kHalf = 0;                   // kMax / 2 of smileDsp_initIrdft: harmonics 1 .. kHalf-1 enter the sum
+  int padLeft = 0;                 // zeros in front of the frame (cTransformFFT.zeroPadSymmetric)
+  float halfK = 256.0f;            // the sum is divided by K / 2
   int p = 8;                       // cLpc.p
   double T = 0;                    // base period of the cLpc level = 1 / targetFs
   int nFormants = 0;
@@ -264,6 +270,7 @@ bool build_pitch_chain(const osm_b200_specscale &sc, const osm_b200_pitchshs &ps
                        int nMag, double fftFrameSizeSec, PitchChainOp &op, std::string &err);
 
 // fe = front end of the windower level the chain's cTransformFFT reads; zeroPadSymmetric = that cTransformFFT's switch
+void build_ref_fft_tables(std::vector<float> &wc);
 bool build_formant(const osm_b200_specresample &rs, const osm_b200_lpc &lp, const osm_b200_formantlpc &fl, const FrontEnd &fe,
                    bool zeroPadSymmetric, FormantOp &op, std::string &err);
 

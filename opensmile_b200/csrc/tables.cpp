@@ -6,6 +6,7 @@
 // Citations are relative to /root/reference/src.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.hpp"
@@ -557,8 +558,26 @@ bool build_formant(const osm_b200_specresample &rs, const osm_b200_lpc &lp, cons
   const int J = kMax / 2 - 1;                                                           // harmonics k = 1 .. J
   const int pad = zeroPadSymmetric ? (K - N) / 2 : 0;
   op.nIn = N; op.nRes = I; op.nResPad = (I + 31) / 32 * 32;
-  op.D.assign((size_t)N * op.nResPad, 0.0f);
   const double twoPi = 2.0 * M_PI, scale = 1.0 / (double)(K / 2);
+  if (K == 512 && I < K && !getenv("OSM_B200_FORMANT_COMPOSED")) {
+    // Reference-order path: the spectrum is computed with the reference's own rounding sequence (fft_ref_order.cuh) and the
+    // inverse sum runs over the reference's float tables in its order (smileDsp_initIrdft / smileDsp_irdft,
+    // smileutil/smileUtil.c:1752-1820): cos / sin of (2 pi (k i)) / nd evaluated in double, stored as float.
+    op.refOrder = true; op.kHalf = kMax / 2; op.padLeft = pad; op.halfK = (float)(K / 2);
+    std::vector<float> wc;
+    build_ref_fft_tables(wc);
+    const size_t plane = (size_t)op.kHalf * op.nResPad;
+    op.D.assign(wc.size() + 2 * plane, 0.0f);
+    std::copy(wc.begin(), wc.end(), op.D.begin());
+    float *ct = op.D.data() + wc.size(), *st = ct + plane;
+    for (int i = 0; i < I; i++)
+      for (long k2 = 1; k2 < op.kHalf; k2++) {
+        const double kn = twoPi * (double)(k2 * (long)i) / nd;
+        ct[(size_t)k2 * op.nResPad + i] = (float)cos(kn);
+        st[(size_t)k2 * op.nResPad + i] = (float)sin(kn);
+      }
+  } else {
+  op.D.assign((size_t)N * op.nResPad, 0.0f);
   for (int m = 0; m < N; m++) {
     const int n = pad + m;
     for (int i = 0; i < I; i++) {
@@ -576,6 +595,7 @@ bool build_formant(const osm_b200_specresample &rs, const osm_b200_lpc &lp, cons
       op.D[(size_t)m * op.nResPad + i] = (float)(acc * scale);
     }
   }
+  }
   op.p = lp.p;
   int nF = fl.nFormants;                                                                // formantLpc.cpp:160-167
   if (nF > lp.p - 1) nF = lp.p - 1;
@@ -591,6 +611,52 @@ bool build_formant(const osm_b200_specresample &rs, const osm_b200_lpc &lp, cons
   op.nOut = (op.saveNValid ? 1 : 0) + (op.saveFormants ? nF : 0) + (op.saveBandwidths ? nF : 0);
   if (op.nOut < 1) { err = "cFormantLpc produces no output"; return false; }
   return true;
+}
+
+// Twiddle tables of the reference's real FFT for n = 512 (fft_ref_order.cuh): w[nw = 128] followed by c[nc = 128], element for
+// element what Ooura's initialisation produces (dspcore/fftsg.c: makewt :660-718, makect :741-757) with FLOAT_TYPE_FFT = float
+// (src/include/dspcore/fftXg.h:16): the angle step is a FLOAT quotient, its multiples are FLOAT products that are widened to
+// double for libm's cos / sin, and the results are rounded back to float.  The sub-tables of the coarser levels are copies of
+// every other entry group; only their two interpolation constants are recomputed (float division).
+void build_ref_fft_tables(std::vector<float> &wc)
+{
+  const int nw = 128, nc = 128;
+  wc.assign(nw + nc, 0.0f);
+  float *w = wc.data(), *c = w + nw;
+  int nwh = nw >> 1;
+  const float delta = (float)atan(1.0) / (float)nwh;
+  const float wn4r = (float)cos((double)(delta * (float)nwh));
+  w[0] = 1.0f; w[1] = wn4r;
+  w[2] = (float)(0.5 / cos((double)(delta * 2.0f)));
+  w[3] = (float)(0.5 / cos((double)(delta * 6.0f)));
+  for (int j = 4; j < nwh; j += 4) {
+    const float d1 = delta * (float)j, d3 = (3.0f * delta) * (float)j;
+    w[j] = (float)cos((double)d1);
+    w[j + 1] = (float)sin((double)d1);
+    w[j + 2] = (float)cos((double)d3);
+    w[j + 3] = (float)(-sin((double)d3));
+  }
+  int nw0 = 0;
+  while (nwh > 2) {
+    const int nw1 = nw0 + nwh;
+    nwh >>= 1;
+    w[nw1] = 1.0f; w[nw1 + 1] = wn4r;
+    if (nwh == 4) { w[nw1 + 2] = w[nw0 + 4]; w[nw1 + 3] = w[nw0 + 5]; }
+    else if (nwh > 4) {
+      w[nw1 + 2] = 0.5f / w[nw0 + 4];
+      w[nw1 + 3] = 0.5f / w[nw0 + 6];
+      for (int j = 4; j < nwh; j += 4) for (int e = 0; e < 4; e++) w[nw1 + j + e] = w[nw0 + 2 * j + e];
+    }
+    nw0 = nw1;
+  }
+  const int nch = nc >> 1;
+  const float dc = (float)atan(1.0) / (float)nch;
+  c[0] = (float)cos((double)(dc * (float)nch));
+  c[nch] = 0.5f * c[0];
+  for (int j = 1; j < nch; j++) {
+    c[j] = (float)(0.5 * cos((double)(dc * (float)j)));
+    c[nc - j] = (float)(0.5 * sin((double)(dc * (float)j)));
+  }
 }
 
 }  // namespace osm

@@ -40,7 +40,7 @@ def cases():
         if any(k.startswith("compare_") for k in R.files):
             out.append(("ComParE_2016.conf (BASELINE configs[3])", "compare16/ComParE_2016.conf", {"lldcsvoutput": "x.csv"},
                         [(key + " (%d Hz)" % int(R["sr_" + key]), R["pcm_" + key], int(R["sr_" + key]), 1, R["compare_" + key])
-                         for key in sorted(k[4:] for k in R.files if k.startswith("pcm_"))]))
+                         for key in sorted(k[4:] for k in R.files if k.startswith("pcm_")) if "compare_" + key in R.files]))
     return out
 
 
@@ -61,11 +61,16 @@ def main():
     summary = {}
     for title, conf, opts, sigs in cases():
         for label, pcm, sr, nc, ref in sigs:
-            s = Session(os.path.join(REFCONF, conf), options=opts, device=0)
-            names = s.element_names(float(sr), nc)
-            rows, fo = s.extract_pcm(np.concatenate([pcm, np.zeros(8 * nc, np.int16)]), np.array([0, len(pcm) // nc], np.int64), float(sr), nc)
-            s.close()
             lines += ["## %s -- %s: %d rows x %d columns" % (title, label, ref.shape[0], ref.shape[1]), ""]
+            try:
+                s = Session(os.path.join(REFCONF, conf), options=opts, device=0)
+                names = s.element_names(float(sr), nc)
+                rows, fo = s.extract_pcm(np.concatenate([pcm, np.zeros(8 * nc, np.int16)]), np.array([0, len(pcm) // nc], np.int64), float(sr), nc)
+                s.close()
+            except Exception as e:                                   # an unsupported format is reported, not hidden
+                lines += ["NOT RUN: %s" % e, ""]
+                summary[title + " / " + label] = "not run: %s" % e
+                continue
             if rows.shape != ref.shape:
                 lines += ["SHAPE MISMATCH got %s ref %s" % (rows.shape, ref.shape), ""]
                 summary[title + " / " + label] = "shape mismatch"

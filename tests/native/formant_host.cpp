@@ -4,6 +4,7 @@
 //   g++ -O2 -ffp-contract=off -shared -fPIC -o formant_host.so formant_host.cpp
 #include "../../opensmile_b200/csrc/formant_math.cuh"
 #include "../../opensmile_b200/csrc/harmonics_math.cuh"
+#include "../../opensmile_b200/csrc/fft_ref_order.cuh"
 #include <vector>
 
 using namespace osm::fm;
@@ -88,7 +89,32 @@ int fmh_resample(double sampleRate, int N, int nfft, double frameSizeSec, int ze
   std::string err;
   if (!osm::build_formant(rs, lp, fl, fe, zeroPadSymmetric != 0, op, err)) return -1;
   if (Tper) *Tper = op.T;
-  if (res)
+  if (res && op.refOrder) {
+    // the kernel's reference-order path (formant.cu): 512-point transform of the zero padded frame, then the float inverse sum
+    using namespace osm::ro;
+    const float *wc = op.D.data(), *cosT = wc + kNw + kNc, *sinT = cosT + (size_t)op.kHalf * op.nResPad;
+    std::vector<float> buf(4 * kPlane);
+    Planes a{buf.data(), buf.data() + kPlane}, b{buf.data() + 2 * kPlane, buf.data() + 3 * kPlane};
+    for (int t = 0; t < T; t++) {
+      for (int n = 0; n < kN; n++) {
+        const int m = n - op.padLeft;
+        const float v = (m >= 0 && m < N) ? xw[(size_t)t * N + m] : 0.0f;
+        ((n & 1) ? a.im : a.re)[phys(n >> 1)] = v;
+      }
+      for (int i = 0; i < kItemsA; i++) phase_a(a, wc, i);
+      for (int i = 0; i < kItemsB; i++) phase_b(a, wc, i);
+      for (int i = 0; i < kItemsC; i++) phase_c(a, wc, i);
+      for (int i = 0; i < kItemsD; i++) phase_d(a, b, wc + kNw, i);
+      for (int i = 0; i < op.nRes; i++) {
+        float acc = b.re[0];
+        for (int k2 = 1; k2 < op.kHalf; k2++) {
+          acc = acc + b.re[phys(k2)] * cosT[(size_t)k2 * op.nResPad + i];
+          acc = acc + b.im[phys(k2)] * sinT[(size_t)k2 * op.nResPad + i];
+        }
+        res[(size_t)t * op.nRes + i] = acc / op.halfK;
+      }
+    }
+  } else if (res)
     for (int t = 0; t < T; t++)
       for (int i = 0; i < op.nRes; i++) {
         float acc = 0.0f;

@@ -61,18 +61,41 @@ def test_degenerate_frames():
     assert abs(f[0] - ang / (2 * np.pi) * 11000.0) < 1e-2 and abs(f[5] - (-np.log(0.9) * 11000.0 / np.pi)) < 1e-2 and not f[1:5].any()
 
 
-def test_resampling_table_against_the_reference_level():
+def test_resampled_frames_are_bit_identical_to_the_reference_level():
+    """FFT size 512: the kernel's statements (reference-order FFT, fft_ref_order.cuh, + the float inverse sum in the reference's
+    order) reproduce the reference's cSpecResample level bit for bit"""
     pcm = mixed_pcm(24000, 16000, seed=3)
     xw, nfft = fh.windowed_frames(pcm)
     res, per = fh.resample(xw, 16000.0, nfft, 0.020, 11000.0)
     assert res.shape == G["res"].shape and per == 1.0 / 11000.0
-    assert np.abs(res - G["res"]).max() / np.abs(G["res"]).max() < 2e-6
+    assert np.array_equal(res.view(np.uint32), G["res"].view(np.uint32))
 
 
-def test_end_to_end_deviation_is_the_conditioning_of_lpc():
-    """The 1e-6 difference of the resampled frames (above) reaches the formants through an order-11 float Durbin recursion:
-    typical rows agree to 1e-5, rows with poles next to each other move by percents (the same happens between two builds of
-    the reference with different FFT rounding).  Recorded here so a change of the table path shows up."""
+def test_composed_table_path_against_the_reference_level(monkeypatch):
+    """other FFT sizes use the composed table (zero padding, FFT and inverse sum folded into one matrix in double): 2e-6"""
+    monkeypatch.setenv("OSM_B200_FORMANT_COMPOSED", "1")
+    pcm = mixed_pcm(24000, 16000, seed=3)
+    xw, nfft = fh.windowed_frames(pcm)
+    res, per = fh.resample(xw, 16000.0, nfft, 0.020, 11000.0)
+    assert res.shape == G["res"].shape and per == 1.0 / 11000.0
+    err = np.abs(res - G["res"]).max() / np.abs(G["res"]).max()
+    assert 0 < err < 2e-6
+
+
+def test_end_to_end_formants_equal_the_reference_level():
+    """PCM -> formant frequencies / bandwidths through the kernel's statements: equal to the reference's cFormantLpc level on
+    every frame (the reference-order FFT removed the 1e-3 .. 1e-2 deviations that order-11 LPC made of 2e-7 spectral noise)"""
+    got = fh.formant_chain(mixed_pcm(24000, 16000, seed=3))
+    ref = G["fmt"]
+    assert got.shape == ref.shape
+    assert (np.abs(got - ref) / np.abs(ref).max(axis=0)).max() < 1e-6
+
+
+def test_composed_path_deviation_is_the_conditioning_of_lpc(monkeypatch):
+    """kept for the FFT sizes without a reference-order transform: a 1e-6 difference of the resampled frames reaches the
+    formants through an order-11 float Durbin recursion -- typical rows agree to 1e-5, rows with poles next to each other move
+    by percents"""
+    monkeypatch.setenv("OSM_B200_FORMANT_COMPOSED", "1")
     got = fh.formant_chain(mixed_pcm(24000, 16000, seed=3))
     ref = G["fmt"]
     err = np.abs(got - ref) / np.abs(ref).max(axis=0)

@@ -2,8 +2,7 @@
 through osm_b200_session_extract_files_arff on the GPU: file structure identical to the reference's files
 (headers, instance name, time stamps incl. the repeated one of the appended last row), values within 1e-5 of each
 column's scale.  (Named to run last: it exercises file I/O on top of paths the other GPU tests already cover.)
-Written after the last GPU run of its round: opt-in through OSM_B200_RUN_UNVERIFIED=1 until it has run on a device once
-(scripts/next_round_gpu.sh); the writers themselves are pinned byte for byte on the CPU (tests/test_pitch_cpu.py)."""
+The writers themselves are pinned byte for byte on the CPU (tests/test_pitch_cpu.py)."""
 import os
 
 import numpy as np
@@ -11,9 +10,7 @@ import pytest
 
 from opensmile_b200.synth import voiced_pcm
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OSM_B200_RUN_UNVERIFIED") != "1",
-                                 reason="ARFF session path not yet run on a device (set OSM_B200_RUN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 G = np.load(os.path.join(HERE, "golden", "pitch_goldens.npz"))
 CONF = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "config", "compare16", "ComParE_2016.conf")

@@ -1,7 +1,6 @@
 """tests/configs/gemaps_sel.conf (cDataSelector over the pitch and jitter / shimmer levels of the reference's shipped GeMAPS
 graph + the shipped selector gemapsv01b_lldsetE) on the GPU against the reference's CSV rows.  The selector only regroups
-columns of kernels the other GPU tests cover, but this grouping has not run on a device yet (written after the round's GPU
-budget was spent): opt-in through OSM_B200_RUN_UNVERIFIED=1 like tests/test_zzz_formant_gpu.py."""
+columns of kernels the other GPU tests cover."""
 import os
 
 import numpy as np
@@ -9,9 +8,7 @@ import pytest
 
 from opensmile_b200.synth import mixed_pcm, voiced_pcm
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OSM_B200_RUN_UNVERIFIED") != "1",
-                                 reason="selector grouping not yet run on a device (set OSM_B200_RUN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REFCONF = os.path.join(ROOT, "oracle", "_ref", "config")

@@ -1,13 +1,11 @@
 """Formant chain on the GPU (cWindower -> cTransformFFT -> cSpecResample -> cLpc -> cFormantLpc as one kernel,
 opensmile_b200/csrc/formant.cu) through the session C ABI.
 
-The kernel was written after this round's GPU budget was spent: it compiles for sm_100a and its arithmetic is pinned on the
-CPU (tests/test_formant_kernel_cpu.py), but it has not run on a device yet.  Until it has, this file only runs when
-OSM_B200_RUN_UNVERIFIED=1 is set (scripts/formant_gpu_check.sh); it is named to sort last.
-
-Bar: the device rows equal the host build of the same statements (tests/formant_harness.py: same table, same fmaf order, same
-recursions) to 1e-6 of each column's scale -- the resampled frames are bit-identical by construction, the roots differ only
-through libm (start values, atan2 / log).  The host build itself is held against the reference's level taps stage by stage."""
+At FFT size 512 (16 kHz, 20 ms frames: every GeMAPS-family configuration) the kernel transforms with the reference's rounding
+sequence (fft_ref_order.cuh) and resamples with the reference's float inverse sum, so the resampled frames are bit-identical to
+the reference's and the formants follow: the bar against the reference's own formant level is 1e-5 of each column's scale on
+EVERY row (the roots differ from the reference's QR iteration at the 1e-7 level only).  The kernel is also held to 1e-6 against
+the host build of the same statements (tests/formant_harness.py)."""
 import os
 
 import numpy as np
@@ -16,9 +14,7 @@ import pytest
 import formant_harness as fh
 from opensmile_b200.synth import mixed_pcm, voiced_pcm
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OSM_B200_RUN_UNVERIFIED") != "1",
-                                 reason="formant kernel not yet run on a device (set OSM_B200_RUN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 CONF = os.path.join(HERE, "configs", "formant_chain.conf")
 
@@ -46,11 +42,10 @@ def test_formant_rows_equal_the_host_build():
 
 
 def test_formant_rows_against_the_reference_taps():
-    """end to end against the reference's own formant level: typical rows to 1e-4, the ill-conditioned ones bounded in number
-    (tests/test_formant_kernel_cpu.py::test_end_to_end_deviation_is_the_conditioning_of_lpc)"""
+    """end to end against the reference's own cFormantLpc level: every row, every column within 1e-5"""
     G = np.load(os.path.join(HERE, "golden", "formant_goldens.npz"))
     got = _run([mixed_pcm(24000, 16000, seed=3)])[0]
     ref = G["fmt"]
     assert got.shape == ref.shape
     err = np.abs(got - ref) / np.abs(ref).max(axis=0)
-    assert np.median(err) < 1e-4 and (err.max(axis=1) > 1e-3).mean() < 0.25
+    assert err.max() < 1e-5

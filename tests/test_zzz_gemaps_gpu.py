@@ -1,9 +1,8 @@
-"""The shipped GeMAPSv01b.conf / eGeMAPSv02.conf (BASELINE configs[2]) end to end on the GPU against the reference's LLD files.
-
-Opt-in (OSM_B200_RUN_UNVERIFIED=1, scripts/formant_gpu_check.sh): formant.cu and harmonics.cu have not run on a device yet.
-Columns that do not read the formant chain are held to 1e-5 of the column scale; the formant-dependent ones (F1-F3 frequency /
-bandwidth / amplitude, H1-A3) to the conditioning bound documented in DESIGN.md 3.6 (median 1e-4, < 25 % of the rows beyond
-1e-3), the bound the CPU tests establish for the host build of the same statements."""
+"""The shipped GeMAPSv01a/b.conf, eGeMAPSv01a/b.conf, eGeMAPSv02.conf (BASELINE configs[2]) end to end on the GPU against the
+reference's LLD files: EVERY column -- including the formant frequencies / bandwidths / amplitudes and H1-A3 that read the
+order-11 LPC chain -- within 1e-5 of the column's scale on every row (north_star's bar).  The formant branch gets there
+through the reference-order FFT of fft_ref_order.cuh; scripts/parity_report.py prints the per-column table."""
+import json
 import os
 
 import numpy as np
@@ -11,11 +10,14 @@ import pytest
 
 from opensmile_b200.synth import mixed_pcm
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("OSM_B200_RUN_UNVERIFIED") != "1",
-                                 reason="formant / harmonics kernels not yet run on a device (set OSM_B200_RUN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "config")
+TOL = 1e-5
+
+
+def _percol(got, ref):
+    return np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)
 
 
 @pytest.mark.parametrize("conf,opts,key", [("gemaps/v01b/GeMAPSv01b.conf", {"lldhtkoutput": "x.htk"}, "gemaps_lld"),
@@ -31,19 +33,16 @@ def test_shipped_configuration_rows(conf, opts, key):
     names = s.element_names()
     rows, fo = s.extract_pcm(np.concatenate(pcms + [np.zeros(8, np.int16)]), off, 16000.0, 1)
     s.close()
-    fdep = [i for i, n in enumerate(names) if n.startswith(("F1", "F2", "F3")) or "H1-A3" in n]
-    rest = [i for i in range(len(names)) if i not in fdep]
     for i, k in enumerate((key + "_m24k", key + "_m40k")):
         got, ref = rows[fo[i]:fo[i + 1]], G[k]
         assert got.shape == ref.shape
-        err = np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-30)
-        assert err[:, rest].max() < 1e-5
-        assert np.median(err[:, fdep]) < 1e-4 and (err[:, fdep].max(axis=1) > 1e-3).mean() < 0.25
+        err = _percol(got, ref)
+        worst = {names[j]: float(err[:, j].max()) for j in range(len(names)) if err[:, j].max() >= TOL}
+        assert not worst, worst
 
 
 def test_all_shipped_gemaps_family_rows():
     """the five shipped feature-set files (v01a / v01b / v02) against the reference's LLD rows (tests/golden/gemaps_family.npz)"""
-    import json
     from opensmile_b200.session import Session
     if not os.path.isdir(REF):
         pytest.skip("reference configuration files not built (make -C oracle ref)")
@@ -57,8 +56,6 @@ def test_all_shipped_gemaps_family_rows():
         s.close()
         ref = R[os.path.splitext(os.path.basename(conf))[0]]
         assert names == g["names"] and rows.shape == ref.shape
-        fdep = [i for i, n in enumerate(names) if n.startswith(("F1", "F2", "F3")) or "H1-A3" in n]
-        rest = [i for i in range(len(names)) if i not in fdep]
-        err = np.abs(rows - ref) / (np.abs(ref).max(axis=0) + 1e-30)
-        assert err[:, rest].max() < 1e-5
-        assert np.median(err[:, fdep]) < 1e-4 and (err[:, fdep].max(axis=1) > 1e-3).mean() < 0.25
+        err = _percol(rows, ref)
+        worst = {names[j]: float(err[:, j].max()) for j in range(len(names)) if err[:, j].max() >= TOL}
+        assert not worst, (conf, worst)
