@@ -434,6 +434,12 @@ OSM_B200_API float       osm_b200_plan_last_kernel_ms(osm_b200_plan *plan);
 OSM_B200_API osm_b200_status osm_b200_plan_last_kernel_times(osm_b200_plan *plan, float *lld_ms,
                                                              float *post_ms);
 
+/* Per-kernel profiling of run_device (measurement aid, bench.py): when on, the auxiliary stream is not used and a CUDA
+ * event follows every kernel launch; after a run, entry idx names the idx-th launch of the step and its device time in ms. */
+OSM_B200_API void            osm_b200_plan_set_profiling(osm_b200_plan *plan, int32_t on);
+OSM_B200_API int32_t         osm_b200_plan_profile_count(osm_b200_plan *plan);
+OSM_B200_API osm_b200_status osm_b200_plan_profile_entry(osm_b200_plan *plan, int32_t idx, const char **name, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

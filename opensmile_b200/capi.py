@@ -258,7 +258,7 @@ EXPORTS = [
     "osm_b200_plan_frame_step_samples", "osm_b200_plan_fft_size", "osm_b200_plan_num_frames", "osm_b200_plan_num_time_frames",
     "osm_b200_plan_frame_offsets", "osm_b200_plan_run_device", "osm_b200_plan_run_host",
     "osm_b200_plan_last_launch_count", "osm_b200_plan_take_device_flags", "osm_b200_plan_last_kernel_ms",
-    "osm_b200_plan_last_kernel_times",
+    "osm_b200_plan_last_kernel_times", "osm_b200_plan_set_profiling", "osm_b200_plan_profile_count", "osm_b200_plan_profile_entry",
     # include/osm_b200_host.h
     "osm_b200_session_open", "osm_b200_session_close", "osm_b200_session_num_elements",
     "osm_b200_session_element_name", "osm_b200_session_extract_files", "osm_b200_session_extract_files_arff", "osm_b200_session_sink_options",
@@ -311,6 +311,10 @@ def lib():
     L.osm_b200_plan_last_kernel_ms.argtypes = [vp]
     L.osm_b200_plan_last_kernel_ms.restype = C.c_float
     L.osm_b200_plan_last_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.osm_b200_plan_set_profiling.argtypes = [vp, i32]
+    L.osm_b200_plan_set_profiling.restype = None
+    L.osm_b200_plan_profile_count.argtypes = [vp]
+    L.osm_b200_plan_profile_entry.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     # host front end (include/osm_b200_host.h)
     cpp = C.POINTER(C.c_char_p)
     L.osm_b200_session_open.argtypes = [C.c_char_p, i32, cpp, cpp, C.c_char_p, i32, C.POINTER(vp)]

@@ -163,6 +163,11 @@ struct osm_b200_plan {
   cudaStream_t hostStream = nullptr, h2dStream = nullptr, d2hStream = nullptr;
   std::vector<cudaEvent_t> evPiece;   // 2 per pipeline piece: PCM landed / rows computed
   int lastLaunches = 0;
+  // per-kernel profiling mode (osm_b200_plan_set_profiling): one event after every launch, everything on one stream
+  bool profile = false;
+  std::vector<cudaEvent_t> profEv;
+  std::vector<const char *> profName;
+  int profN = 0;
   LldLaunchInfo lastInfo{};
 };
 extern "C" {
@@ -857,6 +862,7 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
   if (pl->h2dStream) cudaStreamDestroy(pl->h2dStream);
   if (pl->d2hStream) cudaStreamDestroy(pl->d2hStream);
   for (cudaEvent_t e : pl->evPiece) cudaEventDestroy(e);
+  for (cudaEvent_t e : pl->profEv) cudaEventDestroy(e);
   cudaDeviceSynchronize();
   for (StreamRt &s : pl->st) {
     if (s.dConst) cudaFree(s.dConst);
@@ -1022,6 +1028,21 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
   return OSM_B200_OK;
 }
 
+static cudaError_t prof_mark(osm_b200_plan *pl, const char *name, cudaStream_t st)
+{
+  if (!pl->profile) return cudaSuccess;
+  if (pl->profN >= (int)pl->profEv.size()) {
+    cudaEvent_t e;
+    cudaError_t r = cudaEventCreate(&e);
+    if (r != cudaSuccess) return r;
+    pl->profEv.push_back(e);
+    pl->profName.push_back(name);
+  }
+  pl->profName[pl->profN] = name;
+  return cudaEventRecord(pl->profEv[pl->profN++], st);
+}
+#define PROF(name) CU(prof_mark(pl, name, st))
+
 // launch the kernels for utterances [u0, u1) of the prepared batch
 static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float *d_out, int n_utt, int u0, int u1,
                                     cudaStream_t st)
@@ -1029,6 +1050,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
   const PlanDesc &d = pl->d;
   const size_t nm = (size_t)(n_utt + 1);
   const long long *dU = pl->dMeta.p, *dR = dU + nm, *dS = dR + nm;
+  PROF("begin");
   // 1. per stream: FFT front end (+ fused band op / magnitude dump)
   for (size_t si = 0; si < pl->st.size(); si++) {
     StreamRt &rt = pl->st[si];
@@ -1057,12 +1079,15 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       }
       CU(launch_lld(kp, d.streams[si].fe.nfft, pl->numSMs, st, &pl->lastInfo));
       pl->lastLaunches++;
+      PROF("lld_kernel");
       if (pr.rasta) {
         RastaParams rp = pr.rp;
         rp.band = pr.dBand.p; rp.uttOff = dU; rp.statOff = dS;
         CU(launch_rasta(rp, u0, u1, st));
+        PROF("rasta_kernel");
         CU(launch_plp_tail(pr.tail, pr.dBand.p, pl->dStat.p, d.nStatic, d.ops[pr.op].outCol, row0, row1, st));
         pl->lastLaunches += 2;
+        PROF("plp_tail_kernel");
       }
     }
   }
@@ -1071,7 +1096,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
   bool forked = false;
   for (OpRt &o : pl->ops) {
     StreamRt &rt = pl->st[o.stream];
-    if ((o.kind == SOP_PITCH || o.kind == SOP_JITTER) && pl->auxStream && !forked) {
+    if ((o.kind == SOP_PITCH || o.kind == SOP_JITTER) && pl->auxStream && !forked && !pl->profile) {
       // everything the chain reads (magnitude level, selector energy) has been launched on `st` by now
       CU(cudaEventRecord(pl->evFork, st));
       CU(cudaStreamWaitEvent(pl->auxStream, pl->evFork, 0));
@@ -1083,6 +1108,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       const long long *hS = pl->hMeta.p + 2 * nm;
       CU(launch_vecop_ll1(pl->dStat.p, d.nStatic, o.vSrcCol, o.vN, o.vOutCol, hS[u0], hS[u1], st));
       pl->lastLaunches++;
+      PROF("vecop_kernel");
       continue;
     }
     const int t0 = rt.uttTile0[u0], t1 = rt.uttTile0[u1];
@@ -1091,6 +1117,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       CU(launch_mag_rows(rt.dMag.p + (size_t)t0 * o.vN * rt.tileF, rt.dTiles.p + t0, t1 - t0, rt.tileF, o.vN, dS,
                          pl->dStat.p, d.nStatic, o.vOutCol, st));
       pl->lastLaunches++;
+      PROF("mag_rows_kernel");
       continue;
     }
     if (o.kind == SOP_SPECTRAL) {
@@ -1099,6 +1126,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       sp.tiles = rt.dTiles.p + t0; sp.nTiles = t1 - t0;
       sp.statOff = dS; sp.stat = pl->dStat.p;
       CU(launch_spectral(sp, st));
+      PROF("spectral_kernel");
     } else if (o.kind == SOP_PITCH) {
       ShsParams sh = o.shs;
       CU(o.dShs.reserve((size_t)pl->totalStat * sh.nShsCols + 64));
@@ -1107,15 +1135,18 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       sh.tiles = rt.dTiles.p + t0; sh.nTiles = t1 - t0;
       sh.statOff = dS; sh.shs = o.dShs.p;
       CU(launch_shs(sh, ks));
+      PROF("shs_kernel");
       ViterbiParams vp = o.vit;
       vp.shs = o.dShs.p; vp.uttOff = dU; vp.statOff = dS; vp.stat = pl->dStat.p; vp.lag = o.dLag.p;
       CU(launch_viterbi(vp, u0, u1, ks));
       pl->lastLaunches++;
+      PROF("viterbi_kernel");
     } else if (o.kind == SOP_JITTER) {
       JitterParams jp = o.jit;
       jp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
       jp.uttOff = dU; jp.statOff = dS; jp.stat = pl->dStat.p; jp.errFlag = pl->dErr;
       CU(launch_jitter(jp, u0, u1, ks));
+      PROF("jitter_kernel");
     } else if (o.kind == SOP_PITCHACF) {
       AcfPitchParams ap = o.ap;
       CU(o.dRaw.reserve((size_t)pl->totalStat + 64));
@@ -1123,16 +1154,21 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       ap.tiles = rt.dTiles.p + t0; ap.nTiles = t1 - t0;
       ap.statOff = dS; ap.uttOff = dU; ap.raw = o.dRaw.p; ap.stat = pl->dStat.p; ap.nUtt = n_utt;
       CU(launch_acf_pitch(ap, st));
+      PROF("acf_pitch_kernel");
       CU(launch_pitch_smooth(ap, u0, u1, st));
       pl->lastLaunches++;
+      PROF("pitch_smooth_kernel");
     } else {
       TimeOpParams tp = o.tp;
       tp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
       tp.uttOff = dU; tp.statOff = dS;
       tp.tiles = rt.dTiles.p + t0; tp.nTiles = t1 - t0;
       tp.stat = pl->dStat.p;
-      if (o.kind == SOP_FORMANT) { FormantParams fp = o.fmt; fp.tp = tp; CU(launch_formant(fp, st)); }
-      else CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : (o.kind == SOP_INTENSITY ? launch_intensity(tp, st) : launch_mzcr(tp, st)));
+      if (o.kind == SOP_FORMANT) { FormantParams fp = o.fmt; fp.tp = tp; CU(launch_formant(fp, st)); PROF("formant_kernel"); }
+      else {
+        CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : (o.kind == SOP_INTENSITY ? launch_intensity(tp, st) : launch_mzcr(tp, st)));
+        PROF(o.kind == SOP_ENERGY ? "energy_kernel" : (o.kind == SOP_INTENSITY ? "intensity_kernel" : "mzcr_kernel"));
+      }
     }
     pl->lastLaunches++;
   }
@@ -1151,6 +1187,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
     hp.statOff = dS; hp.stat = pl->dStat.p;
     CU(launch_harmonics(hp, st));
     pl->lastLaunches++;
+    PROF("harmonics_kernel");
   }
   // 3. temporal stages + assembly of the output rows
   if (pl->pp.nGroups > 0 && !pl->fused) {
@@ -1164,11 +1201,13 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       CU(pl->dMeans.reserve((size_t)n_utt * d.nStatic + 64));
       CU(launch_cms_means(pp, pl->dMeans.p, u0, u1, st));
       pl->lastLaunches++;
+      PROF("cms_means_kernel");
       pp.means = pl->dMeans.p;
     }
     if (pp.nTiles > 0) {
       CU(launch_post(pp, st));
       pl->lastLaunches++;
+      PROF("post_kernel");
     }
   }
   // 4. levels behind the Viterbi-smoothed pitch chain
@@ -1178,6 +1217,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
     sq.out = d_out; sq.outStride = d.nOut; sq.lag = pl->ops[pl->seqLagOp].dLag.p;
     CU(launch_seq_post(sq, u0, u1, st));
     pl->lastLaunches++;
+    PROF("seq_post_kernel");
   }
   return OSM_B200_OK;
 }
@@ -1191,6 +1231,7 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
   CU(cudaSetDevice(pl->device));
   pl->lastLaunches = 0;
   pl->timed = false;
+  pl->profN = 0;
   osm_b200_status s = prepare_batch(pl, utt_offsets, n_utt, frame_offsets, st);
   if (s != OSM_B200_OK) return s;
   if (pl->totalRows == 0 || pl->totalWork == 0) return OSM_B200_OK;
@@ -1303,6 +1344,22 @@ float osm_b200_plan_last_kernel_ms(osm_b200_plan *pl)
   float ms = -1.f;
   if (cudaEventElapsedTime(&ms, pl->evK0, pl->evK1) != cudaSuccess) return -1.f;
   return ms;
+}
+
+void osm_b200_plan_set_profiling(osm_b200_plan *pl, int32_t on) { if (pl) pl->profile = on != 0; }
+
+int32_t osm_b200_plan_profile_count(osm_b200_plan *pl) { return (pl && pl->profN > 1) ? pl->profN - 1 : 0; }
+
+osm_b200_status osm_b200_plan_profile_entry(osm_b200_plan *pl, int32_t idx, const char **name, float *ms)
+{
+  if (!pl || idx < 0 || idx + 1 >= pl->profN) return fail(OSM_B200_ERR_INVALID, "profile entry out of range");
+  CU(cudaSetDevice(pl->device));
+  CU(cudaEventSynchronize(pl->profEv[idx + 1]));
+  float t = 0.0f;
+  CU(cudaEventElapsedTime(&t, pl->profEv[idx], pl->profEv[idx + 1]));
+  if (name) *name = pl->profName[idx + 1];
+  if (ms) *ms = t;
+  return OSM_B200_OK;
 }
 
 osm_b200_status osm_b200_plan_last_kernel_times(osm_b200_plan *pl, float *lld_ms, float *post_ms)

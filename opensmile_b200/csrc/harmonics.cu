@@ -8,9 +8,9 @@
 //     fs / F0 (getClosestPeak).  Only those lags are evaluated here, each as a cosine sum over the bins with the lanes
 //     of the warp striding the bins (double accumulation, table of cos(2 pi m / N)); every lane holds the reduced
 //     value, so the peak search runs uniformly on all lanes;
-//   - the harmonic peak search is inherently sequential (each harmonic starts where the previous one ended): lane 0,
-//     on the shared-memory copy, statements of harmonics_math.cuh.
-// Compiled with -fmad=false.  Status: built, first device run pending.
+//   - harmonic peak search with one lane per harmonic (the reference's "start at the previous harmonic's bin" never binds on
+//     a linear frequency axis; checked per frame, sequential fallback), log magnitudes per lane, warp arg-max per formant.
+// Compiled with -fmad=false.
 #include "kernels.cuh"
 #include "harmonics_math.cuh"
 
@@ -74,20 +74,63 @@ __global__ void __launch_bounds__(kHmThreads) harmonics_kernel(const HarmonicsPa
         if (lane == 0) dst[o] = v;
         o++;
       }
-      if (lane == 0) {
-        if (F0 > 0.0f) {
-          hm::Harm *H = HS + (size_t)warp * p.nHarm;
-          MagS M{m};
-          hm::find_harmonics(F0, M, nb, p.binHz, p.nHarm, H);
-          int fa[hm::kMaxFormants];
-          for (int k = 0; k < p.nFmt; k++) fa[k] = hm::formant_harmonic(H, p.nHarm, srow[p.fmtCol + k]);
+      if (F0 > 0.0f) {
+        // Harmonic peaks, lane = harmonic (i = lane, lane + 32, ...).  The reference searches harmonic i upward from the
+        // candidate bin of harmonic i-1 (freqToBin's start argument).  On the linear axis that lower bound never binds
+        // (candidate i-1 <= first bin above (i f0) <= the bin freqToBin finds for any later frequency), so every lane takes
+        // its predecessor's candidate from the closed form; each lane checks that its own candidate equals that closed form,
+        // and if any lane disagrees the warp falls back to the sequential statements on lane 0.
+        hm::Harm *H = HS + (size_t)warp * p.nHarm;
+        MagS M{m};
+        const int last0 = hm::freq_to_bin(p.binHz, nb, 0.5f * F0, 1);
+        const int first = hm::freq_to_bin(p.binHz, nb, 0.5f * F0, last0);
+        bool consistent = true;
+        for (int i = lane; i < p.nHarm; i += 32) {
+          const int prev = i == 0 ? last0 : hm::freq_to_bin(p.binHz, nb, (float)i * F0, 0);
+          hm::Harm h;
+          const int cand = hm::find_one_harmonic(F0, M, nb, p.binHz, i, prev, first, &h);
+          consistent = consistent && cand == hm::freq_to_bin(p.binHz, nb, (float)(i + 1) * F0, 0);
+          H[i] = h;
+        }
+        consistent = __all_sync(0xffffffffu, consistent);
+        __syncwarp();
+        if (!consistent) {
+          if (lane == 0) hm::find_harmonics(F0, M, nb, p.binHz, p.nHarm, H);
+        } else {
+          const float m0 = H[0].mag;
+          const bool logRel = m0 != 0.0f;
+          const float m0log = logRel ? log10f(m0) : 0.0f;
+          __syncwarp();
+          for (int i = lane; i < p.nHarm; i += 32) H[i].lr = i == 0 ? 0.0f : hm::log_rel(H[i].magi, logRel, m0log);
+          __syncwarp();
+          if (lane == 0) hm::dedup(H, p.nHarm);
+        }
+        __syncwarp();
+        // strongest harmonic within +-20 % of each formant (getFormantAmplitudeIndices): lanes stride the harmonics, warp
+        // arg-max with the lowest index among equal magnitudes (the sequential scan keeps the first of the largest)
+        int fa[hm::kMaxFormants];
+        for (int k = 0; k < p.nFmt; k++) {
+          const float f = srow[p.fmtCol + k], lo = 0.8f * f, hi = 1.2f * f;
+          int best = -1;
+          float bm = 0.0f;
+          for (int h = lane; h < p.nHarm; h += 32)
+            if (lo <= H[h].fi && H[h].fi <= hi && H[h].mag > bm) { best = h; bm = H[h].mag; }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, bm, off);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+            if (ob >= 0 && (best < 0 || om > bm || (om == bm && ob < best))) { bm = om; best = ob; }
+          }
+          fa[k] = best;
+        }
+        if (lane == 0) {
           for (int i = 0; i < p.nDiffs; i++)
             dst[o++] = hm::harmonic_difference(H, p.nHarm, fa, p.nFmt, hm::Diff{p.diffs[4 * i], p.diffs[4 * i + 1], p.diffs[4 * i + 2], p.diffs[4 * i + 3]});
           if (p.doFa) for (int k = p.faStart; k <= p.faEnd; k++) dst[o++] = (k >= 1 && k <= p.nFmt && fa[k - 1] >= 0) ? H[fa[k - 1]].lr : 0.0f;
-        } else {
-          for (int i = 0; i < p.nDiffs; i++) dst[o++] = 0.0f;
-          if (p.doFa) for (int k = p.faStart; k <= p.faEnd; k++) dst[o++] = p.floorUnvoiced;
         }
+      } else if (lane == 0) {
+        for (int i = 0; i < p.nDiffs; i++) dst[o++] = 0.0f;
+        if (p.doFa) for (int k = p.faStart; k <= p.faEnd; k++) dst[o++] = p.floorUnvoiced;
       }
     }
     __syncthreads();

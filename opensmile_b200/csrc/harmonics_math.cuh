@@ -68,17 +68,43 @@ OSM_HM_HD void quad3(double x1, double y1, double x2, double y2, double x3, doub
   *xo = x1; *yo = y1;
 }
 
-// findHarmonicPeaks, branch with a frequency axis (:476-545) + postProcessHarmonics with logRelMagnitude (:550-588).
-// M(b) = magnitude of bin b.
-template <class M>
-OSM_HM_HD void find_harmonics(float pitch, const M &mag, int nb, double binHz, int nHarm, Harm *H)
+// postProcessHarmonics with logRelMagnitude (:550-588), split in two so that a warp can share the work:
+// log magnitude of harmonic i >= 1 relative to the fundamental (log10 of a float argument is the float function in the
+// reference's build: log10f, widened afterwards) ...
+OSM_HM_HD float log_rel(float magi, bool logRel, float m0log)
 {
-  int last = freq_to_bin(binHz, nb, 0.5f * pitch, 1);
-  const int first = freq_to_bin(binHz, nb, 0.5f * pitch, last);
-  for (int i = 0; i < nHarm; i++) {
+  if (!logRel) return -201.0f;
+  if (magi > 0.0f) {
+    const double t = (double)log10f(magi);
+    const float v = (float)(20.0 * (t - (double)m0log));
+    return v >= -200.0f ? v : -200.0f;
+  }
+  return -200.0f;
+}
+// ... and the removal of duplicates, which compares with the (possibly already cleared) predecessor: sequential
+OSM_HM_HD void dedup(Harm *H, int nHarm)
+{
+  for (int i = 1; i < nHarm; i++)
+    if (H[i].bin == H[i - 1].bin) H[i] = Harm{0, 0.0f, 0.0f, 0.0f, -201.0f};
+}
+OSM_HM_HD void post_process(Harm *H, int nHarm)
+{
+  const float m0 = H[0].mag;
+  const bool logRel = m0 != 0.0f;
+  const float m0log = logRel ? log10f(m0) : 0.0f;
+  H[0].lr = 0.0f;                                             // unconditional in the reference (:561)
+  for (int i = 1; i < nHarm; i++) H[i].lr = log_rel(H[i].magi, logRel, m0log);
+  dedup(H, nHarm);
+}
+
+// one harmonic of findHarmonicPeaks, branch with a frequency axis (:476-545): `last` = the previous harmonic's candidate
+// bin (lower bound of this one's search), returns this harmonic's candidate bin.  M(b) = magnitude of bin b.
+template <class M>
+OSM_HM_HD int find_one_harmonic(float pitch, const M &mag, int nb, double binHz, int i, int last, int first, Harm *out)
+{
     Harm h{-1, 0.0f, 0.0f, 0.0f, -201.0f};
     const int cand = freq_to_bin(binHz, nb, (float)(i + 1) * pitch, last);
-    if (cand >= nb) { H[i] = h; continue; }
+    if (cand >= nb) { *out = h; return last; }
     int peak = -1;
     if (is_peak(mag, nb, cand)) peak = cand;
     else {
@@ -98,23 +124,18 @@ OSM_HM_HD void find_harmonics(float pitch, const M &mag, int nb, double binHz, i
             (double)mag(peak + 1), &x, &y);
       h.fi = (float)x; h.magi = (float)y;
     } else h.bin = cand;
-    last = cand;
-    H[i] = h;
-  }
-  bool logRel = true;
-  float m0 = H[0].mag;
-  if (m0 == 0.0f) logRel = false;
-  else { m0 = log10f(m0); H[0].lr = 0.0f; }
-  for (int i = 1; i < nHarm; i++) {
-    if (logRel) {
-      if (H[i].magi > 0.0f) {
-        const double t = log10((double)H[i].magi);
-        const float v = (float)(20.0 * (t - (double)m0));
-        H[i].lr = v >= -200.0f ? v : -200.0f;
-      } else H[i].lr = -200.0f;
-    } else H[i].lr = -201.0f;
-    if (H[i].bin == H[i - 1].bin) H[i] = Harm{0, 0.0f, 0.0f, 0.0f, -201.0f};
-  }
+    *out = h;
+    return cand;
+}
+
+// findHarmonicPeaks + postProcessHarmonics, sequential form (host build, and the kernel's fallback)
+template <class M>
+OSM_HM_HD void find_harmonics(float pitch, const M &mag, int nb, double binHz, int nHarm, Harm *H)
+{
+  int last = freq_to_bin(binHz, nb, 0.5f * pitch, 1);
+  const int first = freq_to_bin(binHz, nb, 0.5f * pitch, last);
+  for (int i = 0; i < nHarm; i++) last = find_one_harmonic(pitch, mag, nb, binHz, i, last, first, &H[i]);
+  post_process(H, nHarm);
 }
 
 // the strongest harmonic within +-20 % of a formant frequency (getFormantAmplitudeIndices, :714-741); -1 = none

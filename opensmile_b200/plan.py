@@ -229,6 +229,21 @@ class Plan:
         return a.value, b.value
 
 
+    def set_profiling(self, on):
+        """per-kernel CUDA-event timing of run_device (serialises the step on one stream)"""
+        self._L.osm_b200_plan_set_profiling(self._h, 1 if on else 0)
+
+    def kernel_profile(self):
+        """[(kernel name, ms)] of the last profiled run_device, in launch order"""
+        out = []
+        for i in range(self._L.osm_b200_plan_profile_count(self._h)):
+            nm, ms = C.c_char_p(), C.c_float(0)
+            if self._L.osm_b200_plan_profile_entry(self._h, i, C.byref(nm), C.byref(ms)) != capi.OK:
+                raise RuntimeError(capi.last_error())
+            out.append((nm.value.decode(), ms.value))
+        return out
+
+
 def _addr(buf):
     if hasattr(buf, "data_ptr"):
         return C.c_void_p(buf.data_ptr())
