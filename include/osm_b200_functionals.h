@@ -1,0 +1,105 @@
+/*
+ * osm_b200_functionals.h -- cFunctionals on the GPU: per-utterance summaries of resident LLD rows.
+ *
+ * Mirrors the reference's cFunctionals component in full-input mode (frameMode = full: one output vector per utterance,
+ * src/functionals/functionals.cpp:284-330) with the sub-components
+ *     cFunctionalExtremes     src/functionals/functionalExtremes.cpp:89-132
+ *     cFunctionalMeans        src/functionals/functionalMeans.cpp:104-262
+ *     cFunctionalMoments      src/functionals/functionalMoments.cpp:89-168
+ *     cFunctionalPercentiles  src/functionals/functionalPercentiles.cpp:299-430
+ *     cFunctionalRegression   src/functionals/functionalRegression.cpp:141-428
+ * Field names and defaults are the reference's configuration fields (`[x:cFunctionals]` section: functionalsEnabled,
+ * nonZeroFuncts, functNameAppend, masterTimeNorm, and `<Functional>.<field>` for the sub-components).
+ *
+ * The input is the row-major LLD matrix a plan leaves in HBM ([sum rows][row_stride] float32, utterance u owns rows
+ * row_offsets[u] .. row_offsets[u] + n_rows[u]); the output is one row of num_elements floats per utterance, laid out like the
+ * reference's functionals level: for every input element, its enabled values in functionalsEnabled order
+ * (src/functionals/functionals.cpp:215-256 for the names).  One warp per (utterance, element).
+ * No CPU fallback: device < 0 gives a description-only object (names / counts) that cannot run.
+ */
+#ifndef OSM_B200_FUNCTIONALS_H
+#define OSM_B200_FUNCTIONALS_H
+
+#include "osm_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  OSM_B200_F_EXTREMES = 0, OSM_B200_F_MEANS, OSM_B200_F_MOMENTS, OSM_B200_F_PERCENTILES, OSM_B200_F_REGRESSION,
+  OSM_B200_F_COUNT_
+} osm_b200_functional_type;
+
+/* time normalisation (src/include/functionals/functionalComponent.hpp:27-35) */
+#define OSM_B200_TIMENORM_UNSET   (-1)
+#define OSM_B200_TIMENORM_SEGMENT 0
+#define OSM_B200_TIMENORM_SECOND  1
+#define OSM_B200_TIMENORM_FRAME   2
+
+#define OSM_B200_F_MAX_ENABLED 8
+#define OSM_B200_F_MAX_PCTL 8
+
+typedef struct {
+  /* [x:cFunctionals] */
+  int32_t n_enabled;                               /* entries of functionalsEnabled */
+  int32_t enabled[OSM_B200_F_MAX_ENABLED];         /* osm_b200_functional_type, in the order of the array */
+  int32_t nonZeroFuncts;                           /* 0; 1 = values != 0 only; 2 = values > 0 only */
+  int32_t masterTimeNorm;                          /* OSM_B200_TIMENORM_*, UNSET when the field is absent */
+  char    functNameAppend[OSM_B200_NAME_LEN];      /* "" = none */
+  struct {                                         /* Extremes.* : 1,1,1,1,1,0,1,1 ; norm "frames" */
+    int32_t max, min, range, maxpos, minpos, amean, maxameandist, minameandist;
+    int32_t norm, normIsSet;                       /* own `norm` field and whether the configuration sets it */
+  } extremes;
+  struct {                                         /* Means.* : 1,1,1,1,1,1,1,1,0,... ; norm "frames" */
+    int32_t amean, absmean, qmean, nzamean, nzabsmean, nzqmean, nzgmean, nnz, flatness, posamean, negamean,
+            posqmean, posrqmean, negqmean, negrqmean, rqmean, nzrqmean;
+    int32_t norm, normIsSet;
+  } means;
+  struct {                                         /* Moments.* : 1,1,1,1,0, stddevNorm 0 (1 = / |mean|, 2 = / mean) */
+    int32_t variance, stddev, skewness, kurtosis, amean, stddevNorm, doRatioLimit;
+  } moments;
+  struct {                                         /* Percentiles.* */
+    int32_t quartile1, quartile2, quartile3, iqr12, iqr23, iqr13;
+    int32_t n_percentile;  double percentile[OSM_B200_F_MAX_PCTL];
+    int32_t n_pctlrange;   int32_t pctlrange[OSM_B200_F_MAX_PCTL][2];
+    int32_t interp;                                /* 1 */
+  } percentiles;
+  struct {                                         /* Regression.* : nine values + centroid on by default */
+    int32_t linregc1, linregc2, linregerrA, linregerrQ, qregc1, qregc2, qregc3, qregerrA, qregerrQ, centroid;
+    int32_t centroidNorm;                          /* SEGMENT */
+    int32_t centroidUseAbsValues, centroidRatioLimit;   /* 1, 1 (the limiter is not implemented: must be 0 when centroid = 1) */
+    int32_t normRegCoeff, normInputs, oldBuggyQerr, doRatioLimit;   /* 0, 0, 1, 0 */
+  } regression;
+} osm_b200_functionals_spec;
+
+typedef struct osm_b200_functionals osm_b200_functionals;
+
+/* the reference's defaults (no functional enabled) */
+OSM_B200_API void osm_b200_functionals_defaults(osm_b200_functionals_spec *spec);
+
+/* in_names: the n_in element names of the input level (osm_b200_plan_element_name); input_period: frame period of that
+ * level in seconds (osm_b200_plan_frame_period).  device < 0: description only. */
+OSM_B200_API osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spec, int32_t n_in,
+                                                         const char *const *in_names, double input_period, int32_t device,
+                                                         osm_b200_functionals **f);
+OSM_B200_API void            osm_b200_functionals_destroy(osm_b200_functionals *f);
+OSM_B200_API int32_t         osm_b200_functionals_num_values(const osm_b200_functionals *f);     /* per input element */
+OSM_B200_API int32_t         osm_b200_functionals_num_elements(const osm_b200_functionals *f);   /* n_in * num_values */
+OSM_B200_API const char     *osm_b200_functionals_element_name(const osm_b200_functionals *f, int32_t idx);
+
+/* d_rows: device LLD matrix, row_stride floats per row, the first n_in columns are summarised.  row_offsets / n_rows: HOST arrays
+ * of n_utt entries (first row and number of rows of every utterance; n_rows[u] = 0 gives an all-zero output row).
+ * d_out: device [n_utt][num_elements].  Asynchronous on `stream` (cudaStream_t). */
+OSM_B200_API osm_b200_status osm_b200_functionals_run_device(osm_b200_functionals *f, const float *d_rows, int32_t row_stride,
+                                                             const int64_t *row_offsets, const int64_t *n_rows, int32_t n_utt,
+                                                             float *d_out, void *stream);
+/* same with host buffers (copies in, runs, copies out, synchronises) */
+OSM_B200_API osm_b200_status osm_b200_functionals_run_host(osm_b200_functionals *f, const float *rows, int32_t row_stride,
+                                                           const int64_t *row_offsets, const int64_t *n_rows, int32_t n_utt,
+                                                           int64_t total_rows, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
