@@ -393,6 +393,11 @@ OSM_B200_API int32_t     osm_b200_plan_fft_size(const osm_b200_plan *plan);
  * concat = min over inputs) */
 OSM_B200_API int64_t     osm_b200_plan_num_frames(const osm_b200_plan *plan, int64_t n_sample_frames);
 
+/* rows of the output level that exist when a full-input reader (cFunctionals, frameMode = full) ticks for the first time at
+ * end of input: the window processors of the level have each appended one frame by then, not yet all of them
+ * (blocksize 1, core/windowProcessor.cpp:167-230); that is the contour the reference's functionals summarise */
+OSM_B200_API int64_t     osm_b200_plan_num_frames_first_eoi(const osm_b200_plan *plan, int64_t n_sample_frames);
+
 /* number of distinct time stamps of those rows: frames of the level the first output field comes from, before its
  * window processors.  The rows a window processor appends at the end of input repeat the time stamp of the last
  * real frame (their tmeta is a copy, src/core/dataMemoryLevel.cpp:1698-1708), so row r of a sink's file carries the
@@ -419,6 +424,11 @@ OSM_B200_API osm_b200_status osm_b200_plan_run_host(osm_b200_plan *plan, const v
                                        const int64_t *utt_offsets, int32_t n_utt,
                                        const int64_t *frame_offsets, float *out);
 
+/* like run_host, but the rows stay in HBM: *d_rows = the plan's own device row buffer [rows][num_elements], valid until
+ * the plan's next run (hand-over to osm_b200_functionals_run_device, include/osm_b200_functionals.h) */
+OSM_B200_API osm_b200_status osm_b200_plan_run_host_resident(osm_b200_plan *plan, const void *pcm,
+                                            const int64_t *utt_offsets, int32_t n_utt,
+                                            const int64_t *frame_offsets, const float **d_rows);
 /* number of CUDA kernels the last run_* call launched (for bench.py's gpu_launches) */
 OSM_B200_API int32_t     osm_b200_plan_last_launch_count(const osm_b200_plan *plan);
 /* Device-side condition flags of the runs since the last call (synchronises the device, then clears them).

@@ -75,6 +75,8 @@ typedef struct {
 
 typedef struct osm_b200_functionals osm_b200_functionals;
 
+/* sizeof(osm_b200_functionals_spec) as compiled (bindings check their mirror against it) */
+OSM_B200_API int32_t osm_b200_functionals_sizeof_spec(void);
 /* the reference's defaults (no functional enabled) */
 OSM_B200_API void osm_b200_functionals_defaults(osm_b200_functionals_spec *spec);
 

@@ -256,7 +256,12 @@ EXPORTS = [
     "osm_b200_plan_destroy", "osm_b200_plan_num_elements", "osm_b200_plan_element_name",
     "osm_b200_plan_frame_period", "osm_b200_plan_frame_size_samples",
     "osm_b200_plan_frame_step_samples", "osm_b200_plan_fft_size", "osm_b200_plan_num_frames", "osm_b200_plan_num_time_frames",
-    "osm_b200_plan_frame_offsets", "osm_b200_plan_run_device", "osm_b200_plan_run_host",
+    "osm_b200_plan_frame_offsets", "osm_b200_plan_run_device", "osm_b200_plan_run_host", "osm_b200_plan_run_host_resident",
+    "osm_b200_plan_num_frames_first_eoi",
+    # include/osm_b200_functionals.h
+    "osm_b200_functionals_defaults", "osm_b200_functionals_create", "osm_b200_functionals_destroy", "osm_b200_functionals_num_values",
+    "osm_b200_functionals_num_elements", "osm_b200_functionals_element_name", "osm_b200_functionals_run_device", "osm_b200_functionals_run_host",
+    "osm_b200_functionals_sizeof_spec",
     "osm_b200_plan_last_launch_count", "osm_b200_plan_take_device_flags", "osm_b200_plan_last_kernel_ms",
     "osm_b200_plan_last_kernel_times", "osm_b200_plan_set_profiling", "osm_b200_plan_profile_count", "osm_b200_plan_profile_entry",
     # include/osm_b200_host.h
@@ -305,6 +310,8 @@ def lib():
     L.osm_b200_plan_num_frames.restype = C.c_int64
     L.osm_b200_plan_num_time_frames.argtypes = [vp, C.c_int64]
     L.osm_b200_plan_num_time_frames.restype = C.c_int64
+    L.osm_b200_plan_num_frames_first_eoi.argtypes = [vp, C.c_int64]
+    L.osm_b200_plan_num_frames_first_eoi.restype = C.c_int64
     L.osm_b200_plan_frame_offsets.argtypes = [vp, i64p, i32, i64p]
     L.osm_b200_plan_run_device.argtypes = [vp, vp, i64p, i32, i64p, vp, vp]
     L.osm_b200_plan_run_host.argtypes = [vp, vp, i64p, i32, i64p, vp]

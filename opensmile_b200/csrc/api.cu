@@ -17,14 +17,14 @@
 using namespace osm;
 
 namespace {
-
 thread_local std::string g_err;
-
-osm_b200_status fail(osm_b200_status st, const std::string &msg)
-{
-  g_err = msg;
-  return st;
 }
+// shared with the other translation units of the library (functionals.cu): the message osm_b200_last_error() returns
+namespace osm { osm_b200_status set_last_error(osm_b200_status st, const std::string &msg) { g_err = msg; return st; } }
+
+namespace {
+
+osm_b200_status fail(osm_b200_status st, const std::string &msg) { return osm::set_last_error(st, msg); }
 
 osm_b200_status cuda_fail(cudaError_t e, const char *what)
 {
@@ -1249,8 +1249,8 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
 // streams: H2D of piece k+1, kernels of piece k and D2H of piece k-1 overlap (the two copy
 // directions use separate copy engines).  Host memory should be pinned (cudaHostAlloc /
 // torch pin_memory) for the copies to be asynchronous; pageable memory works but serialises.
-osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const int64_t *utt_offsets, int32_t n_utt,
-                                       const int64_t *frame_offsets, float *out)
+static osm_b200_status run_host_impl(osm_b200_plan *pl, const void *pcm, const int64_t *utt_offsets, int32_t n_utt,
+                                     const int64_t *frame_offsets, float *out, bool resident)
 {
   if (!pl || !utt_offsets || n_utt < 0) return fail(OSM_B200_ERR_INVALID, "null argument");
   if (pl->device < 0) return fail(OSM_B200_ERR_CUDA, "description-only plan (device < 0) cannot run; no CPU fallback");
@@ -1267,7 +1267,7 @@ osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const
   if (s != OSM_B200_OK) return s;
   const long long rows = pl->totalRows;
   if (rows == 0 || pl->totalWork == 0) return OSM_B200_OK;
-  if (!pcm || !out) return fail(OSM_B200_ERR_INVALID, "null host buffer");
+  if (!pcm || (!out && !resident)) return fail(OSM_B200_ERR_INVALID, "null host buffer");
   const int nChan = pl->d.fe0().nChan, nOut = pl->d.nOut;
   const int64_t nSamp = utt_offsets[n_utt] * nChan;
   CU(pl->dPcm.reserve((size_t)nSamp + 16));
@@ -1305,7 +1305,7 @@ osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const
     CU(cudaEventRecord(pl->evPiece[2 * k + 1], st));
     CU(cudaStreamWaitEvent(pl->d2hStream, pl->evPiece[2 * k + 1], 0));
     const long long ra = hR[u0], rb = hR[u1];
-    if (rb > ra)
+    if (rb > ra && out)
       CU(cudaMemcpyAsync(out + ra * nOut, pl->dOut.p + ra * nOut, (size_t)(rb - ra) * nOut * sizeof(float),
                          cudaMemcpyDeviceToHost, pl->d2hStream));
     u0 = u1;
@@ -1324,6 +1324,27 @@ osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const
   }
   return OSM_B200_OK;
 }
+
+osm_b200_status osm_b200_plan_run_host(osm_b200_plan *pl, const void *pcm, const int64_t *utt_offsets, int32_t n_utt,
+                                       const int64_t *frame_offsets, float *out)
+{
+  return run_host_impl(pl, pcm, utt_offsets, n_utt, frame_offsets, out, false);
+}
+
+// Host PCM in, rows left in HBM: the H2D pipeline and kernels of run_host without the copy back.  *d_rows = the plan's own
+// row buffer ([rows][num_elements], valid until the plan's next run): the hand-over point to a consumer that summarises the
+// rows on the device (osm_b200_functionals_run_device).
+osm_b200_status osm_b200_plan_run_host_resident(osm_b200_plan *pl, const void *pcm, const int64_t *utt_offsets, int32_t n_utt,
+                                                const int64_t *frame_offsets, const float **d_rows)
+{
+  if (!d_rows) return fail(OSM_B200_ERR_INVALID, "null argument");
+  *d_rows = nullptr;
+  osm_b200_status s = run_host_impl(pl, pcm, utt_offsets, n_utt, frame_offsets, nullptr, true);
+  if (s == OSM_B200_OK) *d_rows = pl->dOut.p;
+  return s;
+}
+
+int64_t osm_b200_plan_num_frames_first_eoi(const osm_b200_plan *pl, int64_t n) { return pl ? desc_num_frames_first_eoi(pl->d, n) : 0; }
 
 int32_t osm_b200_plan_last_launch_count(const osm_b200_plan *pl) { return pl ? pl->lastLaunches : 0; }
 

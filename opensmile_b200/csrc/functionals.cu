@@ -1,0 +1,549 @@
+// functionals.cu -- cFunctionals in full-input mode on the GPU (include/osm_b200_functionals.h).
+//
+// One warp per contour = (utterance, LLD element).  The contour is streamed from the row-major LLD matrix in chunks of 32
+// frames (lane = frame); the reference's nonZeroFuncts filter (functionals.cpp:286-299) becomes an order-preserving warp
+// compaction on the fly (ballot + prefix popcount give every kept value its index in the filtered contour, which the position
+// and regression functionals need).  Two passes:
+//   pass 1  count, sum, min / max with first positions, the power / sign / log sums of cFunctionalMeans, the moment sums
+//           sum x i, sum x i^2 of cFunctionalRegression; the filtered contour is copied to shared memory when percentiles are
+//           enabled
+//   pass 2  central moments about the float mean (functionalMoments.cpp:96-108) and the regression residuals
+//           (functionalRegression.cpp:263-290), which need the results of pass 1
+// then a warp-wide bitonic sort of the shared copy for cFunctionalPercentiles (the reference sorts with std::sort,
+// functionals.cpp:296-299), and lane 0 assembles the values in the reference's order.
+// All accumulators are double like the reference's; the reference adds sequentially, a warp adds 32 strided partial sums and
+// combines them by shuffles -- a reordering of double additions, 1e-16 relative, invisible in the float results.
+// Compiled with -fmad=false (the float expressions of the percentile interpolation keep their two roundings).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/osm_b200_functionals.h"
+#include "plan.hpp"
+
+namespace osm {
+namespace {
+
+constexpr int kFnWarps = 4;
+constexpr int kFnThreads = kFnWarps * 32;
+constexpr int kMaxSort = 8192;              // longest filtered contour with percentiles enabled (32 KB per warp)
+
+struct FnParams {
+  const float *rows; int rowStride; int nIn;
+  const long long *rowOff, *nRows;          // device [nUtt]
+  float *out; int nVals;                    // out[u][e * nVals + v]
+  int sortCap;                              // floats per warp in shared memory (0: no percentiles)
+  float period; double periodD;             // input level period as FLOAT_DMEM and as double
+  osm_b200_functionals_spec s;
+  int extNorm, meanNorm;                    // resolved time normalisations
+  int needReg, enQreg;
+};
+
+__device__ __forceinline__ double wsum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long wsumll(long long v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct Keep {
+  int mode;
+  __device__ __forceinline__ bool operator()(float x) const { return mode == 0 || (mode == 2 ? x > 0.0f : x != 0.0f); }
+};
+
+// getInterpPctl (functionalPercentiles.cpp:317-336)
+__device__ float interp_pctl(double p, const float *s, long long N)
+{
+  const double idx = p * (double)(N - 1);
+  long long i1 = (long long)floor(idx), i2 = (long long)ceil(idx);
+  i1 = i1 < 0 ? 0 : (i1 >= N ? N - 1 : i1);
+  i2 = i2 < 0 ? 0 : (i2 >= N ? N - 1 : i2);
+  if (i1 != i2) {
+    const double w1 = idx - (double)i1, w2 = (double)i2 - idx;
+    return __fadd_rn(__fmul_rn(s[i1], (float)w2), __fmul_rn(s[i2], (float)w1));
+  }
+  return s[i1];
+}
+__device__ float index_pctl(double p, const float *s, long long N)          // getPctlIdx (:309-315): C round()
+{
+  long long r = (long long)round(p * (double)(N - 1));
+  r = r < 0 ? 0 : (r >= N ? N - 1 : r);
+  return s[r];
+}
+
+__global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams p)
+{
+  extern __shared__ float fnSort[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = (p.nIn + kFnWarps - 1) / kFnWarps;
+  const int u = blockIdx.x / groups, e = (blockIdx.x % groups) * kFnWarps + warp;
+  if (e >= p.nIn) return;
+  const long long T = p.nRows[u];
+  const float *col = p.rows + p.rowOff[u] * (long long)p.rowStride + e;
+  float *out = p.out + ((long long)u * p.nIn + e) * p.nVals;
+  float *sbuf = fnSort + (size_t)warp * p.sortCap;
+  const Keep keep{p.s.nonZeroFuncts};
+  const unsigned ltMask = (1u << lane) - 1u;
+
+  // ---------------- pass 1 ----------------
+  long long cnt = 0;
+  double sum = 0, sAbs = 0, sSq = 0, sLog = 0, sPos = 0, sNeg = 0, sPosSq = 0, sNegSq = 0, sNz = 0, sNzAbs = 0, sNzSq = 0;
+  double num = 0, num2 = 0, numAbs = 0;
+  long long nPos = 0, nNeg = 0, nNz = 0;
+  float mn = INFINITY, mx = -INFINITY;
+  long long mnI = 0x7fffffffffffffffLL, mxI = 0x7fffffffffffffffLL;
+  for (long long t0 = 0; t0 < T; t0 += 32) {
+    const long long t = t0 + lane;
+    const float x = t < T ? col[t * p.rowStride] : 0.0f;
+    const bool k = t < T && keep(x);
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const long long i = cnt + __popc(m & ltMask);
+      const double xd = (double)x, fa = fabs(xd), ii = (double)i;
+      sum += xd; sAbs += fa;
+      if (x < mn) { mn = x; mnI = i; }
+      if (x > mx) { mx = x; mxI = i; }
+      if (x > 0.0f) { sPos += xd; sPosSq += xd * xd; nPos++; }
+      if (x < 0.0f) { sNeg += xd; sNegSq += xd * xd; nNeg++; }
+      if (x != 0.0f) { sNz += xd; sNzAbs += fa; sNzSq += xd * xd; sLog += log(fa); nNz++; sSq += xd * xd; }
+      double tmp = xd * ii;
+      num += tmp; num2 += tmp * ii;
+      numAbs += fa * ii;
+      if (p.sortCap > 0 && i < p.sortCap) sbuf[i] = x;
+    }
+    cnt += __popc(m);
+  }
+  const long long N = cnt;                 // uniform
+  if (N == 0) {                            // every sub-component returns nothing: zero fill (functionals.cpp:316-320)
+    for (int v = lane; v < p.nVals; v += 32) out[v] = 0.0f;
+    return;
+  }
+  sum = wsum(sum); sAbs = wsum(sAbs); sSq = wsum(sSq); sLog = wsum(sLog); sPos = wsum(sPos); sNeg = wsum(sNeg);
+  sPosSq = wsum(sPosSq); sNegSq = wsum(sNegSq); sNz = wsum(sNz); sNzAbs = wsum(sNzAbs); sNzSq = wsum(sNzSq);
+  num = wsum(num); num2 = wsum(num2); numAbs = wsum(numAbs);
+  nPos = wsumll(nPos); nNeg = wsumll(nNeg); nNz = wsumll(nNz);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {       // extremes with the first position (functionalExtremes.cpp:96-101)
+    const float omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
+    const long long omnI = __shfl_xor_sync(0xffffffffu, mnI, o), omxI = __shfl_xor_sync(0xffffffffu, mxI, o);
+    if (omn < mn || (omn == mn && omnI < mnI)) { mn = omn; mnI = omnI; }
+    if (omx > mx || (omx == mx && omxI < mxI)) { mx = omx; mxI = omxI; }
+  }
+  const double Nd = (double)N;
+  const float mean = (float)(sum / Nd);    // functionals.cpp:300-306, handed on as FLOAT_DMEM
+  const double meanD = (double)mean;
+
+  // ---------------- regression coefficients (functionalRegression.cpp:150-262) ----------------
+  const auto &R = p.s.regression;
+  double rm = 0, rt = 0, ra = 0, rb = 0, rc = 0, rinv = 0, centroid = 0;
+  const double asum = meanD * Nd;
+  if (p.needReg) {
+    const double range = (double)__fsub_rn(mx, mn);         // max - min is a FLOAT_DMEM expression (:151)
+    rinv = range > 0.0 ? 1.0 / range : 0.0;
+    if (R.centroidUseAbsValues) centroid = sAbs != 0.0 ? numAbs / sAbs : 0.0;
+    else centroid = asum != 0.0 ? num / asum : 0.0;
+    if (R.centroidNorm == OSM_B200_TIMENORM_SECOND) centroid *= p.periodD;
+    else if (R.centroidNorm == OSM_B200_TIMENORM_SEGMENT) centroid /= Nd;
+    if (N > 1) {
+      const double NNm1 = Nd * (Nd - 1.0);
+      const double S1 = NNm1 / 2.0, S2 = NNm1 * (2.0 * Nd - 1.0) / 6.0;
+      const double S1dS2 = S1 / S2;
+      const double tmp = Nd - S1 * S1dS2;
+      rt = tmp == 0.0 ? 0.0 : (asum - num * S1dS2) / tmp;
+      rm = (num - rt * S1) / S2;
+      const double S3 = S1 * S1, Nind1 = Nd - 1.0;
+      const double S4 = S2 * (3.0 * (Nind1 * Nind1 + Nind1) - 1.0) / 5.0;
+      if (p.enQreg) {
+        const double S3S3 = S3 * S3, S2S2 = S2 * S2, S1S2 = S1 * S2, S1S1 = S3;
+        const double det = S4 * S2 * Nd + 2.0 * S3 * S1S2 - S2S2 * S2 - S3S3 * Nd - S1S1 * S4;
+        if (det != 0.0) {
+          ra = ((S2 * Nd - S1S1) * num2 + (S1S2 - S3 * Nd) * num + (S3 * S1 - S2S2) * asum) / det;
+          rb = ((S1S2 - S3 * Nd) * num2 + (S4 * Nd - S2S2) * num + (S3 * S2 - S4 * S1) * asum) / det;
+          rc = ((S3 * S1 - S2S2) * num2 + (S3 * S2 - S4 * S1) * num + (S4 * S2 - S3S3) * asum) / det;
+        }
+      }
+    } else {
+      // a contour of one value: m = 0, t = c = that value
+      float x0 = 0.0f;
+      for (long long t = 0; t < T; t++) { const float x = col[t * p.rowStride]; if (keep(x)) { x0 = x; break; } }
+      rm = 0.0; rt = rc = (double)x0;
+    }
+  }
+
+  // ---------------- pass 2 ----------------
+  double m2 = 0, m3 = 0, m4 = 0, lea = 0, leq = 0, qea = 0, qeq = 0;
+  cnt = 0;
+  for (long long t0 = 0; t0 < T; t0 += 32) {
+    const long long t = t0 + lane;
+    const float x = t < T ? col[t * p.rowStride] : 0.0f;
+    const bool k = t < T && keep(x);
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const double xd = (double)x, ii = (double)(cnt + __popc(m & ltMask));
+      const double d = xd - meanD;
+      double d2 = d * d;
+      m2 += d2; d2 *= d; m3 += d2; m4 += d2 * d;
+      if (p.needReg) {
+        double er = xd - (rm * ii + rt);
+        if (R.normInputs) er *= rinv;
+        lea += fabs(er); leq += er * er;
+        if (p.enQreg) {
+          double eq = xd - (ra * ii * ii + rb * ii + rc);
+          if (R.normInputs) eq *= rinv;
+          qea += fabs(eq); qeq += eq * eq;
+        }
+      }
+    }
+    cnt += __popc(m);
+  }
+  m2 = wsum(m2); m3 = wsum(m3); m4 = wsum(m4);
+  lea = wsum(lea); leq = wsum(leq); qea = wsum(qea); qeq = wsum(qeq);
+
+  // ---------------- sorted copy for the percentiles ----------------
+  bool needSort = false;
+  for (int i = 0; i < p.s.n_enabled; i++) needSort = needSort || p.s.enabled[i] == OSM_B200_F_PERCENTILES;
+  if (needSort) {
+    int n2 = 32;
+    while (n2 < N) n2 <<= 1;
+    __syncwarp();
+    for (int i = (int)N + lane; i < n2; i += 32) sbuf[i] = INFINITY;
+    __syncwarp();
+    for (int k = 2; k <= n2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < n2; i += 32) {
+          const int q = i ^ j;
+          if (q > i) {
+            const float a = sbuf[i], b = sbuf[q];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) { sbuf[i] = b; sbuf[q] = a; }
+          }
+        }
+        __syncwarp();
+      }
+  }
+  if (lane != 0) return;
+
+  // ---------------- values, in the order of functionalsEnabled ----------------
+  int n = 0;
+  for (int fi = 0; fi < p.s.n_enabled; fi++) {
+    switch (p.s.enabled[fi]) {
+      case OSM_B200_F_EXTREMES: {
+        const auto &E = p.s.extremes;
+        float maxpos = (float)mxI, minpos = (float)mnI;
+        if (p.extNorm == OSM_B200_TIMENORM_SEGMENT) { maxpos = __fdiv_rn(maxpos, (float)N); minpos = __fdiv_rn(minpos, (float)N); }
+        else if (p.extNorm == OSM_B200_TIMENORM_SECOND && p.period != 0.0f) { maxpos = __fmul_rn(maxpos, p.period); minpos = __fmul_rn(minpos, p.period); }
+        if (E.max) out[n++] = mx;
+        if (E.min) out[n++] = mn;
+        if (E.range) out[n++] = __fsub_rn(mx, mn);
+        if (E.maxpos) out[n++] = maxpos;
+        if (E.minpos) out[n++] = minpos;
+        if (E.amean) out[n++] = mean;
+        if (E.maxameandist) out[n++] = __fsub_rn(mx, mean);
+        if (E.minameandist) out[n++] = __fsub_rn(mean, mn);
+      } break;
+      case OSM_B200_F_MEANS: {
+        const auto &M = p.s.means;
+        const double absmean = sAbs / Nd, qmean = sSq / Nd;
+        double nzamean = 0, nzabsmean = 0, nzqmean = 0, nzgmean = 0;
+        if (nNz > 0) { const double d = (double)nNz; nzamean = sNz / d; nzabsmean = sNzAbs / d; nzqmean = sNzSq / d; nzgmean = exp(sLog / d); }
+        const double posamean = nPos > 0 ? sPos / (double)nPos : 0.0, posqmean = nPos > 0 ? sPosSq / (double)nPos : 0.0;
+        const double negamean = nNeg > 0 ? sNeg / (double)nNeg : 0.0, negqmean = nNeg > 0 ? sNegSq / (double)nNeg : 0.0;
+        if (M.amean) out[n++] = mean;
+        if (M.absmean) out[n++] = (float)absmean;
+        if (M.qmean) out[n++] = (float)qmean;
+        if (M.nzamean) out[n++] = (float)nzamean;
+        if (M.nzabsmean) out[n++] = (float)nzabsmean;
+        if (M.nzqmean) out[n++] = (float)nzqmean;
+        if (M.nzgmean) out[n++] = (float)nzgmean;
+        if (M.nnz) {
+          const float c = (float)nNz;
+          out[n++] = p.meanNorm == OSM_B200_TIMENORM_FRAME ? c : (p.meanNorm == OSM_B200_TIMENORM_SEGMENT ? __fdiv_rn(c, (float)N) : __fdiv_rn(c, p.period));
+        }
+        if (M.flatness) out[n++] = absmean != 0.0 ? (float)(nzgmean / absmean) : 1.0f;
+        if (M.posamean) out[n++] = (float)posamean;
+        if (M.negamean) out[n++] = (float)negamean;
+        if (M.posqmean) out[n++] = (float)posqmean;
+        if (M.posrqmean) out[n++] = (float)sqrt(posqmean);
+        if (M.negqmean) out[n++] = (float)negqmean;
+        if (M.negrqmean) out[n++] = (float)sqrt(negqmean);
+        if (M.rqmean) out[n++] = (float)sqrt(qmean);
+        if (M.nzrqmean) out[n++] = (float)sqrt(nzqmean);
+      } break;
+      case OSM_B200_F_MOMENTS: {
+        const auto &M = p.s.moments;
+        const double v2 = m2 / Nd, sq = sqrt(v2);
+        if (M.variance) out[n++] = (float)v2;
+        if (M.stddev) out[n++] = v2 > 0.0 ? (float)sq : 0.0f;
+        if (M.skewness) out[n++] = v2 > 0.0 ? (float)(m3 / (Nd * v2 * sq)) : 0.0f;
+        if (M.kurtosis) out[n++] = v2 > 0.0 ? (float)(m4 / (Nd * v2 * v2)) : 0.0f;
+        if (M.amean) out[n++] = mean;
+        if (M.stddevNorm == 1 || M.stddevNorm == 2) {
+          if (v2 > 0.0) {
+            double ml = M.stddevNorm == 1 ? (double)fabsf(mean) : meanD;
+            if (ml == 0.0) ml = 1.0;
+            out[n++] = (float)(sq / ml);
+          } else out[n++] = 0.0f;
+        }
+      } break;
+      case OSM_B200_F_PERCENTILES: {
+        const auto &P = p.s.percentiles;
+        const float q1 = P.interp ? interp_pctl(0.25, sbuf, N) : index_pctl(0.25, sbuf, N);
+        const float q2 = P.interp ? interp_pctl(0.50, sbuf, N) : index_pctl(0.50, sbuf, N);
+        const float q3 = P.interp ? interp_pctl(0.75, sbuf, N) : index_pctl(0.75, sbuf, N);
+        if (P.quartile1) out[n++] = q1;
+        if (P.quartile2) out[n++] = q2;
+        if (P.quartile3) out[n++] = q3;
+        if (P.iqr12) out[n++] = __fsub_rn(q2, q1);
+        if (P.iqr23) out[n++] = __fsub_rn(q3, q2);
+        if (P.iqr13) out[n++] = __fsub_rn(q3, q1);
+        const int n0 = n;
+        for (int i = 0; i < P.n_percentile; i++) out[n++] = P.interp ? interp_pctl(P.percentile[i], sbuf, N) : index_pctl(P.percentile[i], sbuf, N);
+        for (int i = 0; i < P.n_pctlrange; i++) out[n++] = fabsf(__fsub_rn(out[n0 + P.pctlrange[i][1]], out[n0 + P.pctlrange[i][0]]));
+      } break;
+      case OSM_B200_F_REGRESSION: {
+        double m = rm, t = rt, a = ra, b = rb, c = rc;
+        if (R.normRegCoeff == 1) { m *= Nd - 1.0; a *= (Nd - 1.0) * (Nd - 1.0); b *= Nd - 1.0; }
+        else if (R.normRegCoeff == 2) { const double one = 1.0 / p.periodD; m *= one; a *= one * one; b *= one; }
+        if (R.normInputs) { m *= rinv; t = (t - (double)mn) * rinv; a *= rinv; b *= rinv; c = (c - (double)mn) * rinv; }
+        auto fin = [](double v) { return isfinite(v) ? v : 0.0; };
+        if (R.linregc1) out[n++] = (float)fin(m);
+        if (R.linregc2) out[n++] = (float)fin(t);
+        if (R.linregerrA) out[n++] = (float)(isfinite(lea / Nd) ? lea / Nd : 0.0);
+        if (R.linregerrQ) out[n++] = (float)(isfinite(leq / Nd) ? leq / Nd : 0.0);
+        if (R.qregc1) out[n++] = (float)fin(a);
+        if (R.qregc2) out[n++] = (float)fin(b);
+        if (R.qregc3) out[n++] = (float)fin(c);
+        const double qa = isfinite(qea / Nd) ? qea : 0.0, qq = isfinite(qeq / Nd) ? qeq : 0.0;
+        if (R.qregerrA) out[n++] = (float)(R.oldBuggyQerr ? qa : qa / Nd);
+        if (R.qregerrQ) out[n++] = (float)(R.oldBuggyQerr ? qq : qq / Nd);
+        if (R.centroid) out[n++] = (float)fin(centroid);
+      } break;
+    }
+  }
+}
+
+int resolve_norm(int own, int ownSet, int master)            // functionalComponent.hpp:67-76
+{
+  if (ownSet) return own;
+  return master != OSM_B200_TIMENORM_UNSET ? master : own;
+}
+
+}  // namespace
+}  // namespace osm
+
+using namespace osm;
+
+struct osm_b200_functionals {
+  osm_b200_functionals_spec spec;
+  int nIn = 0, nVals = 0, device = -1;
+  double period = 0;
+  std::vector<std::string> names;
+  bool hasPct = false;
+  long long *dMeta = nullptr; size_t metaCap = 0;
+  float *dIn = nullptr; size_t inCap = 0;
+  float *dOut = nullptr; size_t outCap = 0;
+};
+
+namespace {
+
+#define FCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { char b_[256]; snprintf(b_, sizeof b_, "CUDA error in %s: %s", #call, cudaGetErrorString(e_)); return set_last_error(OSM_B200_ERR_CUDA, b_); } } while (0)
+
+std::vector<std::string> value_names(const osm_b200_functionals_spec &s)
+{
+  std::vector<std::string> v;
+  char buf[64];
+  for (int i = 0; i < s.n_enabled; i++) {
+    switch (s.enabled[i]) {
+      case OSM_B200_F_EXTREMES: {
+        const auto &E = s.extremes;
+        const int on[8] = {E.max, E.min, E.range, E.maxpos, E.minpos, E.amean, E.maxameandist, E.minameandist};
+        const char *nm[8] = {"max", "min", "range", "maxPos", "minPos", "amean", "maxameandist", "minameandist"};   // functionalExtremes.cpp:37
+        for (int k = 0; k < 8; k++) if (on[k]) v.push_back(nm[k]);
+      } break;
+      case OSM_B200_F_MEANS: {
+        const auto &M = s.means;
+        const int on[17] = {M.amean, M.absmean, M.qmean, M.nzamean, M.nzabsmean, M.nzqmean, M.nzgmean, M.nnz, M.flatness, M.posamean, M.negamean,
+                            M.posqmean, M.posrqmean, M.negqmean, M.negrqmean, M.rqmean, M.nzrqmean};
+        const char *nm[17] = {"amean", "absmean", "qmean", "nzamean", "nzabsmean", "nzqmean", "nzgmean", "nnz", "flatness", "posamean", "negamean",
+                              "posqmean", "posrqmean", "negqmean", "negrqmean", "rqmean", "nzrqmean"};                  // functionalMeans.cpp:45
+        for (int k = 0; k < 17; k++) if (on[k]) v.push_back(nm[k]);
+      } break;
+      case OSM_B200_F_MOMENTS: {
+        const auto &M = s.moments;
+        if (M.variance) v.push_back("variance");
+        if (M.stddev) v.push_back("stddev");
+        if (M.skewness) v.push_back("skewness");
+        if (M.kurtosis) v.push_back("kurtosis");
+        if (M.amean) v.push_back("amean");
+        if (M.stddevNorm == 2) v.push_back("stddevNorm");
+        else if (M.stddevNorm == 1) v.push_back("coeffOfVariation");                                                    // functionalMoments.cpp:34
+      } break;
+      case OSM_B200_F_PERCENTILES: {
+        const auto &P = s.percentiles;
+        if (P.quartile1) v.push_back("quartile1");
+        if (P.quartile2) v.push_back("quartile2");
+        if (P.quartile3) v.push_back("quartile3");
+        if (P.iqr12) v.push_back("iqr1-2");
+        if (P.iqr23) v.push_back("iqr2-3");
+        if (P.iqr13) v.push_back("iqr1-3");
+        for (int k = 0; k < P.n_percentile; k++) { snprintf(buf, sizeof buf, "percentile%.1f", P.percentile[k] * 100.0); v.push_back(buf); }   // :268-290
+        for (int k = 0; k < P.n_pctlrange; k++) { snprintf(buf, sizeof buf, "pctlrange%i-%i", P.pctlrange[k][0], P.pctlrange[k][1]); v.push_back(buf); }
+      } break;
+      case OSM_B200_F_REGRESSION: {
+        const auto &R = s.regression;
+        const int on[10] = {R.linregc1, R.linregc2, R.linregerrA, R.linregerrQ, R.qregc1, R.qregc2, R.qregc3, R.qregerrA, R.qregerrQ, R.centroid};
+        const char *nm[10] = {"linregc1", "linregc2", "linregerrA", "linregerrQ", "qregc1", "qregc2", "qregc3", "qregerrA", "qregerrQ", "centroid"};
+        for (int k = 0; k < 10; k++) if (on[k]) v.push_back(nm[k]);
+      } break;
+    }
+  }
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t osm_b200_functionals_sizeof_spec(void) { return (int32_t)sizeof(osm_b200_functionals_spec); }
+
+void osm_b200_functionals_defaults(osm_b200_functionals_spec *s)
+{
+  if (!s) return;
+  memset(s, 0, sizeof *s);
+  s->masterTimeNorm = OSM_B200_TIMENORM_UNSET;
+  auto &E = s->extremes;
+  E.max = E.min = E.range = E.maxpos = E.minpos = E.maxameandist = E.minameandist = 1; E.amean = 0; E.norm = OSM_B200_TIMENORM_FRAME;
+  auto &M = s->means;
+  M.amean = M.absmean = M.qmean = M.nzamean = M.nzabsmean = M.nzqmean = M.nzgmean = M.nnz = 1; M.norm = OSM_B200_TIMENORM_FRAME;
+  auto &Q = s->moments;
+  Q.variance = Q.stddev = Q.skewness = Q.kurtosis = 1;
+  s->percentiles.interp = 1;
+  auto &R = s->regression;
+  R.linregc1 = R.linregc2 = R.linregerrA = R.linregerrQ = R.qregc1 = R.qregc2 = R.qregc3 = R.qregerrA = R.qregerrQ = R.centroid = 1;
+  R.centroidNorm = OSM_B200_TIMENORM_SEGMENT; R.centroidUseAbsValues = 1; R.centroidRatioLimit = 1; R.oldBuggyQerr = 1;
+}
+
+osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spec, int32_t n_in, const char *const *in_names,
+                                            double input_period, int32_t device, osm_b200_functionals **out)
+{
+  if (!spec || !out || n_in <= 0 || !in_names) return set_last_error(OSM_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const auto &s = *spec;
+  if (s.n_enabled <= 0 || s.n_enabled > OSM_B200_F_MAX_ENABLED) return set_last_error(OSM_B200_ERR_INVALID, "cFunctionals: functionalsEnabled is empty");
+  for (int i = 0; i < s.n_enabled; i++)
+    if (s.enabled[i] < 0 || s.enabled[i] >= OSM_B200_F_COUNT_) return set_last_error(OSM_B200_ERR_INVALID, "cFunctionals: unknown functional");
+  if (s.nonZeroFuncts < 0 || s.nonZeroFuncts > 2) return set_last_error(OSM_B200_ERR_INVALID, "cFunctionals.nonZeroFuncts must be 0, 1 or 2");
+  if (s.moments.doRatioLimit || s.regression.doRatioLimit) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionals: doRatioLimit = 1 is not supported");
+  if (s.regression.centroid && s.regression.centroidRatioLimit)
+    for (int i = 0; i < s.n_enabled; i++)
+      if (s.enabled[i] == OSM_B200_F_REGRESSION) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalRegression: centroid with centroidRatioLimit = 1 is not supported (set centroidRatioLimit = 0 or centroid = 0)");
+  const auto &P = s.percentiles;
+  if (P.n_percentile < 0 || P.n_percentile > OSM_B200_F_MAX_PCTL || P.n_pctlrange < 0 || P.n_pctlrange > OSM_B200_F_MAX_PCTL)
+    return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalPercentiles: at most 8 percentiles / ranges");
+  for (int i = 0; i < P.n_pctlrange; i++)
+    if (P.pctlrange[i][0] < 0 || P.pctlrange[i][0] >= P.n_percentile || P.pctlrange[i][1] < 0 || P.pctlrange[i][1] >= P.n_percentile)
+      return set_last_error(OSM_B200_ERR_INVALID, "cFunctionalPercentiles.pctlrange refers to a percentile that does not exist");
+  osm_b200_functionals *f = new osm_b200_functionals();
+  f->spec = s; f->nIn = n_in; f->device = device; f->period = input_period;
+  const std::vector<std::string> vn = value_names(s);
+  f->nVals = (int)vn.size();
+  if (f->nVals == 0) { delete f; return set_last_error(OSM_B200_ERR_INVALID, "cFunctionals: no value enabled"); }
+  for (int e = 0; e < n_in; e++)
+    for (const std::string &v : vn)                                    // functionals.cpp:222-228
+      f->names.push_back(s.functNameAppend[0] ? std::string(in_names[e]) + "__" + s.functNameAppend + "_" + v : std::string(in_names[e]) + "_" + v);
+  for (int i = 0; i < s.n_enabled; i++) f->hasPct = f->hasPct || s.enabled[i] == OSM_B200_F_PERCENTILES;
+  if (device >= 0) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) { delete f; return set_last_error(OSM_B200_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)"); }
+  }
+  *out = f;
+  return OSM_B200_OK;
+}
+
+void osm_b200_functionals_destroy(osm_b200_functionals *f)
+{
+  if (!f) return;
+  if (f->device >= 0) { cudaSetDevice(f->device); if (f->dMeta) cudaFree(f->dMeta); if (f->dIn) cudaFree(f->dIn); if (f->dOut) cudaFree(f->dOut); }
+  delete f;
+}
+
+int32_t osm_b200_functionals_num_values(const osm_b200_functionals *f) { return f ? f->nVals : 0; }
+int32_t osm_b200_functionals_num_elements(const osm_b200_functionals *f) { return f ? f->nVals * f->nIn : 0; }
+const char *osm_b200_functionals_element_name(const osm_b200_functionals *f, int32_t idx)
+{
+  return (f && idx >= 0 && idx < (int)f->names.size()) ? f->names[idx].c_str() : nullptr;
+}
+
+osm_b200_status osm_b200_functionals_run_device(osm_b200_functionals *f, const float *d_rows, int32_t row_stride, const int64_t *row_offsets,
+                                                const int64_t *n_rows, int32_t n_utt, float *d_out, void *stream)
+{
+  if (!f || !row_offsets || !n_rows || n_utt < 0) return set_last_error(OSM_B200_ERR_INVALID, "null argument");
+  if (f->device < 0) return set_last_error(OSM_B200_ERR_CUDA, "description-only functionals object (device < 0) cannot run; no CPU fallback");
+  if (n_utt == 0) return OSM_B200_OK;
+  if (!d_rows || !d_out || row_stride < f->nIn) return set_last_error(OSM_B200_ERR_INVALID, "bad row buffer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  FCU(cudaSetDevice(f->device));
+  long long maxT = 0;
+  std::vector<long long> meta(2 * (size_t)n_utt);
+  for (int u = 0; u < n_utt; u++) {
+    if (n_rows[u] < 0 || row_offsets[u] < 0) return set_last_error(OSM_B200_ERR_INVALID, "negative row offset / count");
+    meta[u] = row_offsets[u]; meta[n_utt + u] = n_rows[u];
+    maxT = std::max<long long>(maxT, n_rows[u]);
+  }
+  int sortCap = 0;
+  if (f->hasPct) {
+    if (maxT > kMaxSort) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalPercentiles: contours longer than 8192 frames are not supported");
+    sortCap = 32;
+    while (sortCap < maxT) sortCap <<= 1;
+  }
+  if (f->metaCap < meta.size()) {
+    if (f->dMeta) cudaFree(f->dMeta);
+    f->dMeta = nullptr; f->metaCap = 0;
+    FCU(cudaMalloc(&f->dMeta, meta.size() * sizeof(long long)));
+    f->metaCap = meta.size();
+  }
+  FCU(cudaMemcpyAsync(f->dMeta, meta.data(), meta.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+  FCU(cudaStreamSynchronize(st));                  // `meta` is a local: the copy must have left the host buffer
+  FnParams p;
+  memset(&p, 0, sizeof p);
+  p.rows = d_rows; p.rowStride = row_stride; p.nIn = f->nIn; p.rowOff = f->dMeta; p.nRows = f->dMeta + n_utt;
+  p.out = d_out; p.nVals = f->nVals; p.sortCap = sortCap; p.period = (float)f->period; p.periodD = f->period; p.s = f->spec;
+  p.extNorm = resolve_norm(f->spec.extremes.norm, f->spec.extremes.normIsSet, f->spec.masterTimeNorm);
+  p.meanNorm = resolve_norm(f->spec.means.norm, f->spec.means.normIsSet, f->spec.masterTimeNorm);
+  const auto &R = f->spec.regression;
+  for (int i = 0; i < f->spec.n_enabled; i++) p.needReg = p.needReg || f->spec.enabled[i] == OSM_B200_F_REGRESSION;
+  p.enQreg = R.qregc1 || R.qregc2 || R.qregc3 || R.qregerrA || R.qregerrQ || R.centroid;     // functionalRegression.cpp:108-117
+  const size_t smem = (size_t)kFnWarps * sortCap * sizeof(float);
+  if (smem > 48 * 1024) FCU(cudaFuncSetAttribute(functionals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int groups = (f->nIn + kFnWarps - 1) / kFnWarps;
+  functionals_kernel<<<(unsigned)((long long)n_utt * groups), kFnThreads, smem, st>>>(p);
+  FCU(cudaGetLastError());
+  return OSM_B200_OK;
+}
+
+osm_b200_status osm_b200_functionals_run_host(osm_b200_functionals *f, const float *rows, int32_t row_stride, const int64_t *row_offsets,
+                                              const int64_t *n_rows, int32_t n_utt, int64_t total_rows, float *out)
+{
+  if (!f || !rows || !out || total_rows < 0) return set_last_error(OSM_B200_ERR_INVALID, "null argument");
+  if (f->device < 0) return set_last_error(OSM_B200_ERR_CUDA, "description-only functionals object (device < 0) cannot run; no CPU fallback");
+  FCU(cudaSetDevice(f->device));
+  const size_t nIn = (size_t)total_rows * row_stride, nOut = (size_t)n_utt * f->nVals * f->nIn;
+  if (f->inCap < nIn) { if (f->dIn) cudaFree(f->dIn); f->dIn = nullptr; f->inCap = 0; FCU(cudaMalloc(&f->dIn, (nIn + 1) * sizeof(float))); f->inCap = nIn; }
+  if (f->outCap < nOut) { if (f->dOut) cudaFree(f->dOut); f->dOut = nullptr; f->outCap = 0; FCU(cudaMalloc(&f->dOut, (nOut + 1) * sizeof(float))); f->outCap = nOut; }
+  FCU(cudaMemcpy(f->dIn, rows, nIn * sizeof(float), cudaMemcpyHostToDevice));
+  osm_b200_status st = osm_b200_functionals_run_device(f, f->dIn, row_stride, row_offsets, n_rows, n_utt, f->dOut, nullptr);
+  if (st != OSM_B200_OK) return st;
+  FCU(cudaMemcpy(out, f->dOut, nOut * sizeof(float), cudaMemcpyDeviceToHost));
+  return OSM_B200_OK;
+}
+
+}  // extern "C"

@@ -100,6 +100,28 @@ int64_t desc_num_frames(const PlanDesc &d, int64_t L)
   return best < 0 ? 0 : best;
 }
 
+// Frames of the output level that exist when a full-input reader (cFunctionals with frameMode = full) ticks for the first time
+// after end of input was raised.  The reference's window processors run with blocksize 1: stage s has produced
+// c0_s = max(c0_{s-1} - W_s, 0) frames before EOI (tick-order model, see post_kernel) and adds exactly one more in the first EOI
+// tick before the components behind it tick; the reader then takes what is there (core/dataReader.cpp:560-585) and, having read
+// once, never reads again -- so the frames the window processors append later are NOT part of the summary unless the
+// configuration sets EOIlevel (the shipped IS09 / IS10 files do not).  Verified against the reference's functionals rows
+// (tests/test_functionals_cpu.py).
+int64_t desc_num_frames_first_eoi(const PlanDesc &d, int64_t L)
+{
+  int64_t best = -1;
+  for (const auto &g : d.groups) {
+    int64_t t = desc_num_static_frames(d, g.stream, L);
+    for (int ls : g.limitStreams) t = std::min<int64_t>(t, desc_num_static_frames(d, ls, L));
+    if (t <= 0) return 0;
+    int64_t c0 = t, fin = t;
+    for (const auto &s : g.stages) { c0 = std::max<int64_t>(c0 - s.win, 0); fin += s.win; }
+    const int64_t avail = g.stages.empty() ? t : std::min<int64_t>(c0 + 1, fin);
+    if (best < 0 || avail < best) best = avail;
+  }
+  return best < 0 ? 0 : best;
+}
+
 namespace {
 
 struct ChainInfo {               // resolved front-end chain below a static producer

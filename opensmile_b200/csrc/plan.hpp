@@ -255,6 +255,7 @@ struct PlanDesc {
 osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char *outputLevel,
                               PlanDesc &out, std::string &err);
 int64_t desc_num_frames(const PlanDesc &d, int64_t nSampleFrames);
+int64_t desc_num_frames_first_eoi(const PlanDesc &d, int64_t nSampleFrames);
 int64_t desc_num_static_frames(const PlanDesc &d, int stream, int64_t nSampleFrames);
 int64_t desc_max_static_frames(const PlanDesc &d, int64_t nSampleFrames);
 
@@ -271,6 +272,7 @@ bool build_pitch_chain(const osm_b200_specscale &sc, const osm_b200_pitchshs &ps
 
 // fe = front end of the windower level the chain's cTransformFFT reads; zeroPadSymmetric = that cTransformFFT's switch
 void build_ref_fft_tables(std::vector<float> &wc);
+osm_b200_status set_last_error(osm_b200_status st, const std::string &msg);   // api.cu
 bool build_formant(const osm_b200_specresample &rs, const osm_b200_lpc &lp, const osm_b200_formantlpc &fl, const FrontEnd &fe,
                    bool zeroPadSymmetric, FormantOp &op, std::string &err);
 

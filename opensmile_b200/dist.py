@@ -43,3 +43,39 @@ def gather_row_counts(local_rows, dist=None, device=None):
     out = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
     dist.all_gather(out, mine)
     return [int(x[0]) for x in out]
+
+
+def gather_functionals(local_rows, local_indices, n_total, dist=None, device=None, dst=0):
+    """The one data exchange of a sharded extraction (BASELINE.json north_star: "NCCL only for the final functionals
+    reduction"): every rank holds one functionals row per utterance it owns (`local_rows` [n_local, K] float32 tensor on
+    `device`, `local_indices` = the global utterance indices of those rows); rank `dst` receives the [n_total, K] matrix in
+    global utterance order, the other ranks get None.  The reference has no counterpart (it summarises one file per process
+    and the sink appends to a shared ARFF / CSV file); this replaces that file-level merge by one gather over NVLink:
+    all_gather of the row counts, then gather of the (padded) rows and of their indices (NCCL on GPUs, gloo in the CPU tests).
+    """
+    import torch
+    local_rows = torch.as_tensor(local_rows, dtype=torch.float32, device=device)
+    idx = torch.as_tensor(np.asarray(local_indices, dtype=np.int64), device=device)
+    K = int(local_rows.shape[1]) if local_rows.dim() == 2 else 0
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        out = torch.zeros((n_total, K), dtype=torch.float32, device=device)
+        out[idx] = local_rows
+        return out
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = gather_row_counts(int(local_rows.shape[0]), dist, device)
+    cap = max(max(counts), 1)
+    pad_rows = torch.zeros((cap, K), dtype=torch.float32, device=device)
+    pad_idx = torch.full((cap,), -1, dtype=torch.int64, device=device)
+    pad_rows[:local_rows.shape[0]] = local_rows
+    pad_idx[:idx.shape[0]] = idx
+    rows_list = [torch.zeros_like(pad_rows) for _ in range(world)] if rank == dst else None
+    idx_list = [torch.zeros_like(pad_idx) for _ in range(world)] if rank == dst else None
+    dist.gather(pad_rows, rows_list, dst=dst)
+    dist.gather(pad_idx, idx_list, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.zeros((n_total, K), dtype=torch.float32, device=device)
+    for r in range(world):
+        n = counts[r]
+        out[idx_list[r][:n]] = rows_list[r][:n]
+    return out

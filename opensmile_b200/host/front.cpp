@@ -18,6 +18,8 @@
 #include <vector>
 
 #include "../../include/osm_b200_host.h"
+#include "../../include/osm_b200_functionals.h"
+#include <cuda_runtime_api.h>
 
 namespace {
 
@@ -594,6 +596,121 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
 }
 
 // ------------------------------------------------------------------------------------------
+// [x:cFunctionals] -> osm_b200_functionals_spec (src/functionals/functionals.cpp:33-100, the sub-components' registerComponent
+// blocks for the field names).  Only full-input mode (frameMode = full, shared/FrameModeFunctionals.conf.inc) is executed.
+// ------------------------------------------------------------------------------------------
+int time_norm(const std::string &v)          // functionalComponent.cpp:51-64: prefix match
+{
+  if (v.compare(0, 3, "tur") == 0 || v.compare(0, 3, "seg") == 0) return OSM_B200_TIMENORM_SEGMENT;
+  if (v.compare(0, 3, "sec") == 0) return OSM_B200_TIMENORM_SECOND;
+  if (v.compare(0, 3, "fra") == 0) return OSM_B200_TIMENORM_FRAME;
+  return OSM_B200_TIMENORM_UNSET;
+}
+
+bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string &err)
+{
+  osm_b200_functionals_defaults(&fs);
+  std::map<int, std::string> enabledIdx;         // functionalsEnabled[i] entries
+  std::string enabledList;
+  std::map<int, double> pct;
+  std::map<int, std::string> pctRange;
+  bool quartilesSet = false, iqrSet = false;
+  int quartiles = 0, iqr = 0;
+  auto &E = fs.extremes; auto &M = fs.means; auto &Q = fs.moments; auto &P = fs.percentiles; auto &R = fs.regression;
+  struct IntField { const char *name; int32_t *dst; };
+  const IntField fields[] = {
+    {"Extremes.max", &E.max}, {"Extremes.min", &E.min}, {"Extremes.range", &E.range}, {"Extremes.maxpos", &E.maxpos}, {"Extremes.minpos", &E.minpos},
+    {"Extremes.amean", &E.amean}, {"Extremes.maxameandist", &E.maxameandist}, {"Extremes.minameandist", &E.minameandist},
+    {"Means.amean", &M.amean}, {"Means.absmean", &M.absmean}, {"Means.qmean", &M.qmean}, {"Means.nzamean", &M.nzamean}, {"Means.nzabsmean", &M.nzabsmean},
+    {"Means.nzqmean", &M.nzqmean}, {"Means.nzgmean", &M.nzgmean}, {"Means.nnz", &M.nnz}, {"Means.flatness", &M.flatness}, {"Means.posamean", &M.posamean},
+    {"Means.negamean", &M.negamean}, {"Means.posqmean", &M.posqmean}, {"Means.posrqmean", &M.posrqmean}, {"Means.negqmean", &M.negqmean},
+    {"Means.negrqmean", &M.negrqmean}, {"Means.rqmean", &M.rqmean}, {"Means.nzrqmean", &M.nzrqmean},
+    {"Moments.variance", &Q.variance}, {"Moments.stddev", &Q.stddev}, {"Moments.skewness", &Q.skewness}, {"Moments.kurtosis", &Q.kurtosis},
+    {"Moments.amean", &Q.amean}, {"Moments.stddevNorm", &Q.stddevNorm}, {"Moments.doRatioLimit", &Q.doRatioLimit},
+    {"Percentiles.quartile1", &P.quartile1}, {"Percentiles.quartile2", &P.quartile2}, {"Percentiles.quartile3", &P.quartile3},
+    {"Percentiles.iqr12", &P.iqr12}, {"Percentiles.iqr23", &P.iqr23}, {"Percentiles.iqr13", &P.iqr13}, {"Percentiles.interp", &P.interp},
+    {"Regression.linregc1", &R.linregc1}, {"Regression.linregc2", &R.linregc2}, {"Regression.linregerrA", &R.linregerrA}, {"Regression.linregerrQ", &R.linregerrQ},
+    {"Regression.qregc1", &R.qregc1}, {"Regression.qregc2", &R.qregc2}, {"Regression.qregc3", &R.qregc3}, {"Regression.qregerrA", &R.qregerrA},
+    {"Regression.qregerrQ", &R.qregerrQ}, {"Regression.centroid", &R.centroid}, {"Regression.centroidUseAbsValues", &R.centroidUseAbsValues},
+    {"Regression.centroidRatioLimit", &R.centroidRatioLimit}, {"Regression.normRegCoeff", &R.normRegCoeff}, {"Regression.normInputs", &R.normInputs},
+    {"Regression.oldBuggyQerr", &R.oldBuggyQerr}, {"Regression.doRatioLimit", &R.doRatioLimit}};
+  for (const auto &kv : s.kv) {
+    const std::string &f = kv.first, &v = kv.second;
+    if (is_common(f) || f == "noPostEOIprocessing" || f == "allowLastFrameIncomplete" || f == "frameListFile" || f == "frameList") continue;
+    if (f == "frameMode") { if (v.compare(0, 3, "ful") != 0) { err = "cFunctionals.frameMode=" + v + " is not supported (only full-input summaries)"; return false; } continue; }
+    if (f == "frameSize" || f == "frameStep" || f == "frameCenterSpecial" || f == "frameSizeFrames" || f == "frameStepFrames" || f == "frameCenter" || f == "frameCenterFrames") continue;
+    if (f == "functionalsEnabled") { enabledList = v; continue; }
+    if (f.compare(0, 19, "functionalsEnabled[") == 0) { enabledIdx[atoi(f.c_str() + 19)] = v; continue; }
+    if (f == "nonZeroFuncts") { fs.nonZeroFuncts = inum(v); continue; }
+    if (f == "functNameAppend") { snprintf(fs.functNameAppend, sizeof fs.functNameAppend, "%s", v.c_str()); continue; }
+    if (f == "masterTimeNorm") { fs.masterTimeNorm = time_norm(v); continue; }
+    if (f == "preserveFields") { if (inum(v)) { err = "cFunctionals.preserveFields=1 is not supported"; return false; } continue; }
+    if (f == "Extremes.norm") { E.norm = time_norm(v); E.normIsSet = 1; continue; }
+    if (f == "Means.norm") { M.norm = time_norm(v); M.normIsSet = 1; continue; }
+    if (f == "Regression.centroidNorm") { R.centroidNorm = time_norm(v); continue; }
+    if (f == "Percentiles.quartiles") { quartilesSet = true; quartiles = inum(v); continue; }
+    if (f == "Percentiles.iqr") { iqrSet = true; iqr = inum(v); continue; }
+    if (f.compare(0, 23, "Percentiles.percentile[") == 0) { pct[atoi(f.c_str() + 23)] = num(v); continue; }
+    if (f.compare(0, 22, "Percentiles.pctlrange[") == 0) { pctRange[atoi(f.c_str() + 22)] = v; continue; }
+    if (f.compare(0, 24, "Percentiles.pctlquotient") == 0 || f.compare(0, 15, "Percentiles.iqq") == 0) { err = "cFunctionalPercentiles: quotients are not supported"; return false; }
+    if (f.compare(0, 15, "Regression.qreg") == 0 && (f == "Regression.qregls" || f == "Regression.qregrs" || f == "Regression.qregx0" || f == "Regression.qregy0" ||
+        f == "Regression.qregyr" || f == "Regression.qregy0nn" || f == "Regression.qregc3nn" || f == "Regression.qregyrnn")) {
+      if (inum(v)) { err = "cFunctionalRegression." + f.substr(11) + " is not supported"; return false; }
+      continue;
+    }
+    bool hit = false;
+    for (const IntField &fd : fields) if (f == fd.name) { *fd.dst = inum(v); hit = true; break; }
+    if (hit) continue;
+    // a sub-configuration of a functional that is not implemented is only an error if that functional is enabled (below)
+    const size_t dot = f.find('.');
+    if (dot != std::string::npos) {
+      const std::string sub = f.substr(0, dot);
+      static const char *known[] = {"Crossings", "DCT", "Lpc", "Modulation", "Onset", "Peaks", "Peaks2", "Samples", "Segments", "Times"};
+      bool other = false;
+      for (const char *k : known) other = other || sub == k;
+      if (other) continue;
+    }
+    err = "unknown field '" + f + "' in section [" + s.name + ":cFunctionals]";
+    return false;
+  }
+  if (quartilesSet) P.quartile1 = P.quartile2 = P.quartile3 = quartiles;          // functionalPercentiles.cpp:112-116
+  if (iqrSet) P.iqr12 = P.iqr23 = P.iqr13 = iqr;
+  std::vector<std::string> names;
+  if (!enabledIdx.empty()) for (const auto &kv : enabledIdx) names.push_back(trim(kv.second));
+  else {
+    std::stringstream ss(enabledList);
+    std::string one;
+    while (std::getline(ss, one, ';')) { one = trim(one); if (!one.empty()) names.push_back(one); }
+  }
+  if (names.empty()) { err = "cFunctionals '" + s.name + "': functionalsEnabled is empty"; return false; }
+  if (names.size() > OSM_B200_F_MAX_ENABLED) { err = "cFunctionals: too many enabled functionals"; return false; }
+  fs.n_enabled = 0;
+  for (const std::string &n : names) {
+    int t = -1;
+    if (n == "Extremes") t = OSM_B200_F_EXTREMES;
+    else if (n == "Means") t = OSM_B200_F_MEANS;
+    else if (n == "Moments") t = OSM_B200_F_MOMENTS;
+    else if (n == "Percentiles") t = OSM_B200_F_PERCENTILES;
+    else if (n == "Regression") t = OSM_B200_F_REGRESSION;
+    else { err = "cFunctional" + n + " (instance '" + s.name + "') is not supported on the GPU path (Extremes, Means, Moments, Percentiles, Regression are)"; return false; }
+    fs.enabled[fs.n_enabled++] = t;
+  }
+  P.n_percentile = 0;
+  for (const auto &kv : pct) {
+    if (P.n_percentile >= OSM_B200_F_MAX_PCTL) { err = "cFunctionalPercentiles: more than 8 percentiles"; return false; }
+    P.percentile[P.n_percentile++] = std::min(1.0, std::max(0.0, kv.second));
+  }
+  P.n_pctlrange = 0;
+  if (P.n_percentile > 0)
+    for (const auto &kv : pctRange) {
+      double a, b;
+      if (P.n_pctlrange >= OSM_B200_F_MAX_PCTL || !parse_range(kv.second, a, b)) { err = "cFunctionalPercentiles.pctlrange: expected X-Y"; return false; }
+      P.pctlrange[P.n_pctlrange][0] = (int)a; P.pctlrange[P.n_pctlrange][1] = (int)b; P.n_pctlrange++;
+    }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
 // WAV in, HTK / CSV out
 // ------------------------------------------------------------------------------------------
 struct Wav { int sampleRate = 0, nChan = 0; std::vector<int16_t> pcm; };
@@ -828,6 +945,13 @@ struct osm_b200_session {
   std::map<std::pair<long, int>, osm_b200_plan *> plans;
   osm_b200_plan *cur = nullptr;
   std::vector<osm_b200_component> curComps;
+  // a cFunctionals summary between the LLD level and the sink (full-input mode): the plan then produces the functionals'
+  // input level, which stays in HBM, and one functionals object per input format summarises it (osm_b200_functionals.h)
+  bool hasFunc = false;
+  osm_b200_functionals_spec fspec;
+  std::map<std::pair<long, int>, osm_b200_functionals *> funcs;
+  osm_b200_functionals *curFunc = nullptr;
+  float *dFuncOut = nullptr; size_t funcOutCap = 0;
 };
 
 static osm_b200_status get_plan(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan **out)
@@ -845,6 +969,24 @@ static osm_b200_status get_plan(osm_b200_session *s, double sampleRate, int nCha
     s->curComps = cs;
   }
   s->cur = it->second;
+  *out = it->second;
+  return OSM_B200_OK;
+}
+
+static osm_b200_status get_func(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan *p, osm_b200_functionals **out)
+{
+  const auto key = std::make_pair((long)lround(sampleRate * 1000.0), nChan);
+  auto it = s->funcs.find(key);
+  if (it == s->funcs.end()) {
+    const int K = osm_b200_plan_num_elements(p);
+    std::vector<const char *> names(K);
+    for (int i = 0; i < K; i++) names[i] = osm_b200_plan_element_name(p, i);
+    osm_b200_functionals *f = nullptr;
+    osm_b200_status st = osm_b200_functionals_create(&s->fspec, K, names.data(), osm_b200_plan_frame_period(p), s->device, &f);
+    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    it = s->funcs.insert({key, f}).first;
+  }
+  s->curFunc = it->second;
   *out = it->second;
   return OSM_B200_OK;
 }
@@ -942,6 +1084,29 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
     if (sinkLevels.empty()) { delete s; return hfail(OSM_B200_ERR_INVALID, "no active sink: pass output_level or enable a sink (-O / -csvoutput)"); }
     lvl = sinkLevels[0];
   }
+  // A summary level: [sink level] <- (single-input cVectorConcat)* <- cFunctionals <- LLD level(s).  The plan computes the
+  // functionals' input level(s); the summary itself runs on the resident rows (functionals.cu).
+  if (lvl.find(';') == std::string::npos) {
+    std::map<std::string, const Section *> writerOfAll;
+    for (const Section *sec : compute) if (const std::string *w = sec->get("writer.dmLevel")) writerOfAll[*w] = sec;
+    std::string cur = lvl;
+    for (int guard = 0; guard < 16; guard++) {
+      auto it = writerOfAll.find(cur);
+      if (it == writerOfAll.end()) break;
+      const Section *w = it->second;
+      if (w->type == "cFunctionals") {
+        if (!to_functionals(*w, s->fspec, err)) { delete s; return hfail(err.find("not supported") != std::string::npos ? OSM_B200_ERR_UNSUPPORTED : OSM_B200_ERR_INVALID, err); }
+        const std::string *r = w->get("reader.dmLevel");
+        if (!r) { delete s; return hfail(OSM_B200_ERR_INVALID, "cFunctionals '" + w->name + "' has no reader.dmLevel"); }
+        s->hasFunc = true;
+        lvl = *r;
+        break;
+      }
+      const std::string *r = w->get("reader.dmLevel");
+      if (w->type == "cVectorConcat" && r && r->find(';') == std::string::npos) { cur = trim(*r); continue; }
+      break;
+    }
+  }
   // Only the components the output level depends on are part of the plan: the shipped feature-set
   // configurations carry sinks and summaries (cFunctionals ...) that stay idle when their output file is
   // not requested (filename = ?), exactly like the reference leaves those sinks unwritten.
@@ -1003,6 +1168,15 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
     osm_b200_plan *p = nullptr;
     osm_b200_status st = osm_b200_plan_create(cs.data(), (int)cs.size(), s->outputLevel.c_str(), -1, &p);
     if (st != OSM_B200_OK) { const std::string m = osm_b200_last_error(); delete s; return hfail(st, m); }
+    if (s->hasFunc) {
+      const int K = osm_b200_plan_num_elements(p);
+      std::vector<const char *> names(K);
+      for (int i = 0; i < K; i++) names[i] = osm_b200_plan_element_name(p, i);
+      osm_b200_functionals *f = nullptr;
+      st = osm_b200_functionals_create(&s->fspec, K, names.data(), osm_b200_plan_frame_period(p), -1, &f);
+      if (st != OSM_B200_OK) { const std::string m = osm_b200_last_error(); osm_b200_plan_destroy(p); delete s; return hfail(st, m); }
+      osm_b200_functionals_destroy(f);
+    }
     osm_b200_plan_destroy(p);
   }
   *session = s;
@@ -1013,6 +1187,8 @@ void osm_b200_session_close(osm_b200_session *s)
 {
   if (!s) return;
   for (auto &kv : s->plans) osm_b200_plan_destroy(kv.second);
+  for (auto &kv : s->funcs) osm_b200_functionals_destroy(kv.second);
+  if (s->dFuncOut) cudaFree(s->dFuncOut);
   delete s;
 }
 
@@ -1021,11 +1197,17 @@ int32_t osm_b200_session_num_elements(osm_b200_session *s, double sampleRate, in
   if (!s) return 0;
   osm_b200_plan *p;
   if (get_plan(s, sampleRate, nChan, &p) != OSM_B200_OK) return 0;
+  if (s->hasFunc) {
+    osm_b200_functionals *f;
+    if (get_func(s, sampleRate, nChan, p, &f) != OSM_B200_OK) return 0;
+    return osm_b200_functionals_num_elements(f);
+  }
   return osm_b200_plan_num_elements(p);
 }
 
 const char *osm_b200_session_element_name(osm_b200_session *s, int32_t idx)
 {
+  if (s && s->hasFunc) return s->curFunc ? osm_b200_functionals_element_name(s->curFunc, idx) : nullptr;
   return (s && s->cur) ? osm_b200_plan_element_name(s->cur, idx) : nullptr;
 }
 
@@ -1054,6 +1236,41 @@ osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t 
   osm_b200_plan *p;
   osm_b200_status st = get_plan(s, sampleRate, nChan, &p);
   if (st != OSM_B200_OK) return st;
+  if (s->hasFunc) {
+    // one summary row per utterance that has frames; the rows a plan run leaves in HBM are summarised in place.  The
+    // contour of utterance u = its first osm_b200_plan_num_frames_first_eoi() rows (what the reference's functionals see).
+    osm_b200_functionals *f;
+    st = get_func(s, sampleRate, nChan, p, &f);
+    if (st != OSM_B200_OK) return st;
+    std::vector<int64_t> lldOff((size_t)nUtt + 1), nRows((size_t)nUtt), rowOff((size_t)nUtt);
+    st = osm_b200_plan_frame_offsets(p, uttOff, nUtt, lldOff.data());
+    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    std::vector<int> live;
+    frameOff[0] = 0;
+    for (int u = 0; u < nUtt; u++) {
+      const int64_t n = osm_b200_plan_num_frames_first_eoi(p, uttOff[u + 1] - uttOff[u]);
+      if (n > 0) { rowOff[live.size()] = lldOff[u]; nRows[live.size()] = std::min<int64_t>(n, lldOff[u + 1] - lldOff[u]); live.push_back(u); }
+      frameOff[u + 1] = frameOff[u] + (n > 0 ? 1 : 0);
+    }
+    if (!out) return OSM_B200_OK;
+    if (frameOff[nUtt] > maxRows) return hfail(OSM_B200_ERR_INVALID, "output buffer too small");
+    if (live.empty()) return OSM_B200_OK;
+    const float *dRows = nullptr;
+    st = osm_b200_plan_run_host_resident(p, pcm, uttOff, nUtt, lldOff.data(), &dRows);
+    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    const int KF = osm_b200_functionals_num_elements(f);
+    const size_t need = live.size() * (size_t)KF;
+    if (s->funcOutCap < need) {
+      if (s->dFuncOut) cudaFree(s->dFuncOut);
+      s->dFuncOut = nullptr; s->funcOutCap = 0;
+      if (cudaMalloc(reinterpret_cast<void **>(&s->dFuncOut), need * sizeof(float)) != cudaSuccess) return hfail(OSM_B200_ERR_NOMEM, "out of device memory (functionals rows)");
+      s->funcOutCap = need;
+    }
+    st = osm_b200_functionals_run_device(f, dRows, osm_b200_plan_num_elements(p), rowOff.data(), nRows.data(), (int)live.size(), s->dFuncOut, nullptr);
+    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    if (cudaMemcpy(out, s->dFuncOut, need * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return hfail(OSM_B200_ERR_CUDA, "copy of the functionals rows failed");
+    return OSM_B200_OK;
+  }
   st = osm_b200_plan_frame_offsets(p, uttOff, nUtt, frameOff);
   if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
   if (!out) return OSM_B200_OK;

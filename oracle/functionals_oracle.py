@@ -178,7 +178,7 @@ def contour(spec, x, period):
         elif f == "Regression":                                    # functionalRegression.cpp:141-428
             r = spec.regression
             Nd = float(N)
-            rng = float(mx) - float(mn)
+            rng = float(F32(mx - mn))                                # FLOAT_DMEM expression
             rinv = 1.0 / rng if rng > 0 else 0.0
             ii = np.arange(N, dtype=np.float64)
             num, num2 = (xd * ii).sum(), (xd * ii * ii).sum()

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from opensmile_b200 import Plan, components_mfcc12_0_d_a
-from opensmile_b200.dist import gather_row_counts, reduce_counters, shard_utterances
+from opensmile_b200.dist import gather_functionals, gather_row_counts, reduce_counters, shard_utterances
 
 
 def _free_port():
@@ -32,7 +32,11 @@ def _worker(rank, world, port, lengths, q):
     rows = int(plan.frame_offsets(off)[-1])
     total, tmax = reduce_counters(rows, 0.5 + rank, dist)
     counts = gather_row_counts(rows, dist)
-    q.put((rank, mine.tolist(), rows, total, tmax, counts))
+    # the functionals gather: row i of the global matrix is [i, 2 i, 3 i] whichever rank owns utterance i
+    local = np.stack([np.array([i, 2 * i, 3 * i], np.float32) for i in mine]) if len(mine) else np.zeros((0, 3), np.float32)
+    glob = gather_functionals(local, mine, len(lengths), dist)
+    ok = None if glob is None else bool(np.array_equal(glob.numpy(), np.arange(len(lengths), dtype=np.float32)[:, None] * np.array([1, 2, 3], np.float32)))
+    q.put((rank, mine.tolist(), rows, total, tmax, counts, ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,6 +62,7 @@ def test_two_rank_sharding_gloo():
     assert res[0][3] == res[1][3] == expect == res[0][2] + res[1][2]     # SUM reduction == single-rank count
     assert res[0][4] == res[1][4] == 1.5                             # MAX over ranks
     assert res[0][5] == res[1][5] == [res[0][2], res[1][2]]
+    assert res[0][6] is True and res[1][6] is None                   # rank 0 holds the gathered functionals matrix, in global order
     loads = [sum(lengths[i] for i in r[1]) for r in res]
     assert abs(loads[0] - loads[1]) <= max(lengths)                  # balanced
 

@@ -1,0 +1,117 @@
+"""cFunctionals: the CPU restatement (oracle/functionals_oracle.py) against rows of the UNMODIFIED reference
+(tests/golden/functionals_goldens.npz, scripts/make_golden_functionals.py), and the host side of the product -- the shipped
+config/is09-13/IS09_emotion.conf (384 features) and tests/configs/func_variants.conf open unchanged with the reference's element
+names; functionals the GPU path does not implement are refused loudly."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import functionals_oracle as fo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REFCONF = os.path.join(ROOT, "oracle", "_ref", "config")
+G = np.load(os.path.join(HERE, "golden", "functionals_goldens.npz"))
+S, SEC, FR = fo.SEGMENT, fo.SECOND, fo.FRAME
+
+SPEC_A = fo.Spec(["Means"], master_norm=SEC, means=dict(flatness=1, posamean=1, negamean=1, posqmean=1, posrqmean=1, negqmean=1, negrqmean=1,
+                                                            rqmean=1, nzrqmean=1))
+SPEC_B = fo.Spec(["Percentiles", "Moments", "Extremes"], non_zero=1, master_norm=S,
+                 percentiles=dict(quartile1=1, quartile2=1, quartile3=1, iqr12=1, iqr23=1, iqr13=1, percentile=[0.2, 0.5, 0.8], pctlrange=[(0, 2)], interp=1),
+                 moments=dict(variance=1, stddev=0, skewness=0, kurtosis=0, amean=1, stddevNorm=2),
+                 extremes=dict(max=0, min=0, range=1, maxpos=1, minpos=1, amean=0, maxameandist=1, minameandist=1))
+SPEC_C = fo.Spec(["Regression", "Percentiles", "Means"], non_zero=2, name_append="x",
+                 regression=dict(centroidNorm=SEC, centroidUseAbsValues=1, normRegCoeff=1, normInputs=1, oldBuggyQerr=0),
+                 percentiles=dict(quartile1=1, quartile2=1, quartile3=1, interp=0),
+                 means=dict(amean=1, absmean=0, qmean=0, nzamean=0, nzabsmean=0, nzqmean=0, nzgmean=0, nnz=1, norm=S, norm_set=True))
+# (tag, spec, columns of the 32-column lld;lld_de level, frames the functionals see relative to T = static frames)
+LEVELS = [("is09", fo.IS09, slice(0, 32), -2, "is09_func"), ("A", SPEC_A, slice(0, 32), -2, "varA"), ("B", SPEC_B, slice(0, 16), 0, "varB"),
+          ("C", SPEC_C, slice(16, 32), -2, "varC")]
+
+
+def contour_rows(lld, dn):
+    """the rows a full-input reader sees when it first ticks at end of input (graph.cpp:desc_num_frames_first_eoi): the smoothed
+    level (T + 1 rows in the end) holds T rows then, the delta level behind it T - 2"""
+    T = lld.shape[0] - 1                      # the lld;lld_de sink level has T + 1 rows
+    return lld[:T + dn]
+
+
+@pytest.mark.parametrize("key", ["m24k", "v32k", "rec"])
+def test_oracle_reproduces_the_reference_rows(key):
+    lld = G["is09_lld_" + key]
+    names = list(G["is09_lld_names"])
+    for tag, spec, cols, dn, gk in LEVELS:
+        got = fo.functionals(spec, contour_rows(lld, dn)[:, cols], 0.01)
+        ref = G["%s_%s" % (gk, key)][0]
+        assert fo.element_names(spec, names[cols]) == list(G["is09_func_names"] if tag == "is09" else G[gk + "_names"])
+        # the reference's CSV prints 7 significant digits
+        assert np.all(np.abs(got - ref) <= 1e-6 * np.abs(ref) + 1e-12), tag
+
+
+def test_zero_and_single_value_contours():
+    spec = fo.Spec(["Extremes", "Moments", "Regression", "Percentiles"], non_zero=1, percentiles=dict(quartile2=1),
+                   regression=dict(centroid=0))
+    assert not np.any(fo.functionals(spec, np.zeros((20, 2), np.float32), 0.01))        # nothing survives the filter: zero fill
+    x = np.zeros((9, 1), np.float32); x[4] = 3.5
+    v = dict(zip(fo.value_names(spec), fo.functionals(spec, x, 0.01)))
+    assert v["max"] == v["min"] == v["quartile2"] == v["linregc2"] == np.float32(3.5) and v["linregc1"] == 0 and v["stddev"] == 0 and v["maxPos"] == 0
+
+
+def _session(conf, opts):
+    from opensmile_b200.session import Session
+    return Session(conf, options=opts, device=-1)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "is09-13")), reason="reference configuration files not built (make -C oracle ref)")
+def test_shipped_is09_configuration_opens_unchanged():
+    s = _session(os.path.join(REFCONF, "is09-13", "IS09_emotion.conf"), {"csvoutput": "f.csv"})
+    assert s.element_names() == list(G["is09_func_names"])                              # 384 features, the reference's header
+    # one summary row per utterance with at least one frame
+    fo_ = s.frame_offsets(np.array([0, 24000, 24100, 24100 + 32000, 24100 + 32000 + 400], np.int64), 16000.0, 1)
+    assert list(fo_) == [0, 1, 1, 2, 3]
+    s.close()
+    s = _session(os.path.join(REFCONF, "is09-13", "IS09_emotion.conf"), {"lldcsvoutput": "l.csv"})   # the LLD sinks still work
+    assert s.element_names() == list(G["is09_lld_names"])
+    s.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "is09-13")), reason="reference configuration files not built (make -C oracle ref)")
+def test_variant_configuration_names(tmp_path):
+    conf = tmp_path / "v.conf"
+    conf.write_text(open(os.path.join(HERE, "configs", "func_variants.conf")).read().replace("REFCONF", REFCONF))
+    for opt, key in (("outA", "varA"), ("outB", "varB"), ("outC", "varC")):
+        s = _session(str(conf), {opt: "x.csv"})
+        assert s.element_names() == list(G[key + "_names"])
+        s.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "is09-13")), reason="reference configuration files not built (make -C oracle ref)")
+def test_unimplemented_functionals_are_refused_loudly(tmp_path):
+    from opensmile_b200.session import SessionError
+    from opensmile_b200 import capi
+    txt = open(os.path.join(HERE, "configs", "func_variants.conf")).read().replace("REFCONF", REFCONF)
+    bad = tmp_path / "bad.conf"
+    bad.write_text(txt.replace("functionalsEnabled = Means\n", "functionalsEnabled = Means ; Peaks2\n"))
+    with pytest.raises(SessionError) as e:
+        _session(str(bad), {"outA": "x.csv"})
+    assert e.value.status == capi.ERR_UNSUPPORTED and "cFunctionalPeaks2" in str(e.value)
+    bad.write_text(txt.replace("nonZeroFuncts = 0\n", "nonZeroFuncts = 0\nbogusField = 1\n"))
+    with pytest.raises(SessionError) as e:
+        _session(str(bad), {"outA": "x.csv"})
+    assert "bogusField" in str(e.value)
+    # the shipped eGeMAPS summary needs Peaks2 / Segments: the LLD output works, the functionals output says what is missing
+    with pytest.raises(SessionError) as e:
+        _session(os.path.join(REFCONF, "egemaps", "v02", "eGeMAPSv02.conf"), {"csvoutput": "x.csv"})
+    assert e.value.status == capi.ERR_UNSUPPORTED
+
+
+def test_spec_mirror_and_descriptions():
+    from opensmile_b200 import functionals as F
+    sp = F.spec(["Extremes", "Regression", "Moments"], extremes=dict(amean=1, maxameandist=0, minameandist=0, norm=2, normIsSet=1),
+                regression=dict(linregerrA=0, qregc1=0, qregc2=0, qregc3=0, qregerrA=0, qregerrQ=0, centroid=0), moments=dict(variance=0))
+    f = F.Functionals(sp, list(G["is09_lld_names"]), 0.01, device=-1)
+    assert f.num_values == 12 and f.element_names() == list(G["is09_func_names"])
+    with pytest.raises(RuntimeError):                                                   # description-only objects never compute
+        f.run_host(np.zeros((4, 32), np.float32), [0], [4])
+    f.close()

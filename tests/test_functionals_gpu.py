@@ -1,0 +1,92 @@
+"""cFunctionals on the GPU (opensmile_b200/csrc/functionals.cu) through the C ABI: the kernel on the reference's own LLD rows
+against the reference's functionals rows and the pinned oracle; the shipped IS09_emotion.conf end to end from PCM (LLD plan ->
+rows resident in HBM -> summary -> one row per utterance) against the reference's -csvoutput row."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import functionals_oracle as fo
+from opensmile_b200 import functionals as F
+from opensmile_b200.synth import mixed_pcm, voiced_pcm
+from test_functionals_cpu import G, LEVELS, REFCONF, contour_rows
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _cspec(spec):
+    """oracle Spec -> ctypes spec"""
+    ex = {k: v for k, v in spec.extremes.items() if k not in ("norm_set",)}
+    ex["normIsSet"] = int(spec.extremes["norm_set"])
+    me = {k: v for k, v in spec.means.items() if k not in ("norm_set",)}
+    me["normIsSet"] = int(spec.means["norm_set"])
+    rg = dict(spec.regression)
+    rg["centroidRatioLimit"] = 0
+    return F.spec(spec.enabled, non_zero=spec.non_zero, master_norm=-1 if spec.master_norm is None else spec.master_norm,
+                  name_append=spec.name_append or "", extremes=ex, means=me, moments=dict(spec.moments),
+                  percentiles=dict(spec.percentiles), regression=rg)
+
+
+def _close(got, ref, rtol):
+    # a summary value is compared relative to its own magnitude, with the magnitude of the largest value of the row's
+    # functional family as floor for values near zero (a skewness of 1e-4 next to one of 1.0)
+    return np.abs(got - ref) <= rtol * (np.abs(ref) + 1e-3 * np.abs(ref).max()) + 1e-12
+
+
+@pytest.mark.parametrize("key", ["m24k", "v32k", "rec"])
+def test_kernel_on_the_reference_lld_rows(key):
+    lld = G["is09_lld_" + key]
+    names = list(G["is09_lld_names"])
+    for tag, spec, cols, dn, gk in LEVELS:
+        rows = np.ascontiguousarray(contour_rows(lld, dn)[:, cols])
+        f = F.Functionals(_cspec(spec), names[cols], 0.01, device=0)
+        assert f.element_names() == list(G["is09_func_names"] if tag == "is09" else G[gk + "_names"])
+        got = f.run_host(rows, [0], [rows.shape[0]])[0]
+        f.close()
+        ora = fo.functionals(spec, rows, 0.01)
+        assert np.all(np.abs(got - ora) <= 2e-6 * np.abs(ora) + 1e-9), tag       # double reductions in another order, float log10 / exp
+        ref = G["%s_%s" % (gk, key)][0]
+        assert np.all(np.abs(got - ref) <= 2e-6 * np.abs(ref) + 1e-9), tag       # the reference's CSV: 7 significant digits
+
+
+def test_ragged_batch_and_degenerate_contours():
+    rng = np.random.default_rng(3)
+    lens = [300, 1, 2, 0, 33, 64, 4097]
+    K = 5
+    rows = rng.standard_normal((sum(lens), K)).astype(np.float32)
+    rows[:, 1] = 0                                    # a contour without any non-zero value
+    rows[::3, 2] = 0                                  # zeros spread over a contour
+    rows[:, 3] = 2.5                                  # a constant contour
+    off = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    for spec in (fo.Spec(["Extremes", "Means", "Moments", "Percentiles", "Regression"], non_zero=nz, master_norm=fo.SEGMENT,
+                         percentiles=dict(quartile1=1, quartile2=1, quartile3=1, iqr13=1, percentile=[0.05, 0.95], pctlrange=[(0, 1)], interp=ip),
+                         regression=dict(centroidUseAbsValues=ab), moments=dict(stddevNorm=1, amean=1))
+                 for nz, ip, ab in ((0, 1, 1), (1, 0, 0), (2, 1, 1))):
+        f = F.Functionals(_cspec(spec), ["c%d" % i for i in range(K)], 0.01, device=0)
+        got = f.run_host(rows, off, lens)
+        f.close()
+        for u, (o, n) in enumerate(zip(off, lens)):
+            ora = fo.functionals(spec, rows[o:o + n], 0.01) if n else np.zeros(got.shape[1], np.float32)
+            assert np.all(_close(got[u], ora, 1e-5)), (spec.non_zero, u)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "is09-13")), reason="reference configuration files not built (make -C oracle ref)")
+def test_shipped_is09_configuration_end_to_end():
+    from opensmile_b200.session import Session
+    rec = np.load(os.path.join(HERE, "golden", "egemaps_recordings.npz"))["pcm_opensmile_16k"]
+    pcms = [mixed_pcm(24000, 16000, seed=3), np.zeros(100, np.int16), voiced_pcm(32000, 16000, seed=7), rec]
+    off = np.concatenate([[0], np.cumsum([len(x) for x in pcms])]).astype(np.int64)
+    s = Session(os.path.join(REFCONF, "is09-13", "IS09_emotion.conf"), options={"csvoutput": "f.csv"}, device=0)
+    assert s.element_names() == list(G["is09_func_names"])
+    rows, fo_ = s.extract_pcm(np.concatenate(pcms + [np.zeros(8, np.int16)]), off, 16000.0, 1)
+    s.close()
+    assert list(fo_) == [0, 1, 1, 2, 3] and rows.shape == (3, 384)
+    names = list(G["is09_func_names"])
+    for r, key in enumerate(("m24k", "v32k", "rec")):
+        ref = G["is09_func_" + key][0]
+        # Per functional family (12 values per contour): 1e-5 of the family's largest magnitude over the 32 contours.
+        fam = np.abs(ref).reshape(32, 12).max(axis=0)
+        err = (np.abs(rows[r] - ref).reshape(32, 12) / (fam + 1e-12))
+        worst = {names[int(i) * 12 + int(j)]: float(err[i, j]) for i, j in zip(*np.nonzero(err >= 1e-5))}
+        assert not worst, (key, worst)
