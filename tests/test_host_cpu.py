@@ -15,7 +15,8 @@ from opensmile_b200.plan import _comp
 
 
 def test_library_exports_every_declared_symbol():
-    hdr = open(os.path.join(ROOT, "include", "osm_b200.h")).read() + open(os.path.join(ROOT, "include", "osm_b200_host.h")).read()
+    inc = os.path.join(ROOT, "include")
+    hdr = "".join(open(os.path.join(inc, f)).read() for f in sorted(os.listdir(inc)) if f.endswith(".h"))
     declared = set(re.findall(r"OSM_B200_API[^;]*?\b(osm_b200_\w+)\s*\(", hdr))
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
     L = C.CDLL(capi.LIB_PATH)

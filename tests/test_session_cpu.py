@@ -90,23 +90,26 @@ def test_concat_drops_single_element_fields_by_default(tmp_path):
 
 @pytest.mark.parametrize("text,status,needle", [
     ("[frame:cFramer]\nreader.dmLevel=wave\nwriter.dmLevel=frames\nframeSizee = 0.025\n", capi.ERR_INVALID, "unknown field"),
-    ("[x:cFunctionals]\nreader.dmLevel=wave\nwriter.dmLevel=func\n", capi.ERR_UNSUPPORTED, "cFunctionals"),
+    ("[x:cChroma]\nreader.dmLevel=wave\nwriter.dmLevel=func\n", capi.ERR_UNSUPPORTED, "cChroma"),
+    ("[x:cFunctionals]\nreader.dmLevel=wave\nwriter.dmLevel=func\n", capi.ERR_INVALID, "functionalsEnabled"),
     ("[frame:cFramer]\nreader.dmLevel=wave\nwriter.dmLevel=frames\nframeSize = \\cm[fs:frame size]\n", capi.ERR_INVALID, "no value"),
     ("\\{does_not_exist.conf.inc}\n", capi.ERR_INVALID, "cannot open"),
     ("[frame:cFramer]\nreader.dmLevel=wave\nwriter.dmLevel=frames\nframeMode = list\n", capi.ERR_INVALID, "frameMode"),
 ])
 def test_config_errors_are_loud(tmp_path, text, status, needle):
     head = ("[componentInstances:cComponentManager]\ninstance[dataMemory].type=cDataMemory\ninstance[waveIn].type=cWaveSource\n"
-            "instance[frame].type=cFramer\ninstance[x].type=cFunctionals\n[waveIn:cWaveSource]\nwriter.dmLevel=wave\n")
-    if "cFunctionals" not in text:
-        head = head.replace("instance[x].type=cFunctionals\n", "")
+            "instance[frame].type=cFramer\ninstance[x].type=%s\n[waveIn:cWaveSource]\nwriter.dmLevel=wave\n")
+    xt = "cChroma" if "cChroma" in text else "cFunctionals"
+    head = head % xt
+    if "[x:" not in text:
+        head = head.replace("instance[x].type=%s\n" % xt, "")
     if "[frame:" not in text:
         head = head.replace("instance[frame].type=cFramer\n", "")
     (tmp_path / "bad.conf").write_text(head + text)
     with pytest.raises(SessionError) as e:
         # a component off the supported LLD path is rejected when the requested level depends on it (components
         # the output level does not depend on stay idle, like the reference's sinks without a file name)
-        Session(str(tmp_path / "bad.conf"), output_level="func" if "cFunctionals" in text else "frames", device=-1)
+        Session(str(tmp_path / "bad.conf"), output_level="func" if "[x:" in text else "frames", device=-1)
     assert e.value.status == status and needle in str(e.value), str(e.value)
 
 
