@@ -106,6 +106,10 @@ struct LldLaunchInfo { int grid, block; size_t smem; };
 // returns cudaSuccess or the launch error; fills `info`
 cudaError_t launch_lld(const LldParams &p, int nfft, int numSMs, cudaStream_t st, LldLaunchInfo *info);
 cudaError_t launch_post(const PostParams &p, cudaStream_t st);
+// lld_fast.cu: the specialised 512-point mono MFCC instance (same contract and results as lld_kernel); launch_lld selects it
+// unless OSM_B200_LLD_FAST=0
+bool lld_fast_applies(const LldParams &p, int nfft);
+cudaError_t launch_lld_fast(const LldParams &p, int numSMs, cudaStream_t st, LldLaunchInfo *info);
 // output rows per post_kernel CTA: 64, or fewer when a wide static level would not fit shared memory
 int post_tile_rows(int nStat, int maxN, int halo);
 // smem bytes the fused kernel needs for a given geometry (host helper, used for diagnostics)

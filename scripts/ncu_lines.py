@@ -109,7 +109,12 @@ def main():
         return L[l - 1].strip() if 0 < l <= len(L) else ""
 
     if phases:
-        kfile = next((f for (f, l) in agg if f.endswith("kernels.cu")), None)
+        # the kernel's own source file: the one most outer lines belong to (kernels.cu, lld_fast.cu, ...)
+        cnt = {}
+        for (f, l), a in agg.items():
+            if f.endswith(".cu"):
+                cnt[f] = cnt.get(f, 0) + a["inst"]
+        kfile = max(cnt, key=cnt.get) if cnt else None
         marks = []
         if kfile:
             for i, ln in enumerate(open(kfile).read().splitlines(), 1):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Opcode histogram per kernel phase (or for one source line) of an ncu capture.
-usage: ncu_ops.py <report> <mangled-kernel-substring> [--line N] [--frames NFRAMES]"""
+usage: ncu_ops.py <report> <mangled-kernel-substring> [--line N] [--frames NFRAMES] [--src file.cu]"""
 import collections, csv, re, subprocess, sys, os
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import ncu_lines as nl
@@ -23,8 +23,9 @@ if fn is None:
     fn = list(fns)[0]
     print("warning: no instance with %d instructions, using %s" % (len(body), fn), file=sys.stderr)
 offs = sorted(k[1] for k in table if k[0] == fn)
+srcname = sys.argv[sys.argv.index("--src") + 1] if "--src" in sys.argv else "kernels.cu"
 marks = []
-for i, ln in enumerate(open(os.path.join(nl.ROOT, "opensmile_b200", "csrc", "kernels.cu")).read().splitlines(), 1):
+for i, ln in enumerate(open(os.path.join(nl.ROOT, "opensmile_b200", "csrc", srcname)).read().splitlines(), 1):
     m = re.search(r"// =================\s*(.*?)\s*=*$", ln)
     if m:
         marks.append((i, m.group(1)[:28]))
@@ -39,7 +40,7 @@ for idx, r in enumerate(body):
         name = "line %d" % line
     else:
         name = "(other)"
-        if outer[0].endswith("kernels.cu"):
+        if outer[0].endswith(srcname):
             for i, nm in marks:
                 if outer[1] >= i:
                     name = nm
