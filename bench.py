@@ -502,7 +502,9 @@ def measure(w, args, rank, world, local_rank, dist, steps, with_cpu, sampler=Non
         if w.key == "mfcc12":
             k_ms = statistics.mean(lld_ms)
             roof = {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "traffic": profile_traffic(), "kernel": "lld_kernel<256,32,256,2,VEC2,MFCC>", "kernel_ms": k_ms,
+                    "traffic": profile_traffic(),
+                    "kernel": "lld_kernel<256,32,256,2,VEC2,MFCC>" if os.environ.get("OSM_B200_LLD_FAST", "1")[:1] == "0" else "lld512_kernel<13>",
+                    "kernel_ms": k_ms,
                     "post_kernel_ms": statistics.mean(post_ms), "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}
         else:
             roof = {"bound": "hbm", "achieved": alg / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "traffic": None,

@@ -397,9 +397,11 @@ static osm_b200_status build_pass(osm_b200_plan *pl, int si, int opIdx, bool dum
       {
         const int nvw = lld_virtual_warps(fe.nfft);
         const int nB = mb.nBands;
+        // the 512-point MFCC instance (lld_fast.cu) also adds every finished band into its DCT partial sums (~20 more)
+        const double bandCost = (!isPlp && !dumps && lld_fast_applies(kp, fe.nfft)) ? 70.0 : 50.0;
         auto cost = [&](int bs, int be) -> double {          // bands [bs, be) visit ranges bs..be
           if (be <= bs) return 0.0;
-          return 6.0 * (mb.rangeBegin[be + 1] - mb.rangeBegin[bs]) + 50.0 * (be - bs) + 12.0;
+          return 6.0 * (mb.rangeBegin[be + 1] - mb.rangeBegin[bs]) + bandCost * (be - bs) + 12.0;
         };
         // best[w][b] = minimal max-cost of covering bands [0, b) with w groups
         std::vector<std::vector<double>> best(nvw + 1, std::vector<double>(nB + 1, 1e30));

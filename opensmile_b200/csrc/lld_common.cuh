@@ -59,7 +59,8 @@ __host__ __device__ inline SmemLayout make_layout(const LldParams &p, int M, int
   L.melCoef = o; o += (p.melVCount + 4) * 8;   // visit list: (w, 1-w) per visited bin, ranges padded to x4
   L.melRange = o; o += 2 * (p.nBands + 2) * 4;  // first bin / first visit entry of every range
   o = align_up(o, 16);
-  L.dctCos = o; o += p.dctRows * p.dctStride * 4;
+  // MFCC: the fast 512-point instance keeps the DCT table transposed, [nBands][16]
+  L.dctCos = o; o += max(p.dctRows * p.dctStride, p.opKind == 0 ? p.nBands * 16 : 0) * 4;
   L.dctLift = o; o += p.nStat * 4;
   L.eql = o; o += (p.opKind == 1 ? p.nBands : 0) * 4;
   o = align_up(o, 16);

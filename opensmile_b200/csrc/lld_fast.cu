@@ -13,15 +13,26 @@
 //            back and never re-read (one Z round trip and one barrier less than lld_kernel).  The two self-paired
 //            butterflies (t = 0: k and 256 - k both = 0 mod 16; t = 8) go to warp 0, which reorders its registers into the
 //            same (a_q, b_{15-q}) pairing so that every warp executes the same code.
-//   mel      visit list read as float4 (two bins per load)
+//   mel+DCT  visit list read as float4 (two bins per load); a warp adds its finished log band values straight into partial
+//            DCT sums in registers, a short second step adds the eight warps' partial sums: the DCT is balanced like the
+//            band work (13 coefficients do not divide over 8 warps) and the band level never goes through shared memory
 //
 // Reference rows as in kernels.cu (SURVEY.md 8a-1 ... a-8, a-13, a-15).
 #include "lld_common.cuh"
+
+// A/B switch: 1 = a warp adds its finished log band values straight into partial DCT sums (balanced, no band level in
+// shared memory) -- 4 % faster, but the partial sums reorder the reference's sequential m = 0..25 accumulation, which moves
+// 0.3 % of the delta-delta values past 1e-5 of their column's scale (measured, profiles/r02_v3_*).  Default: reference order.
+#ifndef OSM_FAST_FUSED_DCT
+#define OSM_FAST_FUSED_DCT 0
+#endif
 
 namespace osm {
 namespace {
 
 constexpr int kM = 256, kF = 32, kNT = 256, kNW = 8;
+constexpr int kKMax = 16;             // static outputs per frame the in-register DCT accumulates (nStat <= 16)
+constexpr int kPartOff = 9216;        // float offset of the DCT partial sums inside the FFT tile: behind P (257 x 32 floats)
 
 // t1 -+ i t3 helper of the radix-4 butterfly whose fourth input is zero: d == 0 on entry
 __device__ __forceinline__ void dft4_d0(float2 &a, float2 &b, float2 &c, float2 &d)
@@ -82,6 +93,7 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
   using D16 = Dft<16>;
 
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ ChunkCtx sCx[2];
   const SmemLayout L = make_layout(p, M, F);
   float2 *Z = reinterpret_cast<float2 *>(smem + L.zbuf);
   float *P = reinterpret_cast<float *>(smem + L.zbuf);
@@ -96,7 +108,6 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
   int *sMelRange = reinterpret_cast<int *>(smem + L.melRange);
   float *sDct = reinterpret_cast<float *>(smem + L.dctCos);
   float *sLift = reinterpret_cast<float *>(smem + L.dctLift);
-  float *melS = reinterpret_cast<float *>(smem + L.melS);
   float *ring = reinterpret_cast<float *>(smem + L.ring);
   float *Dbuf = reinterpret_cast<float *>(smem + L.zbuf);
 
@@ -109,7 +120,10 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
   for (int i = tid; i < M / 2 + 1; i += NT) sSplit[i] = p.splitTw[i];
   for (int i = tid; i < p.melVCount; i += NT) sMelCoef[i] = p.melVisit[i];
   for (int i = tid; i < p.nBands + 2; i += NT) { sMelRange[i] = p.melRange[i]; sMelRange[p.nBands + 2 + i] = p.melVB[i]; }
-  for (int i = tid; i < p.dctRows * p.dctStride; i += NT) sDct[i] = p.dctCos[i];
+  for (int i = tid; i < p.nBands * kKMax; i += NT) {            // transposed, zero padded: sDct[band][kKMax]
+    const int m = i / kKMax, c = i - m * kKMax;
+    sDct[i] = (c < p.nStat) ? p.dctCos[c * p.dctStride + m] : 0.f;
+  }
   for (int i = tid; i < p.nStat; i += NT) sLift[i] = p.dctLift[i];
   for (int i = tid; i < L.sampFloats; i += NT) samp[i] = 0.f;
   __syncthreads();
@@ -118,16 +132,20 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
   const int S = hop + p.sPad;
   uint32_t phase = 0;
 
+  // The chunk context is CTA-uniform: it lives in shared memory (current / next chunk, alternating) instead of a dozen
+  // registers per thread; thread 0 fills the next slot when it prefetches that chunk's first tile.
   int chunk = blockIdx.x;
   if (chunk >= p.nChunks) return;
-  ChunkCtx cx = load_chunk<F>(p, chunk);
-  int j = 0;
-  int emitted = cx.a;
+  int cpar = 0;
   if (tid == 0) {
-    const TileGeom g0 = tile_geom<F>(p, cx, 0);
+    sCx[0] = load_chunk<F>(p, chunk);
+    const TileGeom g0 = tile_geom<F>(p, sCx[0], 0);
     mbar_expect_tx(mbar, g0.bytes);
     bulk_g2s(rawPcm, g0.src, g0.bytes, mbar);
   }
+  __syncthreads();
+  int j = 0;
+  int emitted = sCx[0].a;
 
   // pass 2: butterflies of this warp; bins of the pair slots (see the file header).  Slots 0..7 hold k = wl + 16 q
   // (and M - k = 256 - wl - 16 q), slots 8..15 hold k = 256 - wh - 16 q (and M - k = wh + 16 q): warps 1..7 have
@@ -137,13 +155,14 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
   const int melBs = p.melSplit[warp], melBe = p.melSplit[warp + 1];
 
   while (chunk < p.nChunks) {
-    const TileGeom tg = tile_geom<F>(p, cx, j);
-    const int nf = tg.nf, count = tg.count;
+    const ChunkCtx &cx = sCx[cpar];
 
     // ================= stage: PCM (landing zone) -> float -> pre-emphasis -> sample tile =================
     mbar_wait(mbar, phase);
     phase ^= 1;
     {
+      const TileGeom tg = tile_geom<F>(p, cx, j);
+      const int count = tg.count;
       const int16_t *rp = reinterpret_cast<const int16_t *>(rawPcm + tg.mis) + tg.lead;
       const bool aligned = (tg.mis == 0);
       const bool hasLead = tg.lead > 0;
@@ -189,6 +208,7 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
         bulk_g2s(rawPcm, gn.src, gn.bytes, mbar);
       } else if (chunk + (int)gridDim.x < p.nChunks) {
         const ChunkCtx cn = load_chunk<F>(p, chunk + gridDim.x);
+        sCx[cpar ^ 1] = cn;                           // read by everyone after the barriers of this tile
         const TileGeom gn = tile_geom<F>(p, cn, 0);
         mbar_expect_tx(mbar, gn.bytes);
         bulk_g2s(rawPcm, gn.src, gn.bytes, mbar);
@@ -282,7 +302,70 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
     }
     __syncthreads();
 
+#if OSM_FAST_FUSED_DCT
+    // ================= mel filterbank (melspec.cpp:543-569) + log (mfcc.cpp:239-243) + DCT-II partial sums =================
+    // Every warp owns a contiguous band group (cost-balanced on the host).  A finished log band value goes straight into
+    // the warp's partial DCT sums (mfcc.cpp:251-272: sum_m log[m] cos(...), here grouped by warp: bands ascending inside a
+    // warp, warps ascending in the final sum), so the DCT work is balanced like the band work and the band level never
+    // touches shared memory.
+    {
+      float acc[kKMax];
+#pragma unroll
+      for (int c = 0; c < kKMax; c++) acc[c] = 0.f;
+      if (melBs < melBe) {
+        const int *sVB = sMelRange + p.nBands + 2;
+        float cur = 0.f;
+        for (int r = melBs; r <= melBe; r++) {
+          float nxt = 0.f;
+          const float *pp = P + sMelRange[r] * F + f;
+          const int v0 = sVB[r];
+          const float4 *cp = reinterpret_cast<const float4 *>(sMelCoef + v0);
+#pragma unroll 1
+          for (int q = (sVB[r + 1] - v0) >> 2; q > 0; q--, pp += 4 * F, cp += 2) {
+            const float p0 = pp[0], p1 = pp[F], p2 = pp[2 * F], p3 = pp[3 * F];
+            const float4 wa = cp[0], wb = cp[1];
+            cur = __fmaf_rn(p0, wa.x, cur); nxt = __fmaf_rn(p0, wa.y, nxt);
+            cur = __fmaf_rn(p1, wa.z, cur); nxt = __fmaf_rn(p1, wa.w, nxt);
+            cur = __fmaf_rn(p2, wb.x, cur); nxt = __fmaf_rn(p2, wb.y, nxt);
+            cur = __fmaf_rn(p3, wb.z, cur); nxt = __fmaf_rn(p3, wb.w, nxt);
+          }
+          if (r > melBs) {
+            float mval = __fmul_rn(cur, p.melScale);
+            if (p.doLog) mval = (mval < p.melfloor) ? p.logMelfloor : logf(mval);
+            const float4 *dt = reinterpret_cast<const float4 *>(sDct + (r - 1) * kKMax);
+#pragma unroll
+            for (int c4 = 0; c4 < kKMax / 4; c4++) {
+              const float4 d = dt[c4];
+              acc[4 * c4 + 0] = __fmaf_rn(mval, d.x, acc[4 * c4 + 0]);
+              acc[4 * c4 + 1] = __fmaf_rn(mval, d.y, acc[4 * c4 + 1]);
+              acc[4 * c4 + 2] = __fmaf_rn(mval, d.z, acc[4 * c4 + 2]);
+              acc[4 * c4 + 3] = __fmaf_rn(mval, d.w, acc[4 * c4 + 3]);
+            }
+          }
+          cur = nxt;
+        }
+      }
+      float *part = P + kPartOff + warp * (kKMax * F) + f;      // [warp][kKMax][F], behind the power spectrum
+#pragma unroll
+      for (int c = 0; c < kKMax; c++) part[c * F] = acc[c];
+    }
+    __syncthreads();
+
+    // ================= DCT-II: sum of the warps' partial sums, lifter (mfcc.cpp:268-272) =================
+    const int ringBase = (j & 1) * F;
+    for (int c = warp; c < p.nStat; c += NW) {
+      const float *pp = P + kPartOff + c * F + f;
+      float a = pp[0];
+#pragma unroll
+      for (int w = 1; w < NW; w++) a = __fadd_rn(a, pp[w * (kKMax * F)]);
+      ring[c * (2 * F) + ringBase + f] = __fmul_rn(a, sLift[c]);
+    }
+    __syncthreads();
+
+#else
     // ================= mel filterbank (melspec.cpp:543-569) + log (mfcc.cpp:239-243) =================
+    // the band level lives behind the power spectrum (P + kPartOff), not in the sample tile
+    float *melS = P + kPartOff;
     if (melBs < melBe) {
       const int *sVB = sMelRange + p.nBands + 2;
       float cur = 0.f;
@@ -310,47 +393,42 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
     }
     __syncthreads();
 
-    // ================= DCT-II + lifter (mfcc.cpp:251-272) =================
+    // ================= DCT-II + lifter (mfcc.cpp:251-272), the reference's m = 0 .. nBands-1 accumulation order =================
+    // table transposed and zero padded, sDct[band][kKMax]: warp w evaluates coefficients 2w and 2w+1 together (one 8-byte
+    // table read and one band value feed two dot products); the padding columns are zero
     const int ringBase = (j & 1) * F;
-    for (int i = warp; i < p.nStat; i += 2 * NW) {
-      const int i1 = i + NW;
-      const bool two = i1 < p.nStat;
-      const float4 *c0 = reinterpret_cast<const float4 *>(sDct + i * p.dctStride);
-      const float4 *c1 = reinterpret_cast<const float4 *>(sDct + (two ? i1 : i) * p.dctStride);
-      const float *lp = melS + f;
-      float a0 = 0.f, a1 = 0.f;
-      int m = 0;
+    {
+      const int i = 2 * warp;
+      if (i < p.nStat) {
+        const float2 *cc = reinterpret_cast<const float2 *>(sDct + i);
+        const float *lp = melS + f;
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll 2
-      for (; m + 4 <= p.nBands; m += 4, lp += 4 * F) {
-        const float4 w0 = *c0++, w1 = *c1++;
-        const float l0 = lp[0], l1 = lp[F], l2 = lp[2 * F], l3 = lp[3 * F];
-        a0 = __fmaf_rn(l0, w0.x, a0); a1 = __fmaf_rn(l0, w1.x, a1);
-        a0 = __fmaf_rn(l1, w0.y, a0); a1 = __fmaf_rn(l1, w1.y, a1);
-        a0 = __fmaf_rn(l2, w0.z, a0); a1 = __fmaf_rn(l2, w1.z, a1);
-        a0 = __fmaf_rn(l3, w0.w, a0); a1 = __fmaf_rn(l3, w1.w, a1);
+        for (int m = 0; m < p.nBands; m++, lp += F, cc += kKMax / 2) {
+          const float l0 = lp[0];
+          const float2 c = cc[0];
+          a0 = __fmaf_rn(l0, c.x, a0); a1 = __fmaf_rn(l0, c.y, a1);
+        }
+        ring[i * (2 * F) + ringBase + f] = __fmul_rn(a0, sLift[i]);
+        if (i + 1 < p.nStat) ring[(i + 1) * (2 * F) + ringBase + f] = __fmul_rn(a1, sLift[i + 1]);
       }
-      const float *r0 = reinterpret_cast<const float *>(c0), *r1 = reinterpret_cast<const float *>(c1);
-      for (int k = 0; m < p.nBands; m++, k++, lp += F) {
-        const float l0 = lp[0];
-        a0 = __fmaf_rn(l0, r0[k], a0); a1 = __fmaf_rn(l0, r1[k], a1);
-      }
-      ring[i * (2 * F) + ringBase + f] = __fmul_rn(a0, sLift[i]);
-      if (two) ring[i1 * (2 * F) + ringBase + f] = __fmul_rn(a1, sLift[i1]);
     }
     __syncthreads();
 
+#endif
     // ================= store (same statements as lld_kernel) =================
+    const int tfs = cx.s0 + j * F;                    // first static frame of this tile
     if (!p.fused) {
-      const int tot = nf * p.nStat;
+      const int tot = min(F, cx.sEnd - tfs) * p.nStat;
       for (int idx = tid; idx < tot; idx += NT) {
         const int ff = idx / p.nStat, c = idx - ff * p.nStat;
-        p.out[(cx.row0 + tg.fs + ff) * p.outStride + p.outCol + c] = ring[c * (2 * F) + ringBase + ff];
+        p.out[(cx.row0 + tfs + ff) * p.outStride + p.outCol + c] = ring[c * (2 * F) + ringBase + ff];
       }
     } else {
       const int K = p.nStat, W1 = p.fW1, W2 = p.fW2, H = W1 + W2;
       const int T = cx.T;
       const int r0 = emitted;
-      const int r1 = (j + 1 == cx.nT) ? cx.b : min(tg.fs + F - H, cx.b);
+      const int r1 = (j + 1 == cx.nT) ? cx.b : min(tfs + F - H, cx.b);
       const int T1 = T + W1, c01 = max(T - W1, 0), c02 = max(c01 - W2, 0);
       const float norm1 = p.fNorm1, norm2 = p.fNorm2;
       const int d0 = max(r0 - W2, 0), d1 = min(r1 + W2, T1);
@@ -377,7 +455,8 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
     if (j == cx.nT) {
       chunk += gridDim.x;
       j = 0;
-      if (chunk < p.nChunks) { cx = load_chunk<F>(p, chunk); emitted = cx.a; }
+      cpar ^= 1;
+      if (chunk < p.nChunks) emitted = sCx[cpar].a;
     }
   }
 }
@@ -406,7 +485,7 @@ cudaError_t launch_fast_t(const LldParams &p, int numSMs, cudaStream_t st, LldLa
 bool lld_fast_applies(const LldParams &p, int nfft)
 {
   return nfft == 512 && !p.narrow && p.opKind == 0 && p.magOut == nullptr && p.melUsePower && p.nChan == 1 &&
-         p.frameStep % 8 == 0 && p.frameSize % 8 == 0 && p.frameSize <= 512 && !p.hasWinOffset &&
+         p.frameStep % 8 == 0 && p.frameSize % 8 == 0 && p.frameSize <= 512 && !p.hasWinOffset && p.nStat <= kKMax &&
          ((p.frameStep + p.sPad) % 2) == 0;
 }
 

@@ -1,8 +1,13 @@
 """CPU restatement of cFunctionals (frameMode = full) with the sub-components cFunctionalExtremes, cFunctionalMeans,
-cFunctionalMoments, cFunctionalPercentiles and cFunctionalRegression -- numpy, float64 accumulators like the reference.
+cFunctionalMoments, cFunctionalPercentiles, cFunctionalRegression (numpy, float64 accumulators like the reference) and
+cFunctionalTimes, cFunctionalLpc, cFunctionalSegments (relTh / nonX / eqX), cFunctionalPeaks2 (float32 statement by statement:
+their reference code works in FLOAT_DMEM).
 
 TEST INFRASTRUCTURE ONLY (tests/, smoke, bench parity).  Pinned against the unmodified reference's -csvoutput / -arffoutput
 rows: tests/golden/functionals_goldens.npz (scripts/make_golden_functionals.py), tests/test_functionals_cpu.py.
+
+The second group is pinned by tests/golden/functionals_goldens2.npz (tests/configs/func_variants2.conf: the option sets of the
+shipped ComParE_2016 / GeMAPS functionals blocks).
 
 Citations relative to /root/reference/src/functionals.  One contour = one LLD column of one utterance:
   functionals.cpp:284-330  non-zero filter (nonZeroFuncts 1: != 0, 2: > 0), sorted copy, min / max / mean (double sum, divided
@@ -29,7 +34,7 @@ class Spec:
     """mirror of include/osm_b200_functionals.h (field names = the reference's configuration fields)"""
 
     def __init__(self, enabled, non_zero=0, master_norm=None, name_append=None, extremes=None, means=None, moments=None,
-                 percentiles=None, regression=None):
+                 percentiles=None, regression=None, times=None, lpc=None, segments=None, peaks2=None):
         self.enabled, self.non_zero, self.master_norm, self.name_append = list(enabled), non_zero, master_norm, name_append
         self.extremes = dict(max=1, min=1, range=1, maxpos=1, minpos=1, amean=0, maxameandist=1, minameandist=1, norm=FRAME, norm_set=False)
         self.extremes.update(extremes or {})
@@ -43,6 +48,19 @@ class Spec:
         self.regression = dict(linregc1=1, linregc2=1, linregerrA=1, linregerrQ=1, qregc1=1, qregc2=1, qregc3=1, qregerrA=1, qregerrQ=1,
                                centroid=1, centroidNorm=SEGMENT, centroidUseAbsValues=1, normRegCoeff=0, normInputs=0, oldBuggyQerr=1)
         self.regression.update(regression or {})
+        self.times = dict(upleveltime25=1, downleveltime25=1, upleveltime50=1, downleveltime50=1, upleveltime75=1, downleveltime75=1,
+                          upleveltime90=1, downleveltime90=1, risetime=1, falltime=1, leftctime=1, rightctime=1, duration=1,
+                          buggySecNorm=1, norm=SEGMENT, norm_set=False)
+        self.times.update(times or {})
+        self.lpc = dict(lpGain=0, lpc=1, firstCoeff=0, order=5)
+        self.lpc.update(lpc or {})
+        self.segments = dict(maxNumSeg=20, segmentationAlgorithm="delta", thresholds=[0.0], X=0.0, XisRel=0, rangeRelThreshold=0.2,
+                             numSegments=0, meanSegLen=0, maxSegLen=0, minSegLen=0, segLenStddev=0, segMinLng=3, segMinLng_set=False,
+                             pauseMinLng=2, norm=SEGMENT, norm_set=False)
+        self.segments.update(segments or {})
+        self.peaks2 = {k: 0 for k in PEAKS2_NAMES}
+        self.peaks2.update(dict(norm=FRAME, norm_set=False, relThresh=0.1, dynRelThresh=0, absThresh=None, doRatioLimit=1))
+        self.peaks2.update(peaks2 or {})
 
 
 EXT_NAMES = ["max", "min", "range", "maxPos", "minPos", "amean", "maxameandist", "minameandist"]
@@ -50,6 +68,16 @@ EXT_KEYS = ["max", "min", "range", "maxpos", "minpos", "amean", "maxameandist", 
 MEAN_NAMES = ["amean", "absmean", "qmean", "nzamean", "nzabsmean", "nzqmean", "nzgmean", "nnz", "flatness", "posamean", "negamean",
               "posqmean", "posrqmean", "negqmean", "negrqmean", "rqmean", "nzrqmean"]
 MOM_NAMES = ["variance", "stddev", "skewness", "kurtosis", "amean"]
+TIMES_NAMES = ["upleveltime25", "downleveltime25", "upleveltime50", "downleveltime50", "upleveltime75", "downleveltime75",
+               "upleveltime90", "downleveltime90", "risetime", "falltime", "leftctime", "rightctime", "duration"]
+SEG_NAMES = ["numSegments", "meanSegLen", "maxSegLen", "minSegLen", "segLenStddev"]
+# functionalPeaks2.cpp:24-73: output order = index order of the FUNCT_* constants; the configuration field of a value is its
+# name except for the three marked ones
+PEAKS2_NAMES = ["numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs", "peakRangeRel", "peakMeanAbs",
+                "peakMeanMeanDist", "peakMeanRel", "ptpAmpMeanAbs", "ptpAmpMeanRel", "ptpAmpStddevAbs", "ptpAmpStddevRel", "minRangeAbs",
+                "minRangeRel", "minMeanAbs", "minMeanMeanDist", "minMeanRel", "mtmAmpMeanAbs", "mtmAmpMeanRel", "mtmAmpStddevAbs",
+                "mtmAmpStddevRel", "meanRisingSlope", "maxRisingSlope", "minRisingSlope", "stddevRisingSlope", "meanFallingSlope",
+                "maxFallingSlope", "minFallingSlope", "stddevFallingSlope", "covFallingSlope", "covRisingSlope"]
 REG_NAMES = ["linregc1", "linregc2", "linregerrA", "linregerrQ", "qregc1", "qregc2", "qregc3", "qregerrA", "qregerrQ", "centroid"]
 
 
@@ -74,6 +102,15 @@ def value_names(spec):
             out += ["pctlrange%d-%d" % tuple(r) for r in p["pctlrange"]]
         elif f == "Regression":
             out += [n for n in REG_NAMES if spec.regression[n]]
+        elif f == "Times":
+            out += [n for n in TIMES_NAMES if spec.times[n]]
+        elif f == "Lpc":                                           # functionalLpc.cpp:84-96
+            l = spec.lpc
+            out += (["lpgain"] if l["lpGain"] else []) + (["lpc%d" % i for i in range(l["firstCoeff"], l["order"])] if l["lpc"] else [])
+        elif f == "Segments":
+            out += [n for n in SEG_NAMES if spec.segments[n]]
+        elif f == "Peaks2":
+            out += [n for n in PEAKS2_NAMES if spec.peaks2[n]]
         else:
             raise ValueError(f)
     return out
@@ -234,8 +271,492 @@ def contour(spec, x, period):
                         qregc3=fin(c), qregerrA=fin(qea) if r["oldBuggyQerr"] else fin(qea / Nd),
                         qregerrQ=fin(qeq) if r["oldBuggyQerr"] else fin(qeq / Nd), centroid=fin(centroid))
             out += [F32(vals[k]) for k in REG_NAMES if r[k]]
+        elif f == "Times":
+            out += _times(spec, x, mn, mx, period)
+        elif f == "Lpc":
+            out += _lpc(spec, x)
+        elif f == "Segments":
+            out += _segments(spec, x, mn, mx, mean, period)
+        elif f == "Peaks2":
+            out += _peaks2(spec, x, mn, mx, mean, period)
     assert len(out) == nvals
     return out
+
+
+def _times(spec, x, mn, mx, period):
+    """functionalTimes.cpp:245-371 (upleveltime[] / downleveltime[] arrays and useRobustPercentileRange are not restated)"""
+    t = spec.times
+    N = len(x)
+    Nind = F32(N)
+    Norm, Norm1, Norm2 = Nind, F32(Nind - F32(1)), F32(Nind - F32(2))
+    nrm = _norm(t["norm"], t["norm_set"], spec.master_norm)
+    T = F32(1)
+    if nrm == SECOND:
+        T = F32(period)
+        if T != 0:
+            if t["buggySecNorm"]:
+                Norm, Norm1, Norm2 = F32(Norm / T), F32(Norm1 / T), F32(Norm2 / T)
+            else:
+                Norm = F32(F32(1.0) / T)
+                Norm1 = F32(Norm1 / F32(Nind * T))
+                Norm2 = F32(Norm2 / F32(Nind * T))
+    if nrm == FRAME:
+        Norm, Norm1, Norm2 = F32(1), F32(Norm1 / Nind), F32(Norm2 / Nind)
+    rng = F32(mx - mn)
+    lv = [F32(F32(F32(q) * rng) + mn) for q in (0.25, 0.50, 0.75, 0.90)]
+    n25, n50, n75, n90 = [int((x <= l).sum()) for l in lv]
+    nR, nF = int((x[:-1] < x[1:]).sum()), int((x[:-1] > x[1:]).sum())
+    a1, a2 = (x[1:-1] - x[:-2]).astype(np.float32), (x[2:] - x[1:-1]).astype(np.float32)
+    nRC, nLC = int((a2 < a1).sum()), int((a1 < a2).sum())
+    v = {}
+    for nm, cnt in (("25", n25), ("50", n50), ("75", n75), ("90", n90)):
+        v["upleveltime" + nm] = F32(F32(N - cnt) / Norm)
+        v["downleveltime" + nm] = F32(F32(cnt) / Norm)
+    v["risetime"] = F32(F32(nR) / Norm1) if Norm1 != 0 else F32(0)
+    v["falltime"] = F32(F32(nF) / Norm1) if Norm1 != 0 else F32(0)
+    v["leftctime"] = F32(F32(nLC) / Norm2) if Norm2 != 0 else F32(0)
+    v["rightctime"] = F32(F32(nRC) / Norm2) if Norm2 != 0 else F32(0)
+    v["duration"] = F32(F32(N) * T) if nrm == SECOND else F32(N)
+    return [v[k] for k in TIMES_NAMES if t[k]]
+
+
+def _durbin(r, p):
+    """smileDsp_calcLpcAcf (smileutil/smileUtil.c:1572-1627), float: predictor coefficients a[0..p-1] and the final error"""
+    a = [F32(0)] * (p + 1)
+    if r[0] == 0:
+        return a[:p], F32(0)
+    e = F32(r[0])
+    for m in range(1, p + 1):
+        s = F32(F32(1.0) * r[m])
+        for i in range(1, m):
+            s = F32(s + F32(a[i - 1] * r[m - i]))
+        km = F32(F32(F32(-1.0) / e) * s)
+        a[m - 1] = km
+        for i in range(1, m // 2 + 1):
+            xx = a[i - 1]
+            a[i - 1] = F32(a[i - 1] + F32(km * a[m - i - 1]))
+            if i < m // 2 or (m & 1) == 1:
+                a[m - i - 1] = F32(a[m - i - 1] + F32(km * xx))
+        e = F32(e * F32(F32(1.0) - F32(km * km)))
+        if e == 0:
+            for i in range(m, p + 1):
+                a[i] = F32(0)
+            break
+    return a[:p], e
+
+
+def _lpc(spec, x):
+    """functionalLpc.cpp:98-125: smileDsp_autoCorr (smileUtil.c:1560-1569, sequential float sums) + Durbin on the contour"""
+    l = spec.lpc
+    order, N = l["order"], len(x)
+    acf = []
+    for lag in range(order + 1):
+        acc = F32(0)
+        for i in range(lag, N):
+            acc = F32(acc + F32(x[i] * x[i - lag]))
+        acf.append(acc)
+    a, gain = _durbin(acf, order)
+    out = []
+    if l["lpGain"]:
+        out.append(F32(gain / F32(N)))
+    if l["lpc"]:
+        out += [F32(a[i]) for i in range(l["firstCoeff"], order)]
+    return out
+
+
+def _segments(spec, x, mn, mx, mean, period):
+    """functionalSegments.cpp: relTh (process_SegThresh :305-367), nonX (:658-726), eqX (:729-797), statistics + output :800-960"""
+    g = spec.segments
+    N = len(x)
+    maxNumSeg = g["maxNumSeg"]
+    seglens = []
+    st = dict(mean=0, mx=0, mn=0)
+
+    def add(i, last):                                   # addNewSegment :240-262
+        L = i - last
+        if len(seglens) < maxNumSeg:
+            st["mean"] += L
+            seglens.append(L)
+            if L > st["mx"]:
+                st["mx"] = L
+            if st["mn"] == 0 or L < st["mn"]:
+                st["mn"] = L
+        return i
+
+    rng = F32(mx - mn)
+    alg = g["segmentationAlgorithm"]
+    if alg == "relTh":
+        th = [F32(mn + F32(rng * F32(t))) for t in g["thresholds"]]
+        segMinLng = max(g["segMinLng"], 1)
+        if not g["segMinLng_set"]:
+            segMinLng = max(N // maxNumSeg - 1, 2)
+        ravgLng = 3                                     # :333 (the ravgLng option is not used by this method)
+        lastSeg = int(-segMinLng / 2)                   # C integer division truncates toward zero
+        ravg, raLast = F32(0), F32(0)
+        for i in range(N):
+            ravg = F32(ravg + x[i])
+            if i >= ravgLng:
+                ravg = F32(ravg - x[i - ravgLng])
+            ra = F32(ravg / F32(min(i + 1, ravgLng)))
+            cross = any((ra > t and raLast <= t) or (ra < t and raLast >= t) for t in th)
+            raLast = ra
+            if cross and i - lastSeg > segMinLng:
+                lastSeg = add(i, lastSeg)
+    elif alg in ("nonX", "eqX"):
+        X = F32(mn + F32(rng * F32(g["X"]))) if g["XisRel"] else F32(g["X"])
+        segMinLng, pauseMinLng = max(g["segMinLng"], 1), max(g["pauseMinLng"], 1)
+        inSeg = segStart = segEnd = 0
+        startIdx = 0
+        for i in range(N):
+            hit = (x[i] != X) if alg == "nonX" else (x[i] == X)
+            if hit:
+                if inSeg == 1:
+                    segEnd = 0
+                    segStart += 1
+                    if segStart >= segMinLng:
+                        segStart = 0
+                        inSeg = 2
+                elif inSeg == 0:
+                    segStart += 1
+                    startIdx = i
+                    inSeg = 1
+                else:
+                    segEnd = 0
+            else:
+                if inSeg == 2:
+                    segStart = 0
+                    segEnd += 1
+                    if segEnd >= pauseMinLng:
+                        inSeg = 0
+                        add(i - segEnd, startIdx)
+                        segEnd = 0
+                elif inSeg == 1:
+                    segEnd += 1
+                    if segEnd >= pauseMinLng:
+                        inSeg = segEnd = segStart = 0
+        if inSeg == 2:
+            segEnd += 1
+            add(N - segEnd, startIdx)
+    else:
+        raise ValueError(alg)
+    nS = len(seglens)
+    m = F32(F32(st["mean"]) / F32(nS)) if nS > 1 else F32(st["mean"])
+    dev = F32(0)
+    for L in seglens:
+        d = F32(F32(L) - m)
+        dev = F32(dev + F32(d * d))
+    dev = F32(math.sqrt(F32(dev / F32(nS)))) if nS > 1 else F32(0)      # sqrt(double(float)) -> float
+    nrm = _norm(g["norm"], g["norm_set"], spec.master_norm)
+    T = F32(period)
+    Tn = T if T != 0 else F32(1)
+    v = {}
+    if nrm == SECOND:
+        v["numSegments"] = F32(F32(nS) / F32(Tn * F32(N)))
+        v["meanSegLen"], v["maxSegLen"], v["minSegLen"], v["segLenStddev"] = F32(m * Tn), F32(F32(st["mx"]) * Tn), F32(F32(st["mn"]) * Tn), F32(dev * Tn)
+    elif nrm == SEGMENT:
+        v["numSegments"] = F32(F32(nS) / F32(maxNumSeg))
+        v["meanSegLen"], v["maxSegLen"], v["minSegLen"], v["segLenStddev"] = F32(m / F32(N)), F32(F32(st["mx"]) / F32(N)), F32(F32(st["mn"]) / F32(N)), F32(dev / F32(N))
+    else:
+        v["numSegments"] = F32(nS)
+        v["meanSegLen"], v["maxSegLen"], v["minSegLen"], v["segLenStddev"] = m, F32(st["mx"]), F32(st["mn"]), dev
+    return [v[k] for k in SEG_NAMES if g[k]]
+
+
+def _ratio_limit(x, lim1=10.0, lim2=10.0):
+    """smileMath_ratioLimit (smileutil/smileUtil.c:602-614) with smileMath_tanh / smileMath_logistic (:590-600): the argument of
+    tanh is a FLOAT_DMEM, the logistic is evaluated in double and returned as FLOAT_DMEM"""
+    def tanh_(a):
+        a = F32(a)
+        z = F32(F32(2.0) * a)
+        lim = F32(math.log(float(np.finfo(np.float32).max)))
+        lg = F32(1.0) if z > lim else (F32(0.0) if z < -lim else F32(1.0 / (1.0 + math.exp(-float(z)))))
+        return F32(F32(F32(2.0) * lg) - F32(1.0))
+    x = F32(x)
+    l1, l2 = F32(lim1), F32(lim2)
+    if x > l1:
+        return F32(F32(tanh_((math.sqrt(float(x) - float(l1) + 1.0) - 1.0) / (float(l2) * 0.5)) * l2) + l1)
+    if x < -l1:
+        return F32(F32(tanh_(-(math.sqrt(-1.0 * (float(x) + float(l1)) + 1.0) - 1.0) / (float(l2) * 0.5)) * l2) - l1)
+    return x
+
+
+def _peaks2(spec, x, mn, mx, mean, period):
+    """functionalPeaks2.cpp:296-915.  The reference's doubly linked list of extrema becomes a Python list of [type, x, y] with
+    removal by identity; the statement order of the three pruning passes and of the statistics is kept, FLOAT_DMEM = float32."""
+    c = spec.peaks2
+    N = len(x)
+    rng = F32(mx - mn)
+    absT = F32(c["absThresh"]) if c["absThresh"] is not None else F32(F32(c["relThresh"]) * rng)
+    dyn = c["dynRelThresh"] and c["absThresh"] is None
+    relT = F32(c["relThresh"])
+
+    def below(diff, base):                              # isBelowThresh :270-294
+        if dyn:
+            if base == 0:
+                return diff != 0
+            return abs(float(F32(diff / base))) < relT  # fabs of a float quotient, compared with the float threshold
+        return diff < absT
+
+    lst = []
+    for i in range(2, N - 2):                           # step 1 :320-327
+        if x[i] > x[i - 1] and x[i] > x[i + 1]:
+            lst.append([1, i, F32(x[i])])
+        elif x[i] < x[i - 1] and x[i] < x[i + 1]:
+            lst.append([0, i, F32(x[i])])
+
+    def remove(el):
+        for k, e in enumerate(lst):
+            if e is el:
+                del lst[k]
+                return
+
+    # step 2a :330-392
+    lastVal = lastMin = lastMax = F32(x[0])
+    maxFlag = minFlag = 0
+    lastMaxPtr = None
+    k = 0
+    while k < len(lst):
+        el = lst[k]
+        nxt = lst[k + 1] if k + 1 < len(lst) else None
+        if el[0] == 1:
+            if below(F32(abs(F32(el[2] - lastVal))), min(el[2], lastVal)):
+                if below(F32(el[2] - lastMin), lastMin):
+                    remove(el)
+                else:
+                    if float(el[2]) > float(lastMax) * 1.05:        # FLOAT_DMEM * double literal: compared in double
+                        if lastMaxPtr is not None:
+                            remove(lastMaxPtr)
+                        lastMax = el[2]
+                        lastMaxPtr = el
+                    else:
+                        if minFlag:
+                            lastMax = el[2]
+                            lastMaxPtr = el
+                        else:
+                            remove(el)
+                    maxFlag, minFlag = 1, 0
+            else:
+                maxFlag, minFlag = 1, 0
+                lastMax = el[2]
+                lastMaxPtr = el
+        else:
+            if not below(F32(abs(F32(el[2] - lastVal))), min(el[2], lastVal)):
+                minFlag, maxFlag = 1, 0
+                lastMin = el[2]
+        lastVal = el[2]
+        k = next((q for q, e in enumerate(lst) if e is nxt), len(lst)) if nxt is not None else len(lst)
+    # step 2b :395-412
+    lastMax = F32(x[0])
+    for el in list(lst):
+        if el[0] == 0:
+            if below(F32(lastMax - el[2]), el[2]):
+                remove(el)
+        else:
+            lastMax = el[2]
+    # step 3 :415-466
+    lastMax = lastMin = F32(x[0])
+    minFlag = 0
+    init = 1
+    lastMinPtr = lastMaxPtr = None
+    for el in list(lst):
+        if not any(e is el for e in lst):
+            continue
+        if el[0] == 0:
+            if not minFlag or init:
+                lastMin, lastMinPtr, minFlag, init = el[2], el, 1, 0
+            else:
+                if el[2] >= lastMin:
+                    remove(el)
+                else:
+                    if lastMinPtr is not el:
+                        remove(lastMinPtr)
+                        lastMinPtr, lastMin = el, el[2]
+        else:
+            if minFlag or init:
+                lastMax, lastMaxPtr, minFlag, init = el[2], el, 0, 0
+            else:
+                if el[2] <= lastMax:
+                    remove(el)
+                else:
+                    if lastMaxPtr is not el:
+                        remove(lastMaxPtr)
+                        lastMaxPtr, lastMax = el, el[2]
+    # statistics, first pass :470-545
+    Z = F32(0)
+    peakMax = peakMin = peakDist = peakDiff = peakMean = Z
+    minMax = minMin = minDist = minDiff = minMean = Z
+    nPeakDist = nPeaks = nMinDist = nMins = 0
+    lastMaxPtr = lastMinPtr = None
+    for el in lst:
+        if el[0] == 0:
+            if lastMinPtr is None:
+                lastMinPtr, minMin, minMax = el, el[2], el[2]
+            else:
+                nMinDist += 1
+                minDist = F32(minDist + F32(el[1] - lastMinPtr[1]))
+                minDiff = F32(minDiff + F32(abs(F32(el[2] - lastMinPtr[2]))))
+                minMin, minMax = min(minMin, el[2]), max(minMax, el[2])
+                lastMinPtr = el
+            minMean = F32(minMean + el[2])
+            nMins += 1
+        else:
+            if lastMaxPtr is None:
+                lastMaxPtr, peakMin, peakMax = el, el[2], el[2]
+            else:
+                nPeakDist += 1
+                peakDist = F32(peakDist + F32(el[1] - lastMaxPtr[1]))
+                peakDiff = F32(peakDiff + F32(abs(F32(el[2] - lastMaxPtr[2]))))
+                peakMin, peakMax = min(peakMin, el[2]), max(peakMax, el[2])
+                lastMaxPtr = el
+            peakMean = F32(peakMean + el[2])
+            nPeaks += 1
+    if nPeaks > 1:                                      # :548-561 (sic: a single peak keeps its sum, minima divide from one on)
+        peakMean = F32(peakMean / F32(nPeaks))
+        if nPeakDist > 1:
+            peakDist, peakDiff = F32(peakDist / F32(nPeakDist)), F32(peakDiff / F32(nPeakDist))
+    if nMins > 0:
+        minMean = F32(minMean / F32(nMins))
+        if nMinDist > 1:
+            minDist, minDiff = F32(minDist / F32(nMinDist)), F32(minDiff / F32(nMinDist))
+    # second pass :564-594 (sic: the peak deviations are taken against the last MINIMUM)
+    peakSdDist = peakSdDiff = minSdDist = minSdDiff = Z
+    lastMaxPtr = lastMinPtr = None
+    for el in lst:
+        if el[0] == 0:
+            if lastMinPtr is None:
+                lastMinPtr = el
+            else:
+                d = F32(F32(el[1] - lastMinPtr[1]) - minDist)
+                minSdDist = F32(minSdDist + F32(d * d))
+                d = F32(F32(abs(F32(el[2] - lastMinPtr[2]))) - minDiff)
+                minSdDiff = F32(minSdDiff + F32(d * d))
+                lastMinPtr = el
+        else:
+            if lastMaxPtr is None:
+                lastMaxPtr = el
+            else:
+                d = F32(F32(el[1] - lastMinPtr[1]) - peakDist)
+                peakSdDist = F32(peakSdDist + F32(d * d))
+                d = F32(F32(abs(F32(el[2] - lastMinPtr[2]))) - peakDiff)
+                peakSdDiff = F32(peakSdDiff + F32(d * d))
+                lastMaxPtr = el
+    sq = lambda v: F32(math.sqrt(float(v))) if v > 0 else F32(0)
+    if nPeakDist > 1:
+        peakSdDist, peakSdDiff = F32(peakSdDist / F32(nPeakDist)), F32(peakSdDiff / F32(nPeakDist))
+    peakSdDist, peakSdDiff = sq(peakSdDist), sq(peakSdDiff)
+    if nMinDist > 1:
+        minSdDist, minSdDiff = F32(minSdDist / F32(nMinDist)), F32(minSdDiff / F32(nMinDist))
+    minSdDist, minSdDiff = sq(minSdDist), sq(minSdDiff)
+    # slopes :610-730
+    meanRise = meanFall = minRise = maxRise = minFall = maxFall = sdRise = sdFall = Z
+    nRising = nFalling = 0
+    enabSlope = any(c[k] for k in PEAKS2_NAMES[22:])
+    if enabSlope:
+        T = F32(period)
+        lastIsMax = -1
+        lastMax = lastMin = F32(x[0])
+        lastMaxPos = lastMinPos = 0
+
+        def rise(s):
+            nonlocal meanRise, minRise, maxRise, nRising
+            meanRise = F32(meanRise + s)
+            if nRising == 0:
+                minRise = maxRise = s
+            else:
+                minRise, maxRise = min(minRise, s), max(maxRise, s)
+            nRising += 1
+
+        def fall(s):
+            nonlocal meanFall, minFall, maxFall, nFalling
+            meanFall = F32(meanFall + s)
+            if nFalling == 0:
+                minFall = maxFall = s
+            else:
+                minFall, maxFall = min(minFall, s), max(maxFall, s)
+            nFalling += 1
+
+        for el in lst:
+            if el[0] == 0:
+                lastMin, lastMinPos = el[2], el[1]
+                if lastMinPos - lastMaxPos > 0:
+                    fall(F32(F32(lastMax - lastMin) / F32(F32(lastMinPos - lastMaxPos) * T)))
+                    lastIsMax = 0
+            else:
+                lastMax, lastMaxPos = el[2], el[1]
+                if lastMaxPos - lastMinPos > 0:
+                    rise(F32(F32(lastMax - lastMin) / F32(F32(lastMaxPos - lastMinPos) * T)))
+                    lastIsMax = 1
+        if lastIsMax == 1:
+            if N - 1 - lastMaxPos > 0:
+                fall(F32(F32(x[N - 1] - lastMax) / F32(F32(N - 1 - lastMaxPos) * T)))
+        elif lastIsMax == 0:
+            if N - 1 - lastMinPos > 0:
+                rise(F32(F32(x[N - 1] - lastMin) / F32(F32(N - 1 - lastMinPos) * T)))
+        else:
+            s_ = F32(F32(x[N - 1] - x[0]) / F32(N))
+            if s_ > 0:
+                meanRise = maxRise = minRise = s_
+                nRising = 1
+            elif s_ < 0:
+                meanFall = maxFall = minFall = s_
+                nFalling = 1
+        if nRising > 1:
+            meanRise = F32(meanRise / F32(nRising))
+        if nFalling > 1:
+            meanFall = F32(meanFall / F32(nFalling))
+        lastMax = lastMin = F32(x[0])
+        lastMaxPos = lastMinPos = 0
+        for el in lst:
+            if el[0] == 0:
+                lastMin, lastMinPos = el[2], el[1]
+                if lastMinPos - lastMaxPos > 0:
+                    s_ = F32(F32(lastMax - lastMin) / F32(F32(lastMinPos - lastMaxPos) * T))
+                    d = F32(s_ - meanFall)
+                    sdFall = F32(sdFall + F32(d * d))
+            else:
+                lastMax, lastMaxPos = el[2], el[1]
+                if lastMaxPos - lastMinPos:
+                    s_ = F32(F32(lastMax - lastMin) / F32(F32(lastMaxPos - lastMinPos) * T))
+                    d = F32(s_ - meanRise)
+                    sdRise = F32(sdRise + F32(d * d))
+        if nRising > 1:
+            sdRise = F32(sdRise / F32(nRising))
+        if nFalling > 1:
+            sdFall = F32(sdFall / F32(nFalling))
+        sdRise, sdFall = sq(sdRise), sq(sdFall)
+    nrm = _norm(c["norm"], c["norm_set"], spec.master_norm)
+    P_ = F32(period)
+    if nrm == SECOND:
+        peakDist, peakSdDist, minDist, minSdDist = F32(peakDist * P_), F32(peakSdDist * P_), F32(minDist * P_), F32(minSdDist * P_)
+    elif nrm == SEGMENT:
+        peakDist, peakSdDist, minDist, minSdDist = F32(peakDist / F32(N)), F32(peakSdDist / F32(N)), F32(minDist / F32(N)), F32(minSdDist / F32(N))
+    lim = (lambda v: _ratio_limit(v)) if c["doRatioLimit"] else (lambda v: F32(v))
+    limMax = (lambda alt: F32(20.0)) if c["doRatioLimit"] else (lambda alt: F32(alt))
+    unity = (lambda v: min(max(F32(v), F32(-1)), F32(1))) if c["doRatioLimit"] else (lambda v: F32(v))
+    v = {}
+    v["numPeaks"] = F32(F32(nPeaks) / F32(F32(N) * P_)) if nrm == SECOND else F32(nPeaks)
+    v["meanPeakDist"], v["meanPeakDistDelta"], v["peakDistStddev"] = peakDist, F32(0), peakSdDist
+    v["peakRangeAbs"] = F32(peakMax - peakMin)
+    v["peakRangeRel"] = unity(F32(abs(F32(F32(peakMax - peakMin) / rng)))) if rng != 0 else F32(peakMax - peakMin)
+    v["peakMeanAbs"], v["peakMeanMeanDist"] = peakMean, F32(peakMean - mean)
+    v["peakMeanRel"] = lim(F32(peakMean / mean)) if mean != 0 else limMax(peakMean)
+    v["ptpAmpMeanAbs"] = peakDiff
+    v["ptpAmpMeanRel"] = unity(F32(peakDiff / rng)) if rng != 0 else peakDiff
+    v["ptpAmpStddevAbs"] = peakSdDiff
+    v["ptpAmpStddevRel"] = unity(F32(peakSdDiff / rng)) if rng != 0 else peakSdDiff
+    v["minRangeAbs"] = F32(minMax - minMin)
+    v["minRangeRel"] = unity(F32(abs(F32(F32(minMax - minMin) / rng)))) if rng != 0 else F32(minMax - minMin)
+    v["minMeanAbs"], v["minMeanMeanDist"] = minMean, F32(mean - minMean)
+    v["minMeanRel"] = lim(F32(minMean / mean)) if mean != 0 else limMax(minMean)
+    v["mtmAmpMeanAbs"] = minDiff
+    v["mtmAmpMeanRel"] = unity(F32(minDiff / rng)) if rng != 0 else minDiff
+    v["mtmAmpStddevAbs"] = minSdDiff
+    v["mtmAmpStddevRel"] = unity(F32(minSdDiff / rng)) if rng != 0 else minSdDiff
+    v["meanRisingSlope"], v["maxRisingSlope"], v["minRisingSlope"], v["stddevRisingSlope"] = meanRise, maxRise, minRise, sdRise
+    v["meanFallingSlope"], v["maxFallingSlope"], v["minFallingSlope"], v["stddevFallingSlope"] = meanFall, maxFall, minFall, sdFall
+    v["covFallingSlope"] = lim(F32(sdFall / meanFall)) if meanFall > 0 else F32(0)
+    v["covRisingSlope"] = lim(F32(sdRise / meanRise)) if meanRise > 0 else F32(0)
+    return [F32(v[k]) for k in PEAKS2_NAMES if c[k]]
 
 
 def functionals(spec, rows, period):
