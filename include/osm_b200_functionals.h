@@ -8,6 +8,10 @@
  *     cFunctionalMoments      src/functionals/functionalMoments.cpp:89-168
  *     cFunctionalPercentiles  src/functionals/functionalPercentiles.cpp:299-430
  *     cFunctionalRegression   src/functionals/functionalRegression.cpp:141-428
+ *     cFunctionalTimes        src/functionals/functionalTimes.cpp:245-371
+ *     cFunctionalLpc          src/functionals/functionalLpc.cpp:98-125
+ *     cFunctionalSegments     src/functionals/functionalSegments.cpp:305-367 (relTh), :658-797 (nonX / eqX), :800-960
+ *     cFunctionalPeaks2       src/functionals/functionalPeaks2.cpp:296-915
  * Field names and defaults are the reference's configuration fields (`[x:cFunctionals]` section: functionalsEnabled,
  * nonZeroFuncts, functNameAppend, masterTimeNorm, and `<Functional>.<field>` for the sub-components).
  *
@@ -28,6 +32,7 @@ extern "C" {
 
 typedef enum {
   OSM_B200_F_EXTREMES = 0, OSM_B200_F_MEANS, OSM_B200_F_MOMENTS, OSM_B200_F_PERCENTILES, OSM_B200_F_REGRESSION,
+  OSM_B200_F_TIMES, OSM_B200_F_LPC, OSM_B200_F_SEGMENTS, OSM_B200_F_PEAKS2,
   OSM_B200_F_COUNT_
 } osm_b200_functional_type;
 
@@ -39,6 +44,14 @@ typedef enum {
 
 #define OSM_B200_F_MAX_ENABLED 8
 #define OSM_B200_F_MAX_PCTL 8
+#define OSM_B200_F_MAX_THRESH 8
+#define OSM_B200_F_MAX_LPC 16
+#define OSM_B200_F_PEAKS2_VALUES 32
+
+/* cFunctionalSegments.segmentationAlgorithm (the three the shipped ComParE_2016 / GeMAPS blocks use) */
+#define OSM_B200_SEG_RELTH 0
+#define OSM_B200_SEG_NONX  1
+#define OSM_B200_SEG_EQX   2
 
 typedef struct {
   /* [x:cFunctionals] */
@@ -71,6 +84,35 @@ typedef struct {
     int32_t centroidUseAbsValues, centroidRatioLimit;   /* 1, 1 (the limiter is not implemented: must be 0 when centroid = 1) */
     int32_t normRegCoeff, normInputs, oldBuggyQerr, doRatioLimit;   /* 0, 0, 1, 0 */
   } regression;
+  struct {                                         /* Times.* : every value on; norm "segment"; buggySecNorm 1 */
+    int32_t upleveltime25, downleveltime25, upleveltime50, downleveltime50, upleveltime75, downleveltime75, upleveltime90,
+            downleveltime90, risetime, falltime, leftctime, rightctime, duration;
+    int32_t buggySecNorm;
+    int32_t norm, normIsSet;
+  } times;
+  struct {                                         /* Lpc.* : lpGain 0, lpc 1, firstCoeff 0, order 5 */
+    int32_t lpGain, lpc, firstCoeff, order;
+  } lpc;
+  struct {                                         /* Segments.* : every value off; maxNumSeg 20; segMinLng 3; pauseMinLng 2; norm "segment" */
+    int32_t numSegments, meanSegLen, maxSegLen, minSegLen, segLenStddev;
+    int32_t algorithm;                             /* OSM_B200_SEG_* */
+    int32_t maxNumSeg;
+    int32_t n_thresholds; float thresholds[OSM_B200_F_MAX_THRESH];   /* relTh: relative to the contour's range */
+    float   X; int32_t XisRel;                     /* nonX / eqX */
+    int32_t segMinLng, segMinLngIsSet, pauseMinLng;
+    int32_t norm, normIsSet;
+  } segments;
+  struct {                                         /* Peaks2.* : every value off; norm "frames"; relThresh 0.1; doRatioLimit 1 */
+    int32_t value[OSM_B200_F_PEAKS2_VALUES];       /* in the reference's output order: numPeaks, meanPeakDist, meanPeakDistDelta,
+                                                      peakDistStddev, peakRangeAbs, peakRangeRel, peakMeanAbs, peakMeanMeanDist, peakMeanRel,
+                                                      ptpAmpMeanAbs, ptpAmpMeanRel, ptpAmpStddevAbs, ptpAmpStddevRel, minRangeAbs, minRangeRel,
+                                                      minMeanAbs, minMeanMeanDist, minMeanRel, mtmAmpMeanAbs, mtmAmpMeanRel, mtmAmpStddevAbs,
+                                                      mtmAmpStddevRel, meanRisingSlope, maxRisingSlope, minRisingSlope, stddevRisingSlope,
+                                                      meanFallingSlope, maxFallingSlope, minFallingSlope, stddevFallingSlope, covFallingSlope,
+                                                      covRisingSlope (functionalPeaks2.cpp:24-73) */
+    float   relThresh, absThresh; int32_t useAbsThresh, dynRelThresh, doRatioLimit;
+    int32_t norm, normIsSet;
+  } peaks2;
 } osm_b200_functionals_spec;
 
 typedef struct osm_b200_functionals osm_b200_functionals;

@@ -7,6 +7,10 @@
 //   pass 1  count, sum, min / max with first positions, the power / sign / log sums of cFunctionalMeans, the moment sums
 //           sum x i, sum x i^2 of cFunctionalRegression; the filtered contour is copied to shared memory when percentiles are
 //           enabled
+//   seq     the order-dependent functionals (functionals_seq.cuh) read the shared copy: cFunctionalTimes counts in parallel,
+//           cFunctionalLpc with one lane per autocorrelation lag (the reference's sequential float sums), cFunctionalPeaks2
+//           collects the local extrema in parallel (ordered compaction) and prunes them on lane 0, cFunctionalSegments runs
+//           its state machine on lane 0
 //   pass 2  central moments about the float mean (functionalMoments.cpp:96-108) and the regression residuals
 //           (functionalRegression.cpp:263-290), which need the results of pass 1
 // then a warp-wide bitonic sort of the shared copy for cFunctionalPercentiles (the reference sorts with std::sort,
@@ -22,6 +26,7 @@
 #include <vector>
 
 #include "../../include/osm_b200_functionals.h"
+#include "functionals_seq.cuh"
 #include "plan.hpp"
 
 namespace osm {
@@ -35,7 +40,11 @@ struct FnParams {
   const float *rows; int rowStride; int nIn;
   const long long *rowOff, *nRows;          // device [nUtt]
   float *out; int nVals;                    // out[u][e * nVals + v]
-  int sortCap;                              // floats per warp in shared memory (0: no percentiles)
+  int sortCap;                              // floats of the contour copy per warp in shared memory (0: not needed)
+  int perWarp;                              // floats per warp in shared memory: contour copy + extrema list + segment lengths
+  int listOff, lensOff;                     // float offsets of the Peaks2 list / Segments lengths inside a warp's block
+  int valOff[OSM_B200_F_MAX_ENABLED];       // first value of every enabled functional inside a contour's output
+  int timesNorm, segNorm, peaksNorm;
   float period; double periodD;             // input level period as FLOAT_DMEM and as double
   osm_b200_functionals_spec s;
   int extNorm, meanNorm;                    // resolved time normalisations
@@ -84,13 +93,14 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
 {
   extern __shared__ float fnSort[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int groups = (p.nIn + kFnWarps - 1) / kFnWarps;
-  const int u = blockIdx.x / groups, e = (blockIdx.x % groups) * kFnWarps + warp;
+  const int nW = blockDim.x >> 5;                                   // 1 .. kFnWarps: fewer when long contours need the shared memory
+  const int groups = (p.nIn + nW - 1) / nW;
+  const int u = blockIdx.x / groups, e = (blockIdx.x % groups) * nW + warp;
   if (e >= p.nIn) return;
   const long long T = p.nRows[u];
   const float *col = p.rows + p.rowOff[u] * (long long)p.rowStride + e;
   float *out = p.out + ((long long)u * p.nIn + e) * p.nVals;
-  float *sbuf = fnSort + (size_t)warp * p.sortCap;
+  float *sbuf = fnSort + (size_t)warp * p.perWarp;
   const Keep keep{p.s.nonZeroFuncts};
   const unsigned ltMask = (1u << lane) - 1u;
 
@@ -179,6 +189,94 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
     }
   }
 
+  // ---------------- order-dependent functionals on the shared copy of the filtered contour ----------------
+  __syncwarp();
+  for (int fi = 0; fi < p.s.n_enabled; fi++) {
+    float *o = out + p.valOff[fi];
+    const int kind = p.s.enabled[fi];
+    if (kind == OSM_B200_F_TIMES) {                                   // functionalTimes.cpp:245-371
+      const auto &Tm = p.s.times;
+      const float Nind = (float)N;
+      float Norm = Nind, Norm1 = Nind - 1.0f, Norm2 = Nind - 2.0f, Tp = 1.0f;
+      if (p.timesNorm == OSM_B200_TIMENORM_SECOND) {
+        Tp = p.period;
+        if (Tp != 0.0f) {
+          if (Tm.buggySecNorm) { Norm = Norm / Tp; Norm1 = Norm1 / Tp; Norm2 = Norm2 / Tp; }
+          else { Norm = 1.0f / Tp; Norm1 = Norm1 / (Nind * Tp); Norm2 = Norm2 / (Nind * Tp); }
+        }
+      }
+      if (p.timesNorm == OSM_B200_TIMENORM_FRAME) { Norm = 1.0f; Norm1 = Norm1 / Nind; Norm2 = Norm2 / Nind; }
+      const float range = mx - mn;
+      const float l25 = 0.25f * range + mn, l50 = 0.50f * range + mn, l75 = 0.75f * range + mn, l90 = 0.90f * range + mn;
+      long long n25 = 0, n50 = 0, n75 = 0, n90 = 0, nR = 0, nF = 0, nLC = 0, nRC = 0;
+      for (long long i = lane; i < N; i += 32) {
+        const float x = sbuf[i];
+        n25 += x <= l25; n50 += x <= l50; n75 += x <= l75; n90 += x <= l90;
+        if (i >= 1) {
+          const float xp = sbuf[i - 1];
+          nR += xp < x; nF += xp > x;
+          if (i + 1 < N) {
+            const float a1 = x - xp, a2 = sbuf[i + 1] - x;
+            nRC += a2 < a1; nLC += a1 < a2;
+          }
+        }
+      }
+      n25 = wsumll(n25); n50 = wsumll(n50); n75 = wsumll(n75); n90 = wsumll(n90);
+      nR = wsumll(nR); nF = wsumll(nF); nLC = wsumll(nLC); nRC = wsumll(nRC);
+      if (lane == 0) {
+        int n = 0;
+        if (Tm.upleveltime25) o[n++] = (float)(N - n25) / Norm;
+        if (Tm.downleveltime25) o[n++] = (float)n25 / Norm;
+        if (Tm.upleveltime50) o[n++] = (float)(N - n50) / Norm;
+        if (Tm.downleveltime50) o[n++] = (float)n50 / Norm;
+        if (Tm.upleveltime75) o[n++] = (float)(N - n75) / Norm;
+        if (Tm.downleveltime75) o[n++] = (float)n75 / Norm;
+        if (Tm.upleveltime90) o[n++] = (float)(N - n90) / Norm;
+        if (Tm.downleveltime90) o[n++] = (float)n90 / Norm;
+        if (Tm.risetime) o[n++] = Norm1 != 0.0f ? (float)nR / Norm1 : 0.0f;
+        if (Tm.falltime) o[n++] = Norm1 != 0.0f ? (float)nF / Norm1 : 0.0f;
+        if (Tm.leftctime) o[n++] = Norm2 != 0.0f ? (float)nLC / Norm2 : 0.0f;
+        if (Tm.rightctime) o[n++] = Norm2 != 0.0f ? (float)nRC / Norm2 : 0.0f;
+        if (Tm.duration) o[n++] = p.timesNorm == OSM_B200_TIMENORM_SECOND ? (float)N * Tp : (float)N;
+      }
+    } else if (kind == OSM_B200_F_LPC) {                              // functionalLpc.cpp:98-125
+      const int order = p.s.lpc.order;
+      float *acf = sbuf + p.lensOff;                                   // the segment-length scratch doubles as the lag buffer
+      if (lane <= order) {                                            // smileDsp_autoCorr (smileUtil.c:1560-1569): sequential float sum per lag
+        float acc = 0.0f;
+        for (long long i = lane; i < N; i++) acc = acc + sbuf[i] * sbuf[i - lane];
+        acf[lane] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) fseq::lpc(p.s.lpc, acf, (long)N, o);
+      __syncwarp();
+    } else if (kind == OSM_B200_F_PEAKS2) {                           // functionalPeaks2.cpp:320-327 in parallel, then :330-915 on lane 0
+      float *ly = sbuf + p.listOff;
+      int *lx = reinterpret_cast<int *>(ly + p.sortCap);              // up to N - 4 extrema (a zigzag)
+      int nl = 0;
+      for (long long i0 = 2; i0 < N - 2; i0 += 32) {
+        const long long i = i0 + lane;
+        int type = -1;
+        float x = 0.0f;
+        if (i < N - 2) {
+          x = sbuf[i];
+          const float a = sbuf[i - 1], b = sbuf[i + 1];
+          if (x > a && x > b) type = 1;
+          else if (x < a && x < b) type = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, type >= 0);
+        if (type >= 0) { const int k = nl + __popc(m & ltMask); ly[k] = x; lx[k] = (int)(i << 1) | type; }
+        nl += __popc(m);
+      }
+      __syncwarp();
+      if (lane == 0) fseq::peaks2(p.s.peaks2, sbuf, (long)N, mn, mx, mean, p.period, p.peaksNorm, ly, lx, nl, o);
+      __syncwarp();
+    } else if (kind == OSM_B200_F_SEGMENTS) {
+      if (lane == 0) fseq::segments(p.s.segments, sbuf, (long)N, mn, mx, p.period, p.segNorm, sbuf + p.lensOff, o);
+      __syncwarp();
+    }
+  }
+
   // ---------------- pass 2 ----------------
   double m2 = 0, m3 = 0, m4 = 0, lea = 0, leq = 0, qea = 0, qeq = 0;
   cnt = 0;
@@ -233,8 +331,8 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
   if (lane != 0) return;
 
   // ---------------- values, in the order of functionalsEnabled ----------------
-  int n = 0;
   for (int fi = 0; fi < p.s.n_enabled; fi++) {
+    int n = p.valOff[fi];
     switch (p.s.enabled[fi]) {
       case OSM_B200_F_EXTREMES: {
         const auto &E = p.s.extremes;
@@ -347,7 +445,7 @@ struct osm_b200_functionals {
   int nIn = 0, nVals = 0, device = -1;
   double period = 0;
   std::vector<std::string> names;
-  bool hasPct = false;
+  bool hasPct = false, hasSeq = false, hasPeaks = false, hasSeg = false;
   long long *dMeta = nullptr; size_t metaCap = 0;
   float *dIn = nullptr; size_t inCap = 0;
   float *dOut = nullptr; size_t outCap = 0;
@@ -404,9 +502,43 @@ std::vector<std::string> value_names(const osm_b200_functionals_spec &s)
         const char *nm[10] = {"linregc1", "linregc2", "linregerrA", "linregerrQ", "qregc1", "qregc2", "qregc3", "qregerrA", "qregerrQ", "centroid"};
         for (int k = 0; k < 10; k++) if (on[k]) v.push_back(nm[k]);
       } break;
+      case OSM_B200_F_TIMES: {
+        const auto &T = s.times;
+        const int on[13] = {T.upleveltime25, T.downleveltime25, T.upleveltime50, T.downleveltime50, T.upleveltime75, T.downleveltime75,
+                            T.upleveltime90, T.downleveltime90, T.risetime, T.falltime, T.leftctime, T.rightctime, T.duration};
+        const char *nm[13] = {"upleveltime25", "downleveltime25", "upleveltime50", "downleveltime50", "upleveltime75", "downleveltime75",
+                              "upleveltime90", "downleveltime90", "risetime", "falltime", "leftctime", "rightctime", "duration"};   // functionalTimes.cpp:39
+        for (int k = 0; k < 13; k++) if (on[k]) v.push_back(nm[k]);
+      } break;
+      case OSM_B200_F_LPC: {                                                                                            // functionalLpc.cpp:84-96
+        if (s.lpc.lpGain) v.push_back("lpgain");
+        if (s.lpc.lpc) for (int k = s.lpc.firstCoeff; k < s.lpc.order; k++) { snprintf(buf, sizeof buf, "lpc%i", k); v.push_back(buf); }
+      } break;
+      case OSM_B200_F_SEGMENTS: {
+        const auto &G = s.segments;
+        const int on[5] = {G.numSegments, G.meanSegLen, G.maxSegLen, G.minSegLen, G.segLenStddev};
+        const char *nm[5] = {"numSegments", "meanSegLen", "maxSegLen", "minSegLen", "segLenStddev"};                    // functionalSegments.cpp:39
+        for (int k = 0; k < 5; k++) if (on[k]) v.push_back(nm[k]);
+      } break;
+      case OSM_B200_F_PEAKS2: {
+        const char *nm[OSM_B200_F_PEAKS2_VALUES] = {"numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs", "peakRangeRel",
+            "peakMeanAbs", "peakMeanMeanDist", "peakMeanRel", "ptpAmpMeanAbs", "ptpAmpMeanRel", "ptpAmpStddevAbs", "ptpAmpStddevRel", "minRangeAbs",
+            "minRangeRel", "minMeanAbs", "minMeanMeanDist", "minMeanRel", "mtmAmpMeanAbs", "mtmAmpMeanRel", "mtmAmpStddevAbs", "mtmAmpStddevRel",
+            "meanRisingSlope", "maxRisingSlope", "minRisingSlope", "stddevRisingSlope", "meanFallingSlope", "maxFallingSlope", "minFallingSlope",
+            "stddevFallingSlope", "covFallingSlope", "covRisingSlope"};                                                  // functionalPeaks2.cpp:58-66
+        for (int k = 0; k < OSM_B200_F_PEAKS2_VALUES; k++) if (s.peaks2.value[k]) v.push_back(nm[k]);
+      } break;
     }
   }
   return v;
+}
+
+// number of values functional `fi` of the enabled list contributes
+int value_count(const osm_b200_functionals_spec &s, int fi)
+{
+  osm_b200_functionals_spec one = s;
+  one.n_enabled = 1; one.enabled[0] = s.enabled[fi];
+  return (int)value_names(one).size();
 }
 
 }  // namespace
@@ -430,6 +562,15 @@ void osm_b200_functionals_defaults(osm_b200_functionals_spec *s)
   auto &R = s->regression;
   R.linregc1 = R.linregc2 = R.linregerrA = R.linregerrQ = R.qregc1 = R.qregc2 = R.qregc3 = R.qregerrA = R.qregerrQ = R.centroid = 1;
   R.centroidNorm = OSM_B200_TIMENORM_SEGMENT; R.centroidUseAbsValues = 1; R.centroidRatioLimit = 1; R.oldBuggyQerr = 1;
+  auto &T = s->times;                                             // functionalTimes.cpp:60-78
+  T.upleveltime25 = T.downleveltime25 = T.upleveltime50 = T.downleveltime50 = T.upleveltime75 = T.downleveltime75 = T.upleveltime90 =
+      T.downleveltime90 = T.risetime = T.falltime = T.leftctime = T.rightctime = T.duration = 1;
+  T.buggySecNorm = 1; T.norm = OSM_B200_TIMENORM_SEGMENT;
+  s->lpc.lpc = 1; s->lpc.order = 5;                                // functionalLpc.cpp:38-41
+  auto &G = s->segments;                                          // functionalSegments.cpp:48-73
+  G.maxNumSeg = 20; G.segMinLng = 3; G.pauseMinLng = 2; G.norm = OSM_B200_TIMENORM_SEGMENT; G.algorithm = OSM_B200_SEG_RELTH;
+  auto &K = s->peaks2;                                            // functionalPeaks2.cpp:84-130
+  K.relThresh = 0.1f; K.doRatioLimit = 1; K.norm = OSM_B200_TIMENORM_FRAME;
 }
 
 osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spec, int32_t n_in, const char *const *in_names,
@@ -452,6 +593,16 @@ osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spe
   for (int i = 0; i < P.n_pctlrange; i++)
     if (P.pctlrange[i][0] < 0 || P.pctlrange[i][0] >= P.n_percentile || P.pctlrange[i][1] < 0 || P.pctlrange[i][1] >= P.n_percentile)
       return set_last_error(OSM_B200_ERR_INVALID, "cFunctionalPercentiles.pctlrange refers to a percentile that does not exist");
+  for (int i = 0; i < s.n_enabled; i++) {
+    if (s.enabled[i] == OSM_B200_F_LPC && (s.lpc.order < 1 || s.lpc.order > OSM_B200_F_MAX_LPC || s.lpc.firstCoeff < 0 || s.lpc.firstCoeff >= s.lpc.order))
+      return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalLpc: 0 <= firstCoeff < order <= 16");
+    if (s.enabled[i] == OSM_B200_F_SEGMENTS) {
+      const auto &G = s.segments;
+      if (G.algorithm < OSM_B200_SEG_RELTH || G.algorithm > OSM_B200_SEG_EQX) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSegments: segmentationAlgorithm must be relTh, nonX or eqX");
+      if (G.maxNumSeg < 1 || G.maxNumSeg > 4096) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSegments: 1 <= maxNumSeg <= 4096");
+      if (G.n_thresholds < 0 || G.n_thresholds > OSM_B200_F_MAX_THRESH) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSegments: at most 8 thresholds");
+    }
+  }
   osm_b200_functionals *f = new osm_b200_functionals();
   f->spec = s; f->nIn = n_in; f->device = device; f->period = input_period;
   const std::vector<std::string> vn = value_names(s);
@@ -460,7 +611,12 @@ osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spe
   for (int e = 0; e < n_in; e++)
     for (const std::string &v : vn)                                    // functionals.cpp:222-228
       f->names.push_back(s.functNameAppend[0] ? std::string(in_names[e]) + "__" + s.functNameAppend + "_" + v : std::string(in_names[e]) + "_" + v);
-  for (int i = 0; i < s.n_enabled; i++) f->hasPct = f->hasPct || s.enabled[i] == OSM_B200_F_PERCENTILES;
+  for (int i = 0; i < s.n_enabled; i++) {
+    f->hasPct = f->hasPct || s.enabled[i] == OSM_B200_F_PERCENTILES;
+    f->hasSeq = f->hasSeq || s.enabled[i] >= OSM_B200_F_TIMES;
+    f->hasPeaks = f->hasPeaks || s.enabled[i] == OSM_B200_F_PEAKS2;
+    f->hasSeg = f->hasSeg || s.enabled[i] == OSM_B200_F_SEGMENTS;
+  }
   if (device >= 0) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || device >= n) { delete f; return set_last_error(OSM_B200_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)"); }
@@ -500,11 +656,18 @@ osm_b200_status osm_b200_functionals_run_device(osm_b200_functionals *f, const f
     maxT = std::max<long long>(maxT, n_rows[u]);
   }
   int sortCap = 0;
-  if (f->hasPct) {
-    if (maxT > kMaxSort) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalPercentiles: contours longer than 8192 frames are not supported");
+  if (f->hasPct || f->hasSeq) {
+    if (maxT > kMaxSort) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionals (Percentiles, Times, Lpc, Segments, Peaks2): contours longer than 8192 frames are not supported");
     sortCap = 32;
     while (sortCap < maxT) sortCap <<= 1;
   }
+  // per-warp shared memory: contour copy | Peaks2 extrema (values, then positions) | segment lengths / lag buffer
+  const int listFloats = f->hasPeaks ? 2 * sortCap : 0;
+  const int lensFloats = f->hasSeq ? std::max(32, f->hasSeg ? f->spec.segments.maxNumSeg : 0) : 0;
+  const int perWarp = sortCap + listFloats + lensFloats;
+  int nWarps = kFnWarps;
+  while (nWarps > 1 && (size_t)nWarps * perWarp * sizeof(float) > 200 * 1024) nWarps--;
+  if ((size_t)nWarps * perWarp * sizeof(float) > 200 * 1024) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionals: contour too long for the shared-memory work space");
   if (f->metaCap < meta.size()) {
     if (f->dMeta) cudaFree(f->dMeta);
     f->dMeta = nullptr; f->metaCap = 0;
@@ -516,16 +679,21 @@ osm_b200_status osm_b200_functionals_run_device(osm_b200_functionals *f, const f
   FnParams p;
   memset(&p, 0, sizeof p);
   p.rows = d_rows; p.rowStride = row_stride; p.nIn = f->nIn; p.rowOff = f->dMeta; p.nRows = f->dMeta + n_utt;
+  p.perWarp = perWarp; p.listOff = sortCap; p.lensOff = sortCap + listFloats;
+  for (int i = 0, o = 0; i < f->spec.n_enabled; i++) { p.valOff[i] = o; o += value_count(f->spec, i); }
+  p.timesNorm = resolve_norm(f->spec.times.norm, f->spec.times.normIsSet, f->spec.masterTimeNorm);
+  p.segNorm = resolve_norm(f->spec.segments.norm, f->spec.segments.normIsSet, f->spec.masterTimeNorm);
+  p.peaksNorm = resolve_norm(f->spec.peaks2.norm, f->spec.peaks2.normIsSet, f->spec.masterTimeNorm);
   p.out = d_out; p.nVals = f->nVals; p.sortCap = sortCap; p.period = (float)f->period; p.periodD = f->period; p.s = f->spec;
   p.extNorm = resolve_norm(f->spec.extremes.norm, f->spec.extremes.normIsSet, f->spec.masterTimeNorm);
   p.meanNorm = resolve_norm(f->spec.means.norm, f->spec.means.normIsSet, f->spec.masterTimeNorm);
   const auto &R = f->spec.regression;
   for (int i = 0; i < f->spec.n_enabled; i++) p.needReg = p.needReg || f->spec.enabled[i] == OSM_B200_F_REGRESSION;
   p.enQreg = R.qregc1 || R.qregc2 || R.qregc3 || R.qregerrA || R.qregerrQ || R.centroid;     // functionalRegression.cpp:108-117
-  const size_t smem = (size_t)kFnWarps * sortCap * sizeof(float);
+  const size_t smem = (size_t)nWarps * perWarp * sizeof(float);
   if (smem > 48 * 1024) FCU(cudaFuncSetAttribute(functionals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int groups = (f->nIn + kFnWarps - 1) / kFnWarps;
-  functionals_kernel<<<(unsigned)((long long)n_utt * groups), kFnThreads, smem, st>>>(p);
+  const int groups = (f->nIn + nWarps - 1) / nWarps;
+  functionals_kernel<<<(unsigned)((long long)n_utt * groups), nWarps * 32, smem, st>>>(p);
   FCU(cudaGetLastError());
   return OSM_B200_OK;
 }

@@ -9,9 +9,17 @@ import numpy as np
 
 from . import capi
 
-i32, f64 = C.c_int32, C.c_double
-F_EXTREMES, F_MEANS, F_MOMENTS, F_PERCENTILES, F_REGRESSION = range(5)
-TYPE_BY_NAME = {"Extremes": F_EXTREMES, "Means": F_MEANS, "Moments": F_MOMENTS, "Percentiles": F_PERCENTILES, "Regression": F_REGRESSION}
+i32, f64, f32 = C.c_int32, C.c_double, C.c_float
+F_EXTREMES, F_MEANS, F_MOMENTS, F_PERCENTILES, F_REGRESSION, F_TIMES, F_LPC, F_SEGMENTS, F_PEAKS2 = range(9)
+TYPE_BY_NAME = {"Extremes": F_EXTREMES, "Means": F_MEANS, "Moments": F_MOMENTS, "Percentiles": F_PERCENTILES, "Regression": F_REGRESSION,
+                "Times": F_TIMES, "Lpc": F_LPC, "Segments": F_SEGMENTS, "Peaks2": F_PEAKS2}
+SEG_RELTH, SEG_NONX, SEG_EQX = 0, 1, 2
+SEG_BY_NAME = {"relTh": SEG_RELTH, "nonX": SEG_NONX, "eqX": SEG_EQX}
+PEAKS2_NAMES = ["numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs", "peakRangeRel", "peakMeanAbs",
+                "peakMeanMeanDist", "peakMeanRel", "ptpAmpMeanAbs", "ptpAmpMeanRel", "ptpAmpStddevAbs", "ptpAmpStddevRel", "minRangeAbs",
+                "minRangeRel", "minMeanAbs", "minMeanMeanDist", "minMeanRel", "mtmAmpMeanAbs", "mtmAmpMeanRel", "mtmAmpStddevAbs",
+                "mtmAmpStddevRel", "meanRisingSlope", "maxRisingSlope", "minRisingSlope", "stddevRisingSlope", "meanFallingSlope",
+                "maxFallingSlope", "minFallingSlope", "stddevFallingSlope", "covFallingSlope", "covRisingSlope"]
 TIMENORM_UNSET, TIMENORM_SEGMENT, TIMENORM_SECOND, TIMENORM_FRAME = -1, 0, 1, 2
 
 
@@ -39,10 +47,31 @@ class _Regression(C.Structure):
                                     "oldBuggyQerr", "doRatioLimit")]
 
 
+class _Times(C.Structure):
+    _fields_ = [(n, i32) for n in ("upleveltime25", "downleveltime25", "upleveltime50", "downleveltime50", "upleveltime75", "downleveltime75",
+                                    "upleveltime90", "downleveltime90", "risetime", "falltime", "leftctime", "rightctime", "duration",
+                                    "buggySecNorm", "norm", "normIsSet")]
+
+
+class _Lpc(C.Structure):
+    _fields_ = [(n, i32) for n in ("lpGain", "lpc", "firstCoeff", "order")]
+
+
+class _Segments(C.Structure):
+    _fields_ = [(n, i32) for n in ("numSegments", "meanSegLen", "maxSegLen", "minSegLen", "segLenStddev", "algorithm", "maxNumSeg", "n_thresholds")] + \
+               [("thresholds", f32 * 8), ("X", f32)] + [(n, i32) for n in ("XisRel", "segMinLng", "segMinLngIsSet", "pauseMinLng", "norm", "normIsSet")]
+
+
+class _Peaks2(C.Structure):
+    _fields_ = [("value", i32 * 32), ("relThresh", f32), ("absThresh", f32)] + \
+               [(n, i32) for n in ("useAbsThresh", "dynRelThresh", "doRatioLimit", "norm", "normIsSet")]
+
+
 class Spec(C.Structure):
     _fields_ = [("n_enabled", i32), ("enabled", i32 * 8), ("nonZeroFuncts", i32), ("masterTimeNorm", i32),
                 ("functNameAppend", C.c_char * capi.NAME_LEN), ("extremes", _Extremes), ("means", _Means), ("moments", _Moments),
-                ("percentiles", _Percentiles), ("regression", _Regression)]
+                ("percentiles", _Percentiles), ("regression", _Regression), ("times", _Times), ("lpc", _Lpc), ("segments", _Segments),
+                ("peaks2", _Peaks2)]
 
 
 def _bind(L):
@@ -91,6 +120,14 @@ def spec(enabled, non_zero=0, master_norm=TIMENORM_UNSET, name_append="", **sub)
                 blk.n_pctlrange = len(v)
                 for i, (a, b) in enumerate(v):
                     blk.pctlrange[i][0], blk.pctlrange[i][1] = a, b
+            elif k == "thresholds":
+                blk.n_thresholds = len(v)
+                for i, x in enumerate(v):
+                    blk.thresholds[i] = x
+            elif k == "segmentationAlgorithm":
+                blk.algorithm = SEG_BY_NAME[v]
+            elif part == "peaks2" and k in PEAKS2_NAMES:
+                blk.value[PEAKS2_NAMES.index(k)] = v
             else:
                 setattr(blk, k, v)
     return s

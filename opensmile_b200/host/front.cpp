@@ -617,6 +617,15 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
   bool quartilesSet = false, iqrSet = false;
   int quartiles = 0, iqr = 0;
   auto &E = fs.extremes; auto &M = fs.means; auto &Q = fs.moments; auto &P = fs.percentiles; auto &R = fs.regression;
+  auto &TI = fs.times; auto &LP = fs.lpc; auto &SG = fs.segments; auto &PK = fs.peaks2;
+  std::map<int, double> segThresh;
+  std::string segThreshList, segAlgo = "delta";
+  bool unsupportedTimes = false, unsupportedSeg = false, unsupportedPeaks = false;
+  static const char *peaksNames[OSM_B200_F_PEAKS2_VALUES] = {"numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs",
+      "peakRangeRel", "peakMeanAbs", "peakMeanMeanDist", "peakMeanRel", "ptpAmpMeanAbs", "ptpAmpMeanRel", "ptpAmpStddevAbs", "ptpAmpStddevRel",
+      "minRangeAbs", "minRangeRel", "minMeanAbs", "minMeanMeanDist", "minMeanRel", "mtmAmpMeanAbs", "mtmAmpMeanRel", "mtmAmpStddevAbs",
+      "mtmAmpStddevRel", "meanRisingSlope", "maxRisingSlope", "minRisingSlope", "stddevRisingSlope", "meanFallingSlope", "maxFallingSlope",
+      "minFallingSlope", "stddevFallingSlope", "covFallingSlope", "covRisingSlope"};   // configuration field = value name (functionalPeaks2.cpp:84-118)
   struct IntField { const char *name; int32_t *dst; };
   const IntField fields[] = {
     {"Extremes.max", &E.max}, {"Extremes.min", &E.min}, {"Extremes.range", &E.range}, {"Extremes.maxpos", &E.maxpos}, {"Extremes.minpos", &E.minpos},
@@ -633,7 +642,17 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     {"Regression.qregc1", &R.qregc1}, {"Regression.qregc2", &R.qregc2}, {"Regression.qregc3", &R.qregc3}, {"Regression.qregerrA", &R.qregerrA},
     {"Regression.qregerrQ", &R.qregerrQ}, {"Regression.centroid", &R.centroid}, {"Regression.centroidUseAbsValues", &R.centroidUseAbsValues},
     {"Regression.centroidRatioLimit", &R.centroidRatioLimit}, {"Regression.normRegCoeff", &R.normRegCoeff}, {"Regression.normInputs", &R.normInputs},
-    {"Regression.oldBuggyQerr", &R.oldBuggyQerr}, {"Regression.doRatioLimit", &R.doRatioLimit}};
+    {"Regression.oldBuggyQerr", &R.oldBuggyQerr}, {"Regression.doRatioLimit", &R.doRatioLimit},
+    {"Times.upleveltime25", &TI.upleveltime25}, {"Times.downleveltime25", &TI.downleveltime25}, {"Times.upleveltime50", &TI.upleveltime50},
+    {"Times.downleveltime50", &TI.downleveltime50}, {"Times.upleveltime75", &TI.upleveltime75}, {"Times.downleveltime75", &TI.downleveltime75},
+    {"Times.upleveltime90", &TI.upleveltime90}, {"Times.downleveltime90", &TI.downleveltime90}, {"Times.risetime", &TI.risetime},
+    {"Times.falltime", &TI.falltime}, {"Times.leftctime", &TI.leftctime}, {"Times.rightctime", &TI.rightctime}, {"Times.duration", &TI.duration},
+    {"Times.buggySecNorm", &TI.buggySecNorm},
+    {"Lpc.lpGain", &LP.lpGain}, {"Lpc.lpc", &LP.lpc}, {"Lpc.firstCoeff", &LP.firstCoeff}, {"Lpc.order", &LP.order},
+    {"Segments.numSegments", &SG.numSegments}, {"Segments.meanSegLen", &SG.meanSegLen}, {"Segments.maxSegLen", &SG.maxSegLen},
+    {"Segments.minSegLen", &SG.minSegLen}, {"Segments.segLenStddev", &SG.segLenStddev}, {"Segments.maxNumSeg", &SG.maxNumSeg},
+    {"Segments.XisRel", &SG.XisRel}, {"Segments.pauseMinLng", &SG.pauseMinLng},
+    {"Peaks2.dynRelThresh", &PK.dynRelThresh}, {"Peaks2.doRatioLimit", &PK.doRatioLimit}};
   for (const auto &kv : s.kv) {
     const std::string &f = kv.first, &v = kv.second;
     if (is_common(f) || f == "noPostEOIprocessing" || f == "allowLastFrameIncomplete" || f == "frameListFile" || f == "frameList") continue;
@@ -648,6 +667,32 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     if (f == "Extremes.norm") { E.norm = time_norm(v); E.normIsSet = 1; continue; }
     if (f == "Means.norm") { M.norm = time_norm(v); M.normIsSet = 1; continue; }
     if (f == "Regression.centroidNorm") { R.centroidNorm = time_norm(v); continue; }
+    if (f == "Times.norm") { TI.norm = time_norm(v); TI.normIsSet = 1; continue; }
+    if (f == "Segments.norm") { SG.norm = time_norm(v); SG.normIsSet = 1; continue; }
+    if (f == "Peaks2.norm") { PK.norm = time_norm(v); PK.normIsSet = 1; continue; }
+    if (f.compare(0, 17, "Times.upleveltime") == 0 || f.compare(0, 19, "Times.downleveltime") == 0) {
+      bool fixedName = false;
+      for (const char *sfx : {"25", "50", "75", "90"}) fixedName = fixedName || f == std::string("Times.upleveltime") + sfx || f == std::string("Times.downleveltime") + sfx;
+      if (!fixedName) { unsupportedTimes = true; continue; }         // the upleveltime[] / downleveltime[] arrays
+    }
+    if (f == "Times.useRobustPercentileRange") { if (inum(v)) unsupportedTimes = true; continue; }
+    if (f == "Times.pctlRangeMargin") continue;
+    if (f == "Segments.segmentationAlgorithm") { segAlgo = v; continue; }
+    if (f == "Segments.thresholds") { segThreshList = v; continue; }
+    if (f.compare(0, 20, "Segments.thresholds[") == 0) { segThresh[atoi(f.c_str() + 20)] = num(v); continue; }
+    if (f == "Segments.X") { SG.X = (float)num(v); continue; }
+    if (f == "Segments.segMinLng") { SG.segMinLng = inum(v); SG.segMinLngIsSet = 1; continue; }
+    if (f == "Segments.ravgLng" || f == "Segments.rangeRelThreshold" || f == "Segments.dbgPrint") continue;   // not read by relTh / nonX / eqX
+    if (f == "Segments.useOldBuggyChX" || f == "Segments.growDynSegBuffer") { if (inum(v)) unsupportedSeg = true; continue; }
+    if (f == "Peaks2.relThresh") { PK.relThresh = (float)num(v); continue; }
+    if (f == "Peaks2.absThresh") { PK.absThresh = (float)num(v); PK.useAbsThresh = 1; continue; }
+    if (f == "Peaks2.noClearPeakList") { if (inum(v)) unsupportedPeaks = true; continue; }
+    if (f == "Peaks2.posDbgOutp" || f == "Peaks2.posDbgAppend" || f == "Peaks2.consoleDbg") continue;
+    if (f.compare(0, 7, "Peaks2.") == 0) {
+      bool hitP = false;
+      for (int k = 0; k < OSM_B200_F_PEAKS2_VALUES; k++) if (f.compare(7, std::string::npos, peaksNames[k]) == 0) { PK.value[k] = inum(v); hitP = true; break; }
+      if (hitP) continue;
+    }
     if (f == "Percentiles.quartiles") { quartilesSet = true; quartiles = inum(v); continue; }
     if (f == "Percentiles.iqr") { iqrSet = true; iqr = inum(v); continue; }
     if (f.compare(0, 23, "Percentiles.percentile[") == 0) { pct[atoi(f.c_str() + 23)] = num(v); continue; }
@@ -665,7 +710,7 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     const size_t dot = f.find('.');
     if (dot != std::string::npos) {
       const std::string sub = f.substr(0, dot);
-      static const char *known[] = {"Crossings", "DCT", "Lpc", "Modulation", "Onset", "Peaks", "Peaks2", "Samples", "Segments", "Times"};
+      static const char *known[] = {"Crossings", "DCT", "Modulation", "Onset", "Peaks", "Samples"};
       bool other = false;
       for (const char *k : known) other = other || sub == k;
       if (other) continue;
@@ -692,8 +737,33 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     else if (n == "Moments") t = OSM_B200_F_MOMENTS;
     else if (n == "Percentiles") t = OSM_B200_F_PERCENTILES;
     else if (n == "Regression") t = OSM_B200_F_REGRESSION;
-    else { err = "cFunctional" + n + " (instance '" + s.name + "') is not supported on the GPU path (Extremes, Means, Moments, Percentiles, Regression are)"; return false; }
+    else if (n == "Times") t = OSM_B200_F_TIMES;
+    else if (n == "Lpc") t = OSM_B200_F_LPC;
+    else if (n == "Segments") t = OSM_B200_F_SEGMENTS;
+    else if (n == "Peaks2") t = OSM_B200_F_PEAKS2;
+    else { err = "cFunctional" + n + " (instance '" + s.name + "') is not supported on the GPU path (Extremes, Means, Moments, Percentiles, Regression, Times, Lpc, Segments, Peaks2 are)"; return false; }
     fs.enabled[fs.n_enabled++] = t;
+    if (t == OSM_B200_F_TIMES && unsupportedTimes) { err = "cFunctionalTimes: upleveltime[] / downleveltime[] arrays and useRobustPercentileRange are not supported"; return false; }
+    if (t == OSM_B200_F_PEAKS2 && unsupportedPeaks) { err = "cFunctionalPeaks2.noClearPeakList = 1 is not supported"; return false; }
+    if (t == OSM_B200_F_SEGMENTS) {
+      if (unsupportedSeg) { err = "cFunctionalSegments: useOldBuggyChX / growDynSegBuffer are not supported"; return false; }
+      // functionalSegments.cpp:124-158: prefix match in this order
+      if (segAlgo.compare(0, 5, "relTh") == 0) SG.algorithm = OSM_B200_SEG_RELTH;
+      else if (segAlgo.compare(0, 4, "nonX") == 0) SG.algorithm = OSM_B200_SEG_NONX;
+      else if (segAlgo.compare(0, 3, "eqX") == 0) SG.algorithm = OSM_B200_SEG_EQX;
+      else { err = "cFunctionalSegments.segmentationAlgorithm = " + segAlgo + " is not supported (relTh, nonX, eqX are)"; return false; }
+      std::vector<double> th;
+      if (!segThresh.empty()) for (const auto &kv : segThresh) th.push_back(kv.second);
+      else {
+        std::stringstream ss(segThreshList);
+        std::string one;
+        while (std::getline(ss, one, ';')) { one = trim(one); if (!one.empty()) th.push_back(num(one)); }
+      }
+      if (SG.algorithm == OSM_B200_SEG_RELTH && th.empty()) th.push_back(0.0);       // the field's default value
+      if (th.size() > OSM_B200_F_MAX_THRESH) { err = "cFunctionalSegments: more than 8 thresholds"; return false; }
+      SG.n_thresholds = (int)th.size();
+      for (size_t k = 0; k < th.size(); k++) SG.thresholds[k] = (float)std::min(1.0, std::max(0.0, th[k]));   // :198-207
+    }
   }
   P.n_percentile = 0;
   for (const auto &kv : pct) {

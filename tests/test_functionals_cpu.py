@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REFCONF = os.path.join(ROOT, "oracle", "_ref", "config")
 G = np.load(os.path.join(HERE, "golden", "functionals_goldens.npz"))
+G2 = np.load(os.path.join(HERE, "golden", "functionals_goldens2.npz"))
 S, SEC, FR = fo.SEGMENT, fo.SECOND, fo.FRAME
 
 SPEC_A = fo.Spec(["Means"], master_norm=SEC, means=dict(flatness=1, posamean=1, negamean=1, posqmean=1, posrqmean=1, negqmean=1, negrqmean=1,
@@ -25,6 +26,30 @@ SPEC_C = fo.Spec(["Regression", "Percentiles", "Means"], non_zero=2, name_append
                  regression=dict(centroidNorm=SEC, centroidUseAbsValues=1, normRegCoeff=1, normInputs=1, oldBuggyQerr=0),
                  percentiles=dict(quartile1=1, quartile2=1, quartile3=1, interp=0),
                  means=dict(amean=1, absmean=0, qmean=0, nzamean=0, nzabsmean=0, nzqmean=0, nzgmean=0, nnz=1, norm=S, norm_set=True))
+# second set (tests/configs/func_variants2.conf): the Times / Lpc / Segments / Peaks2 option sets of the shipped ComParE_2016 and
+# GeMAPS functionals blocks
+_CMP_PEAKS = ["meanPeakDist", "peakDistStddev", "peakRangeAbs", "peakRangeRel", "peakMeanAbs", "peakMeanMeanDist", "peakMeanRel", "minRangeRel",
+              "meanRisingSlope", "stddevRisingSlope", "meanFallingSlope", "stddevFallingSlope"]
+SPEC_D = fo.Spec(["Extremes", "Segments", "Times", "Lpc"], master_norm=S,
+                 extremes=dict(max=0, min=0, range=1, maxpos=1, minpos=1, amean=0, maxameandist=0, minameandist=0),
+                 segments=dict(maxNumSeg=100, segmentationAlgorithm="relTh", thresholds=[0.25, 0.75], meanSegLen=1, maxSegLen=1, minSegLen=1,
+                               segLenStddev=1, norm=SEC, norm_set=True),
+                 times=dict(downleveltime25=0, downleveltime50=0, downleveltime75=0, downleveltime90=0, falltime=0, rightctime=0, duration=0,
+                            buggySecNorm=0, norm=S, norm_set=True),
+                 lpc=dict(lpGain=1, lpc=1, firstCoeff=0, order=5))
+SPEC_E = fo.Spec(["Means", "Segments", "Peaks2"], master_norm=S,
+                 means=dict(amean=0, absmean=0, qmean=0, nzamean=0, nzabsmean=0, nzqmean=0, nzgmean=0, nnz=1, norm=S, norm_set=True),
+                 segments=dict(maxNumSeg=100, segmentationAlgorithm="nonX", X=0.0, numSegments=1, meanSegLen=1, maxSegLen=1, minSegLen=1,
+                               segLenStddev=1, norm=SEC, norm_set=True),
+                 peaks2=dict(numPeaks=1, norm=SEC, norm_set=True, relThresh=0.1))
+SPEC_F = fo.Spec(["Peaks2", "Times"], master_norm=SEC, peaks2=dict({k: 1 for k in _CMP_PEAKS}, norm=SEC, norm_set=True, relThresh=0.1, doRatioLimit=1),
+                 times=dict(norm=SEC, norm_set=True))
+SPEC_G = fo.Spec(["Segments", "Peaks2", "Times"], master_norm=SEC, name_append="g",
+                 segments=dict(maxNumSeg=1000, segmentationAlgorithm="eqX", X=0.0, numSegments=1, meanSegLen=1, segLenStddev=1, norm=SEC, norm_set=True),
+                 peaks2=dict({k: 1 for k in fo.PEAKS2_NAMES}, norm=FR, norm_set=True, relThresh=0.35, dynRelThresh=1, doRatioLimit=0),
+                 times=dict(norm=FR, norm_set=True, buggySecNorm=0))
+LEVELS2 = [("D", SPEC_D, slice(0, 32), -2), ("E", SPEC_E, slice(0, 16), 0), ("F", SPEC_F, slice(0, 32), -2), ("G", SPEC_G, slice(0, 16), 0)]
+
 # (tag, spec, columns of the 32-column lld;lld_de level, frames the functionals see relative to T = static frames)
 LEVELS = [("is09", fo.IS09, slice(0, 32), -2, "is09_func"), ("A", SPEC_A, slice(0, 32), -2, "varA"), ("B", SPEC_B, slice(0, 16), 0, "varB"),
           ("C", SPEC_C, slice(16, 32), -2, "varC")]
@@ -47,6 +72,69 @@ def test_oracle_reproduces_the_reference_rows(key):
         assert fo.element_names(spec, names[cols]) == list(G["is09_func_names"] if tag == "is09" else G[gk + "_names"])
         # the reference's CSV prints 7 significant digits
         assert np.all(np.abs(got - ref) <= 1e-6 * np.abs(ref) + 1e-12), tag
+
+
+@pytest.mark.parametrize("key", ["m24k", "v32k", "rec"])
+def test_oracle_reproduces_the_reference_rows_times_lpc_segments_peaks2(key):
+    lld = G["is09_lld_" + key]
+    names = list(G["is09_lld_names"])
+    for tag, spec, cols, dn in LEVELS2:
+        got = fo.functionals(spec, contour_rows(lld, dn)[:, cols], 0.01)
+        ref = G2["var%s_%s" % (tag, key)][0]
+        assert fo.element_names(spec, names[cols]) == list(G2["var%s_names" % tag])
+        assert np.all(np.abs(got - ref) <= 1e-6 * np.abs(ref) + 1e-12), tag
+
+
+def to_c_spec(spec):
+    """oracle Spec -> ctypes mirror of osm_b200_functionals_spec"""
+    from opensmile_b200 import functionals as F
+    norm = lambda d: dict(norm=d["norm"], normIsSet=int(d["norm_set"]))
+    sub = {}
+    sub["extremes"] = {k: v for k, v in spec.extremes.items() if k not in ("norm", "norm_set")} | norm(spec.extremes)
+    sub["means"] = {k: v for k, v in spec.means.items() if k not in ("norm", "norm_set")} | norm(spec.means)
+    sub["moments"] = dict(spec.moments)
+    sub["percentiles"] = dict(spec.percentiles)
+    sub["regression"] = dict(spec.regression)
+    sub["times"] = {k: v for k, v in spec.times.items() if k not in ("norm", "norm_set")} | norm(spec.times)
+    sub["lpc"] = dict(spec.lpc)
+    g = spec.segments
+    sub["segments"] = dict(numSegments=g["numSegments"], meanSegLen=g["meanSegLen"], maxSegLen=g["maxSegLen"], minSegLen=g["minSegLen"],
+                           segLenStddev=g["segLenStddev"], maxNumSeg=g["maxNumSeg"], X=g["X"], XisRel=g["XisRel"], segMinLng=g["segMinLng"],
+                           segMinLngIsSet=int(g["segMinLng_set"]), pauseMinLng=g["pauseMinLng"], **norm(g))
+    if g["segmentationAlgorithm"] in F.SEG_BY_NAME:
+        sub["segments"]["segmentationAlgorithm"] = g["segmentationAlgorithm"]
+        sub["segments"]["thresholds"] = list(g["thresholds"])
+    c = spec.peaks2
+    sub["peaks2"] = {k: c[k] for k in fo.PEAKS2_NAMES} | dict(relThresh=c["relThresh"], dynRelThresh=c["dynRelThresh"], doRatioLimit=c["doRatioLimit"],
+                                                              useAbsThresh=int(c["absThresh"] is not None), absThresh=c["absThresh"] or 0.0, **norm(c))
+    return F.spec(spec.enabled, non_zero=spec.non_zero, master_norm=-1 if spec.master_norm is None else spec.master_norm,
+                  name_append=spec.name_append or "", **sub)
+
+
+def test_device_statements_of_the_sequential_functionals_on_the_host():
+    """opensmile_b200/csrc/functionals_seq.cuh compiled for the host: bit-identical to the oracle on the reference's contours and on
+    random ones (zigzags, plateaus, constant and very short contours)"""
+    import functionals_harness as fh
+    rng = np.random.RandomState(5)
+    contours = [G["is09_lld_rec"][:-1, c] for c in range(16)]
+    contours += [np.cumsum(rng.randn(n)).astype(np.float32) for n in (5, 6, 9, 40, 300, 1200)]
+    contours += [np.round(rng.rand(200) * 4).astype(np.float32), np.zeros(50, np.float32), np.ones(7, np.float32),
+                 (rng.rand(300) > 0.5).astype(np.float32) * rng.rand(300).astype(np.float32), np.array([1, 3, 2, 4, 1, 5, 0, 6, 2, 7, 1], np.float32)]
+    for spec in (SPEC_D, SPEC_E, SPEC_F, SPEC_G):
+        cs = to_c_spec(spec)
+        for x in contours:
+            mn, mx = np.float32(x.min()), np.float32(x.max())
+            mean = np.float32(x.astype(np.float64).sum() / len(x))
+            if "Segments" in spec.enabled:
+                nrm = fo._norm(spec.segments["norm"], spec.segments["norm_set"], spec.master_norm)
+                assert np.array_equal(fh.segments(cs, x, 0.01, nrm), np.array(fo._segments(spec, x, mn, mx, mean, 0.01), np.float32))
+            if "Peaks2" in spec.enabled:
+                nrm = fo._norm(spec.peaks2["norm"], spec.peaks2["norm_set"], spec.master_norm)
+                a, b = fh.peaks2(cs, x, 0.01, nrm), np.array(fo._peaks2(spec, x, mn, mx, mean, 0.01), np.float32)
+                assert np.array_equal(a, b, equal_nan=True), (a, b)
+            if "Lpc" in spec.enabled:
+                a, b = fh.lpc(cs, x), np.array(fo._lpc(spec, x), np.float32)
+                assert np.array_equal(a, b, equal_nan=True), (a, b)
 
 
 def test_zero_and_single_value_contours():
@@ -87,15 +175,25 @@ def test_variant_configuration_names(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "is09-13")), reason="reference configuration files not built (make -C oracle ref)")
+def test_second_variant_configuration_names(tmp_path):
+    conf = tmp_path / "v.conf"
+    conf.write_text(open(os.path.join(HERE, "configs", "func_variants2.conf")).read().replace("REFCONF", REFCONF))
+    for lv in "DEFG":
+        s = _session(str(conf), {"out" + lv: "x.csv"})
+        assert s.element_names() == list(G2["var%s_names" % lv])
+        s.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "is09-13")), reason="reference configuration files not built (make -C oracle ref)")
 def test_unimplemented_functionals_are_refused_loudly(tmp_path):
     from opensmile_b200.session import SessionError
     from opensmile_b200 import capi
     txt = open(os.path.join(HERE, "configs", "func_variants.conf")).read().replace("REFCONF", REFCONF)
     bad = tmp_path / "bad.conf"
-    bad.write_text(txt.replace("functionalsEnabled = Means\n", "functionalsEnabled = Means ; Peaks2\n"))
+    bad.write_text(txt.replace("functionalsEnabled = Means\n", "functionalsEnabled = Means ; Onset\n"))
     with pytest.raises(SessionError) as e:
         _session(str(bad), {"outA": "x.csv"})
-    assert e.value.status == capi.ERR_UNSUPPORTED and "cFunctionalPeaks2" in str(e.value)
+    assert e.value.status == capi.ERR_UNSUPPORTED and "cFunctionalOnset" in str(e.value)
     bad.write_text(txt.replace("nonZeroFuncts = 0\n", "nonZeroFuncts = 0\nbogusField = 1\n"))
     with pytest.raises(SessionError) as e:
         _session(str(bad), {"outA": "x.csv"})

@@ -9,7 +9,7 @@ import pytest
 from oracle import functionals_oracle as fo
 from opensmile_b200 import functionals as F
 from opensmile_b200.synth import mixed_pcm, voiced_pcm
-from test_functionals_cpu import G, LEVELS, REFCONF, contour_rows
+from test_functionals_cpu import G, G2, LEVELS, LEVELS2, REFCONF, contour_rows, to_c_spec
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -48,6 +48,53 @@ def test_kernel_on_the_reference_lld_rows(key):
         assert np.all(np.abs(got - ora) <= 2e-6 * np.abs(ora) + 1e-9), tag       # double reductions in another order, float log10 / exp
         ref = G["%s_%s" % (gk, key)][0]
         assert np.all(np.abs(got - ref) <= 2e-6 * np.abs(ref) + 1e-9), tag       # the reference's CSV: 7 significant digits
+
+
+@pytest.mark.parametrize("key", ["m24k", "v32k", "rec"])
+def test_times_lpc_segments_peaks2_on_the_reference_lld_rows(key):
+    """tests/configs/func_variants2.conf (the ComParE_2016 / GeMAPS option sets): float statements in the reference's order -> equal
+    to the oracle bit for bit except where a double reduction feeds them (the contour mean), and to the reference's CSV digits"""
+    lld = G["is09_lld_" + key]
+    names = list(G["is09_lld_names"])
+    for tag, spec, cols, dn in LEVELS2:
+        rows = np.ascontiguousarray(contour_rows(lld, dn)[:, cols])
+        f = F.Functionals(to_c_spec(spec), names[cols], 0.01, device=0)
+        assert f.element_names() == list(G2["var%s_names" % tag])
+        got = f.run_host(rows, [0], [rows.shape[0]])[0]
+        f.close()
+        ora = fo.functionals(spec, rows, 0.01)
+        assert np.all(np.abs(got - ora) <= 2e-6 * np.abs(ora) + 1e-9), (tag, np.nonzero(~(np.abs(got - ora) <= 2e-6 * np.abs(ora) + 1e-9))[0][:8])
+        ref = G2["var%s_%s" % (tag, key)][0]
+        assert np.all(np.abs(got - ref) <= 2e-6 * np.abs(ref) + 1e-9), tag
+
+
+def test_sequential_functionals_on_ragged_and_degenerate_contours():
+    rng = np.random.default_rng(11)
+    lens = [300, 1, 2, 0, 5, 33, 64, 2500]
+    K = 6
+    rows = np.cumsum(rng.standard_normal((sum(lens), K)), axis=0).astype(np.float32)
+    rows[:, 1] = 0
+    rows[::3, 2] = 0
+    rows[:, 3] = 2.5
+    rows[:, 4] = np.where(rng.random(sum(lens)) > 0.6, 0, rows[:, 4])           # pauses for nonX / eqX
+    rows[:, 5] = np.round(rows[:, 5])                                            # plateaus
+    off = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    pk = {k: 1 for k in fo.PEAKS2_NAMES}
+    specs = [fo.Spec(["Times", "Lpc", "Segments", "Peaks2", "Percentiles"], non_zero=nz, master_norm=mn, percentiles=dict(quartile2=1),
+                     times=dict(buggySecNorm=bs), lpc=dict(lpGain=1, order=od),
+                     segments=dict(segmentationAlgorithm=al, thresholds=[0.3, 0.6], maxNumSeg=50, numSegments=1, meanSegLen=1, maxSegLen=1,
+                                   minSegLen=1, segLenStddev=1),
+                     peaks2=dict(pk, relThresh=rt, dynRelThresh=dy, doRatioLimit=rl))
+             for nz, mn, bs, od, al, rt, dy, rl in ((0, fo.SEGMENT, 0, 5, "relTh", 0.1, 0, 1), (1, fo.SECOND, 1, 8, "nonX", 0.35, 1, 0),
+                                                    (0, fo.FRAME, 0, 3, "eqX", 0.0, 0, 1))]
+    for spec in specs:
+        f = F.Functionals(to_c_spec(spec), ["c%d" % i for i in range(K)], 0.01, device=0)
+        got = f.run_host(rows, off, lens)
+        f.close()
+        for u, (o, n) in enumerate(zip(off, lens)):
+            ora = fo.functionals(spec, rows[o:o + n], 0.01) if n else np.zeros(got.shape[1], np.float32)
+            ok = (np.abs(got[u] - ora) <= 2e-6 * np.abs(ora) + 1e-9) | (np.isnan(got[u]) & np.isnan(ora))
+            assert np.all(ok), (spec.segments["segmentationAlgorithm"], u, np.nonzero(~ok)[0][:8], got[u][~ok][:4], ora[~ok][:4])
 
 
 def test_ragged_batch_and_degenerate_contours():
