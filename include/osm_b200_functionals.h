@@ -81,7 +81,7 @@ typedef struct {
   struct {                                         /* Regression.* : nine values + centroid on by default */
     int32_t linregc1, linregc2, linregerrA, linregerrQ, qregc1, qregc2, qregc3, qregerrA, qregerrQ, centroid;
     int32_t centroidNorm;                          /* SEGMENT */
-    int32_t centroidUseAbsValues, centroidRatioLimit;   /* 1, 1 (the limiter is not implemented: must be 0 when centroid = 1) */
+    int32_t centroidUseAbsValues, centroidRatioLimit;   /* 1, 1 */
     int32_t normRegCoeff, normInputs, oldBuggyQerr, doRatioLimit;   /* 0, 0, 1, 0 */
   } regression;
   struct {                                         /* Times.* : every value on; norm "segment"; buggySecNorm 1 */
@@ -138,6 +138,13 @@ OSM_B200_API const char     *osm_b200_functionals_element_name(const osm_b200_fu
 OSM_B200_API osm_b200_status osm_b200_functionals_run_device(osm_b200_functionals *f, const float *d_rows, int32_t row_stride,
                                                              const int64_t *row_offsets, const int64_t *n_rows, int32_t n_utt,
                                                              float *d_out, void *stream);
+/* the same for an input level that is a subset / permutation of the row's columns (several cFunctionals instances on one resident
+ * LLD matrix, a cVectorConcat of their outputs behind them): cols = HOST array of n_in column indices (NULL: 0 .. n_in-1);
+ * utterance u writes its num_elements values at d_out + u * out_stride (out_stride >= num_elements: the caller lays the instances
+ * of a concatenated summary row side by side by offsetting d_out) */
+OSM_B200_API osm_b200_status osm_b200_functionals_run_device_cols(osm_b200_functionals *f, const float *d_rows, int32_t row_stride,
+                                                                  const int32_t *cols, const int64_t *row_offsets, const int64_t *n_rows,
+                                                                  int32_t n_utt, float *d_out, int64_t out_stride, void *stream);
 /* same with host buffers (copies in, runs, copies out, synchronises) */
 OSM_B200_API osm_b200_status osm_b200_functionals_run_host(osm_b200_functionals *f, const float *rows, int32_t row_stride,
                                                            const int64_t *row_offsets, const int64_t *n_rows, int32_t n_utt,

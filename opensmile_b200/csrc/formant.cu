@@ -21,8 +21,10 @@ namespace osm {
 
 namespace {
 
-constexpr int kFmtWarps = 8;               // frames in flight per CTA (one warp each in the per-frame phase)
+constexpr int kFmtWarps = 8;               // warps per CTA = frames per transform / resampling batch
 constexpr int kFmtThreads = kFmtWarps * 32;
+constexpr int kFmtFpw = 2;                 // frames per warp in the per-frame phase: a half warp each (one lane per lag / root, p <= 15)
+constexpr int kFmtBatch = kFmtWarps * kFmtFpw;
 
 struct FmtWarpWs {                          // per-warp scratch of the per-frame phase
   double c[fm::kMaxLpcOrder];               // polynomial, ascending powers (monic)
@@ -40,14 +42,21 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
   const TimeOpParams &tp = p.tp;
   const int N = tp.frameSize, I = p.nRes, IP = p.nResPad;
   FmtWarpWs *ws = reinterpret_cast<FmtWarpWs *>(fmtSmem);
-  float *xw = reinterpret_cast<float *>(ws + kFmtWarps);        // [kFmtWarps][N]
-  float *res = xw + (size_t)kFmtWarps * (p.refOrder ? 4 * ro::kPlane : N);   // [kFmtWarps][IP]
+  float *xw = reinterpret_cast<float *>(ws + kFmtBatch);        // [kFmtWarps][N]
+  float *res0 = xw + (size_t)kFmtWarps * (p.refOrder ? 4 * ro::kPlane : N);  // [kFmtBatch][IP]
   const OpTile tl = tp.tiles[blockIdx.x];
   const long long uo = tp.uttOff[tl.utt];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int fb = 0; fb < tl.nf; fb += kFmtWarps) {
+  // two frames per warp need a half warp per frame: one lane per lag 0..p
+  const int fpw = (p.p + 1 <= 16) ? kFmtFpw : 1;
+  for (int fb0 = 0; fb0 < tl.nf; fb0 += kFmtWarps * fpw) {
+   // transform + resampling in batches of kFmtWarps frames; the per-frame phase then takes fpw batches at once
+   for (int part = 0; part < fpw; part++) {
+    const int fb = fb0 + part * kFmtWarps;
     const int nb = min(kFmtWarps, tl.nf - fb);
+    if (nb <= 0) break;
+    float *res = res0 + (size_t)part * kFmtWarps * IP;
     if (p.refOrder) {
       // Reference-order path (fft_ref_order.cuh): the zero padded windowed frame goes through a 512-point real FFT with the
       // reference's rounding sequence; then cSpecResample's inverse sum over the reference's float tables, in its order.
@@ -115,48 +124,55 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
     }
     __syncthreads();
     }
-    // 3. one warp per frame
-    if (warp < nb) {
-      FmtWarpWs &w = ws[warp];
-      const float *x = res + warp * IP;
+   }
+    // 3. one (half) warp per frame
+    {
+      const int h = (fpw == 2) ? (lane >> 4) : 0, hl = (fpw == 2) ? (lane & 15) : lane;
+      const unsigned hm = (fpw == 2) ? (0xffffu << (16 * h)) : 0xffffffffu;
+      const int fi = warp * fpw + h;                                   // frame of the batch [fb0, fb0 + kFmtWarps * fpw)
+      const int part = fi / kFmtWarps, fin = fi - part * kFmtWarps;    // resampled by batch `part` as its frame `fin`
+      // frames are dealt so that a warp's two frames come from the two batches: fi -> (part, fin) below keeps res contiguous
+      if (fb0 + fi < tl.nf) {
+      FmtWarpWs &w = ws[fi];
+      const float *x = res0 + ((size_t)part * kFmtWarps + fin) * IP;
       const int P = p.p;
-      if (lane <= P) w.r[lane] = fm::acf_lag(x, I, lane);            // lld/lpc.cpp:156-215 (method acf)
-      __syncwarp();
-      if (lane == 0) {
+      if (hl <= P) w.r[hl] = fm::acf_lag(x, I, hl);                    // lld/lpc.cpp:156-215 (method acf)
+      __syncwarp(hm);
+      if (hl == 0) {
         fm::durbin(w.r, P, w.a);
         for (int i = 0; i < P; i++) w.c[i] = -(double)w.a[P - 1 - i];  // lld/formantLpc.cpp:258-262
         int z0 = 0;
         while (z0 < P && w.c[z0] == 0.0) z0++;                         // roots at the origin yield no candidate
         w.z0 = z0; w.n = P - z0;
       }
-      __syncwarp();
+      __syncwarp(hm);
       const int n = w.n;
       const double *c = w.c + w.z0;
       double zr = 0.0, zi = 0.0, prev = 1e300;
-      if (lane < n) { fm::aberth_init(c, n, lane, &zr, &zi); w.zr[lane] = zr; w.zi[lane] = zi; }
-      __syncwarp();
+      if (hl < n) { fm::aberth_init(c, n, hl, &zr, &zi); w.zr[hl] = zr; w.zi[hl] = zi; }
+      __syncwarp(hm);
       bool last = false;
       for (int it = 0; it < fm::kAberthMaxIter && n > 0; it++) {
         bool done = true;
-        if (lane < n) {
-          const double c2 = fm::aberth_step(c, n, w.zr, w.zi, lane, &zr, &zi);
+        if (hl < n) {
+          const double c2 = fm::aberth_step(c, n, w.zr, w.zi, hl, &zr, &zi);
           done = fm::aberth_done(c2, prev, zr, zi);
           prev = c2;
         }
-        __syncwarp();
-        if (lane < n) { w.zr[lane] = zr; w.zi[lane] = zi; }
-        const bool all = __all_sync(0xffffffffu, done);
-        __syncwarp();
+        __syncwarp(hm);
+        if (hl < n) { w.zr[hl] = zr; w.zi[hl] = zi; }
+        const bool all = __all_sync(hm, done);
+        __syncwarp(hm);
         if (last) break;
         last = all;
       }
-      if (lane < n) {
+      if (hl < n) {
         double f = 0.0, b = 0.0;
-        w.ok[lane] = fm::root_to_formant(zr, zi, p.T, p.minF, p.maxF, &f, &b) ? 1 : 0;
-        w.f[lane] = f; w.b[lane] = b;
+        w.ok[hl] = fm::root_to_formant(zr, zi, p.T, p.minF, p.maxF, &f, &b) ? 1 : 0;
+        w.f[hl] = f; w.b[hl] = b;
       }
-      __syncwarp();
-      if (lane == 0) {
+      __syncwarp(hm);
+      if (hl == 0) {
         // smileDsp_lpcrootsToFormants (smileutil/smileUtil.c:2019-2054): candidates in root order, then the
         // ascending sort of lld/formantLpc.cpp:277-296 over the leading non-zero entries
         double f[fm::kMaxLpcOrder], b[fm::kMaxLpcOrder];
@@ -169,11 +185,12 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
         for (int i = 0; i < nz; i++)
           for (int j = i + 1; j < nz; j++)
             if (f[j] < f[i]) { double t = f[j]; f[j] = f[i]; f[i] = t; t = b[j]; b[j] = b[i]; b[i] = t; }
-        float *dst = tp.stat + (tp.statOff[tl.utt] + tl.f0 + fb + warp) * (long long)tp.statStride + tp.outCol;
+        float *dst = tp.stat + (tp.statOff[tl.utt] + tl.f0 + fb0 + fi) * (long long)tp.statStride + tp.outCol;
         int o = 0;
         if (p.saveNValid) dst[o++] = (float)nv;                        // lld/formantLpc.cpp:376-392
         if (p.saveFormants) for (int i = 0; i < nF; i++) dst[o++] = (float)f[i];
         if (p.saveBandwidths) for (int i = 0; i < nF; i++) dst[o++] = (float)b[i];
+      }
       }
     }
     __syncthreads();
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
 size_t formant_smem_bytes(const FormantParams &p)
 {
   const size_t perFrame = p.refOrder ? (size_t)4 * ro::kPlane : (size_t)p.tp.frameSize;
-  return sizeof(FmtWarpWs) * kFmtWarps + (size_t)kFmtWarps * (perFrame + p.nResPad) * sizeof(float);
+  return sizeof(FmtWarpWs) * kFmtBatch + ((size_t)kFmtWarps * perFrame + (size_t)kFmtBatch * p.nResPad) * sizeof(float);
 }
 
 cudaError_t launch_formant(const FormantParams &p, cudaStream_t st)

@@ -74,33 +74,36 @@ OSM_FM_HD void aberth_init(const double *c, int n, int k, double *zr, double *zi
 OSM_FM_HD double aberth_step(const double *c, int n, const double *zr, const double *zi, int k, double *outR, double *outI)
 {
   const double x = zr[k], y = zi[k];
-  // Horner for p and p'
+  // Horner for p and p' (explicit fused multiply-adds: this solver is not a restatement of reference arithmetic, any accurate
+  // evaluation serves; the translation unit is otherwise compiled without contraction)
   double pr = 1.0, pi = 0.0, dr = 0.0, di = 0.0;
   for (int j = n - 1; j >= 0; j--) {
-    const double ndr = dr * x - di * y + pr, ndi = dr * y + di * x + pi;
+    const double ndr = fma(dr, x, fma(-di, y, pr)), ndi = fma(dr, y, fma(di, x, pi));
     dr = ndr; di = ndi;
-    const double npr = pr * x - pi * y + c[j], npi = pr * y + pi * x;
+    const double npr = fma(pr, x, fma(-pi, y, c[j])), npi = fma(pr, y, pi * x);
     pr = npr; pi = npi;
   }
   // w = p / p'
-  double den = dr * dr + di * di;
+  double den = fma(dr, dr, di * di);
   if (den == 0.0) { *outR = x + 1e-3; *outI = y + 1e-3; return 1.0; }
-  const double wr = (pr * dr + pi * di) / den, wi = (pi * dr - pr * di) / den;
-  // s = sum_{j != k} 1 / (z_k - z_j)
+  double inv = 1.0 / den;
+  const double wr = fma(pr, dr, pi * di) * inv, wi = fma(pi, dr, -(pr * di)) * inv;
+  // s = sum_{j != k} 1 / (z_k - z_j): one division per term
   double sr = 0.0, si = 0.0;
   for (int j = 0; j < n; j++) {
     if (j == k) continue;
     const double ar = x - zr[j], ai = y - zi[j];
-    const double ad = ar * ar + ai * ai;
+    const double ad = fma(ar, ar, ai * ai);
     if (ad == 0.0) continue;
-    sr += ar / ad; si -= ai / ad;
+    const double ia = 1.0 / ad;
+    sr = fma(ar, ia, sr); si = fma(-ai, ia, si);
   }
   // z_k -= w / (1 - w s)
-  const double qr = 1.0 - (wr * sr - wi * si), qi = -(wr * si + wi * sr);
-  den = qr * qr + qi * qi;
+  const double qr = 1.0 - fma(wr, sr, -(wi * si)), qi = -fma(wr, si, wi * sr);
+  den = fma(qr, qr, qi * qi);
   double cr, ci;
   if (den == 0.0) { cr = wr; ci = wi; }
-  else { cr = (wr * qr + wi * qi) / den; ci = (wi * qr - wr * qi) / den; }
+  else { inv = 1.0 / den; cr = fma(wr, qr, wi * qi) * inv; ci = fma(wi, qr, -(wr * qi)) * inv; }
   *outR = x - cr; *outI = y - ci;
   return cr * cr + ci * ci;
 }

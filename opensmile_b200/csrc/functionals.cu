@@ -38,6 +38,8 @@ constexpr int kMaxSort = 8192;              // longest filtered contour with per
 
 struct FnParams {
   const float *rows; int rowStride; int nIn;
+  const int *cols;                          // device [nIn] column of every input element inside a row, or null (0 .. nIn-1)
+  long long outStride;                      // floats between the output rows of consecutive utterances
   const long long *rowOff, *nRows;          // device [nUtt]
   float *out; int nVals;                    // out[u][e * nVals + v]
   int sortCap;                              // floats of the contour copy per warp in shared memory (0: not needed)
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
   const int u = blockIdx.x / groups, e = (blockIdx.x % groups) * nW + warp;
   if (e >= p.nIn) return;
   const long long T = p.nRows[u];
-  const float *col = p.rows + p.rowOff[u] * (long long)p.rowStride + e;
-  float *out = p.out + ((long long)u * p.nIn + e) * p.nVals;
+  const float *col = p.rows + p.rowOff[u] * (long long)p.rowStride + (p.cols ? p.cols[e] : e);
+  float *out = p.out + (long long)u * p.outStride + (long long)e * p.nVals;
   float *sbuf = fnSort + (size_t)warp * p.perWarp;
   const Keep keep{p.s.nonZeroFuncts};
   const unsigned ltMask = (1u << lane) - 1u;
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
     rinv = range > 0.0 ? 1.0 / range : 0.0;
     if (R.centroidUseAbsValues) centroid = sAbs != 0.0 ? numAbs / sAbs : 0.0;
     else centroid = asum != 0.0 ? num / asum : 0.0;
+    if (R.centroidRatioLimit) centroid = (double)fseq::ratio_limit((float)centroid, (float)Nd, (float)Nd);   // :206-209
     if (R.centroidNorm == OSM_B200_TIMENORM_SECOND) centroid *= p.periodD;
     else if (R.centroidNorm == OSM_B200_TIMENORM_SEGMENT) centroid /= Nd;
     if (N > 1) {
@@ -387,8 +390,12 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
         if (M.stddevNorm == 1 || M.stddevNorm == 2) {
           if (v2 > 0.0) {
             double ml = M.stddevNorm == 1 ? (double)fabsf(mean) : meanD;
-            if (ml == 0.0) ml = 1.0;
-            out[n++] = (float)(sq / ml);
+            if (M.doRatioLimit) {                                      // functionalMoments.cpp:144-151
+              out[n++] = ml != 0.0 ? fseq::ratio_limit((float)(sq / ml), 10.0f, 20.0f) : 20.0f;
+            } else {
+              if (ml == 0.0) ml = 1.0;
+              out[n++] = (float)(sq / ml);
+            }
           } else out[n++] = 0.0f;
         }
       } break;
@@ -409,6 +416,13 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
       } break;
       case OSM_B200_F_REGRESSION: {
         double m = rm, t = rt, a = ra, b = rb, c = rc;
+        if (R.doRatioLimit) {                                          // functionalRegression.cpp:328-335
+          double rg = (double)__fsub_rn(mx, mn);
+          if (rg <= 0.0) rg = 1.0;
+          m = (double)fseq::ratio_limit((float)m, (float)(rg / 10.0), (float)(rg / 10.0 + 0.01));
+          a = (double)fseq::ratio_limit((float)a, (float)sqrt(rg / 10.0), (float)(sqrt(rg / 10.0) + 0.01));
+          b = (double)fseq::ratio_limit((float)b, (float)(rg / 10.0), (float)(rg / 10.0 + 0.01));
+        }
         if (R.normRegCoeff == 1) { m *= Nd - 1.0; a *= (Nd - 1.0) * (Nd - 1.0); b *= Nd - 1.0; }
         else if (R.normRegCoeff == 2) { const double one = 1.0 / p.periodD; m *= one; a *= one * one; b *= one; }
         if (R.normInputs) { m *= rinv; t = (t - (double)mn) * rinv; a *= rinv; b *= rinv; c = (c - (double)mn) * rinv; }
@@ -449,6 +463,7 @@ struct osm_b200_functionals {
   long long *dMeta = nullptr; size_t metaCap = 0;
   float *dIn = nullptr; size_t inCap = 0;
   float *dOut = nullptr; size_t outCap = 0;
+  int *dCols = nullptr; std::vector<int> hCols;
 };
 
 namespace {
@@ -583,10 +598,6 @@ osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spe
   for (int i = 0; i < s.n_enabled; i++)
     if (s.enabled[i] < 0 || s.enabled[i] >= OSM_B200_F_COUNT_) return set_last_error(OSM_B200_ERR_INVALID, "cFunctionals: unknown functional");
   if (s.nonZeroFuncts < 0 || s.nonZeroFuncts > 2) return set_last_error(OSM_B200_ERR_INVALID, "cFunctionals.nonZeroFuncts must be 0, 1 or 2");
-  if (s.moments.doRatioLimit || s.regression.doRatioLimit) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionals: doRatioLimit = 1 is not supported");
-  if (s.regression.centroid && s.regression.centroidRatioLimit)
-    for (int i = 0; i < s.n_enabled; i++)
-      if (s.enabled[i] == OSM_B200_F_REGRESSION) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalRegression: centroid with centroidRatioLimit = 1 is not supported (set centroidRatioLimit = 0 or centroid = 0)");
   const auto &P = s.percentiles;
   if (P.n_percentile < 0 || P.n_percentile > OSM_B200_F_MAX_PCTL || P.n_pctlrange < 0 || P.n_pctlrange > OSM_B200_F_MAX_PCTL)
     return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalPercentiles: at most 8 percentiles / ranges");
@@ -628,7 +639,7 @@ osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spe
 void osm_b200_functionals_destroy(osm_b200_functionals *f)
 {
   if (!f) return;
-  if (f->device >= 0) { cudaSetDevice(f->device); if (f->dMeta) cudaFree(f->dMeta); if (f->dIn) cudaFree(f->dIn); if (f->dOut) cudaFree(f->dOut); }
+  if (f->device >= 0) { cudaSetDevice(f->device); if (f->dMeta) cudaFree(f->dMeta); if (f->dIn) cudaFree(f->dIn); if (f->dOut) cudaFree(f->dOut); if (f->dCols) cudaFree(f->dCols); }
   delete f;
 }
 
@@ -642,12 +653,28 @@ const char *osm_b200_functionals_element_name(const osm_b200_functionals *f, int
 osm_b200_status osm_b200_functionals_run_device(osm_b200_functionals *f, const float *d_rows, int32_t row_stride, const int64_t *row_offsets,
                                                 const int64_t *n_rows, int32_t n_utt, float *d_out, void *stream)
 {
+  return osm_b200_functionals_run_device_cols(f, d_rows, row_stride, nullptr, row_offsets, n_rows, n_utt, d_out,
+                                              f ? (int64_t)f->nVals * f->nIn : 0, stream);
+}
+
+osm_b200_status osm_b200_functionals_run_device_cols(osm_b200_functionals *f, const float *d_rows, int32_t row_stride, const int32_t *cols,
+                                                     const int64_t *row_offsets, const int64_t *n_rows, int32_t n_utt, float *d_out,
+                                                     int64_t out_stride, void *stream)
+{
   if (!f || !row_offsets || !n_rows || n_utt < 0) return set_last_error(OSM_B200_ERR_INVALID, "null argument");
   if (f->device < 0) return set_last_error(OSM_B200_ERR_CUDA, "description-only functionals object (device < 0) cannot run; no CPU fallback");
   if (n_utt == 0) return OSM_B200_OK;
-  if (!d_rows || !d_out || row_stride < f->nIn) return set_last_error(OSM_B200_ERR_INVALID, "bad row buffer");
+  if (!d_rows || !d_out || (!cols && row_stride < f->nIn) || out_stride < (int64_t)f->nVals * f->nIn) return set_last_error(OSM_B200_ERR_INVALID, "bad row buffer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   FCU(cudaSetDevice(f->device));
+  if (cols) {
+    for (int e = 0; e < f->nIn; e++) if (cols[e] < 0 || cols[e] >= row_stride) return set_last_error(OSM_B200_ERR_INVALID, "column index outside the row");
+    if (!f->dCols || f->hCols.size() != (size_t)f->nIn || memcmp(f->hCols.data(), cols, sizeof(int) * f->nIn) != 0) {
+      if (!f->dCols) FCU(cudaMalloc(&f->dCols, sizeof(int) * (size_t)f->nIn));
+      f->hCols.assign(cols, cols + f->nIn);
+      FCU(cudaMemcpy(f->dCols, f->hCols.data(), sizeof(int) * (size_t)f->nIn, cudaMemcpyHostToDevice));
+    }
+  }
   long long maxT = 0;
   std::vector<long long> meta(2 * (size_t)n_utt);
   for (int u = 0; u < n_utt; u++) {
@@ -678,6 +705,7 @@ osm_b200_status osm_b200_functionals_run_device(osm_b200_functionals *f, const f
   FCU(cudaStreamSynchronize(st));                  // `meta` is a local: the copy must have left the host buffer
   FnParams p;
   memset(&p, 0, sizeof p);
+  p.cols = cols ? f->dCols : nullptr; p.outStride = out_stride;
   p.rows = d_rows; p.rowStride = row_stride; p.nIn = f->nIn; p.rowOff = f->dMeta; p.nRows = f->dMeta + n_utt;
   p.perWarp = perWarp; p.listOff = sortCap; p.lensOff = sortCap + listFloats;
   for (int i = 0, o = 0; i < f->spec.n_enabled; i++) { p.valOff[i] = o; o += value_count(f->spec, i); }

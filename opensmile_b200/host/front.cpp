@@ -1017,12 +1017,35 @@ struct osm_b200_session {
   std::vector<osm_b200_component> curComps;
   // a cFunctionals summary between the LLD level and the sink (full-input mode): the plan then produces the functionals'
   // input level, which stays in HBM, and one functionals object per input format summarises it (osm_b200_functionals.h)
+  // One instance (the shipped IS09 graph) or several behind a cVectorConcat / multi-level sink reader (ComParE_2016: six instances on
+  // column subsets of the LLD rows): the plan's output level is the union of the instances' reader levels.
   bool hasFunc = false;
-  osm_b200_functionals_spec fspec;
-  std::map<std::pair<long, int>, osm_b200_functionals *> funcs;
-  osm_b200_functionals *curFunc = nullptr;
+  // a reader level of an instance: a level of the plan, or the view a cDataSelector (`selected` names + nameAppend) gives of one
+  struct FuncReader { std::string level; std::vector<std::string> sel; std::string nameAppend;
+                      bool operator==(const FuncReader &o) const { return level == o.level && sel == o.sel && nameAppend == o.nameAppend; } };
+  struct FuncInst { osm_b200_functionals_spec spec; std::vector<FuncReader> readers; };
+  std::vector<FuncInst> finsts;              // in the order of the summary row
+  std::vector<std::string> unionLevels;      // levels of the plan's output level, in order
+  struct FuncRt {                            // per input format
+    std::vector<osm_b200_functionals *> f;
+    std::vector<std::vector<int32_t>> cols;  // columns of every instance's input elements inside the plan's rows
+    std::vector<std::vector<std::string>> inNames;
+    std::vector<osm_b200_plan *> desc;       // description-only plan over the instance's reader levels (its frame-count rule); null = the main plan
+    std::vector<int> off;                    // first value of every instance inside the summary row
+    std::vector<std::string> names;
+    int total = 0;
+  };
+  std::map<std::pair<long, int>, FuncRt> funcs;
+  FuncRt *curFunc = nullptr;
   float *dFuncOut = nullptr; size_t funcOutCap = 0;
 };
+
+static void split_levels(const std::string &v, std::vector<std::string> &out)
+{
+  std::stringstream ss(v);
+  std::string one;
+  while (std::getline(ss, one, ';')) { one = trim(one); if (!one.empty()) out.push_back(one); }
+}
 
 static osm_b200_status get_plan(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan **out)
 {
@@ -1043,21 +1066,110 @@ static osm_b200_status get_plan(osm_b200_session *s, double sampleRate, int nCha
   return OSM_B200_OK;
 }
 
-static osm_b200_status get_func(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan *p, osm_b200_functionals **out)
+// description-only plan (names, counts, frame rules) of the session's graph with `levels` as output level
+static osm_b200_status desc_plan(osm_b200_session *s, double sampleRate, int nChan, const std::vector<std::string> &levels, osm_b200_plan **out)
+{
+  std::vector<osm_b200_component> cs;
+  for (const osm_b200_component &c : s->comps) if (strcmp(c.name, "_sinkconcat") != 0) cs.push_back(c);
+  int wave = -1;
+  for (size_t i = 0; i < cs.size(); i++) if (cs[i].type == OSM_B200_C_WAVESOURCE) wave = (int)i;
+  cs[wave].u.wavesource.sampleRate = sampleRate;
+  cs[wave].u.wavesource.nChannels = nChan;
+  std::string lvl = levels[0];
+  if (levels.size() > 1) {
+    if (levels.size() > OSM_B200_MAX_INPUTS) return hfail(OSM_B200_ERR_UNSUPPORTED, "more than 8 levels in one reader");
+    osm_b200_component c;
+    osm_b200_component_defaults(OSM_B200_C_VECTORCONCAT, &c);
+    snprintf(c.name, sizeof c.name, "%s", "_fconcat");
+    for (const std::string &l : levels) snprintf(c.reader_dmLevel[c.n_inputs++], OSM_B200_NAME_LEN, "%s", l.c_str());
+    snprintf(c.writer_dmLevel, sizeof c.writer_dmLevel, "%s", "_fconcat");
+    c.u.vectorconcat.processArrayFields = 0;
+    cs.push_back(c);
+    lvl = "_fconcat";
+  }
+  osm_b200_status st = osm_b200_plan_create(cs.data(), (int)cs.size(), lvl.c_str(), -1, out);
+  if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+  return OSM_B200_OK;
+}
+
+static void free_func_rt(osm_b200_session::FuncRt &rt)
+{
+  for (osm_b200_functionals *f : rt.f) osm_b200_functionals_destroy(f);
+  for (osm_b200_plan *d : rt.desc) if (d) osm_b200_plan_destroy(d);
+  rt.f.clear(); rt.desc.clear();
+}
+
+// the functionals objects of the session for one input format; device < 0: names / counts only
+static osm_b200_status build_func_rt(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan *p, int device, osm_b200_session::FuncRt &rt)
+{
+  const int K = osm_b200_plan_num_elements(p);
+  // columns of every level of the plan's output level
+  std::map<std::string, std::pair<int, int>> range;
+  if (s->unionLevels.size() == 1) range[s->unionLevels[0]] = {0, K};
+  else {
+    int o = 0;
+    for (const std::string &l : s->unionLevels) {
+      osm_b200_plan *d = nullptr;
+      osm_b200_status st = desc_plan(s, sampleRate, nChan, {l}, &d);
+      if (st != OSM_B200_OK) return st;
+      const int n = osm_b200_plan_num_elements(d);
+      osm_b200_plan_destroy(d);
+      range[l] = {o, n};
+      o += n;
+    }
+    if (o != K) return hfail(OSM_B200_ERR_INVALID, "cFunctionals: the levels of the summary's inputs do not add up to the plan's row");
+  }
+  rt.total = 0;
+  for (const osm_b200_session::FuncInst &fi : s->finsts) {
+    std::vector<int32_t> cols;
+    std::vector<std::string> inNames;
+    std::vector<std::string> plain;                                    // the levels behind the readers (frame-count rule)
+    for (const osm_b200_session::FuncReader &rd : fi.readers) {
+      const auto r = range[rd.level];
+      plain.push_back(rd.level);
+      if (rd.sel.empty()) {
+        for (int c = 0; c < r.second; c++) { cols.push_back(r.first + c); inNames.push_back(osm_b200_plan_element_name(p, r.first + c)); }
+      } else {
+        // cDataSelector (core/dataSelector.cpp:296-366, elementMode): the selected elements in the order of `selected`
+        for (const std::string &want : rd.sel) {
+          int hit = -1;
+          for (int c = 0; c < r.second && hit < 0; c++) if (want == osm_b200_plan_element_name(p, r.first + c)) hit = r.first + c;
+          if (hit < 0) { free_func_rt(rt); return hfail(OSM_B200_ERR_INVALID, "cDataSelector: element '" + want + "' not found in level '" + rd.level + "'"); }
+          cols.push_back(hit);
+          inNames.push_back(rd.nameAppend.empty() ? want : want + "_" + rd.nameAppend);
+        }
+      }
+    }
+    std::vector<const char *> names(cols.size());
+    for (size_t i = 0; i < cols.size(); i++) names[i] = inNames[i].c_str();
+    osm_b200_functionals *f = nullptr;
+    osm_b200_status st = osm_b200_functionals_create(&fi.spec, (int)cols.size(), names.data(), osm_b200_plan_frame_period(p), device, &f);
+    if (st != OSM_B200_OK) { const std::string m = osm_b200_last_error(); free_func_rt(rt); return hfail(st, m); }
+    osm_b200_plan *d = nullptr;
+    if (plain != s->unionLevels) {
+      st = desc_plan(s, sampleRate, nChan, plain, &d);
+      if (st != OSM_B200_OK) { osm_b200_functionals_destroy(f); free_func_rt(rt); return st; }
+    }
+    rt.f.push_back(f); rt.cols.push_back(cols); rt.desc.push_back(d); rt.off.push_back(rt.total);
+    const int n = osm_b200_functionals_num_elements(f);
+    for (int i = 0; i < n; i++) rt.names.push_back(osm_b200_functionals_element_name(f, i));
+    rt.total += n;
+  }
+  return OSM_B200_OK;
+}
+
+static osm_b200_status get_func(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan *p, osm_b200_session::FuncRt **out)
 {
   const auto key = std::make_pair((long)lround(sampleRate * 1000.0), nChan);
   auto it = s->funcs.find(key);
   if (it == s->funcs.end()) {
-    const int K = osm_b200_plan_num_elements(p);
-    std::vector<const char *> names(K);
-    for (int i = 0; i < K; i++) names[i] = osm_b200_plan_element_name(p, i);
-    osm_b200_functionals *f = nullptr;
-    osm_b200_status st = osm_b200_functionals_create(&s->fspec, K, names.data(), osm_b200_plan_frame_period(p), s->device, &f);
-    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
-    it = s->funcs.insert({key, f}).first;
+    osm_b200_session::FuncRt rt;
+    osm_b200_status st = build_func_rt(s, sampleRate, nChan, p, s->device, rt);
+    if (st != OSM_B200_OK) return st;
+    it = s->funcs.insert({key, rt}).first;
   }
-  s->curFunc = it->second;
-  *out = it->second;
+  s->curFunc = &it->second;
+  *out = &it->second;
   return OSM_B200_OK;
 }
 
@@ -1154,27 +1266,90 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
     if (sinkLevels.empty()) { delete s; return hfail(OSM_B200_ERR_INVALID, "no active sink: pass output_level or enable a sink (-O / -csvoutput)"); }
     lvl = sinkLevels[0];
   }
-  // A summary level: [sink level] <- (single-input cVectorConcat)* <- cFunctionals <- LLD level(s).  The plan computes the
-  // functionals' input level(s); the summary itself runs on the resident rows (functionals.cu).
-  if (lvl.find(';') == std::string::npos) {
+  // A summary level: [sink level] <- (single-input cVectorConcat)* <- cFunctionals <- LLD level(s), or several such chains behind
+  // one cVectorConcat / multi-level sink reader.  The plan computes the union of the functionals' input levels; the summaries
+  // run on the resident rows (functionals.cu), each instance on its columns.
+  {
     std::map<std::string, const Section *> writerOfAll;
     for (const Section *sec : compute) if (const std::string *w = sec->get("writer.dmLevel")) writerOfAll[*w] = sec;
-    std::string cur = lvl;
-    for (int guard = 0; guard < 16; guard++) {
-      auto it = writerOfAll.find(cur);
-      if (it == writerOfAll.end()) break;
-      const Section *w = it->second;
-      if (w->type == "cFunctionals") {
-        if (!to_functionals(*w, s->fspec, err)) { delete s; return hfail(err.find("not supported") != std::string::npos ? OSM_B200_ERR_UNSUPPORTED : OSM_B200_ERR_INVALID, err); }
+    // level -> the cFunctionals section behind it (through single-input concats), or null
+    auto func_behind = [&](std::string cur) -> const Section * {
+      for (int guard = 0; guard < 16; guard++) {
+        auto it = writerOfAll.find(cur);
+        if (it == writerOfAll.end()) return nullptr;
+        const Section *w = it->second;
+        if (w->type == "cFunctionals") return w;
         const std::string *r = w->get("reader.dmLevel");
-        if (!r) { delete s; return hfail(OSM_B200_ERR_INVALID, "cFunctionals '" + w->name + "' has no reader.dmLevel"); }
-        s->hasFunc = true;
-        lvl = *r;
+        if (w->type == "cVectorConcat" && r && r->find(';') == std::string::npos) { cur = trim(*r); continue; }
+        return nullptr;
+      }
+      return nullptr;
+    };
+    // the levels the summary row is made of: the sink's reader list, with one multi-input cVectorConcat expanded
+    std::vector<std::string> parts;
+    split_levels(lvl, parts);
+    if (parts.size() == 1 && !func_behind(parts[0])) {
+      std::string cur = parts[0];
+      for (int guard = 0; guard < 16; guard++) {
+        auto it = writerOfAll.find(cur);
+        if (it == writerOfAll.end() || it->second->type != "cVectorConcat") break;
+        const std::string *r = it->second->get("reader.dmLevel");
+        if (!r) break;
+        if (r->find(';') == std::string::npos) { cur = trim(*r); continue; }
+        parts.clear();
+        split_levels(*r, parts);
         break;
       }
-      const std::string *r = w->get("reader.dmLevel");
-      if (w->type == "cVectorConcat" && r && r->find(';') == std::string::npos) { cur = trim(*r); continue; }
-      break;
+    }
+    std::vector<const Section *> fsecs;
+    for (const std::string &pl : parts) fsecs.push_back(func_behind(pl));
+    const bool allFunc = !fsecs.empty() && std::all_of(fsecs.begin(), fsecs.end(), [](const Section *x) { return x != nullptr; });
+    const bool anyFunc = std::any_of(fsecs.begin(), fsecs.end(), [](const Section *x) { return x != nullptr; });
+    if (anyFunc && !allFunc) { delete s; return hfail(OSM_B200_ERR_UNSUPPORTED, "a level that mixes cFunctionals summaries with other levels is not supported"); }
+    if (allFunc) {
+      for (const Section *w : fsecs) {
+        osm_b200_session::FuncInst fi;
+        if (!to_functionals(*w, fi.spec, err)) { delete s; return hfail(err.find("not supported") != std::string::npos ? OSM_B200_ERR_UNSUPPORTED : OSM_B200_ERR_INVALID, err); }
+        const std::string *r = w->get("reader.dmLevel");
+        if (!r) { delete s; return hfail(OSM_B200_ERR_INVALID, "cFunctionals '" + w->name + "' has no reader.dmLevel"); }
+        std::vector<std::string> rl;
+        split_levels(*r, rl);
+        for (const std::string &l : rl) {
+          osm_b200_session::FuncReader rd;
+          rd.level = l;
+          // a cDataSelector that only picks named elements (and appends to their names) is a view of its input level
+          auto itw = writerOfAll.find(l);
+          if (itw != writerOfAll.end() && itw->second->type == "cDataSelector") {
+            const Section *ds = itw->second;
+            bool simple = true;
+            std::map<int, std::string> selIdx;
+            std::string selList;
+            for (const auto &kv : ds->kv) {
+              const std::string &f = kv.first;
+              if (f == "nameAppend") { rd.nameAppend = kv.second; continue; }
+              if (is_common(f) || f == "reader.dmLevel" || f == "writer.dmLevel") continue;
+              if (f == "selected") selList = kv.second;
+              else if (f.compare(0, 9, "selected[") == 0) selIdx[atoi(f.c_str() + 9)] = kv.second;
+              else if (f == "nameAppend") rd.nameAppend = kv.second;
+              else if (f == "elementMode") simple = simple && inum(kv.second) == 1;
+              else if (f == "copyInputName") simple = simple && inum(kv.second) == 1;
+              else simple = false;
+            }
+            const std::string *base = ds->get("reader.dmLevel");
+            if (!selIdx.empty()) for (const auto &kv : selIdx) rd.sel.push_back(trim(kv.second));
+            else split_levels(selList, rd.sel);
+            if (simple && base && base->find(';') == std::string::npos && !rd.sel.empty()) rd.level = trim(*base);
+            else { rd.sel.clear(); rd.nameAppend.clear(); }
+          }
+          fi.readers.push_back(rd);
+          if (std::find(s->unionLevels.begin(), s->unionLevels.end(), rd.level) == s->unionLevels.end()) s->unionLevels.push_back(rd.level);
+        }
+        s->finsts.push_back(fi);
+      }
+      if (s->unionLevels.size() > OSM_B200_MAX_INPUTS) { delete s; return hfail(OSM_B200_ERR_UNSUPPORTED, "cFunctionals: more than 8 input levels in total"); }
+      s->hasFunc = true;
+      lvl.clear();
+      for (const std::string &l : s->unionLevels) lvl += (lvl.empty() ? "" : ";") + l;
     }
   }
   // Only the components the output level depends on are part of the plan: the shipped feature-set
@@ -1239,13 +1414,10 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
     osm_b200_status st = osm_b200_plan_create(cs.data(), (int)cs.size(), s->outputLevel.c_str(), -1, &p);
     if (st != OSM_B200_OK) { const std::string m = osm_b200_last_error(); delete s; return hfail(st, m); }
     if (s->hasFunc) {
-      const int K = osm_b200_plan_num_elements(p);
-      std::vector<const char *> names(K);
-      for (int i = 0; i < K; i++) names[i] = osm_b200_plan_element_name(p, i);
-      osm_b200_functionals *f = nullptr;
-      st = osm_b200_functionals_create(&s->fspec, K, names.data(), osm_b200_plan_frame_period(p), -1, &f);
-      if (st != OSM_B200_OK) { const std::string m = osm_b200_last_error(); osm_b200_plan_destroy(p); delete s; return hfail(st, m); }
-      osm_b200_functionals_destroy(f);
+      osm_b200_session::FuncRt rt;
+      st = build_func_rt(s, 16000, 1, p, -1, rt);
+      if (st != OSM_B200_OK) { const std::string m = osm_b200_host_last_error(); osm_b200_plan_destroy(p); delete s; return hfail(st, m); }
+      free_func_rt(rt);
     }
     osm_b200_plan_destroy(p);
   }
@@ -1257,7 +1429,7 @@ void osm_b200_session_close(osm_b200_session *s)
 {
   if (!s) return;
   for (auto &kv : s->plans) osm_b200_plan_destroy(kv.second);
-  for (auto &kv : s->funcs) osm_b200_functionals_destroy(kv.second);
+  for (auto &kv : s->funcs) free_func_rt(kv.second);
   if (s->dFuncOut) cudaFree(s->dFuncOut);
   delete s;
 }
@@ -1268,16 +1440,16 @@ int32_t osm_b200_session_num_elements(osm_b200_session *s, double sampleRate, in
   osm_b200_plan *p;
   if (get_plan(s, sampleRate, nChan, &p) != OSM_B200_OK) return 0;
   if (s->hasFunc) {
-    osm_b200_functionals *f;
+    osm_b200_session::FuncRt *f;
     if (get_func(s, sampleRate, nChan, p, &f) != OSM_B200_OK) return 0;
-    return osm_b200_functionals_num_elements(f);
+    return f->total;
   }
   return osm_b200_plan_num_elements(p);
 }
 
 const char *osm_b200_session_element_name(osm_b200_session *s, int32_t idx)
 {
-  if (s && s->hasFunc) return s->curFunc ? osm_b200_functionals_element_name(s->curFunc, idx) : nullptr;
+  if (s && s->hasFunc) return (s->curFunc && idx >= 0 && idx < s->curFunc->total) ? s->curFunc->names[idx].c_str() : nullptr;
   return (s && s->cur) ? osm_b200_plan_element_name(s->cur, idx) : nullptr;
 }
 
@@ -1309,18 +1481,27 @@ osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t 
   if (s->hasFunc) {
     // one summary row per utterance that has frames; the rows a plan run leaves in HBM are summarised in place.  The
     // contour of utterance u = its first osm_b200_plan_num_frames_first_eoi() rows (what the reference's functionals see).
-    osm_b200_functionals *f;
+    osm_b200_session::FuncRt *f;
     st = get_func(s, sampleRate, nChan, p, &f);
     if (st != OSM_B200_OK) return st;
-    std::vector<int64_t> lldOff((size_t)nUtt + 1), nRows((size_t)nUtt), rowOff((size_t)nUtt);
+    const size_t nI = f->f.size();
+    std::vector<int64_t> lldOff((size_t)nUtt + 1), rowOff((size_t)nUtt);
+    std::vector<std::vector<int64_t>> nRows(nI, std::vector<int64_t>((size_t)nUtt));
     st = osm_b200_plan_frame_offsets(p, uttOff, nUtt, lldOff.data());
     if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
     std::vector<int> live;
     frameOff[0] = 0;
     for (int u = 0; u < nUtt; u++) {
-      const int64_t n = osm_b200_plan_num_frames_first_eoi(p, uttOff[u + 1] - uttOff[u]);
-      if (n > 0) { rowOff[live.size()] = lldOff[u]; nRows[live.size()] = std::min<int64_t>(n, lldOff[u + 1] - lldOff[u]); live.push_back(u); }
-      frameOff[u + 1] = frameOff[u] + (n > 0 ? 1 : 0);
+      // every instance sees the rows its own reader holds when end of input is first signalled; a summary row exists when
+      // every instance has at least one frame
+      bool all = true;
+      for (size_t i = 0; i < nI; i++) {
+        const int64_t n = std::min<int64_t>(osm_b200_plan_num_frames_first_eoi(f->desc[i] ? f->desc[i] : p, uttOff[u + 1] - uttOff[u]), lldOff[u + 1] - lldOff[u]);
+        nRows[i][live.size()] = n;
+        all = all && n > 0;
+      }
+      if (all) { rowOff[live.size()] = lldOff[u]; live.push_back(u); }
+      frameOff[u + 1] = frameOff[u] + (all ? 1 : 0);
     }
     if (!out) return OSM_B200_OK;
     if (frameOff[nUtt] > maxRows) return hfail(OSM_B200_ERR_INVALID, "output buffer too small");
@@ -1328,7 +1509,7 @@ osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t 
     const float *dRows = nullptr;
     st = osm_b200_plan_run_host_resident(p, pcm, uttOff, nUtt, lldOff.data(), &dRows);
     if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
-    const int KF = osm_b200_functionals_num_elements(f);
+    const int KF = f->total;
     const size_t need = live.size() * (size_t)KF;
     if (s->funcOutCap < need) {
       if (s->dFuncOut) cudaFree(s->dFuncOut);
@@ -1336,8 +1517,11 @@ osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t 
       if (cudaMalloc(reinterpret_cast<void **>(&s->dFuncOut), need * sizeof(float)) != cudaSuccess) return hfail(OSM_B200_ERR_NOMEM, "out of device memory (functionals rows)");
       s->funcOutCap = need;
     }
-    st = osm_b200_functionals_run_device(f, dRows, osm_b200_plan_num_elements(p), rowOff.data(), nRows.data(), (int)live.size(), s->dFuncOut, nullptr);
-    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    for (size_t i = 0; i < nI; i++) {
+      st = osm_b200_functionals_run_device_cols(f->f[i], dRows, osm_b200_plan_num_elements(p), f->cols[i].data(), rowOff.data(), nRows[i].data(),
+                                                (int)live.size(), s->dFuncOut + f->off[i], KF, nullptr);
+      if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    }
     if (cudaMemcpy(out, s->dFuncOut, need * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return hfail(OSM_B200_ERR_CUDA, "copy of the functionals rows failed");
     return OSM_B200_OK;
   }

@@ -41,12 +41,13 @@ class Spec:
         self.means = dict(amean=1, absmean=1, qmean=1, nzamean=1, nzabsmean=1, nzqmean=1, nzgmean=1, nnz=1, flatness=0, posamean=0,
                           negamean=0, posqmean=0, posrqmean=0, negqmean=0, negrqmean=0, rqmean=0, nzrqmean=0, norm=FRAME, norm_set=False)
         self.means.update(means or {})
-        self.moments = dict(variance=1, stddev=1, skewness=1, kurtosis=1, amean=0, stddevNorm=0)
+        self.moments = dict(variance=1, stddev=1, skewness=1, kurtosis=1, amean=0, stddevNorm=0, doRatioLimit=0)
         self.moments.update(moments or {})
         self.percentiles = dict(quartile1=0, quartile2=0, quartile3=0, iqr12=0, iqr23=0, iqr13=0, percentile=[], pctlrange=[], interp=1)
         self.percentiles.update(percentiles or {})
         self.regression = dict(linregc1=1, linregc2=1, linregerrA=1, linregerrQ=1, qregc1=1, qregc2=1, qregc3=1, qregerrA=1, qregerrQ=1,
-                               centroid=1, centroidNorm=SEGMENT, centroidUseAbsValues=1, normRegCoeff=0, normInputs=0, oldBuggyQerr=1)
+                               centroid=1, centroidNorm=SEGMENT, centroidUseAbsValues=1, normRegCoeff=0, normInputs=0, oldBuggyQerr=1,
+                               centroidRatioLimit=1, doRatioLimit=0)
         self.regression.update(regression or {})
         self.times = dict(upleveltime25=1, downleveltime25=1, upleveltime50=1, downleveltime50=1, upleveltime75=1, downleveltime75=1,
                           upleveltime90=1, downleveltime90=1, risetime=1, falltime=1, leftctime=1, rightctime=1, duration=1,
@@ -199,7 +200,10 @@ def contour(spec, x, period):
             if m["stddevNorm"]:
                 if m2 > 0:
                     ml = float(abs(mean)) if m["stddevNorm"] == 1 else float(mean)
-                    out.append(F32(sq / (ml if ml != 0 else 1.0)))
+                    if m["doRatioLimit"]:                          # functionalMoments.cpp:144-151
+                        out.append(_ratio_limit(F32(sq / ml), 10.0, 20.0) if ml != 0 else F32(20.0))
+                    else:
+                        out.append(F32(sq / (ml if ml != 0 else 1.0)))
                 else:
                     out.append(F32(0))
         elif f == "Percentiles":                                   # functionalPercentiles.cpp:338-430
@@ -217,6 +221,8 @@ def contour(spec, x, period):
             Nd = float(N)
             rng = float(F32(mx - mn))                                # FLOAT_DMEM expression
             rinv = 1.0 / rng if rng > 0 else 0.0
+            if rng <= 0:
+                rng = 1.0                                            # :151-157
             ii = np.arange(N, dtype=np.float64)
             num, num2 = (xd * ii).sum(), (xd * ii * ii).sum()
             asum = float(mean) * Nd
@@ -225,6 +231,8 @@ def contour(spec, x, period):
                 centroid = (np.abs(xd) * ii).sum() / asa if asa != 0 else 0.0
             else:
                 centroid = num / asum if asum != 0 else 0.0
+            if r["centroidRatioLimit"]:                              # :206-209, before the time normalisation
+                centroid = float(_ratio_limit(F32(centroid), float(F32(Nd)), float(F32(Nd))))
             if r["centroidNorm"] == SECOND:
                 centroid *= period
             elif r["centroidNorm"] == SEGMENT:
@@ -259,6 +267,11 @@ def contour(spec, x, period):
                 if r["normInputs"]:
                     e = e * rinv
                 qea, qeq = np.abs(e).sum(), (e * e).sum()
+            if r["doRatioLimit"]:                                    # :328-335
+                l1 = float(F32(rng / 10.0))
+                m = float(_ratio_limit(F32(m), l1, float(F32(rng / 10.0 + 0.01))))
+                a = float(_ratio_limit(F32(a), float(F32(math.sqrt(rng / 10.0))), float(F32(math.sqrt(rng / 10.0) + 0.01))))
+                b = float(_ratio_limit(F32(b), l1, float(F32(rng / 10.0 + 0.01))))
             if r["normRegCoeff"] == 1:
                 m *= Nd - 1.0; a *= (Nd - 1.0) ** 2; b *= Nd - 1.0
             elif r["normRegCoeff"] == 2:

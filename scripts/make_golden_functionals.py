@@ -66,10 +66,10 @@ def main():
             refrun.write_wav(wav, pcm, 16000, 1)
             open(os.path.join(d, "v.conf"), "w").write(var2)
             cmd = [refrun.SMILEXTRACT, "-C", os.path.join(d, "v.conf"), "-I", wav, "-l", "0"]
-            for lv in "DEFG":
+            for lv in "DEFGH":
                 cmd += ["-out" + lv, os.path.join(d, lv + ".csv")]
             subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            for lv in "DEFG":
+            for lv in "DEFGH":
                 n, r = csv_rows(os.path.join(d, lv + ".csv"))
                 out2["var%s_names" % lv] = np.array(n)
                 out2["var%s_%s" % (lv, key)] = r

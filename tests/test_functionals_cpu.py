@@ -23,7 +23,7 @@ SPEC_B = fo.Spec(["Percentiles", "Moments", "Extremes"], non_zero=1, master_norm
                  moments=dict(variance=1, stddev=0, skewness=0, kurtosis=0, amean=1, stddevNorm=2),
                  extremes=dict(max=0, min=0, range=1, maxpos=1, minpos=1, amean=0, maxameandist=1, minameandist=1))
 SPEC_C = fo.Spec(["Regression", "Percentiles", "Means"], non_zero=2, name_append="x",
-                 regression=dict(centroidNorm=SEC, centroidUseAbsValues=1, normRegCoeff=1, normInputs=1, oldBuggyQerr=0),
+                 regression=dict(centroidNorm=SEC, centroidUseAbsValues=1, centroidRatioLimit=0, normRegCoeff=1, normInputs=1, oldBuggyQerr=0),
                  percentiles=dict(quartile1=1, quartile2=1, quartile3=1, interp=0),
                  means=dict(amean=1, absmean=0, qmean=0, nzamean=0, nzabsmean=0, nzqmean=0, nzgmean=0, nnz=1, norm=S, norm_set=True))
 # second set (tests/configs/func_variants2.conf): the Times / Lpc / Segments / Peaks2 option sets of the shipped ComParE_2016 and
@@ -48,7 +48,12 @@ SPEC_G = fo.Spec(["Segments", "Peaks2", "Times"], master_norm=SEC, name_append="
                  segments=dict(maxNumSeg=1000, segmentationAlgorithm="eqX", X=0.0, numSegments=1, meanSegLen=1, segLenStddev=1, norm=SEC, norm_set=True),
                  peaks2=dict({k: 1 for k in fo.PEAKS2_NAMES}, norm=FR, norm_set=True, relThresh=0.35, dynRelThresh=1, doRatioLimit=0),
                  times=dict(norm=FR, norm_set=True, buggySecNorm=0))
-LEVELS2 = [("D", SPEC_D, slice(0, 32), -2), ("E", SPEC_E, slice(0, 16), 0), ("F", SPEC_F, slice(0, 32), -2), ("G", SPEC_G, slice(0, 16), 0)]
+SPEC_H = fo.Spec(["Regression", "Moments"], master_norm=S,
+                 regression=dict(linregerrA=0, qregerrA=0, centroid=1, centroidUseAbsValues=1, centroidRatioLimit=1, normRegCoeff=2, normInputs=1,
+                                 oldBuggyQerr=0, doRatioLimit=1),
+                 moments=dict(variance=0, stddev=1, skewness=0, kurtosis=0, amean=0, stddevNorm=1, doRatioLimit=1))
+LEVELS2 = [("D", SPEC_D, slice(0, 32), -2), ("E", SPEC_E, slice(0, 16), 0), ("F", SPEC_F, slice(0, 32), -2), ("G", SPEC_G, slice(0, 16), 0),
+           ("H", SPEC_H, slice(0, 32), -2)]
 
 # (tag, spec, columns of the 32-column lld;lld_de level, frames the functionals see relative to T = static frames)
 LEVELS = [("is09", fo.IS09, slice(0, 32), -2, "is09_func"), ("A", SPEC_A, slice(0, 32), -2, "varA"), ("B", SPEC_B, slice(0, 16), 0, "varB"),
@@ -178,7 +183,7 @@ def test_variant_configuration_names(tmp_path):
 def test_second_variant_configuration_names(tmp_path):
     conf = tmp_path / "v.conf"
     conf.write_text(open(os.path.join(HERE, "configs", "func_variants2.conf")).read().replace("REFCONF", REFCONF))
-    for lv in "DEFG":
+    for lv in "DEFGH":
         s = _session(str(conf), {"out" + lv: "x.csv"})
         assert s.element_names() == list(G2["var%s_names" % lv])
         s.close()

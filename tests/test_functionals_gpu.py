@@ -17,15 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def _cspec(spec):
     """oracle Spec -> ctypes spec"""
-    ex = {k: v for k, v in spec.extremes.items() if k not in ("norm_set",)}
-    ex["normIsSet"] = int(spec.extremes["norm_set"])
-    me = {k: v for k, v in spec.means.items() if k not in ("norm_set",)}
-    me["normIsSet"] = int(spec.means["norm_set"])
-    rg = dict(spec.regression)
-    rg["centroidRatioLimit"] = 0
-    return F.spec(spec.enabled, non_zero=spec.non_zero, master_norm=-1 if spec.master_norm is None else spec.master_norm,
-                  name_append=spec.name_append or "", extremes=ex, means=me, moments=dict(spec.moments),
-                  percentiles=dict(spec.percentiles), regression=rg)
+    return to_c_spec(spec)
 
 
 def _close(got, ref, rtol):
