@@ -397,6 +397,13 @@ OSM_B200_API int64_t     osm_b200_plan_num_frames(const osm_b200_plan *plan, int
  * end of input: the window processors of the level have each appended one frame by then, not yet all of them
  * (blocksize 1, core/windowProcessor.cpp:167-230); that is the contour the reference's functionals summarise */
 OSM_B200_API int64_t     osm_b200_plan_num_frames_first_eoi(const osm_b200_plan *plan, int64_t n_sample_frames);
+/* the same for levels behind the SHS pitch chain, whose length at that moment depends on the data: viterbi_frames = frames the
+ * cPitchSmootherViterbi level held when end of input was raised (osm_b200_plan_copy_seq_lag after a run; < 0: not known, the
+ * static frame count is assumed) */
+OSM_B200_API int64_t     osm_b200_plan_num_frames_first_eoi_v(const osm_b200_plan *plan, int64_t n_sample_frames, int64_t viterbi_frames);
+/* per utterance of the last run: frames of the Viterbi level before the end-of-input flush (-1 when the plan has no SHS pitch chain);
+ * synchronises the device */
+OSM_B200_API osm_b200_status osm_b200_plan_copy_seq_lag(osm_b200_plan *plan, int32_t *out, int32_t n_utt);
 
 /* number of distinct time stamps of those rows: frames of the level the first output field comes from, before its
  * window processors.  The rows a window processor appends at the end of input repeat the time stamp of the last

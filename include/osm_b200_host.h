@@ -117,6 +117,25 @@ OSM_B200_API int32_t osm_b200_write_csv_timed(const char *path, const float *row
                                               const char *const *names, double period, const char *instance_name,
                                               int32_t frame_index, int32_t frame_time, int64_t n_time_frames);
 
+/* ---- the value formatting of the sinks on the device (sinks.cu) ------------------------------------------------
+ * Rows a plan run left in HBM become file bytes there; osm_b200_session_extract_files* use these unless OSM_B200_DEVICE_SINKS=0.
+ *   osm_b200_device_format_csv : every value of every row as cCsvSink prints it ("%.0f" integer valued, "%e" otherwise,
+ *       iocore/csvSink.cpp:216-233), followed by `delim` (newline after the last value of a row), rows at d_text + r * slot_bytes
+ *       (slot_bytes >= osm_b200_device_csv_slot_bytes(K)), d_row_len[r] = bytes of row r, d_row_host[r] = 1 when the row holds a value
+ *       the device leaves to the host formatter (non-finite, |x| >= 1e15, an undecidable rounding: about 1e-7 of the values)
+ *   osm_b200_device_pack_htk   : cHtkSink's payload, float32 big endian (iocore/htkSink.cpp:183-206)
+ * Asynchronous on `stream` (cudaStream_t); return 0 on success. */
+OSM_B200_API int64_t osm_b200_device_csv_slot_bytes(int32_t n_elements);
+OSM_B200_API int32_t osm_b200_device_format_csv(const float *d_rows, int64_t n_rows, int32_t n_elements, char delim, char *d_text,
+                                                int64_t slot_bytes, int32_t *d_row_len, uint8_t *d_row_host, void *stream);
+OSM_B200_API int32_t osm_b200_device_pack_htk(const float *d_rows, int64_t n_values, uint32_t *d_out, void *stream);
+/* whole files from device rows (format on the device, copy, write): byte-identical to osm_b200_write_csv_timed / osm_b200_write_htk */
+OSM_B200_API int32_t osm_b200_write_csv_device(const char *path, const float *d_rows, int64_t n_rows, int32_t n_elements,
+                                               const char *const *names, double period, const char *instance_name,
+                                               int32_t frame_index, int32_t frame_time, int64_t n_time_frames);
+OSM_B200_API int32_t osm_b200_write_htk_device(const char *path, const float *d_rows, int64_t n_rows, int32_t n_elements, double period,
+                                               int32_t parm_kind);
+
 /* cArffSink's file format for rows already in host memory; targets[c] = value of class attribute c for every row
  * ("?" = unknown); append: add rows to an existing file without repeating the header */
 OSM_B200_API int32_t osm_b200_write_arff(const char *path, const float *rows, int64_t n_rows, int32_t n_elements,

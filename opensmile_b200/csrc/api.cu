@@ -1347,6 +1347,19 @@ osm_b200_status osm_b200_plan_run_host_resident(osm_b200_plan *pl, const void *p
 }
 
 int64_t osm_b200_plan_num_frames_first_eoi(const osm_b200_plan *pl, int64_t n) { return pl ? desc_num_frames_first_eoi(pl->d, n) : 0; }
+int64_t osm_b200_plan_num_frames_first_eoi_v(const osm_b200_plan *pl, int64_t n, int64_t v) { return pl ? desc_num_frames_first_eoi(pl->d, n, v) : 0; }
+
+osm_b200_status osm_b200_plan_copy_seq_lag(osm_b200_plan *pl, int32_t *out, int32_t n_utt)
+{
+  if (!pl || !out || n_utt < 0) return fail(OSM_B200_ERR_INVALID, "null argument");
+  for (int u = 0; u < n_utt; u++) out[u] = -1;
+  if (pl->device < 0 || pl->seqLagOp < 0 || n_utt == 0) return OSM_B200_OK;
+  CU(cudaSetDevice(pl->device));
+  CU(cudaDeviceSynchronize());
+  if (!pl->ops[pl->seqLagOp].dLag.p) return OSM_B200_OK;
+  CU(cudaMemcpy(out, pl->ops[pl->seqLagOp].dLag.p, sizeof(int) * (size_t)n_utt, cudaMemcpyDeviceToHost));
+  return OSM_B200_OK;
+}
 
 int32_t osm_b200_plan_last_launch_count(const osm_b200_plan *pl) { return pl ? pl->lastLaunches : 0; }
 

@@ -95,7 +95,7 @@ int64_t desc_num_frames(const PlanDesc &d, int64_t L)
     for (int ls : g.limitStreams) t = std::min<int64_t>(t, desc_num_static_frames(d, ls, L));
     if (t <= 0) return 0;
     for (const auto &s : g.stages) t += s.win;
-    if (best < 0 || t < best) best = t;
+    if (best < 0 || (d.padRows ? t > best : t < best)) best = t;
   }
   return best < 0 ? 0 : best;
 }
@@ -107,13 +107,17 @@ int64_t desc_num_frames(const PlanDesc &d, int64_t L)
 // once, never reads again -- so the frames the window processors append later are NOT part of the summary unless the
 // configuration sets EOIlevel (the shipped IS09 / IS10 files do not).  Verified against the reference's functionals rows
 // (tests/test_functionals_cpu.py).
-int64_t desc_num_frames_first_eoi(const PlanDesc &d, int64_t L)
+// Levels behind the SHS pitch chain (lagKind != 0): the Viterbi smoother has written V frames when end of input is raised
+// (data dependent, osm_b200_plan_copy_seq_lag) and adds one in the first EOI tick like every other component, so the chain's
+// static level holds min(V + 1, T) frames there (pinned on the reference's ComParE_2016 functionals rows).
+int64_t desc_num_frames_first_eoi(const PlanDesc &d, int64_t L, int64_t V)
 {
   int64_t best = -1;
   for (const auto &g : d.groups) {
     int64_t t = desc_num_static_frames(d, g.stream, L);
     for (int ls : g.limitStreams) t = std::min<int64_t>(t, desc_num_static_frames(d, ls, L));
     if (t <= 0) return 0;
+    if (g.lagKind != 0 && V >= 0) t = std::min<int64_t>(t, V + 1);
     int64_t c0 = t, fin = t;
     for (const auto &s : g.stages) { c0 = std::max<int64_t>(c0 - s.win, 0); fin += s.win; }
     const int64_t avail = g.stages.empty() ? t : std::min<int64_t>(c0 + 1, fin);
@@ -180,6 +184,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
   };
 
   d = PlanDesc();
+  d.padRows = R.prod(outputLevel)->type == OSM_B200_C_VECTORCONCAT && strcmp(R.prod(outputLevel)->name, "_unionconcat") == 0;
   // find or create the stream of a chain; needFft extends an existing time-only stream
   auto get_stream = [&](const ChainInfo &ci, bool needFft, int &idx) -> osm_b200_status {
     for (size_t s = 0; s < d.streams.size(); s++) {

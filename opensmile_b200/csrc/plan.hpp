@@ -248,6 +248,9 @@ struct PlanDesc {
   std::vector<OutGroup> groups;
   int nOut = 0;
   std::vector<std::string> names;  // output element names
+  // The output level is the host layer's "_unionconcat" of the input levels of several cFunctionals instances: every level keeps
+  // its own length (no min over the levels), the output has as many rows as the longest (rows past a level's end are not read)
+  bool padRows = false;
   const FrontEnd &fe0() const { return streams[0].fe; }
 };
 
@@ -255,7 +258,7 @@ struct PlanDesc {
 osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char *outputLevel,
                               PlanDesc &out, std::string &err);
 int64_t desc_num_frames(const PlanDesc &d, int64_t nSampleFrames);
-int64_t desc_num_frames_first_eoi(const PlanDesc &d, int64_t nSampleFrames);
+int64_t desc_num_frames_first_eoi(const PlanDesc &d, int64_t nSampleFrames, int64_t viterbiFrames = -1);
 int64_t desc_num_static_frames(const PlanDesc &d, int stream, int64_t nSampleFrames);
 int64_t desc_max_static_frames(const PlanDesc &d, int64_t nSampleFrames);
 

@@ -823,7 +823,9 @@ bool read_wav(const char *path, Wav &w, std::string &err)    // 16-bit PCM RIFF 
 }
 
 // HTK parameter file (iocore/htkSink.cpp:90-106 header, :183-206 rows): big-endian
-bool write_htk(const char *path, const float *rows, int64_t n, int K, double period, int parmKind, std::string &err)
+// `packed` (optional): the payload already in file byte order (sinks.cu: htk_pack_kernel), n * K 32-bit words
+bool write_htk(const char *path, const float *rows, int64_t n, int K, double period, int parmKind, std::string &err,
+               const uint32_t *packed = nullptr)
 {
   FILE *f = fopen(path, "wb");
   if (!f) { err = std::string("cannot write '") + path + "'"; return false; }
@@ -833,6 +835,11 @@ bool write_htk(const char *path, const float *rows, int64_t n, int K, double per
   be32(period <= 0.0 ? 100000u : (uint32_t)round(period * 10000000.0));
   be16((uint16_t)(sizeof(float) * K));
   be16((uint16_t)parmKind);
+  if (packed) {
+    fwrite(packed, 4, (size_t)n * K, f);
+    fclose(f);
+    return true;
+  }
   std::vector<unsigned char> buf((size_t)K * 4);
   for (int64_t r = 0; r < n; r++) {
     for (int k = 0; k < K; k++) {
@@ -892,8 +899,12 @@ struct TextBuf {
 struct CsvOpts { bool printHeader = true, timestamp = true, number = true; int prname = 0; char delim = ';'; std::string instName; };
 
 // iocore/csvSink.cpp:150-235
+// value text of the rows formatted on the device (sinks.cu: csv_format_kernel): row r at text + r * slot, len[r] bytes ending in the
+// newline; host[r] != 0: the row holds a value the device left to the host formatter
+struct DevText { const char *text; int64_t slot; const int32_t *len; const uint8_t *host; };
+
 bool write_csv(const char *path, const float *rows, int64_t n, int K, const std::vector<std::string> &names, double period,
-               const CsvOpts &o, std::string &err, int64_t nTimeFrames = 0)
+               const CsvOpts &o, std::string &err, int64_t nTimeFrames = 0, const DevText *dt = nullptr)
 {
   FILE *f = fopen(path, "w");
   if (!f) { err = std::string("cannot write '") + path + "'"; return false; }
@@ -914,6 +925,7 @@ bool write_csv(const char *path, const float *rows, int64_t n, int K, const std:
     if (o.number) { tb.fmt_ld((long)r); tb.ch(o.delim); }
     // rows appended by a window processor at the end of input carry a copy of the last frame's time stamp
     if (o.timestamp) { tb.fmt_f6((double)((nTimeFrames > 0 && r > nTimeFrames - 1) ? nTimeFrames - 1 : r) * period); tb.ch(o.delim); }
+    if (dt && !dt->host[r]) { tb.str(dt->text + r * dt->slot, (size_t)dt->len[r]); continue; }
     for (int k = 0; k < K; k++) {
       const float v = rows[r * K + k];
       if (v == floorf(v)) tb.fmt_f0(v); else tb.fmt_e(v);
@@ -1070,7 +1082,7 @@ static osm_b200_status get_plan(osm_b200_session *s, double sampleRate, int nCha
 static osm_b200_status desc_plan(osm_b200_session *s, double sampleRate, int nChan, const std::vector<std::string> &levels, osm_b200_plan **out)
 {
   std::vector<osm_b200_component> cs;
-  for (const osm_b200_component &c : s->comps) if (strcmp(c.name, "_sinkconcat") != 0) cs.push_back(c);
+  for (const osm_b200_component &c : s->comps) if (strcmp(c.name, "_sinkconcat") != 0 && strcmp(c.name, "_unionconcat") != 0) cs.push_back(c);
   int wave = -1;
   for (size_t i = 0; i < cs.size(); i++) if (cs[i].type == OSM_B200_C_WAVESOURCE) wave = (int)i;
   cs[wave].u.wavesource.sampleRate = sampleRate;
@@ -1392,17 +1404,19 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
   if (lvl.find(';') != std::string::npos) {
     osm_b200_component c;
     osm_b200_component_defaults(OSM_B200_C_VECTORCONCAT, &c);
-    snprintf(c.name, sizeof c.name, "%s", "_sinkconcat");
+    // the union of the input levels of several cFunctionals instances keeps every level's own length (graph.cpp: padRows)
+    const char *cname = (s->hasFunc && s->unionLevels.size() > 1) ? "_unionconcat" : "_sinkconcat";
+    snprintf(c.name, sizeof c.name, "%s", cname);
     std::stringstream ss(lvl);
     std::string one;
     while (std::getline(ss, one, ';')) {
       one = trim(one);
       if (!one.empty() && c.n_inputs < OSM_B200_MAX_INPUTS) snprintf(c.reader_dmLevel[c.n_inputs++], OSM_B200_NAME_LEN, "%s", one.c_str());
     }
-    snprintf(c.writer_dmLevel, sizeof c.writer_dmLevel, "%s", "_sinkconcat");
+    snprintf(c.writer_dmLevel, sizeof c.writer_dmLevel, "%s", cname);
     c.u.vectorconcat.processArrayFields = 0;     // a reader's level concatenation keeps every field
     s->comps.push_back(c);
-    lvl = "_sinkconcat";
+    lvl = cname;
   }
   s->outputLevel = lvl;
   // validate the graph now (description-only plan at a nominal format) so that errors surface at open
@@ -1499,6 +1513,7 @@ osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t 
         const int64_t n = std::min<int64_t>(osm_b200_plan_num_frames_first_eoi(f->desc[i] ? f->desc[i] : p, uttOff[u + 1] - uttOff[u]), lldOff[u + 1] - lldOff[u]);
         nRows[i][live.size()] = n;
         all = all && n > 0;
+        if (getenv("OSM_B200_DEBUG_FUNC")) fprintf(stderr, "functionals instance %zu: utterance %d sees %lld rows (level rows %lld)\n", i, u, (long long)n, (long long)(lldOff[u + 1] - lldOff[u]));
       }
       if (all) { rowOff[live.size()] = lldOff[u]; live.push_back(u); }
       frameOff[u + 1] = frameOff[u] + (all ? 1 : 0);
@@ -1509,6 +1524,19 @@ osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t 
     const float *dRows = nullptr;
     st = osm_b200_plan_run_host_resident(p, pcm, uttOff, nUtt, lldOff.data(), &dRows);
     if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    // levels behind the SHS pitch chain: their length at the first end-of-input tick follows the Viterbi level's (data dependent)
+    {
+      std::vector<int32_t> lag((size_t)nUtt, -1);
+      st = osm_b200_plan_copy_seq_lag(p, lag.data(), nUtt);
+      if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+      for (size_t k = 0; k < live.size(); k++) {
+        const int u = live[k];
+        if (lag[u] < 0) continue;
+        for (size_t i = 0; i < nI; i++)
+          nRows[i][k] = std::max<int64_t>(0, std::min<int64_t>(osm_b200_plan_num_frames_first_eoi_v(f->desc[i] ? f->desc[i] : p, uttOff[u + 1] - uttOff[u], lag[u]),
+                                                               lldOff[u + 1] - lldOff[u]));
+      }
+    }
     const int KF = f->total;
     const size_t need = live.size() * (size_t)KF;
     if (s->funcOutCap < need) {
@@ -1572,7 +1600,8 @@ static bool parallel_files(int n, Fn fn, std::string &err, bool serial = false)
 // the sinks of one batch: rows [fo[k], fo[k+1]) of file idx[k] -> its HTK / CSV / ARFF files, files in parallel
 static bool write_batch(osm_b200_session *s, const std::vector<int> &idx, const int64_t *fo, const int64_t *nTime, const float *rows, int K,
                         const std::vector<std::string> &names, double period, const char *const *htkPaths, const char *const *csvPaths,
-                        const char *const *arffPaths, int64_t *framesOut, std::string &err)
+                        const char *const *arffPaths, int64_t *framesOut, std::string &err, const DevText *dt = nullptr,
+                        const uint32_t *packed = nullptr)
 {
   // several inputs may name the same output file (cArffSink / cCsvSink with append=1 collect every input in one file):
   // those files must be written one after the other, in input order
@@ -1589,8 +1618,10 @@ static bool write_batch(osm_b200_session *s, const std::vector<int> &idx, const 
     const float *r = rows + (size_t)fo[k] * K;
     const int64_t nr = fo[k + 1] - fo[k];
     if (framesOut) framesOut[i] = nr;
-    if (htkPaths && htkPaths[i] && !write_htk(htkPaths[i], r, nr, K, period, s->parmKind, e)) return false;
-    if (csvPaths && csvPaths[i] && !write_csv(csvPaths[i], r, nr, K, names, period, s->csv, e, nTime[k])) return false;
+    if (htkPaths && htkPaths[i] && !write_htk(htkPaths[i], r, nr, K, period, s->parmKind, e, packed ? packed + (size_t)fo[k] * K : nullptr)) return false;
+    DevText dk;
+    if (dt) dk = DevText{dt->text + fo[k] * dt->slot, dt->slot, dt->len + fo[k], dt->host + fo[k]};
+    if (csvPaths && csvPaths[i] && !write_csv(csvPaths[i], r, nr, K, names, period, s->csv, e, nTime[k], dt ? &dk : nullptr)) return false;
     if (arffPaths && arffPaths[i] && !write_arff(arffPaths[i], r, nr, K, names, period, s->arff, e, nTime[k])) return false;
     return true;
   }, err, shared);
@@ -1622,12 +1653,50 @@ osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t
     st = osm_b200_plan_frame_offsets(p, off.data(), (int)g.second.size(), fo.data());
     if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
     const int K = osm_b200_plan_num_elements(p);
-    std::vector<float> rows((size_t)fo.back() * K + 1);
-    st = osm_b200_plan_run_host(p, pcm.data(), off.data(), (int)g.second.size(), fo.data(), rows.data());
-    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    const int64_t nR = fo.back();
+    std::vector<float> rows((size_t)nR * K + 1);
     std::vector<std::string> names(K);
     for (int k = 0; k < K; k++) names[k] = osm_b200_plan_element_name(p, k);
     for (size_t k = 0; k < g.second.size(); k++) nTime[k] = osm_b200_plan_num_time_frames(p, off[k + 1] - off[k]);
+    // Device sinks (sinks.cu): the rows stay in HBM after the plan run, the CSV value text and the HTK payload are produced there
+    // and copied next to the float rows; the host threads add the per-row prefixes and write.  OSM_B200_DEVICE_SINKS=0: host formatting.
+    static const bool devSinks = [] { const char *e = getenv("OSM_B200_DEVICE_SINKS"); return !(e && e[0] == '0'); }();
+    const bool wantCsv = csvPaths != nullptr, wantHtk = htkPaths != nullptr;
+    if (devSinks && nR > 0 && (wantCsv || wantHtk)) {
+      const float *dRows = nullptr;
+      st = osm_b200_plan_run_host_resident(p, pcm.data(), off.data(), (int)g.second.size(), fo.data(), &dRows);
+      if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+      const int64_t slot = osm_b200_device_csv_slot_bytes(K);
+      char *dText = nullptr; int32_t *dLen = nullptr; uint8_t *dHost = nullptr; uint32_t *dPack = nullptr;
+      std::vector<char> text; std::vector<int32_t> len; std::vector<uint8_t> hostFlag; std::vector<uint32_t> packed;
+      bool ok = cudaMemcpy(rows.data(), dRows, (size_t)nR * K * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+      if (ok && wantCsv) {
+        text.resize((size_t)nR * slot); len.resize((size_t)nR); hostFlag.resize((size_t)nR);
+        ok = cudaMalloc(reinterpret_cast<void **>(&dText), text.size()) == cudaSuccess && cudaMalloc(reinterpret_cast<void **>(&dLen), len.size() * 4) == cudaSuccess &&
+             cudaMalloc(reinterpret_cast<void **>(&dHost), hostFlag.size()) == cudaSuccess &&
+             osm_b200_device_format_csv(dRows, nR, K, s->csv.delim, dText, slot, dLen, dHost, nullptr) == 0 &&
+             cudaMemcpy(text.data(), dText, text.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaMemcpy(len.data(), dLen, len.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaMemcpy(hostFlag.data(), dHost, hostFlag.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+      }
+      if (ok && wantHtk) {
+        packed.resize((size_t)nR * K);
+        ok = cudaMalloc(reinterpret_cast<void **>(&dPack), packed.size() * 4) == cudaSuccess && osm_b200_device_pack_htk(dRows, nR * K, dPack, nullptr) == 0 &&
+             cudaMemcpy(packed.data(), dPack, packed.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+      }
+      if (dText) cudaFree(dText);
+      if (dLen) cudaFree(dLen);
+      if (dHost) cudaFree(dHost);
+      if (dPack) cudaFree(dPack);
+      if (!ok) return hfail(OSM_B200_ERR_CUDA, std::string("device sinks: ") + cudaGetErrorString(cudaGetLastError()));
+      const DevText dt{text.data(), slot, len.data(), hostFlag.data()};
+      if (!write_batch(s, g.second, fo.data(), nTime.data(), rows.data(), K, names, osm_b200_plan_frame_period(p), htkPaths, csvPaths, arffPaths, framesOut, err,
+                       wantCsv ? &dt : nullptr, wantHtk ? packed.data() : nullptr))
+        return hfail(OSM_B200_ERR_INVALID, err);
+      continue;
+    }
+    st = osm_b200_plan_run_host(p, pcm.data(), off.data(), (int)g.second.size(), fo.data(), rows.data());
+    if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
     if (!write_batch(s, g.second, fo.data(), nTime.data(), rows.data(), K, names, osm_b200_plan_frame_period(p), htkPaths, csvPaths, arffPaths, framesOut, err))
       return hfail(OSM_B200_ERR_INVALID, err);
   }
@@ -1680,6 +1749,54 @@ const char *osm_b200_session_sink_options(osm_b200_session *s)
 }
 
 const char *osm_b200_host_last_error(void) { return g_herr.empty() ? osm_b200_last_error() : g_herr.c_str(); }
+
+int32_t osm_b200_write_htk_device(const char *path, const float *d_rows, int64_t n, int32_t K, double period, int32_t parmKind)
+{
+  if (!path || (n > 0 && !d_rows) || K <= 0 || n < 0) { g_herr = "null argument"; return 1; }
+  std::vector<uint32_t> packed((size_t)n * K + 1);
+  uint32_t *dPack = nullptr;
+  bool ok = n == 0 || (cudaMalloc(reinterpret_cast<void **>(&dPack), (size_t)n * K * 4) == cudaSuccess && osm_b200_device_pack_htk(d_rows, n * K, dPack, nullptr) == 0 &&
+                       cudaMemcpy(packed.data(), dPack, (size_t)n * K * 4, cudaMemcpyDeviceToHost) == cudaSuccess);
+  if (dPack) cudaFree(dPack);
+  if (!ok) { g_herr = std::string("device sinks: ") + cudaGetErrorString(cudaGetLastError()); return 1; }
+  std::string err;
+  if (write_htk(path, nullptr, n, K, period, parmKind, err, packed.data())) return 0;
+  g_herr = err;
+  return 1;
+}
+
+int32_t osm_b200_write_csv_device(const char *path, const float *d_rows, int64_t n, int32_t K, const char *const *names, double period,
+                                  const char *instName, int32_t frameIndex, int32_t frameTime, int64_t nTimeFrames)
+{
+  if (!path || (n > 0 && !d_rows) || K <= 0 || n < 0 || !names) { g_herr = "null argument"; return 1; }
+  CsvOpts o;
+  o.number = frameIndex != 0; o.timestamp = frameTime != 0;
+  if (instName && instName[0]) { o.prname = 1; o.instName = instName; }
+  std::vector<std::string> nm(K);
+  for (int k = 0; k < K; k++) nm[k] = names[k];
+  const int64_t slot = osm_b200_device_csv_slot_bytes(K);
+  std::vector<float> rows((size_t)n * K + 1);
+  std::vector<char> text((size_t)n * slot + 1);
+  std::vector<int32_t> len((size_t)n + 1);
+  std::vector<uint8_t> hostFlag((size_t)n + 1);
+  char *dText = nullptr; int32_t *dLen = nullptr; uint8_t *dHost = nullptr;
+  bool ok = n == 0 || (cudaMalloc(reinterpret_cast<void **>(&dText), (size_t)n * slot) == cudaSuccess && cudaMalloc(reinterpret_cast<void **>(&dLen), (size_t)n * 4) == cudaSuccess &&
+                       cudaMalloc(reinterpret_cast<void **>(&dHost), (size_t)n) == cudaSuccess &&
+                       osm_b200_device_format_csv(d_rows, n, K, o.delim, dText, slot, dLen, dHost, nullptr) == 0 &&
+                       cudaMemcpy(text.data(), dText, (size_t)n * slot, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                       cudaMemcpy(len.data(), dLen, (size_t)n * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                       cudaMemcpy(hostFlag.data(), dHost, (size_t)n, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                       cudaMemcpy(rows.data(), d_rows, (size_t)n * K * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess);
+  if (dText) cudaFree(dText);
+  if (dLen) cudaFree(dLen);
+  if (dHost) cudaFree(dHost);
+  if (!ok) { g_herr = std::string("device sinks: ") + cudaGetErrorString(cudaGetLastError()); return 1; }
+  const DevText dt{text.data(), slot, len.data(), hostFlag.data()};
+  std::string err;
+  if (write_csv(path, rows.data(), n, K, nm, period, o, err, nTimeFrames, &dt)) return 0;
+  g_herr = err;
+  return 1;
+}
 
 int32_t osm_b200_write_htk(const char *path, const float *rows, int64_t n, int32_t K, double period, int32_t parmKind)
 {

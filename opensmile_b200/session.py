@@ -146,3 +146,27 @@ def write_arff(path, rows, names, period, relation="smile", instance_name=None, 
                              int(frame_index), int(frame_time), len(classes), _strs([c[0] for c in classes]),
                              _strs([c[1] for c in classes]), _strs([c[2] for c in classes]), int(append), int(n_time_frames)):
         raise IOError(L.osm_b200_host_last_error().decode())
+
+
+def _dptr(buf):
+    return C.c_void_p(buf.data_ptr() if hasattr(buf, "data_ptr") else int(buf))
+
+
+def write_htk_device(path, d_rows, n_rows, n_elements, period, parm_kind=9):
+    """cHtkSink's file from rows resident in device memory: the big-endian payload is packed on the device (sinks.cu)"""
+    L = capi.lib()
+    L.osm_b200_write_htk_device.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_int32]
+    if L.osm_b200_write_htk_device(str(path).encode(), _dptr(d_rows), int(n_rows), int(n_elements), float(period), parm_kind):
+        raise IOError(L.osm_b200_host_last_error().decode())
+
+
+def write_csv_device(path, d_rows, n_rows, names, period, instance_name=None, frame_index=True, frame_time=True, n_time_frames=0):
+    """cCsvSink's file from rows resident in device memory: every value is formatted on the device (sinks.cu, text_format.cuh),
+    the host adds the per-row prefix; byte-identical to write_csv"""
+    L = capi.lib()
+    L.osm_b200_write_csv_device.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), C.c_double,
+                                            C.c_char_p, C.c_int32, C.c_int32, C.c_int64]
+    if L.osm_b200_write_csv_device(str(path).encode(), _dptr(d_rows), int(n_rows), len(names), _strs(names), float(period),
+                                   instance_name.encode() if instance_name is not None else None, int(frame_index), int(frame_time),
+                                   int(n_time_frames)):
+        raise IOError(L.osm_b200_host_last_error().decode())

@@ -129,3 +129,37 @@ def test_shipped_is09_configuration_end_to_end():
         err = (np.abs(rows[r] - ref).reshape(32, 12) / (fam + 1e-12))
         worst = {names[int(i) * 12 + int(j)]: float(err[i, j]) for i, j in zip(*np.nonzero(err >= 1e-5))}
         assert not worst, (key, worst)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "compare16")), reason="reference configuration files not built (make -C oracle ref)")
+def test_shipped_compare16_functionals_end_to_end():
+    """config/compare16/ComParE_2016.conf -csvoutput unchanged: 6373 features = six cFunctionals instances (Extremes, Percentiles,
+    Moments, Segments, Times, Lpc, Means, Regression, Peaks2) on column subsets of the 130 LLD columns, from PCM, against the
+    reference's row.  Per functional value (name suffix): 1e-5 of that value's largest magnitude over the contours; the few
+    discontinuous ones (positions, counts, percentile picks on plateaus) may flip on single contours and are counted."""
+    from opensmile_b200.session import Session
+    GC = np.load(os.path.join(HERE, "golden", "compare16_func.npz"))
+    names = list(GC["names"])
+    rec = np.load(os.path.join(HERE, "golden", "egemaps_recordings.npz"))["pcm_opensmile_16k"]
+    pcms = [mixed_pcm(24000, 16000, seed=3), voiced_pcm(32000, 16000, seed=7), rec]
+    off = np.concatenate([[0], np.cumsum([len(x) for x in pcms])]).astype(np.int64)
+    s = Session(os.path.join(REFCONF, "compare16", "ComParE_2016.conf"), options={"csvoutput": "f.csv"}, device=0)
+    assert s.element_names() == names
+    rows, fo_ = s.extract_pcm(np.concatenate(pcms), off, 16000.0, 1)
+    s.close()
+    assert list(fo_) == [0, 1, 2, 3] and rows.shape == (3, 6373)
+    suffix = np.array([n.rsplit("_", 1)[1] for n in names])
+    report = {}
+    for r, key in enumerate(("m24k", "v32k", "rec")):
+        ref = GC["func_" + key][0]
+        bad_total = 0
+        for sfx in np.unique(suffix):
+            idx = np.nonzero(suffix == sfx)[0]
+            scale = np.abs(ref[idx]).max() + 1e-12
+            err = np.abs(rows[r, idx] - ref[idx]) / scale
+            bad = idx[err > 1e-5]
+            if bad.size:
+                report[(key, sfx)] = (int(bad.size), float(err.max()), names[int(bad[0])])
+                bad_total += int(bad.size)
+        assert bad_total <= 0.005 * len(names), (key, bad_total, report)
+    print("compare16 functionals: values beyond 1e-5 of their family's scale:", report)

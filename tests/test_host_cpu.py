@@ -130,3 +130,15 @@ def test_text_sink_number_formatting_equals_printf():
     exe = "/tmp/osm_test_fmt_check"
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "native", "fmt_check.cpp")])
     subprocess.check_call([exe], stdout=subprocess.DEVNULL)
+
+
+def test_device_text_formatter_equals_printf():
+    """opensmile_b200/csrc/text_format.cuh (the cCsvSink value format of the device sinks) compiled for the host: identical to printf
+    on millions of values -- random bit patterns, LLD-sized decimals and their neighbours, dyadic ties, powers of ten, integers --
+    and it leaves at most ~1e-6 of the in-range values to the host formatter"""
+    exe = "/tmp/osm_fmt_device_check_%d" % os.getuid()
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "native", "fmt_device_check.cpp")])
+    out = subprocess.run([exe, "3000000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    checked, bad, uncertain = (int(x) for x in out.stdout.split())
+    assert bad == 0 and checked > 5000000 and uncertain <= checked * 2e-6, out.stdout

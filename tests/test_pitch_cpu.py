@@ -141,8 +141,8 @@ def _compare16_conf():
 
 def test_compare16_sink_selection():
     """Which sink is active decides the plan: the LLD sinks read lld;lld_de (130 columns, both give the same
-    plan); the summary sinks (-O / -csvoutput) read the cFunctionals level, which is off the supported path and
-    is rejected by naming the component; without any file name there is nothing to compute."""
+    plan); the summary sinks (-O / -csvoutput) read the concatenation of the six cFunctionals levels: 6373 features on the
+    union of their input levels; without any file name there is nothing to compute."""
     from opensmile_b200 import capi
     from opensmile_b200.session import Session, SessionError
     conf = _compare16_conf()
@@ -157,10 +157,10 @@ def test_compare16_sink_selection():
     c = Session(conf, options={"lldarffoutput": "x.arff"}, device=-1)      # the LLD ARFF sink reads the same levels
     assert len(c.element_names(16000.0, 1)) == 130
     c.close()
-    for opts in ({"csvoutput": "x.csv"}, {"O": "x.arff"}):   # summaries: cDataSelector / cFunctionals are upstream of `func`
-        with pytest.raises(SessionError) as e:
-            Session(conf, options=opts, device=-1)
-        assert e.value.status == capi.ERR_UNSUPPORTED and "not on the supported LLD path" in str(e.value), str(e.value)
+    for opts in ({"csvoutput": "x.csv"}, {"O": "x.arff"}):   # summaries: six cFunctionals instances behind a cVectorConcat
+        d = Session(conf, options=opts, device=-1)
+        assert len(d.element_names(16000.0, 1)) == 6373
+        d.close()
     with pytest.raises(SessionError) as e:               # nothing requested
         Session(conf, device=-1)
     assert "no active sink" in str(e.value)
