@@ -108,8 +108,9 @@ int64_t desc_num_frames(const PlanDesc &d, int64_t L)
 // configuration sets EOIlevel (the shipped IS09 / IS10 files do not).  Verified against the reference's functionals rows
 // (tests/test_functionals_cpu.py).
 // Levels behind the SHS pitch chain (lagKind != 0): the Viterbi smoother has written V frames when end of input is raised
-// (data dependent, osm_b200_plan_copy_seq_lag) and adds one in the first EOI tick like every other component, so the chain's
-// static level holds min(V + 1, T) frames there (pinned on the reference's ComParE_2016 functionals rows).
+// (data dependent, osm_b200_plan_copy_seq_lag); cPitchJitter does not run while end of input is set (lld/pitchJitter.cpp:593), so the
+// chain's static level still holds min(V, T) frames in the first EOI tick: a smoother behind it ends at V rows, its delta at V - 2
+// (pinned on the reference's ComParE_2016 functionals rows: V = 143 / 193 / 198 -> 143 | 141, 193 | 191, 198 | 196).
 int64_t desc_num_frames_first_eoi(const PlanDesc &d, int64_t L, int64_t V)
 {
   int64_t best = -1;
@@ -117,7 +118,7 @@ int64_t desc_num_frames_first_eoi(const PlanDesc &d, int64_t L, int64_t V)
     int64_t t = desc_num_static_frames(d, g.stream, L);
     for (int ls : g.limitStreams) t = std::min<int64_t>(t, desc_num_static_frames(d, ls, L));
     if (t <= 0) return 0;
-    if (g.lagKind != 0 && V >= 0) t = std::min<int64_t>(t, V + 1);
+    if (g.lagKind != 0 && V >= 0) t = std::min<int64_t>(t, V);
     int64_t c0 = t, fin = t;
     for (const auto &s : g.stages) { c0 = std::max<int64_t>(c0 - s.win, 0); fin += s.win; }
     const int64_t avail = g.stages.empty() ? t : std::min<int64_t>(c0 + 1, fin);

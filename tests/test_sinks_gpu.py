@@ -17,12 +17,14 @@ def _rows(seed, n, k):
     rng = np.random.default_rng(seed)
     r = (rng.standard_normal((n, k)) * 10.0 ** rng.integers(-9, 6, size=(1, k))).astype(np.float32)
     r[:, 0] = np.round(r[:, 0])                                  # integer valued -> "%.0f"
-    r[:, 1] = np.ldexp(rng.integers(1, 4096, n) * 2 + 1, rng.integers(-40, 10, n)).astype(np.float32)   # dyadic: exact ties
-    r[::7, 2] = 0.0
-    r[1::7, 2] = -0.0
-    r[:, 3] = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)            # any bit pattern (nan / inf / denormal)
-    r[5, 4] = 1e16
-    r[6, 4] = 9.9999995e6
+    if k > 3:
+        r[:, 1] = np.ldexp(rng.integers(1, 4096, n) * 2 + 1, rng.integers(-40, 10, n)).astype(np.float32)   # dyadic: exact ties
+        r[::7, 2] = 0.0
+        r[1::7, 2] = -0.0
+        r[:, 3] = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)            # any bit pattern (nan / inf / denormal)
+    if n > 6 and k > 4:
+        r[5, 4] = 1e16
+        r[6, 4] = 9.9999995e6
     return r
 
 
