@@ -27,14 +27,25 @@ struct MagS { const float *m; __device__ __forceinline__ float operator()(int b)
 // |p0/2 + p(N/2)/2 (-1)^j + sum_{k=1}^{N/2-1} p_k cos(2 pi j k / N)| / nb, p_k = mag_k^2 (float product)
 struct AcfWarp {
   const float *m; int nb, N; const double *cosTab; int lane;
+  // The peak search probes neighbouring lags again and again (isPeak reads x(n) twice and x(n-1), x(n+1); the outward walk then
+  // moves by one): the last four lags are kept.  Every lane holds the same (lag, value) pairs, so the look-up is warp uniform.
+  mutable int cj0 = -1, cj1 = -1, cj2 = -1, cj3 = -1, nextSlot = 0;
+  mutable float cv0 = 0.f, cv1 = 0.f, cv2 = 0.f, cv3 = 0.f;
   __device__ __forceinline__ float operator()(int j) const
   {
+    if (j == cj0) return cv0;
+    if (j == cj1) return cv1;
+    if (j == cj2) return cv2;
+    if (j == cj3) return cv3;
     double s = 0.0;
     for (int k = 1 + lane; k < N / 2; k += 32) s += (double)(m[k] * m[k]) * cosTab[(j * k) & (N - 1)];
     if (lane == 0) s += 0.5 * (double)(m[0] * m[0]) + 0.5 * (double)(m[N / 2] * m[N / 2]) * ((j & 1) ? -1.0 : 1.0);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    return (float)fabs(s) / (float)nb;
+    const float v = (float)fabs(s) / (float)nb;
+    if (nextSlot == 0) { cj0 = j; cv0 = v; } else if (nextSlot == 1) { cj1 = j; cv1 = v; } else if (nextSlot == 2) { cj2 = j; cv2 = v; } else { cj3 = j; cv3 = v; }
+    nextSlot = (nextSlot + 1) & 3;
+    return v;
   }
 };
 

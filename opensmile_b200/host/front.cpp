@@ -789,32 +789,44 @@ bool read_wav(const char *path, Wav &w, std::string &err)    // 16-bit PCM RIFF 
 {
   FILE *f = fopen(path, "rb");
   if (!f) { err = std::string("cannot open '") + path + "'"; return false; }
+  // chunk sizes come from the file: every one is clamped to what the file still holds before anything is allocated
+  long fileSize = 0;
+  if (fseek(f, 0, SEEK_END) == 0) fileSize = ftell(f);
+  if (fileSize < 12 || fseek(f, 0, SEEK_SET) != 0) { fclose(f); err = std::string(path) + ": not a RIFF/WAVE file"; return false; }
   unsigned char h[12];
   if (fread(h, 1, 12, f) != 12 || memcmp(h, "RIFF", 4) || memcmp(h + 8, "WAVE", 4)) { fclose(f); err = std::string(path) + ": not a RIFF/WAVE file"; return false; }
   bool fmtOk = false;
-  int bits = 0, fmtTag = 0;
+  int bits = 0, fmtTag = 0, blockAlign = 0;
   for (;;) {
     unsigned char ch[8];
     if (fread(ch, 1, 8, f) != 8) break;
-    const uint32_t sz = ch[4] | (ch[5] << 8) | (ch[6] << 16) | ((uint32_t)ch[7] << 24);
+    uint32_t sz = ch[4] | (ch[5] << 8) | (ch[6] << 16) | ((uint32_t)ch[7] << 24);
+    const long here = ftell(f);
+    if (here < 0) break;
+    const uint32_t left = (uint32_t)std::min<long>(fileSize - here, 0x7fffffffL);
     if (!memcmp(ch, "fmt ", 4)) {
+      if (sz < 16 || sz > left || sz > 4096) break;
       std::vector<unsigned char> b(sz);
-      if (fread(b.data(), 1, sz, f) != sz || sz < 16) break;
+      if (fread(b.data(), 1, sz, f) != sz) break;
       fmtTag = b[0] | (b[1] << 8); w.nChan = b[2] | (b[3] << 8);
       w.sampleRate = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+      blockAlign = b[12] | (b[13] << 8);
       bits = b[14] | (b[15] << 8);
+      if (w.nChan <= 0 || w.sampleRate <= 0) { fclose(f); err = std::string(path) + ": invalid WAV header (channels / sample rate)"; return false; }
       fmtOk = true;
-      if (sz & 1) fseek(f, 1, SEEK_CUR);
+      if ((sz & 1) && fseek(f, 1, SEEK_CUR) != 0) break;
     } else if (!memcmp(ch, "data", 4)) {
       if (!fmtOk) break;
       if (!(fmtTag == 1 || fmtTag == 0xFFFE) || bits != 16) { fclose(f); err = std::string(path) + ": only 16-bit integer PCM is supported"; return false; }
-      w.pcm.resize(sz / 2);
+      if (blockAlign != 2 * w.nChan) { fclose(f); err = std::string(path) + ": invalid WAV header (block alignment)"; return false; }
+      if (sz == 0 || sz == 0xFFFFFFFFu || sz > left) sz = left;        // streamed files: the data chunk runs to the end of the file
+      try { w.pcm.resize(sz / 2); } catch (const std::exception &) { fclose(f); err = std::string(path) + ": out of memory"; return false; }
       const size_t got = fread(w.pcm.data(), 2, sz / 2, f);
-      w.pcm.resize(got - got % (size_t)std::max(w.nChan, 1));
+      w.pcm.resize(got - got % (size_t)w.nChan);
       fclose(f);
       return true;
     } else {
-      fseek(f, sz + (sz & 1), SEEK_CUR);
+      if (sz > left || fseek(f, (long)sz + (long)(sz & 1), SEEK_CUR) != 0) break;
     }
   }
   fclose(f);
@@ -836,8 +848,8 @@ bool write_htk(const char *path, const float *rows, int64_t n, int K, double per
   be16((uint16_t)(sizeof(float) * K));
   be16((uint16_t)parmKind);
   if (packed) {
-    fwrite(packed, 4, (size_t)n * K, f);
-    fclose(f);
+    const bool okw = fwrite(packed, 4, (size_t)n * K, f) == (size_t)n * K;
+    if (fclose(f) != 0 || !okw) { err = std::string("write error on '") + path + "'"; return false; }
     return true;
   }
   std::vector<unsigned char> buf((size_t)K * 4);
@@ -850,7 +862,8 @@ bool write_htk(const char *path, const float *rows, int64_t n, int K, double per
     }
     fwrite(buf.data(), 1, buf.size(), f);
   }
-  fclose(f);
+  const bool bad = ferror(f) != 0;
+  if (fclose(f) != 0 || bad) { err = std::string("write error on '") + path + "'"; return false; }
   return true;
 }
 
@@ -866,7 +879,8 @@ struct TextBuf {
   size_t n = 0;
   explicit TextBuf(FILE *fp) : f(fp), b(1 << 20) {}
   void room(size_t need) { if (n + need > b.size()) flush(); if (need > b.size()) b.resize(need * 2); }
-  void flush() { if (n) fwrite(b.data(), 1, n, f); n = 0; }
+  void flush() { if (n && fwrite(b.data(), 1, n, f) != n) failed = true; n = 0; }
+  bool failed = false;
   void ch(char c) { room(1); b[n++] = c; }
   void str(const char *s, size_t len) { room(len); memcpy(b.data() + n, s, len); n += len; }
   void str(const std::string &s) { str(s.data(), s.size()); }
@@ -933,7 +947,8 @@ bool write_csv(const char *path, const float *rows, int64_t n, int K, const std:
     }
   }
   tb.flush();
-  fclose(f);
+  const bool bad = tb.failed || ferror(f) != 0;
+  if (fclose(f) != 0 || bad) { err = std::string("write error on '") + path + "'"; return false; }
   return true;
 }
 
@@ -1485,7 +1500,7 @@ osm_b200_status osm_b200_session_plan(osm_b200_session *s, double sampleRate, in
   return get_plan(s, sampleRate, nChan, plan);
 }
 
-osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t *pcm, const int64_t *uttOff, int32_t nUtt,
+static osm_b200_status osm_b200_session_extract_pcm_impl(osm_b200_session *s, const int16_t *pcm, const int64_t *uttOff, int32_t nUtt,
                                              double sampleRate, int32_t nChan, int64_t *frameOff, float *out, int64_t maxRows)
 {
   if (!s || !uttOff || !frameOff) return hfail(OSM_B200_ERR_INVALID, "null argument");
@@ -1562,6 +1577,16 @@ osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t 
   return OSM_B200_OK;
 }
 
+osm_b200_status osm_b200_session_extract_pcm(osm_b200_session *s, const int16_t *pcm, const int64_t *uttOff, int32_t nUtt,
+                                             double sampleRate, int32_t nChan, int64_t *frameOff, float *out, int64_t maxRows)
+{
+  // no exception crosses the C boundary (allocation failures on hostile inputs, std::filesystem / stream errors)
+  try { return osm_b200_session_extract_pcm_impl(s, pcm, uttOff, nUtt, sampleRate, nChan, frameOff, out, maxRows); }
+  catch (const std::bad_alloc &) { return hfail(OSM_B200_ERR_NOMEM, "out of host memory"); }
+  catch (const std::exception &e) { return hfail(OSM_B200_ERR_INVALID, e.what()); }
+}
+
+
 osm_b200_status osm_b200_session_extract_files(osm_b200_session *s, int32_t n, const char *const *wavPaths,
                                                const char *const *htkPaths, const char *const *csvPaths, int64_t *framesOut)
 {
@@ -1628,7 +1653,7 @@ static bool write_batch(osm_b200_session *s, const std::vector<int> &idx, const 
 }
 }  // extern "C++"
 
-osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t n, const char *const *wavPaths,
+static osm_b200_status osm_b200_session_extract_files_arff_impl(osm_b200_session *s, int32_t n, const char *const *wavPaths,
                                                     const char *const *htkPaths, const char *const *csvPaths,
                                                     const char *const *arffPaths, int64_t *framesOut)
 {
@@ -1702,6 +1727,17 @@ osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t
   }
   return OSM_B200_OK;
 }
+
+osm_b200_status osm_b200_session_extract_files_arff(osm_b200_session *s, int32_t n, const char *const *wavPaths,
+                                                    const char *const *htkPaths, const char *const *csvPaths,
+                                                    const char *const *arffPaths, int64_t *framesOut)
+{
+  // no exception crosses the C boundary (allocation failures on hostile inputs, std::filesystem / stream errors)
+  try { return osm_b200_session_extract_files_arff_impl(s, n, wavPaths, htkPaths, csvPaths, arffPaths, framesOut); }
+  catch (const std::bad_alloc &) { return hfail(OSM_B200_ERR_NOMEM, "out of host memory"); }
+  catch (const std::exception &e) { return hfail(OSM_B200_ERR_INVALID, e.what()); }
+}
+
 
 // The sink half of osm_b200_session_extract_files_arff on rows the caller already holds (e.g. from
 // osm_b200_session_extract_pcm): file i gets rows [frame_offsets[i], frame_offsets[i+1]) of `rows` ([.., num_elements]);
