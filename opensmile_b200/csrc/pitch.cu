@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
         const int q = (i - lo) * 32 + lane;
         if (i >= 1 && i <= N - 2) { a = p.fwdA[q]; b = p.fwdP6[q] * ((yS[i + 1] - yS[i]) * p.r1[q] - (yS[i] - yS[i - 1]) * p.r2[q]); }
         B = a * B + b; A = a * A;
+        uS[i] = b;                              // the second pass of the scan reads it back instead of rebuilding it from four tables
       }
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -152,10 +153,8 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
       double u = __shfl_up_sync(kFull, B, 1);
       if (lane == 0) u = 0.0;
       for (int i = lo; i < hi; i++) {
-        double a = 0.0, b = 0.0;
-        const int q = (i - lo) * 32 + lane;
-        if (i >= 1 && i <= N - 2) { a = p.fwdA[q]; b = p.fwdP6[q] * ((yS[i + 1] - yS[i]) * p.r1[q] - (yS[i] - yS[i - 1]) * p.r2[q]); }
-        u = a * u + b;
+        const double a = (i >= 1 && i <= N - 2) ? p.fwdA[(i - lo) * 32 + lane] : 0.0;
+        u = a * u + uS[i];
         uS[i] = u;
       }
       __syncwarp();
@@ -641,9 +640,18 @@ __global__ void __launch_bounds__(kJitWarps * 32, 5) jitter_kernel(const JitterP
             const double P2a = PB1 + (q1 - g1), P2b = PB2 + (q2 - g2);  // P(2 tf)
             if (tf <= tmax) {
               const float *x = w, *y = w + tf;
-              double Sxy = 0.0;
-#pragma unroll 4
-              for (int i = 0; i < tf; i++) Sxy += (double)x[i] * (double)y[i];
+              // four independent partial sums (the products are exact in double; regrouping the additions moves the sum by
+              // ~1e-16 relative, like the one-pass form itself): the loop is bound by the latency of the dependent additions
+              double xy0 = 0.0, xy1 = 0.0, xy2 = 0.0, xy3 = 0.0;
+              int i = 0;
+              for (; i + 4 <= tf; i += 4) {
+                xy0 += (double)x[i] * (double)y[i];
+                xy1 += (double)x[i + 1] * (double)y[i + 1];
+                xy2 += (double)x[i + 2] * (double)y[i + 2];
+                xy3 += (double)x[i + 3] * (double)y[i + 3];
+              }
+              for (; i < tf; i++) xy0 += (double)x[i] * (double)y[i];
+              const double Sxy = (xy0 + xy1) + (xy2 + xy3);
               const double N = (double)tf, Sy = P2a - Sx, Syy = P2b - Sxx;
               cc[tf - tmin] = (Sxy - Sx * Sy / N) / (sqrt(Sxx - Sx * Sx / N) * sqrt(Syy - Sy * Sy / N));
             }
