@@ -930,6 +930,9 @@ static osm_b200_status prepare_batch(osm_b200_plan *pl, const int64_t *uttOff, i
   const bool same = (int)pl->cachedUttOff.size() == nUtt + 1 &&
                     memcmp(pl->cachedUttOff.data(), uttOff, sizeof(int64_t) * (nUtt + 1)) == 0;
   if (!same) {
+    // the host tables below are rewritten in place: until the rebuild has completed no layout counts as cached (a rebuild that
+    // fails half way must not be mistaken for the previous one)
+    pl->cachedUttOff.clear();
     if (pl->metaPending) { CU(cudaEventSynchronize(pl->evMetaDone)); pl->metaPending = false; }
     const size_t nm = (size_t)(nUtt + 1);
     CU(pl->hMeta.reserve(3 * nm));

@@ -1292,6 +1292,9 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
   if (lvl.empty()) {
     if (sinkLevels.empty()) { delete s; return hfail(OSM_B200_ERR_INVALID, "no active sink: pass output_level or enable a sink (-O / -csvoutput)"); }
     lvl = sinkLevels[0];
+    // every active sink gets the rows of ONE plan run: sinks that read different levels cannot be served together
+    for (const std::string &l : sinkLevels)
+      if (l != lvl) { delete s; return hfail(OSM_B200_ERR_UNSUPPORTED, "the active sinks read different levels ('" + lvl + "' and '" + l + "'): enable the sinks of one level per session"); }
   }
   // A summary level: [sink level] <- (single-input cVectorConcat)* <- cFunctionals <- LLD level(s), or several such chains behind
   // one cVectorConcat / multi-level sink reader.  The plan computes the union of the functionals' input levels; the summaries
