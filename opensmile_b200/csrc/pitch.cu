@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
       }
       __syncwarp();
     }
+#pragma unroll 4                                 // independent points: four iterations' table loads (5 per point, from L2) in flight
     for (int i = lane; i < M; i += 32) {                                         // smileUtilSpline.c:355-368, specScale.cpp:343-368
       const int k = p.ik[i];
       const double a = p.ia[i], b = 1.0 - a;
@@ -190,16 +191,29 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
     // sub-harmonic summation (lld/pitchShs.cpp:238-258)
     float *SS = reinterpret_cast<float *>(uS);
     double part = 0.0;
-    for (int j = lane; j < M; j += 32) {
-      float s = hps[j];
+    // two points per lane and iteration: the 15-fold shift-add of a point is one dependent float chain (the reference's order),
+    // two independent chains hide its latency; the lane's running sum still takes its points in ascending order
+    for (int j = lane; j < M; j += 64) {
+      const int j2 = j + 32;
+      const bool two = j2 < M;
+      float s = hps[j], s2 = two ? hps[j2] : 0.0f;
       for (int h = 0; h < p.nHarm - 1; h++) {
-        const int q = j + p.shift[h];
-        if (q < M) s = s + hps[q] * p.hscale[h];
+        const int sh = p.shift[h];
+        const float hs = p.hscale[h];
+        const int q = j + sh, q2 = j2 + sh;
+        if (q < M) s = s + hps[q] * hs;
+        if (q2 < M) s2 = s2 + hps[q2] * hs;
       }
       s = s / (float)p.nHarm;
       if (s < 0) s = 0.0f;
       SS[j] = s;
       part += (double)s;
+      if (two) {
+        s2 = s2 / (float)p.nHarm;
+        if (s2 < 0) s2 = 0.0f;
+        SS[j2] = s2;
+        part += (double)s2;
+      }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(kFull, part, d);
@@ -640,18 +654,10 @@ __global__ void __launch_bounds__(kJitWarps * 32, 5) jitter_kernel(const JitterP
             const double P2a = PB1 + (q1 - g1), P2b = PB2 + (q2 - g2);  // P(2 tf)
             if (tf <= tmax) {
               const float *x = w, *y = w + tf;
-              // four independent partial sums (the products are exact in double; regrouping the additions moves the sum by
-              // ~1e-16 relative, like the one-pass form itself): the loop is bound by the latency of the dependent additions
-              double xy0 = 0.0, xy1 = 0.0, xy2 = 0.0, xy3 = 0.0;
-              int i = 0;
-              for (; i + 4 <= tf; i += 4) {
-                xy0 += (double)x[i] * (double)y[i];
-                xy1 += (double)x[i + 1] * (double)y[i + 1];
-                xy2 += (double)x[i + 2] * (double)y[i + 2];
-                xy3 += (double)x[i + 3] * (double)y[i + 3];
-              }
-              for (; i < tf; i++) xy0 += (double)x[i] * (double)y[i];
-              const double Sxy = (xy0 + xy1) + (xy2 + xy3);
+              // (splitting this sum into four independent partial sums was measured: 54.1 -> 59.5 ms, slower)
+              double Sxy = 0.0;
+#pragma unroll 4
+              for (int i = 0; i < tf; i++) Sxy += (double)x[i] * (double)y[i];
               const double N = (double)tf, Sy = P2a - Sx, Syy = P2b - Sxx;
               cc[tf - tmin] = (Sxy - Sx * Sy / N) / (sqrt(Sxx - Sx * Sx / N) * sqrt(Syy - Sy * Sy / N));
             }
@@ -773,8 +779,13 @@ __global__ void __launch_bounds__(kJitWarps * 32, 5) jitter_kernel(const JitterP
       lastPeriod = toRead0; lastMis = 0;
       lastT0 = 0.0f; lastDiff = 0.0f; lastJitterDDP = 0.0f; lastJitterLocal = 0.0f; lastShimmerLocal = 0.0f;
       if (p.noiseERMS || p.linearHNR || p.logHNR) {
+        // energy of an unvoiced frame: float products summed in double (lld/pitchJitter.cpp:930-936).  The lanes take strided
+        // partial sums (a regrouping of double additions of exact float values: ~1e-16 relative, gone in the float result)
+        // instead of every lane walking all nT samples
         double E = 0.0;
-        for (int i = 0; i < nT; i++) E += wav[i] * wav[i];
+        for (int i = lane; i < nT; i += 32) E += wav[i] * wav[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) E += __shfl_xor_sync(kFull, E, d);
         E /= (double)nT;
         eH = 0.0f; HNR = 0.0f; eN = (float)sqrt(E); lgHNR = p.lgHNRfloor;
       }

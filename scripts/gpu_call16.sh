@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, GPU call 16: per-column parity asserts (tests + smoke), pitch chain changes (shs two chains, jitter unvoiced energy in parallel)
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -8 | cut -c1-2500 | tee gpurun_out/c16_gpu_suite.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/c16_smoke.txt
+for w in compare16 egemaps; do
+timeout 900 python bench.py --workload $w --no-others --steps 3 --warmup 2 2> gpurun_out/c16_bench_$w.err | tail -1 > gpurun_out/c16_bench_$w.json
+python - <<PY
+import json
+l=json.loads(open("gpurun_out/c16_bench_$w.json").read())
+print("$w value %.2f M ms %.1f parity %s" % (l["value"]/1e6, l["ms_per_step"], l.get("parity",{}).get("ok")))
+print(l["roofline"]["kernels_ms"])
+PY
+done

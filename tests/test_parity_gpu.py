@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLD, rel_to_frame_scale
+from conftest import GOLD, assert_columns_close, rel_to_frame_scale
 from opensmile_b200 import Plan, components_mfcc12_0_d_a, pack_utterances
 from opensmile_b200.synth import voiced_pcm
 from oracle import oracle
@@ -33,6 +33,7 @@ def test_golden_example_wav_config0(plan44):
     out = plan44.run_host(g["pcm"], np.array([0, g["pcm"].size], np.int64))
     assert out.shape == (202, 39)                       # bit-exact frame count
     assert rel_to_frame_scale(out, g["lld"]) < TOL
+    assert_columns_close(out, g["lld"])                 # every column against its own scale
 
 
 def test_golden_synth16k(plan16):
@@ -41,6 +42,7 @@ def test_golden_synth16k(plan16):
     out = plan16.run_host(pcm, np.array([0, pcm.size], np.int64))
     assert out.shape == (498, 39)
     assert rel_to_frame_scale(out, g["lld"]) < TOL
+    assert_columns_close(out, g["lld"])
     # the regression stages are exact float arithmetic on the statics: recomputing them on the
     # CPU from the GPU's own statics must match the GPU's delta columns bit for bit
     d = oracle.delta(out[:, :13], 2)
