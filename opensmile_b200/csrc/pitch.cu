@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
   const int nWarps = blockDim.x >> 5;
   for (int f = warp; f < tl.nf; f += nWarps) {
     const float *mg = p.mag + ((size_t)blockIdx.x * N) * p.F + f;
+#pragma unroll 4
     for (int j = lane; j < N; j += 32) yS[j] = (double)mg[(size_t)j * p.F];      // dsp/specScale.cpp:329-331
     __syncwarp();
     if (p.enhance) {                                                             // smileUtil.c:1965-2003
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(kShsWarps * 32) shs_kernel(const ShsParams p)
     {
       double A = 1.0, B = 0.0;
       // (coefficient tables are stored lane-interleaved: entry of (lane, step k) at [k * 32 + lane] -> coalesced)
+#pragma unroll 4                                // the table loads (L2) of four steps in flight; only A, B carry a dependency
       for (int i = lo; i < hi; i++) {
         double a = 0.0, b = 0.0;
         const int q = (i - lo) * 32 + lane;
@@ -654,7 +656,8 @@ __global__ void __launch_bounds__(kJitWarps * 32, 5) jitter_kernel(const JitterP
             const double P2a = PB1 + (q1 - g1), P2b = PB2 + (q2 - g2);  // P(2 tf)
             if (tf <= tmax) {
               const float *x = w, *y = w + tf;
-              // (splitting this sum into four independent partial sums was measured: 54.1 -> 59.5 ms, slower)
+              // (measured alternatives, both slower at the kernel's 96-register budget: four independent partial sums 54.1 -> 59.5 ms;
+              // an explicit double FMA -- exact here, float products are exact in double -- with the PCM loads unrolled 55.0 -> 58.8 ms)
               double Sxy = 0.0;
 #pragma unroll 4
               for (int i = 0; i < tf; i++) Sxy += (double)x[i] * (double)y[i];
