@@ -104,7 +104,8 @@ typedef enum {
 /* window functions, cWindower.winFunc (src/dspcore/windower.cpp:60-80) */
 typedef enum {
   OSM_B200_WIN_RECTANGLE = 0, OSM_B200_WIN_HANNING, OSM_B200_WIN_HAMMING, OSM_B200_WIN_GAUSS,
-  OSM_B200_WIN_SINE, OSM_B200_WIN_TRIANGLE, OSM_B200_WIN_BARTLETT
+  OSM_B200_WIN_SINE, OSM_B200_WIN_TRIANGLE, OSM_B200_WIN_BARTLETT,
+  OSM_B200_WIN_BLACKMAN, OSM_B200_WIN_BLACKHARR, OSM_B200_WIN_BARTHANN, OSM_B200_WIN_LANCZOS
 } osm_b200_winfunc;
 
 typedef enum { OSM_B200_PCM_S16 = 0, OSM_B200_PCM_F32 = 1 } osm_b200_pcm_format;
@@ -132,6 +133,12 @@ typedef struct { double k; int32_t de; } osm_b200_vectorpreemphasis;  /* 0.97, 0
 typedef struct {            /* cWindower */
   int32_t winFunc;          /* osm_b200_winfunc, default Hanning */
   double  gain, offset, sigma;    /* 1, 0, 0.4 */
+  /* Blackman / Blackman-Harris / Bartlett-Hann coefficients as the reference resolves them (dspcore/windower.cpp:83-113):
+   * Blackman (1-alpha)/2, 1/2, alpha/2 with alpha = 0.16 unless alpha0..2 are all set; Blackman-Harris 0.35875, 0.48829, 0.14128,
+   * 0.01168; Bartlett-Hann 0.62, 0.48, 0.38.  osm_b200_component_defaults() fills the Blackman values. */
+  double  alpha0, alpha1, alpha2, alpha3;
+  double  fade;             /* 0: fraction (<= 0.5) of the window faded in / out with a half raised cosine (:201-208) */
+  int32_t squareRoot;       /* 0; 1 = square root of the window function (:178-188) */
 } osm_b200_windower;
 
 typedef struct { int32_t inverse; int32_t zeroPadSymmetric; } osm_b200_transformfft; /* 0, 1 */
@@ -396,6 +403,9 @@ OSM_B200_API int64_t     osm_b200_plan_num_frames(const osm_b200_plan *plan, int
 /* rows of the output level that exist when a full-input reader (cFunctionals, frameMode = full) ticks for the first time at
  * end of input: the window processors of the level have each appended one frame by then, not yet all of them
  * (blocksize 1, core/windowProcessor.cpp:167-230); that is the contour the reference's functionals summarise */
+/* the window table cWindower multiplies a frame of n samples with (dspcore/windower.cpp:159-217: window function, squareRoot,
+ * fade, gain), as float: what osm_b200_plan_create stages for the kernels (bindings, tests) */
+OSM_B200_API osm_b200_status osm_b200_window_table(const osm_b200_windower *cfg, int32_t n, float *out);
 OSM_B200_API int64_t     osm_b200_plan_num_frames_first_eoi(const osm_b200_plan *plan, int64_t n_sample_frames);
 /* the same for levels behind the SHS pitch chain, whose length at that moment depends on the data: viterbi_frames = frames the
  * cPitchSmootherViterbi level held when end of input was raised (osm_b200_plan_copy_seq_lag after a run; < 0: not known, the

@@ -59,7 +59,8 @@ class VectorPreemphasis(C.Structure):
 
 
 class Windower(C.Structure):
-    _fields_ = [("winFunc", i32), ("gain", f64), ("offset", f64), ("sigma", f64)]
+    _fields_ = [("winFunc", i32), ("gain", f64), ("offset", f64), ("sigma", f64), ("alpha0", f64), ("alpha1", f64), ("alpha2", f64),
+                ("alpha3", f64), ("fade", f64), ("squareRoot", i32)]
 
 
 class TransformFFT(C.Structure):
@@ -257,7 +258,7 @@ EXPORTS = [
     "osm_b200_plan_frame_period", "osm_b200_plan_frame_size_samples",
     "osm_b200_plan_frame_step_samples", "osm_b200_plan_fft_size", "osm_b200_plan_num_frames", "osm_b200_plan_num_time_frames",
     "osm_b200_plan_frame_offsets", "osm_b200_plan_run_device", "osm_b200_plan_run_host", "osm_b200_plan_run_host_resident",
-    "osm_b200_plan_num_frames_first_eoi", "osm_b200_plan_num_frames_first_eoi_v", "osm_b200_plan_copy_seq_lag",
+    "osm_b200_window_table", "osm_b200_plan_num_frames_first_eoi", "osm_b200_plan_num_frames_first_eoi_v", "osm_b200_plan_copy_seq_lag",
     # include/osm_b200_functionals.h
     "osm_b200_functionals_defaults", "osm_b200_functionals_create", "osm_b200_functionals_destroy", "osm_b200_functionals_num_values",
     "osm_b200_functionals_num_elements", "osm_b200_functionals_element_name", "osm_b200_functionals_run_device", "osm_b200_functionals_run_device_cols", "osm_b200_device_csv_slot_bytes", "osm_b200_device_format_csv",

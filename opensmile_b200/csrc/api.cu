@@ -204,6 +204,8 @@ osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
     case OSM_B200_C_WINDOWER:
       c->u.windower.winFunc = OSM_B200_WIN_HANNING; c->u.windower.gain = 1.0; c->u.windower.offset = 0.0;
       c->u.windower.sigma = 0.4;
+      c->u.windower.alpha0 = (1.0 - 0.16) * 0.5; c->u.windower.alpha1 = 0.5; c->u.windower.alpha2 = 0.16 * 0.5; c->u.windower.alpha3 = 0.0;
+      c->u.windower.fade = 0.0; c->u.windower.squareRoot = 0;
       break;
     case OSM_B200_C_TRANSFORMFFT: c->u.transformfft.inverse = 0; c->u.transformfft.zeroPadSymmetric = 1; break;
     case OSM_B200_C_FFTMAGPHASE: c->u.fftmagphase.magnitude = 1; break;
@@ -1347,6 +1349,17 @@ osm_b200_status osm_b200_plan_run_host_resident(osm_b200_plan *pl, const void *p
   osm_b200_status s = run_host_impl(pl, pcm, utt_offsets, n_utt, frame_offsets, nullptr, true);
   if (s == OSM_B200_OK) *d_rows = pl->dOut.p;
   return s;
+}
+
+osm_b200_status osm_b200_window_table(const osm_b200_windower *w, int32_t n, float *out)
+{
+  if (!w || !out || n <= 0) return fail(OSM_B200_ERR_INVALID, "null argument");
+  if (w->winFunc < OSM_B200_WIN_RECTANGLE || w->winFunc > OSM_B200_WIN_LANCZOS) return fail(OSM_B200_ERR_INVALID, "unknown window function");
+  const double al[4] = {w->alpha0, w->alpha1, w->alpha2, w->alpha3};
+  std::vector<float> t;
+  build_window(w->winFunc, n, w->sigma, w->gain, t, al, w->squareRoot, std::min(std::max(w->fade, 0.0), 0.5));
+  memcpy(out, t.data(), sizeof(float) * (size_t)n);
+  return OSM_B200_OK;
 }
 
 int64_t osm_b200_plan_num_frames_first_eoi(const osm_b200_plan *pl, int64_t n) { return pl ? desc_num_frames_first_eoi(pl->d, n) : 0; }

@@ -225,7 +225,8 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     }
     if (ci.win) {
       const auto &wnp = ci.win->u.windower;
-      build_window(wnp.winFunc, fe.frameSize, wnp.sigma, wnp.gain, fe.window);
+      { const double al[4] = {wnp.alpha0, wnp.alpha1, wnp.alpha2, wnp.alpha3};
+        build_window(wnp.winFunc, fe.frameSize, wnp.sigma, wnp.gain, fe.window, al, wnp.squareRoot, std::min(std::max(wnp.fade, 0.0), 0.5)); }
       fe.winOffset = (float)wnp.offset;
       st.hasWindow = true;
     } else {

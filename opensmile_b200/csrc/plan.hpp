@@ -263,7 +263,7 @@ int64_t desc_num_static_frames(const PlanDesc &d, int stream, int64_t nSampleFra
 int64_t desc_max_static_frames(const PlanDesc &d, int64_t nSampleFrames);
 
 // tables.cpp
-void build_window(int winFunc, int N, double sigma, double gain, std::vector<float> &w);
+void build_window(int winFunc, int N, double sigma, double gain, std::vector<float> &w, const double *alpha = nullptr, int squareRoot = 0, double fade = 0.0);
 void build_mel(const osm_b200_melspec &cfg, int nBins, double frameSizeSec, MelBank &mb);
 void build_mfcc(const osm_b200_mfcc &cfg, int nBands, MfccOp &op);
 bool build_plp(const osm_b200_plp &cfg, const MelBank &mb, double levelPeriod, PlpOp &op, std::string &err);

@@ -19,7 +19,7 @@ namespace osm {
 
 // cWindower::precomputeWinFunc (dspcore/windower.cpp:159-217) over the double tables of
 // smileutil/smileUtil.c:1218-1349; the per-sample use casts to float (windower.cpp:226).
-void build_window(int winFunc, int N, double sigma, double gain, std::vector<float> &out)
+void build_window(int winFunc, int N, double sigma, double gain, std::vector<float> &out, const double *alpha, int squareRoot, double fade)
 {
   std::vector<double> w(N);
   const double NN = (double)N;
@@ -50,9 +50,37 @@ void build_window(int winFunc, int N, double sigma, double gain, std::vector<flo
         w[n] = (n < N / 2) ? 2.0 * (double)n / (double)(N - 1)
                            : 2.0 * (double)(N - 1 - n) / (double)(N - 1);
         break;
+      case OSM_B200_WIN_BLACKMAN: {   // smileUtil.c:1352-1367
+        const double tmp = (2.0 * M_PI * i) / (NN - 1.0);
+        w[n] = alpha[0] - alpha[1] * cos(tmp) + alpha[2] * cos(2.0 * tmp);
+        break;
+      }
+      case OSM_B200_WIN_BLACKHARR: {  // smileUtil.c:1386-1402
+        const double tmp = (2.0 * M_PI * i) / (NN - 1.0);
+        w[n] = alpha[0] - alpha[1] * cos(tmp) + alpha[2] * cos(2.0 * tmp) - alpha[3] * cos(3.0 * tmp);
+        break;
+      }
+      case OSM_B200_WIN_BARTHANN:     // smileUtil.c:1370-1383
+        w[n] = alpha[0] - alpha[1] * fabs(i / (NN - 1.0) - 0.5) - alpha[2] * cos((2.0 * M_PI * i) / (NN - 1.0));
+        break;
+      case OSM_B200_WIN_LANCZOS: {    // smileUtil.c:1320-1331, smileDsp_lcSinc :1205-1209 (0/0 at the centre of an odd window, like the reference)
+        const double y = M_PI * ((2.0 * i) / (NN - 1.0) - 1.0);
+        w[n] = sin(y) / y;
+        break;
+      }
       default:                     // rectangle, smileUtil.c:1218-1228
         w[n] = 1.0;
         break;
+    }
+  }
+  if (squareRoot)                  // dspcore/windower.cpp:178-188 (negative values become 0)
+    for (int n = 0; n < N; n++) w[n] = w[n] >= 0.0 ? sqrt(w[n]) : 0.0;
+  if (fade > 0.0) {                // :201-208
+    const long fadeSize = (long)((double)N * fade);
+    for (long k = 0; k < fadeSize; k++) {
+      const double a = -0.5 * (cos(M_PI * (double)k / (double)fadeSize) - 1.0);
+      w[k] *= a;
+      w[N - k - 1] *= a;
     }
   }
   if (gain != 1.0)

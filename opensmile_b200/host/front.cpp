@@ -203,7 +203,11 @@ int win_func(const std::string &s)
   if (l.compare(0, 3, "gau") == 0) return OSM_B200_WIN_GAUSS;
   if (l.compare(0, 3, "sin") == 0 || l.compare(0, 3, "cos") == 0) return OSM_B200_WIN_SINE;
   if (l.compare(0, 3, "tri") == 0) return OSM_B200_WIN_TRIANGLE;
+  if (l.compare(0, 3, "bah") == 0 || l.compare(0, 10, "bartlett-h") == 0) return OSM_B200_WIN_BARTHANN;
   if (l.compare(0, 3, "bar") == 0) return OSM_B200_WIN_BARTLETT;
+  if (l.compare(0, 3, "blh") == 0 || l.compare(0, 10, "blackman-h") == 0) return OSM_B200_WIN_BLACKHARR;
+  if (l.compare(0, 3, "bla") == 0) return OSM_B200_WIN_BLACKMAN;
+  if (l.compare(0, 3, "lac") == 0 || l.compare(0, 3, "lan") == 0) return OSM_B200_WIN_LANCZOS;
   return -1;
 }
 
@@ -294,10 +298,11 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
       case OSM_B200_C_WINDOWER:
         SETD("gain", c.u.windower.gain) SETD("offset", c.u.windower.offset) SETD("sigma", c.u.windower.sigma)
         if (f == "winFunc") { c.u.windower.winFunc = win_func(v); if (c.u.windower.winFunc < 0) { err = "cWindower.winFunc=" + v + " is not supported"; return false; } continue; }
-        if (f == "xscale" || f == "xshift" || f == "fade" || f == "squareRoot" || f == "alpha") {
+        SETD("fade", c.u.windower.fade) SETI("squareRoot", c.u.windower.squareRoot)
+        if (f == "alpha" || f == "alpha0" || f == "alpha1" || f == "alpha2" || f == "alpha3") continue;   // resolved below (they depend on winFunc)
+        if (f == "xscale" || f == "xshift") {
           const double d = num(v);
-          const bool dflt = (f == "xscale" && d == 1.0) || (f == "alpha" && d == 0.16) || ((f == "xshift" || f == "fade" || f == "squareRoot") && d == 0.0);
-          if (!dflt && f != "alpha") { err = "cWindower." + f + " is not supported"; return false; }
+          if (!((f == "xscale" && d == 1.0) || (f == "xshift" && d == 0.0))) { err = "cWindower." + f + " is not supported"; return false; }
           continue;
         }
         break;
@@ -591,6 +596,18 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
   if (t == OSM_B200_C_MFCC && c.u.mfcc.lastMfcc <= -1000)          // lastMfcc = firstMfcc + nMfcc - 1 (lldcore/mfcc.cpp:77-82)
     c.u.mfcc.lastMfcc = c.u.mfcc.firstMfcc + (-1000 - c.u.mfcc.lastMfcc) - 1;
   if (t == OSM_B200_C_ACF && c.u.acf.cepstrum && !usePowerSet) c.u.acf.usePower = 0;   // dspcore/acf.cpp:91-99
+  if (t == OSM_B200_C_WINDOWER) {                                  // window coefficients, dspcore/windower.cpp:83-113
+    auto &w = c.u.windower;
+    const std::string *a = s.get("alpha"), *a0 = s.get("alpha0"), *a1 = s.get("alpha1"), *a2 = s.get("alpha2"), *a3 = s.get("alpha3");
+    if (w.winFunc == OSM_B200_WIN_BLACKMAN) {
+      if (a0 && a1 && a2) { w.alpha0 = num(*a0); w.alpha1 = num(*a1); w.alpha2 = num(*a2); }
+      else { const double al = a ? num(*a) : 0.16; w.alpha0 = (1.0 - al) * 0.5; w.alpha1 = 0.5; w.alpha2 = al * 0.5; }
+    } else if (w.winFunc == OSM_B200_WIN_BLACKHARR) {
+      w.alpha0 = a0 ? num(*a0) : 0.35875; w.alpha1 = a1 ? num(*a1) : 0.48829; w.alpha2 = a2 ? num(*a2) : 0.14128; w.alpha3 = a3 ? num(*a3) : 0.01168;
+    } else if (w.winFunc == OSM_B200_WIN_BARTHANN) {
+      w.alpha0 = a0 ? num(*a0) : 0.62; w.alpha1 = a1 ? num(*a1) : 0.48; w.alpha2 = a2 ? num(*a2) : 0.38;
+    }
+  }
   if (t == OSM_B200_C_VECTOROPERATION && c.u.vectoroperation.operation < 0) { err = "cVectorOperation.operation=norm (the default) is not supported (ll1 only)"; return false; }
   return true;
 }

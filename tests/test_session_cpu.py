@@ -269,3 +269,26 @@ def test_inputs_sharing_one_output_file_are_written_in_order(tmp_path):
     assert len(data) == int(fo[-1])
     first = [int(float(ln.split(",")[2])) for ln in data]          # name, frameTime, then the values
     assert first == sorted(first) and first[0] == 1 and first[-1] == len(n_samples)
+
+
+@pytest.mark.parametrize("case", ["bla", "bla_alpha", "bla_a012", "blh", "bah", "lac", "han_sqrt", "ham_fade", "blh_gain_sqrt_fade", "gau", "tri"])
+def test_window_tables_equal_the_reference(tmp_path, case):
+    """cWindower's table through the conf front end (names, defaults and coefficient rules of dspcore/windower.cpp:60-113) and the
+    table builder, against the reference's cWindower level of a constant signal (tests/golden/window_goldens.npz,
+    scripts/make_golden_windows.py): Blackman, Blackman-Harris, Bartlett-Hann, Lanczos, squareRoot, fade, custom coefficients"""
+    import ctypes as C
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "window_goldens.npz"))
+    (tmp_path / "inc").mkdir()
+    inc = open(os.path.join(CONF, "inc", "htk_frontend.conf.inc")).read().replace("winFunc = ham\n", str(g[case + "_conf"]) + "\n")
+    (tmp_path / "inc" / "htk_frontend.conf.inc").write_text(inc)
+    (tmp_path / "inc" / "ft0_d_a_out.conf.inc").write_text(open(os.path.join(CONF, "inc", "ft0_d_a_out.conf.inc")).read())
+    (tmp_path / "c.conf").write_text(open(os.path.join(CONF, "mfcc_0_d_a.conf")).read())
+    s = Session(str(tmp_path / "c.conf"), device=-1)
+    comps, _ = s.components(16000.0, 1)
+    win = [c for c in comps if c.type == capi.C_WINDOWER][0]
+    out = np.zeros(400, np.float32)
+    assert capi.lib().osm_b200_window_table(C.byref(win.u.windower), 400, out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    s.close()
+    ref = g[case]
+    # the reference's CSV prints 7 significant digits of the float product 1.0 * (float)w
+    assert np.all(np.abs(out - ref) <= 1e-6 * np.abs(ref) + 1e-12), (case, float(np.abs(out - ref).max()))
