@@ -83,18 +83,56 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
         ro::phase_d(frame_planes(it / ro::kItemsD, 0), frame_planes(it / ro::kItemsD, 1), wc + ro::kNw, it % ro::kItemsD);
       __syncthreads();
       // smileDsp_irdft (smileutil/smileUtil.c:1800-1820): out = DC; out += Re_k cos; out += Im_k sin (k ascending); out /= K/2
+      // The bins the sum reads are first gathered per bin as (Re of the 8 frames | Im of the 8 frames) into the transform's input
+      // planes, which are dead now (34 rows of 16 floats in each of the first four frames' input planes): the sum then reads four
+      // 128-bit words per bin instead of sixteen scalars.  Same operands, same order per frame.
+      constexpr int kRowsPerPiece = (2 * ro::kPlane) / 16;
+      const bool gathered = p.kHalf <= 4 * kRowsPerPiece;
+      if (gathered) {
+        for (int idx = tid; idx < p.kHalf * 16; idx += kFmtThreads) {
+          const int k2 = idx >> 4, c = idx & 15, f = c & 7, im = c >> 3;
+          planes[(size_t)(k2 / kRowsPerPiece) * 4 * ro::kPlane + (k2 % kRowsPerPiece) * 16 + c] =
+              planes[((size_t)f * 4 + 2 + im) * ro::kPlane + ro::phys(k2)];
+        }
+        __syncthreads();
+      }
       for (int i = tid; i < I; i += kFmtThreads) {
         float acc[kFmtWarps];
+        if (gathered) {
+          {
+            const float4 *r4 = reinterpret_cast<const float4 *>(planes);                 // bin 0: DC of every frame
+            const float4 a = r4[0], b = r4[1];
+            acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w; acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w;
+          }
+          const float *row = planes + 16;
+          int within = 1;
+          for (int k2 = 1; k2 < p.kHalf; k2++) {
+            const float cv = __ldg(cosT + (size_t)k2 * IP + i), sv = __ldg(sinT + (size_t)k2 * IP + i);
+            const float4 *r4 = reinterpret_cast<const float4 *>(row);
+            const float4 re0 = r4[0], re1 = r4[1], im0 = r4[2], im1 = r4[3];
+            acc[0] = __fadd_rn(acc[0], __fmul_rn(re0.x, cv)); acc[0] = __fadd_rn(acc[0], __fmul_rn(im0.x, sv));
+            acc[1] = __fadd_rn(acc[1], __fmul_rn(re0.y, cv)); acc[1] = __fadd_rn(acc[1], __fmul_rn(im0.y, sv));
+            acc[2] = __fadd_rn(acc[2], __fmul_rn(re0.z, cv)); acc[2] = __fadd_rn(acc[2], __fmul_rn(im0.z, sv));
+            acc[3] = __fadd_rn(acc[3], __fmul_rn(re0.w, cv)); acc[3] = __fadd_rn(acc[3], __fmul_rn(im0.w, sv));
+            acc[4] = __fadd_rn(acc[4], __fmul_rn(re1.x, cv)); acc[4] = __fadd_rn(acc[4], __fmul_rn(im1.x, sv));
+            acc[5] = __fadd_rn(acc[5], __fmul_rn(re1.y, cv)); acc[5] = __fadd_rn(acc[5], __fmul_rn(im1.y, sv));
+            acc[6] = __fadd_rn(acc[6], __fmul_rn(re1.z, cv)); acc[6] = __fadd_rn(acc[6], __fmul_rn(im1.z, sv));
+            acc[7] = __fadd_rn(acc[7], __fmul_rn(re1.w, cv)); acc[7] = __fadd_rn(acc[7], __fmul_rn(im1.w, sv));
+            row += 16;
+            if (++within == kRowsPerPiece) { within = 0; row += 4 * ro::kPlane - kRowsPerPiece * 16; }
+          }
+        } else {
 #pragma unroll
-        for (int f = 0; f < kFmtWarps; f++) acc[f] = planes[((size_t)f * 4 + 2) * ro::kPlane];
-        for (int k2 = 1; k2 < p.kHalf; k2++) {
-          const float cv = __ldg(cosT + (size_t)k2 * IP + i), sv = __ldg(sinT + (size_t)k2 * IP + i);
-          const int ph = ro::phys(k2);
+          for (int f = 0; f < kFmtWarps; f++) acc[f] = planes[((size_t)f * 4 + 2) * ro::kPlane];
+          for (int k2 = 1; k2 < p.kHalf; k2++) {
+            const float cv = __ldg(cosT + (size_t)k2 * IP + i), sv = __ldg(sinT + (size_t)k2 * IP + i);
+            const int ph = ro::phys(k2);
 #pragma unroll
-          for (int f = 0; f < kFmtWarps; f++) {
-            const float *b = planes + ((size_t)f * 4 + 2) * ro::kPlane;
-            acc[f] = __fadd_rn(acc[f], __fmul_rn(b[ph], cv));
-            acc[f] = __fadd_rn(acc[f], __fmul_rn(b[ro::kPlane + ph], sv));
+            for (int f = 0; f < kFmtWarps; f++) {
+              const float *b = planes + ((size_t)f * 4 + 2) * ro::kPlane;
+              acc[f] = __fadd_rn(acc[f], __fmul_rn(b[ph], cv));
+              acc[f] = __fadd_rn(acc[f], __fmul_rn(b[ro::kPlane + ph], sv));
+            }
           }
         }
 #pragma unroll

@@ -11,7 +11,7 @@ namespace osm {
 // ------------------------------------------------------------------------------------------
 // cSpectral (lldcore/spectral.cpp:586-1555), magnitude input with a linear bin-frequency axis
 // ------------------------------------------------------------------------------------------
-constexpr int kSpecWarps = 4;
+constexpr int kSpecWarps = 8;                    // staging and the log spectrum use all of them, the descriptors the first four
 constexpr int kSpecThreads = 32 * kSpecWarps;   // one CTA = one tile; lane = frame, warps split the descriptors
 
 struct SpecView {
@@ -36,7 +36,7 @@ struct SpecView {
 };
 
 // The tile's magnitudes (and, when needed, its log spectrum) are staged in shared memory once;
-// the descriptors are then distributed over the four warps of the CTA.  Every descriptor is still
+// (by all eight warps); the descriptors are then distributed over the first four warps.  Every descriptor is still
 // evaluated by ONE thread per frame in the reference's loop order and accumulator types; a warp
 // that needs a shared prerequisite (frame sum, sum of the spectrum, centroid) recomputes it with the
 // same loop, so the split does not change any result.
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kSpecThreads) spectral_kernel(const SpectralPa
         put(cSlope, p.oldSlopeScale ? (float)(slope * (Nind - 1.0)) : (float)slope);
       }
     }
-  } else {
+  } else if (warp == 3) {
     // ---- band slopes, alpha ratio, Hammarberg index, extrema, harmonicity, flatness ----
     for (int b = 0; b < p.nSlopes; b++) {                               // :873-993
       const int iL = p.slopeIL[b], iR = p.slopeIR[b];
