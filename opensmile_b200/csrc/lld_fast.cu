@@ -26,6 +26,22 @@
 #ifndef OSM_FAST_FUSED_DCT
 #define OSM_FAST_FUSED_DCT 0
 #endif
+// further A/B switches (scripts/ab_lld512.py): unroll factors of the two passes' butterfly loops, of the mel group loop and of the
+// DCT loop.  The defaults are what was measured fastest.
+#ifndef OSM_FAST_P1_UNROLL
+#define OSM_FAST_P1_UNROLL 1
+#endif
+#ifndef OSM_FAST_P2_UNROLL
+#define OSM_FAST_P2_UNROLL 1
+#endif
+#ifndef OSM_FAST_MEL_UNROLL
+#define OSM_FAST_MEL_UNROLL 1
+#endif
+#ifndef OSM_FAST_DCT_UNROLL
+#define OSM_FAST_DCT_UNROLL 2
+#endif
+#define OSM_PRAGMA_(x) _Pragma(#x)
+#define OSM_UNROLL(n) OSM_PRAGMA_(unroll n)
 
 namespace osm {
 namespace {
@@ -219,7 +235,7 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
     {
       const float *sampF = samp + f * S;
       const float2 *tw0 = sTw + p.twOff[0];
-#pragma unroll 1
+      OSM_UNROLL(OSM_FAST_P1_UNROLL)
       for (int t = warp; t < 16; t += NW) {
         float2 v[16];
 #pragma unroll
@@ -248,7 +264,7 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
     // ================= FFT pass 2 + real-FFT split + power, in registers =================
     {
       float2 A[16], v[16];
-#pragma unroll 1
+      OSM_UNROLL(OSM_FAST_P2_UNROLL)
       for (int h = 0; h < 2; h++) {
         const float2 *zp = Z + ((h ? tB : tA) * 16) * F + f;
 #pragma unroll
@@ -320,7 +336,7 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
           const float *pp = P + sMelRange[r] * F + f;
           const int v0 = sVB[r];
           const float4 *cp = reinterpret_cast<const float4 *>(sMelCoef + v0);
-#pragma unroll 1
+          OSM_UNROLL(OSM_FAST_MEL_UNROLL)
           for (int q = (sVB[r + 1] - v0) >> 2; q > 0; q--, pp += 4 * F, cp += 2) {
             const float p0 = pp[0], p1 = pp[F], p2 = pp[2 * F], p3 = pp[3 * F];
             const float4 wa = cp[0], wb = cp[1];
@@ -374,7 +390,7 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
         const float *pp = P + sMelRange[r] * F + f;
         const int v0 = sVB[r];
         const float4 *cp = reinterpret_cast<const float4 *>(sMelCoef + v0);
-#pragma unroll 1
+        OSM_UNROLL(OSM_FAST_MEL_UNROLL)
         for (int q = (sVB[r + 1] - v0) >> 2; q > 0; q--, pp += 4 * F, cp += 2) {
           const float p0 = pp[0], p1 = pp[F], p2 = pp[2 * F], p3 = pp[3 * F];
           const float4 wa = cp[0], wb = cp[1];
@@ -403,7 +419,7 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
         const float2 *cc = reinterpret_cast<const float2 *>(sDct + i);
         const float *lp = melS + f;
         float a0 = 0.f, a1 = 0.f;
-#pragma unroll 2
+        OSM_UNROLL(OSM_FAST_DCT_UNROLL)
         for (int m = 0; m < p.nBands; m++, lp += F, cc += kKMax / 2) {
           const float l0 = lp[0];
           const float2 c = cc[0];
