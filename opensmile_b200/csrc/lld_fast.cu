@@ -32,13 +32,19 @@
 #define OSM_FAST_P1_UNROLL 1
 #endif
 #ifndef OSM_FAST_P2_UNROLL
-#define OSM_FAST_P2_UNROLL 1
+#define OSM_FAST_P2_UNROLL 2
 #endif
 #ifndef OSM_FAST_MEL_UNROLL
 #define OSM_FAST_MEL_UNROLL 1
 #endif
 #ifndef OSM_FAST_DCT_UNROLL
-#define OSM_FAST_DCT_UNROLL 2
+#define OSM_FAST_DCT_UNROLL 4
+#endif
+#ifndef OSM_FAST_STAGE_UNROLL
+#define OSM_FAST_STAGE_UNROLL 1
+#endif
+#ifndef OSM_FAST_EMIT_K13
+#define OSM_FAST_EMIT_K13 0
 #endif
 #define OSM_PRAGMA_(x) _Pragma(#x)
 #define OSM_UNROLL(n) OSM_PRAGMA_(unroll n)
@@ -183,6 +189,7 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
       const bool aligned = (tg.mis == 0);
       const bool hasLead = tg.lead > 0;
       const float ks = p.preDe ? p.preK : -p.preK;
+      OSM_UNROLL(OSM_FAST_STAGE_UNROLL)
       for (int i = tid * 8; i < count; i += NT * 8) {
         int wds[4];
         if (aligned) {
@@ -455,6 +462,10 @@ __global__ void __launch_bounds__(kNT, 2) lld512_kernel(const LldParams p)
       const bool interior1 = (d0 >= W1) && (d1 + W1 <= T);
       const bool interior2 = (r0 >= W2) && (r1 <= c02);
       if (interior1 && interior2 && W1 == 2 && W2 == 2 && nr == F) {
+#if OSM_FAST_EMIT_K13
+        if (K == 13) emit_interior<F, NT, 13>(ring, Dbuf, outS, K, dRows, d0 - cx.s0, r0 - cx.s0, norm1, p.fRcp1, norm2, p.fRcp2, tid);
+        else
+#endif
         emit_interior<F, NT, 0>(ring, Dbuf, outS, K, dRows, d0 - cx.s0, r0 - cx.s0, norm1, p.fRcp1, norm2, p.fRcp2, tid);
       } else {
         emit_edge<F, NW>(ring, Dbuf, outS, K, W1, W2, T, T1, c01, c02, cx.s0, r0, r1, d0, d1, dRows, norm1, p.fRcp1, norm2, p.fRcp2, warp, f);
