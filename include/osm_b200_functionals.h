@@ -145,6 +145,17 @@ OSM_B200_API osm_b200_status osm_b200_functionals_run_device(osm_b200_functional
 OSM_B200_API osm_b200_status osm_b200_functionals_run_device_cols(osm_b200_functionals *f, const float *d_rows, int32_t row_stride,
                                                                   const int32_t *cols, const int64_t *row_offsets, const int64_t *n_rows,
                                                                   int32_t n_utt, float *d_out, int64_t out_stride, void *stream);
+/* The glue the shipped summary graphs put behind their cFunctionals instances (config/gemaps/v01b/GeMAPSv01b_core.func.conf.inc:
+ * 133-139 cDataSelector picks and renames summary values, config/egemaps/v02/eGeMAPSv02_core.func.conf.inc:34-42 cVectorOperation
+ * turns the mean energy into dB, eGeMAPSv02.conf:31-34 cVectorConcat orders the row): out[r][k] = op_k(in[r][src[k]]) for r < n_rows,
+ * k < n_out.  src / op / log_floor: HOST arrays of n_out entries (n_out <= OSM_B200_SUMMARY_MAX_OUT); op = OSM_B200_VOP_*:
+ * COPY, DBP = 10 / ln 10 * ln(max(x, log_floor)), DBV = 20 / ln 10 * ln(...) (other/vectorOperation.cpp:508-527, float arithmetic).
+ * d_in: device [n_rows][in_stride], d_out: device [n_rows][out_stride].  Asynchronous on `stream`. */
+enum { OSM_B200_VOP_COPY = 0, OSM_B200_VOP_DBP = 1, OSM_B200_VOP_DBV = 2 };
+#define OSM_B200_SUMMARY_MAX_OUT 320
+OSM_B200_API osm_b200_status osm_b200_summary_assemble_device(const float *d_in, int64_t in_stride, const int32_t *src, const int32_t *op,
+                                                              const float *log_floor, int32_t n_out, int64_t n_rows, float *d_out,
+                                                              int64_t out_stride, void *stream);
 /* same with host buffers (copies in, runs, copies out, synchronises) */
 OSM_B200_API osm_b200_status osm_b200_functionals_run_host(osm_b200_functionals *f, const float *rows, int32_t row_stride,
                                                            const int64_t *row_offsets, const int64_t *n_rows, int32_t n_utt,

@@ -574,13 +574,14 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       G.noZero = g.stages[0].flags & 1;
       G.deltaWin = g.stages.size() > 1 ? g.stages[1].win : 0;
       G.segId = g.segId;
+      G.gateCol = g.gateCol; G.gateFlags = (g.gateInvert ? 1 : 0) | (g.gateAllowEqual ? 2 : 0); G.gateThr = g.gateThreshold; G.gateOut = g.gateOutVal;
       if (G.nStages == 2 && G.deltaWin != 2) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cDeltaRegression(onlyInSegments) behind the pitch chain: deltawin must be 2"); }
       if (G.nStages == 2) {
         int segCols = 0;
         for (int q = 0; q < sq.nGroups; q++) if (sq.groups[q].nStages == 2 && sq.groups[q].segId == G.segId) segCols += sq.groups[q].n;
         if (segCols > 32) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "cDeltaRegression(onlyInSegments): more than 32 elements"); }
       }
-      if (G.segId >= kMaxSeqGroups) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many onlyInSegments delta components"); }
+      if (G.segId >= kMaxSegIds) { osm_b200_plan_destroy(pl); return fail(OSM_B200_ERR_UNSUPPORTED, "too many onlyInSegments delta components"); }
       sq.frameSize = d.streams[g.stream].fe.frameSize; sq.frameStep = d.streams[g.stream].fe.frameStep;
       continue;
     }

@@ -19,6 +19,7 @@
 // combines them by shuffles -- a reordering of double additions, 1e-16 relative, invisible in the float results.
 // Compiled with -fmad=false (the float expressions of the percentile interpolation keep their two roundings).
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <math.h>
 #include <string.h>
 
@@ -449,6 +450,33 @@ int resolve_norm(int own, int ownSet, int master)            // functionalCompon
   return master != OSM_B200_TIMENORM_UNSET ? master : own;
 }
 
+// summary glue: gather + cVectorOperation dBp / dBv (other/vectorOperation.cpp:508-527)
+struct AssembleParams {
+  const float *in; float *out;
+  long long inStride, outStride, nRows;
+  int nOut;
+  short src[OSM_B200_SUMMARY_MAX_OUT];
+  unsigned char op[OSM_B200_SUMMARY_MAX_OUT];
+  float floorv[OSM_B200_SUMMARY_MAX_OUT];
+};
+
+__global__ void __launch_bounds__(128) summary_assemble_kernel(const __grid_constant__ AssembleParams p)
+{
+  const long long total = p.nRows * p.nOut;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / p.nOut;
+    const int k = (int)(i - r * p.nOut);
+    float x = p.in[r * p.inStride + p.src[k]];
+    const int op = p.op[k];
+    if (op != OSM_B200_VOP_COPY) {
+      const float factor = op == OSM_B200_VOP_DBP ? (float)(10.0 / 2.302585092994046) : (float)(20.0 / 2.302585092994046);
+      const float fl = p.floorv[k];
+      x = factor * logf(x > fl ? x : fl);
+    }
+    p.out[r * p.outStride + k] = x;
+  }
+}
+
 }  // namespace
 }  // namespace osm
 
@@ -723,6 +751,28 @@ osm_b200_status osm_b200_functionals_run_device_cols(osm_b200_functionals *f, co
   const int groups = (f->nIn + nWarps - 1) / nWarps;
   functionals_kernel<<<(unsigned)((long long)n_utt * groups), nWarps * 32, smem, st>>>(p);
   FCU(cudaGetLastError());
+  return OSM_B200_OK;
+}
+
+osm_b200_status osm_b200_summary_assemble_device(const float *d_in, int64_t in_stride, const int32_t *src, const int32_t *op, const float *log_floor,
+                                                 int32_t n_out, int64_t n_rows, float *d_out, int64_t out_stride, void *stream)
+{
+  if (!d_in || !d_out || !src || n_out < 1 || n_rows < 0) return set_last_error(OSM_B200_ERR_INVALID, "summary_assemble: null argument");
+  if (n_out > OSM_B200_SUMMARY_MAX_OUT) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "summary_assemble: more than OSM_B200_SUMMARY_MAX_OUT output values");
+  if (n_rows == 0) return OSM_B200_OK;
+  AssembleParams p;
+  p.in = d_in; p.out = d_out; p.inStride = in_stride; p.outStride = out_stride; p.nRows = n_rows; p.nOut = n_out;
+  for (int k = 0; k < n_out; k++) {
+    if (src[k] < 0 || src[k] >= in_stride || src[k] > 32767) return set_last_error(OSM_B200_ERR_INVALID, "summary_assemble: source index out of range");
+    const int o = op ? op[k] : OSM_B200_VOP_COPY;
+    if (o < OSM_B200_VOP_COPY || o > OSM_B200_VOP_DBV) return set_last_error(OSM_B200_ERR_INVALID, "summary_assemble: unknown operation");
+    p.src[k] = (short)src[k]; p.op[k] = (unsigned char)o; p.floorv[k] = log_floor ? log_floor[k] : 1e-12f;
+  }
+  const long long total = n_rows * n_out;
+  const int blocks = (int)std::min<long long>((total + 127) / 128, 148LL * 8);
+  summary_assemble_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_last_error(OSM_B200_ERR_CUDA, std::string("summary_assemble: ") + cudaGetErrorString(e));
   return OSM_B200_OK;
 }
 

@@ -263,6 +263,9 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
   struct SelScope { const osm_b200_component *c; size_t l0, l1, above; };   // leaves [l0, l1) sit below selector c, `above` stages above it
   std::vector<SelScope> selScopes;
   bool inSelector = false;
+  // leaves [l0, l1) are the data levels of a cValbasedSelector (zeroVec = 1) that gates them element-wise with a column of the pitch level
+  struct GateScope { const osm_b200_component *c; size_t l0, l1, above; };
+  std::vector<GateScope> gateScopes;
   std::vector<std::vector<std::string>> leafSelNames;   // per leaf: element names as a selector above it sees them
   std::function<osm_b200_status(const std::string &, std::vector<const osm_b200_component *>, int, bool)> expand =
     [&](const std::string &lvl, std::vector<const osm_b200_component *> above, int depth, bool arraysOnly) -> osm_b200_status {
@@ -300,6 +303,30 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       inSelector = false;
       if (!stageComps.empty() && c->n_inputs > 1) concatChecks.push_back({l0, leaves.size(), stageComps.size()});
       selScopes.push_back(SelScope{c, l0, leaves.size(), stageComps.size()});
+      return OSM_B200_OK;
+    }
+    if (c->type == OSM_B200_C_VALBASEDSELECTOR && !multi &&
+        !(c->n_inputs == 2 && R.prod(c->reader_dmLevel[1]) && R.prod(c->reader_dmLevel[1])->type == OSM_B200_C_PITCHSMOOTHERVITERBI)) {
+      // cValbasedSelector over [selector level ; data levels ...] with zeroVec = 1 (GeMAPSv01b_core.lld.conf.inc:395-433: formants /
+      // spectral parameters of the voiced resp. unvoiced frames): every frame is written, its elements either copied or set to
+      // outputVal, so the gate works element by element like the temporal stages above it.  The pitch chain's own selector
+      // ([energy ; cPitchSmootherViterbi level]) is part of the SHS pitch op (get_op).
+      const auto &q = c->u.valbasedselector;
+      if (c->n_inputs < 2) { err = "cValbasedSelector must read at least two levels: selector;data"; return OSM_B200_ERR_UNSUPPORTED; }
+      if (q.idx != 0 || !q.removeIdx || !q.zeroVec || q.adaptiveThreshold) { err = "cValbasedSelector: only idx=0, removeIdx=1, zeroVec=1, adaptiveThreshold=0 are supported"; return OSM_B200_ERR_UNSUPPORTED; }
+      if (arraysOnly) { err = "cValbasedSelector below a cVectorConcat that drops single-element fields is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+      for (const GateScope &gs : gateScopes) if (gs.l1 == (size_t)-1) { err = "nested cValbasedSelector levels are not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+      const size_t l0 = leaves.size();
+      gateScopes.push_back(GateScope{c, l0, (size_t)-1, stageComps.size()});
+      const size_t me = gateScopes.size() - 1;
+      for (int i = 1; i < c->n_inputs; i++) {
+        osm_b200_status s2 = expand(c->reader_dmLevel[i], stageComps, depth + 1, false);
+        if (s2 != OSM_B200_OK) return s2;
+      }
+      gateScopes[me].l1 = leaves.size();
+      for (size_t l = l0; l < leaves.size(); l++)
+        if (leaves[l].stages.size() != stageComps.size()) { err = "cValbasedSelector reading an already smoothed level is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+      if (!stageComps.empty() && c->n_inputs > 2) concatChecks.push_back({l0, leaves.size(), stageComps.size()});
       return OSM_B200_OK;
     }
     if (c->type == OSM_B200_C_VECTORCONCAT || multi) {
@@ -758,6 +785,33 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     return OSM_B200_OK;
   };
 
+  // ---- cValbasedSelector gates: the selector value must be one column of the SHS pitch level (directly, or through a cDataSelector
+  // that picks it: GeMAPSv01b_core.lld.conf.inc:385-391) ----
+  struct GateInfo { int col, pitchOp; };
+  std::vector<GateInfo> gateInfo;
+  for (const GateScope &gs : gateScopes) {
+    const osm_b200_component *sl = R.prod(gs.c->reader_dmLevel[0]);
+    if (!sl) { err = std::string("level '") + gs.c->reader_dmLevel[0] + "' has no writer"; return OSM_B200_ERR_INVALID; }
+    const char *want = nullptr;
+    if (sl->type == OSM_B200_C_DATASELECTOR) {
+      if (sl->u.dataselector.nSelected != 1 || sl->n_inputs != 1 || !sl->u.dataselector.elementMode) { err = "cValbasedSelector: a cDataSelector selector level must pick exactly one element of one level"; return OSM_B200_ERR_UNSUPPORTED; }
+      want = sl->u.dataselector.selected[0];
+      sl = R.prod(sl->reader_dmLevel[0]);
+      if (!sl) { err = "cValbasedSelector: the selector level has no writer"; return OSM_B200_ERR_INVALID; }
+    }
+    int so = -1;
+    osm_b200_status s3 = get_op(sl, so);
+    if (s3 != OSM_B200_OK) return s3;
+    if (d.ops[so].kind != SOP_PITCH) { err = "cValbasedSelector: the selector level must come from the SHS pitch chain (cPitchSmootherViterbi)"; return OSM_B200_ERR_UNSUPPORTED; }
+    int col = -1, cc = d.ops[so].outCol;
+    for (const FieldName &f : d.ops[so].fields) {
+      if (f.n == 1 && (want ? f.name == want : d.ops[so].nOut == 1)) { col = cc; break; }
+      cc += f.n;
+    }
+    if (col < 0) { err = want ? std::string("cValbasedSelector: selector element '") + want + "' not found in the pitch level" : std::string("cValbasedSelector: the selector level must hold exactly one element"); return OSM_B200_ERR_UNSUPPORTED; }
+    gateInfo.push_back(GateInfo{col, so});
+  }
+
   std::vector<const osm_b200_component *> segComps;     // cDeltaRegression instances with onlyInSegments=1
   for (const Leaf &leaf : leaves) {
     const osm_b200_component *c = leaf.c;
@@ -773,6 +827,9 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     std::vector<FieldName> fields = d.ops[opIdx].fields;
     int segId = -1;
     const size_t leafIdx = (size_t)(&leaf - &leaves[0]);
+    long gateIdx = -1;
+    for (size_t q = 0; q < gateScopes.size(); q++) if (leafIdx >= gateScopes[q].l0 && leafIdx < gateScopes[q].l1) gateIdx = (long)q;
+    if (gateIdx >= 0) for (auto &f : fields) f.name = name_append_auto(*gateScopes[gateIdx].c, f.name, nullptr);   // other/valbasedSelector.cpp:84-97
     long selAbove = -1;                                  // stages above the selector this leaf sits below, -1 = none
     for (const SelScope &sc : selScopes) if (leafIdx >= sc.l0 && leafIdx < sc.l1) selAbove = (long)sc.above;
     auto element_names = [&](const std::vector<FieldName> &fs) {
@@ -833,6 +890,16 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
           if (d.ops[opIdx].kind == SOP_PITCH) { g.lagKind = 1; g.lagOp = opIdx; }
           if (d.ops[opIdx].kind == SOP_JITTER) { g.lagKind = 2; g.lagOp = d.ops[opIdx].jitter.pitchOp; }
           if (d.ops[opIdx].kind == SOP_HARMONICS) { g.lagKind = 1; g.lagOp = d.ops[opIdx].harmonics.pitchOp; }
+          if (gateIdx >= 0) {
+            const auto &q = gateScopes[gateIdx].c->u.valbasedselector;
+            g.gateCol = gateInfo[gateIdx].col;
+            g.gateThreshold = (float)q.threshold; g.gateOutVal = (float)q.outputVal;
+            g.gateInvert = q.invert != 0; g.gateAllowEqual = q.allowEqual != 0;
+            // the gate reads the pitch level: its output ends where that level ends (truncating reader) and lags with it
+            if (g.lagKind == 0) g.lagKind = 1;
+            if (g.lagOp >= 0 && g.lagOp != gateInfo[gateIdx].pitchOp) { err = "cValbasedSelector: data behind another pitch chain than the selector's"; return OSM_B200_ERR_UNSUPPORTED; }
+            g.lagOp = gateInfo[gateIdx].pitchOp;
+          }
           g.segId = segId;
           d.groups.push_back(g);
           open = true;
@@ -972,6 +1039,23 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     d.groups.swap(ng);
     d.names.swap(nn);
     d.nOut = outCol;
+  }
+
+  // ---- gated groups: every data level must deliver at least the rows of the pitch level (same step, frames not longer), the gate's
+  // output then has the pitch level's length ----
+  for (OutGroup &g : d.groups) {
+    if (g.gateCol < 0) continue;
+    const int ps = d.ops[g.lagOp].stream;
+    const FrontEnd &fp = d.streams[ps].fe;
+    std::vector<int> chk = g.limitStreams;
+    chk.push_back(g.stream);
+    for (int sidx : chk) {
+      const FrontEnd &fx = d.streams[sidx].fe;
+      if (fx.frameStep != fp.frameStep || fx.frameSize > fp.frameSize) { err = "cValbasedSelector: a data level of another frame step / longer frames than the pitch level is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+    }
+    g.limitStreams.clear();
+    g.stream = ps;
+    if (g.stages.empty()) { err = "a cValbasedSelector level as output level (no cContourSmoother behind it) is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
   }
 
   // ---- groups behind a Viterbi-smoothed pitch level (seq_post_kernel) ----

@@ -298,8 +298,10 @@ struct JitterParams {
 };
 cudaError_t launch_jitter(const JitterParams &p, int u0, int u1, cudaStream_t st);
 
-struct SeqGroup { int srcCol, n, outCol, lagKind, nStages, deltaWin, noZero, segId; };
-constexpr int kMaxSeqGroups = 16;
+// gateCol >= 0: cValbasedSelector (zeroVec) in front of the smoother -- the value of row i is the source value when the selector
+// column passes the threshold (gateFlags bit 0 = invert, bit 1 = allowEqual), else gateOut (other/valbasedSelector.cpp:195-233)
+struct SeqGroup { int srcCol, n, outCol, lagKind, nStages, deltaWin, noZero, segId, gateCol, gateFlags; float gateThr, gateOut; };
+constexpr int kMaxSeqGroups = 56, kMaxSegIds = 16;
 struct SeqPostParams {
   const float *stat; int statStride;
   const long long *statOff, *rowOff, *uttOff;

@@ -846,12 +846,18 @@ struct SeqCtx { const float *x; int stride; int T; int V; };
 // cContourSmoother (smaWin = 3) value of row m, column c (dspcore/contourSmoother.cpp:84-117) with the
 // end-of-input behaviour of a reader over [pitch level ; jitter level]: rows V-1 and V are produced during the
 // reference's first EOI pass, when the jitter level (lagKind 2) still ends at its row V-1
-__device__ float seq_sma(const SeqCtx &c, int col, int m, int lagKind, int noZero)
+__device__ float seq_sma(const SeqCtx &c, const SeqGroup &G, int k, int m)
 {
+  const int col = G.srcCol + k, lagKind = G.lagKind, noZero = G.noZero;
   const bool lagged = lagKind == 2 && c.V >= 1 && (m == c.V - 1 || m == c.V);   // V == 0: nothing runs in the first pass
   auto g = [&](int i) -> float {
     i = min(max(i, 0), c.T - 1);
     if (lagged && i > c.V - 1) i = c.V - 1;
+    if (G.gateCol >= 0) {                                                         // other/valbasedSelector.cpp:195-233
+      const float sel = c.x[(size_t)i * c.stride + G.gateCol];
+      const bool pass = ((G.gateFlags & 1) ? sel < G.gateThr : sel > G.gateThr) || ((G.gateFlags & 2) && sel == G.gateThr);
+      if (!pass) return G.gateOut;
+    }
     return c.x[(size_t)i * c.stride + col];
   };
   const float x0 = g(m);
@@ -891,7 +897,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) seq_post_kernel(const SeqPostP
     const SeqGroup &G = p.groups[g];
     if (G.nStages != 1) continue;
     for (int m = lane; m <= T && m < R; m += 32)
-      for (int k = 0; k < G.n; k++) out[(size_t)m * p.outStride + G.outCol + k] = seq_sma(c, G.srcCol + k, m, G.lagKind, G.noZero);
+      for (int k = 0; k < G.n; k++) out[(size_t)m * p.outStride + G.outCol + k] = seq_sma(c, G, k, m);
   }
   // 2. deltas with onlyInSegments: one running norm per delta component (dspcore/deltaRegression.cpp:77-79,123-141),
   //    rows in order, elements in column order: norm(n, k) = 2*sum i^2 + (i^2 of every accepted pair before and
@@ -899,7 +905,7 @@ __global__ void __launch_bounds__(kSeqWarps * 32) seq_post_kernel(const SeqPostP
   //    Rows V-1..V+2 are produced during the reference's first EOI pass, when the smoothed level ends at its row V;
   //    row V+3 (for T-5 <= V <= T-2) in the first tick of the second pass, when it ends at row T-1
   //    (core/dataMemoryLevel.cpp:1020-1027,1698-1708).
-  for (int seg = 0; seg < kMaxSeqGroups; seg++) {
+  for (int seg = 0; seg < kMaxSegIds; seg++) {
     int W = 0;
     for (int g = 0; g < p.nGroups; g++) if (p.groups[g].nStages == 2 && p.groups[g].segId == seg) W = p.groups[g].deltaWin;
     if (W == 0) continue;
@@ -923,8 +929,8 @@ __global__ void __launch_bounds__(kSeqWarps * 32) seq_post_kernel(const SeqPostP
           float nm = 0.0f; int ct = 0;
           if (live) {
             for (int i = 1; i <= W; i++) {
-              const float a = seq_sma(c, G.srcCol + k, min(max(n - i, 0), last), G.lagKind, G.noZero);
-              const float b = seq_sma(c, G.srcCol + k, min(max(n + i, 0), last), G.lagKind, G.noZero);
+              const float a = seq_sma(c, G, k, min(max(n - i, 0), last));
+              const float b = seq_sma(c, G, k, min(max(n + i, 0), last));
               if (!(a == 0.0f || a != a || b == 0.0f || b != b)) { nm += (float)i * (b - a); ct += i * i; }
             }
           }

@@ -228,6 +228,11 @@ struct OutGroup {
   // reference's first end-of-input pass), lagOp = the pitch chain op that supplies the per-utterance lag,
   // segId >= 0 = groups sharing one onlyInSegments delta component (one running norm, in column order)
   int lagKind = 0, lagOp = -1, segId = -1;
+  // cValbasedSelector in front of the stages (other/valbasedSelector.cpp:153-233, zeroVec = 1): the element of row i is the source
+  // value when the selector value sel[i] (static column gateCol) passes the threshold, else gateOutVal
+  int gateCol = -1;
+  float gateThreshold = 0.f, gateOutVal = 0.f;
+  bool gateInvert = false, gateAllowEqual = false;
 };
 
 // one framer -> [pre-emphasis] -> [window] -> [FFT -> magnitude] chain

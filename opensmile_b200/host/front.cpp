@@ -16,6 +16,7 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include <functional>
 
 #include "../../include/osm_b200_host.h"
 #include "../../include/osm_b200_functionals.h"
@@ -680,7 +681,7 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     if (f == "nonZeroFuncts") { fs.nonZeroFuncts = inum(v); continue; }
     if (f == "functNameAppend") { snprintf(fs.functNameAppend, sizeof fs.functNameAppend, "%s", v.c_str()); continue; }
     if (f == "masterTimeNorm") { fs.masterTimeNorm = time_norm(v); continue; }
-    if (f == "preserveFields") { if (inum(v)) { err = "cFunctionals.preserveFields=1 is not supported"; return false; } continue; }
+    if (f == "preserveFields") continue;             // checked by the session against the input level (single-element fields only)
     if (f == "Extremes.norm") { E.norm = time_norm(v); E.normIsSet = 1; continue; }
     if (f == "Means.norm") { M.norm = time_norm(v); M.normIsSet = 1; continue; }
     if (f == "Regression.centroidNorm") { R.centroidNorm = time_norm(v); continue; }
@@ -1067,21 +1068,41 @@ struct osm_b200_session {
   // a reader level of an instance: a level of the plan, or the view a cDataSelector (`selected` names + nameAppend) gives of one
   struct FuncReader { std::string level; std::vector<std::string> sel; std::string nameAppend;
                       bool operator==(const FuncReader &o) const { return level == o.level && sel == o.sel && nameAppend == o.nameAppend; } };
-  struct FuncInst { osm_b200_functionals_spec spec; std::vector<FuncReader> readers; };
-  std::vector<FuncInst> finsts;              // in the order of the summary row
+  struct FuncInst { osm_b200_functionals_spec spec; std::vector<FuncReader> readers; bool preserveFields = false; };
+  std::vector<FuncInst> finsts;              // in the order of their first appearance in the summary row
+  // what sits between the cFunctionals levels and the sink (the shipped GeMAPS / eGeMAPS summary graphs): cVectorConcat (any depth),
+  // cDataSelector (picks and renames summary values, core/dataSelector.cpp:296-366), cVectorOperation dBp / dBv
+  // (other/vectorOperation.cpp:508-527).  All of it works value by value on the summary row, so the instances write their values
+  // side by side into a scratch row and one gather pass (osm_b200_summary_assemble_device) produces the sink's row.
+  struct SummNode {
+    int kind = 0;                            // 0 cFunctionals instance, 1 concat, 2 cDataSelector, 3 cVectorOperation
+    int inst = -1;
+    std::vector<int> kids;
+    std::vector<std::string> sel, newNames;  // cDataSelector
+    std::string nameAppend;                  // cDataSelector / cVectorOperation (the operation name when appendOperationToName = 1)
+    std::string nameBase;                    // cVectorOperation
+    bool copyInputName = true;
+    int op = 0; float logfloor = 1e-12f;     // OSM_B200_VOP_*
+  };
+  std::vector<SummNode> snodes;
+  int sroot = -1;
   std::vector<std::string> unionLevels;      // levels of the plan's output level, in order
   struct FuncRt {                            // per input format
     std::vector<osm_b200_functionals *> f;
     std::vector<std::vector<int32_t>> cols;  // columns of every instance's input elements inside the plan's rows
     std::vector<std::vector<std::string>> inNames;
     std::vector<osm_b200_plan *> desc;       // description-only plan over the instance's reader levels (its frame-count rule); null = the main plan
-    std::vector<int> off;                    // first value of every instance inside the summary row
-    std::vector<std::string> names;
+    std::vector<int> off;                    // first value of every instance inside the scratch row
+    int scratch = 0;                         // values per scratch row (all instances side by side)
+    std::vector<std::string> names;          // the sink's row
     int total = 0;
+    bool identity = true;                    // the sink's row is the scratch row
+    std::vector<int32_t> gSrc, gOp; std::vector<float> gFloor;
   };
   std::map<std::pair<long, int>, FuncRt> funcs;
   FuncRt *curFunc = nullptr;
   float *dFuncOut = nullptr; size_t funcOutCap = 0;
+  float *dFuncScratch = nullptr; size_t funcScratchCap = 0;
 };
 
 static void split_levels(const std::string &v, std::vector<std::string> &out)
@@ -1163,7 +1184,7 @@ static osm_b200_status build_func_rt(osm_b200_session *s, double sampleRate, int
     }
     if (o != K) return hfail(OSM_B200_ERR_INVALID, "cFunctionals: the levels of the summary's inputs do not add up to the plan's row");
   }
-  rt.total = 0;
+  rt.total = 0; rt.scratch = 0;
   for (const osm_b200_session::FuncInst &fi : s->finsts) {
     std::vector<int32_t> cols;
     std::vector<std::string> inNames;
@@ -1194,11 +1215,60 @@ static osm_b200_status build_func_rt(osm_b200_session *s, double sampleRate, int
       st = desc_plan(s, sampleRate, nChan, plain, &d);
       if (st != OSM_B200_OK) { osm_b200_functionals_destroy(f); free_func_rt(rt); return st; }
     }
-    rt.f.push_back(f); rt.cols.push_back(cols); rt.desc.push_back(d); rt.off.push_back(rt.total);
-    const int n = osm_b200_functionals_num_elements(f);
-    for (int i = 0; i < n; i++) rt.names.push_back(osm_b200_functionals_element_name(f, i));
-    rt.total += n;
+    if (fi.preserveFields && cols.size() != 1) {
+      // preserveFields = 1 keeps the field structure of the input (functionals.cpp:133-137); for single-element fields that is the
+      // same row, which is all the shipped graphs ask for (eGeMAPSv02_core.func.conf.inc:14-19)
+      osm_b200_functionals_destroy(f); if (d) osm_b200_plan_destroy(d); free_func_rt(rt);
+      return hfail(OSM_B200_ERR_UNSUPPORTED, "cFunctionals.preserveFields=1 on more than one input element is not supported");
+    }
+    rt.f.push_back(f); rt.cols.push_back(cols); rt.desc.push_back(d); rt.off.push_back(rt.scratch);
+    rt.scratch += osm_b200_functionals_num_elements(f);
   }
+  // the sink's row: walk the summary graph over the instances' values
+  struct El { int src; int op; float fl; std::string name; };
+  std::string terr;
+  std::function<bool(int, std::vector<El> &)> eval = [&](int ni, std::vector<El> &out) -> bool {
+    const osm_b200_session::SummNode &nd = s->snodes[(size_t)ni];
+    if (nd.kind == 0) {
+      const int n = osm_b200_functionals_num_elements(rt.f[(size_t)nd.inst]);
+      for (int j = 0; j < n; j++) out.push_back(El{rt.off[(size_t)nd.inst] + j, OSM_B200_VOP_COPY, 0.f, osm_b200_functionals_element_name(rt.f[(size_t)nd.inst], j)});
+      return true;
+    }
+    std::vector<El> in;
+    for (int k : nd.kids) if (!eval(k, in)) return false;
+    if (nd.kind == 1) { out.insert(out.end(), in.begin(), in.end()); return true; }
+    if (nd.kind == 2) {                                               // core/dataSelector.cpp:296-366 (elementMode)
+      for (size_t k = 0; k < nd.sel.size(); k++) {
+        const El *hit = nullptr;
+        for (const El &e : in) if (e.name == nd.sel[k]) { hit = &e; break; }
+        if (!hit) { terr = "cDataSelector: element '" + nd.sel[k] + "' not found in the summary levels it reads"; return false; }
+        El e = *hit;
+        if (k < nd.newNames.size() && !nd.newNames[k].empty()) e.name = nd.newNames[k];
+        else if (!nd.nameAppend.empty()) e.name += "_" + nd.nameAppend;
+        out.push_back(e);
+      }
+      return true;
+    }
+    for (El e : in) {                                                 // other/vectorOperation.cpp:226-249 + core/dataProcessor.cpp:250-269
+      if (e.op != OSM_B200_VOP_COPY) { terr = "chained cVectorOperation instances behind cFunctionals are not supported"; return false; }
+      const std::string base = !nd.nameBase.empty() ? nd.nameBase : e.name;
+      if (!nd.nameAppend.empty()) e.name = (nd.copyInputName && !base.empty()) ? base + "_" + nd.nameAppend : nd.nameAppend;
+      else e.name = (nd.copyInputName && !base.empty()) ? base : std::string("noname");
+      e.op = nd.op; e.fl = nd.logfloor;
+      out.push_back(e);
+    }
+    return true;
+  };
+  std::vector<El> els;
+  if (!eval(s->sroot, els)) { free_func_rt(rt); return hfail(OSM_B200_ERR_INVALID, terr); }
+  if (els.empty()) { free_func_rt(rt); return hfail(OSM_B200_ERR_INVALID, "the summary level has no elements"); }
+  rt.total = (int)els.size();
+  rt.identity = rt.total == rt.scratch;
+  for (size_t k = 0; k < els.size(); k++) {
+    rt.names.push_back(els[k].name); rt.gSrc.push_back(els[k].src); rt.gOp.push_back(els[k].op); rt.gFloor.push_back(els[k].fl);
+    if (els[k].src != (int)k || els[k].op != OSM_B200_VOP_COPY) rt.identity = false;
+  }
+  if (!rt.identity && rt.total > OSM_B200_SUMMARY_MAX_OUT) { free_func_rt(rt); return hfail(OSM_B200_ERR_UNSUPPORTED, "a re-ordered / transformed summary row of more than OSM_B200_SUMMARY_MAX_OUT values is not supported"); }
   return OSM_B200_OK;
 }
 
@@ -1319,46 +1389,31 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
   {
     std::map<std::string, const Section *> writerOfAll;
     for (const Section *sec : compute) if (const std::string *w = sec->get("writer.dmLevel")) writerOfAll[*w] = sec;
-    // level -> the cFunctionals section behind it (through single-input concats), or null
-    auto func_behind = [&](std::string cur) -> const Section * {
-      for (int guard = 0; guard < 16; guard++) {
-        auto it = writerOfAll.find(cur);
-        if (it == writerOfAll.end()) return nullptr;
-        const Section *w = it->second;
-        if (w->type == "cFunctionals") return w;
-        const std::string *r = w->get("reader.dmLevel");
-        if (w->type == "cVectorConcat" && r && r->find(';') == std::string::npos) { cur = trim(*r); continue; }
-        return nullptr;
-      }
-      return nullptr;
+    // the summary graph behind the sink: cFunctionals levels below cVectorConcat / cDataSelector / cVectorOperation nodes
+    std::function<bool(const std::string &, int)> has_func = [&](const std::string &cur, int depth) -> bool {
+      auto it = writerOfAll.find(cur);
+      if (it == writerOfAll.end() || depth > 16) return false;
+      const Section *w = it->second;
+      if (w->type == "cFunctionals") return true;
+      if (w->type != "cVectorConcat" && w->type != "cDataSelector" && w->type != "cVectorOperation") return false;
+      const std::string *r = w->get("reader.dmLevel");
+      if (!r) return false;
+      std::vector<std::string> rl;
+      split_levels(*r, rl);
+      for (const std::string &l : rl) if (has_func(l, depth + 1)) return true;
+      return false;
     };
-    // the levels the summary row is made of: the sink's reader list, with one multi-input cVectorConcat expanded
-    std::vector<std::string> parts;
-    split_levels(lvl, parts);
-    if (parts.size() == 1 && !func_behind(parts[0])) {
-      std::string cur = parts[0];
-      for (int guard = 0; guard < 16; guard++) {
-        auto it = writerOfAll.find(cur);
-        if (it == writerOfAll.end() || it->second->type != "cVectorConcat") break;
-        const std::string *r = it->second->get("reader.dmLevel");
-        if (!r) break;
-        if (r->find(';') == std::string::npos) { cur = trim(*r); continue; }
-        parts.clear();
-        split_levels(*r, parts);
-        break;
-      }
-    }
-    std::vector<const Section *> fsecs;
-    for (const std::string &pl : parts) fsecs.push_back(func_behind(pl));
-    const bool allFunc = !fsecs.empty() && std::all_of(fsecs.begin(), fsecs.end(), [](const Section *x) { return x != nullptr; });
-    const bool anyFunc = std::any_of(fsecs.begin(), fsecs.end(), [](const Section *x) { return x != nullptr; });
-    if (anyFunc && !allFunc) { delete s; return hfail(OSM_B200_ERR_UNSUPPORTED, "a level that mixes cFunctionals summaries with other levels is not supported"); }
-    if (allFunc) {
-      for (const Section *w : fsecs) {
-        osm_b200_session::FuncInst fi;
-        if (!to_functionals(*w, fi.spec, err)) { delete s; return hfail(err.find("not supported") != std::string::npos ? OSM_B200_ERR_UNSUPPORTED : OSM_B200_ERR_INVALID, err); }
+    std::string terr;
+    osm_b200_status tst = OSM_B200_ERR_UNSUPPORTED;
+    std::map<const Section *, int> instOf;
+    auto add_inst = [&](const Section *w) -> int {
+      auto it = instOf.find(w);
+      if (it != instOf.end()) return it->second;
+      osm_b200_session::FuncInst fi;
+      if (!to_functionals(*w, fi.spec, terr)) { tst = terr.find("not supported") != std::string::npos ? OSM_B200_ERR_UNSUPPORTED : OSM_B200_ERR_INVALID; return -1; }
+      if (const std::string *x = w->get("preserveFields")) fi.preserveFields = inum(*x) != 0;
         const std::string *r = w->get("reader.dmLevel");
-        if (!r) { delete s; return hfail(OSM_B200_ERR_INVALID, "cFunctionals '" + w->name + "' has no reader.dmLevel"); }
+        if (!r) { terr = "cFunctionals '" + w->name + "' has no reader.dmLevel"; tst = OSM_B200_ERR_INVALID; return -1; }
         std::vector<std::string> rl;
         split_levels(*r, rl);
         for (const std::string &l : rl) {
@@ -1392,7 +1447,97 @@ osm_b200_status osm_b200_session_open(const char *conf_path, int32_t n_opts, con
           if (std::find(s->unionLevels.begin(), s->unionLevels.end(), rd.level) == s->unionLevels.end()) s->unionLevels.push_back(rd.level);
         }
         s->finsts.push_back(fi);
+      instOf[w] = (int)s->finsts.size() - 1;
+      return (int)s->finsts.size() - 1;
+    };
+    std::function<int(const std::string &, int)> build = [&](const std::string &cur, int depth) -> int {
+      auto it = writerOfAll.find(cur);
+      if (it == writerOfAll.end() || depth > 16) { terr = "level '" + cur + "' has no writer"; tst = OSM_B200_ERR_INVALID; return -1; }
+      const Section *w = it->second;
+      osm_b200_session::SummNode nd;
+      if (w->type == "cFunctionals") {
+        nd.kind = 0;
+        nd.inst = add_inst(w);
+        if (nd.inst < 0) return -1;
+        s->snodes.push_back(nd);
+        return (int)s->snodes.size() - 1;
       }
+      const std::string *r = w->get("reader.dmLevel");
+      if (!r || (w->type != "cVectorConcat" && w->type != "cDataSelector" && w->type != "cVectorOperation")) {
+        terr = "a level that mixes cFunctionals summaries with other levels is not supported (level '" + cur + "')"; tst = OSM_B200_ERR_UNSUPPORTED; return -1;
+      }
+      std::vector<std::string> rl;
+      split_levels(*r, rl);
+      for (const std::string &l : rl) { const int k = build(l, depth + 1); if (k < 0) return -1; nd.kids.push_back(k); }
+      if (w->type == "cVectorConcat") {
+        // summary levels hold single-element fields: a cVectorConcat that keeps only array fields (its default) would be empty
+        nd.kind = 1;
+        int paf = 1, incl = 0;
+        if (const std::string *x = w->get("processArrayFields")) paf = inum(*x);
+        if (const std::string *x = w->get("includeSingleElementFields")) incl = inum(*x);
+        if (paf == 1 && !incl && rl.size() > 1) { terr = "cVectorConcat '" + w->name + "' behind cFunctionals drops single-element fields (includeSingleElementFields = 0)"; tst = OSM_B200_ERR_UNSUPPORTED; return -1; }
+      } else if (w->type == "cDataSelector") {
+        nd.kind = 2;
+        std::map<int, std::string> selIdx, newIdx;
+        std::string selList, newList;
+        for (const auto &kv : w->kv) {
+          const std::string &f = kv.first;
+          if (f == "nameAppend") { nd.nameAppend = kv.second; continue; }
+          if (is_common(f) || f == "reader.dmLevel" || f == "writer.dmLevel") continue;
+          if (f == "selected") selList = kv.second;
+          else if (f.compare(0, 9, "selected[") == 0) selIdx[atoi(f.c_str() + 9)] = kv.second;
+          else if (f == "newNames") newList = kv.second;
+          else if (f.compare(0, 9, "newNames[") == 0) newIdx[atoi(f.c_str() + 9)] = kv.second;
+          else if (f == "elementMode") { if (inum(kv.second) != 1) { terr = "cDataSelector.elementMode=0 is not supported"; return -1; } }
+          else if (f == "copyInputName") { if (inum(kv.second) != 1) { terr = "cDataSelector.copyInputName=0 is not supported"; return -1; } }
+          else { terr = "cDataSelector '" + w->name + "': field '" + f + "' is not supported"; return -1; }
+        }
+        if (!selIdx.empty()) for (const auto &kv : selIdx) nd.sel.push_back(trim(kv.second)); else split_levels(selList, nd.sel);
+        if (!newIdx.empty()) { nd.newNames.assign(nd.sel.size(), ""); for (const auto &kv : newIdx) if (kv.first >= 0 && (size_t)kv.first < nd.newNames.size()) nd.newNames[(size_t)kv.first] = trim(kv.second); }
+        else split_levels(newList, nd.newNames);
+        if (nd.sel.empty()) { terr = "cDataSelector '" + w->name + "': no elements selected"; tst = OSM_B200_ERR_INVALID; return -1; }
+      } else {
+        nd.kind = 3;                                                  // other/vectorOperation.cpp:42-48,136-139,210-222
+        std::string opn = "norm";
+        int appendOp = 0;
+        double lf = 1e-12;                                            // default of `logfloor`
+        for (const auto &kv : w->kv) {
+          const std::string &f = kv.first;
+          if (f == "nameAppend") { nd.nameAppend = kv.second; continue; }
+          if (f == "copyInputName") { nd.copyInputName = inum(kv.second) != 0; continue; }
+          if (is_common(f) || f == "reader.dmLevel" || f == "writer.dmLevel") continue;
+          if (f == "operation") opn = kv.second;
+          else if (f == "nameBase") nd.nameBase = kv.second;
+          else if (f == "appendOperationToName") appendOp = inum(kv.second);
+          else if (f == "logfloor") lf = atof(kv.second.c_str());
+          else if (f == "processArrayFields" || f == "includeSingleElementFields" || f == "param1" || f == "param2" || f == "powOnlyPos") continue;
+          else { terr = "cVectorOperation '" + w->name + "': field '" + f + "' is not supported"; return -1; }
+        }
+        if (opn.compare(0, 3, "dBp") == 0) nd.op = OSM_B200_VOP_DBP;
+        else if (opn.compare(0, 3, "dBv") == 0) nd.op = OSM_B200_VOP_DBV;
+        else { terr = "cVectorOperation behind cFunctionals: only operation = dBp / dBv is supported (got '" + opn + "')"; return -1; }
+        if (appendOp) nd.nameAppend = opn;                             // overrides nameAppend (:210-216, :240-243)
+        if (lf <= 0) lf = 0.000000000001;                              // :219-223
+        nd.logfloor = (float)lf;
+        if (rl.size() != 1) { terr = "cVectorOperation must read exactly one level"; return -1; }
+      }
+      s->snodes.push_back(nd);
+      return (int)s->snodes.size() - 1;
+    };
+    std::vector<std::string> parts;
+    split_levels(lvl, parts);
+    bool anyFunc = false;
+    for (const std::string &pl : parts) anyFunc = anyFunc || has_func(pl, 0);
+    if (anyFunc) {
+      if (parts.size() == 1) s->sroot = build(parts[0], 0);
+      else {
+        osm_b200_session::SummNode root;
+        root.kind = 1;
+        bool ok = true;
+        for (const std::string &pl : parts) { const int k = build(pl, 0); if (k < 0) { ok = false; break; } root.kids.push_back(k); }
+        if (ok) { s->snodes.push_back(root); s->sroot = (int)s->snodes.size() - 1; }
+      }
+      if (s->sroot < 0) { delete s; return hfail(tst, terr); }
       if (s->unionLevels.size() > OSM_B200_MAX_INPUTS) { delete s; return hfail(OSM_B200_ERR_UNSUPPORTED, "cFunctionals: more than 8 input levels in total"); }
       s->hasFunc = true;
       lvl.clear();
@@ -1480,6 +1625,7 @@ void osm_b200_session_close(osm_b200_session *s)
   for (auto &kv : s->plans) osm_b200_plan_destroy(kv.second);
   for (auto &kv : s->funcs) free_func_rt(kv.second);
   if (s->dFuncOut) cudaFree(s->dFuncOut);
+  if (s->dFuncScratch) cudaFree(s->dFuncScratch);
   delete s;
 }
 
@@ -1572,8 +1718,19 @@ static osm_b200_status osm_b200_session_extract_pcm_impl(osm_b200_session *s, co
                                                                lldOff[u + 1] - lldOff[u]));
       }
     }
-    const int KF = f->total;
+    const int KF = f->total, KS = f->scratch;
     const size_t need = live.size() * (size_t)KF;
+    float *dInst = nullptr;                                            // where the instances write: the sink's row or the scratch row
+    if (!f->identity) {
+      const size_t needS = live.size() * (size_t)KS;
+      if (s->funcScratchCap < needS) {
+        if (s->dFuncScratch) cudaFree(s->dFuncScratch);
+        s->dFuncScratch = nullptr; s->funcScratchCap = 0;
+        if (cudaMalloc(reinterpret_cast<void **>(&s->dFuncScratch), needS * sizeof(float)) != cudaSuccess) return hfail(OSM_B200_ERR_NOMEM, "out of device memory (functionals scratch rows)");
+        s->funcScratchCap = needS;
+      }
+      dInst = s->dFuncScratch;
+    }
     if (s->funcOutCap < need) {
       if (s->dFuncOut) cudaFree(s->dFuncOut);
       s->dFuncOut = nullptr; s->funcOutCap = 0;
@@ -1582,7 +1739,11 @@ static osm_b200_status osm_b200_session_extract_pcm_impl(osm_b200_session *s, co
     }
     for (size_t i = 0; i < nI; i++) {
       st = osm_b200_functionals_run_device_cols(f->f[i], dRows, osm_b200_plan_num_elements(p), f->cols[i].data(), rowOff.data(), nRows[i].data(),
-                                                (int)live.size(), s->dFuncOut + f->off[i], KF, nullptr);
+                                                (int)live.size(), (dInst ? dInst : s->dFuncOut) + f->off[i], KS, nullptr);
+      if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    }
+    if (dInst) {
+      st = osm_b200_summary_assemble_device(dInst, KS, f->gSrc.data(), f->gOp.data(), f->gFloor.data(), KF, (int64_t)live.size(), s->dFuncOut, KF, nullptr);
       if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
     }
     if (cudaMemcpy(out, s->dFuncOut, need * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return hfail(OSM_B200_ERR_CUDA, "copy of the functionals rows failed");

@@ -203,10 +203,29 @@ def test_unimplemented_functionals_are_refused_loudly(tmp_path):
     with pytest.raises(SessionError) as e:
         _session(str(bad), {"outA": "x.csv"})
     assert "bogusField" in str(e.value)
-    # the shipped eGeMAPS summary needs Peaks2 / Segments: the LLD output works, the functionals output says what is missing
-    with pytest.raises(SessionError) as e:
-        _session(os.path.join(REFCONF, "egemaps", "v02", "eGeMAPSv02.conf"), {"csvoutput": "x.csv"})
-    assert e.value.status == capi.ERR_UNSUPPORTED
+    # glue the summary graphs do not use stays refused: another cVectorOperation behind the functionals, a concat that drops the fields
+    ege = open(os.path.join(REFCONF, "egemaps", "v02", "eGeMAPSv02.conf")).read()
+    for a, b, needle in (("includeSingleElementFields = 1\n\n\\{../../shared/standard_data_output_no_lld_de", "includeSingleElementFields = 0\n\n\\{../../shared/standard_data_output_no_lld_de", "drops single-element fields"),):
+        assert a in ege
+        d = tmp_path / "egemaps" / "v02"
+        d.mkdir(parents=True, exist_ok=True)
+        (d / "bad.conf").write_text(ege.replace(a, b).replace("\\{../../", "\\{" + REFCONF + "/").replace("\\{eGeMAPSv02_core", "\\{" + REFCONF + "/egemaps/v02/eGeMAPSv02_core"))
+        with pytest.raises(SessionError) as e:
+            _session(str(d / "bad.conf"), {"csvoutput": "x.csv"})
+        assert e.value.status == capi.ERR_UNSUPPORTED and needle in str(e.value)
+
+
+GGF = np.load(os.path.join(HERE, "golden", "gemaps_func.npz"))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "egemaps")), reason="reference configuration files not built (make -C oracle ref)")
+@pytest.mark.parametrize("conf,tag", [("egemaps/v02/eGeMAPSv02.conf", "egemaps"), ("gemaps/v01b/GeMAPSv01b.conf", "gemaps")])
+def test_gemaps_summary_names(conf, tag):
+    """the shipped GeMAPS / eGeMAPS files open unchanged with -csvoutput: cVectorConcat / cDataSelector (newNames) / cVectorOperation
+    (dBp) behind eight cFunctionals instances, cValbasedSelector gates in front of them -- the reference's 62 / 88 names"""
+    s = _session(os.path.join(REFCONF, conf), {"csvoutput": "x.csv"})
+    assert s.element_names() == [str(x) for x in GGF["names_" + tag]]
+    s.close()
 
 
 def test_spec_mirror_and_descriptions():
@@ -218,3 +237,44 @@ def test_spec_mirror_and_descriptions():
     with pytest.raises(RuntimeError):                                                   # description-only objects never compute
         f.run_host(np.zeros((4, 32), np.float32), [0], [4])
     f.close()
+
+
+def test_gemaps_summary_oracle_on_the_reference_levels():
+    """oracle/gemaps_summary_oracle.py (eight cFunctionals instances + cDataSelector renaming + dBp) on the reference's own dumps of the
+    seven input levels reproduces the reference's 88-value eGeMAPSv02 row.  The rows every instance sees at the first end-of-input
+    tick (graph.cpp:desc_num_frames_first_eoi): static level T, smoothed level T (of T + 1), levels behind the Viterbi smoother V =
+    143 / 193 / 198 -- the same lags the ComParE_2016 rows pin (tests/golden/compare16_func.npz)."""
+    from oracle import gemaps_summary_oracle as go
+    GL = np.load(os.path.join(HERE, "golden", "gemaps_func_levels.npz"))
+    lvls = sorted({k.split("_", 1)[1] for k in GL.files if not k.startswith("names_")})
+    names = {l: [str(x) for x in GL["names_" + l]] for l in lvls}
+    for key, V in (("m24k", 143), ("v32k", 193), ("rec", 198)):
+        lv = {}
+        for l in lvls:
+            full = GL["%s_%s" % (key, l)]
+            if l.endswith("energyRMS"): n = len(full)
+            elif l in ("gemapsv01b_loudness_smo", "egemapsv02_lldSetNoF0AndLoudnessZ_smo"): n = len(full) - 1
+            else: n = min(V, len(full))
+            lv[l] = full[:n]
+        nm, val = go.egemaps_summary(lv, names)
+        ref = GGF["egemaps_" + key][0]
+        assert nm == [str(x) for x in GGF["names_egemaps"]]
+        rel = np.abs(val - ref) / (np.abs(ref) + 1e-6)
+        assert rel.max() < 2e-5, (key, nm[int(np.argmax(rel))], float(rel.max()))   # the CSV rows carry 7 significant digits
+
+
+def test_valbased_gate_oracle_on_the_reference_levels():
+    """the voiced / unvoiced gates (other/valbasedSelector.cpp:195-233): in the reference's dumps a frame of the smoothed F0 level that
+    is zero together with its neighbours has all-zero voiced parameters; the unvoiced spectral parameters are zero where F0 and its
+    neighbours are voiced -- the gate oracle on the F0 contour predicts both supports"""
+    from oracle import gemaps_summary_oracle as go
+    GL = np.load(os.path.join(HERE, "golden", "gemaps_func_levels.npz"))
+    for key in ("m24k", "v32k", "rec"):
+        f0 = GL[key + "_gemapsv01b_lld_single_logF0_smo"][:, 0]
+        snz = GL[key + "_egemapsv02_lldSetSpectralNz_smo"]
+        sz = GL[key + "_egemapsv02_lldSetSpectralZ_smo"]
+        n = min(len(f0), len(snz), len(sz))
+        voiced = go.valbased_gate(f0[:n], np.ones((n, 1), np.float32))[:, 0] > 0          # smoothed F0 > 0 <=> raw F0 > 0 (noZeroSma)
+        assert np.all(snz[:n][~voiced] == 0) and np.all(sz[:n][voiced] == 0)
+        inv = go.valbased_gate(f0[:n], np.ones((n, 1), np.float32), invert=True)[:, 0] > 0
+        assert np.array_equal(inv, ~voiced)

@@ -170,3 +170,54 @@ def test_shipped_compare16_functionals_end_to_end():
                 bad_total += int(bad.size)
         assert bad_total <= 0.005 * len(names), (key, bad_total, sorted(report.items(), key=lambda kv: -kv[1][0])[:12])
     print("compare16 functionals: values beyond 1e-5 of their family's scale:", report)
+
+
+def _gemaps_inputs():
+    rec = np.load(os.path.join(HERE, "golden", "egemaps_recordings.npz"))["pcm_opensmile_16k"]
+    pcms = [mixed_pcm(24000, 16000, seed=3), voiced_pcm(32000, 16000, seed=7), rec]
+    off = np.concatenate([[0], np.cumsum([len(x) for x in pcms])]).astype(np.int64)
+    return np.concatenate(pcms), off
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "egemaps")), reason="reference configuration files not built (make -C oracle ref)")
+def test_gemaps_functionals_input_levels_equal_the_reference():
+    """the seven levels the eGeMAPSv02 functionals read -- smoothed F0 / loudness, the cValbasedSelector-gated voiced / unvoiced
+    parameter sets behind cDataSelector + cContourSmoother, the frame energy -- row by row against the unmodified reference's dumps
+    (tests/golden/gemaps_func_levels.npz): same row counts, every column within 1e-5 of its scale"""
+    from opensmile_b200.session import Session
+    GL = np.load(os.path.join(HERE, "golden", "gemaps_func_levels.npz"))
+    pcm, off = _gemaps_inputs()
+    conf = os.path.join(REFCONF, "egemaps", "v02", "eGeMAPSv02.conf")
+    for lv in sorted({k.split("_", 1)[1] for k in GL.files if not k.startswith("names_")}):
+        s = Session(conf, output_level=lv, device=0)
+        assert s.element_names() == [str(x) for x in GL["names_" + lv]]
+        rows, fo_ = s.extract_pcm(pcm, off, 16000.0, 1)
+        s.close()
+        for u, key in enumerate(("m24k", "v32k", "rec")):
+            ref = GL["%s_%s" % (key, lv)]
+            got = rows[fo_[u]:fo_[u + 1]]
+            assert got.shape == ref.shape, (lv, key, got.shape, ref.shape)
+            err = np.abs(got - ref) / (np.abs(ref).max(axis=0) + 1e-12)
+            assert err.max() < 1e-5, (lv, key, float(err.max()))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "egemaps")), reason="reference configuration files not built (make -C oracle ref)")
+@pytest.mark.parametrize("conf,tag,n", [("egemaps/v02/eGeMAPSv02.conf", "egemaps", 88), ("gemaps/v01b/GeMAPSv01b.conf", "gemaps", 62)])
+def test_shipped_gemaps_summaries_end_to_end(conf, tag, n):
+    """config/egemaps/v02/eGeMAPSv02.conf and config/gemaps/v01b/GeMAPSv01b.conf -csvoutput unchanged, from PCM, three utterances in
+    one batch, against the reference's rows: nine (seven) cFunctionals instances on the gated / smoothed levels, cDataSelector
+    renaming, cVectorOperation dBp, cVectorConcat order.  Every value within 1e-4 of its own magnitude (the reference's CSV row
+    carries 7 digits; the summaries amplify the 1e-6 LLD differences: stddevNorm, slopes)."""
+    from opensmile_b200.session import Session
+    GF = np.load(os.path.join(HERE, "golden", "gemaps_func.npz"))
+    pcm, off = _gemaps_inputs()
+    s = Session(os.path.join(REFCONF, conf), options={"csvoutput": "f.csv"}, device=0)
+    names = s.element_names()
+    assert names == [str(x) for x in GF["names_" + tag]] and len(names) == n
+    rows, fo_ = s.extract_pcm(pcm, off, 16000.0, 1)
+    s.close()
+    assert list(fo_) == [0, 1, 2, 3] and rows.shape == (3, n)
+    for u, key in enumerate(("m24k", "v32k", "rec")):
+        ref = GF["%s_%s" % (tag, key)][0]
+        rel = np.abs(rows[u] - ref) / (np.abs(ref) + 1e-6)
+        assert rel.max() < 1e-4, (key, names[int(np.argmax(rel))], float(rows[u][int(np.argmax(rel))]), float(ref[int(np.argmax(rel))]))
