@@ -532,7 +532,10 @@ __device__ void jit_extrema(const float *x, int N, int lane, float &mx, int &mI,
 }
 
 // 5 CTAs / SM: 96 registers per thread (a few spilled words outside the loops) -> 20 warps / SM instead of 16
-__global__ void __launch_bounds__(kJitWarps * 32, 5) jitter_kernel(const JitterParams p, int u0, int u1)
+#ifndef OSM_JIT_MIN_BLOCKS
+#define OSM_JIT_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(kJitWarps * 32, OSM_JIT_MIN_BLOCKS) jitter_kernel(const JitterParams p, int u0, int u1)
 {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include <functional>
+#include <chrono>
 
 #include "../../include/osm_b200_host.h"
 #include "../../include/osm_b200_functionals.h"
@@ -1703,8 +1704,14 @@ static osm_b200_status osm_b200_session_extract_pcm_impl(osm_b200_session *s, co
     if (frameOff[nUtt] > maxRows) return hfail(OSM_B200_ERR_INVALID, "output buffer too small");
     if (live.empty()) return OSM_B200_OK;
     const float *dRows = nullptr;
+    const bool timing = getenv("OSM_B200_FUNC_TIMING") != nullptr;       // dev aid: host wall clock of the phases, to stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     st = osm_b200_plan_run_host_resident(p, pcm, uttOff, nUtt, lldOff.data(), &dRows);
     if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
+    if (timing) cudaDeviceSynchronize();
+    const auto t1 = now();
     // levels behind the SHS pitch chain: their length at the first end-of-input tick follows the Viterbi level's (data dependent)
     {
       std::vector<int32_t> lag((size_t)nUtt, -1);
@@ -1718,6 +1725,7 @@ static osm_b200_status osm_b200_session_extract_pcm_impl(osm_b200_session *s, co
                                                                lldOff[u + 1] - lldOff[u]));
       }
     }
+    const auto t2 = now();
     const int KF = f->total, KS = f->scratch;
     const size_t need = live.size() * (size_t)KF;
     float *dInst = nullptr;                                            // where the instances write: the sink's row or the scratch row
@@ -1746,7 +1754,11 @@ static osm_b200_status osm_b200_session_extract_pcm_impl(osm_b200_session *s, co
       st = osm_b200_summary_assemble_device(dInst, KS, f->gSrc.data(), f->gOp.data(), f->gFloor.data(), KF, (int64_t)live.size(), s->dFuncOut, KF, nullptr);
       if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
     }
+    if (timing) cudaDeviceSynchronize();
+    const auto t3 = now();
     if (cudaMemcpy(out, s->dFuncOut, need * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return hfail(OSM_B200_ERR_CUDA, "copy of the functionals rows failed");
+    if (timing) fprintf(stderr, "summary timing: LLD plan (H2D + kernels) %.2f ms, row counts %.2f ms, %zu cFunctionals instances + assemble %.2f ms, D2H %.2f ms\n",
+                        ms(t0, t1), ms(t1, t2), nI, ms(t2, t3), ms(t3, now()));
     return OSM_B200_OK;
   }
   st = osm_b200_plan_frame_offsets(p, uttOff, nUtt, frameOff);

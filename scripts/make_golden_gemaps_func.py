@@ -19,7 +19,13 @@ REF = "/root/reference/config"
 
 def main():
     rec = np.load(os.path.join(ROOT, "tests", "golden", "egemaps_recordings.npz"))
-    sigs = {"m24k": mixed_pcm(24000, 16000, seed=3), "v32k": voiced_pcm(32000, 16000, seed=7), "rec": rec["pcm_opensmile_16k"]}
+    rng = np.random.RandomState(11)
+    # degenerate contours: digital silence, unvoiced noise only, an utterance shorter than the Viterbi buffer, a single voiced burst
+    burst = np.zeros(20000, np.int16)
+    burst[6000:12000] = voiced_pcm(6000, 16000, seed=5)
+    sigs = {"m24k": mixed_pcm(24000, 16000, seed=3), "v32k": voiced_pcm(32000, 16000, seed=7), "rec": rec["pcm_opensmile_16k"],
+            "silence": np.zeros(16000, np.int16), "noise": (rng.randn(16000) * 800).astype(np.int16), "short": voiced_pcm(4000, 16000, seed=9),
+            "burst": burst}
     out = {}
     for tag, conf in (("egemaps", "egemaps/v02/eGeMAPSv02.conf"), ("gemaps", "gemaps/v01b/GeMAPSv01b.conf")):
         for key, pcm in sigs.items():

@@ -1,5 +1,6 @@
-"""Time the ComParE_2016 summary (LLD plan + six cFunctionals instances, 6 373 features per utterance) end to end from host PCM:
-python scripts/time_functionals.py [n_utt]   -- dev helper, prints utterances / s and the share of the functionals kernels."""
+"""Time a summary configuration (LLD plan + cFunctionals instances) end to end from host PCM: ComParE_2016 (6 373 features per
+utterance) or eGeMAPSv02 (88):
+python scripts/time_functionals.py [n_utt] [compare16|egemaps]   -- dev helper, prints utterances / s with and without the summary."""
 import os
 import sys
 import time
@@ -12,7 +13,8 @@ from opensmile_b200.session import Session  # noqa: E402
 from opensmile_b200.synth import mixed_pcm  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-conf = os.path.join(ROOT, "oracle", "_ref", "config", "compare16", "ComParE_2016.conf")
+which = sys.argv[2] if len(sys.argv) > 2 else "compare16"
+conf = os.path.join(ROOT, "oracle", "_ref", "config", *{"compare16": ("compare16", "ComParE_2016.conf"), "egemaps": ("egemaps", "v02", "eGeMAPSv02.conf")}[which])
 base = [mixed_pcm(48000, 16000, seed=s) for s in range(8)]
 pcm = np.concatenate([base[i % 8] for i in range(n)])
 off = np.arange(n + 1, dtype=np.int64) * 48000

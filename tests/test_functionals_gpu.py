@@ -221,3 +221,31 @@ def test_shipped_gemaps_summaries_end_to_end(conf, tag, n):
         ref = GF["%s_%s" % (tag, key)][0]
         rel = np.abs(rows[u] - ref) / (np.abs(ref) + 1e-6)
         assert rel.max() < 1e-4, (key, names[int(np.argmax(rel))], float(rows[u][int(np.argmax(rel))]), float(ref[int(np.argmax(rel))]))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "egemaps")), reason="reference configuration files not built (make -C oracle ref)")
+@pytest.mark.parametrize("conf,tag", [("egemaps/v02/eGeMAPSv02.conf", "egemaps"), ("gemaps/v01b/GeMAPSv01b.conf", "gemaps")])
+def test_gemaps_summaries_on_degenerate_inputs(conf, tag):
+    """digital silence, unvoiced noise, an utterance shorter than the Viterbi buffer (the smoother never emits before end of input:
+    V = 0), one voiced burst between silence -- ragged batch, against the reference's rows (empty voiced sets: the non-zero filter
+    leaves nothing, functionals.cpp:286-330 then writes zeros; no voiced / unvoiced segment at all)"""
+    from opensmile_b200.session import Session
+    GF = np.load(os.path.join(HERE, "golden", "gemaps_func.npz"))
+    rng = np.random.RandomState(11)
+    burst = np.zeros(20000, np.int16)
+    burst[6000:12000] = voiced_pcm(6000, 16000, seed=5)
+    sig = {"silence": np.zeros(16000, np.int16), "noise": (rng.randn(16000) * 800).astype(np.int16), "short": voiced_pcm(4000, 16000, seed=9),
+           "burst": burst}
+    keys = ["silence", "noise", "short", "burst"]
+    off = np.concatenate([[0], np.cumsum([len(sig[k]) for k in keys])]).astype(np.int64)
+    s = Session(os.path.join(REFCONF, conf), options={"csvoutput": "f.csv"}, device=0)
+    names = s.element_names()
+    rows, fo_ = s.extract_pcm(np.concatenate([sig[k] for k in keys]), off, 16000.0, 1)
+    s.close()
+    assert list(fo_) == [0, 1, 2, 3, 4]
+    for u, key in enumerate(keys):
+        ref = GF["%s_%s" % (tag, key)][0]
+        assert np.all(np.isfinite(rows[u]))
+        err = np.abs(rows[u] - ref) / (np.abs(ref) + 1e-4)
+        i = int(np.argmax(err))
+        assert err[i] < 2e-4, (key, names[i], float(rows[u][i]), float(ref[i]))
