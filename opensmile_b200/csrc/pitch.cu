@@ -533,7 +533,7 @@ __device__ void jit_extrema(const float *x, int N, int lane, float &mx, int &mI,
 
 // 5 CTAs / SM: 96 registers per thread (a few spilled words outside the loops) -> 20 warps / SM instead of 16
 #ifndef OSM_JIT_MIN_BLOCKS
-#define OSM_JIT_MIN_BLOCKS 5
+#define OSM_JIT_MIN_BLOCKS 6   // 80 registers: six CTAs (24 warps) per SM; A/B on B200 (ComParE, 10 k utterances): 55.0 -> 52.6 ms
 #endif
 __global__ void __launch_bounds__(kJitWarps * 32, OSM_JIT_MIN_BLOCKS) jitter_kernel(const JitterParams p, int u0, int u1)
 {

@@ -1868,6 +1868,21 @@ static osm_b200_status osm_b200_session_extract_files_arff_impl(osm_b200_session
     osm_b200_plan *p;
     osm_b200_status st = get_plan(s, sr, nc, &p);
     if (st != OSM_B200_OK) return st;
+    if (s->hasFunc) {
+      // a summary configuration (cFunctionals behind the sink's level): one row per input that has frames, as the reference's sinks
+      // write it -- instance name, time stamp 0 (the summary's segment starts at 0), the values
+      osm_b200_session::FuncRt *f;
+      st = get_func(s, sr, nc, p, &f);
+      if (st != OSM_B200_OK) return st;
+      const int KF = f->total;
+      std::vector<float> frows(g.second.size() * (size_t)KF + 1);
+      st = osm_b200_session_extract_pcm_impl(s, pcm.data(), off.data(), (int)g.second.size(), sr, nc, fo.data(), frows.data(), (int64_t)g.second.size());
+      if (st != OSM_B200_OK) return st;
+      for (size_t k = 0; k < g.second.size(); k++) nTime[k] = fo[k + 1] - fo[k];
+      if (!write_batch(s, g.second, fo.data(), nTime.data(), frows.data(), KF, f->names, osm_b200_plan_frame_period(p), htkPaths, csvPaths, arffPaths, framesOut, err))
+        return hfail(OSM_B200_ERR_INVALID, err);
+      continue;
+    }
     st = osm_b200_plan_frame_offsets(p, off.data(), (int)g.second.size(), fo.data());
     if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
     const int K = osm_b200_plan_num_elements(p);
@@ -1944,12 +1959,19 @@ osm_b200_status osm_b200_session_write_files(osm_b200_session *s, double sampleR
   osm_b200_plan *p;
   osm_b200_status st = get_plan(s, sampleRate, nChan, &p);
   if (st != OSM_B200_OK) return st;
-  const int K = osm_b200_plan_num_elements(p);
+  int K = osm_b200_plan_num_elements(p);
   std::vector<std::string> names(K);
   for (int k = 0; k < K; k++) names[k] = osm_b200_plan_element_name(p, k);
   std::vector<int> idx(n);
   std::vector<int64_t> nTime(n, 0);
   for (int i = 0; i < n; i++) { idx[i] = i; nTime[i] = nSamples ? osm_b200_plan_num_time_frames(p, nSamples[i]) : 0; }
+  if (s->hasFunc) {                                  // summary rows (osm_b200_session_extract_pcm of a cFunctionals configuration)
+    osm_b200_session::FuncRt *f;
+    st = get_func(s, sampleRate, nChan, p, &f);
+    if (st != OSM_B200_OK) return st;
+    K = f->total; names = f->names;
+    for (int i = 0; i < n; i++) nTime[i] = frameOff[i + 1] - frameOff[i];
+  }
   std::string err;
   if (!write_batch(s, idx, frameOff, nTime.data(), rows, K, names, osm_b200_plan_frame_period(p), htkPaths, csvPaths, arffPaths, nullptr, err))
     return hfail(OSM_B200_ERR_INVALID, err);

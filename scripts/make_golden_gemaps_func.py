@@ -35,6 +35,8 @@ def main():
                 subprocess.run([refrun.SMILEXTRACT, "-C", os.path.join(REF, conf), "-I", wav, "-csvoutput", os.path.join(d, "f.csv"),
                                 "-l", "0"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
                 n, r = csv_rows(os.path.join(d, "f.csv"))
+                if key == "m24k":
+                    out["csv_" + tag + "_m24k"] = np.frombuffer(open(os.path.join(d, "f.csv"), "rb").read(), np.uint8)   # the sink's file as written
                 out["names_" + tag] = np.array(n)
                 out[tag + "_" + key] = r
     for k, v in out.items():

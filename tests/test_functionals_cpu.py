@@ -278,3 +278,25 @@ def test_valbased_gate_oracle_on_the_reference_levels():
         assert np.all(snz[:n][~voiced] == 0) and np.all(sz[:n][voiced] == 0)
         inv = go.valbased_gate(f0[:n], np.ones((n, 1), np.float32), invert=True)[:, 0] > 0
         assert np.array_equal(inv, ~voiced)
+
+
+def _csv_close(got_text, ref_text, rtol):
+    """same header line, same row prefix (instance name ; time stamp), values equal within rtol of their magnitude"""
+    g, r = got_text.strip().split("\n"), ref_text.strip().split("\n")
+    assert g[0] == r[0] and len(g) == len(r)
+    for a, b in zip(g[1:], r[1:]):
+        fa, fb = a.split(";"), b.split(";")
+        assert fa[:2] == fb[:2] and len(fa) == len(fb)
+        va, vb = np.array(fa[2:], np.float64), np.array(fb[2:], np.float64)
+        assert np.all(np.abs(va - vb) <= rtol * (np.abs(vb) + 1e-6)), (a[:80], b[:80])
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "egemaps")), reason="reference configuration files not built (make -C oracle ref)")
+def test_summary_rows_are_written_like_the_reference_sink(tmp_path):
+    """osm_b200_session_write_files on a cFunctionals session: the sink's file has the summary's names, one row per input,
+    `'unknown';0.000000;values` -- the reference's file for the same input (the values here are the reference's own, re-printed)"""
+    s = _session(os.path.join(REFCONF, "egemaps", "v02", "eGeMAPSv02.conf"), {"csvoutput": "x.csv"})
+    out = tmp_path / "f.csv"
+    s.write_files(GGF["egemaps_m24k"], [0, 1], 16000.0, 1, n_samples=[24000], csv_paths=[str(out)])
+    s.close()
+    _csv_close(out.read_text(), GGF["csv_egemaps_m24k"].tobytes().decode(), 2e-7)

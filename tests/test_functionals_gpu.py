@@ -249,3 +249,28 @@ def test_gemaps_summaries_on_degenerate_inputs(conf, tag):
         err = np.abs(rows[u] - ref) / (np.abs(ref) + 1e-4)
         i = int(np.argmax(err))
         assert err[i] < 2e-4, (key, names[i], float(rows[u][i]), float(ref[i]))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "egemaps")), reason="reference configuration files not built (make -C oracle ref)")
+def test_summary_configuration_from_wav_files_to_csv(tmp_path):
+    """the file route of a summary configuration (what the command line front end runs): WAV files in, one CSV per input with the
+    reference sink's layout and the reference's values (eGeMAPSv02.conf -I x.wav -csvoutput x.csv)"""
+    from oracle import refrun
+    from opensmile_b200.session import Session
+    from test_functionals_cpu import _csv_close
+    GF = np.load(os.path.join(HERE, "golden", "gemaps_func.npz"))
+    wavs, outs = [], []
+    for i, pcm in enumerate((mixed_pcm(24000, 16000, seed=3), voiced_pcm(32000, 16000, seed=7))):
+        wavs.append(str(tmp_path / ("in%d.wav" % i)))
+        outs.append(str(tmp_path / ("out%d.csv" % i)))
+        refrun.write_wav(wavs[-1], pcm, 16000, 1)
+    s = Session(os.path.join(REFCONF, "egemaps", "v02", "eGeMAPSv02.conf"), options={"csvoutput": "f.csv"}, device=0)
+    frames = s.extract_files(wavs, csv_paths=outs)
+    s.close()
+    assert list(frames) == [1, 1]
+    _csv_close(open(outs[0]).read(), GF["csv_egemaps_m24k"].tobytes().decode(), 1e-4)
+    head = open(outs[1]).read().split("\n")
+    assert head[0] == GF["csv_egemaps_m24k"].tobytes().decode().split("\n")[0] and head[1].startswith("'unknown';0.000000;")
+    vals = np.array(head[1].split(";")[2:], np.float64)
+    ref = GF["egemaps_v32k"][0]
+    assert np.all(np.abs(vals - ref) <= 1e-4 * (np.abs(ref) + 1e-6))
