@@ -108,7 +108,18 @@ typedef enum {
   OSM_B200_WIN_BLACKMAN, OSM_B200_WIN_BLACKHARR, OSM_B200_WIN_BARTHANN, OSM_B200_WIN_LANCZOS
 } osm_b200_winfunc;
 
-typedef enum { OSM_B200_PCM_S16 = 0, OSM_B200_PCM_F32 = 1 } osm_b200_pcm_format;
+/* sample formats of the PCM buffers handed to osm_b200_plan_run_*: what smilePcm_convertSamples / smilePcm_convertFloatSamples accept
+ * (src/smileutil/smileUtil.c:2500-2680), interleaved channels, little endian.  A sample frame = nChannels samples.
+ *   S16    int16                      x / 32767                       (read by the kernels directly)
+ *   F32    IEEE float                 x
+ *   S8     int8 (the reference reads 8-bit WAV data as SIGNED bytes)  x / 127
+ *   S24    3 bytes per sample         x / (32767 * 256)
+ *   S24_32 24 valid bits in 4 bytes   (x & 0xFFFFFF) / (32767 * 256)  -- no sign extension, as the reference (smileUtil.c:2559)
+ *   S32    int32                      x / 2147483647
+ * With several channels the reference sums the float samples in channel order and divides by the channel count first
+ * (monoMixdown).  Every format but S16 is converted on the device by one pre-pass (pcm_convert_kernel) into mono floats. */
+typedef enum { OSM_B200_PCM_S16 = 0, OSM_B200_PCM_F32 = 1, OSM_B200_PCM_S8 = 2, OSM_B200_PCM_S24 = 3, OSM_B200_PCM_S24_32 = 4,
+               OSM_B200_PCM_S32 = 5 } osm_b200_pcm_format;
 
 /* ---- per-type parameter blocks.  Field names and defaults = the reference's config
  * schema; osm_b200_component_defaults() fills the defaults. ---- */
@@ -446,6 +457,8 @@ OSM_B200_API osm_b200_status osm_b200_plan_run_host(osm_b200_plan *plan, const v
 OSM_B200_API osm_b200_status osm_b200_plan_run_host_resident(osm_b200_plan *plan, const void *pcm,
                                             const int64_t *utt_offsets, int32_t n_utt,
                                             const int64_t *frame_offsets, const float **d_rows);
+/* bytes of one sample frame of the plan's input (nChannels * bytes per sample of cWaveSource.format) */
+OSM_B200_API int32_t     osm_b200_plan_sample_frame_bytes(const osm_b200_plan *plan);
 /* number of CUDA kernels the last run_* call launched (for bench.py's gpu_launches) */
 OSM_B200_API int32_t     osm_b200_plan_last_launch_count(const osm_b200_plan *plan);
 /* Device-side condition flags of the runs since the last call (synchronises the device, then clears them).

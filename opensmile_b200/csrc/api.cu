@@ -39,6 +39,67 @@ osm_b200_status cuda_fail(cudaError_t e, const char *what)
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);       \
   } while (0)
 
+// ---- input formats (cWaveSource.format) ----
+int sample_bytes(int format)
+{
+  switch (format) {
+    case OSM_B200_PCM_S8: return 1;
+    case OSM_B200_PCM_S16: return 2;
+    case OSM_B200_PCM_S24: return 3;
+    default: return 4;                 // F32, S24_32, S32
+  }
+}
+// channel count the kernels see: 16-bit input is read in place; every other format is pre-converted to mono floats, whose 4-byte
+// sample frame the kernels address as "two int16 per frame" (LldParams::pcmF32)
+int kernel_nchan(const FrontEnd &fe) { return fe.format == OSM_B200_PCM_S16 ? fe.nChan : 2; }
+
+// smilePcm_convertSamples / smilePcm_convertFloatSamples with monoMixdown (smileutil/smileUtil.c:2518-2580, 2651-2661): the channel
+// values are converted to float and summed in channel order starting from 0.0f, the sum is divided by the channel count, then by
+// the format's full scale -- two IEEE divisions, exactly the reference's statement.  One thread per sample frame.
+__global__ void __launch_bounds__(256) pcm_convert_kernel(const unsigned char *in, int format, int nChan, long long nFrames, float *out)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nFrames) return;
+  float tmp = 0.0f;
+  float scale = 1.0f;
+  switch (format) {
+    case OSM_B200_PCM_S8: {
+      const signed char *b = reinterpret_cast<const signed char *>(in) + i * nChan;
+      for (int c = 0; c < nChan; c++) tmp = __fadd_rn(tmp, (float)b[c]);
+      scale = 127.0f;
+      break;
+    }
+    case OSM_B200_PCM_S24: {
+      const unsigned char *b = in + i * nChan * 3;
+      for (int c = 0; c < nChan; c++) {                                             // :2543-2552 (byte assembly, arithmetic shift)
+        const unsigned int is = ((unsigned int)b[3 * c] << 8) | ((unsigned int)b[3 * c + 1] << 16) | ((unsigned int)b[3 * c + 2] << 24);
+        tmp = __fadd_rn(tmp, (float)((int)is >> 8));
+      }
+      scale = 8388352.0f;                                                           // (float)(32767.0 * 256.0)
+      break;
+    }
+    case OSM_B200_PCM_S24_32: {
+      const int *b = reinterpret_cast<const int *>(in) + i * nChan;
+      for (int c = 0; c < nChan; c++) tmp = __fadd_rn(tmp, (float)(b[c] & 0xFFFFFF));   // :2559 (no sign extension)
+      scale = 8388352.0f;
+      break;
+    }
+    case OSM_B200_PCM_S32: {
+      const int *b = reinterpret_cast<const int *>(in) + i * nChan;
+      for (int c = 0; c < nChan; c++) tmp = __fadd_rn(tmp, (float)b[c]);
+      scale = 2147483648.0f;                                                        // (float)2147483647.0
+      break;
+    }
+    default: {                                                                      // OSM_B200_PCM_F32: no full-scale division (:2658)
+      const float *b = reinterpret_cast<const float *>(in) + i * nChan;
+      for (int c = 0; c < nChan; c++) tmp = __fadd_rn(tmp, b[c]);
+      out[i] = __fdiv_rn(tmp, (float)nChan);
+      return;
+    }
+  }
+  out[i] = __fdiv_rn(__fdiv_rn(tmp, (float)nChan), scale);
+}
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
@@ -159,6 +220,7 @@ struct osm_b200_plan {
   bool metaPending = false, timed = false;
   // run_host buffers
   DevBuf<int16_t> dPcm;
+  DevBuf<float> dPcmF;             // mono float samples of the batch (inputs in another format than 16-bit integer)
   DevBuf<float> dOut;
   cudaStream_t hostStream = nullptr, h2dStream = nullptr, d2hStream = nullptr;
   std::vector<cudaEvent_t> evPiece;   // 2 per pipeline piece: PCM landed / rows computed
@@ -330,7 +392,7 @@ static osm_b200_status build_pass(osm_b200_plan *pl, int si, int opIdx, bool dum
   pr.op = opIdx;
   memset(&kp, 0, sizeof kp);
   kp.opKind = -1;
-  kp.nChan = fe.nChan;
+  kp.nChan = kernel_nchan(fe); kp.pcmF32 = fe.format != OSM_B200_PCM_S16;
   kp.frameSize = fe.frameSize; kp.frameStep = fe.frameStep;
   kp.hopMagic = (unsigned)((0x100000000ull + (unsigned long long)fe.frameStep - 1) / (unsigned long long)fe.frameStep);
   // per-lane stride S = frameStep + sPad of the shared-memory sample tile: odd S (scalar loads)
@@ -752,7 +814,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
       const JitterOp &jo = op.jitter;
       JitterParams &jp = rt.jit;
       memset(&jp, 0, sizeof jp);
-      jp.nChan = fe.nChan; jp.frameSize = fe.frameSize; jp.frameStep = fe.frameStep;
+      jp.nChan = kernel_nchan(fe); jp.pcmF32 = fe.format != OSM_B200_PCM_S16; jp.frameSize = fe.frameSize; jp.frameStep = fe.frameStep;
       jp.Ts = 1.0 / fe.sampleRate;                               // period of the wave level
       jp.pitchT = fe.frameStepSec;                               // period of the F0 level (core/winToVecProcessor.cpp:563)
       jp.statStride = d.nStatic; jp.f0Col = d.ops[jo.pitchOp].outCol + jo.f0Col; jp.outCol = op.outCol;
@@ -808,7 +870,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     } else {
       TimeOpParams &tp = rt.tp;
       memset(&tp, 0, sizeof tp);
-      tp.nChan = fe.nChan; tp.F = srt.tileF; tp.statStride = d.nStatic; tp.outCol = op.outCol;
+      tp.nChan = kernel_nchan(fe); tp.pcmF32 = fe.format != OSM_B200_PCM_S16; tp.F = srt.tileF; tp.statStride = d.nStatic; tp.outCol = op.outCol;
       tp.frameSize = fe.frameSize; tp.frameStep = fe.frameStep;
       tp.windowed = op.windowed; tp.preemph = op.windowed && fe.preemph; tp.preDe = fe.preDe; tp.preK = fe.preK;
       tp.oneMinusK = 1 - fe.preK; tp.winOffset = fe.winOffset; tp.window = srt.dWindow;
@@ -881,7 +943,7 @@ void osm_b200_plan_destroy(osm_b200_plan *pl)
   if (pl->evFork) cudaEventDestroy(pl->evFork);
   if (pl->evJoin) cudaEventDestroy(pl->evJoin);
   pl->hMeta.release(); pl->dMeta.release(); pl->hPost.release(); pl->dPost.release(); pl->dStat.release(); pl->dMeans.release();
-  pl->dPcm.release(); pl->dOut.release();
+  pl->dPcm.release(); pl->dPcmF.release(); pl->dOut.release();
   if (pl->evMetaDone) cudaEventDestroy(pl->evMetaDone);
   if (pl->evK0) cudaEventDestroy(pl->evK0);
   if (pl->evK1) cudaEventDestroy(pl->evK1);
@@ -1059,6 +1121,20 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
   const size_t nm = (size_t)(n_utt + 1);
   const long long *dU = pl->dMeta.p, *dR = dU + nm, *dS = dR + nm;
   PROF("begin");
+  if (d.fe0().format != OSM_B200_PCM_S16) {
+    // inputs in another format than 16-bit integer: one conversion pass into mono floats (the caller reserved dPcmF)
+    const long long *hU = pl->hMeta.p;
+    const long long f0 = hU[u0], f1 = hU[u1];
+    const int nc = d.fe0().nChan;
+    if (f1 > f0) {
+      pcm_convert_kernel<<<(unsigned)((f1 - f0 + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const unsigned char *>(d_pcm) + (size_t)f0 * nc * sample_bytes(d.fe0().format), d.fe0().format, nc, f1 - f0, pl->dPcmF.p + f0);
+      CU(cudaGetLastError());
+      pl->lastLaunches++;
+    }
+    d_pcm = pl->dPcmF.p;
+    PROF("pcm_convert_kernel");
+  }
   // 1. per stream: FFT front end (+ fused band op / magnitude dump)
   for (size_t si = 0; si < pl->st.size(); si++) {
     StreamRt &rt = pl->st[si];
@@ -1244,6 +1320,7 @@ osm_b200_status osm_b200_plan_run_device(osm_b200_plan *pl, const void *d_pcm, c
   if (s != OSM_B200_OK) return s;
   if (pl->totalRows == 0 || pl->totalWork == 0) return OSM_B200_OK;
   if (!d_pcm || !d_out) return fail(OSM_B200_ERR_INVALID, "null device buffer");
+  if (pl->d.fe0().format != OSM_B200_PCM_S16) CU(pl->dPcmF.reserve((size_t)utt_offsets[n_utt] + 16));
   if (!pl->staticDirect) CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic + 64));
   CU(cudaEventRecord(pl->evK0, st));
   s = launch_range(pl, d_pcm, d_out, n_utt, 0, n_utt, st);
@@ -1276,15 +1353,16 @@ static osm_b200_status run_host_impl(osm_b200_plan *pl, const void *pcm, const i
   const long long rows = pl->totalRows;
   if (rows == 0 || pl->totalWork == 0) return OSM_B200_OK;
   if (!pcm || (!out && !resident)) return fail(OSM_B200_ERR_INVALID, "null host buffer");
-  const int nChan = pl->d.fe0().nChan, nOut = pl->d.nOut;
-  const int64_t nSamp = utt_offsets[n_utt] * nChan;
-  CU(pl->dPcm.reserve((size_t)nSamp + 16));
+  const int nOut = pl->d.nOut;
+  const int64_t frameBytes = (int64_t)pl->d.fe0().nChan * sample_bytes(pl->d.fe0().format);
+  const int64_t totalBytes = utt_offsets[n_utt] * frameBytes;
+  CU(pl->dPcm.reserve((size_t)(totalBytes + 1) / 2 + 16));
+  if (pl->d.fe0().format != OSM_B200_PCM_S16) CU(pl->dPcmF.reserve((size_t)utt_offsets[n_utt] + 16));
   CU(pl->dOut.reserve((size_t)rows * nOut));
   if (!pl->staticDirect) CU(pl->dStat.reserve((size_t)pl->totalStat * pl->d.nStatic + 64));
   const long long *hR = pl->hMeta.p + (size_t)(n_utt + 1);
 
   // pieces of ~24 MB of PCM, at most 16, cut at utterance boundaries
-  const int64_t totalBytes = nSamp * 2;
   // (plans with per-utterance sequential kernels -- Viterbi, jitter -- get their parallelism from the number of
   // utterances in flight: fewer, larger pieces)
   const int64_t maxPieces = pl->sp.nGroups > 0 ? 4 : 16;
@@ -1303,8 +1381,8 @@ static osm_b200_status run_host_impl(osm_b200_plan *pl, const void *pcm, const i
     while (u1 < n_utt && (utt_offsets[u1 + 1] <= target || u1 == u0)) u1++;
     if (k == nPieces - 1) u1 = n_utt;
     if (u1 == u0) continue;
-    const int64_t sa = utt_offsets[u0] * nChan, sb = utt_offsets[u1] * nChan;
-    CU(cudaMemcpyAsync(pl->dPcm.p + sa, reinterpret_cast<const int16_t *>(pcm) + sa, (size_t)(sb - sa) * sizeof(int16_t),
+    const int64_t sa = utt_offsets[u0] * frameBytes, sb = utt_offsets[u1] * frameBytes;
+    CU(cudaMemcpyAsync(reinterpret_cast<unsigned char *>(pl->dPcm.p) + sa, reinterpret_cast<const unsigned char *>(pcm) + sa, (size_t)(sb - sa),
                        cudaMemcpyHostToDevice, pl->h2dStream));
     CU(cudaEventRecord(pl->evPiece[2 * k], pl->h2dStream));
     CU(cudaStreamWaitEvent(st, pl->evPiece[2 * k], 0));
@@ -1379,6 +1457,8 @@ osm_b200_status osm_b200_plan_copy_seq_lag(osm_b200_plan *pl, int32_t *out, int3
 }
 
 int32_t osm_b200_plan_last_launch_count(const osm_b200_plan *pl) { return pl ? pl->lastLaunches : 0; }
+
+int32_t osm_b200_plan_sample_frame_bytes(const osm_b200_plan *pl) { return pl ? pl->d.fe0().nChan * sample_bytes(pl->d.fe0().format) : 0; }
 
 int32_t osm_b200_plan_take_device_flags(osm_b200_plan *pl)
 {

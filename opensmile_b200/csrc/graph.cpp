@@ -203,7 +203,7 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     const auto &wp = ci.wav->u.wavesource;
     if (wp.sampleRate <= 0 || wp.nChannels < 1) { err = "cWaveSource: bad sampleRate/nChannels"; return OSM_B200_ERR_INVALID; }
     if (wp.nChannels > 1 && !wp.monoMixdown) { err = "multi-channel without monoMixdown is not supported"; return OSM_B200_ERR_UNSUPPORTED; }
-    if (wp.format != OSM_B200_PCM_S16) { err = "only 16-bit integer PCM is supported"; return OSM_B200_ERR_UNSUPPORTED; }
+    if (wp.format < OSM_B200_PCM_S16 || wp.format > OSM_B200_PCM_S32) { err = "cWaveSource: unknown sample format"; return OSM_B200_ERR_INVALID; }
     fe.sampleRate = wp.sampleRate; fe.nChan = wp.nChannels; fe.format = wp.format; fe.mixdown = true;
     // cWinToVecProcessor::configureWriter (core/winToVecProcessor.cpp:435-456)
     const auto &fp = ci.frm->u.framer;

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     phase ^= 1;
     {
       const int16_t *rp = reinterpret_cast<const int16_t *>(rawPcm + tg.mis) + tg.lead * nChan;   // sample frame 0 of the tile
-      const bool fastLoad = (tg.mis == 0) && (nChan <= 2);
+      const bool fastLoad = (tg.mis == 0) && (nChan <= 2) && !p.pcmF32;
       const bool fastStore = (p.sPad == 0) || (hop % 8 == 0);
       for (int c = tid; c * 8 < count; c += NT) {
         const int i = c * 8;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           }
         } else {
 #pragma unroll
-          for (int jj = 0; jj < 8; jj++) x[jj] = (jj < nvalid) ? pcm_to_float_slow(rp + (i + jj) * nChan, nChan) : 0.f;
+          for (int jj = 0; jj < 8; jj++) x[jj] = (jj < nvalid) ? pcm_to_float_slow(rp + (i + jj) * nChan, nChan, p.pcmF32) : 0.f;
         }
         float y[8];
         if (p.preemph) {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
           float xprev = 0.f;
           if (i > 0 || tg.lead > 0) {
             if (nChan == 1) xprev = div32767((float)rp[i - 1]);
-            else xprev = pcm_to_float_slow(rp + (i - 1) * nChan, nChan);
+            else xprev = pcm_to_float_slow(rp + (i - 1) * nChan, nChan, p.pcmF32);
           }
           // x - k*xp == x + (-k)*xp exactly: one signed coefficient instead of a per-sample select
           const float ks = p.preDe ? p.preK : -p.preK;

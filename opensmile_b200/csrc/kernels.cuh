@@ -20,6 +20,9 @@ struct LldParams {
   const ChunkRef *chunks;
   int nChunks;
   int nChan;
+  // 1: `pcm` holds pre-converted mono float samples (pcm_convert_kernel: every input format but 16-bit integer).  The sample
+  // frame is 4 bytes wide, so nChan is 2 here -- all offset arithmetic stays in int16 units -- and only the conversion differs.
+  int pcmF32;
   // fused temporal stages (static | delta(W1) | delta(W1,W2)); halo = W1 + W2, 0 when not fused
   unsigned hopMagic;             // ceil(2^32 / frameStep): i / frameStep == __umulhi(i, hopMagic) for i * frameStep < 2^32
   int narrow;                    // 1: half-width tiles (F/2 frames), used when the full tile does not fit shared memory
@@ -145,7 +148,7 @@ struct SpectralParams {
 };
 
 struct TimeOpParams {            // cEnergy / cMZcr on the framer or windower level
-  const int16_t *pcm; int nChan;
+  const int16_t *pcm; int nChan; int pcmF32;   // pcmF32: see LldParams
   const long long *uttOff, *statOff;
   const OpTile *tiles; int nTiles; int F;
   float *stat; int statStride, outCol;
@@ -283,7 +286,7 @@ struct ViterbiParams {
 cudaError_t launch_viterbi(const ViterbiParams &p, int u0, int u1, cudaStream_t st);
 
 struct JitterParams {
-  const int16_t *pcm; int nChan;
+  const int16_t *pcm; int nChan; int pcmF32;   // pcmF32: see LldParams
   const long long *uttOff, *statOff;
   int frameSize, frameStep;
   double Ts, pitchT;             // wave sample period, period of the F0 level

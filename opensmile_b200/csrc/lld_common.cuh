@@ -88,8 +88,9 @@ __device__ __forceinline__ float div32767(float x)
 }
 
 #define OSM_COLD __noinline__     // rarely executed paths stay out of the hot instruction stream
-__device__ __forceinline__ float pcm_to_float_generic(const int16_t *s, int nChan)
+__device__ __forceinline__ float pcm_to_float_generic(const int16_t *s, int nChan, int f32 = 0)
 {
+  if (f32) return *reinterpret_cast<const float *>(s);      // pre-converted mono float sample (LldParams::pcmF32)
   float tmp = (float)s[0];
   for (int c = 1; c < nChan; c++) tmp = __fadd_rn(tmp, (float)s[c]);
   if (nChan == 1) return div32767(tmp);
@@ -97,7 +98,7 @@ __device__ __forceinline__ float pcm_to_float_generic(const int16_t *s, int nCha
   return __fdiv_rn(__fdiv_rn(tmp, (float)nChan), 32767.0f);
 }
 // out-of-line copy for the rarely taken staging paths (unaligned / partial chunks, >2 channels)
-static __device__ OSM_COLD float pcm_to_float_slow(const int16_t *s, int nChan) { return pcm_to_float_generic(s, nChan); }
+static __device__ OSM_COLD float pcm_to_float_slow(const int16_t *s, int nChan, int f32 = 0) { return pcm_to_float_generic(s, nChan, f32); }
 
 // ------------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (TMA unit, SASS UBLKCP) wrappers

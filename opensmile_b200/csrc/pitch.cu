@@ -487,8 +487,9 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
 
 constexpr int kJitWarps = 4;
 
-__device__ __forceinline__ float jit_pcm(const int16_t *s, int nChan)       // smileutil/smileUtil.c:2520-2534
+__device__ __forceinline__ float jit_pcm(const int16_t *s, int nChan, int f32)       // smileutil/smileUtil.c:2520-2534
 {
+  if (f32) return *reinterpret_cast<const float *>(s);      // pre-converted mono float sample
   float tmp = (float)s[0];
   for (int c = 1; c < nChan; c++) tmp = tmp + (float)s[c];
   if (nChan > 1) tmp = tmp / (float)nChan;
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(kJitWarps * 32, OSM_JIT_MIN_BLOCKS) jitter_ker
     }
     const int nT = (int)toRead;
     __syncwarp();
-    for (int i = lane; i < nT; i += 32) wav[i] = jit_pcm(pcm + (lastIdx + i) * p.nChan, p.nChan);
+    for (int i = lane; i < nT; i += 32) wav[i] = jit_pcm(pcm + (lastIdx + i) * p.nChan, p.nChan, p.pcmF32);
     __syncwarp();
 
     float nPeriodsLocal = 0, nPeriodsDDP = 0, nPeriods = 0, avgPeriod = 0.0f, JitterDDP = 0.0f, JitterLocal = 0.0f;

@@ -802,9 +802,13 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
 // ------------------------------------------------------------------------------------------
 // WAV in, HTK / CSV out
 // ------------------------------------------------------------------------------------------
-struct Wav { int sampleRate = 0, nChan = 0; std::vector<int16_t> pcm; };
+// data chunk as it is in the file (interleaved sample frames of `format`, an osm_b200_pcm_format); the device converts
+struct Wav { int sampleRate = 0, nChan = 0, format = OSM_B200_PCM_S16, frameBytes = 2; std::vector<unsigned char> pcm;
+             size_t frames() const { return pcm.size() / (size_t)frameBytes; } };
 
-bool read_wav(const char *path, Wav &w, std::string &err)    // 16-bit PCM RIFF (iocore/waveSource.cpp, smileUtil.c:2390-2495)
+// RIFF/WAVE as smilePcm_readWaveHeader accepts it (smileUtil.c:2381-2481): AudioFormat 1 (integer PCM: 8 / 16 / 24 bit, 32-bit
+// containers with 24 or 32 valid bits) or 3 (IEEE float, 32 bit); bytes per sample = BlockAlign / NumChannels (:2473)
+bool read_wav(const char *path, Wav &w, std::string &err)
 {
   FILE *f = fopen(path, "rb");
   if (!f) { err = std::string("cannot open '") + path + "'"; return false; }
@@ -836,12 +840,26 @@ bool read_wav(const char *path, Wav &w, std::string &err)    // 16-bit PCM RIFF 
       if ((sz & 1) && fseek(f, 1, SEEK_CUR) != 0) break;
     } else if (!memcmp(ch, "data", 4)) {
       if (!fmtOk) break;
-      if (!(fmtTag == 1 || fmtTag == 0xFFFE) || bits != 16) { fclose(f); err = std::string(path) + ": only 16-bit integer PCM is supported"; return false; }
-      if (blockAlign != 2 * w.nChan) { fclose(f); err = std::string(path) + ": invalid WAV header (block alignment)"; return false; }
+      if (blockAlign <= 0 || blockAlign % w.nChan != 0) { fclose(f); err = std::string(path) + ": invalid WAV header (block alignment)"; return false; }
+      const int bps = blockAlign / w.nChan;
+      w.format = -1;
+      if (fmtTag == 1 || (fmtTag == 0xFFFE && bits == 16 && bps == 2)) {     // (the extensible tag was accepted for 16-bit files before)
+        if (bps == 1) w.format = OSM_B200_PCM_S8;
+        else if (bps == 2) w.format = OSM_B200_PCM_S16;
+        else if (bps == 3) w.format = OSM_B200_PCM_S24;
+        else if (bps == 4 && bits == 24) w.format = OSM_B200_PCM_S24_32;
+        else if (bps == 4 && bits == 32) w.format = OSM_B200_PCM_S32;
+      } else if (fmtTag == 3 && bps == 4 && bits == 32) w.format = OSM_B200_PCM_F32;
+      if (w.format < 0) {
+        char b[160];
+        snprintf(b, sizeof b, ": unsupported sample format (format tag %d, %d bits, %d bytes per sample); integer PCM 8/16/24/32 bit and 32-bit float are supported", fmtTag, bits, bps);
+        fclose(f); err = std::string(path) + b; return false;
+      }
+      w.frameBytes = blockAlign;
       if (sz == 0 || sz == 0xFFFFFFFFu || sz > left) sz = left;        // streamed files: the data chunk runs to the end of the file
-      try { w.pcm.resize(sz / 2); } catch (const std::exception &) { fclose(f); err = std::string(path) + ": out of memory"; return false; }
-      const size_t got = fread(w.pcm.data(), 2, sz / 2, f);
-      w.pcm.resize(got - got % (size_t)w.nChan);
+      try { w.pcm.resize(sz); } catch (const std::exception &) { fclose(f); err = std::string(path) + ": out of memory"; return false; }
+      const size_t got = fread(w.pcm.data(), 1, sz, f);
+      w.pcm.resize(got - got % (size_t)blockAlign);
       fclose(f);
       return true;
     } else {
@@ -1113,14 +1131,15 @@ static void split_levels(const std::string &v, std::vector<std::string> &out)
   while (std::getline(ss, one, ';')) { one = trim(one); if (!one.empty()) out.push_back(one); }
 }
 
-static osm_b200_status get_plan(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan **out)
+static osm_b200_status get_plan(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan **out, int format = OSM_B200_PCM_S16)
 {
-  const auto key = std::make_pair((long)lround(sampleRate * 1000.0), nChan);
+  const auto key = std::make_pair((long)lround(sampleRate * 1000.0), nChan + 4096 * format);
   auto it = s->plans.find(key);
   if (it == s->plans.end()) {
     std::vector<osm_b200_component> cs = s->comps;
     cs[s->waveIdx].u.wavesource.sampleRate = sampleRate;
     cs[s->waveIdx].u.wavesource.nChannels = nChan;
+    cs[s->waveIdx].u.wavesource.format = format;
     osm_b200_plan *p = nullptr;
     osm_b200_status st = osm_b200_plan_create(cs.data(), (int)cs.size(), s->outputLevel.c_str(), s->device, &p);
     if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
@@ -1275,7 +1294,7 @@ static osm_b200_status build_func_rt(osm_b200_session *s, double sampleRate, int
 
 static osm_b200_status get_func(osm_b200_session *s, double sampleRate, int nChan, osm_b200_plan *p, osm_b200_session::FuncRt **out)
 {
-  const auto key = std::make_pair((long)lround(sampleRate * 1000.0), nChan);
+  const auto key = std::make_pair((long)lround(sampleRate * 1000.0), nChan);      // names / counts do not depend on the sample format
   auto it = s->funcs.find(key);
   if (it == s->funcs.end()) {
     osm_b200_session::FuncRt rt;
@@ -1667,12 +1686,13 @@ osm_b200_status osm_b200_session_plan(osm_b200_session *s, double sampleRate, in
   return get_plan(s, sampleRate, nChan, plan);
 }
 
-static osm_b200_status osm_b200_session_extract_pcm_impl(osm_b200_session *s, const int16_t *pcm, const int64_t *uttOff, int32_t nUtt,
-                                             double sampleRate, int32_t nChan, int64_t *frameOff, float *out, int64_t maxRows)
+static osm_b200_status osm_b200_session_extract_pcm_impl(osm_b200_session *s, const void *pcm, const int64_t *uttOff, int32_t nUtt,
+                                             double sampleRate, int32_t nChan, int64_t *frameOff, float *out, int64_t maxRows,
+                                             int format = OSM_B200_PCM_S16)
 {
   if (!s || !uttOff || !frameOff) return hfail(OSM_B200_ERR_INVALID, "null argument");
   osm_b200_plan *p;
-  osm_b200_status st = get_plan(s, sampleRate, nChan, &p);
+  osm_b200_status st = get_plan(s, sampleRate, nChan, &p, format);
   if (st != OSM_B200_OK) return st;
   if (s->hasFunc) {
     // one summary row per utterance that has frames; the rows a plan run leaves in HBM are summarised in place.  The
@@ -1856,17 +1876,17 @@ static osm_b200_status osm_b200_session_extract_files_arff_impl(osm_b200_session
   std::string err;
   if (!parallel_files(n, [&](int i, std::string &e) { return read_wav(wavPaths[i], wavs[i], e); }, err)) return hfail(OSM_B200_ERR_INVALID, err);
   std::map<std::pair<int, int>, std::vector<int>> groups;
-  for (int i = 0; i < n; i++) groups[{wavs[i].sampleRate, wavs[i].nChan}].push_back(i);
+  for (int i = 0; i < n; i++) groups[{wavs[i].sampleRate, wavs[i].nChan + 4096 * wavs[i].format}].push_back(i);
   for (auto &g : groups) {
-    const int sr = g.first.first, nc = g.first.second;
+    const int sr = g.first.first, nc = g.first.second % 4096, fmt = g.first.second / 4096;
     std::vector<int64_t> off(g.second.size() + 1, 0), fo(g.second.size() + 1, 0), nTime(g.second.size(), 0);
     size_t total = 0;
-    for (size_t k = 0; k < g.second.size(); k++) { total += wavs[g.second[k]].pcm.size(); off[k + 1] = off[k] + (int64_t)(wavs[g.second[k]].pcm.size() / nc); }
-    std::vector<int16_t> pcm(total + 8);
+    for (size_t k = 0; k < g.second.size(); k++) { total += wavs[g.second[k]].pcm.size(); off[k + 1] = off[k] + (int64_t)wavs[g.second[k]].frames(); }
+    std::vector<unsigned char> pcm(total + 16);
     size_t at = 0;
-    for (int idx : g.second) { memcpy(pcm.data() + at, wavs[idx].pcm.data(), wavs[idx].pcm.size() * 2); at += wavs[idx].pcm.size(); }
+    for (int idx : g.second) { memcpy(pcm.data() + at, wavs[idx].pcm.data(), wavs[idx].pcm.size()); at += wavs[idx].pcm.size(); }
     osm_b200_plan *p;
-    osm_b200_status st = get_plan(s, sr, nc, &p);
+    osm_b200_status st = get_plan(s, sr, nc, &p, fmt);
     if (st != OSM_B200_OK) return st;
     if (s->hasFunc) {
       // a summary configuration (cFunctionals behind the sink's level): one row per input that has frames, as the reference's sinks
@@ -1876,7 +1896,7 @@ static osm_b200_status osm_b200_session_extract_files_arff_impl(osm_b200_session
       if (st != OSM_B200_OK) return st;
       const int KF = f->total;
       std::vector<float> frows(g.second.size() * (size_t)KF + 1);
-      st = osm_b200_session_extract_pcm_impl(s, pcm.data(), off.data(), (int)g.second.size(), sr, nc, fo.data(), frows.data(), (int64_t)g.second.size());
+      st = osm_b200_session_extract_pcm_impl(s, pcm.data(), off.data(), (int)g.second.size(), sr, nc, fo.data(), frows.data(), (int64_t)g.second.size(), fmt);
       if (st != OSM_B200_OK) return st;
       for (size_t k = 0; k < g.second.size(); k++) nTime[k] = fo[k + 1] - fo[k];
       if (!write_batch(s, g.second, fo.data(), nTime.data(), frows.data(), KF, f->names, osm_b200_plan_frame_period(p), htkPaths, csvPaths, arffPaths, framesOut, err))

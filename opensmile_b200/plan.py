@@ -39,12 +39,13 @@ def _comp(ctype, name, reader, writer, **fields):
     return c
 
 
-def components_mfcc12_0_d_a(sample_rate=16000.0, n_channels=1):
-    """config/mfcc/MFCC12_0_D_A.conf (+ shared/standard_wave_input.conf.inc) as a component list."""
+def components_mfcc12_0_d_a(sample_rate=16000.0, n_channels=1, pcm_format=0):
+    """config/mfcc/MFCC12_0_D_A.conf (+ shared/standard_wave_input.conf.inc) as a component list.
+    pcm_format: osm_b200_pcm_format of the buffers handed to run_* (0 int16, 1 float32, 2 int8, 3 packed 24 bit, 4 24 in 32, 5 int32)"""
     T = capi
     return [
         _comp(T.C_WAVESOURCE, "waveIn", "", "wave", sampleRate=float(sample_rate),
-              nChannels=n_channels, monoMixdown=1),
+              nChannels=n_channels, monoMixdown=1, format=pcm_format),
         _comp(T.C_FRAMER, "frame", "wave", "frames", frameSize=0.025, frameStep=0.010),
         _comp(T.C_VECTORPREEMPHASIS, "pe", "frames", "framespe", k=0.97, de=0),
         _comp(T.C_WINDOWER, "win", "framespe", "winframes", winFunc=T.WIN_BY_NAME["ham"], gain=1.0, offset=0.0),
@@ -139,6 +140,7 @@ class Plan:
         self._h = h
         self.device = device
         self.num_elements = self._L.osm_b200_plan_num_elements(h)
+        self.sample_frame_bytes = self._L.osm_b200_plan_sample_frame_bytes(h)
         self.frame_size = self._L.osm_b200_plan_frame_size_samples(h)
         self.frame_step = self._L.osm_b200_plan_frame_step_samples(h)
         self.fft_size = self._L.osm_b200_plan_fft_size(h)

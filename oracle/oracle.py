@@ -216,6 +216,20 @@ def _fp(a):
 # ---- config presets mirroring the shipped .conf files (values read from
 # /root/reference/config/mfcc/MFCC12_0_D_A.conf, config/plp/PLP_0_D_A.conf) ----
 
+def pcm_to_float(buf, fmt, n_chan=1):
+    """a-1 for every sample format (osm_or_pcm_to_float): buf = the bytes of interleaved sample frames, fmt = osm_b200_pcm_format
+    (0 int16, 1 float32, 2 int8, 3 packed 24 bit, 4 24 bit in 32, 5 int32) -> mono float32 samples"""
+    raw = np.ascontiguousarray(np.frombuffer(bytes(buf), np.uint8))
+    bps = {0: 2, 1: 4, 2: 1, 3: 3, 4: 4, 5: 4}[fmt]
+    n = raw.size // (bps * n_chan)
+    out = np.empty(n, np.float32)
+    L = lib()
+    L.osm_or_pcm_to_float.argtypes = [C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_void_p]
+    L.osm_or_pcm_to_float.restype = None
+    L.osm_or_pcm_to_float(raw.ctypes.data, fmt, n, n_chan, out.ctypes.data)
+    return out
+
+
 def mfcc12_0_d_a(sample_rate):
     fe = Frontend(sample_rate, 0.025, 0.010, 1, 0.97, WIN["ham"], 0.4, 1.0, 0.0, 0)
     ms = Melspec(26, 0.0, 8000.0, 1, 1)

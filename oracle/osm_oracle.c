@@ -75,6 +75,47 @@ void osm_or_pcm16_to_float(const int16_t *pcm, long n_samples, int n_chan, float
   }
 }
 
+/* every sample format cWaveSource accepts, monoMixdown = 1 (smileutil/smileUtil.c:2518-2580 integer formats, :2651-2661 IEEE float).
+ * format: 0 int16, 1 float32, 2 int8 (the reference reads 8-bit data as SIGNED bytes, :2507), 3 three bytes per sample (:2543-2552),
+ * 4 32-bit container with 24 valid bits (masked, NOT sign extended, :2559), 5 int32.  Statement order of the reference: the channel
+ * values are summed as floats from 0.0, divided by the channel count, then by the full scale (the float format has no full scale). */
+void osm_or_pcm_to_float(const void *buf, int format, long n_samples, int n_chan, float *out)
+{
+  const int8_t *b8 = (const int8_t *)buf;
+  const uint8_t *bu8 = (const uint8_t *)buf;
+  const int16_t *b16 = (const int16_t *)buf;
+  const int32_t *b32 = (const int32_t *)buf;
+  const float *bf = (const float *)buf;
+  for (long i = 0; i < n_samples; i++) {
+    float tmp = 0.0f;
+    for (int c = 0; c < n_chan; c++) {
+      const long k = i * n_chan + c;
+      switch (format) {
+        case 0: tmp += (float)b16[k]; break;
+        case 1: tmp += bf[k]; break;
+        case 2: tmp += (float)b8[k]; break;
+        case 3: {
+          uint32_t is = 0;
+          is |= (uint32_t)bu8[k * 3] << 8;
+          is |= (uint32_t)bu8[k * 3 + 1] << 16;
+          is |= (uint32_t)bu8[k * 3 + 2] << 24;
+          tmp += (float)((int32_t)is >> 8);
+          break;
+        }
+        case 4: tmp += (float)(b32[k] & 0xFFFFFF); break;
+        default: tmp += (float)b32[k]; break;
+      }
+    }
+    switch (format) {
+      case 0: out[i] = (tmp / (float)n_chan) / (float)32767.0; break;
+      case 1: out[i] = tmp / (float)n_chan; break;
+      case 2: out[i] = (tmp / (float)n_chan) / (float)127.0; break;
+      case 3: case 4: out[i] = (tmp / (float)n_chan) / (float)(32767.0 * 256.0); break;
+      default: out[i] = (tmp / (float)n_chan) / (float)2147483647.0; break;
+    }
+  }
+}
+
 /* ------------------------------------------------------------------ a-4 window table */
 
 /* smileutil/smileUtil.c:1218-1349, dspcore/windower.cpp:159-217 (gain only; no sqrt /

@@ -111,6 +111,7 @@ long osm_or_num_frames(long n_samples, long frame_size, long frame_step);
 
 /* ---- stage by stage ---- */
 void osm_or_pcm16_to_float(const int16_t *pcm, long n_samples, int n_chan, float *out);
+void osm_or_pcm_to_float(const void *buf, int format, long n_samples, int n_chan, float *out);
 void osm_or_window_table(int win_func, long n, double sigma, double gain, double *w);
 /* one frame: raw float samples (frame_size) -> magnitude spectrum (nfft/2+1) */
 void osm_or_frame_to_mag(const osm_or_frontend *fe, const float *x, long frame_size,
