@@ -33,6 +33,7 @@ extern "C" {
 typedef enum {
   OSM_B200_F_EXTREMES = 0, OSM_B200_F_MEANS, OSM_B200_F_MOMENTS, OSM_B200_F_PERCENTILES, OSM_B200_F_REGRESSION,
   OSM_B200_F_TIMES, OSM_B200_F_LPC, OSM_B200_F_SEGMENTS, OSM_B200_F_PEAKS2,
+  OSM_B200_F_ONSET, OSM_B200_F_PEAKS, OSM_B200_F_CROSSINGS,
   OSM_B200_F_COUNT_
 } osm_b200_functional_type;
 
@@ -113,6 +114,19 @@ typedef struct {
     float   relThresh, absThresh; int32_t useAbsThresh, dynRelThresh, doRatioLimit;
     int32_t norm, normIsSet;
   } peaks2;
+  struct {                                         /* Onset.* (functionalOnset.cpp:43-54): 0,0,1,0,0 ; thresholds 0 ; norm "segment" */
+    int32_t onsetPos, offsetPos, numOnsets, numOffsets, onsetRate;
+    float   thresholdOnset, thresholdOffset;       /* `threshold` sets both, thresholdOnset / thresholdOffset override it */
+    int32_t useAbsVal;
+    int32_t norm, normIsSet;
+  } onset;
+  struct {                                         /* Peaks.* (functionalPeaks.cpp:45-53): 1,1,1,1,0 ; norm "frames"; overlapFlag = 1 only */
+    int32_t numPeaks, meanPeakDist, peakMean, peakMeanMeanDist, peakDistStddev;
+    int32_t norm, normIsSet;
+  } peaks;
+  struct {                                         /* Crossings.* (functionalCrossings.cpp:42-46): 1,1,0 */
+    int32_t zcr, mcr, amean;
+  } crossings;
 } osm_b200_functionals_spec;
 
 typedef struct osm_b200_functionals osm_b200_functionals;

@@ -47,7 +47,7 @@ struct FnParams {
   int perWarp;                              // floats per warp in shared memory: contour copy + extrema list + segment lengths
   int listOff, lensOff;                     // float offsets of the Peaks2 list / Segments lengths inside a warp's block
   int valOff[OSM_B200_F_MAX_ENABLED];       // first value of every enabled functional inside a contour's output
-  int timesNorm, segNorm, peaksNorm;
+  int timesNorm, segNorm, peaksNorm; int onsetNorm, peaksOldNorm;
   float period; double periodD;             // input level period as FLOAT_DMEM and as double
   osm_b200_functionals_spec s;
   int extNorm, meanNorm;                    // resolved time normalisations
@@ -277,6 +277,15 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
       __syncwarp();
     } else if (kind == OSM_B200_F_SEGMENTS) {
       if (lane == 0) fseq::segments(p.s.segments, sbuf, (long)N, mn, mx, p.period, p.segNorm, sbuf + p.lensOff, o);
+      __syncwarp();
+    } else if (kind == OSM_B200_F_ONSET) {                            // state machines / float running sums in frame order: lane 0
+      if (lane == 0) fseq::onset(p.s.onset, sbuf, (long)N, p.period, p.onsetNorm, o);
+      __syncwarp();
+    } else if (kind == OSM_B200_F_PEAKS) {
+      if (lane == 0) fseq::peaks(p.s.peaks, sbuf, (long)N, p.period, p.peaksOldNorm, reinterpret_cast<int *>(sbuf + p.listOff), o);
+      __syncwarp();
+    } else if (kind == OSM_B200_F_CROSSINGS) {
+      if (lane == 0) fseq::crossings(p.s.crossings, sbuf, (long)N, o);
       __syncwarp();
     }
   }
@@ -571,6 +580,23 @@ std::vector<std::string> value_names(const osm_b200_functionals_spec &s)
             "stddevFallingSlope", "covFallingSlope", "covRisingSlope"};                                                  // functionalPeaks2.cpp:58-66
         for (int k = 0; k < OSM_B200_F_PEAKS2_VALUES; k++) if (s.peaks2.value[k]) v.push_back(nm[k]);
       } break;
+      case OSM_B200_F_ONSET: {                                                                                          // functionalOnset.cpp:29
+        const auto &O = s.onset;
+        const int on[5] = {O.onsetPos, O.offsetPos, O.numOnsets, O.numOffsets, O.onsetRate};
+        const char *nm[5] = {"onsetPos", "offsetPos", "numOnsets", "numOffsets", "onsetRate"};
+        for (int k = 0; k < 5; k++) if (on[k]) v.push_back(nm[k]);
+      } break;
+      case OSM_B200_F_PEAKS: {                                                                                          // functionalPeaks.cpp:29
+        const auto &K = s.peaks;
+        const int on[5] = {K.numPeaks, K.meanPeakDist, K.peakMean, K.peakMeanMeanDist, K.peakDistStddev};
+        const char *nm[5] = {"numPeaks", "meanPeakDist", "peakMean", "peakMeanMeanDist", "peakDistStddev"};
+        for (int k = 0; k < 5; k++) if (on[k]) v.push_back(nm[k]);
+      } break;
+      case OSM_B200_F_CROSSINGS: {                                                                                      // functionalCrossings.cpp:26
+        if (s.crossings.zcr) v.push_back("zcr");
+        if (s.crossings.mcr) v.push_back("mcr");
+        if (s.crossings.amean) v.push_back("amean");
+      } break;
     }
   }
   return v;
@@ -614,6 +640,10 @@ void osm_b200_functionals_defaults(osm_b200_functionals_spec *s)
   G.maxNumSeg = 20; G.segMinLng = 3; G.pauseMinLng = 2; G.norm = OSM_B200_TIMENORM_SEGMENT; G.algorithm = OSM_B200_SEG_RELTH;
   auto &K = s->peaks2;                                            // functionalPeaks2.cpp:84-130
   K.relThresh = 0.1f; K.doRatioLimit = 1; K.norm = OSM_B200_TIMENORM_FRAME;
+  s->onset.numOnsets = 1; s->onset.norm = OSM_B200_TIMENORM_SEGMENT;                                    // functionalOnset.cpp:43-54
+  auto &QP = s->peaks;                                            // functionalPeaks.cpp:45-53
+  QP.numPeaks = QP.meanPeakDist = QP.peakMean = QP.peakMeanMeanDist = 1; QP.norm = OSM_B200_TIMENORM_FRAME;
+  s->crossings.zcr = s->crossings.mcr = 1;                        // functionalCrossings.cpp:42-46
 }
 
 osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spec, int32_t n_in, const char *const *in_names,
@@ -653,7 +683,7 @@ osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spe
   for (int i = 0; i < s.n_enabled; i++) {
     f->hasPct = f->hasPct || s.enabled[i] == OSM_B200_F_PERCENTILES;
     f->hasSeq = f->hasSeq || s.enabled[i] >= OSM_B200_F_TIMES;
-    f->hasPeaks = f->hasPeaks || s.enabled[i] == OSM_B200_F_PEAKS2;
+    f->hasPeaks = f->hasPeaks || s.enabled[i] == OSM_B200_F_PEAKS2 || s.enabled[i] == OSM_B200_F_PEAKS;   // the extrema / distance list
     f->hasSeg = f->hasSeg || s.enabled[i] == OSM_B200_F_SEGMENTS;
   }
   if (device >= 0) {
@@ -740,6 +770,8 @@ osm_b200_status osm_b200_functionals_run_device_cols(osm_b200_functionals *f, co
   p.timesNorm = resolve_norm(f->spec.times.norm, f->spec.times.normIsSet, f->spec.masterTimeNorm);
   p.segNorm = resolve_norm(f->spec.segments.norm, f->spec.segments.normIsSet, f->spec.masterTimeNorm);
   p.peaksNorm = resolve_norm(f->spec.peaks2.norm, f->spec.peaks2.normIsSet, f->spec.masterTimeNorm);
+  p.onsetNorm = resolve_norm(f->spec.onset.norm, f->spec.onset.normIsSet, f->spec.masterTimeNorm);
+  p.peaksOldNorm = resolve_norm(f->spec.peaks.norm, f->spec.peaks.normIsSet, f->spec.masterTimeNorm);
   p.out = d_out; p.nVals = f->nVals; p.sortCap = sortCap; p.period = (float)f->period; p.periodD = f->period; p.s = f->spec;
   p.extNorm = resolve_norm(f->spec.extremes.norm, f->spec.extremes.normIsSet, f->spec.masterTimeNorm);
   p.meanNorm = resolve_norm(f->spec.means.norm, f->spec.means.normIsSet, f->spec.masterTimeNorm);

@@ -421,5 +421,113 @@ OSM_FS_HD int lpc(const Spec &l, const float *acf, long N, float *out)
   return n;
 }
 
+// cFunctionalOnset::process (functionalOnset.cpp:95-153)
+template <class Spec>
+OSM_FS_HD int onset(const Spec &c, const float *x, long N, float period, int timeNorm, float *out)
+{
+  long onsetPos = -1, offsetPos = -1, nOnsets = 0, nOffsets = 0;
+  int oo = x[0] > c.thresholdOnset ? 1 : 0;
+  for (long i = 1; i < N; i++) {
+    const float cur = c.useAbsVal ? fabsf(x[i]) : x[i];
+    if (cur > c.thresholdOnset && oo == 0) { nOnsets++; if (onsetPos == -1) onsetPos = i; oo = 1; }
+    if (cur <= c.thresholdOffset && oo == 1) { nOffsets++; offsetPos = i; oo = 0; }
+  }
+  if (offsetPos == -1) offsetPos = N - 1;
+  if (onsetPos == -1) onsetPos = 0;
+  int n = 0;
+  if (timeNorm == OSM_B200_TIMENORM_SEGMENT) {
+    if (c.onsetPos) out[n++] = (float)onsetPos / (float)N;
+    if (c.offsetPos) out[n++] = (float)offsetPos / (float)N;
+  } else if (timeNorm == OSM_B200_TIMENORM_SECOND) {
+    if (c.onsetPos) out[n++] = (float)onsetPos * period;
+    if (c.offsetPos) out[n++] = (float)offsetPos * period;
+  } else {
+    if (c.onsetPos) out[n++] = (float)onsetPos;
+    if (c.offsetPos) out[n++] = (float)offsetPos;
+  }
+  if (c.numOnsets) out[n++] = (float)nOnsets;
+  if (c.numOffsets) out[n++] = (float)nOffsets;
+  if (c.onsetRate) out[n++] = (float)nOnsets / ((float)N * period);
+  return n;
+}
+
+// cFunctionalPeaks::process (functionalPeaks.cpp:96-213) with overlapFlag = 1 (its default: the two-sample history restarts with
+// every contour).  dists: work space for the peak distances (at most N / 2 entries)
+template <class Spec>
+OSM_FS_HD int peaks(const Spec &c, const float *x, long N, float period, int timeNorm, int *dists, float *out)
+{
+  float mxv = x[0], mnv = x[0], mean = x[0];
+  for (long i = 1; i < N; i++) { if (x[i] < mnv) mnv = x[i]; if (x[i] > mxv) mxv = x[i]; mean = mean + x[i]; }
+  mean = mean / (float)N;
+  const float range = mxv - mnv;
+  float peakDist = 0.0f, peakMean = 0.0f, lastMin = 0.0f, lastMax = 0.0f;
+  long nPeakDist = 0, nPeaks = 0, curmaxPos = 0, lastmaxPos = -1;
+  int peakflag = 0;
+  float lastlastVal = x[0], lastVal = N > 1 ? x[1] : 0.0f;
+  for (long i = 2; i < N; i++) {
+    if (lastlastVal < lastVal && lastVal > x[i]) {                                        // max
+      if (!peakflag) lastMax = x[i];
+      else if (x[i] > lastMax) { lastMax = x[i]; curmaxPos = i; }
+      if ((double)(lastMax - lastMin) > 0.11 * (double)range) { peakflag = 1; curmaxPos = i; }
+    } else if (lastlastVal > lastVal && lastVal < x[i]) lastMin = x[i];                   // min
+    if (peakflag && ((double)x[i] < (double)lastMax - 0.09 * (double)range || i == N - 1)) {
+      nPeaks++;
+      peakMean = peakMean + lastMax;
+      if (lastmaxPos >= 0) {
+        const float dist = (float)(curmaxPos - lastmaxPos);
+        peakDist = peakDist + dist;
+        dists[nPeakDist++] = (int)dist;
+      }
+      lastmaxPos = curmaxPos;
+      peakflag = 0;
+    }
+    lastlastVal = lastVal;
+    lastVal = x[i];
+  }
+  float stddev = 0.0f;
+  if (nPeakDist > 0) {
+    peakDist = peakDist / (float)nPeakDist;
+    for (long i = 0; i < nPeakDist; i++) stddev = stddev + ((float)dists[i] - peakDist) * ((float)dists[i] - peakDist);
+    stddev = stddev / (float)nPeakDist;
+    stddev = sqrtf(stddev);
+  } else { peakDist = (float)(N + 1); stddev = 0.0f; }
+  int n = 0;
+  if (c.numPeaks) out[n++] = (float)nPeaks;
+  if (timeNorm == OSM_B200_TIMENORM_SECOND) { peakDist = peakDist * period; stddev = stddev * period; }
+  else if (timeNorm == OSM_B200_TIMENORM_SEGMENT) { peakDist = peakDist / (float)N; stddev = stddev / (float)N; }
+  if (c.meanPeakDist) out[n++] = peakDist;
+  peakMean = nPeaks > 0 ? peakMean / (float)nPeaks : 0.0f;
+  if (c.peakMean) out[n++] = peakMean;
+  if (c.peakMeanMeanDist) out[n++] = peakMean - mean;
+  if (c.peakDistStddev) out[n++] = stddev;
+  return n;
+}
+
+// cFunctionalCrossings::process (functionalCrossings.cpp:64-97): products in float, the mean-crossing terms in double
+template <class Spec>
+OSM_FS_HD int crossings(const Spec &c, const float *x, long N, float *out)
+{
+  double amean = 0.0;
+  if (c.mcr || c.amean) {
+    amean = (double)x[0];
+    for (long i = 1; i < N; i++) amean += (double)x[i];
+    amean /= (double)N;
+  }
+  long zcr = 0, mcr = 0;
+  for (long i = 1; i < N - 1; i++) {
+    const float a = x[i - 1], b = x[i], d = x[i + 1];
+    if ((a * d <= 0.0f && b == 0.0f) || a * b < 0.0f) zcr++;
+    if (c.mcr) {
+      const double am = (double)a - amean, bm = (double)b - amean, dm = (double)d - amean;
+      if ((am * dm <= 0.0 && bm == 0.0) || am * bm < 0.0) mcr++;
+    }
+  }
+  int n = 0;
+  if (c.zcr) out[n++] = (float)((double)zcr / (double)N);
+  if (c.mcr) out[n++] = (float)((double)mcr / (double)N);
+  if (c.amean) out[n++] = (float)amean;
+  return n;
+}
+
 }  // namespace fseq
 }  // namespace osm

@@ -10,9 +10,10 @@ import numpy as np
 from . import capi
 
 i32, f64, f32 = C.c_int32, C.c_double, C.c_float
-F_EXTREMES, F_MEANS, F_MOMENTS, F_PERCENTILES, F_REGRESSION, F_TIMES, F_LPC, F_SEGMENTS, F_PEAKS2 = range(9)
+F_EXTREMES, F_MEANS, F_MOMENTS, F_PERCENTILES, F_REGRESSION, F_TIMES, F_LPC, F_SEGMENTS, F_PEAKS2, F_ONSET, F_PEAKS, F_CROSSINGS = range(12)
 TYPE_BY_NAME = {"Extremes": F_EXTREMES, "Means": F_MEANS, "Moments": F_MOMENTS, "Percentiles": F_PERCENTILES, "Regression": F_REGRESSION,
-                "Times": F_TIMES, "Lpc": F_LPC, "Segments": F_SEGMENTS, "Peaks2": F_PEAKS2}
+                "Times": F_TIMES, "Lpc": F_LPC, "Segments": F_SEGMENTS, "Peaks2": F_PEAKS2, "Onset": F_ONSET, "Peaks": F_PEAKS,
+                "Crossings": F_CROSSINGS}
 SEG_RELTH, SEG_NONX, SEG_EQX = 0, 1, 2
 SEG_BY_NAME = {"relTh": SEG_RELTH, "nonX": SEG_NONX, "eqX": SEG_EQX}
 PEAKS2_NAMES = ["numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs", "peakRangeRel", "peakMeanAbs",
@@ -67,11 +68,24 @@ class _Peaks2(C.Structure):
                [(n, i32) for n in ("useAbsThresh", "dynRelThresh", "doRatioLimit", "norm", "normIsSet")]
 
 
+class _Onset(C.Structure):
+    _fields_ = [(n, i32) for n in ("onsetPos", "offsetPos", "numOnsets", "numOffsets", "onsetRate")] + \
+               [("thresholdOnset", f32), ("thresholdOffset", f32)] + [(n, i32) for n in ("useAbsVal", "norm", "normIsSet")]
+
+
+class _Peaks(C.Structure):
+    _fields_ = [(n, i32) for n in ("numPeaks", "meanPeakDist", "peakMean", "peakMeanMeanDist", "peakDistStddev", "norm", "normIsSet")]
+
+
+class _Crossings(C.Structure):
+    _fields_ = [(n, i32) for n in ("zcr", "mcr", "amean")]
+
+
 class Spec(C.Structure):
     _fields_ = [("n_enabled", i32), ("enabled", i32 * 8), ("nonZeroFuncts", i32), ("masterTimeNorm", i32),
                 ("functNameAppend", C.c_char * capi.NAME_LEN), ("extremes", _Extremes), ("means", _Means), ("moments", _Moments),
                 ("percentiles", _Percentiles), ("regression", _Regression), ("times", _Times), ("lpc", _Lpc), ("segments", _Segments),
-                ("peaks2", _Peaks2)]
+                ("peaks2", _Peaks2), ("onset", _Onset), ("peaks", _Peaks), ("crossings", _Crossings)]
 
 
 def _bind(L):

@@ -639,7 +639,10 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
   auto &TI = fs.times; auto &LP = fs.lpc; auto &SG = fs.segments; auto &PK = fs.peaks2;
   std::map<int, double> segThresh;
   std::string segThreshList, segAlgo = "delta";
-  bool unsupportedTimes = false, unsupportedSeg = false, unsupportedPeaks = false;
+  bool unsupportedTimes = false, unsupportedSeg = false, unsupportedPeaks = false, peaksNoOverlap = false;
+  double onsetThr = 0.0, onsetThrOn = 0.0, onsetThrOff = 0.0;
+  bool onsetThrOnSet = false, onsetThrOffSet = false;
+  auto &ON = fs.onset; auto &PO = fs.peaks; auto &CR = fs.crossings;
   static const char *peaksNames[OSM_B200_F_PEAKS2_VALUES] = {"numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs",
       "peakRangeRel", "peakMeanAbs", "peakMeanMeanDist", "peakMeanRel", "ptpAmpMeanAbs", "ptpAmpMeanRel", "ptpAmpStddevAbs", "ptpAmpStddevRel",
       "minRangeAbs", "minRangeRel", "minMeanAbs", "minMeanMeanDist", "minMeanRel", "mtmAmpMeanAbs", "mtmAmpMeanRel", "mtmAmpStddevAbs",
@@ -671,7 +674,12 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     {"Segments.numSegments", &SG.numSegments}, {"Segments.meanSegLen", &SG.meanSegLen}, {"Segments.maxSegLen", &SG.maxSegLen},
     {"Segments.minSegLen", &SG.minSegLen}, {"Segments.segLenStddev", &SG.segLenStddev}, {"Segments.maxNumSeg", &SG.maxNumSeg},
     {"Segments.XisRel", &SG.XisRel}, {"Segments.pauseMinLng", &SG.pauseMinLng},
-    {"Peaks2.dynRelThresh", &PK.dynRelThresh}, {"Peaks2.doRatioLimit", &PK.doRatioLimit}};
+    {"Peaks2.dynRelThresh", &PK.dynRelThresh}, {"Peaks2.doRatioLimit", &PK.doRatioLimit},
+    {"Onset.onsetPos", &ON.onsetPos}, {"Onset.offsetPos", &ON.offsetPos}, {"Onset.numOnsets", &ON.numOnsets}, {"Onset.numOffsets", &ON.numOffsets},
+    {"Onset.onsetRate", &ON.onsetRate}, {"Onset.useAbsVal", &ON.useAbsVal},
+    {"Peaks.numPeaks", &PO.numPeaks}, {"Peaks.meanPeakDist", &PO.meanPeakDist}, {"Peaks.peakMean", &PO.peakMean},
+    {"Peaks.peakMeanMeanDist", &PO.peakMeanMeanDist}, {"Peaks.peakDistStddev", &PO.peakDistStddev},
+    {"Crossings.zcr", &CR.zcr}, {"Crossings.mcr", &CR.mcr}, {"Crossings.amean", &CR.amean}};
   for (const auto &kv : s.kv) {
     const std::string &f = kv.first, &v = kv.second;
     if (is_common(f) || f == "noPostEOIprocessing" || f == "allowLastFrameIncomplete" || f == "frameListFile" || f == "frameList") continue;
@@ -712,10 +720,23 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
       for (int k = 0; k < OSM_B200_F_PEAKS2_VALUES; k++) if (f.compare(7, std::string::npos, peaksNames[k]) == 0) { PK.value[k] = inum(v); hitP = true; break; }
       if (hitP) continue;
     }
+    if (f == "Onset.threshold") { onsetThr = num(v); continue; }
+    if (f == "Onset.thresholdOnset") { onsetThrOn = num(v); onsetThrOnSet = true; continue; }
+    if (f == "Onset.thresholdOffset") { onsetThrOff = num(v); onsetThrOffSet = true; continue; }
+    if (f == "Onset.norm") { fs.onset.norm = time_norm(v); fs.onset.normIsSet = 1; continue; }
+    if (f == "Peaks.norm") { fs.peaks.norm = time_norm(v); fs.peaks.normIsSet = 1; continue; }
+    if (f == "Peaks.overlapFlag") { peaksNoOverlap = inum(v) == 0; continue; }
     if (f == "Percentiles.quartiles") { quartilesSet = true; quartiles = inum(v); continue; }
     if (f == "Percentiles.iqr") { iqrSet = true; iqr = inum(v); continue; }
     if (f.compare(0, 23, "Percentiles.percentile[") == 0) { pct[atoi(f.c_str() + 23)] = num(v); continue; }
     if (f.compare(0, 22, "Percentiles.pctlrange[") == 0) { pctRange[atoi(f.c_str() + 22)] = v; continue; }
+    // array fields given as one `a;b;c` list (core/configManager.cpp:2229-2262: the elements are assigned in order from index 0)
+    if (f == "Percentiles.percentile" || f == "Percentiles.pctlrange") {
+      std::vector<std::string> items;
+      { std::stringstream ss(v); std::string one; while (std::getline(ss, one, ';')) { one = trim(one); if (!one.empty()) items.push_back(one); } }
+      for (size_t k = 0; k < items.size(); k++) { if (f == "Percentiles.percentile") pct[(int)k] = num(items[k]); else pctRange[(int)k] = items[k]; }
+      continue;
+    }
     if (f.compare(0, 24, "Percentiles.pctlquotient") == 0 || f.compare(0, 15, "Percentiles.iqq") == 0) { err = "cFunctionalPercentiles: quotients are not supported"; return false; }
     if (f.compare(0, 15, "Regression.qreg") == 0 && (f == "Regression.qregls" || f == "Regression.qregrs" || f == "Regression.qregx0" || f == "Regression.qregy0" ||
         f == "Regression.qregyr" || f == "Regression.qregy0nn" || f == "Regression.qregc3nn" || f == "Regression.qregyrnn")) {
@@ -737,6 +758,8 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     err = "unknown field '" + f + "' in section [" + s.name + ":cFunctionals]";
     return false;
   }
+  ON.thresholdOnset = (float)(onsetThrOnSet ? onsetThrOn : onsetThr);               // functionalOnset.cpp:77-81
+  ON.thresholdOffset = (float)(onsetThrOffSet ? onsetThrOff : onsetThr);
   if (quartilesSet) P.quartile1 = P.quartile2 = P.quartile3 = quartiles;          // functionalPercentiles.cpp:112-116
   if (iqrSet) P.iqr12 = P.iqr23 = P.iqr13 = iqr;
   std::vector<std::string> names;
@@ -760,7 +783,11 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     else if (n == "Lpc") t = OSM_B200_F_LPC;
     else if (n == "Segments") t = OSM_B200_F_SEGMENTS;
     else if (n == "Peaks2") t = OSM_B200_F_PEAKS2;
-    else { err = "cFunctional" + n + " (instance '" + s.name + "') is not supported on the GPU path (Extremes, Means, Moments, Percentiles, Regression, Times, Lpc, Segments, Peaks2 are)"; return false; }
+    else if (n == "Onset") t = OSM_B200_F_ONSET;
+    else if (n == "Peaks") t = OSM_B200_F_PEAKS;
+    else if (n == "Crossings") t = OSM_B200_F_CROSSINGS;
+    else { err = "cFunctional" + n + " (instance '" + s.name + "') is not supported on the GPU path (Extremes, Means, Moments, Percentiles, Regression, Times, Lpc, Segments, Peaks2, Onset, Peaks, Crossings are)"; return false; }
+    if (t == OSM_B200_F_PEAKS && peaksNoOverlap) { err = "cFunctionalPeaks.overlapFlag = 0 (peak history carried from one contour to the next) is not supported"; return false; }
     fs.enabled[fs.n_enabled++] = t;
     if (t == OSM_B200_F_TIMES && unsupportedTimes) { err = "cFunctionalTimes: upleveltime[] / downleveltime[] arrays and useRobustPercentileRange are not supported"; return false; }
     if (t == OSM_B200_F_PEAKS2 && unsupportedPeaks) { err = "cFunctionalPeaks2.noClearPeakList = 1 is not supported"; return false; }

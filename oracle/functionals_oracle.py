@@ -34,7 +34,7 @@ class Spec:
     """mirror of include/osm_b200_functionals.h (field names = the reference's configuration fields)"""
 
     def __init__(self, enabled, non_zero=0, master_norm=None, name_append=None, extremes=None, means=None, moments=None,
-                 percentiles=None, regression=None, times=None, lpc=None, segments=None, peaks2=None):
+                 percentiles=None, regression=None, times=None, lpc=None, segments=None, peaks2=None, onset=None, peaks=None, crossings=None):
         self.enabled, self.non_zero, self.master_norm, self.name_append = list(enabled), non_zero, master_norm, name_append
         self.extremes = dict(max=1, min=1, range=1, maxpos=1, minpos=1, amean=0, maxameandist=1, minameandist=1, norm=FRAME, norm_set=False)
         self.extremes.update(extremes or {})
@@ -62,6 +62,13 @@ class Spec:
         self.peaks2 = {k: 0 for k in PEAKS2_NAMES}
         self.peaks2.update(dict(norm=FRAME, norm_set=False, relThresh=0.1, dynRelThresh=0, absThresh=None, doRatioLimit=1))
         self.peaks2.update(peaks2 or {})
+        self.onset = dict(onsetPos=0, offsetPos=0, numOnsets=1, numOffsets=0, onsetRate=0, threshold=0.0, thresholdOnset=None, thresholdOffset=None,
+                          useAbsVal=0, norm=SEGMENT, norm_set=False)
+        self.onset.update(onset or {})
+        self.peaks = dict(numPeaks=1, meanPeakDist=1, peakMean=1, peakMeanMeanDist=1, peakDistStddev=0, norm=FRAME, norm_set=False)
+        self.peaks.update(peaks or {})
+        self.crossings = dict(zcr=1, mcr=1, amean=0)
+        self.crossings.update(crossings or {})
 
 
 EXT_NAMES = ["max", "min", "range", "maxPos", "minPos", "amean", "maxameandist", "minameandist"]
@@ -72,6 +79,9 @@ MOM_NAMES = ["variance", "stddev", "skewness", "kurtosis", "amean"]
 TIMES_NAMES = ["upleveltime25", "downleveltime25", "upleveltime50", "downleveltime50", "upleveltime75", "downleveltime75",
                "upleveltime90", "downleveltime90", "risetime", "falltime", "leftctime", "rightctime", "duration"]
 SEG_NAMES = ["numSegments", "meanSegLen", "maxSegLen", "minSegLen", "segLenStddev"]
+ONSET_NAMES = ["onsetPos", "offsetPos", "numOnsets", "numOffsets", "onsetRate"]                  # functionalOnset.cpp:29
+PEAKS_NAMES = ["numPeaks", "meanPeakDist", "peakMean", "peakMeanMeanDist", "peakDistStddev"]     # functionalPeaks.cpp:29
+CROSS_NAMES = ["zcr", "mcr", "amean"]                                                            # functionalCrossings.cpp:26
 # functionalPeaks2.cpp:24-73: output order = index order of the FUNCT_* constants; the configuration field of a value is its
 # name except for the three marked ones
 PEAKS2_NAMES = ["numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs", "peakRangeRel", "peakMeanAbs",
@@ -112,6 +122,12 @@ def value_names(spec):
             out += [n for n in SEG_NAMES if spec.segments[n]]
         elif f == "Peaks2":
             out += [n for n in PEAKS2_NAMES if spec.peaks2[n]]
+        elif f == "Onset":
+            out += [n for n in ONSET_NAMES if spec.onset[n]]
+        elif f == "Peaks":
+            out += [n for n in PEAKS_NAMES if spec.peaks[n]]
+        elif f == "Crossings":
+            out += [n for n in CROSS_NAMES if spec.crossings[n]]
         else:
             raise ValueError(f)
     return out
@@ -292,8 +308,124 @@ def contour(spec, x, period):
             out += _segments(spec, x, mn, mx, mean, period)
         elif f == "Peaks2":
             out += _peaks2(spec, x, mn, mx, mean, period)
+        elif f == "Onset":
+            out += _onset(spec, x, period)
+        elif f == "Peaks":
+            out += _peaks_old(spec, x, period)
+        elif f == "Crossings":
+            out += _crossings(spec, x)
     assert len(out) == nvals
     return out
+
+
+def _onset(spec, x, period):
+    """functionalOnset.cpp:95-153: a two-state machine over the contour (thresholdOnset / thresholdOffset, :77-81)"""
+    o = spec.onset
+    thr_on = F32(o["threshold"] if o["thresholdOnset"] is None else o["thresholdOnset"])
+    thr_off = F32(o["threshold"] if o["thresholdOffset"] is None else o["thresholdOffset"])
+    N = len(x)
+    onset_pos = offset_pos = -1
+    n_on = n_off = 0
+    oo = 1 if x[0] > thr_on else 0
+    for i in range(1, N):
+        cur = F32(abs(x[i])) if o["useAbsVal"] else x[i]
+        if cur > thr_on and oo == 0:
+            n_on += 1
+            if onset_pos == -1:
+                onset_pos = i
+            oo = 1
+        if cur <= thr_off and oo == 1:
+            n_off += 1
+            offset_pos = i
+            oo = 0
+    if offset_pos == -1:
+        offset_pos = N - 1
+    if onset_pos == -1:
+        onset_pos = 0
+    nrm = _norm(o["norm"], o["norm_set"], spec.master_norm)
+    T = F32(period)
+    if nrm == SEGMENT:
+        pos = [F32(F32(onset_pos) / F32(N)), F32(F32(offset_pos) / F32(N))]
+    elif nrm == SECOND:
+        pos = [F32(F32(onset_pos) * T), F32(F32(offset_pos) * T)]
+    else:
+        pos = [F32(onset_pos), F32(offset_pos)]
+    vals = dict(onsetPos=pos[0], offsetPos=pos[1], numOnsets=F32(n_on), numOffsets=F32(n_off), onsetRate=F32(F32(n_on) / F32(F32(N) * T)))
+    return [vals[k] for k in ONSET_NAMES if o[k]]
+
+
+def _peaks_old(spec, x, period):
+    """functionalPeaks.cpp:96-213 with overlapFlag = 1 (the default): float running sums, the 0.11 / 0.09 range tests in double"""
+    k = spec.peaks
+    N = len(x)
+    mean = x[0]
+    for i in range(1, N):
+        mean = F32(mean + x[i])
+    mean = F32(mean / F32(N))
+    rng = F32(x.max() - x.min())
+    peak_dist, peak_mean, last_min, last_max = F32(0), F32(0), F32(0), F32(0)
+    dists = []
+    n_peaks, curmax, lastmax_pos, flag = 0, 0, -1, 0
+    llv, lv = x[0], (x[1] if N > 1 else F32(0))
+    for i in range(2, N):
+        if llv < lv and lv > x[i]:
+            if not flag:
+                last_max = x[i]
+            elif x[i] > last_max:
+                last_max, curmax = x[i], i
+            if float(F32(last_max - last_min)) > 0.11 * float(rng):
+                flag, curmax = 1, i
+        elif llv > lv and lv < x[i]:
+            last_min = x[i]
+        if flag and (float(x[i]) < float(last_max) - 0.09 * float(rng) or i == N - 1):
+            n_peaks += 1
+            peak_mean = F32(peak_mean + last_max)
+            if lastmax_pos >= 0:
+                d = F32(curmax - lastmax_pos)
+                peak_dist = F32(peak_dist + d)
+                dists.append(int(d))
+            lastmax_pos, flag = curmax, 0
+        llv, lv = lv, x[i]
+    stddev = F32(0)
+    if dists:
+        peak_dist = F32(peak_dist / F32(len(dists)))
+        for d in dists:
+            t = F32(F32(d) - peak_dist)
+            stddev = F32(stddev + F32(t * t))
+        stddev = F32(np.sqrt(F32(stddev / F32(len(dists)))))
+    else:
+        peak_dist = F32(N + 1)
+    nrm = _norm(k["norm"], k["norm_set"], spec.master_norm)
+    if nrm == SECOND:
+        peak_dist, stddev = F32(peak_dist * F32(period)), F32(stddev * F32(period))
+    elif nrm == SEGMENT:
+        peak_dist, stddev = F32(peak_dist / F32(N)), F32(stddev / F32(N))
+    peak_mean = F32(peak_mean / F32(n_peaks)) if n_peaks > 0 else F32(0)
+    vals = dict(numPeaks=F32(n_peaks), meanPeakDist=peak_dist, peakMean=peak_mean, peakMeanMeanDist=F32(peak_mean - mean), peakDistStddev=stddev)
+    return [vals[n] for n in PEAKS_NAMES if k[n]]
+
+
+def _crossings(spec, x):
+    """functionalCrossings.cpp:64-97: zero crossings on float products, mean crossings on double differences"""
+    c = spec.crossings
+    N = len(x)
+    amean = 0.0
+    if c["mcr"] or c["amean"]:
+        amean = float(x[0])
+        for i in range(1, N):
+            amean += float(x[i])
+        amean /= float(N)
+    zcr = mcr = 0
+    for i in range(1, N - 1):
+        a, b, d = x[i - 1], x[i], x[i + 1]
+        if (F32(a * d) <= 0 and b == 0) or F32(a * b) < 0:
+            zcr += 1
+        if c["mcr"]:
+            am, bm, dm = float(a) - amean, float(b) - amean, float(d) - amean
+            if (am * dm <= 0.0 and bm == 0.0) or am * bm < 0.0:
+                mcr += 1
+    vals = dict(zcr=F32(zcr / float(N)), mcr=F32(mcr / float(N)), amean=F32(amean))
+    return [vals[n] for n in CROSS_NAMES if c[n]]
 
 
 def _times(spec, x, mn, mx, period):

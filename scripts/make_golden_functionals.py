@@ -55,7 +55,7 @@ def main():
                 out["var%s_%s" % (lv.upper(), key)] = r
     for k, v in out.items():
         print(k, v.shape)
-    if "--second-only" not in sys.argv:
+    if "--second-only" not in sys.argv and "--third-only" not in sys.argv:
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", "functionals_goldens.npz"), **out)
     # second set (tests/configs/func_variants2.conf): Times, Lpc, Segments, Peaks2
     out2 = {}
@@ -75,7 +75,27 @@ def main():
                 out2["var%s_%s" % (lv, key)] = r
     for k, v in out2.items():
         print(k, v.shape)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "functionals_goldens2.npz"), **out2)
+    if "--third-only" not in sys.argv:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "functionals_goldens2.npz"), **out2)
+    # third set (tests/configs/func_variants3.conf): Onset, Peaks, Crossings
+    out3 = {}
+    var3 = open(os.path.join(ROOT, "tests", "configs", "func_variants3.conf")).read().replace("REFCONF", REF)
+    for key, pcm in sigs.items():
+        with tempfile.TemporaryDirectory() as d:
+            wav = os.path.join(d, "in.wav")
+            refrun.write_wav(wav, pcm, 16000, 1)
+            open(os.path.join(d, "v.conf"), "w").write(var3)
+            cmd = [refrun.SMILEXTRACT, "-C", os.path.join(d, "v.conf"), "-I", wav, "-l", "0"]
+            for lv in "IJK":
+                cmd += ["-out" + lv, os.path.join(d, lv + ".csv")]
+            subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            for lv in "IJK":
+                n, r = csv_rows(os.path.join(d, lv + ".csv"))
+                out3["var%s_names" % lv] = np.array(n)
+                out3["var%s_%s" % (lv, key)] = r
+    for k, v in out3.items():
+        print(k, v.shape)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "functionals_goldens3.npz"), **out3)
 
 
 if __name__ == "__main__":

@@ -64,5 +64,6 @@ def column_scale_report(got, ref):
 
 
 def assert_columns_close(got, ref):
+    """the MFCC / PLP rule; on samples of fewer than 2 000 values "0.1 %" would be less than two values, so two are allowed there"""
     worst, share = column_scale_report(got, ref)
-    assert worst < 5e-5 and share <= 1e-3, (worst, share)
+    assert worst < 5e-5 and share <= max(1e-3, 2.0 / max(got.size, 1)), (worst, share)

@@ -48,3 +48,24 @@ def lpc(spec, x):
     out = np.zeros(20, np.float32)
     n = lib().fsh_lpc(C.byref(spec), _fp(x), C.c_long(len(x)), _fp(out))
     return out[:n]
+
+
+def onset(spec, x, period, norm):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(8, np.float32)
+    n = lib().fsh_onset(C.byref(spec), _fp(x), C.c_long(len(x)), C.c_float(period), norm, _fp(out))
+    return out[:n]
+
+
+def peaks(spec, x, period, norm):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(8, np.float32)
+    n = lib().fsh_peaks(C.byref(spec), _fp(x), C.c_long(len(x)), C.c_float(period), norm, _fp(out))
+    return out[:n]
+
+
+def crossings(spec, x):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(4, np.float32)
+    n = lib().fsh_crossings(C.byref(spec), _fp(x), C.c_long(len(x)), _fp(out))
+    return out[:n]

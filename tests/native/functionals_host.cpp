@@ -40,4 +40,20 @@ int fsh_lpc(const osm_b200_functionals_spec *s, const float *x, long N, float *o
   return fseq::lpc(s->lpc, acf, N, out);
 }
 
+int fsh_onset(const osm_b200_functionals_spec *s, const float *x, long N, float period, int timeNorm, float *out)
+{
+  return fseq::onset(s->onset, x, N, period, timeNorm, out);
+}
+
+int fsh_peaks(const osm_b200_functionals_spec *s, const float *x, long N, float period, int timeNorm, float *out)
+{
+  std::vector<int> dists((size_t)N + 1);
+  return fseq::peaks(s->peaks, x, N, period, timeNorm, dists.data(), out);
+}
+
+int fsh_crossings(const osm_b200_functionals_spec *s, const float *x, long N, float *out)
+{
+  return fseq::crossings(s->crossings, x, N, out);
+}
+
 }  // extern "C"

@@ -52,6 +52,18 @@ SPEC_H = fo.Spec(["Regression", "Moments"], master_norm=S,
                  regression=dict(linregerrA=0, qregerrA=0, centroid=1, centroidUseAbsValues=1, centroidRatioLimit=1, normRegCoeff=2, normInputs=1,
                                  oldBuggyQerr=0, doRatioLimit=1),
                  moments=dict(variance=0, stddev=1, skewness=0, kurtosis=0, amean=0, stddevNorm=1, doRatioLimit=1))
+# tests/configs/func_variants3.conf: Onset / Peaks / Crossings
+SPEC_I = fo.Spec(["Onset", "Times", "Peaks", "Crossings"], name_append="Turn",
+                 onset=dict(threshold=0.0, thresholdOnset=0.0, thresholdOffset=0.0, numOnsets=1),
+                 times=dict({k: 0 for k in fo.TIMES_NAMES}, duration=1, norm=SEC, norm_set=True), peaks=dict(), crossings=dict())
+SPEC_J = fo.Spec(["Crossings", "Peaks", "Onset"], master_norm=SEC,
+                 onset=dict(threshold=0.05, thresholdOffset=0.01, useAbsVal=1, onsetPos=1, offsetPos=1, numOnsets=1, numOffsets=1, onsetRate=1),
+                 peaks=dict(peakDistStddev=1), crossings=dict(amean=1))
+SPEC_K = fo.Spec(["Peaks", "Onset", "Crossings"], non_zero=1, master_norm=SEC,
+                 onset=dict(threshold=0.2, onsetPos=1, offsetPos=1, numOnsets=1, onsetRate=1, norm=FR, norm_set=True),
+                 peaks=dict(peakMean=0, peakMeanMeanDist=0, peakDistStddev=1, norm=S, norm_set=True), crossings=dict(zcr=0, mcr=1, amean=1))
+LEVELS3 = [("I", SPEC_I, slice(0, 32), -2), ("J", SPEC_J, slice(0, 16), 0), ("K", SPEC_K, slice(0, 16), 0)]
+G3 = np.load(os.path.join(HERE, "golden", "functionals_goldens3.npz"))
 LEVELS2 = [("D", SPEC_D, slice(0, 32), -2), ("E", SPEC_E, slice(0, 16), 0), ("F", SPEC_F, slice(0, 32), -2), ("G", SPEC_G, slice(0, 16), 0),
            ("H", SPEC_H, slice(0, 32), -2)]
 
@@ -90,6 +102,17 @@ def test_oracle_reproduces_the_reference_rows_times_lpc_segments_peaks2(key):
         assert np.all(np.abs(got - ref) <= 1e-6 * np.abs(ref) + 1e-12), tag
 
 
+@pytest.mark.parametrize("key", ["m24k", "v32k", "rec"])
+def test_oracle_reproduces_the_reference_rows_onset_peaks_crossings(key):
+    lld = G["is09_lld_" + key]
+    names = list(G["is09_lld_names"])
+    for tag, spec, cols, dn in LEVELS3:
+        got = fo.functionals(spec, contour_rows(lld, dn)[:, cols], 0.01)
+        ref = G3["var%s_%s" % (tag, key)][0]
+        assert fo.element_names(spec, names[cols]) == list(G3["var%s_names" % tag])
+        assert np.all(np.abs(got - ref) <= 1e-6 * np.abs(ref) + 1e-12), (tag, [(n, a, b) for n, a, b in zip(G3["var%s_names" % tag], got, ref) if abs(a - b) > 1e-6 * abs(b) + 1e-12][:5])
+
+
 def to_c_spec(spec):
     """oracle Spec -> ctypes mirror of osm_b200_functionals_spec"""
     from opensmile_b200 import functionals as F
@@ -112,6 +135,12 @@ def to_c_spec(spec):
     c = spec.peaks2
     sub["peaks2"] = {k: c[k] for k in fo.PEAKS2_NAMES} | dict(relThresh=c["relThresh"], dynRelThresh=c["dynRelThresh"], doRatioLimit=c["doRatioLimit"],
                                                               useAbsThresh=int(c["absThresh"] is not None), absThresh=c["absThresh"] or 0.0, **norm(c))
+    o = spec.onset
+    sub["onset"] = dict(onsetPos=o["onsetPos"], offsetPos=o["offsetPos"], numOnsets=o["numOnsets"], numOffsets=o["numOffsets"], onsetRate=o["onsetRate"],
+                        thresholdOnset=o["threshold"] if o["thresholdOnset"] is None else o["thresholdOnset"],
+                        thresholdOffset=o["threshold"] if o["thresholdOffset"] is None else o["thresholdOffset"], useAbsVal=o["useAbsVal"], **norm(o))
+    sub["peaks"] = {k: spec.peaks[k] for k in fo.PEAKS_NAMES} | norm(spec.peaks)
+    sub["crossings"] = dict(spec.crossings)
     return F.spec(spec.enabled, non_zero=spec.non_zero, master_norm=-1 if spec.master_norm is None else spec.master_norm,
                   name_append=spec.name_append or "", **sub)
 
@@ -140,6 +169,17 @@ def test_device_statements_of_the_sequential_functionals_on_the_host():
             if "Lpc" in spec.enabled:
                 a, b = fh.lpc(cs, x), np.array(fo._lpc(spec, x), np.float32)
                 assert np.array_equal(a, b, equal_nan=True), (a, b)
+    for spec in (SPEC_I, SPEC_J, SPEC_K):
+        cs = to_c_spec(spec)
+        for x in contours:
+            nrm = fo._norm(spec.onset["norm"], spec.onset["norm_set"], spec.master_norm)
+            a, b = fh.onset(cs, x, 0.01, nrm), np.array(fo._onset(spec, x, 0.01), np.float32)
+            assert np.array_equal(a, b, equal_nan=True), (a, b)
+            nrm = fo._norm(spec.peaks["norm"], spec.peaks["norm_set"], spec.master_norm)
+            a, b = fh.peaks(cs, x, 0.01, nrm), np.array(fo._peaks_old(spec, x, 0.01), np.float32)
+            assert np.array_equal(a, b, equal_nan=True), (a, b)
+            a, b = fh.crossings(cs, x), np.array(fo._crossings(spec, x), np.float32)
+            assert np.array_equal(a, b, equal_nan=True), (a, b)
 
 
 def test_zero_and_single_value_contours():
@@ -195,10 +235,10 @@ def test_unimplemented_functionals_are_refused_loudly(tmp_path):
     from opensmile_b200 import capi
     txt = open(os.path.join(HERE, "configs", "func_variants.conf")).read().replace("REFCONF", REFCONF)
     bad = tmp_path / "bad.conf"
-    bad.write_text(txt.replace("functionalsEnabled = Means\n", "functionalsEnabled = Means ; Onset\n"))
+    bad.write_text(txt.replace("functionalsEnabled = Means\n", "functionalsEnabled = Means ; Samples\n"))
     with pytest.raises(SessionError) as e:
         _session(str(bad), {"outA": "x.csv"})
-    assert e.value.status == capi.ERR_UNSUPPORTED and "cFunctionalOnset" in str(e.value)
+    assert e.value.status == capi.ERR_UNSUPPORTED and "cFunctionalSamples" in str(e.value)
     bad.write_text(txt.replace("nonZeroFuncts = 0\n", "nonZeroFuncts = 0\nbogusField = 1\n"))
     with pytest.raises(SessionError) as e:
         _session(str(bad), {"outA": "x.csv"})

@@ -9,7 +9,7 @@ import pytest
 from oracle import functionals_oracle as fo
 from opensmile_b200 import functionals as F
 from opensmile_b200.synth import mixed_pcm, voiced_pcm
-from test_functionals_cpu import G, G2, LEVELS, LEVELS2, REFCONF, contour_rows, to_c_spec
+from test_functionals_cpu import G, G2, G3, LEVELS, LEVELS2, LEVELS3, REFCONF, contour_rows, to_c_spec
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -60,6 +60,24 @@ def test_times_lpc_segments_peaks2_on_the_reference_lld_rows(key):
         assert np.all(np.abs(got - ref) <= 2e-6 * np.abs(ref) + 1e-9), tag
 
 
+@pytest.mark.parametrize("key", ["m24k", "v32k", "rec"])
+def test_onset_peaks_crossings_on_the_reference_lld_rows(key):
+    """tests/configs/func_variants3.conf (cFunctionalOnset / cFunctionalPeaks / cFunctionalCrossings with the IS10_paraling and emo_large
+    option sets and their other norms): equal to the oracle and to the reference's CSV digits"""
+    lld = G["is09_lld_" + key]
+    names = list(G["is09_lld_names"])
+    for tag, spec, cols, dn in LEVELS3:
+        rows = np.ascontiguousarray(contour_rows(lld, dn)[:, cols])
+        f = F.Functionals(to_c_spec(spec), names[cols], 0.01, device=0)
+        assert f.element_names() == list(G3["var%s_names" % tag])
+        got = f.run_host(rows, [0], [rows.shape[0]])[0]
+        f.close()
+        ora = fo.functionals(spec, rows, 0.01)
+        assert np.all(np.abs(got - ora) <= 2e-6 * np.abs(ora) + 1e-9), (tag, np.nonzero(~(np.abs(got - ora) <= 2e-6 * np.abs(ora) + 1e-9))[0][:8])
+        ref = G3["var%s_%s" % (tag, key)][0]
+        assert np.all(np.abs(got - ref) <= 2e-6 * np.abs(ref) + 1e-9), tag
+
+
 def test_sequential_functionals_on_ragged_and_degenerate_contours():
     rng = np.random.default_rng(11)
     lens = [300, 1, 2, 0, 5, 33, 64, 2500]
@@ -79,6 +97,10 @@ def test_sequential_functionals_on_ragged_and_degenerate_contours():
                      peaks2=dict(pk, relThresh=rt, dynRelThresh=dy, doRatioLimit=rl))
              for nz, mn, bs, od, al, rt, dy, rl in ((0, fo.SEGMENT, 0, 5, "relTh", 0.1, 0, 1), (1, fo.SECOND, 1, 8, "nonX", 0.35, 1, 0),
                                                     (0, fo.FRAME, 0, 3, "eqX", 0.0, 0, 1))]
+    specs += [fo.Spec(["Onset", "Peaks", "Crossings", "Percentiles"], non_zero=nz, master_norm=mn, percentiles=dict(quartile2=1),
+                      onset=dict(threshold=th, useAbsVal=ab, onsetPos=1, offsetPos=1, numOnsets=1, numOffsets=1, onsetRate=1),
+                      peaks=dict(peakDistStddev=1), crossings=dict(amean=1))
+              for nz, mn, th, ab in ((0, fo.SEGMENT, 0.0, 0), (1, fo.SECOND, 1.5, 1), (0, fo.FRAME, -2.0, 0))]
     for spec in specs:
         f = F.Functionals(to_c_spec(spec), ["c%d" % i for i in range(K)], 0.01, device=0)
         got = f.run_host(rows, off, lens)
@@ -86,7 +108,7 @@ def test_sequential_functionals_on_ragged_and_degenerate_contours():
         for u, (o, n) in enumerate(zip(off, lens)):
             ora = fo.functionals(spec, rows[o:o + n], 0.01) if n else np.zeros(got.shape[1], np.float32)
             ok = (np.abs(got[u] - ora) <= 2e-6 * np.abs(ora) + 1e-9) | (np.isnan(got[u]) & np.isnan(ora))
-            assert np.all(ok), (spec.segments["segmentationAlgorithm"], u, np.nonzero(~ok)[0][:8], got[u][~ok][:4], ora[~ok][:4])
+            assert np.all(ok), (spec.enabled, spec.segments["segmentationAlgorithm"], u, np.nonzero(~ok)[0][:8], got[u][~ok][:4], ora[~ok][:4])
 
 
 def test_ragged_batch_and_degenerate_contours():
