@@ -483,6 +483,179 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
   }
 }
 
+// The same smoother with one WARP per utterance (the default; OSM_VITERBI_WARP=0 builds the launcher around the one-thread kernel
+// above for A/B runs).  What is sequential in the reference stays sequential and is executed redundantly by all lanes on shared
+// operands: the (i, j) transition walk with its running `lastChange` (hpp:224-252).  Everything around it is spread over the lanes:
+// the nCand^2 + nStates double logarithms of a frame pair, the copy of the nStates best paths (bytes in shared memory), the search
+// for the frames on which all paths agree (one candidate frame per lane, ballot), and the output rows of the frames that became
+// final.  Every double operation is the one of viterbi_kernel, in the same order: the results are bit-identical.
+#ifndef OSM_VITERBI_WARP
+#define OSM_VITERBI_WARP 1
+#endif
+constexpr int kVitWarps = 4;
+struct VitWarpSmem {
+  double rr[kVitStates * kVitStates];
+  double lc[kVitStates];
+  double cost[2][kVitStates];
+  unsigned char path[2][kVitStates][kVitBuf];
+  unsigned char best[kVitBuf];
+  unsigned char minState[kVitStates + 7];
+};
+
+__global__ void __launch_bounds__(kVitWarps * 32) viterbi_warp_kernel(const ViterbiParams p, int u0, int u1)
+{
+  __shared__ VitWarpSmem smAll[kVitWarps];
+  const int lane = threadIdx.x & 31;
+  const int u = u0 + blockIdx.x * kVitWarps + (threadIdx.x >> 5);
+  if (u >= u1) return;
+  VitWarpSmem &sm = smAll[threadIdx.x >> 5];
+  const int T = frames_of(p.uttOff[u + 1] - p.uttOff[u], p.frameSize, p.frameStep);
+  if (T <= 0) { if (lane == 0) p.lag[u] = 0; return; }
+  const long long row0 = p.statOff[u];
+  const int nC = p.nCand, nS = nC + 1, last = nC, bl = p.bufLen;
+  double lastChange = 1.0;
+  int pathBuf = 0, pathIdx = 0, convIdx = -1, rdIdx = 0;
+  float lastValidf0 = 0.0f;
+  const double thrD = (double)p.voiceThresh;
+  const bool envOut = p.oF0finalEnv || p.oF0finalEnvLog;
+
+  auto local_cost = [&](int i, const float *fr) -> double {              // hpp:202-221; fr[1+k] = F0, fr[1+nC+k] = voicing
+    if (i < last) {
+      double pv = (double)fr[1 + nC + i];
+      double thr = 0.0;
+      if (pv < 0.01) pv = 0.01;
+      if (pv > 1.00) pv = 1.00;
+      if (pv < thrD) thr = p.wThr;
+      return (-log(pv) + thr) * p.wLocal + vit_fweight(fr[1 + i]) * p.wRange;
+    }
+    double flag = 0.0;
+    for (int j = 0; j < nC; j++) if (fr[1 + nC + j] >= p.voiceThresh) { flag = p.wThr; break; }
+    return p.wLocal * flag;
+  };
+  // one output row (lld/pitchSmootherViterbi.cpp:470-545); lastValid: the running value of the envelope outputs (in / out)
+  auto emit_row = [&](int r, float &lastValid) {
+    const int state = sm.best[r % bl];
+    const float *b = p.shs + (size_t)(row0 + r) * p.nShsCols;
+    float f0 = state < last ? b[1 + state] : 0.0f;
+    const float vp = state < nC ? b[1 + nC + state] : b[1 + nC];
+    float *o = p.stat + (size_t)(row0 + r) * p.statStride + p.outCol;
+    bool copy = true;
+    if (p.hasSel) {                                                         // other/valbasedSelector.cpp:153-233
+      const float val = p.stat[(size_t)(row0 + r) * p.statStride + p.selCol];
+      copy = (!p.selInvert && val > p.selThreshold) || (p.selInvert && val < p.selThreshold) || (p.selAllowEqual && val == p.selThreshold);
+    }
+    int n = 0;
+    auto semitone = [](float f) -> float { return f > 29.136 ? 12.0f * logf(f / 27.5f) / logf(2.0f) : (f > 0.0 ? 1.0f : 0.0f); };
+    if (p.oF0final) o[n++] = copy ? f0 : p.selOutputVal;
+    if (p.oF0finalLog) o[n++] = copy ? semitone(f0) : p.selOutputVal;
+    if (p.oF0finalEnv || p.oF0finalEnvLog) {
+      if (f0 <= 0.0) f0 = lastValid; else lastValid = f0;
+      if (p.oF0finalEnv) o[n++] = copy ? f0 : p.selOutputVal;
+      if (p.oF0finalEnvLog) o[n++] = copy ? semitone(f0) : p.selOutputVal;
+    }
+    if (p.oVClipped) o[n++] = copy ? (vp >= p.voiceThresh ? vp : 0.0f) : p.selOutputVal;
+    if (p.oVUnclipped) o[n++] = copy ? vp : p.selOutputVal;
+  };
+  auto drain = [&]() {            // rows rdIdx .. convIdx became final (sm.best holds their states; the caller synchronised the warp)
+    if (rdIdx > convIdx) return;
+    if (envOut) {                 // the envelope carries the last voiced F0 from row to row: in order, on lane 0
+      if (lane == 0) for (int r = rdIdx; r <= convIdx; r++) emit_row(r, lastValidf0);
+      lastValidf0 = __shfl_sync(kFull, lastValidf0, 0);
+    } else {
+      float dummy = 0.0f;
+      for (int r = rdIdx + lane; r <= convIdx; r += 32) emit_row(r, dummy);
+    }
+    rdIdx = convIdx + 1;
+  };
+  auto argmin_cost = [&]() -> int {
+    int m = 0;
+    for (int i = 1; i < nS; i++) if (sm.cost[pathBuf][i] < sm.cost[pathBuf][m]) m = i;
+    return m;
+  };
+
+  for (int t = 0; t < T; t++) {                                               // lld/pitchSmootherViterbi.cpp:79-183
+    const float *cur = p.shs + (size_t)(row0 + t) * p.nShsCols;
+    const float *prv = cur - p.nShsCols;
+    if (pathIdx == 0) {
+      convIdx = -1;
+      if (lane < nS) sm.cost[pathBuf][lane] = local_cost(lane, cur);
+      for (int idx = lane; idx < nS * bl; idx += 32) { const int i = idx / bl, k = idx - i * bl; sm.path[pathBuf][i][k] = (unsigned char)(k == 0 ? i : 0); }
+    } else {
+      const int nb = pathBuf ^ 1;
+      for (int idx = lane; idx < nC * nC; idx += 32) {                         // log(f1_i / f0_j), NaN = empty candidate
+        const int i = idx / nC, j = idx - i * nC;
+        const float f0 = prv[1 + j], f1 = cur[1 + i];
+        sm.rr[i * kVitStates + j] = (f0 == 0 || f1 == 0) ? nan("") : log((double)(f1 / f0));
+      }
+      if (lane >= 32 - nS) sm.lc[lane - (32 - nS)] = local_cost(lane - (32 - nS), cur);   // the upper lanes: in parallel with the ratios
+      __syncwarp();
+      for (int i = 0; i < nS; i++) {                                         // all lanes, redundantly: keeps `lastChange` in every lane
+        int minState = 0;
+        double minCost = 0.0;
+        for (int j = 0; j < nS; j++) {
+          double tc;                                                          // hpp:224-252 (i = current state, j = previous state)
+          if ((int)(i == j) == last) tc = p.wTuu;                             // the reference's `i == j == nStates-1`
+          else if (i < last && j < last) {
+            const double r = sm.rr[i * kVitStates + j];
+            if (r != r) tc = 999.0;
+            else {
+              tc = p.wTvv * fabs(r) + p.wTvvd * fabs(r - lastChange);
+              lastChange = r;
+            }
+          } else if ((i == last && j < last) || (i < last && j == last)) { lastChange = 0.0; tc = p.wTvuv; }
+          else tc = 1.0;
+          const double c = tc + sm.cost[pathBuf][j];
+          if (j == 0 || c < minCost) { minState = j; minCost = c; }
+        }
+        if (lane == 0) { sm.cost[nb][i] = minCost + sm.lc[i]; sm.minState[i] = (unsigned char)minState; }
+      }
+      __syncwarp();
+      const int kNow = pathIdx % bl;
+      for (int idx = lane; idx < nS * bl; idx += 32) {
+        const int i = idx / bl, k = idx - i * bl;
+        sm.path[nb][i][k] = (k == kNow) ? (unsigned char)i : sm.path[pathBuf][sm.minState[i]][k];
+      }
+      pathBuf = nb;
+    }
+    __syncwarp();
+    pathIdx++;
+    if (pathIdx - convIdx > bl) {
+      const int minState = argmin_cost();
+      convIdx++;
+      if (lane == 0) sm.best[convIdx % bl] = sm.path[pathBuf][minState][convIdx % bl];
+    } else {
+      // frames convIdx+1 .. pathIdx-1 on which every state's best path passes through the same state, up to the first that differs
+      bool go = true;
+      while (go && convIdx + 1 < pathIdx) {
+        const int n = convIdx + 1 + lane;
+        bool match = false;
+        int x = 0;
+        if (n < pathIdx) {
+          x = sm.path[pathBuf][0][n % bl];
+          match = true;
+          for (int i = 1; i < nS; i++) if (x != sm.path[pathBuf][i][n % bl]) { match = false; break; }
+        }
+        const unsigned bal = __ballot_sync(kFull, match);
+        const int cnt = (bal == 0xffffffffu) ? 32 : __ffs(~bal) - 1;          // leading matches
+        if (lane < cnt) sm.best[n % bl] = (unsigned char)x;
+        convIdx += cnt;
+        go = cnt == 32;
+      }
+    }
+    __syncwarp();
+    drain();
+  }
+  if (lane == 0) p.lag[u] = rdIdx;        // frames written before the end of input is signalled
+  {                                       // flushTrellis (hpp:105-125)
+    const int minState = argmin_cost();
+    // at most bufLen entries are pending (forced decisions keep pathIdx - convIdx <= bufLen), so the ring is intact
+    for (int n = convIdx + 1 + lane; n < pathIdx; n += 32) sm.best[n % bl] = sm.path[pathBuf][minState][n % bl];
+    if (convIdx + 1 < pathIdx) convIdx = pathIdx - 1;
+    __syncwarp();
+    drain();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ jitter_kernel
 
 constexpr int kJitWarps = 4;
@@ -980,7 +1153,11 @@ cudaError_t launch_viterbi(const ViterbiParams &p, int u0, int u1, cudaStream_t 
 {
   if (u1 <= u0) return cudaSuccess;
   if (p.nCand + 1 > kVitStates || p.bufLen > kVitBuf) return cudaErrorInvalidValue;
+#if OSM_VITERBI_WARP
+  viterbi_warp_kernel<<<(u1 - u0 + kVitWarps - 1) / kVitWarps, kVitWarps * 32, 0, st>>>(p, u0, u1);
+#else
   viterbi_kernel<<<(u1 - u0 + 63) / 64, 64, 0, st>>>(p, u0, u1);
+#endif
   return cudaGetLastError();
 }
 
