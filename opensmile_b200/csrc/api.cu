@@ -1387,7 +1387,11 @@ static osm_b200_status run_host_impl(osm_b200_plan *pl, const void *pcm, const i
     CU(cudaEventRecord(pl->evPiece[2 * k], pl->h2dStream));
     CU(cudaStreamWaitEvent(st, pl->evPiece[2 * k], 0));
     s = launch_range(pl, pl->dPcm.p, pl->dOut.p, n_utt, u0, u1, st);
-    if (s != OSM_B200_OK) return s;
+    if (s != OSM_B200_OK) {
+      // copies of earlier pieces into the caller's buffers may still be in flight: let them land before reporting the error
+      cudaStreamSynchronize(pl->h2dStream); cudaStreamSynchronize(st); cudaStreamSynchronize(pl->d2hStream);
+      return s;
+    }
     CU(cudaEventRecord(pl->evPiece[2 * k + 1], st));
     CU(cudaStreamWaitEvent(pl->d2hStream, pl->evPiece[2 * k + 1], 0));
     const long long ra = hR[u0], rb = hR[u1];

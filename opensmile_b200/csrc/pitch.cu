@@ -483,14 +483,17 @@ __global__ void __launch_bounds__(64) viterbi_kernel(const ViterbiParams p, int 
   }
 }
 
-// The same smoother with one WARP per utterance (the default; OSM_VITERBI_WARP=0 builds the launcher around the one-thread kernel
-// above for A/B runs).  What is sequential in the reference stays sequential and is executed redundantly by all lanes on shared
+// The same smoother with one WARP per utterance -- an A/B variant (-DOSM_VITERBI_WARP=1), NOT the default: measured on the B200
+// (ComParE workload, 10 000 utterances x 296 frames, profiles/r02_v10_viterbi_ab.txt) it takes 9.2 ms against 7.3 ms for the
+// one-thread kernel above.  A thread-per-utterance warp instruction advances 32 utterances; here it advances one, and what the lanes
+// share (13 logarithms, 120 path bytes, <= 30 candidate frames) fills a fraction of them, so ~6x more instructions are issued for the
+// same work and 64 resident warps per SM do not make up for it.  What is sequential in the reference stays sequential and is executed redundantly by all lanes on shared
 // operands: the (i, j) transition walk with its running `lastChange` (hpp:224-252).  Everything around it is spread over the lanes:
 // the nCand^2 + nStates double logarithms of a frame pair, the copy of the nStates best paths (bytes in shared memory), the search
 // for the frames on which all paths agree (one candidate frame per lane, ballot), and the output rows of the frames that became
 // final.  Every double operation is the one of viterbi_kernel, in the same order: the results are bit-identical.
 #ifndef OSM_VITERBI_WARP
-#define OSM_VITERBI_WARP 1
+#define OSM_VITERBI_WARP 0
 #endif
 constexpr int kVitWarps = 4;
 struct VitWarpSmem {

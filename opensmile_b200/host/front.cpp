@@ -1902,8 +1902,27 @@ static osm_b200_status osm_b200_session_extract_files_arff_impl(osm_b200_session
   std::vector<Wav> wavs(n);
   std::string err;
   if (!parallel_files(n, [&](int i, std::string &e) { return read_wav(wavPaths[i], wavs[i], e); }, err)) return hfail(OSM_B200_ERR_INVALID, err);
-  std::map<std::pair<int, int>, std::vector<int>> groups;
-  for (int i = 0; i < n; i++) groups[{wavs[i].sampleRate, wavs[i].nChan + 4096 * wavs[i].format}].push_back(i);
+  // Inputs that share an output file (append-mode ARFF / CSV) must reach it in input order: within one group write_batch does
+  // that; when such a batch mixes formats, every input becomes its own group, taken in input order (one plan run each).
+  bool sharedAcross = false;
+  {
+    std::map<std::string, std::pair<int, int>> owner;                 // path -> (rate, channels/format) of its first writer
+    for (const char *const *paths : {htkPaths, csvPaths, arffPaths})
+      if (paths)
+        for (int i = 0; i < n; i++) {
+          if (!paths[i]) continue;
+          const std::pair<int, int> key{wavs[i].sampleRate, wavs[i].nChan + 4096 * wavs[i].format};
+          auto it = owner.find(paths[i]);
+          if (it == owner.end()) owner[paths[i]] = key; else if (it->second != key) sharedAcross = true;
+        }
+  }
+  std::vector<std::pair<std::pair<int, int>, std::vector<int>>> groups;
+  if (sharedAcross) for (int i = 0; i < n; i++) groups.push_back({{wavs[i].sampleRate, wavs[i].nChan + 4096 * wavs[i].format}, {i}});
+  else {
+    std::map<std::pair<int, int>, std::vector<int>> byFormat;
+    for (int i = 0; i < n; i++) byFormat[{wavs[i].sampleRate, wavs[i].nChan + 4096 * wavs[i].format}].push_back(i);
+    for (auto &g : byFormat) groups.push_back({g.first, g.second});
+  }
   for (auto &g : groups) {
     const int sr = g.first.first, nc = g.first.second % 4096, fmt = g.first.second / 4096;
     std::vector<int64_t> off(g.second.size() + 1, 0), fo(g.second.size() + 1, 0), nTime(g.second.size(), 0);

@@ -48,6 +48,13 @@ int main(int argc, char **argv)
              "       [-filelist list.txt] [-device N] [-level lld] [-<config option> value ...]\n");
       return 0;
     }
+    else if (a == "-d" || a == "-debug" || a == "-L" || a == "-components" || a == "-cfgFileTemplate" || a == "-cfgFileDescriptions" || a == "-c" ||
+             a == "-ccmdHelp" || a == "-exportHelp" || a == "-noconsoleoutput" || a == "-appendLogfile" || a == "-nologfile") {
+      // the reference's boolean switches (progsrc/smilextract/SMILExtract.cpp:60-72) take no value unless an explicit 0 / 1 follows;
+      // they steer logging and help output, which this front end does not have: accepted and ignored
+      if (i + 1 < argc) { const std::string nx = argv[i + 1]; if (nx == "0" || nx == "1" || nx == "yes" || nx == "no" || nx == "true" || nx == "false") i++; }
+    }
+    else if (a == "-l" || a == "-loglevel" || a == "-t" || a == "-nticks" || a == "-logfile") (void)val();   // logging / tick limit: accepted, ignored
     else if (a.size() > 1 && a[0] == '-') {
       const std::string n = a.substr(1), v = val();
       optN.push_back(n); optV.push_back(v);

@@ -164,6 +164,10 @@ def test_cli_fails_loudly_without_a_gpu(tmp_path):
     r = subprocess.run([exe, "-C", os.path.join(CONF, "mfcc_e_d_a.conf"), "-I", str(tmp_path / "t.wav"), "-O", str(tmp_path / "o.htk")],
                        capture_output=True, text=True)
     assert r.returncode != 0 and "CUDA" in r.stderr and not (tmp_path / "o.htk").exists()
+    # the reference's value-less switches (SMILExtract.cpp:60-72) do not swallow the argument behind them: the run gets just as far
+    r = subprocess.run([exe, "-nologfile", "-C", os.path.join(CONF, "mfcc_e_d_a.conf"), "-noconsoleoutput", "-I", str(tmp_path / "t.wav"), "-l", "0",
+                        "-appendLogfile", "1", "-O", str(tmp_path / "o.htk")], capture_output=True, text=True)
+    assert r.returncode != 0 and "CUDA" in r.stderr and "required" not in r.stderr
 
 
 def _conf_with(tmp_path, extra_instances, extra_sections, level):
