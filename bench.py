@@ -21,6 +21,9 @@ path has no data-path collective, NCCL only carries the timing / counter reducti
   roofline     : algorithmic bytes over the measured time vs the measured HBM copy bandwidth -- for mfcc12 of
                  the one fused kernel, for the multi-kernel workloads of the WHOLE step, naming the dominant kernel and its share
                  (per-kernel CUDA events, osm_b200_plan_set_profiling)
+  summaries    : (default run, one GPU) the shipped summary configurations end to end -- eGeMAPSv02.conf / ComParE_2016.conf with
+                 -csvoutput, 1 000 utterances x 3 s from host PCM to one row of 88 / 6 373 values each (utterances/s); an extra,
+                 not a headline number
   parity       : rows of bench utterances (200 for mfcc12) taken from the e2e run's output are compared with the UNMODIFIED
                  reference's rows for the same PCM (per column, 1e-5 of the column scale)
   cpu_baseline : the UNMODIFIED reference on the box's host cores on a bounded sample of the same workload.  Two legs:
@@ -537,6 +540,36 @@ def measure(w, args, rank, world, local_rank, dist, steps, with_cpu, sampler=Non
     return res
 
 
+def measure_summaries(n_utt=1000):
+    """SURVEY.md 8(f)-3, reported beside the LLD workloads (not a headline number): the shipped summary configurations end to end
+    through the session API from host PCM -- LLD plan, rows resident in HBM, cFunctionals instances + glue, one row per utterance
+    copied back.  Wall clock around the blocking call (it synchronises), after one warm-up call."""
+    import time
+    import numpy as np
+    from opensmile_b200 import Session
+    from opensmile_b200.synth import mixed_pcm
+    out = []
+    base = [mixed_pcm(48000, 16000, seed=s) for s in range(8)]
+    pcm = np.concatenate([base[i % 8] for i in range(n_utt)])
+    off = np.arange(n_utt + 1, dtype=np.int64) * 48000
+    for rel, tag in (("egemaps/v02/eGeMAPSv02.conf", "eGeMAPSv02.conf -csvoutput"), ("compare16/ComParE_2016.conf", "ComParE_2016.conf -csvoutput")):
+        conf = os.path.join(ROOT, "oracle", "_ref", "config", rel)
+        if not os.path.exists(conf):
+            continue
+        try:
+            s = Session(conf, options={"csvoutput": "x.csv"}, device=0)
+            s.extract_pcm(pcm[:48000 * 8], off[:9], 16000.0, 1)
+            t0 = time.perf_counter()
+            rows, _ = s.extract_pcm(pcm, off, 16000.0, 1)
+            dt = time.perf_counter() - t0
+            s.close()
+            out.append({"config": tag, "utterances": n_utt, "seconds_of_audio": 3.0 * n_utt, "values_per_utterance": int(rows.shape[1]),
+                        "wall_s": dt, "utterances_per_s": n_utt / dt, "api": "osm_b200_session_extract_pcm (host PCM in, summary rows out)"})
+        except Exception as e:      # a reported extra: never takes the bench line down
+            out.append({"config": tag, "error": str(e)[:200]})
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     torch.cuda.set_device(local_rank)
@@ -555,10 +588,13 @@ def run_ours(args, rank, world, local_rank):
             if r is not None:
                 others.append({k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "config", "e2e", "gpu_launches", "roofline",
                                                  "parity", "cpu_baseline") if k in r})
+    summaries = measure_summaries() if (world == 1 and not args.no_others and args.workload == "mfcc12") else []
     if rank == 0:
         line["config"]["numa"] = numa
         if others:
             line["other_workloads"] = others
+        if summaries:
+            line["summaries"] = summaries
         if line.get("parity", {}).get("ok") is False or any(o.get("parity", {}).get("ok") is False for o in others):
             line["parity_failed"] = True
         print(json.dumps(line))

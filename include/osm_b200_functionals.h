@@ -33,7 +33,7 @@ extern "C" {
 typedef enum {
   OSM_B200_F_EXTREMES = 0, OSM_B200_F_MEANS, OSM_B200_F_MOMENTS, OSM_B200_F_PERCENTILES, OSM_B200_F_REGRESSION,
   OSM_B200_F_TIMES, OSM_B200_F_LPC, OSM_B200_F_SEGMENTS, OSM_B200_F_PEAKS2,
-  OSM_B200_F_ONSET, OSM_B200_F_PEAKS, OSM_B200_F_CROSSINGS,
+  OSM_B200_F_ONSET, OSM_B200_F_PEAKS, OSM_B200_F_CROSSINGS, OSM_B200_F_SAMPLES, OSM_B200_F_DCT,
   OSM_B200_F_COUNT_
 } osm_b200_functional_type;
 
@@ -48,6 +48,8 @@ typedef enum {
 #define OSM_B200_F_MAX_THRESH 8
 #define OSM_B200_F_MAX_LPC 16
 #define OSM_B200_F_PEAKS2_VALUES 32
+#define OSM_B200_F_MAX_SAMPLES 16
+#define OSM_B200_F_MAX_DCT 32
 
 /* cFunctionalSegments.segmentationAlgorithm (the three the shipped ComParE_2016 / GeMAPS blocks use) */
 #define OSM_B200_SEG_RELTH 0
@@ -127,6 +129,13 @@ typedef struct {
   struct {                                         /* Crossings.* (functionalCrossings.cpp:42-46): 1,1,0 */
     int32_t zcr, mcr, amean;
   } crossings;
+  struct {                                         /* Samples.samplepos[] (functionalSamples.cpp:38-78): relative positions in [0, 1];
+                                                      none given = 0, 0.25, 0.5, 0.75, 1 */
+    int32_t n_samplepos; double samplepos[OSM_B200_F_MAX_SAMPLES];
+  } samples;
+  struct {                                         /* DCT.firstCoeff / lastCoeff (functionalDCT.cpp:38-72): 1, 6; nCoeffs overrides lastCoeff */
+    int32_t firstCoeff, lastCoeff;
+  } dct;
 } osm_b200_functionals_spec;
 
 typedef struct osm_b200_functionals osm_b200_functionals;

@@ -287,6 +287,12 @@ __global__ void __launch_bounds__(kFnThreads) functionals_kernel(const FnParams 
     } else if (kind == OSM_B200_F_CROSSINGS) {
       if (lane == 0) fseq::crossings(p.s.crossings, sbuf, (long)N, o);
       __syncwarp();
+    } else if (kind == OSM_B200_F_SAMPLES) {
+      if (lane == 0) fseq::samples(p.s.samples, sbuf, (long)N, o);
+      __syncwarp();
+    } else if (kind == OSM_B200_F_DCT) {                              // one coefficient per lane, each a sequential float sum over the contour
+      for (int k = p.s.dct.firstCoeff + lane; k <= p.s.dct.lastCoeff; k += 32) o[k - p.s.dct.firstCoeff] = fseq::dct_coeff(sbuf, (long)N, k);
+      __syncwarp();
     }
   }
 
@@ -597,6 +603,12 @@ std::vector<std::string> value_names(const osm_b200_functionals_spec &s)
         if (s.crossings.mcr) v.push_back("mcr");
         if (s.crossings.amean) v.push_back("amean");
       } break;
+      case OSM_B200_F_SAMPLES: {                                                                                        // functionalSamples.cpp:89-95
+        for (int k = 0; k < s.samples.n_samplepos; k++) { snprintf(buf, sizeof buf, "samples%.3f", s.samples.samplepos[k]); v.push_back(buf); }
+      } break;
+      case OSM_B200_F_DCT: {                                                                                            // functionalDCT.cpp:103-110
+        for (int k = s.dct.firstCoeff; k <= s.dct.lastCoeff; k++) { snprintf(buf, sizeof buf, "dct%i", k); v.push_back(buf); }
+      } break;
     }
   }
   return v;
@@ -644,6 +656,9 @@ void osm_b200_functionals_defaults(osm_b200_functionals_spec *s)
   auto &QP = s->peaks;                                            // functionalPeaks.cpp:45-53
   QP.numPeaks = QP.meanPeakDist = QP.peakMean = QP.peakMeanMeanDist = 1; QP.norm = OSM_B200_TIMENORM_FRAME;
   s->crossings.zcr = s->crossings.mcr = 1;                        // functionalCrossings.cpp:42-46
+  s->samples.n_samplepos = 5;                                     // functionalSamples.cpp:24,68-75
+  for (int i = 0; i < 5; i++) s->samples.samplepos[i] = (double)i / (5 - 1.0);
+  s->dct.firstCoeff = 1; s->dct.lastCoeff = 6;                    // functionalDCT.cpp:38-40
 }
 
 osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spec, int32_t n_in, const char *const *in_names,
@@ -665,6 +680,10 @@ osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spe
   for (int i = 0; i < s.n_enabled; i++) {
     if (s.enabled[i] == OSM_B200_F_LPC && (s.lpc.order < 1 || s.lpc.order > OSM_B200_F_MAX_LPC || s.lpc.firstCoeff < 0 || s.lpc.firstCoeff >= s.lpc.order))
       return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalLpc: 0 <= firstCoeff < order <= 16");
+    if (s.enabled[i] == OSM_B200_F_SAMPLES && (s.samples.n_samplepos < 1 || s.samples.n_samplepos > OSM_B200_F_MAX_SAMPLES))
+      return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSamples: 1 .. 16 sample positions");
+    if (s.enabled[i] == OSM_B200_F_DCT && (s.dct.firstCoeff < 0 || s.dct.lastCoeff < s.dct.firstCoeff || s.dct.lastCoeff - s.dct.firstCoeff + 1 > OSM_B200_F_MAX_DCT))
+      return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalDCT: 0 <= firstCoeff <= lastCoeff, at most 32 coefficients");
     if (s.enabled[i] == OSM_B200_F_SEGMENTS) {
       const auto &G = s.segments;
       if (G.algorithm < OSM_B200_SEG_RELTH || G.algorithm > OSM_B200_SEG_EQX) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSegments: segmentationAlgorithm must be relTh, nonX or eqX");

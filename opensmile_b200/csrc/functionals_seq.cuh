@@ -529,5 +529,29 @@ OSM_FS_HD int crossings(const Spec &c, const float *x, long N, float *out)
   return n;
 }
 
+// cFunctionalSamples::process (functionalSamples.cpp:99-116): the contour's value at relative positions
+template <class Spec>
+OSM_FS_HD int samples(const Spec &c, const float *x, long N, float *out)
+{
+  const float Nind = (float)N;
+  for (int k = 0; k < c.n_samplepos; k++) out[k] = x[(int)(((double)Nind - 1.0) * c.samplepos[k])];
+  return c.n_samplepos;
+}
+
+// cFunctionalDCT::process (functionalDCT.cpp:85-135), coefficient `coeff` (absolute index): the table entry is
+// (float)cos(pi * i / N * ((float)m + 0.5)) in double, the sum runs in float over m = 0 .. N-1, times (float)sqrt(2 / N)
+OSM_FS_HD float dct_coeff(const float *x, long N, int coeff)
+{
+  float acc = 0.0f;
+  const double w = M_PI * (double)coeff / (double)N;
+  for (long m = 0; m < N; m++) {
+    const float ct = (float)cos(w * ((double)(float)m + 0.5));
+    const float pr = x[m] * ct;
+    acc = acc + pr;
+  }
+  acc = acc * (float)sqrt(2.0 / (double)N);
+  return isfinite(acc) ? acc : 0.0f;
+}
+
 }  // namespace fseq
 }  // namespace osm

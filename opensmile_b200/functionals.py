@@ -10,10 +10,10 @@ import numpy as np
 from . import capi
 
 i32, f64, f32 = C.c_int32, C.c_double, C.c_float
-F_EXTREMES, F_MEANS, F_MOMENTS, F_PERCENTILES, F_REGRESSION, F_TIMES, F_LPC, F_SEGMENTS, F_PEAKS2, F_ONSET, F_PEAKS, F_CROSSINGS = range(12)
+F_EXTREMES, F_MEANS, F_MOMENTS, F_PERCENTILES, F_REGRESSION, F_TIMES, F_LPC, F_SEGMENTS, F_PEAKS2, F_ONSET, F_PEAKS, F_CROSSINGS, F_SAMPLES, F_DCT = range(14)
 TYPE_BY_NAME = {"Extremes": F_EXTREMES, "Means": F_MEANS, "Moments": F_MOMENTS, "Percentiles": F_PERCENTILES, "Regression": F_REGRESSION,
                 "Times": F_TIMES, "Lpc": F_LPC, "Segments": F_SEGMENTS, "Peaks2": F_PEAKS2, "Onset": F_ONSET, "Peaks": F_PEAKS,
-                "Crossings": F_CROSSINGS}
+                "Crossings": F_CROSSINGS, "Samples": F_SAMPLES, "DCT": F_DCT}
 SEG_RELTH, SEG_NONX, SEG_EQX = 0, 1, 2
 SEG_BY_NAME = {"relTh": SEG_RELTH, "nonX": SEG_NONX, "eqX": SEG_EQX}
 PEAKS2_NAMES = ["numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs", "peakRangeRel", "peakMeanAbs",
@@ -81,11 +81,20 @@ class _Crossings(C.Structure):
     _fields_ = [(n, i32) for n in ("zcr", "mcr", "amean")]
 
 
+class _Samples(C.Structure):
+    _fields_ = [("n_samplepos", i32), ("samplepos", f64 * 16)]
+
+
+class _Dct(C.Structure):
+    _fields_ = [("firstCoeff", i32), ("lastCoeff", i32)]
+
+
 class Spec(C.Structure):
     _fields_ = [("n_enabled", i32), ("enabled", i32 * 8), ("nonZeroFuncts", i32), ("masterTimeNorm", i32),
                 ("functNameAppend", C.c_char * capi.NAME_LEN), ("extremes", _Extremes), ("means", _Means), ("moments", _Moments),
                 ("percentiles", _Percentiles), ("regression", _Regression), ("times", _Times), ("lpc", _Lpc), ("segments", _Segments),
-                ("peaks2", _Peaks2), ("onset", _Onset), ("peaks", _Peaks), ("crossings", _Crossings)]
+                ("peaks2", _Peaks2), ("onset", _Onset), ("peaks", _Peaks), ("crossings", _Crossings),
+                ("samples", _Samples), ("dct", _Dct)]
 
 
 def _bind(L):
@@ -134,6 +143,10 @@ def spec(enabled, non_zero=0, master_norm=TIMENORM_UNSET, name_append="", **sub)
                 blk.n_pctlrange = len(v)
                 for i, (a, b) in enumerate(v):
                     blk.pctlrange[i][0], blk.pctlrange[i][1] = a, b
+            elif k == "samplepos":
+                blk.n_samplepos = len(v)
+                for i, x in enumerate(v):
+                    blk.samplepos[i] = x
             elif k == "thresholds":
                 blk.n_thresholds = len(v)
                 for i, x in enumerate(v):

@@ -640,6 +640,8 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
   std::map<int, double> segThresh;
   std::string segThreshList, segAlgo = "delta";
   bool unsupportedTimes = false, unsupportedSeg = false, unsupportedPeaks = false, peaksNoOverlap = false;
+  std::map<int, double> samplePos;
+  int dctLast = 6, dctN = -1;
   double onsetThr = 0.0, onsetThrOn = 0.0, onsetThrOff = 0.0;
   bool onsetThrOnSet = false, onsetThrOffSet = false;
   auto &ON = fs.onset; auto &PO = fs.peaks; auto &CR = fs.crossings;
@@ -720,6 +722,15 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
       for (int k = 0; k < OSM_B200_F_PEAKS2_VALUES; k++) if (f.compare(7, std::string::npos, peaksNames[k]) == 0) { PK.value[k] = inum(v); hitP = true; break; }
       if (hitP) continue;
     }
+    if (f.compare(0, 18, "Samples.samplepos[") == 0) { samplePos[atoi(f.c_str() + 18)] = num(v); continue; }
+    if (f == "Samples.samplepos") {
+      std::stringstream ss(v); std::string one; int k = 0;
+      while (std::getline(ss, one, ';')) { one = trim(one); if (!one.empty()) samplePos[k++] = num(one); }
+      continue;
+    }
+    if (f == "DCT.firstCoeff") { fs.dct.firstCoeff = std::max(0, inum(v)); continue; }          // functionalDCT.cpp:58-62
+    if (f == "DCT.lastCoeff") { dctLast = inum(v); continue; }
+    if (f == "DCT.nCoeffs") { dctN = inum(v); continue; }
     if (f == "Onset.threshold") { onsetThr = num(v); continue; }
     if (f == "Onset.thresholdOnset") { onsetThrOn = num(v); onsetThrOnSet = true; continue; }
     if (f == "Onset.thresholdOffset") { onsetThrOff = num(v); onsetThrOffSet = true; continue; }
@@ -758,6 +769,12 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     err = "unknown field '" + f + "' in section [" + s.name + ":cFunctionals]";
     return false;
   }
+  fs.dct.lastCoeff = dctN >= 0 ? fs.dct.firstCoeff + dctN - 1 : dctLast;            // functionalDCT.cpp:63-68
+  if (!samplePos.empty()) {                                                         // functionalSamples.cpp:50-66 (clipped to [0, 1])
+    if (samplePos.size() > OSM_B200_F_MAX_SAMPLES) { err = "cFunctionalSamples: more than 16 sample positions"; return false; }
+    fs.samples.n_samplepos = 0;
+    for (const auto &kv : samplePos) fs.samples.samplepos[fs.samples.n_samplepos++] = std::min(1.0, std::max(0.0, kv.second));
+  }
   ON.thresholdOnset = (float)(onsetThrOnSet ? onsetThrOn : onsetThr);               // functionalOnset.cpp:77-81
   ON.thresholdOffset = (float)(onsetThrOffSet ? onsetThrOff : onsetThr);
   if (quartilesSet) P.quartile1 = P.quartile2 = P.quartile3 = quartiles;          // functionalPercentiles.cpp:112-116
@@ -786,7 +803,9 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     else if (n == "Onset") t = OSM_B200_F_ONSET;
     else if (n == "Peaks") t = OSM_B200_F_PEAKS;
     else if (n == "Crossings") t = OSM_B200_F_CROSSINGS;
-    else { err = "cFunctional" + n + " (instance '" + s.name + "') is not supported on the GPU path (Extremes, Means, Moments, Percentiles, Regression, Times, Lpc, Segments, Peaks2, Onset, Peaks, Crossings are)"; return false; }
+    else if (n == "Samples") t = OSM_B200_F_SAMPLES;
+    else if (n == "DCT") t = OSM_B200_F_DCT;
+    else { err = "cFunctional" + n + " (instance '" + s.name + "') is not supported on the GPU path (Extremes, Means, Moments, Percentiles, Regression, Times, Lpc, Segments, Peaks2, Onset, Peaks, Crossings, Samples, DCT are)"; return false; }
     if (t == OSM_B200_F_PEAKS && peaksNoOverlap) { err = "cFunctionalPeaks.overlapFlag = 0 (peak history carried from one contour to the next) is not supported"; return false; }
     fs.enabled[fs.n_enabled++] = t;
     if (t == OSM_B200_F_TIMES && unsupportedTimes) { err = "cFunctionalTimes: upleveltime[] / downleveltime[] arrays and useRobustPercentileRange are not supported"; return false; }

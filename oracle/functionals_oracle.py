@@ -34,7 +34,7 @@ class Spec:
     """mirror of include/osm_b200_functionals.h (field names = the reference's configuration fields)"""
 
     def __init__(self, enabled, non_zero=0, master_norm=None, name_append=None, extremes=None, means=None, moments=None,
-                 percentiles=None, regression=None, times=None, lpc=None, segments=None, peaks2=None, onset=None, peaks=None, crossings=None):
+                 percentiles=None, regression=None, times=None, lpc=None, segments=None, peaks2=None, onset=None, peaks=None, crossings=None, samples=None, dct=None):
         self.enabled, self.non_zero, self.master_norm, self.name_append = list(enabled), non_zero, master_norm, name_append
         self.extremes = dict(max=1, min=1, range=1, maxpos=1, minpos=1, amean=0, maxameandist=1, minameandist=1, norm=FRAME, norm_set=False)
         self.extremes.update(extremes or {})
@@ -69,6 +69,10 @@ class Spec:
         self.peaks.update(peaks or {})
         self.crossings = dict(zcr=1, mcr=1, amean=0)
         self.crossings.update(crossings or {})
+        self.samples = dict(samplepos=[i / 4.0 for i in range(5)])                  # functionalSamples.cpp:24,68-75
+        self.samples.update(samples or {})
+        self.dct = dict(firstCoeff=1, lastCoeff=6)                                  # functionalDCT.cpp:38-40
+        self.dct.update(dct or {})
 
 
 EXT_NAMES = ["max", "min", "range", "maxPos", "minPos", "amean", "maxameandist", "minameandist"]
@@ -128,6 +132,10 @@ def value_names(spec):
             out += [n for n in PEAKS_NAMES if spec.peaks[n]]
         elif f == "Crossings":
             out += [n for n in CROSS_NAMES if spec.crossings[n]]
+        elif f == "Samples":                                       # functionalSamples.cpp:89-95
+            out += ["samples%.3f" % x for x in spec.samples["samplepos"]]
+        elif f == "DCT":                                           # functionalDCT.cpp:103-110
+            out += ["dct%d" % k for k in range(spec.dct["firstCoeff"], spec.dct["lastCoeff"] + 1)]
         else:
             raise ValueError(f)
     return out
@@ -314,6 +322,10 @@ def contour(spec, x, period):
             out += _peaks_old(spec, x, period)
         elif f == "Crossings":
             out += _crossings(spec, x)
+        elif f == "Samples":                                       # functionalSamples.cpp:99-116
+            out += [x[int((float(F32(N)) - 1.0) * float(pos))] for pos in spec.samples["samplepos"]]
+        elif f == "DCT":
+            out += _dct(spec, x)
     assert len(out) == nvals
     return out
 
@@ -426,6 +438,21 @@ def _crossings(spec, x):
                 mcr += 1
     vals = dict(zcr=F32(zcr / float(N)), mcr=F32(mcr / float(N)), amean=F32(amean))
     return [vals[n] for n in CROSS_NAMES if c[n]]
+
+
+def _dct(spec, x):
+    """functionalDCT.cpp:85-135: table (float)cos(pi * i / N * ((float)m + 0.5)), float sum over the contour, times (float)sqrt(2 / N)"""
+    N = len(x)
+    m = np.arange(N, dtype=np.float32).astype(np.float64) + 0.5
+    out = []
+    for i in range(spec.dct["firstCoeff"], spec.dct["lastCoeff"] + 1):
+        tab = np.cos(math.pi * float(i) / float(N) * m).astype(np.float32)
+        acc = F32(0)
+        for v in (x * tab).astype(np.float32):                     # float product, float running sum
+            acc = F32(acc + v)
+        acc = F32(acc * F32(math.sqrt(2.0 / float(N))))
+        out.append(acc if np.isfinite(acc) else F32(0))
+    return out
 
 
 def _times(spec, x, mn, mx, period):

@@ -86,10 +86,10 @@ def main():
             refrun.write_wav(wav, pcm, 16000, 1)
             open(os.path.join(d, "v.conf"), "w").write(var3)
             cmd = [refrun.SMILEXTRACT, "-C", os.path.join(d, "v.conf"), "-I", wav, "-l", "0"]
-            for lv in "IJK":
+            for lv in "IJKL":
                 cmd += ["-out" + lv, os.path.join(d, lv + ".csv")]
             subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            for lv in "IJK":
+            for lv in "IJKL":
                 n, r = csv_rows(os.path.join(d, lv + ".csv"))
                 out3["var%s_names" % lv] = np.array(n)
                 out3["var%s_%s" % (lv, key)] = r

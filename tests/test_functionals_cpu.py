@@ -62,7 +62,9 @@ SPEC_J = fo.Spec(["Crossings", "Peaks", "Onset"], master_norm=SEC,
 SPEC_K = fo.Spec(["Peaks", "Onset", "Crossings"], non_zero=1, master_norm=SEC,
                  onset=dict(threshold=0.2, onsetPos=1, offsetPos=1, numOnsets=1, onsetRate=1, norm=FR, norm_set=True),
                  peaks=dict(peakMean=0, peakMeanMeanDist=0, peakDistStddev=1, norm=S, norm_set=True), crossings=dict(zcr=0, mcr=1, amean=1))
-LEVELS3 = [("I", SPEC_I, slice(0, 32), -2), ("J", SPEC_J, slice(0, 16), 0), ("K", SPEC_K, slice(0, 16), 0)]
+SPEC_L = fo.Spec(["Samples", "Moments", "DCT"], samples=dict(samplepos=[0, 0.1, 0.33, 0.5, 0.999, 1.0, 1.0]),
+                 moments=dict(variance=0, stddev=1, skewness=0, kurtosis=0, amean=0), dct=dict(firstCoeff=0, lastCoeff=8))
+LEVELS3 = [("I", SPEC_I, slice(0, 32), -2), ("J", SPEC_J, slice(0, 16), 0), ("K", SPEC_K, slice(0, 16), 0), ("L", SPEC_L, slice(0, 16), 0)]
 G3 = np.load(os.path.join(HERE, "golden", "functionals_goldens3.npz"))
 LEVELS2 = [("D", SPEC_D, slice(0, 32), -2), ("E", SPEC_E, slice(0, 16), 0), ("F", SPEC_F, slice(0, 32), -2), ("G", SPEC_G, slice(0, 16), 0),
            ("H", SPEC_H, slice(0, 32), -2)]
@@ -141,6 +143,8 @@ def to_c_spec(spec):
                         thresholdOffset=o["threshold"] if o["thresholdOffset"] is None else o["thresholdOffset"], useAbsVal=o["useAbsVal"], **norm(o))
     sub["peaks"] = {k: spec.peaks[k] for k in fo.PEAKS_NAMES} | norm(spec.peaks)
     sub["crossings"] = dict(spec.crossings)
+    sub["samples"] = dict(samplepos=[float(x) for x in spec.samples["samplepos"]])
+    sub["dct"] = dict(spec.dct)
     return F.spec(spec.enabled, non_zero=spec.non_zero, master_norm=-1 if spec.master_norm is None else spec.master_norm,
                   name_append=spec.name_append or "", **sub)
 
@@ -235,10 +239,10 @@ def test_unimplemented_functionals_are_refused_loudly(tmp_path):
     from opensmile_b200 import capi
     txt = open(os.path.join(HERE, "configs", "func_variants.conf")).read().replace("REFCONF", REFCONF)
     bad = tmp_path / "bad.conf"
-    bad.write_text(txt.replace("functionalsEnabled = Means\n", "functionalsEnabled = Means ; Samples\n"))
+    bad.write_text(txt.replace("functionalsEnabled = Means\n", "functionalsEnabled = Means ; Modulation\n"))
     with pytest.raises(SessionError) as e:
         _session(str(bad), {"outA": "x.csv"})
-    assert e.value.status == capi.ERR_UNSUPPORTED and "cFunctionalSamples" in str(e.value)
+    assert e.value.status == capi.ERR_UNSUPPORTED and "cFunctionalModulation" in str(e.value)
     bad.write_text(txt.replace("nonZeroFuncts = 0\n", "nonZeroFuncts = 0\nbogusField = 1\n"))
     with pytest.raises(SessionError) as e:
         _session(str(bad), {"outA": "x.csv"})
