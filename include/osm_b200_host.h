@@ -123,11 +123,15 @@ OSM_B200_API int32_t osm_b200_write_csv_timed(const char *path, const float *row
  *       iocore/csvSink.cpp:216-233), followed by `delim` (newline after the last value of a row), rows at d_text + r * slot_bytes
  *       (slot_bytes >= osm_b200_device_csv_slot_bytes(K)), d_row_len[r] = bytes of row r, d_row_host[r] = 1 when the row holds a value
  *       the device leaves to the host formatter (non-finite, |x| >= 1e15, an undecidable rounding: about 1e-7 of the values)
+ *   osm_b200_device_format_rows: the same with always_e = 1 for cArffSink, which prints every value with "%e"
+ *       (iocore/arffSink.cpp:300-312; delim ','); integer values >= 1e7 are then left to the host as well
  *   osm_b200_device_pack_htk   : cHtkSink's payload, float32 big endian (iocore/htkSink.cpp:183-206)
  * Asynchronous on `stream` (cudaStream_t); return 0 on success. */
 OSM_B200_API int64_t osm_b200_device_csv_slot_bytes(int32_t n_elements);
 OSM_B200_API int32_t osm_b200_device_format_csv(const float *d_rows, int64_t n_rows, int32_t n_elements, char delim, char *d_text,
                                                 int64_t slot_bytes, int32_t *d_row_len, uint8_t *d_row_host, void *stream);
+OSM_B200_API int32_t osm_b200_device_format_rows(const float *d_rows, int64_t n_rows, int32_t n_elements, char delim, int32_t always_e,
+                                                 char *d_text, int64_t slot_bytes, int32_t *d_row_len, uint8_t *d_row_host, void *stream);
 OSM_B200_API int32_t osm_b200_device_pack_htk(const float *d_rows, int64_t n_values, uint32_t *d_out, void *stream);
 /* whole files from device rows (format on the device, copy, write): byte-identical to osm_b200_write_csv_timed / osm_b200_write_htk */
 OSM_B200_API int32_t osm_b200_write_csv_device(const char *path, const float *d_rows, int64_t n_rows, int32_t n_elements,

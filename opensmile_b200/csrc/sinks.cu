@@ -6,6 +6,8 @@
 //             every finite float it accepts), ordered by a warp prefix sum of the lengths into the row's slot of the text buffer.
 //             Rows with a value the device leaves to the host (non-finite, |x| >= 1e15, an undecidable rounding: ~1e-7 of the
 //             values) are flagged and formatted by the host writer.
+//   cArffSink (iocore/arffSink.cpp:300-312): every value "%e", ',' between them -> the same kernel with alwaysE (integers >= 1e7 go to
+//             the host writer as well)
 #include <cuda_runtime.h>
 
 #include "../../include/osm_b200_host.h"
@@ -18,7 +20,7 @@ constexpr int kSinkWarps = 8;
 
 __global__ void __launch_bounds__(kSinkWarps * 32) csv_format_kernel(const float *__restrict__ rows, long long nRows, int K, char delim,
                                                                       char *__restrict__ text, long long slot, int *__restrict__ rowLen,
-                                                                      unsigned char *__restrict__ rowHost)
+                                                                      unsigned char *__restrict__ rowHost, int alwaysE)
 {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * kSinkWarps + (threadIdx.x >> 5);
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(kSinkWarps * 32) csv_format_kernel(const float
     char buf[tf::kMaxValueChars + 1];
     int n = 0;
     if (k < K) {
-      n = tf::fmt_value(row[k], buf);
+      n = tf::fmt_value(row[k], buf, alwaysE != 0);
       if (n < 0) { host = true; n = 0; }
       buf[n++] = (k == K - 1) ? '\n' : delim;
     }
@@ -65,11 +67,17 @@ int64_t osm_b200_device_csv_slot_bytes(int32_t K) { return (int64_t)K * (tf::kMa
 int32_t osm_b200_device_format_csv(const float *d_rows, int64_t n_rows, int32_t K, char delim, char *d_text, int64_t slot_bytes,
                                    int32_t *d_row_len, uint8_t *d_row_host, void *stream)
 {
+  return osm_b200_device_format_rows(d_rows, n_rows, K, delim, 0, d_text, slot_bytes, d_row_len, d_row_host, stream);
+}
+
+int32_t osm_b200_device_format_rows(const float *d_rows, int64_t n_rows, int32_t K, char delim, int32_t always_e, char *d_text, int64_t slot_bytes,
+                                    int32_t *d_row_len, uint8_t *d_row_host, void *stream)
+{
   if (n_rows <= 0) return 0;
   if (!d_rows || !d_text || !d_row_len || !d_row_host || K <= 0 || slot_bytes < osm_b200_device_csv_slot_bytes(K)) return 1;
   const long long blocks = (n_rows + kSinkWarps - 1) / kSinkWarps;
   csv_format_kernel<<<(unsigned)blocks, kSinkWarps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_rows, n_rows, K, delim, d_text, slot_bytes,
-                                                                                                       d_row_len, d_row_host);
+                                                                                                       d_row_len, d_row_host, always_e);
   return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 

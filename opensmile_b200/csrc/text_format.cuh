@@ -31,13 +31,18 @@ OSM_TF_HD double pow10_exact(int p)     // 10^p, exact for 0 <= p <= 22
 }
 
 // writes the characters of v to dst (at most kMaxValueChars), returns their number, or -1 when the host has to format this value
-OSM_TF_HD int fmt_value(float v, char *dst)
+// alwaysE: cArffSink prints every value with "%e" (iocore/arffSink.cpp:300-312), cCsvSink only the non-integer ones
+OSM_TF_HD int fmt_value(float v, char *dst, bool alwaysE = false)
 {
   if (!(fabsf(v) <= 3.402823466e+38f)) return -1;                       // nan / inf
   int n = 0;
   if (signbit(v)) dst[n++] = '-';
   const float a = fabsf(v);
-  if (a == floorf(a)) {                                                  // "%.0f"
+  if (alwaysE) {
+    if (a == 0.0f) { const char z[] = "0.000000e+00"; for (int i = 0; i < 12; i++) dst[n++] = z[i]; return n; }
+    if (a >= 1e7f) return -1;                                            // integers beyond the 7 printed digits: exact big-number rounding, left to the host
+  }
+  if (!alwaysE && a == floorf(a)) {                                      // "%.0f"
     if (a >= 1e15f) return -1;
     unsigned long long u = (unsigned long long)a;
     char tmp[16];
@@ -46,7 +51,7 @@ OSM_TF_HD int fmt_value(float v, char *dst)
     while (k > 0) dst[n++] = tmp[--k];
     return n;
   }
-  // "%e": a is not an integer, so a < 2^23 and p = 6 - E10 >= 0
+  // "%e": a is not an integer (a < 2^23) or, with alwaysE, below 1e7: p = 6 - E10 >= 0
   const double x = (double)a;
   int E10 = (int)floor(log10(x));
   double s;

@@ -1064,7 +1064,7 @@ std::string arff_escape(const std::string &str)               // iocore/arffSink
 }
 
 bool write_arff(const char *path, const float *rows, int64_t n, int K, const std::vector<std::string> &names, double period,
-                const ArffOpts &o, std::string &err, int64_t nTimeFrames = 0)
+                const ArffOpts &o, std::string &err, int64_t nTimeFrames = 0, const DevText *dt = nullptr)
 {
   bool header = true;
   if (o.append) {                                             // :244-256: append to an existing file without a header
@@ -1092,8 +1092,11 @@ bool write_arff(const char *path, const float *rows, int64_t n, int K, const std
     else if (o.prname == 2) { char b[512]; snprintf(b, sizeof b, "%s_%ld", o.instName.c_str(), (long)r); fprintf(f, "%s,", arff_escape(b).c_str()); }
     if (o.number) fprintf(f, "%ld,", (long)r);
     if (o.timestamp) fprintf(f, "%f,", (double)((nTimeFrames > 0 && r > nTimeFrames - 1) ? nTimeFrames - 1 : r) * period + o.frameTimeAdd);
-    tb.fmt_e(rows[r * K]);
-    for (int k = 1; k < K; k++) { tb.ch(','); tb.fmt_e(rows[r * K + k]); }
+    if (dt && !dt->host[r]) tb.str(dt->text + r * dt->slot, (size_t)dt->len[r] - 1);   // the device's row text without its newline
+    else {
+      tb.fmt_e(rows[r * K]);
+      for (int k = 1; k < K; k++) { tb.ch(','); tb.fmt_e(rows[r * K + k]); }
+    }
     tb.flush();                          // keeps the order with the fprintf calls around it (both end in the FILE buffer)
     if (!o.classes.empty()) {
       for (size_t c = 0; c < o.classes.size(); c++) {
@@ -1885,7 +1888,7 @@ static bool parallel_files(int n, Fn fn, std::string &err, bool serial = false)
 static bool write_batch(osm_b200_session *s, const std::vector<int> &idx, const int64_t *fo, const int64_t *nTime, const float *rows, int K,
                         const std::vector<std::string> &names, double period, const char *const *htkPaths, const char *const *csvPaths,
                         const char *const *arffPaths, int64_t *framesOut, std::string &err, const DevText *dt = nullptr,
-                        const uint32_t *packed = nullptr)
+                        const uint32_t *packed = nullptr, const DevText *dtArff = nullptr)
 {
   // several inputs may name the same output file (cArffSink / cCsvSink with append=1 collect every input in one file):
   // those files must be written one after the other, in input order
@@ -1906,7 +1909,9 @@ static bool write_batch(osm_b200_session *s, const std::vector<int> &idx, const 
     DevText dk;
     if (dt) dk = DevText{dt->text + fo[k] * dt->slot, dt->slot, dt->len + fo[k], dt->host + fo[k]};
     if (csvPaths && csvPaths[i] && !write_csv(csvPaths[i], r, nr, K, names, period, s->csv, e, nTime[k], dt ? &dk : nullptr)) return false;
-    if (arffPaths && arffPaths[i] && !write_arff(arffPaths[i], r, nr, K, names, period, s->arff, e, nTime[k])) return false;
+    DevText da;
+    if (dtArff) da = DevText{dtArff->text + fo[k] * dtArff->slot, dtArff->slot, dtArff->len + fo[k], dtArff->host + fo[k]};
+    if (arffPaths && arffPaths[i] && !write_arff(arffPaths[i], r, nr, K, names, period, s->arff, e, nTime[k], dtArff ? &da : nullptr)) return false;
     return true;
   }, err, shared);
 }
@@ -1979,8 +1984,8 @@ static osm_b200_status osm_b200_session_extract_files_arff_impl(osm_b200_session
     // Device sinks (sinks.cu): the rows stay in HBM after the plan run, the CSV value text and the HTK payload are produced there
     // and copied next to the float rows; the host threads add the per-row prefixes and write.  OSM_B200_DEVICE_SINKS=0: host formatting.
     static const bool devSinks = [] { const char *e = getenv("OSM_B200_DEVICE_SINKS"); return !(e && e[0] == '0'); }();
-    const bool wantCsv = csvPaths != nullptr, wantHtk = htkPaths != nullptr;
-    if (devSinks && nR > 0 && (wantCsv || wantHtk)) {
+    const bool wantCsv = csvPaths != nullptr, wantHtk = htkPaths != nullptr, wantArff = arffPaths != nullptr;
+    if (devSinks && nR > 0 && (wantCsv || wantHtk || wantArff)) {
       const float *dRows = nullptr;
       st = osm_b200_plan_run_host_resident(p, pcm.data(), off.data(), (int)g.second.size(), fo.data(), &dRows);
       if (st != OSM_B200_OK) return hfail(st, osm_b200_last_error());
@@ -1997,6 +2002,20 @@ static osm_b200_status osm_b200_session_extract_files_arff_impl(osm_b200_session
              cudaMemcpy(len.data(), dLen, len.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
              cudaMemcpy(hostFlag.data(), dHost, hostFlag.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
       }
+      char *dTextA = nullptr; int32_t *dLenA = nullptr; uint8_t *dHostA = nullptr;
+      std::vector<char> textA; std::vector<int32_t> lenA; std::vector<uint8_t> hostFlagA;
+      if (ok && wantArff) {                                 // cArffSink: every value "%e", ',' between them (iocore/arffSink.cpp:300-312)
+        textA.resize((size_t)nR * slot); lenA.resize((size_t)nR); hostFlagA.resize((size_t)nR);
+        ok = cudaMalloc(reinterpret_cast<void **>(&dTextA), textA.size()) == cudaSuccess && cudaMalloc(reinterpret_cast<void **>(&dLenA), lenA.size() * 4) == cudaSuccess &&
+             cudaMalloc(reinterpret_cast<void **>(&dHostA), hostFlagA.size()) == cudaSuccess &&
+             osm_b200_device_format_rows(dRows, nR, K, ',', 1, dTextA, slot, dLenA, dHostA, nullptr) == 0 &&
+             cudaMemcpy(textA.data(), dTextA, textA.size(), cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaMemcpy(lenA.data(), dLenA, lenA.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess &&
+             cudaMemcpy(hostFlagA.data(), dHostA, hostFlagA.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+      }
+      if (dTextA) cudaFree(dTextA);
+      if (dLenA) cudaFree(dLenA);
+      if (dHostA) cudaFree(dHostA);
       if (ok && wantHtk) {
         packed.resize((size_t)nR * K);
         ok = cudaMalloc(reinterpret_cast<void **>(&dPack), packed.size() * 4) == cudaSuccess && osm_b200_device_pack_htk(dRows, nR * K, dPack, nullptr) == 0 &&
@@ -2008,8 +2027,9 @@ static osm_b200_status osm_b200_session_extract_files_arff_impl(osm_b200_session
       if (dPack) cudaFree(dPack);
       if (!ok) return hfail(OSM_B200_ERR_CUDA, std::string("device sinks: ") + cudaGetErrorString(cudaGetLastError()));
       const DevText dt{text.data(), slot, len.data(), hostFlag.data()};
+      const DevText dtA{textA.data(), slot, lenA.data(), hostFlagA.data()};
       if (!write_batch(s, g.second, fo.data(), nTime.data(), rows.data(), K, names, osm_b200_plan_frame_period(p), htkPaths, csvPaths, arffPaths, framesOut, err,
-                       wantCsv ? &dt : nullptr, wantHtk ? packed.data() : nullptr))
+                       wantCsv ? &dt : nullptr, wantHtk ? packed.data() : nullptr, wantArff ? &dtA : nullptr))
         return hfail(OSM_B200_ERR_INVALID, err);
       continue;
     }

@@ -16,6 +16,12 @@ static void check(float v)
   a[n] = 0;
   if (v == floorf(v)) snprintf(b, sizeof b, "%.0f", (double)v); else snprintf(b, sizeof b, "%e", (double)v);
   if (strcmp(a, b) != 0) { if (bad < 10) fprintf(stderr, "mismatch %a: got %s want %s\n", v, a, b); bad++; }
+  // cArffSink's mode: "%e" for every value (integers included, below 1e7; the rest is the host's)
+  const int m = osm::tf::fmt_value(v, a, true);
+  if (m < 0) { if (fabsf(v) < 1e7f) { unc++; if (unc <= 5) fprintf(stderr, "uncertain (always %%e) %a = %.9e\n", v, (double)v); } return; }
+  a[m] = 0;
+  snprintf(b, sizeof b, "%e", (double)v);
+  if (strcmp(a, b) != 0) { if (bad < 10) fprintf(stderr, "mismatch (always %%e) %a: got %s want %s\n", v, a, b); bad++; }
 }
 
 int main(int argc, char **argv)

@@ -259,12 +259,14 @@ def test_gemaps_summaries_on_degenerate_inputs(conf, tag):
     sig = {"silence": np.zeros(16000, np.int16), "noise": (rng.randn(16000) * 800).astype(np.int16), "short": voiced_pcm(4000, 16000, seed=9),
            "burst": burst}
     keys = ["silence", "noise", "short", "burst"]
-    off = np.concatenate([[0], np.cumsum([len(sig[k]) for k in keys])]).astype(np.int64)
+    sig["tiny"] = voiced_pcm(300, 16000, seed=2)          # shorter than one 20 ms frame: no frame, hence no summary row for this input
+    order = ["silence", "noise", "tiny", "short", "burst"]
+    off = np.concatenate([[0], np.cumsum([len(sig[k]) for k in order])]).astype(np.int64)
     s = Session(os.path.join(REFCONF, conf), options={"csvoutput": "f.csv"}, device=0)
     names = s.element_names()
-    rows, fo_ = s.extract_pcm(np.concatenate([sig[k] for k in keys]), off, 16000.0, 1)
+    rows, fo_ = s.extract_pcm(np.concatenate([sig[k] for k in order]), off, 16000.0, 1)
     s.close()
-    assert list(fo_) == [0, 1, 2, 3, 4]
+    assert list(fo_) == [0, 1, 2, 2, 3, 4]
     for u, key in enumerate(keys):
         ref = GF["%s_%s" % (tag, key)][0]
         assert np.all(np.isfinite(rows[u]))

@@ -44,7 +44,8 @@ def test_device_writers_equal_the_host_writers(tmp_path, n, k):
 
 
 def test_session_files_come_from_the_device_sinks(tmp_path):
-    """extract_files (device sinks) against write_files on the rows of extract_pcm (host formatting): identical files"""
+    """extract_files (device sinks: HTK payload, CSV and ARFF value text) against write_files on the rows of extract_pcm (host
+    formatting): identical files"""
     import wave
     from opensmile_b200.session import Session
     conf = os.path.join(HERE, "configs", "mfcc_e_d_a.conf")
@@ -56,13 +57,15 @@ def test_session_files_come_from_the_device_sinks(tmp_path):
             f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(np.ascontiguousarray(x, dtype="<i2").tobytes())
         wavs.append(str(w))
     s = Session(conf, options={"instname": "utt7"}, device=0)
-    frames = s.extract_files(wavs, [str(tmp_path / ("d%d.htk" % i)) for i in range(2)], [str(tmp_path / ("d%d.csv" % i)) for i in range(2)])
+    frames = s.extract_files(wavs, [str(tmp_path / ("d%d.htk" % i)) for i in range(2)], [str(tmp_path / ("d%d.csv" % i)) for i in range(2)],
+                             [str(tmp_path / ("d%d.arff" % i)) for i in range(2)])
     off = np.concatenate([[0], np.cumsum([len(x) for x in pcms])]).astype(np.int64)
     rows, fo = s.extract_pcm(np.concatenate(pcms), off, 16000.0, 1)
     assert list(frames) == list(np.diff(fo))
     s.write_files(rows, fo, 16000.0, 1, n_samples=[len(x) for x in pcms], htk_paths=[str(tmp_path / ("h%d.htk" % i)) for i in range(2)],
-                  csv_paths=[str(tmp_path / ("h%d.csv" % i)) for i in range(2)])
+                  csv_paths=[str(tmp_path / ("h%d.csv" % i)) for i in range(2)], arff_paths=[str(tmp_path / ("h%d.arff" % i)) for i in range(2)])
     s.close()
     for i in range(2):
         assert (tmp_path / ("d%d.htk" % i)).read_bytes() == (tmp_path / ("h%d.htk" % i)).read_bytes()
         assert (tmp_path / ("d%d.csv" % i)).read_bytes() == (tmp_path / ("h%d.csv" % i)).read_bytes()
+        assert (tmp_path / ("d%d.arff" % i)).read_bytes() == (tmp_path / ("h%d.arff" % i)).read_bytes()      # every value "%e" (cArffSink)
