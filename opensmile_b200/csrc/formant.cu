@@ -25,6 +25,9 @@ constexpr int kFmtWarps = 8;               // warps per CTA = frames per transfo
 constexpr int kFmtThreads = kFmtWarps * 32;
 constexpr int kFmtFpw = 2;                 // frames per warp in the per-frame phase: a half warp each (one lane per lag / root, p <= 15)
 constexpr int kFmtBatch = kFmtWarps * kFmtFpw;
+#ifndef OSM_FMT_BATCHED
+#define OSM_FMT_BATCHED 1
+#endif
 
 struct FmtWarpWs {                          // per-warp scratch of the per-frame phase
   double c[fm::kMaxLpcOrder];               // polynomial, ascending powers (monic)
@@ -170,20 +173,54 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
       const int fi = warp * fpw + h;                                   // frame of the batch [fb0, fb0 + kFmtWarps * fpw)
       const int part = fi / kFmtWarps, fin = fi - part * kFmtWarps;    // resampled by batch `part` as its frame `fin`
       // frames are dealt so that a warp's two frames come from the two batches: fi -> (part, fin) below keeps res contiguous
-      if (fb0 + fi < tl.nf) {
-      FmtWarpWs &w = ws[fi];
-      const float *x = res0 + ((size_t)part * kFmtWarps + fin) * IP;
+      // The sequential per-frame steps (Durbin recursion, candidate selection / sort / store) run as "one LANE per frame" on the
+      // first warp for the whole batch of frames -- one instruction stream for up to 16 frames instead of one per half warp with a
+      // single active lane (ncu: those two steps were 45 % of the kernel's warp-instructions) -- the steps with per-frame
+      // parallelism (autocorrelation lags, the simultaneous root refinement) stay "one half warp per frame".  OSM_FMT_BATCHED=0
+      // builds the previous flow for A/B runs.
+      const bool live = fb0 + fi < tl.nf;
+      FmtWarpWs &w = ws[live ? fi : 0];
       const int P = p.p;
-      if (hl <= P) w.r[hl] = fm::acf_lag(x, I, hl);                    // lld/lpc.cpp:156-215 (method acf)
-      __syncwarp(hm);
-      if (hl == 0) {
-        fm::durbin(w.r, P, w.a);
-        for (int i = 0; i < P; i++) w.c[i] = -(double)w.a[P - 1 - i];  // lld/formantLpc.cpp:258-262
+      auto lpc_setup = [&](FmtWarpWs &q) {
+        fm::durbin(q.r, P, q.a);
+        for (int i = 0; i < P; i++) q.c[i] = -(double)q.a[P - 1 - i];  // lld/formantLpc.cpp:258-262
         int z0 = 0;
-        while (z0 < P && w.c[z0] == 0.0) z0++;                         // roots at the origin yield no candidate
-        w.z0 = z0; w.n = P - z0;
+        while (z0 < P && q.c[z0] == 0.0) z0++;                         // roots at the origin yield no candidate
+        q.z0 = z0; q.n = P - z0;
+      };
+      auto emit = [&](FmtWarpWs &q, int frameInBatch) {
+        // smileDsp_lpcrootsToFormants (smileutil/smileUtil.c:2019-2054): candidates in root order, then the
+        // ascending sort of lld/formantLpc.cpp:277-296 over the leading non-zero entries
+        double f[fm::kMaxLpcOrder], b[fm::kMaxLpcOrder];
+        const int nF = p.nFormants, n = q.n;
+        int nv = 0;
+        for (int k = 0; k < n && nv < nF; k++) if (q.ok[k]) { f[nv] = q.f[k]; b[nv] = q.b[k]; nv++; }
+        for (int i = nv; i < nF; i++) { f[i] = 0.0; b[i] = 0.0; }
+        int nz = 0;
+        while (nz < nF && f[nz] != 0.0) nz++;
+        for (int i = 0; i < nz; i++)
+          for (int j = i + 1; j < nz; j++)
+            if (f[j] < f[i]) { double t = f[j]; f[j] = f[i]; f[i] = t; t = b[j]; b[j] = b[i]; b[i] = t; }
+        float *dst = tp.stat + (tp.statOff[tl.utt] + tl.f0 + fb0 + frameInBatch) * (long long)tp.statStride + tp.outCol;
+        int o = 0;
+        if (p.saveNValid) dst[o++] = (float)nv;                        // lld/formantLpc.cpp:376-392
+        if (p.saveFormants) for (int i = 0; i < nF; i++) dst[o++] = (float)f[i];
+        if (p.saveBandwidths) for (int i = 0; i < nF; i++) dst[o++] = (float)b[i];
+      };
+      if (live) {
+        const float *x = res0 + ((size_t)part * kFmtWarps + fin) * IP;
+        if (hl <= P) w.r[hl] = fm::acf_lag(x, I, hl);                  // lld/lpc.cpp:156-215 (method acf)
       }
+#if OSM_FMT_BATCHED
+      __syncthreads();
+      if (warp == 0 && lane < kFmtWarps * fpw && fb0 + lane < tl.nf) lpc_setup(ws[lane]);
+      __syncthreads();
+#else
       __syncwarp(hm);
+      if (live && hl == 0) lpc_setup(w);
+      __syncwarp(hm);
+#endif
+      if (live) {
       const int n = w.n;
       const double *c = w.c + w.z0;
       double zr = 0.0, zi = 0.0, prev = 1e300;
@@ -209,27 +246,15 @@ __global__ void __launch_bounds__(kFmtThreads) formant_kernel(const FormantParam
         w.ok[hl] = fm::root_to_formant(zr, zi, p.T, p.minF, p.maxF, &f, &b) ? 1 : 0;
         w.f[hl] = f; w.b[hl] = b;
       }
+#if !OSM_FMT_BATCHED
       __syncwarp(hm);
-      if (hl == 0) {
-        // smileDsp_lpcrootsToFormants (smileutil/smileUtil.c:2019-2054): candidates in root order, then the
-        // ascending sort of lld/formantLpc.cpp:277-296 over the leading non-zero entries
-        double f[fm::kMaxLpcOrder], b[fm::kMaxLpcOrder];
-        const int nF = p.nFormants;
-        int nv = 0;
-        for (int k = 0; k < n && nv < nF; k++) if (w.ok[k]) { f[nv] = w.f[k]; b[nv] = w.b[k]; nv++; }
-        for (int i = nv; i < nF; i++) { f[i] = 0.0; b[i] = 0.0; }
-        int nz = 0;
-        while (nz < nF && f[nz] != 0.0) nz++;
-        for (int i = 0; i < nz; i++)
-          for (int j = i + 1; j < nz; j++)
-            if (f[j] < f[i]) { double t = f[j]; f[j] = f[i]; f[i] = t; t = b[j]; b[j] = b[i]; b[i] = t; }
-        float *dst = tp.stat + (tp.statOff[tl.utt] + tl.f0 + fb0 + fi) * (long long)tp.statStride + tp.outCol;
-        int o = 0;
-        if (p.saveNValid) dst[o++] = (float)nv;                        // lld/formantLpc.cpp:376-392
-        if (p.saveFormants) for (int i = 0; i < nF; i++) dst[o++] = (float)f[i];
-        if (p.saveBandwidths) for (int i = 0; i < nF; i++) dst[o++] = (float)b[i];
+      if (hl == 0) emit(w, fi);
+#endif
       }
-      }
+#if OSM_FMT_BATCHED
+      __syncthreads();
+      if (warp == 0 && lane < kFmtWarps * fpw && fb0 + lane < tl.nf) emit(ws[lane], lane);
+#endif
     }
     __syncthreads();
   }
