@@ -55,6 +55,7 @@ typedef enum {
 #define OSM_B200_SEG_RELTH 0
 #define OSM_B200_SEG_NONX  1
 #define OSM_B200_SEG_EQX   2
+#define OSM_B200_SEG_NARELTH 3   /* relTh on the samples themselves, no 3-frame running average (process_SegThreshNoavg, functionalSegments.cpp:369-413) */
 
 typedef struct {
   /* [x:cFunctionals] */

@@ -686,7 +686,7 @@ osm_b200_status osm_b200_functionals_create(const osm_b200_functionals_spec *spe
       return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalDCT: 0 <= firstCoeff <= lastCoeff, at most 32 coefficients");
     if (s.enabled[i] == OSM_B200_F_SEGMENTS) {
       const auto &G = s.segments;
-      if (G.algorithm < OSM_B200_SEG_RELTH || G.algorithm > OSM_B200_SEG_EQX) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSegments: segmentationAlgorithm must be relTh, nonX or eqX");
+      if (G.algorithm < OSM_B200_SEG_RELTH || G.algorithm > OSM_B200_SEG_NARELTH) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSegments: segmentationAlgorithm must be relTh, NArelTh, nonX or eqX");
       if (G.maxNumSeg < 1 || G.maxNumSeg > 4096) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSegments: 1 <= maxNumSeg <= 4096");
       if (G.n_thresholds < 0 || G.n_thresholds > OSM_B200_F_MAX_THRESH) return set_last_error(OSM_B200_ERR_UNSUPPORTED, "cFunctionalSegments: at most 8 thresholds");
     }

@@ -83,6 +83,18 @@ OSM_FS_HD int segments(const Spec &g, const float *x, long N, float mn, float mx
       raLast = ra;
       if (cross && i - lastSeg > segMinLng) lastSeg = seg_add(st, i, lastSeg);
     }
+  } else if (g.algorithm == OSM_B200_SEG_NARELTH) {                  // process_SegThreshNoavg :369-413
+    float th[OSM_B200_F_MAX_THRESH];
+    for (int j = 0; j < g.n_thresholds; j++) th[j] = mn + range * g.thresholds[j];
+    long segMinLng = g.segMinLng < 1 ? 1 : g.segMinLng;
+    if (!g.segMinLngIsSet) { segMinLng = N / g.maxNumSeg - 1; if (segMinLng < 2) segMinLng = 2; }
+    long lastSeg = -segMinLng / 2;
+    for (long i = 1; i < N; i++) {
+      bool cross = false;
+      for (int j = 0; j < g.n_thresholds; j++)
+        if ((x[i] > th[j] && x[i - 1] <= th[j]) || (x[i] < th[j] && x[i - 1] >= th[j])) cross = true;
+      if (cross && i - lastSeg > segMinLng) lastSeg = seg_add(st, i, lastSeg);
+    }
   } else {
     const float X = g.XisRel ? mn + range * g.X : g.X;
     const int segMinLng = g.segMinLng < 1 ? 1 : g.segMinLng, pauseMinLng = g.pauseMinLng < 1 ? 1 : g.pauseMinLng;

@@ -14,8 +14,8 @@ F_EXTREMES, F_MEANS, F_MOMENTS, F_PERCENTILES, F_REGRESSION, F_TIMES, F_LPC, F_S
 TYPE_BY_NAME = {"Extremes": F_EXTREMES, "Means": F_MEANS, "Moments": F_MOMENTS, "Percentiles": F_PERCENTILES, "Regression": F_REGRESSION,
                 "Times": F_TIMES, "Lpc": F_LPC, "Segments": F_SEGMENTS, "Peaks2": F_PEAKS2, "Onset": F_ONSET, "Peaks": F_PEAKS,
                 "Crossings": F_CROSSINGS, "Samples": F_SAMPLES, "DCT": F_DCT}
-SEG_RELTH, SEG_NONX, SEG_EQX = 0, 1, 2
-SEG_BY_NAME = {"relTh": SEG_RELTH, "nonX": SEG_NONX, "eqX": SEG_EQX}
+SEG_RELTH, SEG_NONX, SEG_EQX, SEG_NARELTH = 0, 1, 2, 3
+SEG_BY_NAME = {"relTh": SEG_RELTH, "nonX": SEG_NONX, "eqX": SEG_EQX, "NArelTh": SEG_NARELTH}
 PEAKS2_NAMES = ["numPeaks", "meanPeakDist", "meanPeakDistDelta", "peakDistStddev", "peakRangeAbs", "peakRangeRel", "peakMeanAbs",
                 "peakMeanMeanDist", "peakMeanRel", "ptpAmpMeanAbs", "ptpAmpMeanRel", "ptpAmpStddevAbs", "ptpAmpStddevRel", "minRangeAbs",
                 "minRangeRel", "minMeanAbs", "minMeanMeanDist", "minMeanRel", "mtmAmpMeanAbs", "mtmAmpMeanRel", "mtmAmpStddevAbs",

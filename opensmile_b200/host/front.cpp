@@ -816,7 +816,8 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
       if (segAlgo.compare(0, 5, "relTh") == 0) SG.algorithm = OSM_B200_SEG_RELTH;
       else if (segAlgo.compare(0, 4, "nonX") == 0) SG.algorithm = OSM_B200_SEG_NONX;
       else if (segAlgo.compare(0, 3, "eqX") == 0) SG.algorithm = OSM_B200_SEG_EQX;
-      else { err = "cFunctionalSegments.segmentationAlgorithm = " + segAlgo + " is not supported (relTh, nonX, eqX are)"; return false; }
+      else if (segAlgo.compare(0, 7, "NArelTh") == 0) SG.algorithm = OSM_B200_SEG_NARELTH;
+      else { err = "cFunctionalSegments.segmentationAlgorithm = " + segAlgo + " is not supported (relTh, NArelTh, nonX, eqX are)"; return false; }
       std::vector<double> th;
       if (!segThresh.empty()) for (const auto &kv : segThresh) th.push_back(kv.second);
       else {

@@ -574,6 +574,16 @@ def _segments(spec, x, mn, mx, mean, period):
             raLast = ra
             if cross and i - lastSeg > segMinLng:
                 lastSeg = add(i, lastSeg)
+    elif alg == "NArelTh":                              # process_SegThreshNoavg :369-413: the samples themselves, from frame 1
+        th = [F32(mn + F32(rng * F32(t))) for t in g["thresholds"]]
+        segMinLng = max(g["segMinLng"], 1)
+        if not g["segMinLng_set"]:
+            segMinLng = max(N // maxNumSeg - 1, 2)
+        lastSeg = int(-segMinLng / 2)
+        for i in range(1, N):
+            cross = any((x[i] > t and x[i - 1] <= t) or (x[i] < t and x[i - 1] >= t) for t in th)
+            if cross and i - lastSeg > segMinLng:
+                lastSeg = add(i, lastSeg)
     elif alg in ("nonX", "eqX"):
         X = F32(mn + F32(rng * F32(g["X"]))) if g["XisRel"] else F32(g["X"])
         segMinLng, pauseMinLng = max(g["segMinLng"], 1), max(g["pauseMinLng"], 1)

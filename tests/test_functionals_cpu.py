@@ -56,7 +56,9 @@ SPEC_H = fo.Spec(["Regression", "Moments"], master_norm=S,
 SPEC_I = fo.Spec(["Onset", "Times", "Peaks", "Crossings"], name_append="Turn",
                  onset=dict(threshold=0.0, thresholdOnset=0.0, thresholdOffset=0.0, numOnsets=1),
                  times=dict({k: 0 for k in fo.TIMES_NAMES}, duration=1, norm=SEC, norm_set=True), peaks=dict(), crossings=dict())
-SPEC_J = fo.Spec(["Crossings", "Peaks", "Onset"], master_norm=SEC,
+SPEC_J = fo.Spec(["Crossings", "Peaks", "Onset", "Segments"], master_norm=SEC,
+                 segments=dict(maxNumSeg=100, segmentationAlgorithm="NArelTh", thresholds=[0.25, 0.5, 0.75], numSegments=1, meanSegLen=1, maxSegLen=1,
+                               minSegLen=1, segLenStddev=1),
                  onset=dict(threshold=0.05, thresholdOffset=0.01, useAbsVal=1, onsetPos=1, offsetPos=1, numOnsets=1, numOffsets=1, onsetRate=1),
                  peaks=dict(peakDistStddev=1), crossings=dict(amean=1))
 SPEC_K = fo.Spec(["Peaks", "Onset", "Crossings"], non_zero=1, master_norm=SEC,
