@@ -158,11 +158,18 @@ typedef struct {            /* cFFTmagphase */
   int32_t magnitude, phase, normalise, power, dBpsd;  /* 1,0,0,0,0 */
 } osm_b200_fftmagphase;
 
+/* cMelspec.specScale (lldcore/melspec.cpp:100-135; smileutil/smileUtil.c:1097-1204): the frequency scale the band centres are
+ * equidistant on.  Only read when htkcompatible = 0 (HTK compatibility forces mel). */
+typedef enum { OSM_B200_SCALE_MEL = 0, OSM_B200_SCALE_BARK, OSM_B200_SCALE_BARK_SPEEX, OSM_B200_SCALE_BARK_SCHROED, OSM_B200_SCALE_SEMITONE,
+               OSM_B200_SCALE_LINEAR, OSM_B200_SCALE_LOG } osm_b200_specscale_kind;
+
 typedef struct {            /* cMelspec */
   int32_t nBands;           /* 26 */
   double  lofreq, hifreq;   /* 20, 8000 */
   int32_t usePower;         /* 0 */
   int32_t htkcompatible;    /* 1 */
+  int32_t specScale;        /* OSM_B200_SCALE_MEL */
+  double  scaleParam;       /* semitone: firstNote (27.5); log: logScaleBase (2.0, values <= 0 or == 1 become 2.0) */
 } osm_b200_melspec;
 
 typedef struct {            /* cMfcc */

@@ -73,7 +73,7 @@ class FFTmagphase(C.Structure):
 
 class Melspec(C.Structure):
     _fields_ = [("nBands", i32), ("lofreq", f64), ("hifreq", f64), ("usePower", i32),
-                ("htkcompatible", i32)]
+                ("htkcompatible", i32), ("specScale", i32), ("scaleParam", f64)]
 
 
 class Mfcc(C.Structure):

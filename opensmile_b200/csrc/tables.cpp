@@ -92,12 +92,52 @@ void build_window(int winFunc, int N, double sigma, double gain, std::vector<flo
 // smileDsp_specScaleTransfFwd / Inv for SPECTSCALE_MEL (smileutil/smileUtil.c:1139-1142,1197)
 static double mel_fwd(double x) { return x > 0.0 ? 1127.0 * log(1.0 + x / 700.0) : 0.0; }
 static double mel_inv(double x) { return 700.0 * (exp(x / 1127.0) - 1.0); }
+// smileDsp_specScaleTransfFwd / Inv (smileutil/smileUtil.c:1097-1204)
+static double scale_fwd(double x, int scale, double param)
+{
+  switch (scale) {
+    case OSM_B200_SCALE_LOG: return x > 0 ? log(x) / log(param) : 0.0;
+    case OSM_B200_SCALE_SEMITONE: return x / param > 1.0 ? 12.0 * (log(x / param) / log(2.0)) : 0.0;     // smileMath_log2 = log(x) / log(2)
+    case OSM_B200_SCALE_BARK: {
+      if (!(x > 0)) return 0.0;
+      const double zz = (26.81 / (1.0 + 1960.0 / x)) - 0.53;
+      if (zz < 2) return 0.85 * zz + 0.3;
+      if (zz > 20.1) return 1.22 * zz - 0.22 * 20.1;
+      return zz;
+    }
+    case OSM_B200_SCALE_BARK_SCHROED: { if (!(x > 0)) return 0.0; const double f6 = x / 600.0; return 6.0 * log(f6 + sqrt(f6 * f6 + 1.0)); }
+    case OSM_B200_SCALE_BARK_SPEEX: return 13.1 * atan(.00074 * x) + 2.24 * atan(x * x * 1.85e-8) + 1e-4 * x;
+    case OSM_B200_SCALE_LINEAR: return x;
+    default: return mel_fwd(x);
+  }
+}
+static double scale_inv(double x, int scale, double param)
+{
+  switch (scale) {
+    case OSM_B200_SCALE_LOG: return exp(x * log(param));
+    case OSM_B200_SCALE_SEMITONE: return param * pow(2.0, x / 12.0);
+    case OSM_B200_SCALE_BARK: {
+      double zz = x;
+      if (x > 20.1) zz = (x + 0.22 * 20.1) / 1.22;
+      else if (x < 2) zz = (x - 0.3) / 0.85;
+      const double z0 = 26.81 / (zz + 0.53);
+      return z0 != 1.0 ? 1960.0 / (z0 - 1.0) : 0.0;
+    }
+    case OSM_B200_SCALE_BARK_SCHROED: return 600.0 * sinh(x / 6.0);
+    case OSM_B200_SCALE_LINEAR: return x;
+    default: return mel_inv(x);                  // mel; bark_speex has no inverse in the reference and falls through to mel (:1187-1190)
+  }
+}
 
 // cMelspec::computeFilters, standard triangular bank (lldcore/melspec.cpp:184-240,391-447),
 // specScale = mel (forced when htkcompatible, melspec.cpp:127-131).
 void build_mel(const osm_b200_melspec &cfg, int blocksize, double frameSizeSec, MelBank &mb)
 {
   const int nBands = cfg.nBands;
+  const int scale = cfg.htkcompatible ? (int)OSM_B200_SCALE_MEL : cfg.specScale;     // melspec.cpp:127-131
+  double param = 0.0;                                                                // :133-135
+  if (scale == OSM_B200_SCALE_LOG) param = (cfg.scaleParam <= 0.0 || cfg.scaleParam == 1.0) ? 2.0 : cfg.scaleParam;   // :117-121
+  else if (scale == OSM_B200_SCALE_SEMITONE) param = cfg.scaleParam;
   mb.nBands = nBands;
   mb.nBins = blocksize;
   mb.coef.assign(blocksize, 0.f);
@@ -112,8 +152,8 @@ void build_mel(const osm_b200_melspec &cfg, int blocksize, double frameSizeSec, 
   float lofreq = (float)cfg.lofreq, hifreq = (float)cfg.hifreq;  // FLOAT_DMEM members, melspec.hpp:48
   if ((lofreq < 0.0) || (lofreq > Fs / 2.0) || (lofreq > hifreq)) lofreq = 0.0;             // :224
   if ((hifreq < lofreq) || (hifreq > Fs / 2.0) || (hifreq <= 0.0)) hifreq = Fs / (float)2.0; // :226
-  const float LoF = (float)mel_fwd(lofreq);                   // :228
-  const float HiF = (float)mel_fwd(hifreq);                   // :230
+  const float LoF = (float)scale_fwd(lofreq, scale, param);                   // :228
+  const float HiF = (float)scale_fwd(hifreq, scale, param);                   // :230
   long nLoF = (long)round((double)(lofreq / F0));             // FtoN, melspec.hpp:107-110
   long nHiF = (long)round((double)(hifreq / F0));
   if (nLoF > blocksize) nLoF = blocksize;
@@ -125,7 +165,7 @@ void build_mel(const osm_b200_melspec &cfg, int blocksize, double frameSizeSec, 
 
   const float mBandw = (HiF - LoF) / (M + (float)1.0);        // :394
   for (int m = 0; m <= nBands + 1; m++) cfs[m] = LoF + (float)m * mBandw;   // :395-397
-  for (int m = 1; m <= nBands; m++) mb.bandHz[m - 1] = mel_inv(cfs[m]);     // :408-411
+  for (int m = 1; m <= nBands; m++) mb.bandHz[m - 1] = scale_inv(cfs[m], scale, param);     // :408-411
 
   // channel map :427-438 ; NtoFmel(n,F0) = (float)fwd((float)n * F0), melspec.hpp:119-122
   int m = 0;
@@ -133,7 +173,7 @@ void build_mel(const osm_b200_melspec &cfg, int blocksize, double frameSizeSec, 
     if ((n <= nLoF) || (n >= nHiF)) {
       mb.chanMap[n] = -3;
     } else {
-      while (cfs[m] < (float)mel_fwd(((float)n) * F0)) {
+      while (cfs[m] < (float)scale_fwd(((float)n) * F0, scale, param)) {
         if (m > nBands) break;
         m++;
       }
@@ -143,7 +183,7 @@ void build_mel(const osm_b200_melspec &cfg, int blocksize, double frameSizeSec, 
   // rising-slope weights :441-447
   m = 0;
   for (long n = nLoF; n < nHiF; n++) {
-    const float nM = (float)mel_fwd(((float)n) * F0);
+    const float nM = (float)scale_fwd(((float)n) * F0, scale, param);
     while ((nM > cfs[m + 1]) && (m <= nBands)) m++;
     mb.coef[n] = (cfs[m + 1] - nM) / (cfs[m + 1] - cfs[m]);
   }

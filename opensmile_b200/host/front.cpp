@@ -255,6 +255,7 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
   if (osm_b200_component_defaults(t, &c) != OSM_B200_OK) { err = osm_b200_last_error(); return false; }
   snprintf(c.name, sizeof c.name, "%s", s.name.c_str());
   bool usePowerSet = false;
+  double melFirstNote = 27.5, melLogBase = 2.0;                  // cMelspec defaults (lldcore/melspec.cpp:48-49)
   if (t == OSM_B200_C_VECTOROPERATION) c.u.vectoroperation.operation = -1;   // the reference's default is "norm"
   for (const auto &kv : s.kv) {
     const std::string &f = kv.first, &v = kv.second;
@@ -320,10 +321,24 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
       case OSM_B200_C_MELSPEC:
         SETI("nBands", c.u.melspec.nBands) SETD("lofreq", c.u.melspec.lofreq) SETD("hifreq", c.u.melspec.hifreq)
         SETI("usePower", c.u.melspec.usePower) SETI("htkcompatible", c.u.melspec.htkcompatible)
-        if (f == "specScale") { if (v != "mel") { err = "cMelspec.specScale=" + v + " is not supported"; return false; } continue; }
+        if (f == "specScale") {                              // lldcore/melspec.cpp:100-126 (case-insensitive; semi / lin / log by prefix)
+          std::string lv = v;
+          for (char &ch : lv) ch = (char)tolower((unsigned char)ch);
+          if (lv == "mel") c.u.melspec.specScale = OSM_B200_SCALE_MEL;
+          else if (lv == "bark") c.u.melspec.specScale = OSM_B200_SCALE_BARK;
+          else if (lv == "bark_speex") c.u.melspec.specScale = OSM_B200_SCALE_BARK_SPEEX;
+          else if (lv == "bark_schroed") c.u.melspec.specScale = OSM_B200_SCALE_BARK_SCHROED;
+          else if (lv.compare(0, 4, "semi") == 0) c.u.melspec.specScale = OSM_B200_SCALE_SEMITONE;
+          else if (lv.compare(0, 3, "lin") == 0) c.u.melspec.specScale = OSM_B200_SCALE_LINEAR;
+          else if (lv.compare(0, 3, "log") == 0) c.u.melspec.specScale = OSM_B200_SCALE_LOG;
+          else c.u.melspec.specScale = OSM_B200_SCALE_MEL;   // unknown: the reference logs an error and assumes mel (:123-125)
+          continue;
+        }
+        if (f == "firstNote") { melFirstNote = num(v); continue; }
+        if (f == "logScaleBase") { melLogBase = num(v); continue; }
         if (f == "bwMethod") { if (v.compare(0, 2, "lr") != 0) { err = "cMelspec.bwMethod=" + v + " is not supported"; return false; } continue; }
         if (f == "inverse") { if (inum(v)) { err = "cMelspec.inverse is not supported"; return false; } continue; }
-        if (f == "showFbank" || f == "halfBwTarg" || f == "logScaleBase" || f == "firstNote") continue;
+        if (f == "showFbank" || f == "halfBwTarg") continue;
         break;
       case OSM_B200_C_MFCC:
         SETI("firstMfcc", c.u.mfcc.firstMfcc) SETI("lastMfcc", c.u.mfcc.lastMfcc) SETD("melfloor", c.u.mfcc.melfloor)
@@ -598,6 +613,8 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
   if (t == OSM_B200_C_MFCC && c.u.mfcc.lastMfcc <= -1000)          // lastMfcc = firstMfcc + nMfcc - 1 (lldcore/mfcc.cpp:77-82)
     c.u.mfcc.lastMfcc = c.u.mfcc.firstMfcc + (-1000 - c.u.mfcc.lastMfcc) - 1;
   if (t == OSM_B200_C_ACF && c.u.acf.cepstrum && !usePowerSet) c.u.acf.usePower = 0;   // dspcore/acf.cpp:91-99
+  if (t == OSM_B200_C_MELSPEC)
+    c.u.melspec.scaleParam = c.u.melspec.specScale == OSM_B200_SCALE_SEMITONE ? melFirstNote : (c.u.melspec.specScale == OSM_B200_SCALE_LOG ? melLogBase : 0.0);
   if (t == OSM_B200_C_WINDOWER) {                                  // window coefficients, dspcore/windower.cpp:83-113
     auto &w = c.u.windower;
     const std::string *a = s.get("alpha"), *a0 = s.get("alpha0"), *a1 = s.get("alpha1"), *a2 = s.get("alpha2"), *a3 = s.get("alpha3");

@@ -24,7 +24,7 @@ class Frontend(C.Structure):
 
 class Melspec(C.Structure):
     _fields_ = [("n_bands", C.c_int), ("lofreq", C.c_double), ("hifreq", C.c_double),
-                ("use_power", C.c_int), ("htkcompatible", C.c_int)]
+                ("use_power", C.c_int), ("htkcompatible", C.c_int), ("spec_scale", C.c_int), ("scale_param", C.c_double)]
 
 
 class Mfcc(C.Structure):

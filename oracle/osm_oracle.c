@@ -245,11 +245,53 @@ static double mel_fwd(double x) { return x > 0.0 ? 1127.0 * log(1.0 + x / 700.0)
 /* smileutil/smileUtil.c:1197-1198 (inverse) */
 static double mel_inv(double x) { return 700.0 * (exp(x / 1127.0) - 1.0); }
 
+/* smileDsp_specScaleTransfFwd (smileutil/smileUtil.c:1097-1147); scale numbering of osm_or_melspec.spec_scale */
+static double scale_fwd(double x, int scale, double param)
+{
+  double zz, f6;
+  switch (scale) {
+    case 6: return x > 0 ? log(x) / log(param) : 0.0;
+    case 4: return x / param > 1.0 ? 12.0 * (log(x / param) / log(2.0)) : 0.0;       /* smileMath_log2 */
+    case 1:
+      if (!(x > 0)) return 0.0;
+      zz = (26.81 / (1.0 + 1960.0 / x)) - 0.53;
+      if (zz < 2) return 0.85 * zz + 0.3;
+      if (zz > 20.1) return 1.22 * zz - 0.22 * 20.1;
+      return zz;
+    case 3: if (!(x > 0)) return 0.0; f6 = x / 600.0; return 6.0 * log(f6 + sqrt(f6 * f6 + 1.0));
+    case 2: return 13.1 * atan(.00074 * x) + 2.24 * atan(x * x * 1.85e-8) + 1e-4 * x;
+    case 5: return x;
+    default: return mel_fwd(x);
+  }
+}
+/* smileDsp_specScaleTransfInv (:1158-1204); bark_speex has no inverse there and falls through to the mel inverse */
+static double scale_inv(double x, int scale, double param)
+{
+  double zz, z0;
+  switch (scale) {
+    case 6: return exp(x * log(param));
+    case 4: return param * pow(2.0, x / 12.0);
+    case 1:
+      zz = x;
+      if (x > 20.1) zz = (x + 0.22 * 20.1) / 1.22;
+      else if (x < 2) zz = (x - 0.3) / 0.85;
+      z0 = 26.81 / (zz + 0.53);
+      return z0 != 1.0 ? 1960.0 / (z0 - 1.0) : 0.0;
+    case 3: return 600.0 * sinh(x / 6.0);
+    case 5: return x;
+    default: return mel_inv(x);
+  }
+}
+
 /* lldcore/melspec.cpp:184-455, standard (non-ERB) triangular bank, specScale=mel.
  * float/double casts follow the reference line by line. */
 static void mel_design(const osm_or_melspec *ms, long blocksize, double frame_size_sec, mel_bank *mb)
 {
   int nBands = ms->n_bands;
+  const int scale = ms->htkcompatible ? 0 : ms->spec_scale;   /* melspec.cpp:127-131 */
+  double param = 0.0;                                          /* :133-135 */
+  if (scale == 6) param = (ms->scale_param <= 0.0 || ms->scale_param == 1.0) ? 2.0 : ms->scale_param;
+  else if (scale == 4) param = ms->scale_param;
   mb->n_bins = blocksize; mb->n_bands = nBands;
   mb->coef = (float *)calloc(blocksize, sizeof(float));
   mb->chan_map = (long *)malloc(sizeof(long) * blocksize);
@@ -263,8 +305,8 @@ static void mel_design(const osm_or_melspec *ms, long blocksize, double frame_si
   float lofreq = (float)ms->lofreq, hifreq = (float)ms->hifreq; /* melspec.hpp:48 FLOAT_DMEM */
   if ((lofreq < 0.0) || (lofreq > Fs / 2.0) || (lofreq > hifreq)) lofreq = 0.0;      /* :224-225 */
   if ((hifreq < lofreq) || (hifreq > Fs / 2.0) || (hifreq <= 0.0)) hifreq = Fs / (float)2.0; /* :226-227 */
-  float LoF = (float)mel_fwd(lofreq);                     /* :228-229 */
-  float HiF = (float)mel_fwd(hifreq);                     /* :230-231 */
+  float LoF = (float)scale_fwd(lofreq, scale, param);                     /* :228-229 */
+  float HiF = (float)scale_fwd(hifreq, scale, param);                     /* :230-231 */
   long nLoF = (long)round((double)(lofreq / F0));         /* :232 + melspec.hpp:107-110 */
   long nHiF = (long)round((double)(hifreq / F0));
   if (nLoF > blocksize) nLoF = blocksize;
@@ -275,14 +317,14 @@ static void mel_design(const osm_or_melspec *ms, long blocksize, double frame_si
 
   float mBandw = (HiF - LoF) / (M + (float)1.0);          /* :394 */
   for (int m = 0; m <= nBands + 1; m++) mb->cfs[m] = LoF + (float)m * mBandw; /* :395-397 */
-  for (int m = 1; m <= nBands; m++) mb->band_hz[m - 1] = mel_inv(mb->cfs[m]); /* :408-411 */
+  for (int m = 1; m <= nBands; m++) mb->band_hz[m - 1] = scale_inv(mb->cfs[m], scale, param); /* :408-411 */
 
   /* channel map :427-438 ; NtoFmel(n,F0) = (float)mel_fwd((float)n * F0) (melspec.hpp:119-122) */
   int m = 0;
   for (long n = 0; n < blocksize; n++) {
     if ((n <= nLoF) || (n >= nHiF)) mb->chan_map[n] = -3;
     else {
-      while (mb->cfs[m] < (float)mel_fwd(((float)n) * F0)) {
+      while (mb->cfs[m] < (float)scale_fwd(((float)n) * F0, scale, param)) {
         if (m > nBands) break;
         m++;
       }
@@ -292,7 +334,7 @@ static void mel_design(const osm_or_melspec *ms, long blocksize, double frame_si
   /* rising slope weights :441-447 */
   m = 0;
   for (long n = nLoF; n < nHiF; n++) {
-    float nM = (float)mel_fwd(((float)n) * F0);
+    float nM = (float)scale_fwd(((float)n) * F0, scale, param);
     while ((nM > mb->cfs[m + 1]) && (m <= nBands)) m++;
     mb->coef[n] = (mb->cfs[m + 1] - nM) / (mb->cfs[m + 1] - mb->cfs[m]);
   }

@@ -50,6 +50,8 @@ typedef struct {
   double lofreq, hifreq;   /* cMelspec.lofreq / hifreq */
   int    use_power;        /* cMelspec.usePower */
   int    htkcompatible;    /* cMelspec.htkcompatible */
+  int    spec_scale;       /* cMelspec.specScale when htkcompatible = 0: 0 mel, 1 bark, 2 bark_speex, 3 bark_schroed, 4 semitone, 5 linear, 6 log */
+  double scale_param;      /* firstNote (semitone) / logScaleBase (log) */
 } osm_or_melspec;
 
 typedef struct {
