@@ -361,7 +361,34 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       ChainInfo ci;
       std::string base;
       auto wave_name = [&]() { return std::string(ci.wav->u.wavesource.outFieldName[0] ? ci.wav->u.wavesource.outFieldName : "pcm"); };
-      if (c->type == OSM_B200_C_MFCC || c->type == OSM_B200_C_PLP) {
+      if (c->type == OSM_B200_C_MELSPEC) {
+        // the band level itself as an output (log-mel spectrogram style graphs): the band values behind the kernel's filterbank
+        // phase, i.e. the cPlp back end with every stage switched off (doLog = doAud = doInvLog = doIDFT = doLP = doLpToCeps = 0
+        // hands the bands through, lldcore/plp.cpp:416-593) -- the band sums and the htk scaling are cMelspec's own (a-7)
+        const osm_b200_component *mel = c;
+        if (!resolve_mag_chain(single_input(mel), ci)) return OSM_B200_ERR_UNSUPPORTED;
+        osm_b200_status s2 = get_stream(ci, true, op.stream);
+        if (s2 != OSM_B200_OK) return s2;
+        const FrontEnd &fe = d.streams[op.stream].fe;
+        base = name_append_auto(*ci.mag, wave_name(), "fftMag");        // dspcore/fftmagphase.cpp:154
+        const auto &melp = mel->u.melspec;
+        if (melp.nBands < 1 || melp.nBands > 64 || melp.nBands >= fe.nBins) { err = "cMelspec.nBands out of range"; return OSM_B200_ERR_UNSUPPORTED; }
+        MelBank mb;
+        build_mel(melp, fe.nBins, fe.fftFrameSizeSec, mb);
+        d.mels.push_back(mb);
+        osm_b200_plp off;
+        memset(&off, 0, sizeof off);
+        off.firstCC = 0; off.lastCC = -1; off.nCeps = -1; off.compression = 1.0;
+        op.kind = SOP_PLP;
+        if (!build_plp(off, d.mels.back(), fe.frameStepSec, op.plp, err)) return OSM_B200_ERR_UNSUPPORTED;
+        op.plp.melIdx = (int)d.mels.size() - 1;
+        op.nOut = op.plp.nOut;
+        if (op.nOut != melp.nBands) { err = "internal: cMelspec pass-through width"; return OSM_B200_ERR_INVALID; }
+        FieldName fn;
+        fn.name = name_append_auto(*mel, base, nullptr);                // lldcore/melspec.cpp:175-178 (no default nameAppend)
+        fn.n = op.nOut; fn.arrNameOffset = 0;
+        op.fields.push_back(fn);
+      } else if (c->type == OSM_B200_C_MFCC || c->type == OSM_B200_C_PLP) {
         const osm_b200_component *mel = single_input(c);
         if (!mel || mel->type != OSM_B200_C_MELSPEC) { err = "cMfcc / cPlp must read a cMelspec level"; return OSM_B200_ERR_UNSUPPORTED; }
         if (!resolve_mag_chain(single_input(mel), ci)) return OSM_B200_ERR_UNSUPPORTED;

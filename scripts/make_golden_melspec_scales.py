@@ -35,6 +35,21 @@ def main():
             rows, _ = refrun.read_htk(o)
             out["mfcc_" + name] = rows.astype(np.float32)
             print(name, rows.shape, float(np.abs(rows).max()))
+        # the band level itself (cMelspec as the level a sink reads): exact values through an extra cHtkSink, names through a cCsvSink
+        for name, opts in (("mel", ["-scale", "mel"]), ("bark", ["-scale", "bark"]), ("htk", ["-melhtk", "1"])):
+            txt = open(conf).read() + ("\n[componentInstances:cComponentManager]\ninstance[mh].type=cHtkSink\ninstance[mc].type=cCsvSink\n"
+                                       "[mh:cHtkSink]\nreader.dmLevel=melspec\nfilename=%s\nparmKind=9\n"
+                                       "[mc:cCsvSink]\nreader.dmLevel=melspec\nfilename=%s\n" % (os.path.join(d, "m.htk"), os.path.join(d, "m.csv")))
+            c2 = os.path.join(d, "m.conf")
+            open(c2, "w").write(txt)
+            r = subprocess.run([refrun.SMILEXTRACT, "-C", c2, "-I", wav, "-O", os.path.join(d, "x.htk"), "-l", "1"] + opts, capture_output=True, text=True)
+            if r.returncode:
+                print(r.stderr[-2000:])
+                sys.exit(1)
+            rows, _ = refrun.read_htk(os.path.join(d, "m.htk"))
+            out["melspec_" + name] = rows.astype(np.float32)
+            out["melspec_names"] = np.array(open(os.path.join(d, "m.csv")).readline().strip().split(";")[2:])
+            print("melspec", name, rows.shape, float(np.abs(rows).max()), out["melspec_names"][:2])
     out["variants"] = np.array(list(VARIANTS))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "melspec_scales.npz"), **out)
 

@@ -61,3 +61,28 @@ def test_session_on_every_scale_equals_the_reference(name):
     ref = G["mfcc_" + name]
     assert rows.shape == ref.shape
     _close(rows, ref)
+
+
+def test_band_level_as_output_level_names():
+    """cMelspec as the level a sink reads (log-mel spectrogram style graphs): nBands elements named like the magnitude field
+    (lldcore/melspec.cpp:175-178: no default nameAppend)"""
+    from opensmile_b200.session import Session
+    s = Session(CONF, output_level="melspec", device=-1)
+    assert s.element_names() == [str(x) for x in G["melspec_names"]]
+    s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,opts", [("mel", {"scale": "mel"}), ("bark", {"scale": "bark"}), ("htk", {"melhtk": "1"})])
+def test_band_level_as_output_level(name, opts):
+    """the band sums themselves (two-tap filterbank, double product per bin, htk scaling 32767^2) against the reference's melspec
+    level: every band within 1e-5 of its scale"""
+    from opensmile_b200.session import Session
+    pcm = mixed_pcm(24000, 16000, seed=3)
+    s = Session(CONF, options=dict(opts), output_level="melspec", device=0)
+    rows, fo = s.extract_pcm(pcm, np.array([0, pcm.size], np.int64), 16000.0, 1)
+    s.close()
+    ref = G["melspec_" + name]
+    assert rows.shape == ref.shape
+    err = np.abs(rows - ref) / np.abs(ref).max(axis=0, keepdims=True)
+    assert err.max() < 1e-5, float(err.max())
