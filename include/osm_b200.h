@@ -156,6 +156,9 @@ typedef struct { int32_t inverse; int32_t zeroPadSymmetric; } osm_b200_transform
 
 typedef struct {            /* cFFTmagphase */
   int32_t magnitude, phase, normalise, power, dBpsd;  /* 1,0,0,0,0 */
+  /* normalise / power / dBpsd (dspcore/fftmagphase.cpp:223-255) are served where the level is the OUTPUT level (spectrogram.conf);
+   * the consumers on the path (cMelspec, cSpectral, cAcf, cSpecScale ...) read the plain magnitude */
+  double  dBpnorm, mindBp;  /* 90.302, -102.0 (mindBp is raised to dBpnorm - 120, :95-98) */
 } osm_b200_fftmagphase;
 
 /* cMelspec.specScale (lldcore/melspec.cpp:100-135; smileutil/smileUtil.c:1097-1204): the frequency scale the band centres are

@@ -68,7 +68,7 @@ class TransformFFT(C.Structure):
 
 
 class FFTmagphase(C.Structure):
-    _fields_ = [("magnitude", i32), ("phase", i32), ("normalise", i32), ("power", i32), ("dBpsd", i32)]
+    _fields_ = [("magnitude", i32), ("phase", i32), ("normalise", i32), ("power", i32), ("dBpsd", i32), ("dBpnorm", f64), ("mindBp", f64)]
 
 
 class Melspec(C.Structure):

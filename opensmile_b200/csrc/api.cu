@@ -168,6 +168,7 @@ struct StreamRt {
 struct OpRt {
   int kind = 0, stream = 0;
   int vSrcCol = 0, vN = 0, vOutCol = 0;     // SOP_VECOP
+  int magMode = 0; float magN = 1.f, magDbNorm = 0.f, magMinDb = 0.f;   // SOP_MAG: cFFTmagphase normalise / power / dBpsd
   SpectralParams sp;
   TimeOpParams tp;
   AcfPitchParams ap;
@@ -270,7 +271,7 @@ osm_b200_status osm_b200_component_defaults(int32_t type, osm_b200_component *c)
       c->u.windower.fade = 0.0; c->u.windower.squareRoot = 0;
       break;
     case OSM_B200_C_TRANSFORMFFT: c->u.transformfft.inverse = 0; c->u.transformfft.zeroPadSymmetric = 1; break;
-    case OSM_B200_C_FFTMAGPHASE: c->u.fftmagphase.magnitude = 1; break;
+    case OSM_B200_C_FFTMAGPHASE: c->u.fftmagphase.magnitude = 1; c->u.fftmagphase.dBpnorm = 90.302; c->u.fftmagphase.mindBp = -102.0; break;   // dspcore/fftmagphase.cpp:44-49
     case OSM_B200_C_MELSPEC:
       c->u.melspec.nBands = 26; c->u.melspec.lofreq = 20; c->u.melspec.hifreq = 8000;
       c->u.melspec.usePower = 0; c->u.melspec.htkcompatible = 1;
@@ -705,6 +706,7 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
     if (op.kind == SOP_MAG) {
       pl->st[op.stream].needTiles = true;
       rt.vN = d.streams[op.stream].fe.nBins; rt.vOutCol = op.outCol;
+      rt.magMode = op.magMode; rt.magN = (float)d.streams[op.stream].fe.nfft; rt.magDbNorm = op.magDbNorm; rt.magMinDb = op.magMinDb;
       pl->ops.push_back(rt);
       continue;
     }
@@ -1199,7 +1201,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
     if (t1 <= t0) continue;
     if (o.kind == SOP_MAG) {
       CU(launch_mag_rows(rt.dMag.p + (size_t)t0 * o.vN * rt.tileF, rt.dTiles.p + t0, t1 - t0, rt.tileF, o.vN, dS,
-                         pl->dStat.p, d.nStatic, o.vOutCol, st));
+                         pl->dStat.p, d.nStatic, o.vOutCol, st, o.magMode, o.magN, o.magDbNorm, o.magMinDb));
       pl->lastLaunches++;
       PROF("mag_rows_kernel");
       continue;

@@ -169,12 +169,13 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
     if (!ci.wav || ci.wav->type != OSM_B200_C_WAVESOURCE) { err = "cFramer must read the cWaveSource level"; return false; }
     return true;
   };
-  auto resolve_mag_chain = [&](const osm_b200_component *mag, ChainInfo &ci) -> bool {
+  auto resolve_mag_chain = [&](const osm_b200_component *mag, ChainInfo &ci, bool asOutput = false) -> bool {
     if (!mag || mag->type != OSM_B200_C_FFTMAGPHASE) { err = "expected a cFFTmagphase level"; return false; }
     ci.mag = mag;
     const auto &mp = mag->u.fftmagphase;
-    if (!mp.magnitude || mp.phase || mp.normalise || mp.power || mp.dBpsd) {
-      err = "cFFTmagphase: only magnitude=1 (no phase/normalise/power/dBpsd) is supported"; return false;
+    if ((!mp.magnitude && !mp.dBpsd) || mp.phase) { err = "cFFTmagphase: only magnitude=1 without phase is supported"; return false; }
+    if (!asOutput && (mp.normalise || mp.power || mp.dBpsd)) {
+      err = "cFFTmagphase: normalise / power / dBpsd are supported where the level is the output level only (its consumers read the plain magnitude)"; return false;
     }
     ci.fft = single_input(mag);
     if (!ci.fft || ci.fft->type != OSM_B200_C_TRANSFORMFFT) { err = "cFFTmagphase must read a cTransformFFT level"; return false; }
@@ -548,13 +549,20 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
         if (op.nOut < 1) { err = "component produces no output"; return OSM_B200_ERR_INVALID; }
       } else if (c->type == OSM_B200_C_FFTMAGPHASE) {
         // the magnitude level itself as an output (config/spectrum/spectrogram.conf): nBins elements
-        if (!resolve_mag_chain(c, ci)) return OSM_B200_ERR_UNSUPPORTED;
+        if (!resolve_mag_chain(c, ci, true)) return OSM_B200_ERR_UNSUPPORTED;
         osm_b200_status s2 = get_stream(ci, true, op.stream);
         if (s2 != OSM_B200_OK) return s2;
         op.kind = SOP_MAG;
         op.nOut = d.streams[op.stream].fe.nBins;
+        const auto &mp = c->u.fftmagphase;
+        const bool norm = mp.normalise || mp.dBpsd;                          // dBpsd implies normalise (:92)
+        op.magMode = mp.dBpsd ? 4 : (norm && mp.power ? 3 : (mp.power ? 2 : (norm ? 1 : 0)));
+        op.magDbNorm = (float)mp.dBpnorm;
+        op.magMinDb = (float)mp.mindBp;
+        if (op.magMinDb - op.magDbNorm < -120.0f) op.magMinDb = -120.0f + op.magDbNorm;      // :95-98
+        const char *fixed = mp.dBpsd ? "fftMag_dBsplPSD" : (mp.power && !norm ? "fftMag_PowSpec" : (mp.power ? "fftMag_PowSpecDens" : (norm ? "fftMag_SpecDens" : "fftMag")));   // :141-155
         FieldName fn;
-        fn.name = name_append_auto(*c, wave_name(), "fftMag");              // dspcore/fftmagphase.cpp:154
+        fn.name = name_append_auto(*c, wave_name(), fixed);
         fn.n = op.nOut; fn.arrNameOffset = 0;
         op.fields.push_back(fn);
       } else if (c->type == OSM_B200_C_VECTOROPERATION) {

@@ -209,7 +209,8 @@ cudaError_t launch_vecop_ll1(float *stat, int statStride, int srcCol, int n, int
 cudaError_t launch_spectral(const SpectralParams &p, cudaStream_t st);
 // cFFTmagphase as an output level: tile-major magnitude level [tile][nSrc][F] -> columns of the static rows
 cudaError_t launch_mag_rows(const float *mag, const OpTile *tiles, int nTiles, int F, int nSrc, const long long *statOff,
-                            float *stat, int statStride, int outCol, cudaStream_t st);
+                            float *stat, int statStride, int outCol, cudaStream_t st, int mode = 0, float fftN = 1.f, float dBpnorm = 0.f,
+                            float mindBp = 0.f);
 cudaError_t launch_energy(const TimeOpParams &p, cudaStream_t st);
 cudaError_t launch_mzcr(const TimeOpParams &p, cudaStream_t st);
 cudaError_t launch_intensity(const TimeOpParams &p, cudaStream_t st);

@@ -344,8 +344,27 @@ cudaError_t launch_spectral(const SpectralParams &p, cudaStream_t st)
 
 // cFFTmagphase as an output level (spectrogram): transposes a magnitude tile [nSrc][F] into rows of the
 // static level, 32 bins at a time through shared memory so that both sides are coalesced
+// mode (dspcore/fftmagphase.cpp:215-255, float statements): 0 magnitude, 1 normalise (|X| / N), 2 power, 3 normalise + power
+// (|X|^2 / N^2), 4 dBpsd = max(mindBp, dBpnorm + 10 log10(|X|^2 / N^2)) (bins 0 and N/2: 20 log10(|X| / N)); N = FFT size
+__device__ __forceinline__ float mag_variant(float m, int mode, bool edgeBin, float N, float dBpnorm, float mindBp)
+{
+  switch (mode) {
+    case 1: return __fmul_rn(__fdiv_rn(1.0f, N), m);
+    case 2: return __fmul_rn(m, m);
+    case 3: if (edgeBin) { const float v = __fmul_rn(__fdiv_rn(1.0f, N), m); return __fmul_rn(v, v); }
+            return __fmul_rn(__fdiv_rn(1.0f, __fmul_rn(N, N)), __fmul_rn(m, m));
+    case 4: {
+      const float v = edgeBin ? __fadd_rn(dBpnorm, __fmul_rn(20.0f, log10f(__fmul_rn(__fdiv_rn(1.0f, N), m))))
+                              : __fadd_rn(dBpnorm, __fmul_rn(10.0f, log10f(__fmul_rn(__fdiv_rn(1.0f, __fmul_rn(N, N)), __fmul_rn(m, m)))));
+      return v > mindBp ? v : mindBp;                 // MAX(mindBp, v): a NaN (log10 of 0 * ...) compares false and yields mindBp like the macro
+    }
+    default: return m;
+  }
+}
+
 __global__ void __launch_bounds__(256) mag_rows_kernel(const float *mag, const OpTile *tiles, int F, int nSrc,
-                                                       const long long *statOff, float *stat, int statStride, int outCol)
+                                                       const long long *statOff, float *stat, int statStride, int outCol,
+                                                       int mode, float fftN, float dBpnorm, float mindBp)
 {
   __shared__ float t[32][33];
   const OpTile tl = tiles[blockIdx.x];
@@ -357,16 +376,16 @@ __global__ void __launch_bounds__(256) mag_rows_kernel(const float *mag, const O
       t[kk][tx] = (k0 + kk < nSrc && tx < F) ? src[(size_t)(k0 + kk) * F + tx] : 0.f;
     __syncthreads();
     for (int ff = ty; ff < tl.nf; ff += 8)
-      if (k0 + tx < nSrc) dst[(long long)ff * statStride + k0 + tx] = t[tx][ff];
+      if (k0 + tx < nSrc) dst[(long long)ff * statStride + k0 + tx] = mag_variant(t[tx][ff], mode, k0 + tx == 0 || k0 + tx == nSrc - 1, fftN, dBpnorm, mindBp);
     __syncthreads();
   }
 }
 
 cudaError_t launch_mag_rows(const float *mag, const OpTile *tiles, int nTiles, int F, int nSrc, const long long *statOff,
-                            float *stat, int statStride, int outCol, cudaStream_t st)
+                            float *stat, int statStride, int outCol, cudaStream_t st, int mode, float fftN, float dBpnorm, float mindBp)
 {
   if (nTiles <= 0) return cudaSuccess;
-  mag_rows_kernel<<<nTiles, 256, 0, st>>>(mag, tiles, F, nSrc, statOff, stat, statStride, outCol);
+  mag_rows_kernel<<<nTiles, 256, 0, st>>>(mag, tiles, F, nSrc, statOff, stat, statStride, outCol, mode, fftN, dBpnorm, mindBp);
   return cudaGetLastError();
 }
 

@@ -198,6 +198,8 @@ struct StaticOp {
   int outCol = 0, nOut = 0;
   std::vector<FieldName> fields;   // names of the produced level
   int srcOp = -1;                  // SOP_VECOP: op whose columns of the static level are reduced (ll1)
+  int magMode = 0;                 // SOP_MAG: 0 magnitude, 1 normalise, 2 power, 3 both, 4 dBpsd (dspcore/fftmagphase.cpp:215-255)
+  float magDbNorm = 0.f, magMinDb = 0.f;
   MfccOp mfcc;
   PlpOp plp;
   SpectralOp spectral;

@@ -316,7 +316,7 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
         SETI("magnitude", c.u.fftmagphase.magnitude) SETI("phase", c.u.fftmagphase.phase) SETI("normalise", c.u.fftmagphase.normalise)
         SETI("power", c.u.fftmagphase.power) SETI("dBpsd", c.u.fftmagphase.dBpsd)
         if (f == "inverse" || f == "joinMagphase") { if (inum(v)) { err = "cFFTmagphase." + f + " is not supported"; return false; } continue; }
-        if (f == "dBpnorm" || f == "mindBp") continue;
+        SETD("dBpnorm", c.u.fftmagphase.dBpnorm) SETD("mindBp", c.u.fftmagphase.mindBp)
         break;
       case OSM_B200_C_MELSPEC:
         SETI("nBands", c.u.melspec.nBands) SETD("lofreq", c.u.melspec.lofreq) SETD("hifreq", c.u.melspec.hifreq)
