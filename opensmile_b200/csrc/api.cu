@@ -667,7 +667,8 @@ osm_b200_status osm_b200_plan_create(const osm_b200_component *comps, int32_t n_
                          g1.srcCol == 0 && g2.srcCol == 0 && g1.n == d.nStatic && g2.n == d.nStatic &&
                          g1.outCol == d.nStatic && g2.outCol == 2 * d.nStatic &&
                          g1.stages[0].kind == ST_DELTA && g2.stages[0].kind == ST_DELTA && g2.stages[1].kind == ST_DELTA &&
-                         g1.stages[0].win == g2.stages[0].win;
+                         g1.stages[0].win == g2.stages[0].win &&
+                         g1.stages[0].flags == 0 && g2.stages[0].flags == 0 && g2.stages[1].flags == 0;   // plain regression only
       // OSM_B200_NO_FUSE=1 forces the two-kernel path (used by the tests to cross-check both)
       const char *nf = getenv("OSM_B200_NO_FUSE");
       // the kernel keeps the statics of two tiles (2F frames): a row needs 2*halo+1 of them

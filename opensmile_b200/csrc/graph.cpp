@@ -882,11 +882,12 @@ osm_b200_status compile_graph(const osm_b200_component *comps, int n, const char
       Stage st;
       if (s->type == OSM_B200_C_DELTAREGRESSION) {
         const auto &p = s->u.deltaregression;
-        if (p.absOutput || p.halfWaveRect || p.relativeDelta) {
-          err = "cDeltaRegression: absOutput/halfWaveRect/relativeDelta are not supported"; return OSM_B200_ERR_UNSUPPORTED;
-        }
         if (p.deltawin < 1 || p.deltawin > 8) { err = "cDeltaRegression.deltawin must be 1..8"; return OSM_B200_ERR_UNSUPPORTED; }
-        st = Stage{ST_DELTA, p.deltawin, p.onlyInSegments ? 1 : 0};
+        // flags: bit 0 onlyInSegments, bit 1 relativeDelta, bit 2 absOutput, bit 3 halfWaveRect (dspcore/deltaRegression.cpp:100-168;
+        // halfWaveRect wins over absOutput, :157-165)
+        const int variant = (p.relativeDelta ? 2 : 0) | (p.halfWaveRect ? 8 : (p.absOutput ? 4 : 0));
+        if (variant && p.onlyInSegments) { err = "cDeltaRegression: relativeDelta / absOutput / halfWaveRect together with onlyInSegments are not supported"; return OSM_B200_ERR_UNSUPPORTED; }
+        st = Stage{ST_DELTA, p.deltawin, (p.onlyInSegments ? 1 : 0) | variant};
         if (p.onlyInSegments) {
           segId = -1;
           for (size_t q = 0; q < segComps.size(); q++) if (segComps[q] == s) segId = (int)q;

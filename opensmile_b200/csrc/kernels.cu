@@ -549,12 +549,17 @@ __global__ void __launch_bounds__(kPostThreads) post_kernel(const PostParams p)
         } else if (g.kind[s] == 0) {
           // deltaRegression.cpp:139-146 : num = sum_i i*(x[t+i]-x[t-i]) ; y = num / norm
           float num = 0.f;
+          const int fl = g.flags[s];                 // bit 1 relativeDelta, bit 2 absOutput, bit 3 halfWaveRect (:100-108,157-165)
           for (int i = 1; i <= W; i++) {
             const float later = post_read(cur, n, rowBase, t, W, navail, t + i, c);
             const float prior = post_read(cur, n, rowBase, t, W, navail, t - i, c);
-            num = __fadd_rn(num, __fmul_rn((float)i, __fsub_rn(later, prior)));
+            float delta = __fsub_rn(later, prior);
+            if (fl & 2) delta = prior != 0.0f ? __fdiv_rn(delta, fabsf(prior)) : 0.0f;
+            num = __fadd_rn(num, __fmul_rn((float)i, delta));
           }
           y = __fdiv_rn(num, norm);
+          if (fl & 8) { if (y < 0.0f) y = 0.0f; }
+          else if (fl & 4) { if (y < 0.0f) y = -y; }
         } else {
           // contourSmoother.cpp:84-117 : y = x[n]; y += x[n-w]; y += x[n+w]; y /= smaWin
           const int noZero = g.flags[s];

@@ -325,6 +325,17 @@ def delta(x, win):
     return out[:r]
 
 
+def delta_variant(x, win, relative=0, abs_output=0, half_wave=0):
+    """cDeltaRegression with relativeDelta / absOutput / halfWaveRect on a complete level"""
+    x = np.ascontiguousarray(x, np.float32)
+    T, K = x.shape
+    out = np.zeros((T + win, K), np.float32)
+    L = lib()
+    L.osm_or_delta_variant.restype = C.c_long
+    r = L.osm_or_delta_variant(_fp(x), C.c_long(T), C.c_int(K), C.c_int(win), C.c_int(relative), C.c_int(abs_output), C.c_int(half_wave), _fp(out))
+    return out[:r]
+
+
 def delta_chained(x, win, n0):
     """Stage reading a level of which only n0 frames exist when EOI is raised.
     Returns (out, c0) with c0 = the same quantity for the produced level."""

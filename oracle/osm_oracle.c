@@ -474,6 +474,34 @@ static long delta_stage(const float *in, long T, long n0, int K, int W, float *o
   return To;
 }
 
+/* cDeltaRegression with relativeDelta / absOutput / halfWaveRect (dspcore/deltaRegression.cpp:100-108 computeDelta, :157-165 the
+ * rectifications; halfWaveRect wins over absOutput), input level complete (n0 = T) */
+long osm_or_delta_variant(const float *in, long T, int K, int W, int relative, int abs_output, int half_wave, float *out)
+{
+  if (T <= 0) return 0;
+  float norm = 0.0f;
+  for (int i = 1; i <= W; i++) norm += (float)i * (float)i;
+  norm *= 2.0;
+  long To = T + W, c0 = T - W > 0 ? T - W : 0;
+  for (long t = 0; t < To; t++) {
+    long na = win_navail(t, T, c0, T);
+    for (int k = 0; k < K; k++) {
+      float num = 0.0f;
+      for (int i = 1; i <= W; i++) {
+        float prior = row_win(in, na, K, t, W, t - i)[k], later = row_win(in, na, K, t, W, t + i)[k];
+        float delta = later - prior;
+        if (relative) delta = prior != 0.0 ? delta / fabsf(prior) : 0.0;
+        num += (float)i * delta;
+      }
+      float y = num / norm;
+      if (half_wave) { if (y < 0.0) y = 0.0; }
+      else if (abs_output) { if (y < 0.0) y = -y; }
+      out[t * K + k] = y;
+    }
+  }
+  return To;
+}
+
 /* cDeltaRegression with onlyInSegments=1 (dspcore/deltaRegression.cpp:123-141, hpp:41-45): a pair
  * enters the sum only when neither value is 0 / NaN, and the member `norm` (initialised to
  * 2*sum i^2, :77-79) GROWS by i^2 for every accepted pair and is never reset, in

@@ -168,6 +168,7 @@ long osm_or_mzcr(const osm_or_frontend *fe, const osm_or_mzcr_cfg *mz, int windo
 /* cDeltaRegression with the reference's edge/phantom-frame semantics.
  * in: T x K ; out: (T + win) x K.  Returns T + win. */
 long osm_or_delta(const float *in, long T, int K, int win, float *out);
+long osm_or_delta_variant(const float *in, long T, int K, int W, int relative, int abs_output, int half_wave, float *out);
 /* cContourSmoother: in T x K ; out (T + (smaWin-1)/2) x K */
 long osm_or_sma(const float *in, long T, int K, int sma_win, int no_zero_sma, float *out);
 /* chained variants: `n0` = frames of the input level already written when EOI is raised
