@@ -74,8 +74,11 @@ def test_graph_errors():
     with pytest.raises(RuntimeError, match="exactly one cWaveSource"):
         Plan(comps[1:], "lld", device=-1)
     bad = components_mfcc12_0_d_a(16000.0)
-    bad[8] = _comp(capi.C_DELTAREGRESSION, "delta", "ft0", "ft0de", deltawin=2, relativeDelta=1)
+    bad[8] = _comp(capi.C_DELTAREGRESSION, "delta", "ft0", "ft0de", deltawin=2, relativeDelta=1, onlyInSegments=1)
     with pytest.raises(RuntimeError, match="not supported"):
+        Plan(bad, "lld", device=-1)
+    bad[8] = _comp(capi.C_DELTAREGRESSION, "delta", "ft0", "ft0de", deltawin=0)          # simple difference: refused
+    with pytest.raises(RuntimeError, match="deltawin"):
         Plan(bad, "lld", device=-1)
 
 
