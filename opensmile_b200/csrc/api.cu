@@ -16,6 +16,16 @@
 
 using namespace osm;
 
+// the _f32 builds of the PCM-reading launchers (kernels.cuh: OSM_F32_VARIANT), for plans whose input is not 16-bit integer
+namespace osm {
+cudaError_t launch_lld_f32(const LldParams &p, int nfft, int numSMs, cudaStream_t st, LldLaunchInfo *info);
+cudaError_t launch_energy_f32(const TimeOpParams &p, cudaStream_t st);
+cudaError_t launch_mzcr_f32(const TimeOpParams &p, cudaStream_t st);
+cudaError_t launch_intensity_f32(const TimeOpParams &p, cudaStream_t st);
+cudaError_t launch_formant_f32(const FormantParams &p, cudaStream_t st);
+cudaError_t launch_jitter_f32(const JitterParams &p, int u0, int u1, cudaStream_t st);
+}
+
 namespace {
 thread_local std::string g_err;
 }
@@ -1124,7 +1134,8 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
   const size_t nm = (size_t)(n_utt + 1);
   const long long *dU = pl->dMeta.p, *dR = dU + nm, *dS = dR + nm;
   PROF("begin");
-  if (d.fe0().format != OSM_B200_PCM_S16) {
+  const bool f32in = d.fe0().format != OSM_B200_PCM_S16;
+  if (f32in) {
     // inputs in another format than 16-bit integer: one conversion pass into mono floats (the caller reserved dPcmF)
     const long long *hU = pl->hMeta.p;
     const long long f0 = hU[u0], f1 = hU[u1];
@@ -1164,7 +1175,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
         CU(pr.dBand.reserve((size_t)pl->totalStat * kp.nBands + 64));
         kp.out = pr.dBand.p; kp.outStride = kp.nBands; kp.outCol = 0; kp.rowOff = dS;
       }
-      CU(launch_lld(kp, d.streams[si].fe.nfft, pl->numSMs, st, &pl->lastInfo));
+      CU((f32in ? launch_lld_f32 : launch_lld)(kp, d.streams[si].fe.nfft, pl->numSMs, st, &pl->lastInfo));
       pl->lastLaunches++;
       PROF("lld_kernel");
       if (pr.rasta) {
@@ -1232,7 +1243,7 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       JitterParams jp = o.jit;
       jp.pcm = reinterpret_cast<const int16_t *>(d_pcm);
       jp.uttOff = dU; jp.statOff = dS; jp.stat = pl->dStat.p; jp.errFlag = pl->dErr;
-      CU(launch_jitter(jp, u0, u1, ks));
+      CU((f32in ? launch_jitter_f32 : launch_jitter)(jp, u0, u1, ks));
       PROF("jitter_kernel");
     } else if (o.kind == SOP_PITCHACF) {
       AcfPitchParams ap = o.ap;
@@ -1251,9 +1262,10 @@ static osm_b200_status launch_range(osm_b200_plan *pl, const void *d_pcm, float 
       tp.uttOff = dU; tp.statOff = dS;
       tp.tiles = rt.dTiles.p + t0; tp.nTiles = t1 - t0;
       tp.stat = pl->dStat.p;
-      if (o.kind == SOP_FORMANT) { FormantParams fp = o.fmt; fp.tp = tp; CU(launch_formant(fp, st)); PROF("formant_kernel"); }
+      if (o.kind == SOP_FORMANT) { FormantParams fp = o.fmt; fp.tp = tp; CU((f32in ? launch_formant_f32 : launch_formant)(fp, st)); PROF("formant_kernel"); }
       else {
-        CU(o.kind == SOP_ENERGY ? launch_energy(tp, st) : (o.kind == SOP_INTENSITY ? launch_intensity(tp, st) : launch_mzcr(tp, st)));
+        CU(o.kind == SOP_ENERGY ? (f32in ? launch_energy_f32 : launch_energy)(tp, st)
+                                : (o.kind == SOP_INTENSITY ? (f32in ? launch_intensity_f32 : launch_intensity)(tp, st) : (f32in ? launch_mzcr_f32 : launch_mzcr)(tp, st)));
         PROF(o.kind == SOP_ENERGY ? "energy_kernel" : (o.kind == SOP_INTENSITY ? "intensity_kernel" : "mzcr_kernel"));
       }
     }

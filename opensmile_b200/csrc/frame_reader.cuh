@@ -11,7 +11,7 @@ namespace osm {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float td_pcm(const TimeOpParams &p, const int16_t *s)
 {
-  if (p.pcmF32) return *reinterpret_cast<const float *>(s);   // pre-converted mono float sample
+  if (OSM_PCM_F32_SUPPORT && p.pcmF32) return *reinterpret_cast<const float *>(s);   // pre-converted mono float sample
   // smileutil/smileUtil.c:2520-2534 : ((sum_c (float)x_c) / nChan) / 32767
   float tmp = (float)s[0];
   for (int c = 1; c < p.nChan; c++) tmp = __fadd_rn(tmp, (float)s[c]);

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(NT, MINB) lld_kernel(const LldParams p)
     phase ^= 1;
     {
       const int16_t *rp = reinterpret_cast<const int16_t *>(rawPcm + tg.mis) + tg.lead * nChan;   // sample frame 0 of the tile
-      const bool fastLoad = (tg.mis == 0) && (nChan <= 2) && !p.pcmF32;
+      const bool fastLoad = (tg.mis == 0) && (nChan <= 2) && !(OSM_PCM_F32_SUPPORT && p.pcmF32);
       const bool fastStore = (p.sPad == 0) || (hop % 8 == 0);
       for (int c = tid; c * 8 < count; c += NT) {
         const int i = c * 8;

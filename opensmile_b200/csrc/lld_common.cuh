@@ -90,7 +90,7 @@ __device__ __forceinline__ float div32767(float x)
 #define OSM_COLD __noinline__     // rarely executed paths stay out of the hot instruction stream
 __device__ __forceinline__ float pcm_to_float_generic(const int16_t *s, int nChan, int f32 = 0)
 {
-  if (f32) return *reinterpret_cast<const float *>(s);      // pre-converted mono float sample (LldParams::pcmF32)
+  if (OSM_PCM_F32_SUPPORT && f32) return *reinterpret_cast<const float *>(s);      // pre-converted mono float sample (LldParams::pcmF32)
   float tmp = (float)s[0];
   for (int c = 1; c < nChan; c++) tmp = __fadd_rn(tmp, (float)s[c]);
   if (nChan == 1) return div32767(tmp);

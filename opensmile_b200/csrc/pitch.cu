@@ -665,7 +665,7 @@ constexpr int kJitWarps = 4;
 
 __device__ __forceinline__ float jit_pcm(const int16_t *s, int nChan, int f32)       // smileutil/smileUtil.c:2520-2534
 {
-  if (f32) return *reinterpret_cast<const float *>(s);      // pre-converted mono float sample
+  if (OSM_PCM_F32_SUPPORT && f32) return *reinterpret_cast<const float *>(s);      // pre-converted mono float sample
   float tmp = (float)s[0];
   for (int c = 1; c < nChan; c++) tmp = tmp + (float)s[c];
   if (nChan > 1) tmp = tmp / (float)nChan;
