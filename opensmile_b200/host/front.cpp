@@ -659,6 +659,7 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
   bool unsupportedTimes = false, unsupportedSeg = false, unsupportedPeaks = false, peaksNoOverlap = false;
   std::map<int, double> samplePos;
   int dctLast = 6, dctN = -1;
+  bool frameModeFull = false, subWindow = false;
   double onsetThr = 0.0, onsetThrOn = 0.0, onsetThrOff = 0.0;
   bool onsetThrOnSet = false, onsetThrOffSet = false;
   auto &ON = fs.onset; auto &PO = fs.peaks; auto &CR = fs.crossings;
@@ -702,8 +703,9 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
   for (const auto &kv : s.kv) {
     const std::string &f = kv.first, &v = kv.second;
     if (is_common(f) || f == "noPostEOIprocessing" || f == "allowLastFrameIncomplete" || f == "frameListFile" || f == "frameList") continue;
-    if (f == "frameMode") { if (v.compare(0, 3, "ful") != 0) { err = "cFunctionals.frameMode=" + v + " is not supported (only full-input summaries)"; return false; } continue; }
-    if (f == "frameSize" || f == "frameStep" || f == "frameCenterSpecial" || f == "frameSizeFrames" || f == "frameStepFrames" || f == "frameCenter" || f == "frameCenterFrames") continue;
+    if (f == "frameMode") { frameModeFull = true; if (v.compare(0, 3, "ful") != 0) { err = "cFunctionals.frameMode=" + v + " is not supported (only full-input summaries)"; return false; } continue; }
+    if (f == "frameSize" || f == "frameStep" || f == "frameSizeFrames" || f == "frameStepFrames") { if (num(v) != 0.0) subWindow = true; continue; }
+    if (f == "frameCenterSpecial" || f == "frameCenter" || f == "frameCenterFrames") continue;
     if (f == "functionalsEnabled") { enabledList = v; continue; }
     if (f.compare(0, 19, "functionalsEnabled[") == 0) { enabledIdx[atoi(f.c_str() + 19)] = v; continue; }
     if (f == "nonZeroFuncts") { fs.nonZeroFuncts = inum(v); continue; }
@@ -804,6 +806,10 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     while (std::getline(ss, one, ';')) { one = trim(one); if (!one.empty()) names.push_back(one); }
   }
   if (names.empty()) { err = "cFunctionals '" + s.name + "': functionalsEnabled is empty"; return false; }
+  // the reference's default frameMode is "fixed" (core/winToVecProcessor.cpp:66): a section that does not say frameMode = full
+  // summarises sub-windows of frameSize seconds (MediaEval_Audio_IS12based_subwin2.conf: 2 s) -- not the full-input summary built here
+  if (!frameModeFull) { err = std::string("cFunctionals '") + s.name + "': frameMode = fixed (the default" + (subWindow ? ", with a frameSize" : "") + ") is not supported (only full-input summaries: frameMode = full)"; return false; }
+
   if (names.size() > OSM_B200_F_MAX_ENABLED) { err = "cFunctionals: too many enabled functionals"; return false; }
   fs.n_enabled = 0;
   for (const std::string &n : names) {

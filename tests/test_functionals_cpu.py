@@ -346,3 +346,35 @@ def test_summary_rows_are_written_like_the_reference_sink(tmp_path):
     s.write_files(GGF["egemaps_m24k"], [0, 1], 16000.0, 1, n_samples=[24000], csv_paths=[str(out)])
     s.close()
     _csv_close(out.read_text(), GGF["csv_egemaps_m24k"].tobytes().decode(), 2e-7)
+
+
+GMS = np.load(os.path.join(HERE, "golden", "more_summaries.npz"))
+MORE = [("is09-13/IS12_speaker_trait.conf", "IS12_speaker_trait", 5757), ("is09-13/IS13_ComParE.conf", "IS13_ComParE", 6373),
+        ("egemaps/v01a/eGeMAPSv01a.conf", "eGeMAPSv01a", 88), ("egemaps/v01b/eGeMAPSv01b.conf", "eGeMAPSv01b", 88),
+        ("gemaps/v01a/GeMAPSv01a.conf", "GeMAPSv01a", 62)]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "is09-13")), reason="reference configuration files not built (make -C oracle ref)")
+@pytest.mark.parametrize("conf,tag,n", MORE)
+def test_more_shipped_summary_configurations_open_with_the_reference_names(conf, tag, n):
+    if not os.path.exists(os.path.join(REFCONF, conf)):
+        pytest.skip("not among the configuration files copied next to the oracle build")
+    s = _session(os.path.join(REFCONF, conf), {"csvoutput": "x.csv"})
+    assert s.element_names() == [str(x) for x in GMS["names_" + tag]] and len(s.element_names()) == n
+    s.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "is09-13")), reason="reference configuration files not built (make -C oracle ref)")
+def test_sub_window_functionals_are_refused(tmp_path):
+    """the reference's default frameMode is "fixed": a cFunctionals section without frameMode = full summarises sub-windows (the
+    MediaEval configurations: frameSize = 2.0) -- refused by name instead of silently summarising the whole input"""
+    from opensmile_b200.session import SessionError
+    from opensmile_b200 import capi
+    txt = open(os.path.join(HERE, "configs", "func_variants.conf")).read().replace("REFCONF", REFCONF)
+    inc = "\\{REFCONF/shared/FrameModeFunctionals.conf.inc}".replace("REFCONF", REFCONF)
+    assert inc in txt
+    bad = tmp_path / "sub.conf"
+    bad.write_text(txt.replace(inc, "frameSize = 2.0\nframeStep = 2.0"))
+    with pytest.raises(SessionError) as e:
+        _session(str(bad), {"outA": "x.csv"})
+    assert e.value.status == capi.ERR_UNSUPPORTED and "frameMode = fixed" in str(e.value)

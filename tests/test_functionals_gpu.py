@@ -298,3 +298,24 @@ def test_summary_configuration_from_wav_files_to_csv(tmp_path):
     vals = np.array(head[1].split(";")[2:], np.float64)
     ref = GF["egemaps_v32k"][0]
     assert np.all(np.abs(vals - ref) <= 1e-4 * (np.abs(ref) + 1e-6))
+
+
+GMS = np.load(os.path.join(HERE, "golden", "more_summaries.npz"))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFCONF, "egemaps")), reason="reference configuration files not built (make -C oracle ref)")
+@pytest.mark.parametrize("conf,tag", [("egemaps/v01a/eGeMAPSv01a.conf", "eGeMAPSv01a"), ("egemaps/v01b/eGeMAPSv01b.conf", "eGeMAPSv01b"),
+                                      ("gemaps/v01a/GeMAPSv01a.conf", "GeMAPSv01a")])
+def test_earlier_gemaps_versions_end_to_end(conf, tag):
+    """the other shipped members of the GeMAPS family (same graphs as v01b / v02 with fewer parameters) against the reference's row for
+    one utterance: every value within 1e-4 of its own magnitude"""
+    from opensmile_b200.session import Session
+    pcm = mixed_pcm(24000, 16000, seed=3)
+    s = Session(os.path.join(REFCONF, conf), options={"csvoutput": "f.csv"}, device=0)
+    assert s.element_names() == [str(x) for x in GMS["names_" + tag]]
+    rows, fo_ = s.extract_pcm(pcm, np.array([0, pcm.size], np.int64), 16000.0, 1)
+    s.close()
+    ref = GMS["row_" + tag][0]
+    assert rows.shape == (1, len(ref))
+    rel = np.abs(rows[0] - ref) / (np.abs(ref) + 1e-6)
+    assert rel.max() < 1e-4, (s and None, str(GMS["names_" + tag][int(np.argmax(rel))]), float(rows[0][int(np.argmax(rel))]), float(ref[int(np.argmax(rel))]))
