@@ -702,6 +702,10 @@ bool to_functionals(const Section &s, osm_b200_functionals_spec &fs, std::string
     {"Crossings.zcr", &CR.zcr}, {"Crossings.mcr", &CR.mcr}, {"Crossings.amean", &CR.amean}};
   for (const auto &kv : s.kv) {
     const std::string &f = kv.first, &v = kv.second;
+    // EOIlevel > 0 makes the summary wait for later end-of-input passes (more rows of the window processors behind it); a frame list
+    // cuts the input into several summaries: both change what the rows mean and are refused rather than ignored
+    if (f == "EOIlevel" && inum(v) != 0) { err = "cFunctionals.EOIlevel != 0 is not supported (the summary is taken at the first end-of-input tick)"; return false; }
+    if ((f == "frameListFile" || f == "frameList") && !trim(v).empty()) { err = "cFunctionals." + f + " is not supported"; return false; }
     if (is_common(f) || f == "noPostEOIprocessing" || f == "allowLastFrameIncomplete" || f == "frameListFile" || f == "frameList") continue;
     if (f == "frameMode") { frameModeFull = true; if (v.compare(0, 3, "ful") != 0) { err = "cFunctionals.frameMode=" + v + " is not supported (only full-input summaries)"; return false; } continue; }
     if (f == "frameSize" || f == "frameStep" || f == "frameSizeFrames" || f == "frameStepFrames") { if (num(v) != 0.0) subWindow = true; continue; }

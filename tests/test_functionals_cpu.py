@@ -378,3 +378,8 @@ def test_sub_window_functionals_are_refused(tmp_path):
     with pytest.raises(SessionError) as e:
         _session(str(bad), {"outA": "x.csv"})
     assert e.value.status == capi.ERR_UNSUPPORTED and "frameMode = fixed" in str(e.value)
+    # EOIlevel > 0 would let the summary see the rows the window processors append in later end-of-input passes
+    bad.write_text(txt.replace("functionalsEnabled = Means\n", "functionalsEnabled = Means\nEOIlevel = 1\n"))
+    with pytest.raises(SessionError) as e:
+        _session(str(bad), {"outA": "x.csv"})
+    assert e.value.status == capi.ERR_UNSUPPORTED and "EOIlevel" in str(e.value)
