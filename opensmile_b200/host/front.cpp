@@ -284,8 +284,18 @@ bool to_component(const Section &s, osm_b200_component &c, std::string &err)
       case OSM_B200_C_WAVESOURCE:
         SETI("monoMixdown", c.u.wavesource.monoMixdown)
         if (f == "outFieldName") { snprintf(c.u.wavesource.outFieldName, OSM_B200_NAME_LEN, "%s", v.c_str()); continue; }
-        if (f == "filename" || f == "start" || f == "end" || f == "endrel" || f == "startSamples" || f == "endSamples" ||
-            f == "endrelSamples" || f == "noHeader" || f == "properTimestamps" || f == "period" || f == "sampleRate" ||
+        // reading a part of the file (iocore/waveSource.cpp:48-58) or header-less PCM changes the samples the graph sees: refused
+        // unless left at the defaults (start 0, end -1 = to the end, endrel 0, noHeader 0), never silently ignored
+        if (f == "start" || f == "startSamples" || f == "endrel" || f == "endrelSamples") {
+          if (num(v) != 0.0) { err = "cWaveSource." + f + " != 0 is not supported (whole files are read)"; return false; }
+          continue;
+        }
+        if (f == "end" || f == "endSamples") {
+          if (num(v) >= 0.0) { err = "cWaveSource." + f + " is not supported (whole files are read)"; return false; }
+          continue;
+        }
+        if (f == "noHeader") { if (inum(v)) { err = "cWaveSource.noHeader=1 (raw PCM files) is not supported"; return false; } continue; }
+        if (f == "filename" || f == "properTimestamps" || f == "period" || f == "sampleRate" ||
             f == "channels" || f == "nBits" || f == "nBPS" || f == "fieldName") continue;
         break;
       case OSM_B200_C_FRAMER:

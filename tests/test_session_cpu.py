@@ -296,3 +296,17 @@ def test_window_tables_equal_the_reference(tmp_path, case):
     ref = g[case]
     # the reference's CSV prints 7 significant digits of the float product 1.0 * (float)w
     assert np.all(np.abs(out - ref) <= 1e-6 * np.abs(ref) + 1e-12), (case, float(np.abs(out - ref).max()))
+
+
+def test_partial_file_options_are_refused_not_ignored():
+    """cWaveSource.start / end / endrel select a part of the input file in the reference (iocore/waveSource.cpp:48-58); whole files
+    are read here, so any value but the defaults is an error instead of a silently different result"""
+    conf = os.path.join(REF_CONF, "mfcc", "MFCC12_0_D_A.conf")
+    if not os.path.exists(conf):
+        pytest.skip("reference configs not built into oracle/_ref")
+    Session(conf, options={"O": "x.htk", "start": "0", "end": "-1"}, device=-1).close()
+    for opts, needle in (({"start": "1.5"}, "start"), ({"end": "2.0"}, "end")):
+        with pytest.raises(SessionError) as e:
+            Session(conf, options=dict(opts, O="x.htk"), device=-1)
+        assert e.value.status == capi.ERR_UNSUPPORTED or e.value.status == capi.ERR_INVALID
+        assert needle in str(e.value)
