@@ -86,3 +86,16 @@ def test_band_level_as_output_level(name, opts):
     assert rows.shape == ref.shape
     err = np.abs(rows - ref) / np.abs(ref).max(axis=0, keepdims=True)
     assert err.max() < 1e-5, float(err.max())
+
+
+@pytest.mark.parametrize("name,scale,htk", [("mel", 0, 0), ("bark", 1, 0), ("htk", 0, 1)])
+def test_oracle_band_level_equals_the_reference_melspec_level(name, scale, htk):
+    """the oracle's band sums (tap of oracle.mfcc_d_a) against the reference's melspec level, incl. the htk scaling 32767^2"""
+    fe = oracle.Frontend(16000.0, 0.025, 0.010, 0, 0.0, oracle.WIN["ham"], 0.4, 1.0, 0.0, 0)
+    ms = oracle.Melspec(26, 20.0, 8000.0, 1, htk, scale, 0.0)
+    mf = oracle.Mfcc(0, 12, 22.0, 1e-8, 0)
+    _, _, mel = oracle.mfcc_d_a(mixed_pcm(24000, 16000, seed=3), 16000, cfg=(fe, ms, mf), taps=True)
+    ref = G["melspec_" + name]
+    assert mel.shape == ref.shape
+    err = np.abs(mel - ref) / np.abs(ref).max(axis=0, keepdims=True)
+    assert err.max() < 1e-5, float(err.max())

@@ -55,3 +55,22 @@ def test_values_equal_the_reference(name):
         peak = np.abs(ref).max(axis=1, keepdims=True)                  # per frame: the FFT's error scales with the frame's peak
         lin = 2.0 if "pow" in name else 1.0
         assert (np.abs(rows - ref) / peak).max() < 2e-6 * lin, float((np.abs(rows - ref) / peak).max())
+
+
+def test_oracle_restatement_of_the_variants_on_the_reference_magnitudes():
+    """oracle-side restatement (numpy, float32) of dspcore/fftmagphase.cpp:223-255 applied to the reference's own magnitude rows
+    reproduces its variant rows (the reference squares re / im directly, so the power forms differ from |X|^2 by an ulp or two)"""
+    mag = G["rows_mag"].astype(np.float32)
+    N = np.float32(512.0)
+    edge = np.zeros(mag.shape[1], bool); edge[0] = edge[-1] = True
+    dens = (np.float32(1.0) / N) * mag
+    powd = np.where(edge, dens * dens, (np.float32(1.0) / (N * N)) * (mag * mag))
+    for name, got in (("specdens", dens), ("powspec", mag * mag), ("powspecdens", powd)):
+        ref = G["rows_" + name]
+        assert np.all(np.abs(got - ref) <= 4e-7 * np.abs(ref) + 1e-30), name
+    for name, norm, floor in (("dbpsd", 90.302, -102.0), ("dbpsd_floor", 60.0, -20.0)):
+        floor = max(floor, norm - 120.0)
+        with np.errstate(divide="ignore"):
+            v = np.where(edge, np.float32(norm) + np.float32(20.0) * np.log10(dens), np.float32(norm) + np.float32(10.0) * np.log10(powd))
+        got = np.maximum(np.float32(floor), v.astype(np.float32))
+        assert np.abs(got - G["rows_" + name]).max() < 2e-4, name
