@@ -543,7 +543,7 @@ def measure(w, args, rank, world, local_rank, dist, steps, with_cpu, sampler=Non
 def measure_summaries(n_utt=1000):
     """SURVEY.md 8(f)-3, reported beside the LLD workloads (not a headline number): the shipped summary configurations end to end
     through the session API from host PCM -- LLD plan, rows resident in HBM, cFunctionals instances + glue, one row per utterance
-    copied back.  Wall clock around the blocking call (it synchronises), after one warm-up call."""
+    copied back.  Wall clock around the blocking call (it synchronises), after one warm-up call on the same batch."""
     import time
     import numpy as np
     from opensmile_b200 import Session
@@ -558,7 +558,7 @@ def measure_summaries(n_utt=1000):
             continue
         try:
             s = Session(conf, options={"csvoutput": "x.csv"}, device=0)
-            s.extract_pcm(pcm[:48000 * 8], off[:9], 16000.0, 1)
+            s.extract_pcm(pcm, off, 16000.0, 1)                  # warm-up with the same batch: buffers sized, modules loaded
             t0 = time.perf_counter()
             rows, _ = s.extract_pcm(pcm, off, 16000.0, 1)
             dt = time.perf_counter() - t0
